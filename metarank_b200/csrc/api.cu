@@ -1,0 +1,471 @@
+// C ABI of libmrgpu.so (include/mr_b200.h): context, booster handles, predictMat.
+// Everything here is host code around the kernels; exceptions are converted to
+// mr_status at the boundary and never escape.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "gbdt_kernels.cuh"
+#include "gbdt_model.h"
+
+using namespace mr;
+
+namespace {
+thread_local std::string t_last_error;
+
+template <class F> mr_status guard(F &&f) {
+  try {
+    f();
+    return MR_OK;
+  } catch (const Error &e) {
+    t_last_error = e.what();
+    return e.code;
+  } catch (const std::bad_alloc &) {
+    t_last_error = "out of host memory";
+    return MR_ERR_INVALID_ARG;
+  } catch (const std::exception &e) {
+    t_last_error = e.what();
+    return MR_ERR_INVALID_ARG;
+  } catch (...) {
+    t_last_error = "unknown error";
+    return MR_ERR_INVALID_ARG;
+  }
+}
+}  // namespace
+
+// A Lane is what one in-flight host call needs: a stream, pinned staging and device
+// scratch.  Lanes are checked out from the context's pool, so concurrent JVM threads
+// never share buffers and never allocate on the hot path once warmed up.
+struct Lane {
+  cudaStream_t stream = nullptr;
+  uint8_t *h_pinned = nullptr;
+  size_t h_bytes = 0;
+  uint8_t *d_buf = nullptr;
+  size_t d_bytes = 0;
+  void ensure(size_t hb, size_t db) {
+    if (hb > h_bytes) {
+      if (h_pinned) cudaFreeHost(h_pinned);
+      h_pinned = nullptr;
+      h_bytes = 0;
+      size_t n = std::max(hb, h_bytes * 2);
+      MR_CUDA_CHECK(cudaMallocHost((void **)&h_pinned, n));
+      h_bytes = n;
+    }
+    if (db > d_bytes) {
+      if (d_buf) cudaFree(d_buf);
+      d_buf = nullptr;
+      d_bytes = 0;
+      size_t n = std::max(db, d_bytes * 2);
+      MR_CUDA_CHECK(cudaMalloc((void **)&d_buf, n));
+      d_bytes = n;
+    }
+  }
+};
+
+struct mr_ctx {
+  int device = 0;
+  int num_sms = 0;
+  std::mutex mu;
+  std::vector<std::unique_ptr<Lane>> free_lanes;
+  std::atomic<int> live_models{0};
+
+  std::unique_ptr<Lane> checkout() {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      if (!free_lanes.empty()) {
+        auto l = std::move(free_lanes.back());
+        free_lanes.pop_back();
+        return l;
+      }
+    }
+    auto l = std::make_unique<Lane>();
+    MR_CUDA_CHECK(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
+    return l;
+  }
+  void checkin(std::unique_ptr<Lane> l) {
+    std::lock_guard<std::mutex> g(mu);
+    free_lanes.push_back(std::move(l));
+  }
+};
+
+struct LaneGuard {
+  mr_ctx *ctx;
+  std::unique_ptr<Lane> lane;
+  explicit LaneGuard(mr_ctx *c) : ctx(c), lane(c->checkout()) {}
+  ~LaneGuard() {
+    if (lane) ctx->checkin(std::move(lane));
+  }
+  Lane *operator->() { return lane.get(); }
+};
+
+struct mr_model {
+  mr_ctx *ctx = nullptr;
+  HostModel host;
+  PackedModel packed;
+  uint8_t *d_model = nullptr;
+  ChunkDesc *d_chunks = nullptr;
+  std::atomic<bool> closed{false};
+  std::atomic<int> inflight{0};
+  std::mutex mu;  // guards repacking / device buffers
+  int opt_threads = 0, opt_variant = -1, opt_ilp = 0, opt_chunk_kb = 0;
+
+  void upload() {
+    if (d_model) cudaFree(d_model);
+    if (d_chunks) cudaFree(d_chunks);
+    d_model = nullptr;
+    d_chunks = nullptr;
+    MR_CUDA_CHECK(cudaMalloc((void **)&d_model, packed.bytes.size()));
+    MR_CUDA_CHECK(cudaMemcpy(d_model, packed.bytes.data(), packed.bytes.size(), cudaMemcpyHostToDevice));
+    MR_CUDA_CHECK(cudaMalloc((void **)&d_chunks, packed.chunks.size() * sizeof(ChunkDesc)));
+    MR_CUDA_CHECK(cudaMemcpy(d_chunks, packed.chunks.data(), packed.chunks.size() * sizeof(ChunkDesc),
+                             cudaMemcpyHostToDevice));
+  }
+  void repack() {
+    // Default policy: keep the whole ensemble resident in shared memory when it leaves room
+    // for a feature tile; otherwise stream it in ~32 KB chunks (two buffers in flight).
+    size_t budget;
+    if (opt_chunk_kb > 0) {
+      budget = (size_t)opt_chunk_kb * 1024;
+    } else {
+      budget = 32 * 1024;
+    }
+    packed = pack_model(host, budget);
+    upload();
+  }
+  void release_device() {
+    if (d_model) cudaFree(d_model);
+    if (d_chunks) cudaFree(d_chunks);
+    d_model = nullptr;
+    d_chunks = nullptr;
+  }
+  ScoreLaunch launch_desc(const double *d_values, int rows, int cols, double *d_out) const {
+    ScoreLaunch L;
+    L.d_model = d_model;
+    L.d_chunks = d_chunks;
+    L.n_chunks = (int)packed.chunks.size();
+    L.max_chunk_bytes = packed.max_chunk_bytes;
+    L.kind = host.kind;
+    L.has_cat = host.has_cat;
+    L.has_zero = host.has_zero_missing;
+    L.base_score = host.base_score;
+    L.n_features = host.n_features;
+    L.d_values = d_values;
+    L.rows = rows;
+    L.cols = cols;
+    L.d_out = d_out;
+    L.threads = opt_threads;
+    L.variant = opt_variant;
+    L.ilp = opt_ilp;
+    return L;
+  }
+};
+
+namespace {
+
+struct InflightGuard {
+  mr_model *m;
+  explicit InflightGuard(mr_model *mm) : m(mm) { m->inflight++; }
+  ~InflightGuard() { m->inflight--; }
+};
+
+void check_model(mr_model *m) {
+  if (!m) fail(MR_ERR_INVALID_ARG, "model handle is null");
+  if (m->closed.load()) fail(MR_ERR_CLOSED, "booster is closed");
+}
+
+void check_matrix(mr_model *m, const void *values, int rows, int cols, const void *out) {
+  if (rows < 0 || cols < 0) fail(MR_ERR_INVALID_ARG, "negative matrix dimension");
+  if (rows > 0 && (!values || !out)) fail(MR_ERR_INVALID_ARG, "null matrix or output pointer");
+  if (rows > 0 && cols != m->host.n_features)
+    fail(MR_ERR_INVALID_ARG, "matrix has %d columns, the booster was trained with %d features", cols,
+         m->host.n_features);
+  if ((int64_t)rows * cols >= (int64_t)INT32_MAX)
+    fail(MR_ERR_INVALID_ARG, "matrix of %d x %d exceeds the 2^31 cell limit", rows, cols);
+}
+
+mr_model *make_model(mr_ctx *ctx, HostModel &&hm, int n_features) {
+  if (n_features > 0 && hm.n_features != n_features)
+    fail(MR_ERR_FEATURE_MISMATCH, "booster reads %d features, dataset descriptor has %d", hm.n_features, n_features);
+  auto m = std::make_unique<mr_model>();
+  m->ctx = ctx;
+  m->host = std::move(hm);
+  MR_CUDA_CHECK(cudaSetDevice(ctx->device));
+  m->repack();
+  ctx->live_models++;
+  return m.release();
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *mr_last_error(void) { return t_last_error.c_str(); }
+const char *mr_version(void) { return "libmrgpu 0.1.0 sm_100a"; }
+int64_t mr_kernel_launches(void) { return (int64_t)g_kernel_launches; }
+
+mr_status mr_init(int32_t device, mr_ctx **out) {
+  return guard([&] {
+    if (!out) fail(MR_ERR_INVALID_ARG, "out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+      fail(MR_ERR_NO_DEVICE, "no CUDA device available (%s); libmrgpu has no CPU fallback",
+           e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) fail(MR_ERR_INVALID_ARG, "device %d out of range [0,%d)", device, n);
+    cudaDeviceProp prop;
+    MR_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+      fail(MR_ERR_NO_DEVICE, "device %d is sm_%d%d; libmrgpu is built for sm_100a only", device, prop.major, prop.minor);
+    MR_CUDA_CHECK(cudaSetDevice(device));
+    auto ctx = std::make_unique<mr_ctx>();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    *out = ctx.release();
+  });
+}
+
+mr_status mr_shutdown(mr_ctx *ctx) {
+  return guard([&] {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto &l : ctx->free_lanes) {
+      if (l->h_pinned) cudaFreeHost(l->h_pinned);
+      if (l->d_buf) cudaFree(l->d_buf);
+      if (l->stream) cudaStreamDestroy(l->stream);
+    }
+    delete ctx;
+  });
+}
+
+mr_status mr_model_load(mr_ctx *ctx, int32_t kind, const uint8_t *blob, size_t len, int32_t n_features,
+                        mr_model **out) {
+  return guard([&] {
+    if (!ctx || !blob || !out) fail(MR_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    HostModel hm;
+    if (kind == MR_BOOSTER_LIGHTGBM) hm = parse_lightgbm_text(blob, len);
+    else if (kind == MR_BOOSTER_XGBOOST) hm = parse_xgboost_model(blob, len);
+    else fail(MR_ERR_UNSUPPORTED, "unsupported booster tag %d", kind);
+    *out = make_model(ctx, std::move(hm), n_features);
+  });
+}
+
+mr_status mr_model_load_metarank(mr_ctx *ctx, const uint8_t *blob, size_t len, const char *const *feature_names,
+                                 int32_t n_names, mr_model **out) {
+  return guard([&] {
+    if (!ctx || !blob || !out) fail(MR_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    std::vector<std::string> names;
+    int kind = 0;
+    size_t b = 0, e = 0;
+    parse_metarank_frame(blob, len, names, kind, b, e);
+    if (n_names >= 0) {
+      bool same = (size_t)n_names == names.size();
+      for (int i = 0; same && i < n_names; i++) same = feature_names && feature_names[i] && names[i] == feature_names[i];
+      if (!same) {
+        std::string exp, act;
+        for (auto &s : names) exp += (exp.empty() ? "" : ", ") + s;
+        for (int i = 0; i < n_names; i++) act += (act.empty() ? "" : ", ") + std::string(feature_names && feature_names[i] ? feature_names[i] : "<null>");
+        fail(MR_ERR_FEATURE_MISMATCH,
+             "booster trained with List(%s) features, but config defines List(%s)\nYou may need to retrain the model with the newer config",
+             exp.c_str(), act.c_str());
+      }
+    }
+    HostModel hm = kind == 0 ? parse_lightgbm_text(blob + b, e - b) : parse_xgboost_model(blob + b, e - b);
+    *out = make_model(ctx, std::move(hm), 0);
+  });
+}
+
+mr_status mr_model_predict_mat_device(mr_model *m, const double *d_values, int32_t rows, int32_t cols,
+                                      double *d_out_scores, void *cuda_stream) {
+  return guard([&] {
+    check_model(m);
+    InflightGuard ig(m);
+    check_matrix(m, d_values, rows, cols, d_out_scores);
+    if (rows == 0) return;
+    ScoreLaunch L = m->launch_desc(d_values, rows, cols, d_out_scores);
+    launch_gbdt_score(L, m->ctx->num_sms, (cudaStream_t)cuda_stream);
+  });
+}
+
+mr_status mr_model_predict_mat(mr_model *m, const double *values, int32_t rows, int32_t cols, double *out_scores) {
+  return guard([&] {
+    check_model(m);
+    InflightGuard ig(m);
+    check_matrix(m, values, rows, cols, out_scores);
+    if (rows == 0) return;
+    MR_CUDA_CHECK(cudaSetDevice(m->ctx->device));
+    LaneGuard lane(m->ctx);
+    const size_t in_bytes = (size_t)rows * cols * sizeof(double), out_bytes = (size_t)rows * sizeof(double);
+    const size_t d_in_off = 0, d_out_off = (in_bytes + 255) & ~size_t(255);
+    lane->ensure(in_bytes + out_bytes, d_out_off + out_bytes);
+    // stage through pinned memory so both copies are truly asynchronous DMA
+    memcpy(lane->h_pinned, values, in_bytes);
+    double *d_in = (double *)(lane->d_buf + d_in_off), *d_out = (double *)(lane->d_buf + d_out_off);
+    MR_CUDA_CHECK(cudaMemcpyAsync(d_in, lane->h_pinned, in_bytes, cudaMemcpyHostToDevice, lane->stream));
+    ScoreLaunch L = m->launch_desc(d_in, rows, cols, d_out);
+    launch_gbdt_score(L, m->ctx->num_sms, lane->stream);
+    MR_CUDA_CHECK(cudaMemcpyAsync(lane->h_pinned + in_bytes, d_out, out_bytes, cudaMemcpyDeviceToHost, lane->stream));
+    MR_CUDA_CHECK(cudaStreamSynchronize(lane->stream));
+    memcpy(out_scores, lane->h_pinned + in_bytes, out_bytes);
+  });
+}
+
+mr_status mr_model_count_path(mr_model *m, const double *values, int32_t rows, int32_t cols, double *mean_path) {
+  return guard([&] {
+    check_model(m);
+    InflightGuard ig(m);
+    if (!mean_path) fail(MR_ERR_INVALID_ARG, "mean_path is null");
+    std::vector<double> scratch((size_t)std::max(rows, 1));
+    check_matrix(m, values, rows, cols, scratch.data());
+    *mean_path = 0.0;
+    if (rows == 0 || m->host.trees.empty()) return;
+    MR_CUDA_CHECK(cudaSetDevice(m->ctx->device));
+    LaneGuard lane(m->ctx);
+    const size_t in_bytes = (size_t)rows * cols * sizeof(double), out_bytes = (size_t)rows * sizeof(double);
+    const size_t d_out_off = (in_bytes + 255) & ~size_t(255), d_cnt_off = (d_out_off + out_bytes + 255) & ~size_t(255);
+    lane->ensure(in_bytes + 8, d_cnt_off + 8);
+    memcpy(lane->h_pinned, values, in_bytes);
+    MR_CUDA_CHECK(cudaMemcpyAsync(lane->d_buf, lane->h_pinned, in_bytes, cudaMemcpyHostToDevice, lane->stream));
+    MR_CUDA_CHECK(cudaMemsetAsync(lane->d_buf + d_cnt_off, 0, 8, lane->stream));
+    ScoreLaunch L = m->launch_desc((double *)lane->d_buf, rows, cols, (double *)(lane->d_buf + d_out_off));
+    L.d_visited = (unsigned long long *)(lane->d_buf + d_cnt_off);
+    launch_gbdt_score(L, m->ctx->num_sms, lane->stream);
+    unsigned long long cnt = 0;
+    MR_CUDA_CHECK(cudaMemcpyAsync(lane->h_pinned, lane->d_buf + d_cnt_off, 8, cudaMemcpyDeviceToHost, lane->stream));
+    MR_CUDA_CHECK(cudaStreamSynchronize(lane->stream));
+    memcpy(&cnt, lane->h_pinned, 8);
+    *mean_path = (double)cnt / ((double)rows * (double)m->host.trees.size());
+  });
+}
+
+mr_status mr_model_save(mr_model *m, const uint8_t **blob, size_t *len) {
+  return guard([&] {
+    check_model(m);
+    if (!blob || !len) fail(MR_ERR_INVALID_ARG, "null argument");
+    *blob = m->host.blob.data();
+    *len = m->host.blob.size();
+  });
+}
+
+mr_status mr_model_weights(mr_model *m, double *out, int32_t n) {
+  return guard([&] {
+    check_model(m);
+    if (!out || n < m->host.n_features) fail(MR_ERR_INVALID_ARG, "weights buffer too small");
+    std::fill(out, out + n, 0.0);
+    for (auto &t : m->host.trees)
+      for (int f : t.feat) out[f] += 1.0;
+  });
+}
+
+mr_status mr_model_get_info(mr_model *m, mr_model_info *out) {
+  return guard([&] {
+    if (!m || !out) fail(MR_ERR_INVALID_ARG, "null argument");
+    out->kind = m->host.kind;
+    out->n_features = m->host.n_features;
+    out->n_trees = (int32_t)m->host.trees.size();
+    out->max_leaves = m->host.max_leaves;
+    out->n_chunks = (int32_t)m->packed.chunks.size();
+    out->has_categorical = m->host.has_cat;
+    out->n_internal_nodes = m->host.n_internal;
+    out->device_bytes = (int64_t)m->packed.bytes.size();
+  });
+}
+
+mr_status mr_model_inspect(int32_t kind, const uint8_t *blob, size_t len, int32_t chunk_kb, mr_model_info *out) {
+  return guard([&] {
+    if (!blob || !out) fail(MR_ERR_INVALID_ARG, "null argument");
+    HostModel hm;
+    if (kind == MR_BOOSTER_LIGHTGBM) hm = parse_lightgbm_text(blob, len);
+    else if (kind == MR_BOOSTER_XGBOOST) hm = parse_xgboost_model(blob, len);
+    else fail(MR_ERR_UNSUPPORTED, "unsupported booster tag %d", kind);
+    PackedModel pk = pack_model(hm, (size_t)(chunk_kb > 0 ? chunk_kb : 32) * 1024);
+    out->kind = hm.kind;
+    out->n_features = hm.n_features;
+    out->n_trees = (int32_t)hm.trees.size();
+    out->max_leaves = hm.max_leaves;
+    out->n_chunks = (int32_t)pk.chunks.size();
+    out->has_categorical = hm.has_cat;
+    out->n_internal_nodes = hm.n_internal;
+    out->device_bytes = (int64_t)pk.bytes.size();
+  });
+}
+
+mr_status mr_model_set_option(mr_model *m, const char *key, int32_t value) {
+  return guard([&] {
+    check_model(m);
+    if (!key) fail(MR_ERR_INVALID_ARG, "key is null");
+    std::lock_guard<std::mutex> g(m->mu);
+    std::string k(key);
+    if (k == "threads") m->opt_threads = value;
+    else if (k == "variant") m->opt_variant = value;
+    else if (k == "ilp") m->opt_ilp = value;
+    else if (k == "chunk_kb") {
+      m->opt_chunk_kb = value;
+      MR_CUDA_CHECK(cudaSetDevice(m->ctx->device));
+      MR_CUDA_CHECK(cudaDeviceSynchronize());
+      m->repack();
+    } else fail(MR_ERR_NOT_FOUND, "unknown option '%s'", key);
+  });
+}
+
+mr_status mr_model_close(mr_model *m) {
+  return guard([&] {
+    if (!m) fail(MR_ERR_INVALID_ARG, "model handle is null");
+    bool was = m->closed.exchange(true);
+    if (was) return;  // idempotent
+    // in-flight predicts hold `inflight`; wait for them, then drop device memory
+    while (m->inflight.load() > 0) std::this_thread::yield();
+    cudaSetDevice(m->ctx->device);
+    cudaDeviceSynchronize();
+    m->release_device();
+    m->ctx->live_models--;
+  });
+}
+
+int32_t mr_model_is_closed(mr_model *m) { return (!m || m->closed.load()) ? 1 : 0; }
+
+mr_status mr_model_free(mr_model *m) {
+  if (!m) return MR_OK;
+  mr_status s = mr_model_close(m);
+  delete m;
+  return s;
+}
+
+mr_status mr_rank_order(mr_ctx *ctx, const double *scores, const int32_t *offsets, int32_t n_requests,
+                        int32_t *order) {
+  return guard([&] {
+    (void)ctx;
+    if (n_requests < 0) fail(MR_ERR_INVALID_ARG, "negative request count");
+    if (n_requests > 0 && (!scores || !offsets || !order)) fail(MR_ERR_INVALID_ARG, "null argument");
+    for (int r = 0; r < n_requests; r++) {
+      const int b = offsets[r], e = offsets[r + 1];
+      if (e < b) fail(MR_ERR_INVALID_ARG, "offsets must be non-decreasing");
+      int32_t *o = order + b;
+      for (int i = 0; i < e - b; i++) o[i] = i;
+      const double *s = scores + b;
+      // java.lang.Double.compare on -score: total order with NaN last, -0.0 < 0.0
+      auto key = [](double x) -> int64_t {
+        x = -x;
+        if (x != x) return INT64_MAX;
+        int64_t bits;
+        memcpy(&bits, &x, 8);
+        return bits < 0 ? (bits ^ INT64_MAX) : bits;
+      };
+      std::stable_sort(o, o + (e - b), [&](int32_t a, int32_t c) { return key(s[a]) < key(s[c]); });
+    }
+  });
+}
+
+}  // extern "C"

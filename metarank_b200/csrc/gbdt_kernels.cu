@@ -1,0 +1,358 @@
+// GBDT ensemble scoring on sm_100a — the device side of Booster.predictMat
+// (reference call site S/ml/rank/LambdaMARTRanker.scala:348; LightGBM / XGBoost
+// prediction semantics restated in oracle/gbdt_oracle.c).
+//
+// Mapping.  One THREAD owns one item and walks every tree in tree order, so the score
+// is accumulated in exactly the order the CPU libraries use (f64 `+=` per tree for
+// LightGBM, f32 for XGBoost): scores are bit-identical to the sequential reference,
+// which is what makes the final ordering bit-exact.  A CTA owns a tile of W items:
+//   * the tile's features live in shared memory TRANSPOSED, xs[f][item]; thread `tid`
+//     reads xs[f*W + tid], so any per-lane feature index is bank-conflict free;
+//   * the ensemble is streamed through shared memory in CHUNKS by the TMA engine
+//     (cp.async.bulk global->shared, mbarrier complete_tx), double-buffered so the
+//     copy of chunk c+1 overlaps the traversal of chunk c; a model that fits in one
+//     chunk is staged once per CTA and stays resident across item tiles;
+//   * CTAs are persistent: grid = min(#tiles, SMs x resident CTAs), tiles strided.
+// Node visit = one 16-byte LDS (node) + one LDS (feature) + compare/select.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+
+#include "gbdt_kernels.cuh"
+
+namespace mr {
+
+long long g_kernel_launches = 0;
+
+namespace {
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk copy global -> shared (SASS: UBLKCP), completion on an mbarrier.
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+struct KParams {
+  const uint8_t *model;
+  const ChunkDesc *chunks;
+  const double *values;
+  double *out;
+  unsigned long long *visited;
+  int n_chunks;
+  uint32_t chunk_stride;  // bytes reserved per shared-memory chunk buffer
+  int rows, cols, n_features;
+  float base_score;
+};
+
+template <typename Real> struct Acc;
+template <> struct Acc<double> { using type = double; };
+template <> struct Acc<float> { using type = float; };
+
+template <typename Real> __device__ __forceinline__ Real cvt_feature(double v);
+template <> __device__ __forceinline__ double cvt_feature<double>(double v) { return v; }
+// XGBoost reads the matrix as binary32 (DMatrix of floats): round-to-nearest-even once.
+template <> __device__ __forceinline__ float cvt_feature<float>(double v) { return __double2float_rn(v); }
+
+// One decision.  nd = {thr.lo, thr.hi, feature|flags<<24, left|right<<16}.
+template <typename Real, bool HAS_CAT, bool HAS_ZERO>
+__device__ __forceinline__ int step(const uint4 nd, const Real x, const uint8_t *chunk) {
+  const uint32_t flags = nd.z >> 24;
+  bool left;
+  if constexpr (sizeof(Real) == 8) {
+    // LightGBM Tree::NumericalDecision / CategoricalDecision
+    const double xd = (double)x;
+    if (HAS_CAT && (flags & NF_CATEGORICAL)) {
+      left = false;
+      if (xd == xd) {
+        // static_cast<int>(fval); values outside int range behave as negative (x86 cvttsd2si)
+        const bool in_range = (xd < 2147483648.0) && (xd > -2147483649.0);
+        const int iv = in_range ? __double2int_rz(xd) : -1;
+        if (iv >= 0) {
+          const uint32_t w = (uint32_t)iv >> 5;
+          if (w < nd.y) left = (reinterpret_cast<const uint32_t *>(chunk)[nd.x + w] >> (iv & 31)) & 1u;
+        }
+      }
+    } else {
+      const double thr = __hiloint2double((int)nd.y, (int)nd.x);
+      left = xd <= thr;  // false when xd is NaN
+      if (HAS_ZERO) {
+        // missing_type == Zero: |x| <= kZeroThreshold (= (double)1e-35f) takes the default side
+        const double kZero = (double)1e-35f;
+        if (((flags >> NF_MISSING_SHIFT) & 3u) == 1u && xd >= -kZero && xd <= kZero)
+          left = (flags & NF_DEFAULT_LEFT) != 0;
+      }
+      if (xd != xd) left = (flags & NF_NAN_LEFT) != 0;
+    }
+  } else {
+    // XGBoost: fvalue < split_cond goes left; missing (NaN) takes default_left
+    const float thr = __uint_as_float(nd.x);
+    left = x < thr;
+    if (x != x) left = (flags & NF_NAN_LEFT) != 0;
+  }
+  const int l = (int)(short)(nd.w & 0xFFFFu), r = (int)(short)(nd.w >> 16);
+  return left ? l : r;
+}
+
+// VARIANT 0: lock-step — every lane walks tree t at the same time (ILP trees in flight);
+//            node loads of a warp stay inside one tree (mostly broadcast / conflict free).
+// VARIANT 1: free-running — a lane moves to its next tree as soon as it hits a leaf, so no
+//            lane idles while the deepest path of the warp finishes.
+template <typename Real, bool HAS_CAT, bool HAS_ZERO, int VARIANT, int ILP, bool STAGE, bool COUNT>
+__global__ void __launch_bounds__(256) gbdt_score_kernel(const KParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  using AccT = typename Acc<Real>::type;
+  const int W = blockDim.x;
+  const int tid = threadIdx.x;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+  const bool resident = p.n_chunks == 1;
+  uint8_t *cbuf0 = smem + 128;
+  uint8_t *cbuf1 = cbuf0 + (resident ? 0u : p.chunk_stride);
+  Real *xs = reinterpret_cast<Real *>(cbuf1 + p.chunk_stride);
+
+  const int n_tiles = (p.rows + W - 1) / W;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0 && (int)blockIdx.x < n_tiles) {
+    const ChunkDesc cd = p.chunks[0];
+    mbar_arrive_expect_tx(&bars[0], cd.bytes);
+    tma_bulk_g2s(cbuf0, p.model + cd.byte_off, cd.bytes, &bars[0]);
+  }
+
+  uint32_t it = 0;
+  unsigned long long visited = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int item = tile * W + tid;
+    const double *row = p.values + (size_t)item * p.cols;
+    if (STAGE) {
+      // transposed feature tile: xs[f*W + tid]
+      if (item < p.rows) {
+        if ((p.cols & 1) == 0) {
+          const double2 *row2 = reinterpret_cast<const double2 *>(row);
+          int f = 0;
+          for (; f + 1 < p.n_features; f += 2) {
+            const double2 v = __ldg(row2 + (f >> 1));
+            xs[f * W + tid] = cvt_feature<Real>(v.x);
+            xs[(f + 1) * W + tid] = cvt_feature<Real>(v.y);
+          }
+          if (f < p.n_features) xs[f * W + tid] = cvt_feature<Real>(__ldg(row + f));
+        } else {
+          for (int f = 0; f < p.n_features; f++) xs[f * W + tid] = cvt_feature<Real>(__ldg(row + f));
+        }
+      } else {
+        for (int f = 0; f < p.n_features; f++) xs[f * W + tid] = (Real)0;
+      }
+    }
+    __syncthreads();
+
+    AccT acc = (sizeof(Real) == 4) ? (AccT)p.base_score : (AccT)0;
+    for (int c = 0; c < p.n_chunks; ++c, ++it) {
+      if (!resident && tid == 0) {
+        const bool more = (c + 1 < p.n_chunks) || (tile + (int)gridDim.x < n_tiles);
+        if (more) {
+          const int nc = (c + 1 < p.n_chunks) ? c + 1 : 0;
+          const ChunkDesc cd = p.chunks[nc];
+          uint64_t *bar = &bars[(it + 1) & 1];
+          fence_proxy_async();  // generic-proxy reads of that buffer (iteration it-1) precede the async write
+          mbar_arrive_expect_tx(bar, cd.bytes);
+          tma_bulk_g2s(((it + 1) & 1) ? cbuf1 : cbuf0, p.model + cd.byte_off, cd.bytes, bar);
+        }
+      }
+      if (!resident || it == 0) mbar_wait(&bars[it & 1], (it >> 1) & 1);
+      const uint8_t *cb = (!resident && (it & 1)) ? cbuf1 : cbuf0;
+      const int ntree = (int)*reinterpret_cast<const uint32_t *>(cb);
+      const uint2 *tab = reinterpret_cast<const uint2 *>(cb + 16);
+
+      auto feat = [&](uint32_t f) -> Real {
+        if (STAGE) return xs[f * W + tid];
+        return (item < p.rows) ? cvt_feature<Real>(__ldg(row + f)) : (Real)0;
+      };
+
+      if (VARIANT == 0) {
+        int t = 0;
+        for (; t + ILP <= ntree; t += ILP) {
+          const uint4 *nodes[ILP];
+          const Real *leaves[ILP];
+          int n[ILP];
+#pragma unroll
+          for (int k = 0; k < ILP; k++) {
+            const uint2 to = tab[t + k];
+            nodes[k] = reinterpret_cast<const uint4 *>(cb + to.x);
+            leaves[k] = reinterpret_cast<const Real *>(cb + to.y);
+            n[k] = 0;
+          }
+          bool any = true;
+          while (any) {
+            any = false;
+#pragma unroll
+            for (int k = 0; k < ILP; k++) {
+              if (n[k] >= 0) {
+                const uint4 nd = nodes[k][n[k]];
+                n[k] = step<Real, HAS_CAT, HAS_ZERO>(nd, feat(nd.z & 0xFFFFFFu), cb);
+                if (COUNT) visited++;
+                any |= n[k] >= 0;
+              }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < ILP; k++) acc += (AccT)leaves[k][~n[k]];
+        }
+        for (; t < ntree; t++) {
+          const uint2 to = tab[t];
+          const uint4 *nodes = reinterpret_cast<const uint4 *>(cb + to.x);
+          const Real *leaves = reinterpret_cast<const Real *>(cb + to.y);
+          int n = 0;
+          do {
+            const uint4 nd = nodes[n];
+            n = step<Real, HAS_CAT, HAS_ZERO>(nd, feat(nd.z & 0xFFFFFFu), cb);
+            if (COUNT) visited++;
+          } while (n >= 0);
+          acc += (AccT)leaves[~n];
+        }
+      } else {
+        int t = 0, n = 0;
+        uint2 to = ntree > 0 ? tab[0] : make_uint2(0, 0);
+        while (t < ntree) {
+          const uint4 nd = reinterpret_cast<const uint4 *>(cb + to.x)[n];
+          n = step<Real, HAS_CAT, HAS_ZERO>(nd, feat(nd.z & 0xFFFFFFu), cb);
+          if (COUNT) visited++;
+          if (n < 0) {
+            acc += (AccT) reinterpret_cast<const Real *>(cb + to.y)[~n];
+            t++;
+            n = 0;
+            if (t < ntree) to = tab[t];
+          }
+        }
+      }
+      __syncthreads();  // the buffer may be overwritten by the next prefetch; xs by the next tile
+    }
+    if (item < p.rows) {
+      p.out[item] = (double)acc;
+      if (COUNT) atomicAdd(p.visited, visited);
+    }
+    visited = 0;
+  }
+}
+
+template <typename Real, bool HAS_CAT, bool HAS_ZERO, int VARIANT, int ILP, bool STAGE, bool COUNT>
+void launch_inst(const KParams &p, int threads, size_t smem, int num_sms, cudaStream_t stream) {
+  auto kern = gbdt_score_kernel<Real, HAS_CAT, HAS_ZERO, VARIANT, ILP, STAGE, COUNT>;
+  MR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  MR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  if (per_sm < 1) fail(MR_ERR_CUDA, "gbdt_score kernel does not fit on an SM (smem %zu, threads %d)", smem, threads);
+  const int n_tiles = (p.rows + threads - 1) / threads;
+  const int grid = std::max(1, std::min(n_tiles, num_sms * per_sm));
+  kern<<<grid, threads, smem, stream>>>(p);
+  MR_CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+}
+
+template <typename Real, bool HAS_CAT, bool HAS_ZERO, bool STAGE, bool COUNT>
+void launch_variant(const KParams &p, int variant, int ilp, int threads, size_t smem, int num_sms, cudaStream_t s) {
+  if (variant == 1) return launch_inst<Real, HAS_CAT, HAS_ZERO, 1, 1, STAGE, COUNT>(p, threads, smem, num_sms, s);
+  switch (ilp) {
+    case 1: return launch_inst<Real, HAS_CAT, HAS_ZERO, 0, 1, STAGE, COUNT>(p, threads, smem, num_sms, s);
+    case 4: return launch_inst<Real, HAS_CAT, HAS_ZERO, 0, 4, STAGE, COUNT>(p, threads, smem, num_sms, s);
+    default: return launch_inst<Real, HAS_CAT, HAS_ZERO, 0, 2, STAGE, COUNT>(p, threads, smem, num_sms, s);
+  }
+}
+
+template <typename Real, bool STAGE, bool COUNT>
+void launch_flags(const KParams &p, bool cat, bool zero, int variant, int ilp, int threads, size_t smem, int num_sms,
+                  cudaStream_t s) {
+  if constexpr (sizeof(Real) == 4) {
+    return launch_variant<Real, false, false, STAGE, COUNT>(p, variant, ilp, threads, smem, num_sms, s);
+  } else {
+    if (cat || zero) return launch_variant<Real, true, true, STAGE, COUNT>(p, variant, ilp, threads, smem, num_sms, s);
+    return launch_variant<Real, false, false, STAGE, COUNT>(p, variant, ilp, threads, smem, num_sms, s);
+  }
+}
+
+}  // namespace
+
+void launch_gbdt_score(const ScoreLaunch &L, int num_sms, cudaStream_t stream) {
+  if (L.rows <= 0) return;
+  KParams p;
+  p.model = L.d_model;
+  p.chunks = L.d_chunks;
+  p.values = L.d_values;
+  p.out = L.d_out;
+  p.visited = L.d_visited;
+  p.n_chunks = L.n_chunks;
+  p.chunk_stride = (L.max_chunk_bytes + 127u) & ~127u;
+  p.rows = L.rows;
+  p.cols = L.cols;
+  p.n_features = L.n_features;
+  p.base_score = L.base_score;
+
+  const bool f32 = L.kind == MR_BOOSTER_XGBOOST;
+  const size_t real_sz = f32 ? 4 : 8;
+  const size_t kMaxSmem = 227 * 1024;
+  const size_t fixed = 128 + (size_t)p.chunk_stride * (L.n_chunks == 1 ? 1 : 2);
+
+  int threads = L.threads;
+  if (threads <= 0) {
+    threads = 256;
+    // keep at least ~2 tiles per SM so the persistent grid covers the chip
+    while (threads > 32 && (L.rows + threads - 1) / threads < 2 * num_sms) threads >>= 1;
+  }
+  threads = std::max(32, std::min(256, (threads / 32) * 32));
+  bool stage = true;
+  while (fixed + (size_t)threads * L.n_features * real_sz > kMaxSmem && threads > 32) threads >>= 1;
+  if (fixed + (size_t)threads * L.n_features * real_sz > kMaxSmem) stage = false;  // very wide rows: read HBM/L1 directly
+  if (fixed > kMaxSmem) fail(MR_ERR_UNSUPPORTED, "model chunk of %u bytes does not fit in shared memory", L.max_chunk_bytes);
+  const size_t smem = fixed + (stage ? (size_t)threads * L.n_features * real_sz : 0);
+
+  int variant = L.variant < 0 ? 0 : L.variant;
+  int ilp = L.ilp <= 0 ? 2 : L.ilp;
+  const bool count = L.d_visited != nullptr;
+
+#define MR_DISPATCH(REAL)                                                                                        \
+  do {                                                                                                           \
+    if (stage) {                                                                                                 \
+      if (count) launch_flags<REAL, true, true>(p, L.has_cat, L.has_zero, variant, ilp, threads, smem, num_sms, stream); \
+      else launch_flags<REAL, true, false>(p, L.has_cat, L.has_zero, variant, ilp, threads, smem, num_sms, stream);      \
+    } else {                                                                                                     \
+      if (count) launch_flags<REAL, false, true>(p, L.has_cat, L.has_zero, variant, ilp, threads, smem, num_sms, stream); \
+      else launch_flags<REAL, false, false>(p, L.has_cat, L.has_zero, variant, ilp, threads, smem, num_sms, stream);      \
+    }                                                                                                            \
+  } while (0)
+  if (f32) MR_DISPATCH(float);
+  else MR_DISPATCH(double);
+#undef MR_DISPATCH
+}
+
+}  // namespace mr

@@ -1,0 +1,37 @@
+// Launch interface of the GBDT scoring kernels (gbdt_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "gbdt_model.h"
+
+namespace mr {
+
+struct ScoreLaunch {
+  // model
+  const uint8_t *d_model = nullptr;       // packed chunks in HBM
+  const ChunkDesc *d_chunks = nullptr;    // chunk table in HBM
+  int n_chunks = 0;
+  uint32_t max_chunk_bytes = 0;
+  int kind = 0;                           // MR_BOOSTER_*
+  bool has_cat = false, has_zero = false;
+  float base_score = 0.f;
+  int n_features = 0;
+  // batch
+  const double *d_values = nullptr;       // row-major rows x cols
+  int rows = 0, cols = 0;
+  double *d_out = nullptr;
+  unsigned long long *d_visited = nullptr;  // non-null: also count evaluated internal nodes
+  // tuning (0 = choose)
+  int threads = 0;
+  int variant = -1;
+  int ilp = 0;
+};
+
+// Enqueues the scoring kernel on `stream`.  Throws mr::Error on failure.
+void launch_gbdt_score(const ScoreLaunch &L, int num_sms, cudaStream_t stream);
+
+extern long long g_kernel_launches;
+
+}  // namespace mr

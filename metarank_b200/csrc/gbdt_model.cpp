@@ -1,0 +1,401 @@
+// Parsers for the booster blobs + packing into TMA-stageable chunks.  See gbdt_model.h.
+//
+// Format notes (public formats of the third-party boosters; the arithmetic is not in
+// the reference tree — see oracle/gbdt_oracle.c for the citation chain):
+//  * LightGBM model text: "key=value" header, then "Tree=<i>" blocks with num_leaves,
+//    num_cat, split_feature, threshold, decision_type, left_child, right_child,
+//    leaf_value, [cat_boundaries, cat_threshold], terminated by "end of trees".
+//  * XGBoost JSON/UBJSON: learner.gradient_booster.model.trees[] with left_children,
+//    right_children, split_indices, split_conditions, default_left; leaf <=> left == -1,
+//    leaf value = split_conditions[i]; learner_model_param.base_score / num_feature.
+#include "gbdt_model.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <unordered_map>
+
+#include "json.h"
+
+namespace mr {
+
+int HostTree::depth() const {
+  if (feat.empty()) return 0;
+  std::vector<std::pair<int, int>> st{{0, 1}};
+  int best = 0;
+  while (!st.empty()) {
+    auto [n, d] = st.back();
+    st.pop_back();
+    best = std::max(best, d);
+    if (left[n] >= 0) st.push_back({left[n], d + 1});
+    if (right[n] >= 0) st.push_back({right[n], d + 1});
+  }
+  return best;
+}
+
+namespace {
+
+struct Line {
+  const char *p;
+  size_t n;
+};
+
+bool starts(const Line &l, const char *s) {
+  size_t n = strlen(s);
+  return l.n >= n && memcmp(l.p, s, n) == 0;
+}
+
+// whitespace-separated list -> numbers.  strtod/strtol are correctly rounded, like the
+// fast_double_parser path LightGBM >= 3.2 uses when it reads its own model text.
+template <class T, class F>
+std::vector<T> split_nums(const std::string &s, size_t expect, const char *key, F conv) {
+  std::vector<T> out;
+  out.reserve(expect);
+  const char *p = s.c_str();
+  while (*p) {
+    while (*p == ' ' || *p == '\t' || *p == '\r') p++;
+    if (!*p) break;
+    char *end = nullptr;
+    T v = conv(p, &end);
+    if (end == p) fail(MR_ERR_PARSE, "lightgbm: bad number in '%s'", key);
+    out.push_back(v);
+    p = end;
+  }
+  if (out.size() != expect)
+    fail(MR_ERR_PARSE, "lightgbm: '%s' has %zu values, expected %zu", key, out.size(), expect);
+  return out;
+}
+
+void finalize(HostModel &m) {
+  m.n_internal = 0;
+  m.max_leaves = 0;
+  m.max_depth = 0;
+  m.has_cat = m.has_zero_missing = false;
+  for (auto &t : m.trees) {
+    m.n_internal += (int64_t)t.feat.size();
+    m.max_leaves = std::max<int>(m.max_leaves, (int)t.leaf.size());
+    m.max_depth = std::max(m.max_depth, t.depth());
+    for (size_t i = 0; i < t.feat.size(); i++) {
+      if (t.flags[i] & NF_CATEGORICAL) m.has_cat = true;
+      else if (((t.flags[i] >> NF_MISSING_SHIFT) & 3) == 1) m.has_zero_missing = true;
+      if (t.feat[i] < 0 || t.feat[i] >= m.n_features)
+        fail(MR_ERR_PARSE, "split feature %d outside [0,%d)", t.feat[i], m.n_features);
+      int nl = (int)t.leaf.size(), ni = (int)t.feat.size();
+      for (int c : {t.left[i], t.right[i]}) {
+        if (c >= 0 ? c >= ni : ~c >= nl) fail(MR_ERR_PARSE, "child index out of range");
+      }
+    }
+    if (t.leaf.size() > 32768) fail(MR_ERR_UNSUPPORTED, "trees with more than 32768 leaves are not supported");
+  }
+}
+
+}  // namespace
+
+HostModel parse_lightgbm_text(const uint8_t *blob, size_t len) {
+  HostModel m;
+  m.kind = MR_BOOSTER_LIGHTGBM;
+  m.blob.assign(blob, blob + len);
+  // split into lines
+  std::vector<Line> lines;
+  {
+    const char *p = (const char *)blob, *e = p + len;
+    while (p < e) {
+      const char *q = (const char *)memchr(p, '\n', (size_t)(e - p));
+      if (!q) q = e;
+      size_t n = (size_t)(q - p);
+      while (n && (p[n - 1] == '\r' || p[n - 1] == ' ')) n--;
+      lines.push_back({p, n});
+      p = q + 1;
+    }
+  }
+  size_t i = 0;
+  int max_feature_idx = -1, num_class = 1, per_iter = 1;
+  for (; i < lines.size() && !starts(lines[i], "Tree="); i++) {
+    std::string s(lines[i].p, lines[i].n);
+    if (starts(lines[i], "max_feature_idx=")) max_feature_idx = atoi(s.c_str() + 16);
+    else if (starts(lines[i], "num_class=")) num_class = atoi(s.c_str() + 10);
+    else if (starts(lines[i], "num_tree_per_iteration=")) per_iter = atoi(s.c_str() + 23);
+  }
+  if (max_feature_idx < 0) fail(MR_ERR_PARSE, "lightgbm: max_feature_idx missing (not a LightGBM model text)");
+  if (num_class != 1 || per_iter != 1) fail(MR_ERR_UNSUPPORTED, "lightgbm: multiclass models are not supported");
+  m.n_features = max_feature_idx + 1;
+
+  std::unordered_map<std::string, std::string> kv;
+  auto flush = [&]() {
+    if (kv.empty()) return;
+    auto need = [&](const char *k) -> const std::string & {
+      auto it = kv.find(k);
+      if (it == kv.end()) fail(MR_ERR_PARSE, "lightgbm: tree block lacks '%s'", k);
+      return it->second;
+    };
+    int nl = atoi(need("num_leaves").c_str());
+    if (nl < 1) fail(MR_ERR_PARSE, "lightgbm: num_leaves < 1");
+    if (kv.count("is_linear") && atoi(kv["is_linear"].c_str()) != 0)
+      fail(MR_ERR_UNSUPPORTED, "lightgbm: linear trees are not supported");
+    HostTree t;
+    auto d = [](const char *p, char **e) { return strtod(p, e); };
+    auto l = [](const char *p, char **e) { return (int32_t)strtol(p, e, 10); };
+    auto u = [](const char *p, char **e) { return (uint32_t)strtoul(p, e, 10); };
+    t.leaf = split_nums<double>(need("leaf_value"), (size_t)nl, "leaf_value", d);
+    size_t ni = (size_t)nl - 1;
+    if (ni > 0) {
+      t.feat = split_nums<int32_t>(need("split_feature"), ni, "split_feature", l);
+      t.thr = split_nums<double>(need("threshold"), ni, "threshold", d);
+      auto dt = split_nums<int32_t>(need("decision_type"), ni, "decision_type", l);
+      t.left = split_nums<int32_t>(need("left_child"), ni, "left_child", l);
+      t.right = split_nums<int32_t>(need("right_child"), ni, "right_child", l);
+      int ncat = kv.count("num_cat") ? atoi(kv["num_cat"].c_str()) : 0;
+      std::vector<int32_t> cb;
+      std::vector<uint32_t> ct;
+      if (ncat > 0) {
+        cb = split_nums<int32_t>(need("cat_boundaries"), (size_t)ncat + 1, "cat_boundaries", l);
+        if (cb.back() < 0) fail(MR_ERR_PARSE, "lightgbm: bad cat_boundaries");
+        ct = split_nums<uint32_t>(need("cat_threshold"), (size_t)cb.back(), "cat_threshold", u);
+      }
+      t.flags.resize(ni);
+      t.cat_begin.assign(ni, 0);
+      t.cat_n.assign(ni, 0);
+      for (size_t k = 0; k < ni; k++) {
+        uint32_t f = (uint32_t)dt[k] & 0xF;
+        if (f & NF_CATEGORICAL) {
+          int ci = (int)t.thr[k];
+          if (ci < 0 || ci >= ncat) fail(MR_ERR_PARSE, "lightgbm: categorical threshold index out of range");
+          if (cb[ci] < 0 || cb[ci + 1] < cb[ci] || cb[ci + 1] > (int)ct.size())
+            fail(MR_ERR_PARSE, "lightgbm: bad cat_boundaries");
+          t.cat_begin[k] = (int32_t)t.cat_words.size();
+          t.cat_n[k] = cb[ci + 1] - cb[ci];
+          t.cat_words.insert(t.cat_words.end(), ct.begin() + cb[ci], ct.begin() + cb[ci + 1]);
+        } else {
+          // where does NaN go?  Tree::NumericalDecision: NaN -> 0.0 unless missing_type == NaN;
+          // then Zero/NaN missing types take the default side, otherwise 0.0 <= threshold.
+          uint32_t mt = (f >> NF_MISSING_SHIFT) & 3;
+          bool nan_left = (mt == 0) ? (0.0 <= t.thr[k]) : ((f & NF_DEFAULT_LEFT) != 0);
+          if (nan_left) f |= NF_NAN_LEFT;
+        }
+        t.flags[k] = (uint8_t)f;
+      }
+    }
+    m.trees.push_back(std::move(t));
+    kv.clear();
+  };
+  bool in_tree = false;
+  for (; i < lines.size(); i++) {
+    const Line &ln = lines[i];
+    if (starts(ln, "Tree=")) {
+      flush();
+      in_tree = true;
+      kv["Tree"] = std::string(ln.p + 5, ln.n - 5);
+      continue;
+    }
+    if (starts(ln, "end of trees")) break;
+    if (!in_tree) continue;
+    const char *eq = (const char *)memchr(ln.p, '=', ln.n);
+    if (!eq) continue;
+    kv[std::string(ln.p, (size_t)(eq - ln.p))] = std::string(eq + 1, ln.n - (size_t)(eq - ln.p) - 1);
+  }
+  flush();
+  finalize(m);
+  return m;
+}
+
+HostModel parse_xgboost_model(const uint8_t *blob, size_t len) {
+  HostModel m;
+  m.kind = MR_BOOSTER_XGBOOST;
+  m.blob.assign(blob, blob + len);
+  size_t s = 0;
+  while (s < len && (blob[s] == ' ' || blob[s] == '\n' || blob[s] == '\r' || blob[s] == '\t')) s++;
+  if (s >= len || blob[s] != '{')
+    fail(MR_ERR_UNSUPPORTED, "xgboost: unsupported model encoding (only JSON and UBJSON; legacy binary is not)");
+  JValue doc;
+  size_t k = s + 1;
+  while (k < len && (blob[k] == ' ' || blob[k] == '\n' || blob[k] == '\r' || blob[k] == '\t')) k++;
+  if (k < len && (blob[k] == '"' || blob[k] == '}')) doc = JsonParser(blob + s, len - s).parse();
+  else doc = UbjParser(blob + s, len - s).parse();
+
+  const JValue &learner = doc.at("learner");
+  const JValue &gb = learner.at("gradient_booster");
+  if (gb.at("name").str != "gbtree") fail(MR_ERR_UNSUPPORTED, "xgboost: booster '%s' not supported", gb.at("name").str.c_str());
+  const JValue &lmp = learner.at("learner_model_param");
+  m.base_score = lmp.at("base_score").as_f32();
+  m.n_features = (int)lmp.at("num_feature").as_int();
+  if (const JValue *nc = lmp.get("num_class"))
+    if (nc->as_int() > 1) fail(MR_ERR_UNSUPPORTED, "xgboost: multiclass models are not supported");
+  const JValue &trees = gb.at("model").at("trees");
+  if (trees.kind != JValue::Arr) fail(MR_ERR_PARSE, "xgboost: trees is not an array");
+  for (const JValue &jt : trees.arr) {
+    const auto &L = jt.at("left_children").arr, &R = jt.at("right_children").arr;
+    const auto &SI = jt.at("split_indices").arr, &SC = jt.at("split_conditions").arr, &DL = jt.at("default_left").arr;
+    size_t n = L.size();
+    if (R.size() != n || SI.size() != n || SC.size() != n || DL.size() != n || n == 0)
+      fail(MR_ERR_PARSE, "xgboost: tree arrays have inconsistent sizes");
+    if (const JValue *st = jt.get("split_type"))
+      for (auto &v : st->arr)
+        if (v.as_int() != 0) fail(MR_ERR_UNSUPPORTED, "xgboost: categorical splits are not supported");
+    // renumber: internal nodes and leaves get separate index spaces
+    std::vector<int32_t> id(n);
+    int ni = 0, nl = 0;
+    for (size_t i = 0; i < n; i++) id[i] = (L[i].as_int() == -1) ? ~(nl++) : ni++;
+    HostTree t;
+    t.feat.resize(ni); t.thr.resize(ni); t.flags.resize(ni); t.left.resize(ni); t.right.resize(ni);
+    t.cat_begin.assign(ni, 0); t.cat_n.assign(ni, 0);
+    t.leaf.resize(nl);
+    for (size_t i = 0; i < n; i++) {
+      if (id[i] < 0) {
+        t.leaf[~id[i]] = (double)SC[i].as_f32();
+      } else {
+        int64_t l = L[i].as_int(), r = R[i].as_int();
+        if (l < 0 || r < 0 || (size_t)l >= n || (size_t)r >= n) fail(MR_ERR_PARSE, "xgboost: child out of range");
+        int k2 = id[i];
+        t.feat[k2] = (int32_t)SI[i].as_int();
+        t.thr[k2] = (double)SC[i].as_f32();
+        bool dl = DL[i].as_int() != 0;
+        t.flags[k2] = (uint8_t)((dl ? NF_DEFAULT_LEFT | NF_NAN_LEFT : 0) | (2u << NF_MISSING_SHIFT));
+        t.left[k2] = id[l];
+        t.right[k2] = id[r];
+      }
+    }
+    m.trees.push_back(std::move(t));
+  }
+  finalize(m);
+  return m;
+}
+
+void parse_metarank_frame(const uint8_t *blob, size_t len, std::vector<std::string> &names, int &kind,
+                          size_t &begin, size_t &end) {
+  // java.io.DataInputStream: big-endian; readUTF = u16 length + modified UTF-8
+  size_t p = 0;
+  auto need = [&](size_t n) {
+    if (len - p < n) fail(MR_ERR_PARSE, "metarank model blob truncated");
+  };
+  auto i32 = [&]() {
+    need(4);
+    int32_t v = (int32_t)((uint32_t)blob[p] << 24 | (uint32_t)blob[p + 1] << 16 | (uint32_t)blob[p + 2] << 8 | blob[p + 3]);
+    p += 4;
+    return v;
+  };
+  need(1);
+  int version = (int8_t)blob[p++];
+  if (version != 2 && version != 3) fail(MR_ERR_PARSE, "unsupported bitstream version %d", version);
+  int32_t nf = i32();
+  if (nf < 0) fail(MR_ERR_PARSE, "negative feature count");
+  names.clear();
+  for (int i = 0; i < nf; i++) {
+    need(2);
+    size_t n = (size_t)blob[p] << 8 | blob[p + 1];
+    p += 2;
+    need(n);
+    names.emplace_back((const char *)blob + p, n);
+    p += n;
+  }
+  need(1);
+  kind = (int8_t)blob[p++];
+  int32_t size = i32();
+  if (size < 0) fail(MR_ERR_PARSE, "negative booster size");
+  need((size_t)size);
+  begin = p;
+  end = p + (size_t)size;
+  if (kind != 0 && kind != 1) fail(MR_ERR_UNSUPPORTED, "unsupported booster tag %d", kind);
+}
+
+// ------------------------------------------------------------------ packing
+
+namespace {
+inline size_t al16(size_t x) { return (x + 15) & ~size_t(15); }
+
+struct DNodeHost {
+  union {
+    double thr64;
+    struct { float thr32; uint32_t pad; } f;
+    struct { uint32_t cat_off, cat_n; } c;
+  };
+  uint32_t ff;
+  int16_t left, right;
+};
+static_assert(sizeof(DNodeHost) == 16, "DNode must be 16 bytes");
+}  // namespace
+
+PackedModel pack_model(const HostModel &m, size_t chunk_budget) {
+  PackedModel pk;
+  const bool f32 = m.kind == MR_BOOSTER_XGBOOST;
+  const size_t leaf_sz = f32 ? 4 : 8;
+  // a single-leaf tree becomes one dummy node whose two children are leaf 0
+  auto n_nodes = [](const HostTree &t) { return t.feat.empty() ? size_t(1) : t.feat.size(); };
+  auto tree_bytes = [&](const HostTree &t) {
+    return n_nodes(t) * 16 + al16(t.leaf.size() * leaf_sz) + al16(t.cat_words.size() * 4);
+  };
+  size_t i = 0, nt = m.trees.size();
+  if (nt == 0) {
+    // empty ensemble: one empty chunk so the kernel still writes base scores
+    ChunkDesc cd{0, 16, 0, 0};
+    pk.bytes.assign(16, 0);
+    pk.chunks.push_back(cd);
+    pk.max_chunk_bytes = 16;
+    return pk;
+  }
+  while (i < nt) {
+    size_t j = i, body = 0;
+    while (j < nt) {
+      size_t nb = body + tree_bytes(m.trees[j]);
+      size_t hdr = 16 + al16((j - i + 1) * 8);
+      if (j > i && hdr + nb > chunk_budget) break;
+      body = nb;
+      j++;
+    }
+    size_t n = j - i;
+    size_t hdr = 16 + al16(n * 8);
+    size_t total = hdr + body;
+    if (total >= (1u << 20)) fail(MR_ERR_UNSUPPORTED, "a single tree needs %zu bytes of shared memory", total);
+    size_t base = pk.bytes.size();
+    pk.bytes.resize(base + total, 0);
+    uint8_t *c = pk.bytes.data() + base;
+    uint32_t hn = (uint32_t)n;
+    memcpy(c, &hn, 4);
+    uint32_t *tab = (uint32_t *)(c + 16);
+    size_t off = hdr;
+    for (size_t k = 0; k < n; k++) {
+      const HostTree &t = m.trees[i + k];
+      size_t nn = n_nodes(t);
+      size_t node_off = off, leaf_off = off + nn * 16;
+      size_t cat_off = leaf_off + al16(t.leaf.size() * leaf_sz);
+      tab[2 * k] = (uint32_t)node_off;
+      tab[2 * k + 1] = (uint32_t)leaf_off;
+      DNodeHost *nodes = (DNodeHost *)(c + node_off);
+      if (t.feat.empty()) {
+        nodes[0].thr64 = 0.0;
+        nodes[0].ff = 0;
+        nodes[0].left = nodes[0].right = (int16_t)~0;
+      }
+      for (size_t q = 0; q < t.feat.size(); q++) {
+        DNodeHost &d = nodes[q];
+        if (t.flags[q] & NF_CATEGORICAL) {
+          d.c.cat_off = (uint32_t)((cat_off / 4) + (size_t)t.cat_begin[q]);
+          d.c.cat_n = (uint32_t)t.cat_n[q];
+        } else if (f32) {
+          d.f.thr32 = (float)t.thr[q];
+          d.f.pad = 0;
+        } else {
+          d.thr64 = t.thr[q];
+        }
+        d.ff = (uint32_t)t.feat[q] | ((uint32_t)t.flags[q] << 24);
+        d.left = (int16_t)t.left[q];
+        d.right = (int16_t)t.right[q];
+      }
+      if (f32) {
+        float *lv = (float *)(c + leaf_off);
+        for (size_t q = 0; q < t.leaf.size(); q++) lv[q] = (float)t.leaf[q];
+      } else {
+        memcpy(c + leaf_off, t.leaf.data(), t.leaf.size() * 8);
+      }
+      if (!t.cat_words.empty()) memcpy(c + cat_off, t.cat_words.data(), t.cat_words.size() * 4);
+      off = cat_off + al16(t.cat_words.size() * 4);
+    }
+    ChunkDesc cd{(uint32_t)base, (uint32_t)total, (uint32_t)n, (uint32_t)i};
+    pk.chunks.push_back(cd);
+    pk.max_chunk_bytes = std::max<uint32_t>(pk.max_chunk_bytes, (uint32_t)total);
+    i = j;
+  }
+  return pk;
+}
+
+}  // namespace mr

@@ -1,0 +1,86 @@
+// Host-side booster representation, parsers and the HBM packing of the tree ensemble.
+//
+// Replaces ltrlib's `LightGBMBooster(bytes)` / `XGBoostBooster(bytes)` constructors
+// (reference S/ml/rank/LambdaMARTRanker.scala:228-232).  The blobs are the public
+// LightGBM model text / XGBoost JSON|UBJSON model formats.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "common.h"
+
+namespace mr {
+
+// decision flags shared by host and device (low 8 bits of DNode::ff >> 24)
+enum : uint32_t {
+  NF_CATEGORICAL = 1u,     // LightGBM kCategoricalMask
+  NF_DEFAULT_LEFT = 2u,    // LightGBM kDefaultLeftMask / XGBoost default_left
+  NF_MISSING_SHIFT = 2,    // bits 2-3: 0 None, 1 Zero, 2 NaN
+  NF_NAN_LEFT = 16u,       // precomputed: where a NaN input goes at this node
+};
+
+// One decision tree in the unified form both parsers produce: internal nodes
+// 0..n-1 with children >= 0 (internal) or < 0 (leaf ~c), leaves separate.
+struct HostTree {
+  std::vector<int32_t> feat;
+  std::vector<double> thr;      // f64 threshold (LightGBM) or the exact f32 split_condition widened
+  std::vector<uint8_t> flags;
+  std::vector<int32_t> left, right;
+  std::vector<double> leaf;     // f64 leaf (LightGBM) or f32 leaf widened (XGBoost)
+  // categorical nodes: thr[i] is unused; cat_begin/cat_n index cat_words
+  std::vector<int32_t> cat_begin, cat_n;  // per internal node (0,0 for numerical)
+  std::vector<uint32_t> cat_words;
+  int depth() const;
+};
+
+struct HostModel {
+  int kind = 0;            // MR_BOOSTER_*
+  int n_features = 0;
+  float base_score = 0.f;  // XGBoost only
+  std::vector<HostTree> trees;
+  bool has_cat = false, has_zero_missing = false;
+  int64_t n_internal = 0;
+  int max_leaves = 0, max_depth = 0;
+  std::vector<uint8_t> blob;  // original bytes for Booster.save()
+};
+
+HostModel parse_lightgbm_text(const uint8_t *blob, size_t len);
+HostModel parse_xgboost_model(const uint8_t *blob, size_t len);
+
+// Metarank model framing (LambdaMARTPredictor.load). Returns the booster kind and the
+// [begin,end) byte range of the booster blob; fills names.
+void parse_metarank_frame(const uint8_t *blob, size_t len, std::vector<std::string> &names, int &kind,
+                          size_t &begin, size_t &end);
+
+// ---- device layout -------------------------------------------------------------
+// A model is a sequence of CHUNKS, each one contiguous, 16-byte aligned byte range that
+// a single cp.async.bulk (TMA 1-D bulk copy) stages into shared memory:
+//
+//   +0   u32 n_trees, u32 reserved[3]
+//   +16  u32 tab[2*n_trees]  {byte offset of tree's node array, byte offset of its leaves}
+//        (padded to 16 B)
+//   ...  per tree: DNode nodes[n_internal]   (16 B each)
+//                  Real  leaves[n_leaves]    (f64 LightGBM / f32 XGBoost; padded to 16 B)
+//   ...  u32 cat_words[] of the chunk's categorical nodes (padded to 16 B)
+//
+// DNode (16 B): { f64 thr | f32 thr | {u32 cat_word_off, u32 cat_n_words} ;
+//                 u32 ff = feature | flags << 24 ; i16 left ; i16 right }
+// children: >= 0 internal node index within the tree, < 0 leaf ~c.
+struct ChunkDesc {
+  uint32_t byte_off;   // from model base
+  uint32_t bytes;      // multiple of 16
+  uint32_t n_trees;
+  uint32_t first_tree;
+};
+
+struct PackedModel {
+  std::vector<uint8_t> bytes;
+  std::vector<ChunkDesc> chunks;
+  uint32_t max_chunk_bytes = 0;
+};
+
+// chunk_budget: maximum bytes per chunk (a single tree larger than it gets its own chunk).
+PackedModel pack_model(const HostModel &m, size_t chunk_budget);
+
+}  // namespace mr

@@ -1,0 +1,335 @@
+"""Seeded synthetic models and inputs for the /rank hot path.
+
+Nothing here is an oracle or a kernel: it only *writes* LightGBM model text /
+XGBoost model JSON in the public formats those libraries save (the blobs the
+reference hands to ``LightGBMBooster(bytes)`` / ``XGBoostBooster(bytes)``,
+reference S/ml/rank/LambdaMARTRanker.scala:228-232) and draws feature matrices
+of the shapes BASELINE.json names.  All randomness is
+``numpy.random.Generator(PCG64(seed))``.
+"""
+from __future__ import annotations
+
+import json
+import struct
+from dataclasses import dataclass
+
+import numpy as np
+
+__all__ = [
+    "feature_matrix", "column_kinds", "lightgbm_model_text", "xgboost_model_json",
+    "xgboost_model_ubj", "metarank_model_blob", "CONFIGS",
+]
+
+# BASELINE.json configs (rows × features × trees); see SURVEY.md §8 shorthand.
+CONFIGS = {
+    "C2": dict(items=100, features=30, trees=500, leaves=16, max_depth=8, kind="lightgbm"),
+    "C4": dict(items=256, features=16, trees=200, depth=6, kind="xgboost"),
+    "C5": dict(items=10_000, features=64, trees=2000, leaves=16, max_depth=8, kind="lightgbm"),
+}
+
+_KINDS = ("normal", "lognormal", "count", "ctr", "nan5")
+
+
+def column_kinds(n_features: int) -> list[str]:
+    """Columns cycle through {N(0,1), logN(0,1), U{0..1000}, Beta(2,50), N(0,1)+5% NaN}."""
+    return [_KINDS[j % len(_KINDS)] for j in range(n_features)]
+
+
+def _draw_column(rng: np.random.Generator, kind: str, n: int) -> np.ndarray:
+    if kind == "normal":
+        return rng.standard_normal(n)
+    if kind == "lognormal":
+        return rng.lognormal(0.0, 1.0, n)
+    if kind == "count":
+        return rng.integers(0, 1001, n).astype(np.float64)
+    if kind == "ctr":
+        return rng.beta(2.0, 50.0, n)
+    if kind == "nan5":
+        x = rng.standard_normal(n)
+        x[rng.random(n) < 0.05] = np.nan
+        return x
+    raise ValueError(kind)
+
+
+def feature_matrix(rows: int, n_features: int, seed: int = 42) -> np.ndarray:
+    """Row-major f64[rows × n_features], the layout of ltrlib ``Query.values``
+    (reference S/flow/ClickthroughQuery.scala:50-74)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    kinds = column_kinds(n_features)
+    out = np.empty((rows, n_features), dtype=np.float64)
+    for j, k in enumerate(kinds):
+        out[:, j] = _draw_column(rng, k, rows)
+    return out
+
+
+def _quantile_threshold(rng: np.random.Generator, kind: str) -> float:
+    """A split threshold = a uniformly drawn quantile of the column's distribution."""
+    sample = _draw_column(rng, "normal" if kind == "nan5" else kind, 64)
+    v = float(sample[int(rng.integers(0, 64))])
+    if kind == "count":
+        v = float(np.floor(v)) + 0.5  # LightGBM puts thresholds between observed values
+    return v
+
+
+def _fmt(x: float) -> str:
+    return repr(float(x)) if np.isfinite(x) else ("nan" if np.isnan(x) else ("inf" if x > 0 else "-inf"))
+
+
+@dataclass
+class _Tree:
+    split_feature: list
+    threshold: list
+    decision_type: list
+    left_child: list
+    right_child: list
+    leaf_value: list
+    cat_boundaries: list
+    cat_threshold: list
+
+
+def _grow_lightgbm_tree(rng, n_features, kinds, num_leaves, max_depth, cat_features, shrinkage,
+                        zero_missing=False):
+    """Random leaf-wise growth with LightGBM's node numbering: split #s turns leaf `l`
+    into internal node s whose left child keeps leaf id l and right child is leaf s+1."""
+    leaf_depth = {0: 0}
+    leaf_parent = {0: (-1, 0)}  # leaf -> (parent node, is_right)
+    sf, thr, dt, lc, rc = [], [], [], [], []
+    cat_b, cat_t = [0], []
+    n_leaves = 1
+    while n_leaves < num_leaves:
+        cands = [l for l, d in leaf_depth.items() if max_depth <= 0 or d < max_depth]
+        if not cands:
+            break
+        leaf = cands[int(rng.integers(0, len(cands)))]
+        node = n_leaves - 1
+        f = int(rng.integers(0, n_features))
+        default_left = int(rng.random() < 0.5)
+        if f in cat_features:
+            n_cat = cat_features[f]
+            n_words = (n_cat + 31) // 32
+            words = [int(rng.integers(0, 2**32)) for _ in range(n_words)]
+            cat_idx = len(cat_b) - 1
+            cat_t.extend(words)
+            cat_b.append(len(cat_t))
+            sf.append(f); thr.append(float(cat_idx)); dt.append(1)  # categorical, missing None
+        else:
+            kind = kinds[f]
+            t = _quantile_threshold(rng, kind)
+            if kind == "nan5":
+                missing = 2
+            elif zero_missing and kind == "count":
+                missing = 1
+            else:
+                missing = 0
+            sf.append(f); thr.append(t); dt.append((default_left << 1) | (missing << 2))
+        lc.append(~leaf); rc.append(~n_leaves)
+        p, is_right = leaf_parent[leaf]
+        if p >= 0:
+            if is_right:
+                rc[p] = node
+            else:
+                lc[p] = node
+        d = leaf_depth[leaf] + 1
+        leaf_depth[leaf] = d
+        leaf_depth[n_leaves] = d
+        leaf_parent[leaf] = (node, 0)
+        leaf_parent[n_leaves] = (node, 1)
+        n_leaves += 1
+    lv = (rng.standard_normal(n_leaves) * 0.1 * shrinkage).tolist()
+    return _Tree(sf, thr, dt, lc, rc, lv, cat_b, cat_t)
+
+
+def lightgbm_model_text(n_trees: int, n_features: int, num_leaves: int = 16, max_depth: int = 8,
+                        seed: int = 1234, cat_features: dict | None = None,
+                        shrinkage: float = 0.1, zero_missing: bool = False,
+                        stump_every: int = 0) -> bytes:
+    """LightGBM ``SaveModelToString`` text (v4 header) for a lambdarank model.
+
+    cat_features: {column -> n_categories} columns split with categorical bitsets.
+    stump_every: every k-th tree is a single-leaf tree (num_leaves=1), which real
+    models contain after early convergence.
+    """
+    rng = np.random.Generator(np.random.PCG64(seed))
+    kinds = column_kinds(n_features)
+    cat_features = cat_features or {}
+    blocks = []
+    for t in range(n_trees):
+        if stump_every and t % stump_every == stump_every - 1:
+            tr = _Tree([], [], [], [], [], [float(rng.standard_normal() * 0.01)], [0], [])
+        else:
+            tr = _grow_lightgbm_tree(rng, n_features, kinds, num_leaves, max_depth, cat_features,
+                                     shrinkage, zero_missing)
+        nl = len(tr.leaf_value)
+        n_cat = len(tr.cat_boundaries) - 1
+        lines = [f"Tree={t}", f"num_leaves={nl}", f"num_cat={n_cat}"]
+        if nl > 1:
+            ni = nl - 1
+            lines += [
+                "split_feature=" + " ".join(map(str, tr.split_feature)),
+                "split_gain=" + " ".join("1" for _ in range(ni)),
+                "threshold=" + " ".join(_fmt(x) for x in tr.threshold),
+                "decision_type=" + " ".join(map(str, tr.decision_type)),
+                "left_child=" + " ".join(map(str, tr.left_child)),
+                "right_child=" + " ".join(map(str, tr.right_child)),
+                "leaf_value=" + " ".join(_fmt(x) for x in tr.leaf_value),
+                "leaf_weight=" + " ".join("1" for _ in range(nl)),
+                "leaf_count=" + " ".join("10" for _ in range(nl)),
+                "internal_value=" + " ".join("0" for _ in range(ni)),
+                "internal_weight=" + " ".join("1" for _ in range(ni)),
+                "internal_count=" + " ".join("20" for _ in range(ni)),
+            ]
+            if n_cat > 0:
+                lines += [
+                    "cat_boundaries=" + " ".join(map(str, tr.cat_boundaries)),
+                    "cat_threshold=" + " ".join(map(str, tr.cat_threshold)),
+                ]
+        else:
+            lines += ["leaf_value=" + _fmt(tr.leaf_value[0])]
+        lines += ["is_linear=0", f"shrinkage={_fmt(shrinkage)}", "", ""]
+        blocks.append("\n".join(lines))
+    header = [
+        "tree", "version=v4", "num_class=1", "num_tree_per_iteration=1", "label_index=0",
+        f"max_feature_idx={n_features - 1}", "objective=lambdarank",
+        "feature_names=" + " ".join(f"Column_{j}" for j in range(n_features)),
+        "feature_infos=" + " ".join("[-10:10]" for _ in range(n_features)),
+        "tree_sizes=" + " ".join(str(len(b) + 1) for b in blocks),
+        "", "",
+    ]
+    tail = ["end of trees", "", "feature_importances:", "", "parameters:", "[boosting: gbdt]",
+            "[objective: lambdarank]", "end of parameters", "", "pandas_categorical:null", ""]
+    return ("\n".join(header) + "\n".join(blocks) + "\n" + "\n".join(tail)).encode("utf-8")
+
+
+# --------------------------------------------------------------------------- XGBoost
+
+def _grow_xgb_tree(rng, n_features, kinds, depth, full, shrinkage):
+    """XGBoost RegTree arrays (BFS ids, leaf <=> left_children == -1)."""
+    left, right, sidx, scond, dleft = [], [], [], [], []
+
+    def new_node():
+        left.append(-1); right.append(-1); sidx.append(0); scond.append(0.0); dleft.append(0)
+        return len(left) - 1
+
+    root = new_node()
+    frontier = [(root, 0)]
+    while frontier:
+        nid, d = frontier.pop(0)
+        split = d < depth and (full or d < 2 or rng.random() < 0.75)
+        if split:
+            f = int(rng.integers(0, n_features))
+            sidx[nid] = f
+            scond[nid] = float(np.float32(_quantile_threshold(rng, kinds[f])))
+            dleft[nid] = int(rng.random() < 0.5)
+            l = new_node(); r = new_node()
+            left[nid] = l; right[nid] = r
+            frontier.append((l, d + 1)); frontier.append((r, d + 1))
+        else:
+            scond[nid] = float(np.float32(rng.standard_normal() * 0.1 * shrinkage))
+    return left, right, sidx, scond, dleft
+
+
+def _xgb_model_dict(n_trees, n_features, depth, seed, full, base_score, shrinkage):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    kinds = column_kinds(n_features)
+    trees = []
+    for t in range(n_trees):
+        l, r, si, sc, dl = _grow_xgb_tree(rng, n_features, kinds, depth, full, shrinkage)
+        n = len(l)
+        parents = [2147483647] * n
+        for i in range(n):
+            if l[i] >= 0:
+                parents[l[i]] = i; parents[r[i]] = i
+        trees.append({
+            "base_weights": [0.0] * n, "categories": [], "categories_nodes": [],
+            "categories_segments": [], "categories_sizes": [],
+            "default_left": dl, "id": t, "left_children": l, "loss_changes": [0.0] * n,
+            "parents": parents, "right_children": r, "split_conditions": sc,
+            "split_indices": si, "split_type": [0] * n, "sum_hessian": [1.0] * n,
+            "tree_param": {"num_deleted": "0", "num_feature": str(n_features),
+                           "num_nodes": str(n), "size_leaf_vector": "1"},
+        })
+    bs = np.float32(base_score)
+    return {
+        "learner": {
+            "attributes": {}, "feature_names": [], "feature_types": [],
+            "gradient_booster": {
+                "model": {
+                    "gbtree_model_param": {"num_parallel_tree": "1", "num_trees": str(n_trees)},
+                    "iteration_indptr": list(range(n_trees + 1)),
+                    "tree_info": [0] * n_trees, "trees": trees,
+                },
+                "name": "gbtree",
+            },
+            "learner_model_param": {
+                "base_score": np.format_float_scientific(bs, unique=True, exp_digits=1).upper(),
+                "boost_from_average": "1", "num_class": "0", "num_feature": str(n_features),
+                "num_target": "1",
+            },
+            "objective": {"name": "rank:ndcg", "lambdarank_param": {}},
+        },
+        "version": [2, 1, 4],
+    }
+
+
+def xgboost_model_json(n_trees: int, n_features: int, depth: int = 6, seed: int = 1234,
+                       full: bool = True, base_score: float = 0.5, shrinkage: float = 0.1) -> bytes:
+    """XGBoost ≥1.x JSON model (``save_raw("json")``) for a rank:ndcg gbtree."""
+    d = _xgb_model_dict(n_trees, n_features, depth, seed, full, base_score, shrinkage)
+    return json.dumps(d, separators=(",", ":")).encode("utf-8")
+
+
+def _ubj(obj, float_ctx: str | None = None) -> bytes:
+    """Minimal UBJSON writer in the dialect XGBoost emits (typed arrays for numeric lists)."""
+    if isinstance(obj, dict):
+        out = [b"{"]
+        for k, v in obj.items():
+            kb = k.encode()
+            out.append(b"L" + struct.pack(">q", len(kb)) + kb)
+            out.append(_ubj(v, k))
+        out.append(b"}")
+        return b"".join(out)
+    if isinstance(obj, list):
+        if obj and all(isinstance(x, float) for x in obj):
+            return b"[$d#L" + struct.pack(">q", len(obj)) + b"".join(struct.pack(">f", x) for x in obj)
+        if obj and all(isinstance(x, int) and not isinstance(x, bool) for x in obj):
+            if float_ctx == "default_left" or float_ctx == "split_type":
+                return b"[$U#L" + struct.pack(">q", len(obj)) + bytes(obj)
+            if float_ctx in ("iteration_indptr",) or max(abs(x) for x in obj) >= 2**31:
+                return b"[$L#L" + struct.pack(">q", len(obj)) + b"".join(struct.pack(">q", x) for x in obj)
+            return b"[$l#L" + struct.pack(">q", len(obj)) + b"".join(struct.pack(">i", x) for x in obj)
+        return b"[" + b"".join(_ubj(x) for x in obj) + b"]"
+    if isinstance(obj, str):
+        b = obj.encode()
+        return b"SL" + struct.pack(">q", len(b)) + b
+    if isinstance(obj, bool):
+        return b"T" if obj else b"F"
+    if isinstance(obj, int):
+        return b"l" + struct.pack(">i", obj) if abs(obj) < 2**31 else b"L" + struct.pack(">q", obj)
+    if isinstance(obj, float):
+        return b"d" + struct.pack(">f", obj)
+    if obj is None:
+        return b"Z"
+    raise TypeError(type(obj))
+
+
+def xgboost_model_ubj(n_trees: int, n_features: int, depth: int = 6, seed: int = 1234,
+                      full: bool = True, base_score: float = 0.5, shrinkage: float = 0.1) -> bytes:
+    """Same model as :func:`xgboost_model_json`, UBJSON-encoded (``save_raw("ubj")``)."""
+    return _ubj(_xgb_model_dict(n_trees, n_features, depth, seed, full, base_score, shrinkage))
+
+
+def metarank_model_blob(feature_names: list[str], booster_kind: int, booster_bytes: bytes,
+                        version: int = 3) -> bytes:
+    """Metarank's model framing (reference S/ml/rank/LambdaMARTRanker.scala:367-389):
+    byte version, int nFeatures, writeUTF names, byte boosterType, int size, bytes,
+    (v3) int nWarmup — big-endian DataOutputStream."""
+    out = [struct.pack(">b", version), struct.pack(">i", len(feature_names))]
+    for n in feature_names:
+        b = n.encode("utf-8")  # modified UTF-8 == UTF-8 for BMP text without NUL
+        out.append(struct.pack(">H", len(b)) + b)
+    out.append(struct.pack(">b", booster_kind))
+    out.append(struct.pack(">i", len(booster_bytes)))
+    out.append(booster_bytes)
+    if version >= 3:
+        out.append(struct.pack(">i", 0))
+    return b"".join(out)

@@ -1,0 +1,203 @@
+"""GPU parity of Booster.predictMat (through the C ABI) against the CPU oracle.
+
+Bar (BASELINE.json north_star): ordering bit-exact, |Δscore| <= 1e-5.  The kernel
+accumulates per item in tree order in the library's own precision, so we assert the
+stronger property: scores are BIT-IDENTICAL to the oracle.
+"""
+import numpy as np
+import pytest
+
+from metarank_b200 import synth
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # the stated tolerance; the tests below additionally require exact equality
+
+
+def _check(ctx, kind, blob, X, **opts):
+    import metarank_b200 as mb
+
+    ob = oracle.OracleBooster(kind, blob)
+    want = ob.predictMat(X, *X.shape)
+    b = mb.B200Booster(ctx, blob, kind=kind, n_features=X.shape[1])
+    try:
+        for k, v in opts.items():
+            b.set_option(k, v)
+        got = b.predictMat(X, *X.shape)
+    finally:
+        b.free()
+    assert got.shape == want.shape
+    assert np.all(np.abs(got - want) <= TOL)
+    assert np.array_equal(got, want), f"max |Δ| = {np.max(np.abs(got - want))}"
+    assert np.array_equal(ctx.rank_order(got), oracle.rank_order(want))
+    return got
+
+
+@pytest.mark.parametrize("variant,ilp", [(0, 1), (0, 2), (0, 4), (1, 1)])
+@pytest.mark.parametrize("threads", [32, 128, 256])
+def test_c2_lightgbm_100x30x500(ctx, variant, ilp, threads):
+    blob = synth.lightgbm_model_text(500, 30, seed=1234 + 2)
+    X = synth.feature_matrix(100, 30, seed=42 + 2)
+    _check(ctx, 0, blob, X, variant=variant, ilp=ilp, threads=threads)
+
+
+@pytest.mark.parametrize("chunk_kb", [4, 32, 200])
+def test_chunking_is_invisible(ctx, chunk_kb):
+    blob = synth.lightgbm_model_text(500, 30, seed=7)
+    X = synth.feature_matrix(3000, 30, seed=8)
+    _check(ctx, 0, blob, X, chunk_kb=chunk_kb)
+
+
+@pytest.mark.parametrize("rows", [1, 2, 31, 32, 33, 255, 257, 1000, 4097])
+def test_ragged_row_counts(ctx, rows):
+    blob = synth.lightgbm_model_text(64, 13, seed=3)  # odd column count: scalar tile loads
+    X = synth.feature_matrix(rows, 13, seed=rows)
+    _check(ctx, 0, blob, X)
+
+
+def test_categorical_zero_missing_and_stumps(ctx):
+    cat = {2: 40, 7: 100}
+    blob = synth.lightgbm_model_text(120, 10, seed=11, cat_features=cat, zero_missing=True, stump_every=7)
+    rng = np.random.Generator(np.random.PCG64(5))
+    X = synth.feature_matrix(2000, 10, seed=6)
+    X[:, 2] = rng.integers(-2, 45, 2000)  # negative and out-of-bitset categories
+    X[:, 7] = rng.integers(0, 130, 2000)
+    X[rng.random(2000) < 0.1, 2] = np.nan
+    X[rng.random(2000) < 0.05, 7] = 3e10  # beyond int range -> right child
+    X[rng.random(2000) < 0.2, 0] = 0.0
+    X[rng.random(2000) < 0.1, 1] = np.nan
+    X[rng.random(2000) < 0.05, 3] = np.inf
+    X[rng.random(2000) < 0.05, 4] = -np.inf
+    X[rng.random(2000) < 0.05, 5] = 1e-36  # inside LightGBM's zero band
+    for variant in (0, 1):
+        _check(ctx, 0, blob, X, variant=variant)
+
+
+def test_deep_unbalanced_lightgbm(ctx):
+    blob = synth.lightgbm_model_text(50, 20, num_leaves=255, max_depth=0, seed=21)
+    X = synth.feature_matrix(777, 20, seed=22)
+    _check(ctx, 0, blob, X)
+
+
+@pytest.mark.parametrize("fmt", ["json", "ubj"])
+@pytest.mark.parametrize("depth,full", [(6, True), (8, False)])
+def test_c4_xgboost(ctx, fmt, depth, full):
+    gen = synth.xgboost_model_json if fmt == "json" else synth.xgboost_model_ubj
+    blob = gen(200, 16, depth=depth, seed=1234 + 4, full=full)
+    X = synth.feature_matrix(256, 16, seed=42 + 4)
+    for variant in (0, 1):
+        _check(ctx, 1, blob, X, variant=variant)
+
+
+def test_xgboost_f32_rounding_of_inputs(ctx):
+    # values that differ only below binary32 precision must route identically to the oracle
+    blob = synth.xgboost_model_json(50, 4, depth=5, seed=9)
+    rng = np.random.Generator(np.random.PCG64(10))
+    X = rng.standard_normal((500, 4))
+    X += rng.standard_normal((500, 4)) * 1e-9
+    _check(ctx, 1, blob, X)
+
+
+def test_wide_rows_fall_back_to_global_reads(ctx):
+    blob = synth.lightgbm_model_text(20, 1200, seed=31)
+    X = synth.feature_matrix(300, 1200, seed=32)
+    _check(ctx, 0, blob, X)
+
+
+def test_c5_mega_request_properties(ctx):
+    """BASELINE config #5 shape at full size: 10 000 x 64, 2000 trees."""
+    import metarank_b200 as mb
+
+    blob = synth.lightgbm_model_text(2000, 64, seed=1234 + 5)
+    X = synth.feature_matrix(10_000, 64, seed=42 + 5)
+    got = _check(ctx, 0, blob, X)
+    # size-independent properties: row permutation equivariance, duplication
+    b = mb.B200Booster(ctx, blob, kind=0)
+    perm = np.random.Generator(np.random.PCG64(1)).permutation(X.shape[0])
+    got_p = b.predictMat(X[perm], *X.shape)
+    assert np.array_equal(got_p, got[perm])
+    twice = b.predictMat(np.concatenate([X[:100], X[:100]]), 200, 64)
+    assert np.array_equal(twice[:100], twice[100:])
+    b.free()
+
+
+def test_empty_and_errors(ctx):
+    import metarank_b200 as mb
+
+    blob = synth.lightgbm_model_text(5, 4, seed=1)
+    b = mb.B200Booster(ctx, blob, kind=0)
+    assert b.predictMat(np.zeros((0, 4)), 0, 4).shape == (0,)
+    with pytest.raises(mb.MrError) as e:
+        b.predictMat(np.zeros((3, 5)), 3, 5)
+    assert e.value.status == 1
+    assert b.save() == blob
+    assert b.weights().sum() == b.info().n_internal_nodes
+    assert not b.isClosed()
+    b.close()
+    b.close()  # idempotent
+    assert b.isClosed()
+    with pytest.raises(mb.MrError) as e:
+        b.predictMat(np.zeros((1, 4)), 1, 4)
+    assert e.value.status == 4
+    with pytest.raises(mb.MrError):
+        mb.B200Booster(ctx, b"not a model", kind=0)
+    with pytest.raises(mb.MrError) as e:
+        mb.B200Booster(ctx, blob, kind=0, n_features=9)
+    assert e.value.status == 6
+
+
+def test_metarank_blob_framing(ctx):
+    import metarank_b200 as mb
+
+    names = [f"f{i}" for i in range(6)]
+    lgb = synth.lightgbm_model_text(10, 6, seed=2)
+    X = synth.feature_matrix(50, 6, seed=3)
+    want = oracle.OracleBooster(0, lgb).predictMat(X, 50, 6)
+    for version in (2, 3):
+        blob = synth.metarank_model_blob(names, 0, lgb, version=version)
+        b = mb.B200Booster.from_metarank_blob(ctx, blob, names)
+        assert np.array_equal(b.predictMat(X, 50, 6), want)
+        b.free()
+    with pytest.raises(mb.MrError) as e:
+        mb.B200Booster.from_metarank_blob(ctx, blob, names[:-1] + ["other"])
+    assert e.value.status == 6 and "booster trained with" in e.value.message
+
+
+def test_mean_path_matches_oracle(ctx):
+    import metarank_b200 as mb
+
+    blob = synth.lightgbm_model_text(100, 30, seed=4)
+    X = synth.feature_matrix(500, 30, seed=5)
+    ob = oracle.OracleBooster(0, blob)
+    ob.predictMat(X, 500, 30)
+    b = mb.B200Booster(ctx, blob, kind=0)
+    # single-leaf trees cost one dummy node on the device; none here
+    assert b.mean_path(X, 500, 30) == pytest.approx(ob.visited / (500 * 100), rel=1e-12)
+    b.free()
+
+
+def test_concurrent_predicts(ctx):
+    import threading
+
+    import metarank_b200 as mb
+
+    blob = synth.lightgbm_model_text(200, 30, seed=6)
+    b = mb.B200Booster(ctx, blob, kind=0)
+    ob = oracle.OracleBooster(0, blob)
+    errs = []
+
+    def work(seed):
+        try:
+            X = synth.feature_matrix(100 + seed, 30, seed=seed)
+            want = ob.predictMat(X, *X.shape)
+            for _ in range(20):
+                assert np.array_equal(b.predictMat(X, *X.shape), want)
+        except Exception as ex:  # noqa: BLE001
+            errs.append(ex)
+
+    ts = [threading.Thread(target=work, args=(s,)) for s in range(8)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    b.free()
+    assert not errs, errs
