@@ -1,0 +1,79 @@
+"""CPU-side checks of libmrgpu.so: it loads, exports every symbol the header declares,
+its host parsers accept/reject what the oracle's parsers accept/reject, and the GPU
+entry points fail loudly (no CPU fallback) when no device is present."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import metarank_b200 as mb
+from metarank_b200 import _capi, synth
+from metarank_b200.booster import inspect_model
+from oracle import model_parse
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _capi.lib()
+    names = _capi.declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), n
+    assert b"sm_100a" in lib.mr_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(mb.MrError) as e:
+        mb.Context(0)
+    assert e.value.status == 8 and "no CPU fallback" in e.value.message
+
+
+@pytest.mark.parametrize("kind,blob", [
+    (0, synth.lightgbm_model_text(500, 30, seed=1236)),
+    (0, synth.lightgbm_model_text(9, 6, cat_features={2: 40}, stump_every=3, zero_missing=True)),
+    (1, synth.xgboost_model_json(200, 16, depth=6)),
+    (1, synth.xgboost_model_ubj(20, 16, depth=8, full=False)),
+])
+def test_host_parser_agrees_with_oracle_parser_on_shape(kind, blob):
+    inf = inspect_model(kind, blob)
+    om = model_parse.parse_lightgbm_text(blob) if kind == 0 else model_parse.parse_xgboost(blob)
+    assert inf.n_features == om["n_features"]
+    assert inf.n_trees == len(om["trees"])
+    if kind == 0:
+        assert inf.n_internal_nodes == sum(t["num_leaves"] - 1 for t in om["trees"])
+        assert inf.max_leaves == max(t["num_leaves"] for t in om["trees"])
+        assert inf.has_categorical == int(any((t["decision_type"] & 1).any() for t in om["trees"]))
+    else:
+        assert inf.n_internal_nodes == sum(int((t["left"] != -1).sum()) for t in om["trees"])
+    assert inf.device_bytes % 16 == 0 and inf.n_chunks >= 1
+
+
+def test_chunk_budget_controls_chunk_count():
+    blob = synth.lightgbm_model_text(500, 30, seed=1)
+    assert inspect_model(0, blob, chunk_kb=1024).n_chunks == 1
+    assert inspect_model(0, blob, chunk_kb=4).n_chunks > 40
+
+
+@pytest.mark.parametrize("kind,blob,status", [
+    (0, b"", 2), (0, b"tree\nversion=v4\n", 2), (1, b"binf....", 5), (1, b'{"learner": {}}', 2), (7, b"x", 5),
+    (0, synth.lightgbm_model_text(2, 3).replace(b"num_class=1", b"num_class=3"), 5),
+    (0, synth.lightgbm_model_text(2, 3).replace(b"is_linear=0", b"is_linear=1"), 5),
+    (0, synth.lightgbm_model_text(2, 3).replace(b"max_feature_idx=2", b"max_feature_idx=0"), 2),
+])
+def test_bad_models_are_rejected_with_a_status(kind, blob, status):
+    with pytest.raises(mb.MrError) as e:
+        inspect_model(kind, blob)
+    assert e.value.status == status, e.value
+
+
+def test_truncated_lightgbm_arrays_are_parse_errors():
+    blob = synth.lightgbm_model_text(1, 3, seed=5)
+    lines = blob.decode().split("\n")
+    i = next(k for k, l in enumerate(lines) if l.startswith("threshold="))
+    lines[i] = " ".join(lines[i].split(" ")[:-1])
+    with pytest.raises(mb.MrError) as e:
+        inspect_model(0, "\n".join(lines).encode())
+    assert e.value.status == 2 and "threshold" in e.value.message

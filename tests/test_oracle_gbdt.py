@@ -1,0 +1,216 @@
+"""Pins the GBDT oracle on hand-computed known answers.
+
+The reference holds NO golden score for Booster.predictMat ("parity
+unpinned"), so these cases are derived by hand from the published LightGBM / XGBoost
+decision rules — each expected value below can be checked with pencil and paper
+against the model text in the test.
+"""
+import json
+import math
+
+import numpy as np
+import pytest
+
+from metarank_b200 import synth
+from oracle import model_parse, oracle
+
+LGB_TEMPLATE = """tree
+version=v4
+num_class=1
+num_tree_per_iteration=1
+label_index=0
+max_feature_idx=2
+objective=lambdarank
+feature_names=a b c
+feature_infos=[0:1] [0:1] 0:1:2:3:40
+tree_sizes=0
+
+{trees}
+end of trees
+
+feature_importances:
+a=1
+
+parameters:
+end of parameters
+
+pandas_categorical:null
+"""
+
+
+def lgb(*trees):
+    return LGB_TEMPLATE.format(trees="\n\n".join(trees)).encode()
+
+
+# node 0: a <= 0.5 ? node 1 : leaf 2 ; node 1: b <= 1.5 ? leaf 0 : leaf 1
+T_NUM = lambda dt0, dt1: f"""Tree=0
+num_leaves=3
+num_cat=0
+split_feature=0 1
+split_gain=1 1
+threshold=0.5 1.5
+decision_type={dt0} {dt1}
+left_child=1 -1
+right_child=-3 -2
+leaf_value=10 20 30
+leaf_weight=1 1 1
+leaf_count=1 1 1
+internal_value=0 0
+internal_weight=1 1
+internal_count=2 2
+is_linear=0
+shrinkage=1
+"""
+
+NAN = float("nan")
+
+
+def predict(blob, rows):
+    X = np.array(rows, dtype=np.float64)
+    return oracle.OracleBooster(0, blob).predictMat(X, *X.shape).tolist()
+
+
+def test_lightgbm_numerical_le_threshold():
+    # decision_type 0: missing None, default right
+    got = predict(lgb(T_NUM(0, 0)), [[0.5, 1.5, 0], [0.5000001, 0, 0], [0.4, 1.6, 0], [-1e300, -1e300, 0]])
+    assert got == [10.0, 30.0, 20.0, 10.0]  # x <= thr goes LEFT (inclusive)
+
+
+def test_lightgbm_nan_with_missing_none_becomes_zero():
+    # missing None: NaN -> 0.0, then 0.0 <= 0.5 -> left ; 0.0 <= 1.5 -> left
+    assert predict(lgb(T_NUM(0, 0)), [[NAN, NAN, 0]]) == [10.0]
+    # threshold below zero: NaN -> 0.0 > -1 -> right
+    t = T_NUM(0, 0).replace("threshold=0.5 1.5", "threshold=-1 1.5")
+    assert predict(lgb(t), [[NAN, 0, 0]]) == [30.0]
+
+
+def test_lightgbm_missing_nan_uses_default_direction():
+    # decision_type 8 = missing NaN, default right ; 10 = missing NaN, default left
+    assert predict(lgb(T_NUM(8, 8)), [[NAN, 0, 0], [0.1, NAN, 0]]) == [30.0, 20.0]
+    assert predict(lgb(T_NUM(10, 10)), [[NAN, 99, 0], [0.1, NAN, 0]]) == [20.0, 10.0]
+
+
+def test_lightgbm_missing_zero_band():
+    # decision_type 4 = missing Zero, default right ; 6 = default left.  |x| <= 1e-35f is "zero"
+    assert predict(lgb(T_NUM(4, 4)), [[0.0, 0.0, 0], [1e-36, 1.0, 0], [-1e-36, 1.0, 0], [1e-34, 1.0, 0]]) == \
+        [30.0, 30.0, 30.0, 10.0]
+    assert predict(lgb(T_NUM(6, 6)), [[0.0, 5.0, 0], [0.0, 0.0, 0]]) == [20.0, 10.0]
+    # NaN with missing Zero: NaN -> 0.0 -> zero band -> default side
+    assert predict(lgb(T_NUM(4, 4)), [[NAN, 0, 0]]) == [30.0]
+    assert predict(lgb(T_NUM(6, 6)), [[NAN, NAN, 0]]) == [10.0]
+
+
+T_CAT = """Tree=0
+num_leaves=2
+num_cat=1
+split_feature=2
+split_gain=1
+threshold=0
+decision_type=1
+left_child=-1
+right_child=-2
+leaf_value=1 2
+leaf_weight=1 1
+leaf_count=1 1
+internal_value=0
+internal_weight=1
+internal_count=2
+cat_boundaries=0 2
+cat_threshold=10 1
+is_linear=0
+shrinkage=1
+"""
+
+
+def test_lightgbm_categorical_bitset():
+    # bitset words [10 (bits 1,3), 1 (bit 32)] -> categories {1, 3, 32} go left
+    rows = [[0, 0, c] for c in (0, 1, 2, 3, 3.9, 31, 32, 33, 64, 1000, -1, NAN, 3e10, -0.5)]
+    # 3.9 truncates to 3 (left); -0.5 truncates to 0 (not in set); -1 < 0 -> right
+    want = [2, 1, 2, 1, 1, 2, 1, 2, 2, 2, 2, 2, 2, 2]
+    assert predict(lgb(T_CAT), rows) == [float(w) for w in want]
+
+
+def test_lightgbm_sum_is_f64_in_tree_order():
+    # 0.1 + 0.2 + 0.3 in f64, left to right: (0.1 + 0.2) + 0.3 != 0.1 + (0.2 + 0.3)
+    def stump(i, v):
+        return f"Tree={i}\nnum_leaves=1\nnum_cat=0\nleaf_value={v!r}\nis_linear=0\nshrinkage=1\n"
+
+    got = predict(lgb(stump(0, 0.1), stump(1, 0.2), stump(2, 0.3)), [[0, 0, 0]])
+    assert got == [(0.1 + 0.2) + 0.3]
+    assert got != [0.1 + (0.2 + 0.3)]
+
+
+def test_lightgbm_threshold_parse_is_correctly_rounded():
+    t = T_NUM(0, 0).replace("threshold=0.5 1.5", "threshold=0.1000000000000000055511151231257827 1.5")
+    assert predict(lgb(t), [[0.1, 0, 0], [np.nextafter(0.1, 1), 0, 0]]) == [10.0, 30.0]
+
+
+def _xgb(trees, base="5E-1", nf=2):
+    return json.dumps({"learner": {
+        "gradient_booster": {"name": "gbtree", "model": {"trees": trees, "tree_info": [0] * len(trees)}},
+        "learner_model_param": {"base_score": base, "num_feature": str(nf), "num_class": "0"},
+        "objective": {"name": "rank:ndcg"}}, "version": [2, 1, 4]}).encode()
+
+
+def _xtree(split_cond, default_left):
+    return {"left_children": [1, -1, -1], "right_children": [2, -1, -1], "split_indices": [0, 0, 0],
+            "split_conditions": split_cond, "default_left": default_left, "split_type": [0, 0, 0]}
+
+
+def test_xgboost_strict_less_default_and_f32():
+    blob = _xgb([_xtree([0.5, 1.0, 2.0], [1, 0, 0])])
+    X = np.array([[0.5, 0], [0.4999999, 0], [NAN, 0], [0.5 - 1e-12, 0]])
+    got = oracle.OracleBooster(1, blob).predictMat(X, 4, 2).tolist()
+    # 0.5 < 0.5 false -> right (2.0); 0.4999999 -> left; NaN -> default left;
+    # 0.5-1e-12 rounds to 0.5f as binary32 -> NOT less -> right
+    assert got == [2.5, 1.5, 1.5, 2.5]
+    blob = _xgb([_xtree([0.5, 1.0, 2.0], [0, 0, 0])])
+    assert oracle.OracleBooster(1, blob).predictMat(np.array([[NAN, 0.0]]), 1, 2).tolist() == [2.5]
+
+
+def test_xgboost_f32_sequential_sum_from_base_score():
+    leaves = [0.1, 0.2, 0.3, 1e-8, 1e-8]
+    trees = [{"left_children": [-1], "right_children": [-1], "split_indices": [0], "split_conditions": [v],
+              "default_left": [0], "split_type": [0]} for v in leaves]
+    got = oracle.OracleBooster(1, _xgb(trees)).predictMat(np.zeros((1, 2)), 1, 2)[0]
+    s = np.float32(0.5)
+    for v in leaves:
+        s = np.float32(s + np.float32(v))
+    assert got == float(s)
+    assert got != 0.5 + sum(leaves)  # f64 arithmetic would differ
+
+
+def test_parsers_agree_json_ubj_and_reject_garbage():
+    a = model_parse.parse_xgboost(synth.xgboost_model_json(5, 6, depth=4, seed=1))
+    b = model_parse.parse_xgboost(synth.xgboost_model_ubj(5, 6, depth=4, seed=1))
+    for ta, tb in zip(a["trees"], b["trees"]):
+        for k in ta:
+            assert np.array_equal(ta[k], tb[k])
+    with pytest.raises(ValueError):
+        model_parse.parse_xgboost(b"binf\x00\x00")
+    with pytest.raises(ValueError):
+        model_parse.parse_lightgbm_text(b"hello")
+
+
+def test_metarank_blob_roundtrip():
+    names = ["popularity", "ctr", "genre"]
+    inner = synth.lightgbm_model_text(2, 3, seed=1)
+    for v in (2, 3):
+        ver, got_names, kind, booster = model_parse.parse_metarank_blob(synth.metarank_model_blob(names, 0, inner, v))
+        assert (ver, got_names, kind, booster) == (v, names, 0, inner)
+    with pytest.raises(ValueError):
+        model_parse.parse_metarank_blob(b"\x07" + b"\0" * 20)
+
+
+def test_rank_order_is_stable_descending_total_order():
+    s = [0.1, 0.5, 0.5, NAN, -0.0, 0.0, 2.0, -math.inf, math.inf]
+    assert oracle.rank_order(s).tolist() == [8, 6, 1, 2, 0, 5, 4, 7, 3]
+    assert oracle.rank_order([]).tolist() == []
+    assert oracle.rank_order([1.0] * 5).tolist() == [0, 1, 2, 3, 4]
+
+
+def test_openmp_path_equals_scalar_path():
+    blob = synth.lightgbm_model_text(50, 12, seed=3, cat_features={4: 20}, zero_missing=True)
+    X = synth.feature_matrix(3000, 12, seed=4)
+    ob = oracle.OracleBooster(0, blob)
+    assert np.array_equal(ob.predictMat(X, *X.shape, threads=1), ob.predictMat(X, *X.shape, threads=0))

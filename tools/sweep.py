@@ -1,7 +1,7 @@
 """Scratch sweep of kernel variants on the GPU (not part of the product)."""
 import sys, time, json
 import numpy as np, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import metarank_b200 as mb
 from metarank_b200 import synth
 from oracle import oracle
