@@ -130,13 +130,14 @@ struct mr_model {
                              cudaMemcpyHostToDevice));
   }
   void repack() {
-    // Default policy: keep the whole ensemble resident in shared memory when it leaves room
-    // for a feature tile; otherwise stream it in ~32 KB chunks (two buffers in flight).
+    // Default policy: stream the ensemble through two small shared-memory buffers (TMA bulk
+    // copies overlap the traversal).  Small chunks leave shared memory for the feature tile,
+    // i.e. for resident warps, which is what bounds this kernel (profiles/ round-1 notes).
     size_t budget;
     if (opt_chunk_kb > 0) {
       budget = (size_t)opt_chunk_kb * 1024;
     } else {
-      budget = 32 * 1024;
+      budget = 8 * 1024;  // small chunks leave shared memory for the feature tile (occupancy)
     }
     packed = pack_model(host, budget);
     upload();
@@ -299,6 +300,20 @@ mr_status mr_model_predict_mat_device(mr_model *m, const double *d_values, int32
   });
 }
 
+// Host-buffer predictMat.  Large batches are cut into slices that alternate between two
+// lanes (stream + buffers) so the H2D copy of slice i+1 overlaps the kernel of slice i and
+// the D2H of slice i-1.  Page-locked caller buffers are DMA'd directly; pageable ones are
+// staged through the lane's pinned buffer.
+static bool is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
 mr_status mr_model_predict_mat(mr_model *m, const double *values, int32_t rows, int32_t cols, double *out_scores) {
   return guard([&] {
     check_model(m);
@@ -306,19 +321,48 @@ mr_status mr_model_predict_mat(mr_model *m, const double *values, int32_t rows, 
     check_matrix(m, values, rows, cols, out_scores);
     if (rows == 0) return;
     MR_CUDA_CHECK(cudaSetDevice(m->ctx->device));
-    LaneGuard lane(m->ctx);
-    const size_t in_bytes = (size_t)rows * cols * sizeof(double), out_bytes = (size_t)rows * sizeof(double);
-    const size_t d_in_off = 0, d_out_off = (in_bytes + 255) & ~size_t(255);
-    lane->ensure(in_bytes + out_bytes, d_out_off + out_bytes);
-    // stage through pinned memory so both copies are truly asynchronous DMA
-    memcpy(lane->h_pinned, values, in_bytes);
-    double *d_in = (double *)(lane->d_buf + d_in_off), *d_out = (double *)(lane->d_buf + d_out_off);
-    MR_CUDA_CHECK(cudaMemcpyAsync(d_in, lane->h_pinned, in_bytes, cudaMemcpyHostToDevice, lane->stream));
-    ScoreLaunch L = m->launch_desc(d_in, rows, cols, d_out);
-    launch_gbdt_score(L, m->ctx->num_sms, lane->stream);
-    MR_CUDA_CHECK(cudaMemcpyAsync(lane->h_pinned + in_bytes, d_out, out_bytes, cudaMemcpyDeviceToHost, lane->stream));
-    MR_CUDA_CHECK(cudaStreamSynchronize(lane->stream));
-    memcpy(out_scores, lane->h_pinned + in_bytes, out_bytes);
+    const int kSlice = 1 << 17;  // rows per slice
+    const int n_slices = (rows + kSlice - 1) / kSlice;
+    const bool direct_in = is_pinned(values), direct_out = is_pinned(out_scores);
+    LaneGuard lane0(m->ctx);
+    std::unique_ptr<LaneGuard> lane1;
+    if (n_slices > 1) lane1 = std::make_unique<LaneGuard>(m->ctx);
+    Lane *lanes[2] = {lane0.lane.get(), lane1 ? lane1->lane.get() : lane0.lane.get()};
+    const int slice_rows = std::min(rows, kSlice);
+    const size_t in_cap = (size_t)slice_rows * cols * sizeof(double), out_cap = (size_t)slice_rows * sizeof(double);
+    const size_t d_out_off = (in_cap + 255) & ~size_t(255);
+    for (int l = 0; l < (n_slices > 1 ? 2 : 1); l++)
+      lanes[l]->ensure((direct_in ? 0 : in_cap) + (direct_out ? 0 : out_cap) + 16, d_out_off + out_cap);
+    struct Pending { int r0, n; };
+    Pending pend[2] = {{0, 0}, {0, 0}};
+    auto drain = [&](int l) {
+      if (pend[l].n == 0) return;
+      MR_CUDA_CHECK(cudaStreamSynchronize(lanes[l]->stream));
+      if (!direct_out)
+        memcpy(out_scores + pend[l].r0, lanes[l]->h_pinned + (direct_in ? 0 : in_cap), (size_t)pend[l].n * sizeof(double));
+      pend[l].n = 0;
+    };
+    for (int i = 0; i < n_slices; i++) {
+      const int l = i & 1;
+      Lane *ln = lanes[l];
+      drain(l);  // buffers of this lane are free again
+      const int r0 = i * kSlice, n = std::min(kSlice, rows - r0);
+      const size_t in_bytes = (size_t)n * cols * sizeof(double), out_bytes = (size_t)n * sizeof(double);
+      const double *src = values + (size_t)r0 * cols;
+      if (!direct_in) {
+        memcpy(ln->h_pinned, src, in_bytes);
+        src = (const double *)ln->h_pinned;
+      }
+      double *d_in = (double *)ln->d_buf, *d_out = (double *)(ln->d_buf + d_out_off);
+      MR_CUDA_CHECK(cudaMemcpyAsync(d_in, src, in_bytes, cudaMemcpyHostToDevice, ln->stream));
+      ScoreLaunch L = m->launch_desc(d_in, n, cols, d_out);
+      launch_gbdt_score(L, m->ctx->num_sms, ln->stream);
+      double *dst = direct_out ? out_scores + r0 : (double *)(ln->h_pinned + (direct_in ? 0 : in_cap));
+      MR_CUDA_CHECK(cudaMemcpyAsync(dst, d_out, out_bytes, cudaMemcpyDeviceToHost, ln->stream));
+      pend[l] = {r0, n};
+    }
+    drain(0);
+    drain(1);
   });
 }
 
@@ -390,7 +434,7 @@ mr_status mr_model_inspect(int32_t kind, const uint8_t *blob, size_t len, int32_
     if (kind == MR_BOOSTER_LIGHTGBM) hm = parse_lightgbm_text(blob, len);
     else if (kind == MR_BOOSTER_XGBOOST) hm = parse_xgboost_model(blob, len);
     else fail(MR_ERR_UNSUPPORTED, "unsupported booster tag %d", kind);
-    PackedModel pk = pack_model(hm, (size_t)(chunk_kb > 0 ? chunk_kb : 32) * 1024);
+    PackedModel pk = pack_model(hm, (size_t)(chunk_kb > 0 ? chunk_kb : 8) * 1024);
     out->kind = hm.kind;
     out->n_features = hm.n_features;
     out->n_trees = (int32_t)hm.trees.size();

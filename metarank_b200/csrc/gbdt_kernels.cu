@@ -127,7 +127,7 @@ __device__ __forceinline__ int step(const uint4 nd, const Real x, const uint8_t 
 // VARIANT 1: free-running — a lane moves to its next tree as soon as it hits a leaf, so no
 //            lane idles while the deepest path of the warp finishes.
 template <typename Real, bool HAS_CAT, bool HAS_ZERO, int VARIANT, int ILP, bool STAGE, bool COUNT>
-__global__ void __launch_bounds__(256) gbdt_score_kernel(const KParams p) {
+__global__ void __launch_bounds__(1024) gbdt_score_kernel(const KParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   using AccT = typename Acc<Real>::type;
   const int W = blockDim.x;
@@ -215,15 +215,21 @@ __global__ void __launch_bounds__(256) gbdt_score_kernel(const KParams p) {
           }
           bool any = true;
           while (any) {
+            // all ILP node loads, then all feature loads, are issued before any is consumed;
+            // a tree that already reached its leaf re-reads its root (harmless) and keeps n
+            uint4 nd[ILP];
+            Real x[ILP];
+#pragma unroll
+            for (int k = 0; k < ILP; k++) nd[k] = nodes[k][n[k] < 0 ? 0 : n[k]];
+#pragma unroll
+            for (int k = 0; k < ILP; k++) x[k] = feat(nd[k].z & 0xFFFFFFu);
             any = false;
 #pragma unroll
             for (int k = 0; k < ILP; k++) {
-              if (n[k] >= 0) {
-                const uint4 nd = nodes[k][n[k]];
-                n[k] = step<Real, HAS_CAT, HAS_ZERO>(nd, feat(nd.z & 0xFFFFFFu), cb);
-                if (COUNT) visited++;
-                any |= n[k] >= 0;
-              }
+              const int nx = step<Real, HAS_CAT, HAS_ZERO>(nd[k], x[k], cb);
+              if (COUNT) visited += n[k] >= 0;
+              n[k] = n[k] >= 0 ? nx : n[k];
+              any |= n[k] >= 0;
             }
           }
 #pragma unroll
@@ -323,21 +329,45 @@ void launch_gbdt_score(const ScoreLaunch &L, int num_sms, cudaStream_t stream) {
   const size_t kMaxSmem = 227 * 1024;
   const size_t fixed = 128 + (size_t)p.chunk_stride * (L.n_chunks == 1 ? 1 : 2);
 
+  // Occupancy is what this kernel lives on (every node visit is a dependent
+  // LDS -> LDS -> compare chain), and shared memory is what limits it: each item in
+  // flight pins n_features * sizeof(Real) bytes of tile.  Pick the CTA shape that
+  // keeps the most warps resident per SM.
+  const size_t per_item = (size_t)L.n_features * real_sz;
+  auto fit_threads = [&](int n_cta) -> int {
+    const size_t per_cta = kMaxSmem / (size_t)n_cta;
+    const size_t reserve = 1024;  // driver-reserved shared memory per CTA
+    if (per_cta < fixed + reserve + 32 * per_item) return 0;
+    size_t t = (per_cta - fixed - reserve) / std::max<size_t>(per_item, 1);
+    t = std::min<size_t>(t, 1024) & ~size_t(31);
+    return (int)t;
+  };
   int threads = L.threads;
   if (threads <= 0) {
-    threads = 256;
-    // keep at least ~2 tiles per SM so the persistent grid covers the chip
-    while (threads > 32 && (L.rows + threads - 1) / threads < 2 * num_sms) threads >>= 1;
+    int best_warps = 0;
+    threads = 0;
+    for (int n_cta = 1; n_cta <= 4; n_cta++) {
+      const int t = fit_threads(n_cta);
+      if (t < 32) continue;
+      const int warps = std::min(64, n_cta * (t / 32));
+      if (warps >= best_warps) {  // ties: prefer more, smaller CTAs (cheaper barriers)
+        best_warps = warps;
+        threads = t;
+      }
+    }
+    if (threads == 0) threads = 32;
+    // small batches: shrink the tile until the persistent grid covers the chip
+    while (threads > 32 && (L.rows + threads - 1) / threads < num_sms) threads = ((threads / 2) + 31) & ~31;
   }
-  threads = std::max(32, std::min(256, (threads / 32) * 32));
+  threads = std::max(32, std::min(1024, (threads / 32) * 32));
   bool stage = true;
-  while (fixed + (size_t)threads * L.n_features * real_sz > kMaxSmem && threads > 32) threads >>= 1;
-  if (fixed + (size_t)threads * L.n_features * real_sz > kMaxSmem) stage = false;  // very wide rows: read HBM/L1 directly
+  while (fixed + (size_t)threads * per_item > kMaxSmem && threads > 32) threads = ((threads / 2) + 31) & ~31;
+  if (fixed + (size_t)threads * per_item > kMaxSmem) stage = false;  // very wide rows: read HBM/L1 directly
   if (fixed > kMaxSmem) fail(MR_ERR_UNSUPPORTED, "model chunk of %u bytes does not fit in shared memory", L.max_chunk_bytes);
-  const size_t smem = fixed + (stage ? (size_t)threads * L.n_features * real_sz : 0);
+  const size_t smem = fixed + (stage ? (size_t)threads * per_item : 0);
 
   int variant = L.variant < 0 ? 0 : L.variant;
-  int ilp = L.ilp <= 0 ? 2 : L.ilp;
+  int ilp = L.ilp <= 0 ? (per_item > 384 ? 4 : 2) : L.ilp;
   const bool count = L.d_visited != nullptr;
 
 #define MR_DISPATCH(REAL)                                                                                        \

@@ -20,9 +20,9 @@ for name, kind, blob, F in cfgs:
     b = mb.B200Booster(ctx, blob, kind=kind)
     print(name, "mean path", b.mean_path(X[:4096], 4096, F), flush=True)
     st = torch.cuda.current_stream().cuda_stream
-    for chunk_kb in (16, 32, 64, 200):
+    for chunk_kb in (8, 16):
         b.set_option("chunk_kb", chunk_kb)
-        for threads in (64, 128, 256):
+        for threads in (256, 384, 512, 768):
             for variant, ilp in ((0, 1), (0, 2), (0, 4), (1, 1)):
                 b.set_option("threads", threads); b.set_option("variant", variant); b.set_option("ilp", ilp)
                 try:
