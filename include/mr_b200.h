@@ -153,6 +153,117 @@ MR_API mr_status mr_model_set_option(mr_model *m, const char *key, int32_t value
 MR_API mr_status mr_rank_order(mr_ctx *ctx, const double *scores, const int32_t *offsets, int32_t n_requests,
                         int32_t *order);
 
+/* ------------------------------------------------------------------ feature assembly */
+
+/* All strings that identify things at run time (item / user / session ids, field values,
+ * tags) cross the ABI as 64-bit hashes produced by mr_hash64 (the JVM hashes while it
+ * decodes the request JSON).  0 is reserved for "absent" (None). */
+MR_API uint64_t mr_hash64(const void *bytes, size_t len);
+
+/* WordCountFeature.tokenCount (S/feature/WordCountFeature.scala:73-76):
+ * "\\s+".split(s).length with java.util.regex semantics (a leading whitespace run yields
+ * an empty first token, trailing empty tokens are dropped, "" -> 1).  Host helper for the
+ * ranking-scoped word_count input. */
+MR_API int32_t mr_token_count(const char *utf8, size_t len);
+
+/* FeatureMapping for one model (S/FeatureMapping.scala:56-99).  `json` is
+ *   {"features": [<Metarank FeatureSchema JSON, polymorphic on "type">, ...],
+ *    "model_features": ["name", ...]}
+ * i.e. the `features:` section of the Metarank config (YAML -> JSON unchanged) and the
+ * model's `features:` list.  The dense column layout is DatasetDescriptor's: model feature
+ * order, widths = each extractor's dim (S/FeatureMapping.scala:89-99).  Supported types:
+ * number, word_count, string (index|onehot), interaction_count, window_count, rate,
+ * interacted_with, relevancy, position, diversity, field_match/bi-encoder.  Anything
+ * else fails with MR_ERR_UNSUPPORTED naming the feature. */
+MR_API mr_status mr_schema_create(mr_ctx *ctx, const char *json, size_t len, mr_schema **out);
+MR_API mr_status mr_schema_free(mr_schema *s);
+/* DatasetDescriptor.dim */
+MR_API int32_t mr_schema_dim(const mr_schema *s);
+/* DatasetDescriptor.offsets(feature): first column of a model feature, -1 if unknown;
+ * *dim_out (optional) receives its width. */
+MR_API int32_t mr_schema_feature_offset(const mr_schema *s, const char *feature, int32_t *dim_out);
+
+/* Request-side inputs the schema needs (what the extractors read from the RankingEvent
+ * itself rather than from state).  kind: */
+enum {
+  MR_IN_REQ_F64 = 0,  /* one double per request  (number/word_count with scope ranking, string on a
+                         ranking field -> encoded category index)                      */
+  MR_IN_REQ_U64 = 1,  /* one hash per request    (rate scoped ranking.<field>: hash of the field value) */
+  MR_IN_REQ_VEC = 2,  /* one f32[dim] per request (bi-encoder query embedding)          */
+  MR_IN_ITEM_F64 = 3  /* one double per item, NaN = absent (relevancy; per-item field overrides of
+                         number / string-index features, S/feature/NumberFeature.scala:84-93) */
+};
+/* Slot index of `feature` within the inputs of `kind`, or -1 when the feature reads no such
+ * input.  n_out (optional) receives the total number of slots of that kind. */
+MR_API int32_t mr_schema_input_slot(const mr_schema *s, int32_t kind, const char *feature, int32_t *n_out);
+/* Total f32 elements per request across all MR_IN_REQ_VEC slots, and the element offset of a slot. */
+MR_API int32_t mr_schema_vec_stride(const mr_schema *s);
+MR_API int32_t mr_schema_vec_offset(const mr_schema *s, int32_t slot, int32_t *dim_out);
+
+/* Device-resident replacement for Persistence.values: KVStore[Key, FeatureValue]
+ * (S/fstore/Persistence.scala:39,85-89) restricted to the state the schema's extractors
+ * read.  Tables live in HBM; mr_state_upsert is KVStore.put, the two batched gets of
+ * FeatureValueLoader.fromStateBackend (S/fstore/FeatureValueLoader.scala:11-25) become
+ * hash probes + row gathers inside the assemble kernel. */
+MR_API mr_status mr_state_create(mr_ctx *ctx, mr_schema *schema, mr_state **out);
+MR_API mr_status mr_state_free(mr_state *st);
+
+/* KVStore.put(Map[Key, FeatureValue]) in a packed little-endian wire format, records
+ * back to back:
+ *   u16 name_len, name bytes     feature-state name == Key.feature, e.g. "ctr_click_norm"
+ *   u8  scope                    0 global | 1 item | 2 user | 3 session | 4 field | 5 irf | 6 ranking
+ *   scope payload                1/2/3/6: u64 id hash | 4: u64 value hash |
+ *                                5: u64 value hash, u64 item hash | 0: nothing
+ *   u8  kind                     0 SDouble | 1 SString | 2 SStringList | 3 SDoubleList |
+ *                                4 Counter | 5 PeriodicCounter | 6 BoundedList
+ *   payload                      0: f64 | 1: u64 hash | 2: u32 n, n x u64 hash | 3: u32 n, n x f64 |
+ *                                4: i64 | 5: u32 n, n x i64 (PeriodicValue.value, S/model/FeatureValue.scala:30-43) |
+ *                                6: u32 n, n x u64 item-id hash, newest first (BoundedListValue.values)
+ * Records whose name no extractor of the schema reads are skipped (counted in *skipped).
+ * Visible to mr_rank after mr_state_flush. */
+MR_API mr_status mr_state_upsert(mr_state *st, const uint8_t *packed, size_t len, int64_t *applied, int64_t *skipped);
+/* Uploads pending upserts to HBM (synchronous). */
+MR_API mr_status mr_state_flush(mr_state *st);
+typedef struct mr_state_info {
+  int64_t rows[6];        /* global, item, user, session, field, irf */
+  int64_t device_bytes;
+  int64_t item_row_bytes; /* fixed-width bytes gathered per item row */
+} mr_state_info;
+MR_API mr_status mr_state_get_info(mr_state *st, mr_state_info *out);
+
+/* A batch of RankingEvents (S/model/Event.scala:44-67) reduced to what the hot path reads. */
+typedef struct mr_rank_batch {
+  int32_t n_requests;
+  const int32_t *item_offsets; /* n_requests + 1; request r owns items [off[r], off[r+1]) */
+  const uint64_t *item_ids;    /* mr_hash64(RankItem.id) */
+  const uint64_t *user_ids;    /* per request, 0 = None; may be NULL */
+  const uint64_t *session_ids; /* per request, 0 = None; may be NULL */
+  const double *req_f64;       /* [n_requests x n(MR_IN_REQ_F64)], NaN = absent */
+  const uint64_t *req_u64;     /* [n_requests x n(MR_IN_REQ_U64)], 0 = absent */
+  const float *req_vec;        /* [n_requests x mr_schema_vec_stride] */
+  const uint8_t *req_vec_present; /* [n_requests x n(MR_IN_REQ_VEC)] */
+  const double *item_f64;      /* [total_items x n(MR_IN_ITEM_F64)], NaN = absent */
+} mr_rank_batch;
+
+/* Ranker.rerank for a batch of requests (S/ml/Ranker.scala:27-83): makeQuery
+ * (FeatureValueLoader + ItemValue.fromState + ClickthroughQuery) -> model.predict ->
+ * sortBy(-score).  All buffers are HOST memory; copies are part of the call.
+ *   out_scores   [total_items]  score per item in request order (required)
+ *   out_order    [total_items]  optional: per request, item indices (relative to the request)
+ *                               in response order (stable descending)
+ *   out_features [total_items x dim] optional: the assembled dense matrix (explain=true)
+ * model may be NULL: then only features are assembled (TrainBuffer / explain use). */
+MR_API mr_status mr_rank(mr_state *st, mr_model *model, const mr_rank_batch *batch, double *out_scores,
+                         int32_t *out_order, double *out_features);
+
+/* Same, with every pointer in `batch` and the outputs being DEVICE memory and the work
+ * enqueued on `cuda_stream` without synchronising (bench.py's HBM-resident `value`).
+ * Arithmetic errors (MR_ERR_ARITHMETIC) are reported by mr_rank_device_status. */
+MR_API mr_status mr_rank_device(mr_state *st, mr_model *model, const mr_rank_batch *d_batch, int32_t total_items,
+                                double *d_out_scores, int32_t *d_out_order, double *d_out_features,
+                                void *cuda_stream);
+MR_API mr_status mr_rank_device_status(mr_state *st, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,696 @@
+// Feature-vector assembly on sm_100a: the device side of
+//   FeatureValueLoader.fromStateBackend  (S/fstore/FeatureValueLoader.scala:11-25)
+//   ItemValue.fromState                  (S/model/ItemValue.scala:25-72)
+//   ClickthroughQuery.collectFeatureValues (S/flow/ClickthroughQuery.scala:50-74)
+// and of each hot extractor's value()/values().
+//
+// Kernels (all HBM gather/scan work; no tensor cores anywhere on this path):
+//   lookup_kernel   thread per item: request index, hash probe item-id -> item row;
+//                   thread per request: user/session rows
+//   cosine_kernel   thread per item: bi-encoder cosine in the reference's exact operation order
+//   prepass_kernel  CTA per request: sorted tag multisets (interacted_with, diversity strings),
+//                   diversity median, cosine min-max / position normalisation
+//   assemble_kernel thread per item, uniform loop over the extractor plan -> dense f64 row
+//   order_kernel    CTA per request: stable descending rank of the scores
+// Java arithmetic is strict IEEE (no fused multiply-add), so every a*b+c below is spelled
+// with __dmul_rn/__dadd_rn to keep nvcc from contracting it.
+#include "assemble_kernels.cuh"
+
+#include <algorithm>
+
+#include "gbdt_kernels.cuh"  // g_kernel_launches
+
+namespace mr {
+namespace {
+
+constexpr uint32_t kNoRow = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t probe(const DTable &t, uint64_t key) {
+  if (t.mask == 0 || t.keys == nullptr) return kNoRow;
+  if (key == 0) key = 1;
+  uint32_t i = (uint32_t)mix64(key) & t.mask;
+  for (;;) {
+    const uint64_t k = __ldg(t.keys + i);
+    if (k == key) return __ldg(t.vals + i);
+    if (k == 0) return kNoRow;
+    i = (i + 1) & t.mask;
+  }
+}
+
+__device__ __forceinline__ uint64_t d_hash_combine(uint64_t a, uint64_t b) {
+  uint64_t x = a ^ (b + 0x9E3779B97F4A7C15ull + (a << 6) + (a >> 2));
+  x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32;
+  return x ? x : 1;
+}
+
+__device__ __forceinline__ const uint64_t *row_ptr(const DTable &t, uint32_t row) {
+  return t.rows + (size_t)row * t.row_words;
+}
+__device__ __forceinline__ bool present(const uint64_t *row, int bit) {
+  return (__ldg(row + (bit >> 6)) >> (bit & 63)) & 1ull;
+}
+__device__ __forceinline__ double nan_d() { return __longlong_as_double(0x7FF8000000000000ll); }
+
+// java.lang.Double.compare as a sortable key (NaN largest, -0.0 < 0.0)
+__device__ __forceinline__ long long total_order_key(double x) {
+  if (x != x) return 0x7FFFFFFFFFFFFFFFll;
+  long long b = __double_as_longlong(x);
+  return b < 0 ? (b ^ 0x7FFFFFFFFFFFFFFFll) : b;
+}
+
+// ------------------------------------------------------------------ lookup
+__global__ void lookup_kernel(RankArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < a.total_items) {
+    // owning request: last r with off[r] <= i
+    int lo = 0, hi = a.n_requests;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(a.item_offsets + mid) <= i) lo = mid; else hi = mid;
+    }
+    a.item_req[i] = lo;
+    a.item_row[i] = probe(a.st.t[SC_ITEM], __ldg(a.item_ids + i));
+  }
+  if (i < a.n_requests) {
+    const uint64_t u = a.user_ids ? __ldg(a.user_ids + i) : 0, s = a.session_ids ? __ldg(a.session_ids + i) : 0;
+    a.visitor_row[2 * i] = u ? probe(a.st.t[SC_USER], u) : kNoRow;
+    a.visitor_row[2 * i + 1] = s ? probe(a.st.t[SC_SESSION], s) : kNoRow;
+  }
+  if (i == 0) *a.hist_cursor = 0;
+}
+
+// ------------------------------------------------------------------ cosine
+// CosineDistance.dist (S/ml/onnx/distance/DistanceFunction.scala:13-27): sequential sums,
+// query(i)*query(i) is a FLOAT product, the other two are double products.
+__global__ void cosine_kernel(RankArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.total_items) return;
+  const int r = a.item_req[i];
+  const uint32_t ir = a.item_row[i];
+  for (int f = 0; f < a.n_plan; f++) {
+    const DFeature d = a.plan[f];
+    if (d.kind != FK_COSINE) continue;
+    double out = nan_d();
+    const bool q_ok = a.req_vec_present && a.req_vec_present[(size_t)r * a.n_req_vec + d.in0];
+    if (q_ok && ir != kNoRow && present(row_ptr(a.st.t[SC_ITEM], ir), d.b[0])) {
+      const int dim = d.aux0;
+      int voff = 0;
+      // element offset of this vector slot = sum of dims of earlier slots; stored in uparam's side dims
+      for (int g = 0; g < f; g++) if (a.plan[g].kind == FK_COSINE) voff += a.plan[g].aux0;
+      const float *q = a.req_vec + (size_t)r * a.vec_stride + voff;
+      const double *e = a.st.side[(int)d.uparam] + (size_t)ir * dim;
+      double top = 0.0, as = 0.0, bs = 0.0;
+      for (int k = 0; k < dim; k++) {
+        const float qk = __ldg(q + k);
+        const double ek = __ldg(e + k);
+        top = __dadd_rn(top, __dmul_rn((double)qk, ek));
+        as = __dadd_rn(as, (double)__fmul_rn(qk, qk));
+        bs = __dadd_rn(bs, __dmul_rn(ek, ek));
+      }
+      out = __ddiv_rn(top, __dmul_rn(__dsqrt_rn(as), __dsqrt_rn(bs)));
+    }
+    a.cos[(size_t)d.aux2 * a.total_items + i] = out;
+    a.cos[(size_t)(a.n_cos + d.aux2) * a.total_items + i] = out;  // normalised copy (noop default)
+  }
+}
+
+// ------------------------------------------------------------------ per-request prepass
+constexpr int kSortCap = 4096;  // u64 keys sorted in shared memory (32 KB)
+
+__device__ void block_sort_u64(uint64_t *s, int n_pow2) {
+  // in-place bitonic sort of n_pow2 keys in shared memory
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const uint64_t x = s[i], y = s[l];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) { s[i] = y; s[l] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Reserves `n` pool entries for histogram (r,h); returns the offset or 0xFFFFFFFF on overflow.
+__device__ uint32_t hist_alloc(const RankArgs &a, uint32_t n) {
+  __shared__ uint32_t s_off;
+  if (threadIdx.x == 0) {
+    uint32_t off = atomicAdd(a.hist_cursor, n);
+    if (off + n > a.hist_pool_cap || off + n < off) {
+      atomicExch(a.error_flag, -1);
+      off = 0xFFFFFFFFu;
+    }
+    s_off = off;
+  }
+  __syncthreads();
+  const uint32_t o = s_off;
+  __syncthreads();
+  return o;
+}
+
+__device__ void hist_finish(const RankArgs &a, int r, int h, uint32_t off, uint32_t n, uint64_t *s_sort) {
+  // sort the multiset so that per-item counting is two binary searches
+  uint32_t flags = 0;
+  if (n > 1 && n <= (uint32_t)kSortCap) {
+    int p2 = 1;
+    while (p2 < (int)n) p2 <<= 1;
+    for (int i = threadIdx.x; i < p2; i += blockDim.x) s_sort[i] = i < (int)n ? a.hist_pool[off + i] : ~0ull;
+    __syncthreads();
+    block_sort_u64(s_sort, p2);
+    for (int i = threadIdx.x; i < (int)n; i += blockDim.x) a.hist_pool[off + i] = s_sort[i];
+  } else if (n > (uint32_t)kSortCap) {
+    flags = 0x80000000u;  // too large for the shared-memory sort: readers scan linearly
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) a.hist_desc[(size_t)r * a.n_hist + h] = make_uint2(off, n | flags);
+}
+
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_scan, uint32_t *total) {
+  // exclusive scan over blockDim.x (<= 1024) values
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t x = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) s_scan[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = lane < (int)((blockDim.x + 31) >> 5) ? s_scan[lane] : 0;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o);
+      if (lane >= o) w += y;
+    }
+    s_scan[lane] = w;
+  }
+  __syncthreads();
+  const uint32_t base = wid ? s_scan[wid - 1] : 0;
+  *total = s_scan[((blockDim.x + 31) >> 5) - 1];
+  __syncthreads();
+  return base + x - v;
+}
+
+__global__ void __launch_bounds__(256) prepass_kernel(RankArgs a) {
+  __shared__ uint64_t s_sort[kSortCap];
+  __shared__ uint32_t s_scan[32];
+  __shared__ int s_i[4];
+  __shared__ double s_d[4];
+  const int r = blockIdx.x;
+  const int i0 = a.item_offsets[r], n_items = a.item_offsets[r + 1] - i0;
+  const DTable &IT = a.st.t[SC_ITEM];
+
+  for (int f = 0; f < a.n_plan; f++) {
+    const DFeature d = a.plan[f];
+    if (d.kind == FK_INTERACTED) {
+      // visitor's interacted items -> multiset of their values of this field
+      // (InteractedWithFeature.values :134-147)
+      const int tb = d.scope;  // SC_USER | SC_SESSION
+      const uint32_t vr = a.visitor_row[2 * r + (tb == SC_SESSION ? 1 : 0)];
+      uint32_t hoff = 0, hlen = 0;
+      const uint64_t *hist_items = nullptr;
+      if (vr != kNoRow) {
+        const uint64_t *vrow = row_ptr(a.st.t[tb], vr);
+        if (present(vrow, d.b[1])) {
+          const uint64_t desc = vrow[d.w[1]];
+          hoff = (uint32_t)desc;
+          hlen = (uint32_t)(desc >> 32);
+          hist_items = a.st.t[tb].pool + hoff;
+        }
+      }
+      // pass 1: count, pass 2: fill (chunks of blockDim history items)
+      uint32_t total = 0;
+      for (uint32_t base = 0; base < hlen; base += blockDim.x) {
+        const uint32_t j = base + threadIdx.x;
+        uint32_t cnt = 0;
+        if (j < hlen) {
+          const uint32_t row = probe(IT, hist_items[j]);
+          if (row != kNoRow) {
+            const uint64_t *rp = row_ptr(IT, row);
+            if (present(rp, d.b[0])) cnt = (uint32_t)(rp[d.w[0]] >> 32);
+          }
+        }
+        uint32_t chunk_total;
+        block_excl_scan(cnt, s_scan, &chunk_total);
+        total += chunk_total;
+      }
+      uint32_t off = total ? hist_alloc(a, total) : 0;
+      if (off == 0xFFFFFFFFu) { if (threadIdx.x == 0) a.hist_desc[(size_t)r * a.n_hist + d.aux0] = make_uint2(0, 0); continue; }
+      uint32_t run = 0;
+      for (uint32_t base = 0; base < hlen && total; base += blockDim.x) {
+        const uint32_t j = base + threadIdx.x;
+        uint32_t cnt = 0, src = 0;
+        if (j < hlen) {
+          const uint32_t row = probe(IT, hist_items[j]);
+          if (row != kNoRow) {
+            const uint64_t *rp = row_ptr(IT, row);
+            if (present(rp, d.b[0])) { const uint64_t desc = rp[d.w[0]]; cnt = (uint32_t)(desc >> 32); src = (uint32_t)desc; }
+          }
+        }
+        uint32_t chunk_total;
+        const uint32_t my = block_excl_scan(cnt, s_scan, &chunk_total);
+        for (uint32_t k = 0; k < cnt; k++) a.hist_pool[off + run + my + k] = IT.pool[src + k];
+        run += chunk_total;
+      }
+      __syncthreads();
+      hist_finish(a, r, d.aux0, off, total, s_sort);
+    } else if (d.kind == FK_DIVERSITY) {
+      // DiversityFeature.values (:67-130): items WITH state, in request order; the first one's
+      // scalar type selects the mode; aggregates over the first `top` items of that type.
+      double *agg = a.reqagg + ((size_t)r * a.n_reqagg + d.aux2) * 4;
+      // head = first item with state
+      if (threadIdx.x == 0) { s_i[0] = 0x7FFFFFFF; }
+      __syncthreads();
+      for (int base = 0; base < n_items; base += blockDim.x) {
+        const int j = base + threadIdx.x;
+        if (j < n_items) {
+          const uint32_t row = a.item_row[i0 + j];
+          if (row != kNoRow && present(row_ptr(IT, row), d.b[0])) atomicMin(&s_i[0], j);
+        }
+        __syncthreads();
+        const int seen = s_i[0];
+        __syncthreads();  // everyone has read s_i[0] before the next chunk's atomicMin
+        if (seen != 0x7FFFFFFF) break;
+      }
+      const int head = s_i[0];
+      __syncthreads();
+      int mode = 0;
+      if (head != 0x7FFFFFFF) {
+        const uint64_t kd = row_ptr(IT, a.item_row[i0 + head])[d.w[0]];
+        mode = kd == 1 ? 1 : kd == 2 ? 2 : 0;
+      }
+      const int top = d.aux0;
+      if (mode == 0) {
+        if (threadIdx.x == 0) { agg[0] = 0.0; agg[1] = 0.0; agg[2] = 0.0; a.hist_desc[(size_t)r * a.n_hist + d.aux1] = make_uint2(0, 0); }
+        continue;
+      }
+      // ordinal of every matching item (prefix count in request order); selected iff ordinal < top
+      if (mode == 1) {
+        // collect the selected doubles into the pool (as bits), then LEGACY percentile(50)
+        uint32_t n_sel = 0;
+        {
+          uint32_t run = 0;
+          // count first
+          for (int base = 0; base < n_items && run < (uint32_t)top; base += blockDim.x) {
+            const int j = base + threadIdx.x;
+            uint32_t m = 0;
+            if (j < n_items) {
+              const uint32_t row = a.item_row[i0 + j];
+              if (row != kNoRow) { const uint64_t *rp = row_ptr(IT, row); m = present(rp, d.b[0]) && rp[d.w[0]] == 1; }
+            }
+            uint32_t ct;
+            block_excl_scan(m, s_scan, &ct);
+            run += ct;
+          }
+          n_sel = run < (uint32_t)top ? run : (uint32_t)top;
+        }
+        const uint32_t off = hist_alloc(a, n_sel);
+        if (off == 0xFFFFFFFFu) { if (threadIdx.x == 0) { agg[0] = 0; agg[1] = 0; agg[2] = 0; } continue; }
+        uint32_t run = 0;
+        for (int base = 0; base < n_items && run < (uint32_t)top; base += blockDim.x) {
+          const int j = base + threadIdx.x;
+          uint32_t m = 0;
+          uint64_t bits = 0;
+          if (j < n_items) {
+            const uint32_t row = a.item_row[i0 + j];
+            if (row != kNoRow) {
+              const uint64_t *rp = row_ptr(IT, row);
+              if (present(rp, d.b[0]) && rp[d.w[0]] == 1) { m = 1; bits = rp[d.w[0] + 1]; }
+            }
+          }
+          uint32_t ct;
+          const uint32_t my = block_excl_scan(m, s_scan, &ct);
+          if (m && run + my < (uint32_t)top) a.hist_pool[off + run + my] = bits;
+          run += ct;
+        }
+        __syncthreads();
+        // commons-math3 Percentile (LEGACY estimation, NaNs removed), p = 50:
+        //   n == 1 -> the value;  work = non-NaN values;  pos = 0.5 * (n' + 1)
+        //   pos < 1 -> min; pos >= n' -> max; else lower + (pos - floor(pos)) * (upper - lower)
+        const uint64_t *vals = a.hist_pool + off;
+        if (threadIdx.x == 0) { s_i[1] = 0; s_d[0] = nan_d(); s_d[1] = nan_d(); }
+        __syncthreads();
+        uint32_t nn = 0;
+        for (uint32_t k = threadIdx.x; k < n_sel; k += blockDim.x) { const double v = __longlong_as_double((long long)vals[k]); if (v == v) nn++; }
+        atomicAdd(&s_i[1], (int)nn);
+        __syncthreads();
+        const int np = s_i[1];
+        double median = nan_d();
+        if (n_sel == 1) {
+          median = __longlong_as_double((long long)vals[0]);
+        } else if (np > 0) {
+          const double pos = 0.5 * (double)(np + 1);
+          const double fpos = floor(pos);
+          const int ip = (int)fpos;
+          int k_lo, k_hi;
+          if (pos < 1.0) k_lo = k_hi = 0;
+          else if (pos >= (double)np) k_lo = k_hi = np - 1;
+          else { k_lo = ip - 1; k_hi = ip; }
+          // k-th smallest by rank counting (ties broken by position) over the non-NaN values
+          for (uint32_t k = threadIdx.x; k < n_sel; k += blockDim.x) {
+            const double v = __longlong_as_double((long long)vals[k]);
+            if (v != v) continue;
+            int rank = 0;
+            for (uint32_t q = 0; q < n_sel; q++) {
+              const double u = __longlong_as_double((long long)vals[q]);
+              if (u != u) continue;
+              rank += (u < v) || (u == v && q < k);
+            }
+            if (rank == k_lo) s_d[0] = v;
+            if (rank == k_hi) s_d[1] = v;
+          }
+          __syncthreads();
+          const double lower = s_d[0], upper = s_d[1];
+          median = (k_lo == k_hi) ? lower : __dadd_rn(lower, __dmul_rn(pos - fpos, __dadd_rn(upper, -lower)));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { agg[0] = 1.0; agg[1] = median; agg[2] = 0.0; a.hist_desc[(size_t)r * a.n_hist + d.aux1] = make_uint2(0, 0); }
+      } else {
+        // strings: multiset of the tags of the first `top` string-typed items; sum = its size
+        uint32_t total = 0, run = 0;
+        for (int base = 0; base < n_items && run < (uint32_t)top; base += blockDim.x) {
+          const int j = base + threadIdx.x;
+          uint32_t m = 0, cnt = 0;
+          if (j < n_items) {
+            const uint32_t row = a.item_row[i0 + j];
+            if (row != kNoRow) {
+              const uint64_t *rp = row_ptr(IT, row);
+              if (present(rp, d.b[0]) && rp[d.w[0]] == 2) { m = 1; cnt = (uint32_t)(rp[d.w[0] + 1] >> 32); }
+            }
+          }
+          uint32_t ct, tt;
+          const uint32_t ord = block_excl_scan(m, s_scan, &ct);
+          if (!(m && run + ord < (uint32_t)top)) cnt = 0;
+          block_excl_scan(cnt, s_scan, &tt);
+          total += tt;
+          run += ct;
+        }
+        const uint32_t off = total ? hist_alloc(a, total) : 0;
+        if (off == 0xFFFFFFFFu) { if (threadIdx.x == 0) { agg[0] = 0; agg[1] = 0; agg[2] = 0; a.hist_desc[(size_t)r * a.n_hist + d.aux1] = make_uint2(0, 0); } continue; }
+        uint32_t filled = 0;
+        run = 0;
+        for (int base = 0; base < n_items && run < (uint32_t)top && total; base += blockDim.x) {
+          const int j = base + threadIdx.x;
+          uint32_t m = 0, cnt = 0, src = 0;
+          if (j < n_items) {
+            const uint32_t row = a.item_row[i0 + j];
+            if (row != kNoRow) {
+              const uint64_t *rp = row_ptr(IT, row);
+              if (present(rp, d.b[0]) && rp[d.w[0]] == 2) { m = 1; const uint64_t ds = rp[d.w[0] + 1]; cnt = (uint32_t)(ds >> 32); src = (uint32_t)ds; }
+            }
+          }
+          uint32_t ct, tt;
+          const uint32_t ord = block_excl_scan(m, s_scan, &ct);
+          if (!(m && run + ord < (uint32_t)top)) cnt = 0;
+          const uint32_t my = block_excl_scan(cnt, s_scan, &tt);
+          for (uint32_t k = 0; k < cnt; k++) a.hist_pool[off + filled + my + k] = IT.pool[src + k];
+          filled += tt;
+          run += ct;
+        }
+        __syncthreads();
+        hist_finish(a, r, d.aux1, off, total, s_sort);
+        if (threadIdx.x == 0) { agg[0] = 2.0; agg[1] = 0.0; agg[2] = (double)total; }
+      }
+    } else if (d.kind == FK_COSINE && d.aux1 != 0) {
+      // Normalize.scale over the request's N raw values (S/ml/onnx/Normalize.scala:13-46)
+      const double *raw = a.cos + (size_t)d.aux2 * a.total_items + i0;
+      double *nrm = a.cos + (size_t)(a.n_cos + d.aux2) * a.total_items + i0;
+      if (d.aux1 == 1) {
+        // MinMax over non-NaN values; none -> unchanged
+        if (threadIdx.x == 0) { s_i[0] = 0; }
+        __syncthreads();
+        double mn = 0, mx = 0;
+        bool any = false;
+        for (int j = threadIdx.x; j < n_items; j += blockDim.x) {
+          const double v = raw[j];
+          if (v == v) { if (!any) { mn = mx = v; any = true; } else { mn = fmin(mn, v); mx = fmax(mx, v); } }
+        }
+        // block reduce through shared memory (tiny): serialise by warp leaders
+        for (int o = 16; o > 0; o >>= 1) {
+          const double omn = __shfl_down_sync(0xFFFFFFFFu, mn, o), omx = __shfl_down_sync(0xFFFFFFFFu, mx, o);
+          const int oany = __shfl_down_sync(0xFFFFFFFFu, (int)any, o);
+          if (oany) { if (!any) { mn = omn; mx = omx; any = true; } else { mn = fmin(mn, omn); mx = fmax(mx, omx); } }
+        }
+        __shared__ double w_mn[8], w_mx[8];
+        __shared__ int w_any[8];
+        if ((threadIdx.x & 31) == 0) { w_mn[threadIdx.x >> 5] = mn; w_mx[threadIdx.x >> 5] = mx; w_any[threadIdx.x >> 5] = any; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          bool A = false; double MN = 0, MX = 0;
+          for (int w = 0; w < (int)(blockDim.x >> 5); w++) if (w_any[w]) { if (!A) { MN = w_mn[w]; MX = w_mx[w]; A = true; } else { MN = fmin(MN, w_mn[w]); MX = fmax(MX, w_mx[w]); } }
+          s_i[0] = A; s_d[0] = MN; s_d[1] = MX;
+        }
+        __syncthreads();
+        if (s_i[0]) {
+          const double MN = s_d[0], MX = s_d[1];
+          for (int j = threadIdx.x; j < n_items; j += blockDim.x) nrm[j] = __ddiv_rn(__dadd_rn(raw[j], -MN), __dadd_rn(MX, -MN));
+        }
+        __syncthreads();
+      } else {
+        // Position: stable sort by value (NaN last), value -> sortedIndex / size, NaN stays NaN
+        const double size = (double)n_items;
+        for (int j = threadIdx.x; j < n_items; j += blockDim.x) {
+          const double v = raw[j];
+          if (v != v) { nrm[j] = v; continue; }
+          const long long kj = total_order_key(v);
+          int rank = 0;
+          for (int q = 0; q < n_items; q++) {
+            const long long kq = total_order_key(raw[q]);
+            rank += (kq < kj) || (kq == kj && q < j);
+          }
+          nrm[j] = __ddiv_rn((double)rank, size);
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
+// number of occurrences of `tag` in histogram (r,h)
+__device__ __forceinline__ uint32_t hist_count(const RankArgs &a, int r, int h, uint64_t tag) {
+  const uint2 hd = a.hist_desc[(size_t)r * a.n_hist + h];
+  const uint32_t n = hd.y & 0x7FFFFFFFu;
+  if (n == 0) return 0;
+  const uint64_t *p = a.hist_pool + hd.x;
+  if (hd.y & 0x80000000u) {
+    uint32_t c = 0;
+    for (uint32_t k = 0; k < n; k++) c += p[k] == tag;
+    return c;
+  }
+  uint32_t lo = 0, hi = n;  // lower_bound
+  while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (p[m] < tag) lo = m + 1; else hi = m; }
+  const uint32_t first = lo;
+  hi = n;  // upper_bound
+  while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (p[m] <= tag) lo = m + 1; else hi = m; }
+  return lo - first;
+}
+
+// ------------------------------------------------------------------ assemble
+__global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.total_items) return;
+  const int r = a.item_req[i];
+  const uint32_t ir = a.item_row[i];
+  const DTable &IT = a.st.t[SC_ITEM];
+  const uint64_t *irow = ir != kNoRow ? row_ptr(IT, ir) : nullptr;
+  double *out = a.out_features + (size_t)i * a.dim;
+  const double *ov = a.item_f64 ? a.item_f64 + (size_t)i * a.n_item_f64 : nullptr;
+  const double kNaN = nan_d();
+
+  auto scoped_row = [&](int scope) -> const uint64_t * {
+    switch (scope) {
+      case SC_ITEM: return irow;
+      case SC_GLOBAL: return a.st.t[SC_GLOBAL].n_rows ? a.st.t[SC_GLOBAL].rows : nullptr;
+      case SC_USER: { const uint32_t v = a.visitor_row[2 * r]; return v != kNoRow ? row_ptr(a.st.t[SC_USER], v) : nullptr; }
+      case SC_SESSION: { const uint32_t v = a.visitor_row[2 * r + 1]; return v != kNoRow ? row_ptr(a.st.t[SC_SESSION], v) : nullptr; }
+    }
+    return nullptr;
+  };
+
+  for (int f = 0; f < a.n_plan; f++) {
+    const DFeature d = a.plan[f];
+    switch (d.kind) {
+      case FK_NUMBER: {
+        // NumberFeature.values :84-93 (request-item field override) then value :58-69; WordCountFeature.value :63-68
+        double v = kNaN;
+        const double o = (d.in0 >= 0 && ov) ? ov[d.in0] : kNaN;
+        if (o == o) v = o;
+        else { const uint64_t *rp = scoped_row(d.scope); if (rp && present(rp, d.b[0])) v = __longlong_as_double((long long)rp[d.w[0]]); }
+        out[d.col] = v;
+        break;
+      }
+      case FK_CATEGORY: {
+        // IndexCategoricalEncoder: index + 1, 0 = nil (StringFeature.scala:124-137); CategoryValue -> index.toDouble
+        double v = 0.0;
+        const double o = (d.in0 >= 0 && ov) ? ov[d.in0] : kNaN;
+        if (o == o) v = o;
+        else { const uint64_t *rp = scoped_row(d.scope); if (rp && present(rp, d.b[0])) v = (double)(int)rp[d.w[0]]; }
+        out[d.col] = v;
+        break;
+      }
+      case FK_ONEHOT: {
+        const double o = (d.in0 >= 0 && ov) ? ov[d.in0] : kNaN;
+        if (o == o) { for (int k = 0; k < d.dim; k++) out[d.col + k] = ov[d.in0 + k]; break; }
+        uint64_t mask = 0;
+        const uint64_t *rp = scoped_row(d.scope);
+        if (rp && present(rp, d.b[0])) mask = rp[d.w[0]];
+        for (int k = 0; k < d.dim; k++) out[d.col + k] = (mask >> k) & 1ull ? 1.0 : 0.0;
+        break;
+      }
+      case FK_COUNT: {
+        // InteractionCountFeature.value :44-59 — missing is 0.0, not NaN
+        const uint64_t *rp = scoped_row(d.scope);
+        out[d.col] = (rp && present(rp, d.b[0])) ? (double)(long long)rp[d.w[0]] : 0.0;
+        break;
+      }
+      case FK_WINDOW: {
+        // WindowInteractionCountFeature.value :50-63
+        const uint64_t *rp = scoped_row(d.scope);
+        const bool ok = rp && present(rp, d.b[0]);
+        for (int k = 0; k < d.dim; k++) out[d.col + k] = ok ? (double)(long long)rp[d.w[0] + k] : kNaN;
+        break;
+      }
+      case FK_RATE: {
+        // RateFeature.value :290-356
+        const uint64_t *tr = nullptr;
+        if (d.scope == SC_ITEM) tr = irow;
+        else if (d.scope == SC_FIELD) {
+          if (irow && present(irow, d.aux2)) {
+            const uint32_t row = probe(a.st.t[SC_FIELD], d_hash_combine(d.uparam, irow[d.aux1]));
+            if (row != kNoRow) tr = row_ptr(a.st.t[SC_FIELD], row);
+          }
+        } else {
+          const uint64_t fv = a.req_u64 ? a.req_u64[(size_t)r * a.n_req_u64 + d.in1] : 0;
+          if (fv) {
+            const uint32_t row = probe(a.st.t[SC_IRF], d_hash_combine(d_hash_combine(d.uparam, fv), a.item_ids[i]));
+            if (row != kNoRow) tr = row_ptr(a.st.t[SC_IRF], row);
+          }
+        }
+        bool ok = tr && present(tr, d.b[0]) && present(tr, d.b[1]);
+        const uint64_t *gr = nullptr;
+        if (d.aux0) {
+          gr = scoped_row(SC_GLOBAL);
+          ok = ok && gr && present(gr, d.b[2]) && present(gr, d.b[3]);
+        }
+        for (int k = 0; k < d.dim; k++) {
+          double v = kNaN;
+          if (ok) {
+            const long long top = (long long)tr[d.w[0] + k], bot = (long long)tr[d.w[1] + k];
+            if (!d.aux0) {
+              v = __ddiv_rn((double)top, (double)bot);  // Long / Double: 0/0 -> NaN, x/0 -> +-Inf
+            } else {
+              const long long tg = (long long)gr[d.w[2] + k], bg = (long long)gr[d.w[3] + k];
+              if (tg == 0) {
+                atomicExch(a.error_flag, MR_ERR_ARITHMETIC);  // java.lang.ArithmeticException: / by zero
+              } else {
+                const long long q = (tg == -1) ? -bg : bg / tg;  // Long division truncates toward zero
+                v = __ddiv_rn(__dadd_rn(d.dparam, (double)top),
+                              __dadd_rn(__dmul_rn(d.dparam, (double)q), (double)bot));
+              }
+            }
+          }
+          out[d.col + k] = v;
+        }
+        break;
+      }
+      case FK_INTERACTED: {
+        // sum over the item's values of this field of the visitor's histogram count (:152-161)
+        double cnt = 0.0;
+        if (irow && present(irow, d.b[0])) {
+          const uint64_t desc = irow[d.w[0]];
+          const uint32_t off = (uint32_t)desc, n = (uint32_t)(desc >> 32);
+          for (uint32_t k = 0; k < n; k++) cnt = __dadd_rn(cnt, (double)hist_count(a, r, d.aux0, IT.pool[off + k]));
+        }
+        out[d.col] = cnt;
+        break;
+      }
+      case FK_RELEVANCY:
+        out[d.col] = ov ? ov[d.in0] : kNaN;
+        break;
+      case FK_POSITION:
+        out[d.col] = d.dparam;  // ValueMode.OnlineInference (PositionFeature.scala:32)
+        break;
+      case FK_DIVERSITY: {
+        const double *agg = a.reqagg + ((size_t)r * a.n_reqagg + d.aux2) * 4;
+        const int mode = (int)agg[0];
+        double v = 0.0;  // emptyResponse
+        if (mode == 1) {
+          v = (irow && present(irow, d.b[0]) && irow[d.w[0]] == 1)
+                  ? __dadd_rn(__longlong_as_double((long long)irow[d.w[0] + 1]), -agg[1]) : kNaN;
+        } else if (mode == 2) {
+          if (irow && present(irow, d.b[0]) && irow[d.w[0]] == 2) {
+            const uint64_t desc = irow[d.w[0] + 1];
+            const uint32_t off = (uint32_t)desc, n = (uint32_t)(desc >> 32);
+            double s = 0.0;
+            for (uint32_t k = 0; k < n; k++) s = __dadd_rn(s, (double)hist_count(a, r, d.aux1, IT.pool[off + k]));
+            v = __ddiv_rn(s, agg[2]);
+          } else v = kNaN;
+        }
+        out[d.col] = v;
+        break;
+      }
+      case FK_COSINE:
+        out[d.col] = a.cos[(size_t)(a.n_cos + d.aux2) * a.total_items + i];
+        break;
+      case FK_CONST_REQ:
+        for (int k = 0; k < d.dim; k++) out[d.col + k] = a.req_f64 ? a.req_f64[(size_t)r * a.n_req_f64 + d.in0 + k] : kNaN;
+        break;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ ordering
+__global__ void __launch_bounds__(256) order_kernel(const double *scores, const int32_t *offsets, int32_t *order) {
+  const int r = blockIdx.x;
+  const int b = offsets[r], n = offsets[r + 1] - b;
+  extern __shared__ long long s_keys[];
+  const int cap = 4096;
+  const bool in_smem = n <= cap;
+  for (int j = threadIdx.x; j < n && in_smem; j += blockDim.x) s_keys[j] = total_order_key(-scores[b + j]);
+  __syncthreads();
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const long long kj = in_smem ? s_keys[j] : total_order_key(-scores[b + j]);
+    int rank = 0;
+    for (int q = 0; q < n; q++) {
+      const long long kq = in_smem ? s_keys[q] : total_order_key(-scores[b + q]);
+      rank += (kq < kj) || (kq == kj && q < j);
+    }
+    order[b + rank] = j;
+  }
+}
+
+}  // namespace
+
+void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t stream) {
+  if (a.total_items <= 0 && a.n_requests <= 0) return;
+  const int n = std::max(a.total_items, a.n_requests);
+  lookup_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a);
+  MR_CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+  if (a.total_items <= 0) return;
+  if (schema.needs_cosine) {
+    cosine_kernel<<<(a.total_items + 127) / 128, 128, 0, stream>>>(a);
+    MR_CUDA_CHECK(cudaGetLastError());
+    g_kernel_launches++;
+  }
+  if (schema.needs_prepass && a.n_requests > 0) {
+    prepass_kernel<<<a.n_requests, 256, 0, stream>>>(a);
+    MR_CUDA_CHECK(cudaGetLastError());
+    g_kernel_launches++;
+  }
+  assemble_kernel<<<(a.total_items + 127) / 128, 128, 0, stream>>>(a);
+  MR_CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+}
+
+void launch_rank_order(const double *d_scores, const int32_t *d_item_offsets, int n_requests, int total_items,
+                       int32_t *d_order, cudaStream_t stream) {
+  if (n_requests <= 0 || total_items <= 0) return;
+  order_kernel<<<n_requests, 256, 4096 * sizeof(long long), stream>>>(d_scores, d_item_offsets, d_order);
+  MR_CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+}
+
+}  // namespace mr

@@ -1,0 +1,46 @@
+// Launch interface of the feature-assembly kernels (assemble_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "schema.h"
+#include "state.h"
+
+namespace mr {
+
+struct RankArgs {
+  DState st;
+  const DFeature *plan;  // device copy of Schema::plan
+  int n_plan, dim;
+  // batch (device pointers)
+  int n_requests, total_items;
+  const int32_t *item_offsets;
+  const uint64_t *item_ids, *user_ids, *session_ids;
+  const double *req_f64;
+  const uint64_t *req_u64;
+  const float *req_vec;
+  const uint8_t *req_vec_present;
+  const double *item_f64;
+  int n_req_f64, n_req_u64, n_req_vec, vec_stride, n_item_f64;
+  // scratch (device)
+  int32_t *item_req;      // [total_items] owning request
+  uint32_t *item_row;     // [total_items] row in the item table or 0xFFFFFFFF
+  uint32_t *visitor_row;  // [n_requests x 2] user row, session row
+  double *cos;            // [2 x n_cos x total_items] raw, then normalised
+  double *reqagg;         // [n_requests x n_reqagg x 4]
+  uint2 *hist_desc;       // [n_requests x n_hist] {offset, length | unsorted << 31}
+  uint64_t *hist_pool;
+  uint32_t hist_pool_cap;
+  uint32_t *hist_cursor;
+  int32_t *error_flag;    // 0 ok | MR_ERR_ARITHMETIC | -1 histogram pool overflow
+  int n_hist, n_reqagg, n_cos;
+  // output
+  double *out_features;   // [total_items x dim] row-major (ltrlib Query.values)
+};
+
+// Enqueues lookup -> cosine -> per-request prepass -> assemble on `stream`.
+void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t stream);
+// Ranker.rerank's sortBy(-score): order[off[r] + k] = index (within the request) of the k-th item.
+void launch_rank_order(const double *d_scores, const int32_t *d_item_offsets, int n_requests, int total_items,
+                       int32_t *d_order, cudaStream_t stream);
+
+}  // namespace mr

@@ -1,0 +1,179 @@
+// Internal definitions shared by the C-ABI translation units (api.cu, rank_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.h"
+#include "gbdt_kernels.cuh"
+#include "gbdt_model.h"
+
+namespace mr {
+extern thread_local std::string t_last_error;
+
+template <class F> mr_status guard(F &&f) {
+  try {
+    f();
+    return MR_OK;
+  } catch (const Error &e) {
+    t_last_error = e.what();
+    return e.code;
+  } catch (const std::bad_alloc &) {
+    t_last_error = "out of host memory";
+    return MR_ERR_INVALID_ARG;
+  } catch (const std::exception &e) {
+    t_last_error = e.what();
+    return MR_ERR_INVALID_ARG;
+  } catch (...) {
+    t_last_error = "unknown error";
+    return MR_ERR_INVALID_ARG;
+  }
+}
+}  // namespace mr
+
+using namespace mr;
+
+// A Lane is what one in-flight host call needs: a stream, pinned staging and device
+// scratch.  Lanes are checked out from the context's pool, so concurrent JVM threads
+// never share buffers and never allocate on the hot path once warmed up.
+struct Lane {
+  cudaStream_t stream = nullptr;
+  uint8_t *h_pinned = nullptr;
+  size_t h_bytes = 0;
+  uint8_t *d_buf = nullptr;
+  size_t d_bytes = 0;
+  void ensure(size_t hb, size_t db) {
+    if (hb > h_bytes) {
+      if (h_pinned) cudaFreeHost(h_pinned);
+      h_pinned = nullptr;
+      h_bytes = 0;
+      size_t n = std::max(hb, h_bytes * 2);
+      MR_CUDA_CHECK(cudaMallocHost((void **)&h_pinned, n));
+      h_bytes = n;
+    }
+    if (db > d_bytes) {
+      if (d_buf) cudaFree(d_buf);
+      d_buf = nullptr;
+      d_bytes = 0;
+      size_t n = std::max(db, d_bytes * 2);
+      MR_CUDA_CHECK(cudaMalloc((void **)&d_buf, n));
+      d_bytes = n;
+    }
+  }
+};
+
+struct mr_ctx {
+  int device = 0;
+  int num_sms = 0;
+  std::mutex mu;
+  std::vector<std::unique_ptr<Lane>> free_lanes;
+  std::atomic<int> live_models{0};
+
+  std::unique_ptr<Lane> checkout() {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      if (!free_lanes.empty()) {
+        auto l = std::move(free_lanes.back());
+        free_lanes.pop_back();
+        return l;
+      }
+    }
+    auto l = std::make_unique<Lane>();
+    MR_CUDA_CHECK(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
+    return l;
+  }
+  void checkin(std::unique_ptr<Lane> l) {
+    std::lock_guard<std::mutex> g(mu);
+    free_lanes.push_back(std::move(l));
+  }
+};
+
+struct LaneGuard {
+  mr_ctx *ctx;
+  std::unique_ptr<Lane> lane;
+  explicit LaneGuard(mr_ctx *c) : ctx(c), lane(c->checkout()) {}
+  ~LaneGuard() {
+    if (lane) ctx->checkin(std::move(lane));
+  }
+  Lane *operator->() { return lane.get(); }
+};
+
+struct mr_model {
+  mr_ctx *ctx = nullptr;
+  HostModel host;
+  PackedModel packed;
+  uint8_t *d_model = nullptr;
+  ChunkDesc *d_chunks = nullptr;
+  std::atomic<bool> closed{false};
+  std::atomic<int> inflight{0};
+  std::mutex mu;  // guards repacking / device buffers
+  int opt_threads = 0, opt_variant = -1, opt_ilp = 0, opt_chunk_kb = 0;
+
+  void upload() {
+    if (d_model) cudaFree(d_model);
+    if (d_chunks) cudaFree(d_chunks);
+    d_model = nullptr;
+    d_chunks = nullptr;
+    MR_CUDA_CHECK(cudaMalloc((void **)&d_model, packed.bytes.size()));
+    MR_CUDA_CHECK(cudaMemcpy(d_model, packed.bytes.data(), packed.bytes.size(), cudaMemcpyHostToDevice));
+    MR_CUDA_CHECK(cudaMalloc((void **)&d_chunks, packed.chunks.size() * sizeof(ChunkDesc)));
+    MR_CUDA_CHECK(cudaMemcpy(d_chunks, packed.chunks.data(), packed.chunks.size() * sizeof(ChunkDesc),
+                             cudaMemcpyHostToDevice));
+  }
+  void repack() {
+    // Default policy: stream the ensemble through two small shared-memory buffers (TMA bulk
+    // copies overlap the traversal).  Small chunks leave shared memory for the feature tile,
+    // i.e. for resident warps, which is what bounds this kernel (profiles/ round-1 notes).
+    size_t budget;
+    if (opt_chunk_kb > 0) {
+      budget = (size_t)opt_chunk_kb * 1024;
+    } else {
+      budget = 8 * 1024;  // small chunks leave shared memory for the feature tile (occupancy)
+    }
+    packed = pack_model(host, budget);
+    upload();
+  }
+  void release_device() {
+    if (d_model) cudaFree(d_model);
+    if (d_chunks) cudaFree(d_chunks);
+    d_model = nullptr;
+    d_chunks = nullptr;
+  }
+  ScoreLaunch launch_desc(const double *d_values, int rows, int cols, double *d_out) const {
+    ScoreLaunch L;
+    L.d_model = d_model;
+    L.d_chunks = d_chunks;
+    L.n_chunks = (int)packed.chunks.size();
+    L.max_chunk_bytes = packed.max_chunk_bytes;
+    L.kind = host.kind;
+    L.has_cat = host.has_cat;
+    L.has_zero = host.has_zero_missing;
+    L.base_score = host.base_score;
+    L.n_features = host.n_features;
+    L.d_values = d_values;
+    L.rows = rows;
+    L.cols = cols;
+    L.d_out = d_out;
+    L.threads = opt_threads;
+    L.variant = opt_variant;
+    L.ilp = opt_ilp;
+    return L;
+  }
+};
+
+
+namespace mr {
+struct InflightGuard {
+  mr_model *m;
+  explicit InflightGuard(mr_model *mm) : m(mm) { m->inflight++; }
+  ~InflightGuard() { m->inflight--; }
+};
+void check_model(mr_model *m);
+}  // namespace mr

@@ -1,0 +1,394 @@
+// C ABI for feature assembly + the full rerank path: mr_schema_*, mr_state_*, mr_rank*.
+// Host mirror of Ranker.rerank (reference S/ml/Ranker.scala:27-83):
+//   makeQuery  = lookup/cosine/prepass/assemble kernels over the device-resident state
+//   predict    = gbdt_score kernel on the assembled matrix (never leaves HBM)
+//   sortBy     = order kernel
+#include "assemble_kernels.cuh"
+#include "internal.h"
+#include "schema.h"
+#include "state.h"
+
+using namespace mr;
+
+struct mr_schema {
+  Schema s;
+  mr_ctx *ctx = nullptr;
+  DFeature *d_plan = nullptr;
+};
+
+struct RankScratch {  // per-lane device scratch for one in-flight mr_rank
+  uint8_t *buf = nullptr;
+  size_t cap = 0;
+};
+
+struct mr_state {
+  mr_ctx *ctx = nullptr;
+  mr_schema *schema = nullptr;
+  std::unique_ptr<StateStore> store;
+  bool dirty = false;
+  uint32_t hist_pool_per_hist = 256;  // average tag-multiset entries reserved per (request, histogram)
+  // device-batch API scratch (single stream use)
+  uint8_t *d_scratch = nullptr;
+  size_t d_scratch_cap = 0;
+  int32_t *d_error = nullptr;
+};
+
+namespace {
+
+inline size_t al(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct ScratchPlan {
+  size_t item_req, item_row, visitor_row, cos, reqagg, hist_desc, hist_pool, hist_cursor, error_flag, features, total;
+  uint32_t hist_pool_cap;
+};
+
+ScratchPlan plan_scratch(const Schema &S, int n_requests, int total_items, uint32_t per_hist, bool own_features) {
+  ScratchPlan p{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += al(bytes); return r; };
+  int n_cos = 0;
+  for (auto &d : S.plan) n_cos += d.kind == FK_COSINE;
+  p.item_req = take((size_t)total_items * 4);
+  p.item_row = take((size_t)total_items * 4);
+  p.visitor_row = take((size_t)n_requests * 8);
+  p.cos = take((size_t)2 * n_cos * total_items * 8);
+  p.reqagg = take((size_t)n_requests * std::max(S.n_reqagg, 1) * 32);
+  p.hist_desc = take((size_t)n_requests * std::max(S.n_hist, 1) * 8);
+  uint64_t cap = (uint64_t)n_requests * S.n_hist * per_hist;
+  cap = std::min<uint64_t>(std::max<uint64_t>(cap, S.n_hist ? 4096 : 0), 0x7FFFFFF0ull);
+  p.hist_pool_cap = (uint32_t)cap;
+  p.hist_pool = take((size_t)cap * 8);
+  p.hist_cursor = take(4);
+  p.error_flag = take(4);
+  p.features = own_features ? take((size_t)total_items * std::max(S.dim, 1) * 8) : 0;
+  p.total = o;
+  return p;
+}
+
+void fill_args(RankArgs &a, mr_state *st, uint8_t *scratch, const ScratchPlan &sp) {
+  const Schema &S = st->store->schema;
+  a.st = st->store->view();
+  a.plan = st->schema->d_plan;
+  a.n_plan = (int)S.plan.size();
+  a.dim = S.dim;
+  a.n_req_f64 = (int)S.in_req_f64.size();
+  a.n_req_u64 = (int)S.in_req_u64.size();
+  a.n_req_vec = (int)S.in_req_vec.size();
+  a.vec_stride = S.vec_stride;
+  a.n_item_f64 = (int)S.in_item_f64.size();
+  a.item_req = (int32_t *)(scratch + sp.item_req);
+  a.item_row = (uint32_t *)(scratch + sp.item_row);
+  a.visitor_row = (uint32_t *)(scratch + sp.visitor_row);
+  a.cos = (double *)(scratch + sp.cos);
+  a.reqagg = (double *)(scratch + sp.reqagg);
+  a.hist_desc = (uint2 *)(scratch + sp.hist_desc);
+  a.hist_pool = (uint64_t *)(scratch + sp.hist_pool);
+  a.hist_pool_cap = sp.hist_pool_cap;
+  a.hist_cursor = (uint32_t *)(scratch + sp.hist_cursor);
+  a.error_flag = (int32_t *)(scratch + sp.error_flag);
+  a.n_hist = S.n_hist;
+  a.n_reqagg = S.n_reqagg;
+  int n_cos = 0;
+  for (auto &d : S.plan) n_cos += d.kind == FK_COSINE;
+  a.n_cos = n_cos;
+}
+
+void ensure_flushed(mr_state *st) {
+  if (st->dirty) {
+    st->store->flush();
+    st->dirty = false;
+  }
+}
+
+void check_scored_dim(mr_state *st, mr_model *model) {
+  if (model && model->host.n_features != st->store->schema.dim)
+    fail(MR_ERR_FEATURE_MISMATCH, "booster reads %d features, the schema's dataset descriptor has %d columns",
+         model->host.n_features, st->store->schema.dim);
+}
+
+}  // namespace
+
+extern "C" {
+
+uint64_t mr_hash64(const void *bytes, size_t len) { return hash64(bytes, len); }
+int32_t mr_token_count(const char *utf8, size_t len) { return token_count(utf8, len); }
+
+mr_status mr_schema_create(mr_ctx *ctx, const char *json, size_t len, mr_schema **out) {
+  return guard([&] {
+    if (!json || !out) fail(MR_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    auto s = std::make_unique<mr_schema>();
+    s->s = parse_schema_json(json, len);
+    s->ctx = ctx;
+    if (ctx) {  // ctx may be NULL for host-only validation of a config
+      MR_CUDA_CHECK(cudaSetDevice(ctx->device));
+      const size_t bytes = std::max<size_t>(s->s.plan.size(), 1) * sizeof(DFeature);
+      MR_CUDA_CHECK(cudaMalloc((void **)&s->d_plan, bytes));
+      if (!s->s.plan.empty())
+        MR_CUDA_CHECK(cudaMemcpy(s->d_plan, s->s.plan.data(), s->s.plan.size() * sizeof(DFeature), cudaMemcpyHostToDevice));
+    }
+    *out = s.release();
+  });
+}
+
+mr_status mr_schema_free(mr_schema *s) {
+  if (!s) return MR_OK;
+  if (s->d_plan) cudaFree(s->d_plan);
+  delete s;
+  return MR_OK;
+}
+
+int32_t mr_schema_dim(const mr_schema *s) { return s ? s->s.dim : -1; }
+
+int32_t mr_schema_feature_offset(const mr_schema *s, const char *feature, int32_t *dim_out) {
+  if (!s || !feature) return -1;
+  auto it = s->s.col_of.find(feature);
+  if (it == s->s.col_of.end()) return -1;
+  if (dim_out) *dim_out = it->second.second;
+  return it->second.first;
+}
+
+int32_t mr_schema_input_slot(const mr_schema *s, int32_t kind, const char *feature, int32_t *n_out) {
+  if (!s) return -1;
+  const std::vector<std::string> *v = nullptr;
+  std::vector<std::string> vec_names;
+  switch (kind) {
+    case MR_IN_REQ_F64: v = &s->s.in_req_f64; break;
+    case MR_IN_REQ_U64: v = &s->s.in_req_u64; break;
+    case MR_IN_ITEM_F64: v = &s->s.in_item_f64; break;
+    case MR_IN_REQ_VEC:
+      for (auto &x : s->s.in_req_vec) vec_names.push_back(x.feature);
+      v = &vec_names;
+      break;
+    default: return -1;
+  }
+  if (n_out) *n_out = (int32_t)v->size();
+  if (!feature) return -1;
+  for (size_t i = 0; i < v->size(); i++)
+    if ((*v)[i] == feature) return (int32_t)i;
+  return -1;
+}
+
+int32_t mr_schema_vec_stride(const mr_schema *s) { return s ? s->s.vec_stride : -1; }
+int32_t mr_schema_vec_offset(const mr_schema *s, int32_t slot, int32_t *dim_out) {
+  if (!s || slot < 0 || slot >= (int)s->s.in_req_vec.size()) return -1;
+  if (dim_out) *dim_out = s->s.in_req_vec[slot].dim;
+  return s->s.in_req_vec[slot].offset;
+}
+
+mr_status mr_state_create(mr_ctx *ctx, mr_schema *schema, mr_state **out) {
+  return guard([&] {
+    if (!ctx || !schema || !out) fail(MR_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (!schema->d_plan) fail(MR_ERR_INVALID_ARG, "schema was created without a context");
+    auto st = std::make_unique<mr_state>();
+    st->ctx = ctx;
+    st->schema = schema;
+    st->store = std::make_unique<StateStore>(schema->s);
+    st->store->device = ctx->device;
+    st->dirty = true;
+    MR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    MR_CUDA_CHECK(cudaMalloc((void **)&st->d_error, 4));
+    *out = st.release();
+  });
+}
+
+mr_status mr_state_free(mr_state *st) {
+  if (!st) return MR_OK;
+  cudaSetDevice(st->ctx->device);
+  cudaDeviceSynchronize();
+  if (st->d_scratch) cudaFree(st->d_scratch);
+  if (st->d_error) cudaFree(st->d_error);
+  delete st;
+  return MR_OK;
+}
+
+mr_status mr_state_upsert(mr_state *st, const uint8_t *packed, size_t len, int64_t *applied, int64_t *skipped) {
+  return guard([&] {
+    if (!st || (!packed && len)) fail(MR_ERR_INVALID_ARG, "null argument");
+    st->store->upsert(packed, len, applied, skipped);
+    st->dirty = true;
+  });
+}
+
+mr_status mr_state_flush(mr_state *st) {
+  return guard([&] {
+    if (!st) fail(MR_ERR_INVALID_ARG, "null argument");
+    st->store->flush();
+    st->dirty = false;
+  });
+}
+
+mr_status mr_state_get_info(mr_state *st, mr_state_info *out) {
+  return guard([&] {
+    if (!st || !out) fail(MR_ERR_INVALID_ARG, "null argument");
+    for (int t = 0; t < SC_N_TABLES; t++) out->rows[t] = (int64_t)st->store->tables[t].n_rows;
+    out->device_bytes = st->store->device_bytes;
+    out->item_row_bytes = (int64_t)st->store->tables[SC_ITEM].row_words * 8;
+  });
+}
+
+mr_status mr_rank(mr_state *st, mr_model *model, const mr_rank_batch *b, double *out_scores, int32_t *out_order,
+                  double *out_features) {
+  return guard([&] {
+    if (!st || !b) fail(MR_ERR_INVALID_ARG, "null argument");
+    if (model) check_model(model);
+    if (b->n_requests < 0) fail(MR_ERR_INVALID_ARG, "negative request count");
+    if (b->n_requests == 0) return;
+    if (!b->item_offsets || (!b->item_ids && b->item_offsets[b->n_requests] > 0)) fail(MR_ERR_INVALID_ARG, "null item arrays");
+    const int R = b->n_requests;
+    if (b->item_offsets[0] != 0) fail(MR_ERR_INVALID_ARG, "item_offsets[0] must be 0");
+    for (int r = 0; r < R; r++)
+      if (b->item_offsets[r + 1] < b->item_offsets[r]) fail(MR_ERR_INVALID_ARG, "item_offsets must be non-decreasing");
+    const int N = b->item_offsets[R];
+    if (model && !out_scores && N > 0) fail(MR_ERR_INVALID_ARG, "out_scores is null");
+    check_scored_dim(st, model);
+    const Schema &S = st->store->schema;
+    if (!S.in_req_f64.empty() && !b->req_f64) fail(MR_ERR_INVALID_ARG, "schema needs req_f64 inputs");
+    if (!S.in_req_u64.empty() && !b->req_u64) fail(MR_ERR_INVALID_ARG, "schema needs req_u64 inputs");
+    if (!S.in_req_vec.empty() && (!b->req_vec || !b->req_vec_present)) fail(MR_ERR_INVALID_ARG, "schema needs req_vec inputs");
+    if (N == 0) return;
+    std::unique_ptr<InflightGuard> ig;
+    if (model) ig = std::make_unique<InflightGuard>(model);
+    MR_CUDA_CHECK(cudaSetDevice(st->ctx->device));
+    std::shared_lock<std::shared_mutex> read_guard(st->store->mu);  // no flush while kernels read the tables
+    if (st->dirty) fail(MR_ERR_INVALID_ARG, "state has pending upserts: call mr_state_flush before mr_rank");
+
+    // ---- pack the batch into one pinned blob -> one H2D copy
+    struct Seg { const void *src; size_t bytes, off; };
+    std::vector<Seg> segs;
+    size_t in_bytes = 0;
+    auto seg = [&](const void *p, size_t bytes) { Seg s{p, p ? bytes : 0, in_bytes}; in_bytes += al(s.bytes); segs.push_back(s); return segs.size() - 1; };
+    const size_t s_off = seg(b->item_offsets, (size_t)(R + 1) * 4);
+    const size_t s_ids = seg(b->item_ids, (size_t)N * 8);
+    const size_t s_usr = seg(b->user_ids, (size_t)R * 8);
+    const size_t s_ses = seg(b->session_ids, (size_t)R * 8);
+    const size_t s_rf = seg(b->req_f64, (size_t)R * S.in_req_f64.size() * 8);
+    const size_t s_ru = seg(b->req_u64, (size_t)R * S.in_req_u64.size() * 8);
+    const size_t s_rv = seg(b->req_vec, (size_t)R * S.vec_stride * 4);
+    const size_t s_rp = seg(b->req_vec_present, (size_t)R * S.in_req_vec.size());
+    const size_t s_if = seg(b->item_f64, (size_t)N * S.in_item_f64.size() * 8);
+
+    for (int attempt = 0;; attempt++) {
+      ScratchPlan sp = plan_scratch(S, R, N, st->hist_pool_per_hist, true);
+      const size_t scores_off = al(in_bytes) + sp.total, order_off = scores_off + al((size_t)N * 8);
+      const size_t d_total = order_off + al((size_t)N * 4);
+      const size_t out_bytes = al((size_t)N * 8) + al((size_t)N * 4) + (out_features ? al((size_t)N * S.dim * 8) : 0) + 16;
+      LaneGuard lane(st->ctx);
+      lane->ensure(in_bytes + out_bytes, d_total);
+      for (auto &s : segs) if (s.bytes) memcpy(lane->h_pinned + s.off, s.src, s.bytes);
+      uint8_t *d_in = lane->d_buf, *scratch = lane->d_buf + al(in_bytes);
+      MR_CUDA_CHECK(cudaMemcpyAsync(d_in, lane->h_pinned, in_bytes, cudaMemcpyHostToDevice, lane->stream));
+      auto dp = [&](size_t si) -> const void * { return segs[si].bytes ? d_in + segs[si].off : nullptr; };
+      RankArgs a{};
+      fill_args(a, st, scratch, sp);
+      a.n_requests = R;
+      a.total_items = N;
+      a.item_offsets = (const int32_t *)dp(s_off);
+      a.item_ids = (const uint64_t *)dp(s_ids);
+      a.user_ids = (const uint64_t *)dp(s_usr);
+      a.session_ids = (const uint64_t *)dp(s_ses);
+      a.req_f64 = (const double *)dp(s_rf);
+      a.req_u64 = (const uint64_t *)dp(s_ru);
+      a.req_vec = (const float *)dp(s_rv);
+      a.req_vec_present = (const uint8_t *)dp(s_rp);
+      a.item_f64 = (const double *)dp(s_if);
+      a.out_features = (double *)(scratch + sp.features);
+      MR_CUDA_CHECK(cudaMemsetAsync(a.error_flag, 0, 4, lane->stream));
+      launch_assemble(a, S, lane->stream);
+      double *d_scores = (double *)(lane->d_buf + scores_off);
+      int32_t *d_order = (int32_t *)(lane->d_buf + order_off);
+      uint8_t *h_out = lane->h_pinned + in_bytes;
+      size_t ho = 0;
+      if (model) {
+        ScoreLaunch L = model->launch_desc(a.out_features, N, S.dim, d_scores);
+        launch_gbdt_score(L, st->ctx->num_sms, lane->stream);
+        if (out_order) launch_rank_order(d_scores, a.item_offsets, R, N, d_order, lane->stream);
+        MR_CUDA_CHECK(cudaMemcpyAsync(h_out + ho, d_scores, (size_t)N * 8, cudaMemcpyDeviceToHost, lane->stream));
+      }
+      const size_t ho_scores = ho; ho += al((size_t)N * 8);
+      if (model && out_order) MR_CUDA_CHECK(cudaMemcpyAsync(h_out + ho, d_order, (size_t)N * 4, cudaMemcpyDeviceToHost, lane->stream));
+      const size_t ho_order = ho; ho += al((size_t)N * 4);
+      const size_t ho_feat = ho;
+      if (out_features) { MR_CUDA_CHECK(cudaMemcpyAsync(h_out + ho, a.out_features, (size_t)N * S.dim * 8, cudaMemcpyDeviceToHost, lane->stream)); ho += al((size_t)N * S.dim * 8); }
+      MR_CUDA_CHECK(cudaMemcpyAsync(h_out + ho, a.error_flag, 4, cudaMemcpyDeviceToHost, lane->stream));
+      MR_CUDA_CHECK(cudaStreamSynchronize(lane->stream));
+      int32_t err;
+      memcpy(&err, h_out + ho, 4);
+      if (err == -1 && attempt < 6) {  // tag-multiset pool too small: grow and redo this batch
+        st->hist_pool_per_hist *= 4;
+        continue;
+      }
+      if (err == -1) fail(MR_ERR_UNSUPPORTED, "per-request tag histograms exceed the scratch pool");
+      if (err == MR_ERR_ARITHMETIC)
+        fail(MR_ERR_ARITHMETIC, "/ by zero: normalized rate with a global '%s' counter of 0 (java.lang.ArithmeticException in RateFeature.value)", "top");
+      if (model && out_scores) memcpy(out_scores, h_out + ho_scores, (size_t)N * 8);
+      if (model && out_order) memcpy(out_order, h_out + ho_order, (size_t)N * 4);
+      if (out_features) memcpy(out_features, h_out + ho_feat, (size_t)N * S.dim * 8);
+      break;
+    }
+  });
+}
+
+mr_status mr_rank_device(mr_state *st, mr_model *model, const mr_rank_batch *b, int32_t total_items,
+                         double *d_out_scores, int32_t *d_out_order, double *d_out_features, void *cuda_stream) {
+  return guard([&] {
+    if (!st || !b) fail(MR_ERR_INVALID_ARG, "null argument");
+    if (model) check_model(model);
+    check_scored_dim(st, model);
+    const int R = b->n_requests, N = total_items;
+    if (R <= 0 || N <= 0) return;
+    const Schema &S = st->store->schema;
+    MR_CUDA_CHECK(cudaSetDevice(st->ctx->device));
+    if (st->dirty) fail(MR_ERR_INVALID_ARG, "state has pending upserts: call mr_state_flush before mr_rank_device");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    ScratchPlan sp = plan_scratch(S, R, N, st->hist_pool_per_hist, d_out_features == nullptr);
+    if (sp.total > st->d_scratch_cap) {
+      MR_CUDA_CHECK(cudaDeviceSynchronize());
+      if (st->d_scratch) cudaFree(st->d_scratch);
+      st->d_scratch = nullptr;
+      MR_CUDA_CHECK(cudaMalloc((void **)&st->d_scratch, sp.total));
+      st->d_scratch_cap = sp.total;
+    }
+    RankArgs a{};
+    fill_args(a, st, st->d_scratch, sp);
+    a.error_flag = st->d_error;
+    a.n_requests = R;
+    a.total_items = N;
+    a.item_offsets = b->item_offsets;
+    a.item_ids = b->item_ids;
+    a.user_ids = b->user_ids;
+    a.session_ids = b->session_ids;
+    a.req_f64 = b->req_f64;
+    a.req_u64 = b->req_u64;
+    a.req_vec = b->req_vec;
+    a.req_vec_present = b->req_vec_present;
+    a.item_f64 = b->item_f64;
+    a.out_features = d_out_features ? d_out_features : (double *)(st->d_scratch + sp.features);
+    MR_CUDA_CHECK(cudaMemsetAsync(a.error_flag, 0, 4, stream));
+    launch_assemble(a, S, stream);
+    if (model) {
+      if (!d_out_scores) fail(MR_ERR_INVALID_ARG, "d_out_scores is null");
+      ScoreLaunch L = model->launch_desc(a.out_features, N, S.dim, d_out_scores);
+      launch_gbdt_score(L, st->ctx->num_sms, stream);
+      if (d_out_order) launch_rank_order(d_out_scores, a.item_offsets, R, N, d_out_order, stream);
+    }
+  });
+}
+
+mr_status mr_rank_device_status(mr_state *st, void *cuda_stream) {
+  return guard([&] {
+    if (!st) fail(MR_ERR_INVALID_ARG, "null argument");
+    MR_CUDA_CHECK(cudaSetDevice(st->ctx->device));
+    MR_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+    int32_t err = 0;
+    MR_CUDA_CHECK(cudaMemcpy(&err, st->d_error, 4, cudaMemcpyDeviceToHost));
+    if (err == -1) {
+      st->hist_pool_per_hist *= 4;
+      fail(MR_ERR_UNSUPPORTED, "per-request tag histograms exceeded the scratch pool; pool grown, resubmit the batch");
+    }
+    if (err == MR_ERR_ARITHMETIC) fail(MR_ERR_ARITHMETIC, "/ by zero in normalized rate (global top counter is 0)");
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// FeatureMapping for one model: parsed Metarank feature schemas -> extractor plan, state
+// slots and the dense column layout.  Mirrors S/FeatureMapping.scala:56-99 (feature list,
+// Schema of state configs, DatasetDescriptor in model-feature order) for the extractors on
+// the /rank hot path.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.h"
+
+namespace mr {
+
+enum FeatKind : int32_t {
+  FK_NUMBER = 0,      // number, word_count (stored SDouble)     S/feature/NumberFeature.scala, WordCountFeature.scala
+  FK_CATEGORY = 1,    // string, encode: index                   S/feature/StringFeature.scala:124-137
+  FK_ONEHOT = 2,      // string, encode: onehot                  S/feature/StringFeature.scala:118-122
+  FK_COUNT = 3,       // interaction_count                       S/feature/InteractionCountFeature.scala:44-59
+  FK_WINDOW = 4,      // window_count                            S/feature/WindowInteractionCountFeature.scala:50-63
+  FK_RATE = 5,        // rate (plain + normalized)               S/feature/RateFeature.scala:290-356
+  FK_INTERACTED = 6,  // interacted_with, one entry per field    S/feature/InteractedWithFeature.scala:133-164
+  FK_RELEVANCY = 7,   // relevancy                               S/feature/RelevancyFeature.scala:36-51
+  FK_POSITION = 8,    // position (online: constant)             S/feature/PositionFeature.scala:30-35
+  FK_DIVERSITY = 9,   // diversity                               S/feature/DiversityFeature.scala:67-130
+  FK_COSINE = 10,     // field_match / bi-encoder                S/feature/FieldMatchBiencoderFeature.scala:80-109
+  FK_CONST_REQ = 11,  // number/word_count/string with scope ranking: one value per request
+};
+
+enum ScopeT : int32_t { SC_GLOBAL = 0, SC_ITEM = 1, SC_USER = 2, SC_SESSION = 3, SC_FIELD = 4, SC_IRF = 5, SC_RANKING = 6, SC_N_TABLES = 6 };
+
+enum SlotKind : int32_t {
+  SK_F64 = 0,        // ScalarValue(SDouble)                  1 word
+  SK_STRID = 1,      // ScalarValue(SString) as hash          1 word
+  SK_CAT = 2,        // SStringList pre-encoded: index+1 / onehot mask   1 word
+  SK_COUNTER = 3,    // CounterValue                          1 word
+  SK_PCOUNTER = 4,   // PeriodicCounterValue                  P words (+ presence only if length == P)
+  SK_STRLIST = 5,    // ScalarValue(SStringList|SString) hashes: {u32 off, u32 len} into the table's pool
+  SK_BLIST = 6,      // BoundedListValue item hashes:          {u32 off, u32 len}
+  SK_F64LIST = 7,    // ScalarValue(SDoubleList) dim doubles in a side array (presence bit only)
+  SK_DIVERSITY = 8,  // 2 words: {kind 1 double | 2 strings, payload f64 | {off,len}}
+};
+
+struct Slot {
+  std::string name;  // Key.feature
+  int table = 0;     // ScopeT (< SC_N_TABLES)
+  int kind = 0;
+  int word = 0;      // first payload word within the row
+  int n_words = 1;
+  int bit = 0;       // presence bit index
+  int p = 0;         // periods (PCOUNTER) / dim (F64LIST)
+  int side = -1;     // side-array index (F64LIST)
+  int feature = -1;  // owning feature (for CAT encoding)
+};
+
+// Device-visible extractor descriptor (POD).
+struct DFeature {
+  int32_t kind, col, dim, scope;
+  int32_t w[4], b[4];  // slot words / presence bits (meaning depends on kind)
+  int32_t in0, in1;    // request-input slot indices (-1 none)
+  int32_t aux0, aux1, aux2, aux3;
+  double dparam;
+  uint64_t uparam;
+};
+
+struct FeatureDef {  // host-side description of one configured feature
+  std::string name, type;
+  int kind = 0;
+  int dim = 1;
+  int scope = SC_ITEM;
+  std::string scope_field;  // item.<field> / ranking.<field>
+  std::vector<std::string> cat_values;
+  std::vector<uint64_t> cat_hashes;
+  int col = -1;  // first dense column, -1 when not in the model
+  std::vector<int> slots;  // indices into Schema::slots
+};
+
+struct TableLayout {
+  int n_slots = 0;
+  int presence_words = 0;
+  int row_words = 0;  // total u64 words per row
+};
+
+struct SideArray { int table; int dim; int slot; };
+
+struct Schema {
+  std::vector<FeatureDef> features;          // config order
+  std::vector<std::string> model_features;   // model order
+  std::vector<Slot> slots;
+  std::unordered_map<std::string, int> slot_by_name;
+  TableLayout tables[SC_N_TABLES];
+  std::vector<SideArray> sides;
+  std::vector<DFeature> plan;                // extractor entries in column order
+  int dim = 0;
+  // request inputs
+  std::vector<std::string> in_req_f64, in_req_u64, in_item_f64;  // owning feature names
+  struct VecIn { std::string feature; int dim; int offset; };
+  std::vector<VecIn> in_req_vec;
+  int vec_stride = 0;
+  // per-request aggregates
+  int n_hist = 0;       // sorted tag multisets (interacted_with fields, diversity strings)
+  int n_reqagg = 0;     // per-request scalar aggregates (diversity median / totals, cosine min/max)
+  bool needs_prepass = false, needs_cosine = false, needs_visitor = false;
+  std::unordered_map<std::string, std::pair<int, int>> col_of;  // model feature -> (offset, dim)
+};
+
+Schema parse_schema_json(const char *json, size_t len);
+
+uint64_t hash64(const void *bytes, size_t len);
+int32_t token_count(const char *s, size_t len);
+inline uint64_t hash_combine(uint64_t a, uint64_t b) {
+  uint64_t x = a ^ (b + 0x9E3779B97F4A7C15ull + (a << 6) + (a >> 2));
+  x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32;
+  return x ? x : 1;
+}
+
+}  // namespace mr

@@ -1,0 +1,306 @@
+// See state.h.  Wire format of mr_state_upsert is documented in include/mr_b200.h; the
+// FeatureValue kinds are those of reference S/model/FeatureValue.scala:18-50.
+#include "state.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace mr {
+
+uint32_t HostTable::find(uint64_t key) const {
+  if (keys.empty()) return UINT32_MAX;
+  const size_t mask = keys.size() - 1;
+  size_t i = (size_t)mix64(key) & mask;
+  for (;;) {
+    if (keys[i] == key) return vals[i];
+    if (keys[i] == 0) return UINT32_MAX;
+    i = (i + 1) & mask;
+  }
+}
+
+void HostTable::grow_map() {
+  const size_t cap = keys.empty() ? 1024 : keys.size() * 2;
+  std::vector<uint64_t> nk(cap, 0);
+  std::vector<uint32_t> nv(cap, 0);
+  for (size_t i = 0; i < keys.size(); i++) {
+    if (!keys[i]) continue;
+    size_t j = (size_t)mix64(keys[i]) & (cap - 1);
+    while (nk[j]) j = (j + 1) & (cap - 1);
+    nk[j] = keys[i];
+    nv[j] = vals[i];
+  }
+  keys.swap(nk);
+  vals.swap(nv);
+  map_dirty = true;
+}
+
+uint32_t HostTable::find_or_insert(uint64_t key) {
+  if (key == 0) key = 1;
+  if (keys.empty() || (n_rows + 1) * 2 > keys.size()) grow_map();
+  const size_t mask = keys.size() - 1;
+  size_t i = (size_t)mix64(key) & mask;
+  for (;;) {
+    if (keys[i] == key) return vals[i];
+    if (keys[i] == 0) break;
+    i = (i + 1) & mask;
+  }
+  if (n_rows >= (size_t)UINT32_MAX - 1) fail(MR_ERR_UNSUPPORTED, "state table is full");
+  const uint32_t row = (uint32_t)n_rows++;
+  keys[i] = key;
+  vals[i] = row;
+  map_dirty = true;
+  rows.resize(n_rows * (size_t)row_words, 0);
+  return row;
+}
+
+StateStore::StateStore(const Schema &s) : schema(s) {
+  for (int t = 0; t < SC_N_TABLES; t++) tables[t].row_words = schema.tables[t].row_words;
+  if (schema.sides.size() > (size_t)kMaxSides) fail(MR_ERR_UNSUPPORTED, "at most %d embedding features are supported", kMaxSides);
+  for (size_t i = 0; i < schema.sides.size(); i++) {
+    HostTable &T = tables[schema.sides[i].table];
+    T.side_ids.push_back((int)i);
+    T.sides.emplace_back();
+    T.d_sides.push_back(nullptr);
+    T.d_sides_cap.push_back(0);
+  }
+  // the global scope always has its single row
+  tables[SC_GLOBAL].find_or_insert(1);
+}
+
+StateStore::~StateStore() {
+  for (auto &T : tables) {
+    if (T.d_keys) cudaFree(T.d_keys);
+    if (T.d_vals) cudaFree(T.d_vals);
+    if (T.d_rows) cudaFree(T.d_rows);
+    if (T.d_pool) cudaFree(T.d_pool);
+    for (auto p : T.d_sides) if (p) cudaFree(p);
+  }
+}
+
+namespace {
+struct Reader {
+  const uint8_t *p, *e;
+  template <class T> T get() {
+    if ((size_t)(e - p) < sizeof(T)) fail(MR_ERR_PARSE, "state record truncated");
+    T v;
+    memcpy(&v, p, sizeof(T));
+    p += sizeof(T);
+    return v;
+  }
+  const uint8_t *bytes(size_t n) {
+    if ((size_t)(e - p) < n) fail(MR_ERR_PARSE, "state record truncated");
+    const uint8_t *q = p;
+    p += n;
+    return q;
+  }
+};
+}  // namespace
+
+void StateStore::upsert(const uint8_t *buf, size_t len, int64_t *applied, int64_t *skipped) {
+  std::unique_lock<std::shared_mutex> g(mu);
+  Reader r{buf, buf + len};
+  int64_t n_ok = 0, n_skip = 0;
+  while (r.p < r.e) {
+    const uint16_t nl = r.get<uint16_t>();
+    std::string name((const char *)r.bytes(nl), nl);
+    const uint8_t scope = r.get<uint8_t>();
+    uint64_t id0 = 0, id1 = 0;
+    switch (scope) {
+      case SC_GLOBAL: break;
+      case SC_ITEM: case SC_USER: case SC_SESSION: case SC_RANKING: case SC_FIELD: id0 = r.get<uint64_t>(); break;
+      case SC_IRF: id0 = r.get<uint64_t>(); id1 = r.get<uint64_t>(); break;
+      default: fail(MR_ERR_PARSE, "state record: bad scope tag %d", (int)scope);
+    }
+    const uint8_t kind = r.get<uint8_t>();
+    // payload view
+    double f64 = 0; uint64_t u64 = 0; int64_t i64 = 0; uint32_t n = 0; const uint8_t *arr = nullptr;
+    switch (kind) {
+      case 0: f64 = r.get<double>(); break;
+      case 1: u64 = r.get<uint64_t>(); break;
+      case 2: case 6: n = r.get<uint32_t>(); arr = r.bytes((size_t)n * 8); break;
+      case 3: n = r.get<uint32_t>(); arr = r.bytes((size_t)n * 8); break;
+      case 4: i64 = r.get<int64_t>(); break;
+      case 5: n = r.get<uint32_t>(); arr = r.bytes((size_t)n * 8); break;
+      default: fail(MR_ERR_PARSE, "state record: bad value kind %d", (int)kind);
+    }
+    auto it = schema.slot_by_name.find(name);
+    if (it == schema.slot_by_name.end()) { n_skip++; continue; }
+    const Slot &sl = schema.slots[it->second];
+    if (sl.table != (int)scope) { n_skip++; continue; }  // same name under another scope: not what the extractor reads
+    HostTable &T = tables[sl.table];
+    uint64_t key;
+    if (scope == SC_GLOBAL) key = 1;
+    else if (scope == SC_FIELD) {
+      const FeatureDef &fd = schema.features[sl.feature];
+      key = hash_combine(hash64(fd.scope_field.data(), fd.scope_field.size()), id0);
+    } else if (scope == SC_IRF) {
+      const FeatureDef &fd = schema.features[sl.feature];
+      key = hash_combine(hash_combine(hash64(fd.scope_field.data(), fd.scope_field.size()), id0), id1);
+    } else key = id0 ? id0 : 1;
+    const uint32_t row = T.find_or_insert(key);
+    uint64_t *w = T.rows.data() + (size_t)row * T.row_words;
+    auto set_present = [&](bool on) {
+      if (on) w[sl.bit >> 6] |= 1ull << (sl.bit & 63);
+      else w[sl.bit >> 6] &= ~(1ull << (sl.bit & 63));
+    };
+    auto put_list = [&](uint64_t *dst) {
+      const uint32_t off = (uint32_t)T.pool.size();
+      if (T.pool.size() + n > (size_t)UINT32_MAX) fail(MR_ERR_UNSUPPORTED, "state pool is full");
+      T.pool.resize(T.pool.size() + n);
+      if (n) memcpy(T.pool.data() + off, arr, (size_t)n * 8);
+      *dst = (uint64_t)off | ((uint64_t)n << 32);
+    };
+    bool ok = true;
+    switch (sl.kind) {
+      case SK_F64:
+        if (kind == 0) { memcpy(&w[sl.word], &f64, 8); set_present(true); }
+        else set_present(false);  // a non-SDouble scalar reads as missing (NumberFeature.value's match)
+        break;
+      case SK_STRID:
+        if (kind == 1) { w[sl.word] = u64; set_present(true); } else set_present(false);
+        break;
+      case SK_CAT: {
+        // StringFeature stores SStringList; the encoder is applied here, once, instead of per request
+        if (kind != 2 && kind != 1) { set_present(false); break; }
+        const FeatureDef &fd = schema.features[sl.feature];
+        std::vector<uint64_t> vals;
+        if (kind == 1) vals.push_back(u64);
+        else { vals.resize(n); if (n) memcpy(vals.data(), arr, (size_t)n * 8); }
+        const bool onehot = fd.kind == FK_ONEHOT;
+        uint64_t enc = 0;
+        if (!onehot) {
+          // IndexCategoricalEncoder: first value -> index + 1, unknown / empty -> 0
+          if (!vals.empty())
+            for (size_t k = 0; k < fd.cat_hashes.size(); k++)
+              if (fd.cat_hashes[k] == vals[0]) { enc = k + 1; break; }
+        } else {
+          for (uint64_t v : vals)
+            for (size_t k = 0; k < fd.cat_hashes.size(); k++)
+              if (fd.cat_hashes[k] == v) { enc |= 1ull << k; break; }  // indexOf: first match
+        }
+        w[sl.word] = enc;
+        set_present(true);
+        break;
+      }
+      case SK_COUNTER:
+        if (kind == 4) { memcpy(&w[sl.word], &i64, 8); set_present(true); } else set_present(false);
+        break;
+      case SK_PCOUNTER:
+        // readers require values.length == dim (e.g. S/feature/RateFeature.scala:318-319); a value
+        // of another length behaves as missing
+        if (kind == 5 && (int)n == sl.p) { memcpy(&w[sl.word], arr, (size_t)n * 8); set_present(true); }
+        else set_present(false);
+        break;
+      case SK_STRLIST:
+        if (kind == 2) { put_list(&w[sl.word]); set_present(true); }
+        else set_present(false);  // InteractedWith collects only SStringList
+        break;
+      case SK_BLIST:
+        if (kind == 6) { put_list(&w[sl.word]); set_present(true); } else set_present(false);
+        break;
+      case SK_F64LIST: {
+        if (kind != 3) { set_present(false); break; }
+        if ((int)n != sl.p) fail(MR_ERR_INVALID_ARG, "embedding '%s' has %u values, the schema says dim %d", name.c_str(), n, sl.p);
+        int local = -1;
+        for (size_t k = 0; k < T.side_ids.size(); k++) if (T.side_ids[k] == sl.side) local = (int)k;
+        auto &S = T.sides[local];
+        if (S.size() < (size_t)T.n_rows * sl.p) S.resize((size_t)T.n_rows * sl.p, 0.0);
+        memcpy(S.data() + (size_t)row * sl.p, arr, (size_t)n * 8);
+        set_present(true);
+        break;
+      }
+      case SK_DIVERSITY:
+        // DiversityFeature keeps whatever scalar the item field had: number | string | string[]
+        if (kind == 0) { w[sl.word] = 1; memcpy(&w[sl.word + 1], &f64, 8); set_present(true); }
+        else if (kind == 1) { n = 1; arr = (const uint8_t *)&u64; w[sl.word] = 2; put_list(&w[sl.word + 1]); set_present(true); }
+        else if (kind == 2) { w[sl.word] = 2; put_list(&w[sl.word + 1]); set_present(true); }
+        else if (kind == 3) { w[sl.word] = 3; set_present(true); }  // "other" scalar kinds -> emptyResponse when first
+        else set_present(false);
+        break;
+      default: ok = false;
+    }
+    if (ok) { T.touch(row); n_ok++; } else n_skip++;
+  }
+  if (applied) *applied = n_ok;
+  if (skipped) *skipped = n_skip;
+}
+
+template <class T> static void ensure_dev(T *&d, size_t &cap, size_t need, size_t keep, int64_t &bytes) {
+  if (need <= cap) return;
+  size_t ncap = std::max(need, cap * 2);
+  T *nd = nullptr;
+  MR_CUDA_CHECK(cudaMalloc((void **)&nd, ncap * sizeof(T)));
+  if (d && keep) MR_CUDA_CHECK(cudaMemcpy(nd, d, keep * sizeof(T), cudaMemcpyDeviceToDevice));
+  if (d) cudaFree(d);
+  bytes += (int64_t)(ncap - cap) * (int64_t)sizeof(T);
+  d = nd;
+  cap = ncap;
+}
+
+void StateStore::flush() {
+  std::unique_lock<std::shared_mutex> g(mu);
+  MR_CUDA_CHECK(cudaSetDevice(device));
+  MR_CUDA_CHECK(cudaDeviceSynchronize());  // no kernel may be reading while rows move
+  for (auto &T : tables) {
+    if (T.map_dirty) {
+      size_t cap0 = T.d_cap, cap1 = T.d_cap;
+      ensure_dev(T.d_keys, cap0, T.keys.size(), 0, device_bytes);
+      ensure_dev(T.d_vals, cap1, T.keys.size(), 0, device_bytes);
+      T.d_cap = cap0;
+      MR_CUDA_CHECK(cudaMemcpy(T.d_keys, T.keys.data(), T.keys.size() * 8, cudaMemcpyHostToDevice));
+      MR_CUDA_CHECK(cudaMemcpy(T.d_vals, T.vals.data(), T.vals.size() * 4, cudaMemcpyHostToDevice));
+      T.map_dirty = false;
+    }
+    if (T.dirty_lo < T.dirty_hi) {
+      const size_t had = T.d_rows_cap;
+      ensure_dev(T.d_rows, T.d_rows_cap, T.rows.size(), 0, device_bytes);
+      size_t lo = T.dirty_lo, hi = T.dirty_hi;
+      if (T.d_rows_cap != had) { lo = 0; hi = T.n_rows; }  // reallocated: upload everything
+      MR_CUDA_CHECK(cudaMemcpy(T.d_rows + lo * T.row_words, T.rows.data() + lo * T.row_words,
+                               (hi - lo) * T.row_words * 8, cudaMemcpyHostToDevice));
+      for (size_t s = 0; s < T.sides.size(); s++) {
+        const int dim = schema.sides[T.side_ids[s]].dim;
+        if (T.sides[s].size() < T.n_rows * (size_t)dim) T.sides[s].resize(T.n_rows * (size_t)dim, 0.0);
+        const size_t had_s = T.d_sides_cap[s];
+        ensure_dev(T.d_sides[s], T.d_sides_cap[s], T.sides[s].size(), 0, device_bytes);
+        size_t slo = T.dirty_lo, shi = T.dirty_hi;
+        if (T.d_sides_cap[s] != had_s) { slo = 0; shi = T.n_rows; }
+        MR_CUDA_CHECK(cudaMemcpy(T.d_sides[s] + slo * dim, T.sides[s].data() + slo * dim, (shi - slo) * dim * 8,
+                                 cudaMemcpyHostToDevice));
+      }
+      T.dirty_lo = SIZE_MAX;
+      T.dirty_hi = 0;
+    }
+    if (T.pool_uploaded < T.pool.size()) {
+      const size_t had = T.d_pool_cap;
+      ensure_dev(T.d_pool, T.d_pool_cap, T.pool.size(), T.pool_uploaded, device_bytes);
+      (void)had;
+      MR_CUDA_CHECK(cudaMemcpy(T.d_pool + T.pool_uploaded, T.pool.data() + T.pool_uploaded,
+                               (T.pool.size() - T.pool_uploaded) * 8, cudaMemcpyHostToDevice));
+      T.pool_uploaded = T.pool.size();
+    }
+  }
+}
+
+DState StateStore::view() const {
+  DState v;
+  memset(&v, 0, sizeof v);
+  for (int t = 0; t < SC_N_TABLES; t++) {
+    const HostTable &T = tables[t];
+    v.t[t].keys = T.d_keys;
+    v.t[t].vals = T.d_vals;
+    v.t[t].mask = T.d_keys ? (uint32_t)(T.keys.size() - 1) : 0;
+    v.t[t].n_rows = T.d_rows ? (uint32_t)T.n_rows : 0;
+    v.t[t].rows = T.d_rows;
+    v.t[t].pool = T.d_pool;
+    v.t[t].row_words = T.row_words;
+    for (size_t s = 0; s < T.side_ids.size(); s++) {
+      v.side[T.side_ids[s]] = T.d_sides[s];
+      v.side_dim[T.side_ids[s]] = schema.sides[T.side_ids[s]].dim;
+    }
+  }
+  return v;
+}
+
+}  // namespace mr

@@ -1,0 +1,80 @@
+// Device-resident feature state: the replacement for Persistence.values
+// (KVStore[Key, FeatureValue], reference S/fstore/Persistence.scala:39,85-89) on the read
+// path.  One table per scope kind; a table = open-addressing hash map (scope hash -> row)
+// + fixed-width rows of u64 words (presence bits, then every slot of that scope) + a pool
+// for variable-length payloads (tag hashes, bounded lists) + dense side arrays for
+// embeddings.  The host keeps a shadow copy and uploads dirty ranges on flush.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <mutex>
+#include <shared_mutex>
+#include <vector>
+
+#include "schema.h"
+
+namespace mr {
+
+constexpr int kMaxSides = 4;
+
+struct DTable {  // device view, passed to kernels by value
+  const uint64_t *keys;
+  const uint32_t *vals;
+  uint32_t mask;       // capacity - 1 (capacity is a power of two); 0 when empty
+  uint32_t n_rows;
+  const uint64_t *rows;
+  const uint64_t *pool;
+  int32_t row_words;
+  int32_t pad;
+};
+
+struct DState {
+  DTable t[SC_N_TABLES];
+  const double *side[kMaxSides];
+  int32_t side_dim[kMaxSides];
+};
+
+__host__ __device__ inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xFF51AFD7ED558CCDull; x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ull; x ^= x >> 33;
+  return x;
+}
+
+struct HostTable {
+  std::vector<uint64_t> keys;   // 0 = empty
+  std::vector<uint32_t> vals;
+  size_t n_rows = 0;
+  int row_words = 1;
+  std::vector<uint64_t> rows;
+  std::vector<uint64_t> pool;
+  std::vector<std::vector<double>> sides;  // one per side array of this table
+  std::vector<int> side_ids;
+  // device mirrors
+  uint64_t *d_keys = nullptr; uint32_t *d_vals = nullptr; size_t d_cap = 0;
+  uint64_t *d_rows = nullptr; size_t d_rows_cap = 0;
+  uint64_t *d_pool = nullptr; size_t d_pool_cap = 0, pool_uploaded = 0;
+  std::vector<double *> d_sides; std::vector<size_t> d_sides_cap;
+  bool map_dirty = false;
+  size_t dirty_lo = SIZE_MAX, dirty_hi = 0;  // row range touched since the last flush
+
+  uint32_t find(uint64_t key) const;
+  uint32_t find_or_insert(uint64_t key);
+  void grow_map();
+  void touch(size_t row) { dirty_lo = std::min(dirty_lo, row); dirty_hi = std::max(dirty_hi, row + 1); }
+};
+
+struct StateStore {
+  Schema schema;
+  HostTable tables[SC_N_TABLES];
+  std::shared_mutex mu;  // shared: kernels reading the tables; exclusive: upsert / flush
+  int device = 0;
+  int64_t device_bytes = 0;
+
+  explicit StateStore(const Schema &s);
+  ~StateStore();
+  void upsert(const uint8_t *p, size_t len, int64_t *applied, int64_t *skipped);
+  void flush();
+  DState view() const;
+};
+
+}  // namespace mr

@@ -1,0 +1,312 @@
+"""Host-side mirror of the reference's feature plumbing on the /rank path, over the C ABI:
+
+    FeatureMapping   S/FeatureMapping.scala:56-99       -> mr_schema (columns, inputs)
+    DeviceState      Persistence.values (KVStore.put)   -> mr_state_upsert / mr_state_flush
+    Ranker.rerank    S/ml/Ranker.scala:27-83            -> mr_rank
+
+This is what the JVM shim does in Scala; here it is Python so the
+parity tests can drive the CUDA path with the same literal events/requests as the oracle.
+Plain-data conventions (shared with the tests, no shared code with oracle/):
+  Key   = (scope, feature_name); scope = ("global",) | ("item", id) | ("user", id) | ("session", id) |
+          ("field", name, value) | ("irf", name, value, item) | ("ranking", id)
+  Value = ("scalar", float|str|list[str]|list[float]) | ("counter", int) | ("pcounter", [int]) | ("blist", [ids])
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import struct
+
+import numpy as np
+
+from . import _capi
+from ._capi import check, lib
+
+MR_IN_REQ_F64, MR_IN_REQ_U64, MR_IN_REQ_VEC, MR_IN_ITEM_F64 = 0, 1, 2, 3
+_SCOPE_TAG = {"global": 0, "item": 1, "user": 2, "session": 3, "field": 4, "irf": 5, "ranking": 6}
+
+
+def hash64(s) -> int:
+    b = s.encode("utf-8") if isinstance(s, str) else bytes(s)
+    lib().mr_hash64.restype = C.c_uint64
+    return int(lib().mr_hash64(b, C.c_size_t(len(b))))
+
+
+def token_count(s: str) -> int:
+    b = s.encode("utf-8")
+    lib().mr_token_count.restype = C.c_int32
+    return int(lib().mr_token_count(b, C.c_size_t(len(b))))
+
+
+def _field_name(s: str) -> tuple[str, str]:
+    ev, fld = s.split(".", 1)
+    return ("item" if ev == "metadata" else ev), fld
+
+
+class RankBatch(C.Structure):
+    _fields_ = [("n_requests", C.c_int32), ("item_offsets", C.c_void_p), ("item_ids", C.c_void_p),
+                ("user_ids", C.c_void_p), ("session_ids", C.c_void_p), ("req_f64", C.c_void_p),
+                ("req_u64", C.c_void_p), ("req_vec", C.c_void_p), ("req_vec_present", C.c_void_p),
+                ("item_f64", C.c_void_p)]
+
+
+class StateInfo(C.Structure):
+    _fields_ = [("rows", C.c_int64 * 6), ("device_bytes", C.c_int64), ("item_row_bytes", C.c_int64)]
+
+
+class FeatureMapping:
+    """mr_schema: features config (list of Metarank feature dicts) + the model's feature list."""
+
+    def __init__(self, ctx, features: list[dict], model_features: list[str]):
+        self.ctx = ctx
+        self.features = [dict(f) for f in features]
+        self.model_features = list(model_features)
+        doc = json.dumps({"features": self.features, "model_features": self.model_features}).encode()
+        self._h = C.c_void_p()
+        check(lib().mr_schema_create(ctx.handle if ctx is not None else None, doc, C.c_size_t(len(doc)),
+                                     C.byref(self._h)))
+        self.dim = int(lib().mr_schema_dim(self._h))
+        self.by_name = {f["name"]: f for f in self.features}
+        self.n_req_f64 = self._n(MR_IN_REQ_F64)
+        self.n_req_u64 = self._n(MR_IN_REQ_U64)
+        self.n_req_vec = self._n(MR_IN_REQ_VEC)
+        self.n_item_f64 = self._n(MR_IN_ITEM_F64)
+        self.vec_stride = int(lib().mr_schema_vec_stride(self._h))
+
+    def _n(self, kind):
+        n = C.c_int32(0)
+        lib().mr_schema_input_slot(self._h, C.c_int32(kind), None, C.byref(n))
+        return n.value
+
+    def offset(self, feature: str):
+        d = C.c_int32(0)
+        o = int(lib().mr_schema_feature_offset(self._h, feature.encode(), C.byref(d)))
+        return (o, d.value) if o >= 0 else None
+
+    def input_slot(self, kind: int, feature: str) -> int:
+        return int(lib().mr_schema_input_slot(self._h, C.c_int32(kind), feature.encode(), None))
+
+    def vec_offset(self, slot: int):
+        d = C.c_int32(0)
+        o = int(lib().mr_schema_vec_offset(self._h, C.c_int32(slot), C.byref(d)))
+        return o, d.value
+
+    def free(self):
+        if self._h:
+            lib().mr_schema_free(self._h)
+            self._h = C.c_void_p()
+
+    # ---- request -> inputs (the JVM shim's job) -------------------------------------
+    def _encode_string(self, conf, values):
+        possible = conf["values"]
+        if conf.get("encode", "onehot") == "index":
+            return [float(possible.index(values[0]) + 1) if values and values[0] in possible else 0.0]
+        out = [0.0] * len(possible)
+        for v in values:
+            if v in possible:
+                out[possible.index(v)] = 1.0
+        return out
+
+    def pack_requests(self, requests: list[dict]):
+        """RankingEvents -> the flat arrays of mr_rank_batch (numpy, kept alive by the caller)."""
+        R = len(requests)
+        offs = np.zeros(R + 1, dtype=np.int32)
+        for r, q in enumerate(requests):
+            offs[r + 1] = offs[r] + len(q["items"])
+        N = int(offs[R])
+        ids = np.zeros(max(N, 1), dtype=np.uint64)
+        users = np.zeros(max(R, 1), dtype=np.uint64)
+        sessions = np.zeros(max(R, 1), dtype=np.uint64)
+        req_f64 = np.full((max(R, 1), max(self.n_req_f64, 1)), np.nan)
+        req_u64 = np.zeros((max(R, 1), max(self.n_req_u64, 1)), dtype=np.uint64)
+        req_vec = np.zeros((max(R, 1), max(self.vec_stride, 1)), dtype=np.float32)
+        req_vp = np.zeros((max(R, 1), max(self.n_req_vec, 1)), dtype=np.uint8)
+        item_f64 = np.full((max(N, 1), max(self.n_item_f64, 1)), np.nan)
+        num = lambda v: isinstance(v, (int, float)) and not isinstance(v, bool)  # noqa: E731
+        strl = lambda v: isinstance(v, list) and all(isinstance(x, str) for x in v)  # noqa: E731
+        for r, q in enumerate(requests):
+            if q.get("user") is not None:
+                users[r] = hash64(q["user"])
+            if q.get("session") is not None:
+                sessions[r] = hash64(q["session"])
+            rf = {n: v for n, v in q.get("fields", [])}  # fieldsMap: last duplicate wins
+            rfirst = {}
+            for n, v in q.get("fields", []):
+                rfirst.setdefault(n, v)
+            for name in self.model_features:
+                conf = self.by_name.get(name)
+                if conf is None:
+                    continue
+                t = conf["type"]
+                if t in ("number", "word_count") and conf.get("scope") == "ranking":
+                    slot = self.input_slot(MR_IN_REQ_F64, name)
+                    v = rf.get(_field_name(conf.get("source", conf.get("field")))[1])
+                    if t == "number" and num(v):
+                        req_f64[r, slot] = float(v)
+                    if t == "word_count" and isinstance(v, str):
+                        req_f64[r, slot] = float(token_count(v))
+                elif t == "string" and _field_name(conf.get("source", conf.get("field")))[0] == "ranking":
+                    slot = self.input_slot(MR_IN_REQ_F64, name)
+                    v = rfirst.get(_field_name(conf.get("source", conf.get("field")))[1])
+                    enc = self._encode_string(conf, [v] if isinstance(v, str) else v if strl(v) else [])
+                    req_f64[r, slot:slot + len(enc)] = enc
+                elif t == "rate" and str(conf.get("scope", "item")).startswith("ranking."):
+                    slot = self.input_slot(MR_IN_REQ_U64, name)
+                    v = rf.get(conf["scope"].split(".", 1)[1])
+                    if isinstance(v, str):
+                        req_u64[r, slot] = hash64(v)
+                elif t == "field_match":
+                    slot = self.input_slot(MR_IN_REQ_VEC, name)
+                    q_emb = (q.get("embeddings") or {}).get(name)
+                    if q_emb is not None:
+                        o, d = self.vec_offset(slot)
+                        req_vec[r, o:o + d] = np.asarray(q_emb, dtype=np.float32)
+                        req_vp[r, slot] = 1
+            for j, it in enumerate(q["items"]):
+                i = int(offs[r]) + j
+                ids[i] = hash64(it["id"])
+                flds = it.get("fields", [])
+                for name in self.model_features:
+                    conf = self.by_name.get(name)
+                    if conf is None:
+                        continue
+                    t = conf["type"]
+                    if t == "relevancy":
+                        first = next(((n, v) for n, v in flds if n == "relevancy"), None)
+                        if first is not None and num(first[1]):
+                            item_f64[i, self.input_slot(MR_IN_ITEM_F64, name)] = float(first[1])
+                    elif t == "number" and conf.get("scope") != "ranking":
+                        fld = _field_name(conf.get("source", conf.get("field")))[1]
+                        ov = next((v for n, v in flds if n == fld and num(v)), None)
+                        if ov is not None:
+                            item_f64[i, self.input_slot(MR_IN_ITEM_F64, name)] = float(ov)
+                    elif t == "string" and _field_name(conf.get("source", conf.get("field")))[0] != "ranking":
+                        fld = _field_name(conf.get("source", conf.get("field")))[1]
+                        ov = next(([v] if isinstance(v, str) else list(v) for n, v in flds
+                                   if n == fld and (isinstance(v, str) or strl(v))), None)
+                        if ov is not None:
+                            slot = self.input_slot(MR_IN_ITEM_F64, name)
+                            enc = self._encode_string(conf, ov)
+                            item_f64[i, slot:slot + len(enc)] = enc
+        return dict(offsets=offs, ids=ids, users=users, sessions=sessions, req_f64=req_f64, req_u64=req_u64,
+                    req_vec=req_vec, req_vp=req_vp, item_f64=item_f64, n_requests=R, total_items=N)
+
+
+def pack_feature_values(values: dict) -> bytes:
+    """Map[Key, FeatureValue] -> mr_state_upsert wire format (include/mr_b200.h)."""
+    out = []
+    for (scope, name), (kind, v) in values.items():
+        nb = name.encode("utf-8")
+        out.append(struct.pack("<H", len(nb)) + nb)
+        tag = _SCOPE_TAG[scope[0]]
+        out.append(struct.pack("<B", tag))
+        if tag in (1, 2, 3, 6):
+            out.append(struct.pack("<Q", hash64(scope[1])))
+        elif tag == 4:
+            out.append(struct.pack("<Q", hash64(scope[2])))
+        elif tag == 5:
+            out.append(struct.pack("<QQ", hash64(scope[2]), hash64(scope[3])))
+        if kind == "scalar":
+            if isinstance(v, bool):
+                raise ValueError("SBoolean is not read by any supported extractor")
+            if isinstance(v, (int, float)):
+                out.append(struct.pack("<Bd", 0, float(v)))
+            elif isinstance(v, str):
+                out.append(struct.pack("<BQ", 1, hash64(v)))
+            elif isinstance(v, (list, tuple, np.ndarray)) and len(v) and not isinstance(v[0], str):
+                a = np.asarray(v, dtype=np.float64)
+                out.append(struct.pack("<BI", 3, a.size) + a.tobytes())
+            else:
+                hs = np.array([hash64(x) for x in v], dtype=np.uint64)
+                out.append(struct.pack("<BI", 2, hs.size) + hs.tobytes())
+        elif kind == "counter":
+            out.append(struct.pack("<Bq", 4, int(v)))
+        elif kind == "pcounter":
+            a = np.asarray(v, dtype=np.int64)
+            out.append(struct.pack("<BI", 5, a.size) + a.tobytes())
+        elif kind == "blist":
+            hs = np.array([hash64(x) for x in v], dtype=np.uint64)
+            out.append(struct.pack("<BI", 6, hs.size) + hs.tobytes())
+        else:
+            raise ValueError(kind)
+    return b"".join(out)
+
+
+class DeviceState:
+    """mr_state: device-resident Persistence.values for one FeatureMapping."""
+
+    def __init__(self, ctx, mapping: FeatureMapping):
+        self.mapping = mapping
+        self._h = C.c_void_p()
+        check(lib().mr_state_create(ctx.handle, mapping._h, C.byref(self._h)))
+
+    def put_packed(self, blob: bytes):
+        a, s = C.c_int64(0), C.c_int64(0)
+        buf = (C.c_uint8 * max(len(blob), 1)).from_buffer_copy(blob if blob else b"\0")
+        check(lib().mr_state_upsert(self._h, buf, C.c_size_t(len(blob)), C.byref(a), C.byref(s)))
+        return a.value, s.value
+
+    def put(self, values: dict):
+        """KVStore.put(Map[Key, FeatureValue])"""
+        return self.put_packed(pack_feature_values(values))
+
+    def flush(self):
+        check(lib().mr_state_flush(self._h))
+
+    def info(self) -> StateInfo:
+        inf = StateInfo()
+        check(lib().mr_state_get_info(self._h, C.byref(inf)))
+        return inf
+
+    def free(self):
+        if self._h:
+            lib().mr_state_free(self._h)
+            self._h = C.c_void_p()
+
+
+class Ranker:
+    """Ranker(mapping, store).rerank (S/ml/Ranker.scala:27-83), batched."""
+
+    def __init__(self, mapping: FeatureMapping, state: DeviceState):
+        self.mapping, self.state = mapping, state
+
+    def rank_arrays(self, arrays: dict, model=None, want_order=True, want_features=False):
+        """mr_rank on already-packed arrays; returns (scores, order, features)."""
+        N = arrays["total_items"]
+        b = RankBatch(arrays["n_requests"], arrays["offsets"].ctypes.data, arrays["ids"].ctypes.data,
+                      arrays["users"].ctypes.data, arrays["sessions"].ctypes.data, arrays["req_f64"].ctypes.data,
+                      arrays["req_u64"].ctypes.data, arrays["req_vec"].ctypes.data, arrays["req_vp"].ctypes.data,
+                      arrays["item_f64"].ctypes.data)
+        scores = np.empty(max(N, 1), dtype=np.float64)
+        order = np.empty(max(N, 1), dtype=np.int32) if want_order and model is not None else None
+        feats = np.empty((max(N, 1), max(self.mapping.dim, 1)), dtype=np.float64) if want_features else None
+        check(lib().mr_rank(self.state._h, model._h if model is not None else None, C.byref(b),
+                            C.c_void_p(scores.ctypes.data),
+                            C.c_void_p(order.ctypes.data) if order is not None else None,
+                            C.c_void_p(feats.ctypes.data) if feats is not None else None))
+        return (scores[:N] if model is not None else None, order[:N] if order is not None else None,
+                feats[:N, :self.mapping.dim] if feats is not None else None)
+
+    def make_query(self, requests: list[dict]) -> list[np.ndarray]:
+        """Ranker.makeQuery: the dense f64[N x dim] matrix per request (ltrlib Query.values)."""
+        arrays = self.mapping.pack_requests(requests)
+        _, _, feats = self.rank_arrays(arrays, None, want_order=False, want_features=True)
+        offs = arrays["offsets"]
+        return [feats[offs[r]:offs[r + 1]] for r in range(len(requests))]
+
+    def rerank(self, requests: list[dict], model, explain: bool = False) -> list[dict]:
+        """One RankResponse-shaped dict per request: items sorted by -score (stable)."""
+        arrays = self.mapping.pack_requests(requests)
+        scores, order, feats = self.rank_arrays(arrays, model, want_order=True, want_features=explain)
+        offs = arrays["offsets"]
+        out = []
+        for r, q in enumerate(requests):
+            b = int(offs[r])
+            items = []
+            for k in order[b:int(offs[r + 1])]:
+                e = {"item": q["items"][k]["id"], "score": float(scores[b + k])}
+                if explain:
+                    e["features"] = feats[b + k].tolist()
+                items.append(e)
+            out.append({"items": items})
+        return out

@@ -333,3 +333,140 @@ def metarank_model_blob(feature_names: list[str], booster_kind: int, booster_byt
     if version >= 3:
         out.append(struct.pack(">i", 0))
     return b"".join(out)
+
+
+# --------------------------------------------------------------------------- ranklens-shaped state (config #3)
+
+RANKLENS_GENRES = ["drama", "comedy", "thriller", "action", "adventure", "romance", "crime", "science fiction",
+                   "fantasy", "family", "horror", "mystery", "animation", "history", "music"]
+
+
+def ranklens_config():
+    """The ranklens feature set of the reference (src/test/resources/ranklens/config.yml:27-58 and the
+    `features:` section), as the JSON-able dicts Metarank's config decoders accept.  24 columns."""
+    num = lambda n, f: dict(name=n, type="number", scope="item", source=f"metadata.{f}")  # noqa: E731
+    rate = dict(type="rate", top="click", bottom="impression", bucket="24h", periods=[7, 30])
+    feats = [
+        dict(rate, name="ctr_tag", scope="item.tag"),
+        dict(rate, name="ctr_genre", scope="item.genre"),
+        dict(name="position", type="position", position=5),
+        num("popularity", "popularity"), num("vote_avg", "vote_avg"), num("vote_cnt", "vote_cnt"),
+        num("budget", "budget"), num("release_date", "release_date"), num("runtime", "runtime"),
+        dict(name="title_length", type="word_count", source="metadata.title", scope="item"),
+        dict(name="genre", type="string", scope="item", source="metadata.genres", encode="index",
+             values=RANKLENS_GENRES),
+        dict(rate, name="ctr", normalize={"weight": 10}),
+        dict(name="profile", type="interacted_with", interaction="click",
+             field=["item.genres", "item.actors", "item.tags", "item.director"], scope="session", count=100,
+             duration="24h"),
+        dict(name="divers_genres", type="diversity", source="metadata.genres"),
+        dict(name="divers_actors", type="diversity", source="metadata.actors"),
+        dict(name="divers_tags", type="diversity", source="metadata.tags"),
+        dict(name="divers_year", type="diversity", source="metadata.release_date"),
+        dict(name="divers_popularity", type="diversity", source="metadata.popularity"),
+        dict(name="visitor_click_count", type="interaction_count", interaction="click", scope="session"),
+        dict(name="global_item_click_count", type="interaction_count", interaction="click", scope="item"),
+        dict(name="day_item_click_count", type="window_count", interaction="click", scope="item", bucket="24h",
+             periods=[1]),
+    ]
+    model = ["popularity", "vote_avg", "vote_cnt", "budget", "release_date", "runtime", "title_length", "genre",
+             "ctr", "profile", "position", "divers_genres", "divers_actors", "divers_tags", "divers_year",
+             "divers_popularity", "ctr_tag", "ctr_genre"]
+    return feats, model
+
+
+def _zipf_draw(rng, n_vocab, k):
+    p = 1.0 / np.arange(1, n_vocab + 1) ** 1.2
+    p /= p.sum()
+    return rng.choice(n_vocab, size=k, replace=False, p=p)
+
+
+def ranklens_state(n_items: int = 1000, n_sessions: int = 100, seed: int = 45, missing: float = 0.03,
+                   with_field_scalars: bool = True):
+    """FeatureValues (plain Key -> Value dict, see metarank_b200/features.py) of a ranklens-shaped
+    catalogue, SURVEY.md §8d: per item 6 numeric scalars, title word count, 1-3 genres / 3-8 actors /
+    2-10 tags / 1 director drawn Zipf(1.2) from vocabularies of 20/5000/1000/2000, click/impression
+    windows for periods [7, 30] per item, per tag/genre value and globally; sessions with 0-100
+    clicked items.  `missing` = fraction of state entries left out (exercises NaN paths)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    st = {}
+    drop = lambda: rng.random() < missing  # noqa: E731
+    genres_v = RANKLENS_GENRES + [f"g{i}" for i in range(5)]
+    item_ids = [f"m{i}" for i in range(n_items)]
+    tag_first, genre_first = {}, {}
+    for i, it in enumerate(item_ids):
+        sc = ("item", it)
+        nums = dict(popularity=rng.lognormal(2, 1), vote_avg=rng.uniform(0, 10), vote_cnt=float(rng.integers(0, 20000)),
+                    budget=float(rng.integers(0, 3 * 10**8)), release_date=float(rng.integers(0, 1_600_000_000)),
+                    runtime=float(rng.integers(40, 240)))
+        for k, v in nums.items():
+            if not drop():
+                st[(sc, k)] = ("scalar", float(v))
+        if not drop():
+            st[(sc, "title_length")] = ("scalar", float(rng.integers(1, 9)))
+        genres = [genres_v[j] for j in _zipf_draw(rng, len(genres_v), int(rng.integers(1, 4)))]
+        actors = [f"a{j}" for j in _zipf_draw(rng, 5000, int(rng.integers(3, 9)))]
+        tags = [f"t{j}" for j in _zipf_draw(rng, 1000, int(rng.integers(2, 11)))]
+        director = [f"d{j}" for j in _zipf_draw(rng, 2000, 1)]
+        if not drop():
+            st[(sc, "genre")] = ("scalar", genres)
+        for fld, vals in (("genres", genres), ("actors", actors), ("tags", tags), ("director", director)):
+            if not drop():
+                st[(sc, f"profile_{fld}")] = ("scalar", vals)
+        for fld, vals in (("genres", genres), ("actors", actors), ("tags", tags)):
+            if not drop():
+                st[(sc, f"divers_{fld}")] = ("scalar", vals)
+        if (sc, "release_date") in st and not drop():
+            st[(sc, "divers_year")] = st[(sc, "release_date")]
+        if (sc, "popularity") in st and not drop():
+            st[(sc, "divers_popularity")] = st[(sc, "popularity")]
+        imp = rng.poisson([40.0, 160.0])
+        clk = np.minimum(rng.poisson([3.0, 12.0]), imp)
+        if not drop():
+            st[(sc, "ctr_click")] = ("pcounter", [int(x) for x in clk])
+        if not drop():
+            st[(sc, "ctr_impression")] = ("pcounter", [int(x) for x in imp])
+        if with_field_scalars and not drop():
+            # the real ranklens events carry no singular `tag`/`genre` field, so on the real data
+            # these two scalars never exist and ctr_tag/ctr_genre are NaN (SURVEY.md appendix B);
+            # synthetic data exercises the populated path too
+            st[(sc, "ctr_tag_field")] = ("scalar", tags[0])
+            st[(sc, "ctr_genre_field")] = ("scalar", genres[0])
+            tag_first[tags[0]] = 1
+            genre_first[genres[0]] = 1
+    for name, vocab in (("tag", tag_first), ("genre", genre_first)):
+        for v in vocab:
+            imp = rng.poisson([400.0, 1600.0])
+            clk = np.minimum(rng.poisson([30.0, 120.0]), imp)
+            sc = ("field", name, v)
+            if not drop():
+                st[(sc, f"ctr_{name}_click")] = ("pcounter", [int(x) for x in clk])
+            if not drop():
+                st[(sc, f"ctr_{name}_impression")] = ("pcounter", [int(x) for x in imp])
+    st[(("global",), "ctr_click_norm")] = ("pcounter", [int(n_items * 3), int(n_items * 12)])
+    st[(("global",), "ctr_impression_norm")] = ("pcounter", [int(n_items * 40), int(n_items * 160)])
+    sessions = [f"s{i}" for i in range(n_sessions)]
+    for s in sessions:
+        n = int(min(100, rng.geometric(0.08) - 1))
+        if n > 0:
+            hist = [item_ids[int(j)] for j in rng.integers(0, n_items, n)]
+            if rng.random() < 0.1:
+                hist.append("unknown-item")  # an interacted item that has no state
+            st[(("session", s), "profile_interactions")] = ("blist", hist)
+    return st, item_ids, sessions
+
+
+def ranklens_requests(item_ids, sessions, n_requests: int, items_per_request: int, seed: int = 46,
+                      unknown: float = 0.02):
+    """LatencyBenchmark.RandomRequest-shaped RankingEvents (T/util/benchmark/LatencyBenchmark.scala:44-58):
+    distinct random items + a random session."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = []
+    for r in range(n_requests):
+        k = min(items_per_request, len(item_ids))
+        ids = [item_ids[int(j)] for j in rng.choice(len(item_ids), size=k, replace=False)]
+        ids = [f"nope{r}_{j}" if rng.random() < unknown else x for j, x in enumerate(ids)]
+        sess = sessions[int(rng.integers(0, len(sessions)))] if rng.random() > 0.05 else None
+        out.append(dict(event="ranking", id=f"req{r}", timestamp=0, user=sess, session=sess, fields=[],
+                        items=[dict(id=i, fields=[("relevancy", 0.0)]) for i in ids]))
+    return out

@@ -1,0 +1,153 @@
+"""Golden vectors transcribed from the reference's own tests (src/test/scala/ai/metarank/...).
+
+Each case = (feature config dicts, events replayed through the write path, ranking request,
+expected per-feature values) with the reference file:line it was taken from.  They pin the
+CPU oracle (tests/test_features_golden.py) and, through the oracle AND directly, the CUDA
+path (tests/test_features_gpu.py).
+"""
+import itertools
+
+NOW = 1622505601000  # Timestamp.date(2021, 6, 1, 0, 0, 1), T/fstore/FeatureSuite.scala:14
+_ids = itertools.count()
+
+
+def item_event(item, fields=()):
+    """T/util/TestItemEvent.scala"""
+    return dict(event="item", id=f"e{next(_ids)}", item=item, timestamp=NOW, fields=list(fields))
+
+
+def interaction(item, ranking, typ="click", user="u1", session="s1", ts=NOW):
+    """T/util/TestInteractionEvent.scala"""
+    return dict(event="interaction", id=f"e{next(_ids)}", item=item, timestamp=ts, ranking=ranking, user=user,
+                session=session, type=typ, fields=[])
+
+
+def ranking(items, fields=(), rid=None, user="u1", session="s1", item_fields=None):
+    """T/util/TestRankingEvent.scala: every item carries relevancy 1.0"""
+    return dict(event="ranking", id=rid or f"r{next(_ids)}", timestamp=NOW, user=user, session=session,
+                fields=list(fields),
+                items=[dict(id=i, fields=[("relevancy", 1.0)] + list((item_fields or {}).get(i, []))) for i in items])
+
+
+CASES = []
+
+
+def case(name, ref, features, events, request, expected, model_features=None):
+    CASES.append(dict(name=name, ref=ref, features=features, events=events, request=request, expected=expected,
+                      model_features=model_features or [f["name"] for f in features]))
+
+
+RATE = dict(name="ctr", type="rate", top="click", bottom="impression", bucket="24h", periods=[7, 14], refresh="0s")
+
+case("rate_plain", "T/feature/RateFeatureTest.scala:61-74", [RATE],
+     [interaction("p1", "x", "impression")] * 4 + [interaction("p1", "x", "click")],
+     ranking(["p1"]), {"ctr": [[0.25, 0.25]]})
+
+case("rate_normalized_integer_division", "T/feature/NormRateFeatureTest.scala:64-81",
+     [dict(RATE, normalize={"weight": 10})],
+     [interaction("p1", "x", "impression")] * 3 + [interaction("p1", "x", "click")]
+     + [interaction("p2", "x", "impression")] * 90 + [interaction("p2", "x", "click")] * 9,
+     ranking(["p1"]), {"ctr": [[0.11827956989247312, 0.11827956989247312]]})
+
+_scoped_events = [
+    item_event("p1", [("color", "red")]), item_event("p2", [("color", "red")]), item_event("p3", [("color", "red")]),
+    item_event("p4", [("color", "green")]), item_event("p5", [("size", "xl")]),
+    interaction("p1", "x", "impression"), interaction("p2", "x", "impression"), interaction("p3", "x", "impression"),
+    interaction("p2", "x", "impression"), interaction("p4", "x", "impression"), interaction("p5", "x", "impression"),
+    interaction("p1", "x", "click"), interaction("p4", "x", "click"), interaction("p5", "x", "click"),
+]
+case("rate_item_field_scope", "T/feature/ScopedRateFeatureTest.scala:60-83", [dict(RATE, scope="item.color")],
+     _scoped_events, ranking(["p1"]), {"ctr": [[0.25, 0.25]]})
+case("rate_item_field_scope_string_lists", "T/feature/ScopedRateFeatureTest.scala:85-108", [dict(RATE, scope="item.color")],
+     [item_event("p1", [("color", ["red"])]), item_event("p2", [("color", ["red"])]),
+      item_event("p3", [("color", ["red"])])] + _scoped_events[3:],
+     ranking(["p1"]), {"ctr": [[0.25, 0.25]]})
+
+case("rate_ranking_field_scope", "T/feature/RankFieldScopedRateFeatureTest.scala:48-65",
+     [dict(RATE, scope="ranking.query")],
+     [ranking(["p1", "p2"], [("query", "test")], rid="r1"),
+      interaction("p1", "r1", "impression"), interaction("p2", "r1", "impression"), interaction("p1", "r1", "click"),
+      ranking(["p1", "p2"], [("query", "test")], rid="r2"),
+      interaction("p1", "r2", "impression"), interaction("p2", "r2", "impression"), interaction("p2", "r2", "click")],
+     ranking(["p1"], [("query", "test")]), {"ctr": [[0.5, 0.5]]})
+
+case("window_count", "T/feature/WindowInteractionCountFeatureTest.scala:46-56",
+     [dict(name="cnt", type="window_count", interaction="click", bucket="24h", periods=[1], scope="item")],
+     [interaction("p1", "e0")] * 3, ranking(["p1"]), {"cnt": [[3.0]]})
+
+case("interaction_count", "T/feature/InteractionCountTest.scala:50-57",
+     [dict(name="cnt", type="interaction_count", interaction="click", scope="item")],
+     [interaction("p1", "x")] * 3, ranking(["p1"]), {"cnt": [[3.0]]})
+
+_seen = dict(name="seen", type="interacted_with", interaction="impression", field="item.color", scope="session",
+             count=10, duration="24h")
+_seen_events = [item_event("p1", [("color", "red")]), item_event("p2", [("color", "green")]),
+                interaction("p1", "i1", "impression"), interaction("p2", "i1", "impression")]
+case("interacted_with_one_field", "T/feature/InteractedWithFeatureTest.scala:105-119", [_seen], _seen_events,
+     ranking(["p1", "p2", "p3"]), {"seen": [[1.0], [1.0], [0.0]]})
+case("interacted_with_two_fields", "T/feature/InteractedWithFeatureTest.scala:121-144",
+     [dict(_seen, field=["item.color", "item.tags"])], _seen_events,
+     ranking(["p1", "p2", "p3"]), {"seen": [[1.0, 0.0], [1.0, 0.0], [0.0, 0.0]]})
+
+case("word_count_item", "T/feature/WordCountFeatureItemTest.scala:46-53",
+     [dict(name="title_words", type="word_count", scope="item", source="metadata.title")],
+     [item_event("p1", [("title", "foo, bar, baz!")])], ranking(["p1"]), {"title_words": [[3.0]]})
+case("word_count_ranking", "T/feature/WordCountFeatureRankingTest.scala:36-43",
+     [dict(name="query_words", type="word_count", scope="ranking", source="ranking.query")],
+     [], ranking(["p1"], [("query", "foo bar")]), {"query_words": [[2.0]]})
+
+_rel_req = ranking(["p1", "p2"])
+_rel_req["items"][0]["fields"] = [("relevancy", 1.0)]
+_rel_req["items"][1]["fields"] = [("relevancy", 2.0)]
+case("relevancy", "T/feature/RelevancyTest.scala:16-25", [dict(name="rel", type="relevancy")], [], _rel_req,
+     {"rel": [[1.0], [2.0]]})
+
+case("position_online", "T/feature/PositionFeatureTest.scala:24-28", [dict(name="pos", type="position", position=5)],
+     [], ranking(["p1", "p2", "p3"]), {"pos": [[5.0], [5.0], [5.0]]})
+
+_prices = lambda ps: [item_event(f"p{i + 1}", [("price", p)]) for i, p in enumerate(ps)]  # noqa: E731
+case("diversity_numbers", "T/feature/DiversityFeatureTest.scala:12-32",
+     [dict(name="divnum", type="diversity", source="item.price", top=2147483647)], _prices([10.0, 20.0, 40.0, 15.0, 5.0]),
+     ranking(["p1", "p2", "p3", "p4", "p5"]), {"divnum": [[-5.0], [5.0], [25.0], [0.0], [-10.0]]})
+case("diversity_top3_numbers", "T/feature/DiversityFeatureTest.scala:34-55",
+     [dict(name="divnum", type="diversity", source="item.price", top=3)], _prices([10.0, 20.0, 30.0, 5.0, 1.0]),
+     ranking(["p1", "p2", "p3", "p4", "p5"]), {"divnum": [[-10.0], [0.0], [10.0], [-15.0], [-19.0]]})
+case("diversity_strings", "T/feature/DiversityFeatureTest.scala:57-78",
+     [dict(name="divstr", type="diversity", source="item.cat", top=2147483647)],
+     [item_event(f"p{i + 1}", [("cat", c)]) for i, c in enumerate("abcab")],
+     ranking(["p1", "p2", "p3", "p4", "p5"]), {"divstr": [[0.4], [0.4], [0.2], [0.4], [0.4]]})
+case("diversity_string_lists", "T/feature/DiversityFeatureTest.scala:79-99",
+     [dict(name="divstrl", type="diversity", source="item.cat", top=2147483647)],
+     [item_event("p1", [("cat", ["a"])]), item_event("p2", [("cat", ["b", "c"])]),
+      item_event("p3", [("cat", ["a", "b", "c"])]), item_event("p4", [("cat", ["a", "b", "c", "d"])])],
+     ranking(["p1", "p2", "p3", "p4"]), {"divstrl": [[0.3], [0.6], [0.9], [1.0]]})
+
+# Known-answer cases derived from the reference source where its tests hold no value
+case("number_item_and_override", "S/feature/NumberFeature.scala:58-97 (derived)",
+     [dict(name="price", type="number", scope="item", source="metadata.price")],
+     [item_event("p1", [("price", 10.0)]), item_event("p2", [("price", 20.0)])],
+     ranking(["p1", "p2", "p3"], item_fields={"p2": [("price", 99.0)]}),
+     {"price": [[10.0], [99.0], [float("nan")]]})
+case("string_index_unknown_is_zero", "S/feature/StringFeature.scala:124-137 (derived)",
+     [dict(name="color", type="string", scope="item", source="metadata.color", encode="index", values=["red", "green", "blue"])],
+     [item_event("p1", [("color", "green")]), item_event("p2", [("color", ["pink", "red"])])],
+     ranking(["p1", "p2", "p3"]), {"color": [[2.0], [0.0], [0.0]]})
+case("string_onehot", "S/util/OneHotEncoder.scala:12-24 (derived)",
+     [dict(name="color", type="string", scope="item", source="metadata.color", values=["red", "green", "blue"])],
+     [item_event("p1", [("color", ["blue", "red", "pink"])])],
+     ranking(["p1", "p2"]), {"color": [[1.0, 0.0, 1.0], [0.0, 0.0, 0.0]]})
+
+# ClickthroughQuery dense layout: T/flow/ClickthroughQueryTest.scala:152-159
+LAYOUT_FEATURES = [
+    dict(name="price", type="number", scope="item", source="metadata.price"),
+    dict(name="category", type="string", scope="item", source="metadata.category", encode="index", values=["socks", "shirts"]),
+    dict(RATE, name="ctr"),
+    dict(name="clicked_category", type="interacted_with", interaction="click", field="metadata.category",
+         scope="session", count=10, duration="24h"),
+]
+LAYOUT_ITEM_VALUES = [
+    {"category": [1.0], "ctr": [0.2, 0.1], "price": [10.0], "clicked_category": [1.0]},
+    {"price": [5.0], "ctr": [0.1, 0.05], "category": [2.0], "clicked_category": [0.0]},
+    {"ctr": [0.2, 0.2], "clicked_category": [1.0], "price": [3.0], "category": [1.0]},
+]
+LAYOUT_EXPECTED = [10.0, 1.0, 0.2, 0.1, 1.0, 5.0, 2.0, 0.1, 0.05, 0.0, 3.0, 1.0, 0.2, 0.2, 1.0]

@@ -1,0 +1,213 @@
+"""GPU parity of feature assembly + the full rerank path (through the C ABI) against the
+CPU oracle and the reference's golden vectors.  Bit-exact: the assembled matrix is compared
+with array_equal (NaN == NaN), scores likewise, ordering identical."""
+import numpy as np
+import pytest
+
+import golden_cases as G
+from metarank_b200 import synth
+from oracle import features_oracle as fo
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _eq(a, b):
+    return np.array_equal(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), equal_nan=True)
+
+
+def _device(ctx, features, model_features, state):
+    from metarank_b200 import features as F
+
+    fm = F.FeatureMapping(ctx, features, model_features)
+    ds = F.DeviceState(ctx, fm)
+    applied, skipped = ds.put(state)
+    ds.flush()
+    return fm, ds, F.Ranker(fm, ds), applied, skipped
+
+
+@pytest.mark.parametrize("case", G.CASES, ids=[c["name"] for c in G.CASES])
+def test_golden_vectors_on_device(ctx, case):
+    mapping = fo.FeatureMapping(case["features"], case["model_features"])
+    state = fo.FeatureValueFlow(mapping, always_refresh=True).process(case["events"])
+    want = fo.dense_matrix(mapping, case["request"], state)
+    fm, ds, rk, applied, _ = _device(ctx, case["features"], case["model_features"], state)
+    try:
+        assert fm.dim == mapping.dim
+        got = rk.make_query([case["request"]])[0]
+        assert _eq(got, want), (case["ref"], got, want)
+        for name, exp in case["expected"].items():  # and directly against the reference's numbers
+            o, d = fm.offset(name)
+            assert _eq(got[:, o:o + d], np.array(exp)), (case["ref"], name)
+    finally:
+        ds.free(); fm.free()
+
+
+def test_dense_layout_columns(ctx):
+    from metarank_b200 import features as F
+
+    fm = F.FeatureMapping(ctx, G.LAYOUT_FEATURES, [f["name"] for f in G.LAYOUT_FEATURES])
+    assert fm.dim == 5  # T/flow/ClickthroughQueryTest.scala:152
+    assert [fm.offset(n) for n in ("price", "category", "ctr", "clicked_category")] == [(0, 1), (1, 1), (2, 2), (4, 1)]
+    fm.free()
+
+
+@pytest.mark.parametrize("n_items,per_request", [(300, 24), (2000, 1000)])
+def test_ranklens_shaped_assembly_and_rerank(ctx, n_items, per_request):
+    """BASELINE config #3 shape (1000-item requests over the ranklens feature set, 24 columns)."""
+    import metarank_b200 as mb
+
+    feats, model = synth.ranklens_config()
+    state, item_ids, sessions = synth.ranklens_state(n_items=n_items, n_sessions=40, seed=45)
+    reqs = synth.ranklens_requests(item_ids, sessions, 6, per_request, seed=46)
+    reqs.append(dict(reqs[0], session=None, user=None))  # no visitor
+    reqs.append(dict(reqs[1], items=reqs[1]["items"][:1]))  # single item
+    mapping = fo.FeatureMapping(feats, model)
+    assert mapping.dim == 24
+    fm, ds, rk, applied, skipped = _device(ctx, feats, model, state)
+    blob = synth.lightgbm_model_text(60, 24, seed=9, cat_features={7: 16})
+    booster = mb.LightGBMBooster(ctx, blob, n_features=24)
+    ob = oracle.OracleBooster(0, blob)
+    try:
+        assert fm.dim == 24 and applied > 0
+        got = rk.make_query(reqs)
+        resp = rk.rerank(reqs, booster, explain=True)
+        for r, q in enumerate(reqs):
+            want = fo.dense_matrix(mapping, q, state)
+            assert _eq(got[r], want), f"request {r}: first diff col {np.argwhere(~((got[r] == want) | ((got[r] != got[r]) & (want != want))))[:5]}"
+            scores = ob.predictMat(want, *want.shape)
+            order = oracle.rank_order(scores)
+            assert [e["item"] for e in resp[r]["items"]] == [q["items"][k]["id"] for k in order]
+            assert _eq([e["score"] for e in resp[r]["items"]], scores[order])
+            assert _eq([e["features"] for e in resp[r]["items"]], want[order])
+    finally:
+        booster.free(); ds.free(); fm.free()
+
+
+def test_cosine_biencoder_c4(ctx):
+    """BASELINE config #4 shape: cosine(384-d) + scalar columns, 256 items, XGBoost scorer."""
+    import metarank_b200 as mb
+
+    rng = np.random.Generator(np.random.PCG64(77))
+    dim = 384
+    feats = [dict(name="sim", type="field_match", rankingField="ranking.query", itemField="item.title",
+                  method=dict(type="bi-encoder", dim=dim), distance="cos")]
+    feats += [dict(name=f"n{k}", type="number", scope="item", source=f"metadata.n{k}") for k in range(15)]
+    model = [f["name"] for f in feats]
+    state, ids = {}, [f"i{k}" for k in range(300)]
+    for it in ids:
+        e = rng.standard_normal(dim).astype(np.float32)
+        e /= np.linalg.norm(e)
+        if rng.random() > 0.05:
+            state[(("item", it), "sim")] = ("scalar", e.astype(np.float64).tolist())
+        for k in range(15):
+            state[(("item", it), f"n{k}")] = ("scalar", float(rng.standard_normal()))
+    for norm in ("noop", "linear", "position"):
+        feats[0] = dict(feats[0], norm=norm)
+        reqs = []
+        for r in range(3):
+            pick = [ids[int(j)] for j in rng.choice(300, 256, replace=False)]
+            q = rng.standard_normal(dim).astype(np.float32)
+            reqs.append(dict(event="ranking", id=f"r{r}", timestamp=0, user=None, session=None,
+                             fields=[("query", "some text")], embeddings={"sim": q.tolist()},
+                             items=[dict(id=i, fields=[]) for i in pick]))
+        reqs.append(dict(reqs[0], embeddings={}))  # no query embedding -> NaN column
+        mapping = fo.FeatureMapping(feats, model)
+        fm, ds, rk, _, _ = _device(ctx, feats, model, state)
+        blob = synth.xgboost_model_json(200, 16, depth=6, seed=1234 + 4)
+        bx = mb.XGBoostBooster(ctx, blob, n_features=16)
+        try:
+            got = rk.make_query(reqs)
+            resp = rk.rerank(reqs, bx)
+            for r, q in enumerate(reqs):
+                want = fo.dense_matrix(mapping, q, state)
+                assert _eq(got[r], want), (norm, r)
+                scores = oracle.OracleBooster(1, blob).predictMat(want, *want.shape)
+                order = oracle.rank_order(scores)
+                assert [e["item"] for e in resp[r]["items"]] == [q["items"][k]["id"] for k in order]
+        finally:
+            bx.free(); ds.free(); fm.free()
+
+
+def test_scopes_user_session_global_and_request_inputs(ctx):
+    feats = [
+        dict(name="u_clicks", type="interaction_count", interaction="click", scope="user"),
+        dict(name="s_win", type="window_count", interaction="click", scope="session", bucket="24h", periods=[1, 7]),
+        dict(name="g_num", type="number", scope="global", source="metadata.x"),
+        dict(name="q_len", type="word_count", scope="ranking", source="ranking.query"),
+        dict(name="q_num", type="number", scope="ranking", source="ranking.boost"),
+        dict(name="q_cat", type="string", scope="item", source="ranking.kind", encode="index", values=["web", "app"]),
+        dict(name="q_hot", type="string", scope="item", source="ranking.kind", values=["web", "app", "tv"]),
+        dict(name="color", type="string", scope="item", source="item.color", encode="index", values=["red", "green"]),
+        dict(name="rel", type="relevancy"),
+        dict(G.RATE, name="rq", scope="ranking.query"),
+    ]
+    model = [f["name"] for f in feats]
+    state = {
+        (("user", "u1"), "u_clicks"): ("counter", 7), (("session", "s1"), "s_win"): ("pcounter", [2, 9]),
+        (("session", "s2"), "s_win"): ("pcounter", [2]),  # wrong length -> NaN
+        (("global",), "g_num"): ("scalar", 3.5), (("item", "a"), "color"): ("scalar", ["green"]),
+        (("irf", "query", "shoes", "a"), "rq_click"): ("pcounter", [1, 2]),
+        (("irf", "query", "shoes", "a"), "rq_impression"): ("pcounter", [4, 4]),
+    }
+    reqs = [
+        dict(event="ranking", id="r1", timestamp=0, user="u1", session="s1",
+             fields=[("query", "shoes"), ("boost", 2.0), ("kind", "app")],
+             items=[dict(id="a", fields=[("relevancy", 0.5)]), dict(id="b", fields=[("color", "red")]), dict(id="c", fields=[])]),
+        dict(event="ranking", id="r2", timestamp=0, user="nobody", session="s2", fields=[("query", "  red   shoes ")],
+             items=[dict(id="a", fields=[])]),
+        dict(event="ranking", id="r3", timestamp=0, user=None, session=None, fields=[("kind", ["tv", "web"])],
+             items=[dict(id="a", fields=[]), dict(id="zz", fields=[])]),
+    ]
+    mapping = fo.FeatureMapping(feats, model)
+    fm, ds, rk, _, _ = _device(ctx, feats, model, state)
+    try:
+        got = rk.make_query(reqs)
+        for r, q in enumerate(reqs):
+            assert _eq(got[r], fo.dense_matrix(mapping, q, state)), r
+    finally:
+        ds.free(); fm.free()
+
+
+def test_normalized_rate_zero_global_is_arithmetic_error(ctx):
+    import metarank_b200 as mb
+
+    feats = [dict(G.RATE, normalize={"weight": 10})]
+    state = {(("item", "p1"), "ctr_click"): ("pcounter", [0, 0]), (("item", "p1"), "ctr_impression"): ("pcounter", [3, 3]),
+             (("global",), "ctr_click_norm"): ("pcounter", [0, 0]), (("global",), "ctr_impression_norm"): ("pcounter", [3, 3])}
+    fm, ds, rk, _, _ = _device(ctx, feats, ["ctr"], state)
+    try:
+        with pytest.raises(mb.MrError) as e:  # java.lang.ArithmeticException -> HTTP 500 in the reference
+            rk.make_query([G.ranking(["p1"])])
+        assert e.value.status == 7
+        assert _eq(rk.make_query([G.ranking(["p2"])])[0], [[np.nan, np.nan]])  # item without state never divides
+    finally:
+        ds.free(); fm.free()
+
+
+def test_state_updates_are_visible_after_flush(ctx):
+    feats = [dict(name="price", type="number", scope="item", source="metadata.price")]
+    fm, ds, rk, _, _ = _device(ctx, feats, ["price"], {(("item", "p1"), "price"): ("scalar", 1.0)})
+    try:
+        assert _eq(rk.make_query([G.ranking(["p1", "p2"])])[0], [[1.0], [np.nan]])
+        ds.put({(("item", "p2"), "price"): ("scalar", 2.0), (("item", "p1"), "price"): ("scalar", 5.0),
+                (("item", "p1"), "unrelated"): ("scalar", 9.0)})
+        ds.flush()
+        assert _eq(rk.make_query([G.ranking(["p1", "p2"])])[0], [[5.0], [2.0]])
+        many = {(("item", f"x{i}"), "price"): ("scalar", float(i)) for i in range(5000)}  # forces table growth
+        ds.put(many)
+        ds.flush()
+        got = rk.make_query([G.ranking([f"x{i}" for i in range(0, 5000, 7)] + ["p1"])])[0]
+        assert _eq(got[:, 0], [float(i) for i in range(0, 5000, 7)] + [5.0])
+        assert ds.info().rows[1] == 5002
+    finally:
+        ds.free(); fm.free()
+
+
+def test_unsupported_feature_types_fail_loudly(ctx):
+    import metarank_b200 as mb
+    from metarank_b200 import features as F
+
+    with pytest.raises(mb.MrError) as e:
+        F.FeatureMapping(ctx, [dict(name="ua", type="ua", field="platform", source="ranking.ua")], ["ua"])
+    assert e.value.status == 5 and "ua" in e.value.message
