@@ -34,6 +34,7 @@ ITEMS = 100
 FEATURES = 30
 TREES = 500
 REQUESTS_PER_STEP = 16384
+CATALOGUE = 1_000_000
 MODEL_SEED = 1234 + 2
 DATA_SEED = 42 + 2
 METRIC = "items/sec reranked (100-item req, 500-tree LambdaMART)"
@@ -48,6 +49,15 @@ def _model_blob():
 def _matrix(rows, seed):
     from metarank_b200 import synth
     return synth.feature_matrix(rows, FEATURES, seed=seed)
+
+
+def _splitmix(x):
+    """item-id hashes for the synthetic catalogue (any non-zero u64 is a valid mr_hash64 value)"""
+    x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    x = x ^ (x >> np.uint64(31))
+    return np.where(x == 0, np.uint64(1), x).astype(np.uint64)
 
 
 def _peaks():
@@ -120,13 +130,15 @@ def run_reference(args, rank, world):
     blob = _model_blob()
     ob = oracle.OracleBooster(0, blob)
     cores = os.cpu_count() or 1
-    sample_requests = 1000
+    sample_requests = max(1000, cores * 40)
     rows = sample_requests * ITEMS
-    X = _matrix(rows, DATA_SEED)
+    cat = _matrix(CATALOGUE, DATA_SEED)
+    pick = np.random.Generator(np.random.PCG64(DATA_SEED + 1000)).integers(0, CATALOGUE, rows)
     for _ in range(args.warmup):
-        ob.predictMat(X, rows, FEATURES, threads=0)
+        ob.predictMat(cat[pick], rows, FEATURES, threads=0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
+        X = cat[pick]  # feature assembly on the CPU = row gather of the stored scalars
         ob.predictMat(X, rows, FEATURES, threads=0)
     dt = time.perf_counter() - t0
     v = rows * args.steps / dt
@@ -135,9 +147,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: 100-item requests x 30 scalar features x 500-tree LightGBM LambdaMART "
-                               "(predictMat on the assembled matrix)", "items_per_request": ITEMS,
-                   "features": FEATURES, "trees": TREES, "requests_per_step": sample_requests},
+        "config": {"workload": "C2: 100-item /rank requests, 30 scalar (number) features gathered from a "
+                               "1M-item state table, 500-tree LightGBM LambdaMART", "items_per_request": ITEMS,
+                   "features": FEATURES, "trees": TREES, "catalogue_items": CATALOGUE,
+                   "requests_per_step": sample_requests},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference scorer (ltrlib -> LightGBM JNI) is not installable here (no JVM, no jars); "
@@ -178,129 +191,172 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from metarank_b200 import features as F
+
     ctx = mb.Context(local)
     blob = _model_blob()
     booster = mb.LightGBMBooster(ctx, blob, n_features=FEATURES)
 
+    # ---- device-resident state: CATALOGUE items x 30 `number` features (Persistence.values on HBM)
+    names = [f"f{j}" for j in range(FEATURES)]
+    feats = [dict(name=n, type="number", scope="item", source=f"metadata.{n}") for n in names]
+    mapping = F.FeatureMapping(ctx, feats, names)
+    state = F.DeviceState(ctx, mapping)
+    cat = _matrix(CATALOGUE, DATA_SEED)  # same column recipe as SURVEY.md 8d (5 % NaN = missing state)
+    item_ids = _splitmix(np.arange(1, CATALOGUE + 1, dtype=np.uint64))
+    t_up = time.perf_counter()
+    for j0 in range(0, FEATURES, 5):
+        state.put_packed(F.pack_number_columns(names[j0:j0 + 5], item_ids, cat[:, j0:j0 + 5]))
+    state.flush()
+    t_up = time.perf_counter() - t_up
+
     R = args.requests_per_step
     rows = R * ITEMS
-    X_host = _matrix(rows, DATA_SEED + rank)  # every rank scores its own requests (weak scaling)
-    d_X = torch.from_numpy(X_host).cuda()
+    rng = np.random.Generator(np.random.PCG64(DATA_SEED + 1000 + rank))  # every rank ranks its own requests
+    pick = rng.integers(0, CATALOGUE, rows)
+    ids_host = item_ids[pick]
+    offs_host = (np.arange(R + 1, dtype=np.int32) * ITEMS).astype(np.int32)
+    d_ids = torch.from_numpy(ids_host.view(np.int64)).cuda()
+    d_offs = torch.from_numpy(offs_host).cuda()
     d_out = torch.empty(rows, dtype=torch.float64, device="cuda")
+    d_order = torch.empty(rows, dtype=torch.int32, device="cuda")
+    d_feat = torch.empty(rows * FEATURES, dtype=torch.float64, device="cuda")
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
 
     def step():
-        booster.predict_device(d_X.data_ptr(), rows, FEATURES, d_out.data_ptr(), sptr)
+        F.rank_device(state, booster, R, rows, d_offs.data_ptr(), d_ids.data_ptr(), d_out.data_ptr(),
+                      d_order.data_ptr(), d_feat.data_ptr(), sptr)
 
-    launches0 = mb._capi.lib().mr_kernel_launches()
     for _ in range(args.warmup):
         step()
+    F.rank_device_status(state, sptr)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches1 = mb._capi.lib().mr_kernel_launches()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for a, b in evs:
-        a.record(stream)
+    for _ in range(args.steps):
         step()
-        b.record(stream)
     e1.record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     gpu_launches = mb._capi.lib().mr_kernel_launches() - launches1
     total_ms = e0.elapsed_time(e1)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = rows * world * args.steps / (total_ms / 1e3)
 
-    # parity spot check against the oracle on the first requests of this rank (outside the timer)
-    got = d_out[: 20 * ITEMS].cpu().numpy()
+    # ---- dominant kernel alone (gbdt_score on the assembled matrix), CUDA events on the launching stream
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in evs:
+        a.record(stream)
+        booster.predict_device(d_feat.data_ptr(), rows, FEATURES, d_out.data_ptr(), sptr)
+        b.record(stream)
+    # ... and assembly alone (model = None)
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record(stream)
+    for _ in range(args.steps):
+        F.rank_device(state, None, R, rows, d_offs.data_ptr(), d_ids.data_ptr(), 0, 0, d_feat.data_ptr(), sptr)
+    a1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    assemble_ms = a0.elapsed_time(a1) / args.steps
+    step()
+    F.rank_device_status(state, sptr)
+    n_chk = 20
+    got = d_out[: n_chk * ITEMS].cpu().numpy()
+    got_order = d_order[: n_chk * ITEMS].cpu().numpy()
+    got_feat = d_feat[: n_chk * ITEMS * FEATURES].cpu().numpy().reshape(-1, FEATURES)
 
-    # ---- e2e: same metric through the C ABI with host buffers (pinned), H2D + D2H inside the timer
-    Xp = torch.from_numpy(X_host).pin_memory()
-    out_p = torch.empty(rows, dtype=torch.float64).pin_memory()
+    # ---- e2e: the same metric through mr_rank with HOST buffers (item-id hashes in, scores + order out)
+    rk = F.Ranker(mapping, state)
+    arrays = dict(offsets=offs_host, ids=ids_host, users=np.zeros(R, dtype=np.uint64),
+                  sessions=np.zeros(R, dtype=np.uint64), req_f64=np.zeros((R, 1)), req_u64=np.zeros((R, 1), dtype=np.uint64),
+                  req_vec=np.zeros((R, 1), dtype=np.float32), req_vp=np.zeros((R, 1), dtype=np.uint8), item_f64=None,
+                  n_requests=R, total_items=rows)
     e2e_steps = max(3, min(args.steps, 10))
-    lib = mb._capi.lib()
-    import ctypes as C
-
-    def e2e_step():
-        mb._capi.check(lib.mr_model_predict_mat(booster._h, C.c_void_p(Xp.data_ptr()), C.c_int32(rows),
-                                                C.c_int32(FEATURES), C.c_void_p(out_p.data_ptr())))
     for _ in range(2):
-        e2e_step()
+        sc_h, ord_h, _ = rk.rank_arrays(arrays, booster, want_order=True)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
+        sc_h, ord_h, _ = rk.rank_arrays(arrays, booster, want_order=True)
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = rows * world * e2e_steps / float(t.item())
-    e2e_ok = bool(np.array_equal(out_p[: 20 * ITEMS].numpy(), got))
+    e2e_ok = bool(np.array_equal(sc_h[: n_chk * ITEMS], got) and np.array_equal(ord_h[: n_chk * ITEMS], got_order))
 
     # ---- single-request latency through the C ABI (p50 of 300 calls, 100 items, host buffers)
     lat = None
     if rank == 0:
-        x1 = np.ascontiguousarray(X_host[:ITEMS])
+        one = dict(arrays, offsets=offs_host[:2].copy(), ids=ids_host[:ITEMS].copy(), n_requests=1, total_items=ITEMS)
         for _ in range(20):
-            booster.predictMat(x1, ITEMS, FEATURES)
+            rk.rank_arrays(one, booster, want_order=True)
         ts = []
         for _ in range(300):
             a = time.perf_counter()
-            booster.predictMat(x1, ITEMS, FEATURES)
+            rk.rank_arrays(one, booster, want_order=True)
             ts.append(time.perf_counter() - a)
         lat = {"p50_ms": float(np.percentile(ts, 50) * 1e3), "p99_ms": float(np.percentile(ts, 99) * 1e3),
-               "what": "mr_model_predict_mat, 1 request x 100 items, host buffers, incl. H2D/D2H + ctypes"}
+               "what": "mr_rank, 1 request x 100 items: id hashes in -> scores + order out, host buffers, via ctypes"}
 
     if rank == 0:
         from oracle import oracle
         ob = oracle.OracleBooster(0, blob)
-        want = ob.predictMat(X_host[: 20 * ITEMS], 20 * ITEMS, FEATURES)
+        want_feat = cat[pick[: n_chk * ITEMS]]  # the oracle's assembly of `number` features is the stored scalar
+        want = ob.predictMat(want_feat, n_chk * ITEMS, FEATURES)
+        feat_ok = bool(np.array_equal(got_feat, want_feat, equal_nan=True))
         parity = bool(np.array_equal(got, want))
-        order_ok = all(np.array_equal(ctx.rank_order(got[i * ITEMS:(i + 1) * ITEMS]),
-                                      oracle.rank_order(want[i * ITEMS:(i + 1) * ITEMS])) for i in range(20))
-        # roofline: algorithmic bytes per item, SURVEY.md §8(d): 8F + T*(dbar*16 + 8) + 8
-        dbar = booster.mean_path(X_host[:8192], 8192, FEATURES)
+        order_ok = all(np.array_equal(got_order[i * ITEMS:(i + 1) * ITEMS],
+                                      oracle.rank_order(want[i * ITEMS:(i + 1) * ITEMS])) for i in range(n_chk))
+        # roofline of the dominant kernel: algorithmic bytes per item, SURVEY.md 8(d): 8F + T*(dbar*16 + 8) + 8
+        dbar = booster.mean_path(want_feat[:2000], 2000, FEATURES)
         b_item = 8 * FEATURES + TREES * (dbar * 16 + 8) + 8
         peak, peak_src = _peaks()
         achieved = b_item * rows / (kernel_ms / 1e3) / 1e9
-        # CPU baseline on a bounded sample, all host cores (~10-30 s of CPU work)
+        # CPU baseline on a bounded sample, all host cores: hash lookup + row gather + tree walk
         cores = os.cpu_count() or 1
-        cpu_rows = 2000 * ITEMS
-        Xc = X_host[:cpu_rows]
+        cpu_rows = min(rows, max(2000 * ITEMS, cores * 40 * ITEMS))
+        Xc = cat[pick[:cpu_rows]]
         ob.predictMat(Xc[:10000], 10000, FEATURES, threads=0)
         c0 = time.perf_counter()
+        Xc = cat[pick[:cpu_rows]]  # the gather is part of the CPU path too
         ob.predictMat(Xc, cpu_rows, FEATURES, threads=0)
         cpu_dt = time.perf_counter() - c0
+        info = state.info()
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2: 100-item requests x 30 scalar features x 500-tree LightGBM LambdaMART "
-                                   "(predictMat on the assembled matrix)",
-                       "items_per_request": ITEMS, "features": FEATURES, "trees": TREES,
-                       "requests_per_step": R, "parallelism": f"requests sharded over {world} GPU(s), no collective",
-                       "l2": "inputs (393 MB/step/GPU) larger than the 126 MB L2; no flush needed"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": rows * FEATURES * 8,
-                    "d2h_bytes_per_step": rows * 8, "steps": e2e_steps, "parity_ok": e2e_ok,
-                    "what": "mr_model_predict_mat on pinned host buffers, copies inside the timed region"},
+            "config": {"workload": "C2: 100-item /rank requests, 30 scalar (number) features gathered from a "
+                                   "1M-item device-resident state table, 500-tree LightGBM LambdaMART, "
+                                   "scores + per-request ordering",
+                       "items_per_request": ITEMS, "features": FEATURES, "trees": TREES, "catalogue_items": CATALOGUE,
+                       "requests_per_step": R, "parallelism": f"requests sharded over {world} GPU(s), state replicated, no collective",
+                       "l2": "per step the item table (248 MB) is gathered at random and a 393 MB feature matrix "
+                             "is written and re-read: both exceed the 126 MB L2, no flush needed"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ids_host.nbytes + offs_host.nbytes + 2 * R * 8),
+                    "d2h_bytes_per_step": rows * 12, "steps": e2e_steps, "parity_ok": e2e_ok,
+                    "what": "mr_rank: item-id hashes in host memory -> scores + order in host memory, copies inside the timer"},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "bytes_per_item": b_item, "mean_path": dbar,
-                         "kernel_ms": kernel_ms, "kernel": "gbdt_score_kernel"},
+                         "kernel_ms": kernel_ms, "kernel": "gbdt_score_kernel",
+                         "step_share": kernel_ms / (total_ms / args.steps), "assemble_ms": assemble_ms},
             "cpu_baseline": {"value": cpu_rows / cpu_dt, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{cpu_rows // ITEMS} requests x {ITEMS} items, OpenMP over rows"},
+                             "sample": f"{cpu_rows // ITEMS} requests x {ITEMS} items: numpy row gather + C oracle, OpenMP over rows"},
             "clocks": clocks, "latency": lat,
-            "parity": {"scores_bit_identical": parity, "ordering_identical": bool(order_ok), "checked_items": 20 * ITEMS},
+            "parity": {"features_bit_identical": feat_ok, "scores_bit_identical": parity,
+                       "ordering_identical": bool(order_ok), "checked_items": n_chk * ITEMS},
+            "state": {"items": int(info.rows[1]), "device_bytes": int(info.device_bytes),
+                      "item_row_bytes": int(info.item_row_bytes), "upload_s": t_up},
         }
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_file):
@@ -310,6 +366,8 @@ def main():
                 pass
         print(json.dumps(out), flush=True)
 
+    state.free()
+    mapping.free()
     booster.free()
     ctx.close()
     if world > 1:

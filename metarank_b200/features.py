@@ -188,6 +188,8 @@ class FeatureMapping:
                             slot = self.input_slot(MR_IN_ITEM_F64, name)
                             enc = self._encode_string(conf, ov)
                             item_f64[i, slot:slot + len(enc)] = enc
+        if self.n_item_f64 == 0 or np.isnan(item_f64).all():
+            item_f64 = None  # mr_rank_batch.item_f64 == NULL: no per-item inputs at all
         return dict(offsets=offs, ids=ids, users=users, sessions=sessions, req_f64=req_f64, req_u64=req_u64,
                     req_vec=req_vec, req_vp=req_vp, item_f64=item_f64, n_requests=R, total_items=N)
 
@@ -276,7 +278,7 @@ class Ranker:
         b = RankBatch(arrays["n_requests"], arrays["offsets"].ctypes.data, arrays["ids"].ctypes.data,
                       arrays["users"].ctypes.data, arrays["sessions"].ctypes.data, arrays["req_f64"].ctypes.data,
                       arrays["req_u64"].ctypes.data, arrays["req_vec"].ctypes.data, arrays["req_vp"].ctypes.data,
-                      arrays["item_f64"].ctypes.data)
+                      arrays["item_f64"].ctypes.data if arrays["item_f64"] is not None else None)
         scores = np.empty(max(N, 1), dtype=np.float64)
         order = np.empty(max(N, 1), dtype=np.int32) if want_order and model is not None else None
         feats = np.empty((max(N, 1), max(self.mapping.dim, 1)), dtype=np.float64) if want_features else None
@@ -310,3 +312,40 @@ class Ranker:
                 items.append(e)
             out.append({"items": items})
         return out
+
+
+def pack_number_columns(names: list[str], ids_u64: np.ndarray, columns: np.ndarray) -> bytes:
+    """Vectorised mr_state_upsert packing of item-scoped SDouble scalars: one record per
+    (item, feature) for a dense [n_items x n_features] matrix (NaN entries are skipped = missing)."""
+    out = []
+    ids_u64 = np.ascontiguousarray(ids_u64, dtype=np.uint64)
+    for j, name in enumerate(names):
+        nb = name.encode("utf-8")
+        dt = np.dtype([("nl", "<u2"), ("name", f"S{len(nb)}"), ("scope", "u1"), ("id", "<u8"), ("kind", "u1"),
+                       ("val", "<f8")])
+        col = columns[:, j]
+        keep = ~np.isnan(col)
+        rec = np.zeros(int(keep.sum()), dtype=dt)
+        rec["nl"] = len(nb)
+        rec["name"] = nb
+        rec["scope"] = 1
+        rec["id"] = ids_u64[keep]
+        rec["kind"] = 0
+        rec["val"] = col[keep]
+        out.append(rec.tobytes())
+    return b"".join(out)
+
+
+def rank_device(state: DeviceState, model, n_requests: int, total_items: int, d_offsets: int, d_item_ids: int,
+                d_scores: int, d_order: int = 0, d_features: int = 0, stream: int = 0, d_user_ids: int = 0,
+                d_session_ids: int = 0) -> None:
+    """mr_rank_device: every pointer is a device address; enqueued on `stream`, no sync."""
+    b = RankBatch(n_requests, d_offsets, d_item_ids, d_user_ids or None, d_session_ids or None, None, None, None,
+                  None, None)
+    check(lib().mr_rank_device(state._h, model._h if model is not None else None, C.byref(b),
+                               C.c_int32(total_items), C.c_void_p(d_scores), C.c_void_p(d_order or None),
+                               C.c_void_p(d_features or None), C.c_void_p(stream)))
+
+
+def rank_device_status(state: DeviceState, stream: int = 0) -> None:
+    check(lib().mr_rank_device_status(state._h, C.c_void_p(stream)))
