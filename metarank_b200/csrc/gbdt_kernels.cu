@@ -344,17 +344,21 @@ void launch_gbdt_score(const ScoreLaunch &L, int num_sms, cudaStream_t stream) {
   };
   int threads = L.threads;
   if (threads <= 0) {
+    // Measured on B200 (profiles/sweep_r1.md): two or three mid-sized CTAs per SM beat one huge
+    // CTA with more warps, because every chunk ends in a CTA-wide barrier and a second CTA
+    // fills the bubble.  So: the most warps among >= 2 CTAs/SM, one CTA/SM only if nothing else fits.
     int best_warps = 0;
     threads = 0;
-    for (int n_cta = 1; n_cta <= 4; n_cta++) {
+    for (int n_cta = 2; n_cta <= 4; n_cta++) {
       const int t = fit_threads(n_cta);
-      if (t < 32) continue;
+      if (t < 64) continue;
       const int warps = std::min(64, n_cta * (t / 32));
-      if (warps >= best_warps) {  // ties: prefer more, smaller CTAs (cheaper barriers)
+      if (warps > best_warps) {
         best_warps = warps;
         threads = t;
       }
     }
+    if (threads == 0) threads = fit_threads(1);
     if (threads == 0) threads = 32;
     // small batches: shrink the tile until the persistent grid covers the chip
     while (threads > 32 && (L.rows + threads - 1) / threads < num_sms) threads = ((threads / 2) + 31) & ~31;

@@ -1,0 +1,109 @@
+// JNI shim for libmrgpu (compiled only with -DWITH_JNI -I$JAVA_HOME/include -I$JAVA_HOME/include/linux;
+// there is no JDK / jni.h in the build image, so the default build leaves this file empty).
+// One native method per C-ABI entry point that the Scala adapter in INTEGRATION.md binds.
+// Rules: no JNI critical section is held across a GPU call; a non-zero mr_status becomes a
+// java.lang.RuntimeException carrying mr_last_error() (-> IO.raiseError -> HTTP 500, exactly how
+// the reference surfaces booster failures, S/main/command/Serve.scala:101-103).
+#ifdef WITH_JNI
+#include <jni.h>
+
+#include "../../include/mr_b200.h"
+
+namespace {
+void throw_status(JNIEnv *env, mr_status s) {
+  if (s == MR_OK) return;
+  jclass cls = env->FindClass(s == MR_ERR_ARITHMETIC ? "java/lang/ArithmeticException" : "java/lang/RuntimeException");
+  env->ThrowNew(cls, mr_last_error());
+}
+}  // namespace
+
+extern "C" {
+
+JNIEXPORT jlong JNICALL Java_ai_metarank_b200_Native_init(JNIEnv *env, jclass, jint device) {
+  mr_ctx *ctx = nullptr;
+  throw_status(env, mr_init(device, &ctx));
+  return (jlong)ctx;
+}
+
+JNIEXPORT jlong JNICALL Java_ai_metarank_b200_Native_modelLoad(JNIEnv *env, jclass, jlong ctx, jint kind, jbyteArray blob,
+                                                               jint nFeatures) {
+  jsize n = env->GetArrayLength(blob);
+  jbyte *p = env->GetByteArrayElements(blob, nullptr);
+  mr_model *m = nullptr;
+  mr_status s = mr_model_load((mr_ctx *)ctx, kind, (const uint8_t *)p, (size_t)n, nFeatures, &m);
+  env->ReleaseByteArrayElements(blob, p, JNI_ABORT);
+  throw_status(env, s);
+  return (jlong)m;
+}
+
+// Booster.predictMat(values: Array[Double], rows: Int, cols: Int): Array[Double]
+JNIEXPORT jdoubleArray JNICALL Java_ai_metarank_b200_Native_predictMat(JNIEnv *env, jclass, jlong model, jdoubleArray values,
+                                                                        jint rows, jint cols) {
+  jdoubleArray out = env->NewDoubleArray(rows);
+  jdouble *v = env->GetDoubleArrayElements(values, nullptr);
+  jdouble *o = env->GetDoubleArrayElements(out, nullptr);
+  mr_status s = mr_model_predict_mat((mr_model *)model, v, rows, cols, o);
+  env->ReleaseDoubleArrayElements(values, v, JNI_ABORT);
+  env->ReleaseDoubleArrayElements(out, o, 0);
+  throw_status(env, s);
+  return out;
+}
+
+JNIEXPORT void JNICALL Java_ai_metarank_b200_Native_modelClose(JNIEnv *env, jclass, jlong model) {
+  throw_status(env, mr_model_close((mr_model *)model));
+}
+JNIEXPORT jboolean JNICALL Java_ai_metarank_b200_Native_modelIsClosed(JNIEnv *, jclass, jlong model) {
+  return mr_model_is_closed((mr_model *)model) ? JNI_TRUE : JNI_FALSE;
+}
+
+JNIEXPORT jlong JNICALL Java_ai_metarank_b200_Native_schemaCreate(JNIEnv *env, jclass, jlong ctx, jbyteArray json) {
+  jsize n = env->GetArrayLength(json);
+  jbyte *p = env->GetByteArrayElements(json, nullptr);
+  mr_schema *sc = nullptr;
+  mr_status s = mr_schema_create((mr_ctx *)ctx, (const char *)p, (size_t)n, &sc);
+  env->ReleaseByteArrayElements(json, p, JNI_ABORT);
+  throw_status(env, s);
+  return (jlong)sc;
+}
+
+JNIEXPORT jlong JNICALL Java_ai_metarank_b200_Native_stateCreate(JNIEnv *env, jclass, jlong ctx, jlong schema) {
+  mr_state *st = nullptr;
+  throw_status(env, mr_state_create((mr_ctx *)ctx, (mr_schema *)schema, &st));
+  return (jlong)st;
+}
+
+// KVStore.put: `packed` is a direct ByteBuffer in the wire format of mr_state_upsert
+JNIEXPORT void JNICALL Java_ai_metarank_b200_Native_stateUpsert(JNIEnv *env, jclass, jlong state, jobject packed, jint len,
+                                                                jboolean flush) {
+  const uint8_t *p = (const uint8_t *)env->GetDirectBufferAddress(packed);
+  mr_status s = mr_state_upsert((mr_state *)state, p, (size_t)len, nullptr, nullptr);
+  if (s == MR_OK && flush) s = mr_state_flush((mr_state *)state);
+  throw_status(env, s);
+}
+
+// Ranker.rerank for one request: item-id hashes in, scores + order out (direct buffers, no copies in JNI)
+JNIEXPORT void JNICALL Java_ai_metarank_b200_Native_rank(JNIEnv *env, jclass, jlong state, jlong model, jint nItems,
+                                                         jobject itemIds, jlong user, jlong session, jobject reqF64,
+                                                         jobject reqU64, jobject reqVec, jobject reqVecPresent,
+                                                         jobject itemF64, jobject outScores, jobject outOrder,
+                                                         jobject outFeatures) {
+  auto addr = [&](jobject b) { return b ? env->GetDirectBufferAddress(b) : nullptr; };
+  int32_t offs[2] = {0, nItems};
+  uint64_t u = (uint64_t)user, se = (uint64_t)session;
+  mr_rank_batch b{};
+  b.n_requests = 1;
+  b.item_offsets = offs;
+  b.item_ids = (const uint64_t *)addr(itemIds);
+  b.user_ids = &u;
+  b.session_ids = &se;
+  b.req_f64 = (const double *)addr(reqF64);
+  b.req_u64 = (const uint64_t *)addr(reqU64);
+  b.req_vec = (const float *)addr(reqVec);
+  b.req_vec_present = (const uint8_t *)addr(reqVecPresent);
+  b.item_f64 = (const double *)addr(itemF64);
+  throw_status(env, mr_rank((mr_state *)state, (mr_model *)model, &b, (double *)addr(outScores), (int32_t *)addr(outOrder),
+                            (double *)addr(outFeatures)));
+}
+
+}  // extern "C"
+#endif  // WITH_JNI
