@@ -140,7 +140,8 @@ MR_API int32_t mr_model_is_closed(mr_model *m);
 MR_API mr_status mr_model_free(mr_model *m);
 
 /* Tuning knobs for experiments (bench.py / tests); defaults are chosen per model.
- * key: "threads" (items per CTA), "chunk_kb", "variant" (0 = lock-step, 1 = free-running). */
+ * key: "threads" (items per CTA, 0 = auto), "chunk_kb", "ilp" (trees in flight per thread),
+ * "variant" (-1 = auto, 0 = f64 lock-step, 1 = f64 free-running, 2 = binned integer traversal). */
 MR_API mr_status mr_model_set_option(mr_model *m, const char *key, int32_t value);
 
 /* ------------------------------------------------------------------ final ordering */

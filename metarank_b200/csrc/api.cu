@@ -127,8 +127,7 @@ mr_status mr_model_predict_mat_device(mr_model *m, const double *d_values, int32
     InflightGuard ig(m);
     check_matrix(m, d_values, rows, cols, d_out_scores);
     if (rows == 0) return;
-    ScoreLaunch L = m->launch_desc(d_values, rows, cols, d_out_scores);
-    launch_gbdt_score(L, m->ctx->num_sms, (cudaStream_t)cuda_stream);
+    m->score(d_values, rows, cols, d_out_scores, (cudaStream_t)cuda_stream);
   });
 }
 
@@ -187,8 +186,7 @@ mr_status mr_model_predict_mat(mr_model *m, const double *values, int32_t rows, 
       }
       double *d_in = (double *)ln->d_buf, *d_out = (double *)(ln->d_buf + d_out_off);
       MR_CUDA_CHECK(cudaMemcpyAsync(d_in, src, in_bytes, cudaMemcpyHostToDevice, ln->stream));
-      ScoreLaunch L = m->launch_desc(d_in, n, cols, d_out);
-      launch_gbdt_score(L, m->ctx->num_sms, ln->stream);
+      m->score(d_in, n, cols, d_out, ln->stream);
       double *dst = direct_out ? out_scores + r0 : (double *)(ln->h_pinned + (direct_in ? 0 : in_cap));
       MR_CUDA_CHECK(cudaMemcpyAsync(dst, d_out, out_bytes, cudaMemcpyDeviceToHost, ln->stream));
       pend[l] = {r0, n};

@@ -1,0 +1,325 @@
+// Binned GBDT scoring on sm_100a (see gbdt_model.h "binned layout" for why it is exact).
+//
+//   bin_kernel      X (row-major f64) -> u16 rank codes, laid out [group of 32 items][feature][lane]
+//                   so that a CTA's tile is one contiguous byte range;
+//   score kernel    thread per item, trees in tree order (bit-identical sums, like the f64 kernel),
+//                   per node one 8-byte LDS (node) + one 2-byte LDS (code) + integer compare.
+//                   The tile of codes and the tree chunks are both staged by TMA bulk copies
+//                   (cp.async.bulk + mbarrier complete_tx); chunks are double-buffered.
+// Compared with the f64 kernel this halves the node bytes, quarters the tile bytes (4x more
+// items resident per SM -> more warps to hide the LDS->LDS->compare chain) and takes the
+// FP64 compare pipe out of the loop.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+
+#include "gbdt_kernels.cuh"
+
+namespace mr {
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ------------------------------------------------------------------ binning
+struct BinParams {
+  const double *values;
+  const uint32_t *thr_off;
+  const double *thr;
+  const uint8_t *is_cat;
+  uint16_t *bins;
+  int rows, cols, n_features;
+  int xgb;  // 1: round to binary32 first, strict less (upper_bound)
+};
+
+__device__ __forceinline__ uint16_t code_of(const BinParams &p, int f, double x) {
+  if (p.xgb) x = (double)__double2float_rn(x);
+  if (x != x) return kBinNaN;
+  if (p.is_cat[f]) {
+    // LightGBM CategoricalDecision: static_cast<int>(x), negative / out-of-int-range -> right
+    const bool in_range = (x < 2147483648.0) && (x > -2147483649.0);
+    const int iv = in_range ? __double2int_rz(x) : -1;
+    return (iv >= 0 && iv < 65000) ? (uint16_t)iv : kBinNaN;
+  }
+  const uint32_t b = __ldg(p.thr_off + f), e = __ldg(p.thr_off + f + 1);
+  uint32_t lo = 0, hi = e - b;
+  const double *t = p.thr + b;
+  if (p.xgb) {
+    while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__ldg(t + m) <= x) lo = m + 1; else hi = m; }  // #{t <= x}
+  } else {
+    while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__ldg(t + m) < x) lo = m + 1; else hi = m; }   // #{t < x}
+  }
+  return (uint16_t)lo;
+}
+
+constexpr int kBinGroups = 4;  // groups of 32 items per CTA
+
+__global__ void __launch_bounds__(256) bin_kernel(const BinParams p) {
+  extern __shared__ uint16_t s_codes[];  // [F][kBinGroups*32 + 2]
+  const int F = p.n_features;
+  const int items_per_cta = kBinGroups * 32, pitch = items_per_cta + 2;
+  const long long item0 = (long long)blockIdx.x * items_per_cta;
+  const int n_here = (int)min((long long)items_per_cta, (long long)p.rows - item0);
+  // phase 1: coalesced read of the tile's rows, one element per thread per step
+  const int n_elem = items_per_cta * F;
+  for (int e = threadIdx.x; e < n_elem; e += blockDim.x) {
+    const int it = e / F, f = e - it * F;
+    uint16_t c = 0;
+    if (it < n_here) c = code_of(p, f, __ldg(p.values + (size_t)(item0 + it) * p.cols + f));
+    s_codes[f * pitch + it] = c;
+  }
+  __syncthreads();
+  // phase 2: coalesced write in [group][feature][lane] order
+  uint16_t *out = p.bins + (size_t)blockIdx.x * kBinGroups * F * 32;
+  const long long n_groups_total = (p.rows + 31) / 32;
+  for (int o = threadIdx.x; o < n_elem; o += blockDim.x) {
+    const int g = o / (F * 32), r = o - g * (F * 32), f = r >> 5, lane = r & 31;
+    if ((long long)blockIdx.x * kBinGroups + g < n_groups_total) out[o] = s_codes[f * pitch + g * 32 + lane];
+  }
+}
+
+// ------------------------------------------------------------------ traversal
+struct BParams {
+  const uint8_t *model;
+  const ChunkDesc *chunks;
+  const uint16_t *bins;
+  double *out;
+  int n_chunks;
+  uint32_t chunk_stride;
+  int rows, n_features;
+  float base_score;
+};
+
+template <bool HAS_CAT>
+__device__ __forceinline__ int bstep(const uint2 nd, const uint32_t code, const uint8_t *chunk) {
+  const uint32_t k = nd.x & 0xFFFFu, fl = nd.x >> 28;
+  bool left;
+  if (HAS_CAT && (fl & BF_CATEGORICAL)) {
+    left = false;
+    if (code != kBinNaN) {
+      const uint2 ct = reinterpret_cast<const uint2 *>(chunk)[k];  // {bitset word offset, n words}
+      const uint32_t w = code >> 5;
+      if (w < ct.y) left = (reinterpret_cast<const uint32_t *>(chunk)[ct.x + w] >> (code & 31u)) & 1u;
+    }
+  } else {
+    // k <= 65000 < kBinNaN, so `code <= k` is already false for NaN; NaN then follows NF_NAN_LEFT
+    left = (code <= k) || (code == kBinNaN && (fl & BF_NAN_LEFT));
+  }
+  return left ? (int)(short)(nd.y & 0xFFFFu) : (int)(short)(nd.y >> 16);
+}
+
+template <typename Real, bool HAS_CAT, int ILP>
+__global__ void __launch_bounds__(1024) gbdt_score_binned_kernel(const BParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  using AccT = Real;
+  const int W = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int F = p.n_features;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);  // [0],[1] chunk buffers, [2] tile
+  const bool resident = p.n_chunks == 1;
+  uint8_t *cbuf0 = smem + 128;
+  uint8_t *cbuf1 = cbuf0 + (resident ? 0u : p.chunk_stride);
+  uint16_t *xs = reinterpret_cast<uint16_t *>(cbuf1 + p.chunk_stride);
+  const uint16_t *xw = xs + (size_t)warp * F * 32 + lane;  // this lane's column of codes
+
+  const int n_tiles = (p.rows + W - 1) / W;
+  const int groups_per_tile = W >> 5;
+  const int n_groups = (p.rows + 31) >> 5;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0 && (int)blockIdx.x < n_tiles) {
+    const ChunkDesc cd = p.chunks[0];
+    mbar_arrive_expect_tx(&bars[0], cd.bytes);
+    tma_bulk_g2s(cbuf0, p.model + cd.byte_off, cd.bytes, &bars[0]);
+  }
+
+  uint32_t it = 0, tile_it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+    // the tile's codes are one contiguous range: one TMA bulk copy
+    if (tid == 0) {
+      const int g0 = tile * groups_per_tile, g1 = min(n_groups, g0 + groups_per_tile);
+      const uint32_t bytes = (uint32_t)(g1 - g0) * (uint32_t)F * 64u;
+      fence_proxy_async();
+      mbar_arrive_expect_tx(&bars[2], bytes);
+      tma_bulk_g2s(xs, p.bins + (size_t)g0 * F * 32, bytes, &bars[2]);
+    }
+    mbar_wait(&bars[2], tile_it & 1);
+    const int item = tile * W + tid;
+
+    AccT acc = (sizeof(Real) == 4) ? (AccT)p.base_score : (AccT)0;
+    for (int c = 0; c < p.n_chunks; ++c, ++it) {
+      if (!resident && tid == 0) {
+        const bool more = (c + 1 < p.n_chunks) || (tile + (int)gridDim.x < n_tiles);
+        if (more) {
+          const int nc = (c + 1 < p.n_chunks) ? c + 1 : 0;
+          const ChunkDesc cd = p.chunks[nc];
+          uint64_t *bar = &bars[(it + 1) & 1];
+          fence_proxy_async();
+          mbar_arrive_expect_tx(bar, cd.bytes);
+          tma_bulk_g2s(((it + 1) & 1) ? cbuf1 : cbuf0, p.model + cd.byte_off, cd.bytes, bar);
+        }
+      }
+      if (!resident || it == 0) mbar_wait(&bars[it & 1], (it >> 1) & 1);
+      const uint8_t *cb = (!resident && (it & 1)) ? cbuf1 : cbuf0;
+      const int ntree = (int)*reinterpret_cast<const uint32_t *>(cb);
+      const uint2 *tab = reinterpret_cast<const uint2 *>(cb + 16);
+
+      int t = 0;
+      for (; t + ILP <= ntree; t += ILP) {
+        const uint2 *nodes[ILP];
+        const Real *leaves[ILP];
+        int n[ILP];
+#pragma unroll
+        for (int k = 0; k < ILP; k++) {
+          const uint2 to = tab[t + k];
+          nodes[k] = reinterpret_cast<const uint2 *>(cb + to.x);
+          leaves[k] = reinterpret_cast<const Real *>(cb + to.y);
+          n[k] = 0;
+        }
+        bool any = true;
+        while (any) {
+          uint2 nd[ILP];
+          uint32_t code[ILP];
+#pragma unroll
+          for (int k = 0; k < ILP; k++) nd[k] = nodes[k][n[k] < 0 ? 0 : n[k]];
+#pragma unroll
+          for (int k = 0; k < ILP; k++) code[k] = xw[((nd[k].x >> 16) & 0xFFFu) << 5];
+          any = false;
+#pragma unroll
+          for (int k = 0; k < ILP; k++) {
+            const int nx = bstep<HAS_CAT>(nd[k], code[k], cb);
+            n[k] = n[k] >= 0 ? nx : n[k];
+            any |= n[k] >= 0;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < ILP; k++) acc += (AccT)leaves[k][~n[k]];
+      }
+      for (; t < ntree; t++) {
+        const uint2 to = tab[t];
+        const uint2 *nodes = reinterpret_cast<const uint2 *>(cb + to.x);
+        const Real *leaves = reinterpret_cast<const Real *>(cb + to.y);
+        int n = 0;
+        do {
+          const uint2 nd = nodes[n];
+          n = bstep<HAS_CAT>(nd, xw[((nd.x >> 16) & 0xFFFu) << 5], cb);
+        } while (n >= 0);
+        acc += (AccT)leaves[~n];
+      }
+      __syncthreads();  // chunk buffer (and, after the last chunk, the tile) may be overwritten next
+    }
+    if (item < p.rows) p.out[item] = (double)acc;
+  }
+}
+
+template <typename Real, bool HAS_CAT, int ILP>
+void launch_b(const BParams &p, int threads, size_t smem, int num_sms, cudaStream_t stream) {
+  auto kern = gbdt_score_binned_kernel<Real, HAS_CAT, ILP>;
+  MR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  MR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  if (per_sm < 1) fail(MR_ERR_CUDA, "binned gbdt kernel does not fit on an SM (smem %zu, threads %d)", smem, threads);
+  const int n_tiles = (p.rows + threads - 1) / threads;
+  const int grid = std::max(1, std::min(n_tiles, num_sms * per_sm));
+  kern<<<grid, threads, smem, stream>>>(p);
+  MR_CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+}
+
+template <typename Real, bool HAS_CAT>
+void launch_b_ilp(const BParams &p, int ilp, int threads, size_t smem, int num_sms, cudaStream_t s) {
+  switch (ilp) {
+    case 1: return launch_b<Real, HAS_CAT, 1>(p, threads, smem, num_sms, s);
+    case 4: return launch_b<Real, HAS_CAT, 4>(p, threads, smem, num_sms, s);
+    default: return launch_b<Real, HAS_CAT, 2>(p, threads, smem, num_sms, s);
+  }
+}
+
+}  // namespace
+
+void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream) {
+  if (L.rows <= 0) return;
+  const int F = L.n_features;
+  // ---- pass 1: codes
+  BinParams bp;
+  bp.values = L.d_values; bp.thr_off = L.d_thr_off; bp.thr = L.d_thr; bp.is_cat = L.d_is_cat;
+  bp.bins = L.d_bins; bp.rows = L.rows; bp.cols = L.cols; bp.n_features = F;
+  bp.xgb = L.kind == MR_BOOSTER_XGBOOST;
+  const int items_per_cta = kBinGroups * 32;
+  const size_t bin_smem = (size_t)F * (items_per_cta + 2) * sizeof(uint16_t);
+  if (bin_smem > 200 * 1024) fail(MR_ERR_UNSUPPORTED, "too many features for the binning kernel");
+  MR_CUDA_CHECK(cudaFuncSetAttribute(bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem));
+  bin_kernel<<<(L.rows + items_per_cta - 1) / items_per_cta, 256, bin_smem, stream>>>(bp);
+  MR_CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
+
+  // ---- pass 2: traversal
+  BParams p;
+  p.model = L.d_model; p.chunks = L.d_chunks; p.bins = L.d_bins; p.out = L.d_out;
+  p.n_chunks = L.n_chunks; p.chunk_stride = (L.max_chunk_bytes + 127u) & ~127u;
+  p.rows = L.rows; p.n_features = F; p.base_score = L.base_score;
+  const size_t kMaxSmem = 227 * 1024;
+  const size_t fixed = 128 + (size_t)p.chunk_stride * (L.n_chunks == 1 ? 1 : 2);
+  const size_t per_item = (size_t)F * sizeof(uint16_t);
+  auto fit_threads = [&](int n_cta) -> int {
+    const size_t per_cta = kMaxSmem / (size_t)n_cta, reserve = 1024;
+    if (per_cta < fixed + reserve + 32 * per_item) return 0;
+    size_t t = (per_cta - fixed - reserve) / std::max<size_t>(per_item, 1);
+    t = std::min<size_t>(t, 1024) & ~size_t(31);
+    return (int)t;
+  };
+  int threads = L.threads;
+  if (threads <= 0) {
+    int best_warps = 0;
+    threads = 0;
+    for (int n_cta = 2; n_cta <= 4; n_cta++) {
+      const int t = std::min(fit_threads(n_cta), 2048 / n_cta);
+      if (t < 64) continue;
+      const int warps = std::min(64, n_cta * (t / 32));
+      if (warps > best_warps) { best_warps = warps; threads = t & ~31; }
+    }
+    if (threads == 0) threads = fit_threads(1);
+    while (threads > 32 && (L.rows + threads - 1) / threads < num_sms) threads = ((threads / 2) + 31) & ~31;
+  }
+  threads = std::max(32, std::min(1024, (threads / 32) * 32));
+  while (fixed + (size_t)threads * per_item > kMaxSmem && threads > 32) threads = ((threads / 2) + 31) & ~31;
+  if (fixed + (size_t)threads * per_item > kMaxSmem) fail(MR_ERR_UNSUPPORTED, "binned tile does not fit in shared memory");
+  const size_t smem = fixed + (size_t)threads * per_item;
+  const int ilp = L.ilp <= 0 ? 2 : L.ilp;
+  if (L.kind == MR_BOOSTER_XGBOOST) launch_b_ilp<float, false>(p, ilp, threads, smem, num_sms, stream);
+  else if (L.has_cat) launch_b_ilp<double, true>(p, ilp, threads, smem, num_sms, stream);
+  else launch_b_ilp<double, false>(p, ilp, threads, smem, num_sms, stream);
+}
+
+}  // namespace mr

@@ -32,6 +32,30 @@ struct ScoreLaunch {
 // Enqueues the scoring kernel on `stream`.  Throws mr::Error on failure.
 void launch_gbdt_score(const ScoreLaunch &L, int num_sms, cudaStream_t stream);
 
+// Binned path (gbdt_binned.cu): feature values -> u16 rank codes, then integer traversal.
+struct BinnedLaunch {
+  const uint8_t *d_model = nullptr;     // chunks of BNodes
+  const ChunkDesc *d_chunks = nullptr;
+  int n_chunks = 0;
+  uint32_t max_chunk_bytes = 0;
+  const uint32_t *d_thr_off = nullptr;  // [F + 1]
+  const double *d_thr = nullptr;
+  const uint8_t *d_is_cat = nullptr;    // [F]
+  int kind = 0;
+  bool has_cat = false;
+  float base_score = 0.f;
+  int n_features = 0;
+  const double *d_values = nullptr;
+  int rows = 0, cols = 0;
+  double *d_out = nullptr;
+  uint16_t *d_bins = nullptr;           // scratch: ceil(rows/32) * F * 32 codes
+  int threads = 0, ilp = 0;
+};
+inline size_t binned_scratch_bytes(int rows, int n_features) {
+  return (size_t)((rows + 31) / 32) * (size_t)n_features * 32 * sizeof(uint16_t);
+}
+void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream);
+
 extern long long g_kernel_launches;
 
 }  // namespace mr

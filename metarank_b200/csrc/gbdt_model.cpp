@@ -398,4 +398,120 @@ PackedModel pack_model(const HostModel &m, size_t chunk_budget) {
   return pk;
 }
 
+// ------------------------------------------------------------------ binned packing
+
+BinnedModel pack_binned(const HostModel &m, size_t chunk_budget) {
+  BinnedModel B;
+  const int F = m.n_features;
+  if (F > 4095 || m.has_zero_missing) return B;
+  // per-feature use: numerical thresholds / categorical
+  std::vector<std::vector<double>> thr(F);
+  B.is_cat.assign(F, 0);
+  std::vector<uint8_t> is_num(F, 0);
+  for (auto &t : m.trees)
+    for (size_t q = 0; q < t.feat.size(); q++) {
+      const int f = t.feat[q];
+      if (t.flags[q] & NF_CATEGORICAL) {
+        B.is_cat[f] = 1;
+        if ((size_t)t.cat_n[q] * 32 > 65000) return B;  // category ids must fit the u16 code
+      } else {
+        is_num[f] = 1;
+        thr[f].push_back(t.thr[q]);
+      }
+    }
+  B.thr_off.assign(F + 1, 0);
+  for (int f = 0; f < F; f++) {
+    if (B.is_cat[f] && is_num[f]) return B;  // a column split both ways: not representable by one code
+    auto &v = thr[f];
+    std::sort(v.begin(), v.end());
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+    for (double x : v)
+      if (x != x) return B;  // NaN threshold: comparisons are never true; keep the exact kernel
+    if (v.size() > 65000) return B;
+    B.thr_off[f + 1] = B.thr_off[f] + (uint32_t)v.size();
+    B.thr.insert(B.thr.end(), v.begin(), v.end());
+  }
+  const bool f32 = m.kind == MR_BOOSTER_XGBOOST;
+  const size_t leaf_sz = f32 ? 4 : 8;
+  struct BNodeHost { uint16_t k, ff; int16_t left, right; };
+  static_assert(sizeof(BNodeHost) == 8, "BNode must be 8 bytes");
+  auto n_nodes = [](const HostTree &t) { return t.feat.empty() ? size_t(1) : t.feat.size(); };
+  auto n_cat_nodes = [](const HostTree &t) { size_t c = 0; for (auto fl : t.flags) c += (fl & NF_CATEGORICAL) != 0; return c; };
+  auto tree_bytes = [&](const HostTree &t) {
+    return al16(n_nodes(t) * 8) + al16(t.leaf.size() * leaf_sz) + al16(n_cat_nodes(t) * 8) + al16(t.cat_words.size() * 4);
+  };
+  PackedModel &pk = B.packed;
+  size_t i = 0, nt = m.trees.size();
+  if (nt == 0) {
+    pk.bytes.assign(16, 0);
+    pk.chunks.push_back(ChunkDesc{0, 16, 0, 0});
+    pk.max_chunk_bytes = 16;
+    B.ok = true;
+    return B;
+  }
+  while (i < nt) {
+    size_t j = i, body = 0;
+    while (j < nt) {
+      size_t nb = body + tree_bytes(m.trees[j]);
+      size_t hdr = 16 + al16((j - i + 1) * 8);
+      if (j > i && hdr + nb > chunk_budget) break;
+      body = nb;
+      j++;
+    }
+    const size_t n = j - i, hdr = 16 + al16(n * 8), total = hdr + body;
+    if (total >= (1u << 19)) return B;  // cat-table offsets are u16 in units of 8 bytes
+    const size_t base = pk.bytes.size();
+    pk.bytes.resize(base + total, 0);
+    uint8_t *c = pk.bytes.data() + base;
+    uint32_t hn = (uint32_t)n;
+    memcpy(c, &hn, 4);
+    uint32_t *tab = (uint32_t *)(c + 16);
+    size_t off = hdr;
+    for (size_t k = 0; k < n; k++) {
+      const HostTree &t = m.trees[i + k];
+      const size_t nn = n_nodes(t);
+      const size_t node_off = off, leaf_off = node_off + al16(nn * 8);
+      const size_t ctab_off = leaf_off + al16(t.leaf.size() * leaf_sz);
+      const size_t cw_off = ctab_off + al16(n_cat_nodes(t) * 8);
+      tab[2 * k] = (uint32_t)node_off;
+      tab[2 * k + 1] = (uint32_t)leaf_off;
+      BNodeHost *nodes = (BNodeHost *)(c + node_off);
+      uint32_t *ctab = (uint32_t *)(c + ctab_off);  // {word offset in chunk (u32 units), n words}
+      if (t.feat.empty()) nodes[0] = BNodeHost{0, 0, (int16_t)~0, (int16_t)~0};
+      size_t ci = 0;
+      for (size_t q = 0; q < t.feat.size(); q++) {
+        BNodeHost &d = nodes[q];
+        const int f = t.feat[q];
+        uint32_t fl = (t.flags[q] & NF_NAN_LEFT) ? BF_NAN_LEFT : 0;
+        if (t.flags[q] & NF_CATEGORICAL) {
+          fl = BF_CATEGORICAL;  // NaN always goes right at categorical nodes
+          ctab[2 * ci] = (uint32_t)(cw_off / 4 + (size_t)t.cat_begin[q]);
+          ctab[2 * ci + 1] = (uint32_t)t.cat_n[q];
+          d.k = (uint16_t)((ctab_off + ci * 8) / 8);  // u16 index of the {off, n} pair, in 8-byte units
+          ci++;
+        } else {
+          const double *b = B.thr.data() + B.thr_off[f], *e = B.thr.data() + B.thr_off[f + 1];
+          d.k = (uint16_t)(std::lower_bound(b, e, t.thr[q]) - b);  // exact match exists by construction
+        }
+        d.ff = (uint16_t)((uint32_t)f | (fl << 12));
+        d.left = (int16_t)t.left[q];
+        d.right = (int16_t)t.right[q];
+      }
+      if (f32) {
+        float *lv = (float *)(c + leaf_off);
+        for (size_t q = 0; q < t.leaf.size(); q++) lv[q] = (float)t.leaf[q];
+      } else {
+        memcpy(c + leaf_off, t.leaf.data(), t.leaf.size() * 8);
+      }
+      if (!t.cat_words.empty()) memcpy(c + cw_off, t.cat_words.data(), t.cat_words.size() * 4);
+      off = cw_off + al16(t.cat_words.size() * 4);
+    }
+    pk.chunks.push_back(ChunkDesc{(uint32_t)base, (uint32_t)total, (uint32_t)n, (uint32_t)i});
+    pk.max_chunk_bytes = std::max<uint32_t>(pk.max_chunk_bytes, (uint32_t)total);
+    i = j;
+  }
+  B.ok = true;
+  return B;
+}
+
 }  // namespace mr

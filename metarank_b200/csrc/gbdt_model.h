@@ -83,4 +83,28 @@ struct PackedModel {
 // chunk_budget: maximum bytes per chunk (a single tree larger than it gets its own chunk).
 PackedModel pack_model(const HostModel &m, size_t chunk_budget);
 
+// ---- binned layout ----------------------------------------------------------------
+// Every numerical split `x <= t` (LightGBM) / `x < t` (XGBoost) only asks on which side of t
+// the value lies, so a feature value can be replaced, exactly, by its rank among the sorted
+// distinct thresholds the model uses on that feature: bin(x) = #{t : t < x} (LightGBM,
+// lower_bound) or #{t : t <= x} (XGBoost, upper_bound), and the node test becomes the
+// integer compare `bin <= k` with k = the node threshold's index.  The traversal kernel then
+// reads 8-byte nodes and 2-byte feature codes instead of 16-byte nodes and 8-byte doubles.
+//
+// BNode (8 B): { u16 k | cat-table index ; u16 feature(12) | flags(4) << 12 ; i16 left ; i16 right }
+// feature codes (u16): 0..65533 bin | category value; 0xFFFF = NaN (or a category that is
+// negative / not an int); 0xFFFE = value inside LightGBM's zero band (only when the model has
+// missing_type == Zero nodes, which then also need the numeric bin -> such models fall back).
+enum : uint32_t { BF_NAN_LEFT = 1u, BF_CATEGORICAL = 8u };
+constexpr uint16_t kBinNaN = 0xFFFFu;
+
+struct BinnedModel {
+  bool ok = false;                 // false: model cannot be binned exactly -> use the f64/f32 kernel
+  std::vector<uint32_t> thr_off;   // [n_features + 1] offsets into thr (numerical) per feature
+  std::vector<double> thr;         // sorted distinct thresholds, all features back to back
+  std::vector<uint8_t> is_cat;     // [n_features] feature is split categorically
+  PackedModel packed;              // chunks of BNodes (+ leaves, + categorical tables)
+};
+BinnedModel pack_binned(const HostModel &m, size_t chunk_budget);
+
 }  // namespace mr

@@ -111,6 +111,13 @@ struct mr_model {
   PackedModel packed;
   uint8_t *d_model = nullptr;
   ChunkDesc *d_chunks = nullptr;
+  // binned form (exact integer traversal); binned.ok == false -> always the f64/f32 kernel
+  BinnedModel binned;
+  uint8_t *d_bmodel = nullptr;
+  ChunkDesc *d_bchunks = nullptr;
+  uint32_t *d_thr_off = nullptr;
+  double *d_thr = nullptr;
+  uint8_t *d_is_cat = nullptr;
   std::atomic<bool> closed{false};
   std::atomic<int> inflight{0};
   std::mutex mu;  // guards repacking / device buffers
@@ -127,6 +134,17 @@ struct mr_model {
     MR_CUDA_CHECK(cudaMemcpy(d_chunks, packed.chunks.data(), packed.chunks.size() * sizeof(ChunkDesc),
                              cudaMemcpyHostToDevice));
   }
+  template <class T> static T *to_device(const std::vector<T> &v) {
+    T *d = nullptr;
+    MR_CUDA_CHECK(cudaMalloc((void **)&d, std::max<size_t>(v.size(), 1) * sizeof(T)));
+    if (!v.empty()) MR_CUDA_CHECK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+  }
+  void free_binned() {
+    for (void *p : {(void *)d_bmodel, (void *)d_bchunks, (void *)d_thr_off, (void *)d_thr, (void *)d_is_cat})
+      if (p) cudaFree(p);
+    d_bmodel = nullptr; d_bchunks = nullptr; d_thr_off = nullptr; d_thr = nullptr; d_is_cat = nullptr;
+  }
   void repack() {
     // Default policy: stream the ensemble through two small shared-memory buffers (TMA bulk
     // copies overlap the traversal).  Small chunks leave shared memory for the feature tile,
@@ -139,8 +157,41 @@ struct mr_model {
     }
     packed = pack_model(host, budget);
     upload();
+    free_binned();
+    binned = pack_binned(host, budget);
+    if (binned.ok) {
+      d_bmodel = to_device(binned.packed.bytes);
+      d_bchunks = to_device(binned.packed.chunks);
+      d_thr_off = to_device(binned.thr_off);
+      d_thr = to_device(binned.thr);
+      d_is_cat = to_device(binned.is_cat);
+    }
+  }
+  bool use_binned() const { return binned.ok && (opt_variant < 0 || opt_variant == 2); }
+  // Enqueue scoring of a device-resident matrix on `stream` with whichever kernel applies.
+  void score(const double *d_values, int rows, int cols, double *d_out, cudaStream_t stream) const {
+    if (use_binned()) {
+      BinnedLaunch B;
+      B.d_model = d_bmodel; B.d_chunks = d_bchunks;
+      B.n_chunks = (int)binned.packed.chunks.size();
+      B.max_chunk_bytes = binned.packed.max_chunk_bytes;
+      B.d_thr_off = d_thr_off; B.d_thr = d_thr; B.d_is_cat = d_is_cat;
+      B.kind = host.kind; B.has_cat = host.has_cat; B.base_score = host.base_score;
+      B.n_features = host.n_features;
+      B.d_values = d_values; B.rows = rows; B.cols = cols; B.d_out = d_out;
+      B.threads = opt_threads; B.ilp = opt_ilp;
+      void *bins = nullptr;
+      MR_CUDA_CHECK(cudaMallocAsync(&bins, std::max<size_t>(binned_scratch_bytes(rows, host.n_features), 16), stream));
+      B.d_bins = (uint16_t *)bins;
+      launch_gbdt_binned(B, ctx->num_sms, stream);
+      MR_CUDA_CHECK(cudaFreeAsync(bins, stream));
+    } else {
+      ScoreLaunch L = launch_desc(d_values, rows, cols, d_out);
+      launch_gbdt_score(L, ctx->num_sms, stream);
+    }
   }
   void release_device() {
+    free_binned();
     if (d_model) cudaFree(d_model);
     if (d_chunks) cudaFree(d_chunks);
     d_model = nullptr;

@@ -301,8 +301,7 @@ mr_status mr_rank(mr_state *st, mr_model *model, const mr_rank_batch *b, double 
       uint8_t *h_out = lane->h_pinned + in_bytes;
       size_t ho = 0;
       if (model) {
-        ScoreLaunch L = model->launch_desc(a.out_features, N, S.dim, d_scores);
-        launch_gbdt_score(L, st->ctx->num_sms, lane->stream);
+        model->score(a.out_features, N, S.dim, d_scores, lane->stream);
         if (out_order) launch_rank_order(d_scores, a.item_offsets, R, N, d_order, lane->stream);
         MR_CUDA_CHECK(cudaMemcpyAsync(h_out + ho, d_scores, (size_t)N * 8, cudaMemcpyDeviceToHost, lane->stream));
       }
@@ -369,8 +368,7 @@ mr_status mr_rank_device(mr_state *st, mr_model *model, const mr_rank_batch *b, 
     launch_assemble(a, S, stream);
     if (model) {
       if (!d_out_scores) fail(MR_ERR_INVALID_ARG, "d_out_scores is null");
-      ScoreLaunch L = model->launch_desc(a.out_features, N, S.dim, d_out_scores);
-      launch_gbdt_score(L, st->ctx->num_sms, stream);
+      model->score(a.out_features, N, S.dim, d_out_scores, stream);
       if (d_out_order) launch_rank_order(d_out_scores, a.item_offsets, R, N, d_out_order, stream);
     }
   });

@@ -34,7 +34,7 @@ def _check(ctx, kind, blob, X, **opts):
     return got
 
 
-@pytest.mark.parametrize("variant,ilp", [(0, 1), (0, 2), (0, 4), (1, 1)])
+@pytest.mark.parametrize("variant,ilp", [(0, 1), (0, 2), (0, 4), (1, 1), (2, 1), (2, 2), (2, 4)])
 @pytest.mark.parametrize("threads", [32, 128, 256])
 def test_c2_lightgbm_100x30x500(ctx, variant, ilp, threads):
     blob = synth.lightgbm_model_text(500, 30, seed=1234 + 2)
@@ -70,8 +70,42 @@ def test_categorical_zero_missing_and_stumps(ctx):
     X[rng.random(2000) < 0.05, 3] = np.inf
     X[rng.random(2000) < 0.05, 4] = -np.inf
     X[rng.random(2000) < 0.05, 5] = 1e-36  # inside LightGBM's zero band
-    for variant in (0, 1):
+    for variant in (0, 1, 2):  # zero-band models cannot be binned: variant 2 silently uses the f64 kernel
         _check(ctx, 0, blob, X, variant=variant)
+    blob = synth.lightgbm_model_text(120, 10, seed=12, cat_features=cat, zero_missing=False, stump_every=7)
+    for variant in (0, 2):  # categorical bitsets + NaN routing through the binned kernel
+        for threads in (0, 64):
+            _check(ctx, 0, blob, X, variant=variant, threads=threads)
+
+
+def test_binned_codes_at_threshold_boundaries(ctx):
+    """Values exactly on / one ulp around every threshold must route like the f64 compare."""
+    from oracle import model_parse
+
+    blob = synth.lightgbm_model_text(40, 6, seed=33)
+    m = model_parse.parse_lightgbm_text(blob)
+    rows = []
+    for t in m["trees"]:
+        for f, thr in zip(t["split_feature"], t["threshold"]):
+            for v in (thr, np.nextafter(thr, np.inf), np.nextafter(thr, -np.inf)):
+                r = np.zeros(6)
+                r[f] = v
+                rows.append(r)
+    X = np.array(rows)
+    _check(ctx, 0, blob, X, variant=2)
+    xb = synth.xgboost_model_json(30, 5, depth=5, seed=34)
+    mx = model_parse.parse_xgboost(xb)
+    rows = []
+    for t in mx["trees"]:
+        for f, thr, l in zip(t["split_index"], t["split_cond"], t["left"]):
+            if l == -1:
+                continue
+            for v in (float(thr), float(np.nextafter(np.float32(thr), np.float32(np.inf))),
+                      float(np.nextafter(np.float32(thr), np.float32(-np.inf))), float(thr) + 1e-12, float(thr) - 1e-12):
+                r = np.zeros(5)
+                r[f] = v
+                rows.append(r)
+    _check(ctx, 1, xb, np.array(rows), variant=2)
 
 
 def test_deep_unbalanced_lightgbm(ctx):
@@ -86,7 +120,7 @@ def test_c4_xgboost(ctx, fmt, depth, full):
     gen = synth.xgboost_model_json if fmt == "json" else synth.xgboost_model_ubj
     blob = gen(200, 16, depth=depth, seed=1234 + 4, full=full)
     X = synth.feature_matrix(256, 16, seed=42 + 4)
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         _check(ctx, 1, blob, X, variant=variant)
 
 

@@ -22,8 +22,8 @@ for name, kind, blob, F in cfgs:
     st = torch.cuda.current_stream().cuda_stream
     for chunk_kb in (8, 16):
         b.set_option("chunk_kb", chunk_kb)
-        for threads in (256, 384, 512, 768):
-            for variant, ilp in ((0, 1), (0, 2), (0, 4), (1, 1)):
+        for threads in (0, 256, 384, 512, 768, 1024):
+            for variant, ilp in ((0, 2), (2, 1), (2, 2), (2, 4)):
                 b.set_option("threads", threads); b.set_option("variant", variant); b.set_option("ilp", ilp)
                 try:
                     for _ in range(2): b.predict_device(dX.data_ptr(), rows, F, dO.data_ptr(), st)
