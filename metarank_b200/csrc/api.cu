@@ -264,7 +264,7 @@ mr_status mr_model_inspect(int32_t kind, const uint8_t *blob, size_t len, int32_
     if (kind == MR_BOOSTER_LIGHTGBM) hm = parse_lightgbm_text(blob, len);
     else if (kind == MR_BOOSTER_XGBOOST) hm = parse_xgboost_model(blob, len);
     else fail(MR_ERR_UNSUPPORTED, "unsupported booster tag %d", kind);
-    PackedModel pk = pack_model(hm, (size_t)(chunk_kb > 0 ? chunk_kb : 8) * 1024);
+    PackedModel pk = pack_model(hm, (size_t)(chunk_kb > 0 ? chunk_kb : 16) * 1024);
     out->kind = hm.kind;
     out->n_features = hm.n_features;
     out->n_trees = (int32_t)hm.trees.size();

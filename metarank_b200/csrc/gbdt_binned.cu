@@ -243,6 +243,88 @@ __global__ void __launch_bounds__(1024) gbdt_score_binned_kernel(const BParams p
   }
 }
 
+// ------------------------------------------------------------------ free-running ("threaded") traversal
+// Every lane chases its own pointer through the chunk's flat entry array: internal entry ->
+// child entry, leaf entry -> (add value) -> root of the next tree.  No lane ever idles waiting for
+// the deepest path of its warp, and there is no per-tree loop overhead; the price is that a warp's
+// 32 entry loads hit different addresses (shared-memory bank conflicts instead of broadcasts).
+// A lane still visits its trees strictly in order, so the sum is bit-identical to the sequential one.
+template <typename Real>
+__global__ void __launch_bounds__(1024) gbdt_score_threaded_kernel(const BParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int W = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int F = p.n_features;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+  const bool resident = p.n_chunks == 1;
+  uint8_t *cbuf0 = smem + 128;
+  uint8_t *cbuf1 = cbuf0 + (resident ? 0u : p.chunk_stride);
+  uint16_t *xs = reinterpret_cast<uint16_t *>(cbuf1 + p.chunk_stride);
+  const uint32_t xw_addr = smem_u32(xs) + ((uint32_t)warp * (uint32_t)F * 32u + (uint32_t)lane) * 2u;
+
+  const int n_tiles = (p.rows + W - 1) / W;
+  const int groups_per_tile = W >> 5;
+  const int n_groups = (p.rows + 31) >> 5;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0 && (int)blockIdx.x < n_tiles) {
+    const ChunkDesc cd = p.chunks[0];
+    mbar_arrive_expect_tx(&bars[0], cd.bytes);
+    tma_bulk_g2s(cbuf0, p.model + cd.byte_off, cd.bytes, &bars[0]);
+  }
+  uint32_t it = 0, tile_it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+    if (tid == 0) {
+      const int g0 = tile * groups_per_tile, g1 = min(n_groups, g0 + groups_per_tile);
+      const uint32_t bytes = (uint32_t)(g1 - g0) * (uint32_t)F * 64u;
+      fence_proxy_async();
+      mbar_arrive_expect_tx(&bars[2], bytes);
+      tma_bulk_g2s(xs, p.bins + (size_t)g0 * F * 32, bytes, &bars[2]);
+    }
+    mbar_wait(&bars[2], tile_it & 1);
+    const int item = tile * W + tid;
+    Real acc = (sizeof(Real) == 4) ? (Real)p.base_score : (Real)0;
+    for (int c = 0; c < p.n_chunks; ++c, ++it) {
+      if (!resident && tid == 0) {
+        const bool more = (c + 1 < p.n_chunks) || (tile + (int)gridDim.x < n_tiles);
+        if (more) {
+          const int nc = (c + 1 < p.n_chunks) ? c + 1 : 0;
+          const ChunkDesc cd = p.chunks[nc];
+          uint64_t *bar = &bars[(it + 1) & 1];
+          fence_proxy_async();
+          mbar_arrive_expect_tx(bar, cd.bytes);
+          tma_bulk_g2s(((it + 1) & 1) ? cbuf1 : cbuf0, p.model + cd.byte_off, cd.bytes, bar);
+        }
+      }
+      if (!resident || it == 0) mbar_wait(&bars[it & 1], (it >> 1) & 1);
+      const uint8_t *cb = (!resident && (it & 1)) ? cbuf1 : cbuf0;
+      const uint32_t ent_addr = smem_u32(cb) + 16u;
+      const uint32_t leaf_addr = smem_u32(cb) + reinterpret_cast<const uint32_t *>(cb)[2];
+      uint32_t n = 0;  // first root
+      do {
+        uint32_t w0, w1;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(ent_addr + n * 8u));
+        const uint32_t k = w0 & 0xFFFFu;
+        uint32_t code;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(code) : "r"(xw_addr + ((w0 >> 10) & 0x3FFC0u)));  // feat * 64 bytes
+        const bool left = (code <= k) || (code == kBinNaN && (w0 & (BF_NAN_LEFT << 28)));
+        if (w0 & (BF_LEAF << 28)) {
+          double v;
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(leaf_addr + k * 8u));
+          acc += (Real)v;
+        }
+        n = left ? (w1 & 0xFFFFu) : (w1 >> 16);
+      } while (n != kEntryEnd);
+      __syncthreads();
+    }
+    if (item < p.rows) p.out[item] = (double)acc;
+  }
+}
+
 template <typename Real, bool HAS_CAT, int ILP>
 void launch_b(const BParams &p, int threads, size_t smem, int num_sms, cudaStream_t stream) {
   auto kern = gbdt_score_binned_kernel<Real, HAS_CAT, ILP>;
@@ -316,7 +398,22 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
   while (fixed + (size_t)threads * per_item > kMaxSmem && threads > 32) threads = ((threads / 2) + 31) & ~31;
   if (fixed + (size_t)threads * per_item > kMaxSmem) fail(MR_ERR_UNSUPPORTED, "binned tile does not fit in shared memory");
   const size_t smem = fixed + (size_t)threads * per_item;
-  const int ilp = L.ilp <= 0 ? 2 : L.ilp;
+  if (L.threaded) {
+    auto go = [&](auto kern) {
+      MR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 0;
+      MR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+      if (per_sm < 1) fail(MR_ERR_CUDA, "threaded gbdt kernel does not fit on an SM");
+      const int n_tiles = (p.rows + threads - 1) / threads;
+      kern<<<std::max(1, std::min(n_tiles, num_sms * per_sm)), threads, smem, stream>>>(p);
+      MR_CUDA_CHECK(cudaGetLastError());
+      g_kernel_launches++;
+    };
+    if (L.kind == MR_BOOSTER_XGBOOST) go(gbdt_score_threaded_kernel<float>);
+    else go(gbdt_score_threaded_kernel<double>);
+    return;
+  }
+  const int ilp = L.ilp <= 0 ? 1 : L.ilp;
   if (L.kind == MR_BOOSTER_XGBOOST) launch_b_ilp<float, false>(p, ilp, threads, smem, num_sms, stream);
   else if (L.has_cat) launch_b_ilp<double, true>(p, ilp, threads, smem, num_sms, stream);
   else launch_b_ilp<double, false>(p, ilp, threads, smem, num_sms, stream);

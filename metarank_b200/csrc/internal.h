@@ -112,9 +112,9 @@ struct mr_model {
   uint8_t *d_model = nullptr;
   ChunkDesc *d_chunks = nullptr;
   // binned form (exact integer traversal); binned.ok == false -> always the f64/f32 kernel
-  BinnedModel binned;
-  uint8_t *d_bmodel = nullptr;
-  ChunkDesc *d_bchunks = nullptr;
+  BinnedModel binned, threaded;
+  uint8_t *d_bmodel = nullptr, *d_tmodel = nullptr;
+  ChunkDesc *d_bchunks = nullptr, *d_tchunks = nullptr;
   uint32_t *d_thr_off = nullptr;
   double *d_thr = nullptr;
   uint8_t *d_is_cat = nullptr;
@@ -141,9 +141,11 @@ struct mr_model {
     return d;
   }
   void free_binned() {
-    for (void *p : {(void *)d_bmodel, (void *)d_bchunks, (void *)d_thr_off, (void *)d_thr, (void *)d_is_cat})
+    for (void *p : {(void *)d_bmodel, (void *)d_bchunks, (void *)d_thr_off, (void *)d_thr, (void *)d_is_cat,
+                    (void *)d_tmodel, (void *)d_tchunks})
       if (p) cudaFree(p);
     d_bmodel = nullptr; d_bchunks = nullptr; d_thr_off = nullptr; d_thr = nullptr; d_is_cat = nullptr;
+    d_tmodel = nullptr; d_tchunks = nullptr;
   }
   void repack() {
     // Default policy: stream the ensemble through two small shared-memory buffers (TMA bulk
@@ -153,7 +155,7 @@ struct mr_model {
     if (opt_chunk_kb > 0) {
       budget = (size_t)opt_chunk_kb * 1024;
     } else {
-      budget = 8 * 1024;  // small chunks leave shared memory for the feature tile (occupancy)
+      budget = 16 * 1024;  // small chunks leave shared memory for the feature tile (occupancy)
     }
     packed = pack_model(host, budget);
     upload();
@@ -165,16 +167,31 @@ struct mr_model {
       d_thr_off = to_device(binned.thr_off);
       d_thr = to_device(binned.thr);
       d_is_cat = to_device(binned.is_cat);
+      threaded = pack_threaded(host, binned, budget);
+      if (threaded.ok) {
+        d_tmodel = to_device(threaded.packed.bytes);
+        d_tchunks = to_device(threaded.packed.chunks);
+      }
     }
   }
-  bool use_binned() const { return binned.ok && (opt_variant < 0 || opt_variant == 2); }
+  bool use_threaded() const { return threaded.ok && opt_variant == 3; }
+  bool use_binned() const {
+    if ((size_t)host.n_features * (4 * 32 + 2) * sizeof(uint16_t) > 200 * 1024) return false;  // bin_kernel tile
+    // auto (-1): binned lock-step for LightGBM (f64 -> u16 quarters the tile); XGBoost's features are
+    // already binary32, where the plain f32 kernel measured faster (profiles/sweep_r1.md)
+    if (opt_variant < 0) return binned.ok && host.kind == MR_BOOSTER_LIGHTGBM;
+    return binned.ok && (opt_variant == 2 || use_threaded());
+  }
   // Enqueue scoring of a device-resident matrix on `stream` with whichever kernel applies.
   void score(const double *d_values, int rows, int cols, double *d_out, cudaStream_t stream) const {
     if (use_binned()) {
       BinnedLaunch B;
-      B.d_model = d_bmodel; B.d_chunks = d_bchunks;
-      B.n_chunks = (int)binned.packed.chunks.size();
-      B.max_chunk_bytes = binned.packed.max_chunk_bytes;
+      const bool thr = use_threaded();
+      B.threaded = thr;
+      B.d_model = thr ? d_tmodel : d_bmodel;
+      B.d_chunks = thr ? d_tchunks : d_bchunks;
+      B.n_chunks = (int)(thr ? threaded : binned).packed.chunks.size();
+      B.max_chunk_bytes = (thr ? threaded : binned).packed.max_chunk_bytes;
       B.d_thr_off = d_thr_off; B.d_thr = d_thr; B.d_is_cat = d_is_cat;
       B.kind = host.kind; B.has_cat = host.has_cat; B.base_score = host.base_score;
       B.n_features = host.n_features;

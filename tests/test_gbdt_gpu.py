@@ -34,7 +34,7 @@ def _check(ctx, kind, blob, X, **opts):
     return got
 
 
-@pytest.mark.parametrize("variant,ilp", [(0, 1), (0, 2), (0, 4), (1, 1), (2, 1), (2, 2), (2, 4)])
+@pytest.mark.parametrize("variant,ilp", [(0, 1), (0, 2), (0, 4), (1, 1), (2, 1), (2, 2), (2, 4), (3, 1)])
 @pytest.mark.parametrize("threads", [32, 128, 256])
 def test_c2_lightgbm_100x30x500(ctx, variant, ilp, threads):
     blob = synth.lightgbm_model_text(500, 30, seed=1234 + 2)
@@ -42,11 +42,12 @@ def test_c2_lightgbm_100x30x500(ctx, variant, ilp, threads):
     _check(ctx, 0, blob, X, variant=variant, ilp=ilp, threads=threads)
 
 
+@pytest.mark.parametrize("variant", [0, 2, 3])
 @pytest.mark.parametrize("chunk_kb", [4, 32, 200])
-def test_chunking_is_invisible(ctx, chunk_kb):
-    blob = synth.lightgbm_model_text(500, 30, seed=7)
+def test_chunking_is_invisible(ctx, chunk_kb, variant):
+    blob = synth.lightgbm_model_text(500, 30, seed=7, stump_every=11)
     X = synth.feature_matrix(3000, 30, seed=8)
-    _check(ctx, 0, blob, X, chunk_kb=chunk_kb)
+    _check(ctx, 0, blob, X, chunk_kb=chunk_kb, variant=variant)
 
 
 @pytest.mark.parametrize("rows", [1, 2, 31, 32, 33, 255, 257, 1000, 4097])
@@ -93,6 +94,7 @@ def test_binned_codes_at_threshold_boundaries(ctx):
                 rows.append(r)
     X = np.array(rows)
     _check(ctx, 0, blob, X, variant=2)
+    _check(ctx, 0, blob, X, variant=3)
     xb = synth.xgboost_model_json(30, 5, depth=5, seed=34)
     mx = model_parse.parse_xgboost(xb)
     rows = []
@@ -106,6 +108,7 @@ def test_binned_codes_at_threshold_boundaries(ctx):
                 r[f] = v
                 rows.append(r)
     _check(ctx, 1, xb, np.array(rows), variant=2)
+    _check(ctx, 1, xb, np.array(rows), variant=3)
 
 
 def test_deep_unbalanced_lightgbm(ctx):
@@ -120,7 +123,7 @@ def test_c4_xgboost(ctx, fmt, depth, full):
     gen = synth.xgboost_model_json if fmt == "json" else synth.xgboost_model_ubj
     blob = gen(200, 16, depth=depth, seed=1234 + 4, full=full)
     X = synth.feature_matrix(256, 16, seed=42 + 4)
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         _check(ctx, 1, blob, X, variant=variant)
 
 
@@ -136,7 +139,8 @@ def test_xgboost_f32_rounding_of_inputs(ctx):
 def test_wide_rows_fall_back_to_global_reads(ctx):
     blob = synth.lightgbm_model_text(20, 1200, seed=31)
     X = synth.feature_matrix(300, 1200, seed=32)
-    _check(ctx, 0, blob, X)
+    _check(ctx, 0, blob, X, variant=0)
+    _check(ctx, 0, blob, X)  # auto: too wide for the binning kernel -> exact f64 kernel
 
 
 def test_c5_mega_request_properties(ctx):
