@@ -489,15 +489,47 @@ __device__ __forceinline__ uint32_t hist_count(const RankArgs &a, int r, int h, 
 
 // ------------------------------------------------------------------ assemble
 __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
+  // the extractor plan is read by every thread for every feature: stage it in shared memory
+  extern __shared__ __align__(16) uint8_t s_plan_raw[];
+  DFeature *s_plan = reinterpret_cast<DFeature *>(s_plan_raw);
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(a.plan);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(s_plan_raw);
+    const int n_words = a.n_plan * (int)(sizeof(DFeature) / 4);
+    for (int k = threadIdx.x; k < n_words; k += blockDim.x) dst[k] = __ldg(src + k);
+  }
+  __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.total_items) return;
   const int r = a.item_req[i];
   const uint32_t ir = a.item_row[i];
   const DTable &IT = a.st.t[SC_ITEM];
   const uint64_t *irow = ir != kNoRow ? row_ptr(IT, ir) : nullptr;
-  double *out = a.out_features + (size_t)i * a.dim;
   const double *ov = a.item_f64 ? a.item_f64 + (size_t)i * a.n_item_f64 : nullptr;
   const double kNaN = nan_d();
+  // One assembled value: the dense f64 row (explain / f64 scorer) and/or its exact u16 rank code for
+  // the binned scorer, laid out [group of 32 items][column][lane] so a warp's store is one 64-byte line.
+  struct Emit {
+    double *row;
+    uint16_t *codes;
+    const BinParams *bp;
+    __device__ __forceinline__ void operator()(int col, double v) const {
+      if (row) row[col] = v;
+      if (codes) codes[(size_t)col * 32] = code_of(*bp, col, v);
+    }
+    __device__ __forceinline__ Emit &self() { return *this; }
+  };
+  struct OutProxy {  // lets the extractor code below keep writing out[col] = v
+    const Emit *e; int col;
+    __device__ __forceinline__ void operator=(double v) const { (*e)(col, v); }
+  };
+  struct OutArr {
+    const Emit *e;
+    __device__ __forceinline__ OutProxy operator[](int col) const { return OutProxy{e, col}; }
+  };
+  const Emit emit{a.out_features ? a.out_features + (size_t)i * a.dim : nullptr,
+                  a.codes ? a.codes + ((size_t)(i >> 5) * a.dim) * 32 + (i & 31) : nullptr, &a.bin};
+  const OutArr out{&emit};
 
   auto scoped_row = [&](int scope) -> const uint64_t * {
     switch (scope) {
@@ -510,7 +542,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
   };
 
   for (int f = 0; f < a.n_plan; f++) {
-    const DFeature d = a.plan[f];
+    const DFeature &d = s_plan[f];
     switch (d.kind) {
       case FK_NUMBER: {
         // NumberFeature.values :84-93 (request-item field override) then value :58-69; WordCountFeature.value :63-68
@@ -680,7 +712,7 @@ void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t strea
     MR_CUDA_CHECK(cudaGetLastError());
     g_kernel_launches++;
   }
-  assemble_kernel<<<(a.total_items + 127) / 128, 128, 0, stream>>>(a);
+  assemble_kernel<<<(a.total_items + 127) / 128, 128, (size_t)std::max(a.n_plan, 1) * sizeof(DFeature), stream>>>(a);
   MR_CUDA_CHECK(cudaGetLastError());
   g_kernel_launches++;
 }

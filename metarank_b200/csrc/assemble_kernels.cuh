@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "binning.cuh"
 #include "schema.h"
 #include "state.h"
 
@@ -34,7 +35,9 @@ struct RankArgs {
   int32_t *error_flag;    // 0 ok | MR_ERR_ARITHMETIC | -1 histogram pool overflow
   int n_hist, n_reqagg, n_cos;
   // output
-  double *out_features;   // [total_items x dim] row-major (ltrlib Query.values)
+  double *out_features;   // [total_items x dim] row-major (ltrlib Query.values); may be null when codes != null
+  uint16_t *codes;        // optional: u16 rank codes [group of 32 items][column][lane] for the binned scorer
+  BinParams bin;          // thresholds of the model the codes are for (valid when codes != null)
 };
 
 // Enqueues lookup -> cosine -> per-request prepass -> assemble on `stream`.

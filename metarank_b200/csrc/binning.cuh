@@ -1,0 +1,42 @@
+// Exact value -> u16 rank-code conversion shared by bin_kernel (gbdt_binned.cu) and the fused
+// assemble kernel (assemble_kernels.cu).  See gbdt_model.h "binned layout".
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "gbdt_model.h"
+
+namespace mr {
+
+struct BinParams {
+  const double *values;
+  const uint32_t *thr_off;
+  const double *thr;
+  const uint8_t *is_cat;
+  uint16_t *bins;
+  int rows, cols, n_features;
+  int xgb;  // 1: round to binary32 first, strict less (upper_bound)
+};
+
+__device__ __forceinline__ uint16_t code_of(const BinParams &p, int f, double x) {
+  if (p.xgb) x = (double)__double2float_rn(x);
+  if (x != x) return kBinNaN;
+  if (p.is_cat[f]) {
+    // LightGBM CategoricalDecision: static_cast<int>(x), negative / out-of-int-range -> right
+    const bool in_range = (x < 2147483648.0) && (x > -2147483649.0);
+    const int iv = in_range ? __double2int_rz(x) : -1;
+    return (iv >= 0 && iv < 65000) ? (uint16_t)iv : kBinNaN;
+  }
+  const uint32_t b = __ldg(p.thr_off + f), e = __ldg(p.thr_off + f + 1);
+  uint32_t lo = 0, hi = e - b;
+  const double *t = p.thr + b;
+  if (p.xgb) {
+    while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__ldg(t + m) <= x) lo = m + 1; else hi = m; }  // #{t <= x}
+  } else {
+    while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__ldg(t + m) < x) lo = m + 1; else hi = m; }   // #{t < x}
+  }
+  return (uint16_t)lo;
+}
+
+}  // namespace mr

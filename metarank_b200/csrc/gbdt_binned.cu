@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cstdint>
 
+#include "binning.cuh"
 #include "gbdt_kernels.cuh"
 
 namespace mr {
@@ -49,36 +50,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 
 // ------------------------------------------------------------------ binning
-struct BinParams {
-  const double *values;
-  const uint32_t *thr_off;
-  const double *thr;
-  const uint8_t *is_cat;
-  uint16_t *bins;
-  int rows, cols, n_features;
-  int xgb;  // 1: round to binary32 first, strict less (upper_bound)
-};
-
-__device__ __forceinline__ uint16_t code_of(const BinParams &p, int f, double x) {
-  if (p.xgb) x = (double)__double2float_rn(x);
-  if (x != x) return kBinNaN;
-  if (p.is_cat[f]) {
-    // LightGBM CategoricalDecision: static_cast<int>(x), negative / out-of-int-range -> right
-    const bool in_range = (x < 2147483648.0) && (x > -2147483649.0);
-    const int iv = in_range ? __double2int_rz(x) : -1;
-    return (iv >= 0 && iv < 65000) ? (uint16_t)iv : kBinNaN;
-  }
-  const uint32_t b = __ldg(p.thr_off + f), e = __ldg(p.thr_off + f + 1);
-  uint32_t lo = 0, hi = e - b;
-  const double *t = p.thr + b;
-  if (p.xgb) {
-    while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__ldg(t + m) <= x) lo = m + 1; else hi = m; }  // #{t <= x}
-  } else {
-    while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__ldg(t + m) < x) lo = m + 1; else hi = m; }   // #{t < x}
-  }
-  return (uint16_t)lo;
-}
-
 constexpr int kBinGroups = 4;  // groups of 32 items per CTA
 
 __global__ void __launch_bounds__(256) bin_kernel(const BinParams p) {
@@ -353,7 +324,8 @@ void launch_b_ilp(const BParams &p, int ilp, int threads, size_t smem, int num_s
 void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream) {
   if (L.rows <= 0) return;
   const int F = L.n_features;
-  // ---- pass 1: codes
+  // ---- pass 1: codes (skipped when the caller — the fused assemble kernel — already wrote them)
+  if (!L.codes_ready) {
   BinParams bp;
   bp.values = L.d_values; bp.thr_off = L.d_thr_off; bp.thr = L.d_thr; bp.is_cat = L.d_is_cat;
   bp.bins = L.d_bins; bp.rows = L.rows; bp.cols = L.cols; bp.n_features = F;
@@ -365,6 +337,7 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
   bin_kernel<<<(L.rows + items_per_cta - 1) / items_per_cta, 256, bin_smem, stream>>>(bp);
   MR_CUDA_CHECK(cudaGetLastError());
   g_kernel_launches++;
+  }
 
   // ---- pass 2: traversal
   BParams p;

@@ -182,6 +182,26 @@ struct mr_model {
     if (opt_variant < 0) return binned.ok && host.kind == MR_BOOSTER_LIGHTGBM;
     return binned.ok && (opt_variant == 2 || use_threaded());
   }
+  BinnedLaunch binned_desc() const {
+    BinnedLaunch B;
+    const bool thr = use_threaded();
+    B.threaded = thr;
+    B.d_model = thr ? d_tmodel : d_bmodel;
+    B.d_chunks = thr ? d_tchunks : d_bchunks;
+    B.n_chunks = (int)(thr ? threaded : binned).packed.chunks.size();
+    B.max_chunk_bytes = (thr ? threaded : binned).packed.max_chunk_bytes;
+    B.d_thr_off = d_thr_off; B.d_thr = d_thr; B.d_is_cat = d_is_cat;
+    B.kind = host.kind; B.has_cat = host.has_cat; B.base_score = host.base_score;
+    B.n_features = host.n_features;
+    B.threads = opt_threads; B.ilp = opt_ilp;
+    return B;
+  }
+  // Scores rows whose u16 codes were already written to d_codes (fused assemble path).
+  void score_codes(uint16_t *d_codes, int rows, double *d_out, cudaStream_t stream) const {
+    BinnedLaunch B = binned_desc();
+    B.rows = rows; B.cols = host.n_features; B.d_out = d_out; B.d_bins = d_codes; B.codes_ready = true;
+    launch_gbdt_binned(B, ctx->num_sms, stream);
+  }
   // Enqueue scoring of a device-resident matrix on `stream` with whichever kernel applies.
   void score(const double *d_values, int rows, int cols, double *d_out, cudaStream_t stream) const {
     if (use_binned()) {

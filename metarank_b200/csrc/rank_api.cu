@@ -38,11 +38,12 @@ namespace {
 inline size_t al(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct ScratchPlan {
-  size_t item_req, item_row, visitor_row, cos, reqagg, hist_desc, hist_pool, hist_cursor, error_flag, features, total;
+  size_t item_req, item_row, visitor_row, cos, reqagg, hist_desc, hist_pool, hist_cursor, error_flag, features, codes, total;
   uint32_t hist_pool_cap;
 };
 
-ScratchPlan plan_scratch(const Schema &S, int n_requests, int total_items, uint32_t per_hist, bool own_features) {
+ScratchPlan plan_scratch(const Schema &S, int n_requests, int total_items, uint32_t per_hist, bool own_features,
+                         bool want_codes = false) {
   ScratchPlan p{};
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += al(bytes); return r; };
@@ -61,6 +62,7 @@ ScratchPlan plan_scratch(const Schema &S, int n_requests, int total_items, uint3
   p.hist_cursor = take(4);
   p.error_flag = take(4);
   p.features = own_features ? take((size_t)total_items * std::max(S.dim, 1) * 8) : 0;
+  p.codes = want_codes ? take(binned_scratch_bytes(total_items, std::max(S.dim, 1))) : 0;
   p.total = o;
   return p;
 }
@@ -91,6 +93,20 @@ void fill_args(RankArgs &a, mr_state *st, uint8_t *scratch, const ScratchPlan &s
   int n_cos = 0;
   for (auto &d : S.plan) n_cos += d.kind == FK_COSINE;
   a.n_cos = n_cos;
+}
+
+// The binned scorer consumes u16 rank codes; when it is the scorer, the assemble kernel emits the
+// codes itself and the f64 matrix is only materialised if the caller asked for it (explain).
+bool fused_codes(const mr_model *model) { return model && model->use_binned(); }
+
+void set_codes(RankArgs &a, const mr_model *model, uint8_t *scratch, const ScratchPlan &sp) {
+  a.codes = (uint16_t *)(scratch + sp.codes);
+  a.bin = BinParams{};
+  a.bin.thr_off = model->d_thr_off;
+  a.bin.thr = model->d_thr;
+  a.bin.is_cat = model->d_is_cat;
+  a.bin.n_features = model->host.n_features;
+  a.bin.xgb = model->host.kind == MR_BOOSTER_XGBOOST;
 }
 
 void ensure_flushed(mr_state *st) {
@@ -228,6 +244,118 @@ mr_status mr_state_get_info(mr_state *st, mr_state_info *out) {
   });
 }
 
+}  // extern "C"
+
+namespace {
+
+// One slice of requests in flight on one lane (stream + pinned staging + device scratch).
+struct RankPending {
+  bool active = false;
+  int i0 = 0, n = 0;  // first item / item count of the slice
+  size_t in_bytes = 0, ho_scores = 0, ho_order = 0, ho_feat = 0, ho_err = 0;
+};
+
+void rank_enqueue(mr_state *st, mr_model *model, const mr_rank_batch *b, int r0, int r1, Lane *lane, RankPending &pd,
+                  bool want_order, bool want_features) {
+  const Schema &S = st->store->schema;
+  const int R = r1 - r0, i0 = b->item_offsets[r0], N = b->item_offsets[r1] - i0;
+  pd = RankPending{};
+  pd.active = true;
+  pd.i0 = i0;
+  pd.n = N;
+  // ---- pack the slice into one pinned blob -> one H2D copy
+  struct Seg { const void *src; size_t bytes, off; };
+  Seg segs[9];
+  size_t in_bytes = 0;
+  int ns = 0;
+  auto seg = [&](const void *p, size_t bytes) { segs[ns] = Seg{p, p ? bytes : 0, in_bytes}; in_bytes += al(segs[ns].bytes); return ns++; };
+  const int s_off = seg(b->item_offsets + r0, (size_t)(R + 1) * 4);
+  const int s_ids = seg(b->item_ids + i0, (size_t)N * 8);
+  const int s_usr = seg(b->user_ids ? b->user_ids + r0 : nullptr, (size_t)R * 8);
+  const int s_ses = seg(b->session_ids ? b->session_ids + r0 : nullptr, (size_t)R * 8);
+  const size_t nrf = S.in_req_f64.size(), nru = S.in_req_u64.size(), nrv = S.in_req_vec.size(), nif = S.in_item_f64.size();
+  const int s_rf = seg(b->req_f64 ? b->req_f64 + (size_t)r0 * nrf : nullptr, (size_t)R * nrf * 8);
+  const int s_ru = seg(b->req_u64 ? b->req_u64 + (size_t)r0 * nru : nullptr, (size_t)R * nru * 8);
+  const int s_rv = seg(b->req_vec ? b->req_vec + (size_t)r0 * S.vec_stride : nullptr, (size_t)R * S.vec_stride * 4);
+  const int s_rp = seg(b->req_vec_present ? b->req_vec_present + (size_t)r0 * nrv : nullptr, (size_t)R * nrv);
+  const int s_if = seg(b->item_f64 ? b->item_f64 + (size_t)i0 * nif : nullptr, (size_t)N * nif * 8);
+
+  const bool fused = fused_codes(model);
+  ScratchPlan sp = plan_scratch(S, R, N, st->hist_pool_per_hist, want_features || !fused, fused);
+  const size_t scores_off = al(in_bytes) + sp.total, order_off = scores_off + al((size_t)N * 8);
+  const size_t d_total = order_off + al((size_t)N * 4);
+  const size_t out_bytes = al((size_t)N * 8) + al((size_t)N * 4) + (want_features ? al((size_t)N * S.dim * 8) : 0) + 16;
+  lane->ensure(in_bytes + out_bytes, d_total);
+  for (int k = 0; k < ns; k++)
+    if (segs[k].bytes) memcpy(lane->h_pinned + segs[k].off, segs[k].src, segs[k].bytes);
+  if (i0 != 0) {  // rebase the slice's offsets to start at 0
+    int32_t *o = (int32_t *)(lane->h_pinned + segs[s_off].off);
+    for (int r = 0; r <= R; r++) o[r] -= i0;
+  }
+  uint8_t *d_in = lane->d_buf, *scratch = lane->d_buf + al(in_bytes);
+  MR_CUDA_CHECK(cudaMemcpyAsync(d_in, lane->h_pinned, in_bytes, cudaMemcpyHostToDevice, lane->stream));
+  auto dp = [&](int si) -> const void * { return segs[si].bytes ? d_in + segs[si].off : nullptr; };
+  RankArgs a{};
+  fill_args(a, st, scratch, sp);
+  a.n_requests = R;
+  a.total_items = N;
+  a.item_offsets = (const int32_t *)dp(s_off);
+  a.item_ids = (const uint64_t *)dp(s_ids);
+  a.user_ids = (const uint64_t *)dp(s_usr);
+  a.session_ids = (const uint64_t *)dp(s_ses);
+  a.req_f64 = (const double *)dp(s_rf);
+  a.req_u64 = (const uint64_t *)dp(s_ru);
+  a.req_vec = (const float *)dp(s_rv);
+  a.req_vec_present = (const uint8_t *)dp(s_rp);
+  a.item_f64 = (const double *)dp(s_if);
+  a.out_features = (want_features || !fused) ? (double *)(scratch + sp.features) : nullptr;
+  if (fused) set_codes(a, model, scratch, sp);
+  MR_CUDA_CHECK(cudaMemsetAsync(a.error_flag, 0, 4, lane->stream));
+  launch_assemble(a, S, lane->stream);
+  double *d_scores = (double *)(lane->d_buf + scores_off);
+  int32_t *d_order = (int32_t *)(lane->d_buf + order_off);
+  uint8_t *h_out = lane->h_pinned + in_bytes;
+  size_t ho = 0;
+  pd.in_bytes = in_bytes;
+  if (model) {
+    if (fused) model->score_codes(a.codes, N, d_scores, lane->stream);
+    else model->score(a.out_features, N, S.dim, d_scores, lane->stream);
+    if (want_order) launch_rank_order(d_scores, a.item_offsets, R, N, d_order, lane->stream);
+    MR_CUDA_CHECK(cudaMemcpyAsync(h_out + ho, d_scores, (size_t)N * 8, cudaMemcpyDeviceToHost, lane->stream));
+  }
+  pd.ho_scores = ho; ho += al((size_t)N * 8);
+  if (model && want_order) MR_CUDA_CHECK(cudaMemcpyAsync(h_out + ho, d_order, (size_t)N * 4, cudaMemcpyDeviceToHost, lane->stream));
+  pd.ho_order = ho; ho += al((size_t)N * 4);
+  pd.ho_feat = ho;
+  if (want_features) {
+    MR_CUDA_CHECK(cudaMemcpyAsync(h_out + ho, a.out_features, (size_t)N * S.dim * 8, cudaMemcpyDeviceToHost, lane->stream));
+    ho += al((size_t)N * S.dim * 8);
+  }
+  pd.ho_err = ho;
+  MR_CUDA_CHECK(cudaMemcpyAsync(h_out + ho, a.error_flag, 4, cudaMemcpyDeviceToHost, lane->stream));
+}
+
+// Waits for the slice and copies its outputs to the caller's buffers; returns the device error flag.
+int32_t rank_finish(mr_state *st, mr_model *model, Lane *lane, RankPending &pd, double *out_scores, int32_t *out_order,
+                    double *out_features) {
+  if (!pd.active) return 0;
+  pd.active = false;
+  MR_CUDA_CHECK(cudaStreamSynchronize(lane->stream));
+  const Schema &S = st->store->schema;
+  const uint8_t *h_out = lane->h_pinned + pd.in_bytes;
+  int32_t err;
+  memcpy(&err, h_out + pd.ho_err, 4);
+  if (err != 0) return err;
+  if (model && out_scores) memcpy(out_scores + pd.i0, h_out + pd.ho_scores, (size_t)pd.n * 8);
+  if (model && out_order) memcpy(out_order + pd.i0, h_out + pd.ho_order, (size_t)pd.n * 4);
+  if (out_features) memcpy(out_features + (size_t)pd.i0 * S.dim, h_out + pd.ho_feat, (size_t)pd.n * S.dim * 8);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
 mr_status mr_rank(mr_state *st, mr_model *model, const mr_rank_batch *b, double *out_scores, int32_t *out_order,
                   double *out_features) {
   return guard([&] {
@@ -254,76 +382,37 @@ mr_status mr_rank(mr_state *st, mr_model *model, const mr_rank_batch *b, double 
     std::shared_lock<std::shared_mutex> read_guard(st->store->mu);  // no flush while kernels read the tables
     if (st->dirty) fail(MR_ERR_INVALID_ARG, "state has pending upserts: call mr_state_flush before mr_rank");
 
-    // ---- pack the batch into one pinned blob -> one H2D copy
-    struct Seg { const void *src; size_t bytes, off; };
-    std::vector<Seg> segs;
-    size_t in_bytes = 0;
-    auto seg = [&](const void *p, size_t bytes) { Seg s{p, p ? bytes : 0, in_bytes}; in_bytes += al(s.bytes); segs.push_back(s); return segs.size() - 1; };
-    const size_t s_off = seg(b->item_offsets, (size_t)(R + 1) * 4);
-    const size_t s_ids = seg(b->item_ids, (size_t)N * 8);
-    const size_t s_usr = seg(b->user_ids, (size_t)R * 8);
-    const size_t s_ses = seg(b->session_ids, (size_t)R * 8);
-    const size_t s_rf = seg(b->req_f64, (size_t)R * S.in_req_f64.size() * 8);
-    const size_t s_ru = seg(b->req_u64, (size_t)R * S.in_req_u64.size() * 8);
-    const size_t s_rv = seg(b->req_vec, (size_t)R * S.vec_stride * 4);
-    const size_t s_rp = seg(b->req_vec_present, (size_t)R * S.in_req_vec.size());
-    const size_t s_if = seg(b->item_f64, (size_t)N * S.in_item_f64.size() * 8);
-
+    // Large batches are cut at request boundaries into slices of ~128 K items that alternate
+    // between two lanes, so the H2D copy / kernels / D2H copy of neighbouring slices overlap.
+    const int kSliceItems = 1 << 17;
+    std::vector<int> cuts{0};
+    for (int r = 1; r <= R; r++)
+      if (r == R || b->item_offsets[r + 1] - b->item_offsets[cuts.back()] > kSliceItems) cuts.push_back(r);
+    const int n_slices = (int)cuts.size() - 1;
     for (int attempt = 0;; attempt++) {
-      ScratchPlan sp = plan_scratch(S, R, N, st->hist_pool_per_hist, true);
-      const size_t scores_off = al(in_bytes) + sp.total, order_off = scores_off + al((size_t)N * 8);
-      const size_t d_total = order_off + al((size_t)N * 4);
-      const size_t out_bytes = al((size_t)N * 8) + al((size_t)N * 4) + (out_features ? al((size_t)N * S.dim * 8) : 0) + 16;
-      LaneGuard lane(st->ctx);
-      lane->ensure(in_bytes + out_bytes, d_total);
-      for (auto &s : segs) if (s.bytes) memcpy(lane->h_pinned + s.off, s.src, s.bytes);
-      uint8_t *d_in = lane->d_buf, *scratch = lane->d_buf + al(in_bytes);
-      MR_CUDA_CHECK(cudaMemcpyAsync(d_in, lane->h_pinned, in_bytes, cudaMemcpyHostToDevice, lane->stream));
-      auto dp = [&](size_t si) -> const void * { return segs[si].bytes ? d_in + segs[si].off : nullptr; };
-      RankArgs a{};
-      fill_args(a, st, scratch, sp);
-      a.n_requests = R;
-      a.total_items = N;
-      a.item_offsets = (const int32_t *)dp(s_off);
-      a.item_ids = (const uint64_t *)dp(s_ids);
-      a.user_ids = (const uint64_t *)dp(s_usr);
-      a.session_ids = (const uint64_t *)dp(s_ses);
-      a.req_f64 = (const double *)dp(s_rf);
-      a.req_u64 = (const uint64_t *)dp(s_ru);
-      a.req_vec = (const float *)dp(s_rv);
-      a.req_vec_present = (const uint8_t *)dp(s_rp);
-      a.item_f64 = (const double *)dp(s_if);
-      a.out_features = (double *)(scratch + sp.features);
-      MR_CUDA_CHECK(cudaMemsetAsync(a.error_flag, 0, 4, lane->stream));
-      launch_assemble(a, S, lane->stream);
-      double *d_scores = (double *)(lane->d_buf + scores_off);
-      int32_t *d_order = (int32_t *)(lane->d_buf + order_off);
-      uint8_t *h_out = lane->h_pinned + in_bytes;
-      size_t ho = 0;
-      if (model) {
-        model->score(a.out_features, N, S.dim, d_scores, lane->stream);
-        if (out_order) launch_rank_order(d_scores, a.item_offsets, R, N, d_order, lane->stream);
-        MR_CUDA_CHECK(cudaMemcpyAsync(h_out + ho, d_scores, (size_t)N * 8, cudaMemcpyDeviceToHost, lane->stream));
+      LaneGuard lane0(st->ctx);
+      std::unique_ptr<LaneGuard> lane1;
+      if (n_slices > 1) lane1 = std::make_unique<LaneGuard>(st->ctx);
+      Lane *lanes[2] = {lane0.lane.get(), lane1 ? lane1->lane.get() : lane0.lane.get()};
+      RankPending pend[2];
+      int32_t err = 0;
+      for (int sidx = 0; sidx < n_slices && err == 0; sidx++) {
+        const int l = sidx & 1;
+        err = rank_finish(st, model, lanes[l], pend[l], out_scores, out_order, out_features);
+        if (err) break;
+        rank_enqueue(st, model, b, cuts[sidx], cuts[sidx + 1], lanes[l], pend[l], out_order != nullptr, out_features != nullptr);
       }
-      const size_t ho_scores = ho; ho += al((size_t)N * 8);
-      if (model && out_order) MR_CUDA_CHECK(cudaMemcpyAsync(h_out + ho, d_order, (size_t)N * 4, cudaMemcpyDeviceToHost, lane->stream));
-      const size_t ho_order = ho; ho += al((size_t)N * 4);
-      const size_t ho_feat = ho;
-      if (out_features) { MR_CUDA_CHECK(cudaMemcpyAsync(h_out + ho, a.out_features, (size_t)N * S.dim * 8, cudaMemcpyDeviceToHost, lane->stream)); ho += al((size_t)N * S.dim * 8); }
-      MR_CUDA_CHECK(cudaMemcpyAsync(h_out + ho, a.error_flag, 4, cudaMemcpyDeviceToHost, lane->stream));
-      MR_CUDA_CHECK(cudaStreamSynchronize(lane->stream));
-      int32_t err;
-      memcpy(&err, h_out + ho, 4);
-      if (err == -1 && attempt < 6) {  // tag-multiset pool too small: grow and redo this batch
+      for (int l = 0; l < 2; l++) {
+        const int32_t e = rank_finish(st, model, lanes[l], pend[l], out_scores, out_order, out_features);
+        if (!err) err = e;
+      }
+      if (err == -1 && attempt < 6) {  // tag-multiset pool too small: grow and redo the batch
         st->hist_pool_per_hist *= 4;
         continue;
       }
       if (err == -1) fail(MR_ERR_UNSUPPORTED, "per-request tag histograms exceed the scratch pool");
       if (err == MR_ERR_ARITHMETIC)
-        fail(MR_ERR_ARITHMETIC, "/ by zero: normalized rate with a global '%s' counter of 0 (java.lang.ArithmeticException in RateFeature.value)", "top");
-      if (model && out_scores) memcpy(out_scores, h_out + ho_scores, (size_t)N * 8);
-      if (model && out_order) memcpy(out_order, h_out + ho_order, (size_t)N * 4);
-      if (out_features) memcpy(out_features, h_out + ho_feat, (size_t)N * S.dim * 8);
+        fail(MR_ERR_ARITHMETIC, "/ by zero: normalized rate with a global top counter of 0 (java.lang.ArithmeticException in RateFeature.value)");
       break;
     }
   });
@@ -341,7 +430,8 @@ mr_status mr_rank_device(mr_state *st, mr_model *model, const mr_rank_batch *b, 
     MR_CUDA_CHECK(cudaSetDevice(st->ctx->device));
     if (st->dirty) fail(MR_ERR_INVALID_ARG, "state has pending upserts: call mr_state_flush before mr_rank_device");
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    ScratchPlan sp = plan_scratch(S, R, N, st->hist_pool_per_hist, d_out_features == nullptr);
+    const bool fused = fused_codes(model);
+    ScratchPlan sp = plan_scratch(S, R, N, st->hist_pool_per_hist, d_out_features == nullptr && !fused, fused);
     if (sp.total > st->d_scratch_cap) {
       MR_CUDA_CHECK(cudaDeviceSynchronize());
       if (st->d_scratch) cudaFree(st->d_scratch);
@@ -363,12 +453,14 @@ mr_status mr_rank_device(mr_state *st, mr_model *model, const mr_rank_batch *b, 
     a.req_vec = b->req_vec;
     a.req_vec_present = b->req_vec_present;
     a.item_f64 = b->item_f64;
-    a.out_features = d_out_features ? d_out_features : (double *)(st->d_scratch + sp.features);
+    a.out_features = d_out_features ? d_out_features : (fused ? nullptr : (double *)(st->d_scratch + sp.features));
+    if (fused) set_codes(a, model, st->d_scratch, sp);
     MR_CUDA_CHECK(cudaMemsetAsync(a.error_flag, 0, 4, stream));
     launch_assemble(a, S, stream);
     if (model) {
       if (!d_out_scores) fail(MR_ERR_INVALID_ARG, "d_out_scores is null");
-      model->score(a.out_features, N, S.dim, d_out_scores, stream);
+      if (fused) model->score_codes(a.codes, N, d_out_scores, stream);
+      else model->score(a.out_features, N, S.dim, d_out_scores, stream);
       if (d_out_order) launch_rank_order(d_out_scores, a.item_offsets, R, N, d_out_order, stream);
     }
   });

@@ -351,7 +351,7 @@ Schema parse_schema_json(const char *json, size_t len) {
     L.presence_words = (n + 63) / 64;
     int w = L.presence_words;
     for (auto &sl : S.slots) if (sl.table == tb) { sl.word = w; w += sl.n_words; }
-    L.row_words = std::max(w, 1);
+    L.row_words = std::max((w + 3) & ~3, 4);  // 32-byte sectors: a row never straddles an extra one
   }
   // resolve slot ids in the plan to (word, bit)
   int n_cos = 0;

@@ -211,3 +211,68 @@ def test_unsupported_feature_types_fail_loudly(ctx):
     with pytest.raises(mb.MrError) as e:
         F.FeatureMapping(ctx, [dict(name="ua", type="ua", field="platform", source="ranking.ua")], ["ua"])
     assert e.value.status == 5 and "ua" in e.value.message
+
+
+def test_rank_device_api_matches_host_api(ctx):
+    """mr_rank_device (device pointers, caller's stream) == mr_rank (host buffers), with and without
+    the explain matrix, for the binned (LightGBM) and the f32 (XGBoost) scorer."""
+    import torch
+
+    import metarank_b200 as mb
+    from metarank_b200 import features as F
+
+    feats, model = synth.ranklens_config()
+    state, item_ids, sessions = synth.ranklens_state(n_items=500, n_sessions=30, seed=5)
+    reqs = synth.ranklens_requests(item_ids, sessions, 40, 100, seed=6)
+    fm, ds, rk, _, _ = _device(ctx, feats, model, state)
+    arrays = fm.pack_requests(reqs)
+    N, R = arrays["total_items"], arrays["n_requests"]
+    d = {k: torch.from_numpy(np.ascontiguousarray(v).view(np.int64) if v.dtype == np.uint64 else np.ascontiguousarray(v)).cuda()
+         for k, v in arrays.items() if isinstance(v, np.ndarray)}
+    st = torch.cuda.current_stream().cuda_stream
+    for booster in (mb.LightGBMBooster(ctx, synth.lightgbm_model_text(80, 24, seed=3, cat_features={7: 16})),
+                    mb.XGBoostBooster(ctx, synth.xgboost_model_json(60, 24, depth=5, seed=4))):
+        want_s, want_o, want_f = rk.rank_arrays(arrays, booster, want_order=True, want_features=True)
+        for explain in (False, True):
+            d_s = torch.zeros(N, dtype=torch.float64, device="cuda")
+            d_o = torch.zeros(N, dtype=torch.int32, device="cuda")
+            d_f = torch.zeros(N * fm.dim, dtype=torch.float64, device="cuda")
+            F.rank_device(ds, booster, R, N, d["offsets"].data_ptr(), d["ids"].data_ptr(), d_s.data_ptr(), d_o.data_ptr(),
+                          d_f.data_ptr() if explain else 0, st, d["users"].data_ptr(), d["sessions"].data_ptr())
+            F.rank_device_status(ds, st)
+            assert _eq(d_s.cpu().numpy(), want_s) and np.array_equal(d_o.cpu().numpy(), want_o)
+            if explain:
+                assert _eq(d_f.cpu().numpy().reshape(N, fm.dim), want_f)
+        booster.free()
+    ds.free(); fm.free()
+
+
+def test_large_batch_is_sliced_and_pipelined(ctx):
+    """A batch beyond the 128 K-item slice size goes through two lanes; results must not depend on it."""
+    import metarank_b200 as mb
+    from metarank_b200 import features as F
+
+    names = [f"f{j}" for j in range(8)]
+    feats = [dict(name=n, type="number", scope="item", source=f"metadata.{n}") for n in names]
+    fm = F.FeatureMapping(ctx, feats, names)
+    ds = F.DeviceState(ctx, fm)
+    cat = synth.feature_matrix(5000, 8, seed=1)
+    ids = np.arange(1, 5001, dtype=np.uint64) * np.uint64(2654435761)
+    ds.put_packed(F.pack_number_columns(names, ids, cat))
+    ds.flush()
+    rng = np.random.Generator(np.random.PCG64(2))
+    sizes = rng.integers(1, 400, 2000)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    pick = rng.integers(0, 5000, int(offs[-1]))
+    R = len(sizes)
+    arrays = dict(offsets=offs, ids=ids[pick], users=np.zeros(R, dtype=np.uint64), sessions=np.zeros(R, dtype=np.uint64),
+                  req_f64=np.zeros((R, 1)), req_u64=np.zeros((R, 1), dtype=np.uint64), req_vec=np.zeros((R, 1), dtype=np.float32),
+                  req_vp=np.zeros((R, 1), dtype=np.uint8), item_f64=None, n_requests=R, total_items=int(offs[-1]))
+    blob = synth.lightgbm_model_text(40, 8, seed=3)
+    booster = mb.LightGBMBooster(ctx, blob)
+    scores, order, feats_out = F.Ranker(fm, ds).rank_arrays(arrays, booster, want_order=True, want_features=True)
+    want = oracle.OracleBooster(0, blob).predictMat(cat[pick], len(pick), 8, threads=0)
+    assert _eq(feats_out, cat[pick]) and _eq(scores, want)
+    for r in rng.integers(0, R, 50):
+        assert np.array_equal(order[offs[r]:offs[r + 1]], oracle.rank_order(want[offs[r]:offs[r + 1]]))
+    booster.free(); ds.free(); fm.free()
