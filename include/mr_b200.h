@@ -141,7 +141,8 @@ MR_API mr_status mr_model_free(mr_model *m);
 
 /* Tuning knobs for experiments (bench.py / tests); defaults are chosen per model.
  * key: "threads" (items per CTA, 0 = auto), "chunk_kb", "ilp" (trees in flight per thread),
- * "variant" (-1 = auto, 0 = f64 lock-step, 1 = f64 free-running, 2 = binned integer traversal). */
+ * "variant" (-1 = auto, 0 = f64/f32 lock-step, 1 = f64 free-running, 2 = binned lock-step, 3 = binned
+ * free-running, 4 = binned lock-step on the compact layout). */
 MR_API mr_status mr_model_set_option(mr_model *m, const char *key, int32_t value);
 
 /* ------------------------------------------------------------------ final ordering */

@@ -214,6 +214,108 @@ __global__ void __launch_bounds__(1024) gbdt_score_binned_kernel(const BParams p
   }
 }
 
+// ------------------------------------------------------------------ compact lock-step traversal
+// Same mapping as gbdt_score_binned_kernel, on the compact layout (gbdt_model.h): children are byte
+// offsets (bit 0 = leaf), the feature's byte offset inside the warp's code tile is stored in the
+// node, so one tree level is: LDS.64 node, shift+mask/or, LDS.U16 code, compare, select, test.
+template <typename Real>
+__global__ void __launch_bounds__(1024) gbdt_score_compact_kernel(const BParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int W = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int F = p.n_features;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+  const bool resident = p.n_chunks == 1;
+  uint8_t *cbuf0 = smem + 128;
+  uint8_t *cbuf1 = cbuf0 + (resident ? 0u : p.chunk_stride);
+  uint8_t *xs = cbuf1 + p.chunk_stride;
+  const uint8_t *xwarp = xs + (size_t)warp * F * 64;  // this warp's [feature][lane] u16 codes
+  const uint32_t lane2 = (uint32_t)lane * 2u;
+
+  const int n_tiles = (p.rows + W - 1) / W;
+  const int groups_per_tile = W >> 5;
+  const int n_groups = (p.rows + 31) >> 5;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0 && (int)blockIdx.x < n_tiles) {
+    const ChunkDesc cd = p.chunks[0];
+    mbar_arrive_expect_tx(&bars[0], cd.bytes);
+    tma_bulk_g2s(cbuf0, p.model + cd.byte_off, cd.bytes, &bars[0]);
+  }
+  uint32_t it = 0, tile_it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+    if (tid == 0) {
+      const int g0 = tile * groups_per_tile, g1 = min(n_groups, g0 + groups_per_tile);
+      const uint32_t bytes = (uint32_t)(g1 - g0) * (uint32_t)F * 64u;
+      fence_proxy_async();
+      mbar_arrive_expect_tx(&bars[2], bytes);
+      tma_bulk_g2s(xs, p.bins + (size_t)g0 * F * 32, bytes, &bars[2]);
+    }
+    mbar_wait(&bars[2], tile_it & 1);
+    const int item = tile * W + tid;
+    Real acc = (sizeof(Real) == 4) ? (Real)p.base_score : (Real)0;
+    for (int c = 0; c < p.n_chunks; ++c, ++it) {
+      if (!resident && tid == 0) {
+        const bool more = (c + 1 < p.n_chunks) || (tile + (int)gridDim.x < n_tiles);
+        if (more) {
+          const int nc = (c + 1 < p.n_chunks) ? c + 1 : 0;
+          const ChunkDesc cd = p.chunks[nc];
+          uint64_t *bar = &bars[(it + 1) & 1];
+          fence_proxy_async();
+          mbar_arrive_expect_tx(bar, cd.bytes);
+          tma_bulk_g2s(((it + 1) & 1) ? cbuf1 : cbuf0, p.model + cd.byte_off, cd.bytes, bar);
+        }
+      }
+      if (!resident || it == 0) mbar_wait(&bars[it & 1], (it >> 1) & 1);
+      const uint8_t *cb = (!resident && (it & 1)) ? cbuf1 : cbuf0;
+      const int ntree = (int)*reinterpret_cast<const uint32_t *>(cb);
+      const uint32_t *roots = reinterpret_cast<const uint32_t *>(cb + 16);
+      const uint32_t cb_addr = smem_u32(cb), xwarp_addr = smem_u32(xwarp);
+#pragma unroll 1
+      for (int t = 0; t < ntree; t++) {
+        uint32_t n = roots[t];
+        if (!(n & 1u)) {
+          // one tree level = 12 SASS instructions; spelled in PTX because nvcc otherwise routes the
+          // predicates through integer registers (18 instructions)
+          asm volatile(
+              "{\n"
+              ".reg .pred pl, pn, pf, pq;\n"
+              ".reg .b32 w0, w1, off, code, kk, sel, tmp;\n"
+              "LVL:\n"
+              "add.u32 tmp, %1, %0;\n"
+              "ld.shared.v2.u32 {w0, w1}, [tmp];\n"
+              "lop3.b32 off, w0, 0xFFC0, %3, 0xEA;\n"   // (w0 & 0xFFC0) | lane*2
+              "add.u32 off, off, %2;\n"
+              "ld.shared.u16 code, [off];\n"
+              "shr.u32 kk, w0, 16;\n"
+              "setp.le.u32 pl, code, kk;\n"
+              "setp.eq.u32 pn, code, 0xFFFF;\n"
+              "and.b32 tmp, w0, 1;\n"
+              "setp.ne.u32 pf, tmp, 0;\n"
+              "and.pred pn, pn, pf;\n"
+              "or.pred pl, pl, pn;\n"                    // NaN code is never <= k, so this only adds NaN -> left
+              "selp.b32 sel, 0x4410, 0x4432, pl;\n"
+              "prmt.b32 %0, w1, 0, sel;\n"
+              "and.b32 tmp, %0, 1;\n"
+              "setp.eq.u32 pq, tmp, 0;\n"
+              "@pq bra LVL;\n"
+              "}\n"
+              : "+r"(n)
+              : "r"(cb_addr), "r"(xwarp_addr), "r"(lane2)
+              : "memory");
+        }
+        acc += *reinterpret_cast<const Real *>(cb + (n - 1u));
+      }
+      __syncthreads();
+    }
+    if (item < p.rows) p.out[item] = (double)acc;
+  }
+}
+
 // ------------------------------------------------------------------ free-running ("threaded") traversal
 // Every lane chases its own pointer through the chunk's flat entry array: internal entry ->
 // child entry, leaf entry -> (add value) -> root of the next tree.  No lane ever idles waiting for
@@ -384,6 +486,21 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
     };
     if (L.kind == MR_BOOSTER_XGBOOST) go(gbdt_score_threaded_kernel<float>);
     else go(gbdt_score_threaded_kernel<double>);
+    return;
+  }
+  if (L.compact) {
+    auto go = [&](auto kern) {
+      MR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 0;
+      MR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+      if (per_sm < 1) fail(MR_ERR_CUDA, "compact gbdt kernel does not fit on an SM");
+      const int n_tiles = (p.rows + threads - 1) / threads;
+      kern<<<std::max(1, std::min(n_tiles, num_sms * per_sm)), threads, smem, stream>>>(p);
+      MR_CUDA_CHECK(cudaGetLastError());
+      g_kernel_launches++;
+    };
+    if (L.kind == MR_BOOSTER_XGBOOST) go(gbdt_score_compact_kernel<float>);
+    else go(gbdt_score_compact_kernel<double>);
     return;
   }
   const int ilp = L.ilp <= 0 ? 1 : L.ilp;

@@ -51,6 +51,7 @@ struct BinnedLaunch {
   uint16_t *d_bins = nullptr;           // scratch: ceil(rows/32) * F * 32 codes
   int threads = 0, ilp = 0;
   bool codes_ready = false;             // d_bins already holds the codes (fused assemble): skip bin_kernel
+  bool compact = false;                 // model bytes are pack_compact() chunks -> fast lock-step kernel
   bool threaded = false;                // model bytes are pack_threaded() chunks -> free-running kernel
 };
 inline size_t binned_scratch_bytes(int rows, int n_features) {

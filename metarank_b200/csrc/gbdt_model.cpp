@@ -584,4 +584,65 @@ BinnedModel pack_threaded(const HostModel &m, const BinnedModel &bn, size_t chun
   return T;
 }
 
+// ------------------------------------------------------------------ compact packing
+
+BinnedModel pack_compact(const HostModel &m, const BinnedModel &bn, size_t chunk_budget) {
+  BinnedModel C;
+  if (!bn.ok || m.has_cat || m.n_features > 1023 || m.trees.empty()) return C;
+  C.thr_off = bn.thr_off;
+  C.thr = bn.thr;
+  C.is_cat = bn.is_cat;
+  const bool f32 = m.kind == MR_BOOSTER_XGBOOST;
+  chunk_budget = std::min<size_t>(chunk_budget, 65536 - 16);
+  auto tree_bytes = [](const HostTree &t) { return (t.feat.size() + t.leaf.size()) * 8; };
+  PackedModel &pk = C.packed;
+  size_t i = 0, nt = m.trees.size();
+  while (i < nt) {
+    size_t j = i, body = 0;
+    while (j < nt) {
+      const size_t nb = body + tree_bytes(m.trees[j]);
+      if (j > i && 16 + al16((j - i + 1) * 4) + nb > chunk_budget) break;
+      body = nb;
+      j++;
+    }
+    const size_t n = j - i, hdr = 16 + al16(n * 4), total = al16(hdr + body);
+    if (total > 65536) return C;  // a single tree too large for 16-bit byte offsets
+    const size_t base = pk.bytes.size();
+    pk.bytes.resize(base + total, 0);
+    uint8_t *c = pk.bytes.data() + base;
+    const uint32_t hn = (uint32_t)n;
+    memcpy(c, &hn, 4);
+    uint32_t *roots = (uint32_t *)(c + 16);
+    size_t off = hdr;
+    for (size_t k = 0; k < n; k++) {
+      const HostTree &t = m.trees[i + k];
+      const size_t ni = t.feat.size(), node_off = off, leaf_off = off + ni * 8;
+      auto child = [&](int cidx) -> uint32_t {
+        return cidx >= 0 ? (uint32_t)(node_off + (size_t)cidx * 8) : (uint32_t)((leaf_off + (size_t)(~cidx) * 8) | 1u);
+      };
+      roots[k] = ni ? (uint32_t)node_off : (uint32_t)(leaf_off | 1u);
+      uint32_t *w = (uint32_t *)(c + node_off);
+      for (size_t q = 0; q < ni; q++) {
+        const int f = t.feat[q];
+        const double *b = C.thr.data() + C.thr_off[f], *e = C.thr.data() + C.thr_off[f + 1];
+        const uint32_t kk = (uint32_t)(std::lower_bound(b, e, t.thr[q]) - b);
+        const uint32_t nanl = (t.flags[q] & NF_NAN_LEFT) ? 1u : 0u;
+        w[2 * q] = ((uint32_t)f * 64u | nanl) | (kk << 16);
+        w[2 * q + 1] = child(t.left[q]) | (child(t.right[q]) << 16);
+      }
+      uint8_t *lv = c + leaf_off;
+      for (size_t q = 0; q < t.leaf.size(); q++) {
+        if (f32) { const float v = (float)t.leaf[q]; memcpy(lv + q * 8, &v, 4); }
+        else memcpy(lv + q * 8, &t.leaf[q], 8);
+      }
+      off = leaf_off + t.leaf.size() * 8;
+    }
+    pk.chunks.push_back(ChunkDesc{(uint32_t)base, (uint32_t)total, (uint32_t)n, (uint32_t)i});
+    pk.max_chunk_bytes = std::max<uint32_t>(pk.max_chunk_bytes, (uint32_t)total);
+    i = j;
+  }
+  C.ok = true;
+  return C;
+}
+
 }  // namespace mr

@@ -107,6 +107,15 @@ struct BinnedModel {
 };
 BinnedModel pack_binned(const HostModel &m, size_t chunk_budget);
 
+// "Compact" form of the binned model for the fast lock-step kernel (no categorical nodes, <= 1023
+// features, chunks <= 64 KB).  Children are BYTE offsets inside the chunk, bit 0 set = leaf (the
+// offset then addresses the leaf VALUE), so a level needs no address arithmetic:
+//   CNode (8 B): word0 = feature*64 (bits 6..15) | nan_left (bit 0) | k << 16
+//                word1 = left offset (16) | right offset (16)
+//   chunk: +0 u32 n_trees, pad; +16 u32 root[n_trees] (offset of the root node, or leaf|1 for a
+//          single-leaf tree); then per tree its nodes followed by its leaf values (8-byte slots)
+BinnedModel pack_compact(const HostModel &m, const BinnedModel &binned, size_t chunk_budget);
+
 // "Threaded" form of the binned model for the free-running kernel: one flat array of 8-byte
 // entries per chunk in which LEAVES are entries too.  An internal entry is a BNode whose
 // children are absolute entry indices inside the chunk; a leaf entry has BF_LEAF set and both

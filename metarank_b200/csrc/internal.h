@@ -112,9 +112,9 @@ struct mr_model {
   uint8_t *d_model = nullptr;
   ChunkDesc *d_chunks = nullptr;
   // binned form (exact integer traversal); binned.ok == false -> always the f64/f32 kernel
-  BinnedModel binned, threaded;
-  uint8_t *d_bmodel = nullptr, *d_tmodel = nullptr;
-  ChunkDesc *d_bchunks = nullptr, *d_tchunks = nullptr;
+  BinnedModel binned, threaded, compact;
+  uint8_t *d_bmodel = nullptr, *d_tmodel = nullptr, *d_cmodel = nullptr;
+  ChunkDesc *d_bchunks = nullptr, *d_tchunks = nullptr, *d_cchunks = nullptr;
   uint32_t *d_thr_off = nullptr;
   double *d_thr = nullptr;
   uint8_t *d_is_cat = nullptr;
@@ -142,10 +142,10 @@ struct mr_model {
   }
   void free_binned() {
     for (void *p : {(void *)d_bmodel, (void *)d_bchunks, (void *)d_thr_off, (void *)d_thr, (void *)d_is_cat,
-                    (void *)d_tmodel, (void *)d_tchunks})
+                    (void *)d_tmodel, (void *)d_tchunks, (void *)d_cmodel, (void *)d_cchunks})
       if (p) cudaFree(p);
     d_bmodel = nullptr; d_bchunks = nullptr; d_thr_off = nullptr; d_thr = nullptr; d_is_cat = nullptr;
-    d_tmodel = nullptr; d_tchunks = nullptr;
+    d_tmodel = nullptr; d_tchunks = nullptr; d_cmodel = nullptr; d_cchunks = nullptr;
   }
   void repack() {
     // Default policy: stream the ensemble through two small shared-memory buffers (TMA bulk
@@ -167,6 +167,11 @@ struct mr_model {
       d_thr_off = to_device(binned.thr_off);
       d_thr = to_device(binned.thr);
       d_is_cat = to_device(binned.is_cat);
+      compact = pack_compact(host, binned, budget);
+      if (compact.ok) {
+        d_cmodel = to_device(compact.packed.bytes);
+        d_cchunks = to_device(compact.packed.chunks);
+      }
       threaded = pack_threaded(host, binned, budget);
       if (threaded.ok) {
         d_tmodel = to_device(threaded.packed.bytes);
@@ -175,21 +180,24 @@ struct mr_model {
     }
   }
   bool use_threaded() const { return threaded.ok && opt_variant == 3; }
+  bool use_compact() const { return compact.ok && (opt_variant == 4 || opt_variant < 0); }
   bool use_binned() const {
     if ((size_t)host.n_features * (4 * 32 + 2) * sizeof(uint16_t) > 200 * 1024) return false;  // bin_kernel tile
     // auto (-1): binned lock-step for LightGBM (f64 -> u16 quarters the tile); XGBoost's features are
     // already binary32, where the plain f32 kernel measured faster (profiles/sweep_r1.md)
     if (opt_variant < 0) return binned.ok && host.kind == MR_BOOSTER_LIGHTGBM;
-    return binned.ok && (opt_variant == 2 || use_threaded());
+    return binned.ok && (opt_variant == 2 || opt_variant == 4 || use_threaded());
   }
   BinnedLaunch binned_desc() const {
     BinnedLaunch B;
-    const bool thr = use_threaded();
+    const bool thr = use_threaded(), cmp = !thr && use_compact();
+    const BinnedModel &M = thr ? threaded : cmp ? compact : binned;
     B.threaded = thr;
-    B.d_model = thr ? d_tmodel : d_bmodel;
-    B.d_chunks = thr ? d_tchunks : d_bchunks;
-    B.n_chunks = (int)(thr ? threaded : binned).packed.chunks.size();
-    B.max_chunk_bytes = (thr ? threaded : binned).packed.max_chunk_bytes;
+    B.compact = cmp;
+    B.d_model = thr ? d_tmodel : cmp ? d_cmodel : d_bmodel;
+    B.d_chunks = thr ? d_tchunks : cmp ? d_cchunks : d_bchunks;
+    B.n_chunks = (int)M.packed.chunks.size();
+    B.max_chunk_bytes = M.packed.max_chunk_bytes;
     B.d_thr_off = d_thr_off; B.d_thr = d_thr; B.d_is_cat = d_is_cat;
     B.kind = host.kind; B.has_cat = host.has_cat; B.base_score = host.base_score;
     B.n_features = host.n_features;
@@ -205,18 +213,8 @@ struct mr_model {
   // Enqueue scoring of a device-resident matrix on `stream` with whichever kernel applies.
   void score(const double *d_values, int rows, int cols, double *d_out, cudaStream_t stream) const {
     if (use_binned()) {
-      BinnedLaunch B;
-      const bool thr = use_threaded();
-      B.threaded = thr;
-      B.d_model = thr ? d_tmodel : d_bmodel;
-      B.d_chunks = thr ? d_tchunks : d_bchunks;
-      B.n_chunks = (int)(thr ? threaded : binned).packed.chunks.size();
-      B.max_chunk_bytes = (thr ? threaded : binned).packed.max_chunk_bytes;
-      B.d_thr_off = d_thr_off; B.d_thr = d_thr; B.d_is_cat = d_is_cat;
-      B.kind = host.kind; B.has_cat = host.has_cat; B.base_score = host.base_score;
-      B.n_features = host.n_features;
+      BinnedLaunch B = binned_desc();
       B.d_values = d_values; B.rows = rows; B.cols = cols; B.d_out = d_out;
-      B.threads = opt_threads; B.ilp = opt_ilp;
       void *bins = nullptr;
       MR_CUDA_CHECK(cudaMallocAsync(&bins, std::max<size_t>(binned_scratch_bytes(rows, host.n_features), 16), stream));
       B.d_bins = (uint16_t *)bins;

@@ -34,7 +34,7 @@ def _check(ctx, kind, blob, X, **opts):
     return got
 
 
-@pytest.mark.parametrize("variant,ilp", [(0, 1), (0, 2), (0, 4), (1, 1), (2, 1), (2, 2), (2, 4), (3, 1)])
+@pytest.mark.parametrize("variant,ilp", [(0, 1), (0, 2), (0, 4), (1, 1), (2, 1), (2, 2), (2, 4), (3, 1), (4, 1)])
 @pytest.mark.parametrize("threads", [32, 128, 256])
 def test_c2_lightgbm_100x30x500(ctx, variant, ilp, threads):
     blob = synth.lightgbm_model_text(500, 30, seed=1234 + 2)
@@ -42,7 +42,7 @@ def test_c2_lightgbm_100x30x500(ctx, variant, ilp, threads):
     _check(ctx, 0, blob, X, variant=variant, ilp=ilp, threads=threads)
 
 
-@pytest.mark.parametrize("variant", [0, 2, 3])
+@pytest.mark.parametrize("variant", [0, 2, 3, 4])
 @pytest.mark.parametrize("chunk_kb", [4, 32, 200])
 def test_chunking_is_invisible(ctx, chunk_kb, variant):
     blob = synth.lightgbm_model_text(500, 30, seed=7, stump_every=11)
@@ -93,8 +93,8 @@ def test_binned_codes_at_threshold_boundaries(ctx):
                 r[f] = v
                 rows.append(r)
     X = np.array(rows)
-    _check(ctx, 0, blob, X, variant=2)
-    _check(ctx, 0, blob, X, variant=3)
+    for v in (2, 3, 4):
+        _check(ctx, 0, blob, X, variant=v)
     xb = synth.xgboost_model_json(30, 5, depth=5, seed=34)
     mx = model_parse.parse_xgboost(xb)
     rows = []
@@ -107,14 +107,18 @@ def test_binned_codes_at_threshold_boundaries(ctx):
                 r = np.zeros(5)
                 r[f] = v
                 rows.append(r)
-    _check(ctx, 1, xb, np.array(rows), variant=2)
-    _check(ctx, 1, xb, np.array(rows), variant=3)
+    for v in (2, 3, 4):
+        _check(ctx, 1, xb, np.array(rows), variant=v)
 
 
 def test_deep_unbalanced_lightgbm(ctx):
     blob = synth.lightgbm_model_text(50, 20, num_leaves=255, max_depth=0, seed=21)
     X = synth.feature_matrix(777, 20, seed=22)
-    _check(ctx, 0, blob, X)
+    for v in (-1, 0, 2, 4):
+        _check(ctx, 0, blob, X, variant=v)
+    # one tree of 20 000 leaves: too large for the compact layout's 16-bit offsets -> generic binned kernel
+    big = synth.lightgbm_model_text(2, 20, num_leaves=20000, max_depth=0, seed=23)
+    _check(ctx, 0, big, X, chunk_kb=220)
 
 
 @pytest.mark.parametrize("fmt", ["json", "ubj"])
@@ -123,7 +127,7 @@ def test_c4_xgboost(ctx, fmt, depth, full):
     gen = synth.xgboost_model_json if fmt == "json" else synth.xgboost_model_ubj
     blob = gen(200, 16, depth=depth, seed=1234 + 4, full=full)
     X = synth.feature_matrix(256, 16, seed=42 + 4)
-    for variant in (0, 1, 2, 3):
+    for variant in (0, 1, 2, 3, 4):
         _check(ctx, 1, blob, X, variant=variant)
 
 

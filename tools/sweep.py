@@ -20,10 +20,10 @@ for name, kind, blob, F in cfgs:
     b = mb.B200Booster(ctx, blob, kind=kind)
     print(name, "mean path", b.mean_path(X[:4096], 4096, F), flush=True)
     st = torch.cuda.current_stream().cuda_stream
-    for chunk_kb in (8, 16, 32):
+    for chunk_kb in (8, 16, 32, 60):
         b.set_option("chunk_kb", chunk_kb)
         for threads in (0, 256, 384, 512, 768, 1024):
-            for variant, ilp in ((0, 2), (2, 1), (3, 1)):
+            for variant, ilp in ((2, 1), (4, 1)):
                 b.set_option("threads", threads); b.set_option("variant", variant); b.set_option("ilp", ilp)
                 try:
                     for _ in range(2): b.predict_device(dX.data_ptr(), rows, F, dO.data_ptr(), st)
