@@ -71,6 +71,7 @@ struct KParams {
   uint32_t chunk_stride;  // bytes reserved per shared-memory chunk buffer
   int rows, cols, n_features;
   float base_score;
+  int model_in_global;  // 1: a chunk exceeds shared memory -> nodes are read from HBM/L2 directly
 };
 
 template <typename Real> struct Acc;
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(1024) gbdt_score_kernel(const KParams p) {
     fence_barrier_init();
   }
   __syncthreads();
-  if (tid == 0 && (int)blockIdx.x < n_tiles) {
+  if (tid == 0 && (int)blockIdx.x < n_tiles && !p.model_in_global) {
     const ChunkDesc cd = p.chunks[0];
     mbar_arrive_expect_tx(&bars[0], cd.bytes);
     tma_bulk_g2s(cbuf0, p.model + cd.byte_off, cd.bytes, &bars[0]);
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(1024) gbdt_score_kernel(const KParams p) {
 
     AccT acc = (sizeof(Real) == 4) ? (AccT)p.base_score : (AccT)0;
     for (int c = 0; c < p.n_chunks; ++c, ++it) {
-      if (!resident && tid == 0) {
+      if (!resident && tid == 0 && !p.model_in_global) {
         const bool more = (c + 1 < p.n_chunks) || (tile + (int)gridDim.x < n_tiles);
         if (more) {
           const int nc = (c + 1 < p.n_chunks) ? c + 1 : 0;
@@ -190,8 +191,9 @@ __global__ void __launch_bounds__(1024) gbdt_score_kernel(const KParams p) {
           tma_bulk_g2s(((it + 1) & 1) ? cbuf1 : cbuf0, p.model + cd.byte_off, cd.bytes, bar);
         }
       }
-      if (!resident || it == 0) mbar_wait(&bars[it & 1], (it >> 1) & 1);
-      const uint8_t *cb = (!resident && (it & 1)) ? cbuf1 : cbuf0;
+      if (!p.model_in_global && (!resident || it == 0)) mbar_wait(&bars[it & 1], (it >> 1) & 1);
+      const uint8_t *cb = p.model_in_global ? p.model + p.chunks[c].byte_off
+                                            : ((!resident && (it & 1)) ? cbuf1 : cbuf0);
       const int ntree = (int)*reinterpret_cast<const uint32_t *>(cb);
       const uint2 *tab = reinterpret_cast<const uint2 *>(cb + 16);
 
@@ -323,11 +325,19 @@ void launch_gbdt_score(const ScoreLaunch &L, int num_sms, cudaStream_t stream) {
   p.cols = L.cols;
   p.n_features = L.n_features;
   p.base_score = L.base_score;
+  p.model_in_global = 0;
 
   const bool f32 = L.kind == MR_BOOSTER_XGBOOST;
   const size_t real_sz = f32 ? 4 : 8;
   const size_t kMaxSmem = 227 * 1024;
-  const size_t fixed = 128 + (size_t)p.chunk_stride * (L.n_chunks == 1 ? 1 : 2);
+  size_t fixed = 128 + (size_t)p.chunk_stride * (L.n_chunks == 1 ? 1 : 2);
+  if (fixed + 32 * (size_t)L.n_features * real_sz > kMaxSmem) {
+    // a chunk (= one enormous tree) does not leave room for even a 32-item tile: leave the ensemble
+    // in HBM/L2 and walk it with ordinary loads (slow path; keeps every legal model scorable)
+    p.model_in_global = 1;
+    p.chunk_stride = 0;
+    fixed = 128;
+  }
 
   // Occupancy is what this kernel lives on (every node visit is a dependent
   // LDS -> LDS -> compare chain), and shared memory is what limits it: each item in
@@ -367,7 +377,6 @@ void launch_gbdt_score(const ScoreLaunch &L, int num_sms, cudaStream_t stream) {
   bool stage = true;
   while (fixed + (size_t)threads * per_item > kMaxSmem && threads > 32) threads = ((threads / 2) + 31) & ~31;
   if (fixed + (size_t)threads * per_item > kMaxSmem) stage = false;  // very wide rows: read HBM/L1 directly
-  if (fixed > kMaxSmem) fail(MR_ERR_UNSUPPORTED, "model chunk of %u bytes does not fit in shared memory", L.max_chunk_bytes);
   const size_t smem = fixed + (stage ? (size_t)threads * per_item : 0);
 
   int variant = L.variant < 0 ? 0 : L.variant;

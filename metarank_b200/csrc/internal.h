@@ -155,7 +155,9 @@ struct mr_model {
     if (opt_chunk_kb > 0) {
       budget = (size_t)opt_chunk_kb * 1024;
     } else {
-      budget = 16 * 1024;  // small chunks leave shared memory for the feature tile (occupancy)
+      // measured (profiles/sweep_r1.md): narrow rows leave room for large chunks (fewer CTA-wide
+      // barriers); wide rows need the shared memory for the code tile (occupancy)
+      budget = (host.n_features <= 32 ? 60 : 16) * 1024;
     }
     packed = pack_model(host, budget);
     upload();
@@ -183,9 +185,12 @@ struct mr_model {
   bool use_compact() const { return compact.ok && (opt_variant == 4 || opt_variant < 0); }
   bool use_binned() const {
     if ((size_t)host.n_features * (4 * 32 + 2) * sizeof(uint16_t) > 200 * 1024) return false;  // bin_kernel tile
-    // auto (-1): binned lock-step for LightGBM (f64 -> u16 quarters the tile); XGBoost's features are
-    // already binary32, where the plain f32 kernel measured faster (profiles/sweep_r1.md)
-    if (opt_variant < 0) return binned.ok && host.kind == MR_BOOSTER_LIGHTGBM;
+    if (binned.ok && 2 * (size_t)binned.packed.max_chunk_bytes + 64 * (size_t)host.n_features * 2 > 200 * 1024)
+      return false;  // an enormous tree: the exact kernel's HBM-resident slow path handles it
+    // auto (-1): the compact binned kernel whenever the model allows it (no categorical splits, <= 1023
+    // features); otherwise generic binned for LightGBM (f64 -> u16 quarters the tile) and the plain f32
+    // kernel for XGBoost, whose features are already binary32 (profiles/sweep_r1.md)
+    if (opt_variant < 0) return binned.ok && (compact.ok || host.kind == MR_BOOSTER_LIGHTGBM);
     return binned.ok && (opt_variant == 2 || opt_variant == 4 || use_threaded());
   }
   BinnedLaunch binned_desc() const {
