@@ -103,6 +103,17 @@ MR_API mr_status mr_model_predict_mat(mr_model *m, const double *values, int32_t
 MR_API mr_status mr_model_predict_mat_device(mr_model *m, const double *d_values, int32_t rows, int32_t cols,
                                       double *d_out_scores, void *cuda_stream);
 
+/* The two halves of the binned scorer as separate device-side steps (what mr_model_predict_mat_device
+ * runs back to back when the model can be binned): values -> exact u16 rank codes
+ * ([group of 32 rows][column][lane] layout, mr_model_codes_bytes(rows) bytes), then the tree traversal
+ * on the codes.  mr_model_codes_bytes returns 0 when the model is scored by the f64/f32 kernel
+ * instead (categorical XGBoost splits, zero-as-missing LightGBM nodes, > 4095 columns). */
+MR_API size_t mr_model_codes_bytes(mr_model *m, int32_t rows);
+MR_API mr_status mr_model_bin_device(mr_model *m, const double *d_values, int32_t rows, int32_t cols, void *d_codes,
+                                     void *cuda_stream);
+MR_API mr_status mr_model_score_codes_device(mr_model *m, const void *d_codes, int32_t rows, double *d_out_scores,
+                                             void *cuda_stream);
+
 /* Booster.save(): the original booster bytes (S/ml/rank/LambdaMARTRanker.scala:373).
  * The pointer stays valid until the model is freed. */
 MR_API mr_status mr_model_save(mr_model *m, const uint8_t **blob, size_t *len);

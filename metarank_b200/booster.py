@@ -91,6 +91,18 @@ class B200Booster:
         check(lib().mr_model_predict_mat_device(self._h, C.c_void_p(d_values_ptr), C.c_int32(rows),
                                                 C.c_int32(cols), C.c_void_p(d_out_ptr), C.c_void_p(stream)))
 
+    def codes_bytes(self, rows: int) -> int:
+        lib().mr_model_codes_bytes.restype = C.c_size_t
+        return int(lib().mr_model_codes_bytes(self._h, C.c_int32(rows)))
+
+    def bin_device(self, d_values_ptr: int, rows: int, cols: int, d_codes_ptr: int, stream: int = 0) -> None:
+        check(lib().mr_model_bin_device(self._h, C.c_void_p(d_values_ptr), C.c_int32(rows), C.c_int32(cols),
+                                        C.c_void_p(d_codes_ptr), C.c_void_p(stream)))
+
+    def score_codes_device(self, d_codes_ptr: int, rows: int, d_out_ptr: int, stream: int = 0) -> None:
+        check(lib().mr_model_score_codes_device(self._h, C.c_void_p(d_codes_ptr), C.c_int32(rows),
+                                                C.c_void_p(d_out_ptr), C.c_void_p(stream)))
+
     def save(self) -> bytes:
         p = C.POINTER(C.c_uint8)()
         n = C.c_size_t()

@@ -224,6 +224,38 @@ mr_status mr_model_count_path(mr_model *m, const double *values, int32_t rows, i
   });
 }
 
+size_t mr_model_codes_bytes(mr_model *m, int32_t rows) {
+  if (!m || m->closed.load() || rows <= 0 || !m->use_binned()) return 0;
+  return binned_scratch_bytes(rows, m->host.n_features);
+}
+
+mr_status mr_model_bin_device(mr_model *m, const double *d_values, int32_t rows, int32_t cols, void *d_codes,
+                              void *cuda_stream) {
+  return guard([&] {
+    check_model(m);
+    InflightGuard ig(m);
+    check_matrix(m, d_values, rows, cols, d_codes);
+    if (!m->use_binned()) fail(MR_ERR_UNSUPPORTED, "this model is scored by the f64/f32 kernel, it has no code form");
+    if (rows == 0) return;
+    BinnedLaunch B = m->binned_desc();
+    B.d_values = d_values; B.rows = rows; B.cols = cols; B.d_bins = (uint16_t *)d_codes; B.codes_only = true;
+    launch_gbdt_binned(B, m->ctx->num_sms, (cudaStream_t)cuda_stream);
+  });
+}
+
+mr_status mr_model_score_codes_device(mr_model *m, const void *d_codes, int32_t rows, double *d_out_scores,
+                                      void *cuda_stream) {
+  return guard([&] {
+    check_model(m);
+    InflightGuard ig(m);
+    if (rows < 0) fail(MR_ERR_INVALID_ARG, "negative row count");
+    if (rows > 0 && (!d_codes || !d_out_scores)) fail(MR_ERR_INVALID_ARG, "null pointer");
+    if (!m->use_binned()) fail(MR_ERR_UNSUPPORTED, "this model is scored by the f64/f32 kernel, it has no code form");
+    if (rows == 0) return;
+    m->score_codes((uint16_t *)d_codes, rows, d_out_scores, (cudaStream_t)cuda_stream);
+  });
+}
+
 mr_status mr_model_save(mr_model *m, const uint8_t **blob, size_t *len) {
   return guard([&] {
     check_model(m);

@@ -316,6 +316,72 @@ __global__ void __launch_bounds__(1024) gbdt_score_compact_kernel(const BParams 
   }
 }
 
+// ------------------------------------------------------------------ low-latency path (small batches)
+// A single /rank request is 100 items: one thread per item walking 500 trees is a 100+ us dependent
+// chain on 4 warps of one SM.  For small batches the trees are spread over the chip instead: CTA
+// (chunk c, item group g) walks only chunk c's trees for 128 items and stores every tree's leaf value;
+// a second kernel adds the values per item IN TREE ORDER, so the result is still bit-identical to the
+// sequential sum (a tree-parallel reduction would change the f64 rounding).
+struct LParams {
+  const uint8_t *model;
+  const ChunkDesc *chunks;
+  const uint16_t *bins;
+  double *leafvals;  // [n_trees][rows_padded]
+  double *out;
+  int rows, rows_padded, n_features, n_trees;
+  float base_score;
+};
+
+template <typename Real>
+__global__ void __launch_bounds__(128) gbdt_leaves_kernel(const LParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int F = p.n_features;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+  const ChunkDesc cd = p.chunks[blockIdx.x];
+  uint8_t *cb = smem + 128;
+  uint8_t *xs = cb + ((cd.bytes + 127u) & ~127u);
+  const int n_groups = (p.rows + 31) >> 5;
+  const int g0 = blockIdx.y * 4, g1 = min(n_groups, g0 + 4);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+    const uint32_t tile_bytes = (uint32_t)(g1 - g0) * (uint32_t)F * 64u;
+    mbar_arrive_expect_tx(bar, cd.bytes + tile_bytes);
+    tma_bulk_g2s(cb, p.model + cd.byte_off, cd.bytes, bar);
+    tma_bulk_g2s(xs, p.bins + (size_t)g0 * F * 32, tile_bytes, bar);
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+  if (g0 + warp >= g1) return;
+  const int item = (g0 + warp) * 32 + lane;
+  const uint8_t *xwarp = xs + (size_t)warp * F * 64;
+  const uint32_t lane2 = (uint32_t)lane * 2u;
+  const int ntree = (int)*reinterpret_cast<const uint32_t *>(cb);
+  const uint32_t *roots = reinterpret_cast<const uint32_t *>(cb + 16);
+  for (int t = 0; t < ntree; t++) {
+    uint32_t n = roots[t];
+    while (!(n & 1u)) {
+      const uint2 nd = *reinterpret_cast<const uint2 *>(cb + n);
+      const uint32_t code = *reinterpret_cast<const uint16_t *>(xwarp + ((nd.x & 0xFFC0u) | lane2));
+      const bool left = (code <= (nd.x >> 16)) || (code == kBinNaN && (nd.x & 1u));
+      n = __byte_perm(nd.y, 0u, left ? 0x4410u : 0x4432u);
+    }
+    p.leafvals[(size_t)(cd.first_tree + t) * p.rows_padded + item] = (double)*reinterpret_cast<const Real *>(cb + (n - 1u));
+  }
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(128) gbdt_sum_kernel(const LParams p) {
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= p.rows) return;
+  Real acc = (sizeof(Real) == 4) ? (Real)p.base_score : (Real)0;
+  const double *v = p.leafvals + item;
+#pragma unroll 8
+  for (int t = 0; t < p.n_trees; t++) acc += (Real)v[(size_t)t * p.rows_padded];
+  p.out[item] = (double)acc;
+}
+
 // ------------------------------------------------------------------ free-running ("threaded") traversal
 // Every lane chases its own pointer through the chunk's flat entry array: internal entry ->
 // child entry, leaf entry -> (add value) -> root of the next tree.  No lane ever idles waiting for
@@ -423,6 +489,27 @@ void launch_b_ilp(const BParams &p, int ilp, int threads, size_t smem, int num_s
 
 }  // namespace
 
+void launch_gbdt_latency(const BinnedLaunch &L, int n_trees, double *d_leafvals, cudaStream_t stream) {
+  // L.d_model / d_chunks = the small-chunk compact packing; L.d_bins already holds the codes
+  if (L.rows <= 0) return;
+  LParams p;
+  p.model = L.d_model; p.chunks = L.d_chunks; p.bins = L.d_bins; p.leafvals = d_leafvals; p.out = L.d_out;
+  p.rows = L.rows; p.rows_padded = (L.rows + 127) & ~127; p.n_features = L.n_features; p.n_trees = n_trees;
+  p.base_score = L.base_score;
+  const size_t smem = 128 + ((L.max_chunk_bytes + 127u) & ~127u) + (size_t)4 * L.n_features * 64;
+  dim3 grid((unsigned)L.n_chunks, (unsigned)((L.rows + 127) / 128));
+  auto go = [&](auto leaves, auto sum) {
+    MR_CUDA_CHECK(cudaFuncSetAttribute(leaves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    leaves<<<grid, 128, smem, stream>>>(p);
+    MR_CUDA_CHECK(cudaGetLastError());
+    sum<<<(L.rows + 127) / 128, 128, 0, stream>>>(p);
+    MR_CUDA_CHECK(cudaGetLastError());
+    g_kernel_launches += 2;
+  };
+  if (L.kind == MR_BOOSTER_XGBOOST) go(gbdt_leaves_kernel<float>, gbdt_sum_kernel<float>);
+  else go(gbdt_leaves_kernel<double>, gbdt_sum_kernel<double>);
+}
+
 void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream) {
   if (L.rows <= 0) return;
   const int F = L.n_features;
@@ -441,6 +528,7 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
   g_kernel_launches++;
   }
 
+  if (L.codes_only) return;
   // ---- pass 2: traversal
   BParams p;
   p.model = L.d_model; p.chunks = L.d_chunks; p.bins = L.d_bins; p.out = L.d_out;

@@ -50,6 +50,7 @@ struct BinnedLaunch {
   double *d_out = nullptr;
   uint16_t *d_bins = nullptr;           // scratch: ceil(rows/32) * F * 32 codes
   int threads = 0, ilp = 0;
+  bool codes_only = false;              // run bin_kernel only (no traversal)
   bool codes_ready = false;             // d_bins already holds the codes (fused assemble): skip bin_kernel
   bool compact = false;                 // model bytes are pack_compact() chunks -> fast lock-step kernel
   bool threaded = false;                // model bytes are pack_threaded() chunks -> free-running kernel
@@ -58,6 +59,11 @@ inline size_t binned_scratch_bytes(int rows, int n_features) {
   return (size_t)((rows + 31) / 32) * (size_t)n_features * 32 * sizeof(uint16_t);
 }
 void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream);
+// Low-latency path for small batches: per-tree leaf values spread over (chunk x item-group) CTAs, then an
+// in-order per-item sum.  d_leafvals: n_trees * round_up(rows, 128) doubles of scratch.
+void launch_gbdt_latency(const BinnedLaunch &L, int n_trees, double *d_leafvals, cudaStream_t stream);
+inline size_t latency_scratch_bytes(int rows, int n_trees) { return (size_t)n_trees * (size_t)((rows + 127) & ~127) * 8; }
+constexpr int kLatencyMaxRows = 2048;
 
 extern long long g_kernel_launches;
 

@@ -112,9 +112,9 @@ struct mr_model {
   uint8_t *d_model = nullptr;
   ChunkDesc *d_chunks = nullptr;
   // binned form (exact integer traversal); binned.ok == false -> always the f64/f32 kernel
-  BinnedModel binned, threaded, compact;
-  uint8_t *d_bmodel = nullptr, *d_tmodel = nullptr, *d_cmodel = nullptr;
-  ChunkDesc *d_bchunks = nullptr, *d_tchunks = nullptr, *d_cchunks = nullptr;
+  BinnedModel binned, threaded, compact, lat;  // lat: compact layout in 4 KB chunks for the low-latency path
+  uint8_t *d_bmodel = nullptr, *d_tmodel = nullptr, *d_cmodel = nullptr, *d_lmodel = nullptr;
+  ChunkDesc *d_bchunks = nullptr, *d_tchunks = nullptr, *d_cchunks = nullptr, *d_lchunks = nullptr;
   uint32_t *d_thr_off = nullptr;
   double *d_thr = nullptr;
   uint8_t *d_is_cat = nullptr;
@@ -142,10 +142,11 @@ struct mr_model {
   }
   void free_binned() {
     for (void *p : {(void *)d_bmodel, (void *)d_bchunks, (void *)d_thr_off, (void *)d_thr, (void *)d_is_cat,
-                    (void *)d_tmodel, (void *)d_tchunks, (void *)d_cmodel, (void *)d_cchunks})
+                    (void *)d_tmodel, (void *)d_tchunks, (void *)d_cmodel, (void *)d_cchunks, (void *)d_lmodel,
+                    (void *)d_lchunks})
       if (p) cudaFree(p);
     d_bmodel = nullptr; d_bchunks = nullptr; d_thr_off = nullptr; d_thr = nullptr; d_is_cat = nullptr;
-    d_tmodel = nullptr; d_tchunks = nullptr; d_cmodel = nullptr; d_cchunks = nullptr;
+    d_tmodel = nullptr; d_tchunks = nullptr; d_cmodel = nullptr; d_cchunks = nullptr; d_lmodel = nullptr; d_lchunks = nullptr;
   }
   void repack() {
     // Default policy: stream the ensemble through two small shared-memory buffers (TMA bulk
@@ -173,6 +174,11 @@ struct mr_model {
       if (compact.ok) {
         d_cmodel = to_device(compact.packed.bytes);
         d_cchunks = to_device(compact.packed.chunks);
+      }
+      lat = pack_compact(host, binned, 4 * 1024);
+      if (lat.ok) {
+        d_lmodel = to_device(lat.packed.bytes);
+        d_lchunks = to_device(lat.packed.chunks);
       }
       threaded = pack_threaded(host, binned, budget);
       if (threaded.ok) {
@@ -210,9 +216,23 @@ struct mr_model {
     return B;
   }
   // Scores rows whose u16 codes were already written to d_codes (fused assemble path).
+  bool use_latency(int rows) const {
+    return lat.ok && rows <= kLatencyMaxRows && opt_variant < 0 && opt_threads == 0 &&
+           128 + lat.packed.max_chunk_bytes + 128 + (size_t)4 * host.n_features * 64 <= 200 * 1024;
+  }
   void score_codes(uint16_t *d_codes, int rows, double *d_out, cudaStream_t stream) const {
     BinnedLaunch B = binned_desc();
     B.rows = rows; B.cols = host.n_features; B.d_out = d_out; B.d_bins = d_codes; B.codes_ready = true;
+    if (use_latency(rows)) {
+      B.d_model = d_lmodel; B.d_chunks = d_lchunks;
+      B.n_chunks = (int)lat.packed.chunks.size();
+      B.max_chunk_bytes = lat.packed.max_chunk_bytes;
+      void *lv = nullptr;
+      MR_CUDA_CHECK(cudaMallocAsync(&lv, latency_scratch_bytes(rows, (int)host.trees.size()), stream));
+      launch_gbdt_latency(B, (int)host.trees.size(), (double *)lv, stream);
+      MR_CUDA_CHECK(cudaFreeAsync(lv, stream));
+      return;
+    }
     launch_gbdt_binned(B, ctx->num_sms, stream);
   }
   // Enqueue scoring of a device-resident matrix on `stream` with whichever kernel applies.
@@ -223,7 +243,13 @@ struct mr_model {
       void *bins = nullptr;
       MR_CUDA_CHECK(cudaMallocAsync(&bins, std::max<size_t>(binned_scratch_bytes(rows, host.n_features), 16), stream));
       B.d_bins = (uint16_t *)bins;
-      launch_gbdt_binned(B, ctx->num_sms, stream);
+      if (use_latency(rows)) {
+        B.codes_only = true;
+        launch_gbdt_binned(B, ctx->num_sms, stream);
+        score_codes(B.d_bins, rows, d_out, stream);
+      } else {
+        launch_gbdt_binned(B, ctx->num_sms, stream);
+      }
       MR_CUDA_CHECK(cudaFreeAsync(bins, stream));
     } else {
       ScoreLaunch L = launch_desc(d_values, rows, cols, d_out);

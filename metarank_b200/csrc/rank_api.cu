@@ -248,21 +248,40 @@ mr_status mr_state_get_info(mr_state *st, mr_state_info *out) {
 
 namespace {
 
+bool host_pinned(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// Which caller buffers are page-locked (cudaHostAlloc / cudaHostRegister, e.g. a registered direct
+// ByteBuffer): those are DMA'd in place, everything else is staged through the lane's pinned buffer.
+struct PinInfo {
+  bool ids = false, scores = false, order = false, features = false;
+};
+
 // One slice of requests in flight on one lane (stream + pinned staging + device scratch).
 struct RankPending {
   bool active = false;
   int i0 = 0, n = 0;  // first item / item count of the slice
   size_t in_bytes = 0, ho_scores = 0, ho_order = 0, ho_feat = 0, ho_err = 0;
+  PinInfo pin;
 };
 
 void rank_enqueue(mr_state *st, mr_model *model, const mr_rank_batch *b, int r0, int r1, Lane *lane, RankPending &pd,
-                  bool want_order, bool want_features) {
+                  bool want_order, bool want_features, const PinInfo &pin, double *out_scores, int32_t *out_order,
+                  double *out_features) {
   const Schema &S = st->store->schema;
   const int R = r1 - r0, i0 = b->item_offsets[r0], N = b->item_offsets[r1] - i0;
   pd = RankPending{};
   pd.active = true;
   pd.i0 = i0;
   pd.n = N;
+  pd.pin = pin;
   // ---- pack the slice into one pinned blob -> one H2D copy
   struct Seg { const void *src; size_t bytes, off; };
   Seg segs[9];
@@ -287,13 +306,21 @@ void rank_enqueue(mr_state *st, mr_model *model, const mr_rank_batch *b, int r0,
   const size_t out_bytes = al((size_t)N * 8) + al((size_t)N * 4) + (want_features ? al((size_t)N * S.dim * 8) : 0) + 16;
   lane->ensure(in_bytes + out_bytes, d_total);
   for (int k = 0; k < ns; k++)
-    if (segs[k].bytes) memcpy(lane->h_pinned + segs[k].off, segs[k].src, segs[k].bytes);
+    if (segs[k].bytes && !(k == s_ids && pin.ids)) memcpy(lane->h_pinned + segs[k].off, segs[k].src, segs[k].bytes);
   if (i0 != 0) {  // rebase the slice's offsets to start at 0
     int32_t *o = (int32_t *)(lane->h_pinned + segs[s_off].off);
     for (int r = 0; r <= R; r++) o[r] -= i0;
   }
   uint8_t *d_in = lane->d_buf, *scratch = lane->d_buf + al(in_bytes);
-  MR_CUDA_CHECK(cudaMemcpyAsync(d_in, lane->h_pinned, in_bytes, cudaMemcpyHostToDevice, lane->stream));
+  if (pin.ids) {
+    // ids are the bulk of the request: DMA them straight from the caller's page-locked buffer
+    if (segs[s_ids].off) MR_CUDA_CHECK(cudaMemcpyAsync(d_in, lane->h_pinned, segs[s_ids].off, cudaMemcpyHostToDevice, lane->stream));
+    MR_CUDA_CHECK(cudaMemcpyAsync(d_in + segs[s_ids].off, segs[s_ids].src, segs[s_ids].bytes, cudaMemcpyHostToDevice, lane->stream));
+    const size_t after = segs[s_ids].off + al(segs[s_ids].bytes);
+    if (in_bytes > after) MR_CUDA_CHECK(cudaMemcpyAsync(d_in + after, lane->h_pinned + after, in_bytes - after, cudaMemcpyHostToDevice, lane->stream));
+  } else {
+    MR_CUDA_CHECK(cudaMemcpyAsync(d_in, lane->h_pinned, in_bytes, cudaMemcpyHostToDevice, lane->stream));
+  }
   auto dp = [&](int si) -> const void * { return segs[si].bytes ? d_in + segs[si].off : nullptr; };
   RankArgs a{};
   fill_args(a, st, scratch, sp);
@@ -321,14 +348,18 @@ void rank_enqueue(mr_state *st, mr_model *model, const mr_rank_batch *b, int r0,
     if (fused) model->score_codes(a.codes, N, d_scores, lane->stream);
     else model->score(a.out_features, N, S.dim, d_scores, lane->stream);
     if (want_order) launch_rank_order(d_scores, a.item_offsets, R, N, d_order, lane->stream);
-    MR_CUDA_CHECK(cudaMemcpyAsync(h_out + ho, d_scores, (size_t)N * 8, cudaMemcpyDeviceToHost, lane->stream));
+    MR_CUDA_CHECK(cudaMemcpyAsync(pin.scores ? (void *)(out_scores + i0) : (void *)(h_out + ho), d_scores, (size_t)N * 8,
+                                  cudaMemcpyDeviceToHost, lane->stream));
   }
   pd.ho_scores = ho; ho += al((size_t)N * 8);
-  if (model && want_order) MR_CUDA_CHECK(cudaMemcpyAsync(h_out + ho, d_order, (size_t)N * 4, cudaMemcpyDeviceToHost, lane->stream));
+  if (model && want_order)
+    MR_CUDA_CHECK(cudaMemcpyAsync(pin.order ? (void *)(out_order + i0) : (void *)(h_out + ho), d_order, (size_t)N * 4,
+                                  cudaMemcpyDeviceToHost, lane->stream));
   pd.ho_order = ho; ho += al((size_t)N * 4);
   pd.ho_feat = ho;
   if (want_features) {
-    MR_CUDA_CHECK(cudaMemcpyAsync(h_out + ho, a.out_features, (size_t)N * S.dim * 8, cudaMemcpyDeviceToHost, lane->stream));
+    MR_CUDA_CHECK(cudaMemcpyAsync(pin.features ? (void *)(out_features + (size_t)i0 * S.dim) : (void *)(h_out + ho),
+                                  a.out_features, (size_t)N * S.dim * 8, cudaMemcpyDeviceToHost, lane->stream));
     ho += al((size_t)N * S.dim * 8);
   }
   pd.ho_err = ho;
@@ -346,9 +377,9 @@ int32_t rank_finish(mr_state *st, mr_model *model, Lane *lane, RankPending &pd, 
   int32_t err;
   memcpy(&err, h_out + pd.ho_err, 4);
   if (err != 0) return err;
-  if (model && out_scores) memcpy(out_scores + pd.i0, h_out + pd.ho_scores, (size_t)pd.n * 8);
-  if (model && out_order) memcpy(out_order + pd.i0, h_out + pd.ho_order, (size_t)pd.n * 4);
-  if (out_features) memcpy(out_features + (size_t)pd.i0 * S.dim, h_out + pd.ho_feat, (size_t)pd.n * S.dim * 8);
+  if (model && out_scores && !pd.pin.scores) memcpy(out_scores + pd.i0, h_out + pd.ho_scores, (size_t)pd.n * 8);
+  if (model && out_order && !pd.pin.order) memcpy(out_order + pd.i0, h_out + pd.ho_order, (size_t)pd.n * 4);
+  if (out_features && !pd.pin.features) memcpy(out_features + (size_t)pd.i0 * S.dim, h_out + pd.ho_feat, (size_t)pd.n * S.dim * 8);
   return 0;
 }
 
@@ -389,6 +420,13 @@ mr_status mr_rank(mr_state *st, mr_model *model, const mr_rank_batch *b, double 
     for (int r = 1; r <= R; r++)
       if (r == R || b->item_offsets[r + 1] - b->item_offsets[cuts.back()] > kSliceItems) cuts.push_back(r);
     const int n_slices = (int)cuts.size() - 1;
+    PinInfo pin;
+    if (N >= 4096) {  // only worth four driver queries for sizeable batches
+      pin.ids = host_pinned(b->item_ids);
+      pin.scores = model && host_pinned(out_scores);
+      pin.order = model && out_order && host_pinned(out_order);
+      pin.features = out_features && host_pinned(out_features);
+    }
     for (int attempt = 0;; attempt++) {
       LaneGuard lane0(st->ctx);
       std::unique_ptr<LaneGuard> lane1;
@@ -400,7 +438,8 @@ mr_status mr_rank(mr_state *st, mr_model *model, const mr_rank_batch *b, double 
         const int l = sidx & 1;
         err = rank_finish(st, model, lanes[l], pend[l], out_scores, out_order, out_features);
         if (err) break;
-        rank_enqueue(st, model, b, cuts[sidx], cuts[sidx + 1], lanes[l], pend[l], out_order != nullptr, out_features != nullptr);
+        rank_enqueue(st, model, b, cuts[sidx], cuts[sidx + 1], lanes[l], pend[l], out_order != nullptr, out_features != nullptr,
+                     pin, out_scores, out_order, out_features);
       }
       for (int l = 0; l < 2; l++) {
         const int32_t e = rank_finish(st, model, lanes[l], pend[l], out_scores, out_order, out_features);

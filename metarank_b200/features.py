@@ -272,15 +272,18 @@ class Ranker:
     def __init__(self, mapping: FeatureMapping, state: DeviceState):
         self.mapping, self.state = mapping, state
 
-    def rank_arrays(self, arrays: dict, model=None, want_order=True, want_features=False):
-        """mr_rank on already-packed arrays; returns (scores, order, features)."""
+    def rank_arrays(self, arrays: dict, model=None, want_order=True, want_features=False, out_scores=None,
+                    out_order=None):
+        """mr_rank on already-packed arrays; returns (scores, order, features).  out_scores / out_order may be
+        caller-provided (e.g. page-locked) numpy arrays; page-locked buffers are DMA'd in place."""
         N = arrays["total_items"]
         b = RankBatch(arrays["n_requests"], arrays["offsets"].ctypes.data, arrays["ids"].ctypes.data,
                       arrays["users"].ctypes.data, arrays["sessions"].ctypes.data, arrays["req_f64"].ctypes.data,
                       arrays["req_u64"].ctypes.data, arrays["req_vec"].ctypes.data, arrays["req_vp"].ctypes.data,
                       arrays["item_f64"].ctypes.data if arrays["item_f64"] is not None else None)
-        scores = np.empty(max(N, 1), dtype=np.float64)
-        order = np.empty(max(N, 1), dtype=np.int32) if want_order and model is not None else None
+        scores = out_scores if out_scores is not None else np.empty(max(N, 1), dtype=np.float64)
+        order = (out_order if out_order is not None else np.empty(max(N, 1), dtype=np.int32)) \
+            if want_order and model is not None else None
         feats = np.empty((max(N, 1), max(self.mapping.dim, 1)), dtype=np.float64) if want_features else None
         check(lib().mr_rank(self.state._h, model._h if model is not None else None, C.byref(b),
                             C.c_void_p(scores.ctypes.data),

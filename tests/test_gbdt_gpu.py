@@ -127,8 +127,19 @@ def test_c4_xgboost(ctx, fmt, depth, full):
     gen = synth.xgboost_model_json if fmt == "json" else synth.xgboost_model_ubj
     blob = gen(200, 16, depth=depth, seed=1234 + 4, full=full)
     X = synth.feature_matrix(256, 16, seed=42 + 4)
-    for variant in (0, 1, 2, 3, 4):
+    for variant in (-1, 0, 1, 2, 3, 4):  # -1 on 256 rows = the low-latency tree-parallel path
         _check(ctx, 1, blob, X, variant=variant)
+
+
+def test_low_latency_path_small_batches(ctx):
+    """<= 2048 rows in auto mode: per-tree leaf values over (chunk x group) CTAs + in-order sum."""
+    blob = synth.lightgbm_model_text(500, 30, seed=41, stump_every=13)
+    for rows in (1, 100, 129, 2048, 2049):
+        X = synth.feature_matrix(rows, 30, seed=rows)
+        _check(ctx, 0, blob, X)
+    xb = synth.xgboost_model_ubj(120, 9, depth=7, seed=42, full=False)
+    for rows in (3, 100, 1000):
+        _check(ctx, 1, xb, synth.feature_matrix(rows, 9, seed=rows))
 
 
 def test_xgboost_f32_rounding_of_inputs(ctx):
