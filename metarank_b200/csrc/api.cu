@@ -60,6 +60,15 @@ mr_status mr_init(int32_t device, mr_ctx **out) {
     if (prop.major != 10)
       fail(MR_ERR_NO_DEVICE, "device %d is sm_%d%d; libmrgpu is built for sm_100a only", device, prop.major, prop.minor);
     MR_CUDA_CHECK(cudaSetDevice(device));
+    {  // stream-ordered scratch (cudaMallocAsync) must never give memory back to the OS mid-serving:
+       // a trim at a synchronisation point shows up as a multi-millisecond latency spike
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
+    }
     auto ctx = std::make_unique<mr_ctx>();
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;

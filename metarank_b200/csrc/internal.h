@@ -220,17 +220,21 @@ struct mr_model {
     return lat.ok && rows <= kLatencyMaxRows && opt_variant < 0 && opt_threads == 0 &&
            128 + lat.packed.max_chunk_bytes + 128 + (size_t)4 * host.n_features * 64 <= 200 * 1024;
   }
-  void score_codes(uint16_t *d_codes, int rows, double *d_out, cudaStream_t stream) const {
+  void score_codes(uint16_t *d_codes, int rows, double *d_out, cudaStream_t stream, void *d_leaf_scratch = nullptr) const {
     BinnedLaunch B = binned_desc();
     B.rows = rows; B.cols = host.n_features; B.d_out = d_out; B.d_bins = d_codes; B.codes_ready = true;
     if (use_latency(rows)) {
       B.d_model = d_lmodel; B.d_chunks = d_lchunks;
       B.n_chunks = (int)lat.packed.chunks.size();
       B.max_chunk_bytes = lat.packed.max_chunk_bytes;
-      void *lv = nullptr;
-      MR_CUDA_CHECK(cudaMallocAsync(&lv, latency_scratch_bytes(rows, (int)host.trees.size()), stream));
-      launch_gbdt_latency(B, (int)host.trees.size(), (double *)lv, stream);
-      MR_CUDA_CHECK(cudaFreeAsync(lv, stream));
+      if (d_leaf_scratch) {
+        launch_gbdt_latency(B, (int)host.trees.size(), (double *)d_leaf_scratch, stream);
+      } else {
+        void *lv = nullptr;
+        MR_CUDA_CHECK(cudaMallocAsync(&lv, latency_scratch_bytes(rows, (int)host.trees.size()), stream));
+        launch_gbdt_latency(B, (int)host.trees.size(), (double *)lv, stream);
+        MR_CUDA_CHECK(cudaFreeAsync(lv, stream));
+      }
       return;
     }
     launch_gbdt_binned(B, ctx->num_sms, stream);

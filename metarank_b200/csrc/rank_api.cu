@@ -38,12 +38,12 @@ namespace {
 inline size_t al(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct ScratchPlan {
-  size_t item_req, item_row, visitor_row, cos, reqagg, hist_desc, hist_pool, hist_cursor, error_flag, features, codes, total;
+  size_t item_req, item_row, visitor_row, cos, reqagg, hist_desc, hist_pool, hist_cursor, error_flag, features, codes, leafvals, total;
   uint32_t hist_pool_cap;
 };
 
 ScratchPlan plan_scratch(const Schema &S, int n_requests, int total_items, uint32_t per_hist, bool own_features,
-                         bool want_codes = false) {
+                         bool want_codes = false, size_t leaf_bytes = 0) {
   ScratchPlan p{};
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += al(bytes); return r; };
@@ -63,6 +63,7 @@ ScratchPlan plan_scratch(const Schema &S, int n_requests, int total_items, uint3
   p.error_flag = take(4);
   p.features = own_features ? take((size_t)total_items * std::max(S.dim, 1) * 8) : 0;
   p.codes = want_codes ? take(binned_scratch_bytes(total_items, std::max(S.dim, 1))) : 0;
+  p.leafvals = leaf_bytes ? take(leaf_bytes) : 0;
   p.total = o;
   return p;
 }
@@ -300,7 +301,8 @@ void rank_enqueue(mr_state *st, mr_model *model, const mr_rank_batch *b, int r0,
   const int s_if = seg(b->item_f64 ? b->item_f64 + (size_t)i0 * nif : nullptr, (size_t)N * nif * 8);
 
   const bool fused = fused_codes(model);
-  ScratchPlan sp = plan_scratch(S, R, N, st->hist_pool_per_hist, want_features || !fused, fused);
+  const size_t leaf_bytes = (fused && model->use_latency(N)) ? latency_scratch_bytes(N, (int)model->host.trees.size()) : 0;
+  ScratchPlan sp = plan_scratch(S, R, N, st->hist_pool_per_hist, want_features || !fused, fused, leaf_bytes);
   const size_t scores_off = al(in_bytes) + sp.total, order_off = scores_off + al((size_t)N * 8);
   const size_t d_total = order_off + al((size_t)N * 4);
   const size_t out_bytes = al((size_t)N * 8) + al((size_t)N * 4) + (want_features ? al((size_t)N * S.dim * 8) : 0) + 16;
@@ -345,7 +347,7 @@ void rank_enqueue(mr_state *st, mr_model *model, const mr_rank_batch *b, int r0,
   size_t ho = 0;
   pd.in_bytes = in_bytes;
   if (model) {
-    if (fused) model->score_codes(a.codes, N, d_scores, lane->stream);
+    if (fused) model->score_codes(a.codes, N, d_scores, lane->stream, leaf_bytes ? scratch + sp.leafvals : nullptr);
     else model->score(a.out_features, N, S.dim, d_scores, lane->stream);
     if (want_order) launch_rank_order(d_scores, a.item_offsets, R, N, d_order, lane->stream);
     MR_CUDA_CHECK(cudaMemcpyAsync(pin.scores ? (void *)(out_scores + i0) : (void *)(h_out + ho), d_scores, (size_t)N * 8,
