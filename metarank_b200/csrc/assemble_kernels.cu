@@ -513,12 +513,11 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
     double *row;
     uint16_t *codes;
     const BinParams *bp;
-    double *tile;  // shared-memory staging [col][thread]; null when the row is too wide to stage
     __device__ __forceinline__ void operator()(int col, double v) const {
-      if (tile) { tile[col * 128] = v; return; }
       if (row) row[col] = v;
       if (codes) codes[(size_t)col * 32] = code_of(*bp, col, v);
     }
+    __device__ __forceinline__ Emit &self() { return *this; }
   };
   struct OutProxy {  // lets the extractor code below keep writing out[col] = v
     const Emit *e; int col;
@@ -528,12 +527,8 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
     const Emit *e;
     __device__ __forceinline__ OutProxy operator[](int col) const { return OutProxy{e, col}; }
   };
-  // values are first gathered into a shared-memory column tile; the second pass below (uniform, branch
-  // free) turns them into codes / row stores, so several binary searches are in flight per thread
-  double *tile = a.stage_tile ? reinterpret_cast<double *>(s_plan_raw + ((a.n_plan * sizeof(DFeature) + 15) & ~size_t(15))) + threadIdx.x
-                              : nullptr;
   const Emit emit{a.out_features ? a.out_features + (size_t)i * a.dim : nullptr,
-                  a.codes ? a.codes + ((size_t)(i >> 5) * a.dim) * 32 + (i & 31) : nullptr, &a.bin, tile};
+                  a.codes ? a.codes + ((size_t)(i >> 5) * a.dim) * 32 + (i & 31) : nullptr, &a.bin};
   const OutArr out{&emit};
 
   auto scoped_row = [&](int scope) -> const uint64_t * {
@@ -676,20 +671,6 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
         break;
     }
   }
-  if (tile) {
-    double *row = emit.row;
-    uint16_t *codes = emit.codes;
-    if (codes) {
-#pragma unroll 4
-      for (int col = 0; col < a.dim; col++) {
-        const double v = tile[col * 128];
-        if (row) row[col] = v;
-        codes[(size_t)col * 32] = code_of(a.bin, col, v);
-      }
-    } else {
-      for (int col = 0; col < a.dim; col++) row[col] = tile[col * 128];
-    }
-  }
 }
 
 // ------------------------------------------------------------------ ordering
@@ -731,16 +712,7 @@ void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t strea
     MR_CUDA_CHECK(cudaGetLastError());
     g_kernel_launches++;
   }
-  {
-    RankArgs b = a;
-    const size_t plan_bytes = ((size_t)std::max(a.n_plan, 1) * sizeof(DFeature) + 15) & ~size_t(15);
-    const size_t tile_bytes = (size_t)a.dim * 128 * sizeof(double);
-    b.stage_tile = tile_bytes > 0 && plan_bytes + tile_bytes <= 96 * 1024;
-    const size_t smem = plan_bytes + (b.stage_tile ? tile_bytes : 0);
-    if (smem > 48 * 1024)
-      MR_CUDA_CHECK(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    assemble_kernel<<<(a.total_items + 127) / 128, 128, smem, stream>>>(b);
-  }
+  assemble_kernel<<<(a.total_items + 127) / 128, 128, (size_t)std::max(a.n_plan, 1) * sizeof(DFeature), stream>>>(a);
   MR_CUDA_CHECK(cudaGetLastError());
   g_kernel_launches++;
 }
