@@ -505,6 +505,11 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
   const uint32_t ir = a.item_row[i];
   const DTable &IT = a.st.t[SC_ITEM];
   const uint64_t *irow = ir != kNoRow ? row_ptr(IT, ir) : nullptr;
+  if (irow) {
+    // the extractors below touch the row word by word; without this each of its 32-byte sectors
+    // is a separate, serialised HBM miss.  Pull the whole row towards L2/L1 at once.
+    for (int w = 0; w < IT.row_words; w += 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(irow + w));
+  }
   const double *ov = a.item_f64 ? a.item_f64 + (size_t)i * a.n_item_f64 : nullptr;
   const double kNaN = nan_d();
   // One assembled value: the dense f64 row (explain / f64 scorer) and/or its exact u16 rank code for
