@@ -14,6 +14,8 @@ struct BinParams {
   const uint32_t *thr_off;
   const double *thr;
   const uint8_t *is_cat;
+  const BinMeta *meta;           // [n_features] monotone bucket index (see gbdt_model.h)
+  const uint16_t *bucket_start;
   uint16_t *bins;
   int rows, cols, n_features;
   int xgb;  // 1: round to binary32 first, strict less (upper_bound)
@@ -28,9 +30,16 @@ __device__ __forceinline__ uint16_t code_of(const BinParams &p, int f, double x)
     const int iv = in_range ? __double2int_rz(x) : -1;
     return (iv >= 0 && iv < 65000) ? (uint16_t)iv : kBinNaN;
   }
-  const uint32_t b = __ldg(p.thr_off + f), e = __ldg(p.thr_off + f + 1);
-  uint32_t lo = 0, hi = e - b;
-  const double *t = p.thr + b;
+  // bucket(x) is monotone, so only the thresholds in x's own bucket need comparing
+  const BinMeta M = p.meta[f];
+  uint32_t bk = 0;
+  if (M.g > 1 && x > M.mn) {
+    const double v = __dmul_rn(__dadd_rn(x, -M.mn), M.scale);
+    bk = v >= (double)(M.g - 1) ? M.g - 1 : (uint32_t)v;
+  }
+  const uint16_t *bs = p.bucket_start + M.idx_off + bk;
+  uint32_t lo = __ldg(bs), hi = __ldg(bs + 1);
+  const double *t = p.thr + __ldg(p.thr_off + f);
   if (p.xgb) {
     while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__ldg(t + m) <= x) lo = m + 1; else hi = m; }  // #{t <= x}
   } else {

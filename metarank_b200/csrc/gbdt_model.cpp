@@ -431,6 +431,32 @@ BinnedModel pack_binned(const HostModel &m, size_t chunk_budget) {
     B.thr_off[f + 1] = B.thr_off[f] + (uint32_t)v.size();
     B.thr.insert(B.thr.end(), v.begin(), v.end());
   }
+  // bucket index per column (see BinMeta)
+  B.meta.resize(F);
+  for (int f = 0; f < F; f++) {
+    const double *t = B.thr.data() + B.thr_off[f];
+    const uint32_t mth = B.thr_off[f + 1] - B.thr_off[f];
+    BinMeta &M = B.meta[f];
+    M.mn = 0.0; M.scale = 0.0; M.g = 1; M.idx_off = (uint32_t)B.bucket_start.size();
+    if (mth >= 2 && std::isfinite(t[0]) && std::isfinite(t[mth - 1])) {
+      const double span = t[mth - 1] - t[0];
+      const uint32_t g = std::min<uint32_t>(4 * mth, 32768);
+      const double scale = (double)g / span;
+      if (std::isfinite(span) && span > 0 && std::isfinite(scale) && std::isfinite(span * scale)) {
+        M.mn = t[0]; M.scale = scale; M.g = g;
+      }
+    }
+    auto bucket = [&](double x) -> uint32_t {
+      if (M.g == 1 || x <= M.mn) return 0;
+      const double v = (x - M.mn) * M.scale;
+      return v >= (double)(M.g - 1) ? M.g - 1 : (uint32_t)v;
+    };
+    // prefix counts: bucket_start[b] = #{j : bucket(t_j) < b}
+    std::vector<uint32_t> cnt(M.g + 1, 0);
+    for (uint32_t j = 0; j < mth; j++) cnt[bucket(t[j]) + 1]++;
+    for (uint32_t b = 0; b < M.g; b++) cnt[b + 1] += cnt[b];
+    for (uint32_t b = 0; b <= M.g; b++) B.bucket_start.push_back((uint16_t)cnt[b]);
+  }
   const bool f32 = m.kind == MR_BOOSTER_XGBOOST;
   const size_t leaf_sz = f32 ? 4 : 8;
   struct BNodeHost { uint16_t k, ff; int16_t left, right; };
@@ -522,6 +548,8 @@ BinnedModel pack_threaded(const HostModel &m, const BinnedModel &bn, size_t chun
   T.thr_off = bn.thr_off;
   T.thr = bn.thr;
   T.is_cat = bn.is_cat;
+  T.meta = bn.meta;
+  T.bucket_start = bn.bucket_start;
   const bool f32 = m.kind == MR_BOOSTER_XGBOOST;
   struct Entry { uint16_t k, ff; uint16_t left, right; };
   static_assert(sizeof(Entry) == 8, "entry must be 8 bytes");
@@ -592,6 +620,8 @@ BinnedModel pack_compact(const HostModel &m, const BinnedModel &bn, size_t chunk
   C.thr_off = bn.thr_off;
   C.thr = bn.thr;
   C.is_cat = bn.is_cat;
+  C.meta = bn.meta;
+  C.bucket_start = bn.bucket_start;
   const bool f32 = m.kind == MR_BOOSTER_XGBOOST;
   chunk_budget = std::min<size_t>(chunk_budget, 65536 - 16);
   auto tree_bytes = [](const HostTree &t) { return (t.feat.size() + t.leaf.size()) * 8; };

@@ -98,10 +98,21 @@ PackedModel pack_model(const HostModel &m, size_t chunk_budget);
 enum : uint32_t { BF_NAN_LEFT = 1u, BF_CATEGORICAL = 8u };
 constexpr uint16_t kBinNaN = 0xFFFFu;
 
+// Per-column bucket index that replaces most of the binary search: bucket(x) is a MONOTONE function of
+// x, so every threshold in a lower bucket is < x and every threshold in a higher bucket is > x; only
+// the thresholds sharing x's bucket (usually 0-2) are compared.  Exact for `<` and `<=` alike.
+struct BinMeta {
+  double mn, scale;   // bucket(x) = x <= mn ? 0 : min(g - 1, (int)((x - mn) * scale))
+  uint32_t g;         // number of buckets (>= 1)
+  uint32_t idx_off;   // offset of this column's g + 1 prefix counts in `bucket_start`
+};
+
 struct BinnedModel {
   bool ok = false;                 // false: model cannot be binned exactly -> use the f64/f32 kernel
   std::vector<uint32_t> thr_off;   // [n_features + 1] offsets into thr (numerical) per feature
   std::vector<double> thr;         // sorted distinct thresholds, all features back to back
+  std::vector<BinMeta> meta;       // [n_features]
+  std::vector<uint16_t> bucket_start;
   std::vector<uint8_t> is_cat;     // [n_features] feature is split categorically
   PackedModel packed;              // chunks of BNodes (+ leaves, + categorical tables)
 };
