@@ -276,3 +276,42 @@ def test_large_batch_is_sliced_and_pipelined(ctx):
     for r in rng.integers(0, R, 50):
         assert np.array_equal(order[offs[r]:offs[r + 1]], oracle.rank_order(want[offs[r]:offs[r + 1]]))
     booster.free(); ds.free(); fm.free()
+
+
+def test_sharded_scorer_world1_matches_direct(ctx):
+    """metarank_b200/sharded.py with the CUDA slice scorer (single process: the gather is the identity)."""
+    import metarank_b200 as mb
+    from metarank_b200 import features as F, sharded
+
+    names = [f"f{j}" for j in range(12)]
+    fm = F.FeatureMapping(ctx, [dict(name=n, type="number", scope="item", source=f"metadata.{n}") for n in names], names)
+    ds = F.DeviceState(ctx, fm)
+    cat = synth.feature_matrix(3000, 12, seed=9)
+    ids = np.arange(1, 3001, dtype=np.uint64) * np.uint64(40503)
+    ds.put_packed(F.pack_number_columns(names, ids, cat)); ds.flush()
+    blob = synth.lightgbm_model_text(300, 12, seed=10)
+    booster = mb.LightGBMBooster(ctx, blob)
+    req = dict(event="ranking", id="mega", timestamp=0, user=None, session=None, fields=[],
+               items=[dict(id=None, fields=[]) for _ in range(2500)])
+    # the mapping packs ids by hashing strings; feed hashes directly instead
+    rk = F.Ranker(fm, ds)
+    pick = np.random.Generator(np.random.PCG64(3)).choice(3000, 2500, replace=False)
+    arrays = dict(offsets=np.array([0, 2500], dtype=np.int32), ids=ids[pick], users=np.zeros(1, dtype=np.uint64),
+                  sessions=np.zeros(1, dtype=np.uint64), req_f64=np.zeros((1, 1)), req_u64=np.zeros((1, 1), dtype=np.uint64),
+                  req_vec=np.zeros((1, 1), dtype=np.float32), req_vp=np.zeros((1, 1), dtype=np.uint8), item_f64=None,
+                  n_requests=1, total_items=2500)
+    import torch
+
+    _, _, feats = rk.rank_arrays(arrays, None, want_order=False, want_features=True)
+    d_feat = torch.from_numpy(np.ascontiguousarray(feats)).cuda()
+
+    def score_slice(lo, hi):
+        out = torch.empty(hi - lo, dtype=torch.float64, device="cuda")
+        booster.predict_device(d_feat.data_ptr() + lo * 12 * 8, hi - lo, 12, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        return out
+
+    scores, order = sharded.ShardedScorer(score_slice, ctx.rank_order).rerank(2500)
+    want = oracle.OracleBooster(0, blob).predictMat(cat[pick], 2500, 12)
+    assert _eq(scores, want) and np.array_equal(order, oracle.rank_order(want))
+    del req
+    booster.free(); ds.free(); fm.free()
