@@ -66,23 +66,26 @@ class ShardedScorer:
         return scores_h, self.order_fn(scores_h)
 
 
-def cuda_slice_scorer(ctx, ranker, booster, request):
-    """score_slice for the CUDA path: assemble the whole request on this GPU, score only [lo, hi)."""
+def cuda_slice_scorer(ranker, booster, arrays):
+    """score_slice for the CUDA path, everything device-resident: assemble the whole request on this
+    GPU (mr_rank_device with model = NULL -> dense matrix in HBM), score only rows [lo, hi)."""
     import torch
 
     from . import features as F
 
-    arrays = ranker.mapping.pack_requests([request])
     n, dim = arrays["total_items"], ranker.mapping.dim
-    _, _, feats = ranker.rank_arrays(arrays, None, want_order=False, want_features=True)
-    d_feat = torch.from_numpy(np.ascontiguousarray(feats)).cuda()
+    dev = {k: torch.from_numpy(np.ascontiguousarray(v).view(np.int64) if v.dtype == np.uint64 else np.ascontiguousarray(v)).cuda()
+           for k, v in arrays.items() if isinstance(v, np.ndarray)}
+    d_feat = torch.empty(max(n * dim, 1), dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    F.rank_device(ranker.state, None, arrays["n_requests"], n, dev["offsets"].data_ptr(), dev["ids"].data_ptr(), 0, 0,
+                  d_feat.data_ptr(), stream, dev["users"].data_ptr(), dev["sessions"].data_ptr())
 
     def score_slice(lo, hi):
         out = torch.empty(max(hi - lo, 0), dtype=torch.float64, device="cuda")
         if hi > lo:
-            st = torch.cuda.current_stream().cuda_stream
-            booster.predict_device(d_feat.data_ptr() + lo * dim * 8, hi - lo, dim, out.data_ptr(), st)
+            booster.predict_device(d_feat.data_ptr() + lo * dim * 8, hi - lo, dim, out.data_ptr(), stream)
         return out
 
-    _ = F  # (kept for symmetry with the device-batch API)
+    score_slice.keepalive = (dev, d_feat)
     return score_slice, n

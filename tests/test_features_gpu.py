@@ -300,16 +300,8 @@ def test_sharded_scorer_world1_matches_direct(ctx):
                   sessions=np.zeros(1, dtype=np.uint64), req_f64=np.zeros((1, 1)), req_u64=np.zeros((1, 1), dtype=np.uint64),
                   req_vec=np.zeros((1, 1), dtype=np.float32), req_vp=np.zeros((1, 1), dtype=np.uint8), item_f64=None,
                   n_requests=1, total_items=2500)
-    import torch
-
-    _, _, feats = rk.rank_arrays(arrays, None, want_order=False, want_features=True)
-    d_feat = torch.from_numpy(np.ascontiguousarray(feats)).cuda()
-
-    def score_slice(lo, hi):
-        out = torch.empty(hi - lo, dtype=torch.float64, device="cuda")
-        booster.predict_device(d_feat.data_ptr() + lo * 12 * 8, hi - lo, 12, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
-        return out
-
+    score_slice, n = sharded.cuda_slice_scorer(rk, booster, arrays)
+    assert n == 2500
     scores, order = sharded.ShardedScorer(score_slice, ctx.rank_order).rerank(2500)
     want = oracle.OracleBooster(0, blob).predictMat(cat[pick], 2500, 12)
     assert _eq(scores, want) and np.array_equal(order, oracle.rank_order(want))

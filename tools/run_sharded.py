@@ -30,14 +30,8 @@ arrays = dict(offsets=np.array([0, NI], dtype=np.int32), ids=ids[pick], users=np
               n_requests=1, total_items=NI)
 
 def one():
-    _, _, feats = rk.rank_arrays(arrays, None, want_order=False, want_features=True)   # every rank: full assembly
-    d_feat = torch.from_numpy(np.ascontiguousarray(feats)).cuda()
-    def score_slice(lo, hi):
-        out = torch.empty(max(hi - lo, 0), dtype=torch.float64, device="cuda")
-        if hi > lo:
-            booster.predict_device(d_feat.data_ptr() + lo * NF * 8, hi - lo, NF, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
-        return out
-    return sharded.ShardedScorer(score_slice, ctx.rank_order).rerank(NI)
+    score_slice, n = sharded.cuda_slice_scorer(rk, booster, arrays)   # every rank: full assembly on device
+    return sharded.ShardedScorer(score_slice, ctx.rank_order).rerank(n)
 
 for _ in range(3): scores, order = one()
 torch.cuda.synchronize()
