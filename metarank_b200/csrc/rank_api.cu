@@ -432,21 +432,23 @@ mr_status mr_rank(mr_state *st, mr_model *model, const mr_rank_batch *b, double 
       pin.features = out_features && host_pinned(out_features);
     }
     for (int attempt = 0;; attempt++) {
-      LaneGuard lane0(st->ctx);
-      std::unique_ptr<LaneGuard> lane1;
-      if (n_slices > 1) lane1 = std::make_unique<LaneGuard>(st->ctx);
-      Lane *lanes[2] = {lane0.lane.get(), lane1 ? lane1->lane.get() : lane0.lane.get()};
-      RankPending pend[2];
+      // up to kLanes slices in flight: while the GPU works on some, the host packs / unpacks others
+      constexpr int kLanes = 4;
+      const int n_lanes = std::min(kLanes, n_slices);
+      std::vector<std::unique_ptr<LaneGuard>> guards;
+      for (int l = 0; l < n_lanes; l++) guards.push_back(std::make_unique<LaneGuard>(st->ctx));
+      RankPending pend[kLanes];
       int32_t err = 0;
       for (int sidx = 0; sidx < n_slices && err == 0; sidx++) {
-        const int l = sidx & 1;
-        err = rank_finish(st, model, lanes[l], pend[l], out_scores, out_order, out_features);
+        const int l = sidx % n_lanes;
+        Lane *ln = guards[l]->lane.get();
+        err = rank_finish(st, model, ln, pend[l], out_scores, out_order, out_features);
         if (err) break;
-        rank_enqueue(st, model, b, cuts[sidx], cuts[sidx + 1], lanes[l], pend[l], out_order != nullptr, out_features != nullptr,
+        rank_enqueue(st, model, b, cuts[sidx], cuts[sidx + 1], ln, pend[l], out_order != nullptr, out_features != nullptr,
                      pin, out_scores, out_order, out_features);
       }
-      for (int l = 0; l < 2; l++) {
-        const int32_t e = rank_finish(st, model, lanes[l], pend[l], out_scores, out_order, out_features);
+      for (int l = 0; l < n_lanes; l++) {
+        const int32_t e = rank_finish(st, model, guards[l]->lane.get(), pend[l], out_scores, out_order, out_features);
         if (!err) err = e;
       }
       if (err == -1 && attempt < 6) {  // tag-multiset pool too small: grow and redo the batch
