@@ -186,7 +186,8 @@ MR_API int32_t mr_token_count(const char *utf8, size_t len);
  * model's `features:` list.  The dense column layout is DatasetDescriptor's: model feature
  * order, widths = each extractor's dim (S/FeatureMapping.scala:89-99).  Supported types:
  * number, word_count, string (index|onehot), interaction_count, window_count, rate,
- * interacted_with, relevancy, position, diversity, field_match/bi-encoder.  Anything
+ * interacted_with, relevancy, position, diversity, field_match/bi-encoder, boolean, vector,
+ * item_age, local_time.  Anything
  * else fails with MR_ERR_UNSUPPORTED naming the feature. */
 MR_API mr_status mr_schema_create(mr_ctx *ctx, const char *json, size_t len, mr_schema **out);
 MR_API mr_status mr_schema_free(mr_schema *s);
@@ -200,8 +201,9 @@ MR_API int32_t mr_schema_feature_offset(const mr_schema *s, const char *feature,
  * itself rather than from state).  kind: */
 enum {
   MR_IN_REQ_F64 = 0,  /* one double per request  (number/word_count with scope ranking, string on a
-                         ranking field -> encoded category index)                      */
-  MR_IN_REQ_U64 = 1,  /* one hash per request    (rate scoped ranking.<field>: hash of the field value) */
+                         ranking field -> encoded category index, local_time -> the mapped value) */
+  MR_IN_REQ_U64 = 1,  /* one u64 per request     (rate scoped ranking.<field>: hash of the field value;
+                         item_age: the RankingEvent timestamp in epoch millis)          */
   MR_IN_REQ_VEC = 2,  /* one f32[dim] per request (bi-encoder query embedding)          */
   MR_IN_ITEM_F64 = 3  /* one double per item, NaN = absent (relevancy; per-item field overrides of
                          number / string-index features, S/feature/NumberFeature.scala:84-93) */
@@ -228,8 +230,8 @@ MR_API mr_status mr_state_free(mr_state *st);
  *   scope payload                1/2/3/6: u64 id hash | 4: u64 value hash |
  *                                5: u64 value hash, u64 item hash | 0: nothing
  *   u8  kind                     0 SDouble | 1 SString | 2 SStringList | 3 SDoubleList |
- *                                4 Counter | 5 PeriodicCounter | 6 BoundedList
- *   payload                      0: f64 | 1: u64 hash | 2: u32 n, n x u64 hash | 3: u32 n, n x f64 |
+ *                                4 Counter | 5 PeriodicCounter | 6 BoundedList | 7 SBoolean
+ *   payload                      0: f64 | 1: u64 hash | 2: u32 n, n x u64 hash | 3: u32 n, n x f64 | 7: u8 |
  *                                4: i64 | 5: u32 n, n x i64 (PeriodicValue.value, S/model/FeatureValue.scala:30-43) |
  *                                6: u32 n, n x u64 item-id hash, newest first (BoundedListValue.values)
  * Records whose name no extractor of the schema reads are skipped (counted in *skipped).

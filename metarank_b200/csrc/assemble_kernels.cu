@@ -643,6 +643,32 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
         out[d.col] = cnt;
         break;
       }
+      case FK_VECTOR: {
+        // NumVectorFeature.value :55-70 — the stored (already reduced) list, or NaN x dim
+        const uint64_t *rp = scoped_row(d.scope);
+        const bool ok = rp && present(rp, d.b[0]);
+        for (int k = 0; k < d.dim; k++) out[d.col + k] = ok ? __longlong_as_double((long long)rp[d.w[0] + k]) : kNaN;
+        break;
+      }
+      case FK_ITEM_AGE: {
+        // ItemAgeFeature.value :74-86: updatedAt = Timestamp(math.round(value * 1000));
+        // updatedAt.diff(request.timestamp).toSeconds.toDouble  (|delta| millis, truncated to seconds)
+        double v = kNaN;
+        if (irow && present(irow, d.b[0])) {
+          const double ms = __dmul_rn(__longlong_as_double((long long)irow[d.w[0]]), 1000.0);
+          long long upd;  // java.lang.Math.round: half up, NaN -> 0, saturating
+          if (ms != ms) upd = 0;
+          else if (ms >= 9.2233720368547758e18) upd = 0x7FFFFFFFFFFFFFFFll;
+          else if (ms <= -9.2233720368547758e18) upd = (long long)0x8000000000000000ull;
+          else { const double fl = floor(ms); upd = (long long)fl + ((ms - fl) >= 0.5 ? 1 : 0); }
+          const long long req_ts = a.req_u64 ? (long long)a.req_u64[(size_t)r * a.n_req_u64 + d.in1] : 0;
+          const long long delta = req_ts - upd;
+          const long long ad = delta < 0 ? -delta : delta;  // math.abs
+          v = (double)(ad / 1000);
+        }
+        out[d.col] = v;
+        break;
+      }
       case FK_RELEVANCY:
         out[d.col] = ov ? ov[d.in0] : kNaN;
         break;

@@ -172,6 +172,52 @@ Schema parse_schema_json(const char *json, size_t len) {
           S.in_item_f64.push_back(n);
         }
       }
+    } else if (t == "boolean") {
+      ScopeSpec sc = parse_scope(str_of(o, "scope", n), n);
+      parse_field(o.get("field") ? str_of(o, "field", n) : str_of(o, "source", n), n);
+      if (sc.scope == SC_FIELD || sc.scope == SC_IRF || sc.scope == SC_RANKING)
+        fail(MR_ERR_UNSUPPORTED, "feature %s: scope not supported for boolean features", n.c_str());
+      d.kind = FK_NUMBER; d.scope = sc.scope; fd.scope = sc.scope;  // reads 1.0 / 0.0 / NaN, no per-item override
+      bind(0, add_slot(fi, n, sc.scope, SK_BOOL, 1, 0));
+    } else if (t == "vector") {
+      ScopeSpec sc = parse_scope(str_of(o, "scope", n), n);
+      parse_field(str_of(o, "source", n), n);
+      if (sc.scope == SC_FIELD || sc.scope == SC_IRF || sc.scope == SC_RANKING)
+        fail(MR_ERR_UNSUPPORTED, "feature %s: scope not supported for vector features", n.c_str());
+      int dimv = 0;
+      const JValue *red = o.get("reduce");
+      if (!red || red->kind == JValue::Null) dimv = 4;  // default reducers: min, max, size, avg
+      else if (red->kind == JValue::Arr) {
+        for (auto &r : red->arr) {
+          if (r.kind != JValue::Str) fail(MR_ERR_PARSE, "feature %s: reducers must be strings", n.c_str());
+          static const char *kOne[] = {"first", "last", "min", "max", "avg", "random", "sum", "size", "euclidean_distance"};
+          bool one = false;
+          for (const char *k : kOne) one |= r.str == k;
+          if (one) dimv += 1;
+          else if (r.str.rfind("vector", 0) == 0 && r.str.size() > 6 && r.str.find_first_not_of("0123456789", 6) == std::string::npos)
+            dimv += atoi(r.str.c_str() + 6);
+          else fail(MR_ERR_PARSE, "feature %s: reducer %s is not supported", n.c_str(), r.str.c_str());
+        }
+      } else fail(MR_ERR_PARSE, "feature %s: 'reduce' must be a list", n.c_str());
+      if (dimv <= 0 || dimv > 4096) fail(MR_ERR_PARSE, "feature %s: bad vector dimension %d", n.c_str(), dimv);
+      d.kind = FK_VECTOR; d.scope = sc.scope; d.dim = dimv; fd.scope = sc.scope;
+      bind(0, add_slot(fi, n, sc.scope, SK_F64VEC, dimv, dimv));
+    } else if (t == "item_age") {
+      FieldSpec fs = parse_field(str_of(o, "source", n), n);
+      if (fs.event != "item") fail(MR_ERR_PARSE, "feature %s: can only work with fields from metadata events", n.c_str());
+      d.kind = FK_ITEM_AGE; d.scope = SC_ITEM;
+      bind(0, add_slot(fi, n, SC_ITEM, SK_F64, 1, 0));
+      d.in1 = (int)S.in_req_u64.size();  // the RankingEvent's timestamp (epoch millis)
+      S.in_req_u64.push_back(n);
+    } else if (t == "local_time") {
+      FieldSpec fs = parse_field(str_of(o, "source", n), n);
+      if (fs.event != "ranking") fail(MR_ERR_PARSE, "feature %s: can only work with ranking event fields", n.c_str());
+      std::string pm = str_of(o, "parse", n);
+      if (pm != "time_of_day" && pm != "day_of_week" && pm != "month_of_year" && pm != "year" && pm != "second")
+        fail(MR_ERR_PARSE, "feature %s: parsing method %s is not supported", n.c_str(), pm.c_str());
+      d.kind = FK_CONST_REQ;  // the caller evaluates the DateTimeMapper on the request's timestamp / field
+      d.in0 = (int)S.in_req_f64.size();
+      S.in_req_f64.push_back(n);
     } else if (t == "string") {
       ScopeSpec sc = parse_scope(str_of(o, "scope", n), n);
       std::string src = o.get("source") ? str_of(o, "source", n) : str_of(o, "field", n);

@@ -24,7 +24,9 @@ enum FeatKind : int32_t {
   FK_POSITION = 8,    // position (online: constant)             S/feature/PositionFeature.scala:30-35
   FK_DIVERSITY = 9,   // diversity                               S/feature/DiversityFeature.scala:67-130
   FK_COSINE = 10,     // field_match / bi-encoder                S/feature/FieldMatchBiencoderFeature.scala:80-109
-  FK_CONST_REQ = 11,  // number/word_count/string with scope ranking: one value per request
+  FK_CONST_REQ = 11,  // number/word_count/string with scope ranking, local_time: one value per request
+  FK_VECTOR = 12,     // vector (stored, already reduced SDoubleList)   S/feature/NumVectorFeature.scala:55-70
+  FK_ITEM_AGE = 13,   // item_age                                 S/feature/ItemAgeFeature.scala:74-86
 };
 
 enum ScopeT : int32_t { SC_GLOBAL = 0, SC_ITEM = 1, SC_USER = 2, SC_SESSION = 3, SC_FIELD = 4, SC_IRF = 5, SC_RANKING = 6, SC_N_TABLES = 6 };
@@ -39,6 +41,8 @@ enum SlotKind : int32_t {
   SK_BLIST = 6,      // BoundedListValue item hashes:          {u32 off, u32 len}
   SK_F64LIST = 7,    // ScalarValue(SDoubleList) dim doubles in a side array (presence bit only)
   SK_DIVERSITY = 8,  // 2 words: {kind 1 double | 2 strings, payload f64 | {off,len}}
+  SK_BOOL = 9,       // ScalarValue(SBoolean) stored as the double it reads as (1.0 / 0.0)   1 word
+  SK_F64VEC = 10,    // ScalarValue(SDoubleList) of the feature's dim, inline in the row     dim words
 };
 
 struct Slot {

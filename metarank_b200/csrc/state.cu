@@ -121,6 +121,7 @@ void StateStore::upsert(const uint8_t *buf, size_t len, int64_t *applied, int64_
       case 2: case 6: n = r.get<uint32_t>(); arr = r.bytes((size_t)n * 8); break;
       case 3: n = r.get<uint32_t>(); arr = r.bytes((size_t)n * 8); break;
       case 4: i64 = r.get<int64_t>(); break;
+      case 7: u64 = r.get<uint8_t>(); break;  // SBoolean
       case 5: n = r.get<uint32_t>(); arr = r.bytes((size_t)n * 8); break;
       default: fail(MR_ERR_PARSE, "state record: bad value kind %d", (int)kind);
     }
@@ -156,6 +157,18 @@ void StateStore::upsert(const uint8_t *buf, size_t len, int64_t *applied, int64_
       case SK_F64:
         if (kind == 0) { memcpy(&w[sl.word], &f64, 8); set_present(true); }
         else set_present(false);  // a non-SDouble scalar reads as missing (NumberFeature.value's match)
+        break;
+      case SK_BOOL: {
+        // BooleanFeature.value: SBoolean -> 1.0 / 0.0, anything else reads as missing
+        if (kind == 7) { const double v = u64 ? 1.0 : 0.0; memcpy(&w[sl.word], &v, 8); set_present(true); }
+        else set_present(false);
+        break;
+      }
+      case SK_F64VEC:
+        if (kind != 3) { set_present(false); break; }
+        if ((int)n != sl.p) fail(MR_ERR_INVALID_ARG, "vector '%s' has %u values, the feature's dim is %d", name.c_str(), n, sl.p);
+        memcpy(&w[sl.word], arr, (size_t)n * 8);
+        set_present(true);
         break;
       case SK_STRID:
         if (kind == 1) { w[sl.word] = u64; set_present(true); } else set_present(false);

@@ -38,6 +38,34 @@ def token_count(s: str) -> int:
     return int(lib().mr_token_count(b, C.c_size_t(len(b))))
 
 
+def _parse_iso(s: str):
+    """ZonedDateTime.parse(value, ISO_DATE_TIME) for the local_time extractor (offset required)."""
+    import datetime as dt
+    import re
+
+    s2 = re.sub(r"\[.*\]$", "", s)
+    if s2.endswith("Z"):
+        s2 = s2[:-1] + "+00:00"
+    try:
+        d = dt.datetime.fromisoformat(s2)
+    except ValueError:
+        return None
+    return d if d.tzinfo is not None else None
+
+
+def _map_datetime(parse: str, d) -> float:
+    """LocalDateTimeFeature's DateTimeMapper (S/feature/LocalDateTimeFeature.scala:44-80)."""
+    if parse == "time_of_day":
+        return (d.hour * 3600 + d.minute * 60 + d.second) / 3600.0
+    if parse == "day_of_week":
+        return float(d.isoweekday())
+    if parse == "month_of_year":
+        return float(d.month)
+    if parse == "year":
+        return float(d.year)
+    return float(int(d.timestamp()))  # "second"
+
+
 def _field_name(s: str) -> tuple[str, str]:
     ev, fld = s.split(".", 1)
     return ("item" if ev == "metadata" else ev), fld
@@ -155,6 +183,19 @@ class FeatureMapping:
                     v = rf.get(conf["scope"].split(".", 1)[1])
                     if isinstance(v, str):
                         req_u64[r, slot] = hash64(v)
+                elif t == "item_age":
+                    req_u64[r, self.input_slot(MR_IN_REQ_U64, name)] = np.int64(int(q.get("timestamp", 0))).astype(np.uint64)
+                elif t == "local_time":
+                    import datetime as dt
+
+                    fld = _field_name(conf["source"])[1]
+                    d = None
+                    if fld == "timestamp":
+                        d = dt.datetime.fromtimestamp(int(q.get("timestamp", 0)) // 1000, tz=dt.timezone.utc)
+                    elif isinstance(rf.get(fld), str):
+                        d = _parse_iso(rf[fld])
+                    if d is not None:
+                        req_f64[r, self.input_slot(MR_IN_REQ_F64, name)] = _map_datetime(conf["parse"], d)
                 elif t == "field_match":
                     slot = self.input_slot(MR_IN_REQ_VEC, name)
                     q_emb = (q.get("embeddings") or {}).get(name)
@@ -210,8 +251,8 @@ def pack_feature_values(values: dict) -> bytes:
             out.append(struct.pack("<QQ", hash64(scope[2]), hash64(scope[3])))
         if kind == "scalar":
             if isinstance(v, bool):
-                raise ValueError("SBoolean is not read by any supported extractor")
-            if isinstance(v, (int, float)):
+                out.append(struct.pack("<BB", 7, 1 if v else 0))
+            elif isinstance(v, (int, float)):
                 out.append(struct.pack("<Bd", 0, float(v)))
             elif isinstance(v, str):
                 out.append(struct.pack("<BQ", 1, hash64(v)))

@@ -788,11 +788,217 @@ class FieldMatchBiencoderFeature(BaseFeature):
         return [[v] for v in normalize_scale(self.norm, raw)]
 
 
+class BooleanFeature(BaseFeature):
+    """S/feature/BooleanFeature.scala"""
+
+    def __init__(self, c):
+        self.name = c["name"]
+        self.scope = parse_scope_type(c["scope"])
+        self.field = parse_field_name(c.get("field", c.get("source")))[1]
+
+    def states(self):
+        return {self.name: dict(kind="scalar", scope=self.scope, refresh=0)}
+
+    def writes(self, ev, store):
+        key = self.write_key(ev, self.scope, self.name)
+        if key is None:
+            return []
+        for n, v in ev.get("fields", []):
+            if n == self.field:
+                return [("put", key, ev["timestamp"], bool(v))] if isinstance(v, bool) else []
+        return []
+
+    def value(self, req, state, item):  # :47-62
+        key = self.read_key(req, self.scope, self.name, item["id"])
+        fv = state.get(key) if key is not None else None
+        if fv is not None and fv[0] == "scalar" and isinstance(fv[1], bool):
+            return [1.0 if fv[1] else 0.0]
+        return [NAN]
+
+
+class NumVectorFeature(BaseFeature):
+    """S/feature/NumVectorFeature.scala (reducers are applied on the WRITE side; `random` is not restated)"""
+
+    def __init__(self, c):
+        self.name = c["name"]
+        self.scope = parse_scope_type(c["scope"])
+        self.field = parse_field_name(c["source"])[1]
+        self.reducers = list(c["reduce"]) if c.get("reduce") else ["min", "max", "size", "avg"]
+        self.dim = sum(int(r[6:]) if re.fullmatch(r"vector[0-9]+", r) else 1 for r in self.reducers)
+
+    def states(self):
+        return {self.name: dict(kind="scalar", scope=self.scope, refresh=0)}
+
+    @staticmethod
+    def reduce(name, v):  # :77-168
+        if re.fullmatch(r"vector[0-9]+", name):
+            n = int(name[6:])
+            return (list(v) + [0.0] * n)[:n]  # Arrays.copyOfRange pads with zeros
+        if name == "size":
+            return [float(len(v))]
+        if name == "sum":
+            s = 0.0
+            for x in v:
+                s += x
+            return [s]
+        if name == "euclidean_distance":
+            s = 0.0
+            for x in v:
+                s += x * x
+            return [math.sqrt(s)]
+        if not v:
+            return [0.0]
+        if name == "first":
+            return [v[0]]
+        if name == "last":
+            return [v[-1]]
+        if name == "min":
+            m = 1.7976931348623157e308  # Double.MaxValue
+            for x in v:
+                if x < m:
+                    m = x
+            return [m]
+        if name == "max":
+            m = -1.7976931348623157e308  # scala.Double.MinValue = -Double.MaxValue
+            for x in v:
+                if x > m:
+                    m = x
+            return [m]
+        if name == "avg":
+            s = 0.0
+            for x in v:
+                s += x
+            return [s / len(v)]
+        raise NotImplementedError(name)
+
+    def writes(self, ev, store):
+        key = self.write_key(ev, self.scope, self.name)
+        if key is None:
+            return []
+        for n, v in ev.get("fields", []):
+            if n == self.field:
+                vals = [float(v)] if is_num(v) else [float(x) for x in v] if isinstance(v, list) and all(is_num(x) for x in v) else None
+                if vals is None:
+                    return []
+                out = []
+                for r in self.reducers:
+                    out.extend(self.reduce(r, vals))
+                return [("put", key, ev["timestamp"], out)]
+        return []
+
+    def value(self, req, state, item):  # :55-70
+        key = self.read_key(req, self.scope, self.name, item["id"])
+        fv = state.get(key) if key is not None else None
+        if fv is not None and fv[0] == "scalar" and isinstance(fv[1], (list, np.ndarray)) and (len(fv[1]) == 0 or is_num(fv[1][0])):
+            return [float(x) for x in fv[1]]
+        return [NAN] * self.dim
+
+
+def parse_iso_datetime(s: str):
+    """ZonedDateTime.parse(value, ISO_DATE_TIME): offset date-time with an optional [zone] suffix."""
+    import datetime as _dt
+
+    s2 = re.sub(r"\[.*\]$", "", s)
+    if s2.endswith("Z"):
+        s2 = s2[:-1] + "+00:00"
+    try:
+        d = _dt.datetime.fromisoformat(s2)
+    except ValueError:
+        return None
+    return d if d.tzinfo is not None else None
+
+
+class ItemAgeFeature(BaseFeature):
+    """S/feature/ItemAgeFeature.scala"""
+
+    def __init__(self, c):
+        self.name = c["name"]
+        self.field = parse_field_name(c["source"])[1]
+        self.scope = ("item",)
+
+    def states(self):
+        return {self.name: dict(kind="scalar", scope=("item",), refresh=0)}
+
+    def writes(self, ev, store):  # :33-66
+        key = self.write_key(ev, ("item",), self.name)
+        if key is None:
+            return []
+        if self.field == "timestamp":
+            v = ev["timestamp"] / 1000.0
+        else:
+            v = next((v for n, v in ev.get("fields", []) if n == self.field), None)
+        if is_num(v):
+            out = float(v)
+        elif isinstance(v, str):
+            d = parse_iso_datetime(v)
+            if d is not None:
+                out = float(int(d.timestamp()))
+            else:
+                try:
+                    out = float(v)
+                except ValueError:
+                    return []
+        else:
+            return []
+        return [("put", key, ev["timestamp"], out)]
+
+    def value(self, req, state, item):  # :74-86
+        fv = state.get((("item", item["id"]), self.name))
+        if fv is not None and fv[0] == "scalar" and is_num(fv[1]):
+            ms = float(fv[1]) * 1000.0
+            upd = 0 if ms != ms else int(math.floor(ms + 0.0)) + (1 if (ms - math.floor(ms)) >= 0.5 else 0)  # Math.round
+            return [float(abs(int(req["timestamp"]) - upd) // 1000)]
+        return [NAN]
+
+
+class LocalDateTimeFeature(BaseFeature):
+    """S/feature/LocalDateTimeFeature.scala (a RankingFeature: one value per request)"""
+
+    def __init__(self, c):
+        self.name = c["name"]
+        ev, self.field = parse_field_name(c["source"])
+        if ev != "ranking":
+            raise ValueError("can only work with ranking event fields")
+        self.parse = c["parse"]
+
+    @staticmethod
+    def map_datetime(parse, d) -> float:  # :44-80
+        if parse == "time_of_day":
+            return (d.hour * 3600 + d.minute * 60 + d.second) / 3600.0
+        if parse == "day_of_week":
+            return float(d.isoweekday())
+        if parse == "month_of_year":
+            return float(d.month)
+        if parse == "year":
+            return float(d.year)
+        if parse == "second":
+            return float(int(d.timestamp()))
+        raise ValueError(f"parsing method {parse} is not supported")
+
+    def request_value(self, req) -> float:
+        import datetime as _dt
+
+        if self.field == "timestamp":
+            d = _dt.datetime.fromtimestamp(int(req["timestamp"]) // 1000, tz=_dt.timezone.utc)
+            return self.map_datetime(self.parse, d)
+        v = fields_map(req.get("fields", [])).get(self.field)
+        if isinstance(v, str):
+            d = parse_iso_datetime(v)
+            if d is not None:
+                return self.map_datetime(self.parse, d)
+        return NAN
+
+    def values(self, req, state, mode="online"):
+        v = self.request_value(req)
+        return [[v] for _ in req["items"]]
+
+
 FEATURE_TYPES = {
     "number": NumberFeature, "word_count": WordCountFeature, "string": StringFeature,
     "interaction_count": InteractionCountFeature, "window_count": WindowInteractionCountFeature,
     "rate": RateFeature, "interacted_with": InteractedWithFeature, "relevancy": RelevancyFeature,
-    "position": PositionFeature, "diversity": DiversityFeature,
+    "position": PositionFeature, "diversity": DiversityFeature, "boolean": BooleanFeature,
+    "vector": NumVectorFeature, "item_age": ItemAgeFeature, "local_time": LocalDateTimeFeature,
 }
 
 

@@ -122,7 +122,36 @@ case("diversity_string_lists", "T/feature/DiversityFeatureTest.scala:79-99",
       item_event("p3", [("cat", ["a", "b", "c"])]), item_event("p4", [("cat", ["a", "b", "c", "d"])])],
      ranking(["p1", "p2", "p3", "p4"]), {"divstrl": [[0.3], [0.6], [0.9], [1.0]]})
 
+case("vector_default_reducers", "T/feature/NumVectorFeatureTest.scala:62-70",
+     [dict(name="vec", type="vector", source="item.vec", scope="item")],
+     [item_event("p1", [("vec", [1.0, 2.0, 3.0])])], ranking(["p1", "p2"]),
+     {"vec": [[1.0, 3.0, 3.0, 2.0], [float("nan")] * 4]})
+
+_UPD = 1646085600  # ZonedDateTime.of(2022, 3, 1, 0, 0, 0, 0, UTC+2).toEpochSecond
+_NOWMS = 1648418400000  # ZonedDateTime.of(2022, 3, 28, 0, 0, 0, 0, UTC+2) in epoch millis
+_age_req = ranking(["p1"])
+_age_req["timestamp"] = _NOWMS
+_age_ev = item_event("p1", [("updated_at", "2022-03-01T00:00:00+02:00[UTC+02:00]")])
+_age_ev["timestamp"] = _UPD * 1000
+case("item_age_iso_string", "T/feature/ItemAgeFeatureTest.scala:90-101",
+     [dict(name="itemage", type="item_age", source="item.updated_at")], [_age_ev], _age_req, {"itemage": [[2332800.0]]})
+
+_lt = lambda parse, src="ranking.localts": [dict(name="x", type="local_time", source=src, parse=parse)]  # noqa: E731
+_lt_req = ranking(["p1"], [("localts", "2022-03-28T12:00:00+02:00[UTC+02:00]")])
+for _p, _v in (("time_of_day", 12.0), ("day_of_week", 1.0), ("month_of_year", 3.0), ("year", 2022.0), ("second", 1648461600.0)):
+    case(f"local_time_{_p}", "T/feature/LocalDateTimeFeatureTest.scala:44-62", _lt(_p), [], _lt_req, {"x": [[_v]]})
+_lt_native = ranking(["p1"])
+_lt_native["timestamp"] = 1648461600000
+case("local_time_native_timestamp", "T/feature/LocalDateTimeFeatureTest.scala:64-73", _lt("year", "ranking.timestamp"), [],
+     _lt_native, {"x": [[2022.0]]})
+case("local_time_bad_format_is_missing", "T/feature/LocalDateTimeFeatureTest.scala:33-42", _lt("time_of_day"), [],
+     ranking(["p1"], [("localts", "now")]), {"x": [[float("nan")]]})
+
 # Known-answer cases derived from the reference source where its tests hold no value
+case("boolean_item", "S/feature/BooleanFeature.scala:47-62 (derived)",
+     [dict(name="avail", type="boolean", scope="item", source="item.availability")],
+     [item_event("p1", [("availability", True)]), item_event("p2", [("availability", False)])],
+     ranking(["p1", "p2", "p3"]), {"avail": [[1.0], [0.0], [float("nan")]]})
 case("number_item_and_override", "S/feature/NumberFeature.scala:58-97 (derived)",
      [dict(name="price", type="number", scope="item", source="metadata.price")],
      [item_event("p1", [("price", 10.0)]), item_event("p2", [("price", 20.0)])],
