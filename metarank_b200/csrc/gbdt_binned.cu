@@ -16,38 +16,11 @@
 
 #include "binning.cuh"
 #include "gbdt_kernels.cuh"
+#include "tma.cuh"
 
 namespace mr {
 namespace {
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
 
 // ------------------------------------------------------------------ binning
 constexpr int kBinGroups = 4;  // groups of 32 items per CTA
@@ -218,7 +191,7 @@ __global__ void __launch_bounds__(1024) gbdt_score_binned_kernel(const BParams p
 // Same mapping as gbdt_score_binned_kernel, on the compact layout (gbdt_model.h): children are byte
 // offsets (bit 0 = leaf), the feature's byte offset inside the warp's code tile is stored in the
 // node, so one tree level is: LDS.64 node, shift+mask/or, LDS.U16 code, compare, select, test.
-template <typename Real>
+template <typename Real, bool HAS_CAT>
 __global__ void __launch_bounds__(1024) gbdt_score_compact_kernel(const BParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int W = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -278,7 +251,25 @@ __global__ void __launch_bounds__(1024) gbdt_score_compact_kernel(const BParams 
 #pragma unroll 1
       for (int t = 0; t < ntree; t++) {
         uint32_t n = roots[t];
-        if (!(n & 1u)) {
+        if (HAS_CAT) {
+          // models with categorical splits (e.g. ranklens' `genre`): same layout, plain C++ level loop
+          while (!(n & 1u)) {
+            const uint2 nd = *reinterpret_cast<const uint2 *>(cb + n);
+            const uint32_t code = *reinterpret_cast<const uint16_t *>(xwarp + ((nd.x & 0xFFC0u) | lane2));
+            bool left;
+            if (nd.x & 2u) {
+              left = false;
+              if (code != kBinNaN) {
+                const uint2 ct = reinterpret_cast<const uint2 *>(cb)[nd.x >> 16];
+                const uint32_t w = code >> 5;
+                if (w < ct.y) left = (reinterpret_cast<const uint32_t *>(cb)[ct.x + w] >> (code & 31u)) & 1u;
+              }
+            } else {
+              left = (code <= (nd.x >> 16)) || (code == kBinNaN && (nd.x & 1u));
+            }
+            n = __byte_perm(nd.y, 0u, left ? 0x4410u : 0x4432u);
+          }
+        } else if (!(n & 1u)) {
           // one tree level = 12 SASS instructions; spelled in PTX because nvcc otherwise routes the
           // predicates through integer registers (18 instructions)
           asm volatile(
@@ -364,7 +355,17 @@ __global__ void __launch_bounds__(128) gbdt_leaves_kernel(const LParams p) {
     while (!(n & 1u)) {
       const uint2 nd = *reinterpret_cast<const uint2 *>(cb + n);
       const uint32_t code = *reinterpret_cast<const uint16_t *>(xwarp + ((nd.x & 0xFFC0u) | lane2));
-      const bool left = (code <= (nd.x >> 16)) || (code == kBinNaN && (nd.x & 1u));
+      bool left;
+      if (nd.x & 2u) {  // categorical bitset
+        left = false;
+        if (code != kBinNaN) {
+          const uint2 ct = reinterpret_cast<const uint2 *>(cb)[nd.x >> 16];
+          const uint32_t w = code >> 5;
+          if (w < ct.y) left = (reinterpret_cast<const uint32_t *>(cb)[ct.x + w] >> (code & 31u)) & 1u;
+        }
+      } else {
+        left = (code <= (nd.x >> 16)) || (code == kBinNaN && (nd.x & 1u));
+      }
       n = __byte_perm(nd.y, 0u, left ? 0x4410u : 0x4432u);
     }
     p.leafvals[(size_t)(cd.first_tree + t) * p.rows_padded + item] = (double)*reinterpret_cast<const Real *>(cb + (n - 1u));
@@ -588,8 +589,9 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
       MR_CUDA_CHECK(cudaGetLastError());
       g_kernel_launches++;
     };
-    if (L.kind == MR_BOOSTER_XGBOOST) go(gbdt_score_compact_kernel<float>);
-    else go(gbdt_score_compact_kernel<double>);
+    if (L.kind == MR_BOOSTER_XGBOOST) go(gbdt_score_compact_kernel<float, false>);
+    else if (L.has_cat) go(gbdt_score_compact_kernel<double, true>);
+    else go(gbdt_score_compact_kernel<double, false>);
     return;
   }
   const int ilp = L.ilp <= 0 ? 1 : L.ilp;

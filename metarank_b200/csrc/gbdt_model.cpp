@@ -616,7 +616,7 @@ BinnedModel pack_threaded(const HostModel &m, const BinnedModel &bn, size_t chun
 
 BinnedModel pack_compact(const HostModel &m, const BinnedModel &bn, size_t chunk_budget) {
   BinnedModel C;
-  if (!bn.ok || m.has_cat || m.n_features > 1023 || m.trees.empty()) return C;
+  if (!bn.ok || m.n_features > 1023 || m.trees.empty()) return C;
   C.thr_off = bn.thr_off;
   C.thr = bn.thr;
   C.is_cat = bn.is_cat;
@@ -624,7 +624,10 @@ BinnedModel pack_compact(const HostModel &m, const BinnedModel &bn, size_t chunk
   C.bucket_start = bn.bucket_start;
   const bool f32 = m.kind == MR_BOOSTER_XGBOOST;
   chunk_budget = std::min<size_t>(chunk_budget, 65536 - 16);
-  auto tree_bytes = [](const HostTree &t) { return (t.feat.size() + t.leaf.size()) * 8; };
+  auto n_cat_nodes = [](const HostTree &t) { size_t c = 0; for (auto fl : t.flags) c += (fl & NF_CATEGORICAL) != 0; return c; };
+  auto tree_bytes = [&](const HostTree &t) {
+    return (t.feat.size() + t.leaf.size() + n_cat_nodes(t)) * 8 + ((t.cat_words.size() * 4 + 7) & ~size_t(7));
+  };
   PackedModel &pk = C.packed;
   size_t i = 0, nt = m.trees.size();
   while (i < nt) {
@@ -647,17 +650,28 @@ BinnedModel pack_compact(const HostModel &m, const BinnedModel &bn, size_t chunk
     for (size_t k = 0; k < n; k++) {
       const HostTree &t = m.trees[i + k];
       const size_t ni = t.feat.size(), node_off = off, leaf_off = off + ni * 8;
+      const size_t ctab_off = leaf_off + t.leaf.size() * 8, cw_off = ctab_off + n_cat_nodes(t) * 8;
       auto child = [&](int cidx) -> uint32_t {
         return cidx >= 0 ? (uint32_t)(node_off + (size_t)cidx * 8) : (uint32_t)((leaf_off + (size_t)(~cidx) * 8) | 1u);
       };
       roots[k] = ni ? (uint32_t)node_off : (uint32_t)(leaf_off | 1u);
       uint32_t *w = (uint32_t *)(c + node_off);
+      uint32_t *ctab = (uint32_t *)(c + ctab_off);
+      size_t ci = 0;
       for (size_t q = 0; q < ni; q++) {
         const int f = t.feat[q];
-        const double *b = C.thr.data() + C.thr_off[f], *e = C.thr.data() + C.thr_off[f + 1];
-        const uint32_t kk = (uint32_t)(std::lower_bound(b, e, t.thr[q]) - b);
-        const uint32_t nanl = (t.flags[q] & NF_NAN_LEFT) ? 1u : 0u;
-        w[2 * q] = ((uint32_t)f * 64u | nanl) | (kk << 16);
+        if (t.flags[q] & NF_CATEGORICAL) {
+          // bit 1 = categorical; the k field is the 8-byte index of the node's {bitset word offset, n words}
+          ctab[2 * ci] = (uint32_t)(cw_off / 4 + (size_t)t.cat_begin[q]);
+          ctab[2 * ci + 1] = (uint32_t)t.cat_n[q];
+          w[2 * q] = ((uint32_t)f * 64u | 2u) | ((uint32_t)((ctab_off + ci * 8) / 8) << 16);
+          ci++;
+        } else {
+          const double *b = C.thr.data() + C.thr_off[f], *e = C.thr.data() + C.thr_off[f + 1];
+          const uint32_t kk = (uint32_t)(std::lower_bound(b, e, t.thr[q]) - b);
+          const uint32_t nanl = (t.flags[q] & NF_NAN_LEFT) ? 1u : 0u;
+          w[2 * q] = ((uint32_t)f * 64u | nanl) | (kk << 16);
+        }
         w[2 * q + 1] = child(t.left[q]) | (child(t.right[q]) << 16);
       }
       uint8_t *lv = c + leaf_off;
@@ -665,7 +679,8 @@ BinnedModel pack_compact(const HostModel &m, const BinnedModel &bn, size_t chunk
         if (f32) { const float v = (float)t.leaf[q]; memcpy(lv + q * 8, &v, 4); }
         else memcpy(lv + q * 8, &t.leaf[q], 8);
       }
-      off = leaf_off + t.leaf.size() * 8;
+      if (!t.cat_words.empty()) memcpy(c + cw_off, t.cat_words.data(), t.cat_words.size() * 4);
+      off = cw_off + ((t.cat_words.size() * 4 + 7) & ~size_t(7));
     }
     pk.chunks.push_back(ChunkDesc{(uint32_t)base, (uint32_t)total, (uint32_t)n, (uint32_t)i});
     pk.max_chunk_bytes = std::max<uint32_t>(pk.max_chunk_bytes, (uint32_t)total);

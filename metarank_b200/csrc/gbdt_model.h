@@ -118,11 +118,11 @@ struct BinnedModel {
 };
 BinnedModel pack_binned(const HostModel &m, size_t chunk_budget);
 
-// "Compact" form of the binned model for the fast lock-step kernel (no categorical nodes, <= 1023
-// features, chunks <= 64 KB).  Children are BYTE offsets inside the chunk, bit 0 set = leaf (the
+// "Compact" form of the binned model for the fast lock-step kernel (<= 1023 features, chunks <= 64 KB).  Children are BYTE offsets inside the chunk, bit 0 set = leaf (the
 // offset then addresses the leaf VALUE), so a level needs no address arithmetic:
-//   CNode (8 B): word0 = feature*64 (bits 6..15) | nan_left (bit 0) | k << 16
+//   CNode (8 B): word0 = feature*64 (bits 6..15) | nan_left (bit 0) | categorical (bit 1) | k << 16
 //                word1 = left offset (16) | right offset (16)
+//   a categorical node's k is the 8-byte index (in the chunk) of its {bitset word offset, n words} pair
 //   chunk: +0 u32 n_trees, pad; +16 u32 root[n_trees] (offset of the root node, or leaf|1 for a
 //          single-leaf tree); then per tree its nodes followed by its leaf values (8-byte slots)
 BinnedModel pack_compact(const HostModel &m, const BinnedModel &binned, size_t chunk_budget);

@@ -212,3 +212,58 @@ def parse_xgboost(blob: bytes) -> dict:
         ))
     return dict(kind="xgboost", n_features=n_features, base_score=base_score, trees=trees,
                 objective=learner.get("objective", {}).get("name", ""))
+
+
+# --------------------------------------------------------------------------- second opinion
+
+def predict_python(model: dict, X) -> np.ndarray:
+    """Straight-line pure-Python evaluation of a parsed model, written independently of
+    oracle/gbdt_oracle.c (different language, different data structures) so that the two can be
+    cross-checked on random models: the GBDT boundary has no golden vector in the reference."""
+    X = np.asarray(X, dtype=np.float64)
+    out = np.empty(X.shape[0], dtype=np.float64)
+    if model["kind"] == "lightgbm":
+        k_zero = float(np.float32(1e-35))
+        for r in range(X.shape[0]):
+            s = 0.0
+            for t in model["trees"]:
+                if t["num_leaves"] <= 1:
+                    s += float(t["leaf_value"][0])
+                    continue
+                node = 0
+                while node >= 0:
+                    x = float(X[r, t["split_feature"][node]])
+                    dt = int(t["decision_type"][node])
+                    if dt & 1:  # categorical
+                        left = False
+                        if x == x and -2147483649.0 < x < 2147483648.0 and int(x) >= 0:
+                            iv = int(x)
+                            ci = int(t["threshold"][node])
+                            b, e = int(t["cat_boundaries"][ci]), int(t["cat_boundaries"][ci + 1])
+                            if iv // 32 < e - b:
+                                left = bool((int(t["cat_threshold"][b + iv // 32]) >> (iv % 32)) & 1)
+                    else:
+                        mt = (dt >> 2) & 3
+                        if x != x and mt != 2:
+                            x = 0.0
+                        if (mt == 1 and -k_zero <= x <= k_zero) or (mt == 2 and x != x):
+                            left = bool(dt & 2)
+                        else:
+                            left = x <= float(t["threshold"][node])
+                    node = int(t["left_child"][node] if left else t["right_child"][node])
+                s += float(t["leaf_value"][~node])
+            out[r] = s
+        return out
+    for r in range(X.shape[0]):
+        s = np.float32(model["base_score"])
+        for t in model["trees"]:
+            nid = 0
+            while t["left"][nid] != -1:
+                fv = np.float32(X[r, t["split_index"][nid]])
+                if fv != fv:
+                    nid = int(t["left"][nid] if t["default_left"][nid] else t["right"][nid])
+                else:
+                    nid = int(t["left"][nid] if fv < t["split_cond"][nid] else t["right"][nid])
+            s = np.float32(s + t["split_cond"][nid])
+        out[r] = float(s)
+    return out

@@ -214,3 +214,22 @@ def test_openmp_path_equals_scalar_path():
     X = synth.feature_matrix(3000, 12, seed=4)
     ob = oracle.OracleBooster(0, blob)
     assert np.array_equal(ob.predictMat(X, *X.shape, threads=1), ob.predictMat(X, *X.shape, threads=0))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_c_oracle_agrees_with_independent_python_evaluator(seed):
+    """Two independent restatements (C over flat arrays, pure Python over the parsed dict) must agree
+    bit for bit on random models with every node kind — the only cross-check available for a boundary
+    the reference never asserts a value for."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    blob = synth.lightgbm_model_text(25, 9, seed=seed, cat_features={3: 50}, zero_missing=True, stump_every=6)
+    X = synth.feature_matrix(120, 9, seed=seed + 10)
+    X[:, 3] = rng.integers(-3, 60, 120)
+    X[rng.random(120) < 0.1, 3] = np.nan
+    X[rng.random(120) < 0.2, 2] = 0.0
+    want = model_parse.predict_python(model_parse.parse_lightgbm_text(blob), X)
+    assert np.array_equal(oracle.OracleBooster(0, blob).predictMat(X, *X.shape), want)
+    xb = synth.xgboost_model_json(20, 7, depth=5, seed=seed, full=False)
+    X7 = synth.feature_matrix(100, 7, seed=seed + 20)
+    want = model_parse.predict_python(model_parse.parse_xgboost(xb), X7)
+    assert np.array_equal(oracle.OracleBooster(1, xb).predictMat(X7, *X7.shape), want)
