@@ -82,35 +82,52 @@ __global__ void lookup_kernel(RankArgs a) {
 // ------------------------------------------------------------------ cosine
 // CosineDistance.dist (S/ml/onnx/distance/DistanceFunction.scala:13-27): sequential sums,
 // query(i)*query(i) is a FLOAT product, the other two are double products.
-__global__ void cosine_kernel(RankArgs a) {
+__global__ void __launch_bounds__(128) cosine_kernel(RankArgs a) {
+  // A warp owns 32 items.  Embedding rows are streamed 32 dims at a time with coalesced 256-byte row
+  // segments into a padded shared-memory tile, then every lane walks ITS item's 32 values in index
+  // order, so the three sums are accumulated in exactly the reference's sequence.
+  __shared__ double s_tile[4][32][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.total_items) return;
-  const int r = a.item_req[i];
-  const uint32_t ir = a.item_row[i];
+  const bool live = i < a.total_items;
+  const int r = live ? a.item_req[i] : 0;
+  const uint32_t ir = live ? a.item_row[i] : kNoRow;
+  int voff = 0;
   for (int f = 0; f < a.n_plan; f++) {
     const DFeature d = a.plan[f];
     if (d.kind != FK_COSINE) continue;
-    double out = nan_d();
-    const bool q_ok = a.req_vec_present && a.req_vec_present[(size_t)r * a.n_req_vec + d.in0];
-    if (q_ok && ir != kNoRow && present(row_ptr(a.st.t[SC_ITEM], ir), d.b[0])) {
-      const int dim = d.aux0;
-      int voff = 0;
-      // element offset of this vector slot = sum of dims of earlier slots; stored in uparam's side dims
-      for (int g = 0; g < f; g++) if (a.plan[g].kind == FK_COSINE) voff += a.plan[g].aux0;
-      const float *q = a.req_vec + (size_t)r * a.vec_stride + voff;
-      const double *e = a.st.side[(int)d.uparam] + (size_t)ir * dim;
-      double top = 0.0, as = 0.0, bs = 0.0;
-      for (int k = 0; k < dim; k++) {
-        const float qk = __ldg(q + k);
-        const double ek = __ldg(e + k);
-        top = __dadd_rn(top, __dmul_rn((double)qk, ek));
-        as = __dadd_rn(as, (double)__fmul_rn(qk, qk));
-        bs = __dadd_rn(bs, __dmul_rn(ek, ek));
+    const int dim = d.aux0;
+    const bool q_ok = live && a.req_vec_present && a.req_vec_present[(size_t)r * a.n_req_vec + d.in0];
+    const bool ok = q_ok && ir != kNoRow && present(row_ptr(a.st.t[SC_ITEM], ir), d.b[0]);
+    const float *q = a.req_vec + (size_t)r * a.vec_stride + voff;
+    const double *side = a.st.side[(int)d.uparam];
+    double top = 0.0, as = 0.0, bs = 0.0;
+    for (int d0 = 0; d0 < dim; d0 += 32) {
+      const int nd = min(32, dim - d0);
+      // cooperative, coalesced: row segment of item j of this warp -> s_tile[warp][j][*]
+      for (int j = 0; j < 32; j++) {
+        const uint32_t rj = __shfl_sync(0xFFFFFFFFu, ir, j);
+        const int okj = __shfl_sync(0xFFFFFFFFu, (int)ok, j);
+        if (okj && lane < nd) s_tile[warp][j][lane] = __ldg(side + (size_t)rj * dim + d0 + lane);
       }
-      out = __ddiv_rn(top, __dmul_rn(__dsqrt_rn(as), __dsqrt_rn(bs)));
+      __syncwarp();
+      if (ok) {
+        for (int k = 0; k < nd; k++) {
+          const float qk = __ldg(q + d0 + k);
+          const double ek = s_tile[warp][lane][k];
+          top = __dadd_rn(top, __dmul_rn((double)qk, ek));
+          as = __dadd_rn(as, (double)__fmul_rn(qk, qk));
+          bs = __dadd_rn(bs, __dmul_rn(ek, ek));
+        }
+      }
+      __syncwarp();
     }
-    a.cos[(size_t)d.aux2 * a.total_items + i] = out;
-    a.cos[(size_t)(a.n_cos + d.aux2) * a.total_items + i] = out;  // normalised copy (noop default)
+    if (live) {
+      const double out = ok ? __ddiv_rn(top, __dmul_rn(__dsqrt_rn(as), __dsqrt_rn(bs))) : nan_d();
+      a.cos[(size_t)d.aux2 * a.total_items + i] = out;
+      a.cos[(size_t)(a.n_cos + d.aux2) * a.total_items + i] = out;  // normalised copy (noop default)
+    }
+    voff += dim;
   }
 }
 
@@ -202,7 +219,18 @@ __global__ void __launch_bounds__(256) prepass_kernel(RankArgs a) {
   const int i0 = a.item_offsets[r], n_items = a.item_offsets[r + 1] - i0;
   const DTable &IT = a.st.t[SC_ITEM];
 
-  for (int f = 0; f < a.n_plan; f++) {
+  // grid.y enumerates the plan entries that need a per-request aggregate: one CTA per (request, entry)
+  int f_sel = -1;
+  {
+    int seen = 0;
+    for (int f = 0; f < a.n_plan; f++) {
+      const int k = a.plan[f].kind;
+      const bool agg = k == FK_INTERACTED || k == FK_DIVERSITY || (k == FK_COSINE && a.plan[f].aux1 != 0);
+      if (agg && seen++ == (int)blockIdx.y) { f_sel = f; break; }
+    }
+  }
+  if (f_sel < 0) return;
+  for (int f = f_sel; f <= f_sel; f++) {
     const DFeature d = a.plan[f];
     if (d.kind == FK_INTERACTED) {
       // visitor's interacted items -> multiset of their values of this field
@@ -708,16 +736,47 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
 __global__ void __launch_bounds__(256) order_kernel(const double *scores, const int32_t *offsets, int32_t *order) {
   const int r = blockIdx.x;
   const int b = offsets[r], n = offsets[r + 1] - b;
-  extern __shared__ long long s_keys[];
+  extern __shared__ long long s_keys[];  // [4096] keys, then [4096] int indices
   const int cap = 4096;
-  const bool in_smem = n <= cap;
-  for (int j = threadIdx.x; j < n && in_smem; j += blockDim.x) s_keys[j] = total_order_key(-scores[b + j]);
-  __syncthreads();
+  int *s_idx = reinterpret_cast<int *>(s_keys + cap);
+  if (n <= 1) {
+    if (n == 1 && threadIdx.x == 0) order[b] = 0;
+    return;
+  }
+  if (n <= cap) {
+    // bitonic sort of (total-order key of -score, request index): the index makes every pair distinct,
+    // which is exactly the stability of the reference's sortBy
+    int p2 = 1;
+    while (p2 < n) p2 <<= 1;
+    for (int j = threadIdx.x; j < p2; j += blockDim.x) {
+      s_keys[j] = j < n ? total_order_key(-scores[b + j]) : 0x7FFFFFFFFFFFFFFFll;
+      s_idx[j] = j < n ? j : 0x7FFFFFFF;
+    }
+    __syncthreads();
+    for (int k = 2; k <= p2; k <<= 1) {
+      for (int jj = k >> 1; jj > 0; jj >>= 1) {
+        for (int i = threadIdx.x; i < p2; i += blockDim.x) {
+          const int l = i ^ jj;
+          if (l > i) {
+            const long long ki = s_keys[i], kl = s_keys[l];
+            const int ii = s_idx[i], il = s_idx[l];
+            const bool gt = ki > kl || (ki == kl && ii > il);
+            const bool up = (i & k) == 0;
+            if (gt == up) { s_keys[i] = kl; s_keys[l] = ki; s_idx[i] = il; s_idx[l] = ii; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (int j = threadIdx.x; j < n; j += blockDim.x) order[b + j] = s_idx[j];
+    return;
+  }
+  // very large requests: rank by counting straight from global memory
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    const long long kj = in_smem ? s_keys[j] : total_order_key(-scores[b + j]);
+    const long long kj = total_order_key(-scores[b + j]);
     int rank = 0;
     for (int q = 0; q < n; q++) {
-      const long long kq = in_smem ? s_keys[q] : total_order_key(-scores[b + q]);
+      const long long kq = total_order_key(-scores[b + q]);
       rank += (kq < kj) || (kq == kj && q < j);
     }
     order[b + rank] = j;
@@ -739,7 +798,9 @@ void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t strea
     g_kernel_launches++;
   }
   if (schema.needs_prepass && a.n_requests > 0) {
-    prepass_kernel<<<a.n_requests, 256, 0, stream>>>(a);
+    int n_agg = 0;
+    for (auto &d : schema.plan) n_agg += d.kind == FK_INTERACTED || d.kind == FK_DIVERSITY || (d.kind == FK_COSINE && d.aux1 != 0);
+    prepass_kernel<<<dim3((unsigned)a.n_requests, (unsigned)std::max(n_agg, 1)), 256, 0, stream>>>(a);
     MR_CUDA_CHECK(cudaGetLastError());
     g_kernel_launches++;
   }
@@ -751,7 +812,7 @@ void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t strea
 void launch_rank_order(const double *d_scores, const int32_t *d_item_offsets, int n_requests, int total_items,
                        int32_t *d_order, cudaStream_t stream) {
   if (n_requests <= 0 || total_items <= 0) return;
-  order_kernel<<<n_requests, 256, 4096 * sizeof(long long), stream>>>(d_scores, d_item_offsets, d_order);
+  order_kernel<<<n_requests, 256, 4096 * (sizeof(long long) + sizeof(int)), stream>>>(d_scores, d_item_offsets, d_order);
   MR_CUDA_CHECK(cudaGetLastError());
   g_kernel_launches++;
 }
