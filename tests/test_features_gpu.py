@@ -307,3 +307,40 @@ def test_sharded_scorer_world1_matches_direct(ctx):
     assert _eq(scores, want) and np.array_equal(order, oracle.rank_order(want))
     del req
     booster.free(); ds.free(); fm.free()
+
+
+def test_rank_api_post_rank_like_reference_rank_api_test(ctx):
+    """POST /rank/<model>?explain= in-process, as T/main/api/RankApiTest.scala:36-66 does."""
+    import json
+
+    import metarank_b200 as mb
+    from metarank_b200 import rank_api as ra
+
+    feats, model = synth.ranklens_config()
+    state, item_ids, sessions = synth.ranklens_state(n_items=200, n_sessions=10, seed=5)
+    fm, ds, rk, _, _ = _device(ctx, feats, model, state)
+    blob = synth.lightgbm_model_text(40, 24, seed=3, cat_features={7: 16})
+    booster = mb.LightGBMBooster(ctx, blob, n_features=24)
+    api = ra.RankApi({"xgboost": (fm, ds, booster)})
+    payload = json.dumps({"event": "ranking", "id": "r1", "timestamp": "1599391467000", "user": sessions[0],
+                          "session": sessions[0], "items": [{"id": i, "relevancy": 0} for i in item_ids[:24]]})
+    req = ra.decode_ranking_event(payload)
+    mapping = fo.FeatureMapping(feats, model)
+    want = fo.dense_matrix(mapping, req, state)
+    scores = oracle.OracleBooster(0, blob).predictMat(want, *want.shape)
+    order = oracle.rank_order(scores)
+    for explain in ("true", "false"):
+        status, ctype, body = api.routes("POST", f"/rank/xgboost?explain={explain}", payload)
+        assert status == 200 and ctype == "application/json"
+        resp = json.loads(body)
+        assert [e["item"] for e in resp["items"]] == [item_ids[k] for k in order]
+        assert [e["score"] for e in resp["items"]] == [float(scores[k]) for k in order]
+        assert ("state" in resp) == (explain == "true")
+        assert all(("features" in e) == (explain == "true") for e in resp["items"])
+    # explain payload: names re-attached from the DatasetDescriptor, NaN dropped, category as "cat@index"
+    e0 = json.loads(api.routes("POST", "/rank/xgboost?explain=true", payload)[2])["items"][0]
+    k0 = int(order[0])
+    assert e0["features"]["position"] == 5.0 and len(e0["features"]["profile"]) == 4
+    assert e0["features"]["genre"].endswith("@%d" % int(want[k0, 7]))
+    assert api.routes("POST", "/rank/missing", payload)[0] == 500
+    booster.free(); ds.free(); fm.free()
