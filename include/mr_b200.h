@@ -237,6 +237,17 @@ MR_API mr_status mr_state_free(mr_state *st);
  * Records whose name no extractor of the schema reads are skipped (counted in *skipped).
  * Visible to mr_rank after mr_state_flush. */
 MR_API mr_status mr_state_upsert(mr_state *st, const uint8_t *packed, size_t len, int64_t *applied, int64_t *skipped);
+/* The write path natively: instead of refreshed FeatureValues the caller forwards the
+ * extractors' raw writes (BaseFeature.writes, S/feature/*.scala) and the library keeps the state:
+ * FeatureValueFlow.commitWrite + computeValue (S/flow/FeatureValueFlow.scala:24-92) over the Mem* state
+ * semantics (S/fstore/memory/Mem{ScalarFeature,Counter,PeriodicCounter,BoundedList}.scala,
+ * PeriodicCounterFeature.fromMap S/model/Feature.scala:140-162).  Every write refreshes its value
+ * (refresh interval 0), so reads are never staler than the reference's.  Records, little-endian:
+ *   u16 name_len, name | u8 scope | scope payload (as in mr_state_upsert) | u8 op | i64 ts (epoch ms) | payload
+ *   op 0 Put: u8 kind + value as in mr_state_upsert (kinds 0,1,2,3,7) | op 1 Increment: i64 inc |
+ *   op 2 PeriodicIncrement: i64 inc | op 3 Append: u64 mr_hash64 of the appended string (an item id)
+ * Visible to mr_rank after mr_state_flush. */
+MR_API mr_status mr_state_apply_writes(mr_state *st, const uint8_t *packed, size_t len, int64_t *applied, int64_t *skipped);
 /* Uploads pending upserts to HBM (synchronous). */
 MR_API mr_status mr_state_flush(mr_state *st);
 typedef struct mr_state_info {

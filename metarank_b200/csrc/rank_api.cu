@@ -230,6 +230,14 @@ mr_status mr_state_upsert(mr_state *st, const uint8_t *packed, size_t len, int64
   });
 }
 
+mr_status mr_state_apply_writes(mr_state *st, const uint8_t *packed, size_t len, int64_t *applied, int64_t *skipped) {
+  return guard([&] {
+    if (!st || (!packed && len)) fail(MR_ERR_INVALID_ARG, "null argument");
+    st->store->apply_writes(packed, len, applied, skipped);
+    st->dirty = true;
+  });
+}
+
 mr_status mr_state_flush(mr_state *st) {
   return guard([&] {
     if (!st) fail(MR_ERR_INVALID_ARG, "null argument");

@@ -59,6 +59,21 @@ int32_t token_count(const char *s, size_t len) {
   return tokens < 0 ? 0 : tokens;
 }
 
+int64_t parse_duration_ms(const std::string &s, const std::string &feature) {
+  // ai.metarank.util.DurationJson: "([0-9]+)([smhd]{1})"
+  size_t i = 0;
+  while (i < s.size() && s[i] >= '0' && s[i] <= '9') i++;
+  if (i == 0 || i + 1 != s.size()) fail(MR_ERR_PARSE, "feature %s: duration is in wrong format: %s", feature.c_str(), s.c_str());
+  const int64_t n = strtoll(s.c_str(), nullptr, 10);
+  switch (s[i]) {
+    case 's': return n * 1000;
+    case 'm': return n * 60000;
+    case 'h': return n * 3600000;
+    case 'd': return n * 86400000;
+  }
+  fail(MR_ERR_PARSE, "feature %s: duration is in wrong format: %s", feature.c_str(), s.c_str());
+}
+
 namespace {
 
 struct ScopeSpec { int scope; std::string field; };
@@ -263,7 +278,12 @@ Schema parse_schema_json(const char *json, size_t len) {
       if (per.kind != JValue::Arr || per.arr.empty()) fail(MR_ERR_PARSE, "feature %s: 'periods' must be a non-empty list", n.c_str());
       d.kind = FK_WINDOW; d.scope = sc.scope; fd.scope = sc.scope;
       d.dim = (int)per.arr.size();
-      bind(0, add_slot(fi, n, sc.scope, SK_PCOUNTER, d.dim, d.dim));
+      {
+        const int sl = add_slot(fi, n, sc.scope, SK_PCOUNTER, d.dim, d.dim);
+        bind(0, sl);
+        S.slots[sl].period_ms = parse_duration_ms(str_of(o, "bucket", n), n);
+        for (auto &pv : per.arr) S.slots[sl].ranges.push_back((int)pv.as_int());
+      }
     } else if (t == "rate") {
       std::string top = str_of(o, "top", n), bottom = str_of(o, "bottom", n);
       ScopeSpec sc = o.get("scope") && o.get("scope")->kind == JValue::Str ? parse_scope(o.get("scope")->str, n) : ScopeSpec{SC_ITEM, ""};
@@ -277,6 +297,14 @@ Schema parse_schema_json(const char *json, size_t len) {
       bind(1, add_slot(fi, n + "_" + bottom, sc.scope, SK_PCOUNTER, P, P));
       bind(2, add_slot(fi, n + "_" + top + "_norm", SC_GLOBAL, SK_PCOUNTER, P, P));
       bind(3, add_slot(fi, n + "_" + bottom + "_norm", SC_GLOBAL, SK_PCOUNTER, P, P));
+      {
+        const int64_t bucket = parse_duration_ms(str_of(o, "bucket", n), n);
+        for (int k = 0; k < 4; k++) {
+          Slot &sl = S.slots[d.w[k]];
+          sl.period_ms = bucket;
+          for (auto &pv : per.arr) sl.ranges.push_back((int)pv.as_int());
+        }
+      }
       const JValue *norm = o.get("normalize");
       if (norm && norm->kind == JValue::Obj) {
         d.aux0 = 1;
@@ -315,6 +343,11 @@ Schema parse_schema_json(const char *json, size_t len) {
         for (size_t b2 = a + 1; b2 < fields.size(); b2++)
           if (fields[a] == fields[b2]) fail(MR_ERR_PARSE, "feature %s: duplicate field %s", n.c_str(), fields[a].c_str());
       int vis = add_slot(fi, n + "_interactions", sc.scope, SK_BLIST, 1, 0);
+      {
+        const JValue *cnt = o.get("count"), *dur = o.get("duration");
+        S.slots[vis].list_count = (cnt && cnt->kind == JValue::Num) ? (int)cnt->as_int() : 100;  // getOrElse(100)
+        S.slots[vis].list_duration_ms = (dur && dur->kind == JValue::Str) ? parse_duration_ms(dur->str, n) : 86400000;  // 24.hours
+      }
       fd.dim = (int)fields.size();
       fd.scope = sc.scope;
       S.needs_prepass = true;

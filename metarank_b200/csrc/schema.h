@@ -55,6 +55,11 @@ struct Slot {
   int p = 0;         // periods (PCOUNTER) / dim (F64LIST)
   int side = -1;     // side-array index (F64LIST)
   int feature = -1;  // owning feature (for CAT encoding)
+  // write-path configuration (PeriodicCounterConfig / BoundedListConfig of the owning extractor)
+  int64_t period_ms = 0;          // PCOUNTER: bucket size
+  std::vector<int> ranges;        // PCOUNTER: sumPeriodRanges start offsets (end offset is 0)
+  int list_count = 0;             // BLIST: max entries
+  int64_t list_duration_ms = 0;   // BLIST: max age
 };
 
 // Device-visible extractor descriptor (POD).
@@ -110,6 +115,7 @@ struct Schema {
 
 Schema parse_schema_json(const char *json, size_t len);
 
+int64_t parse_duration_ms(const std::string &s, const std::string &feature);  // DurationJson: "[0-9]+[smhd]"
 uint64_t hash64(const void *bytes, size_t len);
 int32_t token_count(const char *s, size_t len);
 inline uint64_t hash_combine(uint64_t a, uint64_t b) {

@@ -97,6 +97,19 @@ struct Reader {
 };
 }  // namespace
 
+uint32_t StateStore::row_for(const Slot &sl, int scope, uint64_t id0, uint64_t id1) {
+  uint64_t key;
+  if (scope == SC_GLOBAL) key = 1;
+  else if (scope == SC_FIELD) {
+    const FeatureDef &fd = schema.features[sl.feature];
+    key = hash_combine(hash64(fd.scope_field.data(), fd.scope_field.size()), id0);
+  } else if (scope == SC_IRF) {
+    const FeatureDef &fd = schema.features[sl.feature];
+    key = hash_combine(hash_combine(hash64(fd.scope_field.data(), fd.scope_field.size()), id0), id1);
+  } else key = id0 ? id0 : 1;
+  return tables[sl.table].find_or_insert(key);
+}
+
 void StateStore::upsert(const uint8_t *buf, size_t len, int64_t *applied, int64_t *skipped) {
   std::unique_lock<std::shared_mutex> g(mu);
   Reader r{buf, buf + len};
@@ -130,16 +143,7 @@ void StateStore::upsert(const uint8_t *buf, size_t len, int64_t *applied, int64_
     const Slot &sl = schema.slots[it->second];
     if (sl.table != (int)scope) { n_skip++; continue; }  // same name under another scope: not what the extractor reads
     HostTable &T = tables[sl.table];
-    uint64_t key;
-    if (scope == SC_GLOBAL) key = 1;
-    else if (scope == SC_FIELD) {
-      const FeatureDef &fd = schema.features[sl.feature];
-      key = hash_combine(hash64(fd.scope_field.data(), fd.scope_field.size()), id0);
-    } else if (scope == SC_IRF) {
-      const FeatureDef &fd = schema.features[sl.feature];
-      key = hash_combine(hash_combine(hash64(fd.scope_field.data(), fd.scope_field.size()), id0), id1);
-    } else key = id0 ? id0 : 1;
-    const uint32_t row = T.find_or_insert(key);
+    const uint32_t row = row_for(sl, scope, id0, id1);
     uint64_t *w = T.rows.data() + (size_t)row * T.row_words;
     auto set_present = [&](bool on) {
       if (on) w[sl.bit >> 6] |= 1ull << (sl.bit & 63);
@@ -314,6 +318,117 @@ DState StateStore::view() const {
     }
   }
   return v;
+}
+
+// ------------------------------------------------------------------ write path
+// Wire format (little-endian), records back to back:
+//   u16 name_len, name | u8 scope | scope payload (as in upsert) | u8 op | i64 ts (epoch millis) | payload
+//   op 0 Put               payload = u8 kind + value exactly as an upsert record's kind/payload
+//   op 1 Increment         payload = i64 inc                      (MemCounter.put)
+//   op 2 PeriodicIncrement payload = i64 inc                      (MemPeriodicCounter.put + fromMap)
+//   op 3 Append            payload = u64 hash of the appended SString (MemBoundedList.put)
+void StateStore::apply_writes(const uint8_t *buf, size_t len, int64_t *applied, int64_t *skipped) {
+  int64_t n_ok = 0, n_skip = 0;
+  Reader r{buf, buf + len};
+  std::vector<uint8_t> put_rec;
+  while (r.p < r.e) {
+    const uint8_t *rec_begin = r.p;
+    const uint16_t nl = r.get<uint16_t>();
+    std::string name((const char *)r.bytes(nl), nl);
+    const uint8_t scope = r.get<uint8_t>();
+    uint64_t id0 = 0, id1 = 0;
+    switch (scope) {
+      case SC_GLOBAL: break;
+      case SC_ITEM: case SC_USER: case SC_SESSION: case SC_RANKING: case SC_FIELD: id0 = r.get<uint64_t>(); break;
+      case SC_IRF: id0 = r.get<uint64_t>(); id1 = r.get<uint64_t>(); break;
+      default: fail(MR_ERR_PARSE, "write record: bad scope tag %d", (int)scope);
+    }
+    const uint8_t *after_scope = r.p;
+    const uint8_t op = r.get<uint8_t>();
+    const int64_t ts = r.get<int64_t>();
+    if (op == 0) {
+      // Put == KVStore.put of the scalar: re-frame as an upsert record (MemScalarFeature just stores it)
+      const uint8_t *val_begin = r.p;
+      const uint8_t kind = r.get<uint8_t>();
+      switch (kind) {
+        case 0: r.bytes(8); break;
+        case 1: r.bytes(8); break;
+        case 2: case 3: { const uint32_t n = r.get<uint32_t>(); r.bytes((size_t)n * 8); break; }
+        case 7: r.bytes(1); break;
+        default: fail(MR_ERR_PARSE, "Put of value kind %d is not a scalar", (int)kind);
+      }
+      put_rec.assign(rec_begin, after_scope);
+      put_rec.insert(put_rec.end(), val_begin, r.p);
+      int64_t a = 0, s = 0;
+      upsert(put_rec.data(), put_rec.size(), &a, &s);
+      n_ok += a; n_skip += s;
+      continue;
+    }
+    int64_t inc = 0; uint64_t item = 0;
+    if (op == 1 || op == 2) inc = r.get<int64_t>();
+    else if (op == 3) item = r.get<uint64_t>();
+    else fail(MR_ERR_PARSE, "write record: bad op %d", (int)op);
+    auto it = schema.slot_by_name.find(name);
+    if (it == schema.slot_by_name.end() || schema.slots[it->second].table != (int)scope) { n_skip++; continue; }
+    std::unique_lock<std::shared_mutex> g(mu);
+    const Slot &sl = schema.slots[it->second];
+    HostTable &T = tables[sl.table];
+    const uint32_t row = row_for(sl, scope, id0, id1);
+    uint64_t *w = T.rows.data() + (size_t)row * T.row_words;
+    const RawKey rk{((uint64_t)sl.table << 56) ^ ((uint64_t)it->second << 40) ^ (uint64_t)row};
+    auto set_present = [&] { w[sl.bit >> 6] |= 1ull << (sl.bit & 63); };
+    if (op == 1 && sl.kind == SK_COUNTER) {
+      int64_t cur = (w[sl.bit >> 6] >> (sl.bit & 63)) & 1 ? (int64_t)w[sl.word] : 0;
+      cur += inc;
+      memcpy(&w[sl.word], &cur, 8);
+      set_present();
+    } else if (op == 2 && sl.kind == SK_PCOUNTER) {
+      // MemPeriodicCounter.put: bucket = ts.toStartOfPeriod(period) = floor(ts.toDouble / period) * period
+      const int64_t bucket = (int64_t)std::floor((double)ts / (double)sl.period_ms) * sl.period_ms;
+      auto &m = buckets[rk];
+      m[bucket] += inc;
+      // PeriodicCounterFeature.fromMap: windows anchored at the LAST bucket,
+      // [last - period*start, last - period*0 + period], both inclusive
+      const int64_t last = m.rbegin()->first;
+      for (size_t k = 0; k < sl.ranges.size(); k++) {
+        const int64_t start = last - sl.period_ms * sl.ranges[k], end = last + sl.period_ms;
+        int64_t sum = 0;
+        for (auto bi = m.lower_bound(start); bi != m.end() && bi->first <= end; ++bi) sum += bi->second;
+        memcpy(&w[sl.word + k], &sum, 8);
+      }
+      set_present();
+    } else if (op == 3 && sl.kind == SK_BLIST) {
+      // MemBoundedList.put: the first write is stored untrimmed; later ones prepend, drop entries
+      // older than ts - duration, keep `count`
+      auto lit = lists.find(rk);
+      if (lit == lists.end()) {
+        lists[rk].push_front({ts, item});
+        lit = lists.find(rk);
+      } else {
+        auto &L = lit->second;
+        L.push_front({ts, item});
+        std::deque<std::pair<int64_t, uint64_t>> kept;
+        for (auto &tv : L) {
+          if (tv.first >= ts - sl.list_duration_ms) kept.push_back(tv);
+          if ((int)kept.size() >= sl.list_count) break;
+        }
+        L.swap(kept);
+      }
+      auto &L = lit->second;
+      const uint32_t off = (uint32_t)T.pool.size();
+      if (T.pool.size() + L.size() > (size_t)UINT32_MAX) fail(MR_ERR_UNSUPPORTED, "state pool is full");
+      for (auto &tv : L) T.pool.push_back(tv.second);
+      w[sl.word] = (uint64_t)off | ((uint64_t)L.size() << 32);
+      set_present();
+    } else {
+      n_skip++;
+      continue;
+    }
+    T.touch(row);
+    n_ok++;
+  }
+  if (applied) *applied = n_ok;
+  if (skipped) *skipped = n_skip;
 }
 
 }  // namespace mr

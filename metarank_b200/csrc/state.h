@@ -8,8 +8,11 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <deque>
+#include <map>
 #include <mutex>
 #include <shared_mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "schema.h"
@@ -64,6 +67,8 @@ struct HostTable {
 };
 
 struct StateStore {
+  // resolves (slot, scope ids) to the row that holds it, inserting the row when new
+  uint32_t row_for(const Slot &sl, int scope, uint64_t id0, uint64_t id1);
   Schema schema;
   HostTable tables[SC_N_TABLES];
   std::shared_mutex mu;  // shared: kernels reading the tables; exclusive: upsert / flush
@@ -73,6 +78,17 @@ struct StateStore {
   explicit StateStore(const Schema &s);
   ~StateStore();
   void upsert(const uint8_t *p, size_t len, int64_t *applied, int64_t *skipped);
+  // Write path (FeatureValueFlow.commitWrite + computeValue with refresh = always):
+  // Put / Increment / PeriodicIncrement / Append with the reference's Mem* state semantics.
+  void apply_writes(const uint8_t *p, size_t len, int64_t *applied, int64_t *skipped);
+  // raw state behind the refreshed values, keyed by (table, row, slot)
+  struct RawKey {
+    uint64_t v;
+    bool operator==(const RawKey &o) const { return v == o.v; }
+  };
+  struct RawKeyHash { size_t operator()(const RawKey &k) const { return (size_t)mix64(k.v); } };
+  std::unordered_map<RawKey, std::map<int64_t, int64_t>, RawKeyHash> buckets;                // MemPeriodicCounter
+  std::unordered_map<RawKey, std::deque<std::pair<int64_t, uint64_t>>, RawKeyHash> lists;     // MemBoundedList
   void flush();
   DState view() const;
 };

@@ -275,6 +275,42 @@ def pack_feature_values(values: dict) -> bytes:
     return b"".join(out)
 
 
+def _pack_scope(scope) -> bytes:
+    tag = _SCOPE_TAG[scope[0]]
+    out = struct.pack("<B", tag)
+    if tag in (1, 2, 3, 6):
+        out += struct.pack("<Q", hash64(scope[1]))
+    elif tag == 4:
+        out += struct.pack("<Q", hash64(scope[2]))
+    elif tag == 5:
+        out += struct.pack("<QQ", hash64(scope[2]), hash64(scope[3]))
+    return out
+
+
+def pack_writes(writes: list) -> bytes:
+    """The extractors' raw writes -> mr_state_apply_writes wire format.  A write is
+    ("put", key, ts, scalar) | ("inc", key, ts, n) | ("pinc", key, ts, n) | ("append", key, ts, item_id)
+    with key = (scope, feature_name) — Write.{Put, Increment, PeriodicIncrement, Append} (S/model/Write.scala)."""
+    out = []
+    for kind, (scope, name), ts, v in writes:
+        nb = name.encode("utf-8")
+        head = struct.pack("<H", len(nb)) + nb + _pack_scope(scope)
+        if kind == "put":
+            val = pack_feature_values({(scope, name): ("scalar", v)})
+            out.append(head + struct.pack("<Bq", 0, int(ts)) + val[len(head):])
+        elif kind == "inc":
+            out.append(head + struct.pack("<Bqq", 1, int(ts), int(v)))
+        elif kind == "pinc":
+            out.append(head + struct.pack("<Bqq", 2, int(ts), int(v)))
+        elif kind == "append":
+            items = v if isinstance(v, list) else [v]
+            for it in reversed(items):  # a list is prepended as a block, keeping its order (MemBoundedList.put)
+                out.append(head + struct.pack("<BqQ", 3, int(ts), hash64(it)))
+        else:
+            raise ValueError(kind)
+    return b"".join(out)
+
+
 class DeviceState:
     """mr_state: device-resident Persistence.values for one FeatureMapping."""
 
@@ -292,6 +328,14 @@ class DeviceState:
     def put(self, values: dict):
         """KVStore.put(Map[Key, FeatureValue])"""
         return self.put_packed(pack_feature_values(values))
+
+    def apply_writes(self, writes: list):
+        """FeatureValueFlow.commitWrite for a batch of raw writes (see pack_writes)."""
+        blob = pack_writes(writes)
+        a, s = C.c_int64(0), C.c_int64(0)
+        buf = (C.c_uint8 * max(len(blob), 1)).from_buffer_copy(blob if blob else b"\0")
+        check(lib().mr_state_apply_writes(self._h, buf, C.c_size_t(len(blob)), C.byref(a), C.byref(s)))
+        return a.value, s.value
 
     def flush(self):
         check(lib().mr_state_flush(self._h))

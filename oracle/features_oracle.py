@@ -1045,6 +1045,7 @@ class FeatureValueFlow:
         self.store = MemState()
         self.updated = {}
         self.always_refresh = always_refresh
+        self.write_log = []  # every committed write, in order (tests replay them through mr_state_apply_writes)
 
     def process(self, events) -> dict:
         out = {}
@@ -1054,6 +1055,7 @@ class FeatureValueFlow:
                 writes.extend(f.writes(ev, self.store))
             for w in writes:
                 self.store.put(w, self.mapping.configs)
+            self.write_log.extend(writes)
             for w in writes:
                 key, ts = w[1], w[2]
                 last = None if self.always_refresh else self.updated.get(key)

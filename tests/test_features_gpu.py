@@ -344,3 +344,72 @@ def test_rank_api_post_rank_like_reference_rank_api_test(ctx):
     assert e0["features"]["genre"].endswith("@%d" % int(want[k0, 7]))
     assert api.routes("POST", "/rank/missing", payload)[0] == 500
     booster.free(); ds.free(); fm.free()
+
+
+@pytest.mark.parametrize("case", [c for c in G.CASES if c["events"]], ids=[c["name"] for c in G.CASES if c["events"]])
+def test_native_write_path_replays_reference_tests(ctx, case):
+    """the extractors' raw writes (Put / Increment / PeriodicIncrement / Append) go to
+    mr_state_apply_writes instead of refreshed FeatureValues; the library keeps MemCounter /
+    MemPeriodicCounter+fromMap / MemBoundedList semantics itself.  Same golden vectors as the read path."""
+    from metarank_b200 import features as F
+
+    mapping = fo.FeatureMapping(case["features"], case["model_features"])
+    flow = fo.FeatureValueFlow(mapping, always_refresh=True)
+    state = flow.process(case["events"])
+    fm = F.FeatureMapping(ctx, case["features"], case["model_features"])
+    ds = F.DeviceState(ctx, fm)
+    try:
+        applied, skipped = ds.apply_writes(flow.write_log)
+        ds.flush()
+        got = F.Ranker(fm, ds).make_query([case["request"]])[0]
+        assert _eq(got, fo.dense_matrix(mapping, case["request"], state)), case["ref"]
+        for name, exp in case["expected"].items():
+            o, d = fm.offset(name)
+            assert _eq(got[:, o:o + d], np.array(exp)), (case["ref"], name)
+    finally:
+        ds.free(); fm.free()
+
+
+def test_native_write_path_random_event_stream(ctx):
+    """Periodic counters over many days (window anchoring at the last bucket, out-of-order events),
+    bounded lists beyond count/duration, counters in user/session scope — incremental visibility too."""
+    from metarank_b200 import features as F
+
+    rng = np.random.Generator(np.random.PCG64(11))
+    feats = [
+        dict(G.RATE, name="ctr", periods=[1, 7, 30], normalize={"weight": 10}),
+        dict(name="wc", type="window_count", interaction="click", scope="item", bucket="24h", periods=[1, 3]),
+        dict(name="uclicks", type="interaction_count", interaction="click", scope="user"),
+        dict(name="seen", type="interacted_with", interaction="click", field=["item.color", "item.tags"], scope="session",
+             count=5, duration="48h"),
+        dict(name="price", type="number", scope="item", source="metadata.price"),
+    ]
+    model = [f["name"] for f in feats]
+    items = [f"p{i}" for i in range(12)]
+    events = [G.item_event(it, [("color", ["red", "green", "blue"][i % 3]), ("tags", [f"t{i % 4}", f"t{(i * 7) % 5}"]),
+                                ("price", float(i))]) for i, it in enumerate(items)]
+    t = G.NOW - 40 * 86400_000
+    for _ in range(600):
+        t += int(rng.integers(0, 6 * 3600_000))
+        ts = t - (int(rng.integers(0, 3 * 86400_000)) if rng.random() < 0.1 else 0)  # some late events
+        typ = "click" if rng.random() < 0.3 else "impression"
+        events.append(G.interaction(items[int(rng.integers(0, 12))], "r", typ, user=f"u{int(rng.integers(0, 3))}",
+                                    session=f"s{int(rng.integers(0, 4))}", ts=ts))
+    mapping = fo.FeatureMapping(feats, model)
+    flow = fo.FeatureValueFlow(mapping, always_refresh=True)
+    fm = F.FeatureMapping(ctx, feats, model)
+    ds = F.DeviceState(ctx, fm)
+    try:
+        state, done = {}, 0
+        for cut in (len(items), 100, 350, len(events)):
+            state.update(flow.process(events[done:cut]))
+            ds.apply_writes(flow.write_log[len(flow.write_log) - sum(1 for _ in flow.write_log):] if False else flow.write_log)
+            flow.write_log.clear()
+            ds.flush()
+            done = cut
+            for sess, user in (("s0", "u0"), ("s3", "u2"), (None, None)):
+                req = G.ranking(items + ["unknown"], user=user, session=sess)
+                got = F.Ranker(fm, ds).make_query([req])[0]
+                assert _eq(got, fo.dense_matrix(mapping, req, state)), (cut, sess)
+    finally:
+        ds.free(); fm.free()
