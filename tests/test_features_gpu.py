@@ -403,7 +403,7 @@ def test_native_write_path_random_event_stream(ctx):
         state, done = {}, 0
         for cut in (len(items), 100, 350, len(events)):
             state.update(flow.process(events[done:cut]))
-            ds.apply_writes(flow.write_log[len(flow.write_log) - sum(1 for _ in flow.write_log):] if False else flow.write_log)
+            ds.apply_writes(flow.write_log)
             flow.write_log.clear()
             ds.flush()
             done = cut
