@@ -248,7 +248,7 @@ def test_rank_device_api_matches_host_api(ctx):
 
 
 def test_large_batch_is_sliced_and_pipelined(ctx):
-    """A batch beyond the 128 K-item slice size goes through two lanes; results must not depend on it."""
+    """A batch beyond the 256 K-item slice size goes through several lanes; results must not depend on it."""
     import metarank_b200 as mb
     from metarank_b200 import features as F
 
