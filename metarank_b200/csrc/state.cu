@@ -289,6 +289,12 @@ void StateStore::flush() {
       T.dirty_lo = SIZE_MAX;
       T.dirty_hi = 0;
     }
+    if (T.pool_dirty_lo < T.pool_dirty_hi && T.d_pool) {
+      MR_CUDA_CHECK(cudaMemcpy(T.d_pool + T.pool_dirty_lo, T.pool.data() + T.pool_dirty_lo,
+                               (T.pool_dirty_hi - T.pool_dirty_lo) * 8, cudaMemcpyHostToDevice));
+    }
+    T.pool_dirty_lo = SIZE_MAX;
+    T.pool_dirty_hi = 0;
     if (T.pool_uploaded < T.pool.size()) {
       const size_t had = T.d_pool_cap;
       ensure_dev(T.d_pool, T.d_pool_cap, T.pool.size(), T.pool_uploaded, device_bytes);
@@ -415,9 +421,22 @@ void StateStore::apply_writes(const uint8_t *buf, size_t len, int64_t *applied, 
         L.swap(kept);
       }
       auto &L = lit->second;
-      const uint32_t off = (uint32_t)T.pool.size();
-      if (T.pool.size() + L.size() > (size_t)UINT32_MAX) fail(MR_ERR_UNSUPPORTED, "state pool is full");
-      for (auto &tv : L) T.pool.push_back(tv.second);
+      // the list lives in a fixed region of max(count, first-write size) pool entries that is
+      // rewritten in place, so a long event stream does not grow the pool
+      const size_t cap = std::max<size_t>((size_t)std::max(sl.list_count, 1), L.size());
+      auto reg = list_region.find(rk);
+      if (reg == list_region.end()) {
+        if (T.pool.size() + cap > (size_t)UINT32_MAX) fail(MR_ERR_UNSUPPORTED, "state pool is full");
+        reg = list_region.emplace(rk, (uint32_t)T.pool.size()).first;
+        T.pool.resize(T.pool.size() + cap, 0);
+      }
+      const uint32_t off = reg->second;
+      size_t k = 0;
+      for (auto &tv : L) T.pool[off + k++] = tv.second;
+      if (off < T.pool_uploaded) {
+        T.pool_dirty_lo = std::min<size_t>(T.pool_dirty_lo, off);
+        T.pool_dirty_hi = std::max<size_t>(T.pool_dirty_hi, std::min<size_t>(off + cap, T.pool_uploaded));
+      }
       w[sl.word] = (uint64_t)off | ((uint64_t)L.size() << 32);
       set_present();
     } else {

@@ -59,6 +59,7 @@ struct HostTable {
   std::vector<double *> d_sides; std::vector<size_t> d_sides_cap;
   bool map_dirty = false;
   size_t dirty_lo = SIZE_MAX, dirty_hi = 0;  // row range touched since the last flush
+  size_t pool_dirty_lo = SIZE_MAX, pool_dirty_hi = 0;  // pool entries rewritten in place (bounded lists)
 
   uint32_t find(uint64_t key) const;
   uint32_t find_or_insert(uint64_t key);
@@ -89,6 +90,7 @@ struct StateStore {
   struct RawKeyHash { size_t operator()(const RawKey &k) const { return (size_t)mix64(k.v); } };
   std::unordered_map<RawKey, std::map<int64_t, int64_t>, RawKeyHash> buckets;                // MemPeriodicCounter
   std::unordered_map<RawKey, std::deque<std::pair<int64_t, uint64_t>>, RawKeyHash> lists;     // MemBoundedList
+  std::unordered_map<RawKey, uint32_t, RawKeyHash> list_region;  // pool offset of a list's fixed-capacity region
   void flush();
   DState view() const;
 };
