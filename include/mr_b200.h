@@ -238,7 +238,7 @@ MR_API mr_status mr_state_free(mr_state *st);
  * Visible to mr_rank after mr_state_flush. */
 MR_API mr_status mr_state_upsert(mr_state *st, const uint8_t *packed, size_t len, int64_t *applied, int64_t *skipped);
 /* The write path natively: instead of refreshed FeatureValues the caller forwards the
- * extractors' raw writes (BaseFeature.writes, S/feature/*.scala) and the library keeps the state:
+ * extractors' raw writes (BaseFeature.writes, the files under S/feature/) and the library keeps the state:
  * FeatureValueFlow.commitWrite + computeValue (S/flow/FeatureValueFlow.scala:24-92) over the Mem* state
  * semantics (S/fstore/memory/Mem{ScalarFeature,Counter,PeriodicCounter,BoundedList}.scala,
  * PeriodicCounterFeature.fromMap S/model/Feature.scala:140-162).  Every write refreshes its value

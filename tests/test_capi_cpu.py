@@ -77,3 +77,25 @@ def test_truncated_lightgbm_arrays_are_parse_errors():
     with pytest.raises(mb.MrError) as e:
         inspect_model(0, "\n".join(lines).encode())
     assert e.value.status == 2 and "threshold" in e.value.message
+
+
+def test_header_is_plain_c_and_usable_from_c():
+    """include/mr_b200.h compiles as C99 and a C program can drive the host-only entry points."""
+    import os
+    import subprocess
+    import tempfile
+
+    import torch
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "abi_smoke")
+        subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                        os.path.join(root, "tests", "c", "abi_smoke.c"), "-o", exe,
+                        "-L", os.path.join(root, "metarank_b200"), "-lmrgpu",
+                        "-Wl,-rpath," + os.path.join(root, "metarank_b200")], check=True)
+        args = [exe] + ([] if torch.cuda.is_available() else ["--expect-no-gpu"])
+        r = subprocess.run(args, capture_output=True, text=True)
+        assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+        assert "sm_100a ok" in r.stdout
