@@ -413,3 +413,182 @@ def test_native_write_path_random_event_stream(ctx):
                 assert _eq(got, fo.dense_matrix(mapping, req, state)), (cut, sess)
     finally:
         ds.free(); fm.free()
+
+
+def _random_config(rng):
+    """A random feature set over every supported extractor kind and scope, plus state and requests
+    salted with the awkward cases: missing keys, wrong value types, wrong lengths, unknown items."""
+    scopes = ["item", "user", "session", "global"]
+    feats, k = [], 0
+
+    def nm(p):
+        nonlocal k
+        k += 1
+        return f"{p}{k}"
+
+    for _ in range(int(rng.integers(1, 4))):
+        feats.append(dict(name=nm("num"), type="number", scope=str(rng.choice(scopes + ["ranking"])), source="item.price"))
+    feats.append(dict(name=nm("wc"), type="word_count", scope=str(rng.choice(["item", "ranking"])), source="item.title"))
+    feats.append(dict(name=nm("cat"), type="string", scope="item", source="item.color", encode="index", values=["red", "green", "blue"]))
+    feats.append(dict(name=nm("hot"), type="string", scope=str(rng.choice(["item", "user"])), source="item.size", values=["s", "m", "l", "xl"]))
+    feats.append(dict(name=nm("cnt"), type="interaction_count", interaction="click", scope=str(rng.choice(scopes))))
+    feats.append(dict(name=nm("win"), type="window_count", interaction="click", scope=str(rng.choice(scopes)), bucket="24h",
+                      periods=[1, 7, 30][: int(rng.integers(1, 4))]))
+    feats.append(dict(name=nm("rate"), type="rate", top="click", bottom="imp", bucket="24h", periods=[7, 30],
+                      **({"normalize": {"weight": float(rng.integers(1, 20))}} if rng.random() < 0.5 else {}),
+                      **({"scope": str(rng.choice(["item", "item.color", "ranking.query"]))} if rng.random() < 0.8 else {})))
+    feats.append(dict(name=nm("seen"), type="interacted_with", interaction="click", scope=str(rng.choice(["user", "session"])),
+                      field=["item.tags", "item.color"][: int(rng.integers(1, 3))], count=20, duration="24h"))
+    feats.append(dict(name=nm("rel"), type="relevancy"))
+    feats.append(dict(name=nm("pos"), type="position", position=int(rng.integers(0, 9))))
+    feats.append(dict(name=nm("divn"), type="diversity", source="item.price", top=int(rng.choice([1, 3, 20]))))
+    feats.append(dict(name=nm("divs"), type="diversity", source="item.tags"))
+    feats.append(dict(name=nm("flag"), type="boolean", scope=str(rng.choice(["item", "session"])), source="item.ok"))
+    feats.append(dict(name=nm("vec"), type="vector", scope="item", source="item.vec", reduce=["min", "vector2", "avg"]))
+    feats.append(dict(name=nm("age"), type="item_age", source="item.updated"))
+    feats.append(dict(name=nm("tod"), type="local_time", source="ranking.timestamp", parse=str(rng.choice(["time_of_day", "day_of_week", "year"]))))
+    feats.append(dict(name=nm("sim"), type="field_match", rankingField="ranking.query", itemField="item.title",
+                      method=dict(type="bi-encoder", dim=8), norm=str(rng.choice(["noop", "linear", "position"]))))
+    order = rng.permutation(len(feats))
+    model = [feats[i]["name"] for i in order if rng.random() < 0.9]
+    return feats, model
+
+
+def _random_state(rng, feats, items, users, sessions):
+    st = {}
+    tags = [f"t{i}" for i in range(6)]
+
+    def maybe(p=0.85):
+        return rng.random() < p
+
+    def pc(n):
+        return ("pcounter", [int(x) for x in rng.integers(0, 50, n)])
+
+    for f in feats:
+        t, n = f["type"], f["name"]
+        scope_ids = {"item": [("item", i) for i in items], "user": [("user", u) for u in users],
+                     "session": [("session", s) for s in sessions], "global": [("global",)]}
+        sc = f.get("scope", "item")
+        if t == "number" and sc != "ranking":
+            for s in scope_ids[sc]:
+                if maybe():
+                    st[(s, n)] = ("scalar", float(rng.standard_normal())) if maybe(0.9) else ("scalar", "oops")
+        elif t == "word_count" and sc == "item":
+            for s in scope_ids["item"]:
+                if maybe():
+                    st[(s, n)] = ("scalar", float(rng.integers(0, 9)))
+        elif t == "string":
+            for s in scope_ids[sc]:
+                if maybe():
+                    vals = list(rng.choice(f["values"] + ["zzz"], int(rng.integers(0, 3))))
+                    st[(s, n)] = ("scalar", [str(v) for v in vals]) if maybe(0.9) else ("scalar", 3.0)
+        elif t == "interaction_count":
+            for s in scope_ids[sc]:
+                if maybe():
+                    st[(s, n)] = ("counter", int(rng.integers(0, 100)))
+        elif t == "window_count":
+            P = len(f["periods"])
+            for s in scope_ids[sc]:
+                if maybe():
+                    st[(s, n)] = pc(P) if maybe(0.9) else pc(P + 1)
+        elif t == "rate":
+            scope = f.get("scope", "item")
+            for name in (f"{n}_click_norm", f"{n}_imp_norm"):
+                if maybe(0.95):
+                    st[(("global",), name)] = ("pcounter", [int(x) for x in rng.integers(1, 500, 2)])
+            for i in items:
+                if scope == "item":
+                    tgt = ("item", i)
+                elif scope == "item.color":
+                    col = str(rng.choice(["red", "green", "blue"]))
+                    if maybe():
+                        st[(("item", i), f"{n}_field")] = ("scalar", col)
+                    tgt = ("field", "color", col)
+                else:
+                    tgt = ("irf", "query", str(rng.choice(["shoes", "hats"])), i)
+                if maybe():
+                    st[(tgt, f"{n}_click")] = pc(2)
+                if maybe():
+                    st[(tgt, f"{n}_imp")] = pc(2) if maybe(0.95) else pc(3)
+        elif t == "interacted_with":
+            for s in scope_ids[sc]:
+                if maybe(0.7):
+                    st[(s, f"{n}_interactions")] = ("blist", [str(x) for x in rng.choice(items + ["ghost"], int(rng.integers(0, 15)))])
+            for fld in ([f["field"]] if isinstance(f["field"], str) else f["field"]):
+                for i in items:
+                    if maybe():
+                        st[(("item", i), f"{n}_{fld.split('.')[1]}")] = ("scalar", [str(x) for x in rng.choice(tags, int(rng.integers(0, 4)))])
+        elif t == "diversity":
+            numeric = f["source"] == "item.price"
+            for i in items:
+                if maybe(0.8):
+                    st[(("item", i), n)] = ("scalar", float(rng.integers(0, 9))) if numeric else \
+                        ("scalar", [str(x) for x in rng.choice(tags, int(rng.integers(0, 4)))])
+        elif t == "boolean":
+            for s in scope_ids[sc]:
+                if maybe():
+                    st[(s, n)] = ("scalar", bool(rng.random() < 0.5))
+        elif t == "vector":
+            for i in items:
+                if maybe():
+                    st[(("item", i), n)] = ("scalar", [float(x) for x in rng.standard_normal(4)])
+        elif t == "item_age":
+            for i in items:
+                if maybe():
+                    st[(("item", i), n)] = ("scalar", float(1_600_000_000 + int(rng.integers(0, 10**7)) + rng.random()))
+        elif t == "field_match":
+            for i in items:
+                if maybe():
+                    st[(("item", i), n)] = ("scalar", rng.standard_normal(8).astype(np.float32).astype(np.float64))
+    return st
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_feature_configs_match_oracle(ctx, seed):
+    rng = np.random.Generator(np.random.PCG64(1000 + seed))
+    items = [f"i{k}" for k in range(25)]
+    users, sessions = ["u0", "u1"], ["s0", "s1", "s2"]
+    feats, model = _random_config(rng)
+    state = _random_state(rng, feats, items, users, sessions)
+    for key in list(state):  # keep normalized rates away from a zero global top counter (-> ArithmeticException)
+        if key[1].endswith("_click_norm"):
+            state[key] = ("pcounter", [max(1, v) for v in state[key][1]])
+    reqs = []
+    for r in range(6):
+        n = int(rng.integers(1, 40))
+        picks = [str(x) for x in rng.choice(items + ["nope1", "nope2"], n)]  # duplicates and unknown items
+        fields = [("query", str(rng.choice(["shoes", "hats", "socks"])))] if rng.random() < 0.8 else []
+        if rng.random() < 0.5:
+            fields.append(("price", float(rng.integers(0, 5))))
+        if rng.random() < 0.5:
+            fields.append(("title", "  some  words here "))
+        sim = next(f["name"] for f in feats if f["type"] == "field_match")
+        emb = {sim: rng.standard_normal(8).astype(np.float32)} if rng.random() < 0.8 else {}
+        its = []
+        for p in picks:
+            fl = []
+            if rng.random() < 0.7:
+                fl.append(("relevancy", float(rng.integers(0, 4))))
+            if rng.random() < 0.2:
+                fl.append(("price", float(rng.integers(10, 20))))
+            if rng.random() < 0.2:
+                fl.append(("color", str(rng.choice(["red", "zzz"]))))
+            its.append(dict(id=p, fields=fl))
+        reqs.append(dict(event="ranking", id=f"r{r}", timestamp=1_650_000_000_000 + int(rng.integers(0, 10**9)),
+                         user=str(rng.choice(users + ["ux"])) if rng.random() < 0.8 else None,
+                         session=str(rng.choice(sessions + ["sx"])) if rng.random() < 0.8 else None,
+                         fields=fields, embeddings=emb, items=its))
+    mapping = fo.FeatureMapping(feats, model)
+    fm, ds, rk, _, _ = _device(ctx, feats, model, state)
+    try:
+        assert fm.dim == mapping.dim
+        got = rk.make_query(reqs)
+        for r, q in enumerate(reqs):
+            want = fo.dense_matrix(mapping, q, state)
+            if not _eq(got[r], want):
+                bad = np.argwhere(~((got[r] == want) | ((got[r] != got[r]) & (want != want))))
+                cols = {n: mapping.offsets[n] for n in mapping.offsets}
+                raise AssertionError(f"seed {seed} request {r}: mismatch at {bad[:6].tolist()} cols={cols}\n"
+                                     f"got={got[r][bad[0][0]].tolist()}\nwant={want[bad[0][0]].tolist()}")
+    finally:
+        ds.free(); fm.free()
