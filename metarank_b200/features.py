@@ -199,7 +199,8 @@ class FeatureMapping:
                 elif t == "field_match":
                     slot = self.input_slot(MR_IN_REQ_VEC, name)
                     q_emb = (q.get("embeddings") or {}).get(name)
-                    if q_emb is not None:
+                    qf = rf.get(_field_name(conf["rankingField"])[1])
+                    if q_emb is not None and (isinstance(qf, str) or strl(qf)):  # no query field -> feature missing
                         o, d = self.vec_offset(slot)
                         req_vec[r, o:o + d] = np.asarray(q_emb, dtype=np.float32)
                         req_vp[r, slot] = 1

@@ -775,8 +775,12 @@ class FieldMatchBiencoderFeature(BaseFeature):
         return {self.name: dict(kind="scalar", scope=("item",), refresh=0)}
 
     def values(self, req, state, mode="online", query_embedding=None):
+        # the query STRING comes from the ranking field (StringField, or StringListField joined by " ");
+        # without it the feature is missing whatever the caches hold (:84-88)
+        qf = fields_map(req.get("fields", [])).get(self.ranking_field)
+        has_query = isinstance(qf, str) or is_strlist(qf)
         q = (req.get("embeddings") or {}).get(self.name) if query_embedding is None else query_embedding
-        if q is None:
+        if q is None or not has_query:
             return [[NAN] for _ in req["items"]]
         raw = []
         for it in req["items"]:
