@@ -76,7 +76,10 @@ __global__ void lookup_kernel(RankArgs a) {
     a.visitor_row[2 * i] = u ? probe(a.st.t[SC_USER], u) : kNoRow;
     a.visitor_row[2 * i + 1] = s ? probe(a.st.t[SC_SESSION], s) : kNoRow;
   }
-  if (i == 0) *a.hist_cursor = 0;
+  if (i == 0) {  // first kernel of every rank call: reset the per-call device state
+    *a.hist_cursor = 0;
+    *a.error_flag = 0;
+  }
 }
 
 // ------------------------------------------------------------------ cosine

@@ -313,9 +313,11 @@ void rank_enqueue(mr_state *st, mr_model *model, const mr_rank_batch *b, int r0,
   const bool fused = fused_codes(model);
   const size_t leaf_bytes = (fused && model->use_latency(N)) ? latency_scratch_bytes(N, (int)model->host.trees.size()) : 0;
   ScratchPlan sp = plan_scratch(S, R, N, st->hist_pool_per_hist, want_features || !fused, fused, leaf_bytes);
+  // device outputs are laid out [scores | order | error flag] so that the common (unpinned) case is ONE D2H copy
   const size_t scores_off = al(in_bytes) + sp.total, order_off = scores_off + al((size_t)N * 8);
-  const size_t d_total = order_off + al((size_t)N * 4);
-  const size_t out_bytes = al((size_t)N * 8) + al((size_t)N * 4) + (want_features ? al((size_t)N * S.dim * 8) : 0) + 16;
+  const size_t err_off = order_off + al((size_t)N * 4);
+  const size_t d_total = err_off + 256;
+  const size_t out_bytes = al((size_t)N * 8) + al((size_t)N * 4) + 256 + (want_features ? al((size_t)N * S.dim * 8) : 0) + 16;
   lane->ensure(in_bytes + out_bytes, d_total);
   for (int k = 0; k < ns; k++)
     if (segs[k].bytes && !(k == s_ids && pin.ids)) memcpy(lane->h_pinned + segs[k].off, segs[k].src, segs[k].bytes);
@@ -348,34 +350,38 @@ void rank_enqueue(mr_state *st, mr_model *model, const mr_rank_batch *b, int r0,
   a.req_vec_present = (const uint8_t *)dp(s_rp);
   a.item_f64 = (const double *)dp(s_if);
   a.out_features = (want_features || !fused) ? (double *)(scratch + sp.features) : nullptr;
+  a.error_flag = (int32_t *)(lane->d_buf + err_off);  // zeroed by lookup_kernel
   if (fused) set_codes(a, model, scratch, sp);
-  MR_CUDA_CHECK(cudaMemsetAsync(a.error_flag, 0, 4, lane->stream));
   launch_assemble(a, S, lane->stream);
   double *d_scores = (double *)(lane->d_buf + scores_off);
   int32_t *d_order = (int32_t *)(lane->d_buf + order_off);
   uint8_t *h_out = lane->h_pinned + in_bytes;
-  size_t ho = 0;
   pd.in_bytes = in_bytes;
   if (model) {
     if (fused) model->score_codes(a.codes, N, d_scores, lane->stream, leaf_bytes ? scratch + sp.leafvals : nullptr);
     else model->score(a.out_features, N, S.dim, d_scores, lane->stream);
     if (want_order) launch_rank_order(d_scores, a.item_offsets, R, N, d_order, lane->stream);
-    MR_CUDA_CHECK(cudaMemcpyAsync(pin.scores ? (void *)(out_scores + i0) : (void *)(h_out + ho), d_scores, (size_t)N * 8,
-                                  cudaMemcpyDeviceToHost, lane->stream));
   }
-  pd.ho_scores = ho; ho += al((size_t)N * 8);
-  if (model && want_order)
-    MR_CUDA_CHECK(cudaMemcpyAsync(pin.order ? (void *)(out_order + i0) : (void *)(h_out + ho), d_order, (size_t)N * 4,
-                                  cudaMemcpyDeviceToHost, lane->stream));
-  pd.ho_order = ho; ho += al((size_t)N * 4);
-  pd.ho_feat = ho;
-  if (want_features) {
-    MR_CUDA_CHECK(cudaMemcpyAsync(pin.features ? (void *)(out_features + (size_t)i0 * S.dim) : (void *)(h_out + ho),
+  // host staging mirrors the device layout: [scores | order | err | features]
+  pd.ho_scores = 0;
+  pd.ho_order = al((size_t)N * 8);
+  pd.ho_err = pd.ho_order + al((size_t)N * 4);
+  pd.ho_feat = pd.ho_err + 256;
+  const bool any_pinned = pin.scores || pin.order;
+  if (!any_pinned) {
+    MR_CUDA_CHECK(cudaMemcpyAsync(h_out, d_scores, pd.ho_err + 4, cudaMemcpyDeviceToHost, lane->stream));
+  } else {
+    if (model)
+      MR_CUDA_CHECK(cudaMemcpyAsync(pin.scores ? (void *)(out_scores + i0) : (void *)(h_out + pd.ho_scores), d_scores,
+                                    (size_t)N * 8, cudaMemcpyDeviceToHost, lane->stream));
+    if (model && want_order)
+      MR_CUDA_CHECK(cudaMemcpyAsync(pin.order ? (void *)(out_order + i0) : (void *)(h_out + pd.ho_order), d_order,
+                                    (size_t)N * 4, cudaMemcpyDeviceToHost, lane->stream));
+    MR_CUDA_CHECK(cudaMemcpyAsync(h_out + pd.ho_err, a.error_flag, 4, cudaMemcpyDeviceToHost, lane->stream));
+  }
+  if (want_features)
+    MR_CUDA_CHECK(cudaMemcpyAsync(pin.features ? (void *)(out_features + (size_t)i0 * S.dim) : (void *)(h_out + pd.ho_feat),
                                   a.out_features, (size_t)N * S.dim * 8, cudaMemcpyDeviceToHost, lane->stream));
-    ho += al((size_t)N * S.dim * 8);
-  }
-  pd.ho_err = ho;
-  MR_CUDA_CHECK(cudaMemcpyAsync(h_out + ho, a.error_flag, 4, cudaMemcpyDeviceToHost, lane->stream));
 }
 
 // Waits for the slice and copies its outputs to the caller's buffers; returns the device error flag.
@@ -512,7 +518,6 @@ mr_status mr_rank_device(mr_state *st, mr_model *model, const mr_rank_batch *b, 
     a.item_f64 = b->item_f64;
     a.out_features = d_out_features ? d_out_features : (fused ? nullptr : (double *)(st->d_scratch + sp.features));
     if (fused) set_codes(a, model, st->d_scratch, sp);
-    MR_CUDA_CHECK(cudaMemsetAsync(a.error_flag, 0, 4, stream));
     launch_assemble(a, S, stream);
     if (model) {
       if (!d_out_scores) fail(MR_ERR_INVALID_ARG, "d_out_scores is null");
