@@ -251,53 +251,80 @@ __global__ void __launch_bounds__(1024) gbdt_score_compact_kernel(const BParams 
 #pragma unroll 1
       for (int t = 0; t < ntree; t++) {
         uint32_t n = roots[t];
-        if (HAS_CAT) {
-          // models with categorical splits (e.g. ranklens' `genre`): same layout, plain C++ level loop
-          while (!(n & 1u)) {
+        // One tree level = 12 SASS instructions; spelled in PTX because nvcc otherwise routes the
+        // predicates through integer registers (18 instructions).  With HAS_CAT the loop additionally
+        // leaves on a categorical node (bit 1 of word0), which is resolved in C++ below, then re-enters.
+        while (!(n & 1u)) {
+          if (HAS_CAT) {
+            asm volatile(
+                "{\n"
+                ".reg .pred pl, pn, pf, pq, pc;\n"
+                ".reg .b32 w0, w1, off, code, kk, sel, tmp;\n"
+                "LVLC:\n"
+                "add.u32 tmp, %1, %0;\n"
+                "ld.shared.v2.u32 {w0, w1}, [tmp];\n"
+                "and.b32 tmp, w0, 2;\n"
+                "setp.ne.u32 pc, tmp, 0;\n"
+                "@pc bra DONEC;\n"
+                "lop3.b32 off, w0, 0xFFC0, %3, 0xEA;\n"
+                "add.u32 off, off, %2;\n"
+                "ld.shared.u16 code, [off];\n"
+                "shr.u32 kk, w0, 16;\n"
+                "setp.le.u32 pl, code, kk;\n"
+                "setp.eq.u32 pn, code, 0xFFFF;\n"
+                "and.b32 tmp, w0, 1;\n"
+                "setp.ne.u32 pf, tmp, 0;\n"
+                "and.pred pn, pn, pf;\n"
+                "or.pred pl, pl, pn;\n"
+                "selp.b32 sel, 0x4410, 0x4432, pl;\n"
+                "prmt.b32 %0, w1, 0, sel;\n"
+                "and.b32 tmp, %0, 1;\n"
+                "setp.eq.u32 pq, tmp, 0;\n"
+                "@pq bra LVLC;\n"
+                "DONEC:\n"
+                "}\n"
+                : "+r"(n)
+                : "r"(cb_addr), "r"(xwarp_addr), "r"(lane2)
+                : "memory");
+            if (n & 1u) break;
+            // categorical node: NaN / negative / out-of-bitset go right (LightGBM CategoricalDecision)
             const uint2 nd = *reinterpret_cast<const uint2 *>(cb + n);
             const uint32_t code = *reinterpret_cast<const uint16_t *>(xwarp + ((nd.x & 0xFFC0u) | lane2));
-            bool left;
-            if (nd.x & 2u) {
-              left = false;
-              if (code != kBinNaN) {
-                const uint2 ct = reinterpret_cast<const uint2 *>(cb)[nd.x >> 16];
-                const uint32_t w = code >> 5;
-                if (w < ct.y) left = (reinterpret_cast<const uint32_t *>(cb)[ct.x + w] >> (code & 31u)) & 1u;
-              }
-            } else {
-              left = (code <= (nd.x >> 16)) || (code == kBinNaN && (nd.x & 1u));
+            bool left = false;
+            if (code != kBinNaN) {
+              const uint2 ct = reinterpret_cast<const uint2 *>(cb)[nd.x >> 16];
+              const uint32_t w = code >> 5;
+              if (w < ct.y) left = (reinterpret_cast<const uint32_t *>(cb)[ct.x + w] >> (code & 31u)) & 1u;
             }
             n = __byte_perm(nd.y, 0u, left ? 0x4410u : 0x4432u);
+          } else {
+            asm volatile(
+                "{\n"
+                ".reg .pred pl, pn, pf, pq;\n"
+                ".reg .b32 w0, w1, off, code, kk, sel, tmp;\n"
+                "LVL:\n"
+                "add.u32 tmp, %1, %0;\n"
+                "ld.shared.v2.u32 {w0, w1}, [tmp];\n"
+                "lop3.b32 off, w0, 0xFFC0, %3, 0xEA;\n"   // (w0 & 0xFFC0) | lane*2
+                "add.u32 off, off, %2;\n"
+                "ld.shared.u16 code, [off];\n"
+                "shr.u32 kk, w0, 16;\n"
+                "setp.le.u32 pl, code, kk;\n"
+                "setp.eq.u32 pn, code, 0xFFFF;\n"
+                "and.b32 tmp, w0, 1;\n"
+                "setp.ne.u32 pf, tmp, 0;\n"
+                "and.pred pn, pn, pf;\n"
+                "or.pred pl, pl, pn;\n"                    // NaN code is never <= k, so this only adds NaN -> left
+                "selp.b32 sel, 0x4410, 0x4432, pl;\n"
+                "prmt.b32 %0, w1, 0, sel;\n"
+                "and.b32 tmp, %0, 1;\n"
+                "setp.eq.u32 pq, tmp, 0;\n"
+                "@pq bra LVL;\n"
+                "}\n"
+                : "+r"(n)
+                : "r"(cb_addr), "r"(xwarp_addr), "r"(lane2)
+                : "memory");
           }
-        } else if (!(n & 1u)) {
-          // one tree level = 12 SASS instructions; spelled in PTX because nvcc otherwise routes the
-          // predicates through integer registers (18 instructions)
-          asm volatile(
-              "{\n"
-              ".reg .pred pl, pn, pf, pq;\n"
-              ".reg .b32 w0, w1, off, code, kk, sel, tmp;\n"
-              "LVL:\n"
-              "add.u32 tmp, %1, %0;\n"
-              "ld.shared.v2.u32 {w0, w1}, [tmp];\n"
-              "lop3.b32 off, w0, 0xFFC0, %3, 0xEA;\n"   // (w0 & 0xFFC0) | lane*2
-              "add.u32 off, off, %2;\n"
-              "ld.shared.u16 code, [off];\n"
-              "shr.u32 kk, w0, 16;\n"
-              "setp.le.u32 pl, code, kk;\n"
-              "setp.eq.u32 pn, code, 0xFFFF;\n"
-              "and.b32 tmp, w0, 1;\n"
-              "setp.ne.u32 pf, tmp, 0;\n"
-              "and.pred pn, pn, pf;\n"
-              "or.pred pl, pl, pn;\n"                    // NaN code is never <= k, so this only adds NaN -> left
-              "selp.b32 sel, 0x4410, 0x4432, pl;\n"
-              "prmt.b32 %0, w1, 0, sel;\n"
-              "and.b32 tmp, %0, 1;\n"
-              "setp.eq.u32 pq, tmp, 0;\n"
-              "@pq bra LVL;\n"
-              "}\n"
-              : "+r"(n)
-              : "r"(cb_addr), "r"(xwarp_addr), "r"(lane2)
-              : "memory");
         }
         acc += *reinterpret_cast<const Real *>(cb + (n - 1u));
       }
