@@ -553,7 +553,6 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
       if (row) row[col] = v;
       if (codes) codes[(size_t)col * 32] = code_of(*bp, col, v);
     }
-    __device__ __forceinline__ Emit &self() { return *this; }
   };
   struct OutProxy {  // lets the extractor code below keep writing out[col] = v
     const Emit *e; int col;

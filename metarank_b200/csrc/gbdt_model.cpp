@@ -508,7 +508,7 @@ BinnedModel pack_binned(const HostModel &m, size_t chunk_budget) {
       for (size_t q = 0; q < t.feat.size(); q++) {
         BNodeHost &d = nodes[q];
         const int f = t.feat[q];
-        uint32_t fl = (t.flags[q] & NF_NAN_LEFT) ? BF_NAN_LEFT : 0;
+        uint32_t fl = (t.flags[q] & NF_NAN_LEFT) ? (uint32_t)BF_NAN_LEFT : 0u;
         if (t.flags[q] & NF_CATEGORICAL) {
           fl = BF_CATEGORICAL;  // NaN always goes right at categorical nodes
           ctab[2 * ci] = (uint32_t)(cw_off / 4 + (size_t)t.cat_begin[q]);

@@ -112,13 +112,6 @@ void set_codes(RankArgs &a, const mr_model *model, uint8_t *scratch, const Scrat
   a.bin.xgb = model->host.kind == MR_BOOSTER_XGBOOST;
 }
 
-void ensure_flushed(mr_state *st) {
-  if (st->dirty) {
-    st->store->flush();
-    st->dirty = false;
-  }
-}
-
 void check_scored_dim(mr_state *st, mr_model *model) {
   if (model && model->host.n_features != st->store->schema.dim)
     fail(MR_ERR_FEATURE_MISMATCH, "booster reads %d features, the schema's dataset descriptor has %d columns",
