@@ -592,3 +592,35 @@ def test_random_feature_configs_match_oracle(ctx, seed):
                                      f"got={got[r][bad[0][0]].tolist()}\nwant={want[bad[0][0]].tolist()}")
     finally:
         ds.free(); fm.free()
+
+
+def test_two_contexts_in_one_process_on_two_gpus():
+    """A JVM drives all GPUs of the box from one process: one mr_ctx per device, requests round-robin.
+    Skipped on single-GPU boxes."""
+    import torch
+
+    import metarank_b200 as mb
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    blob = synth.lightgbm_model_text(120, 30, seed=5)
+    X = synth.feature_matrix(5000, 30, seed=6)
+    want = oracle.OracleBooster(0, blob).predictMat(X, *X.shape)
+    ctxs = [mb.Context(0), mb.Context(1)]
+    boosters = [mb.LightGBMBooster(c, blob) for c in ctxs]
+    import threading
+
+    out = [None, None]
+
+    def work(k):
+        for _ in range(5):
+            out[k] = boosters[k].predictMat(X, *X.shape)
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert np.array_equal(out[0], want) and np.array_equal(out[1], want)
+    for b in boosters:
+        b.free()
+    for c in ctxs:
+        c.close()
