@@ -248,7 +248,11 @@ def main():
     gpu_launches = mb._capi.lib().mr_kernel_launches() - launches1
     total_ms = e0.elapsed_time(e1)
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    rank_ms = [total_ms / args.steps]
     if world > 1:
+        allt = torch.zeros(world, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allt, t)
+        rank_ms = [float(x) / args.steps for x in allt.cpu()]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = rows * world * args.steps / (total_ms / 1e3)
@@ -366,7 +370,7 @@ def main():
                     "d2h_bytes_per_step": rows * 12, "steps": e2e_steps, "parity_ok": e2e_ok,
                     "what": "mr_rank: item-id hashes in page-locked host memory -> scores + order in page-locked host memory, "
                             "H2D and D2H copies inside the timer"},
-            "gpu_launches": int(gpu_launches),
+            "gpu_launches": int(gpu_launches), "rank_ms_per_step": rank_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "bytes_per_item": b_item, "mean_path": dbar,
                          "kernel_ms": kernel_ms, "kernel": kernel_name,
