@@ -243,6 +243,24 @@ void StateStore::upsert(const uint8_t *buf, size_t len, int64_t *applied, int64_
   if (skipped) *skipped = n_skip;
 }
 
+// Incremental flush: a handful of touched rows are packed [row index][row words] on the host, copied once
+// and scattered into the table by this kernel — instead of re-uploading the span between the first and
+// the last touched row.
+__global__ void scatter_rows_kernel(uint64_t *rows, int row_words, const uint32_t *idx, const uint64_t *packed, int n) {
+  const int r = blockIdx.x;
+  if (r >= n) return;
+  uint64_t *dst = rows + (size_t)idx[r] * row_words;
+  const uint64_t *src = packed + (size_t)r * row_words;
+  for (int w = threadIdx.x; w < row_words; w += blockDim.x) dst[w] = src[w];
+}
+__global__ void scatter_side_kernel(double *side, int dim, const uint32_t *idx, const double *packed, int n) {
+  const int r = blockIdx.x;
+  if (r >= n) return;
+  double *dst = side + (size_t)idx[r] * dim;
+  const double *src = packed + (size_t)r * dim;
+  for (int w = threadIdx.x; w < dim; w += blockDim.x) dst[w] = src[w];
+}
+
 template <class T> static void ensure_dev(T *&d, size_t &cap, size_t need, size_t keep, int64_t &bytes) {
   if (need <= cap) return;
   size_t ncap = std::max(need, cap * 2);
@@ -272,20 +290,60 @@ void StateStore::flush() {
     if (T.dirty_lo < T.dirty_hi) {
       const size_t had = T.d_rows_cap;
       ensure_dev(T.d_rows, T.d_rows_cap, T.rows.size(), 0, device_bytes);
-      size_t lo = T.dirty_lo, hi = T.dirty_hi;
-      if (T.d_rows_cap != had) { lo = 0; hi = T.n_rows; }  // reallocated: upload everything
-      MR_CUDA_CHECK(cudaMemcpy(T.d_rows + lo * T.row_words, T.rows.data() + lo * T.row_words,
-                               (hi - lo) * T.row_words * 8, cudaMemcpyHostToDevice));
+      bool realloc_any = T.d_rows_cap != had;
       for (size_t s = 0; s < T.sides.size(); s++) {
         const int dim = schema.sides[T.side_ids[s]].dim;
         if (T.sides[s].size() < T.n_rows * (size_t)dim) T.sides[s].resize(T.n_rows * (size_t)dim, 0.0);
         const size_t had_s = T.d_sides_cap[s];
         ensure_dev(T.d_sides[s], T.d_sides_cap[s], T.sides[s].size(), 0, device_bytes);
-        size_t slo = T.dirty_lo, shi = T.dirty_hi;
-        if (T.d_sides_cap[s] != had_s) { slo = 0; shi = T.n_rows; }
-        MR_CUDA_CHECK(cudaMemcpy(T.d_sides[s] + slo * dim, T.sides[s].data() + slo * dim, (shi - slo) * dim * 8,
-                                 cudaMemcpyHostToDevice));
+        realloc_any |= T.d_sides_cap[s] != had_s;
       }
+      const size_t n_dirty = T.dirty_rows.size();
+      const bool sparse = !realloc_any && n_dirty * 8 < (T.dirty_hi - T.dirty_lo);  // < 1/8 of the span touched
+      if (sparse) {
+        // scatter path: [idx][packed rows] in one staging blob per table (and per side array)
+        uint32_t *d_idx = nullptr;
+        MR_CUDA_CHECK(cudaMalloc((void **)&d_idx, n_dirty * 4));
+        MR_CUDA_CHECK(cudaMemcpy(d_idx, T.dirty_rows.data(), n_dirty * 4, cudaMemcpyHostToDevice));
+        {
+          std::vector<uint64_t> packed(n_dirty * (size_t)T.row_words);
+          for (size_t k = 0; k < n_dirty; k++)
+            memcpy(packed.data() + k * T.row_words, T.rows.data() + (size_t)T.dirty_rows[k] * T.row_words, (size_t)T.row_words * 8);
+          uint64_t *d_packed = nullptr;
+          MR_CUDA_CHECK(cudaMalloc((void **)&d_packed, packed.size() * 8));
+          MR_CUDA_CHECK(cudaMemcpy(d_packed, packed.data(), packed.size() * 8, cudaMemcpyHostToDevice));
+          scatter_rows_kernel<<<(unsigned)n_dirty, 64>>>(T.d_rows, T.row_words, d_idx, d_packed, (int)n_dirty);
+          MR_CUDA_CHECK(cudaGetLastError());
+          MR_CUDA_CHECK(cudaDeviceSynchronize());
+          cudaFree(d_packed);
+        }
+        for (size_t s = 0; s < T.sides.size(); s++) {
+          const int dim = schema.sides[T.side_ids[s]].dim;
+          std::vector<double> packed(n_dirty * (size_t)dim);
+          for (size_t k = 0; k < n_dirty; k++)
+            memcpy(packed.data() + k * dim, T.sides[s].data() + (size_t)T.dirty_rows[k] * dim, (size_t)dim * 8);
+          double *d_packed = nullptr;
+          MR_CUDA_CHECK(cudaMalloc((void **)&d_packed, packed.size() * 8));
+          MR_CUDA_CHECK(cudaMemcpy(d_packed, packed.data(), packed.size() * 8, cudaMemcpyHostToDevice));
+          scatter_side_kernel<<<(unsigned)n_dirty, 128>>>(T.d_sides[s], dim, d_idx, d_packed, (int)n_dirty);
+          MR_CUDA_CHECK(cudaGetLastError());
+          MR_CUDA_CHECK(cudaDeviceSynchronize());
+          cudaFree(d_packed);
+        }
+        cudaFree(d_idx);
+      } else {
+        size_t lo = T.dirty_lo, hi = T.dirty_hi;
+        if (realloc_any) { lo = 0; hi = T.n_rows; }  // reallocated: upload everything
+        MR_CUDA_CHECK(cudaMemcpy(T.d_rows + lo * T.row_words, T.rows.data() + lo * T.row_words,
+                                 (hi - lo) * T.row_words * 8, cudaMemcpyHostToDevice));
+        for (size_t s = 0; s < T.sides.size(); s++) {
+          const int dim = schema.sides[T.side_ids[s]].dim;
+          MR_CUDA_CHECK(cudaMemcpy(T.d_sides[s] + lo * dim, T.sides[s].data() + lo * dim, (hi - lo) * dim * 8,
+                                   cudaMemcpyHostToDevice));
+        }
+      }
+      for (uint32_t r : T.dirty_rows) T.row_dirty[r] = 0;
+      T.dirty_rows.clear();
       T.dirty_lo = SIZE_MAX;
       T.dirty_hi = 0;
     }

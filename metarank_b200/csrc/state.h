@@ -64,7 +64,14 @@ struct HostTable {
   uint32_t find(uint64_t key) const;
   uint32_t find_or_insert(uint64_t key);
   void grow_map();
-  void touch(size_t row) { dirty_lo = std::min(dirty_lo, row); dirty_hi = std::max(dirty_hi, row + 1); }
+  std::vector<uint8_t> row_dirty;     // per row: touched since the last flush
+  std::vector<uint32_t> dirty_rows;   // the touched rows (each once), for the scatter upload
+  void touch(size_t row) {
+    dirty_lo = std::min(dirty_lo, row);
+    dirty_hi = std::max(dirty_hi, row + 1);
+    if (row_dirty.size() <= row) row_dirty.resize(std::max(row + 1, row_dirty.size() * 2), 0);
+    if (!row_dirty[row]) { row_dirty[row] = 1; dirty_rows.push_back((uint32_t)row); }
+  }
 };
 
 struct StateStore {

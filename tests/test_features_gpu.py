@@ -200,6 +200,31 @@ def test_state_updates_are_visible_after_flush(ctx):
         got = rk.make_query([G.ranking([f"x{i}" for i in range(0, 5000, 7)] + ["p1"])])[0]
         assert _eq(got[:, 0], [float(i) for i in range(0, 5000, 7)] + [5.0])
         assert ds.info().rows[1] == 5002
+        # a few scattered rows of a large table: the scatter-kernel path of mr_state_flush
+        ds.put({(("item", "x3"), "price"): ("scalar", -3.0), (("item", "x4000"), "price"): ("scalar", -4000.0)})
+        ds.flush()
+        got = rk.make_query([G.ranking(["x3", "x4", "x4000", "x4999", "p2"])])[0]
+        assert _eq(got[:, 0], [-3.0, 4.0, -4000.0, 4999.0, 2.0])
+    finally:
+        ds.free(); fm.free()
+
+
+def test_sparse_flush_of_embedding_rows(ctx):
+    feats = [dict(name="sim", type="field_match", rankingField="ranking.query", itemField="item.title",
+                  method=dict(type="bi-encoder", dim=16), distance="cos")]
+    rng = np.random.Generator(np.random.PCG64(3))
+    state = {(("item", f"i{k}"), "sim"): ("scalar", rng.standard_normal(16)) for k in range(400)}
+    fm, ds, rk, _, _ = _device(ctx, feats, ["sim"], state)
+    mapping = fo.FeatureMapping(feats, ["sim"])
+    try:
+        upd = {(("item", "i7"), "sim"): ("scalar", rng.standard_normal(16)), (("item", "i390"), "sim"): ("scalar", rng.standard_normal(16))}
+        state.update(upd)
+        ds.put(upd)
+        ds.flush()
+        req = dict(event="ranking", id="r", timestamp=0, user=None, session=None, fields=[("query", "q")],
+                   embeddings={"sim": rng.standard_normal(16).astype(np.float32)},
+                   items=[dict(id=f"i{k}", fields=[]) for k in (6, 7, 8, 389, 390, 391)])
+        assert _eq(rk.make_query([req])[0], fo.dense_matrix(mapping, req, state))
     finally:
         ds.free(); fm.free()
 
