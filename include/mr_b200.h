@@ -150,7 +150,8 @@ MR_API mr_status mr_model_close(mr_model *m);
 MR_API int32_t mr_model_is_closed(mr_model *m);
 MR_API mr_status mr_model_free(mr_model *m);
 
-/* Tuning knobs for experiments (bench.py / tests); defaults are chosen per model.
+/* Tuning knobs for experiments (bench.py / tests); defaults are chosen per model.  Not synchronised
+ * against concurrent predicts on the same handle: set them before serving.
  * key: "threads" (items per CTA, 0 = auto), "chunk_kb", "ilp" (trees in flight per thread),
  * "variant" (-1 = auto, 0 = f64/f32 lock-step, 1 = f64 free-running, 2 = binned lock-step, 3 = binned
  * free-running, 4 = binned lock-step on the compact layout). */
@@ -248,7 +249,8 @@ MR_API mr_status mr_state_upsert(mr_state *st, const uint8_t *packed, size_t len
  *   op 2 PeriodicIncrement: i64 inc | op 3 Append: u64 mr_hash64 of the appended string (an item id)
  * Visible to mr_rank after mr_state_flush. */
 MR_API mr_status mr_state_apply_writes(mr_state *st, const uint8_t *packed, size_t len, int64_t *applied, int64_t *skipped);
-/* Uploads pending upserts to HBM (synchronous). */
+/* Uploads pending upserts / writes to HBM (synchronous; waits for in-flight mr_rank calls).  A handful of
+ * touched rows are packed and scattered by a kernel; bulk loads copy the touched row range. */
 MR_API mr_status mr_state_flush(mr_state *st);
 typedef struct mr_state_info {
   int64_t rows[6];        /* global, item, user, session, field, irf */
@@ -284,7 +286,10 @@ MR_API mr_status mr_rank(mr_state *st, mr_model *model, const mr_rank_batch *bat
 
 /* Same, with every pointer in `batch` and the outputs being DEVICE memory and the work
  * enqueued on `cuda_stream` without synchronising (bench.py's HBM-resident `value`).
- * Arithmetic errors (MR_ERR_ARITHMETIC) are reported by mr_rank_device_status. */
+ * Arithmetic errors (MR_ERR_ARITHMETIC) are reported by mr_rank_device_status.
+ * Unlike mr_rank (which checks out a private lane per call and may be called concurrently), the
+ * device-batch API keeps ONE scratch area and error flag per mr_state: use one stream at a time per
+ * state, or one mr_state per stream. */
 MR_API mr_status mr_rank_device(mr_state *st, mr_model *model, const mr_rank_batch *d_batch, int32_t total_items,
                                 double *d_out_scores, int32_t *d_out_order, double *d_out_features,
                                 void *cuda_stream);
