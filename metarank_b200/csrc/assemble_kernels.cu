@@ -529,6 +529,16 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
     const int n_words = a.n_plan * (int)(sizeof(DFeature) / 4);
     for (int k = threadIdx.x; k < n_words; k += blockDim.x) dst[k] = __ldg(src + k);
   }
+  // ... and so are the per-column bucket-index headers of the binned scorer (32 B each)
+  BinParams bin = a.bin;
+  if (a.codes && a.stage_meta) {
+    uint8_t *s_meta_raw = s_plan_raw + (((size_t)a.n_plan * sizeof(DFeature) + 15) & ~size_t(15));
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(a.bin.meta);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(s_meta_raw);
+    const int n_words = a.dim * (int)(sizeof(BinMeta) / 4);
+    for (int k = threadIdx.x; k < n_words; k += blockDim.x) dst[k] = __ldg(src + k);
+    bin.meta = reinterpret_cast<const BinMeta *>(s_meta_raw);
+  }
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.total_items) return;
@@ -563,7 +573,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
     __device__ __forceinline__ OutProxy operator[](int col) const { return OutProxy{e, col}; }
   };
   const Emit emit{a.out_features ? a.out_features + (size_t)i * a.dim : nullptr,
-                  a.codes ? a.codes + ((size_t)(i >> 5) * a.dim) * 32 + (i & 31) : nullptr, &a.bin};
+                  a.codes ? a.codes + ((size_t)(i >> 5) * a.dim) * 32 + (i & 31) : nullptr, &bin};
   const OutArr out{&emit};
 
   auto scoped_row = [&](int scope) -> const uint64_t * {
@@ -584,7 +594,13 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
         double v = kNaN;
         const double o = (d.in0 >= 0 && ov) ? ov[d.in0] : kNaN;
         if (o == o) v = o;
-        else { const uint64_t *rp = scoped_row(d.scope); if (rp && present(rp, d.b[0])) v = __longlong_as_double((long long)rp[d.w[0]]); }
+        else {
+          const uint64_t *rp = scoped_row(d.scope);
+          if (rp) {  // presence word and value word are fetched together (same or adjacent sector), then selected
+            const uint64_t pw = __ldg(rp + (d.b[0] >> 6)), vw = __ldg(rp + d.w[0]);
+            if ((pw >> (d.b[0] & 63)) & 1ull) v = __longlong_as_double((long long)vw);
+          }
+        }
         out[d.col] = v;
         break;
       }
@@ -806,7 +822,13 @@ void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t strea
     MR_CUDA_CHECK(cudaGetLastError());
     g_kernel_launches++;
   }
-  assemble_kernel<<<(a.total_items + 127) / 128, 128, (size_t)std::max(a.n_plan, 1) * sizeof(DFeature), stream>>>(a);
+  {
+    RankArgs b = a;
+    const size_t plan_bytes = (((size_t)std::max(a.n_plan, 1) * sizeof(DFeature)) + 15) & ~size_t(15);
+    const size_t meta_bytes = a.codes ? (size_t)a.dim * sizeof(BinMeta) : 0;
+    b.stage_meta = meta_bytes > 0 && plan_bytes + meta_bytes <= 40 * 1024;
+    assemble_kernel<<<(a.total_items + 127) / 128, 128, plan_bytes + (b.stage_meta ? meta_bytes : 0), stream>>>(b);
+  }
   MR_CUDA_CHECK(cudaGetLastError());
   g_kernel_launches++;
 }

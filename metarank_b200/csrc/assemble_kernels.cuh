@@ -38,6 +38,7 @@ struct RankArgs {
   double *out_features;   // [total_items x dim] row-major (ltrlib Query.values); may be null when codes != null
   uint16_t *codes;        // optional: u16 rank codes [group of 32 items][column][lane] for the binned scorer
   BinParams bin;          // thresholds of the model the codes are for (valid when codes != null)
+  int stage_meta;         // set by launch_assemble: bucket-index headers staged in shared memory
 };
 
 // Enqueues lookup -> cosine -> per-request prepass -> assemble on `stream`.

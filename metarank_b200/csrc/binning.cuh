@@ -14,8 +14,8 @@ struct BinParams {
   const uint32_t *thr_off;
   const double *thr;
   const uint8_t *is_cat;
-  const BinMeta *meta;           // [n_features] monotone bucket index (see gbdt_model.h)
-  const uint16_t *bucket_start;
+  const BinMeta *meta;           // [n_features] monotone bucket index (see gbdt_model.h); may point to shared memory
+  const uint32_t *bucket_range;
   uint16_t *bins;
   int rows, cols, n_features;
   int xgb;  // 1: round to binary32 first, strict less (upper_bound)
@@ -37,9 +37,9 @@ __device__ __forceinline__ uint16_t code_of(const BinParams &p, int f, double x)
     const double v = __dmul_rn(__dadd_rn(x, -M.mn), M.scale);
     bk = v >= (double)(M.g - 1) ? M.g - 1 : (uint32_t)v;
   }
-  const uint16_t *bs = p.bucket_start + M.idx_off + bk;
-  uint32_t lo = __ldg(bs), hi = __ldg(bs + 1);
-  const double *t = p.thr + __ldg(p.thr_off + f);
+  const uint32_t range = __ldg(p.bucket_range + M.idx_off + bk);
+  uint32_t lo = range & 0xFFFFu, hi = range >> 16;
+  const double *t = p.thr + M.thr_off;
   if (p.xgb) {
     while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__ldg(t + m) <= x) lo = m + 1; else hi = m; }  // #{t <= x}
   } else {

@@ -545,7 +545,7 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
   if (!L.codes_ready) {
   BinParams bp;
   bp.values = L.d_values; bp.thr_off = L.d_thr_off; bp.thr = L.d_thr; bp.is_cat = L.d_is_cat;
-  bp.meta = L.d_meta; bp.bucket_start = L.d_bucket_start;
+  bp.meta = L.d_meta; bp.bucket_range = L.d_bucket_range;
   bp.bins = L.d_bins; bp.rows = L.rows; bp.cols = L.cols; bp.n_features = F;
   bp.xgb = L.kind == MR_BOOSTER_XGBOOST;
   const int items_per_cta = kBinGroups * 32;

@@ -42,7 +42,7 @@ struct BinnedLaunch {
   const double *d_thr = nullptr;
   const uint8_t *d_is_cat = nullptr;    // [F]
   const BinMeta *d_meta = nullptr;      // [F]
-  const uint16_t *d_bucket_start = nullptr;
+  const uint32_t *d_bucket_range = nullptr;
   int kind = 0;
   bool has_cat = false;
   float base_score = 0.f;

@@ -437,7 +437,8 @@ BinnedModel pack_binned(const HostModel &m, size_t chunk_budget) {
     const double *t = B.thr.data() + B.thr_off[f];
     const uint32_t mth = B.thr_off[f + 1] - B.thr_off[f];
     BinMeta &M = B.meta[f];
-    M.mn = 0.0; M.scale = 0.0; M.g = 1; M.idx_off = (uint32_t)B.bucket_start.size();
+    M.mn = 0.0; M.scale = 0.0; M.g = 1; M.idx_off = (uint32_t)B.bucket_range.size();
+    M.thr_off = B.thr_off[f]; M.pad = 0;
     if (mth >= 2 && std::isfinite(t[0]) && std::isfinite(t[mth - 1])) {
       const double span = t[mth - 1] - t[0];
       const uint32_t g = std::min<uint32_t>(4 * mth, 32768);
@@ -451,11 +452,11 @@ BinnedModel pack_binned(const HostModel &m, size_t chunk_budget) {
       const double v = (x - M.mn) * M.scale;
       return v >= (double)(M.g - 1) ? M.g - 1 : (uint32_t)v;
     };
-    // prefix counts: bucket_start[b] = #{j : bucket(t_j) < b}
+    // prefix counts: cnt[b] = #{j : bucket(t_j) < b}; bucket b owns thresholds [cnt[b], cnt[b+1])
     std::vector<uint32_t> cnt(M.g + 1, 0);
     for (uint32_t j = 0; j < mth; j++) cnt[bucket(t[j]) + 1]++;
     for (uint32_t b = 0; b < M.g; b++) cnt[b + 1] += cnt[b];
-    for (uint32_t b = 0; b <= M.g; b++) B.bucket_start.push_back((uint16_t)cnt[b]);
+    for (uint32_t b = 0; b < M.g; b++) B.bucket_range.push_back(cnt[b] | (cnt[b + 1] << 16));
   }
   const bool f32 = m.kind == MR_BOOSTER_XGBOOST;
   const size_t leaf_sz = f32 ? 4 : 8;
@@ -549,7 +550,7 @@ BinnedModel pack_threaded(const HostModel &m, const BinnedModel &bn, size_t chun
   T.thr = bn.thr;
   T.is_cat = bn.is_cat;
   T.meta = bn.meta;
-  T.bucket_start = bn.bucket_start;
+  T.bucket_range = bn.bucket_range;
   const bool f32 = m.kind == MR_BOOSTER_XGBOOST;
   struct Entry { uint16_t k, ff; uint16_t left, right; };
   static_assert(sizeof(Entry) == 8, "entry must be 8 bytes");
@@ -621,7 +622,7 @@ BinnedModel pack_compact(const HostModel &m, const BinnedModel &bn, size_t chunk
   C.thr = bn.thr;
   C.is_cat = bn.is_cat;
   C.meta = bn.meta;
-  C.bucket_start = bn.bucket_start;
+  C.bucket_range = bn.bucket_range;
   const bool f32 = m.kind == MR_BOOSTER_XGBOOST;
   chunk_budget = std::min<size_t>(chunk_budget, 65536 - 16);
   auto n_cat_nodes = [](const HostTree &t) { size_t c = 0; for (auto fl : t.flags) c += (fl & NF_CATEGORICAL) != 0; return c; };

@@ -104,7 +104,9 @@ constexpr uint16_t kBinNaN = 0xFFFFu;
 struct BinMeta {
   double mn, scale;   // bucket(x) = x <= mn ? 0 : min(g - 1, (int)((x - mn) * scale))
   uint32_t g;         // number of buckets (>= 1)
-  uint32_t idx_off;   // offset of this column's g + 1 prefix counts in `bucket_start`
+  uint32_t idx_off;   // offset of this column's g entries in `bucket_range`
+  uint32_t thr_off;   // offset of this column's thresholds in `thr`
+  uint32_t pad;
 };
 
 struct BinnedModel {
@@ -112,7 +114,7 @@ struct BinnedModel {
   std::vector<uint32_t> thr_off;   // [n_features + 1] offsets into thr (numerical) per feature
   std::vector<double> thr;         // sorted distinct thresholds, all features back to back
   std::vector<BinMeta> meta;       // [n_features]
-  std::vector<uint16_t> bucket_start;
+  std::vector<uint32_t> bucket_range;  // per bucket: first threshold index | one-past-last << 16 (within the column)
   std::vector<uint8_t> is_cat;     // [n_features] feature is split categorically
   PackedModel packed;              // chunks of BNodes (+ leaves, + categorical tables)
 };

@@ -119,7 +119,7 @@ struct mr_model {
   double *d_thr = nullptr;
   uint8_t *d_is_cat = nullptr;
   BinMeta *d_meta = nullptr;
-  uint16_t *d_bucket_start = nullptr;
+  uint32_t *d_bucket_range = nullptr;
   std::atomic<bool> closed{false};
   std::atomic<int> inflight{0};
   std::mutex mu;  // guards repacking / device buffers
@@ -145,10 +145,10 @@ struct mr_model {
   void free_binned() {
     for (void *p : {(void *)d_bmodel, (void *)d_bchunks, (void *)d_thr_off, (void *)d_thr, (void *)d_is_cat,
                     (void *)d_tmodel, (void *)d_tchunks, (void *)d_cmodel, (void *)d_cchunks, (void *)d_lmodel,
-                    (void *)d_lchunks, (void *)d_meta, (void *)d_bucket_start})
+                    (void *)d_lchunks, (void *)d_meta, (void *)d_bucket_range})
       if (p) cudaFree(p);
     d_bmodel = nullptr; d_bchunks = nullptr; d_thr_off = nullptr; d_thr = nullptr; d_is_cat = nullptr;
-    d_tmodel = nullptr; d_tchunks = nullptr; d_cmodel = nullptr; d_cchunks = nullptr; d_lmodel = nullptr; d_lchunks = nullptr; d_meta = nullptr; d_bucket_start = nullptr;
+    d_tmodel = nullptr; d_tchunks = nullptr; d_cmodel = nullptr; d_cchunks = nullptr; d_lmodel = nullptr; d_lchunks = nullptr; d_meta = nullptr; d_bucket_range = nullptr;
   }
   void repack() {
     // Default policy: stream the ensemble through two small shared-memory buffers (TMA bulk
@@ -173,7 +173,7 @@ struct mr_model {
       d_thr = to_device(binned.thr);
       d_is_cat = to_device(binned.is_cat);
       d_meta = to_device(binned.meta);
-      d_bucket_start = to_device(binned.bucket_start);
+      d_bucket_range = to_device(binned.bucket_range);
       compact = pack_compact(host, binned, budget);
       if (compact.ok) {
         d_cmodel = to_device(compact.packed.bytes);
@@ -214,7 +214,7 @@ struct mr_model {
     B.n_chunks = (int)M.packed.chunks.size();
     B.max_chunk_bytes = M.packed.max_chunk_bytes;
     B.d_thr_off = d_thr_off; B.d_thr = d_thr; B.d_is_cat = d_is_cat;
-    B.d_meta = d_meta; B.d_bucket_start = d_bucket_start;
+    B.d_meta = d_meta; B.d_bucket_range = d_bucket_range;
     B.kind = host.kind; B.has_cat = host.has_cat; B.base_score = host.base_score;
     B.n_features = host.n_features;
     B.threads = opt_threads; B.ilp = opt_ilp;

@@ -107,7 +107,7 @@ void set_codes(RankArgs &a, const mr_model *model, uint8_t *scratch, const Scrat
   a.bin.thr = model->d_thr;
   a.bin.is_cat = model->d_is_cat;
   a.bin.meta = model->d_meta;
-  a.bin.bucket_start = model->d_bucket_start;
+  a.bin.bucket_range = model->d_bucket_range;
   a.bin.n_features = model->host.n_features;
   a.bin.xgb = model->host.kind == MR_BOOSTER_XGBOOST;
 }
