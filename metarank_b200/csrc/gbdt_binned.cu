@@ -254,8 +254,8 @@ __global__ void __launch_bounds__(1024) gbdt_score_compact_kernel(const BParams 
         // One tree level = 12 SASS instructions; spelled in PTX because nvcc otherwise routes the
         // predicates through integer registers (18 instructions).  With HAS_CAT the loop additionally
         // leaves on a categorical node (bit 1 of word0), which is resolved in C++ below, then re-enters.
-        while (!(n & 1u)) {
-          if (HAS_CAT) {
+        if (HAS_CAT) {
+          while (!(n & 1u)) {
             asm volatile(
                 "{\n"
                 ".reg .pred pl, pn, pf, pq, pc;\n"
@@ -297,7 +297,9 @@ __global__ void __launch_bounds__(1024) gbdt_score_compact_kernel(const BParams 
               if (w < ct.y) left = (reinterpret_cast<const uint32_t *>(cb)[ct.x + w] >> (code & 31u)) & 1u;
             }
             n = __byte_perm(nd.y, 0u, left ? 0x4410u : 0x4432u);
-          } else {
+          }
+        } else if (!(n & 1u)) {
+          {
             asm volatile(
                 "{\n"
                 ".reg .pred pl, pn, pf, pq;\n"

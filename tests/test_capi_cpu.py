@@ -99,3 +99,29 @@ def test_header_is_plain_c_and_usable_from_c():
         r = subprocess.run(args, capture_output=True, text=True)
         assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
         assert "sm_100a ok" in r.stdout
+
+
+def test_compact_level_loop_stays_at_twelve_sass_instructions():
+    """Performance regression guard (no GPU needed): the per-tree-level loop of the default scorer is
+    hand-written PTX that ptxas schedules into 12 SASS instructions; a careless edit around it once
+    silently grew it to 15 (+19 % kernel time, profiles/ncu_r1_summary.md)."""
+    import os
+    import re
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    obj = os.path.join(root, "metarank_b200", "csrc", "build", "gbdt_binned.o")
+    if not os.path.exists(tool) or not os.path.exists(obj):
+        pytest.skip("cuobjdump or the object file is not available")
+    sass = subprocess.run([tool, "-sass", obj], capture_output=True, text=True).stdout
+    m = re.search(r"Function : \S*compact_kernelIdLb0EE\S*\n(.*?)EXIT", sass, re.S)
+    assert m, "compact kernel <double, no categorical> not found"
+    ins = [re.sub(r"/\*.*?\*/", "", ln).strip() for ln in m.group(1).split("\n") if re.search(r"/\*[0-9a-f]{4}\*/", ln)]
+    ins = [i for i in ins if i]
+    start = next(k for k, i in enumerate(ins) if i.startswith("LDS.64") and "+UR" in i)
+    end = next(k for k in range(start, len(ins)) if "BRA" in ins[k])
+    body = ins[start:end + 1]
+    assert len(body) <= 12, body
+    assert sum("LDS" in i for i in body) == 2 and not any(i.startswith(("DSETP", "DADD", "LDG")) for i in body), body
