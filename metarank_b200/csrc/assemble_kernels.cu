@@ -518,6 +518,87 @@ __device__ __forceinline__ uint32_t hist_count(const RankArgs &a, int r, int h, 
   return lo - first;
 }
 
+// ------------------------------------------------------------------ coalesced row gather (fast columns)
+// Most columns of a typical config are a plain function of one word of the item's row (numbers, word
+// counts, booleans, category indices, counters, windows, stored vectors).  For those a WARP owns a
+// group of 32 items and walks them one by one: the whole row (<= 64 words) arrives with one or two
+// coalesced loads, lane c picks the word of column c out of the warp with a shuffle, converts it and
+// turns it into the scorer's rank code; codes are staged in shared memory and written one 64-byte line
+// per column, the f64 row (explain) as one contiguous run per item.
+constexpr int kGatherWarps = 4;
+
+__global__ void __launch_bounds__(kGatherWarps * 32) row_gather_kernel(RankArgs a) {
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  // [FastCol table][bucket headers (optional)][per warp: codes tile n_fast x 32 u16]
+  FastCol *s_cols = reinterpret_cast<FastCol *>(s_raw);
+  const size_t cols_bytes = ((size_t)a.n_fast * sizeof(FastCol) + 15) & ~size_t(15);
+  BinParams bin = a.bin;
+  size_t off = cols_bytes;
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(a.fast_cols);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(s_raw);
+    for (int k = threadIdx.x; k < a.n_fast * (int)(sizeof(FastCol) / 4); k += blockDim.x) dst[k] = __ldg(src + k);
+  }
+  if (a.codes && a.stage_meta) {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(a.bin.meta);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(s_raw + off);
+    for (int k = threadIdx.x; k < a.dim * (int)(sizeof(BinMeta) / 4); k += blockDim.x) dst[k] = __ldg(src + k);
+    bin.meta = reinterpret_cast<const BinMeta *>(s_raw + off);
+    off += (size_t)a.dim * sizeof(BinMeta);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint16_t *tile = reinterpret_cast<uint16_t *>(s_raw + off) + (size_t)warp * a.n_fast * 32;
+  const int g = blockIdx.x * kGatherWarps + warp;  // group of 32 items
+  const int i0 = g * 32;
+  if (i0 >= a.total_items) return;
+  const DTable &IT = a.st.t[SC_ITEM];
+  const int rw = IT.row_words;
+  const uint32_t my_row = (i0 + lane < a.total_items) ? a.item_row[i0 + lane] : kNoRow;
+  const int n_here = min(32, a.total_items - i0);
+  const double kNaN = nan_d();
+  for (int j = 0; j < n_here; j++) {
+    const uint32_t ir = __shfl_sync(0xFFFFFFFFu, my_row, j);
+    uint64_t w0 = 0, w1 = 0;
+    if (ir != kNoRow) {
+      const uint64_t *rp = IT.rows + (size_t)ir * rw;
+      if (lane < rw) w0 = __ldg(rp + lane);
+      if (lane + 32 < rw) w1 = __ldg(rp + lane + 32);
+    }
+    const int item = i0 + j;
+    for (int c0 = 0; c0 < a.n_fast; c0 += 32) {
+      const int c = c0 + lane;
+      const bool act = c < a.n_fast;
+      const FastCol fc = act ? s_cols[c] : FastCol{};
+      // every lane takes part in the shuffles; inactive lanes read lane 0
+      const int wsrc = act ? fc.word : 0, psrc = act ? (fc.bit >> 6) : 0;
+      const uint64_t vlo = __shfl_sync(0xFFFFFFFFu, w0, wsrc & 31), vhi = __shfl_sync(0xFFFFFFFFu, w1, wsrc & 31);
+      const uint64_t plo = __shfl_sync(0xFFFFFFFFu, w0, psrc & 31), phi = __shfl_sync(0xFFFFFFFFu, w1, psrc & 31);
+      if (!act) continue;
+      const uint64_t vw = wsrc < 32 ? vlo : vhi, pw = psrc < 32 ? plo : phi;
+      double v = fc.missing ? 0.0 : kNaN;
+      if (ir != kNoRow && ((pw >> (fc.bit & 63)) & 1ull)) {
+        v = fc.conv == 0 ? __longlong_as_double((long long)vw)
+            : fc.conv == 1 ? (double)(long long)vw : (double)(int)vw;
+      }
+      if (fc.override_slot >= 0 && a.item_f64) {
+        const double o = __ldg(a.item_f64 + (size_t)item * a.n_item_f64 + fc.override_slot);
+        if (o == o) v = o;
+      }
+      if (a.out_features) a.out_features[(size_t)item * a.dim + fc.col] = v;
+      if (a.codes) tile[c * 32 + j] = code_of(bin, fc.col, v);
+    }
+  }
+  if (a.codes) {
+    __syncwarp();
+    uint16_t *out = a.codes + (size_t)g * a.dim * 32;
+    for (int c = 0; c < a.n_fast; c++) {
+      const int col = s_cols[c].col;
+      if (lane < n_here) out[col * 32 + lane] = tile[c * 32 + lane];
+    }
+  }
+}
+
 // ------------------------------------------------------------------ assemble
 __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
   // the extractor plan is read by every thread for every feature: stage it in shared memory
@@ -588,6 +669,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
 
   for (int f = 0; f < a.n_plan; f++) {
     const DFeature &d = s_plan[f];
+    if (d.fast && a.n_fast > 0) continue;  // produced by row_gather_kernel
     switch (d.kind) {
       case FK_NUMBER: {
         // NumberFeature.values :84-93 (request-item field override) then value :58-69; WordCountFeature.value :63-68
@@ -827,10 +909,27 @@ void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t strea
     const size_t plan_bytes = (((size_t)std::max(a.n_plan, 1) * sizeof(DFeature)) + 15) & ~size_t(15);
     const size_t meta_bytes = a.codes ? (size_t)a.dim * sizeof(BinMeta) : 0;
     b.stage_meta = meta_bytes > 0 && plan_bytes + meta_bytes <= 40 * 1024;
-    assemble_kernel<<<(a.total_items + 127) / 128, 128, plan_bytes + (b.stage_meta ? meta_bytes : 0), stream>>>(b);
+    // row-local columns: coalesced gather kernel; everything else: the generic per-item kernel
+    const size_t cols_bytes = ((size_t)a.n_fast * sizeof(FastCol) + 15) & ~size_t(15);
+    const size_t gather_smem = cols_bytes + (b.stage_meta ? meta_bytes : 0) +
+                               (a.codes ? (size_t)kGatherWarps * a.n_fast * 32 * sizeof(uint16_t) : 0);
+    if (a.n_fast > 0 && gather_smem > 96 * 1024) b.n_fast = 0;  // too many columns for the tile: generic path
+    bool any_generic = false;
+    for (auto &d : schema.plan) any_generic |= !(d.fast && b.n_fast > 0);
+    if (b.n_fast > 0) {
+      if (gather_smem > 48 * 1024)
+        MR_CUDA_CHECK(cudaFuncSetAttribute(row_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gather_smem));
+      const int n_groups = (a.total_items + 31) / 32;
+      row_gather_kernel<<<(n_groups + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, gather_smem, stream>>>(b);
+      MR_CUDA_CHECK(cudaGetLastError());
+      g_kernel_launches++;
+    }
+    if (any_generic) {
+      assemble_kernel<<<(a.total_items + 127) / 128, 128, plan_bytes + (b.stage_meta ? meta_bytes : 0), stream>>>(b);
+      MR_CUDA_CHECK(cudaGetLastError());
+      g_kernel_launches++;
+    }
   }
-  MR_CUDA_CHECK(cudaGetLastError());
-  g_kernel_launches++;
 }
 
 void launch_rank_order(const double *d_scores, const int32_t *d_item_offsets, int n_requests, int total_items,

@@ -39,6 +39,8 @@ struct RankArgs {
   uint16_t *codes;        // optional: u16 rank codes [group of 32 items][column][lane] for the binned scorer
   BinParams bin;          // thresholds of the model the codes are for (valid when codes != null)
   int stage_meta;         // set by launch_assemble: bucket-index headers staged in shared memory
+  const FastCol *fast_cols;  // device copy of Schema::fast_cols (row_gather_kernel)
+  int n_fast;
 };
 
 // Enqueues lookup -> cosine -> per-request prepass -> assemble on `stream`.

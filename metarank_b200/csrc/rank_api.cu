@@ -14,6 +14,7 @@ struct mr_schema {
   Schema s;
   mr_ctx *ctx = nullptr;
   DFeature *d_plan = nullptr;
+  FastCol *d_fast_cols = nullptr;
 };
 
 struct RankScratch {  // per-lane device scratch for one in-flight mr_rank
@@ -73,6 +74,8 @@ void fill_args(RankArgs &a, mr_state *st, uint8_t *scratch, const ScratchPlan &s
   a.st = st->store->view();
   a.plan = st->schema->d_plan;
   a.n_plan = (int)S.plan.size();
+  a.fast_cols = st->schema->d_fast_cols;
+  a.n_fast = (int)S.fast_cols.size();
   a.dim = S.dim;
   a.n_req_f64 = (int)S.in_req_f64.size();
   a.n_req_u64 = (int)S.in_req_u64.size();
@@ -138,6 +141,10 @@ mr_status mr_schema_create(mr_ctx *ctx, const char *json, size_t len, mr_schema 
       MR_CUDA_CHECK(cudaMalloc((void **)&s->d_plan, bytes));
       if (!s->s.plan.empty())
         MR_CUDA_CHECK(cudaMemcpy(s->d_plan, s->s.plan.data(), s->s.plan.size() * sizeof(DFeature), cudaMemcpyHostToDevice));
+      if (!s->s.fast_cols.empty()) {
+        MR_CUDA_CHECK(cudaMalloc((void **)&s->d_fast_cols, s->s.fast_cols.size() * sizeof(FastCol)));
+        MR_CUDA_CHECK(cudaMemcpy(s->d_fast_cols, s->s.fast_cols.data(), s->s.fast_cols.size() * sizeof(FastCol), cudaMemcpyHostToDevice));
+      }
     }
     *out = s.release();
   });
@@ -146,6 +153,7 @@ mr_status mr_schema_create(mr_ctx *ctx, const char *json, size_t len, mr_schema 
 mr_status mr_schema_free(mr_schema *s) {
   if (!s) return MR_OK;
   if (s->d_plan) cudaFree(s->d_plan);
+  if (s->d_fast_cols) cudaFree(s->d_fast_cols);
   delete s;
   return MR_OK;
 }

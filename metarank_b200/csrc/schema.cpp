@@ -450,6 +450,37 @@ Schema parse_schema_json(const char *json, size_t len) {
     }
     if (d.kind == FK_COSINE) d.aux2 = n_cos++;
   }
+  // fast columns: item-scoped entries whose every column is one row word (see FastCol)
+  if (S.tables[SC_ITEM].row_words <= 64 && S.dim <= 65535) {
+    for (auto &d : S.plan) {
+      d.fast = 0;
+      d.pad = 0;
+      if (d.scope != SC_ITEM) continue;
+      int conv = -1, missing = 0;
+      switch (d.kind) {
+        case FK_NUMBER: conv = 0; break;
+        case FK_VECTOR: conv = 0; break;
+        case FK_CATEGORY: conv = 2; missing = 1; break;
+        case FK_COUNT: conv = 1; missing = 1; break;
+        case FK_WINDOW: conv = 1; break;
+        default: break;
+      }
+      if (conv < 0) continue;
+      d.fast = 1;
+      for (int k = 0; k < d.dim; k++) {
+        FastCol c{};
+        c.word = (uint16_t)(d.w[0] + k);
+        c.bit = (uint16_t)d.b[0];
+        c.conv = (uint8_t)conv;
+        c.missing = (uint8_t)missing;
+        c.override_slot = (int16_t)((d.kind == FK_NUMBER || d.kind == FK_CATEGORY) && k == 0 ? d.in0 : -1);
+        c.col = (uint16_t)(d.col + k);
+        S.fast_cols.push_back(c);
+      }
+    }
+  } else {
+    for (auto &d : S.plan) { d.fast = 0; d.pad = 0; }
+  }
   return S;
 }
 

@@ -70,6 +70,21 @@ struct DFeature {
   int32_t aux0, aux1, aux2, aux3;
   double dparam;
   uint64_t uparam;
+  int32_t fast;        // 1: every column of this entry is produced by row_gather_kernel (see FastCol)
+  int32_t pad;
+};
+
+// One output column that is a plain function of ONE word of the item's row: item-scoped number /
+// boolean / word_count (f64), string-index (i32 -> f64), interaction_count and window_count (i64 -> f64),
+// vector (f64).  These are gathered by row_gather_kernel with one coalesced row load per item.
+struct FastCol {
+  uint16_t word;      // row word holding the value
+  uint16_t bit;       // presence bit
+  uint8_t conv;       // 0 f64 bits, 1 i64 -> f64, 2 i32 -> f64
+  uint8_t missing;    // 0 NaN, 1 0.0
+  int16_t override_slot;  // MR_IN_ITEM_F64 slot whose non-NaN value wins, or -1
+  uint16_t col;       // output column
+  uint16_t pad;
 };
 
 struct FeatureDef {  // host-side description of one configured feature
@@ -100,6 +115,7 @@ struct Schema {
   TableLayout tables[SC_N_TABLES];
   std::vector<SideArray> sides;
   std::vector<DFeature> plan;                // extractor entries in column order
+  std::vector<FastCol> fast_cols;            // columns handled by the coalesced row-gather kernel
   int dim = 0;
   // request inputs
   std::vector<std::string> in_req_f64, in_req_u64, in_item_f64;  // owning feature names
