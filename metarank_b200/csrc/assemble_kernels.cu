@@ -548,7 +548,10 @@ __global__ void __launch_bounds__(kGatherWarps * 32) row_gather_kernel(RankArgs 
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint16_t *tile = reinterpret_cast<uint16_t *>(s_raw + off) + (size_t)warp * a.n_fast * 32;
+  // codes tile, item-major with an odd word stride: conflict-free both for the per-item stores
+  // (lane = column) and for the per-column read-back (lane = item)
+  const int tstride = (((a.n_fast + 1) >> 1) | 1) * 2;  // u16 elements per item row
+  uint16_t *tile = reinterpret_cast<uint16_t *>(s_raw + off) + (size_t)warp * 32 * tstride;
   const int g = blockIdx.x * kGatherWarps + warp;  // group of 32 items
   const int i0 = g * 32;
   if (i0 >= a.total_items) return;
@@ -557,26 +560,48 @@ __global__ void __launch_bounds__(kGatherWarps * 32) row_gather_kernel(RankArgs 
   const uint32_t my_row = (i0 + lane < a.total_items) ? a.item_row[i0 + lane] : kNoRow;
   const int n_here = min(32, a.total_items - i0);
   const double kNaN = nan_d();
-  for (int j = 0; j < n_here; j++) {
-    const uint32_t ir = __shfl_sync(0xFFFFFFFFu, my_row, j);
-    uint64_t w0 = 0, w1 = 0;
-    if (ir != kNoRow) {
-      const uint64_t *rp = IT.rows + (size_t)ir * rw;
-      if (lane < rw) w0 = __ldg(rp + lane);
-      if (lane + 32 < rw) w1 = __ldg(rp + lane + 32);
+  for (int c0 = 0; c0 < a.n_fast; c0 += 32) {
+    // this lane's column: descriptor and bucket-index header stay in registers for all 32 items
+    const int c = c0 + lane;
+    const bool act = c < a.n_fast;
+    const FastCol fc = s_cols[act ? c : 0];
+    BinMeta M{};
+    bool cat = false;
+    if (a.codes) { M = bin.meta[fc.col]; cat = __ldg(bin.is_cat + fc.col) != 0; }
+    const int wsrc = fc.word & 31, psrc = (fc.bit >> 6) & 31;
+    const bool whi = fc.word >= 32, phi_ = (fc.bit >> 6) >= 32;
+    const double vmiss = fc.missing ? 0.0 : kNaN;
+    // software pipeline: row j + 1 is in flight while row j is converted
+    uint64_t n0 = 0, n1 = 0;
+    {
+      const uint32_t ir = __shfl_sync(0xFFFFFFFFu, my_row, 0);
+      if (ir != kNoRow) {
+        const uint64_t *rp = IT.rows + (size_t)ir * rw;
+        if (lane < rw) n0 = __ldg(rp + lane);
+        if (lane + 32 < rw) n1 = __ldg(rp + lane + 32);
+      }
     }
-    const int item = i0 + j;
-    for (int c0 = 0; c0 < a.n_fast; c0 += 32) {
-      const int c = c0 + lane;
-      const bool act = c < a.n_fast;
-      const FastCol fc = act ? s_cols[c] : FastCol{};
-      // every lane takes part in the shuffles; inactive lanes read lane 0
-      const int wsrc = act ? fc.word : 0, psrc = act ? (fc.bit >> 6) : 0;
-      const uint64_t vlo = __shfl_sync(0xFFFFFFFFu, w0, wsrc & 31), vhi = __shfl_sync(0xFFFFFFFFu, w1, wsrc & 31);
-      const uint64_t plo = __shfl_sync(0xFFFFFFFFu, w0, psrc & 31), phi = __shfl_sync(0xFFFFFFFFu, w1, psrc & 31);
+    for (int j = 0; j < n_here; j++) {
+      const uint32_t ir = __shfl_sync(0xFFFFFFFFu, my_row, j);
+      const uint64_t w0 = n0, w1 = n1;
+      n0 = 0; n1 = 0;
+      if (j + 1 < n_here) {
+        const uint32_t nr = __shfl_sync(0xFFFFFFFFu, my_row, j + 1);
+        if (nr != kNoRow) {
+          const uint64_t *rp = IT.rows + (size_t)nr * rw;
+          if (lane < rw) n0 = __ldg(rp + lane);
+          if (lane + 32 < rw) n1 = __ldg(rp + lane + 32);
+        }
+      }
+      uint64_t vw = __shfl_sync(0xFFFFFFFFu, w0, wsrc), pw = __shfl_sync(0xFFFFFFFFu, w0, psrc);
+      if (rw > 32) {  // warp-uniform
+        const uint64_t vh = __shfl_sync(0xFFFFFFFFu, w1, wsrc), ph = __shfl_sync(0xFFFFFFFFu, w1, psrc);
+        if (whi) vw = vh;
+        if (phi_) pw = ph;
+      }
       if (!act) continue;
-      const uint64_t vw = wsrc < 32 ? vlo : vhi, pw = psrc < 32 ? plo : phi;
-      double v = fc.missing ? 0.0 : kNaN;
+      const int item = i0 + j;
+      double v = vmiss;
       if (ir != kNoRow && ((pw >> (fc.bit & 63)) & 1ull)) {
         v = fc.conv == 0 ? __longlong_as_double((long long)vw)
             : fc.conv == 1 ? (double)(long long)vw : (double)(int)vw;
@@ -586,7 +611,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) row_gather_kernel(RankArgs 
         if (o == o) v = o;
       }
       if (a.out_features) a.out_features[(size_t)item * a.dim + fc.col] = v;
-      if (a.codes) tile[c * 32 + j] = code_of(bin, fc.col, v);
+      if (a.codes) tile[j * tstride + c] = code_of_col(bin, M, cat, v);
     }
   }
   if (a.codes) {
@@ -594,7 +619,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) row_gather_kernel(RankArgs 
     uint16_t *out = a.codes + (size_t)g * a.dim * 32;
     for (int c = 0; c < a.n_fast; c++) {
       const int col = s_cols[c].col;
-      if (lane < n_here) out[col * 32 + lane] = tile[c * 32 + lane];
+      if (lane < n_here) out[col * 32 + lane] = tile[lane * tstride + c];
     }
   }
 }
@@ -833,53 +858,89 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
 }
 
 // ------------------------------------------------------------------ ordering
-__global__ void __launch_bounds__(256) order_kernel(const double *scores, const int32_t *offsets, int32_t *order) {
-  const int r = blockIdx.x;
-  const int b = offsets[r], n = offsets[r + 1] - b;
+// Requests of up to kSmallOrder items (the usual /rank page): a WARP ranks one request by counting,
+// rank(i) = #{q : key(q) < key(i)} + #{q < i : key(q) == key(i)} — the same total order as the sort
+// below, no barriers, eight requests per CTA.
+constexpr int kSmallOrder = 128;
+constexpr int kOrderWarps = 8;
+
+__global__ void __launch_bounds__(kOrderWarps * 32) order_small_kernel(const double *scores, const int32_t *offsets,
+                                                                       int n_requests, int32_t *order) {
+  __shared__ long long s_k[kOrderWarps][kSmallOrder];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kOrderWarps + warp;
+  if (r >= n_requests) return;
+  const int b = __ldg(offsets + r), n = __ldg(offsets + r + 1) - b;
+  if (n <= 0 || n > kSmallOrder) return;
+  long long k[4];
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    const int i = lane + 32 * m;
+    k[m] = i < n ? total_order_key(-__ldg(scores + b + i)) : 0x7FFFFFFFFFFFFFFFll;
+    if (i < n) s_k[warp][i] = k[m];
+  }
+  __syncwarp();
+  int rank[4] = {0, 0, 0, 0};
+  for (int q = 0; q < n; q++) {
+    const long long kq = s_k[warp][q];
+#pragma unroll
+    for (int m = 0; m < 4; m++) rank[m] += (kq < k[m]) || (kq == k[m] && q < lane + 32 * m);
+  }
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    const int i = lane + 32 * m;
+    if (i < n) order[b + rank[m]] = i;
+  }
+}
+
+__global__ void __launch_bounds__(256) order_kernel(const double *scores, const int32_t *offsets, int n_requests,
+                                                    int32_t *order) {
   extern __shared__ long long s_keys[];  // [4096] keys, then [4096] int indices
   const int cap = 4096;
   int *s_idx = reinterpret_cast<int *>(s_keys + cap);
-  if (n <= 1) {
-    if (n == 1 && threadIdx.x == 0) order[b] = 0;
-    return;
-  }
-  if (n <= cap) {
-    // bitonic sort of (total-order key of -score, request index): the index makes every pair distinct,
-    // which is exactly the stability of the reference's sortBy
-    int p2 = 1;
-    while (p2 < n) p2 <<= 1;
-    for (int j = threadIdx.x; j < p2; j += blockDim.x) {
-      s_keys[j] = j < n ? total_order_key(-scores[b + j]) : 0x7FFFFFFFFFFFFFFFll;
-      s_idx[j] = j < n ? j : 0x7FFFFFFF;
-    }
-    __syncthreads();
-    for (int k = 2; k <= p2; k <<= 1) {
-      for (int jj = k >> 1; jj > 0; jj >>= 1) {
-        for (int i = threadIdx.x; i < p2; i += blockDim.x) {
-          const int l = i ^ jj;
-          if (l > i) {
-            const long long ki = s_keys[i], kl = s_keys[l];
-            const int ii = s_idx[i], il = s_idx[l];
-            const bool gt = ki > kl || (ki == kl && ii > il);
-            const bool up = (i & k) == 0;
-            if (gt == up) { s_keys[i] = kl; s_keys[l] = ki; s_idx[i] = il; s_idx[l] = ii; }
-          }
-        }
-        __syncthreads();
+  // a resident grid walks the requests; the ones order_small_kernel ranked are skipped
+  for (int r = blockIdx.x; r < n_requests; r += gridDim.x) {
+    const int b = __ldg(offsets + r), n = __ldg(offsets + r + 1) - b;
+    if (n <= kSmallOrder) continue;
+    if (n <= cap) {
+      // bitonic sort of (total-order key of -score, request index): the index makes every pair distinct,
+      // which is exactly the stability of the reference's sortBy
+      int p2 = 1;
+      while (p2 < n) p2 <<= 1;
+      __syncthreads();  // the previous request's read-out is complete
+      for (int j = threadIdx.x; j < p2; j += blockDim.x) {
+        s_keys[j] = j < n ? total_order_key(-scores[b + j]) : 0x7FFFFFFFFFFFFFFFll;
+        s_idx[j] = j < n ? j : 0x7FFFFFFF;
       }
+      __syncthreads();
+      for (int k = 2; k <= p2; k <<= 1) {
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+          for (int i = threadIdx.x; i < p2; i += blockDim.x) {
+            const int l = i ^ jj;
+            if (l > i) {
+              const long long ki = s_keys[i], kl = s_keys[l];
+              const int ii = s_idx[i], il = s_idx[l];
+              const bool gt = ki > kl || (ki == kl && ii > il);
+              const bool up = (i & k) == 0;
+              if (gt == up) { s_keys[i] = kl; s_keys[l] = ki; s_idx[i] = il; s_idx[l] = ii; }
+            }
+          }
+          __syncthreads();
+        }
+      }
+      for (int j = threadIdx.x; j < n; j += blockDim.x) order[b + j] = s_idx[j];
+      continue;
     }
-    for (int j = threadIdx.x; j < n; j += blockDim.x) order[b + j] = s_idx[j];
-    return;
-  }
-  // very large requests: rank by counting straight from global memory
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    const long long kj = total_order_key(-scores[b + j]);
-    int rank = 0;
-    for (int q = 0; q < n; q++) {
-      const long long kq = total_order_key(-scores[b + q]);
-      rank += (kq < kj) || (kq == kj && q < j);
+    // very large requests: rank by counting straight from global memory
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const long long kj = total_order_key(-scores[b + j]);
+      int rank = 0;
+      for (int q = 0; q < n; q++) {
+        const long long kq = total_order_key(-scores[b + q]);
+        rank += (kq < kj) || (kq == kj && q < j);
+      }
+      order[b + rank] = j;
     }
-    order[b + rank] = j;
   }
 }
 
@@ -912,7 +973,7 @@ void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t strea
     // row-local columns: coalesced gather kernel; everything else: the generic per-item kernel
     const size_t cols_bytes = ((size_t)a.n_fast * sizeof(FastCol) + 15) & ~size_t(15);
     const size_t gather_smem = cols_bytes + (b.stage_meta ? meta_bytes : 0) +
-                               (a.codes ? (size_t)kGatherWarps * a.n_fast * 32 * sizeof(uint16_t) : 0);
+                               (a.codes ? (size_t)kGatherWarps * 32 * ((((a.n_fast + 1) >> 1) | 1) * 2) * sizeof(uint16_t) : 0);
     if (a.n_fast > 0 && gather_smem > 96 * 1024) b.n_fast = 0;  // too many columns for the tile: generic path
     bool any_generic = false;
     for (auto &d : schema.plan) any_generic |= !(d.fast && b.n_fast > 0);
@@ -933,10 +994,15 @@ void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t strea
 }
 
 void launch_rank_order(const double *d_scores, const int32_t *d_item_offsets, int n_requests, int total_items,
-                       int32_t *d_order, cudaStream_t stream) {
+                       int32_t *d_order, cudaStream_t stream, int max_items_hint) {
   if (n_requests <= 0 || total_items <= 0) return;
-  order_kernel<<<n_requests, 256, 4096 * (sizeof(long long) + sizeof(int)), stream>>>(d_scores, d_item_offsets, d_order);
+  order_small_kernel<<<(n_requests + kOrderWarps - 1) / kOrderWarps, kOrderWarps * 32, 0, stream>>>(d_scores, d_item_offsets, n_requests, d_order);
   MR_CUDA_CHECK(cudaGetLastError());
+  if (max_items_hint <= 0 || max_items_hint > kSmallOrder) {  // larger requests: CTA-wide sort (small ones return at once)
+    order_kernel<<<std::min(n_requests, 148 * 4), 256, 4096 * (sizeof(long long) + sizeof(int)), stream>>>(d_scores, d_item_offsets, n_requests, d_order);
+    MR_CUDA_CHECK(cudaGetLastError());
+    g_kernel_launches++;
+  }
   g_kernel_launches++;
 }
 

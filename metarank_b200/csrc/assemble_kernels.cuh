@@ -47,6 +47,6 @@ struct RankArgs {
 void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t stream);
 // Ranker.rerank's sortBy(-score): order[off[r] + k] = index (within the request) of the k-th item.
 void launch_rank_order(const double *d_scores, const int32_t *d_item_offsets, int n_requests, int total_items,
-                       int32_t *d_order, cudaStream_t stream);
+                       int32_t *d_order, cudaStream_t stream, int max_items_hint = 0);
 
 }  // namespace mr

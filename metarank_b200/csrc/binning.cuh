@@ -21,17 +21,17 @@ struct BinParams {
   int xgb;  // 1: round to binary32 first, strict less (upper_bound)
 };
 
-__device__ __forceinline__ uint16_t code_of(const BinParams &p, int f, double x) {
+// code of x in a column whose header (M, categorical flag) the caller already holds in registers
+__device__ __forceinline__ uint16_t code_of_col(const BinParams &p, const BinMeta &M, bool cat, double x) {
   if (p.xgb) x = (double)__double2float_rn(x);
   if (x != x) return kBinNaN;
-  if (p.is_cat[f]) {
+  if (cat) {
     // LightGBM CategoricalDecision: static_cast<int>(x), negative / out-of-int-range -> right
     const bool in_range = (x < 2147483648.0) && (x > -2147483649.0);
     const int iv = in_range ? __double2int_rz(x) : -1;
     return (iv >= 0 && iv < 65000) ? (uint16_t)iv : kBinNaN;
   }
   // bucket(x) is monotone, so only the thresholds in x's own bucket need comparing
-  const BinMeta M = p.meta[f];
   uint32_t bk = 0;
   if (M.g > 1 && x > M.mn) {
     const double v = __dmul_rn(__dadd_rn(x, -M.mn), M.scale);
@@ -46,6 +46,10 @@ __device__ __forceinline__ uint16_t code_of(const BinParams &p, int f, double x)
     while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__ldg(t + m) < x) lo = m + 1; else hi = m; }   // #{t < x}
   }
   return (uint16_t)lo;
+}
+
+__device__ __forceinline__ uint16_t code_of(const BinParams &p, int f, double x) {
+  return code_of_col(p, p.meta[f], p.is_cat[f] != 0, x);
 }
 
 }  // namespace mr

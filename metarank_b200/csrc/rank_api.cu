@@ -361,7 +361,11 @@ void rank_enqueue(mr_state *st, mr_model *model, const mr_rank_batch *b, int r0,
   if (model) {
     if (fused) model->score_codes(a.codes, N, d_scores, lane->stream, leaf_bytes ? scratch + sp.leafvals : nullptr);
     else model->score(a.out_features, N, S.dim, d_scores, lane->stream);
-    if (want_order) launch_rank_order(d_scores, a.item_offsets, R, N, d_order, lane->stream);
+    if (want_order) {
+      int max_n = 1;  // host offsets are at hand: the CTA-wide sort is only launched when a request needs it
+      for (int r = r0; r < r1; r++) max_n = std::max(max_n, b->item_offsets[r + 1] - b->item_offsets[r]);
+      launch_rank_order(d_scores, a.item_offsets, R, N, d_order, lane->stream, max_n);
+    }
   }
   // host staging mirrors the device layout: [scores | order | err | features]
   pd.ho_scores = 0;

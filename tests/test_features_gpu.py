@@ -649,3 +649,66 @@ def test_two_contexts_in_one_process_on_two_gpus():
         b.free()
     for c in ctxs:
         c.close()
+
+
+def test_ordering_edge_sizes_ties_and_specials(ctx):
+    """Per-request ordering across the three device code paths (warp counting rank <= 128 items, CTA bitonic
+    sort <= 4096, counting from global memory beyond), with heavy ties and NaN scores; through mr_rank
+    (host offsets -> size hint) and mr_rank_device (no hint).  Oracle: stable sortBy(-score),
+    S/ranking/Ranker.scala:58-60."""
+    import torch
+
+    import metarank_b200 as mb
+    from metarank_b200 import features as F
+
+    names = ["a", "b"]
+    fm = F.FeatureMapping(ctx, [dict(name=n, type="number", scope="item", source=f"metadata.{n}") for n in names], names)
+    ds = F.DeviceState(ctx, fm)
+    n_cat = 6000
+    rng = np.random.Generator(np.random.PCG64(11))
+    cat = np.stack([rng.integers(0, 4, n_cat).astype(np.float64), rng.integers(0, 3, n_cat).astype(np.float64)], axis=1)
+    ids = np.arange(1, n_cat + 1, dtype=np.uint64) * np.uint64(11400714819323198485)
+    ds.put_packed(F.pack_number_columns(names, ids, cat)); ds.flush()
+    # two depth-1 trees with leaves that produce ties, a NaN score, and both zeros
+    model = "\n".join([
+        "tree", "version=v3", "num_class=1", "num_tree_per_iteration=1", "label_index=0", "max_feature_idx=1",
+        "objective=lambdarank", "feature_names=a b", "feature_infos=[0:3] [0:2]", "tree_sizes=0 0", "",
+        "Tree=0", "num_leaves=3", "num_cat=0", "split_feature=0 0", "split_gain=1 1", "threshold=0.5 1.5",
+        "decision_type=2 2", "left_child=-1 -2", "right_child=1 -3", "leaf_value=0.0 -0.0 1.0", "leaf_weight=1 1 1",
+        "leaf_count=1 1 1", "internal_value=0 0", "internal_weight=0 0", "internal_count=3 2", "is_linear=0", "shrinkage=1", "",
+        "Tree=1", "num_leaves=3", "num_cat=0", "split_feature=1 1", "split_gain=1 1", "threshold=0.5 1.5",
+        "decision_type=2 2", "left_child=-1 -2", "right_child=1 -3", "leaf_value=0.0 -0.0 nan", "leaf_weight=1 1 1",
+        "leaf_count=1 1 1", "internal_value=0 0", "internal_weight=0 0", "internal_count=3 2", "is_linear=0", "shrinkage=1", "",
+        "end of trees", ""]).encode()
+    booster = mb.LightGBMBooster(ctx, model)
+    sizes = np.array([0, 1, 2, 3, 31, 32, 33, 100, 127, 128, 129, 130, 500, 1024, 4095, 4096, 4097, 5000, 0, 7], dtype=np.int64)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    N, R = int(offs[-1]), len(sizes)
+    pick = rng.integers(0, n_cat, N)
+    arrays = dict(offsets=offs, ids=ids[pick], users=np.zeros(R, dtype=np.uint64), sessions=np.zeros(R, dtype=np.uint64),
+                  req_f64=np.zeros((R, 1)), req_u64=np.zeros((R, 1), dtype=np.uint64), req_vec=np.zeros((R, 1), dtype=np.float32),
+                  req_vp=np.zeros((R, 1), dtype=np.uint8), item_f64=None, n_requests=R, total_items=N)
+    want_s = oracle.OracleBooster(0, model).predictMat(cat[pick], N, 2, threads=0)
+    assert np.isnan(want_s).any() and (want_s == 0).any()  # (a sum that starts at +0.0 never yields -0.0)
+    want_o = np.concatenate([oracle.rank_order(want_s[offs[r]:offs[r + 1]]) for r in range(R)]).astype(np.int32)
+    scores, order, _ = F.Ranker(fm, ds).rank_arrays(arrays, booster, want_order=True)
+    assert _eq(scores, want_s) and np.array_equal(order, want_o)
+    # small requests only: the hint lets mr_rank skip the CTA-wide sort
+    small = sizes <= 128
+    so = np.concatenate([[0], np.cumsum(sizes[small])]).astype(np.int32)
+    sp = np.concatenate([pick[offs[r]:offs[r + 1]] for r in range(R) if small[r]])
+    a2 = dict(arrays, offsets=so, ids=ids[sp], users=arrays["users"][:small.sum()], sessions=arrays["sessions"][:small.sum()],
+              req_f64=np.zeros((small.sum(), 1)), req_u64=np.zeros((small.sum(), 1), dtype=np.uint64),
+              req_vec=np.zeros((small.sum(), 1), dtype=np.float32), req_vp=np.zeros((small.sum(), 1), dtype=np.uint8),
+              n_requests=int(small.sum()), total_items=int(so[-1]))
+    s2, o2, _ = F.Ranker(fm, ds).rank_arrays(a2, booster, want_order=True)
+    w2 = oracle.OracleBooster(0, model).predictMat(cat[sp], len(sp), 2, threads=0)
+    assert np.array_equal(o2, np.concatenate([oracle.rank_order(w2[so[r]:so[r + 1]]) for r in range(len(so) - 1)]))
+    # device entry point
+    d_off = torch.from_numpy(offs).cuda(); d_ids = torch.from_numpy(ids[pick].view(np.int64)).cuda()
+    d_s = torch.zeros(N, dtype=torch.float64, device="cuda"); d_o = torch.full((N,), -1, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    F.rank_device(ds, booster, R, N, d_off.data_ptr(), d_ids.data_ptr(), d_s.data_ptr(), d_o.data_ptr(), 0, st)
+    F.rank_device_status(ds, st)
+    assert _eq(d_s.cpu().numpy(), want_s) and np.array_equal(d_o.cpu().numpy(), want_o)
+    booster.free(); ds.free(); fm.free()
