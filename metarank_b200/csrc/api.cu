@@ -235,7 +235,7 @@ mr_status mr_model_count_path(mr_model *m, const double *values, int32_t rows, i
 
 size_t mr_model_codes_bytes(mr_model *m, int32_t rows) {
   if (!m || m->closed.load() || rows <= 0 || !m->use_binned()) return 0;
-  return binned_scratch_bytes(rows, m->host.n_features);
+  return binned_scratch_bytes(rows, m->code_cols());
 }
 
 mr_status mr_model_bin_device(mr_model *m, const double *d_values, int32_t rows, int32_t cols, void *d_codes,

@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) row_gather_kernel(RankArgs 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // codes tile, item-major with an odd word stride: conflict-free both for the per-item stores
   // (lane = column) and for the per-column read-back (lane = item)
-  const int tstride = (((a.n_fast + 1) >> 1) | 1) * 2;  // u16 elements per item row
+  const int tstride = (a.n_fast | 1) * 2;  // u16 elements per item row: (base, duplicate) per column, odd word stride
   uint16_t *tile = reinterpret_cast<uint16_t *>(s_raw + off) + (size_t)warp * 32 * tstride;
   const int g = blockIdx.x * kGatherWarps + warp;  // group of 32 items
   const int i0 = g * 32;
@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) row_gather_kernel(RankArgs 
     const FastCol fc = s_cols[act ? c : 0];
     BinMeta M{};
     bool cat = false;
-    if (a.codes) { M = bin.meta[fc.col]; cat = __ldg(bin.is_cat + fc.col) != 0; }
+    if (a.codes) { M = bin.meta[fc.col]; cat = (M.flags & kMetaCat) != 0; }
     const int wsrc = fc.word & 31, psrc = (fc.bit >> 6) & 31;
     const bool whi = fc.word >= 32, phi_ = (fc.bit >> 6) >= 32;
     const double vmiss = fc.missing ? 0.0 : kNaN;
@@ -611,15 +611,23 @@ __global__ void __launch_bounds__(kGatherWarps * 32) row_gather_kernel(RankArgs 
         if (o == o) v = o;
       }
       if (a.out_features) a.out_features[(size_t)item * a.dim + fc.col] = v;
-      if (a.codes) tile[j * tstride + c] = code_of_col(bin, M, cat, v);
+      if (a.codes) {
+        const uint16_t cd = code_of_col(bin, M, cat, v);
+        *reinterpret_cast<uint32_t *>(tile + j * tstride + 2 * c) = (uint32_t)base_code(M, cd) | ((uint32_t)dup_code(cd) << 16);
+      }
     }
   }
   if (a.codes) {
     __syncwarp();
-    uint16_t *out = a.codes + (size_t)g * a.dim * 32;
+    uint16_t *out = a.codes + (size_t)g * bin.tile_cols * 32;
     for (int c = 0; c < a.n_fast; c++) {
       const int col = s_cols[c].col;
-      if (lane < n_here) out[col * 32 + lane] = tile[lane * tstride + c];
+      const uint32_t dup = dup_col(bin.meta[col]);  // warp-uniform
+      const uint32_t both = *reinterpret_cast<const uint32_t *>(tile + lane * tstride + 2 * c);
+      if (lane < n_here) {
+        out[col * 32 + lane] = (uint16_t)both;
+        if (dup != kMetaNoDup) out[dup * 32 + lane] = (uint16_t)(both >> 16);
+      }
     }
   }
 }
@@ -667,7 +675,12 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
     const BinParams *bp;
     __device__ __forceinline__ void operator()(int col, double v) const {
       if (row) row[col] = v;
-      if (codes) codes[(size_t)col * 32] = code_of(*bp, col, v);
+      if (codes) {
+        const BinMeta M = bp->meta[col];
+        const uint16_t c = code_of_col(*bp, M, (M.flags & kMetaCat) != 0, v);
+        codes[(size_t)col * 32] = base_code(M, c);
+        if (dup_col(M) != kMetaNoDup) codes[(size_t)dup_col(M) * 32] = dup_code(c);
+      }
     }
   };
   struct OutProxy {  // lets the extractor code below keep writing out[col] = v
@@ -679,7 +692,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
     __device__ __forceinline__ OutProxy operator[](int col) const { return OutProxy{e, col}; }
   };
   const Emit emit{a.out_features ? a.out_features + (size_t)i * a.dim : nullptr,
-                  a.codes ? a.codes + ((size_t)(i >> 5) * a.dim) * 32 + (i & 31) : nullptr, &bin};
+                  a.codes ? a.codes + ((size_t)(i >> 5) * bin.tile_cols) * 32 + (i & 31) : nullptr, &bin};
   const OutArr out{&emit};
 
   auto scoped_row = [&](int scope) -> const uint64_t * {
@@ -973,7 +986,7 @@ void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t strea
     // row-local columns: coalesced gather kernel; everything else: the generic per-item kernel
     const size_t cols_bytes = ((size_t)a.n_fast * sizeof(FastCol) + 15) & ~size_t(15);
     const size_t gather_smem = cols_bytes + (b.stage_meta ? meta_bytes : 0) +
-                               (a.codes ? (size_t)kGatherWarps * 32 * ((((a.n_fast + 1) >> 1) | 1) * 2) * sizeof(uint16_t) : 0);
+                               (a.codes ? (size_t)kGatherWarps * 32 * ((a.n_fast | 1) * 2) * sizeof(uint16_t) : 0);
     if (a.n_fast > 0 && gather_smem > 96 * 1024) b.n_fast = 0;  // too many columns for the tile: generic path
     bool any_generic = false;
     for (auto &d : schema.plan) any_generic |= !(d.fast && b.n_fast > 0);

@@ -18,6 +18,7 @@ struct BinParams {
   const uint32_t *bucket_range;
   uint16_t *bins;
   int rows, cols, n_features;
+  int tile_cols;  // columns of the code tile (>= n_features, see BinMeta::flags)
   int xgb;  // 1: round to binary32 first, strict less (upper_bound)
 };
 
@@ -49,7 +50,16 @@ __device__ __forceinline__ uint16_t code_of_col(const BinParams &p, const BinMet
 }
 
 __device__ __forceinline__ uint16_t code_of(const BinParams &p, int f, double x) {
-  return code_of_col(p, p.meta[f], p.is_cat[f] != 0, x);
+  const BinMeta M = p.meta[f];
+  return code_of_col(p, M, (M.flags & kMetaCat) != 0, x);
 }
+
+// Where a code lands in the scorer's tile (BinMeta::flags): the base column takes the NaN code the
+// feature's nodes agree on; a feature with both NaN directions also fills its duplicate column.
+__device__ __forceinline__ uint16_t base_code(const BinMeta &M, uint16_t c) {
+  return (c == kBinNaN && (M.flags & kMetaNanLow)) ? (uint16_t)0 : c;
+}
+__device__ __forceinline__ uint32_t dup_col(const BinMeta &M) { return M.flags >> 16; }  // kMetaNoDup: none
+__device__ __forceinline__ uint16_t dup_code(uint16_t c) { return c == kBinNaN ? (uint16_t)0 : c; }
 
 }  // namespace mr

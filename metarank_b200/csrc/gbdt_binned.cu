@@ -26,8 +26,8 @@ namespace {
 constexpr int kBinGroups = 4;  // groups of 32 items per CTA
 
 __global__ void __launch_bounds__(256) bin_kernel(const BinParams p) {
-  extern __shared__ uint16_t s_codes[];  // [F][kBinGroups*32 + 2]
-  const int F = p.n_features;
+  extern __shared__ uint16_t s_codes[];  // [tile_cols][kBinGroups*32 + 2]
+  const int F = p.n_features, T = p.tile_cols;
   const int items_per_cta = kBinGroups * 32, pitch = items_per_cta + 2;
   const long long item0 = (long long)blockIdx.x * items_per_cta;
   const int n_here = (int)min((long long)items_per_cta, (long long)p.rows - item0);
@@ -35,16 +35,18 @@ __global__ void __launch_bounds__(256) bin_kernel(const BinParams p) {
   const int n_elem = items_per_cta * F;
   for (int e = threadIdx.x; e < n_elem; e += blockDim.x) {
     const int it = e / F, f = e - it * F;
+    const BinMeta M = p.meta[f];
     uint16_t c = 0;
-    if (it < n_here) c = code_of(p, f, __ldg(p.values + (size_t)(item0 + it) * p.cols + f));
-    s_codes[f * pitch + it] = c;
+    if (it < n_here) c = code_of_col(p, M, (M.flags & kMetaCat) != 0, __ldg(p.values + (size_t)(item0 + it) * p.cols + f));
+    s_codes[f * pitch + it] = base_code(M, c);
+    if (dup_col(M) != kMetaNoDup) s_codes[dup_col(M) * pitch + it] = dup_code(c);
   }
   __syncthreads();
-  // phase 2: coalesced write in [group][feature][lane] order
-  uint16_t *out = p.bins + (size_t)blockIdx.x * kBinGroups * F * 32;
+  // phase 2: coalesced write in [group][column][lane] order
+  uint16_t *out = p.bins + (size_t)blockIdx.x * kBinGroups * T * 32;
   const long long n_groups_total = (p.rows + 31) / 32;
-  for (int o = threadIdx.x; o < n_elem; o += blockDim.x) {
-    const int g = o / (F * 32), r = o - g * (F * 32), f = r >> 5, lane = r & 31;
+  for (int o = threadIdx.x; o < items_per_cta * T; o += blockDim.x) {
+    const int g = o / (T * 32), r = o - g * (T * 32), f = r >> 5, lane = r & 31;
     if ((long long)blockIdx.x * kBinGroups + g < n_groups_total) out[o] = s_codes[f * pitch + g * 32 + lane];
   }
 }
@@ -191,7 +193,9 @@ __global__ void __launch_bounds__(1024) gbdt_score_binned_kernel(const BParams p
 // Same mapping as gbdt_score_binned_kernel, on the compact layout (gbdt_model.h): children are byte
 // offsets (bit 0 = leaf), the feature's byte offset inside the warp's code tile is stored in the
 // node, so one tree level is: LDS.64 node, shift+mask/or, LDS.U16 code, compare, select, test.
-template <typename Real, bool HAS_CAT>
+// ALIGNED (tile_cols a power of two): every warp's tile starts on a multiple of its own size, so the code's
+// address is (column offset | thread base) — one LOP3, no add.
+template <typename Real, bool HAS_CAT, bool ALIGNED>
 __global__ void __launch_bounds__(1024) gbdt_score_compact_kernel(const BParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int W = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -201,6 +205,10 @@ __global__ void __launch_bounds__(1024) gbdt_score_compact_kernel(const BParams 
   uint8_t *cbuf0 = smem + 128;
   uint8_t *cbuf1 = cbuf0 + (resident ? 0u : p.chunk_stride);
   uint8_t *xs = cbuf1 + p.chunk_stride;
+  if (ALIGNED) {
+    const uint32_t wt = (uint32_t)F * 64u, a0 = smem_u32(xs);
+    xs += ((a0 + wt - 1u) & ~(wt - 1u)) - a0;
+  }
   const uint8_t *xwarp = xs + (size_t)warp * F * 64;  // this warp's [feature][lane] u16 codes
   const uint32_t lane2 = (uint32_t)lane * 2u;
 
@@ -251,14 +259,14 @@ __global__ void __launch_bounds__(1024) gbdt_score_compact_kernel(const BParams 
 #pragma unroll 1
       for (int t = 0; t < ntree; t++) {
         uint32_t n = roots[t];
-        // One tree level = 12 SASS instructions; spelled in PTX because nvcc otherwise routes the
+        // One tree level = 10 SASS instructions; spelled in PTX because nvcc otherwise routes the
         // predicates through integer registers (18 instructions).  With HAS_CAT the loop additionally
         // leaves on a categorical node (bit 1 of word0), which is resolved in C++ below, then re-enters.
         if (HAS_CAT) {
           while (!(n & 1u)) {
             asm volatile(
                 "{\n"
-                ".reg .pred pl, pn, pf, pq, pc;\n"
+                ".reg .pred pl, pq, pc;\n"
                 ".reg .b32 w0, w1, off, code, kk, sel, tmp;\n"
                 "LVLC:\n"
                 "add.u32 tmp, %1, %0;\n"
@@ -271,11 +279,6 @@ __global__ void __launch_bounds__(1024) gbdt_score_compact_kernel(const BParams 
                 "ld.shared.u16 code, [off];\n"
                 "shr.u32 kk, w0, 16;\n"
                 "setp.le.u32 pl, code, kk;\n"
-                "setp.eq.u32 pn, code, 0xFFFF;\n"
-                "and.b32 tmp, w0, 1;\n"
-                "setp.ne.u32 pf, tmp, 0;\n"
-                "and.pred pn, pn, pf;\n"
-                "or.pred pl, pl, pn;\n"
                 "selp.b32 sel, 0x4410, 0x4432, pl;\n"
                 "prmt.b32 %0, w1, 0, sel;\n"
                 "and.b32 tmp, %0, 1;\n"
@@ -298,35 +301,50 @@ __global__ void __launch_bounds__(1024) gbdt_score_compact_kernel(const BParams 
             }
             n = __byte_perm(nd.y, 0u, left ? 0x4410u : 0x4432u);
           }
-        } else if (!(n & 1u)) {
-          {
-            asm volatile(
-                "{\n"
-                ".reg .pred pl, pn, pf, pq;\n"
-                ".reg .b32 w0, w1, off, code, kk, sel, tmp;\n"
-                "LVL:\n"
-                "add.u32 tmp, %1, %0;\n"
-                "ld.shared.v2.u32 {w0, w1}, [tmp];\n"
-                "lop3.b32 off, w0, 0xFFC0, %3, 0xEA;\n"   // (w0 & 0xFFC0) | lane*2
-                "add.u32 off, off, %2;\n"
-                "ld.shared.u16 code, [off];\n"
-                "shr.u32 kk, w0, 16;\n"
-                "setp.le.u32 pl, code, kk;\n"
-                "setp.eq.u32 pn, code, 0xFFFF;\n"
-                "and.b32 tmp, w0, 1;\n"
-                "setp.ne.u32 pf, tmp, 0;\n"
-                "and.pred pn, pn, pf;\n"
-                "or.pred pl, pl, pn;\n"                    // NaN code is never <= k, so this only adds NaN -> left
-                "selp.b32 sel, 0x4410, 0x4432, pl;\n"
-                "prmt.b32 %0, w1, 0, sel;\n"
-                "and.b32 tmp, %0, 1;\n"
-                "setp.eq.u32 pq, tmp, 0;\n"
-                "@pq bra LVL;\n"
-                "}\n"
-                : "+r"(n)
-                : "r"(cb_addr), "r"(xwarp_addr), "r"(lane2)
-                : "memory");
-          }
+        } else if (ALIGNED) {
+          // every tree starts at an internal node (single-leaf trees are packed as a dummy split)
+          asm volatile(
+              "{\n"
+              ".reg .pred pl, pq;\n"
+              ".reg .b32 w0, w1, off, code, kk, sel, tmp;\n"
+              "LVLA:\n"
+              "add.u32 tmp, %1, %0;\n"
+              "ld.shared.v2.u32 {w0, w1}, [tmp];\n"
+              "lop3.b32 off, w0, 0xFFC0, %2, 0xEA;\n"   // (w0 & 0xFFC0) | (warp tile base | lane*2)
+              "ld.shared.u16 code, [off];\n"
+              "shr.u32 kk, w0, 16;\n"
+              "setp.le.u32 pl, code, kk;\n"               // the NaN direction is baked into the column (BinMeta::flags)
+              "selp.b32 sel, 0x4410, 0x4432, pl;\n"
+              "prmt.b32 %0, w1, 0, sel;\n"
+              "and.b32 tmp, %0, 1;\n"
+              "setp.eq.u32 pq, tmp, 0;\n"
+              "@pq bra LVLA;\n"
+              "}\n"
+              : "+r"(n)
+              : "r"(cb_addr), "r"(xwarp_addr | lane2)
+              : "memory");
+        } else {
+          asm volatile(
+              "{\n"
+              ".reg .pred pl, pq;\n"
+              ".reg .b32 w0, w1, off, code, kk, sel, tmp;\n"
+              "LVL:\n"
+              "add.u32 tmp, %1, %0;\n"
+              "ld.shared.v2.u32 {w0, w1}, [tmp];\n"
+              "lop3.b32 off, w0, 0xFFC0, %3, 0xEA;\n"   // (w0 & 0xFFC0) | lane*2
+              "add.u32 off, off, %2;\n"
+              "ld.shared.u16 code, [off];\n"
+              "shr.u32 kk, w0, 16;\n"
+              "setp.le.u32 pl, code, kk;\n"
+              "selp.b32 sel, 0x4410, 0x4432, pl;\n"
+              "prmt.b32 %0, w1, 0, sel;\n"
+              "and.b32 tmp, %0, 1;\n"
+              "setp.eq.u32 pq, tmp, 0;\n"
+              "@pq bra LVL;\n"
+              "}\n"
+              : "+r"(n)
+              : "r"(cb_addr), "r"(xwarp_addr), "r"(lane2)
+              : "memory");
         }
         acc += *reinterpret_cast<const Real *>(cb + (n - 1u));
       }
@@ -393,7 +411,7 @@ __global__ void __launch_bounds__(128) gbdt_leaves_kernel(const LParams p) {
           if (w < ct.y) left = (reinterpret_cast<const uint32_t *>(cb)[ct.x + w] >> (code & 31u)) & 1u;
         }
       } else {
-        left = (code <= (nd.x >> 16)) || (code == kBinNaN && (nd.x & 1u));
+        left = code <= (nd.x >> 16);  // NaN direction baked into the column
       }
       n = __byte_perm(nd.y, 0u, left ? 0x4410u : 0x4432u);
     }
@@ -524,9 +542,9 @@ void launch_gbdt_latency(const BinnedLaunch &L, int n_trees, double *d_leafvals,
   if (L.rows <= 0) return;
   LParams p;
   p.model = L.d_model; p.chunks = L.d_chunks; p.bins = L.d_bins; p.leafvals = d_leafvals; p.out = L.d_out;
-  p.rows = L.rows; p.rows_padded = (L.rows + 127) & ~127; p.n_features = L.n_features; p.n_trees = n_trees;
+  p.rows = L.rows; p.rows_padded = (L.rows + 127) & ~127; p.n_features = L.tile_cols; p.n_trees = n_trees;
   p.base_score = L.base_score;
-  const size_t smem = 128 + ((L.max_chunk_bytes + 127u) & ~127u) + (size_t)4 * L.n_features * 64;
+  const size_t smem = 128 + ((L.max_chunk_bytes + 127u) & ~127u) + (size_t)4 * L.tile_cols * 64;
   dim3 grid((unsigned)L.n_chunks, (unsigned)((L.rows + 127) / 128));
   auto go = [&](auto leaves, auto sum) {
     MR_CUDA_CHECK(cudaFuncSetAttribute(leaves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -542,13 +560,13 @@ void launch_gbdt_latency(const BinnedLaunch &L, int n_trees, double *d_leafvals,
 
 void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream) {
   if (L.rows <= 0) return;
-  const int F = L.n_features;
+  const int F = L.tile_cols;  // the traversal only sees tile columns
   // ---- pass 1: codes (skipped when the caller — the fused assemble kernel — already wrote them)
   if (!L.codes_ready) {
   BinParams bp;
   bp.values = L.d_values; bp.thr_off = L.d_thr_off; bp.thr = L.d_thr; bp.is_cat = L.d_is_cat;
   bp.meta = L.d_meta; bp.bucket_range = L.d_bucket_range;
-  bp.bins = L.d_bins; bp.rows = L.rows; bp.cols = L.cols; bp.n_features = F;
+  bp.bins = L.d_bins; bp.rows = L.rows; bp.cols = L.cols; bp.n_features = L.n_features; bp.tile_cols = F;
   bp.xgb = L.kind == MR_BOOSTER_XGBOOST;
   const int items_per_cta = kBinGroups * 32;
   const size_t bin_smem = (size_t)F * (items_per_cta + 2) * sizeof(uint16_t);
@@ -566,7 +584,8 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
   p.n_chunks = L.n_chunks; p.chunk_stride = (L.max_chunk_bytes + 127u) & ~127u;
   p.rows = L.rows; p.n_features = F; p.base_score = L.base_score;
   const size_t kMaxSmem = 227 * 1024;
-  const size_t fixed = 128 + (size_t)p.chunk_stride * (L.n_chunks == 1 ? 1 : 2);
+  const bool aligned_tile = L.compact && !L.has_cat && (F & (F - 1)) == 0;  // + slack to align the tile
+  const size_t fixed = 128 + (size_t)p.chunk_stride * (L.n_chunks == 1 ? 1 : 2) + (aligned_tile ? (size_t)F * 64 : 0);
   const size_t per_item = (size_t)F * sizeof(uint16_t);
   auto fit_threads = [&](int n_cta) -> int {
     const size_t per_cta = kMaxSmem / (size_t)n_cta, reserve = 1024;
@@ -618,9 +637,11 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
       MR_CUDA_CHECK(cudaGetLastError());
       g_kernel_launches++;
     };
-    if (L.kind == MR_BOOSTER_XGBOOST) go(gbdt_score_compact_kernel<float, false>);
-    else if (L.has_cat) go(gbdt_score_compact_kernel<double, true>);
-    else go(gbdt_score_compact_kernel<double, false>);
+    const bool aligned = aligned_tile;
+    if (L.kind == MR_BOOSTER_XGBOOST) { if (aligned) go(gbdt_score_compact_kernel<float, false, true>); else go(gbdt_score_compact_kernel<float, false, false>); }
+    else if (L.has_cat) go(gbdt_score_compact_kernel<double, true, false>);
+    else if (aligned) go(gbdt_score_compact_kernel<double, false, true>);
+    else go(gbdt_score_compact_kernel<double, false, false>);
     return;
   }
   const int ilp = L.ilp <= 0 ? 1 : L.ilp;

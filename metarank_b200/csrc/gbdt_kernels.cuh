@@ -47,18 +47,19 @@ struct BinnedLaunch {
   bool has_cat = false;
   float base_score = 0.f;
   int n_features = 0;
+  int tile_cols = 0;                    // columns of the code tile (BinnedModel::tile_cols)
   const double *d_values = nullptr;
   int rows = 0, cols = 0;
   double *d_out = nullptr;
-  uint16_t *d_bins = nullptr;           // scratch: ceil(rows/32) * F * 32 codes
+  uint16_t *d_bins = nullptr;           // scratch: ceil(rows/32) * tile_cols * 32 codes
   int threads = 0, ilp = 0;
   bool codes_only = false;              // run bin_kernel only (no traversal)
   bool codes_ready = false;             // d_bins already holds the codes (fused assemble): skip bin_kernel
   bool compact = false;                 // model bytes are pack_compact() chunks -> fast lock-step kernel
   bool threaded = false;                // model bytes are pack_threaded() chunks -> free-running kernel
 };
-inline size_t binned_scratch_bytes(int rows, int n_features) {
-  return (size_t)((rows + 31) / 32) * (size_t)n_features * 32 * sizeof(uint16_t);
+inline size_t binned_scratch_bytes(int rows, int tile_cols) {
+  return (size_t)((rows + 31) / 32) * (size_t)tile_cols * 32 * sizeof(uint16_t);
 }
 void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream);
 // Low-latency path for small batches: per-tree leaf values spread over (chunk x item-group) CTAs, then an

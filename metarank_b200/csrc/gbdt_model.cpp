@@ -438,7 +438,7 @@ BinnedModel pack_binned(const HostModel &m, size_t chunk_budget) {
     const uint32_t mth = B.thr_off[f + 1] - B.thr_off[f];
     BinMeta &M = B.meta[f];
     M.mn = 0.0; M.scale = 0.0; M.g = 1; M.idx_off = (uint32_t)B.bucket_range.size();
-    M.thr_off = B.thr_off[f]; M.pad = 0;
+    M.thr_off = B.thr_off[f]; M.flags = (B.is_cat[f] ? kMetaCat : 0u) | (kMetaNoDup << 16);
     if (mth >= 2 && std::isfinite(t[0]) && std::isfinite(t[mth - 1])) {
       const double span = t[mth - 1] - t[0];
       const uint32_t g = std::min<uint32_t>(4 * mth, 32768);
@@ -458,6 +458,7 @@ BinnedModel pack_binned(const HostModel &m, size_t chunk_budget) {
     for (uint32_t b = 0; b < M.g; b++) cnt[b + 1] += cnt[b];
     for (uint32_t b = 0; b < M.g; b++) B.bucket_range.push_back(cnt[b] | (cnt[b + 1] << 16));
   }
+  B.tile_cols = F;
   const bool f32 = m.kind == MR_BOOSTER_XGBOOST;
   const size_t leaf_sz = f32 ? 4 : 8;
   struct BNodeHost { uint16_t k, ff; int16_t left, right; };
@@ -550,6 +551,7 @@ BinnedModel pack_threaded(const HostModel &m, const BinnedModel &bn, size_t chun
   T.thr = bn.thr;
   T.is_cat = bn.is_cat;
   T.meta = bn.meta;
+  T.tile_cols = bn.tile_cols;
   T.bucket_range = bn.bucket_range;
   const bool f32 = m.kind == MR_BOOSTER_XGBOOST;
   struct Entry { uint16_t k, ff; uint16_t left, right; };
@@ -623,11 +625,34 @@ BinnedModel pack_compact(const HostModel &m, const BinnedModel &bn, size_t chunk
   C.is_cat = bn.is_cat;
   C.meta = bn.meta;
   C.bucket_range = bn.bucket_range;
+  // NaN direction per tile column (BinMeta::flags): a feature whose numerical nodes all send NaN the same
+  // way needs one column; a feature with both kinds gets a second column for its NaN-left nodes
+  const int F = m.n_features;
+  std::vector<uint32_t> n_left(F, 0), n_right(F, 0), col_left(F, 0);
+  for (auto &t : m.trees)
+    for (size_t q = 0; q < t.feat.size(); q++)
+      if (!(t.flags[q] & NF_CATEGORICAL)) ((t.flags[q] & NF_NAN_LEFT) ? n_left : n_right)[t.feat[q]]++;
+  C.tile_cols = F;
+  for (int f = 0; f < F; f++) {
+    uint32_t fl = C.is_cat[f] ? kMetaCat : 0u, dup = kMetaNoDup;
+    col_left[f] = (uint32_t)f;
+    if (n_left[f] && !n_right[f]) fl |= kMetaNanLow;
+    else if (n_left[f] && n_right[f]) { dup = (uint32_t)C.tile_cols++; col_left[f] = dup; }
+    C.meta[f].flags = fl | (dup << 16);
+  }
+  {
+    // a power-of-two tile lets the kernel form code addresses with an OR (gbdt_binned.cu, ALIGNED)
+    int p2 = 1;
+    while (p2 < C.tile_cols) p2 <<= 1;
+    if (!m.has_cat && p2 * 3 <= C.tile_cols * 4) C.tile_cols = p2;
+  }
+  if (C.tile_cols > 1023) return C;  // the node's column field is 10 bits
   const bool f32 = m.kind == MR_BOOSTER_XGBOOST;
   chunk_budget = std::min<size_t>(chunk_budget, 65536 - 16);
   auto n_cat_nodes = [](const HostTree &t) { size_t c = 0; for (auto fl : t.flags) c += (fl & NF_CATEGORICAL) != 0; return c; };
   auto tree_bytes = [&](const HostTree &t) {
-    return (t.feat.size() + t.leaf.size() + n_cat_nodes(t)) * 8 + ((t.cat_words.size() * 4 + 7) & ~size_t(7));
+    // a single-leaf tree is stored as one dummy split with both children on its leaf: every walk starts at a node
+    return (std::max<size_t>(t.feat.size(), 1) + t.leaf.size() + n_cat_nodes(t)) * 8 + ((t.cat_words.size() * 4 + 7) & ~size_t(7));
   };
   PackedModel &pk = C.packed;
   size_t i = 0, nt = m.trees.size();
@@ -650,13 +675,14 @@ BinnedModel pack_compact(const HostModel &m, const BinnedModel &bn, size_t chunk
     size_t off = hdr;
     for (size_t k = 0; k < n; k++) {
       const HostTree &t = m.trees[i + k];
-      const size_t ni = t.feat.size(), node_off = off, leaf_off = off + ni * 8;
+      const size_t ni = t.feat.size(), node_off = off, leaf_off = off + std::max<size_t>(ni, 1) * 8;
       const size_t ctab_off = leaf_off + t.leaf.size() * 8, cw_off = ctab_off + n_cat_nodes(t) * 8;
       auto child = [&](int cidx) -> uint32_t {
         return cidx >= 0 ? (uint32_t)(node_off + (size_t)cidx * 8) : (uint32_t)((leaf_off + (size_t)(~cidx) * 8) | 1u);
       };
-      roots[k] = ni ? (uint32_t)node_off : (uint32_t)(leaf_off | 1u);
+      roots[k] = (uint32_t)node_off;
       uint32_t *w = (uint32_t *)(c + node_off);
+      if (ni == 0) { w[0] = 0xFFFFu << 16; w[1] = (uint32_t)(leaf_off | 1u) * 0x10001u; }
       uint32_t *ctab = (uint32_t *)(c + ctab_off);
       size_t ci = 0;
       for (size_t q = 0; q < ni; q++) {
@@ -670,8 +696,8 @@ BinnedModel pack_compact(const HostModel &m, const BinnedModel &bn, size_t chunk
         } else {
           const double *b = C.thr.data() + C.thr_off[f], *e = C.thr.data() + C.thr_off[f + 1];
           const uint32_t kk = (uint32_t)(std::lower_bound(b, e, t.thr[q]) - b);
-          const uint32_t nanl = (t.flags[q] & NF_NAN_LEFT) ? 1u : 0u;
-          w[2 * q] = ((uint32_t)f * 64u | nanl) | (kk << 16);
+          const uint32_t col = (t.flags[q] & NF_NAN_LEFT) ? col_left[f] : (uint32_t)f;
+          w[2 * q] = (col * 64u) | (kk << 16);
         }
         w[2 * q + 1] = child(t.left[q]) | (child(t.right[q]) << 16);
       }

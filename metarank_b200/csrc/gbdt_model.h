@@ -106,8 +106,14 @@ struct BinMeta {
   uint32_t g;         // number of buckets (>= 1)
   uint32_t idx_off;   // offset of this column's g entries in `bucket_range`
   uint32_t thr_off;   // offset of this column's thresholds in `thr`
-  uint32_t pad;
+  // Where the code goes in the scorer's tile.  bit 0: categorical column (code = the integer value);
+  // bit 1: a NaN is stored as code 0 in the base column (every split of this feature sends NaN left),
+  // otherwise as 0xFFFF (never <= k: right); bits 16-31: a second tile column that holds the same codes
+  // with NaN -> 0, referenced by the NaN-left nodes of a feature whose nodes disagree (0xFFFF: none).
+  // With the direction baked into the column the traversal needs no NaN test at all.
+  uint32_t flags;
 };
+constexpr uint32_t kMetaCat = 1u, kMetaNanLow = 2u, kMetaNoDup = 0xFFFFu;
 
 struct BinnedModel {
   bool ok = false;                 // false: model cannot be binned exactly -> use the f64/f32 kernel
@@ -116,6 +122,7 @@ struct BinnedModel {
   std::vector<BinMeta> meta;       // [n_features]
   std::vector<uint32_t> bucket_range;  // per bucket: first threshold index | one-past-last << 16 (within the column)
   std::vector<uint8_t> is_cat;     // [n_features] feature is split categorically
+  int tile_cols = 0;               // columns of the code tile: n_features + duplicated (mixed NaN direction) columns
   PackedModel packed;              // chunks of BNodes (+ leaves, + categorical tables)
 };
 BinnedModel pack_binned(const HostModel &m, size_t chunk_budget);

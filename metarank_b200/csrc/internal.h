@@ -118,7 +118,7 @@ struct mr_model {
   uint32_t *d_thr_off = nullptr;
   double *d_thr = nullptr;
   uint8_t *d_is_cat = nullptr;
-  BinMeta *d_meta = nullptr;
+  BinMeta *d_meta = nullptr, *d_cmeta = nullptr;  // identity tile mapping (binned/threaded) / compact + lat mapping
   uint32_t *d_bucket_range = nullptr;
   std::atomic<bool> closed{false};
   std::atomic<int> inflight{0};
@@ -145,10 +145,10 @@ struct mr_model {
   void free_binned() {
     for (void *p : {(void *)d_bmodel, (void *)d_bchunks, (void *)d_thr_off, (void *)d_thr, (void *)d_is_cat,
                     (void *)d_tmodel, (void *)d_tchunks, (void *)d_cmodel, (void *)d_cchunks, (void *)d_lmodel,
-                    (void *)d_lchunks, (void *)d_meta, (void *)d_bucket_range})
+                    (void *)d_lchunks, (void *)d_meta, (void *)d_cmeta, (void *)d_bucket_range})
       if (p) cudaFree(p);
     d_bmodel = nullptr; d_bchunks = nullptr; d_thr_off = nullptr; d_thr = nullptr; d_is_cat = nullptr;
-    d_tmodel = nullptr; d_tchunks = nullptr; d_cmodel = nullptr; d_cchunks = nullptr; d_lmodel = nullptr; d_lchunks = nullptr; d_meta = nullptr; d_bucket_range = nullptr;
+    d_tmodel = nullptr; d_tchunks = nullptr; d_cmodel = nullptr; d_cchunks = nullptr; d_lmodel = nullptr; d_lchunks = nullptr; d_meta = nullptr; d_cmeta = nullptr; d_bucket_range = nullptr;
   }
   void repack() {
     // Default policy: stream the ensemble through two small shared-memory buffers (TMA bulk
@@ -178,8 +178,10 @@ struct mr_model {
       if (compact.ok) {
         d_cmodel = to_device(compact.packed.bytes);
         d_cchunks = to_device(compact.packed.chunks);
+        d_cmeta = to_device(compact.meta);
       }
       lat = pack_compact(host, binned, 4 * 1024);
+      if (lat.ok && !compact.ok) lat.ok = false;  // same tile mapping as `compact` (d_cmeta) by construction
       if (lat.ok) {
         d_lmodel = to_device(lat.packed.bytes);
         d_lchunks = to_device(lat.packed.chunks);
@@ -193,9 +195,12 @@ struct mr_model {
   }
   bool use_threaded() const { return threaded.ok && opt_variant == 3; }
   bool use_compact() const { return compact.ok && (opt_variant == 4 || opt_variant < 0); }
+  // the code-based scorer that is active and the width of its code tile
+  const BinnedModel &active_binned() const { return use_threaded() ? threaded : use_compact() ? compact : binned; }
+  int code_cols() const { return active_binned().tile_cols; }
   bool use_binned() const {
-    if ((size_t)host.n_features * (4 * 32 + 2) * sizeof(uint16_t) > 200 * 1024) return false;  // bin_kernel tile
-    if (binned.ok && 2 * (size_t)binned.packed.max_chunk_bytes + 64 * (size_t)host.n_features * 2 > 200 * 1024)
+    if ((size_t)2 * host.n_features * (4 * 32 + 2) * sizeof(uint16_t) > 200 * 1024) return false;  // bin_kernel tile
+    if (binned.ok && 2 * (size_t)binned.packed.max_chunk_bytes + 64 * (size_t)2 * host.n_features * 2 > 200 * 1024)
       return false;  // an enormous tree: the exact kernel's HBM-resident slow path handles it
     // auto (-1): the compact binned kernel whenever the model allows it (no categorical splits, <= 1023
     // features); otherwise generic binned for LightGBM (f64 -> u16 quarters the tile) and the plain f32
@@ -214,7 +219,8 @@ struct mr_model {
     B.n_chunks = (int)M.packed.chunks.size();
     B.max_chunk_bytes = M.packed.max_chunk_bytes;
     B.d_thr_off = d_thr_off; B.d_thr = d_thr; B.d_is_cat = d_is_cat;
-    B.d_meta = d_meta; B.d_bucket_range = d_bucket_range;
+    B.d_meta = cmp ? d_cmeta : d_meta; B.d_bucket_range = d_bucket_range;
+    B.tile_cols = M.tile_cols;
     B.kind = host.kind; B.has_cat = host.has_cat; B.base_score = host.base_score;
     B.n_features = host.n_features;
     B.threads = opt_threads; B.ilp = opt_ilp;
@@ -223,7 +229,7 @@ struct mr_model {
   // Scores rows whose u16 codes were already written to d_codes (fused assemble path).
   bool use_latency(int rows) const {
     return lat.ok && rows <= kLatencyMaxRows && opt_variant < 0 && opt_threads == 0 &&
-           128 + lat.packed.max_chunk_bytes + 128 + (size_t)4 * host.n_features * 64 <= 200 * 1024;
+           use_compact() && 128 + lat.packed.max_chunk_bytes + 128 + (size_t)4 * compact.tile_cols * 64 <= 200 * 1024;
   }
   void score_codes(uint16_t *d_codes, int rows, double *d_out, cudaStream_t stream, void *d_leaf_scratch = nullptr) const {
     BinnedLaunch B = binned_desc();
@@ -250,7 +256,7 @@ struct mr_model {
       BinnedLaunch B = binned_desc();
       B.d_values = d_values; B.rows = rows; B.cols = cols; B.d_out = d_out;
       void *bins = nullptr;
-      MR_CUDA_CHECK(cudaMallocAsync(&bins, std::max<size_t>(binned_scratch_bytes(rows, host.n_features), 16), stream));
+      MR_CUDA_CHECK(cudaMallocAsync(&bins, std::max<size_t>(binned_scratch_bytes(rows, code_cols()), 16), stream));
       B.d_bins = (uint16_t *)bins;
       if (use_latency(rows)) {
         B.codes_only = true;

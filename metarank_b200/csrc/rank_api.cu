@@ -44,7 +44,7 @@ struct ScratchPlan {
 };
 
 ScratchPlan plan_scratch(const Schema &S, int n_requests, int total_items, uint32_t per_hist, bool own_features,
-                         bool want_codes = false, size_t leaf_bytes = 0) {
+                         int code_cols = 0, size_t leaf_bytes = 0) {
   ScratchPlan p{};
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += al(bytes); return r; };
@@ -63,7 +63,7 @@ ScratchPlan plan_scratch(const Schema &S, int n_requests, int total_items, uint3
   p.hist_cursor = take(4);
   p.error_flag = take(4);
   p.features = own_features ? take((size_t)total_items * std::max(S.dim, 1) * 8) : 0;
-  p.codes = want_codes ? take(binned_scratch_bytes(total_items, std::max(S.dim, 1))) : 0;
+  p.codes = code_cols > 0 ? take(binned_scratch_bytes(total_items, code_cols)) : 0;
   p.leafvals = leaf_bytes ? take(leaf_bytes) : 0;
   p.total = o;
   return p;
@@ -108,10 +108,12 @@ void set_codes(RankArgs &a, const mr_model *model, uint8_t *scratch, const Scrat
   a.bin = BinParams{};
   a.bin.thr_off = model->d_thr_off;
   a.bin.thr = model->d_thr;
+  const BinnedLaunch B = model->binned_desc();  // the active code-based scorer's tile mapping
   a.bin.is_cat = model->d_is_cat;
-  a.bin.meta = model->d_meta;
+  a.bin.meta = B.d_meta;
   a.bin.bucket_range = model->d_bucket_range;
   a.bin.n_features = model->host.n_features;
+  a.bin.tile_cols = B.tile_cols;
   a.bin.xgb = model->host.kind == MR_BOOSTER_XGBOOST;
 }
 
@@ -313,7 +315,7 @@ void rank_enqueue(mr_state *st, mr_model *model, const mr_rank_batch *b, int r0,
 
   const bool fused = fused_codes(model);
   const size_t leaf_bytes = (fused && model->use_latency(N)) ? latency_scratch_bytes(N, (int)model->host.trees.size()) : 0;
-  ScratchPlan sp = plan_scratch(S, R, N, st->hist_pool_per_hist, want_features || !fused, fused, leaf_bytes);
+  ScratchPlan sp = plan_scratch(S, R, N, st->hist_pool_per_hist, want_features || !fused, fused ? model->code_cols() : 0, leaf_bytes);
   // device outputs are laid out [scores | order | error flag] so that the common (unpinned) case is ONE D2H copy
   const size_t scores_off = al(in_bytes) + sp.total, order_off = scores_off + al((size_t)N * 8);
   const size_t err_off = order_off + al((size_t)N * 4);
@@ -499,7 +501,7 @@ mr_status mr_rank_device(mr_state *st, mr_model *model, const mr_rank_batch *b, 
     if (st->dirty) fail(MR_ERR_INVALID_ARG, "state has pending upserts: call mr_state_flush before mr_rank_device");
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     const bool fused = fused_codes(model);
-    ScratchPlan sp = plan_scratch(S, R, N, st->hist_pool_per_hist, d_out_features == nullptr && !fused, fused);
+    ScratchPlan sp = plan_scratch(S, R, N, st->hist_pool_per_hist, d_out_features == nullptr && !fused, fused ? model->code_cols() : 0);
     if (sp.total > st->d_scratch_cap) {
       MR_CUDA_CHECK(cudaDeviceSynchronize());
       if (st->d_scratch) cudaFree(st->d_scratch);

@@ -101,10 +101,11 @@ def test_header_is_plain_c_and_usable_from_c():
         assert "sm_100a ok" in r.stdout
 
 
-def test_compact_level_loop_stays_at_twelve_sass_instructions():
+def test_compact_level_loop_sass_instruction_budget():
     """Performance regression guard (no GPU needed): the per-tree-level loop of the default scorer is
-    hand-written PTX that ptxas schedules into 12 SASS instructions; a careless edit around it once
-    silently grew it to 15 (+19 % kernel time, profiles/ncu_r1_summary.md)."""
+    hand-written PTX that ptxas schedules into 9 SASS instructions (power-of-two code tile: the code
+    address is a single LOP3) or 10 (otherwise); a careless edit around it once silently grew the then
+    12-instruction loop to 15 (+19 % kernel time, profiles/ncu_r1_summary.md)."""
     import os
     import re
     import shutil
@@ -116,12 +117,13 @@ def test_compact_level_loop_stays_at_twelve_sass_instructions():
     if not os.path.exists(tool) or not os.path.exists(obj):
         pytest.skip("cuobjdump or the object file is not available")
     sass = subprocess.run([tool, "-sass", obj], capture_output=True, text=True).stdout
-    m = re.search(r"Function : \S*compact_kernelIdLb0EE\S*\n(.*?)(?:Function :|\Z)", sass, re.S)
-    assert m, "compact kernel <double, no categorical> not found"
-    ins = [re.sub(r"/\*.*?\*/", "", ln).strip() for ln in m.group(1).split("\n") if re.search(r"/\*[0-9a-f]{4}\*/", ln)]
-    ins = [i for i in ins if i]
-    start = next(k for k, i in enumerate(ins) if i.startswith("LDS.64") and "+UR" in i)
-    end = next(k for k in range(start, len(ins)) if "BRA" in ins[k])
-    body = ins[start:end + 1]
-    assert len(body) <= 12, body
-    assert sum("LDS" in i for i in body) == 2 and not any(i.startswith(("DSETP", "DADD", "LDG")) for i in body), body
+    for aligned, budget in ((1, 9), (0, 10)):
+        m = re.search(r"Function : \S*compact_kernelIdLb0ELb%dEE\S*\n(.*?)(?:Function :|\Z)" % aligned, sass, re.S)
+        assert m, "compact kernel <double, no categorical> not found"
+        ins = [re.sub(r"/\*.*?\*/", "", ln).strip() for ln in m.group(1).split("\n") if re.search(r"/\*[0-9a-f]{4}\*/", ln)]
+        ins = [i for i in ins if i]
+        start = next(k for k, i in enumerate(ins) if i.startswith("LDS.64") and "+UR" in i)
+        end = next(k for k in range(start, len(ins)) if "BRA" in ins[k])
+        body = ins[start:end + 1]
+        assert len(body) <= budget, body
+        assert sum("LDS" in i for i in body) == 2 and not any(i.startswith(("DSETP", "DADD", "LDG")) for i in body), body
