@@ -197,6 +197,9 @@ def main():
     ctx = mb.Context(local)
     blob = _model_blob()
     booster = mb.LightGBMBooster(ctx, blob, n_features=FEATURES)
+    for kv in filter(None, os.environ.get("MR_BENCH_OPTS", "").split(",")):  # tuning aid: "chunk_kb=24,threads=448"
+        key, val = kv.split("=")
+        booster.set_option(key, int(val))
 
     # ---- device-resident state: CATALOGUE items x 30 `number` features (Persistence.values on HBM)
     names = [f"f{j}" for j in range(FEATURES)]

@@ -13,6 +13,8 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 
 #include "binning.cuh"
 #include "gbdt_kernels.cuh"
@@ -595,7 +597,28 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
     return (int)t;
   };
   int threads = L.threads;
-  if (threads <= 0) {
+  int want_per_sm = 0;
+  if (threads <= 0 && L.compact) {
+    // Measured (profiles/sweep_r1.md, fine sweep): time falls with resident warps up to ~48 per SM
+    // (24: 2.81 ms, 32: 2.29, 40: 2.17, 48: 2.05 on C2), then the shared-memory pipe is saturated and
+    // more warps only queue on it (56: 2.07, 64: 2.22).  Take the CTA shape that gets closest to 48 warps,
+    // in CTAs of whole multiples of 4 warps (even over the schedulers); ties go to the shape that wastes
+    // the least of the persistent grid's last round.
+    double best = -1;
+    for (int n_cta = 1; n_cta <= 4; n_cta++) {
+      const int cap = std::min(fit_threads(n_cta), 2048 / n_cta);
+      for (int t = 128; t <= cap; t += 128) {
+        const int warps = n_cta * (t / 32);
+        const double occ = warps <= 48 ? warps : 48 - 0.25 * (warps - 48);
+        const long long tiles = (L.rows + t - 1) / t, slots = (long long)num_sms * n_cta;
+        const double tail = (double)tiles / (double)(((tiles + slots - 1) / slots) * slots);  // 1 = no idle round
+        const double score = occ * (0.9 + 0.1 * tail);
+        if (score > best) { best = score; threads = t; want_per_sm = n_cta; }
+      }
+    }
+    if (threads <= 0) { threads = std::max(32, fit_threads(1)); want_per_sm = 1; }
+    while (threads > 32 && (L.rows + threads - 1) / threads < num_sms) threads = ((threads / 2) + 31) & ~31;
+  } else if (threads <= 0) {
     int best_warps = 0;
     threads = 0;
     for (int n_cta = 2; n_cta <= 4; n_cta++) {
@@ -633,6 +656,11 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
       MR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
       if (per_sm < 1) fail(MR_ERR_CUDA, "compact gbdt kernel does not fit on an SM");
       const int n_tiles = (p.rows + threads - 1) / threads;
+      if (want_per_sm > 0) per_sm = std::min(per_sm, want_per_sm);
+      static const bool debug = getenv("MR_DEBUG_LAUNCH") != nullptr;
+      if (debug)
+        fprintf(stderr, "[mr] compact scorer: rows %d tile_cols %d chunks %d x %u B, %d threads x %d CTAs (%d/SM), %zu B smem\n",
+                p.rows, F, p.n_chunks, p.chunk_stride, threads, std::max(1, std::min(n_tiles, num_sms * per_sm)), per_sm, smem);
       kern<<<std::max(1, std::min(n_tiles, num_sms * per_sm)), threads, smem, stream>>>(p);
       MR_CUDA_CHECK(cudaGetLastError());
       g_kernel_launches++;

@@ -640,14 +640,14 @@ BinnedModel pack_compact(const HostModel &m, const BinnedModel &bn, size_t chunk
     else if (n_left[f] && n_right[f]) { dup = (uint32_t)C.tile_cols++; col_left[f] = dup; }
     C.meta[f].flags = fl | (dup << 16);
   }
-  {
-    // a power-of-two tile lets the kernel form code addresses with an OR (gbdt_binned.cu, ALIGNED)
-    int p2 = 1;
-    while (p2 < C.tile_cols) p2 <<= 1;
-    if (!m.has_cat && p2 * 3 <= C.tile_cols * 4) C.tile_cols = p2;
-  }
   if (C.tile_cols > 1023) return C;  // the node's column field is 10 bits
   const bool f32 = m.kind == MR_BOOSTER_XGBOOST;
+  if (chunk_budget == 0) {
+    // auto: the scorer wants ~48 resident warps per SM (2 CTAs x 768 threads); give the double-buffered
+    // chunks what the code tile of those warps leaves of the 227 KB (profiles/sweep_r1.md)
+    const long long left = (225ll * 1024 - 1536ll * C.tile_cols * 2) / 4;
+    chunk_budget = left >= 24 * 1024 ? 24 * 1024 : left >= 16 * 1024 ? 16 * 1024 : 8 * 1024;
+  }
   chunk_budget = std::min<size_t>(chunk_budget, 65536 - 16);
   auto n_cat_nodes = [](const HostTree &t) { size_t c = 0; for (auto fl : t.flags) c += (fl & NF_CATEGORICAL) != 0; return c; };
   auto tree_bytes = [&](const HostTree &t) {

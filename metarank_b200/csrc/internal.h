@@ -174,7 +174,7 @@ struct mr_model {
       d_is_cat = to_device(binned.is_cat);
       d_meta = to_device(binned.meta);
       d_bucket_range = to_device(binned.bucket_range);
-      compact = pack_compact(host, binned, budget);
+      compact = pack_compact(host, binned, opt_chunk_kb > 0 ? budget : 0);  // 0: sized from the code tile
       if (compact.ok) {
         d_cmodel = to_device(compact.packed.bytes);
         d_cchunks = to_device(compact.packed.chunks);

@@ -11,7 +11,7 @@ cfgs = [("C2", 0, synth.lightgbm_model_text(500, 30, seed=1236), 30)]
 if len(sys.argv) > 1 and sys.argv[1] == "all":
     cfgs += [("C5", 0, synth.lightgbm_model_text(2000, 64, seed=1239), 64),
              ("C4x", 1, synth.xgboost_model_json(200, 16, depth=6, seed=1238), 16)]
-rows = 1 << 20
+rows = 1638400
 for name, kind, blob, F in cfgs:
     X = synth.feature_matrix(rows, F, seed=44)
     want = oracle.OracleBooster(kind, blob).predictMat(X[:4096], 4096, F, threads=0)
@@ -20,22 +20,26 @@ for name, kind, blob, F in cfgs:
     b = mb.B200Booster(ctx, blob, kind=kind)
     print(name, "mean path", b.mean_path(X[:4096], 4096, F), flush=True)
     st = torch.cuda.current_stream().cuda_stream
-    for chunk_kb in (8, 16, 32, 60):
+    for chunk_kb in (16, 24):
         b.set_option("chunk_kb", chunk_kb)
-        for threads in (0, 256, 384, 512, 768, 1024):
-            for variant, ilp in ((2, 1), (4, 1)):
-                b.set_option("threads", threads); b.set_option("variant", variant); b.set_option("ilp", ilp)
+        for stages in (0,):
+            for threads in [0] + list(range(320, 1025, 32)):
+                variant, ilp = 4, 1
+                b.set_option("threads", threads); b.set_option("variant", variant);
                 try:
-                    for _ in range(2): b.predict_device(dX.data_ptr(), rows, F, dO.data_ptr(), st)
+                    n_codes = b.codes_bytes(rows)
+                    d_codes = torch.empty(n_codes, dtype=torch.uint8, device="cuda")
+                    b.bin_device(dX.data_ptr(), rows, F, d_codes.data_ptr(), st)
+                    for _ in range(2): b.score_codes_device(d_codes.data_ptr(), rows, dO.data_ptr(), st)
                     torch.cuda.synchronize()
                     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
                     e0.record()
-                    for _ in range(3): b.predict_device(dX.data_ptr(), rows, F, dO.data_ptr(), st)
+                    for _ in range(5): b.score_codes_device(d_codes.data_ptr(), rows, dO.data_ptr(), st)
                     e1.record(); torch.cuda.synchronize()
-                    ms = e0.elapsed_time(e1) / 3
+                    ms = e0.elapsed_time(e1) / 5
                     ok = np.array_equal(dO[:4096].cpu().numpy(), want)
-                    print(json.dumps(dict(cfg=name, chunk_kb=chunk_kb, nchunks=b.info().n_chunks, threads=threads, variant=variant, ilp=ilp,
+                    print(json.dumps(dict(cfg=name, chunk_kb=chunk_kb, nchunks=b.info().n_chunks, stages=stages, threads=threads,
                                           ms=round(ms, 3), Mitems_s=round(rows / ms / 1e3, 1), ok=bool(ok))), flush=True)
                 except Exception as ex:
-                    print("ERR", chunk_kb, threads, variant, ilp, ex, flush=True)
+                    print("ERR", chunk_kb, stages, threads, ex, flush=True)
     b.free()
