@@ -195,6 +195,100 @@ __global__ void __launch_bounds__(1024) gbdt_score_binned_kernel(const BParams p
 // Same mapping as gbdt_score_binned_kernel, on the compact layout (gbdt_model.h): children are byte
 // offsets (bit 0 = leaf), the feature's byte offset inside the warp's code tile is stored in the
 // node, so one tree level is: LDS.64 node, shift+mask/or, LDS.U16 code, compare, select, test.
+// One tree: from the root's byte offset to the leaf's (offset | 1).  One level = 9 SASS instructions
+// (ALIGNED) or 10; spelled in PTX because nvcc otherwise routes the predicates through integer registers
+// (18 instructions).  With HAS_CAT the PTX loop additionally leaves on a categorical node (bit 1 of
+// word0), which is resolved in C++, then re-enters.  Every tree starts at an internal node (single-leaf
+// trees are packed as a dummy split).
+template <bool HAS_CAT, bool ALIGNED>
+__device__ __forceinline__ uint32_t walk_tree(uint32_t n, const uint8_t *cb, uint32_t cb_addr, const uint8_t *xwarp,
+                                              uint32_t xwarp_addr, uint32_t lane2) {
+  if (HAS_CAT) {
+    do {
+      asm volatile(
+          "{\n"
+          ".reg .pred pl, pq, pc;\n"
+          ".reg .b32 w0, w1, off, code, kk, sel, tmp;\n"
+          "LVLC:\n"
+          "add.u32 tmp, %1, %0;\n"
+          "ld.shared.v2.u32 {w0, w1}, [tmp];\n"
+          "and.b32 tmp, w0, 2;\n"
+          "setp.ne.u32 pc, tmp, 0;\n"
+          "@pc bra DONEC;\n"
+          "lop3.b32 off, w0, 0xFFC0, %3, 0xEA;\n"
+          "add.u32 off, off, %2;\n"
+          "ld.shared.u16 code, [off];\n"
+          "shr.u32 kk, w0, 16;\n"
+          "setp.le.u32 pl, code, kk;\n"
+          "selp.b32 sel, 0x4410, 0x4432, pl;\n"
+          "prmt.b32 %0, w1, 0, sel;\n"
+          "and.b32 tmp, %0, 1;\n"
+          "setp.eq.u32 pq, tmp, 0;\n"
+          "@pq bra LVLC;\n"
+          "DONEC:\n"
+          "}\n"
+          : "+r"(n)
+          : "r"(cb_addr), "r"(xwarp_addr), "r"(lane2)
+          : "memory");
+      if (n & 1u) break;
+      // categorical node: NaN / negative / out-of-bitset go right (LightGBM CategoricalDecision)
+      const uint2 nd = *reinterpret_cast<const uint2 *>(cb + n);
+      const uint32_t code = *reinterpret_cast<const uint16_t *>(xwarp + ((nd.x & 0xFFC0u) | lane2));
+      bool left = false;
+      if (code != kBinNaN) {
+        const uint2 ct = reinterpret_cast<const uint2 *>(cb)[nd.x >> 16];
+        const uint32_t w = code >> 5;
+        if (w < ct.y) left = (reinterpret_cast<const uint32_t *>(cb)[ct.x + w] >> (code & 31u)) & 1u;
+      }
+      n = __byte_perm(nd.y, 0u, left ? 0x4410u : 0x4432u);
+    } while (!(n & 1u));
+  } else if (ALIGNED) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pl, pq;\n"
+        ".reg .b32 w0, w1, off, code, kk, sel, tmp;\n"
+        "LVLA:\n"
+        "add.u32 tmp, %1, %0;\n"
+        "ld.shared.v2.u32 {w0, w1}, [tmp];\n"
+        "lop3.b32 off, w0, 0xFFC0, %2, 0xEA;\n"   // (w0 & 0xFFC0) | (warp tile base | lane*2)
+        "ld.shared.u16 code, [off];\n"
+        "shr.u32 kk, w0, 16;\n"
+        "setp.le.u32 pl, code, kk;\n"               // the NaN direction is baked into the column (BinMeta::flags)
+        "selp.b32 sel, 0x4410, 0x4432, pl;\n"
+        "prmt.b32 %0, w1, 0, sel;\n"
+        "and.b32 tmp, %0, 1;\n"
+        "setp.eq.u32 pq, tmp, 0;\n"
+        "@pq bra LVLA;\n"
+        "}\n"
+        : "+r"(n)
+        : "r"(cb_addr), "r"(xwarp_addr | lane2)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred pl, pq;\n"
+        ".reg .b32 w0, w1, off, code, kk, sel, tmp;\n"
+        "LVL:\n"
+        "add.u32 tmp, %1, %0;\n"
+        "ld.shared.v2.u32 {w0, w1}, [tmp];\n"
+        "lop3.b32 off, w0, 0xFFC0, %3, 0xEA;\n"   // (w0 & 0xFFC0) | lane*2
+        "add.u32 off, off, %2;\n"
+        "ld.shared.u16 code, [off];\n"
+        "shr.u32 kk, w0, 16;\n"
+        "setp.le.u32 pl, code, kk;\n"
+        "selp.b32 sel, 0x4410, 0x4432, pl;\n"
+        "prmt.b32 %0, w1, 0, sel;\n"
+        "and.b32 tmp, %0, 1;\n"
+        "setp.eq.u32 pq, tmp, 0;\n"
+        "@pq bra LVL;\n"
+        "}\n"
+        : "+r"(n)
+        : "r"(cb_addr), "r"(xwarp_addr), "r"(lane2)
+        : "memory");
+  }
+  return n;
+}
+
 // ALIGNED (tile_cols a power of two): every warp's tile starts on a multiple of its own size, so the code's
 // address is (column offset | thread base) — one LOP3, no add.
 template <typename Real, bool HAS_CAT, bool ALIGNED>
@@ -258,98 +352,22 @@ __global__ void __launch_bounds__(1024) gbdt_score_compact_kernel(const BParams 
       const int ntree = (int)*reinterpret_cast<const uint32_t *>(cb);
       const uint32_t *roots = reinterpret_cast<const uint32_t *>(cb + 16);
       const uint32_t cb_addr = smem_u32(cb), xwarp_addr = smem_u32(xwarp);
+      auto walk = [&](uint32_t root) -> Real {
+        const uint32_t n = walk_tree<HAS_CAT, ALIGNED>(root, cb, cb_addr, xwarp, xwarp_addr, lane2);
+        return *reinterpret_cast<const Real *>(cb + (n - 1u));
+      };
+      // four roots per (warp-uniform) LDS.128; the leaf values are still added one by one, in tree order
+      int t = 0;
 #pragma unroll 1
-      for (int t = 0; t < ntree; t++) {
-        uint32_t n = roots[t];
-        // One tree level = 10 SASS instructions; spelled in PTX because nvcc otherwise routes the
-        // predicates through integer registers (18 instructions).  With HAS_CAT the loop additionally
-        // leaves on a categorical node (bit 1 of word0), which is resolved in C++ below, then re-enters.
-        if (HAS_CAT) {
-          while (!(n & 1u)) {
-            asm volatile(
-                "{\n"
-                ".reg .pred pl, pq, pc;\n"
-                ".reg .b32 w0, w1, off, code, kk, sel, tmp;\n"
-                "LVLC:\n"
-                "add.u32 tmp, %1, %0;\n"
-                "ld.shared.v2.u32 {w0, w1}, [tmp];\n"
-                "and.b32 tmp, w0, 2;\n"
-                "setp.ne.u32 pc, tmp, 0;\n"
-                "@pc bra DONEC;\n"
-                "lop3.b32 off, w0, 0xFFC0, %3, 0xEA;\n"
-                "add.u32 off, off, %2;\n"
-                "ld.shared.u16 code, [off];\n"
-                "shr.u32 kk, w0, 16;\n"
-                "setp.le.u32 pl, code, kk;\n"
-                "selp.b32 sel, 0x4410, 0x4432, pl;\n"
-                "prmt.b32 %0, w1, 0, sel;\n"
-                "and.b32 tmp, %0, 1;\n"
-                "setp.eq.u32 pq, tmp, 0;\n"
-                "@pq bra LVLC;\n"
-                "DONEC:\n"
-                "}\n"
-                : "+r"(n)
-                : "r"(cb_addr), "r"(xwarp_addr), "r"(lane2)
-                : "memory");
-            if (n & 1u) break;
-            // categorical node: NaN / negative / out-of-bitset go right (LightGBM CategoricalDecision)
-            const uint2 nd = *reinterpret_cast<const uint2 *>(cb + n);
-            const uint32_t code = *reinterpret_cast<const uint16_t *>(xwarp + ((nd.x & 0xFFC0u) | lane2));
-            bool left = false;
-            if (code != kBinNaN) {
-              const uint2 ct = reinterpret_cast<const uint2 *>(cb)[nd.x >> 16];
-              const uint32_t w = code >> 5;
-              if (w < ct.y) left = (reinterpret_cast<const uint32_t *>(cb)[ct.x + w] >> (code & 31u)) & 1u;
-            }
-            n = __byte_perm(nd.y, 0u, left ? 0x4410u : 0x4432u);
-          }
-        } else if (ALIGNED) {
-          // every tree starts at an internal node (single-leaf trees are packed as a dummy split)
-          asm volatile(
-              "{\n"
-              ".reg .pred pl, pq;\n"
-              ".reg .b32 w0, w1, off, code, kk, sel, tmp;\n"
-              "LVLA:\n"
-              "add.u32 tmp, %1, %0;\n"
-              "ld.shared.v2.u32 {w0, w1}, [tmp];\n"
-              "lop3.b32 off, w0, 0xFFC0, %2, 0xEA;\n"   // (w0 & 0xFFC0) | (warp tile base | lane*2)
-              "ld.shared.u16 code, [off];\n"
-              "shr.u32 kk, w0, 16;\n"
-              "setp.le.u32 pl, code, kk;\n"               // the NaN direction is baked into the column (BinMeta::flags)
-              "selp.b32 sel, 0x4410, 0x4432, pl;\n"
-              "prmt.b32 %0, w1, 0, sel;\n"
-              "and.b32 tmp, %0, 1;\n"
-              "setp.eq.u32 pq, tmp, 0;\n"
-              "@pq bra LVLA;\n"
-              "}\n"
-              : "+r"(n)
-              : "r"(cb_addr), "r"(xwarp_addr | lane2)
-              : "memory");
-        } else {
-          asm volatile(
-              "{\n"
-              ".reg .pred pl, pq;\n"
-              ".reg .b32 w0, w1, off, code, kk, sel, tmp;\n"
-              "LVL:\n"
-              "add.u32 tmp, %1, %0;\n"
-              "ld.shared.v2.u32 {w0, w1}, [tmp];\n"
-              "lop3.b32 off, w0, 0xFFC0, %3, 0xEA;\n"   // (w0 & 0xFFC0) | lane*2
-              "add.u32 off, off, %2;\n"
-              "ld.shared.u16 code, [off];\n"
-              "shr.u32 kk, w0, 16;\n"
-              "setp.le.u32 pl, code, kk;\n"
-              "selp.b32 sel, 0x4410, 0x4432, pl;\n"
-              "prmt.b32 %0, w1, 0, sel;\n"
-              "and.b32 tmp, %0, 1;\n"
-              "setp.eq.u32 pq, tmp, 0;\n"
-              "@pq bra LVL;\n"
-              "}\n"
-              : "+r"(n)
-              : "r"(cb_addr), "r"(xwarp_addr), "r"(lane2)
-              : "memory");
-        }
-        acc += *reinterpret_cast<const Real *>(cb + (n - 1u));
+      for (; t + 4 <= ntree; t += 4) {
+        const uint4 r = *reinterpret_cast<const uint4 *>(roots + t);
+        acc += walk(r.x);
+        acc += walk(r.y);
+        acc += walk(r.z);
+        acc += walk(r.w);
       }
+#pragma unroll 1
+      for (; t < ntree; t++) acc += walk(roots[t]);
       __syncthreads();
     }
     if (item < p.rows) p.out[item] = (double)acc;
