@@ -324,7 +324,7 @@ mr_status mr_model_set_option(mr_model *m, const char *key, int32_t value) {
     std::lock_guard<std::mutex> g(m->mu);
     std::string k(key);
     if (k == "threads") m->opt_threads = value;
-    else if (k == "variant") m->opt_variant = value;
+    else if (k == "variant") { m->opt_variant = value; m->code_gen = mr_model::next_code_gen(); }
     else if (k == "ilp") m->opt_ilp = value;
     else if (k == "chunk_kb") {
       m->opt_chunk_kb = value;

@@ -527,6 +527,8 @@ __device__ __forceinline__ uint32_t hist_count(const RankArgs &a, int r, int h, 
 // per column, the f64 row (explain) as one contiguous run per item.
 constexpr int kGatherWarps = 4;
 
+// CODES: emit the scorer's u16 codes; OUT: emit the dense f64 row; XGB: XGBoost code semantics.
+template <bool CODES, bool OUT, bool XGB>
 __global__ void __launch_bounds__(kGatherWarps * 32) row_gather_kernel(RankArgs a) {
   extern __shared__ __align__(16) uint8_t s_raw[];
   // [FastCol table][bucket headers (optional)][per warp: codes tile n_fast x 32 u16]
@@ -539,7 +541,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) row_gather_kernel(RankArgs 
     uint32_t *dst = reinterpret_cast<uint32_t *>(s_raw);
     for (int k = threadIdx.x; k < a.n_fast * (int)(sizeof(FastCol) / 4); k += blockDim.x) dst[k] = __ldg(src + k);
   }
-  if (a.codes && a.stage_meta) {
+  if (CODES && a.stage_meta) {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(a.bin.meta);
     uint32_t *dst = reinterpret_cast<uint32_t *>(s_raw + off);
     for (int k = threadIdx.x; k < a.dim * (int)(sizeof(BinMeta) / 4); k += blockDim.x) dst[k] = __ldg(src + k);
@@ -567,14 +569,15 @@ __global__ void __launch_bounds__(kGatherWarps * 32) row_gather_kernel(RankArgs 
     const FastCol fc = s_cols[act ? c : 0];
     BinMeta M{};
     bool cat = false;
-    if (a.codes) { M = bin.meta[fc.col]; cat = (M.flags & kMetaCat) != 0; }
+    if (CODES) { M = bin.meta[fc.col]; cat = (M.flags & kMetaCat) != 0; }
     const int wsrc = fc.word & 31, psrc = (fc.bit >> 6) & 31;
     const bool whi = fc.word >= 32, phi_ = (fc.bit >> 6) >= 32;
     const double vmiss = fc.missing ? 0.0 : kNaN;
     // software pipeline: row j + 1 is in flight while row j is converted
     uint64_t n0 = 0, n1 = 0;
+    uint32_t ir_next = __shfl_sync(0xFFFFFFFFu, my_row, 0);
     {
-      const uint32_t ir = __shfl_sync(0xFFFFFFFFu, my_row, 0);
+      const uint32_t ir = ir_next;
       if (ir != kNoRow) {
         const uint64_t *rp = IT.rows + (size_t)ir * rw;
         if (lane < rw) n0 = __ldg(rp + lane);
@@ -582,11 +585,12 @@ __global__ void __launch_bounds__(kGatherWarps * 32) row_gather_kernel(RankArgs 
       }
     }
     for (int j = 0; j < n_here; j++) {
-      const uint32_t ir = __shfl_sync(0xFFFFFFFFu, my_row, j);
+      const uint32_t ir = ir_next;
       const uint64_t w0 = n0, w1 = n1;
       n0 = 0; n1 = 0;
       if (j + 1 < n_here) {
         const uint32_t nr = __shfl_sync(0xFFFFFFFFu, my_row, j + 1);
+        ir_next = nr;
         if (nr != kNoRow) {
           const uint64_t *rp = IT.rows + (size_t)nr * rw;
           if (lane < rw) n0 = __ldg(rp + lane);
@@ -610,14 +614,14 @@ __global__ void __launch_bounds__(kGatherWarps * 32) row_gather_kernel(RankArgs 
         const double o = __ldg(a.item_f64 + (size_t)item * a.n_item_f64 + fc.override_slot);
         if (o == o) v = o;
       }
-      if (a.out_features) a.out_features[(size_t)item * a.dim + fc.col] = v;
-      if (a.codes) {
-        const uint16_t cd = code_of_col(bin, M, cat, v);
+      if (OUT) a.out_features[(size_t)item * a.dim + fc.col] = v;
+      if (CODES) {
+        const uint16_t cd = code_of_col_t<XGB>(bin, M, cat, v);
         *reinterpret_cast<uint32_t *>(tile + j * tstride + 2 * c) = (uint32_t)base_code(M, cd) | ((uint32_t)dup_code(cd) << 16);
       }
     }
   }
-  if (a.codes) {
+  if (CODES) {
     __syncwarp();
     uint16_t *out = a.codes + (size_t)g * bin.tile_cols * 32;
     for (int c = 0; c < a.n_fast; c++) {
@@ -630,6 +634,85 @@ __global__ void __launch_bounds__(kGatherWarps * 32) row_gather_kernel(RankArgs 
       }
     }
   }
+}
+
+// ------------------------------------------------------------------ per-model code rows
+// The fast columns of an item are a function of its row and of the model's thresholds only, so their
+// codes are computed once per (model, row version) into `code_rows` and ranking just copies them:
+// 2 bytes per tile column instead of the 8-byte row words + a bucket/threshold lookup per column.
+template <bool XGB>
+__global__ void __launch_bounds__(kGatherWarps * 32) code_rows_kernel(RankArgs a, uint32_t *code_rows, int crw,
+                                                                      uint32_t n_rows, const uint32_t *idx, uint32_t n_idx) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n_work = idx ? n_idx : n_rows + 1;  // + the unknown-item row
+  const uint32_t w0i = (blockIdx.x * kGatherWarps + warp) * 32u;
+  if (w0i >= n_work) return;
+  const DTable &IT = a.st.t[SC_ITEM];
+  const int rw = IT.row_words;
+  const BinParams &bin = a.bin;
+  uint16_t *out16 = reinterpret_cast<uint16_t *>(code_rows);
+  const double kNaN = nan_d();
+  const uint32_t n_here = min(32u, n_work - w0i);
+  for (int c0 = 0; c0 < a.n_fast; c0 += 32) {
+    const int c = c0 + lane;
+    const bool act = c < a.n_fast;
+    const FastCol fc = a.fast_cols[act ? c : 0];
+    const BinMeta M = bin.meta[fc.col];
+    const bool cat = (M.flags & kMetaCat) != 0;
+    const int wsrc = fc.word & 31, psrc = (fc.bit >> 6) & 31;
+    const bool whi = fc.word >= 32, phi_ = (fc.bit >> 6) >= 32;
+    for (uint32_t j = 0; j < n_here; j++) {
+      // work item -> table row (kNoRow for the unknown-item row, which is the last one of a full build)
+      uint32_t r = idx ? __ldg(idx + w0i + j) : w0i + j;
+      if (!idx && r == n_rows) r = kNoRow;
+      uint64_t w0 = 0, w1 = 0;
+      if (r != kNoRow) {
+        const uint64_t *rp = IT.rows + (size_t)r * rw;
+        if (lane < rw) w0 = __ldg(rp + lane);
+        if (lane + 32 < rw) w1 = __ldg(rp + lane + 32);
+      }
+      uint64_t vw = __shfl_sync(0xFFFFFFFFu, w0, wsrc), pw = __shfl_sync(0xFFFFFFFFu, w0, psrc);
+      if (rw > 32) {
+        const uint64_t vh = __shfl_sync(0xFFFFFFFFu, w1, wsrc), ph = __shfl_sync(0xFFFFFFFFu, w1, psrc);
+        if (whi) vw = vh;
+        if (phi_) pw = ph;
+      }
+      if (!act) continue;
+      double v = fc.missing ? 0.0 : kNaN;
+      if (r != kNoRow && ((pw >> (fc.bit & 63)) & 1ull)) {
+        v = fc.conv == 0 ? __longlong_as_double((long long)vw)
+            : fc.conv == 1 ? (double)(long long)vw : (double)(int)vw;
+      }
+      const uint16_t cd = code_of_col_t<XGB>(bin, M, cat, v);
+      uint16_t *dst = out16 + (size_t)(r + 1u) * crw * 2;  // kNoRow + 1 == 0
+      dst[fc.col] = base_code(M, cd);
+      if (dup_col(M) != kMetaNoDup) dst[dup_col(M)] = dup_code(cd);
+    }
+  }
+}
+
+// Ranking with code rows: a warp copies the code rows of its 32 items (coalesced, independent loads) into
+// a shared-memory tile and writes them out column by column in the scorer's [group][column][lane] layout.
+__global__ void __launch_bounds__(kGatherWarps * 32) code_gather_kernel(RankArgs a) {
+  extern __shared__ __align__(16) uint32_t s_tile[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x * kGatherWarps + warp, i0 = g * 32;
+  if (i0 >= a.total_items) return;
+  const int crw = a.code_row_words, tw = crw | 1;  // odd word stride: conflict-free column reads
+  uint32_t *tile = s_tile + (size_t)warp * 32 * tw;
+  const int n_here = min(32, a.total_items - i0);
+  const uint32_t my = (lane < n_here) ? a.item_row[i0 + lane] + 1u : 0u;  // unknown item (kNoRow) -> row 0
+#pragma unroll 4
+  for (int j = 0; j < n_here; j++) {
+    const uint32_t r = __shfl_sync(0xFFFFFFFFu, my, j);
+    const uint32_t *src = a.code_rows + (size_t)r * crw;
+    for (int l = lane; l < crw; l += 32) tile[j * tw + l] = __ldg(src + l);
+  }
+  __syncwarp();
+  uint16_t *out = a.codes + (size_t)g * a.bin.tile_cols * 32;
+  const uint16_t *t16 = reinterpret_cast<const uint16_t *>(tile);
+  if (lane < n_here)
+    for (int c = 0; c < a.bin.tile_cols; c++) out[c * 32 + lane] = t16[lane * tw * 2 + c];
 }
 
 // ------------------------------------------------------------------ assemble
@@ -990,13 +1073,28 @@ void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t strea
     if (a.n_fast > 0 && gather_smem > 96 * 1024) b.n_fast = 0;  // too many columns for the tile: generic path
     bool any_generic = false;
     for (auto &d : schema.plan) any_generic |= !(d.fast && b.n_fast > 0);
-    if (b.n_fast > 0) {
-      if (gather_smem > 48 * 1024)
-        MR_CUDA_CHECK(cudaFuncSetAttribute(row_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gather_smem));
+    if (b.n_fast > 0 && a.code_rows && a.codes && !a.out_features && !(a.item_f64 && schema.fast_has_override)) {
+      // the fast columns' codes are already materialised per item row: copy them
       const int n_groups = (a.total_items + 31) / 32;
-      row_gather_kernel<<<(n_groups + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, gather_smem, stream>>>(b);
+      const size_t smem = (size_t)kGatherWarps * 32 * (a.code_row_words | 1) * sizeof(uint32_t);
+      if (smem > 48 * 1024)
+        MR_CUDA_CHECK(cudaFuncSetAttribute(code_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      code_gather_kernel<<<(n_groups + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, smem, stream>>>(b);
       MR_CUDA_CHECK(cudaGetLastError());
       g_kernel_launches++;
+    } else if (b.n_fast > 0) {
+      const int n_groups = (a.total_items + 31) / 32;
+      auto go = [&](auto kern) {
+        if (gather_smem > 48 * 1024)
+          MR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gather_smem));
+        kern<<<(n_groups + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, gather_smem, stream>>>(b);
+        MR_CUDA_CHECK(cudaGetLastError());
+        g_kernel_launches++;
+      };
+      const bool xgb = a.codes && a.bin.xgb;
+      if (a.codes && a.out_features) { if (xgb) go(row_gather_kernel<true, true, true>); else go(row_gather_kernel<true, true, false>); }
+      else if (a.codes) { if (xgb) go(row_gather_kernel<true, false, true>); else go(row_gather_kernel<true, false, false>); }
+      else go(row_gather_kernel<false, true, false>);
     }
     if (any_generic) {
       assemble_kernel<<<(a.total_items + 127) / 128, 128, plan_bytes + (b.stage_meta ? meta_bytes : 0), stream>>>(b);
@@ -1004,6 +1102,17 @@ void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t strea
       g_kernel_launches++;
     }
   }
+}
+
+void launch_code_rows(const RankArgs &a, uint32_t *code_rows, int code_row_words, uint32_t n_rows, const uint32_t *d_idx,
+                      uint32_t n_idx, cudaStream_t stream) {
+  const uint32_t n_work = d_idx ? n_idx : n_rows + 1;
+  if (n_work == 0 || a.n_fast <= 0) return;
+  const unsigned grid = (unsigned)((n_work + kGatherWarps * 32 - 1) / (kGatherWarps * 32));
+  if (a.bin.xgb) code_rows_kernel<true><<<grid, kGatherWarps * 32, 0, stream>>>(a, code_rows, code_row_words, n_rows, d_idx, n_idx);
+  else code_rows_kernel<false><<<grid, kGatherWarps * 32, 0, stream>>>(a, code_rows, code_row_words, n_rows, d_idx, n_idx);
+  MR_CUDA_CHECK(cudaGetLastError());
+  g_kernel_launches++;
 }
 
 void launch_rank_order(const double *d_scores, const int32_t *d_item_offsets, int n_requests, int total_items,

@@ -41,11 +41,19 @@ struct RankArgs {
   int stage_meta;         // set by launch_assemble: bucket-index headers staged in shared memory
   const FastCol *fast_cols;  // device copy of Schema::fast_cols (row_gather_kernel)
   int n_fast;
+  // per-model code rows of the item table (rank_api.cu CodeCache): row r + 1 holds item row r's codes for
+  // the fast columns in tile-column order, row 0 the codes of an unknown item.  nullptr: compute from the rows.
+  const uint32_t *code_rows;
+  int code_row_words;        // u32 words per code row
 };
 
 // Enqueues lookup -> cosine -> per-request prepass -> assemble on `stream`.
 void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t stream);
 // Ranker.rerank's sortBy(-score): order[off[r] + k] = index (within the request) of the k-th item.
+// (Re)computes code rows: all item rows [0, n_rows) plus the unknown-item row when idx == nullptr, else the
+// rows listed in idx.  a.st / a.fast_cols / a.n_fast / a.bin describe the source and the model's binning.
+void launch_code_rows(const RankArgs &a, uint32_t *code_rows, int code_row_words, uint32_t n_rows, const uint32_t *d_idx,
+                      uint32_t n_idx, cudaStream_t stream);
 void launch_rank_order(const double *d_scores, const int32_t *d_item_offsets, int n_requests, int total_items,
                        int32_t *d_order, cudaStream_t stream, int max_items_hint = 0);
 

@@ -23,8 +23,9 @@ struct BinParams {
 };
 
 // code of x in a column whose header (M, categorical flag) the caller already holds in registers
-__device__ __forceinline__ uint16_t code_of_col(const BinParams &p, const BinMeta &M, bool cat, double x) {
-  if (p.xgb) x = (double)__double2float_rn(x);
+template <bool XGB>
+__device__ __forceinline__ uint16_t code_of_col_t(const BinParams &p, const BinMeta &M, bool cat, double x) {
+  if (XGB) x = (double)__double2float_rn(x);  // XGBoost compares binary32 values, strict less (upper_bound)
   if (x != x) return kBinNaN;
   if (cat) {
     // LightGBM CategoricalDecision: static_cast<int>(x), negative / out-of-int-range -> right
@@ -41,12 +42,28 @@ __device__ __forceinline__ uint16_t code_of_col(const BinParams &p, const BinMet
   const uint32_t range = __ldg(p.bucket_range + M.idx_off + bk);
   uint32_t lo = range & 0xFFFFu, hi = range >> 16;
   const double *t = p.thr + M.thr_off;
-  if (p.xgb) {
+  const uint32_t n = hi - lo;
+  if (n <= 4) {
+    // the usual case: a handful of thresholds share the bucket.  Fetch them side by side (one memory
+    // latency instead of a chain of dependent probes) and count: the thresholds are sorted, so
+    // #{t < x} (LightGBM) or #{t <= x} (XGBoost) among them is x's rank inside the bucket.
+    const double inf = __longlong_as_double(0x7FF0000000000000ll);
+    const double t0 = n > 0 ? __ldg(t + lo) : inf, t1 = n > 1 ? __ldg(t + lo + 1) : inf;
+    const double t2 = n > 2 ? __ldg(t + lo + 2) : inf, t3 = n > 3 ? __ldg(t + lo + 3) : inf;
+    if (XGB) lo += (uint32_t)(n > 0 && t0 <= x) + (uint32_t)(n > 1 && t1 <= x) + (uint32_t)(n > 2 && t2 <= x) + (uint32_t)(n > 3 && t3 <= x);
+    else lo += (uint32_t)(n > 0 && t0 < x) + (uint32_t)(n > 1 && t1 < x) + (uint32_t)(n > 2 && t2 < x) + (uint32_t)(n > 3 && t3 < x);
+    return (uint16_t)lo;
+  }
+  if (XGB) {
     while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__ldg(t + m) <= x) lo = m + 1; else hi = m; }  // #{t <= x}
   } else {
     while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__ldg(t + m) < x) lo = m + 1; else hi = m; }   // #{t < x}
   }
   return (uint16_t)lo;
+}
+
+__device__ __forceinline__ uint16_t code_of_col(const BinParams &p, const BinMeta &M, bool cat, double x) {
+  return p.xgb ? code_of_col_t<true>(p, M, cat, x) : code_of_col_t<false>(p, M, cat, x);
 }
 
 __device__ __forceinline__ uint16_t code_of(const BinParams &p, int f, double x) {

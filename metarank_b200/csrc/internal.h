@@ -150,7 +150,11 @@ struct mr_model {
     d_bmodel = nullptr; d_bchunks = nullptr; d_thr_off = nullptr; d_thr = nullptr; d_is_cat = nullptr;
     d_tmodel = nullptr; d_tchunks = nullptr; d_cmodel = nullptr; d_cchunks = nullptr; d_lmodel = nullptr; d_lchunks = nullptr; d_meta = nullptr; d_cmeta = nullptr; d_bucket_range = nullptr;
   }
+  // identity of the current code mapping (thresholds + tile columns): consumers that cache codes key on it
+  uint64_t code_gen = 0;
+  static uint64_t next_code_gen() { static std::atomic<uint64_t> g{1}; return g.fetch_add(1); }
   void repack() {
+    code_gen = next_code_gen();
     // Default policy: stream the ensemble through two small shared-memory buffers (TMA bulk
     // copies overlap the traversal).  Small chunks leave shared memory for the feature tile,
     // i.e. for resident warps, which is what bounds this kernel (profiles/ round-1 notes).

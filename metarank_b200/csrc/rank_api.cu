@@ -22,7 +22,19 @@ struct RankScratch {  // per-lane device scratch for one in-flight mr_rank
   size_t cap = 0;
 };
 
+// Per-model code rows of the item table (see code_rows_kernel): built on first use, refreshed from the
+// store's change log after a flush.
+struct CodeCache {
+  uint64_t model_gen = 0, epoch = 0, last_use = 0;
+  uint32_t *d = nullptr;
+  size_t cap_rows = 0;
+  int row_words = 0;
+};
+
 struct mr_state {
+  std::mutex cache_mu;
+  std::vector<CodeCache> caches;
+  uint64_t cache_clock = 0;
   mr_ctx *ctx = nullptr;
   mr_schema *schema = nullptr;
   std::unique_ptr<StateStore> store;
@@ -103,7 +115,9 @@ void fill_args(RankArgs &a, mr_state *st, uint8_t *scratch, const ScratchPlan &s
 // codes itself and the f64 matrix is only materialised if the caller asked for it (explain).
 bool fused_codes(const mr_model *model) { return model && model->use_binned(); }
 
-void set_codes(RankArgs &a, const mr_model *model, uint8_t *scratch, const ScratchPlan &sp) {
+const uint32_t *code_rows_for(mr_state *st, const mr_model *model, int *row_words_out);
+
+void set_codes(RankArgs &a, mr_state *st, const mr_model *model, uint8_t *scratch, const ScratchPlan &sp) {
   a.codes = (uint16_t *)(scratch + sp.codes);
   a.bin = BinParams{};
   a.bin.thr_off = model->d_thr_off;
@@ -115,6 +129,82 @@ void set_codes(RankArgs &a, const mr_model *model, uint8_t *scratch, const Scrat
   a.bin.n_features = model->host.n_features;
   a.bin.tile_cols = B.tile_cols;
   a.bin.xgb = model->host.kind == MR_BOOSTER_XGBOOST;
+  a.code_rows = a.out_features ? nullptr : code_rows_for(st, model, &a.code_row_words);
+}
+
+// Code rows for (state, model), current as of the last flush; nullptr when the path does not apply.
+// Called with the store's shared lock held (no flush can run); builds are synchronous and serialised.
+const uint32_t *code_rows_for(mr_state *st, const mr_model *model, int *row_words_out) {
+  static const bool disabled = [] { const char *e = getenv("MR_CODE_ROWS"); return e && e[0] == '0'; }();
+  const Schema &S = st->store->schema;
+  if (disabled || !model || !model->use_binned() || S.fast_cols.empty()) return nullptr;
+  StateStore &store = *st->store;
+  const size_t n_rows = store.tables[SC_ITEM].n_rows;
+  const BinnedLaunch B = model->binned_desc();
+  const int crw = (B.tile_cols + 1) / 2;
+  std::lock_guard<std::mutex> g(st->cache_mu);
+  CodeCache *cc = nullptr;
+  for (auto &c : st->caches)
+    if (c.model_gen == model->code_gen) cc = &c;
+  if (!cc) {
+    if (st->caches.size() >= 4) {  // evict the least recently used
+      size_t lru = 0;
+      for (size_t k = 1; k < st->caches.size(); k++)
+        if (st->caches[k].last_use < st->caches[lru].last_use) lru = k;
+      MR_CUDA_CHECK(cudaDeviceSynchronize());
+      cudaFree(st->caches[lru].d);
+      st->caches.erase(st->caches.begin() + lru);
+    }
+    st->caches.emplace_back();
+    cc = &st->caches.back();
+    cc->model_gen = model->code_gen;
+  }
+  cc->last_use = ++st->cache_clock;
+  RankArgs a{};
+  a.st = store.view();
+  a.fast_cols = st->schema->d_fast_cols;
+  a.n_fast = (int)S.fast_cols.size();
+  a.bin.thr_off = model->d_thr_off;
+  a.bin.thr = model->d_thr;
+  a.bin.is_cat = model->d_is_cat;
+  a.bin.meta = B.d_meta;
+  a.bin.bucket_range = model->d_bucket_range;
+  a.bin.n_features = model->host.n_features;
+  a.bin.tile_cols = B.tile_cols;
+  a.bin.xgb = model->host.kind == MR_BOOSTER_XGBOOST;
+  bool full = cc->d == nullptr || cc->cap_rows < n_rows + 1 || cc->row_words != crw;
+  std::vector<uint32_t> rows;
+  if (!full && cc->epoch != store.item_epoch) {
+    if (store.item_log.empty() || store.item_log.front().epoch > cc->epoch + 1) full = true;  // log no longer reaches back
+    for (auto &ch : store.item_log) {
+      if (full) break;
+      if (ch.epoch <= cc->epoch) continue;
+      if (ch.all) full = true;
+      else rows.insert(rows.end(), ch.rows.begin(), ch.rows.end());
+    }
+    if (rows.size() * 4 > n_rows) full = true;
+  }
+  if (full) {
+    if (cc->d == nullptr || cc->cap_rows < n_rows + 1 || cc->row_words != crw) {
+      if (cc->d) { MR_CUDA_CHECK(cudaDeviceSynchronize()); cudaFree(cc->d); cc->d = nullptr; }
+      cc->cap_rows = n_rows + 1 + n_rows / 2;
+      cc->row_words = crw;
+      MR_CUDA_CHECK(cudaMalloc((void **)&cc->d, cc->cap_rows * (size_t)crw * 4));
+      MR_CUDA_CHECK(cudaMemset(cc->d, 0, cc->cap_rows * (size_t)crw * 4));
+    }
+    launch_code_rows(a, cc->d, crw, (uint32_t)n_rows, nullptr, 0, 0);
+    MR_CUDA_CHECK(cudaStreamSynchronize(0));
+  } else if (!rows.empty()) {
+    uint32_t *d_idx = nullptr;
+    MR_CUDA_CHECK(cudaMalloc((void **)&d_idx, rows.size() * 4));
+    MR_CUDA_CHECK(cudaMemcpy(d_idx, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice));
+    launch_code_rows(a, cc->d, crw, (uint32_t)n_rows, d_idx, (uint32_t)rows.size(), 0);
+    MR_CUDA_CHECK(cudaStreamSynchronize(0));
+    cudaFree(d_idx);
+  }
+  cc->epoch = store.item_epoch;
+  *row_words_out = crw;
+  return cc->d;
 }
 
 void check_scored_dim(mr_state *st, mr_model *model) {
@@ -221,6 +311,7 @@ mr_status mr_state_free(mr_state *st) {
   cudaDeviceSynchronize();
   if (st->d_scratch) cudaFree(st->d_scratch);
   if (st->d_error) cudaFree(st->d_error);
+  for (auto &c : st->caches) cudaFree(c.d);
   delete st;
   return MR_OK;
 }
@@ -254,6 +345,10 @@ mr_status mr_state_get_info(mr_state *st, mr_state_info *out) {
     if (!st || !out) fail(MR_ERR_INVALID_ARG, "null argument");
     for (int t = 0; t < SC_N_TABLES; t++) out->rows[t] = (int64_t)st->store->tables[t].n_rows;
     out->device_bytes = st->store->device_bytes;
+    {
+      std::lock_guard<std::mutex> g(st->cache_mu);
+      for (auto &c : st->caches) out->device_bytes += (int64_t)(c.cap_rows * (size_t)c.row_words * 4);  // per-model code rows
+    }
     out->item_row_bytes = (int64_t)st->store->tables[SC_ITEM].row_words * 8;
   });
 }
@@ -354,7 +449,7 @@ void rank_enqueue(mr_state *st, mr_model *model, const mr_rank_batch *b, int r0,
   a.item_f64 = (const double *)dp(s_if);
   a.out_features = (want_features || !fused) ? (double *)(scratch + sp.features) : nullptr;
   a.error_flag = (int32_t *)(lane->d_buf + err_off);  // zeroed by lookup_kernel
-  if (fused) set_codes(a, model, scratch, sp);
+  if (fused) set_codes(a, st, model, scratch, sp);
   launch_assemble(a, S, lane->stream);
   double *d_scores = (double *)(lane->d_buf + scores_off);
   int32_t *d_order = (int32_t *)(lane->d_buf + order_off);
@@ -524,7 +619,7 @@ mr_status mr_rank_device(mr_state *st, mr_model *model, const mr_rank_batch *b, 
     a.req_vec_present = b->req_vec_present;
     a.item_f64 = b->item_f64;
     a.out_features = d_out_features ? d_out_features : (fused ? nullptr : (double *)(st->d_scratch + sp.features));
-    if (fused) set_codes(a, model, st->d_scratch, sp);
+    if (fused) set_codes(a, st, model, st->d_scratch, sp);
     launch_assemble(a, S, stream);
     if (model) {
       if (!d_out_scores) fail(MR_ERR_INVALID_ARG, "d_out_scores is null");

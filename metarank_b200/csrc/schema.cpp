@@ -475,6 +475,7 @@ Schema parse_schema_json(const char *json, size_t len) {
         c.missing = (uint8_t)missing;
         c.override_slot = (int16_t)((d.kind == FK_NUMBER || d.kind == FK_CATEGORY) && k == 0 ? d.in0 : -1);
         c.col = (uint16_t)(d.col + k);
+        S.fast_has_override |= c.override_slot >= 0;
         S.fast_cols.push_back(c);
       }
     }

@@ -115,6 +115,7 @@ struct Schema {
   TableLayout tables[SC_N_TABLES];
   std::vector<SideArray> sides;
   std::vector<DFeature> plan;                // extractor entries in column order
+  bool fast_has_override = false;            // some fast column can be overridden by a request-item field
   std::vector<FastCol> fast_cols;            // columns handled by the coalesced row-gather kernel
   int dim = 0;
   // request inputs

@@ -342,6 +342,14 @@ void StateStore::flush() {
                                    cudaMemcpyHostToDevice));
         }
       }
+      if (&T == &tables[SC_ITEM]) {
+        ItemChange ch;
+        ch.epoch = ++item_epoch;
+        ch.all = realloc_any || n_dirty * 4 > T.n_rows;
+        if (!ch.all) ch.rows = T.dirty_rows;
+        item_log.push_back(std::move(ch));
+        if (item_log.size() > kItemLogMax) item_log.pop_front();
+      }
       for (uint32_t r : T.dirty_rows) T.row_dirty[r] = 0;
       T.dirty_rows.clear();
       T.dirty_lo = SIZE_MAX;

@@ -100,6 +100,16 @@ struct StateStore {
   std::unordered_map<RawKey, uint32_t, RawKeyHash> list_region;  // pool offset of a list's fixed-capacity region
   void flush();
   DState view() const;
+  // Item-table change log for consumers that keep derived per-row data on the device (the per-model
+  // code rows, rank_api.cu): one entry per flush that touched item rows.
+  struct ItemChange {
+    uint64_t epoch;
+    bool all;                    // too many rows (or rows moved): rebuild everything
+    std::vector<uint32_t> rows;  // otherwise the rows that changed
+  };
+  uint64_t item_epoch = 0;
+  std::deque<ItemChange> item_log;  // last kItemLogMax flushes
+  static constexpr size_t kItemLogMax = 64;
 };
 
 }  // namespace mr
