@@ -712,3 +712,109 @@ def test_ordering_edge_sizes_ties_and_specials(ctx):
     F.rank_device_status(ds, st)
     assert _eq(d_s.cpu().numpy(), want_s) and np.array_equal(d_o.cpu().numpy(), want_o)
     booster.free(); ds.free(); fm.free()
+
+
+def test_code_rows_follow_state_updates(ctx):
+    """The per-model code rows (materialised u16 codes of the item table, rank_api.cu CodeCache) must track
+    the state: sparse updates (incremental refresh from the flush log), table growth (rebuild), more
+    flushes than the log holds, two models sharing one state, a repacked model, missing values being
+    filled in, and unknown items."""
+    import metarank_b200 as mb
+    from metarank_b200 import features as F
+
+    names = [f"f{j}" for j in range(9)]
+    feats = [dict(name=n, type="number", scope="item", source=f"metadata.{n}") for n in names]
+    fm = F.FeatureMapping(ctx, feats, names)
+    ds = F.DeviceState(ctx, fm)
+    rng = np.random.Generator(np.random.PCG64(77))
+    n0 = 3000
+    cat = synth.feature_matrix(n0 + 4000, 9, seed=5)  # rows beyond n0 are added later
+    ids = np.arange(1, len(cat) + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    ds.put_packed(F.pack_number_columns(names, ids[:n0], cat[:n0])); ds.flush()
+    known = n0
+    lgb_blob = synth.lightgbm_model_text(60, 9, seed=8)
+    xgb_blob = synth.xgboost_model_json(40, 9, depth=5, seed=9)
+    lgb, xgb = mb.LightGBMBooster(ctx, lgb_blob), mb.XGBoostBooster(ctx, xgb_blob)
+    o_lgb, o_xgb = oracle.OracleBooster(0, lgb_blob), oracle.OracleBooster(1, xgb_blob)
+    rk = F.Ranker(fm, ds)
+
+    def check(booster, orc, n_req=40):
+        sizes = rng.integers(1, 60, n_req)
+        offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+        N = int(offs[-1])
+        pick = rng.integers(0, min(known + 50, len(ids)), N)  # some ids are not in the table yet: all-missing rows
+        X = np.where((pick < known)[:, None], cat[pick], np.nan)
+        R = n_req
+        arrays = dict(offsets=offs, ids=ids[pick],
+                      users=np.zeros(R, dtype=np.uint64), sessions=np.zeros(R, dtype=np.uint64), req_f64=np.zeros((R, 1)),
+                      req_u64=np.zeros((R, 1), dtype=np.uint64), req_vec=np.zeros((R, 1), dtype=np.float32),
+                      req_vp=np.zeros((R, 1), dtype=np.uint8), item_f64=None, n_requests=R, total_items=N)
+        # ids beyond `known` but inside `ids` are simply not stored yet -> unknown items
+        scores, order, _ = rk.rank_arrays(arrays, booster, want_order=True)
+        want = orc.predictMat(np.ascontiguousarray(X), N, 9, threads=0)
+        assert _eq(scores, want)
+        for r in range(R):
+            assert np.array_equal(order[offs[r]:offs[r + 1]], oracle.rank_order(want[offs[r]:offs[r + 1]]))
+
+    check(lgb, o_lgb); check(xgb, o_xgb)
+    # sparse update, NaN appearing / disappearing
+    def put(rows, new):  # a NaN entry is "no write": the stored value stays (pack_number_columns skips it)
+        ds.put_packed(F.pack_number_columns(names, ids[rows], new)); ds.flush()
+        cat[rows] = np.where(np.isnan(new), cat[rows], new)
+
+    rows = rng.choice(known, 25, replace=False)
+    put(rows, synth.feature_matrix(25, 9, seed=6))   # also fills values that were missing
+    check(lgb, o_lgb); check(xgb, o_xgb)
+    # many small flushes between two ranks (more than the change log keeps)
+    for k in range(70):
+        r = int(rng.integers(0, known))
+        put(np.array([r]), synth.feature_matrix(1, 9, seed=100 + k))
+    check(lgb, o_lgb)
+    # growth: new items (device rows reallocate)
+    ds.put_packed(F.pack_number_columns(names, ids[known:known + 4000], cat[known:known + 4000])); ds.flush()
+    known += 4000
+    check(lgb, o_lgb); check(xgb, o_xgb)
+    # a repacked model gets fresh rows
+    lgb.set_option("chunk_kb", 8)
+    check(lgb, o_lgb)
+    lgb.set_option("variant", 2)   # generic binned scorer: identity tile mapping
+    check(lgb, o_lgb)
+    lgb.set_option("variant", -1)
+    check(lgb, o_lgb)
+    lgb.free(); xgb.free(); ds.free(); fm.free()
+
+
+def test_request_item_fields_override_stored_values_in_the_scored_path(ctx):
+    """NumberFeature.values (S/feature/NumberFeature.scala:84-93): a field on the ranking item wins over the
+    stored value.  With a model attached the codes normally come from the per-model code rows; a batch that
+    carries item fields for an overridable column must bypass them.  Scores with and without the explain
+    matrix, against the oracle's feature rows."""
+    import metarank_b200 as mb
+    from metarank_b200 import features as F
+
+    feats = [dict(name="price", type="number", scope="item", source="item.price"),
+             dict(name="pop", type="number", scope="item", source="item.pop")]
+    mapping = fo.FeatureMapping(feats, ["price", "pop"])
+    events = [dict(event="item", id=f"e{i}", timestamp=G.NOW, item=f"p{i}", fields=[("price", float(i)), ("pop", float(10 - i))])
+              for i in range(1, 9)]
+    state = fo.FeatureValueFlow(mapping, always_refresh=True).process(events)
+    fm, ds, rk, _, _ = _device(ctx, feats, ["price", "pop"], state)
+    blob = synth.lightgbm_model_text(30, 2, seed=21)
+    booster = mb.LightGBMBooster(ctx, blob)
+    orc = oracle.OracleBooster(0, blob)
+    plain = G.ranking([f"p{i}" for i in range(1, 9)] + ["unknown"])
+    over = G.ranking([f"p{i}" for i in range(1, 9)] + ["unknown"],
+                     item_fields={"p2": [("price", 100.0)], "p5": [("price", -3.5)], "unknown": [("price", 7.0)]})
+    for req in (plain, over, plain):
+        want_x = fo.dense_matrix(mapping, req, state)
+        want_s = orc.predictMat(np.ascontiguousarray(want_x), len(want_x), 2, threads=0)
+        arrays = fm.pack_requests([req])
+        for explain in (False, True):
+            scores, order, fx = rk.rank_arrays(arrays, booster, want_order=True, want_features=explain)
+            assert _eq(scores, want_s), (req is over, explain)
+            assert np.array_equal(order, oracle.rank_order(want_s))
+            if explain:
+                assert _eq(fx, want_x)
+    x_over = fo.dense_matrix(mapping, over, state)
+    assert x_over[1, 0] == 100.0 and x_over[4, 0] == -3.5 and x_over[8, 0] == 7.0 and np.isnan(x_over[8, 1])
+    booster.free(); ds.free(); fm.free()
