@@ -249,6 +249,27 @@ MR_API mr_status mr_state_upsert(mr_state *st, const uint8_t *packed, size_t len
  *   op 2 PeriodicIncrement: i64 inc | op 3 Append: u64 mr_hash64 of the appended string (an item id)
  * Visible to mr_rank after mr_state_flush. */
 MR_API mr_status mr_state_apply_writes(mr_state *st, const uint8_t *packed, size_t len, int64_t *applied, int64_t *skipped);
+/* Bulk load from the reference's BINARY store format: `bytes` is a stream of delimited
+ * FeatureValues exactly as BinaryVCodec(compress = false, FeatureValueCodec).encodeDelimited writes them
+ * (S/fstore/codec/values/BinaryVCodec.scala:45-50, S/fstore/codec/impl/FeatureValueCodec.scala:41-237 — the
+ * value bytes of Persistence.values in Redis / FileKVStore): big-endian i32 length, then tag, binary Key
+ * (scope tag + strings + feature name, DataOutput.writeUTF), varlong timestamp, the value, varlong expire
+ * (absent for the legacy tags 0-6).  Each record is what mr_state_upsert would have received for the same
+ * FeatureValue: strings become mr_hash64 of their UTF-8 bytes; ScalarValue / CounterValue /
+ * PeriodicCounterValue (the PeriodicValue.value column) / BoundedListValue of SStrings are stored,
+ * NumStatsValue / MapValue / FrequencyValue (no supported extractor reads them) and records whose name the
+ * schema does not read count as skipped.  Like decodeDelimited (:52-62) a truncated trailing record ends
+ * the stream: *consumed (optional) receives the bytes of whole records read, so consumed < len says so.
+ * An unknown tag or a record shorter than its fields is MR_ERR_PARSE and nothing is applied.
+ * Visible to mr_rank after mr_state_flush. */
+MR_API mr_status mr_state_load_feature_values(mr_state *st, const uint8_t *bytes, size_t len, int64_t *applied,
+                                              int64_t *skipped, size_t *consumed);
+/* The same decoder without a state (host only): writes the mr_state_upsert records to `out` (capacity
+ * out_cap; pass NULL / 0 to size the buffer) and their byte length to *out_len.  n_records counts decoded
+ * FeatureValues, n_unsupported the classes dropped (see above). */
+MR_API mr_status mr_feature_values_transcode(const uint8_t *bytes, size_t len, uint8_t *out, size_t out_cap,
+                                             size_t *out_len, int64_t *n_records, int64_t *n_unsupported,
+                                             size_t *consumed);
 /* Uploads pending upserts / writes to HBM (synchronous; waits for in-flight mr_rank calls).  A handful of
  * touched rows are packed and scattered by a kernel; bulk loads copy the touched row range. */
 MR_API mr_status mr_state_flush(mr_state *st);

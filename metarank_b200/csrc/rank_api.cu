@@ -4,6 +4,7 @@
 //   predict    = gbdt_score kernel on the assembled matrix (never leaves HBM)
 //   sortBy     = order kernel
 #include "assemble_kernels.cuh"
+#include "fv_codec.h"
 #include "internal.h"
 #include "schema.h"
 #include "state.h"
@@ -329,6 +330,40 @@ mr_status mr_state_apply_writes(mr_state *st, const uint8_t *packed, size_t len,
     if (!st || (!packed && len)) fail(MR_ERR_INVALID_ARG, "null argument");
     st->store->apply_writes(packed, len, applied, skipped);
     st->dirty = true;
+  });
+}
+
+mr_status mr_state_load_feature_values(mr_state *st, const uint8_t *bytes, size_t len, int64_t *applied,
+                                       int64_t *skipped, size_t *consumed) {
+  return guard([&] {
+    if (!st || (!bytes && len)) fail(MR_ERR_INVALID_ARG, "null argument");
+    std::vector<uint8_t> recs;
+    FvStats fs;
+    transcode_feature_values(bytes, len, recs, fs);  // throws before anything is applied
+    int64_t ok = 0, skip = 0;
+    st->store->upsert(recs.data(), recs.size(), &ok, &skip);
+    st->dirty = true;
+    if (applied) *applied = ok;
+    if (skipped) *skipped = skip + fs.unsupported;
+    if (consumed) *consumed = fs.consumed;
+  });
+}
+
+mr_status mr_feature_values_transcode(const uint8_t *bytes, size_t len, uint8_t *out, size_t out_cap, size_t *out_len,
+                                      int64_t *n_records, int64_t *n_unsupported, size_t *consumed) {
+  return guard([&] {
+    if ((!bytes && len) || !out_len) fail(MR_ERR_INVALID_ARG, "null argument");
+    std::vector<uint8_t> recs;
+    FvStats fs;
+    transcode_feature_values(bytes, len, recs, fs);
+    *out_len = recs.size();
+    if (n_records) *n_records = fs.records;
+    if (n_unsupported) *n_unsupported = fs.unsupported;
+    if (consumed) *consumed = fs.consumed;
+    if (out) {
+      if (out_cap < recs.size()) fail(MR_ERR_INVALID_ARG, "output buffer too small: %zu bytes needed", recs.size());
+      if (!recs.empty()) memcpy(out, recs.data(), recs.size());
+    }
   });
 }
 

@@ -276,6 +276,19 @@ def pack_feature_values(values: dict) -> bytes:
     return b"".join(out)
 
 
+def transcode_feature_values(blob: bytes):
+    """mr_feature_values_transcode: reference binary FeatureValue stream -> mr_state_upsert records (host
+    only).  Returns (records bytes, n decoded, n unsupported, consumed bytes)."""
+    n, nr, nu, c = C.c_size_t(0), C.c_int64(0), C.c_int64(0), C.c_size_t(0)
+    src = (C.c_uint8 * max(len(blob), 1)).from_buffer_copy(blob if blob else b"\0")
+    check(lib().mr_feature_values_transcode(src, C.c_size_t(len(blob)), None, C.c_size_t(0), C.byref(n), C.byref(nr),
+                                            C.byref(nu), C.byref(c)))
+    out = (C.c_uint8 * max(n.value, 1))()
+    check(lib().mr_feature_values_transcode(src, C.c_size_t(len(blob)), out, C.c_size_t(n.value), C.byref(n), C.byref(nr),
+                                            C.byref(nu), C.byref(c)))
+    return bytes(out[:n.value]), nr.value, nu.value, c.value
+
+
 def _pack_scope(scope) -> bytes:
     tag = _SCOPE_TAG[scope[0]]
     out = struct.pack("<B", tag)
@@ -329,6 +342,14 @@ class DeviceState:
     def put(self, values: dict):
         """KVStore.put(Map[Key, FeatureValue])"""
         return self.put_packed(pack_feature_values(values))
+
+    def load_feature_values(self, blob: bytes):
+        """Bulk load from the reference's binary store format: a stream of delimited FeatureValues
+        (BinaryVCodec.encodeDelimited over FeatureValueCodec).  Returns (applied, skipped, consumed bytes)."""
+        a, s, c = C.c_int64(0), C.c_int64(0), C.c_size_t(0)
+        buf = (C.c_uint8 * max(len(blob), 1)).from_buffer_copy(blob if blob else b"\0")
+        check(lib().mr_state_load_feature_values(self._h, buf, C.c_size_t(len(blob)), C.byref(a), C.byref(s), C.byref(c)))
+        return a.value, s.value, c.value
 
     def apply_writes(self, writes: list):
         """FeatureValueFlow.commitWrite for a batch of raw writes (see pack_writes)."""

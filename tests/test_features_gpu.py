@@ -818,3 +818,55 @@ def test_request_item_fields_override_stored_values_in_the_scored_path(ctx):
     x_over = fo.dense_matrix(mapping, over, state)
     assert x_over[1, 0] == 100.0 and x_over[4, 0] == -3.5 and x_over[8, 0] == 7.0 and np.isnan(x_over[8, 1])
     booster.free(); ds.free(); fm.free()
+
+
+def _state_to_feature_values(state, legacy=False):
+    """Oracle state {(scope, name): (kind, value)} -> FeatureValue dicts for oracle/codec_oracle.py."""
+    out = []
+    for n, ((scope, name), (kind, v)) in enumerate(state.items()):
+        key = (tuple(scope), name)
+        if kind == "scalar":
+            if isinstance(v, (list, tuple, np.ndarray)) and len(v) == 0:
+                v = ("strings", [])
+            elif isinstance(v, np.ndarray):
+                v = [float(x) for x in v]
+            out.append(dict(type="scalar", key=key, ts=1000 + n, value=v, expire_ms=86400000))
+        elif kind == "counter":
+            out.append(dict(type="counter", key=key, ts=1000 + n, value=int(v), expire_ms=86400000))
+        elif kind == "pcounter":
+            out.append(dict(type="pcounter", key=key, ts=1000 + n, expire_ms=86400000,
+                            values=[dict(start=0, end=86400000, periods=j + 1, value=int(x)) for j, x in enumerate(v)]))
+        elif kind == "blist":
+            out.append(dict(type="blist", key=key, ts=1000 + n, expire_ms=86400000,
+                            values=[(5000 - j, x) for j, x in enumerate(v)]))
+        else:
+            raise ValueError(kind)
+    return out
+
+
+@pytest.mark.parametrize("legacy", [False, True])
+def test_state_loaded_from_the_reference_binary_format(ctx, legacy):
+    """a state exported in the reference's binary store format (delimited FeatureValueCodec
+    records, S/fstore/codec/impl/FeatureValueCodec.scala:41-237) loads natively and ranks exactly like the same
+    state put through mr_state_upsert — ranklens feature set: scalars, string lists, counters, periodic
+    counters, bounded lists, every scope."""
+    from metarank_b200 import features as F
+    from oracle import codec_oracle as co
+
+    feats, model = synth.ranklens_config()
+    state, item_ids, sessions = synth.ranklens_state(n_items=300, n_sessions=20, seed=15)
+    reqs = synth.ranklens_requests(item_ids, sessions, 12, 40, seed=16)
+    blob = co.encode_delimited(_state_to_feature_values(state, legacy), legacy)
+    mapping = fo.FeatureMapping(feats, model)
+    fm = F.FeatureMapping(ctx, feats, model)
+    ds = F.DeviceState(ctx, fm)
+    applied, skipped, consumed = ds.load_feature_values(blob)
+    ds.flush()
+    fm2, ds2, rk2, applied2, skipped2 = _device(ctx, feats, model, state)
+    assert (applied, skipped) == (applied2, skipped2) and consumed == len(blob) and applied > 0
+    rk = F.Ranker(fm, ds)
+    got, ref = rk.make_query(reqs), rk2.make_query(reqs)
+    for r, q in enumerate(reqs):
+        want = fo.dense_matrix(mapping, q, state)
+        assert _eq(got[r], want) and _eq(ref[r], want)
+    ds.free(); fm.free(); ds2.free(); fm2.free()
