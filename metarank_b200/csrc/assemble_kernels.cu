@@ -954,38 +954,69 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
 }
 
 // ------------------------------------------------------------------ ordering
-// Requests of up to kSmallOrder items (the usual /rank page): a WARP ranks one request by counting,
-// rank(i) = #{q : key(q) < key(i)} + #{q < i : key(q) == key(i)} — the same total order as the sort
-// below, no barriers, eight requests per CTA.
+// Requests of up to kSmallOrder items (the usual /rank page): a WARP sorts one request with a bitonic
+// network held entirely in registers — 4 (key, index) pairs per lane, strides below 4 are exchanges inside
+// the lane, larger ones `shfl.xor` with the partner lane.  Keys are (total-order key of -score, index): every
+// pair is distinct, which is the stability of the reference's sortBy.  No shared memory, no barrier, eight
+// requests per CTA.
 constexpr int kSmallOrder = 128;
 constexpr int kOrderWarps = 8;
 
+__device__ __forceinline__ bool pair_gt(long long ka, int ia, long long kb, int ib) {
+  return ka > kb || (ka == kb && ia > ib);
+}
+
 __global__ void __launch_bounds__(kOrderWarps * 32) order_small_kernel(const double *scores, const int32_t *offsets,
                                                                        int n_requests, int32_t *order) {
-  __shared__ long long s_k[kOrderWarps][kSmallOrder];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * kOrderWarps + warp;
   if (r >= n_requests) return;
   const int b = __ldg(offsets + r), n = __ldg(offsets + r + 1) - b;
   if (n <= 0 || n > kSmallOrder) return;
   long long k[4];
+  int id[4];
 #pragma unroll
   for (int m = 0; m < 4; m++) {
-    const int i = lane + 32 * m;
-    k[m] = i < n ? total_order_key(-__ldg(scores + b + i)) : 0x7FFFFFFFFFFFFFFFll;
-    if (i < n) s_k[warp][i] = k[m];
+    const int e = lane * 4 + m;  // blocked layout: element e lives in lane e / 4
+    k[m] = e < n ? total_order_key(-__ldg(scores + b + e)) : 0x7FFFFFFFFFFFFFFFll;
+    id[m] = e < n ? e : 0x7FFFFFFF;
   }
-  __syncwarp();
-  int rank[4] = {0, 0, 0, 0};
-  for (int q = 0; q < n; q++) {
-    const long long kq = s_k[warp][q];
 #pragma unroll
-    for (int m = 0; m < 4; m++) rank[m] += (kq < k[m]) || (kq == k[m] && q < lane + 32 * m);
+  for (int size = 2; size <= kSmallOrder; size <<= 1) {
+#pragma unroll
+    for (int j = size >> 1; j > 0; j >>= 1) {
+      if (j >= 4) {
+        const int pl = j >> 2;  // partner lane distance
+        const bool lower = (lane & pl) == 0;
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          const long long ok = __shfl_xor_sync(0xFFFFFFFFu, k[m], pl);
+          const int oi = __shfl_xor_sync(0xFFFFFFFFu, id[m], pl);
+          const bool up = ((lane * 4 + m) & size) == 0;
+          const bool mine_gt = pair_gt(k[m], id[m], ok, oi);
+          // the lower element of an ascending pair keeps the minimum, the upper one the maximum (and vice versa)
+          const bool take_other = (lower == up) ? mine_gt : !mine_gt;
+          if (take_other) { k[m] = ok; id[m] = oi; }
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          const int l = m ^ j;
+          if (l > m) {
+            const bool up = ((lane * 4 + m) & size) == 0;
+            if (pair_gt(k[m], id[m], k[l], id[l]) == up) {
+              const long long tk = k[m]; k[m] = k[l]; k[l] = tk;
+              const int ti = id[m]; id[m] = id[l]; id[l] = ti;
+            }
+          }
+        }
+      }
+    }
   }
 #pragma unroll
   for (int m = 0; m < 4; m++) {
-    const int i = lane + 32 * m;
-    if (i < n) order[b + rank[m]] = i;
+    const int e = lane * 4 + m;
+    if (e < n) order[b + e] = id[m];
   }
 }
 
