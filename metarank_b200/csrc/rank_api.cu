@@ -36,6 +36,8 @@ struct mr_state {
   std::mutex cache_mu;
   std::vector<CodeCache> caches;
   uint64_t cache_clock = 0;
+  std::atomic<int> ranks_inflight{0};   // mr_rank calls between entry and return
+  std::vector<uint32_t *> graveyard;    // evicted code rows another in-flight rank may still read
   mr_ctx *ctx = nullptr;
   mr_schema *schema = nullptr;
   std::unique_ptr<StateStore> store;
@@ -144,6 +146,12 @@ const uint32_t *code_rows_for(mr_state *st, const mr_model *model, int *row_word
   const BinnedLaunch B = model->binned_desc();
   const int crw = (B.tile_cols + 1) / 2;
   std::lock_guard<std::mutex> g(st->cache_mu);
+  const bool alone = st->ranks_inflight.load() <= 1;  // a rank that fetched a pointer earlier counted itself first
+  if (alone && !st->graveyard.empty()) {
+    MR_CUDA_CHECK(cudaDeviceSynchronize());
+    for (uint32_t *p : st->graveyard) cudaFree(p);
+    st->graveyard.clear();
+  }
   CodeCache *cc = nullptr;
   for (auto &c : st->caches)
     if (c.model_gen == model->code_gen) cc = &c;
@@ -152,8 +160,12 @@ const uint32_t *code_rows_for(mr_state *st, const mr_model *model, int *row_word
       size_t lru = 0;
       for (size_t k = 1; k < st->caches.size(); k++)
         if (st->caches[k].last_use < st->caches[lru].last_use) lru = k;
-      MR_CUDA_CHECK(cudaDeviceSynchronize());
-      cudaFree(st->caches[lru].d);
+      if (alone) {
+        MR_CUDA_CHECK(cudaDeviceSynchronize());
+        cudaFree(st->caches[lru].d);
+      } else if (st->caches[lru].d) {
+        st->graveyard.push_back(st->caches[lru].d);  // freed once no other rank is in flight
+      }
       st->caches.erase(st->caches.begin() + lru);
     }
     st->caches.emplace_back();
@@ -313,6 +325,7 @@ mr_status mr_state_free(mr_state *st) {
   if (st->d_scratch) cudaFree(st->d_scratch);
   if (st->d_error) cudaFree(st->d_error);
   for (auto &c : st->caches) cudaFree(c.d);
+  for (uint32_t *p : st->graveyard) cudaFree(p);
   delete st;
   return MR_OK;
 }
@@ -565,6 +578,11 @@ mr_status mr_rank(mr_state *st, mr_model *model, const mr_rank_batch *b, double 
     std::unique_ptr<InflightGuard> ig;
     if (model) ig = std::make_unique<InflightGuard>(model);
     MR_CUDA_CHECK(cudaSetDevice(st->ctx->device));
+    struct InFlight {
+      mr_state *s;
+      explicit InFlight(mr_state *s_) : s(s_) { s->ranks_inflight.fetch_add(1); }
+      ~InFlight() { s->ranks_inflight.fetch_sub(1); }
+    } inflight(st);
     std::shared_lock<std::shared_mutex> read_guard(st->store->mu);  // no flush while kernels read the tables
     if (st->dirty) fail(MR_ERR_INVALID_ARG, "state has pending upserts: call mr_state_flush before mr_rank");
 

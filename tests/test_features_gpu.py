@@ -870,3 +870,79 @@ def test_state_loaded_from_the_reference_binary_format(ctx, legacy):
         want = fo.dense_matrix(mapping, q, state)
         assert _eq(got[r], want) and _eq(ref[r], want)
     ds.free(); fm.free(); ds2.free(); fm2.free()
+
+
+def test_concurrent_ranks_and_flushes_keep_code_rows_coherent(ctx):
+    """Host threads rank through five models (more than the code-row cache holds -> evictions) while another
+    thread keeps updating and flushing OTHER items; every result must equal the oracle, and after the threads
+    join the updated items must rank with their new values."""
+    import threading
+
+    import metarank_b200 as mb
+    from metarank_b200 import features as F
+
+    names = [f"f{j}" for j in range(6)]
+    fm = F.FeatureMapping(ctx, [dict(name=n, type="number", scope="item", source=f"metadata.{n}") for n in names], names)
+    ds = F.DeviceState(ctx, fm)
+    n_items = 4000
+    cat = synth.feature_matrix(n_items, 6, seed=31)
+    ids = np.arange(1, n_items + 1, dtype=np.uint64) * np.uint64(0xD6E8FEB86659FD93)
+    ds.put_packed(F.pack_number_columns(names, ids, cat)); ds.flush()
+    blobs = [synth.lightgbm_model_text(40, 6, seed=50 + k) for k in range(5)]
+    boosters = [mb.LightGBMBooster(ctx, b) for b in blobs]
+    oracles = [oracle.OracleBooster(0, b) for b in blobs]
+    stable = np.arange(0, 2000)        # never updated
+    hot = np.arange(2000, n_items)     # updated concurrently
+    errors = []
+
+    def ranker(tid):
+        rng = np.random.Generator(np.random.PCG64(100 + tid))
+        rk = F.Ranker(fm, ds)
+        try:
+            for it in range(25):
+                m = int(rng.integers(0, 5))
+                sizes = rng.integers(1, 80, 20)
+                offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+                pick = rng.choice(stable, int(offs[-1]))
+                R = len(sizes)
+                arrays = dict(offsets=offs, ids=ids[pick], users=np.zeros(R, dtype=np.uint64), sessions=np.zeros(R, dtype=np.uint64),
+                              req_f64=np.zeros((R, 1)), req_u64=np.zeros((R, 1), dtype=np.uint64),
+                              req_vec=np.zeros((R, 1), dtype=np.float32), req_vp=np.zeros((R, 1), dtype=np.uint8),
+                              item_f64=None, n_requests=R, total_items=int(offs[-1]))
+                scores, order, _ = rk.rank_arrays(arrays, boosters[m], want_order=True)
+                want = oracles[m].predictMat(np.ascontiguousarray(cat[pick]), len(pick), 6, threads=1)
+                if not _eq(scores, want):
+                    errors.append((tid, it, "scores"))
+        except Exception as e:  # noqa: BLE001
+            errors.append((tid, repr(e)))
+
+    new_hot = synth.feature_matrix(len(hot), 6, seed=77)
+    new_hot = np.where(np.isnan(new_hot), 0.25, new_hot)
+
+    def updater():
+        try:
+            for k in range(0, len(hot), 100):
+                rows = hot[k:k + 100]
+                ds.put_packed(F.pack_number_columns(names, ids[rows], new_hot[k:k + 100]))
+                ds.flush()
+        except Exception as e:  # noqa: BLE001
+            errors.append(("updater", repr(e)))
+
+    threads = [threading.Thread(target=ranker, args=(t,)) for t in range(3)] + [threading.Thread(target=updater)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
+    cat[hot] = new_hot
+    rk = F.Ranker(fm, ds)
+    arrays = dict(offsets=np.array([0, len(hot)], dtype=np.int32), ids=ids[hot], users=np.zeros(1, dtype=np.uint64),
+                  sessions=np.zeros(1, dtype=np.uint64), req_f64=np.zeros((1, 1)), req_u64=np.zeros((1, 1), dtype=np.uint64),
+                  req_vec=np.zeros((1, 1), dtype=np.float32), req_vp=np.zeros((1, 1), dtype=np.uint8), item_f64=None,
+                  n_requests=1, total_items=len(hot))
+    for m in range(5):
+        scores, _, _ = rk.rank_arrays(arrays, boosters[m], want_order=True)
+        assert _eq(scores, oracles[m].predictMat(np.ascontiguousarray(cat[hot]), len(hot), 6, threads=1))
+    for b in boosters:
+        b.free()
+    ds.free(); fm.free()
