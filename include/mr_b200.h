@@ -270,7 +270,8 @@ MR_API mr_status mr_state_load_feature_values(mr_state *st, const uint8_t *bytes
 MR_API mr_status mr_feature_values_transcode(const uint8_t *bytes, size_t len, uint8_t *out, size_t out_cap,
                                              size_t *out_len, int64_t *n_records, int64_t *n_unsupported,
                                              size_t *consumed);
-/* Uploads pending upserts / writes to HBM (synchronous; waits for in-flight mr_rank calls).  A handful of
+/* Uploads pending upserts / writes to HBM (synchronous; waits for in-flight mr_rank calls).  Until then
+ * mr_rank keeps reading the snapshot of the previous flush, so writers and rankers may run concurrently.  A handful of
  * touched rows are packed and scattered by a kernel; bulk loads copy the touched row range. */
 MR_API mr_status mr_state_flush(mr_state *st);
 typedef struct mr_state_info {

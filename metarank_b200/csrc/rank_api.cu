@@ -142,7 +142,7 @@ const uint32_t *code_rows_for(mr_state *st, const mr_model *model, int *row_word
   const Schema &S = st->store->schema;
   if (disabled || !model || !model->use_binned() || S.fast_cols.empty()) return nullptr;
   StateStore &store = *st->store;
-  const size_t n_rows = store.tables[SC_ITEM].n_rows;
+  const size_t n_rows = store.tables[SC_ITEM].d_n_rows;  // rows on the device (pending upserts are not visible yet)
   const BinnedLaunch B = model->binned_desc();
   const int crw = (B.tile_cols + 1) / 2;
   std::lock_guard<std::mutex> g(st->cache_mu);
@@ -584,7 +584,6 @@ mr_status mr_rank(mr_state *st, mr_model *model, const mr_rank_batch *b, double 
       ~InFlight() { s->ranks_inflight.fetch_sub(1); }
     } inflight(st);
     std::shared_lock<std::shared_mutex> read_guard(st->store->mu);  // no flush while kernels read the tables
-    if (st->dirty) fail(MR_ERR_INVALID_ARG, "state has pending upserts: call mr_state_flush before mr_rank");
 
     // Large batches are cut at request boundaries into slices of ~256 K items that alternate
     // between up to four lanes, so the H2D copy / kernels / D2H copy of neighbouring slices overlap.
@@ -646,7 +645,6 @@ mr_status mr_rank_device(mr_state *st, mr_model *model, const mr_rank_batch *b, 
     if (R <= 0 || N <= 0) return;
     const Schema &S = st->store->schema;
     MR_CUDA_CHECK(cudaSetDevice(st->ctx->device));
-    if (st->dirty) fail(MR_ERR_INVALID_ARG, "state has pending upserts: call mr_state_flush before mr_rank_device");
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     const bool fused = fused_codes(model);
     ScratchPlan sp = plan_scratch(S, R, N, st->hist_pool_per_hist, d_out_features == nullptr && !fused, fused ? model->code_cols() : 0);

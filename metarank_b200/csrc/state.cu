@@ -285,6 +285,7 @@ void StateStore::flush() {
       T.d_cap = cap0;
       MR_CUDA_CHECK(cudaMemcpy(T.d_keys, T.keys.data(), T.keys.size() * 8, cudaMemcpyHostToDevice));
       MR_CUDA_CHECK(cudaMemcpy(T.d_vals, T.vals.data(), T.vals.size() * 4, cudaMemcpyHostToDevice));
+      T.d_keys_n = T.keys.size();
       T.map_dirty = false;
     }
     if (T.dirty_lo < T.dirty_hi) {
@@ -361,6 +362,7 @@ void StateStore::flush() {
     }
     T.pool_dirty_lo = SIZE_MAX;
     T.pool_dirty_hi = 0;
+    T.d_n_rows = T.n_rows;
     if (T.pool_uploaded < T.pool.size()) {
       const size_t had = T.d_pool_cap;
       ensure_dev(T.d_pool, T.d_pool_cap, T.pool.size(), T.pool_uploaded, device_bytes);
@@ -379,8 +381,9 @@ DState StateStore::view() const {
     const HostTable &T = tables[t];
     v.t[t].keys = T.d_keys;
     v.t[t].vals = T.d_vals;
-    v.t[t].mask = T.d_keys ? (uint32_t)(T.keys.size() - 1) : 0;
-    v.t[t].n_rows = T.d_rows ? (uint32_t)T.n_rows : 0;
+    // the snapshot of the last flush: upserts that are still pending must not change what kernels index
+    v.t[t].mask = (T.d_keys && T.d_keys_n) ? (uint32_t)(T.d_keys_n - 1) : 0;
+    v.t[t].n_rows = T.d_rows ? (uint32_t)T.d_n_rows : 0;
     v.t[t].rows = T.d_rows;
     v.t[t].pool = T.d_pool;
     v.t[t].row_words = T.row_words;

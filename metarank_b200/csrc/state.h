@@ -57,6 +57,7 @@ struct HostTable {
   uint64_t *d_rows = nullptr; size_t d_rows_cap = 0;
   uint64_t *d_pool = nullptr; size_t d_pool_cap = 0, pool_uploaded = 0;
   std::vector<double *> d_sides; std::vector<size_t> d_sides_cap;
+  size_t d_keys_n = 0, d_n_rows = 0;  // what the device holds as of the last flush (ranking reads this snapshot)
   bool map_dirty = false;
   size_t dirty_lo = SIZE_MAX, dirty_hi = 0;  // row range touched since the last flush
   size_t pool_dirty_lo = SIZE_MAX, pool_dirty_hi = 0;  // pool entries rewritten in place (bounded lists)
