@@ -702,11 +702,19 @@ __global__ void __launch_bounds__(kGatherWarps * 32) code_gather_kernel(RankArgs
   uint32_t *tile = s_tile + (size_t)warp * 32 * tw;
   const int n_here = min(32, a.total_items - i0);
   const uint32_t my = (lane < n_here) ? a.item_row[i0 + lane] + 1u : 0u;  // unknown item (kNoRow) -> row 0
-#pragma unroll 4
-  for (int j = 0; j < n_here; j++) {
-    const uint32_t r = __shfl_sync(0xFFFFFFFFu, my, j);
-    const uint32_t *src = a.code_rows + (size_t)r * crw;
-    for (int l = lane; l < crw; l += 32) tile[j * tw + l] = __ldg(src + l);
+  if (a.total_items <= 4096) {
+    // small batch (a single /rank request): latency matters, bandwidth does not — every lane streams its own
+    // item's row, so all of a warp's 32 rows are in flight at once instead of one after another
+    const uint32_t *src = a.code_rows + (size_t)my * crw;
+#pragma unroll 8
+    for (int l = 0; l < crw; l++) tile[lane * tw + l] = __ldg(src + l);
+  } else {
+#pragma unroll 8
+    for (int j = 0; j < n_here; j++) {
+      const uint32_t r = __shfl_sync(0xFFFFFFFFu, my, j);
+      const uint32_t *src = a.code_rows + (size_t)r * crw;
+      for (int l = lane; l < crw; l += 32) tile[j * tw + l] = __ldg(src + l);
+    }
   }
   __syncwarp();
   uint16_t *out = a.codes + (size_t)g * a.bin.tile_cols * 32;

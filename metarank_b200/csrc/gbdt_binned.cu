@@ -439,14 +439,29 @@ __global__ void __launch_bounds__(128) gbdt_leaves_kernel(const LParams p) {
   }
 }
 
+// The adds are a dependent chain (tree order = the sequential reference's rounding) but the loads are not.
+// ptxas keeps only ~8 register loads in flight, i.e. 60 L2 round trips for 500 trees; cp.async has no such
+// limit: every thread queues kSumBatch 8-byte copies of ITS OWN column into shared memory, waits for its own
+// group (no CTA barrier: nobody else reads them) and adds them in order.
+constexpr int kSumBatch = 48;  // 48 x 128 x 8 B = the 48 KB of static shared memory
+
 template <typename Real>
 __global__ void __launch_bounds__(128) gbdt_sum_kernel(const LParams p) {
+  __shared__ double s_v[kSumBatch][128];
   const int item = blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= p.rows) return;
   Real acc = (sizeof(Real) == 4) ? (Real)p.base_score : (Real)0;
   const double *v = p.leafvals + item;
-#pragma unroll 8
-  for (int t = 0; t < p.n_trees; t++) acc += (Real)v[(size_t)t * p.rows_padded];
+  const uint32_t s_base = smem_u32(&s_v[0][threadIdx.x]);
+  for (int t0 = 0; t0 < p.n_trees; t0 += kSumBatch) {
+    const int nb = min(kSumBatch, p.n_trees - t0);
+    for (int k = 0; k < nb; k++)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s_base + (uint32_t)k * 128u * 8u),
+                   "l"(v + (size_t)(t0 + k) * p.rows_padded)
+                   : "memory");
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    for (int k = 0; k < nb; k++) acc += (Real)s_v[k][threadIdx.x];
+  }
   p.out[item] = (double)acc;
 }
 
