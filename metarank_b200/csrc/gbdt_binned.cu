@@ -204,35 +204,35 @@ template <bool HAS_CAT, bool ALIGNED>
 __device__ __forceinline__ uint32_t walk_tree(uint32_t n, const uint8_t *cb, uint32_t cb_addr, const uint8_t *xwarp,
                                               uint32_t xwarp_addr, uint32_t lane2) {
   if (HAS_CAT) {
+    // pointers carry the kind of their target (bit 0 leaf, bit 1 categorical node): the numeric loop runs until
+    // either bit shows up, categorical nodes are resolved here and the walk re-enters
     do {
-      asm volatile(
-          "{\n"
-          ".reg .pred pl, pq, pc;\n"
-          ".reg .b32 w0, w1, off, code, kk, sel, tmp;\n"
-          "LVLC:\n"
-          "add.u32 tmp, %1, %0;\n"
-          "ld.shared.v2.u32 {w0, w1}, [tmp];\n"
-          "and.b32 tmp, w0, 2;\n"
-          "setp.ne.u32 pc, tmp, 0;\n"
-          "@pc bra DONEC;\n"
-          "lop3.b32 off, w0, 0xFFC0, %3, 0xEA;\n"
-          "add.u32 off, off, %2;\n"
-          "ld.shared.u16 code, [off];\n"
-          "shr.u32 kk, w0, 16;\n"
-          "setp.le.u32 pl, code, kk;\n"
-          "selp.b32 sel, 0x4410, 0x4432, pl;\n"
-          "prmt.b32 %0, w1, 0, sel;\n"
-          "and.b32 tmp, %0, 1;\n"
-          "setp.eq.u32 pq, tmp, 0;\n"
-          "@pq bra LVLC;\n"
-          "DONEC:\n"
-          "}\n"
-          : "+r"(n)
-          : "r"(cb_addr), "r"(xwarp_addr), "r"(lane2)
-          : "memory");
-      if (n & 1u) break;
+      if (!(n & 2u)) {
+        asm volatile(
+            "{\n"
+            ".reg .pred pl, pq;\n"
+            ".reg .b32 w0, w1, off, code, kk, sel, tmp;\n"
+            "LVLC:\n"
+            "add.u32 tmp, %1, %0;\n"
+            "ld.shared.v2.u32 {w0, w1}, [tmp];\n"
+            "lop3.b32 off, w0, 0xFFC0, %3, 0xEA;\n"
+            "add.u32 off, off, %2;\n"
+            "ld.shared.u16 code, [off];\n"
+            "shr.u32 kk, w0, 16;\n"
+            "setp.le.u32 pl, code, kk;\n"
+            "selp.b32 sel, 0x4410, 0x4432, pl;\n"
+            "prmt.b32 %0, w1, 0, sel;\n"
+            "and.b32 tmp, %0, 3;\n"
+            "setp.eq.u32 pq, tmp, 0;\n"
+            "@pq bra LVLC;\n"
+            "}\n"
+            : "+r"(n)
+            : "r"(cb_addr), "r"(xwarp_addr), "r"(lane2)
+            : "memory");
+        if (n & 1u) break;
+      }
       // categorical node: NaN / negative / out-of-bitset go right (LightGBM CategoricalDecision)
-      const uint2 nd = *reinterpret_cast<const uint2 *>(cb + n);
+      const uint2 nd = *reinterpret_cast<const uint2 *>(cb + (n & ~3u));
       const uint32_t code = *reinterpret_cast<const uint16_t *>(xwarp + ((nd.x & 0xFFC0u) | lane2));
       bool left = false;
       if (code != kBinNaN) {
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(128) gbdt_leaves_kernel(const LParams p) {
   for (int t = 0; t < ntree; t++) {
     uint32_t n = roots[t];
     while (!(n & 1u)) {
-      const uint2 nd = *reinterpret_cast<const uint2 *>(cb + n);
+      const uint2 nd = *reinterpret_cast<const uint2 *>(cb + (n & ~2u));  // bit 1 of a pointer: categorical target
       const uint32_t code = *reinterpret_cast<const uint16_t *>(xwarp + ((nd.x & 0xFFC0u) | lane2));
       bool left;
       if (nd.x & 2u) {  // categorical bitset

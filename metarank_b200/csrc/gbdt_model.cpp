@@ -677,10 +677,13 @@ BinnedModel pack_compact(const HostModel &m, const BinnedModel &bn, size_t chunk
       const HostTree &t = m.trees[i + k];
       const size_t ni = t.feat.size(), node_off = off, leaf_off = off + std::max<size_t>(ni, 1) * 8;
       const size_t ctab_off = leaf_off + t.leaf.size() * 8, cw_off = ctab_off + n_cat_nodes(t) * 8;
+      // a pointer to a node says what it points at: bit 0 = leaf value, bit 1 = categorical node — the numeric
+      // level loop then leaves on (n & 3) != 0 with the test it needs anyway, at no cost per level
       auto child = [&](int cidx) -> uint32_t {
-        return cidx >= 0 ? (uint32_t)(node_off + (size_t)cidx * 8) : (uint32_t)((leaf_off + (size_t)(~cidx) * 8) | 1u);
+        if (cidx < 0) return (uint32_t)((leaf_off + (size_t)(~cidx) * 8) | 1u);
+        return (uint32_t)(node_off + (size_t)cidx * 8) | ((t.flags[cidx] & NF_CATEGORICAL) ? 2u : 0u);
       };
-      roots[k] = (uint32_t)node_off;
+      roots[k] = (uint32_t)node_off | ((ni && (t.flags[0] & NF_CATEGORICAL)) ? 2u : 0u);
       uint32_t *w = (uint32_t *)(c + node_off);
       if (ni == 0) { w[0] = 0xFFFFu << 16; w[1] = (uint32_t)(leaf_off | 1u) * 0x10001u; }
       uint32_t *ctab = (uint32_t *)(c + ctab_off);
