@@ -206,8 +206,13 @@ enum {
   MR_IN_REQ_U64 = 1,  /* one u64 per request     (rate scoped ranking.<field>: hash of the field value;
                          item_age: the RankingEvent timestamp in epoch millis)          */
   MR_IN_REQ_VEC = 2,  /* one f32[dim] per request (bi-encoder query embedding)          */
-  MR_IN_ITEM_F64 = 3  /* one double per item, NaN = absent (relevancy; per-item field overrides of
+  MR_IN_ITEM_F64 = 3, /* one double per item, NaN = absent (relevancy; per-item field overrides of
                          number / string-index features, S/feature/NumberFeature.scala:84-93) */
+  MR_IN_REQ_TOKENS = 4 /* one token LIST per request (field_match ngram / term / bm25,
+                         S/feature/FieldMatchFeature.scala:60-93): mr_hash64 of each token the matcher's
+                         tokenize() returned for the ranking field, in that order — the analyzers are Lucene's
+                         and stay with the caller — plus, for bm25, the token's IDF
+                         (S/feature/matcher/BM25Matcher.scala:27) as its weight; an absent field = an empty list */
 };
 /* Slot index of `feature` within the inputs of `kind`, or -1 when the feature reads no such
  * input.  n_out (optional) receives the total number of slots of that kind. */
@@ -293,6 +298,12 @@ typedef struct mr_rank_batch {
   const float *req_vec;        /* [n_requests x mr_schema_vec_stride] */
   const uint8_t *req_vec_present; /* [n_requests x n(MR_IN_REQ_VEC)] */
   const double *item_f64;      /* [total_items x n(MR_IN_ITEM_F64)], NaN = absent */
+  /* MR_IN_REQ_TOKENS (all three may be NULL when the schema has no such slot): request r, slot s owns the
+   * tokens [req_tok_offsets[r * n + s], req_tok_offsets[r * n + s + 1]) of req_tok_hashes / req_tok_weights,
+   * n = n(MR_IN_REQ_TOKENS); offsets are non-decreasing, n_requests * n + 1 of them, the first is 0. */
+  const int32_t *req_tok_offsets;
+  const uint64_t *req_tok_hashes;
+  const double *req_tok_weights; /* bm25 only; may be NULL otherwise */
 } mr_rank_batch;
 
 /* Ranker.rerank for a batch of requests (S/ml/Ranker.scala:27-83): makeQuery

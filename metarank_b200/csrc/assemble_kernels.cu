@@ -900,6 +900,49 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
         out[d.col] = cnt;
         break;
       }
+      case FK_TOKEN_MATCH: {
+        // FieldMatchFeature.values (S/feature/FieldMatchFeature.scala:60-93): no query field / no item state -> 0.
+        // Jaccard of the two token sets (FieldMatcher.score, S/feature/matcher/FieldMatcher.scala:15-49) or BM25
+        // summed over the query's tokens in their order (BM25Matcher.score, matcher/BM25Matcher.scala:19-33;
+        // the per-token IDF arrives as the token's weight).
+        double v = 0.0;
+        int q0 = 0, q1 = 0;
+        if (a.req_tok_off) {
+          const int32_t *qo = a.req_tok_off + (size_t)r * a.n_req_tok + d.in0;
+          q0 = __ldg(qo) - a.req_tok_base;
+          q1 = __ldg(qo + 1) - a.req_tok_base;
+        }
+        if (q1 > q0 && irow && present(irow, d.b[0])) {
+          const uint64_t desc = irow[d.w[0]];
+          const uint32_t off = (uint32_t)desc, n = (uint32_t)(desc >> 32);
+          const uint64_t *doc = IT.pool + off;
+          auto contains = [&](uint64_t h) -> bool {  // the stored set is sorted by hash
+            uint32_t lo = 0, hi = n;
+            while (lo < hi) { const uint32_t m = (lo + hi) >> 1; const uint64_t x = __ldg(doc + m); if (x < h) lo = m + 1; else hi = m; }
+            return lo < n && __ldg(doc + lo) == h;
+          };
+          if (d.aux0 == 0) {
+            if (n > 0) {
+              int inter = 0;
+              for (int q = q0; q < q1; q++) inter += contains(__ldg(a.req_tok_hash + q)) ? 1 : 0;
+              v = __ddiv_rn((double)inter, (double)((q1 - q0) + (int)n - inter));
+            }
+          } else {
+            const double K1 = 1.2, B = 0.75;
+            // K1 * (1.0 - B + B * (doc.length / avgdl)) is the same for every term of this item
+            const double norm = __dmul_rn(K1, __dadd_rn(1.0 - B, __dmul_rn(B, __ddiv_rn((double)n, d.dparam))));
+            double sum = 0.0;
+            for (int q = q0; q < q1; q++) {
+              const double tf = contains(__ldg(a.req_tok_hash + q)) ? 1.0 : 0.0;
+              const double idf = __ldg(a.req_tok_w + q);
+              sum = __dadd_rn(sum, __ddiv_rn(__dmul_rn(idf, __dmul_rn(tf, K1 + 1.0)), __dadd_rn(tf, norm)));
+            }
+            v = sum;
+          }
+        }
+        out[d.col] = v;
+        break;
+      }
       case FK_VECTOR: {
         // NumVectorFeature.value :55-70 — the stored (already reduced) list, or NaN x dim
         const uint64_t *rp = scoped_row(d.scope);

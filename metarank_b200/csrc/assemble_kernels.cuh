@@ -21,7 +21,13 @@ struct RankArgs {
   const float *req_vec;
   const uint8_t *req_vec_present;
   const double *item_f64;
-  int n_req_f64, n_req_u64, n_req_vec, vec_stride, n_item_f64;
+  // per-request token lists (field_match ngram/term/bm25): request r, list slot s owns tokens
+  // [req_tok_off[r * n_req_tok + s], req_tok_off[r * n_req_tok + s + 1]) - req_tok_base of hashes / weights
+  const int32_t *req_tok_off;
+  const uint64_t *req_tok_hash;
+  const double *req_tok_w;
+  int32_t req_tok_base;
+  int n_req_f64, n_req_u64, n_req_vec, vec_stride, n_item_f64, n_req_tok;
   // scratch (device)
   int32_t *item_req;      // [total_items] owning request
   uint32_t *item_row;     // [total_items] row in the item table or 0xFFFFFFFF

@@ -97,6 +97,7 @@ void fill_args(RankArgs &a, mr_state *st, uint8_t *scratch, const ScratchPlan &s
   a.n_req_vec = (int)S.in_req_vec.size();
   a.vec_stride = S.vec_stride;
   a.n_item_f64 = (int)S.in_item_f64.size();
+  a.n_req_tok = (int)S.in_req_tok.size();
   a.item_req = (int32_t *)(scratch + sp.item_req);
   a.item_row = (uint32_t *)(scratch + sp.item_row);
   a.visitor_row = (uint32_t *)(scratch + sp.visitor_row);
@@ -281,6 +282,7 @@ int32_t mr_schema_input_slot(const mr_schema *s, int32_t kind, const char *featu
     case MR_IN_REQ_F64: v = &s->s.in_req_f64; break;
     case MR_IN_REQ_U64: v = &s->s.in_req_u64; break;
     case MR_IN_ITEM_F64: v = &s->s.in_item_f64; break;
+    case MR_IN_REQ_TOKENS: v = &s->s.in_req_tok; break;
     case MR_IN_REQ_VEC:
       for (auto &x : s->s.in_req_vec) vec_names.push_back(x.feature);
       v = &vec_names;
@@ -441,7 +443,7 @@ void rank_enqueue(mr_state *st, mr_model *model, const mr_rank_batch *b, int r0,
   pd.pin = pin;
   // ---- pack the slice into one pinned blob -> one H2D copy
   struct Seg { const void *src; size_t bytes, off; };
-  Seg segs[9];
+  Seg segs[12];
   size_t in_bytes = 0;
   int ns = 0;
   auto seg = [&](const void *p, size_t bytes) { segs[ns] = Seg{p, p ? bytes : 0, in_bytes}; in_bytes += al(segs[ns].bytes); return ns++; };
@@ -455,6 +457,13 @@ void rank_enqueue(mr_state *st, mr_model *model, const mr_rank_batch *b, int r0,
   const int s_rv = seg(b->req_vec ? b->req_vec + (size_t)r0 * S.vec_stride : nullptr, (size_t)R * S.vec_stride * 4);
   const int s_rp = seg(b->req_vec_present ? b->req_vec_present + (size_t)r0 * nrv : nullptr, (size_t)R * nrv);
   const int s_if = seg(b->item_f64 ? b->item_f64 + (size_t)i0 * nif : nullptr, (size_t)N * nif * 8);
+  // token lists of the slice: its offsets verbatim (the kernel subtracts the first), its range of hashes / weights
+  const size_t ntk = S.in_req_tok.size();
+  const bool has_tok = ntk > 0 && b->req_tok_offsets && b->req_tok_hashes;
+  const int32_t t0 = has_tok ? b->req_tok_offsets[(size_t)r0 * ntk] : 0, t1 = has_tok ? b->req_tok_offsets[(size_t)r1 * ntk] : 0;
+  const int s_to = seg(has_tok ? b->req_tok_offsets + (size_t)r0 * ntk : nullptr, ((size_t)R * ntk + 1) * 4);
+  const int s_th = seg(has_tok ? b->req_tok_hashes + t0 : nullptr, (size_t)(t1 - t0) * 8);
+  const int s_tw = seg(has_tok && b->req_tok_weights ? b->req_tok_weights + t0 : nullptr, (size_t)(t1 - t0) * 8);
 
   const bool fused = fused_codes(model);
   const size_t leaf_bytes = (fused && model->use_latency(N)) ? latency_scratch_bytes(N, (int)model->host.trees.size()) : 0;
@@ -495,6 +504,10 @@ void rank_enqueue(mr_state *st, mr_model *model, const mr_rank_batch *b, int r0,
   a.req_vec = (const float *)dp(s_rv);
   a.req_vec_present = (const uint8_t *)dp(s_rp);
   a.item_f64 = (const double *)dp(s_if);
+  a.req_tok_off = has_tok ? (const int32_t *)(d_in + segs[s_to].off) : nullptr;
+  a.req_tok_hash = (const uint64_t *)dp(s_th);
+  a.req_tok_w = (const double *)dp(s_tw);
+  a.req_tok_base = t0;
   a.out_features = (want_features || !fused) ? (double *)(scratch + sp.features) : nullptr;
   a.error_flag = (int32_t *)(lane->d_buf + err_off);  // zeroed by lookup_kernel
   if (fused) set_codes(a, st, model, scratch, sp);
@@ -574,6 +587,16 @@ mr_status mr_rank(mr_state *st, mr_model *model, const mr_rank_batch *b, double 
     if (!S.in_req_f64.empty() && !b->req_f64) fail(MR_ERR_INVALID_ARG, "schema needs req_f64 inputs");
     if (!S.in_req_u64.empty() && !b->req_u64) fail(MR_ERR_INVALID_ARG, "schema needs req_u64 inputs");
     if (!S.in_req_vec.empty() && (!b->req_vec || !b->req_vec_present)) fail(MR_ERR_INVALID_ARG, "schema needs req_vec inputs");
+    if (!S.in_req_tok.empty()) {
+      if (!b->req_tok_offsets || !b->req_tok_hashes) fail(MR_ERR_INVALID_ARG, "schema needs req_tok inputs");
+      const size_t n_off = (size_t)R * S.in_req_tok.size();
+      if (b->req_tok_offsets[0] != 0) fail(MR_ERR_INVALID_ARG, "req_tok_offsets[0] must be 0");
+      for (size_t k = 0; k < n_off; k++)
+        if (b->req_tok_offsets[k + 1] < b->req_tok_offsets[k]) fail(MR_ERR_INVALID_ARG, "req_tok_offsets must be non-decreasing");
+      bool bm25 = false;
+      for (auto &d : S.plan) bm25 |= d.kind == FK_TOKEN_MATCH && d.aux0 == 1;
+      if (bm25 && !b->req_tok_weights) fail(MR_ERR_INVALID_ARG, "a bm25 field_match needs req_tok_weights (the tokens' IDF)");
+    }
     if (N == 0) return;
     std::unique_ptr<InflightGuard> ig;
     if (model) ig = std::make_unique<InflightGuard>(model);
@@ -669,6 +692,10 @@ mr_status mr_rank_device(mr_state *st, mr_model *model, const mr_rank_batch *b, 
     a.req_vec = b->req_vec;
     a.req_vec_present = b->req_vec_present;
     a.item_f64 = b->item_f64;
+    a.req_tok_off = (S.in_req_tok.empty() || !b->req_tok_hashes) ? nullptr : b->req_tok_offsets;
+    a.req_tok_hash = b->req_tok_hashes;
+    a.req_tok_w = b->req_tok_weights;
+    a.req_tok_base = 0;
     a.out_features = d_out_features ? d_out_features : (fused ? nullptr : (double *)(st->d_scratch + sp.features));
     if (fused) set_codes(a, st, model, st->d_scratch, sp);
     launch_assemble(a, S, stream);

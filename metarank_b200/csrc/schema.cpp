@@ -383,10 +383,27 @@ Schema parse_schema_json(const char *json, size_t len) {
     } else if (t == "field_match") {
       const JValue &method = o.at("method");
       std::string mt = str_of(method, "type", n);
-      if (mt != "bi-encoder") fail(MR_ERR_UNSUPPORTED, "feature %s: field_match method %s is not supported on the GPU path", n.c_str(), mt.c_str());
       FieldSpec rf = parse_field(str_of(o, "rankingField", n), n), itf = parse_field(str_of(o, "itemField", n), n);
       if (rf.event != "ranking") fail(MR_ERR_PARSE, "feature %s: expected ranking field", n.c_str());
       if (itf.event != "item") fail(MR_ERR_PARSE, "feature %s: expected item field", n.c_str());
+      if (mt == "ngram" || mt == "term" || mt == "bm25") {
+        // FieldMatchFeature (S/feature/FieldMatchFeature.scala:30-93): the item's token set is stored at write
+        // time as SStringList under "<name>_<itemField>"; the query's tokens arrive with the request
+        // (MR_IN_REQ_TOKENS).  Tokenisation itself (Lucene analyzers) stays with the caller.
+        d.kind = FK_TOKEN_MATCH; d.scope = SC_ITEM;
+        int sl = add_slot(fi, n + "_" + itf.field, SC_ITEM, SK_STRLIST, 1, 1 /* sorted + unique */);
+        bind(0, sl);
+        d.in0 = (int)S.in_req_tok.size();
+        S.in_req_tok.push_back(n);
+        d.aux0 = mt == "bm25" ? 1 : 0;
+        if (mt == "bm25") {
+          // BM25Matcher needs TermFreqDic.avgdl (S/feature/matcher/BM25Matcher.scala:19-33); the per-token IDF
+          // comes with the request as the token's weight
+          if (!method.get("avgdl")) fail(MR_ERR_PARSE, "feature %s: bm25 needs method.avgdl (TermFreqDic.avgdl)", n.c_str());
+          d.dparam = method.at("avgdl").as_double();
+        }
+      } else {
+      if (mt != "bi-encoder") fail(MR_ERR_UNSUPPORTED, "feature %s: field_match method %s is not supported on the GPU path", n.c_str(), mt.c_str());
       std::string dist = str_of(o, "distance", n, "cos");
       if (dist != "cos" && dist != "Cos" && dist != "cosine" && dist != "Cosine")
         fail(MR_ERR_UNSUPPORTED, "feature %s: distance '%s' is not supported", n.c_str(), dist.c_str());
@@ -408,6 +425,7 @@ Schema parse_schema_json(const char *json, size_t len) {
       S.vec_stride += dimv;
       S.needs_cosine = true;
       if (nm != 0) S.needs_prepass = true;
+      }
     } else {
       fail(MR_ERR_UNSUPPORTED, "feature type %s (feature %s) is not supported on the GPU /rank path", t.c_str(), n.c_str());
     }

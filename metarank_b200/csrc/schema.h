@@ -27,6 +27,7 @@ enum FeatKind : int32_t {
   FK_CONST_REQ = 11,  // number/word_count/string with scope ranking, local_time: one value per request
   FK_VECTOR = 12,     // vector (stored, already reduced SDoubleList)   S/feature/NumVectorFeature.scala:55-70
   FK_ITEM_AGE = 13,   // item_age                                 S/feature/ItemAgeFeature.scala:74-86
+  FK_TOKEN_MATCH = 14,  // field_match ngram / term / bm25 over pre-tokenized strings   S/feature/FieldMatchFeature.scala:60-93
 };
 
 enum ScopeT : int32_t { SC_GLOBAL = 0, SC_ITEM = 1, SC_USER = 2, SC_SESSION = 3, SC_FIELD = 4, SC_IRF = 5, SC_RANKING = 6, SC_N_TABLES = 6 };
@@ -38,6 +39,7 @@ enum SlotKind : int32_t {
   SK_COUNTER = 3,    // CounterValue                          1 word
   SK_PCOUNTER = 4,   // PeriodicCounterValue                  P words (+ presence only if length == P)
   SK_STRLIST = 5,    // ScalarValue(SStringList|SString) hashes: {u32 off, u32 len} into the table's pool
+                     // (Slot::p == 1: kept sorted by hash and unique, for field_match's token sets)
   SK_BLIST = 6,      // BoundedListValue item hashes:          {u32 off, u32 len}
   SK_F64LIST = 7,    // ScalarValue(SDoubleList) dim doubles in a side array (presence bit only)
   SK_DIVERSITY = 8,  // 2 words: {kind 1 double | 2 strings, payload f64 | {off,len}}
@@ -120,6 +122,7 @@ struct Schema {
   int dim = 0;
   // request inputs
   std::vector<std::string> in_req_f64, in_req_u64, in_item_f64;  // owning feature names
+  std::vector<std::string> in_req_tok;                           // per-request token lists (field_match ngram/term/bm25)
   struct VecIn { std::string feature; int dim; int offset; };
   std::vector<VecIn> in_req_vec;
   int vec_stride = 0;

@@ -210,8 +210,19 @@ void StateStore::upsert(const uint8_t *buf, size_t len, int64_t *applied, int64_
         else set_present(false);
         break;
       case SK_STRLIST:
-        if (kind == 2) { put_list(&w[sl.word]); set_present(true); }
-        else set_present(false);  // InteractedWith collects only SStringList
+        if (kind == 2 && sl.p == 1) {
+          // field_match token set: kept sorted by hash and unique so the kernel can binary-search it
+          std::vector<uint64_t> v(n);
+          if (n) memcpy(v.data(), arr, (size_t)n * 8);
+          std::sort(v.begin(), v.end());
+          v.erase(std::unique(v.begin(), v.end()), v.end());
+          const uint32_t off = (uint32_t)T.pool.size();
+          if (T.pool.size() + v.size() > (size_t)UINT32_MAX) fail(MR_ERR_UNSUPPORTED, "state pool is full");
+          T.pool.insert(T.pool.end(), v.begin(), v.end());
+          w[sl.word] = (uint64_t)off | ((uint64_t)v.size() << 32);
+          set_present(true);
+        } else if (kind == 2) { put_list(&w[sl.word]); set_present(true); }
+        else set_present(false);  // InteractedWith / FieldMatch collect only SStringList
         break;
       case SK_BLIST:
         if (kind == 6) { put_list(&w[sl.word]); set_present(true); } else set_present(false);

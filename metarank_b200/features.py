@@ -22,7 +22,7 @@ import numpy as np
 from . import _capi
 from ._capi import check, lib
 
-MR_IN_REQ_F64, MR_IN_REQ_U64, MR_IN_REQ_VEC, MR_IN_ITEM_F64 = 0, 1, 2, 3
+MR_IN_REQ_F64, MR_IN_REQ_U64, MR_IN_REQ_VEC, MR_IN_ITEM_F64, MR_IN_REQ_TOKENS = 0, 1, 2, 3, 4
 _SCOPE_TAG = {"global": 0, "item": 1, "user": 2, "session": 3, "field": 4, "irf": 5, "ranking": 6}
 
 
@@ -66,6 +66,30 @@ def _map_datetime(parse: str, d) -> float:
     return float(int(d.timestamp()))  # "second"
 
 
+def match_tokens(conf: dict, text: str) -> list[str]:
+    """FieldMatcher.tokenize for the matchers whose analyzer is first-party enough to mirror here: language
+    "whitespace" (Lucene WhitespaceTokenizer: split on whitespace, nothing else).  NgramMatcher.tokenize
+    (S/feature/matcher/NgramMatcher.scala:9-30): every n-gram of every term; TermMatcher.tokenize
+    (matcher/TermMatcher.scala:7-12): the terms; both sorted and unique (FieldMatcher.unique).  Any other
+    language is a Lucene analyzer and has to be run by the caller (request["tokens"][feature])."""
+    m = conf["method"]
+    if m.get("language") != "whitespace":
+        raise ValueError(f"feature {conf['name']}: language {m.get('language')!r} needs caller-side tokens")
+    terms = text.split()
+    if m["type"] == "ngram":
+        n = int(m["n"])
+        terms = [t[j:j + n] for t in terms for j in range(0, len(t) - n + 1)]
+    return sorted(set(terms))
+
+
+def bm25_idf(method: dict, token: str) -> float:
+    """BM25Matcher.score's termIDF (S/feature/matcher/BM25Matcher.scala:26-27)."""
+    import math
+
+    gtf = method.get("termfreq", {}).get(token, 0)
+    return math.log(1.0 + (method["docs"] - gtf + 0.5) / (gtf + 0.5))
+
+
 def _field_name(s: str) -> tuple[str, str]:
     ev, fld = s.split(".", 1)
     return ("item" if ev == "metadata" else ev), fld
@@ -75,7 +99,8 @@ class RankBatch(C.Structure):
     _fields_ = [("n_requests", C.c_int32), ("item_offsets", C.c_void_p), ("item_ids", C.c_void_p),
                 ("user_ids", C.c_void_p), ("session_ids", C.c_void_p), ("req_f64", C.c_void_p),
                 ("req_u64", C.c_void_p), ("req_vec", C.c_void_p), ("req_vec_present", C.c_void_p),
-                ("item_f64", C.c_void_p)]
+                ("item_f64", C.c_void_p), ("req_tok_offsets", C.c_void_p), ("req_tok_hashes", C.c_void_p),
+                ("req_tok_weights", C.c_void_p)]
 
 
 class StateInfo(C.Structure):
@@ -99,6 +124,7 @@ class FeatureMapping:
         self.n_req_u64 = self._n(MR_IN_REQ_U64)
         self.n_req_vec = self._n(MR_IN_REQ_VEC)
         self.n_item_f64 = self._n(MR_IN_ITEM_F64)
+        self.n_req_tok = self._n(MR_IN_REQ_TOKENS)
         self.vec_stride = int(lib().mr_schema_vec_stride(self._h))
 
     def _n(self, kind):
@@ -150,6 +176,7 @@ class FeatureMapping:
         req_vec = np.zeros((max(R, 1), max(self.vec_stride, 1)), dtype=np.float32)
         req_vp = np.zeros((max(R, 1), max(self.n_req_vec, 1)), dtype=np.uint8)
         item_f64 = np.full((max(N, 1), max(self.n_item_f64, 1)), np.nan)
+        tok_lists = [[[] for _ in range(self.n_req_tok)] for _ in range(R)]  # [request][slot] -> [(hash, weight)]
         num = lambda v: isinstance(v, (int, float)) and not isinstance(v, bool)  # noqa: E731
         strl = lambda v: isinstance(v, list) and all(isinstance(x, str) for x in v)  # noqa: E731
         for r, q in enumerate(requests):
@@ -196,6 +223,15 @@ class FeatureMapping:
                         d = _parse_iso(rf[fld])
                     if d is not None:
                         req_f64[r, self.input_slot(MR_IN_REQ_F64, name)] = _map_datetime(conf["parse"], d)
+                elif t == "field_match" and conf["method"]["type"] in ("ngram", "term", "bm25"):
+                    slot = self.input_slot(MR_IN_REQ_TOKENS, name)
+                    qf = rf.get(_field_name(conf["rankingField"])[1])
+                    if isinstance(qf, str):  # only a StringField is tokenized (FieldMatchFeature.scala:62-68)
+                        toks = (q.get("tokens") or {}).get(name)
+                        if toks is None:
+                            toks = match_tokens(conf, qf)
+                        w = [bm25_idf(conf["method"], tk) for tk in toks] if conf["method"]["type"] == "bm25" else [0.0] * len(toks)
+                        tok_lists[r][slot] = [(hash64(tk), wk) for tk, wk in zip(toks, w)]
                 elif t == "field_match":
                     slot = self.input_slot(MR_IN_REQ_VEC, name)
                     q_emb = (q.get("embeddings") or {}).get(name)
@@ -233,7 +269,20 @@ class FeatureMapping:
         if self.n_item_f64 == 0 or np.isnan(item_f64).all():
             item_f64 = None  # mr_rank_batch.item_f64 == NULL: no per-item inputs at all
         return dict(offsets=offs, ids=ids, users=users, sessions=sessions, req_f64=req_f64, req_u64=req_u64,
-                    req_vec=req_vec, req_vp=req_vp, item_f64=item_f64, n_requests=R, total_items=N)
+                    req_vec=req_vec, req_vp=req_vp, item_f64=item_f64, n_requests=R, total_items=N,
+                    **self._pack_tokens(tok_lists))
+
+    def _pack_tokens(self, tok_lists):
+        if self.n_req_tok == 0:
+            return {}
+        offs, hs, ws = [0], [], []
+        for per_req in tok_lists:
+            for lst in per_req:
+                hs += [h for h, _ in lst]
+                ws += [w for _, w in lst]
+                offs.append(len(hs))
+        return dict(tok_off=np.asarray(offs, dtype=np.int32), tok_hash=np.asarray(hs + [0], dtype=np.uint64),
+                    tok_w=np.asarray(ws + [0.0], dtype=np.float64))
 
 
 def pack_feature_values(values: dict) -> bytes:
@@ -387,7 +436,10 @@ class Ranker:
         b = RankBatch(arrays["n_requests"], arrays["offsets"].ctypes.data, arrays["ids"].ctypes.data,
                       arrays["users"].ctypes.data, arrays["sessions"].ctypes.data, arrays["req_f64"].ctypes.data,
                       arrays["req_u64"].ctypes.data, arrays["req_vec"].ctypes.data, arrays["req_vp"].ctypes.data,
-                      arrays["item_f64"].ctypes.data if arrays["item_f64"] is not None else None)
+                      arrays["item_f64"].ctypes.data if arrays["item_f64"] is not None else None,
+                      arrays["tok_off"].ctypes.data if "tok_off" in arrays else None,
+                      arrays["tok_hash"].ctypes.data if "tok_hash" in arrays else None,
+                      arrays["tok_w"].ctypes.data if "tok_w" in arrays else None)
         scores = out_scores if out_scores is not None else np.empty(max(N, 1), dtype=np.float64)
         order = (out_order if out_order is not None else np.empty(max(N, 1), dtype=np.int32)) \
             if want_order and model is not None else None

@@ -792,6 +792,87 @@ class FieldMatchBiencoderFeature(BaseFeature):
         return [[v] for v in normalize_scale(self.norm, raw)]
 
 
+class FieldMatchTokensFeature(BaseFeature):
+    """S/feature/FieldMatchFeature.scala:30-93 with method ngram / term / bm25.
+
+    Tokenisation is Lucene's (S/util/TextAnalyzer.scala) and therefore NOT restated, except for the
+    `whitespace` analyzer (split on whitespace only): NgramMatcher.tokenize / TermMatcher.tokenize
+    (S/feature/matcher/NgramMatcher.scala:9-30, TermMatcher.scala:7-12) then are pure string code.  For any
+    other language the tokens come with the event / request: event["tokens"][feature], request["tokens"][feature]
+    (what matcher.tokenize(field) returned: sorted, unique).
+    Scoring: FieldMatcher.score (matcher/FieldMatcher.scala:15-49, Jaccard over two sorted unique arrays) and
+    BM25Matcher.score (matcher/BM25Matcher.scala:19-33)."""
+
+    K1, B = 1.2, 0.75
+
+    def __init__(self, c):
+        self.name = c["name"]
+        self.ranking_field = parse_field_name(c["rankingField"])[1]
+        self.item_field = parse_field_name(c["itemField"])[1]
+        self.method = dict(c["method"])
+        self.state_name = self.name + "_" + self.item_field  # conf.name :32
+
+    def states(self):
+        return {self.state_name: dict(kind="scalar", scope=("item",), refresh=0)}
+
+    def tokenize(self, text, given=None):
+        if given is not None:
+            return list(given)
+        if self.method.get("language") != "whitespace":
+            raise NotImplementedError(f"{self.name}: analyzer {self.method.get('language')!r} is Lucene's; pass tokens")
+        terms = text.split()
+        if self.method["type"] == "ngram":  # NgramMatcher.tokenize
+            n = int(self.method["n"])
+            terms = [t[j:j + n] for t in terms for j in range(0, len(t) - n + 1)]
+        return sorted(set(terms))  # FieldMatcher.unique: sort + dedupe
+
+    def writes(self, ev, store):  # :39-54
+        if ev.get("event") != "item":
+            return []
+        key = (("item", ev["item"]), self.state_name)
+        for n, v in ev.get("fields", []):
+            if n == self.item_field:
+                given = (ev.get("tokens") or {}).get(self.name)
+                if isinstance(v, str):
+                    return [("put", key, ev["timestamp"], self.tokenize(v, given))]
+                if is_strlist(v):
+                    return [("put", key, ev["timestamp"], self.tokenize(" ".join(v), given))]
+                return []
+        return []
+
+    def score(self, query, doc):
+        if self.method["type"] == "bm25":  # BM25Matcher.score: no early exit, tf of a unique-token doc is 0/1
+            m = self.method
+            total = 0.0
+            freq = {}
+            for d in doc:
+                freq[d] = freq.get(d, 0) + 1
+            for term in query:
+                tf = freq.get(term, 0)
+                gtf = m.get("termfreq", {}).get(term, 0)
+                idf = math.log(1.0 + (m["docs"] - gtf + 0.5) / (gtf + 0.5))
+                total += idf * (tf * (self.K1 + 1.0)) / (tf + self.K1 * (1.0 - self.B + self.B * (len(doc) / m["avgdl"])))
+            return total
+        if not query or not doc:
+            return 0.0
+        inter = len(set(query) & set(doc))
+        return float(inter) / float(len(set(query) | set(doc)))
+
+    def values(self, req, state, mode="online"):  # :60-93
+        qf = fields_map(req.get("fields", [])).get(self.ranking_field)
+        if not isinstance(qf, str):
+            return [[0.0] for _ in req["items"]]
+        q = self.tokenize(qf, (req.get("tokens") or {}).get(self.name))
+        out = []
+        for it in req["items"]:
+            fv = state.get((("item", it["id"]), self.state_name))
+            if fv is not None and fv[0] == "scalar" and (is_strlist(fv[1]) or (isinstance(fv[1], (list, tuple)) and len(fv[1]) == 0)):
+                out.append([self.score(q, list(fv[1]))])
+            else:
+                out.append([0.0])
+        return out
+
+
 class BooleanFeature(BaseFeature):
     """S/feature/BooleanFeature.scala"""
 
@@ -1009,6 +1090,8 @@ FEATURE_TYPES = {
 def make_feature(conf: dict) -> BaseFeature:
     t = conf["type"]
     if t == "field_match":
+        if conf["method"]["type"] in ("ngram", "term", "bm25"):
+            return FieldMatchTokensFeature(conf)
         if conf["method"]["type"] != "bi-encoder":
             raise NotImplementedError(conf["method"]["type"])
         return FieldMatchBiencoderFeature(conf)

@@ -180,3 +180,39 @@ LAYOUT_ITEM_VALUES = [
     {"ctr": [0.2, 0.2], "clicked_category": [1.0], "price": [3.0], "category": [1.0]},
 ]
 LAYOUT_EXPECTED = [10.0, 1.0, 0.2, 0.1, 1.0, 5.0, 2.0, 0.1, 0.05, 0.0, 3.0, 1.0, 0.2, 0.2, 1.0]
+
+# ---- field_match ngram / term / bm25 (S/feature/FieldMatchFeature.scala).  The reference's tests tokenize with
+# Lucene's English analyzer; tokenisation stays with the caller here, so the cases either use the `whitespace`
+# analyzer on strings the English analyzer leaves untouched, or carry the token lists the reference's tests state.
+_TITLE_MATCH = dict(name="title_match", type="field_match", rankingField="ranking.query", itemField="item.title",
+                    method=dict(type="ngram", n=3, language="whitespace"))
+case("field_match_ngram_score", "T/feature/FieldMatchFeatureTest.scala:61-68 (puts :49-59: [bar, foo, oba, oob])",
+     [_TITLE_MATCH], [item_event("p1", [("title", "foobar")])],
+     ranking(["p1", "p2"], [("query", "foo")]), {"title_match": [[0.25], [0.0]]})
+case("field_match_ngram_no_query_field", "S/feature/FieldMatchFeature.scala:91 (None -> 0 for every item)",
+     [_TITLE_MATCH], [item_event("p1", [("title", "foobar")])], ranking(["p1"]), {"title_match": [[0.0]]})
+case("field_match_ngram_duplicates_and_string_list",
+     "T/feature/matcher/NgramMatcherTest.scala:11-14 ('fooba foo' -> foo, oba, oob); StringListField joined by ' ' (S :46)",
+     [_TITLE_MATCH], [item_event("p1", [("title", ["fooba", "foo"])]), item_event("p2", [("title", 7.0)])],
+     ranking(["p1", "p2"], [("query", "oob zzz")]), {"title_match": [[0.25], [0.0]]})
+_TERM = dict(name="tm", type="field_match", rankingField="ranking.query", itemField="item.title",
+             method=dict(type="term", language="en"))
+_term_item = item_event("p1", [("title", "greetings to hamsters!")])
+_term_item["tokens"] = {"tm": ["greet", "hamster"]}            # TermMatcherTest.scala:11-14
+_term_req = ranking(["p1"], [("query", "greet")])
+_term_req["tokens"] = {"tm": ["greet"]}
+case("field_match_term_half_match", "T/feature/matcher/TermMatcherTest.scala:11-23 (tokens as stated there; {a} vs {a,b} = 0.5)",
+     [_TERM], [_term_item], _term_req, {"tm": [[0.5]]})
+_BM25 = dict(name="bm", type="field_match", rankingField="ranking.query", itemField="item.title",
+             method=dict(type="bm25", language="en", docs=3, avgdl=3.0, termfreq={"foo": 1, "bar": 2, "baz": 3}))
+_bm_items = [item_event("p1", [("title", "bar baz")]), item_event("p2", [("title", "foo")])]
+_bm_items[0]["tokens"] = {"bm": ["bar", "baz"]}
+_bm_items[1]["tokens"] = {"bm": ["foo"]}
+_bm_req = ranking(["p1", "p2", "p3"], [("query", "baz")])
+_bm_req["tokens"] = {"bm": ["baz"]}
+case("field_match_bm25_high_freq_query", "T/feature/matcher/BM25MatcherTest.scala:11-23 (0.15 +- 0.01)",
+     [_BM25], _bm_items, _bm_req, {})
+_bm_req2 = ranking(["p2", "p1"], [("query", "foo")])
+_bm_req2["tokens"] = {"bm": ["foo"]}
+case("field_match_bm25_low_freq_query", "T/feature/matcher/BM25MatcherTest.scala:25-27 (1.34 +- 0.01)",
+     [_BM25], _bm_items, _bm_req2, {})

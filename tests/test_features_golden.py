@@ -100,3 +100,45 @@ def test_rate_plain_division_edge_cases():
     assert math.isnan(v[0]) and v[1] == math.inf
     st[(("item", "p1"), "ctr_click")] = ("pcounter", [1])  # wrong length -> missing
     assert all(math.isnan(x) for x in f.value(G.ranking(["p1"]), st, {"id": "p1"}))
+
+
+def test_bm25_matches_the_reference_test_values():
+    """T/feature/matcher/BM25MatcherTest.scala:21-27: 0.15 +- 0.01 and 1.34 +- 0.01 (the reference's own tolerance:
+    math.log is not bit-reproducible across JVMs either)."""
+    bm = fo.FieldMatchTokensFeature(dict(name="m", rankingField="ranking.q", itemField="item.t",
+                                         method=dict(type="bm25", language="en", docs=3, avgdl=3.0,
+                                                     termfreq={"foo": 1, "bar": 2, "baz": 3})))
+    assert abs(bm.score(["baz"], ["bar", "baz"]) - 0.15) <= 0.01
+    assert abs(bm.score(["foo"], ["foo"]) - 1.34) <= 0.01
+    ng = fo.FieldMatchTokensFeature(dict(name="m", rankingField="ranking.q", itemField="item.t",
+                                         method=dict(type="ngram", n=3, language="whitespace")))
+    assert ng.tokenize("fooba foo") == ["foo", "oba", "oob"]          # NgramMatcherTest.scala:11-14
+    assert ng.tokenize("foobar") == ["bar", "foo", "oba", "oob"]      # :16-19
+    assert (ng.score(list("abc"), list("abc")), ng.score(["a"], ["a", "b"]), ng.score(["c", "d"], ["a", "b"])) == (1.0, 0.5, 0.0)
+
+
+def test_token_match_schema_and_request_packing_on_the_host():
+    """mr_schema_create accepts field_match ngram / term / bm25 and exposes one MR_IN_REQ_TOKENS slot per feature;
+    the Python shim packs the request's token lists the way mr_rank_batch documents."""
+    from metarank_b200 import _capi, features as F
+
+    feats = [dict(name="tm", type="field_match", rankingField="ranking.query", itemField="item.title",
+                  method=dict(type="ngram", n=3, language="whitespace")),
+             dict(name="price", type="number", scope="item", source="item.price"),
+             dict(name="bm", type="field_match", rankingField="ranking.query", itemField="item.title",
+                  method=dict(type="bm25", language="en", docs=3, avgdl=3.0, termfreq={"foo": 1}))]
+    fm = F.FeatureMapping(None, feats, ["tm", "price", "bm"])
+    assert fm.dim == 3 and fm.n_req_tok == 2
+    assert (fm.input_slot(F.MR_IN_REQ_TOKENS, "tm"), fm.input_slot(F.MR_IN_REQ_TOKENS, "bm"),
+            fm.input_slot(F.MR_IN_REQ_TOKENS, "price")) == (0, 1, -1)
+    r1 = G.ranking(["p1", "p2"], [("query", "foobar")])
+    r1["tokens"] = {"bm": ["foo", "zzz"]}
+    r2 = G.ranking(["p3"])  # no query field: empty lists
+    a = fm.pack_requests([r1, r2])
+    assert a["tok_off"].tolist() == [0, 4, 6, 6, 6]
+    assert a["tok_hash"][:6].tolist() == [F.hash64(t) for t in ["bar", "foo", "oba", "oob", "foo", "zzz"]]
+    assert a["tok_w"][:4].tolist() == [0.0] * 4 and a["tok_w"][4] == F.bm25_idf(feats[2]["method"], "foo")
+    fm.free()
+    with pytest.raises(_capi.MrError) as e:
+        F.FeatureMapping(None, [dict(feats[2], method=dict(type="bm25", language="en"))], ["bm"])
+    assert "avgdl" in str(e.value)

@@ -946,3 +946,70 @@ def test_concurrent_ranks_and_flushes_keep_code_rows_coherent(ctx):
     for b in boosters:
         b.free()
     ds.free(); fm.free()
+
+
+def test_token_field_match_random_batches_and_slices(ctx):
+    """field_match ngram / term / bm25 on the device against the oracle: random vocabularies, items without a
+    title or with a non-string one, requests without a query, a batch large enough to be cut into several
+    pipelined slices (the slice's token range is rebased in the kernel), with and without a model."""
+    import metarank_b200 as mb
+    from metarank_b200 import features as F
+
+    rng = np.random.Generator(np.random.PCG64(404))
+    vocab = ["".join(rng.choice(list("abcdefgh"), int(rng.integers(2, 7)))) for _ in range(60)]
+    tf = {w: int(rng.integers(1, 50)) for w in vocab[:40]}
+    feats = [dict(name="ng", type="field_match", rankingField="ranking.query", itemField="item.title",
+                  method=dict(type="ngram", n=2, language="whitespace")),
+             dict(name="tm", type="field_match", rankingField="ranking.query", itemField="item.title",
+                  method=dict(type="term", language="whitespace")),
+             dict(name="bm", type="field_match", rankingField="ranking.q2", itemField="item.title",
+                  method=dict(type="bm25", language="en", docs=50, avgdl=3.5, termfreq=tf)),
+             dict(name="price", type="number", scope="item", source="item.price")]
+    model = ["ng", "price", "bm", "tm"]
+    mapping = fo.FeatureMapping(feats, model)
+    n_items = 1500
+    events = []
+    for i in range(n_items):
+        u = rng.random()
+        words = [str(w) for w in rng.choice(vocab, int(rng.integers(0, 7)))]
+        fields = [("price", float(i % 17))]
+        if u < 0.8:
+            fields.append(("title", " ".join(words)))
+        elif u < 0.9:
+            fields.append(("title", words))          # StringListField: joined by " "
+        elif u < 0.95:
+            fields.append(("title", 3.0))            # wrong type: no write
+        ev = dict(event="item", id=f"e{i}", timestamp=G.NOW, item=f"p{i}", fields=fields)
+        ev["tokens"] = {"bm": sorted(set(words))}    # the English analyzer is the caller's: stand-in tokens
+        events.append(ev)
+    state = fo.FeatureValueFlow(mapping, always_refresh=True).process(events)
+    fm, ds, rk, _, _ = _device(ctx, feats, model, state)
+    reqs = []
+    for r in range(760):
+        n = int(rng.integers(300, 420))
+        items = [f"p{int(k)}" for k in rng.integers(0, n_items + 20, n)]
+        fields = []
+        qwords = [str(w) for w in rng.choice(vocab, int(rng.integers(0, 5)))]
+        if rng.random() < 0.85:
+            fields.append(("query", " ".join(qwords)))
+        q2 = [str(w) for w in rng.choice(vocab, int(rng.integers(0, 4)))]
+        if rng.random() < 0.85:
+            fields.append(("q2", " ".join(q2)))
+        q = G.ranking(items, fields, rid=f"r{r}")
+        q["tokens"] = {"bm": sorted(set(q2))}
+        reqs.append(q)
+    arrays = fm.pack_requests(reqs)
+    assert arrays["total_items"] > (1 << 18)  # more than one slice
+    want = np.concatenate([fo.dense_matrix(mapping, q, state) for q in reqs])
+    assert (want[:, 0] > 0).any() and (want[:, 2] != 0).any() and (want[:, 3] > 0).any()
+    _, _, got = rk.rank_arrays(arrays, None, want_features=True)
+    assert _eq(got, want)
+    blob = synth.lightgbm_model_text(60, 4, seed=12)
+    booster = mb.LightGBMBooster(ctx, blob)
+    scores, order, _ = rk.rank_arrays(arrays, booster, want_order=True)
+    ws = oracle.OracleBooster(0, blob).predictMat(np.ascontiguousarray(want), len(want), 4, threads=0)
+    assert _eq(scores, ws)
+    offs = arrays["offsets"]
+    for r in rng.integers(0, len(reqs), 25):
+        assert np.array_equal(order[offs[r]:offs[r + 1]], oracle.rank_order(ws[offs[r]:offs[r + 1]]))
+    booster.free(); ds.free(); fm.free()
