@@ -136,6 +136,12 @@ void set_codes(RankArgs &a, mr_state *st, const mr_model *model, uint8_t *scratc
   a.code_rows = a.out_features ? nullptr : code_rows_for(st, model, &a.code_row_words);
 }
 
+struct RankInFlight {  // counts a rank call in st->ranks_inflight for its duration (see code_rows_for)
+  mr_state *s;
+  explicit RankInFlight(mr_state *s_) : s(s_) { s->ranks_inflight.fetch_add(1); }
+  ~RankInFlight() { s->ranks_inflight.fetch_sub(1); }
+};
+
 // Code rows for (state, model), current as of the last flush; nullptr when the path does not apply.
 // Called with the store's shared lock held (no flush can run); builds are synchronous and serialised.
 const uint32_t *code_rows_for(mr_state *st, const mr_model *model, int *row_words_out) {
@@ -601,11 +607,7 @@ mr_status mr_rank(mr_state *st, mr_model *model, const mr_rank_batch *b, double 
     std::unique_ptr<InflightGuard> ig;
     if (model) ig = std::make_unique<InflightGuard>(model);
     MR_CUDA_CHECK(cudaSetDevice(st->ctx->device));
-    struct InFlight {
-      mr_state *s;
-      explicit InFlight(mr_state *s_) : s(s_) { s->ranks_inflight.fetch_add(1); }
-      ~InFlight() { s->ranks_inflight.fetch_sub(1); }
-    } inflight(st);
+    RankInFlight inflight(st);
     std::shared_lock<std::shared_mutex> read_guard(st->store->mu);  // no flush while kernels read the tables
 
     // Large batches are cut at request boundaries into slices of ~256 K items that alternate
@@ -668,6 +670,7 @@ mr_status mr_rank_device(mr_state *st, mr_model *model, const mr_rank_batch *b, 
     if (R <= 0 || N <= 0) return;
     const Schema &S = st->store->schema;
     MR_CUDA_CHECK(cudaSetDevice(st->ctx->device));
+    RankInFlight inflight(st);
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     const bool fused = fused_codes(model);
     ScratchPlan sp = plan_scratch(S, R, N, st->hist_pool_per_hist, d_out_features == nullptr && !fused, fused ? model->code_cols() : 0);
