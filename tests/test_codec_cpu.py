@@ -158,3 +158,31 @@ def test_native_decoder_rejects_malformed_records():
     assert "ends inside a field" in str(e.value)
     with pytest.raises(_capi.MrError):
         F.transcode_feature_values(struct.pack(">i", -5) + b"xxxx")
+
+
+def test_native_decoder_survives_corrupted_streams():
+    """Every byte flip / truncation of a valid stream must end in a clean MR_ERR_PARSE or a shorter decode,
+    never in a crash, a hang or an out-of-bounds read (lengths are attacker-controlled varints)."""
+    from metarank_b200 import _capi, features as F
+
+    rng = np.random.Generator(np.random.PCG64(9))
+    base = co.encode_delimited(_sample_values())
+    outcomes = {"ok": 0, "err": 0}
+    for it in range(1500):
+        b = bytearray(base)
+        for _ in range(int(rng.integers(1, 4))):
+            k = int(rng.integers(0, len(b)))
+            b[k] = int(rng.integers(0, 256))
+        if rng.random() < 0.3:
+            b = b[:int(rng.integers(0, len(b)))]
+        try:
+            recs, n, uns, consumed = F.transcode_feature_values(bytes(b))
+            assert consumed <= len(b) and n >= uns >= 0
+            outcomes["ok"] += 1
+        except _capi.MrError:
+            outcomes["err"] += 1
+    assert outcomes["ok"] > 0 and outcomes["err"] > 0
+    # a huge list length must not allocate or loop for long: the record ends first
+    o = co.Out(); o.byte(7); co.write_key(o, (("item", "p"), "f")); o.varlong(1); o.byte(4); o.varint(2 ** 31 - 1)
+    with pytest.raises(_capi.MrError):
+        F.transcode_feature_values(struct.pack(">i", len(o.b)) + o.bytes())
