@@ -81,11 +81,34 @@ JNIEXPORT void JNICALL Java_ai_metarank_b200_Native_stateUpsert(JNIEnv *env, jcl
   throw_status(env, s);
 }
 
-// Ranker.rerank for one request: item-id hashes in, scores + order out (direct buffers, no copies in JNI)
+// Raw extractor writes (Put / Increment / PeriodicIncrement / Append) in the wire format of mr_state_apply_writes
+JNIEXPORT void JNICALL Java_ai_metarank_b200_Native_stateApplyWrites(JNIEnv *env, jclass, jlong state, jobject packed,
+                                                                     jint len, jboolean flush) {
+  const uint8_t *p = (const uint8_t *)env->GetDirectBufferAddress(packed);
+  mr_status s = mr_state_apply_writes((mr_state *)state, p, (size_t)len, nullptr, nullptr);
+  if (s == MR_OK && flush) s = mr_state_flush((mr_state *)state);
+  throw_status(env, s);
+}
+
+// Warm start: a stream of BinaryStoreFormat.featureValue.encodeDelimited(...) records (direct ByteBuffer).
+// Returns the number of bytes consumed (whole records).
+JNIEXPORT jlong JNICALL Java_ai_metarank_b200_Native_stateLoadFeatureValues(JNIEnv *env, jclass, jlong state, jobject bytes,
+                                                                            jlong len, jboolean flush) {
+  const uint8_t *p = (const uint8_t *)env->GetDirectBufferAddress(bytes);
+  size_t consumed = 0;
+  mr_status s = mr_state_load_feature_values((mr_state *)state, p, (size_t)len, nullptr, nullptr, &consumed);
+  if (s == MR_OK && flush) s = mr_state_flush((mr_state *)state);
+  throw_status(env, s);
+  return (jlong)consumed;
+}
+
+// Ranker.rerank for one request: item-id hashes in, scores + order out (direct buffers, no copies in JNI).
+// tokOffsets / tokHashes / tokWeights: the request's MR_IN_REQ_TOKENS lists (field_match ngram/term/bm25) or null.
 JNIEXPORT void JNICALL Java_ai_metarank_b200_Native_rank(JNIEnv *env, jclass, jlong state, jlong model, jint nItems,
                                                          jobject itemIds, jlong user, jlong session, jobject reqF64,
                                                          jobject reqU64, jobject reqVec, jobject reqVecPresent,
-                                                         jobject itemF64, jobject outScores, jobject outOrder,
+                                                         jobject itemF64, jobject tokOffsets, jobject tokHashes,
+                                                         jobject tokWeights, jobject outScores, jobject outOrder,
                                                          jobject outFeatures) {
   auto addr = [&](jobject b) { return b ? env->GetDirectBufferAddress(b) : nullptr; };
   int32_t offs[2] = {0, nItems};
@@ -101,6 +124,9 @@ JNIEXPORT void JNICALL Java_ai_metarank_b200_Native_rank(JNIEnv *env, jclass, jl
   b.req_vec = (const float *)addr(reqVec);
   b.req_vec_present = (const uint8_t *)addr(reqVecPresent);
   b.item_f64 = (const double *)addr(itemF64);
+  b.req_tok_offsets = (const int32_t *)addr(tokOffsets);
+  b.req_tok_hashes = (const uint64_t *)addr(tokHashes);
+  b.req_tok_weights = (const double *)addr(tokWeights);
   throw_status(env, mr_rank((mr_state *)state, (mr_model *)model, &b, (double *)addr(outScores), (int32_t *)addr(outOrder),
                             (double *)addr(outFeatures)));
 }
