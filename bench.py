@@ -34,7 +34,7 @@ ITEMS = 100
 FEATURES = 30
 TREES = 500
 REQUESTS_PER_STEP = 16384
-CATALOGUE = 1_000_000
+CATALOGUE = 2_000_000  # item table 496 MB, per-model code rows 168 MB: both larger than the 126 MB L2
 MODEL_SEED = 1234 + 2
 DATA_SEED = 42 + 2
 METRIC = "items/sec reranked (100-item req, 500-tree LambdaMART)"
@@ -148,7 +148,7 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C2: 100-item /rank requests, 30 scalar (number) features gathered from a "
-                               "1M-item state table, 500-tree LightGBM LambdaMART", "items_per_request": ITEMS,
+                               "2M-item state table, 500-tree LightGBM LambdaMART", "items_per_request": ITEMS,
                    "features": FEATURES, "trees": TREES, "catalogue_items": CATALOGUE,
                    "requests_per_step": sample_requests},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -363,12 +363,11 @@ def main():
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C2: 100-item /rank requests, 30 scalar (number) features gathered from a "
-                                   "1M-item device-resident state table, 500-tree LightGBM LambdaMART, "
+                                   "2M-item device-resident state table, 500-tree LightGBM LambdaMART, "
                                    "scores + per-request ordering",
                        "items_per_request": ITEMS, "features": FEATURES, "trees": TREES, "catalogue_items": CATALOGUE,
                        "requests_per_step": R, "parallelism": f"requests sharded over {world} GPU(s), state replicated, no collective",
-                       "l2": "per step the item table (248 MB) is gathered at random and a 393 MB feature matrix "
-                             "is written and re-read: both exceed the 126 MB L2, no flush needed"},
+                       "l2": "every table a step gathers from at random is larger than the 126 MB L2 (2 M items: item rows 496 MB, per-model code rows 168 MB), and a step writes and re-reads 138 MB of codes plus 33 MB of ids / scores / order: no flush needed"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ids_host.nbytes + offs_host.nbytes + 2 * R * 8),
                     "d2h_bytes_per_step": rows * 12, "steps": e2e_steps, "parity_ok": e2e_ok,
                     "what": "mr_rank: item-id hashes in page-locked host memory -> scores + order in page-locked host memory, "
