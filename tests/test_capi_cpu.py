@@ -127,3 +127,31 @@ def test_compact_level_loop_sass_instruction_budget():
         body = ins[start:end + 1]
         assert len(body) <= budget, body
         assert sum("LDS" in i for i in body) == 2 and not any(i.startswith(("DSETP", "DADD", "LDG")) for i in body), body
+
+
+def test_ctypes_mirrors_match_the_header_layouts():
+    """The Python ctypes structures (metarank_b200/features.py RankBatch, StateInfo) must have the header's
+    layout: a C program prints sizeof / offsetof straight from include/mr_b200.h."""
+    import ctypes
+    import os
+    import subprocess
+    import tempfile
+
+    from metarank_b200 import features as F
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    fields = [n for n, _ in F.RankBatch._fields_]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "mr_b200.h"', 'int main(void) {',
+           '  printf("%zu\\n", sizeof(mr_rank_batch));']
+    src += [f'  printf("%zu\\n", offsetof(mr_rank_batch, {n}));' for n in fields]
+    src += ['  printf("%zu\\n", sizeof(mr_state_info));', '  return 0; }']
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "layout.c")
+        open(c, "w").write("\n".join(src))
+        exe = os.path.join(d, "layout")
+        subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), c, "-o", exe], check=True)
+        out = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(F.RankBatch)
+    assert out[1:1 + len(fields)] == [getattr(F.RankBatch, n).offset for n in fields]
+    assert out[-1] == ctypes.sizeof(F.StateInfo)
