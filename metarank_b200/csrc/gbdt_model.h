@@ -127,13 +127,17 @@ struct BinnedModel {
 };
 BinnedModel pack_binned(const HostModel &m, size_t chunk_budget);
 
-// "Compact" form of the binned model for the fast lock-step kernel (<= 1023 features, chunks <= 64 KB).  Children are BYTE offsets inside the chunk, bit 0 set = leaf (the
-// offset then addresses the leaf VALUE), so a level needs no address arithmetic:
-//   CNode (8 B): word0 = feature*64 (bits 6..15) | nan_left (bit 0) | categorical (bit 1) | k << 16
-//                word1 = left offset (16) | right offset (16)
+// "Compact" form of the binned model for the fast lock-step kernel (<= 1023 tile columns, chunks <= 64 KB).
+// Children are BYTE offsets inside the chunk whose low bits say what they point at — bit 0 = leaf (the offset
+// then addresses the leaf VALUE), bit 1 = categorical node — so a level needs no address arithmetic and the
+// loop's leaf test also catches categorical nodes:
+//   CNode (8 B): word0 = tile_column*64 (bits 6..15) | categorical (bit 1) | k << 16
+//                word1 = left pointer (16) | right pointer (16)
+//   no NaN flag: the direction is a property of the tile column (BinMeta::flags, BinnedModel::tile_cols)
 //   a categorical node's k is the 8-byte index (in the chunk) of its {bitset word offset, n words} pair
-//   chunk: +0 u32 n_trees, pad; +16 u32 root[n_trees] (offset of the root node, or leaf|1 for a
-//          single-leaf tree); then per tree its nodes followed by its leaf values (8-byte slots)
+//   chunk: +0 u32 n_trees, pad; +16 u32 root[n_trees] (pointer to the root node; a single-leaf tree is a dummy
+//          split whose children both are its leaf); then per tree its nodes followed by its leaf values (8-byte slots)
+// chunk_budget 0 = sized from the code tile (what ~48 resident warps leave of the shared memory).
 BinnedModel pack_compact(const HostModel &m, const BinnedModel &binned, size_t chunk_budget);
 
 // "Threaded" form of the binned model for the free-running kernel: one flat array of 8-byte
