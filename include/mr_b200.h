@@ -105,8 +105,10 @@ MR_API mr_status mr_model_predict_mat_device(mr_model *m, const double *d_values
 
 /* The two halves of the binned scorer as separate device-side steps (what mr_model_predict_mat_device
  * runs back to back when the model can be binned): values -> exact u16 rank codes
- * ([group of 32 rows][column][lane] layout, mr_model_codes_bytes(rows) bytes), then the tree traversal
- * on the codes.  mr_model_codes_bytes returns 0 when the model is scored by the f64/f32 kernel
+ * ([group of 32 rows][tile column][lane] layout, mr_model_codes_bytes(rows) bytes; a tile has one column per
+ * feature plus a second one for every feature whose splits send NaN both ways — opaque to the caller, only
+ * valid for the model and options it was produced with), then the tree traversal on the codes.
+ * mr_model_codes_bytes returns 0 when the model is scored by the f64/f32 kernel
  * instead (categorical XGBoost splits, zero-as-missing LightGBM nodes, > 4095 columns). */
 MR_API size_t mr_model_codes_bytes(mr_model *m, int32_t rows);
 MR_API mr_status mr_model_bin_device(mr_model *m, const double *d_values, int32_t rows, int32_t cols, void *d_codes,
