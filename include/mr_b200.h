@@ -308,6 +308,25 @@ typedef struct mr_rank_batch {
   const double *req_tok_weights; /* bm25 only; may be NULL otherwise */
 } mr_rank_batch;
 
+/* Native request decoder: the body of POST /rank — one RankingEvent JSON object, or an array
+ * of them for a batch — decoded with the rules of the reference's circe codecs (S/model/Event.scala:44-99:
+ * id, timestamp as long | numeric string | ISO date-time with a zone, user?, session?, fields?[{name, value}],
+ * items[{id, relevancy?, fields?, label?}]; S/model/Field.scala:36-58) and packed into the arrays of
+ * mr_rank_batch exactly as the extractors read the request: ids / users / sessions through mr_hash64, the
+ * MR_IN_* inputs the schema asks for (ranking-scoped number / word_count / string, rate scoped ranking.<field>,
+ * item_age, local_time, relevancy, per-item overrides, field_match).  Two optional keys carry what stays with the
+ * caller's models: "embeddings": {feature: [f32...]} (bi-encoder query vector) and "tokens": {feature: [...]}
+ * (the analyzer's tokens for field_match ngram / term / bm25; the `whitespace` analyzer is built in).
+ * A body the reference's decoder rejects is MR_ERR_PARSE.  The returned handle owns every array. */
+typedef struct mr_requests mr_requests;
+MR_API mr_status mr_requests_decode(const mr_schema *schema, const char *json, size_t len, mr_requests **out);
+/* The packed batch (valid until mr_requests_free) and its item count: pass them to mr_rank. */
+MR_API const mr_rank_batch *mr_requests_batch(const mr_requests *r, int32_t *total_items);
+/* For the response: the id string of item `index` (0 .. total_items-1, batch order) and a request's timestamp. */
+MR_API const char *mr_requests_item_id(const mr_requests *r, int32_t index, size_t *len);
+MR_API int64_t mr_requests_timestamp(const mr_requests *r, int32_t request);
+MR_API mr_status mr_requests_free(mr_requests *r);
+
 /* Ranker.rerank for a batch of requests (S/ml/Ranker.scala:27-83): makeQuery
  * (FeatureValueLoader + ItemValue.fromState + ClickthroughQuery) -> model.predict ->
  * sortBy(-score).  All buffers are HOST memory; copies are part of the call.

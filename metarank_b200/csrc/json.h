@@ -178,6 +178,17 @@ class JsonParser {
             if (e_ - p_ < 5) bad("bad \\u escape");
             unsigned cp = (unsigned)strtoul(std::string((const char *)p_ + 1, 4).c_str(), nullptr, 16);
             p_ += 4;
+            // a UTF-16 surrogate pair written as two escapes is ONE code point (ids are hashed as UTF-8)
+            if (cp >= 0xD800 && cp <= 0xDBFF && e_ - p_ >= 7 && p_[1] == '\\' && p_[2] == 'u') {
+              const unsigned lo = (unsigned)strtoul(std::string((const char *)p_ + 3, 4).c_str(), nullptr, 16);
+              if (lo >= 0xDC00 && lo <= 0xDFFF) {
+                cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+                p_ += 6;
+                s += (char)(0xF0 | (cp >> 18)); s += (char)(0x80 | ((cp >> 12) & 0x3F));
+                s += (char)(0x80 | ((cp >> 6) & 0x3F)); s += (char)(0x80 | (cp & 0x3F));
+                break;
+              }
+            }
             if (cp < 0x80) s += (char)cp;
             else if (cp < 0x800) { s += (char)(0xC0 | (cp >> 6)); s += (char)(0x80 | (cp & 0x3F)); }
             else { s += (char)(0xE0 | (cp >> 12)); s += (char)(0x80 | ((cp >> 6) & 0x3F)); s += (char)(0x80 | (cp & 0x3F)); }

@@ -5,6 +5,7 @@
 //   sortBy     = order kernel
 #include "assemble_kernels.cuh"
 #include "fv_codec.h"
+#include "request_codec.h"
 #include "internal.h"
 #include "schema.h"
 #include "state.h"
@@ -352,6 +353,42 @@ mr_status mr_state_apply_writes(mr_state *st, const uint8_t *packed, size_t len,
     st->store->apply_writes(packed, len, applied, skipped);
     st->dirty = true;
   });
+}
+
+struct mr_requests {
+  PackedRequests p;
+};
+
+mr_status mr_requests_decode(const mr_schema *schema, const char *json, size_t len, mr_requests **out) {
+  return guard([&] {
+    if (!schema || !json || !out) fail(MR_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    auto r = std::make_unique<mr_requests>();
+    decode_requests(schema->s, json, len, r->p);
+    *out = r.release();
+  });
+}
+
+const mr_rank_batch *mr_requests_batch(const mr_requests *r, int32_t *total_items) {
+  if (!r) return nullptr;
+  if (total_items) *total_items = r->p.total_items;
+  return &r->p.batch;
+}
+
+const char *mr_requests_item_id(const mr_requests *r, int32_t index, size_t *len) {
+  if (!r || index < 0 || index >= (int32_t)r->p.item_ids.size()) return nullptr;
+  if (len) *len = r->p.item_ids[index].size();
+  return r->p.item_ids[index].c_str();
+}
+
+int64_t mr_requests_timestamp(const mr_requests *r, int32_t request) {
+  if (!r || request < 0 || request >= (int32_t)r->p.timestamps.size()) return 0;
+  return r->p.timestamps[request];
+}
+
+mr_status mr_requests_free(mr_requests *r) {
+  delete r;
+  return MR_OK;
 }
 
 mr_status mr_state_load_feature_values(mr_state *st, const uint8_t *bytes, size_t len, int64_t *applied,

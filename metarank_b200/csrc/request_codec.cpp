@@ -1,0 +1,519 @@
+// RankingEvent JSON -> mr_rank_batch arrays.  What each rule follows (S = src/main/scala/ai/metarank):
+//   event shape      S/model/Event.scala:44-99 (id, timestamp, user?, session?, fields?, items[{id, relevancy?,
+//                    fields?, label?}]; `relevancy` is sugar for a leading NumberField("relevancy", r), :84-93)
+//   fields           S/model/Field.scala:36-58 (string | bool | number | string[] | number[]; null / object /
+//                    mixed list are decoding failures)
+//   timestamp        S/model/Timestamp.scala (long | numeric string | ISO date-time with a zone)
+//   request reads    number / word_count on a ranking field (S/feature/NumberFeature.scala:58-69,
+//                    WordCountFeature.scala:63-68), string on a ranking field (StringFeature.scala:96-116),
+//                    rate scoped ranking.<field> (RateFeature.scala), item_age (ItemAgeFeature.scala:74-86),
+//                    local_time (LocalDateTimeFeature.scala:44-80), field_match (FieldMatchFeature.scala:60-68,
+//                    FieldMatchBiencoderFeature.scala:84-88), relevancy (RelevancyFeature.scala:36-51), per-item
+//                    overrides of number / string (NumberFeature.scala:84-93)
+// The Python shim (metarank_b200/features.py pack_requests + rank_api.py decode_ranking_event) is the same logic
+// and is what tests/test_request_codec_cpu.py compares this file with, array for array.
+#include "request_codec.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <unordered_map>
+
+#include "json.h"
+
+namespace mr {
+namespace {
+
+// ---------------------------------------------------------------- decoded event
+struct FieldVal {
+  enum Kind { Str, Bool, Num, StrList, NumList } kind = Str;
+  std::string s;
+  bool b = false;
+  double d = 0;
+  std::vector<std::string> sl;
+  std::vector<double> dl;
+  bool is_str() const { return kind == Str; }
+  bool is_num() const { return kind == Num; }
+  bool is_strlist() const { return kind == StrList; }
+};
+struct Field { std::string name; FieldVal v; };
+
+Field decode_field(const JValue &o) {
+  if (o.kind != JValue::Obj) fail(MR_ERR_PARSE, "field needs a string 'name'");
+  const JValue *n = o.get("name");
+  if (!n || n->kind != JValue::Str) fail(MR_ERR_PARSE, "field needs a string 'name'");
+  Field f;
+  f.name = n->str;
+  const JValue *v = o.get("value");
+  if (!v) fail(MR_ERR_PARSE, "field value not found");
+  switch (v->kind) {
+    case JValue::Null: fail(MR_ERR_PARSE, "null value in field %s", f.name.c_str());
+    case JValue::Bool: f.v.kind = FieldVal::Bool; f.v.b = v->b; break;
+    case JValue::Str: f.v.kind = FieldVal::Str; f.v.s = v->str; break;
+    case JValue::Num: f.v.kind = FieldVal::Num; f.v.d = v->num; break;
+    case JValue::Arr: {
+      bool all_str = true, all_num = true;
+      for (auto &x : v->arr) { all_str &= x.kind == JValue::Str; all_num &= x.kind == JValue::Num; }
+      if (all_str) { f.v.kind = FieldVal::StrList; for (auto &x : v->arr) f.v.sl.push_back(x.str); }
+      else if (all_num) { f.v.kind = FieldVal::NumList; for (auto &x : v->arr) f.v.dl.push_back(x.num); }
+      else fail(MR_ERR_PARSE, "cannot decode field %s: got a mixed list", f.name.c_str());
+      break;
+    }
+    default: fail(MR_ERR_PARSE, "cannot decode field %s: got object", f.name.c_str());
+  }
+  return f;
+}
+
+// days since 1970-01-01 of a proleptic Gregorian date, and back (H. Hinnant's civil algorithms)
+int64_t days_from_civil(int64_t y, unsigned m, unsigned d) {
+  y -= m <= 2;
+  const int64_t era = (y >= 0 ? y : y - 399) / 400;
+  const unsigned yoe = (unsigned)(y - era * 400);
+  const unsigned doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
+  const unsigned doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+  return era * 146097 + (int64_t)doe - 719468;
+}
+void civil_from_days(int64_t z, int64_t &y, unsigned &m, unsigned &d) {
+  z += 719468;
+  const int64_t era = (z >= 0 ? z : z - 146096) / 146097;
+  const unsigned doe = (unsigned)(z - era * 146097);
+  const unsigned yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+  y = (int64_t)yoe + era * 400;
+  const unsigned doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+  const unsigned mp = (5 * doy + 2) / 153;
+  d = doy - (153 * mp + 2) / 5 + 1;
+  m = mp < 10 ? mp + 3 : mp - 9;
+  y += m <= 2;
+}
+
+struct ZonedTime {  // wall-clock fields in the value's own offset + the instant
+  int64_t year = 1970;
+  unsigned month = 1, day = 1, hour = 0, minute = 0, second = 0;
+  int64_t epoch_ms = 0;
+  int iso_weekday() const {  // Monday = 1 .. Sunday = 7 (java.time.DayOfWeek.getValue)
+    const int64_t days = days_from_civil(year, month, day);
+    int64_t wd = (days + 3) % 7;  // 1970-01-01 was a Thursday
+    if (wd < 0) wd += 7;
+    return (int)wd + 1;
+  }
+};
+
+// ZonedDateTime.parse(s, ISO_DATE_TIME): yyyy-MM-ddTHH:mm[:ss[.fraction]] then Z | +HH[:MM[:SS]] | +HHMM, an optional
+// [Region/Id] suffix is dropped.  No zone -> not parsed (the extractor then yields no value).
+bool parse_iso_zoned(const std::string &in, ZonedTime &out) {
+  std::string s = in;
+  if (!s.empty() && s.back() == ']') {
+    const size_t lb = s.find('[');
+    if (lb == std::string::npos) return false;
+    s.resize(lb);
+  }
+  auto digits = [&](size_t pos, int n, int &v) -> bool {
+    if (pos + n > s.size()) return false;
+    v = 0;
+    for (int k = 0; k < n; k++) { const char c = s[pos + k]; if (c < '0' || c > '9') return false; v = v * 10 + (c - '0'); }
+    return true;
+  };
+  int Y, M, D, h, mi, se = 0;
+  if (!digits(0, 4, Y) || s.size() < 16 || s[4] != '-' || !digits(5, 2, M) || s[7] != '-' || !digits(8, 2, D) || s[10] != 'T' ||
+      !digits(11, 2, h) || s[13] != ':' || !digits(14, 2, mi))
+    return false;
+  size_t p = 16;
+  int64_t frac_ms = 0;
+  if (p < s.size() && s[p] == ':') {
+    if (!digits(p + 1, 2, se)) return false;
+    p += 3;
+    if (p < s.size() && (s[p] == '.' || s[p] == ',')) {
+      p++;
+      int nd = 0;
+      while (p < s.size() && s[p] >= '0' && s[p] <= '9') { if (nd < 3) frac_ms = frac_ms * 10 + (s[p] - '0'); nd++; p++; }
+      if (nd == 0) return false;
+      for (; nd < 3; nd++) frac_ms *= 10;
+    }
+  }
+  if (M < 1 || M > 12 || D < 1 || D > 31 || h > 23 || mi > 59 || se > 59) return false;
+  int64_t off_s = 0;
+  if (p >= s.size()) return false;  // zone required
+  if (s[p] == 'Z' || s[p] == 'z') { if (p + 1 != s.size()) return false; }
+  else if (s[p] == '+' || s[p] == '-') {
+    const int sign = s[p] == '-' ? -1 : 1;
+    int oh, om = 0, os = 0;
+    if (!digits(p + 1, 2, oh)) return false;
+    p += 3;
+    if (p < s.size()) {
+      if (s[p] == ':') p++;
+      if (!digits(p, 2, om)) return false;
+      p += 2;
+      if (p < s.size()) {
+        if (s[p] == ':') p++;
+        if (!digits(p, 2, os)) return false;
+        p += 2;
+      }
+    }
+    if (p != s.size()) return false;
+    off_s = sign * ((int64_t)oh * 3600 + om * 60 + os);
+  } else return false;
+  out.year = Y; out.month = (unsigned)M; out.day = (unsigned)D; out.hour = (unsigned)h; out.minute = (unsigned)mi; out.second = (unsigned)se;
+  const int64_t local_s = days_from_civil(Y, (unsigned)M, (unsigned)D) * 86400 + h * 3600 + mi * 60 + se;
+  out.epoch_ms = (local_s - off_s) * 1000 + frac_ms;
+  return true;
+}
+
+ZonedTime utc_from_epoch_seconds(int64_t sec) {
+  ZonedTime z;
+  int64_t days = sec / 86400, rem = sec % 86400;
+  if (rem < 0) { rem += 86400; days -= 1; }
+  civil_from_days(days, z.year, z.month, z.day);
+  z.hour = (unsigned)(rem / 3600); z.minute = (unsigned)((rem % 3600) / 60); z.second = (unsigned)(rem % 60);
+  z.epoch_ms = sec * 1000;
+  return z;
+}
+
+int64_t floor_div(int64_t a, int64_t b) { int64_t q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) q--; return q; }
+
+int64_t decode_timestamp(const JValue &v) {
+  if (v.kind == JValue::Num) {
+    if (v.is_int) return v.i64;
+    if (v.num == std::floor(v.num) && std::fabs(v.num) < 9.2e18) return (int64_t)v.num;
+    fail(MR_ERR_PARSE, "cannot decode timestamp");
+  }
+  if (v.kind == JValue::Str) {
+    size_t a = 0, b = v.str.size();
+    while (a < b && isspace((unsigned char)v.str[a])) a++;
+    while (b > a && isspace((unsigned char)v.str[b - 1])) b--;
+    const std::string s = v.str.substr(a, b - a);
+    bool numeric = !s.empty();
+    for (size_t k = 0; k < s.size(); k++) numeric &= (s[k] >= '0' && s[k] <= '9') || (k == 0 && s[k] == '-' && s.size() > 1);
+    if (numeric) return strtoll(s.c_str(), nullptr, 10);
+    ZonedTime z;
+    if (parse_iso_zoned(s, z)) return z.epoch_ms;
+  }
+  fail(MR_ERR_PARSE, "cannot decode timestamp");
+}
+
+struct Item { std::string id; std::vector<Field> fields; };
+struct Event {
+  std::string id;
+  int64_t ts = 0;
+  bool has_user = false, has_session = false;
+  std::string user, session;
+  std::vector<Field> fields;
+  std::vector<Item> items;
+  const JValue *embeddings = nullptr, *tokens = nullptr;  // extensions: caller-side model outputs / analyzers
+};
+
+Event decode_event(const JValue &o) {
+  if (o.kind != JValue::Obj) fail(MR_ERR_PARSE, "ranking event must be a JSON object");
+  for (const char *k : {"id", "timestamp", "items"})
+    if (!o.get(k)) fail(MR_ERR_PARSE, "required field '%s' missing in JSON", k);
+  Event e;
+  const JValue &id = o.at("id");
+  if (id.kind == JValue::Str) e.id = id.str;
+  else if (id.kind == JValue::Num && id.is_int) e.id = std::to_string(id.i64);
+  else fail(MR_ERR_PARSE, "event id must be a string");
+  e.ts = decode_timestamp(o.at("timestamp"));
+  auto opt_str = [&](const char *k, bool &has, std::string &dst) {
+    const JValue *v = o.get(k);
+    if (!v || v->kind == JValue::Null) return;
+    if (v->kind != JValue::Str) fail(MR_ERR_PARSE, "'%s' must be a string", k);
+    has = true;
+    dst = v->str;
+  };
+  opt_str("user", e.has_user, e.user);
+  opt_str("session", e.has_session, e.session);
+  if (const JValue *f = o.get("fields"))
+    if (f->kind == JValue::Arr) for (auto &x : f->arr) e.fields.push_back(decode_field(x));
+  const JValue &items = o.at("items");
+  if (items.kind != JValue::Arr || items.arr.empty()) fail(MR_ERR_PARSE, "items must be a non-empty list");  // NonEmptyList
+  for (auto &it : items.arr) {
+    const JValue *iid = it.kind == JValue::Obj ? it.get("id") : nullptr;
+    if (!iid || iid->kind != JValue::Str) fail(MR_ERR_PARSE, "item needs a string 'id'");
+    Item I;
+    I.id = iid->str;
+    if (const JValue *rel = it.get("relevancy")) {
+      if (rel->kind != JValue::Null) {
+        if (rel->kind != JValue::Num) fail(MR_ERR_PARSE, "relevancy must be a number");
+        Field f; f.name = "relevancy"; f.v.kind = FieldVal::Num; f.v.d = rel->num;
+        I.fields.push_back(f);
+      }
+    }
+    if (const JValue *f = it.get("fields"))
+      if (f->kind == JValue::Arr) for (auto &x : f->arr) I.fields.push_back(decode_field(x));
+    e.items.push_back(std::move(I));
+  }
+  e.embeddings = o.get("embeddings");
+  e.tokens = o.get("tokens");
+  return e;
+}
+
+// ---------------------------------------------------------------- per-feature request plan (from the schema JSON)
+struct ReqFeature {
+  std::string name, type, scope;
+  std::string src_event, src_field;           // number / word_count / string / boolean: source (or legacy `field`)
+  bool encode_index = false;
+  std::vector<std::string> values;
+  std::string rate_field;                     // rate scoped ranking.<field>
+  std::string lt_field, lt_parse;             // local_time
+  std::string rank_field;                     // field_match: ranking field
+  std::string mtype, language;
+  int n = 0;
+  double docs = 0;
+  std::unordered_map<std::string, double> termfreq;
+  int s_f64 = -1, s_u64 = -1, s_item = -1, s_vec = -1, s_tok = -1, vec_off = 0, vec_dim = 0, dim = 1;
+};
+
+void split_field(const std::string &s, std::string &ev, std::string &fld) {
+  const size_t dot = s.find('.');
+  ev = dot == std::string::npos ? s : s.substr(0, dot);
+  fld = dot == std::string::npos ? "" : s.substr(dot + 1);
+  if (ev == "metadata") ev = "item";
+}
+
+int slot_of(const std::vector<std::string> &v, const std::string &n) {
+  for (size_t k = 0; k < v.size(); k++) if (v[k] == n) return (int)k;
+  return -1;
+}
+
+std::vector<ReqFeature> build_plan(const Schema &S) {
+  JValue doc = JsonParser((const uint8_t *)S.source_json.data(), S.source_json.size()).parse();
+  std::unordered_map<std::string, const JValue *> by_name;
+  for (auto &o : doc.at("features").arr)
+    if (const JValue *n = o.get("name")) by_name[n->str] = &o;
+  std::vector<ReqFeature> plan;
+  auto sget = [](const JValue &o, const char *k) -> std::string { const JValue *v = o.get(k); return v && v->kind == JValue::Str ? v->str : ""; };
+  for (auto &name : S.model_features) {
+    auto it = by_name.find(name);
+    if (it == by_name.end()) continue;
+    const JValue &o = *it->second;
+    ReqFeature f;
+    f.name = name;
+    f.type = sget(o, "type");
+    f.scope = sget(o, "scope");
+    const std::string src = o.get("source") ? sget(o, "source") : sget(o, "field");
+    if (!src.empty()) split_field(src, f.src_event, f.src_field);
+    f.encode_index = sget(o, "encode") == "index";
+    if (const JValue *vals = o.get("values"))
+      if (vals->kind == JValue::Arr) for (auto &x : vals->arr) f.values.push_back(x.str);
+    if (f.type == "rate" && f.scope.rfind("ranking.", 0) == 0) f.rate_field = f.scope.substr(8);
+    if (f.type == "local_time") { std::string ev; split_field(sget(o, "source"), ev, f.lt_field); f.lt_parse = sget(o, "parse"); }
+    if (f.type == "field_match") {
+      std::string ev;
+      split_field(sget(o, "rankingField"), ev, f.rank_field);
+      const JValue &m = o.at("method");
+      f.mtype = sget(m, "type");
+      f.language = sget(m, "language");
+      if (const JValue *n = m.get("n")) f.n = (int)n->as_int();
+      if (const JValue *d = m.get("docs")) f.docs = d->as_double();
+      if (const JValue *tf = m.get("termfreq"))
+        if (tf->kind == JValue::Obj) for (auto &kv : tf->obj) f.termfreq[kv.first] = kv.second.as_double();
+    }
+    f.s_f64 = slot_of(S.in_req_f64, name);
+    f.s_u64 = slot_of(S.in_req_u64, name);
+    f.s_item = slot_of(S.in_item_f64, name);
+    f.s_tok = slot_of(S.in_req_tok, name);
+    for (size_t k = 0; k < S.in_req_vec.size(); k++)
+      if (S.in_req_vec[k].feature == name) { f.s_vec = (int)k; f.vec_off = S.in_req_vec[k].offset; f.vec_dim = S.in_req_vec[k].dim; }
+    auto c = S.col_of.find(name);
+    if (c != S.col_of.end()) f.dim = c->second.second;
+    plan.push_back(std::move(f));
+  }
+  return plan;
+}
+
+// StringFeature encoders on request-side values (StringFeature.scala:118-137)
+void encode_string(const ReqFeature &f, const std::vector<std::string> &vals, double *dst) {
+  auto index_of = [&](const std::string &v) -> int { for (size_t k = 0; k < f.values.size(); k++) if (f.values[k] == v) return (int)k; return -1; };
+  if (f.encode_index) {
+    const int ix = vals.empty() ? -1 : index_of(vals[0]);
+    dst[0] = ix >= 0 ? (double)(ix + 1) : 0.0;
+    return;
+  }
+  for (size_t k = 0; k < f.values.size(); k++) dst[k] = 0.0;
+  for (auto &v : vals) { const int ix = index_of(v); if (ix >= 0) dst[ix] = 1.0; }
+}
+
+// FieldMatcher.tokenize for the `whitespace` analyzer (Lucene WhitespaceTokenizer: split on whitespace only);
+// NgramMatcher.tokenize / TermMatcher.tokenize, then FieldMatcher.unique (sort + dedupe)
+std::vector<std::string> match_tokens(const ReqFeature &f, const std::string &text) {
+  if (f.language != "whitespace")
+    fail(MR_ERR_INVALID_ARG, "feature %s: language '%s' is a Lucene analyzer; the request must carry tokens.%s", f.name.c_str(),
+         f.language.c_str(), f.name.c_str());
+  std::vector<std::string> terms;
+  size_t i = 0;
+  auto is_ws = [](unsigned char c) { return c == ' ' || (c >= 9 && c <= 13) || (c >= 0x1c && c <= 0x1f); };
+  while (i < text.size()) {
+    while (i < text.size() && is_ws((unsigned char)text[i])) i++;
+    size_t j = i;
+    while (j < text.size() && !is_ws((unsigned char)text[j])) j++;
+    if (j > i) terms.push_back(text.substr(i, j - i));
+    i = j;
+  }
+  std::vector<std::string> out;
+  if (f.mtype == "ngram") {
+    for (auto &t : terms) {
+      // String.substring works on UTF-16 units; for BMP text a code point is one unit: walk UTF-8 code points
+      std::vector<size_t> cp;
+      for (size_t k = 0; k < t.size(); k++) if (((unsigned char)t[k] & 0xC0) != 0x80) cp.push_back(k);
+      cp.push_back(t.size());
+      const int L = (int)cp.size() - 1;
+      for (int j = 0; j + f.n <= L; j++) out.push_back(t.substr(cp[j], cp[j + f.n] - cp[j]));
+    }
+  } else {
+    out = terms;
+  }
+  std::sort(out.begin(), out.end());
+  out.erase(std::unique(out.begin(), out.end()), out.end());
+  return out;
+}
+
+double map_datetime(const std::string &parse, const ZonedTime &z) {  // LocalDateTimeFeature.scala:44-80
+  if (parse == "time_of_day") return (double)(z.hour * 3600 + z.minute * 60 + z.second) / 3600.0;
+  if (parse == "day_of_week") return (double)z.iso_weekday();
+  if (parse == "month_of_year") return (double)z.month;
+  if (parse == "year") return (double)z.year;
+  return (double)floor_div(z.epoch_ms, 1000);  // "second"
+}
+
+}  // namespace
+
+void decode_requests(const Schema &S, const char *json, size_t len, PackedRequests &P) {
+  JValue doc = JsonParser((const uint8_t *)json, len).parse();
+  std::vector<Event> events;
+  if (doc.kind == JValue::Arr) for (auto &o : doc.arr) events.push_back(decode_event(o));
+  else events.push_back(decode_event(doc));
+  const std::vector<ReqFeature> plan = build_plan(S);
+  const int R = (int)events.size();
+  const size_t nrf = S.in_req_f64.size(), nru = S.in_req_u64.size(), nrv = S.in_req_vec.size(), nif = S.in_item_f64.size(), ntk = S.in_req_tok.size();
+  const double kNaN = std::nan("");
+  P = PackedRequests{};
+  P.n_requests = R;
+  P.offsets.assign(R + 1, 0);
+  for (int r = 0; r < R; r++) P.offsets[r + 1] = P.offsets[r] + (int32_t)events[r].items.size();
+  const int N = P.total_items = P.offsets[R];
+  P.ids.assign(std::max(N, 1), 0);
+  P.users.assign(std::max(R, 1), 0);
+  P.sessions.assign(std::max(R, 1), 0);
+  P.req_f64.assign((size_t)std::max(R, 1) * std::max<size_t>(nrf, 1), kNaN);
+  P.req_u64.assign((size_t)std::max(R, 1) * std::max<size_t>(nru, 1), 0);
+  P.req_vec.assign((size_t)std::max(R, 1) * std::max(S.vec_stride, 1), 0.f);
+  P.req_vp.assign((size_t)std::max(R, 1) * std::max<size_t>(nrv, 1), 0);
+  P.item_f64.assign((size_t)std::max(N, 1) * std::max<size_t>(nif, 1), kNaN);
+  P.tok_off.assign(1, 0);
+  P.item_ids.reserve(N);
+  std::vector<std::vector<std::pair<uint64_t, double>>> tok((size_t)std::max<size_t>(ntk, 1));
+  bool any_item_f64 = false;
+  for (int r = 0; r < R; r++) {
+    const Event &q = events[r];
+    P.request_ids.push_back(q.id);
+    P.timestamps.push_back(q.ts);
+    if (q.has_user) P.users[r] = hash64(q.user.data(), q.user.size());
+    if (q.has_session) P.sessions[r] = hash64(q.session.data(), q.session.size());
+    auto last = [&](const std::string &n) -> const FieldVal * {  // RankingEvent.fieldsMap: last duplicate wins
+      const FieldVal *v = nullptr;
+      for (auto &f : q.fields) if (f.name == n) v = &f.v;
+      return v;
+    };
+    auto first = [&](const std::string &n) -> const FieldVal * {
+      for (auto &f : q.fields) if (f.name == n) return &f.v;
+      return nullptr;
+    };
+    for (auto &t : tok) t.clear();
+    for (auto &f : plan) {
+      if ((f.type == "number" || f.type == "word_count") && f.scope == "ranking" && f.s_f64 >= 0) {
+        const FieldVal *v = last(f.src_field);
+        double *dst = &P.req_f64[(size_t)r * nrf + f.s_f64];
+        if (f.type == "number" && v && v->is_num()) *dst = v->d;
+        if (f.type == "word_count" && v && v->is_str()) *dst = (double)token_count(v->s.data(), v->s.size());
+      } else if (f.type == "string" && f.src_event == "ranking" && f.s_f64 >= 0) {
+        const FieldVal *v = first(f.src_field);
+        std::vector<std::string> vals;
+        if (v && v->is_str()) vals.push_back(v->s);
+        else if (v && v->is_strlist()) vals = v->sl;
+        encode_string(f, vals, &P.req_f64[(size_t)r * nrf + f.s_f64]);
+      } else if (f.type == "rate" && !f.rate_field.empty() && f.s_u64 >= 0) {
+        const FieldVal *v = last(f.rate_field);
+        if (v && v->is_str()) P.req_u64[(size_t)r * nru + f.s_u64] = hash64(v->s.data(), v->s.size());
+      } else if (f.type == "item_age" && f.s_u64 >= 0) {
+        P.req_u64[(size_t)r * nru + f.s_u64] = (uint64_t)q.ts;
+      } else if (f.type == "local_time" && f.s_f64 >= 0) {
+        ZonedTime z;
+        bool ok = false;
+        if (f.lt_field == "timestamp") { z = utc_from_epoch_seconds(floor_div(q.ts, 1000)); ok = true; }
+        else if (const FieldVal *v = last(f.lt_field)) ok = v->is_str() && parse_iso_zoned(v->s, z);
+        if (ok) P.req_f64[(size_t)r * nrf + f.s_f64] = map_datetime(f.lt_parse, z);
+      } else if (f.type == "field_match" && f.s_tok >= 0) {
+        const FieldVal *qf = last(f.rank_field);
+        if (qf && qf->is_str()) {  // only a StringField is tokenized (FieldMatchFeature.scala:62-68)
+          std::vector<std::string> toks;
+          const JValue *given = q.tokens ? q.tokens->get(f.name.c_str()) : nullptr;
+          if (given && given->kind == JValue::Arr) for (auto &x : given->arr) toks.push_back(x.str);
+          else toks = match_tokens(f, qf->s);
+          for (auto &tk : toks) {
+            double w = 0.0;
+            if (f.mtype == "bm25") {  // BM25Matcher.score's termIDF (BM25Matcher.scala:26-27)
+              auto tf = f.termfreq.find(tk);
+              const double gtf = tf == f.termfreq.end() ? 0.0 : tf->second;
+              w = std::log(1.0 + (f.docs - gtf + 0.5) / (gtf + 0.5));
+            }
+            tok[f.s_tok].push_back({hash64(tk.data(), tk.size()), w});
+          }
+        }
+      } else if (f.type == "field_match" && f.s_vec >= 0) {
+        const JValue *emb = q.embeddings ? q.embeddings->get(f.name.c_str()) : nullptr;
+        const FieldVal *qf = last(f.rank_field);
+        if (emb && emb->kind == JValue::Arr && qf && (qf->is_str() || qf->is_strlist())) {
+          if ((int)emb->arr.size() != f.vec_dim)
+            fail(MR_ERR_INVALID_ARG, "feature %s: query embedding has %zu values, the schema says %d", f.name.c_str(), emb->arr.size(), f.vec_dim);
+          for (int k = 0; k < f.vec_dim; k++) P.req_vec[(size_t)r * S.vec_stride + f.vec_off + k] = (float)emb->arr[k].as_double();
+          P.req_vp[(size_t)r * nrv + f.s_vec] = 1;
+        }
+      }
+    }
+    for (size_t s = 0; s < ntk; s++) {
+      for (auto &hw : tok[s]) { P.tok_hash.push_back(hw.first); P.tok_w.push_back(hw.second); }
+      P.tok_off.push_back((int32_t)P.tok_hash.size());
+    }
+    for (size_t j = 0; j < q.items.size(); j++) {
+      const Item &it = q.items[j];
+      const size_t i = (size_t)P.offsets[r] + j;
+      P.ids[i] = hash64(it.id.data(), it.id.size());
+      P.item_ids.push_back(it.id);
+      for (auto &f : plan) {
+        if (f.s_item < 0) continue;
+        double *dst = &P.item_f64[i * nif + f.s_item];
+        if (f.type == "relevancy") {
+          for (auto &fl : it.fields)
+            if (fl.name == "relevancy") { if (fl.v.is_num()) { *dst = fl.v.d; any_item_f64 = true; } break; }  // the FIRST one decides
+        } else if (f.type == "number" && f.scope != "ranking") {
+          for (auto &fl : it.fields)
+            if (fl.name == f.src_field && fl.v.is_num()) { *dst = fl.v.d; any_item_f64 = true; break; }
+        } else if (f.type == "string" && f.src_event != "ranking") {
+          for (auto &fl : it.fields)
+            if (fl.name == f.src_field && (fl.v.is_str() || fl.v.is_strlist())) {
+              std::vector<std::string> vals = fl.v.is_str() ? std::vector<std::string>{fl.v.s} : fl.v.sl;
+              encode_string(f, vals, dst);
+              any_item_f64 = true;
+              break;
+            }
+        }
+      }
+    }
+  }
+  if (ntk) { P.tok_hash.push_back(0); P.tok_w.push_back(0.0); }
+  P.has_item_f64 = nif > 0 && any_item_f64;
+  mr_rank_batch &b = P.batch;
+  b.n_requests = R;
+  b.item_offsets = P.offsets.data();
+  b.item_ids = P.ids.data();
+  b.user_ids = P.users.data();
+  b.session_ids = P.sessions.data();
+  b.req_f64 = P.req_f64.data();
+  b.req_u64 = P.req_u64.data();
+  b.req_vec = P.req_vec.data();
+  b.req_vec_present = P.req_vp.data();
+  b.item_f64 = P.has_item_f64 ? P.item_f64.data() : nullptr;
+  b.req_tok_offsets = ntk ? P.tok_off.data() : nullptr;
+  b.req_tok_hashes = ntk ? P.tok_hash.data() : nullptr;
+  b.req_tok_weights = ntk ? P.tok_w.data() : nullptr;
+}
+
+}  // namespace mr

@@ -117,6 +117,7 @@ Schema parse_schema_json(const char *json, size_t len) {
   const JValue &jm = doc.at("model_features");
   if (jf.kind != JValue::Arr || jm.kind != JValue::Arr) fail(MR_ERR_PARSE, "schema: 'features' and 'model_features' must be arrays");
   Schema S;
+  S.source_json.assign(json, len);
   for (auto &v : jm.arr) {
     if (v.kind != JValue::Str) fail(MR_ERR_PARSE, "schema: model_features must be strings");
     S.model_features.push_back(v.str);

@@ -110,6 +110,7 @@ struct TableLayout {
 struct SideArray { int table; int dim; int slot; };
 
 struct Schema {
+  std::string source_json;                   // the document handed to mr_schema_create (request decoder re-reads the configs)
   std::vector<FeatureDef> features;          // config order
   std::vector<std::string> model_features;   // model order
   std::vector<Slot> slots;

@@ -325,6 +325,63 @@ def pack_feature_values(values: dict) -> bytes:
     return b"".join(out)
 
 
+class DecodedRequests:
+    """mr_requests_decode: RankingEvent JSON (one object or an array) -> the packed mr_rank_batch, natively."""
+
+    def __init__(self, mapping: "FeatureMapping", body):
+        data = body.encode("utf-8") if isinstance(body, str) else bytes(body)
+        self._h = C.c_void_p()
+        check(lib().mr_requests_decode(mapping._h, data, C.c_size_t(len(data)), C.byref(self._h)))
+        n = C.c_int32(0)
+        lib().mr_requests_batch.restype = C.POINTER(RankBatch)
+        self.batch = lib().mr_requests_batch(self._h, C.byref(n)).contents
+        self.total_items = n.value
+        self.n_requests = self.batch.n_requests
+        self.mapping = mapping
+
+    def arrays(self) -> dict:
+        """Copies of the packed arrays, shaped like FeatureMapping.pack_requests returns them."""
+        m, b, R, N = self.mapping, self.batch, self.n_requests, self.total_items
+
+        def arr(ptr, ctype, count, dtype, shape=None):
+            if not ptr or count == 0:
+                return None
+            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,)).astype(dtype).copy()
+            return a.reshape(shape) if shape else a
+
+        out = dict(n_requests=R, total_items=N, offsets=arr(b.item_offsets, C.c_int32, R + 1, np.int32),
+                   ids=arr(b.item_ids, C.c_uint64, max(N, 1), np.uint64),
+                   users=arr(b.user_ids, C.c_uint64, max(R, 1), np.uint64),
+                   sessions=arr(b.session_ids, C.c_uint64, max(R, 1), np.uint64),
+                   req_f64=arr(b.req_f64, C.c_double, max(R, 1) * max(m.n_req_f64, 1), np.float64, (max(R, 1), max(m.n_req_f64, 1))),
+                   req_u64=arr(b.req_u64, C.c_uint64, max(R, 1) * max(m.n_req_u64, 1), np.uint64, (max(R, 1), max(m.n_req_u64, 1))),
+                   req_vec=arr(b.req_vec, C.c_float, max(R, 1) * max(m.vec_stride, 1), np.float32, (max(R, 1), max(m.vec_stride, 1))),
+                   req_vp=arr(b.req_vec_present, C.c_uint8, max(R, 1) * max(m.n_req_vec, 1), np.uint8, (max(R, 1), max(m.n_req_vec, 1))),
+                   item_f64=arr(b.item_f64, C.c_double, max(N, 1) * max(m.n_item_f64, 1), np.float64, (max(N, 1), max(m.n_item_f64, 1))))
+        if m.n_req_tok:
+            n_off = R * m.n_req_tok + 1
+            out["tok_off"] = arr(b.req_tok_offsets, C.c_int32, n_off, np.int32)
+            n_tok = int(out["tok_off"][-1])
+            out["tok_hash"] = arr(b.req_tok_hashes, C.c_uint64, n_tok + 1, np.uint64)
+            out["tok_w"] = arr(b.req_tok_weights, C.c_double, n_tok + 1, np.float64)
+        return out
+
+    def item_id(self, index: int) -> str:
+        n = C.c_size_t(0)
+        lib().mr_requests_item_id.restype = C.c_void_p
+        p = lib().mr_requests_item_id(self._h, C.c_int32(index), C.byref(n))
+        return C.string_at(p, n.value).decode("utf-8")
+
+    def timestamp(self, request: int) -> int:
+        lib().mr_requests_timestamp.restype = C.c_int64
+        return int(lib().mr_requests_timestamp(self._h, C.c_int32(request)))
+
+    def free(self):
+        if self._h:
+            lib().mr_requests_free(self._h)
+            self._h = C.c_void_p()
+
+
 def transcode_feature_values(blob: bytes):
     """mr_feature_values_transcode: reference binary FeatureValue stream -> mr_state_upsert records (host
     only).  Returns (records bytes, n decoded, n unsupported, consumed bytes)."""
@@ -445,6 +502,19 @@ class Ranker:
             if want_order and model is not None else None
         feats = np.empty((max(N, 1), max(self.mapping.dim, 1)), dtype=np.float64) if want_features else None
         check(lib().mr_rank(self.state._h, model._h if model is not None else None, C.byref(b),
+                            C.c_void_p(scores.ctypes.data),
+                            C.c_void_p(order.ctypes.data) if order is not None else None,
+                            C.c_void_p(feats.ctypes.data) if feats is not None else None))
+        return (scores[:N] if model is not None else None, order[:N] if order is not None else None,
+                feats[:N, :self.mapping.dim] if feats is not None else None)
+
+    def rank_decoded(self, dec: "DecodedRequests", model=None, want_order=True, want_features=False):
+        """mr_rank straight on the batch mr_requests_decode packed (no Python-side packing)."""
+        N = dec.total_items
+        scores = np.empty(max(N, 1), dtype=np.float64)
+        order = np.empty(max(N, 1), dtype=np.int32) if want_order and model is not None else None
+        feats = np.empty((max(N, 1), max(self.mapping.dim, 1)), dtype=np.float64) if want_features else None
+        check(lib().mr_rank(self.state._h, model._h if model is not None else None, C.byref(dec.batch),
                             C.c_void_p(scores.ctypes.data),
                             C.c_void_p(order.ctypes.data) if order is not None else None,
                             C.c_void_p(feats.ctypes.data) if feats is not None else None))

@@ -53,8 +53,8 @@ def decode_timestamp(v) -> int:
             d = _dt.datetime.fromisoformat(s2)
         except ValueError:
             d = None
-        if d is not None and d.tzinfo is not None:
-            return int(d.timestamp() * 1000)
+        if d is not None and d.tzinfo is not None:  # Instant.toEpochMilli: exact, truncated to the millisecond
+            return (d - _dt.datetime(1970, 1, 1, tzinfo=_dt.timezone.utc)) // _dt.timedelta(milliseconds=1)
     raise DecodingFailure(f"cannot decode timestamp {v!r}")
 
 
@@ -104,9 +104,16 @@ def decode_ranking_event(text: str) -> dict:
                 raise DecodingFailure("relevancy must be a number")
             fields = [("relevancy", float(rel))] + fields
         items.append(dict(id=it["id"], fields=fields, label=it.get("label")))
-    return dict(event="ranking", id=str(o["id"]), timestamp=decode_timestamp(o["timestamp"]),
-                user=o.get("user"), session=o.get("session"),
-                fields=[decode_field(f) for f in (o.get("fields") or [])], items=items)
+    for k in ("user", "session"):
+        if o.get(k) is not None and not isinstance(o[k], str):
+            raise DecodingFailure(f"'{k}' must be a string")
+    out = dict(event="ranking", id=str(o["id"]), timestamp=decode_timestamp(o["timestamp"]),
+               user=o.get("user"), session=o.get("session"),
+               fields=[decode_field(f) for f in (o.get("fields") or [])], items=items)
+    for k in ("embeddings", "tokens"):  # extensions: what the caller's models / analyzers produced for this request
+        if isinstance(o.get(k), dict):
+            out[k] = o[k]
+    return out
 
 
 def _num(x: float):

@@ -1013,3 +1013,32 @@ def test_token_field_match_random_batches_and_slices(ctx):
     for r in rng.integers(0, len(reqs), 25):
         assert np.array_equal(order[offs[r]:offs[r + 1]], oracle.rank_order(ws[offs[r]:offs[r + 1]]))
     booster.free(); ds.free(); fm.free()
+
+
+def test_rank_from_natively_decoded_json(ctx):
+    """POST /rank bodies -> mr_requests_decode -> mr_rank, no Python packing in between: same features, scores
+    and order as the Python shim's path, which the other tests hold to the oracle (ranklens feature set)."""
+    import json
+
+    import metarank_b200 as mb
+    from metarank_b200 import features as F
+
+    feats, model = synth.ranklens_config()
+    state, item_ids, sessions = synth.ranklens_state(n_items=400, n_sessions=25, seed=21)
+    reqs = synth.ranklens_requests(item_ids, sessions, 30, 60, seed=22)
+    fm, ds, rk, _, _ = _device(ctx, feats, model, state)
+    bodies = []
+    for q in reqs:  # the request dicts of the oracle -> the JSON the reference's API takes
+        o = dict(id=q["id"], timestamp=q["timestamp"], user=q.get("user"), session=q.get("session"),
+                 fields=[dict(name=n, value=v) for n, v in q.get("fields", [])],
+                 items=[dict(id=it["id"], fields=[dict(name=n, value=v) for n, v in it.get("fields", [])]) for it in q["items"]])
+        bodies.append(o)
+    dec = F.DecodedRequests(fm, json.dumps(bodies))
+    arrays = fm.pack_requests(reqs)
+    booster = mb.LightGBMBooster(ctx, synth.lightgbm_model_text(80, fm.dim, seed=3, cat_features={7: 16}))
+    want = rk.rank_arrays(arrays, booster, want_order=True, want_features=True)
+    got = rk.rank_decoded(dec, booster, want_order=True, want_features=True)
+    assert _eq(got[2], want[2]) and _eq(got[0], want[0]) and np.array_equal(got[1], want[1])
+    for r, q in enumerate(reqs[:5]):
+        assert _eq(got[2][arrays["offsets"][r]:arrays["offsets"][r + 1]], fo.dense_matrix(fo.FeatureMapping(feats, model), q, state))
+    dec.free(); booster.free(); ds.free(); fm.free()

@@ -1,0 +1,164 @@
+"""Native request decoder (metarank_b200/csrc/request_codec.cpp, host only) against the Python
+shim, which the device tests hold to the oracle: JSON body -> decode_ranking_event -> FeatureMapping.pack_requests
+must give the same arrays as mr_requests_decode, value for value, on configs that use every request-side input."""
+import json
+
+import numpy as np
+import pytest
+
+from metarank_b200 import _capi, features as F
+from metarank_b200.rank_api import DecodingFailure, decode_ranking_event
+
+FEATS = [
+    dict(name="price", type="number", scope="item", source="item.price"),
+    dict(name="qlen", type="word_count", scope="ranking", source="ranking.query"),
+    dict(name="budget", type="number", scope="ranking", source="ranking.budget"),
+    dict(name="platform", type="string", scope="ranking", source="ranking.platform", encode="onehot", values=["ios", "android", "web"]),
+    dict(name="country", type="string", scope="ranking", source="ranking.country", encode="index", values=["de", "fr", "us"]),
+    dict(name="color", type="string", scope="item", source="item.color", encode="index", values=["red", "green", "blue"]),
+    dict(name="size", type="string", scope="item", source="item.size", encode="onehot", values=["s", "m", "l", "xl"]),
+    dict(name="ctr", type="rate", top="click", bottom="impression", scope="ranking.query", bucket="24h", periods=[7, 30]),
+    dict(name="rel", type="relevancy"),
+    dict(name="age", type="item_age", source="item.updated_at"),
+    dict(name="tod", type="local_time", source="ranking.timestamp", parse="time_of_day"),
+    dict(name="dow", type="local_time", source="ranking.local_ts", parse="day_of_week"),
+    dict(name="moy", type="local_time", source="ranking.local_ts", parse="month_of_year"),
+    dict(name="yr", type="local_time", source="ranking.local_ts", parse="year"),
+    dict(name="sec", type="local_time", source="ranking.local_ts", parse="second"),
+    dict(name="sim", type="field_match", rankingField="ranking.query", itemField="item.title", distance="cos",
+         method=dict(type="bi-encoder", dim=4)),
+    dict(name="ng", type="field_match", rankingField="ranking.query", itemField="item.title",
+         method=dict(type="ngram", n=3, language="whitespace")),
+    dict(name="tm", type="field_match", rankingField="ranking.query", itemField="item.title",
+         method=dict(type="term", language="en")),
+    dict(name="bm", type="field_match", rankingField="ranking.query", itemField="item.title",
+         method=dict(type="bm25", language="whitespace", docs=40, avgdl=3.5, termfreq={"red": 7, "shoes": 3, "кеды": 1})),
+]
+MODEL = [f["name"] for f in FEATS]
+WORDS = ["red", "shoes", "кеды", "x", "läuft", "😀ok", "blue-ish", "a"]
+
+
+def _random_body(rng, n_events):
+    def field_value(kind):
+        if kind == "str":
+            return " ".join(str(w) for w in rng.choice(WORDS, int(rng.integers(0, 4))))
+        if kind == "num":
+            return float(rng.integers(-5, 50)) if rng.random() < 0.5 else int(rng.integers(0, 9))
+        if kind == "bool":
+            return bool(rng.random() < 0.5)
+        if kind == "strlist":
+            return [str(w) for w in rng.choice(["ios", "web", "red", "blue", "xl", "m"], int(rng.integers(0, 3)))]
+        return [float(x) for x in rng.integers(0, 5, int(rng.integers(1, 3)))]
+
+    events = []
+    for e in range(n_events):
+        fields = []
+        for name, kinds in [("query", ["str", "str", "strlist", "num"]), ("budget", ["num", "num", "str", "bool"]),
+                            ("platform", ["str", "strlist", "num"]), ("country", ["str", "strlist"]),
+                            ("local_ts", ["iso", "iso", "str"])]:
+            for _ in range(int(rng.integers(0, 3))):  # absent, once, or duplicated (first/last-wins rules)
+                k = str(rng.choice(kinds))
+                if name in ("platform", "country") and k == "str":
+                    v = str(rng.choice(["ios", "web", "de", "us", "zz"]))
+                elif k == "iso":
+                    v = str(rng.choice(["2024-03-17T23:59:58+01:00", "2023-12-31T22:00:00.250-05:30[America/Nowhere]",
+                                        "1999-01-01T00:00Z", "2024-02-29T12:34:56,7Z", "2024-03-17T10:00:00", "17.03.2024"]))
+                else:
+                    v = field_value(k)
+                fields.append(dict(name=name, value=v))
+        items = []
+        for j in range(int(rng.integers(1, 6))):
+            it = dict(id=str(rng.choice(["p1", "p2", "товар", "p😀", f"i{j}"])))
+            fl = []
+            if rng.random() < 0.4:
+                it["relevancy"] = float(rng.integers(0, 4))
+            for name, kinds in [("price", ["num", "str"]), ("color", ["str", "strlist", "num"]), ("size", ["strlist", "str"]),
+                                ("relevancy", ["num", "str"])]:
+                if rng.random() < 0.35:
+                    k = str(rng.choice(kinds))
+                    v = str(rng.choice(["red", "blue", "xl", "zz"])) if k == "str" else field_value(k)
+                    fl.append(dict(name=name, value=v))
+            if fl or rng.random() < 0.3:
+                it["fields"] = fl
+            if rng.random() < 0.2:
+                it["label"] = "x"
+            items.append(it)
+        ts = rng.choice(["int", "str", "iso", "float"])
+        ev = dict(id=f"r{e}", items=items, fields=fields,
+                  timestamp={"int": 1710716400123, "str": " 1710716400123 ", "iso": "2024-03-17T23:00:00.123+00:00",
+                             "float": 1710716400000.0}[str(ts)])
+        if rng.random() < 0.7:
+            ev["user"] = str(rng.choice(["alice", "боб"]))
+        if rng.random() < 0.7:
+            ev["session"] = "s1"
+        if rng.random() < 0.3:
+            ev["user"] = None
+        if rng.random() < 0.7:
+            ev["embeddings"] = {"sim": [float(x) for x in rng.normal(size=4)]}
+        ev["tokens"] = {"tm": sorted({str(w) for w in rng.choice(WORDS, int(rng.integers(0, 4)))})}
+        events.append(ev)
+    return events
+
+
+def _python_arrays(fm, events):
+    reqs = [decode_ranking_event(json.dumps(e)) for e in events]
+    return fm.pack_requests(reqs), reqs
+
+
+def _same(a, b, what):
+    if a is None or b is None:
+        assert a is None and b is None, what
+        return
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape and a.dtype == b.dtype, (what, a.shape, b.shape, a.dtype, b.dtype)
+    if a.dtype.kind == "f":
+        assert np.array_equal(a, b, equal_nan=True), (what, a, b)
+    else:
+        assert np.array_equal(a, b), (what, a, b)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_native_decoder_packs_what_the_python_shim_packs(seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    fm = F.FeatureMapping(None, FEATS, MODEL)
+    events = _random_body(rng, int(rng.integers(1, 7)))
+    want, reqs = _python_arrays(fm, events)
+    body = json.dumps(events if len(events) > 1 or seed % 2 else events[0], ensure_ascii=bool(seed % 3))  # \\uXXXX escapes too
+    dec = F.DecodedRequests(fm, body)
+    got = dec.arrays()
+    assert got["n_requests"] == want["n_requests"] and got["total_items"] == want["total_items"]
+    for k in ["offsets", "ids", "users", "sessions", "req_f64", "req_u64", "req_vec", "req_vp", "item_f64", "tok_off"]:
+        _same(got[k], want[k], k)
+    n_tok = int(want["tok_off"][-1])
+    _same(got["tok_hash"][:n_tok], want["tok_hash"][:n_tok], "tok_hash")
+    _same(got["tok_w"][:n_tok], want["tok_w"][:n_tok], "tok_w")
+    i = 0
+    for r, q in enumerate(reqs):
+        assert dec.timestamp(r) == q["timestamp"]
+        for it in q["items"]:
+            assert dec.item_id(i) == it["id"]
+            i += 1
+    dec.free(); fm.free()
+
+
+def test_native_decoder_rejects_what_the_reference_decoder_rejects():
+    fm = F.FeatureMapping(None, FEATS, MODEL)
+    ok = dict(id="r", timestamp=1, items=[dict(id="p1")])
+    bad_bodies = [
+        "[1, 2]", "{}", json.dumps(dict(ok, items=[])), json.dumps(dict(id="r", items=[dict(id="p")])),
+        json.dumps(dict(ok, timestamp=True)), json.dumps(dict(ok, timestamp="yesterday")), json.dumps(dict(ok, timestamp=1.5)),
+        json.dumps(dict(ok, items=[dict(id=5)])), json.dumps(dict(ok, items=[dict(id="p", relevancy="high")])),
+        json.dumps(dict(ok, fields=[dict(name="q", value=None)])), json.dumps(dict(ok, fields=[dict(name="q", value={"a": 1})])),
+        json.dumps(dict(ok, fields=[dict(name="q", value=["a", 1])])), json.dumps(dict(ok, fields=[dict(value="x")])),
+        json.dumps(dict(ok, user=7)), "{not json",
+    ]
+    for body in bad_bodies:
+        with pytest.raises(_capi.MrError):
+            F.DecodedRequests(fm, body)
+        with pytest.raises((DecodingFailure, Exception)):
+            fm.pack_requests([decode_ranking_event(body)])
+    # a Lucene-analyzed field_match without caller-side tokens cannot be served natively: loud, not silent
+    with pytest.raises(_capi.MrError) as e:
+        F.DecodedRequests(fm, json.dumps(dict(ok, fields=[dict(name="query", value="red shoes")])))
+    assert "tokens" in str(e.value)
+    fm.free()
