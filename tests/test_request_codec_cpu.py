@@ -162,3 +162,43 @@ def test_native_decoder_rejects_what_the_reference_decoder_rejects():
         F.DecodedRequests(fm, json.dumps(dict(ok, fields=[dict(name="query", value="red shoes")])))
     assert "tokens" in str(e.value)
     fm.free()
+
+
+def test_native_decoder_on_the_reference_event_json_cases():
+    """T/model/EventJsonTest.scala:86-121 ("decode ranking": string timestamp, user / session, two string fields,
+    three items with the relevancy sugar) and :155-160 (timestamp as long / numeric string / ISO instant)."""
+    body = """{
+      "event": "ranking",
+      "id": "81f46c34-a4bb-469c-8708-f8127cd67d27",
+      "timestamp": "1599391467000",
+      "user": "user1",
+      "session": "session1",
+      "fields": [
+          {"name": "query", "value": "jeans"},
+          {"name": "source", "value": "search"}
+      ],
+      "items": [
+        {"id": "product3", "relevancy":  2.0},
+        {"id": "product1", "relevancy":  1.0},
+        {"id": "product2", "relevancy":  0.5}
+      ]
+    }"""
+    feats = [dict(name="rel", type="relevancy"),
+             dict(name="qwords", type="word_count", scope="ranking", source="ranking.query"),
+             dict(name="src", type="string", scope="ranking", source="ranking.source", encode="index", values=["ads", "search"])]
+    fm = F.FeatureMapping(None, feats, ["rel", "qwords", "src"])
+    dec = F.DecodedRequests(fm, body)
+    a = dec.arrays()
+    assert dec.timestamp(0) == 1599391467000
+    assert a["users"].tolist() == [F.hash64("user1")] and a["sessions"].tolist() == [F.hash64("session1")]
+    assert a["ids"].tolist() == [F.hash64(x) for x in ("product3", "product1", "product2")]
+    assert [dec.item_id(k) for k in range(3)] == ["product3", "product1", "product2"]
+    assert a["item_f64"][:, fm.input_slot(F.MR_IN_ITEM_F64, "rel")].tolist() == [2.0, 1.0, 0.5]
+    assert a["req_f64"][0, fm.input_slot(F.MR_IN_REQ_F64, "qwords")] == 1.0
+    assert a["req_f64"][0, fm.input_slot(F.MR_IN_REQ_F64, "src")] == 2.0   # "search" is the 2nd value: index + 1
+    dec.free()
+    for ts, want in [("123", 123), ('"123"', 123), ('"2022-06-22T11:21:39Z"', 1655896899000)]:
+        d = F.DecodedRequests(fm, '{"id": "r", "timestamp": %s, "items": [{"id": "p"}]}' % ts)
+        assert d.timestamp(0) == want
+        d.free()
+    fm.free()
