@@ -82,8 +82,11 @@ def decode_field(o) -> tuple:
 
 def decode_ranking_event(text: str) -> dict:
     """circe decode[RankingEvent] (the `event` discriminator is optional on this endpoint)."""
+    def _no_constants(name):  # NaN / Infinity are not JSON: circe's parser rejects them (T/model/FieldTest.scala:15-17)
+        raise DecodingFailure(f"{name} is not valid JSON")
+
     try:
-        o = json.loads(text)
+        o = json.loads(text, parse_constant=_no_constants)
     except json.JSONDecodeError as e:
         raise DecodingFailure(str(e)) from e
     if not isinstance(o, dict):

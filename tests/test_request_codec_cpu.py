@@ -151,6 +151,10 @@ def test_native_decoder_rejects_what_the_reference_decoder_rejects():
         json.dumps(dict(ok, fields=[dict(name="q", value=None)])), json.dumps(dict(ok, fields=[dict(name="q", value={"a": 1})])),
         json.dumps(dict(ok, fields=[dict(name="q", value=["a", 1])])), json.dumps(dict(ok, fields=[dict(value="x")])),
         json.dumps(dict(ok, user=7)), "{not json",
+        # T/model/FieldTest.scala:15-17,31-33,40-42: NaN literals and a list of booleans are decoding failures
+        '{"id": "r", "timestamp": 1, "items": [{"id": "p"}], "fields": [{"name": "f", "value": NaN}]}',
+        '{"id": "r", "timestamp": 1, "items": [{"id": "p"}], "fields": [{"name": "f", "value": [1, 2, 3, NaN]}]}',
+        json.dumps(dict(ok, fields=[dict(name="t", value=[True, False])])),
     ]
     for body in bad_bodies:
         with pytest.raises(_capi.MrError):
