@@ -50,10 +50,14 @@ Field decode_field(const JValue &o) {
     case JValue::Null: fail(MR_ERR_PARSE, "null value in field %s", f.name.c_str());
     case JValue::Bool: f.v.kind = FieldVal::Bool; f.v.b = v->b; break;
     case JValue::Str: f.v.kind = FieldVal::Str; f.v.s = v->str; break;
-    case JValue::Num: f.v.kind = FieldVal::Num; f.v.d = v->num; break;
+    case JValue::Num:
+      // the shared JSON reader tolerates NaN / Infinity tokens for XGBoost model files; in a request they are
+      // not JSON and circe rejects them (T/model/FieldTest.scala:15-17)
+      if (!std::isfinite(v->num)) fail(MR_ERR_PARSE, "cannot decode field %s: not a JSON number", f.name.c_str());
+      f.v.kind = FieldVal::Num; f.v.d = v->num; break;
     case JValue::Arr: {
       bool all_str = true, all_num = true;
-      for (auto &x : v->arr) { all_str &= x.kind == JValue::Str; all_num &= x.kind == JValue::Num; }
+      for (auto &x : v->arr) { all_str &= x.kind == JValue::Str; all_num &= x.kind == JValue::Num && std::isfinite(x.num); }
       if (all_str) { f.v.kind = FieldVal::StrList; for (auto &x : v->arr) f.v.sl.push_back(x.str); }
       else if (all_num) { f.v.kind = FieldVal::NumList; for (auto &x : v->arr) f.v.dl.push_back(x.num); }
       else fail(MR_ERR_PARSE, "cannot decode field %s: got a mixed list", f.name.c_str());
@@ -231,7 +235,7 @@ Event decode_event(const JValue &o) {
     I.id = iid->str;
     if (const JValue *rel = it.get("relevancy")) {
       if (rel->kind != JValue::Null) {
-        if (rel->kind != JValue::Num) fail(MR_ERR_PARSE, "relevancy must be a number");
+        if (rel->kind != JValue::Num || !std::isfinite(rel->num)) fail(MR_ERR_PARSE, "relevancy must be a number");
         Field f; f.name = "relevancy"; f.v.kind = FieldVal::Num; f.v.d = rel->num;
         I.fields.push_back(f);
       }
