@@ -1042,3 +1042,45 @@ def test_rank_from_natively_decoded_json(ctx):
     for r, q in enumerate(reqs[:5]):
         assert _eq(got[2][arrays["offsets"][r]:arrays["offsets"][r + 1]], fo.dense_matrix(fo.FeatureMapping(feats, model), q, state))
     dec.free(); booster.free(); ds.free(); fm.free()
+
+
+def _json_body(q):
+    """An oracle request dict -> the JSON body the reference's API takes (plus the embeddings / tokens keys)."""
+    import json
+
+    def val(v):
+        if isinstance(v, np.ndarray):
+            return [float(x) for x in v]
+        if isinstance(v, (np.floating, np.integer)):
+            return float(v)
+        return v
+
+    o = dict(id=q["id"], timestamp=q["timestamp"], fields=[dict(name=n, value=val(v)) for n, v in q.get("fields", [])],
+             items=[dict(id=it["id"], fields=[dict(name=n, value=val(v)) for n, v in it.get("fields", [])]) for it in q["items"]])
+    for k in ("user", "session"):
+        if q.get(k) is not None:
+            o[k] = q[k]
+    if q.get("embeddings"):
+        o["embeddings"] = {k: [float(x) for x in v] for k, v in q["embeddings"].items()}
+    if q.get("tokens"):
+        o["tokens"] = q["tokens"]
+    return json.dumps(o)
+
+
+@pytest.mark.parametrize("case", G.CASES, ids=[c["name"] for c in G.CASES])
+def test_golden_vectors_through_the_native_request_decoder(ctx, case):
+    """The reference's golden vectors again, but the request travels as a JSON body through mr_requests_decode
+    (no Python packing): the assembled matrix must still be the oracle's, bit for bit."""
+    from metarank_b200 import features as F
+
+    mapping = fo.FeatureMapping(case["features"], case["model_features"])
+    state = fo.FeatureValueFlow(mapping, always_refresh=True).process(case["events"])
+    want = fo.dense_matrix(mapping, case["request"], state)
+    fm, ds, rk, _, _ = _device(ctx, case["features"], case["model_features"], state)
+    try:
+        dec = F.DecodedRequests(fm, _json_body(case["request"]))
+        _, _, got = rk.rank_decoded(dec, None, want_features=True)
+        assert _eq(got, want), (case["ref"], got, want)
+        dec.free()
+    finally:
+        ds.free(); fm.free()
