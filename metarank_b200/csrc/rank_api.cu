@@ -13,6 +13,7 @@
 using namespace mr;
 
 struct mr_schema {
+  std::shared_ptr<const RequestPlan> req_plan;  // for mr_requests_decode
   Schema s;
   mr_ctx *ctx = nullptr;
   DFeature *d_plan = nullptr;
@@ -247,6 +248,7 @@ mr_status mr_schema_create(mr_ctx *ctx, const char *json, size_t len, mr_schema 
     *out = nullptr;
     auto s = std::make_unique<mr_schema>();
     s->s = parse_schema_json(json, len);
+    s->req_plan = make_request_plan(s->s);
     s->ctx = ctx;
     if (ctx) {  // ctx may be NULL for host-only validation of a config
       MR_CUDA_CHECK(cudaSetDevice(ctx->device));
@@ -364,7 +366,7 @@ mr_status mr_requests_decode(const mr_schema *schema, const char *json, size_t l
     if (!schema || !json || !out) fail(MR_ERR_INVALID_ARG, "null argument");
     *out = nullptr;
     auto r = std::make_unique<mr_requests>();
-    decode_requests(schema->s, json, len, r->p);
+    decode_requests(schema->s, *schema->req_plan, json, len, r->p);
     *out = r.release();
   });
 }

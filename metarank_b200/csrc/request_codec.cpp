@@ -277,7 +277,7 @@ int slot_of(const std::vector<std::string> &v, const std::string &n) {
   return -1;
 }
 
-std::vector<ReqFeature> build_plan(const Schema &S) {
+std::vector<ReqFeature> build_features(const Schema &S) {
   JValue doc = JsonParser((const uint8_t *)S.source_json.data(), S.source_json.size()).parse();
   std::unordered_map<std::string, const JValue *> by_name;
   for (auto &o : doc.at("features").arr)
@@ -379,12 +379,22 @@ double map_datetime(const std::string &parse, const ZonedTime &z) {  // LocalDat
 
 }  // namespace
 
-void decode_requests(const Schema &S, const char *json, size_t len, PackedRequests &P) {
+struct RequestPlan {
+  std::vector<ReqFeature> features;
+};
+
+std::shared_ptr<const RequestPlan> make_request_plan(const Schema &S) {
+  auto p = std::make_shared<RequestPlan>();
+  p->features = build_features(S);
+  return p;
+}
+
+void decode_requests(const Schema &S, const RequestPlan &rp, const char *json, size_t len, PackedRequests &P) {
   JValue doc = JsonParser((const uint8_t *)json, len).parse();
   std::vector<Event> events;
   if (doc.kind == JValue::Arr) for (auto &o : doc.arr) events.push_back(decode_event(o));
   else events.push_back(decode_event(doc));
-  const std::vector<ReqFeature> plan = build_plan(S);
+  const std::vector<ReqFeature> &plan = rp.features;
   const int R = (int)events.size();
   const size_t nrf = S.in_req_f64.size(), nru = S.in_req_u64.size(), nrv = S.in_req_vec.size(), nif = S.in_item_f64.size(), ntk = S.in_req_tok.size();
   const double kNaN = std::nan("");

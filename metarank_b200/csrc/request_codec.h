@@ -3,6 +3,7 @@
 // S/model/Timestamp.scala) and the per-extractor reads of the request (the files under S/feature/).
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -30,8 +31,13 @@ struct PackedRequests {
   mr_rank_batch batch{};                 // views into the vectors above
 };
 
+// What the decoder needs to know about each model feature (source fields, encoders, matcher settings, input
+// slots), read once from the schema document.
+struct RequestPlan;
+std::shared_ptr<const RequestPlan> make_request_plan(const Schema &S);
+
 // json: one RankingEvent object or an array of them.  Throws mr::Error (MR_ERR_PARSE for a body the reference's
 // decoder rejects, MR_ERR_INVALID_ARG for inputs only this path needs, e.g. missing caller-side tokens).
-void decode_requests(const Schema &S, const char *json, size_t len, PackedRequests &out);
+void decode_requests(const Schema &S, const RequestPlan &plan, const char *json, size_t len, PackedRequests &out);
 
 }  // namespace mr
