@@ -154,6 +154,22 @@ class JsonParser {
     JValue v;
     v.kind = JValue::Num;
     v.is_int = is_int;
+    if (is_int && n <= 15) {
+      // short integers (ids, counts, timestamps): exact in every representation, no libc round trips
+      size_t k = (buf[0] == '-' || buf[0] == '+') ? 1 : 0;
+      bool plain = k < n;
+      int64_t acc = 0;
+      for (size_t j = k; j < n && plain; j++) {
+        if (buf[j] < '0' || buf[j] > '9') plain = false;
+        else acc = acc * 10 + (buf[j] - '0');
+      }
+      if (plain && !(buf[0] == '-' && acc == 0)) {  // "-0" keeps its sign through strtod
+        v.i64 = buf[0] == '-' ? -acc : acc;
+        v.num = (double)v.i64;
+        v.f32 = (float)v.i64;  // |i64| < 2^53: one rounding, same as strtof on the token
+        return v;
+      }
+    }
     char *end = nullptr;
     v.num = strtod(buf, &end);
     if (end == buf) bad("bad number");
@@ -198,7 +214,11 @@ class JsonParser {
         }
         p_++;
       } else {
-        s += (char)*p_++;
+        // bulk-copy the run up to the next quote or escape
+        const uint8_t *q = p_;
+        while (q < e_ && *q != '"' && *q != '\\') q++;
+        s.append((const char *)p_, (size_t)(q - p_));
+        p_ = q;
       }
     }
     if (p_ >= e_) bad("unterminated string");
