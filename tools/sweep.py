@@ -22,7 +22,7 @@ for name, kind, blob, F in cfgs:
     st = torch.cuda.current_stream().cuda_stream
     for chunk_kb in (16, 24):
         b.set_option("chunk_kb", chunk_kb)
-        for stages in (0,):
+        if True:
             for threads in [0] + list(range(320, 1025, 32)):
                 variant, ilp = 4, 1
                 b.set_option("threads", threads); b.set_option("variant", variant);
@@ -38,8 +38,8 @@ for name, kind, blob, F in cfgs:
                     e1.record(); torch.cuda.synchronize()
                     ms = e0.elapsed_time(e1) / 5
                     ok = np.array_equal(dO[:4096].cpu().numpy(), want)
-                    print(json.dumps(dict(cfg=name, chunk_kb=chunk_kb, nchunks=b.info().n_chunks, stages=stages, threads=threads,
+                    print(json.dumps(dict(cfg=name, chunk_kb=chunk_kb, nchunks=b.info().n_chunks, threads=threads,
                                           ms=round(ms, 3), Mitems_s=round(rows / ms / 1e3, 1), ok=bool(ok))), flush=True)
                 except Exception as ex:
-                    print("ERR", chunk_kb, stages, threads, ex, flush=True)
+                    print("ERR", chunk_kb, threads, ex, flush=True)
     b.free()
