@@ -68,6 +68,7 @@ class JsonParser {
     ws();
     return v;
   }
+  const uint8_t *pos() const { return p_; }  // after parse(): first byte behind the value and its trailing blanks
 
  private:
   const uint8_t *p_, *e_;

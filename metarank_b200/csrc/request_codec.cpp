@@ -38,36 +38,6 @@ struct FieldVal {
 };
 struct Field { std::string name; FieldVal v; };
 
-Field decode_field(const JValue &o) {
-  if (o.kind != JValue::Obj) fail(MR_ERR_PARSE, "field needs a string 'name'");
-  const JValue *n = o.get("name");
-  if (!n || n->kind != JValue::Str) fail(MR_ERR_PARSE, "field needs a string 'name'");
-  Field f;
-  f.name = n->str;
-  const JValue *v = o.get("value");
-  if (!v) fail(MR_ERR_PARSE, "field value not found");
-  switch (v->kind) {
-    case JValue::Null: fail(MR_ERR_PARSE, "null value in field %s", f.name.c_str());
-    case JValue::Bool: f.v.kind = FieldVal::Bool; f.v.b = v->b; break;
-    case JValue::Str: f.v.kind = FieldVal::Str; f.v.s = v->str; break;
-    case JValue::Num:
-      // the shared JSON reader tolerates NaN / Infinity tokens for XGBoost model files; in a request they are
-      // not JSON and circe rejects them (T/model/FieldTest.scala:15-17)
-      if (!std::isfinite(v->num)) fail(MR_ERR_PARSE, "cannot decode field %s: not a JSON number", f.name.c_str());
-      f.v.kind = FieldVal::Num; f.v.d = v->num; break;
-    case JValue::Arr: {
-      bool all_str = true, all_num = true;
-      for (auto &x : v->arr) { all_str &= x.kind == JValue::Str; all_num &= x.kind == JValue::Num && std::isfinite(x.num); }
-      if (all_str) { f.v.kind = FieldVal::StrList; for (auto &x : v->arr) f.v.sl.push_back(x.str); }
-      else if (all_num) { f.v.kind = FieldVal::NumList; for (auto &x : v->arr) f.v.dl.push_back(x.num); }
-      else fail(MR_ERR_PARSE, "cannot decode field %s: got a mixed list", f.name.c_str());
-      break;
-    }
-    default: fail(MR_ERR_PARSE, "cannot decode field %s: got object", f.name.c_str());
-  }
-  return f;
-}
-
 // days since 1970-01-01 of a proleptic Gregorian date, and back (H. Hinnant's civil algorithms)
 int64_t days_from_civil(int64_t y, unsigned m, unsigned d) {
   y -= m <= 2;
@@ -202,50 +172,285 @@ struct Event {
   std::string user, session;
   std::vector<Field> fields;
   std::vector<Item> items;
-  const JValue *embeddings = nullptr, *tokens = nullptr;  // extensions: caller-side model outputs / analyzers
+  JValue embeddings, tokens;  // extensions (kept as small DOMs): caller-side model outputs / analyzers
 };
 
-Event decode_event(const JValue &o) {
-  if (o.kind != JValue::Obj) fail(MR_ERR_PARSE, "ranking event must be a JSON object");
-  for (const char *k : {"id", "timestamp", "items"})
-    if (!o.get(k)) fail(MR_ERR_PARSE, "required field '%s' missing in JSON", k);
-  Event e;
-  const JValue &id = o.at("id");
-  if (id.kind == JValue::Str) e.id = id.str;
-  else if (id.kind == JValue::Num && id.is_int) e.id = std::to_string(id.i64);
-  else fail(MR_ERR_PARSE, "event id must be a string");
-  e.ts = decode_timestamp(o.at("timestamp"));
-  auto opt_str = [&](const char *k, bool &has, std::string &dst) {
-    const JValue *v = o.get(k);
-    if (!v || v->kind == JValue::Null) return;
-    if (v->kind != JValue::Str) fail(MR_ERR_PARSE, "'%s' must be a string", k);
-    has = true;
-    dst = v->str;
-  };
-  opt_str("user", e.has_user, e.user);
-  opt_str("session", e.has_session, e.session);
-  if (const JValue *f = o.get("fields"))
-    if (f->kind == JValue::Arr) for (auto &x : f->arr) e.fields.push_back(decode_field(x));
-  const JValue &items = o.at("items");
-  if (items.kind != JValue::Arr || items.arr.empty()) fail(MR_ERR_PARSE, "items must be a non-empty list");  // NonEmptyList
-  for (auto &it : items.arr) {
-    const JValue *iid = it.kind == JValue::Obj ? it.get("id") : nullptr;
-    if (!iid || iid->kind != JValue::Str) fail(MR_ERR_PARSE, "item needs a string 'id'");
-    Item I;
-    I.id = iid->str;
-    if (const JValue *rel = it.get("relevancy")) {
-      if (rel->kind != JValue::Null) {
-        if (rel->kind != JValue::Num || !std::isfinite(rel->num)) fail(MR_ERR_PARSE, "relevancy must be a number");
-        Field f; f.name = "relevancy"; f.v.kind = FieldVal::Num; f.v.d = rel->num;
-        I.fields.push_back(f);
+// The body is walked once with a small tokenizer: no DOM (building ~600 JSON values for a 100-item request was
+// 3/4 of the decoder's time), strings go straight into their destination, unknown keys are skipped in place.
+// Only the rare "embeddings" / "tokens" objects and the timestamp go through the shared JSON reader.
+struct Cur {
+  const uint8_t *p, *e;
+  [[noreturn]] void bad(const char *what) { fail(MR_ERR_PARSE, "json: %s", what); }
+  void ws() { while (p < e && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++; }
+  char peek() { ws(); return p < e ? (char)*p : '\0'; }
+  bool eat(char c) { ws(); if (p < e && *p == (uint8_t)c) { p++; return true; } return false; }
+  void expect(char c, const char *what) { if (!eat(c)) bad(what); }
+  bool lit(const char *w) {
+    const size_t n = strlen(w);
+    if ((size_t)(e - p) >= n && memcmp(p, w, n) == 0) { p += n; return true; }
+    return false;
+  }
+  static void utf8(std::string &out, unsigned cp) {
+    if (cp < 0x80) out += (char)cp;
+    else if (cp < 0x800) { out += (char)(0xC0 | (cp >> 6)); out += (char)(0x80 | (cp & 0x3F)); }
+    else if (cp < 0x10000) { out += (char)(0xE0 | (cp >> 12)); out += (char)(0x80 | ((cp >> 6) & 0x3F)); out += (char)(0x80 | (cp & 0x3F)); }
+    else { out += (char)(0xF0 | (cp >> 18)); out += (char)(0x80 | ((cp >> 12) & 0x3F)); out += (char)(0x80 | ((cp >> 6) & 0x3F)); out += (char)(0x80 | (cp & 0x3F)); }
+  }
+  unsigned hex4() {
+    if (e - p < 4) bad("bad \\u escape");
+    unsigned v = 0;
+    for (int k = 0; k < 4; k++) {
+      const uint8_t c = p[k];
+      v = v * 16 + (c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : 0);
+    }
+    p += 4;
+    return v;
+  }
+  // a JSON string into `out` (cleared first); the same escape rules as json.h (surrogate pairs joined)
+  void str(std::string &out) {
+    ws();
+    if (p >= e || *p != '"') bad("expected a string");
+    p++;
+    out.clear();
+    for (;;) {
+      const uint8_t *q = p;
+      while (q < e && *q != '"' && *q != '\\') q++;
+      out.append((const char *)p, (size_t)(q - p));
+      p = q;
+      if (p >= e) bad("unterminated string");
+      if (*p == '"') { p++; return; }
+      p++;  // backslash
+      if (p >= e) bad("unterminated string");
+      const char c = (char)*p++;
+      switch (c) {
+        case 'n': out += '\n'; break;
+        case 't': out += '\t'; break;
+        case 'r': out += '\r'; break;
+        case 'b': out += '\b'; break;
+        case 'f': out += '\f'; break;
+        case 'u': {
+          unsigned cp = hex4();
+          if (cp >= 0xD800 && cp <= 0xDBFF && e - p >= 6 && p[0] == '\\' && p[1] == 'u') {
+            const uint8_t *save = p;
+            p += 2;
+            const unsigned lo = hex4();
+            if (lo >= 0xDC00 && lo <= 0xDFFF) cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+            else p = save;
+          }
+          utf8(out, cp);
+          break;
+        }
+        default: out += c;  // \" \\ \/ and anything else: the character itself
       }
     }
-    if (const JValue *f = it.get("fields"))
-      if (f->kind == JValue::Arr) for (auto &x : f->arr) I.fields.push_back(decode_field(x));
-    e.items.push_back(std::move(I));
   }
-  e.embeddings = o.get("embeddings");
-  e.tokens = o.get("tokens");
+  // a number token (finite JSON numbers only: NaN / Infinity are not JSON here)
+  void number(double &d, bool &is_int, int64_t &i64) {
+    ws();
+    char buf[64];
+    size_t n = 0;
+    is_int = true;
+    while (p < e && n < sizeof(buf) - 1) {
+      const char c = (char)*p;
+      if ((c >= '0' && c <= '9') || c == '-' || c == '+') {}
+      else if (c == '.' || c == 'e' || c == 'E') is_int = false;
+      else break;
+      buf[n++] = c;
+      p++;
+    }
+    if (n == 0) bad("unexpected character");
+    buf[n] = 0;
+    char *end = nullptr;
+    d = strtod(buf, &end);
+    if (end == buf || *end != 0) bad("bad number");
+    i64 = is_int ? strtoll(buf, nullptr, 10) : 0;
+  }
+  void skip() {  // any value, unparsed
+    switch (peek()) {
+      case '{': {
+        p++;
+        if (eat('}')) return;
+        std::string k;
+        for (;;) { str(k); expect(':', "expected ':'"); skip(); if (eat(',')) continue; expect('}', "expected ',' or '}'"); return; }
+      }
+      case '[': {
+        p++;
+        if (eat(']')) return;
+        for (;;) { skip(); if (eat(',')) continue; expect(']', "expected ',' or ']'"); return; }
+      }
+      case '"': { std::string s; str(s); return; }
+      case 't': if (!lit("true")) bad("bad literal"); return;
+      case 'f': if (!lit("false")) bad("bad literal"); return;
+      case 'n': if (!lit("null")) bad("bad literal"); return;
+      default: { double d; bool ii; int64_t i; number(d, ii, i); return; }
+    }
+  }
+  JValue dom() {  // a whole value through the shared reader (rare keys only)
+    ws();
+    if (p >= e) bad("unexpected end of input");
+    JsonParser jp(p, (size_t)(e - p));
+    JValue v = jp.parse();
+    p = jp.pos();
+    return v;
+  }
+  template <class F> void object(F &&on_key, const char *what) {  // on_key(key) consumes the value
+    if (!eat('{')) fail(MR_ERR_PARSE, "%s", what);
+    if (eat('}')) return;
+    std::string k;
+    for (;;) {
+      str(k);
+      expect(':', "expected ':'");
+      on_key(k);
+      if (eat(',')) continue;
+      expect('}', "expected ',' or '}'");
+      return;
+    }
+  }
+  template <class F> void array(F &&on_elem) {  // caller checked peek() == '['
+    expect('[', "expected '['");
+    if (eat(']')) return;
+    for (;;) {
+      on_elem();
+      if (eat(',')) continue;
+      expect(']', "expected ',' or ']'");
+      return;
+    }
+  }
+};
+
+// the `value` of a Field (S/model/Field.scala:36-58)
+void stream_field_value(Cur &c, const std::string &name, FieldVal &v) {
+  switch (c.peek()) {
+    case 'n': fail(MR_ERR_PARSE, "null value in field %s", name.c_str());
+    case '{': fail(MR_ERR_PARSE, "cannot decode field %s: got object", name.c_str());
+    case '"': v.kind = FieldVal::Str; c.str(v.s); return;
+    case 't': if (!c.lit("true")) c.bad("bad literal"); v.kind = FieldVal::Bool; v.b = true; return;
+    case 'f': if (!c.lit("false")) c.bad("bad literal"); v.kind = FieldVal::Bool; v.b = false; return;
+    case '[': {
+      bool all_str = true, all_num = true;
+      std::string s;
+      c.array([&] {
+        const char k = c.peek();
+        if (k == '"') { c.str(s); v.sl.push_back(s); all_num = false; }
+        else if (k == '{' || k == '[' || k == 't' || k == 'f' || k == 'n') { c.skip(); all_str = all_num = false; }
+        else { double d; bool ii; int64_t i; c.number(d, ii, i); v.dl.push_back(d); all_str = false; }
+      });
+      if (all_str) { v.kind = FieldVal::StrList; v.dl.clear(); }
+      else if (all_num) { v.kind = FieldVal::NumList; v.sl.clear(); }
+      else fail(MR_ERR_PARSE, "cannot decode field %s: got a mixed list", name.c_str());
+      return;
+    }
+    default: {
+      bool ii; int64_t i;
+      c.number(v.d, ii, i);  // NaN / Infinity tokens are not numbers here (T/model/FieldTest.scala:15-17)
+      v.kind = FieldVal::Num;
+      return;
+    }
+  }
+}
+
+void stream_field(Cur &c, Field &f) {
+  bool has_name = false, has_value = false;
+  // "value" may precede "name": remember where it starts and decode it once the name is known
+  const uint8_t *value_at = nullptr;
+  c.object([&](const std::string &k) {
+    if (k == "name" && !has_name) {
+      if (c.peek() != '"') fail(MR_ERR_PARSE, "field needs a string 'name'");
+      c.str(f.name);
+      has_name = true;
+    } else if (k == "value" && !has_value) {
+      c.ws();
+      value_at = c.p;
+      c.skip();
+      has_value = true;
+    } else {
+      c.skip();
+    }
+  }, "field needs a string 'name'");
+  if (!has_name) fail(MR_ERR_PARSE, "field needs a string 'name'");
+  if (!has_value) fail(MR_ERR_PARSE, "field value not found");
+  Cur vc{value_at, c.e};
+  stream_field_value(vc, f.name, f.v);
+}
+
+void stream_fields(Cur &c, std::vector<Field> &out) {
+  if (c.peek() != '[') { c.skip(); return; }  // not a list: ignored
+  c.array([&] { out.emplace_back(); stream_field(c, out.back()); });
+}
+
+Event decode_event(Cur &c) {
+  Event e;
+  bool has_id = false, has_ts = false, has_items = false, seen_user = false, seen_session = false, has_fields = false;
+  c.object([&](const std::string &k) {
+    if (k == "id" && !has_id) {
+      if (c.peek() == '"') c.str(e.id);
+      else {
+        double d; bool ii; int64_t i;
+        c.number(d, ii, i);
+        if (!ii) fail(MR_ERR_PARSE, "event id must be a string");
+        e.id = std::to_string(i);
+      }
+      has_id = true;
+    } else if (k == "timestamp" && !has_ts) {
+      e.ts = decode_timestamp(c.dom());
+      has_ts = true;
+    } else if ((k == "user" && !seen_user) || (k == "session" && !seen_session)) {
+      const bool user = k == "user";
+      (user ? seen_user : seen_session) = true;
+      if (c.peek() == 'n') { if (!c.lit("null")) c.bad("bad literal"); return; }
+      if (c.peek() != '"') fail(MR_ERR_PARSE, "'%s' must be a string", k.c_str());
+      c.str(user ? e.user : e.session);
+      (user ? e.has_user : e.has_session) = true;
+    } else if (k == "fields" && !has_fields) {
+      has_fields = true;
+      stream_fields(c, e.fields);
+    } else if (k == "items" && !has_items) {
+      has_items = true;
+      if (c.peek() != '[') fail(MR_ERR_PARSE, "items must be a non-empty list");
+      c.array([&] {
+        e.items.emplace_back();
+        Item &I = e.items.back();
+        bool has_iid = false, seen_rel = false, has_rel = false, has_ifields = false;
+        double rel = 0;
+        c.object([&](const std::string &ik) {
+          if (ik == "id" && !has_iid) {
+            if (c.peek() != '"') fail(MR_ERR_PARSE, "item needs a string 'id'");
+            c.str(I.id);
+            has_iid = true;
+          } else if (ik == "relevancy" && !seen_rel) {
+            seen_rel = true;
+            const char pk = c.peek();
+            if (pk == 'n') { if (!c.lit("null")) c.bad("bad literal"); return; }
+            if (pk == '"' || pk == '{' || pk == '[' || pk == 't' || pk == 'f') fail(MR_ERR_PARSE, "relevancy must be a number");
+            bool ii; int64_t i;
+            c.number(rel, ii, i);
+            has_rel = true;
+          } else if (ik == "fields" && !has_ifields) {
+            has_ifields = true;
+            stream_fields(c, I.fields);
+          } else {
+            c.skip();  // label and anything else
+          }
+        }, "item needs a string 'id'");
+        if (!has_iid) fail(MR_ERR_PARSE, "item needs a string 'id'");
+        if (has_rel) {  // the sugar comes first (Event.scala:84-93)
+          Field f;
+          f.name = "relevancy"; f.v.kind = FieldVal::Num; f.v.d = rel;
+          I.fields.insert(I.fields.begin(), std::move(f));
+        }
+      });
+      if (e.items.empty()) fail(MR_ERR_PARSE, "items must be a non-empty list");  // NonEmptyList
+    } else if (k == "embeddings" && e.embeddings.kind == JValue::Null) {
+      e.embeddings = c.dom();
+    } else if (k == "tokens" && e.tokens.kind == JValue::Null) {
+      e.tokens = c.dom();
+    } else {
+      c.skip();
+    }
+  }, "ranking event must be a JSON object");
+  if (!has_id) fail(MR_ERR_PARSE, "required field 'id' missing in JSON");
+  if (!has_ts) fail(MR_ERR_PARSE, "required field 'timestamp' missing in JSON");
+  if (!has_items) fail(MR_ERR_PARSE, "required field 'items' missing in JSON");
   return e;
 }
 
@@ -390,10 +595,10 @@ std::shared_ptr<const RequestPlan> make_request_plan(const Schema &S) {
 }
 
 void decode_requests(const Schema &S, const RequestPlan &rp, const char *json, size_t len, PackedRequests &P) {
-  JValue doc = JsonParser((const uint8_t *)json, len).parse();
+  Cur c{(const uint8_t *)json, (const uint8_t *)json + len};
   std::vector<Event> events;
-  if (doc.kind == JValue::Arr) for (auto &o : doc.arr) events.push_back(decode_event(o));
-  else events.push_back(decode_event(doc));
+  if (c.peek() == '[') c.array([&] { events.push_back(decode_event(c)); });
+  else events.push_back(decode_event(c));
   const std::vector<ReqFeature> &plan = rp.features;
   const int R = (int)events.size();
   const size_t nrf = S.in_req_f64.size(), nru = S.in_req_u64.size(), nrv = S.in_req_vec.size(), nif = S.in_item_f64.size(), ntk = S.in_req_tok.size();
@@ -458,7 +663,7 @@ void decode_requests(const Schema &S, const RequestPlan &rp, const char *json, s
         const FieldVal *qf = last(f.rank_field);
         if (qf && qf->is_str()) {  // only a StringField is tokenized (FieldMatchFeature.scala:62-68)
           std::vector<std::string> toks;
-          const JValue *given = q.tokens ? q.tokens->get(f.name.c_str()) : nullptr;
+          const JValue *given = q.tokens.get(f.name.c_str());
           if (given && given->kind == JValue::Arr) for (auto &x : given->arr) toks.push_back(x.str);
           else toks = match_tokens(f, qf->s);
           for (auto &tk : toks) {
@@ -472,7 +677,7 @@ void decode_requests(const Schema &S, const RequestPlan &rp, const char *json, s
           }
         }
       } else if (f.type == "field_match" && f.s_vec >= 0) {
-        const JValue *emb = q.embeddings ? q.embeddings->get(f.name.c_str()) : nullptr;
+        const JValue *emb = q.embeddings.get(f.name.c_str());
         const FieldVal *qf = last(f.rank_field);
         if (emb && emb->kind == JValue::Arr && qf && (qf->is_str() || qf->is_strlist())) {
           if ((int)emb->arr.size() != f.vec_dim)
