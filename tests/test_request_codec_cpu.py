@@ -206,3 +206,24 @@ def test_native_decoder_on_the_reference_event_json_cases():
         assert d.timestamp(0) == want
         d.free()
     fm.free()
+
+
+def test_native_decoder_is_insensitive_to_key_order_whitespace_and_unknown_keys():
+    """`value` before `name`, items before fields, pretty-printing, nested unknown keys: same arrays."""
+    from metarank_b200 import synth
+
+    feats, model = synth.ranklens_config()
+    state, item_ids, sessions = synth.ranklens_state(n_items=200, n_sessions=10, seed=21)
+    reqs = synth.ranklens_requests(item_ids, sessions, 12, 30, seed=22)
+    fm = F.FeatureMapping(None, feats, model)
+    bodies = [dict(items=[dict(fields=[dict(value=v, name=n) for n, v in it.get("fields", [])], id=it["id"], label=1)
+                          for it in q["items"]],
+                   fields=[dict(value=v, extra={"a": [1, {"b": None}]}, name=n) for n, v in q.get("fields", [])],
+                   session=q.get("session"), user=q.get("user"), timestamp=str(q["timestamp"]), id=q["id"],
+                   event="ranking", unknown=[1, 2, {"x": 'y"z\\'}]) for q in reqs]
+    want = fm.pack_requests(reqs)
+    for text in (json.dumps(bodies, indent=3), json.dumps(bodies, separators=(",", ":"))):
+        got = F.DecodedRequests(fm, text).arrays()
+        for k in ["offsets", "ids", "users", "sessions", "req_f64", "req_u64", "item_f64"]:
+            _same(got[k], want[k], k)
+    fm.free()
