@@ -265,18 +265,19 @@ struct Cur {
     if (end == buf || *end != 0) bad("bad number");
     i64 = is_int ? strtoll(buf, nullptr, 10) : 0;
   }
-  void skip() {  // any value, unparsed
+  void skip(int depth = 0) {  // any value, unparsed
+    if (depth > 64) bad("nesting too deep");
     switch (peek()) {
       case '{': {
         p++;
         if (eat('}')) return;
         std::string k;
-        for (;;) { str(k); expect(':', "expected ':'"); skip(); if (eat(',')) continue; expect('}', "expected ',' or '}'"); return; }
+        for (;;) { str(k); expect(':', "expected ':'"); skip(depth + 1); if (eat(',')) continue; expect('}', "expected ',' or '}'"); return; }
       }
       case '[': {
         p++;
         if (eat(']')) return;
-        for (;;) { skip(); if (eat(',')) continue; expect(']', "expected ',' or ']'"); return; }
+        for (;;) { skip(depth + 1); if (eat(',')) continue; expect(']', "expected ',' or ']'"); return; }
       }
       case '"': { std::string s; str(s); return; }
       case 't': if (!lit("true")) bad("bad literal"); return;

@@ -227,3 +227,34 @@ def test_native_decoder_is_insensitive_to_key_order_whitespace_and_unknown_keys(
         for k in ["offsets", "ids", "users", "sessions", "req_f64", "req_u64", "item_f64"]:
             _same(got[k], want[k], k)
     fm.free()
+
+
+def test_native_decoder_survives_corrupted_bodies():
+    """Byte flips, truncations and hostile escapes end in MR_ERR_PARSE / MR_ERR_INVALID_ARG or a valid decode,
+    never in a crash or an out-of-bounds read."""
+    rng = np.random.Generator(np.random.PCG64(77))
+    fm = F.FeatureMapping(None, FEATS, MODEL)
+    base = json.dumps(_random_body(rng, 3), ensure_ascii=True).encode()
+    ok = err = 0
+    for it in range(3000):
+        b = bytearray(base)
+        for _ in range(int(rng.integers(1, 5))):
+            k = int(rng.integers(0, len(b)))
+            b[k] = int(rng.choice([rng.integers(0, 256), ord('"'), ord("\\"), ord("{"), ord("["), ord("u"), ord(",")]))
+        if rng.random() < 0.3:
+            b = b[:int(rng.integers(0, len(b)))]
+        try:
+            d = F.DecodedRequests(fm, bytes(b))
+            a = d.arrays()
+            assert a["offsets"][-1] == a["total_items"]
+            d.free()
+            ok += 1
+        except _capi.MrError:
+            err += 1
+    assert ok > 0 and err > 0
+    for tail in ['"\\u12', '"\\ud83d\\u', '"\\', '"abc', "[[[[[[[[", '{"id": "r", "timestamp": 1, "items": [{"id": "\\ud83d']:
+        with pytest.raises(_capi.MrError):
+            F.DecodedRequests(fm, '{"id": "r", "timestamp": 1, "items": [{"id": "p"}], "fields": [{"name": "q", "value": ' + tail)
+    with pytest.raises(_capi.MrError):  # a megabyte of '[' must not blow the stack
+        F.DecodedRequests(fm, '{"id": "r", "timestamp": 1, "items": [{"id": "p"}], "junk": ' + "[" * 1_000_000)
+    fm.free()
