@@ -73,6 +73,35 @@ void finalize(HostModel &m) {
   m.max_depth = 0;
   m.has_cat = m.has_zero_missing = false;
   for (auto &t : m.trees) {
+    // structure first: everything below (depth, packing, the kernels) walks child pointers without looking back
+    {
+      const int ni = (int)t.feat.size(), nl = (int)t.leaf.size();
+      if (t.left.size() != t.feat.size() || t.right.size() != t.feat.size() || t.flags.size() != t.feat.size() ||
+          t.thr.size() != t.feat.size())
+        fail(MR_ERR_PARSE, "tree arrays disagree in length");
+      if (nl < 1) fail(MR_ERR_PARSE, "a tree needs at least one leaf");
+      std::vector<uint8_t> seen_node(ni, 0), seen_leaf(nl, 0);
+      std::vector<int> st;
+      if (ni > 0) { st.push_back(0); seen_node[0] = 1; }
+      while (!st.empty()) {
+        const int n = st.back();
+        st.pop_back();
+        for (int c : {t.left[n], t.right[n]}) {
+          if (c >= 0) {
+            if (c >= ni) fail(MR_ERR_PARSE, "child index out of range");
+            if (seen_node[c]) fail(MR_ERR_PARSE, "tree node %d is reachable twice (cycle or shared subtree)", c);
+            seen_node[c] = 1;
+            st.push_back(c);
+          } else {
+            if (~c >= nl) fail(MR_ERR_PARSE, "child index out of range");
+            seen_leaf[~c] = 1;
+          }
+        }
+      }
+      for (int n = 0; n < ni; n++)  // unreachable nodes are never walked, but their pointers must still be sane
+        for (int c : {t.left[n], t.right[n]})
+          if (c >= 0 ? c >= ni : ~c >= nl) fail(MR_ERR_PARSE, "child index out of range");
+    }
     m.n_internal += (int64_t)t.feat.size();
     m.max_leaves = std::max<int>(m.max_leaves, (int)t.leaf.size());
     m.max_depth = std::max(m.max_depth, t.depth());

@@ -155,3 +155,45 @@ def test_ctypes_mirrors_match_the_header_layouts():
     assert out[0] == ctypes.sizeof(F.RankBatch)
     assert out[1:1 + len(fields)] == [getattr(F.RankBatch, n).offset for n in fields]
     assert out[-1] == ctypes.sizeof(F.StateInfo)
+
+
+@pytest.mark.timeout(120)
+def test_malformed_tree_structures_are_rejected_not_walked():
+    """A model whose child pointers leave the tree, form a cycle or share a subtree would be walked forever (or
+    out of bounds) by the host-side depth pass and by the kernels: the loader must refuse it.  Host only."""
+    import json
+
+    from metarank_b200 import _capi, synth
+    from metarank_b200 import booster as B
+
+    text = synth.lightgbm_model_text(3, 5, seed=1).decode()
+    assert B.inspect_model(0, text.encode()).n_trees == 3
+
+    def sub(prefix, fn):
+        out, done = [], False
+        for line in text.split("\n"):
+            if line.startswith(prefix) and not done:
+                k, v = line.split("=", 1)
+                line, done = k + "=" + " ".join(fn(v.split(" "))), True
+            out.append(line)
+        return "\n".join(out).encode()
+
+    for blob, what in [(sub("left_child=", lambda v: ["999"] + v[1:]), "out of range"),
+                       (sub("right_child=", lambda v: ["-999"] + v[1:]), "out of range"),
+                       (sub("left_child=", lambda v: ["0"] + v[1:]), "reachable twice"),          # self loop
+                       (sub("left_child=", lambda v: v[:1] + [v[0]] + v[2:]), "reachable twice"),  # shared subtree
+                       (sub("split_feature=", lambda v: ["77"] + v[1:]), "outside")]:
+        with pytest.raises(_capi.MrError) as e:
+            B.inspect_model(0, blob)
+        assert what in str(e.value), (what, str(e.value))
+    # XGBoost JSON: same checks after the node arrays are converted
+    doc = json.loads(synth.xgboost_model_json(3, 5, depth=3, seed=2))
+    tree = doc["learner"]["gradient_booster"]["model"]["trees"][0]
+    assert B.inspect_model(1, json.dumps(doc).encode()).n_trees == 3
+    for key, val, what in [("left_children", 0, "reachable twice"), ("right_children", 10_000, "out of range")]:
+        bad = json.loads(json.dumps(doc))
+        bad["learner"]["gradient_booster"]["model"]["trees"][0][key][0] = val
+        with pytest.raises(_capi.MrError) as e:
+            B.inspect_model(1, json.dumps(bad).encode())
+        assert what in str(e.value) or "range" in str(e.value), str(e.value)
+    assert len(tree["left_children"]) > 1
