@@ -197,3 +197,49 @@ def test_malformed_tree_structures_are_rejected_not_walked():
             B.inspect_model(1, json.dumps(bad).encode())
         assert what in str(e.value) or "range" in str(e.value), str(e.value)
     assert len(tree["left_children"]) > 1
+
+
+@pytest.mark.timeout(300)
+def test_parsers_survive_corrupted_models_and_schemas():
+    """Host-only fuzz: byte flips / truncations of model blobs (LightGBM text, XGBoost JSON and UBJSON) and of
+    schema documents end in an MrError or a clean parse — never a crash, a hang or an out-of-bounds read."""
+    import ctypes as C
+    import json
+
+    from metarank_b200 import _capi, synth
+    from metarank_b200 import booster as B
+
+    rng = np.random.Generator(np.random.PCG64(3))
+    blobs = [(0, synth.lightgbm_model_text(6, 5, seed=1, cat_features={2: 8})), (1, synth.xgboost_model_json(5, 5, depth=3, seed=2)),
+             (1, synth.xgboost_model_ubj(5, 5, depth=3, seed=2))]
+    ok = err = 0
+    for kind, base in blobs:
+        for _ in range(400):
+            b = bytearray(base)
+            for _ in range(int(rng.integers(1, 6))):
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+            if rng.random() < 0.3:
+                b = b[:int(rng.integers(0, len(b)))]
+            try:
+                B.inspect_model(kind, bytes(b))
+                ok += 1
+            except _capi.MrError:
+                err += 1
+    assert ok > 0 and err > 0
+    feats, model = synth.ranklens_config()
+    base = json.dumps({"features": feats, "model_features": model}).encode()
+    lib = _capi.lib()
+    ok = err = 0
+    for _ in range(600):
+        b = bytearray(base)
+        for _ in range(int(rng.integers(1, 5))):
+            b[int(rng.integers(0, len(b)))] = int(rng.choice([rng.integers(32, 127), ord('"'), ord("0"), ord("-"), ord("["), ord(":")]))
+        if rng.random() < 0.2:
+            b = b[:int(rng.integers(0, len(b)))]
+        h = C.c_void_p()
+        if lib.mr_schema_create(None, bytes(b), C.c_size_t(len(b)), C.byref(h)) == 0:
+            lib.mr_schema_free(h)
+            ok += 1
+        else:
+            err += 1
+    assert ok > 0 and err > 0
