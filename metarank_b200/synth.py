@@ -152,13 +152,21 @@ def lightgbm_model_text(n_trees: int, n_features: int, num_leaves: int = 16, max
     rng = np.random.Generator(np.random.PCG64(seed))
     kinds = column_kinds(n_features)
     cat_features = cat_features or {}
-    blocks = []
+    trees = []
     for t in range(n_trees):
         if stump_every and t % stump_every == stump_every - 1:
-            tr = _Tree([], [], [], [], [], [float(rng.standard_normal() * 0.01)], [0], [])
+            trees.append(_Tree([], [], [], [], [], [float(rng.standard_normal() * 0.01)], [0], []))
         else:
-            tr = _grow_lightgbm_tree(rng, n_features, kinds, num_leaves, max_depth, cat_features,
-                                     shrinkage, zero_missing)
+            trees.append(_grow_lightgbm_tree(rng, n_features, kinds, num_leaves, max_depth, cat_features,
+                                             shrinkage, zero_missing))
+    return lightgbm_text_from_trees(trees, n_features, shrinkage)
+
+
+def lightgbm_text_from_trees(trees: list, n_features: int, shrinkage: float = 0.1) -> bytes:
+    """LightGBM model text for explicit trees (`_Tree`: split_feature, threshold, decision_type, left_child,
+    right_child with ~leaf for leaves, leaf_value, cat_boundaries, cat_threshold)."""
+    blocks = []
+    for t, tr in enumerate(trees):
         nl = len(tr.leaf_value)
         n_cat = len(tr.cat_boundaries) - 1
         lines = [f"Tree={t}", f"num_leaves={nl}", f"num_cat={n_cat}"]

@@ -233,3 +233,52 @@ def test_c_oracle_agrees_with_independent_python_evaluator(seed):
     X7 = synth.feature_matrix(100, 7, seed=seed + 20)
     want = model_parse.predict_python(model_parse.parse_xgboost(xb), X7)
     assert np.array_equal(oracle.OracleBooster(1, xb).predictMat(X7, *X7.shape), want)
+
+
+def test_oracle_traversal_and_sum_against_an_independent_gbdt_library():
+    """The reference's scorer (LightGBM behind ltrlib) is not available here, so the GBDT oracle stays "parity
+    unpinned" against it.  What CAN be pinned is the part every GBDT predictor shares — `x <= threshold` goes
+    left, leaf values added in tree order in f64 — against an independent, widely used implementation that IS
+    in the image: scikit-learn's GradientBoostingRegressor.  Its trees are written out as a LightGBM model text
+    (first tree = the constant init prediction, leaf = learning_rate * value, same product sklearn forms) and the
+    oracle's predictions must equal `predict`'s bit for bit on float32-representable inputs (sklearn traverses
+    in float32).  LightGBM's own missing-value / categorical rules are NOT covered by this (no NaN support in
+    GradientBoostingRegressor)."""
+    sklearn_ensemble = pytest.importorskip("sklearn.ensemble")
+    from metarank_b200 import synth
+
+    rng = np.random.Generator(np.random.PCG64(12))
+    n_feat = 7
+    X = rng.normal(size=(900, n_feat)).astype(np.float32).astype(np.float64)
+    y = 2 * X[:, 0] + np.sin(3 * X[:, 1]) + 1.5 * (X[:, 2] > 0.3) - X[:, 3] * X[:, 4] + 0.1 * rng.normal(size=len(X))
+    gb = sklearn_ensemble.GradientBoostingRegressor(n_estimators=60, max_depth=5, learning_rate=0.1, subsample=0.8,
+                                                    random_state=0).fit(X, y)
+    lr = gb.learning_rate
+    trees = [synth._Tree([], [], [], [], [], [float(gb.init_.constant_[0, 0])], [0], [])]
+    for est in gb.estimators_[:, 0]:
+        t = est.tree_
+        internal = [i for i in range(t.node_count) if t.children_left[i] != -1]
+        leaves = [i for i in range(t.node_count) if t.children_left[i] == -1]
+        iid = {n: k for k, n in enumerate(internal)}
+        lid = {n: k for k, n in enumerate(leaves)}
+        ref = lambda c: iid[c] if c in iid else ~lid[c]  # noqa: E731
+        if not internal:
+            trees.append(synth._Tree([], [], [], [], [], [lr * float(t.value[0, 0, 0])], [0], []))
+            continue
+        trees.append(synth._Tree(
+            split_feature=[int(t.feature[n]) for n in internal], threshold=[float(t.threshold[n]) for n in internal],
+            decision_type=[2] * len(internal),  # numerical, default left, missing type None
+            left_child=[ref(int(t.children_left[n])) for n in internal],
+            right_child=[ref(int(t.children_right[n])) for n in internal],
+            leaf_value=[lr * float(t.value[n, 0, 0]) for n in leaves], cat_boundaries=[0], cat_threshold=[]))
+    blob = synth.lightgbm_text_from_trees(trees, n_feat, shrinkage=lr)
+    Xt = rng.normal(size=(4000, n_feat)).astype(np.float32).astype(np.float64)
+    Xt[:50] = X[:50]
+    thr = np.concatenate([np.asarray(t.threshold, dtype=np.float64) for t in trees if t.threshold])
+    Xt[50:50 + min(200, len(thr)), 0] = thr[:200].astype(np.float32)  # values at / next to thresholds
+    got = oracle.OracleBooster(0, blob).predictMat(np.ascontiguousarray(Xt), len(Xt), n_feat, threads=0)
+    want = gb.predict(Xt)
+    assert np.array_equal(got, want), float(np.max(np.abs(got - want)))
+    # and the independent Python evaluator of the same blob agrees as well
+    from oracle import model_parse as mp
+    assert np.array_equal(mp.predict_python(mp.parse_lightgbm_text(blob), Xt[:300]), want[:300])
