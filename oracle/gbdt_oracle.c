@@ -16,6 +16,10 @@
  * PARITY UNPINNED: the reference's own tests assert no score at this boundary
  * (SURVEY.md §8c), so this oracle is anchored on the libraries' documented
  * semantics and on hand-computed known-answer trees (tests/test_oracle_gbdt.py).
+ * The part all GBDT predictors share (x <= threshold goes left, leaves added in tree
+ * order in f64) is additionally held bit for bit to an independent implementation,
+ * scikit-learn's GradientBoostingRegressor, in the same test file; that does not pin
+ * LightGBM's missing-value / categorical rules or XGBoost's binary32 path.
  */
 #include <math.h>
 #include <stdint.h>
