@@ -18,8 +18,10 @@
  * semantics and on hand-computed known-answer trees (tests/test_oracle_gbdt.py).
  * The part all GBDT predictors share (x <= threshold goes left, leaves added in tree
  * order in f64) is additionally held bit for bit to an independent implementation,
- * scikit-learn's GradientBoostingRegressor, in the same test file; that does not pin
- * LightGBM's missing-value / categorical rules or XGBoost's binary32 path.
+ * scikit-learn's GradientBoostingRegressor, and the NaN rule of a node with missing
+ * type NaN (default_left decides) to HistGradientBoostingRegressor, in the same test
+ * file; that does not pin LightGBM's zero-as-missing / categorical rules or XGBoost's
+ * binary32 path.
  */
 #include <math.h>
 #include <stdint.h>

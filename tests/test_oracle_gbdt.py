@@ -282,3 +282,49 @@ def test_oracle_traversal_and_sum_against_an_independent_gbdt_library():
     # and the independent Python evaluator of the same blob agrees as well
     from oracle import model_parse as mp
     assert np.array_equal(mp.predict_python(mp.parse_lightgbm_text(blob), Xt[:300]), want[:300])
+
+
+def test_oracle_nan_routing_against_hist_gradient_boosting():
+    """Same idea for the missing-value rule: scikit-learn's HistGradientBoostingRegressor predicts on raw f64 values
+    with `x <= threshold` and a per-node `missing_go_to_left` for NaN — the semantics of a LightGBM node with
+    missing type NaN and the default-left bit.  Its trees, exported as LightGBM text (decision_type = NaN-missing
+    | default-left), must score bit-identically through the oracle on inputs with NaNs."""
+    sklearn_ensemble = pytest.importorskip("sklearn.ensemble")
+    from metarank_b200 import synth
+
+    rng = np.random.Generator(np.random.PCG64(21))
+    n_feat = 6
+    X = rng.normal(size=(3000, n_feat))
+    X[rng.random(X.shape) < 0.15] = np.nan
+    y = np.nan_to_num(X[:, 0]) * 2 + np.where(np.isnan(X[:, 1]), 1.0, np.sin(3 * np.nan_to_num(X[:, 1]))) + \
+        (np.nan_to_num(X[:, 2]) > 0.3) * 1.5 + 0.1 * rng.normal(size=len(X))
+    hgb = sklearn_ensemble.HistGradientBoostingRegressor(max_iter=50, max_leaf_nodes=15, learning_rate=0.1,
+                                                         early_stopping=False, random_state=0).fit(X, y)
+    trees = [synth._Tree([], [], [], [], [], [float(np.ravel(hgb._baseline_prediction)[0])], [0], [])]
+    n_left = n_right = 0
+    for (pred,) in hgb._predictors:
+        nodes = pred.nodes
+        internal = [i for i in range(len(nodes)) if not nodes[i]["is_leaf"]]
+        leaves = [i for i in range(len(nodes)) if nodes[i]["is_leaf"]]
+        iid = {n: k for k, n in enumerate(internal)}
+        lid = {n: k for k, n in enumerate(leaves)}
+        ref = lambda c: iid[c] if c in iid else ~lid[c]  # noqa: E731
+        assert not any(nodes[n]["is_categorical"] for n in internal)
+        mgl = [bool(nodes[n]["missing_go_to_left"]) for n in internal]
+        n_left += sum(mgl); n_right += len(mgl) - sum(mgl)
+        trees.append(synth._Tree(
+            split_feature=[int(nodes[n]["feature_idx"]) for n in internal],
+            threshold=[float(nodes[n]["num_threshold"]) for n in internal],
+            decision_type=[(2 << 2) | (2 if m else 0) for m in mgl],  # missing type NaN (+ default left)
+            left_child=[ref(int(nodes[n]["left"])) for n in internal],
+            right_child=[ref(int(nodes[n]["right"])) for n in internal],
+            leaf_value=[float(nodes[n]["value"]) for n in leaves], cat_boundaries=[0], cat_threshold=[]))
+    assert n_left > 0 and n_right > 0  # both NaN directions occur
+    blob = synth.lightgbm_text_from_trees(trees, n_feat, shrinkage=0.1)
+    Xt = rng.normal(size=(5000, n_feat))
+    Xt[rng.random(Xt.shape) < 0.2] = np.nan
+    thr = np.concatenate([np.asarray(t.threshold) for t in trees if t.threshold])
+    Xt[:min(300, len(thr)), 1] = thr[:300]  # exactly on thresholds
+    got = oracle.OracleBooster(0, blob).predictMat(np.ascontiguousarray(Xt), len(Xt), n_feat, threads=0)
+    want = hgb.predict(Xt)
+    assert np.array_equal(got, want), float(np.nanmax(np.abs(got - want)))
