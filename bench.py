@@ -1,23 +1,33 @@
 #!/usr/bin/env python
 """bench.py — items/sec reranked on B200 (BASELINE.json metric), one JSON line.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config C2|C3|C4|C5] [--no-extras]
 
-Workload (config.workload): BASELINE configs[1] — synthetic 100-item /rank requests,
-30 scalar features, 500-tree LightGBM-shaped LambdaMART.  One *step* = one pass of the
-hot path over a batch of REQUESTS_PER_STEP such requests (the batch's f64 feature
-matrix, 393 MB, is larger than the 126 MB L2, so no L2 flush is needed between steps).
+Configs are BASELINE.json's (SURVEY.md §8 shorthand); the default and headline is C2:
+  C2  100-item /rank requests, 30 scalar features, 500-tree LightGBM LambdaMART (16 384 requests per step)
+  C3  ranklens feature set (rate / window_count / interacted_with / diversity ...), 1000-item requests
+  C4  bi-encoder cosine (384-d) + 15 numbers, 256-item requests, 200-tree XGBoost
+  C5  ONE 10 000-item request, 64 features, 2000 trees, item-sharded over the N GPUs (mr_group_rank: the
+      scorer stores into every GPU's exchange buffer over NVLink, no collective call on the data path)
+One *step* = one pass of the hot path (lookup -> assemble -> score -> order) over one batch.
 
-  value      whole-job items/s with inputs resident in HBM (device-timed, max over ranks)
-  e2e        the same metric through the C ABI with HOST buffers (H2D/D2H inside the timer)
-  roofline   algorithmic bytes (SURVEY.md §8d B_item with the measured mean path) per launch
-             / kernel duration, against MEASURED_PEAKS.json's HBM copy bandwidth
-  cpu_baseline / --impl reference: the CPU oracle port of the booster arithmetic (the
-             reference's own scorer is a JNI jar that is not in this image) on host cores.
+  value        whole-job items/s with inputs resident in HBM (device-timed with CUDA events, max over ranks)
+  e2e          the same metric through the C ABI with HOST buffers (H2D/D2H inside the timer)
+  roofline     dominant kernel against the pipe that bounds it.  The GBDT scorer serves the ensemble from
+               shared memory (one TMA stage per chunk), so its bound is the SHARED-MEMORY pipe, not HBM:
+               achieved = wavefronts the walk needs (counted in-run by mr_model_walk_stats) x 128 B / kernel time,
+               peak = SMs x 128 B/clk x SM clock.  SURVEY.md 8(d)'s algorithmic-bytes figure is kept under
+               `algorithmic_gbs` (it exceeds the HBM peak by construction and is not a fraction of anything).
+  kernels      every kernel of the step, device time from the library's own per-launch events
+               (mr_profile_begin/end), with algorithmic HBM bytes and the HBM fraction for the HBM-bound ones
+  cpu_baseline / --impl reference: the CPU oracle port (the reference's own scorer is a JNI jar that is not in
+               this image) on the host cores, on a bounded sample of the same workload.
+  other_configs  (default C2 run only) short measurements of C3 / C4 / C5 with their own parity checks.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -30,25 +40,42 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ITEMS = 100
-FEATURES = 30
-TREES = 500
-REQUESTS_PER_STEP = 16384
-CATALOGUE = 2_000_000  # item table 496 MB, per-model code rows 168 MB: both larger than the 126 MB L2
-MODEL_SEED = 1234 + 2
-DATA_SEED = 42 + 2
 METRIC = "items/sec reranked (100-item req, 500-tree LambdaMART)"
 UNIT = "items/s"
+SM_COUNT = 148
+
+CONFIG = {
+    "C2": dict(items=100, features=30, trees=500, requests_per_step=16384, catalogue=2_000_000, model_seed=1236, data_seed=44,
+               workload="C2: 100-item /rank requests, 30 scalar (number) features gathered from a 2M-item device-resident "
+                        "state table, 500-tree LightGBM LambdaMART, scores + per-request ordering"),
+    "C3": dict(items=1000, features=24, trees=500, requests_per_step=256, catalogue=20_000, model_seed=1237, data_seed=45,
+               workload="C3: ranklens feature set (24 columns: numbers, string index, normalized + field-scoped rate, "
+                        "interacted_with over 4 fields, position, 5 diversity features, counts/windows), 1000-item requests, "
+                        "500-tree LightGBM with a categorical column"),
+    "C4": dict(items=256, features=16, trees=200, requests_per_step=512, catalogue=20_000, model_seed=1238, data_seed=77,
+               workload="C4: bi-encoder cosine (384-d item embeddings vs the request's query embedding) + 15 numbers, "
+                        "256-item requests, 200-tree depth-6 XGBoost (f32)"),
+    "C5": dict(items=10_000, features=64, trees=2000, requests_per_step=1, catalogue=50_000, model_seed=1239, data_seed=47,
+               workload="C5: ONE 10 000-item mega-request, 64 scalar features, 2000-tree LightGBM, items split over the "
+                        "GPUs (mr_group_rank: peer stores from the scoring kernel, device-side wait, full ordering on every GPU)"),
+}
 
 
-def _model_blob():
-    from metarank_b200 import synth
-    return synth.lightgbm_model_text(TREES, FEATURES, 16, 8, seed=MODEL_SEED)
-
-
-def _matrix(rows, seed):
-    from metarank_b200 import synth
-    return synth.feature_matrix(rows, FEATURES, seed=seed)
+def config_block(name, world):
+    c = CONFIG[name]
+    d = {"workload": c["workload"], "items_per_request": c["items"], "features": c["features"], "trees": c["trees"],
+         "catalogue_items": c["catalogue"], "requests_per_step": c["requests_per_step"]}
+    if name == "C5":
+        d["parallelism"] = "one request item-sharded over the GPUs (strong scaling), state + model replicated"
+        d["l2"] = "a single request is latency-bound; the 50 000-row table (26 MB) is L2-resident by nature of the workload"
+    else:
+        d["parallelism"] = "requests sharded over the GPUs, state + model replicated, no collective"
+        d["l2"] = ("every table a step gathers from at random is larger than the 126 MB L2 (2 M items: item rows 496 MB, per-model "
+                   "code rows 168 MB), and a step writes and re-reads 138 MB of codes plus 33 MB of ids / scores / order: no flush needed"
+                   if name == "C2" else
+                   "the step's working set (ids, codes, scores, order, per-request scratch) is rewritten every step; the item "
+                   "table is small by the nature of the config and stays L2-resident, as it would in production")
+    return d
 
 
 def _splitmix(x):
@@ -64,42 +91,42 @@ def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured"
+            j = json.load(open(p))
+            return float(j["hbm_gbs"]), float(j.get("sm_max_mhz", 1965.0)), "measured"
         except Exception:
             pass
-    return 6650.0, "fallback"
+    return 6650.0, 1965.0, "fallback"
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (and the repeat of it that follows)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
-        self.device = device
-        self.proc = None
-        self.lines = []
+        self.device, self.proc, self.lines = device, None, []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            time.sleep(0.3)  # nvidia-smi needs a moment before its first sample
         except Exception:
             self.proc = None
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t_begin, t_end):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -107,7 +134,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for t, ln in self.lines:
+            if t < t_begin or t > t_end + 0.05:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -119,12 +148,11 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window_s": t_end - t_begin, "reasons": sorted(reasons)}
 
 
 def _usable_cores():
-    """Threads the CPU arm can really use: os.cpu_count() capped by the affinity mask and the cgroup CPU quota
-    (a 128-CPU host behind a 16-CPU quota runs 128 OpenMP threads slower than 16)."""
+    """Threads the CPU arm can really use: os.cpu_count() capped by the affinity mask and the cgroup CPU quota."""
     n = os.cpu_count() or 1
     try:
         n = min(n, len(os.sched_getaffinity(0)))
@@ -145,56 +173,649 @@ def _usable_cores():
     return max(1, n)
 
 
-def _best_threads(ob, X, rows):
-    """The thread count (usable cores vs. every logical CPU) that scores a sample fastest: the CPU arm gets the
-    better of the two."""
-    cands = sorted({_usable_cores(), os.cpu_count() or 1})
-    best, best_dt = cands[0], None
-    n = min(rows, 20000)
-    for c in cands:
-        ob.predictMat(X[:n], n, FEATURES, threads=c)
+# ======================================================================================= workloads
+class Workload:
+    """One BASELINE config: synthetic state + model + one batch of requests, on this rank's GPU."""
+
+    name = ""
+    kind = 0  # booster kind
+
+    def __init__(self, ctx, rank, world):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.c = CONFIG[self.name]
+        self.R = self.c["requests_per_step"]
+        self.items = self.c["items"]
+        self.rows = self.R * self.items
+
+    # --- to be provided: build(), step(), e2e_step(), parity(), cpu_arm()
+    def total_rows(self):
+        return self.rows * self.world
+
+
+def _dev(arrays):
+    import torch
+    return {k: torch.from_numpy(np.ascontiguousarray(v).view(np.int64) if v.dtype == np.uint64 else np.ascontiguousarray(v)).cuda()
+            for k, v in arrays.items() if isinstance(v, np.ndarray)}
+
+
+class C2(Workload):
+    name = "C2"
+
+    def model_blob(self):
+        from metarank_b200 import synth
+        return synth.lightgbm_model_text(self.c["trees"], self.c["features"], 16, 8, seed=self.c["model_seed"])
+
+    def catalogue(self):
+        from metarank_b200 import synth
+        return synth.feature_matrix(self.c["catalogue"], self.c["features"], seed=self.c["data_seed"])
+
+    def picks(self, rank):
+        return np.random.Generator(np.random.PCG64(self.c["data_seed"] + 1000 + rank)).integers(0, self.c["catalogue"], self.rows)
+
+    def build(self):
+        import torch
+        import metarank_b200 as mb
+        from metarank_b200 import features as F
+        c = self.c
+        self.blob = self.model_blob()
+        self.booster = mb.LightGBMBooster(self.ctx, self.blob, n_features=c["features"])
+        for kv in filter(None, os.environ.get("MR_BENCH_OPTS", "").split(",")):  # tuning aid: "chunk_kb=24,threads=448"
+            key, val = kv.split("=")
+            self.booster.set_option(key, int(val))
+        names = [f"f{j}" for j in range(c["features"])]
+        feats = [dict(name=n, type="number", scope="item", source=f"metadata.{n}") for n in names]
+        self.mapping = F.FeatureMapping(self.ctx, feats, names)
+        self.state = F.DeviceState(self.ctx, self.mapping)
+        self.cat = self.catalogue()  # same column recipe as SURVEY.md 8d (5 % NaN = missing state)
+        self.item_ids = _splitmix(np.arange(1, c["catalogue"] + 1, dtype=np.uint64))
         t0 = time.perf_counter()
-        ob.predictMat(X[:n], n, FEATURES, threads=c)
-        dt = time.perf_counter() - t0
-        if best_dt is None or dt < best_dt:
-            best, best_dt = c, dt
-    return best
+        for j0 in range(0, c["features"], 5):
+            self.state.put_packed(F.pack_number_columns(names[j0:j0 + 5], self.item_ids, self.cat[:, j0:j0 + 5]))
+        self.state.flush()
+        self.upload_s = time.perf_counter() - t0
+        self.pick = self.picks(self.rank)  # every rank ranks its own requests
+        self.ids_host = self.item_ids[self.pick]
+        self.offs_host = (np.arange(self.R + 1, dtype=np.int32) * self.items).astype(np.int32)
+        self.d_ids = torch.from_numpy(self.ids_host.view(np.int64)).cuda()
+        self.d_offs = torch.from_numpy(self.offs_host).cuda()
+        self.d_out = torch.empty(self.rows, dtype=torch.float64, device="cuda")
+        self.d_order = torch.empty(self.rows, dtype=torch.int32, device="cuda")
+        self.d_feat = None
+        self.stream = torch.cuda.current_stream().cuda_stream
+        self.rk = F.Ranker(self.mapping, self.state)
+        self.h2d = int(self.ids_host.nbytes + self.offs_host.nbytes + 2 * self.R * 8)
+        self.d2h = self.rows * 12
+
+    def step(self, explain=False):
+        import torch
+        from metarank_b200 import features as F
+        if explain and self.d_feat is None:
+            self.d_feat = torch.empty(self.rows * self.c["features"], dtype=torch.float64, device="cuda")
+        F.rank_device(self.state, self.booster, self.R, self.rows, self.d_offs.data_ptr(), self.d_ids.data_ptr(),
+                      self.d_out.data_ptr(), self.d_order.data_ptr(), self.d_feat.data_ptr() if explain else 0, self.stream,
+                      max_items=self.items)
+
+    def status(self):
+        from metarank_b200 import features as F
+        F.rank_device_status(self.state, self.stream)
+
+    def e2e_prepare(self):
+        import torch
+        R, rows = self.R, self.rows
+        # page-locked request/response buffers (what a JVM gets from a registered direct ByteBuffer): DMA'd in place
+        self.ids_pin = torch.from_numpy(self.ids_host.view(np.int64)).pin_memory()
+        self.sc_pin = torch.empty(rows, dtype=torch.float64).pin_memory()
+        self.ord_pin = torch.empty(rows, dtype=torch.int32).pin_memory()
+        self.arrays = dict(offsets=self.offs_host, ids=self.ids_pin.numpy().view(np.uint64), users=np.zeros(R, dtype=np.uint64),
+                           sessions=np.zeros(R, dtype=np.uint64), req_f64=np.zeros((R, 1)), req_u64=np.zeros((R, 1), dtype=np.uint64),
+                           req_vec=np.zeros((R, 1), dtype=np.float32), req_vp=np.zeros((R, 1), dtype=np.uint8), item_f64=None,
+                           n_requests=R, total_items=rows)
+
+    def e2e_step(self):
+        return self.rk.rank_arrays(self.arrays, self.booster, want_order=True, out_scores=self.sc_pin.numpy(),
+                                   out_order=self.ord_pin.numpy())[:2]
+
+    def parity(self, n_chk=20):
+        """oracle on the first n_chk requests: assembled features, scores, order — all bit for bit."""
+        from oracle import oracle
+        self.step(explain=True)
+        self.status()
+        n = n_chk * self.items
+        got = self.d_out[:n].cpu().numpy()
+        got_order = self.d_order[:n].cpu().numpy()
+        got_feat = self.d_feat[: n * self.c["features"]].cpu().numpy().reshape(-1, self.c["features"])
+        ob = oracle.OracleBooster(0, self.blob)
+        want_feat = self.cat[self.pick[:n]]  # the oracle's assembly of `number` features is the stored scalar
+        want = ob.predictMat(want_feat, n, self.c["features"])
+        order_ok = all(np.array_equal(got_order[i * self.items:(i + 1) * self.items],
+                                      oracle.rank_order(want[i * self.items:(i + 1) * self.items])) for i in range(n_chk))
+        self._parity_ref = (got, got_order)
+        return {"features_bit_identical": bool(np.array_equal(got_feat, want_feat, equal_nan=True)),
+                "scores_bit_identical": bool(np.array_equal(got, want)), "ordering_identical": bool(order_ok),
+                "checked_items": n}
+
+    def latency(self):
+        one = dict(self.arrays, offsets=self.offs_host[:2].copy(), ids=self.ids_host[:self.items].copy(), n_requests=1,
+                   total_items=self.items)
+        for _ in range(20):
+            self.rk.rank_arrays(one, self.booster, want_order=True)
+        ts = []
+        for _ in range(300):
+            a = time.perf_counter()
+            self.rk.rank_arrays(one, self.booster, want_order=True)
+            ts.append(time.perf_counter() - a)
+        return {"p50_ms": float(np.percentile(ts, 50) * 1e3), "p99_ms": float(np.percentile(ts, 99) * 1e3),
+                "what": "mr_rank, 1 request x 100 items: id hashes in -> scores + order out, host buffers, via ctypes"}
+
+    # --- CPU arm (oracle port): parallel row gather + C oracle scorer + per-request ordering
+    def cpu_setup(self):
+        from oracle import oracle
+        self.ob = oracle.OracleBooster(0, self.model_blob())
+        if not hasattr(self, "cat"):
+            self.cat = self.catalogue()
+        self.cpu_pick = self.picks(0)
+
+    def cpu_run(self, n_requests, threads):
+        from oracle import oracle
+        rows = n_requests * self.items
+        X = oracle.gather_rows(self.cat, self.cpu_pick[:rows], threads)
+        sc = self.ob.predictMat(X, rows, self.c["features"], threads=threads)
+        oracle.rank_order_batch(sc, (np.arange(n_requests + 1, dtype=np.int32) * self.items).astype(np.int32), threads)
+        return rows
+
+    cpu_what = "parallel row gather of the stored scalars + C oracle scorer (OpenMP over rows) + per-request stable ordering"
+
+    def free(self):
+        self.state.free(); self.mapping.free(); self.booster.free()
+
+
+class C5(C2):
+    """One mega-request; `value` = items of the request / its latency.  world > 1: mr_group_rank."""
+    name = "C5"
+
+    def model_blob(self):
+        from metarank_b200 import synth
+        return synth.lightgbm_model_text(self.c["trees"], self.c["features"], seed=self.c["model_seed"])
+
+    def picks(self, rank):  # the SAME request on every rank
+        return np.random.Generator(np.random.PCG64(self.c["data_seed"] + 1)).choice(self.c["catalogue"], self.rows, replace=False)
+
+    def total_rows(self):
+        return self.rows  # strong scaling: the job is one request however many GPUs serve it
+
+    def build(self):
+        super().build()
+        from metarank_b200 import sharded
+        self.group = sharded.Group(self.ctx, self.rank, self.world, self.rows)
+        self.group.connect_distributed()
+
+    def step(self, explain=False):
+        import torch
+        from metarank_b200 import features as F
+        if explain:
+            if self.d_feat is None:
+                self.d_feat = torch.empty(self.rows * self.c["features"], dtype=torch.float64, device="cuda")
+            F.rank_device(self.state, None, 1, self.rows, self.d_offs.data_ptr(), self.d_ids.data_ptr(), 0, 0,
+                          self.d_feat.data_ptr(), self.stream, max_items=self.rows)
+        self.group.rank_device(self.state, self.booster, self.rows, self.d_offs.data_ptr(), self.d_ids.data_ptr(),
+                               self.d_out.data_ptr(), self.d_order.data_ptr(), self.stream)
+
+    def e2e_step(self):
+        return self.group.rank_arrays(self.state, self.booster, self.arrays)
+
+    def latency(self):
+        ts = []
+        for _ in range(5):
+            self.e2e_step()
+        for _ in range(50):
+            a = time.perf_counter()
+            self.e2e_step()
+            ts.append(time.perf_counter() - a)
+        return {"p50_ms": float(np.percentile(ts, 50) * 1e3), "p99_ms": float(np.percentile(ts, 99) * 1e3),
+                "what": f"mr_group_rank on {self.world} GPU(s), one 10 000-item request: id hashes in -> scores + order out, host buffers"}
+
+    def parity(self, n_chk=1):
+        from oracle import oracle
+        self.step(explain=True)
+        self.status()
+        got = self.d_out.cpu().numpy()
+        got_order = self.d_order.cpu().numpy()
+        got_feat = self.d_feat.cpu().numpy().reshape(-1, self.c["features"])
+        want_feat = self.cat[self.pick]
+        want = oracle.OracleBooster(0, self.blob).predictMat(want_feat, self.rows, self.c["features"], threads=_usable_cores())
+        self._parity_ref = (got, got_order)
+        return {"features_bit_identical": bool(np.array_equal(got_feat, want_feat, equal_nan=True)),
+                "scores_bit_identical": bool(np.array_equal(got, want)),
+                "ordering_identical": bool(np.array_equal(got_order, oracle.rank_order(want))), "checked_items": self.rows}
+
+    def free(self):
+        self.group.free()
+        super().free()
+
+
+class GenericWorkload(Workload):
+    """C3 / C4: requests as RankingEvent dicts -> FeatureMapping.pack_requests -> mr_rank_device."""
+
+    def finish_build(self, feats, model, state, reqs, blob, kind):
+        import torch
+        import metarank_b200 as mb
+        from metarank_b200 import features as F
+        self.feats, self.model_names, self.state_dict, self.reqs, self.blob, self.kind = feats, model, state, reqs, blob, kind
+        self.mapping = F.FeatureMapping(self.ctx, feats, model)
+        self.state = F.DeviceState(self.ctx, self.mapping)
+        t0 = time.perf_counter()
+        self.state.put(state)
+        self.state.flush()
+        self.upload_s = time.perf_counter() - t0
+        cls = mb.LightGBMBooster if kind == 0 else mb.XGBoostBooster
+        self.booster = cls(self.ctx, blob, n_features=self.mapping.dim)
+        self.rk = F.Ranker(self.mapping, self.state)
+        self.arrays = self.mapping.pack_requests(reqs)
+        self.rows = self.arrays["total_items"]
+        self.dev = _dev(self.arrays)
+        d = self.dev
+        self.d_out = torch.empty(self.rows, dtype=torch.float64, device="cuda")
+        self.d_order = torch.empty(self.rows, dtype=torch.int32, device="cuda")
+        self.stream = torch.cuda.current_stream().cuda_stream
+        opt = lambda k: d[k].data_ptr() if k in d else None  # noqa: E731
+        self.batch = F.RankBatch(self.arrays["n_requests"], d["offsets"].data_ptr(), d["ids"].data_ptr(), d["users"].data_ptr(),
+                                 d["sessions"].data_ptr(), d["req_f64"].data_ptr(), d["req_u64"].data_ptr(), d["req_vec"].data_ptr(),
+                                 d["req_vp"].data_ptr(), opt("item_f64"), opt("tok_off"), opt("tok_hash"), opt("tok_w"))
+        self.batch.max_items_per_request = self.items
+        self.h2d = int(sum(v.nbytes for v in self.arrays.values() if isinstance(v, np.ndarray)))
+        self.d2h = self.rows * 12
+
+    def step(self, explain=False):
+        import metarank_b200 as mb
+        mb._capi.check(mb._capi.lib().mr_rank_device(self.state._h, self.booster._h, C.byref(self.batch), C.c_int32(self.rows),
+                                                     C.c_void_p(self.d_out.data_ptr()), C.c_void_p(self.d_order.data_ptr()), None,
+                                                     C.c_void_p(self.stream)))
+
+    def status(self):
+        from metarank_b200 import features as F
+        F.rank_device_status(self.state, self.stream)
+
+    def e2e_prepare(self):
+        pass
+
+    def e2e_step(self):
+        return self.rk.rank_arrays(self.arrays, self.booster, want_order=True)[:2]
+
+    def parity(self, n_chk=2):
+        from oracle import features_oracle as fo, oracle
+        self.step()
+        self.status()
+        sc_d = self.d_out.cpu().numpy()
+        od_d = self.d_order.cpu().numpy()
+        mapping = fo.FeatureMapping(self.feats, self.model_names)
+        ob = oracle.OracleBooster(self.kind, self.blob)
+        offs = self.arrays["offsets"]
+        feats = self.rk.make_query(self.reqs[:n_chk])
+        f_ok = s_ok = o_ok = True
+        for r in range(n_chk):
+            want = fo.dense_matrix(mapping, self.reqs[r], self.state_dict)
+            ws = ob.predictMat(want, *want.shape)
+            f_ok &= bool(np.array_equal(feats[r], want, equal_nan=True))
+            s_ok &= bool(np.array_equal(sc_d[offs[r]:offs[r + 1]], ws))
+            o_ok &= bool(np.array_equal(od_d[offs[r]:offs[r + 1]], oracle.rank_order(ws)))
+        self._parity_ref = (sc_d[:offs[n_chk]], od_d[:offs[n_chk]])
+        return {"features_bit_identical": f_ok, "scores_bit_identical": s_ok, "ordering_identical": o_ok,
+                "checked_items": int(offs[n_chk])}
+
+    def latency(self):
+        return None
+
+    def cpu_setup(self):
+        from oracle import features_oracle as fo, oracle
+        self.make()  # host-side data only
+        self.o_mapping = fo.FeatureMapping(self.feats, self.model_names)
+        self.ob = oracle.OracleBooster(self.kind, self.blob)
+
+    def cpu_run(self, n_requests, threads):
+        from oracle import features_oracle as fo, oracle
+        rows = 0
+        for r in range(n_requests):
+            X = fo.dense_matrix(self.o_mapping, self.reqs[r % len(self.reqs)], self.state_dict)
+            sc = self.ob.predictMat(X, *X.shape, threads=threads)
+            oracle.rank_order(sc)
+            rows += X.shape[0]
+        return rows
+
+    cpu_what = ("feature oracle (pure-Python restatement of the extractors, one thread) + C oracle scorer (OpenMP over rows) "
+                "+ stable ordering")
+
+    def free(self):
+        self.state.free(); self.mapping.free(); self.booster.free()
+
+
+class C3(GenericWorkload):
+    name = "C3"
+
+    def make(self):
+        from metarank_b200 import synth
+        c = self.c
+        self.feats, self.model_names = synth.ranklens_config()
+        self.state_dict, item_ids, sessions = synth.ranklens_state(n_items=c["catalogue"], n_sessions=2000, seed=c["data_seed"])
+        self.reqs = synth.ranklens_requests(item_ids, sessions, c["requests_per_step"], c["items"], seed=c["data_seed"] + 1 + self.rank)
+        self.blob = synth.lightgbm_model_text(c["trees"], c["features"], seed=c["model_seed"], cat_features={7: 16})
+        self.kind = 0
+
+    def build(self):
+        self.make()
+        self.finish_build(self.feats, self.model_names, self.state_dict, self.reqs, self.blob, 0)
+
+
+class C4(GenericWorkload):
+    name = "C4"
+    DIM = 384
+
+    def make(self):
+        from metarank_b200 import synth
+        c = self.c
+        rng = np.random.Generator(np.random.PCG64(c["data_seed"]))
+        dim, n = self.DIM, c["catalogue"]
+        feats = [dict(name="sim", type="field_match", rankingField="ranking.query", itemField="item.title",
+                      method=dict(type="bi-encoder", dim=dim), distance="cos")]
+        feats += [dict(name=f"n{k}", type="number", scope="item", source=f"metadata.n{k}") for k in range(15)]
+        ids = [f"i{k}" for k in range(n)]
+        E = rng.standard_normal((n, dim)).astype(np.float32)
+        E /= np.linalg.norm(E, axis=1, keepdims=True)
+        nums = rng.standard_normal((n, 15))
+        state = {}
+        for i, it in enumerate(ids):
+            state[(("item", it), "sim")] = ("scalar", E[i].astype(np.float64))
+            for k in range(15):
+                state[(("item", it), f"n{k}")] = ("scalar", float(nums[i, k]))
+        rq = np.random.Generator(np.random.PCG64(c["data_seed"] + 1 + self.rank))
+        reqs = []
+        for r in range(c["requests_per_step"]):
+            pick = rq.choice(n, c["items"], replace=False)
+            reqs.append(dict(event="ranking", id=f"r{r}", timestamp=0, user=None, session=None, fields=[("query", "q")],
+                             embeddings={"sim": rq.standard_normal(dim).astype(np.float32)},
+                             items=[dict(id=ids[int(j)], fields=[]) for j in pick]))
+        self.feats, self.model_names, self.state_dict, self.reqs = feats, [f["name"] for f in feats], state, reqs
+        self.blob = synth.xgboost_model_json(c["trees"], c["features"], depth=6, seed=c["model_seed"])
+        self.kind = 1
+
+    def build(self):
+        self.make()
+        self.finish_build(self.feats, self.model_names, self.state_dict, self.reqs, self.blob, 1)
+
+
+WORKLOADS = {"C2": C2, "C3": C3, "C4": C4, "C5": C5}
+
+
+# ======================================================================================= measurement
+def device_time(w, steps, warmup, barrier, dist, world):
+    """W warm-up steps, then exactly K timed steps between barrier + synchronize; CUDA events; max over ranks."""
+    import torch
+    stream = torch.cuda.current_stream()
+    for _ in range(warmup):
+        w.step()
+    w.status()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.perf_counter()
+    e0.record(stream)
+    for _ in range(steps):
+        w.step()
+    e1.record(stream)
+    barrier()
+    t_end = time.perf_counter()
+    total_ms = e0.elapsed_time(e1)
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    rank_ms = [total_ms / steps]
+    if world > 1:
+        allt = torch.zeros(world, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allt, t)
+        rank_ms = [float(x) / steps for x in allt.cpu()]
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), rank_ms, t_begin, t_end
+
+
+def kernel_profile(w, steps):
+    """Per-kernel device time over `steps` steps from the library's own per-launch CUDA events."""
+    import metarank_b200 as mb
+    lib = mb._capi.lib()
+    mb._capi.check(lib.mr_profile_begin())
+    for _ in range(steps):
+        w.step()
+    buf = C.create_string_buffer(1 << 16)
+    n = C.c_size_t()
+    mb._capi.check(lib.mr_profile_end(buf, C.c_size_t(len(buf)), C.byref(n)))
+    ks = json.loads(buf.value.decode())
+    for k in ks:
+        k["ms_per_step"] = k.pop("ms") / steps
+        k["launches_per_step"] = k.pop("launches") / steps
+    return ks
+
+
+def scorer_roofline(w, kernels, step_ms, sm_mhz):
+    """The dominant kernel against the pipe that bounds it (see the module docstring)."""
+    import torch
+    b = w.booster
+    c = w.c
+    peak_hbm, sm_max, peak_src = _peaks()
+    clk = (sm_mhz or sm_max) * 1e6
+    dom = max(kernels, key=lambda k: k["ms_per_step"])
+    out = {"kernel": dom["kernel"], "kernel_ms": dom["ms_per_step"], "step_share": dom["ms_per_step"] / step_ms,
+           "peak_source": peak_src}
+    if not dom["kernel"].startswith("gbdt_score_compact"):
+        out.update({"bound": "hbm", "achieved": None, "peak": peak_hbm, "unit": "GB/s", "frac": None, "traffic": None,
+                    "note": "dominant kernel is not the compact scorer; see `kernels` for its HBM fraction"})
+        return out
+    # walk statistics on the codes of this very batch (first <= 262144 rows)
+    rows = min(w.rows, 262144)
+    if getattr(w, "d_feat", None) is None:
+        w.step(explain=True)
+        w.status()
+    n_codes = b.codes_bytes(rows)
+    d_codes = torch.empty(n_codes, dtype=torch.uint8, device="cuda")
+    b.bin_device(w.d_feat.data_ptr(), rows, c["features"], d_codes.data_ptr(), w.stream)
+    import metarank_b200 as mb
+    lane, warp, wt = C.c_double(), C.c_double(), C.c_double()
+    mb._capi.check(mb._capi.lib().mr_model_walk_stats(b._h, C.c_void_p(d_codes.data_ptr()), C.c_int32(rows), C.byref(lane),
+                                                      C.byref(warp), C.byref(wt), C.c_void_p(w.stream)))
+    scale = w.rows / rows
+    levels_per_wt = warp.value / wt.value          # level steps a warp issues per tree (deepest lane)
+    dbar = lane.value / (rows * c["trees"])        # mean path per item per tree
+    lanes_active = lane.value / (32.0 * warp.value)
+    # wavefront floor of the lock-step walk: per level one node load (LDS.64, >= 1 wavefront) and one code load
+    # (LDS.U16, 1 wavefront); per tree one leaf value (LDS.64) and a quarter of a root load (LDS.128 per 4 trees)
+    wavefronts = (2.0 * warp.value + 1.25 * wt.value) * scale
+    t = dom["ms_per_step"] / 1e3
+    smem_peak = SM_COUNT * 128.0 * clk / 1e9       # GB/s
+    achieved = wavefronts * 128.0 / t / 1e9
+    b_item = 8 * c["features"] + c["trees"] * (dbar * 16 + 8) + 8
+    static = {}
+    tf = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tf):
+        try:
+            static = json.load(open(tf))
+        except Exception:
+            static = {}
+    out.update({
+        "bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
+        "what": "shared-memory crossbar: wavefronts the lock-step walk needs at least (counted on this batch by "
+                "mr_model_walk_stats: 2 per warp level step + 1.25 per warp-tree) x 128 B / kernel time, against "
+                "SMs x 128 B/clk x SM clock",
+        "wavefronts_per_launch_floor": wavefronts, "warp_levels_per_tree": levels_per_wt, "mean_path": dbar,
+        "lanes_active_of_32": 32.0 * lanes_active, "sm_clock_mhz": clk / 1e6,
+        "issue": {"frac": None, "what": "see profiles/: issue-slot utilisation comes from ncu (sm__inst_executed), not from this run"},
+        "traffic": static.get("dominant_kernel_c2_bytes_per_launch"),
+        "traffic_source": "static: profiles/traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of one capture), not measured in this run",
+        "ncu_static": {k: static[k] for k in ("smem_wavefronts_per_launch", "l1tex_pipe_pct", "issue_active_pct", "source") if k in static},
+        "algorithmic_gbs": b_item * w.rows / t / 1e9, "algorithmic_bytes_per_item": b_item,
+        "algorithmic_note": "SURVEY.md 8(d) B_item = 8F + T(16 d + 8) + 8: bytes the walk touches; they come from shared memory "
+                            "after one TMA stage per chunk, so this exceeds the HBM peak and is NOT a roofline fraction",
+        "hbm": {"peak": peak_hbm, "unit": "GB/s",
+                "algorithmic_bytes_per_item": (2 * w.tile_cols + 8) if getattr(w, "tile_cols", None) else None,
+                "what": "what the scorer must move through HBM per item: its u16 code tile in, one f64 score out"},
+    })
+    return out
+
+
+def kernel_table(w, kernels):
+    """Algorithmic HBM bytes per kernel launch for the HBM-bound kernels of the step."""
+    peak_hbm, _, _ = _peaks()
+    info = w.state.info()
+    row_b = int(info.item_row_bytes)
+    n = w.rows
+    tc = getattr(w, "tile_cols", None)
+    alg = {
+        "lookup_kernel": n * (8 + 16 + 8 + 4 + 4),                       # id + probe (key, value) + request search + two outputs
+        "code_gather_kernel": n * (2 * 2 * (tc or 0)) if tc else None,   # code row read + tile write
+        "row_gather_kernel": n * (row_b + 2 * (tc or 0)) if tc else n * (row_b + 8 * w.c["features"]),
+        "cosine_kernel": n * (8 * 384 + 16) if w.name == "C4" else None,
+        "order_small_kernel": n * 12,
+        "order_kernel": n * 12,
+    }
+    out = []
+    for k in kernels:
+        e = dict(k)
+        a = alg.get(k["kernel"])
+        if a and k["ms_per_step"] > 0:
+            gbs = a / (k["ms_per_step"] / 1e3) / 1e9  # `a` = bytes per step over all launches of this kernel
+            e.update({"bound": "hbm", "algorithmic_bytes": a, "achieved_gbs": gbs, "frac_hbm": gbs / peak_hbm})
+        elif k["kernel"].startswith("gbdt_"):
+            e["bound"] = "smem" if "compact" in k["kernel"] or "leaves" in k["kernel"] else "latency"
+        out.append(e)
+    return sorted(out, key=lambda e: -e["ms_per_step"])
+
+
+def cpu_baseline(w, budget_s=12.0):
+    """The oracle port on a bounded sample of the same workload, all usable host cores."""
+    w.cpu_setup()
+    cands = sorted({_usable_cores(), os.cpu_count() or 1})
+    n_probe = max(1, min(w.R, 64 if w.name == "C2" else 1))
+    best, best_rate = cands[0], 0.0
+    for c in cands:
+        w.cpu_run(n_probe, c)
+        t0 = time.perf_counter()
+        rows = w.cpu_run(n_probe, c)
+        rate = rows / (time.perf_counter() - t0)
+        if rate > best_rate:
+            best, best_rate = c, rate
+    n_req = int(max(1, min(w.R if w.name != "C5" else 1, best_rate * budget_s / w.items)))
+    t0 = time.perf_counter()
+    rows = w.cpu_run(n_req, best)
+    dt = time.perf_counter() - t0
+    return {"value": rows / dt, "unit": UNIT, "cores": best, "kind": "port",
+            "sample": f"{n_req} request(s) x {w.items} items: {w.cpu_what}"}
 
 
 def run_reference(args, rank, world):
-    """CPU arm: the oracle port on all host cores, bounded sample per step."""
+    """CPU arm: the oracle port on all host cores, bounded sample per step; same config block as the GPU arm."""
     if rank != 0:
         return
-    from oracle import oracle
-    blob = _model_blob()
-    ob = oracle.OracleBooster(0, blob)
-    sample_requests = max(1000, (os.cpu_count() or 1) * 40)
-    rows = sample_requests * ITEMS
-    cat = _matrix(CATALOGUE, DATA_SEED)
-    pick = np.random.Generator(np.random.PCG64(DATA_SEED + 1000)).integers(0, CATALOGUE, rows)
-    cores = _best_threads(ob, cat[pick[:20000]], 20000)
+    w = WORKLOADS[args.config](None, 0, 1)
+    w.cpu_setup()
+    cands = sorted({_usable_cores(), os.cpu_count() or 1})
+    n_probe = 64 if args.config == "C2" else 1
+    best, best_rate = cands[0], 0.0
+    for c in cands:
+        w.cpu_run(n_probe, c)
+        t0 = time.perf_counter()
+        rows = w.cpu_run(n_probe, c)
+        rate = rows / (time.perf_counter() - t0)
+        if rate > best_rate:
+            best, best_rate = c, rate
+    total_steps = max(1, args.steps + args.warmup)
+    n_req = int(max(1, min(w.R if args.config != "C5" else 1, best_rate * 60.0 / total_steps / w.items)))
     for _ in range(args.warmup):
-        ob.predictMat(cat[pick], rows, FEATURES, threads=cores)
+        w.cpu_run(n_req, best)
     t0 = time.perf_counter()
+    rows = 0
     for _ in range(args.steps):
-        X = cat[pick]  # feature assembly on the CPU = row gather of the stored scalars
-        ob.predictMat(X, rows, FEATURES, threads=cores)
+        rows += w.cpu_run(n_req, best)
     dt = time.perf_counter() - t0
-    v = rows * args.steps / dt
-    sample = f"{sample_requests} requests x {ITEMS} items per step (same generator/seed as the GPU arm)"
+    v = rows / dt
+    sample = f"{n_req} request(s) x {w.items} items per step (same generator/seed as the GPU arm): {w.cpu_what}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: 100-item /rank requests, 30 scalar (number) features gathered from a "
-                               "2M-item state table, 500-tree LightGBM LambdaMART", "items_per_request": ITEMS,
-                   "features": FEATURES, "trees": TREES, "catalogue_items": CATALOGUE,
-                   "requests_per_step": sample_requests},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong" if args.config == "C5" else "weak",
+        "vs_baseline": None, "dtype": "f32" if args.config == "C4" else "f64", "data": "synthetic",
+        "config": config_block(args.config, args.gpus),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": best, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference scorer (ltrlib -> LightGBM JNI) is not installable here (no JVM, no jars); "
-                "this is the C oracle port of its arithmetic, OpenMP over rows like LightGBM's predictor",
+        "note": "reference scorer (ltrlib -> LightGBM / XGBoost JNI) is not installable here (no JVM, no jars, no wheels: "
+                "profiles/probe_r2_gbdt_libs.txt); this is the C oracle port of its arithmetic, OpenMP over rows like "
+                "LightGBM's predictor, fed by a parallel row gather",
     }), flush=True)
+
+
+def measure(w, args, rank, world, dist, barrier, full=True):
+    """Timed region + (full) kernel profile, roofline, e2e, latency, parity, CPU baseline."""
+    import torch
+    import metarank_b200 as mb
+    lib = mb._capi.lib()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    sampler = ClockSampler(local)
+    if rank == 0 and full:
+        sampler.start()
+    launches0 = lib.mr_kernel_launches()
+    total_ms, rank_ms, t_begin, t_end = device_time(w, args.steps, args.warmup, barrier, dist, world)
+    gpu_launches = lib.mr_kernel_launches() - launches0
+    value = w.total_rows() * args.steps / (total_ms / 1e3)
+    res = {"value": value, "ms_per_step": total_ms / args.steps, "rank_ms_per_step": rank_ms, "gpu_launches": int(gpu_launches)}
+    if full:
+        # keep the same loop running until the clock record spans >= 1.2 s of load (nvidia-smi samples every 20 ms);
+        # the repeat count derives from the max-over-ranks time, so every rank runs the same number of (collective) steps
+        extra = max(0, int((1200.0 - total_ms) / (total_ms / args.steps)) + 1) if total_ms < 1200.0 else 0
+        for _ in range(extra):
+            w.step()
+        torch.cuda.synchronize()
+        barrier()
+        t_end = time.perf_counter()
+        res["clocks"] = sampler.stop(t_begin, t_end) if rank == 0 else None
+        if res["clocks"]:
+            res["clocks"]["what"] = "sampled over the timed region and the repeats of the same loop that follow it"
+    # e2e: the same metric through the host-buffer API
+    w.e2e_prepare()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        sc_h, ord_h = w.e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sc_h, ord_h = w.e2e_step()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res["parity"] = w.parity()
+    got, got_order = w._parity_ref
+    n = len(got)
+    e2e_ok = bool(np.array_equal(sc_h[:n], got) and np.array_equal(ord_h[:n], got_order))
+    res["e2e"] = {"value": w.total_rows() * e2e_steps / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": w.h2d,
+                  "d2h_bytes_per_step": w.d2h, "steps": e2e_steps, "parity_ok": e2e_ok,
+                  "what": "host buffers in -> scores + order in host buffers, H2D and D2H copies inside the timer"}
+    if w.name == "C5":
+        res["latency"] = w.latency()  # collective: every rank takes part
+    elif rank == 0 and full:
+        res["latency"] = w.latency()
+    barrier()
+    ks = kernel_profile(w, max(2, min(args.steps, 10)))
+    w.status()
+    if rank == 0:
+        try:
+            w.tile_cols = int(w.booster.codes_bytes(32) // 64) or None
+        except Exception:
+            w.tile_cols = None
+        res["kernels"] = kernel_table(w, ks)
+        if full and w.name == "C2":
+            res["roofline"] = scorer_roofline(w, ks, total_ms / args.steps, (res.get("clocks") or {}).get("sm_mhz"))
+        else:
+            dom = max(res["kernels"], key=lambda k: k["ms_per_step"])
+            res["roofline"] = {"bound": dom.get("bound"), "kernel": dom["kernel"], "kernel_ms": dom["ms_per_step"],
+                               "achieved": dom.get("achieved_gbs"), "peak": _peaks()[0], "unit": "GB/s", "frac": dom.get("frac_hbm"),
+                               "traffic": None, "step_share": dom["ms_per_step"] / (total_ms / args.steps)}
+        res["cpu_baseline"] = cpu_baseline(w, 12.0 if full else 4.0)
+        info = w.state.info()
+        res["state"] = {"items": int(info.rows[1]), "device_bytes": int(info.device_bytes),
+                        "item_row_bytes": int(info.item_row_bytes), "upload_s": w.upload_s}
+    return res
 
 
 def main():
@@ -203,9 +824,13 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--requests-per-step", type=int, default=REQUESTS_PER_STEP)
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIG))
+    ap.add_argument("--no-extras", action="store_true", help="default C2 run: skip the short C3 / C4 / C5 measurements")
+    ap.add_argument("--requests-per-step", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
+    if args.requests_per_step > 0:
+        CONFIG[args.config]["requests_per_step"] = args.requests_per_step
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -223,7 +848,6 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -231,209 +855,49 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    from metarank_b200 import features as F
-
     ctx = mb.Context(local)
-    blob = _model_blob()
-    booster = mb.LightGBMBooster(ctx, blob, n_features=FEATURES)
-    for kv in filter(None, os.environ.get("MR_BENCH_OPTS", "").split(",")):  # tuning aid: "chunk_kb=24,threads=448"
-        key, val = kv.split("=")
-        booster.set_option(key, int(val))
+    w = WORKLOADS[args.config](ctx, rank, world)
+    w.build()
+    res = measure(w, args, rank, world, dist, barrier, full=True)
+    w.free()
 
-    # ---- device-resident state: CATALOGUE items x 30 `number` features (Persistence.values on HBM)
-    names = [f"f{j}" for j in range(FEATURES)]
-    feats = [dict(name=n, type="number", scope="item", source=f"metadata.{n}") for n in names]
-    mapping = F.FeatureMapping(ctx, feats, names)
-    state = F.DeviceState(ctx, mapping)
-    cat = _matrix(CATALOGUE, DATA_SEED)  # same column recipe as SURVEY.md 8d (5 % NaN = missing state)
-    item_ids = _splitmix(np.arange(1, CATALOGUE + 1, dtype=np.uint64))
-    t_up = time.perf_counter()
-    for j0 in range(0, FEATURES, 5):
-        state.put_packed(F.pack_number_columns(names[j0:j0 + 5], item_ids, cat[:, j0:j0 + 5]))
-    state.flush()
-    t_up = time.perf_counter() - t_up
-
-    R = args.requests_per_step
-    rows = R * ITEMS
-    rng = np.random.Generator(np.random.PCG64(DATA_SEED + 1000 + rank))  # every rank ranks its own requests
-    pick = rng.integers(0, CATALOGUE, rows)
-    ids_host = item_ids[pick]
-    offs_host = (np.arange(R + 1, dtype=np.int32) * ITEMS).astype(np.int32)
-    d_ids = torch.from_numpy(ids_host.view(np.int64)).cuda()
-    d_offs = torch.from_numpy(offs_host).cuda()
-    d_out = torch.empty(rows, dtype=torch.float64, device="cuda")
-    d_order = torch.empty(rows, dtype=torch.int32, device="cuda")
-    d_feat = torch.empty(rows * FEATURES, dtype=torch.float64, device="cuda")
-    stream = torch.cuda.current_stream()
-    sptr = stream.cuda_stream
-
-    def step(explain=False):
-        # explain=false is the /rank default: the f64 matrix is not materialised, the assemble kernel
-        # emits the binned scorer's u16 codes directly
-        F.rank_device(state, booster, R, rows, d_offs.data_ptr(), d_ids.data_ptr(), d_out.data_ptr(),
-                      d_order.data_ptr(), d_feat.data_ptr() if explain else 0, sptr)
-
-    for _ in range(args.warmup):
-        step()
-    F.rank_device_status(state, sptr)
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches1 = mb._capi.lib().mr_kernel_launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
-    gpu_launches = mb._capi.lib().mr_kernel_launches() - launches1
-    total_ms = e0.elapsed_time(e1)
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    rank_ms = [total_ms / args.steps]
-    if world > 1:
-        allt = torch.zeros(world, dtype=torch.float64, device="cuda")
-        dist.all_gather_into_tensor(allt, t)
-        rank_ms = [float(x) / args.steps for x in allt.cpu()]
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    value = rows * world * args.steps / (total_ms / 1e3)
-
-    # ---- dominant kernel alone (gbdt_score on the assembled matrix), CUDA events on the launching stream
-    step(explain=True)  # materialise the f64 matrix once for the stand-alone kernel timings
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    n_codes = booster.codes_bytes(rows)
-    if n_codes:  # binned scorer: time the traversal kernel alone on precomputed codes
-        d_codes = torch.empty(n_codes, dtype=torch.uint8, device="cuda")
-        booster.bin_device(d_feat.data_ptr(), rows, FEATURES, d_codes.data_ptr(), sptr)
-        kernel_name = "gbdt_score_compact_kernel (u16 rank codes, 8-byte nodes)"
-    else:
-        kernel_name = "gbdt_score_kernel"
-    for a, b in evs:
-        a.record(stream)
-        if n_codes:
-            booster.score_codes_device(d_codes.data_ptr(), rows, d_out.data_ptr(), sptr)
-        else:
-            booster.predict_device(d_feat.data_ptr(), rows, FEATURES, d_out.data_ptr(), sptr)
-        b.record(stream)
-    # ... and assembly alone (model = None)
-    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a0.record(stream)
-    for _ in range(args.steps):
-        F.rank_device(state, None, R, rows, d_offs.data_ptr(), d_ids.data_ptr(), 0, 0, d_feat.data_ptr(), sptr)
-    a1.record(stream)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-    assemble_ms = a0.elapsed_time(a1) / args.steps
-    step(explain=True)
-    F.rank_device_status(state, sptr)
-    n_chk = 20
-    got = d_out[: n_chk * ITEMS].cpu().numpy()
-    got_order = d_order[: n_chk * ITEMS].cpu().numpy()
-    got_feat = d_feat[: n_chk * ITEMS * FEATURES].cpu().numpy().reshape(-1, FEATURES)
-
-    # ---- e2e: the same metric through mr_rank with HOST buffers (item-id hashes in, scores + order out)
-    rk = F.Ranker(mapping, state)
-    # page-locked request/response buffers (what a JVM gets from a registered direct ByteBuffer):
-    # the library DMAs them in place instead of staging
-    ids_pin = torch.from_numpy(ids_host.view(np.int64)).pin_memory()
-    sc_pin = torch.empty(rows, dtype=torch.float64).pin_memory()
-    ord_pin = torch.empty(rows, dtype=torch.int32).pin_memory()
-    ids_pinned_np = ids_pin.numpy().view(np.uint64)
-    arrays = dict(offsets=offs_host, ids=ids_pinned_np, users=np.zeros(R, dtype=np.uint64),
-                  sessions=np.zeros(R, dtype=np.uint64), req_f64=np.zeros((R, 1)), req_u64=np.zeros((R, 1), dtype=np.uint64),
-                  req_vec=np.zeros((R, 1), dtype=np.float32), req_vp=np.zeros((R, 1), dtype=np.uint8), item_f64=None,
-                  n_requests=R, total_items=rows)
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        sc_h, ord_h, _ = rk.rank_arrays(arrays, booster, want_order=True, out_scores=sc_pin.numpy(), out_order=ord_pin.numpy())
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        sc_h, ord_h, _ = rk.rank_arrays(arrays, booster, want_order=True, out_scores=sc_pin.numpy(), out_order=ord_pin.numpy())
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = rows * world * e2e_steps / float(t.item())
-    e2e_ok = bool(np.array_equal(sc_h[: n_chk * ITEMS], got) and np.array_equal(ord_h[: n_chk * ITEMS], got_order))
-
-    # ---- single-request latency through the C ABI (p50 of 300 calls, 100 items, host buffers)
-    lat = None
-    if rank == 0:
-        one = dict(arrays, offsets=offs_host[:2].copy(), ids=ids_host[:ITEMS].copy(), n_requests=1, total_items=ITEMS)
-        for _ in range(20):
-            rk.rank_arrays(one, booster, want_order=True)
-        ts = []
-        for _ in range(300):
-            a = time.perf_counter()
-            rk.rank_arrays(one, booster, want_order=True)
-            ts.append(time.perf_counter() - a)
-        lat = {"p50_ms": float(np.percentile(ts, 50) * 1e3), "p99_ms": float(np.percentile(ts, 99) * 1e3),
-               "what": "mr_rank, 1 request x 100 items: id hashes in -> scores + order out, host buffers, via ctypes"}
-
-    if rank == 0:
-        from oracle import oracle
-        ob = oracle.OracleBooster(0, blob)
-        want_feat = cat[pick[: n_chk * ITEMS]]  # the oracle's assembly of `number` features is the stored scalar
-        want = ob.predictMat(want_feat, n_chk * ITEMS, FEATURES)
-        feat_ok = bool(np.array_equal(got_feat, want_feat, equal_nan=True))
-        parity = bool(np.array_equal(got, want))
-        order_ok = all(np.array_equal(got_order[i * ITEMS:(i + 1) * ITEMS],
-                                      oracle.rank_order(want[i * ITEMS:(i + 1) * ITEMS])) for i in range(n_chk))
-        # roofline of the dominant kernel: algorithmic bytes per item, SURVEY.md 8(d): 8F + T*(dbar*16 + 8) + 8
-        dbar = booster.mean_path(want_feat[:2000], 2000, FEATURES)
-        b_item = 8 * FEATURES + TREES * (dbar * 16 + 8) + 8
-        peak, peak_src = _peaks()
-        achieved = b_item * rows / (kernel_ms / 1e3) / 1e9
-        # CPU baseline on a bounded sample, all host cores: hash lookup + row gather + tree walk
-        cpu_rows = min(rows, max(2000 * ITEMS, (os.cpu_count() or 1) * 40 * ITEMS))
-        Xc = cat[pick[:cpu_rows]]
-        cores = _best_threads(ob, Xc, cpu_rows)
-        c0 = time.perf_counter()
-        Xc = cat[pick[:cpu_rows]]  # the gather is part of the CPU path too
-        ob.predictMat(Xc, cpu_rows, FEATURES, threads=cores)
-        cpu_dt = time.perf_counter() - c0
-        info = state.info()
-        out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2: 100-item /rank requests, 30 scalar (number) features gathered from a "
-                                   "2M-item device-resident state table, 500-tree LightGBM LambdaMART, "
-                                   "scores + per-request ordering",
-                       "items_per_request": ITEMS, "features": FEATURES, "trees": TREES, "catalogue_items": CATALOGUE,
-                       "requests_per_step": R, "parallelism": f"requests sharded over {world} GPU(s), state replicated, no collective",
-                       "l2": "every table a step gathers from at random is larger than the 126 MB L2 (2 M items: item rows 496 MB, per-model code rows 168 MB), and a step writes and re-reads 138 MB of codes plus 33 MB of ids / scores / order: no flush needed"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ids_host.nbytes + offs_host.nbytes + 2 * R * 8),
-                    "d2h_bytes_per_step": rows * 12, "steps": e2e_steps, "parity_ok": e2e_ok,
-                    "what": "mr_rank: item-id hashes in page-locked host memory -> scores + order in page-locked host memory, "
-                            "H2D and D2H copies inside the timer"},
-            "gpu_launches": int(gpu_launches), "rank_ms_per_step": rank_ms,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_item": b_item, "mean_path": dbar,
-                         "kernel_ms": kernel_ms, "kernel": kernel_name,
-                         "step_share": kernel_ms / (total_ms / args.steps), "assemble_ms": assemble_ms},
-            "cpu_baseline": {"value": cpu_rows / cpu_dt, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{cpu_rows // ITEMS} requests x {ITEMS} items: numpy row gather + C oracle, OpenMP over rows"},
-            "clocks": clocks, "latency": lat,
-            "parity": {"features_bit_identical": feat_ok, "scores_bit_identical": parity,
-                       "ordering_identical": bool(order_ok), "checked_items": n_chk * ITEMS},
-            "state": {"items": int(info.rows[1]), "device_bytes": int(info.device_bytes),
-                      "item_row_bytes": int(info.item_row_bytes), "upload_s": t_up},
-        }
-        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(traffic_file):
+    extras = {}
+    if args.config == "C2" and not args.no_extras:
+        short = argparse.Namespace(steps=20, warmup=3)
+        for name in (["C3", "C4", "C5"] if world == 1 else ["C5"]):
             try:
-                out["roofline"]["traffic"] = json.load(open(traffic_file)).get("dominant_kernel_c2_bytes_per_launch")
-            except Exception:
-                pass
+                x = WORKLOADS[name](ctx, rank, world)
+                x.build()
+                r = measure(x, short, rank, world, dist, barrier, full=False)
+                x.free()
+                if rank == 0:
+                    e = {"config": config_block(name, world), "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"],
+                         "steps": short.steps, "n_gpus": world, "scaling": "strong" if name == "C5" else "weak",
+                         "dtype": "f32" if name == "C4" else "f64", "e2e": r["e2e"], "parity": r["parity"],
+                         "kernels": r["kernels"], "roofline": r["roofline"], "cpu_baseline": r["cpu_baseline"],
+                         "gpu_launches": r["gpu_launches"]}
+                    if r.get("latency"):
+                        e["latency"] = r["latency"]
+                    extras[name] = e
+            except Exception as ex:  # an extra must never cost the headline line
+                if rank == 0:
+                    extras[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong" if args.config == "C5" else "weak", "vs_baseline": None,
+            "dtype": "f32" if args.config == "C4" else "f64", "data": "synthetic",
+            "config": config_block(args.config, world), "e2e": res["e2e"], "gpu_launches": res["gpu_launches"],
+            "rank_ms_per_step": res["rank_ms_per_step"], "roofline": res["roofline"], "kernels": res["kernels"],
+            "cpu_baseline": res["cpu_baseline"], "clocks": res.get("clocks"), "latency": res.get("latency"),
+            "parity": res["parity"], "state": res["state"],
+        }
+        if extras:
+            out["other_configs"] = extras
         print(json.dumps(out), flush=True)
 
-    state.free()
-    mapping.free()
-    booster.free()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

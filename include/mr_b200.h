@@ -69,6 +69,14 @@ MR_API const char *mr_version(void);
 /* Number of this library's kernels launched so far by this process (bench.py's
  * gpu_launches claim). */
 MR_API int64_t mr_kernel_launches(void);
+/* Per-kernel device time for bench.py's roofline block.  Between begin and end every kernel this library
+ * launches (any context of the process) is bracketed by two CUDA events on its stream; end waits for the
+ * device and writes a JSON array [{"kernel": name, "launches": n, "ms": total device time}] (NUL-terminated;
+ * *len = its length without the NUL; pass json = NULL to size the buffer — that call also closes the
+ * profile, so size generously instead).  Not for the serving path: the events serialise nothing but cost a
+ * few microseconds per launch. */
+MR_API mr_status mr_profile_begin(void);
+MR_API mr_status mr_profile_end(char *json, size_t cap, size_t *len);
 
 /* ------------------------------------------------------------------ scorer (Booster) */
 
@@ -145,6 +153,14 @@ MR_API mr_status mr_model_inspect(int32_t kind, const uint8_t *blob, size_t len,
  * `rows` scored by mr_model_count_path(): the d̄ of SURVEY.md §8(d)'s B_item. */
 MR_API mr_status mr_model_count_path(mr_model *m, const double *values, int32_t rows, int32_t cols, double *mean_path);
 
+/* What the lock-step scorer executes on `rows` rows of codes (mr_model_bin_device layout; compact scorer only):
+ * lane_levels = the sum of the rows' path lengths (internal nodes visited), warp_levels = the sum over (warp of 32
+ * rows, tree) of the DEEPEST lane's path — the level steps a warp really issues — warp_trees = the number of
+ * (warp, tree) pairs.  lane_levels / (32 * warp_levels) is the fraction of lanes doing useful work;
+ * bench.py's shared-memory roofline is built from these counts.  Synchronous. */
+MR_API mr_status mr_model_walk_stats(mr_model *m, const void *d_codes, int32_t rows, double *lane_levels,
+                                     double *warp_levels, double *warp_trees, void *cuda_stream);
+
 /* Booster.close() / isClosed() (S/ml/rank/LambdaMARTRanker.scala:361-365).  close is
  * idempotent; in-flight predicts finish (CachedModelStore may dispose a model that is
  * still in use, S/fstore/cache/CachedModelStore.scala:39-42).  free releases the handle. */
@@ -154,9 +170,10 @@ MR_API mr_status mr_model_free(mr_model *m);
 
 /* Tuning knobs for experiments (bench.py / tests); defaults are chosen per model.  Not synchronised
  * against concurrent predicts on the same handle: set them before serving.
- * key: "threads" (items per CTA, 0 = auto), "chunk_kb", "ilp" (trees in flight per thread),
- * "variant" (-1 = auto, 0 = f64/f32 lock-step, 1 = f64 free-running, 2 = binned lock-step, 3 = binned
- * free-running, 4 = binned lock-step on the compact layout). */
+ * key: "threads" (items per CTA, 0 = auto), "chunk_kb", "ilp" (trees in flight per thread, exact kernel: 2 | 4),
+ * "variant" (-1 = auto, 0 = exact f64/f32 kernel, 2 = generic binned kernel, 4 = compact binned kernel; any
+ * other value is MR_ERR_INVALID_ARG), "latency_rows" (largest batch the tree-parallel low-latency path takes,
+ * 0 = auto). */
 MR_API mr_status mr_model_set_option(mr_model *m, const char *key, int32_t value);
 
 /* ------------------------------------------------------------------ final ordering */
@@ -306,6 +323,10 @@ typedef struct mr_rank_batch {
   const int32_t *req_tok_offsets;
   const uint64_t *req_tok_hashes;
   const double *req_tok_weights; /* bm25 only; may be NULL otherwise */
+  /* Optional hint for the device-batch API, where the library cannot read item_offsets on the host: the item
+   * count of the largest request (0 = unknown; then every size class of the ordering kernels is enqueued and
+   * returns at once where it does not apply).  Ignored by mr_rank, which reads the offsets. */
+  int32_t max_items_per_request;
 } mr_rank_batch;
 
 /* Native request decoder: the body of POST /rank — one RankingEvent JSON object, or an array
@@ -348,6 +369,42 @@ MR_API mr_status mr_rank_device(mr_state *st, mr_model *model, const mr_rank_bat
                                 double *d_out_scores, int32_t *d_out_order, double *d_out_features,
                                 void *cuda_stream);
 MR_API mr_status mr_rank_device_status(mr_state *st, void *cuda_stream);
+
+/* ------------------------------------------------------------------ mega-request sharding (multi-GPU)
+ *
+ * Ordinary traffic shards by REQUEST: one mr_ctx / mr_state / mr_model per GPU, each ranking its own requests
+ * with mr_rank, nothing exchanged.  Only a request too large for one GPU's latency budget (10 000 items x
+ * 2000 trees) is split by ITEM across the GPUs of the box: an mr_group has one member per GPU; every member
+ * assembles and scores a contiguous item range, its scoring kernel stores each score straight into every
+ * member's exchange buffer over NVLink (peer memory), and each member then orders the full score vector.
+ * The reference has no counterpart (it scores a request on one JVM thread, S/ml/Ranker.scala:27-83); the
+ * result is defined to be identical to mr_rank on one GPU, bit for bit. */
+typedef struct mr_group mr_group;
+#define MR_GROUP_HANDLE_BYTES 64
+/* Member `rank` of a group of `world` (1..8) GPUs, for requests of up to max_items items.  The member lives on
+ * ctx's device.  State and model are replicated by the caller (one mr_state / mr_model per member). */
+MR_API mr_status mr_group_create(mr_ctx *ctx, int32_t rank, int32_t world, int32_t max_items, mr_group **out);
+/* One process per GPU (torchrun): each member exports the CUDA IPC handle of its exchange buffer
+ * (MR_GROUP_HANDLE_BYTES bytes); the caller all-gathers the handles (any transport) and hands every member the
+ * world x MR_GROUP_HANDLE_BYTES table, in rank order. */
+MR_API mr_status mr_group_export(mr_group *g, uint8_t *handle);
+MR_API mr_status mr_group_connect(mr_group *g, const uint8_t *handles);
+/* One process driving several GPUs (a JVM): members[i] is the member of rank i; enables peer access between
+ * their devices.  Members may share a device (tests on a single GPU). */
+MR_API mr_status mr_group_connect_local(mr_group *const *members, int32_t world);
+MR_API mr_status mr_group_free(mr_group *g);
+/* The contiguous item range [*lo, *hi) member `rank` owns of an n_items request: ceil(n_items / world) rounded up
+ * to whole 128-item scorer tiles. */
+MR_API void mr_group_slice(int32_t n_items, int32_t world, int32_t rank, int32_t *lo, int32_t *hi);
+/* Collective: EVERY member calls it with the same single-request batch (n_requests == 1), concurrently — from
+ * its own process, or from one thread per member.  Returns the scores of ALL items in request order and,
+ * optionally, the response order, on every member.  Host buffers; copies are part of the call.  A member that
+ * does not show up within 2 s fails the others with MR_ERR_CUDA instead of hanging them. */
+MR_API mr_status mr_group_rank(mr_group *g, mr_state *st, mr_model *model, const mr_rank_batch *batch,
+                               double *out_scores, int32_t *out_order);
+/* Same with device pointers, enqueued on `cuda_stream` without synchronising (errors via mr_rank_device_status). */
+MR_API mr_status mr_group_rank_device(mr_group *g, mr_state *st, mr_model *model, const mr_rank_batch *d_batch,
+                                      int32_t total_items, double *d_out_scores, int32_t *d_out_order, void *cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -45,6 +45,21 @@ const char *mr_last_error(void) { return t_last_error.c_str(); }
 const char *mr_version(void) { return "libmrgpu 0.1.0 sm_100a"; }
 int64_t mr_kernel_launches(void) { return (int64_t)g_kernel_launches; }
 
+mr_status mr_profile_begin(void) {
+  return guard([&] { profile_begin(); });
+}
+mr_status mr_profile_end(char *json, size_t cap, size_t *len) {
+  return guard([&] {
+    std::string s;
+    profile_end(s);
+    if (len) *len = s.size();
+    if (json) {
+      if (cap < s.size() + 1) fail(MR_ERR_INVALID_ARG, "profile buffer too small: %zu bytes needed", s.size() + 1);
+      memcpy(json, s.c_str(), s.size() + 1);
+    }
+  });
+}
+
 mr_status mr_init(int32_t device, mr_ctx **out) {
   return guard([&] {
     if (!out) fail(MR_ERR_INVALID_ARG, "out is null");
@@ -317,6 +332,25 @@ mr_status mr_model_inspect(int32_t kind, const uint8_t *blob, size_t len, int32_
   });
 }
 
+mr_status mr_model_walk_stats(mr_model *m, const void *d_codes, int32_t rows, double *lane_levels, double *warp_levels,
+                              double *warp_trees, void *cuda_stream) {
+  return guard([&] {
+    check_model(m);
+    if (!d_codes && rows > 0) fail(MR_ERR_INVALID_ARG, "null codes");
+    if (!m->use_binned() || !m->use_compact()) fail(MR_ERR_UNSUPPORTED, "walk statistics exist for the compact binned scorer only");
+    InflightGuard g(m);
+    MR_CUDA_CHECK(cudaSetDevice(m->ctx->device));
+    BinnedLaunch B = m->binned_desc();
+    B.rows = rows;
+    B.d_bins = (uint16_t *)d_codes;
+    unsigned long long out[3] = {0, 0, 0};
+    compact_walk_stats(B, out, (cudaStream_t)cuda_stream);
+    if (lane_levels) *lane_levels = (double)out[0];
+    if (warp_levels) *warp_levels = (double)out[1];
+    if (warp_trees) *warp_trees = (double)out[2];
+  });
+}
+
 mr_status mr_model_set_option(mr_model *m, const char *key, int32_t value) {
   return guard([&] {
     check_model(m);
@@ -324,8 +358,13 @@ mr_status mr_model_set_option(mr_model *m, const char *key, int32_t value) {
     std::lock_guard<std::mutex> g(m->mu);
     std::string k(key);
     if (k == "threads") m->opt_threads = value;
-    else if (k == "variant") { m->opt_variant = value; m->code_gen = mr_model::next_code_gen(); }
+    else if (k == "variant") {
+      if (value != -1 && value != 0 && value != 2 && value != 4) fail(MR_ERR_INVALID_ARG, "variant %d does not exist (-1 auto, 0 exact, 2 binned, 4 compact)", value);
+      m->opt_variant = value;
+      m->code_gen = mr_model::next_code_gen();
+    }
     else if (k == "ilp") m->opt_ilp = value;
+    else if (k == "latency_rows") m->opt_latency_rows = value;
     else if (k == "chunk_kb") {
       m->opt_chunk_kb = value;
       MR_CUDA_CHECK(cudaSetDevice(m->ctx->device));

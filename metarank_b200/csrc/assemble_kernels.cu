@@ -521,11 +521,25 @@ __device__ __forceinline__ uint32_t hist_count(const RankArgs &a, int r, int h, 
 // ------------------------------------------------------------------ coalesced row gather (fast columns)
 // Most columns of a typical config are a plain function of one word of the item's row (numbers, word
 // counts, booleans, category indices, counters, windows, stored vectors).  For those a WARP owns a
-// group of 32 items and walks them one by one: the whole row (<= 64 words) arrives with one or two
+// group of 32 items and walks them one by one: the whole row (<= 128 words) arrives with up to four
 // coalesced loads, lane c picks the word of column c out of the warp with a shuffle, converts it and
 // turns it into the scorer's rank code; codes are staged in shared memory and written one 64-byte line
 // per column, the f64 row (explain) as one contiguous run per item.
 constexpr int kGatherWarps = 4;
+
+// An item row of up to 128 words held across a warp: word w lives in lane (w & 31), register (w >> 5).
+struct RowRegs { uint64_t w[4]; };
+__device__ __forceinline__ void row_load(RowRegs &r, const uint64_t *rp, int rw, int lane) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) r.w[k] = (rp && lane + 32 * k < rw) ? __ldg(rp + lane + 32 * k) : 0ull;
+}
+__device__ __forceinline__ uint64_t row_pick(const RowRegs &r, int word, int rw) {  // rw is warp-uniform
+  uint64_t v = __shfl_sync(0xFFFFFFFFu, r.w[0], word & 31);
+  if (rw > 32) { const uint64_t h = __shfl_sync(0xFFFFFFFFu, r.w[1], word & 31); if ((word >> 5) == 1) v = h; }
+  if (rw > 64) { const uint64_t h = __shfl_sync(0xFFFFFFFFu, r.w[2], word & 31); if ((word >> 5) == 2) v = h; }
+  if (rw > 96) { const uint64_t h = __shfl_sync(0xFFFFFFFFu, r.w[3], word & 31); if ((word >> 5) == 3) v = h; }
+  return v;
+}
 
 // CODES: emit the scorer's u16 codes; OUT: emit the dense f64 row; XGB: XGBoost code semantics.
 template <bool CODES, bool OUT, bool XGB>
@@ -570,39 +584,20 @@ __global__ void __launch_bounds__(kGatherWarps * 32) row_gather_kernel(RankArgs 
     BinMeta M{};
     bool cat = false;
     if (CODES) { M = bin.meta[fc.col]; cat = (M.flags & kMetaCat) != 0; }
-    const int wsrc = fc.word & 31, psrc = (fc.bit >> 6) & 31;
-    const bool whi = fc.word >= 32, phi_ = (fc.bit >> 6) >= 32;
+    const int wsrc = fc.word, psrc = fc.bit >> 6;
     const double vmiss = fc.missing ? 0.0 : kNaN;
     // software pipeline: row j + 1 is in flight while row j is converted
-    uint64_t n0 = 0, n1 = 0;
+    RowRegs nx;
     uint32_t ir_next = __shfl_sync(0xFFFFFFFFu, my_row, 0);
-    {
-      const uint32_t ir = ir_next;
-      if (ir != kNoRow) {
-        const uint64_t *rp = IT.rows + (size_t)ir * rw;
-        if (lane < rw) n0 = __ldg(rp + lane);
-        if (lane + 32 < rw) n1 = __ldg(rp + lane + 32);
-      }
-    }
+    row_load(nx, ir_next != kNoRow ? IT.rows + (size_t)ir_next * rw : nullptr, rw, lane);
     for (int j = 0; j < n_here; j++) {
       const uint32_t ir = ir_next;
-      const uint64_t w0 = n0, w1 = n1;
-      n0 = 0; n1 = 0;
+      const RowRegs cur = nx;
       if (j + 1 < n_here) {
-        const uint32_t nr = __shfl_sync(0xFFFFFFFFu, my_row, j + 1);
-        ir_next = nr;
-        if (nr != kNoRow) {
-          const uint64_t *rp = IT.rows + (size_t)nr * rw;
-          if (lane < rw) n0 = __ldg(rp + lane);
-          if (lane + 32 < rw) n1 = __ldg(rp + lane + 32);
-        }
+        ir_next = __shfl_sync(0xFFFFFFFFu, my_row, j + 1);
+        row_load(nx, ir_next != kNoRow ? IT.rows + (size_t)ir_next * rw : nullptr, rw, lane);
       }
-      uint64_t vw = __shfl_sync(0xFFFFFFFFu, w0, wsrc), pw = __shfl_sync(0xFFFFFFFFu, w0, psrc);
-      if (rw > 32) {  // warp-uniform
-        const uint64_t vh = __shfl_sync(0xFFFFFFFFu, w1, wsrc), ph = __shfl_sync(0xFFFFFFFFu, w1, psrc);
-        if (whi) vw = vh;
-        if (phi_) pw = ph;
-      }
+      const uint64_t vw = row_pick(cur, wsrc, rw), pw = row_pick(cur, psrc, rw);
       if (!act) continue;
       const int item = i0 + j;
       double v = vmiss;
@@ -659,24 +654,14 @@ __global__ void __launch_bounds__(kGatherWarps * 32) code_rows_kernel(RankArgs a
     const FastCol fc = a.fast_cols[act ? c : 0];
     const BinMeta M = bin.meta[fc.col];
     const bool cat = (M.flags & kMetaCat) != 0;
-    const int wsrc = fc.word & 31, psrc = (fc.bit >> 6) & 31;
-    const bool whi = fc.word >= 32, phi_ = (fc.bit >> 6) >= 32;
+    const int wsrc = fc.word, psrc = fc.bit >> 6;
     for (uint32_t j = 0; j < n_here; j++) {
       // work item -> table row (kNoRow for the unknown-item row, which is the last one of a full build)
       uint32_t r = idx ? __ldg(idx + w0i + j) : w0i + j;
       if (!idx && r == n_rows) r = kNoRow;
-      uint64_t w0 = 0, w1 = 0;
-      if (r != kNoRow) {
-        const uint64_t *rp = IT.rows + (size_t)r * rw;
-        if (lane < rw) w0 = __ldg(rp + lane);
-        if (lane + 32 < rw) w1 = __ldg(rp + lane + 32);
-      }
-      uint64_t vw = __shfl_sync(0xFFFFFFFFu, w0, wsrc), pw = __shfl_sync(0xFFFFFFFFu, w0, psrc);
-      if (rw > 32) {
-        const uint64_t vh = __shfl_sync(0xFFFFFFFFu, w1, wsrc), ph = __shfl_sync(0xFFFFFFFFu, w1, psrc);
-        if (whi) vw = vh;
-        if (phi_) pw = ph;
-      }
+      RowRegs cur;
+      row_load(cur, r != kNoRow ? IT.rows + (size_t)r * rw : nullptr, rw, lane);
+      const uint64_t vw = row_pick(cur, wsrc, rw), pw = row_pick(cur, psrc, rw);
       if (!act) continue;
       double v = fc.missing ? 0.0 : kNaN;
       if (r != kNoRow && ((pw >> (fc.bit & 63)) & 1ull)) {
@@ -1079,8 +1064,8 @@ __global__ void __launch_bounds__(256) order_kernel(const double *scores, const 
   // a resident grid walks the requests; the ones order_small_kernel ranked are skipped
   for (int r = blockIdx.x; r < n_requests; r += gridDim.x) {
     const int b = __ldg(offsets + r), n = __ldg(offsets + r + 1) - b;
-    if (n <= kSmallOrder) continue;
-    if (n <= cap) {
+    if (n <= kSmallOrder || n > cap) continue;  // order_small_kernel's / order_big_*'s
+    {
       // bitonic sort of (total-order key of -score, request index): the index makes every pair distinct,
       // which is exactly the stability of the reference's sortBy
       int p2 = 1;
@@ -1109,17 +1094,103 @@ __global__ void __launch_bounds__(256) order_kernel(const double *scores, const 
       for (int j = threadIdx.x; j < n; j += blockDim.x) order[b + j] = s_idx[j];
       continue;
     }
-    // very large requests: rank by counting straight from global memory
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-      const long long kj = total_order_key(-scores[b + j]);
-      int rank = 0;
-      for (int q = 0; q < n; q++) {
-        const long long kq = total_order_key(-scores[b + q]);
-        rank += (kq < kj) || (kq == kj && q < j);
-      }
-      order[b + rank] = j;
-    }
+    // larger requests: order_big_* (below) — a whole grid per request instead of one CTA
   }
+}
+
+// Mega-requests (more items than the CTA sort holds; BASELINE config #5 is one 10 000-item request): the rank of
+// item j is the number of items that sort before it.  The n^2 comparisons are spread over the chip —
+// CTA (x, y) counts, for the 256 items of block x, the earlier items among split y of the request, staged through
+// shared memory as sortable keys — the partial counts meet in `rank` (zeroed by the launcher), and a second
+// kernel scatters.  Ties are broken by the index, i.e. the sort is stable like the reference's sortBy.
+constexpr int kBigOrderMin = 4096;   // requests above this size take this path
+constexpr int kBigOrderSplits = 16;
+constexpr int kBigOrderTile = 1024;  // keys staged per pass
+constexpr int kBigOrderJ = 4;        // items per thread: one staged key is compared against four registers
+
+__device__ __forceinline__ int owning_request(const int32_t *offsets, int n_requests, int i) {
+  int lo = 0, hi = n_requests;  // last r with off[r] <= i
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(offsets + mid) <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// total_order_key with NaN one below the maximum, so that `key + 1` never overflows (no finite key is that large)
+__device__ __forceinline__ long long big_order_key(double x) {
+  const long long k = total_order_key(x);
+  return k == 0x7FFFFFFFFFFFFFFFll ? 0x7FFFFFFFFFFFFFFEll : k;
+}
+
+// CTA (x, y): the 1024 items [1024 x, 1024 x + 1024) against split y of their request.  Thread t owns items
+// 1024 x + t + 256 m (m < 4).  q sorts before j iff key_q < key_j, or the keys tie and q < j: within a block of 256
+// staged keys that is `key_q < key_j + 1` for every q (block entirely before j), `key_q < key_j` for every q (block
+// entirely at or after j), or — only in the one block that holds j — decided per q.
+__global__ void __launch_bounds__(256) order_big_count_kernel(const double *scores, const int32_t *offsets, int n_requests,
+                                                              int total_items, int32_t *rank) {
+  __shared__ long long s_keys[kBigOrderTile];
+  const int j0 = blockIdx.x * (256 * kBigOrderJ), j1 = min(total_items, j0 + 256 * kBigOrderJ);
+  for (int r = owning_request(offsets, n_requests, j0); r < n_requests; r++) {
+    const int b = __ldg(offsets + r), n = __ldg(offsets + r + 1) - b;
+    if (b >= j1) break;
+    if (n <= kBigOrderMin) continue;
+    long long kj[kBigOrderJ];
+    int jj[kBigOrderJ], cnt[kBigOrderJ];
+    bool mine[kBigOrderJ];
+#pragma unroll
+    for (int m = 0; m < kBigOrderJ; m++) {
+      const int j = j0 + (int)threadIdx.x + 256 * m;
+      mine[m] = j < total_items && j >= b && j < b + n;
+      kj[m] = mine[m] ? big_order_key(-scores[j]) : 0;
+      jj[m] = j - b;
+      cnt[m] = 0;
+    }
+    const int per = (((n + gridDim.y - 1) / gridDim.y) + 255) & ~255;  // whole 256-key blocks per split
+    const int q0 = blockIdx.y * per, q1 = min(n, q0 + per);
+    for (int t0 = q0; t0 < q1; t0 += kBigOrderTile) {
+      const int nt = min(kBigOrderTile, q1 - t0);
+      __syncthreads();
+      for (int k = threadIdx.x; k < nt; k += blockDim.x) s_keys[k] = big_order_key(-scores[b + t0 + k]);
+      __syncthreads();
+      for (int c0 = 0; c0 < nt; c0 += 256) {
+        const int c1 = min(nt, c0 + 256), qa = t0 + c0, qb = t0 + c1;  // staged block = q in [qa, qb)
+        long long thr[kBigOrderJ];
+        bool partial = false;
+#pragma unroll
+        for (int m = 0; m < kBigOrderJ; m++) {
+          thr[m] = kj[m] + (jj[m] >= qb ? 1 : 0);
+          partial |= mine[m] && jj[m] > qa && jj[m] < qb;
+        }
+        if (!partial) {
+#pragma unroll 4
+          for (int k = c0; k < c1; k++) {
+            const long long kq = s_keys[k];
+#pragma unroll
+            for (int m = 0; m < kBigOrderJ; m++) cnt[m] += kq < thr[m];
+          }
+        } else {
+          for (int k = c0; k < c1; k++) {
+            const long long kq = s_keys[k];
+#pragma unroll
+            for (int m = 0; m < kBigOrderJ; m++) cnt[m] += kq < kj[m] || (kq == kj[m] && t0 + k < jj[m]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < kBigOrderJ; m++)
+      if (mine[m] && cnt[m]) atomicAdd(rank + j0 + (int)threadIdx.x + 256 * m, cnt[m]);
+  }
+}
+
+__global__ void __launch_bounds__(256) order_big_scatter_kernel(const int32_t *offsets, int n_requests, int total_items,
+                                                                const int32_t *rank, int32_t *order) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= total_items) return;
+  const int r = owning_request(offsets, n_requests, j);
+  const int b = __ldg(offsets + r), n = __ldg(offsets + r + 1) - b;
+  if (n > kBigOrderMin) order[b + rank[j]] = j - b;
 }
 
 }  // namespace
@@ -1127,19 +1198,19 @@ __global__ void __launch_bounds__(256) order_kernel(const double *scores, const 
 void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t stream) {
   if (a.total_items <= 0 && a.n_requests <= 0) return;
   const int n = std::max(a.total_items, a.n_requests);
-  lookup_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a);
+  { ProfScope _ps("lookup_kernel", stream); lookup_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a); }
   MR_CUDA_CHECK(cudaGetLastError());
   g_kernel_launches++;
   if (a.total_items <= 0) return;
   if (schema.needs_cosine) {
-    cosine_kernel<<<(a.total_items + 127) / 128, 128, 0, stream>>>(a);
+    { ProfScope _ps("cosine_kernel", stream); cosine_kernel<<<(a.total_items + 127) / 128, 128, 0, stream>>>(a); }
     MR_CUDA_CHECK(cudaGetLastError());
     g_kernel_launches++;
   }
   if (schema.needs_prepass && a.n_requests > 0) {
     int n_agg = 0;
     for (auto &d : schema.plan) n_agg += d.kind == FK_INTERACTED || d.kind == FK_DIVERSITY || (d.kind == FK_COSINE && d.aux1 != 0);
-    prepass_kernel<<<dim3((unsigned)a.n_requests, (unsigned)std::max(n_agg, 1)), 256, 0, stream>>>(a);
+    { ProfScope _ps("prepass_kernel", stream); prepass_kernel<<<dim3((unsigned)a.n_requests, (unsigned)std::max(n_agg, 1)), 256, 0, stream>>>(a); }
     MR_CUDA_CHECK(cudaGetLastError());
     g_kernel_launches++;
   }
@@ -1161,7 +1232,7 @@ void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t strea
       const size_t smem = (size_t)kGatherWarps * 32 * (a.code_row_words | 1) * sizeof(uint32_t);
       if (smem > 48 * 1024)
         MR_CUDA_CHECK(cudaFuncSetAttribute(code_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      code_gather_kernel<<<(n_groups + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, smem, stream>>>(b);
+      { ProfScope _ps("code_gather_kernel", stream); code_gather_kernel<<<(n_groups + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, smem, stream>>>(b); }
       MR_CUDA_CHECK(cudaGetLastError());
       g_kernel_launches++;
     } else if (b.n_fast > 0) {
@@ -1169,7 +1240,7 @@ void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t strea
       auto go = [&](auto kern) {
         if (gather_smem > 48 * 1024)
           MR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gather_smem));
-        kern<<<(n_groups + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, gather_smem, stream>>>(b);
+        { ProfScope _ps("row_gather_kernel", stream); kern<<<(n_groups + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, gather_smem, stream>>>(b); }
         MR_CUDA_CHECK(cudaGetLastError());
         g_kernel_launches++;
       };
@@ -1179,7 +1250,7 @@ void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t strea
       else go(row_gather_kernel<false, true, false>);
     }
     if (any_generic) {
-      assemble_kernel<<<(a.total_items + 127) / 128, 128, plan_bytes + (b.stage_meta ? meta_bytes : 0), stream>>>(b);
+      { ProfScope _ps("assemble_kernel", stream); assemble_kernel<<<(a.total_items + 127) / 128, 128, plan_bytes + (b.stage_meta ? meta_bytes : 0), stream>>>(b); }
       MR_CUDA_CHECK(cudaGetLastError());
       g_kernel_launches++;
     }
@@ -1191,23 +1262,38 @@ void launch_code_rows(const RankArgs &a, uint32_t *code_rows, int code_row_words
   const uint32_t n_work = d_idx ? n_idx : n_rows + 1;
   if (n_work == 0 || a.n_fast <= 0) return;
   const unsigned grid = (unsigned)((n_work + kGatherWarps * 32 - 1) / (kGatherWarps * 32));
-  if (a.bin.xgb) code_rows_kernel<true><<<grid, kGatherWarps * 32, 0, stream>>>(a, code_rows, code_row_words, n_rows, d_idx, n_idx);
-  else code_rows_kernel<false><<<grid, kGatherWarps * 32, 0, stream>>>(a, code_rows, code_row_words, n_rows, d_idx, n_idx);
+  if (a.bin.xgb) { ProfScope _ps("code_rows_kernel", stream); code_rows_kernel<true><<<grid, kGatherWarps * 32, 0, stream>>>(a, code_rows, code_row_words, n_rows, d_idx, n_idx); }
+  else { ProfScope _ps("code_rows_kernel", stream); code_rows_kernel<false><<<grid, kGatherWarps * 32, 0, stream>>>(a, code_rows, code_row_words, n_rows, d_idx, n_idx); }
   MR_CUDA_CHECK(cudaGetLastError());
   g_kernel_launches++;
 }
 
 void launch_rank_order(const double *d_scores, const int32_t *d_item_offsets, int n_requests, int total_items,
-                       int32_t *d_order, cudaStream_t stream, int max_items_hint) {
+                       int32_t *d_order, cudaStream_t stream, int max_items_hint, int32_t *d_rank_tmp) {
   if (n_requests <= 0 || total_items <= 0) return;
-  order_small_kernel<<<(n_requests + kOrderWarps - 1) / kOrderWarps, kOrderWarps * 32, 0, stream>>>(d_scores, d_item_offsets, n_requests, d_order);
-  MR_CUDA_CHECK(cudaGetLastError());
-  if (max_items_hint <= 0 || max_items_hint > kSmallOrder) {  // larger requests: CTA-wide sort (small ones return at once)
-    order_kernel<<<std::min(n_requests, 148 * 4), 256, 4096 * (sizeof(long long) + sizeof(int)), stream>>>(d_scores, d_item_offsets, n_requests, d_order);
+  const bool unknown = max_items_hint <= 0;
+  if (unknown || max_items_hint <= kSmallOrder || n_requests > 1) {
+    { ProfScope _ps("order_small_kernel", stream); order_small_kernel<<<(n_requests + kOrderWarps - 1) / kOrderWarps, kOrderWarps * 32, 0, stream>>>(d_scores, d_item_offsets, n_requests, d_order); }
     MR_CUDA_CHECK(cudaGetLastError());
     g_kernel_launches++;
   }
-  g_kernel_launches++;
+  if (unknown || max_items_hint > kSmallOrder) {  // larger requests: CTA-wide sort (small ones return at once)
+    { ProfScope _ps("order_kernel", stream); order_kernel<<<std::min(n_requests, 148 * 4), 256, 4096 * (sizeof(long long) + sizeof(int)), stream>>>(d_scores, d_item_offsets, n_requests, d_order); }
+    MR_CUDA_CHECK(cudaGetLastError());
+    g_kernel_launches++;
+  }
+  if ((unknown && total_items > kBigOrderMin) || max_items_hint > kBigOrderMin) {
+    int32_t *tmp = d_rank_tmp;
+    if (!tmp) MR_CUDA_CHECK(cudaMallocAsync((void **)&tmp, (size_t)total_items * 4, stream));
+    MR_CUDA_CHECK(cudaMemsetAsync(tmp, 0, (size_t)total_items * 4, stream));
+    const unsigned gx = (unsigned)((total_items + 255) / 256), gj = (unsigned)((total_items + 256 * kBigOrderJ - 1) / (256 * kBigOrderJ));
+    { ProfScope _ps("order_big_count_kernel", stream); order_big_count_kernel<<<dim3(gj, kBigOrderSplits), 256, 0, stream>>>(d_scores, d_item_offsets, n_requests, total_items, tmp); }
+    MR_CUDA_CHECK(cudaGetLastError());
+    { ProfScope _ps("order_big_scatter_kernel", stream); order_big_scatter_kernel<<<gx, 256, 0, stream>>>(d_item_offsets, n_requests, total_items, tmp, d_order); }
+    MR_CUDA_CHECK(cudaGetLastError());
+    g_kernel_launches += 2;
+    if (!d_rank_tmp) MR_CUDA_CHECK(cudaFreeAsync(tmp, stream));
+  }
 }
 
 }  // namespace mr

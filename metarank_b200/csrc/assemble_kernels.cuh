@@ -60,7 +60,10 @@ void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t strea
 // rows listed in idx.  a.st / a.fast_cols / a.n_fast / a.bin describe the source and the model's binning.
 void launch_code_rows(const RankArgs &a, uint32_t *code_rows, int code_row_words, uint32_t n_rows, const uint32_t *d_idx,
                       uint32_t n_idx, cudaStream_t stream);
+// max_items_hint: the largest request of the batch when the host knows it (0 = unknown: every size class is launched
+// and returns at once where it does not apply).  d_rank_tmp: total_items ints of scratch for the mega-request path
+// (nullptr: stream-ordered allocation when needed).
 void launch_rank_order(const double *d_scores, const int32_t *d_item_offsets, int n_requests, int total_items,
-                       int32_t *d_order, cudaStream_t stream, int max_items_hint = 0);
+                       int32_t *d_order, cudaStream_t stream, int max_items_hint = 0, int32_t *d_rank_tmp = nullptr);
 
 }  // namespace mr

@@ -18,6 +18,7 @@
 
 #include "binning.cuh"
 #include "gbdt_kernels.cuh"
+#include "sinks.cuh"
 #include "tma.cuh"
 
 namespace mr {
@@ -63,6 +64,7 @@ struct BParams {
   uint32_t chunk_stride;
   int rows, n_features;
   float base_score;
+  ScoreSinks sinks;
 };
 
 template <bool HAS_CAT>
@@ -370,8 +372,9 @@ __global__ void __launch_bounds__(1024) gbdt_score_compact_kernel(const BParams 
       for (; t < ntree; t++) acc += walk(roots[t]);
       __syncthreads();
     }
-    if (item < p.rows) p.out[item] = (double)acc;
+    if (item < p.rows) store_score(p.out, p.sinks, item, (double)acc);
   }
+  if (p.sinks.n_peer) publish_when_last(p.sinks);
 }
 
 // ------------------------------------------------------------------ low-latency path (small batches)
@@ -384,7 +387,8 @@ struct LParams {
   const uint8_t *model;
   const ChunkDesc *chunks;
   const uint16_t *bins;
-  double *leafvals;  // [n_trees][rows_padded]
+  uint16_t *leafslots;       // [n_trees][rows_padded]: the leaf each row reached, as its 8-byte slot index in the tree's chunk
+  const uint32_t *tree_off;  // [n_trees] byte offset of the tree's chunk in `model`
   double *out;
   int rows, rows_padded, n_features, n_trees;
   float base_score;
@@ -435,115 +439,108 @@ __global__ void __launch_bounds__(128) gbdt_leaves_kernel(const LParams p) {
       }
       n = __byte_perm(nd.y, 0u, left ? 0x4410u : 0x4432u);
     }
-    p.leafvals[(size_t)(cd.first_tree + t) * p.rows_padded + item] = (double)*reinterpret_cast<const Real *>(cb + (n - 1u));
+    p.leafslots[(size_t)(cd.first_tree + t) * p.rows_padded + item] = (uint16_t)((n - 1u) >> 3);
   }
 }
 
-// The adds are a dependent chain (tree order = the sequential reference's rounding) but the loads are not.
-// ptxas keeps only ~8 register loads in flight, i.e. 60 L2 round trips for 500 trees; cp.async has no such
-// limit: every thread queues kSumBatch 8-byte copies of ITS OWN column into shared memory, waits for its own
-// group (no CTA barrier: nobody else reads them) and adds them in order.
-constexpr int kSumBatch = 48;  // 48 x 128 x 8 B = the 48 KB of static shared memory
+// In-order sum of the per-tree leaf values.  The adds are a dependent chain (tree order = the sequential reference's
+// rounding) but nothing else is: a warp owns 32 rows and streams their leaf SLOTS (2 bytes per row and tree — an
+// eighth of the f64 values themselves) through a kSumStages-deep cp.async pipeline of kSumTrees trees per stage,
+// 16 bytes per copy; the value behind a slot is read from the packed model (a few hundred KB, L1/L2 resident),
+// one 128-byte line per tree for the whole warp.  Small batches use one-warp CTAs so that a single mega-request
+// slice still spreads over the whole chip.
+constexpr int kSumTrees = 64, kSumStages = 4;  // 4 x 4 KB per warp
 
 template <typename Real>
-__global__ void __launch_bounds__(128) gbdt_sum_kernel(const LParams p) {
-  __shared__ double s_v[kSumBatch][128];
-  const int item = blockIdx.x * blockDim.x + threadIdx.x;
-  if (item >= p.rows) return;
-  Real acc = (sizeof(Real) == 4) ? (Real)p.base_score : (Real)0;
-  const double *v = p.leafvals + item;
-  const uint32_t s_base = smem_u32(&s_v[0][threadIdx.x]);
-  for (int t0 = 0; t0 < p.n_trees; t0 += kSumBatch) {
-    const int nb = min(kSumBatch, p.n_trees - t0);
-    for (int k = 0; k < nb; k++)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s_base + (uint32_t)k * 128u * 8u),
-                   "l"(v + (size_t)(t0 + k) * p.rows_padded)
-                   : "memory");
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-    for (int k = 0; k < nb; k++) acc += (Real)s_v[k][threadIdx.x];
-  }
-  p.out[item] = (double)acc;
-}
-
-// ------------------------------------------------------------------ free-running ("threaded") traversal
-// Every lane chases its own pointer through the chunk's flat entry array: internal entry ->
-// child entry, leaf entry -> (add value) -> root of the next tree.  No lane ever idles waiting for
-// the deepest path of its warp, and there is no per-tree loop overhead; the price is that a warp's
-// 32 entry loads hit different addresses (shared-memory bank conflicts instead of broadcasts).
-// A lane still visits its trees strictly in order, so the sum is bit-identical to the sequential one.
-template <typename Real>
-__global__ void __launch_bounds__(1024) gbdt_score_threaded_kernel(const BParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int W = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int F = p.n_features;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
-  const bool resident = p.n_chunks == 1;
-  uint8_t *cbuf0 = smem + 128;
-  uint8_t *cbuf1 = cbuf0 + (resident ? 0u : p.chunk_stride);
-  uint16_t *xs = reinterpret_cast<uint16_t *>(cbuf1 + p.chunk_stride);
-  const uint32_t xw_addr = smem_u32(xs) + ((uint32_t)warp * (uint32_t)F * 32u + (uint32_t)lane) * 2u;
-
-  const int n_tiles = (p.rows + W - 1) / W;
-  const int groups_per_tile = W >> 5;
-  const int n_groups = (p.rows + 31) >> 5;
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_init(&bars[2], 1);
-    fence_barrier_init();
-  }
-  __syncthreads();
-  if (tid == 0 && (int)blockIdx.x < n_tiles) {
-    const ChunkDesc cd = p.chunks[0];
-    mbar_arrive_expect_tx(&bars[0], cd.bytes);
-    tma_bulk_g2s(cbuf0, p.model + cd.byte_off, cd.bytes, &bars[0]);
-  }
-  uint32_t it = 0, tile_it = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
-    if (tid == 0) {
-      const int g0 = tile * groups_per_tile, g1 = min(n_groups, g0 + groups_per_tile);
-      const uint32_t bytes = (uint32_t)(g1 - g0) * (uint32_t)F * 64u;
-      fence_proxy_async();
-      mbar_arrive_expect_tx(&bars[2], bytes);
-      tma_bulk_g2s(xs, p.bins + (size_t)g0 * F * 32, bytes, &bars[2]);
-    }
-    mbar_wait(&bars[2], tile_it & 1);
-    const int item = tile * W + tid;
-    Real acc = (sizeof(Real) == 4) ? (Real)p.base_score : (Real)0;
-    for (int c = 0; c < p.n_chunks; ++c, ++it) {
-      if (!resident && tid == 0) {
-        const bool more = (c + 1 < p.n_chunks) || (tile + (int)gridDim.x < n_tiles);
-        if (more) {
-          const int nc = (c + 1 < p.n_chunks) ? c + 1 : 0;
-          const ChunkDesc cd = p.chunks[nc];
-          uint64_t *bar = &bars[(it + 1) & 1];
-          fence_proxy_async();
-          mbar_arrive_expect_tx(bar, cd.bytes);
-          tma_bulk_g2s(((it + 1) & 1) ? cbuf1 : cbuf0, p.model + cd.byte_off, cd.bytes, bar);
-        }
+__global__ void __launch_bounds__(128) gbdt_sum_kernel(const LParams p, const ScoreSinks sinks) {
+  extern __shared__ __align__(16) uint16_t s_slots[];  // [warps][kSumStages][kSumTrees][32]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + warp) * 32;
+  const int item = row0 + lane;
+  const bool live = item < p.rows, warp_live = row0 < p.rows;
+  uint16_t *tile = s_slots + (size_t)warp * kSumStages * kSumTrees * 32;
+  const int n_groups = (p.n_trees + kSumTrees - 1) / kSumTrees;
+  auto issue = [&](int g) {
+    if (g < n_groups && warp_live) {
+      const int t0 = g * kSumTrees, nb = min(kSumTrees, p.n_trees - t0);
+      const uint32_t dst = smem_u32(tile + (size_t)(g % kSumStages) * kSumTrees * 32);
+      for (int k = lane; k < nb * 4; k += 32) {  // 16-byte piece k: tree k >> 2, rows (k & 3) * 8 .. + 8 of the warp's 32
+        const uint16_t *src = p.leafslots + (size_t)(t0 + (k >> 2)) * p.rows_padded + row0 + (k & 3) * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)k * 16u), "l"(src) : "memory");
       }
-      if (!resident || it == 0) mbar_wait(&bars[it & 1], (it >> 1) & 1);
-      const uint8_t *cb = (!resident && (it & 1)) ? cbuf1 : cbuf0;
-      const uint32_t ent_addr = smem_u32(cb) + 16u;
-      const uint32_t leaf_addr = smem_u32(cb) + reinterpret_cast<const uint32_t *>(cb)[2];
-      uint32_t n = 0;  // first root
-      do {
-        uint32_t w0, w1;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(ent_addr + n * 8u));
-        const uint32_t k = w0 & 0xFFFFu;
-        uint32_t code;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(code) : "r"(xw_addr + ((w0 >> 10) & 0x3FFC0u)));  // feat * 64 bytes
-        const bool left = (code <= k) || (code == kBinNaN && (w0 & (BF_NAN_LEFT << 28)));
-        if (w0 & (BF_LEAF << 28)) {
-          double v;
-          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(leaf_addr + k * 8u));
-          acc += (Real)v;
-        }
-        n = left ? (w1 & 0xFFFFu) : (w1 >> 16);
-      } while (n != kEntryEnd);
-      __syncthreads();
     }
-    if (item < p.rows) p.out[item] = (double)acc;
+    asm volatile("cp.async.commit_group;" ::: "memory");  // an empty group keeps the wait count uniform
+  };
+  Real acc = (sizeof(Real) == 4) ? (Real)p.base_score : (Real)0;
+  for (int g = 0; g < kSumStages - 1; g++) issue(g);
+  for (int g = 0; g < n_groups; g++) {
+    issue(g + kSumStages - 1);
+    asm volatile("cp.async.wait_group %0;" ::"n"(kSumStages - 1) : "memory");
+    __syncwarp();  // the stage was filled by all lanes' copies
+    const int t0 = g * kSumTrees, nb = min(kSumTrees, p.n_trees - t0);
+    const uint16_t *st = tile + (size_t)(g % kSumStages) * kSumTrees * 32 + lane;
+    if (live) {
+#pragma unroll 8
+      for (int k = 0; k < nb; k++) {
+        const uint32_t slot = st[k * 32];
+        acc += *reinterpret_cast<const Real *>(p.model + __ldg(p.tree_off + t0 + k) + slot * 8u);
+      }
+    }
+    __syncwarp();  // before a later issue() overwrites this stage
+  }
+  if (live) store_score(p.out, sinks, item, (double)acc);
+  if (sinks.n_peer) publish_when_last(sinks);
+}
+
+// ------------------------------------------------------------------ walk statistics (bench.py's roofline block)
+// What the lock-step scorer executes on a batch, counted rather than assumed: a warp walks every tree to the
+// depth of its deepest lane, so per (warp, tree) it issues max-depth level steps while its lanes need sum-depth/32
+// of them.  One thread per item straight from HBM/L2 (no staging): a measuring aid, not a scoring path.
+struct WalkStats { unsigned long long lane_levels, warp_levels, warp_trees; };
+
+__global__ void __launch_bounds__(128) compact_walk_stats_kernel(const uint8_t *model, const ChunkDesc *chunks, int n_chunks,
+                                                                 const uint16_t *bins, int rows, int F, WalkStats *out) {
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool live = item < rows;
+  const uint16_t *xw = bins + ((size_t)(item >> 5) * F) * 32 + lane;
+  unsigned long long lane_levels = 0, warp_levels = 0, warp_trees = 0;
+  for (int c = 0; c < n_chunks; c++) {
+    const uint8_t *cb = model + chunks[c].byte_off;
+    const int ntree = (int)*reinterpret_cast<const uint32_t *>(cb);
+    const uint32_t *roots = reinterpret_cast<const uint32_t *>(cb + 16);
+    for (int t = 0; t < ntree; t++) {
+      uint32_t n = roots[t];
+      int depth = 0;
+      while (live && !(n & 1u)) {
+        const uint2 nd = *reinterpret_cast<const uint2 *>(cb + (n & ~2u));
+        const uint32_t code = xw[(nd.x & 0xFFC0u) >> 1];
+        bool left;
+        if (nd.x & 2u) {
+          left = false;
+          if (code != kBinNaN) {
+            const uint2 ct = reinterpret_cast<const uint2 *>(cb)[nd.x >> 16];
+            const uint32_t w = code >> 5;
+            if (w < ct.y) left = (reinterpret_cast<const uint32_t *>(cb)[ct.x + w] >> (code & 31u)) & 1u;
+          }
+        } else {
+          left = code <= (nd.x >> 16);
+        }
+        n = __byte_perm(nd.y, 0u, left ? 0x4410u : 0x4432u);
+        depth++;
+      }
+      lane_levels += depth;
+      warp_levels += __reduce_max_sync(0xFFFFFFFFu, depth);
+      warp_trees++;
+    }
+  }
+  const unsigned long long lanes = lane_levels;
+  unsigned long long tot = lanes;
+  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
+  if (lane == 0) {
+    atomicAdd(&out->lane_levels, tot);
+    atomicAdd(&out->warp_levels, warp_levels);
+    atomicAdd(&out->warp_trees, warp_trees);
   }
 }
 
@@ -556,36 +553,49 @@ void launch_b(const BParams &p, int threads, size_t smem, int num_sms, cudaStrea
   if (per_sm < 1) fail(MR_ERR_CUDA, "binned gbdt kernel does not fit on an SM (smem %zu, threads %d)", smem, threads);
   const int n_tiles = (p.rows + threads - 1) / threads;
   const int grid = std::max(1, std::min(n_tiles, num_sms * per_sm));
-  kern<<<grid, threads, smem, stream>>>(p);
+  { ProfScope _ps("gbdt_score_binned_kernel", stream); kern<<<grid, threads, smem, stream>>>(p); }
   MR_CUDA_CHECK(cudaGetLastError());
   g_kernel_launches++;
 }
 
-template <typename Real, bool HAS_CAT>
-void launch_b_ilp(const BParams &p, int ilp, int threads, size_t smem, int num_sms, cudaStream_t s) {
-  switch (ilp) {
-    case 1: return launch_b<Real, HAS_CAT, 1>(p, threads, smem, num_sms, s);
-    case 4: return launch_b<Real, HAS_CAT, 4>(p, threads, smem, num_sms, s);
-    default: return launch_b<Real, HAS_CAT, 2>(p, threads, smem, num_sms, s);
-  }
-}
 
 }  // namespace
 
-void launch_gbdt_latency(const BinnedLaunch &L, int n_trees, double *d_leafvals, cudaStream_t stream) {
+void compact_walk_stats(const BinnedLaunch &L, unsigned long long out[3], cudaStream_t stream) {
+  WalkStats *d = nullptr;
+  MR_CUDA_CHECK(cudaMalloc((void **)&d, sizeof(WalkStats)));
+  MR_CUDA_CHECK(cudaMemsetAsync(d, 0, sizeof(WalkStats), stream));
+  if (L.rows > 0)
+    compact_walk_stats_kernel<<<(L.rows + 127) / 128, 128, 0, stream>>>(L.d_model, L.d_chunks, L.n_chunks, L.d_bins, L.rows, L.tile_cols, d);
+  cudaError_t e = cudaGetLastError();
+  WalkStats h{};
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFree(d);
+  MR_CUDA_CHECK(e);
+  out[0] = h.lane_levels; out[1] = h.warp_levels; out[2] = h.warp_trees;
+}
+
+void launch_gbdt_latency(const BinnedLaunch &L, int n_trees, const uint32_t *d_tree_off, void *d_leafslots, cudaStream_t stream) {
   // L.d_model / d_chunks = the small-chunk compact packing; L.d_bins already holds the codes
   if (L.rows <= 0) return;
   LParams p;
-  p.model = L.d_model; p.chunks = L.d_chunks; p.bins = L.d_bins; p.leafvals = d_leafvals; p.out = L.d_out;
+  p.model = L.d_model; p.chunks = L.d_chunks; p.bins = L.d_bins; p.leafslots = (uint16_t *)d_leafslots; p.tree_off = d_tree_off;
+  p.out = L.d_out;
   p.rows = L.rows; p.rows_padded = (L.rows + 127) & ~127; p.n_features = L.tile_cols; p.n_trees = n_trees;
   p.base_score = L.base_score;
   const size_t smem = 128 + ((L.max_chunk_bytes + 127u) & ~127u) + (size_t)4 * L.tile_cols * 64;
   dim3 grid((unsigned)L.n_chunks, (unsigned)((L.rows + 127) / 128));
+  // the in-order sum: one-warp CTAs (16 KB of stages each) spread even a 1 000-row slice over 32 SMs
+  const int sum_warps = 1;
+  const size_t sum_smem = (size_t)sum_warps * kSumStages * kSumTrees * 32 * sizeof(uint16_t);
+  const int n_warps = (L.rows + 31) / 32;
   auto go = [&](auto leaves, auto sum) {
     MR_CUDA_CHECK(cudaFuncSetAttribute(leaves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    leaves<<<grid, 128, smem, stream>>>(p);
+    { ProfScope _ps("gbdt_leaves_kernel", stream); leaves<<<grid, 128, smem, stream>>>(p); }
     MR_CUDA_CHECK(cudaGetLastError());
-    sum<<<(L.rows + 127) / 128, 128, 0, stream>>>(p);
+    MR_CUDA_CHECK(cudaFuncSetAttribute(sum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sum_smem));
+    { ProfScope _ps("gbdt_sum_kernel", stream); sum<<<(n_warps + sum_warps - 1) / sum_warps, sum_warps * 32, sum_smem, stream>>>(p, L.sinks); }
     MR_CUDA_CHECK(cudaGetLastError());
     g_kernel_launches += 2;
   };
@@ -607,7 +617,7 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
   const size_t bin_smem = (size_t)F * (items_per_cta + 2) * sizeof(uint16_t);
   if (bin_smem > 200 * 1024) fail(MR_ERR_UNSUPPORTED, "too many features for the binning kernel");
   MR_CUDA_CHECK(cudaFuncSetAttribute(bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem));
-  bin_kernel<<<(L.rows + items_per_cta - 1) / items_per_cta, 256, bin_smem, stream>>>(bp);
+  { ProfScope _ps("bin_kernel", stream); bin_kernel<<<(L.rows + items_per_cta - 1) / items_per_cta, 256, bin_smem, stream>>>(bp); }
   MR_CUDA_CHECK(cudaGetLastError());
   g_kernel_launches++;
   }
@@ -618,6 +628,7 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
   p.model = L.d_model; p.chunks = L.d_chunks; p.bins = L.d_bins; p.out = L.d_out;
   p.n_chunks = L.n_chunks; p.chunk_stride = (L.max_chunk_bytes + 127u) & ~127u;
   p.rows = L.rows; p.n_features = F; p.base_score = L.base_score;
+  p.sinks = L.sinks;
   const size_t kMaxSmem = 227 * 1024;
   const bool aligned_tile = L.compact && !L.has_cat && (F & (F - 1)) == 0;  // + slack to align the tile
   const size_t fixed = 128 + (size_t)p.chunk_stride * (L.n_chunks == 1 ? 1 : 2) + (aligned_tile ? (size_t)F * 64 : 0);
@@ -667,21 +678,6 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
   while (fixed + (size_t)threads * per_item > kMaxSmem && threads > 32) threads = ((threads / 2) + 31) & ~31;
   if (fixed + (size_t)threads * per_item > kMaxSmem) fail(MR_ERR_UNSUPPORTED, "binned tile does not fit in shared memory");
   const size_t smem = fixed + (size_t)threads * per_item;
-  if (L.threaded) {
-    auto go = [&](auto kern) {
-      MR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      int per_sm = 0;
-      MR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-      if (per_sm < 1) fail(MR_ERR_CUDA, "threaded gbdt kernel does not fit on an SM");
-      const int n_tiles = (p.rows + threads - 1) / threads;
-      kern<<<std::max(1, std::min(n_tiles, num_sms * per_sm)), threads, smem, stream>>>(p);
-      MR_CUDA_CHECK(cudaGetLastError());
-      g_kernel_launches++;
-    };
-    if (L.kind == MR_BOOSTER_XGBOOST) go(gbdt_score_threaded_kernel<float>);
-    else go(gbdt_score_threaded_kernel<double>);
-    return;
-  }
   if (L.compact) {
     auto go = [&](auto kern) {
       MR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -694,7 +690,7 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
       if (debug)
         fprintf(stderr, "[mr] compact scorer: rows %d tile_cols %d chunks %d x %u B, %d threads x %d CTAs (%d/SM), %zu B smem\n",
                 p.rows, F, p.n_chunks, p.chunk_stride, threads, std::max(1, std::min(n_tiles, num_sms * per_sm)), per_sm, smem);
-      kern<<<std::max(1, std::min(n_tiles, num_sms * per_sm)), threads, smem, stream>>>(p);
+      { ProfScope _ps("gbdt_score_compact_kernel", stream); kern<<<std::max(1, std::min(n_tiles, num_sms * per_sm)), threads, smem, stream>>>(p); }
       MR_CUDA_CHECK(cudaGetLastError());
       g_kernel_launches++;
     };
@@ -705,10 +701,11 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
     else go(gbdt_score_compact_kernel<double, false, false>);
     return;
   }
-  const int ilp = L.ilp <= 0 ? 1 : L.ilp;
-  if (L.kind == MR_BOOSTER_XGBOOST) launch_b_ilp<float, false>(p, ilp, threads, smem, num_sms, stream);
-  else if (L.has_cat) launch_b_ilp<double, true>(p, ilp, threads, smem, num_sms, stream);
-  else launch_b_ilp<double, false>(p, ilp, threads, smem, num_sms, stream);
+  // generic binned kernel: the fallback for models the compact layout cannot hold (> 1023 columns, oversized
+  // categorical tables); two trees in flight per thread
+  if (L.kind == MR_BOOSTER_XGBOOST) launch_b<float, false, 2>(p, threads, smem, num_sms, stream);
+  else if (L.has_cat) launch_b<double, true, 2>(p, threads, smem, num_sms, stream);
+  else launch_b<double, false, 2>(p, threads, smem, num_sms, stream);
 }
 
 }  // namespace mr

@@ -22,9 +22,67 @@
 #include "gbdt_kernels.cuh"
 #include "tma.cuh"
 
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
 namespace mr {
 
 long long g_kernel_launches = 0;
+
+// ------------------------------------------------------------------ per-kernel profile (bench.py)
+namespace {
+std::atomic<bool> g_prof_on{false};
+std::mutex g_prof_mu;
+struct ProfRec { const char *name; cudaEvent_t e0, e1; };
+std::vector<ProfRec> g_prof;
+}  // namespace
+
+ProfScope::ProfScope(const char *n, cudaStream_t s) : name(n), stream(s) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  if (cudaEventCreate(&e0) != cudaSuccess) { e0 = nullptr; return; }
+  cudaEventRecord(e0, stream);
+}
+ProfScope::~ProfScope() {
+  if (!e0) return;
+  cudaEvent_t e1 = nullptr;
+  if (cudaEventCreate(&e1) != cudaSuccess) { cudaEventDestroy(e0); return; }
+  cudaEventRecord(e1, stream);
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  g_prof.push_back(ProfRec{name, e0, e1});
+}
+void profile_begin() {
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  for (auto &r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof.clear();
+  g_prof_on.store(true);
+}
+void profile_end(std::string &out) {
+  g_prof_on.store(false);
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  std::vector<std::pair<std::string, std::pair<long long, double>>> agg;
+  for (auto &r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+    bool found = false;
+    for (auto &a : agg)
+      if (a.first == r.name) { a.second.first++; a.second.second += ms; found = true; break; }
+    if (!found) agg.push_back({r.name, {1, (double)ms}});
+  }
+  g_prof.clear();
+  out = "[";
+  for (size_t i = 0; i < agg.size(); i++) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s{\"kernel\": \"%s\", \"launches\": %lld, \"ms\": %.6f}", i ? ", " : "", agg[i].first.c_str(),
+             agg[i].second.first, agg[i].second.second);
+    out += buf;
+  }
+  out += "]";
+}
 
 namespace {
 
@@ -91,11 +149,10 @@ __device__ __forceinline__ int step(const uint4 nd, const Real x, const uint8_t 
   return left ? l : r;
 }
 
-// VARIANT 0: lock-step — every lane walks tree t at the same time (ILP trees in flight);
-//            node loads of a warp stay inside one tree (mostly broadcast / conflict free).
-// VARIANT 1: free-running — a lane moves to its next tree as soon as it hits a leaf, so no
-//            lane idles while the deepest path of the warp finishes.
-template <typename Real, bool HAS_CAT, bool HAS_ZERO, int VARIANT, int ILP, bool STAGE, bool COUNT>
+// Lock-step: every lane walks tree t at the same time (ILP trees in flight); node loads of a warp stay inside
+// one tree (mostly broadcast / conflict free).  A free-running variant (a lane moves on to its next tree as soon as
+// it hits a leaf) lost to shared-memory bank conflicts and was removed (profiles/sweep_r1.md).
+template <typename Real, bool HAS_CAT, bool HAS_ZERO, int ILP, bool STAGE, bool COUNT>
 __global__ void __launch_bounds__(1024) gbdt_score_kernel(const KParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   using AccT = typename Acc<Real>::type;
@@ -170,7 +227,7 @@ __global__ void __launch_bounds__(1024) gbdt_score_kernel(const KParams p) {
         return (item < p.rows) ? cvt_feature<Real>(__ldg(row + f)) : (Real)0;
       };
 
-      if (VARIANT == 0) {
+      {
         int t = 0;
         for (; t + ILP <= ntree; t += ILP) {
           const uint4 *nodes[ILP];
@@ -217,20 +274,6 @@ __global__ void __launch_bounds__(1024) gbdt_score_kernel(const KParams p) {
           } while (n >= 0);
           acc += (AccT)leaves[~n];
         }
-      } else {
-        int t = 0, n = 0;
-        uint2 to = ntree > 0 ? tab[0] : make_uint2(0, 0);
-        while (t < ntree) {
-          const uint4 nd = reinterpret_cast<const uint4 *>(cb + to.x)[n];
-          n = step<Real, HAS_CAT, HAS_ZERO>(nd, feat(nd.z & 0xFFFFFFu), cb);
-          if (COUNT) visited++;
-          if (n < 0) {
-            acc += (AccT) reinterpret_cast<const Real *>(cb + to.y)[~n];
-            t++;
-            n = 0;
-            if (t < ntree) to = tab[t];
-          }
-        }
       }
       __syncthreads();  // the buffer may be overwritten by the next prefetch; xs by the next tile
     }
@@ -242,38 +285,37 @@ __global__ void __launch_bounds__(1024) gbdt_score_kernel(const KParams p) {
   }
 }
 
-template <typename Real, bool HAS_CAT, bool HAS_ZERO, int VARIANT, int ILP, bool STAGE, bool COUNT>
+template <typename Real, bool HAS_CAT, bool HAS_ZERO, int ILP, bool STAGE, bool COUNT>
 void launch_inst(const KParams &p, int threads, size_t smem, int num_sms, cudaStream_t stream) {
-  auto kern = gbdt_score_kernel<Real, HAS_CAT, HAS_ZERO, VARIANT, ILP, STAGE, COUNT>;
+  auto kern = gbdt_score_kernel<Real, HAS_CAT, HAS_ZERO, ILP, STAGE, COUNT>;
   MR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   MR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   if (per_sm < 1) fail(MR_ERR_CUDA, "gbdt_score kernel does not fit on an SM (smem %zu, threads %d)", smem, threads);
   const int n_tiles = (p.rows + threads - 1) / threads;
   const int grid = std::max(1, std::min(n_tiles, num_sms * per_sm));
-  kern<<<grid, threads, smem, stream>>>(p);
+  { ProfScope _ps("gbdt_score_kernel", stream); kern<<<grid, threads, smem, stream>>>(p); }
   MR_CUDA_CHECK(cudaGetLastError());
   g_kernel_launches++;
 }
 
-template <typename Real, bool HAS_CAT, bool HAS_ZERO, bool STAGE, bool COUNT>
-void launch_variant(const KParams &p, int variant, int ilp, int threads, size_t smem, int num_sms, cudaStream_t s) {
-  if (variant == 1) return launch_inst<Real, HAS_CAT, HAS_ZERO, 1, 1, STAGE, COUNT>(p, threads, smem, num_sms, s);
-  switch (ilp) {
-    case 1: return launch_inst<Real, HAS_CAT, HAS_ZERO, 0, 1, STAGE, COUNT>(p, threads, smem, num_sms, s);
-    case 4: return launch_inst<Real, HAS_CAT, HAS_ZERO, 0, 4, STAGE, COUNT>(p, threads, smem, num_sms, s);
-    default: return launch_inst<Real, HAS_CAT, HAS_ZERO, 0, 2, STAGE, COUNT>(p, threads, smem, num_sms, s);
-  }
+// Instantiations kept: trees in flight per thread 2 (narrow rows) or 4 (wide rows: fewer resident warps, more ILP);
+// the path-counting build exists once per precision (it only serves mr_model_count_path).
+template <typename Real, bool HAS_CAT, bool HAS_ZERO, bool STAGE>
+void launch_ilp(const KParams &p, int ilp, bool count, int threads, size_t smem, int num_sms, cudaStream_t s) {
+  if (count) return launch_inst<Real, HAS_CAT, HAS_ZERO, 2, STAGE, true>(p, threads, smem, num_sms, s);
+  if (ilp >= 4) return launch_inst<Real, HAS_CAT, HAS_ZERO, 4, STAGE, false>(p, threads, smem, num_sms, s);
+  return launch_inst<Real, HAS_CAT, HAS_ZERO, 2, STAGE, false>(p, threads, smem, num_sms, s);
 }
 
-template <typename Real, bool STAGE, bool COUNT>
-void launch_flags(const KParams &p, bool cat, bool zero, int variant, int ilp, int threads, size_t smem, int num_sms,
+template <typename Real, bool STAGE>
+void launch_flags(const KParams &p, bool cat, bool zero, int ilp, bool count, int threads, size_t smem, int num_sms,
                   cudaStream_t s) {
   if constexpr (sizeof(Real) == 4) {
-    return launch_variant<Real, false, false, STAGE, COUNT>(p, variant, ilp, threads, smem, num_sms, s);
+    return launch_ilp<Real, false, false, STAGE>(p, ilp, count, threads, smem, num_sms, s);
   } else {
-    if (cat || zero) return launch_variant<Real, true, true, STAGE, COUNT>(p, variant, ilp, threads, smem, num_sms, s);
-    return launch_variant<Real, false, false, STAGE, COUNT>(p, variant, ilp, threads, smem, num_sms, s);
+    if (cat || zero) return launch_ilp<Real, true, true, STAGE>(p, ilp, count, threads, smem, num_sms, s);
+    return launch_ilp<Real, false, false, STAGE>(p, ilp, count, threads, smem, num_sms, s);
   }
 }
 
@@ -347,23 +389,15 @@ void launch_gbdt_score(const ScoreLaunch &L, int num_sms, cudaStream_t stream) {
   if (fixed + (size_t)threads * per_item > kMaxSmem) stage = false;  // very wide rows: read HBM/L1 directly
   const size_t smem = fixed + (stage ? (size_t)threads * per_item : 0);
 
-  int variant = L.variant < 0 ? 0 : L.variant;
-  int ilp = L.ilp <= 0 ? (per_item > 384 ? 4 : 2) : L.ilp;
+  const int ilp = L.ilp <= 0 ? (per_item > 384 ? 4 : 2) : L.ilp;
   const bool count = L.d_visited != nullptr;
-
-#define MR_DISPATCH(REAL)                                                                                        \
-  do {                                                                                                           \
-    if (stage) {                                                                                                 \
-      if (count) launch_flags<REAL, true, true>(p, L.has_cat, L.has_zero, variant, ilp, threads, smem, num_sms, stream); \
-      else launch_flags<REAL, true, false>(p, L.has_cat, L.has_zero, variant, ilp, threads, smem, num_sms, stream);      \
-    } else {                                                                                                     \
-      if (count) launch_flags<REAL, false, true>(p, L.has_cat, L.has_zero, variant, ilp, threads, smem, num_sms, stream); \
-      else launch_flags<REAL, false, false>(p, L.has_cat, L.has_zero, variant, ilp, threads, smem, num_sms, stream);      \
-    }                                                                                                            \
-  } while (0)
-  if (f32) MR_DISPATCH(float);
-  else MR_DISPATCH(double);
-#undef MR_DISPATCH
+  if (f32) {
+    if (stage) launch_flags<float, true>(p, L.has_cat, L.has_zero, ilp, count, threads, smem, num_sms, stream);
+    else launch_flags<float, false>(p, L.has_cat, L.has_zero, ilp, count, threads, smem, num_sms, stream);
+  } else {
+    if (stage) launch_flags<double, true>(p, L.has_cat, L.has_zero, ilp, count, threads, smem, num_sms, stream);
+    else launch_flags<double, false>(p, L.has_cat, L.has_zero, ilp, count, threads, smem, num_sms, stream);
+  }
 }
 
 }  // namespace mr

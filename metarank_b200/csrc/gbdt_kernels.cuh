@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <string>
 
 #include "gbdt_model.h"
 
@@ -25,12 +26,23 @@ struct ScoreLaunch {
   unsigned long long *d_visited = nullptr;  // non-null: also count evaluated internal nodes
   // tuning (0 = choose)
   int threads = 0;
-  int variant = -1;
   int ilp = 0;
 };
 
 // Enqueues the scoring kernel on `stream`.  Throws mr::Error on failure.
 void launch_gbdt_score(const ScoreLaunch &L, int num_sms, cudaStream_t stream);
+
+// Where the finished scores go besides d_out.  The mega-request path (rank_api.cu, mr_group_rank) points `peer`
+// at the score buffers of every GPU of the group (peer memory over NVLink): the scorer's final store IS the
+// all-gather.  The CTA that finishes last stores `seq` to flag[g] on every peer (release, system scope).
+struct ScoreSinks {
+  double *peer[8] = {};
+  uint32_t *flag[8] = {};
+  uint32_t *done = nullptr;  // device counter of finished CTAs (zero between launches)
+  uint32_t seq = 0;
+  int n_peer = 0;            // 0: only d_out
+  int item_base = 0;         // index of this slice's first item in the peers' buffers
+};
 
 // Binned path (gbdt_binned.cu): feature values -> u16 rank codes, then integer traversal.
 struct BinnedLaunch {
@@ -56,18 +68,36 @@ struct BinnedLaunch {
   bool codes_only = false;              // run bin_kernel only (no traversal)
   bool codes_ready = false;             // d_bins already holds the codes (fused assemble): skip bin_kernel
   bool compact = false;                 // model bytes are pack_compact() chunks -> fast lock-step kernel
-  bool threaded = false;                // model bytes are pack_threaded() chunks -> free-running kernel
+  ScoreSinks sinks;                     // compact + latency kernels only
 };
 inline size_t binned_scratch_bytes(int rows, int tile_cols) {
   return (size_t)((rows + 31) / 32) * (size_t)tile_cols * 32 * sizeof(uint16_t);
 }
 void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream);
-// Low-latency path for small batches: per-tree leaf values spread over (chunk x item-group) CTAs, then an
-// in-order per-item sum.  d_leafvals: n_trees * round_up(rows, 128) doubles of scratch.
-void launch_gbdt_latency(const BinnedLaunch &L, int n_trees, double *d_leafvals, cudaStream_t stream);
-inline size_t latency_scratch_bytes(int rows, int n_trees) { return (size_t)n_trees * (size_t)((rows + 127) & ~127) * 8; }
+// Low-latency path for small batches: the leaf every row reaches in every tree, spread over (chunk x item-group)
+// CTAs, then an in-order per-item sum of the values behind them.  d_leafslots: latency_scratch_bytes() of scratch;
+// d_tree_off: per tree, the byte offset of its chunk in L.d_model.
+void launch_gbdt_latency(const BinnedLaunch &L, int n_trees, const uint32_t *d_tree_off, void *d_leafslots, cudaStream_t stream);
+// Level steps the lock-step scorer executes on the codes in L.d_bins (compact layout only): out = {sum of the lanes'
+// path lengths, sum over (warp, tree) of the deepest lane's path, number of (warp, tree) pairs}.  Synchronous.
+void compact_walk_stats(const BinnedLaunch &L, unsigned long long out[3], cudaStream_t stream);
+inline size_t latency_scratch_bytes(int rows, int n_trees) { return (size_t)n_trees * (size_t)((rows + 127) & ~127) * 2; }
 constexpr int kLatencyMaxRows = 2048;
 
 extern long long g_kernel_launches;
+
+// Per-kernel timing for bench.py's roofline block (mr_profile_begin / mr_profile_end): while a profile is open,
+// every launch site brackets its kernel with two CUDA events on the launching stream.  Off (one relaxed load per
+// launch) on the serving path.
+struct ProfScope {
+  const char *name;
+  cudaStream_t stream;
+  cudaEvent_t e0 = nullptr;
+  ProfScope(const char *n, cudaStream_t s);
+  ~ProfScope();
+};
+void profile_begin();
+// Waits for the device, then appends one JSON object per kernel name to `out`: {"kernel", "launches", "ms"}.
+void profile_end(std::string &out);
 
 }  // namespace mr

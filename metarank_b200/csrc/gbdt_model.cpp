@@ -571,79 +571,6 @@ BinnedModel pack_binned(const HostModel &m, size_t chunk_budget) {
   return B;
 }
 
-// ------------------------------------------------------------------ threaded packing
-
-BinnedModel pack_threaded(const HostModel &m, const BinnedModel &bn, size_t chunk_budget) {
-  BinnedModel T;
-  if (!bn.ok || m.has_cat) return T;
-  T.thr_off = bn.thr_off;
-  T.thr = bn.thr;
-  T.is_cat = bn.is_cat;
-  T.meta = bn.meta;
-  T.tile_cols = bn.tile_cols;
-  T.bucket_range = bn.bucket_range;
-  const bool f32 = m.kind == MR_BOOSTER_XGBOOST;
-  struct Entry { uint16_t k, ff; uint16_t left, right; };
-  static_assert(sizeof(Entry) == 8, "entry must be 8 bytes");
-  auto n_int = [](const HostTree &t) { return t.feat.size(); };
-  auto tree_entries = [&](const HostTree &t) { return n_int(t) + t.leaf.size(); };
-  PackedModel &pk = T.packed;
-  size_t i = 0, nt = m.trees.size();
-  if (nt == 0) return T;  // empty ensembles use the lock-step kernel (base score only)
-  while (i < nt) {
-    size_t j = i, ne = 0, nl = 0;
-    while (j < nt) {
-      const size_t e2 = ne + tree_entries(m.trees[j]), l2 = nl + m.trees[j].leaf.size();
-      if (j > i && 16 + e2 * 8 + l2 * 8 > chunk_budget) break;
-      ne = e2; nl = l2; j++;
-    }
-    if (ne >= 0xFFF0) return T;  // entry indices are u16
-    // per tree [internal entries..., leaf entries...]; a leaf entry's k field holds the
-    // ordinal of its value in the chunk's dense leaf-value array (8-byte slots)
-    if (nl >= 0xFFF0) return T;
-    const size_t total = al16(16 + ne * 8) + al16(nl * 8);
-    const size_t base = pk.bytes.size();
-    pk.bytes.resize(base + total, 0);
-    uint8_t *c = pk.bytes.data() + base;
-    Entry *ent = (Entry *)(c + 16);
-    const size_t leaf_base = al16(16 + ne * 8);
-    double *lv64 = (double *)(c + leaf_base);
-    size_t lord = 0;
-    size_t e0 = 0;
-    for (size_t k = i; k < j; k++) {
-      const HostTree &t = m.trees[k];
-      const size_t ni = n_int(t), nlv = t.leaf.size();
-      const size_t next_root = (k + 1 < j) ? e0 + ni + nlv : (size_t)kEntryEnd;
-      auto child = [&](int cidx) -> uint16_t { return (uint16_t)(cidx >= 0 ? e0 + (size_t)cidx : e0 + ni + (size_t)(~cidx)); };
-      for (size_t q = 0; q < ni; q++) {
-        const int f = t.feat[q];
-        const double *b = T.thr.data() + T.thr_off[f], *e = T.thr.data() + T.thr_off[f + 1];
-        Entry &d = ent[e0 + q];
-        d.k = (uint16_t)(std::lower_bound(b, e, t.thr[q]) - b);
-        d.ff = (uint16_t)((uint32_t)f | (((t.flags[q] & NF_NAN_LEFT) ? BF_NAN_LEFT : 0u) << 12));
-        d.left = child(t.left[q]);
-        d.right = child(t.right[q]);
-      }
-      for (size_t q = 0; q < nlv; q++) {
-        Entry &d = ent[e0 + ni + q];
-        d.k = (uint16_t)lord;
-        d.ff = (uint16_t)(BF_LEAF << 12);
-        d.left = d.right = (uint16_t)next_root;
-        // f32 leaves are stored widened: the kernel narrows back before the f32 add (exact)
-        lv64[lord++] = f32 ? (double)(float)t.leaf[q] : t.leaf[q];
-      }
-      e0 += ni + nlv;
-    }
-    uint32_t hdr[4] = {(uint32_t)ne, 0u, (uint32_t)leaf_base, 0u};
-    memcpy(c, hdr, 16);
-    pk.chunks.push_back(ChunkDesc{(uint32_t)base, (uint32_t)total, (uint32_t)(j - i), (uint32_t)i});
-    pk.max_chunk_bytes = std::max<uint32_t>(pk.max_chunk_bytes, (uint32_t)total);
-    i = j;
-  }
-  T.ok = true;
-  return T;
-}
-
 // ------------------------------------------------------------------ compact packing
 
 BinnedModel pack_compact(const HostModel &m, const BinnedModel &bn, size_t chunk_budget) {

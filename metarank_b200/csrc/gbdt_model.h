@@ -140,17 +140,4 @@ BinnedModel pack_binned(const HostModel &m, size_t chunk_budget);
 // chunk_budget 0 = sized from the code tile (what ~48 resident warps leave of the shared memory).
 BinnedModel pack_compact(const HostModel &m, const BinnedModel &binned, size_t chunk_budget);
 
-// "Threaded" form of the binned model for the free-running kernel: one flat array of 8-byte
-// entries per chunk in which LEAVES are entries too.  An internal entry is a BNode whose
-// children are absolute entry indices inside the chunk; a leaf entry has BF_LEAF set and both
-// children = the root entry of the NEXT tree (0xFFFF after the chunk's last tree), so a lane
-// that reaches a leaf adds its value and falls through to the next tree with no branch.
-//   chunk: +0 u32 n_entries, u32 first_root, u32 leaf_base_bytes, u32 pad
-//          +16 entries[n_entries] (8 B); then the dense leaf values (8-byte slots: f64, or f32
-//          widened); a leaf entry's k field is the ordinal of its value in that array
-// Categorical nodes are not supported in this form (such models use the lock-step kernel).
-enum : uint32_t { BF_LEAF = 4u };
-constexpr uint16_t kEntryEnd = 0xFFFFu;
-BinnedModel pack_threaded(const HostModel &m, const BinnedModel &binned, size_t chunk_budget);
-
 }  // namespace mr

@@ -112,18 +112,19 @@ struct mr_model {
   uint8_t *d_model = nullptr;
   ChunkDesc *d_chunks = nullptr;
   // binned form (exact integer traversal); binned.ok == false -> always the f64/f32 kernel
-  BinnedModel binned, threaded, compact, lat;  // lat: compact layout in 4 KB chunks for the low-latency path
-  uint8_t *d_bmodel = nullptr, *d_tmodel = nullptr, *d_cmodel = nullptr, *d_lmodel = nullptr;
-  ChunkDesc *d_bchunks = nullptr, *d_tchunks = nullptr, *d_cchunks = nullptr, *d_lchunks = nullptr;
+  BinnedModel binned, compact, lat;  // lat: compact layout in 4 KB chunks for the low-latency path
+  uint8_t *d_bmodel = nullptr, *d_cmodel = nullptr, *d_lmodel = nullptr;
+  ChunkDesc *d_bchunks = nullptr, *d_cchunks = nullptr, *d_lchunks = nullptr;
   uint32_t *d_thr_off = nullptr;
   double *d_thr = nullptr;
   uint8_t *d_is_cat = nullptr;
   BinMeta *d_meta = nullptr, *d_cmeta = nullptr;  // identity tile mapping (binned/threaded) / compact + lat mapping
   uint32_t *d_bucket_range = nullptr;
+  uint32_t *d_ltree_off = nullptr;  // per tree: byte offset of its chunk in d_lmodel (latency path)
   std::atomic<bool> closed{false};
   std::atomic<int> inflight{0};
   std::mutex mu;  // guards repacking / device buffers
-  int opt_threads = 0, opt_variant = -1, opt_ilp = 0, opt_chunk_kb = 0;
+  int opt_threads = 0, opt_variant = -1, opt_ilp = 0, opt_chunk_kb = 0, opt_latency_rows = 0;
 
   void upload() {
     if (d_model) cudaFree(d_model);
@@ -144,11 +145,11 @@ struct mr_model {
   }
   void free_binned() {
     for (void *p : {(void *)d_bmodel, (void *)d_bchunks, (void *)d_thr_off, (void *)d_thr, (void *)d_is_cat,
-                    (void *)d_tmodel, (void *)d_tchunks, (void *)d_cmodel, (void *)d_cchunks, (void *)d_lmodel,
-                    (void *)d_lchunks, (void *)d_meta, (void *)d_cmeta, (void *)d_bucket_range})
+                    (void *)d_cmodel, (void *)d_cchunks, (void *)d_lmodel,
+                    (void *)d_lchunks, (void *)d_ltree_off, (void *)d_meta, (void *)d_cmeta, (void *)d_bucket_range})
       if (p) cudaFree(p);
     d_bmodel = nullptr; d_bchunks = nullptr; d_thr_off = nullptr; d_thr = nullptr; d_is_cat = nullptr;
-    d_tmodel = nullptr; d_tchunks = nullptr; d_cmodel = nullptr; d_cchunks = nullptr; d_lmodel = nullptr; d_lchunks = nullptr; d_meta = nullptr; d_cmeta = nullptr; d_bucket_range = nullptr;
+    d_cmodel = nullptr; d_cchunks = nullptr; d_lmodel = nullptr; d_lchunks = nullptr; d_ltree_off = nullptr; d_meta = nullptr; d_cmeta = nullptr; d_bucket_range = nullptr;
   }
   // identity of the current code mapping (thresholds + tile columns): consumers that cache codes key on it
   uint64_t code_gen = 0;
@@ -189,18 +190,16 @@ struct mr_model {
       if (lat.ok) {
         d_lmodel = to_device(lat.packed.bytes);
         d_lchunks = to_device(lat.packed.chunks);
-      }
-      threaded = pack_threaded(host, binned, budget);
-      if (threaded.ok) {
-        d_tmodel = to_device(threaded.packed.bytes);
-        d_tchunks = to_device(threaded.packed.chunks);
+        std::vector<uint32_t> toff(host.trees.size(), 0);
+        for (auto &cd : lat.packed.chunks)
+          for (uint32_t t = 0; t < cd.n_trees; t++) toff[cd.first_tree + t] = cd.byte_off;
+        d_ltree_off = to_device(toff);
       }
     }
   }
-  bool use_threaded() const { return threaded.ok && opt_variant == 3; }
   bool use_compact() const { return compact.ok && (opt_variant == 4 || opt_variant < 0); }
   // the code-based scorer that is active and the width of its code tile
-  const BinnedModel &active_binned() const { return use_threaded() ? threaded : use_compact() ? compact : binned; }
+  const BinnedModel &active_binned() const { return use_compact() ? compact : binned; }
   int code_cols() const { return active_binned().tile_cols; }
   bool use_binned() const {
     if ((size_t)2 * host.n_features * (4 * 32 + 2) * sizeof(uint16_t) > 200 * 1024) return false;  // bin_kernel tile
@@ -210,16 +209,15 @@ struct mr_model {
     // features); otherwise generic binned for LightGBM (f64 -> u16 quarters the tile) and the plain f32
     // kernel for XGBoost, whose features are already binary32 (profiles/sweep_r1.md)
     if (opt_variant < 0) return binned.ok && (compact.ok || host.kind == MR_BOOSTER_LIGHTGBM);
-    return binned.ok && (opt_variant == 2 || opt_variant == 4 || use_threaded());
+    return binned.ok && (opt_variant == 2 || opt_variant == 4);
   }
   BinnedLaunch binned_desc() const {
     BinnedLaunch B;
-    const bool thr = use_threaded(), cmp = !thr && use_compact();
-    const BinnedModel &M = thr ? threaded : cmp ? compact : binned;
-    B.threaded = thr;
+    const bool cmp = use_compact();
+    const BinnedModel &M = cmp ? compact : binned;
     B.compact = cmp;
-    B.d_model = thr ? d_tmodel : cmp ? d_cmodel : d_bmodel;
-    B.d_chunks = thr ? d_tchunks : cmp ? d_cchunks : d_bchunks;
+    B.d_model = cmp ? d_cmodel : d_bmodel;
+    B.d_chunks = cmp ? d_cchunks : d_bchunks;
     B.n_chunks = (int)M.packed.chunks.size();
     B.max_chunk_bytes = M.packed.max_chunk_bytes;
     B.d_thr_off = d_thr_off; B.d_thr = d_thr; B.d_is_cat = d_is_cat;
@@ -231,23 +229,35 @@ struct mr_model {
     return B;
   }
   // Scores rows whose u16 codes were already written to d_codes (fused assemble path).
+  // The tree-parallel path wins while the batch cannot fill the chip with one thread per item: a thread's walk
+  // through T trees is a T * depth long dependent chain whatever the batch size, the latency path's cost is the
+  // leaf-value round trip (T * rows * 16 B).  Measured crossover: profiles/latency_path_r2.md.
+  int latency_max_rows() const {
+    if (opt_latency_rows > 0) return opt_latency_rows;
+    const long long t = std::max<long long>(1, (long long)host.trees.size());
+    return (int)std::max<long long>(kLatencyMaxRows, std::min<long long>(32768, 48000000ll / t));
+  }
   bool use_latency(int rows) const {
-    return lat.ok && rows <= kLatencyMaxRows && opt_variant < 0 && opt_threads == 0 &&
+    return lat.ok && rows <= latency_max_rows() && opt_variant < 0 && opt_threads == 0 &&
            use_compact() && 128 + lat.packed.max_chunk_bytes + 128 + (size_t)4 * compact.tile_cols * 64 <= 200 * 1024;
   }
-  void score_codes(uint16_t *d_codes, int rows, double *d_out, cudaStream_t stream, void *d_leaf_scratch = nullptr) const {
+  // true: score_codes() can store to peer sinks from inside the scoring kernel
+  bool fuses_sinks(int rows) const { return use_latency(rows) || (use_binned() && use_compact()); }
+  void score_codes(uint16_t *d_codes, int rows, double *d_out, cudaStream_t stream, void *d_leaf_scratch = nullptr,
+                   const ScoreSinks *sinks = nullptr) const {
     BinnedLaunch B = binned_desc();
     B.rows = rows; B.cols = host.n_features; B.d_out = d_out; B.d_bins = d_codes; B.codes_ready = true;
+    if (sinks) B.sinks = *sinks;
     if (use_latency(rows)) {
       B.d_model = d_lmodel; B.d_chunks = d_lchunks;
       B.n_chunks = (int)lat.packed.chunks.size();
       B.max_chunk_bytes = lat.packed.max_chunk_bytes;
       if (d_leaf_scratch) {
-        launch_gbdt_latency(B, (int)host.trees.size(), (double *)d_leaf_scratch, stream);
+        launch_gbdt_latency(B, (int)host.trees.size(), d_ltree_off, d_leaf_scratch, stream);
       } else {
         void *lv = nullptr;
         MR_CUDA_CHECK(cudaMallocAsync(&lv, latency_scratch_bytes(rows, (int)host.trees.size()), stream));
-        launch_gbdt_latency(B, (int)host.trees.size(), (double *)lv, stream);
+        launch_gbdt_latency(B, (int)host.trees.size(), d_ltree_off, lv, stream);
         MR_CUDA_CHECK(cudaFreeAsync(lv, stream));
       }
       return;
@@ -298,7 +308,6 @@ struct mr_model {
     L.cols = cols;
     L.d_out = d_out;
     L.threads = opt_threads;
-    L.variant = opt_variant;
     L.ilp = opt_ilp;
     return L;
   }

@@ -1,5 +1,7 @@
 // JNI shim for libmrgpu (compiled only with -DWITH_JNI -I$JAVA_HOME/include -I$JAVA_HOME/include/linux;
-// there is no JDK / jni.h in the build image, so the default build leaves this file empty).
+// there is no JDK / jni.h in the build image, so the default build leaves this file empty —
+// tests/test_jni_shim_cpu.py compiles it against the test double in tests/c/jni_stub/jni.h, checks the exported
+// Java_ai_metarank_b200_Native_* set against INTEGRATION.md's @native list and drives it with a fake JNIEnv).
 // One native method per C-ABI entry point that the Scala adapter in INTEGRATION.md binds.
 // Rules: no JNI critical section is held across a GPU call; a non-zero mr_status becomes a
 // java.lang.RuntimeException carrying mr_last_error() (-> IO.raiseError -> HTTP 500, exactly how
@@ -36,7 +38,10 @@ JNIEXPORT jlong JNICALL Java_ai_metarank_b200_Native_modelLoad(JNIEnv *env, jcla
   return (jlong)m;
 }
 
-// Booster.predictMat(values: Array[Double], rows: Int, cols: Int): Array[Double]
+// Booster.predictMat(values: Array[Double], rows: Int, cols: Int): Array[Double] — the signature ltrlib's Booster has,
+// so the adapter can be a one-line override.  Get/ReleaseDoubleArrayElements COPY on HotSpot (no pinning of
+// primitive arrays outside critical sections, and no critical section may span a GPU call): 8 * rows * cols bytes each
+// way through the JVM heap before the H2D copy.  predictMatDirect below is the zero-copy variant.
 JNIEXPORT jdoubleArray JNICALL Java_ai_metarank_b200_Native_predictMat(JNIEnv *env, jclass, jlong model, jdoubleArray values,
                                                                         jint rows, jint cols) {
   jdoubleArray out = env->NewDoubleArray(rows);
@@ -47,6 +52,20 @@ JNIEXPORT jdoubleArray JNICALL Java_ai_metarank_b200_Native_predictMat(JNIEnv *e
   env->ReleaseDoubleArrayElements(out, o, 0);
   throw_status(env, s);
   return out;
+}
+
+// Same on direct ByteBuffers (native order, what ByteBuffer.allocateDirect().order(nativeOrder()).asDoubleBuffer()
+// views): nothing is copied in JNI, and a buffer the caller registered with cudaHostRegister is DMA'd in place.
+JNIEXPORT void JNICALL Java_ai_metarank_b200_Native_predictMatDirect(JNIEnv *env, jclass, jlong model, jobject values,
+                                                                    jint rows, jint cols, jobject outScores) {
+  const double *v = (const double *)env->GetDirectBufferAddress(values);
+  double *o = (double *)env->GetDirectBufferAddress(outScores);
+  if (rows > 0 && (!v || !o || env->GetDirectBufferCapacity(values) < (jlong)rows * cols * 8 ||
+                   env->GetDirectBufferCapacity(outScores) < (jlong)rows * 8)) {
+    env->ThrowNew(env->FindClass("java/lang/IllegalArgumentException"), "predictMatDirect: direct buffers too small");
+    return;
+  }
+  throw_status(env, mr_model_predict_mat((mr_model *)model, v, rows, cols, o));
 }
 
 JNIEXPORT void JNICALL Java_ai_metarank_b200_Native_modelClose(JNIEnv *env, jclass, jlong model) {

@@ -8,6 +8,7 @@
 #include "request_codec.h"
 #include "internal.h"
 #include "schema.h"
+#include "sinks.cuh"
 #include "state.h"
 
 using namespace mr;
@@ -56,12 +57,12 @@ namespace {
 inline size_t al(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct ScratchPlan {
-  size_t item_req, item_row, visitor_row, cos, reqagg, hist_desc, hist_pool, hist_cursor, error_flag, features, codes, leafvals, total;
+  size_t item_req, item_row, visitor_row, cos, reqagg, hist_desc, hist_pool, hist_cursor, error_flag, features, codes, leafvals, local_scores, total;
   uint32_t hist_pool_cap;
 };
 
 ScratchPlan plan_scratch(const Schema &S, int n_requests, int total_items, uint32_t per_hist, bool own_features,
-                         int code_cols = 0, size_t leaf_bytes = 0) {
+                         int code_cols = 0, size_t leaf_bytes = 0, size_t local_score_bytes = 0) {
   ScratchPlan p{};
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += al(bytes); return r; };
@@ -82,6 +83,7 @@ ScratchPlan plan_scratch(const Schema &S, int n_requests, int total_items, uint3
   p.features = own_features ? take((size_t)total_items * std::max(S.dim, 1) * 8) : 0;
   p.codes = code_cols > 0 ? take(binned_scratch_bytes(total_items, code_cols)) : 0;
   p.leafvals = leaf_bytes ? take(leaf_bytes) : 0;
+  p.local_scores = local_score_bytes ? take(local_score_bytes) : 0;
   p.total = o;
   return p;
 }
@@ -745,7 +747,7 @@ mr_status mr_rank_device(mr_state *st, mr_model *model, const mr_rank_batch *b, 
       if (!d_out_scores) fail(MR_ERR_INVALID_ARG, "d_out_scores is null");
       if (fused) model->score_codes(a.codes, N, d_out_scores, stream);
       else model->score(a.out_features, N, S.dim, d_out_scores, stream);
-      if (d_out_order) launch_rank_order(d_out_scores, a.item_offsets, R, N, d_out_order, stream);
+      if (d_out_order) launch_rank_order(d_out_scores, a.item_offsets, R, N, d_out_order, stream, b->max_items_per_request);
     }
   });
 }
@@ -762,6 +764,405 @@ mr_status mr_rank_device_status(mr_state *st, void *cuda_stream) {
       fail(MR_ERR_UNSUPPORTED, "per-request tag histograms exceeded the scratch pool; pool grown, resubmit the batch");
     }
     if (err == MR_ERR_ARITHMETIC) fail(MR_ERR_ARITHMETIC, "/ by zero in normalized rate (global top counter is 0)");
+    if (err == -2) fail(MR_ERR_CUDA, "a member of the group did not publish its slice within 2 s (peer process gone?)");
+  });
+}
+
+}  // extern "C"
+
+// =====================================================================================================
+// Mega-request sharding (BASELINE configs[4]: one 10 000-item request, 2000 trees, 8 GPUs).
+//
+// Items are independent given the request, so a request too large for one GPU's latency budget is split into
+// contiguous item ranges, one per member of an mr_group.  Every member assembles and scores ITS range only;
+// the scorer's final store writes each score into the exchange buffer of EVERY member through peer memory
+// (NVLink / NVSwitch; CUDA IPC between processes, direct peer access inside one process) and the last CTA
+// raises the member's flag on every peer — the all-gather is the scorer's epilogue.  A one-warp kernel then
+// waits for the other members' flags and the ordering kernels rank the full score vector.  No host round
+// trip, no NCCL call, no allocation per request.
+//
+// Exchange buffer of a member (cudaMalloc, exported by IPC handle):
+//   +0     u32 flag[2][8]      flag[parity][member] = sequence number of the last request that member published
+//   +256   f64 score[2][cap]   double-buffered by request parity: a member may start request s+1 while a slow
+//                              peer still orders request s (it cannot reach s+2 before that peer published s+1,
+//                              which it does after it finished reading s)
+struct mr_group {
+  mr_ctx *ctx = nullptr;
+  int rank = 0, world = 1, cap = 0;  // cap: item capacity (multiple of 128)
+  uint8_t *xbuf = nullptr;
+  size_t xbytes = 0;
+  uint8_t *peer[8] = {};
+  bool ipc_open[8] = {};
+  bool connected = false;
+  uint32_t seq = 0;
+  uint32_t *d_done = nullptr;   // CTA arrival counter of the publishing kernel
+  int32_t *d_offs = nullptr;    // {0, n_assembled, 0, N}
+  int32_t *d_order = nullptr;   // [cap]
+  int32_t *d_rank_tmp = nullptr;  // [cap] scratch of the mega-request ordering
+  int32_t *d_err = nullptr;
+  std::mutex mu;                // one collective at a time per member
+
+  double *scores(int member, int parity) const { return (double *)(peer[member] + 256) + (size_t)parity * cap; }
+  uint32_t *flag(int member, int parity, int who) const { return (uint32_t *)peer[member] + parity * 8 + who; }
+};
+
+namespace {
+
+// Contiguous slice of member `rank`: ceil(N / G) rounded up to whole 128-item scorer tiles.
+inline void group_slice(int n_items, int world, int rank, int *lo, int *hi) {
+  const int per = ((((n_items + world - 1) / world) + 127) / 128) * 128;
+  *lo = std::min(n_items, rank * per);
+  *hi = std::min(n_items, *lo + per);
+}
+
+__global__ void group_prologue_kernel(int32_t *offs, int n_assembled, int n_total) {
+  offs[0] = 0; offs[1] = n_assembled; offs[2] = 0; offs[3] = n_total;
+}
+
+// Fallback publisher: scorers that cannot store to the sinks themselves (the exact f64/f32 kernel, the generic
+// binned kernel) and empty slices.  local == nullptr publishes nothing but still raises the flags.
+__global__ void __launch_bounds__(256) group_publish_kernel(const double *local, int n, const ScoreSinks s) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (local && i < n) store_score(nullptr, s, i, local[i]);
+  publish_when_last(s);
+}
+
+// One lane per member: spin (acquire, system scope) until its flag carries this request's sequence number.
+// Bounded: a peer that never arrives (crashed process) raises the error flag after `timeout_ns` instead of
+// hanging the GPU.
+__global__ void group_wait_kernel(const uint32_t *flags, int world, uint32_t seq, int32_t *err, unsigned long long timeout_ns) {
+  const int g = threadIdx.x;
+  if (g >= world) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + g) : "memory");
+    if (v == seq) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > timeout_ns) { atomicExch(err, -2); return; }
+    __nanosleep(64);
+  }
+}
+
+struct GroupCall {
+  int N = 0, lo = 0, hi = 0;
+  bool sliced = false;  // only [lo, hi) was assembled (else the whole request)
+};
+
+// Enqueues on `stream`: [assemble] -> score this member's slice (the stores go to every member) -> wait for the
+// other members -> order the full score vector.  `a` carries the device pointers of the assembled item range.
+void group_enqueue(mr_group *g, mr_state *st, mr_model *model, RankArgs &a, const ScratchPlan &sp, uint8_t *scratch,
+                   const GroupCall &gc, cudaStream_t stream) {
+  const Schema &S = st->store->schema;
+  const bool fused = fused_codes(model);
+  const uint32_t seq = g->seq;
+  const int parity = (int)(seq & 1u);
+  const int n_sl = gc.hi - gc.lo, first = gc.sliced ? 0 : gc.lo;
+  { ProfScope _ps("group_prologue_kernel", stream); group_prologue_kernel<<<1, 1, 0, stream>>>(g->d_offs, a.total_items, gc.N); }
+  MR_CUDA_CHECK(cudaGetLastError());
+  a.item_offsets = g->d_offs;
+  a.out_features = fused ? nullptr : (double *)(scratch + sp.features);
+  if (fused) set_codes(a, st, model, scratch, sp);
+  if (a.total_items > 0) launch_assemble(a, S, stream);
+  else MR_CUDA_CHECK(cudaMemsetAsync(a.error_flag, 0, 4, stream));
+  ScoreSinks sk;
+  sk.n_peer = g->world;
+  for (int m = 0; m < g->world; m++) {
+    sk.peer[m] = g->scores(m, parity);
+    sk.flag[m] = g->flag(m, parity, g->rank);
+  }
+  sk.done = g->d_done;
+  sk.seq = seq;
+  sk.item_base = gc.lo;
+  bool published = false;
+  if (n_sl > 0) {
+    if (fused && model->fuses_sinks(n_sl)) {
+      uint16_t *codes = a.codes + (size_t)(first / 32) * model->code_cols() * 32;
+      model->score_codes(codes, n_sl, nullptr, stream, sp.leafvals ? scratch + sp.leafvals : nullptr, &sk);
+      published = true;
+    } else {
+      double *local = (double *)(scratch + sp.local_scores);
+      if (fused) model->score_codes(a.codes + (size_t)(first / 32) * model->code_cols() * 32, n_sl, local, stream);
+      else model->score(a.out_features + (size_t)first * S.dim, n_sl, S.dim, local, stream);
+      { ProfScope _ps("group_publish_kernel", stream); group_publish_kernel<<<(n_sl + 255) / 256, 256, 0, stream>>>(local, n_sl, sk); }
+      MR_CUDA_CHECK(cudaGetLastError());
+      g_kernel_launches++;
+      published = true;
+    }
+  }
+  if (!published) {
+    { ProfScope _ps("group_publish_kernel", stream); group_publish_kernel<<<1, 256, 0, stream>>>(nullptr, 0, sk); }
+    MR_CUDA_CHECK(cudaGetLastError());
+    g_kernel_launches++;
+  }
+  { ProfScope _ps("group_wait_kernel", stream); group_wait_kernel<<<1, 32, 0, stream>>>(g->flag(g->rank, parity, 0), g->world, seq, a.error_flag, 2000000000ull); }
+  MR_CUDA_CHECK(cudaGetLastError());
+  launch_rank_order(g->scores(g->rank, parity), g->d_offs + 2, 1, gc.N, g->d_order, stream, gc.N, g->d_rank_tmp);
+  g_kernel_launches += 2;
+}
+
+void group_check(mr_group *g, mr_state *st, mr_model *model, int n_requests, int N) {
+  if (!g || !st || !model) fail(MR_ERR_INVALID_ARG, "null argument");
+  check_model(model);
+  if (!g->connected) fail(MR_ERR_INVALID_ARG, "group is not connected (mr_group_connect / mr_group_connect_local)");
+  if (st->ctx != g->ctx || model->ctx != g->ctx) fail(MR_ERR_INVALID_ARG, "state / model belong to another context than the group member");
+  if (n_requests != 1) fail(MR_ERR_UNSUPPORTED, "mr_group_rank splits ONE request; batches of ordinary requests are sharded by request (mr_rank per GPU)");
+  if (N < 0 || N > g->cap) fail(MR_ERR_INVALID_ARG, "request has %d items, the group was created for %d", N, g->cap);
+  check_scored_dim(st, model);
+}
+
+}  // namespace
+
+extern "C" {
+
+mr_status mr_group_create(mr_ctx *ctx, int32_t rank, int32_t world, int32_t max_items, mr_group **out) {
+  return guard([&] {
+    if (!ctx || !out) fail(MR_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) fail(MR_ERR_INVALID_ARG, "rank %d / world %d (1..8 members)", rank, world);
+    if (max_items < 1) fail(MR_ERR_INVALID_ARG, "max_items must be positive");
+    auto g = std::make_unique<mr_group>();
+    g->ctx = ctx;
+    g->rank = rank;
+    g->world = world;
+    g->cap = ((max_items + 127) / 128) * 128;
+    g->xbytes = 256 + (size_t)2 * g->cap * 8;
+    MR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    MR_CUDA_CHECK(cudaMalloc((void **)&g->xbuf, g->xbytes));
+    MR_CUDA_CHECK(cudaMemset(g->xbuf, 0, g->xbytes));
+    MR_CUDA_CHECK(cudaMalloc((void **)&g->d_done, 256));
+    MR_CUDA_CHECK(cudaMemset(g->d_done, 0, 256));
+    g->d_offs = (int32_t *)((uint8_t *)g->d_done + 64);
+    g->d_err = (int32_t *)((uint8_t *)g->d_done + 128);
+    MR_CUDA_CHECK(cudaMalloc((void **)&g->d_order, (size_t)g->cap * 4 * 2));
+    g->d_rank_tmp = g->d_order + g->cap;
+    g->peer[rank] = g->xbuf;
+    g->connected = world == 1;
+    *out = g.release();
+  });
+}
+
+mr_status mr_group_export(mr_group *g, uint8_t *handle) {
+  return guard([&] {
+    if (!g || !handle) fail(MR_ERR_INVALID_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == MR_GROUP_HANDLE_BYTES, "handle size");
+    MR_CUDA_CHECK(cudaSetDevice(g->ctx->device));
+    cudaIpcMemHandle_t h;
+    MR_CUDA_CHECK(cudaIpcGetMemHandle(&h, g->xbuf));
+    memcpy(handle, &h, sizeof h);
+  });
+}
+
+mr_status mr_group_connect(mr_group *g, const uint8_t *handles) {
+  return guard([&] {
+    if (!g || !handles) fail(MR_ERR_INVALID_ARG, "null argument");
+    MR_CUDA_CHECK(cudaSetDevice(g->ctx->device));
+    for (int m = 0; m < g->world; m++) {
+      if (m == g->rank || g->peer[m]) continue;
+      cudaIpcMemHandle_t h;
+      memcpy(&h, handles + (size_t)m * MR_GROUP_HANDLE_BYTES, sizeof h);
+      void *p = nullptr;
+      MR_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      g->peer[m] = (uint8_t *)p;
+      g->ipc_open[m] = true;
+    }
+    g->connected = true;
+  });
+}
+
+mr_status mr_group_connect_local(mr_group *const *members, int32_t world) {
+  return guard([&] {
+    if (!members || world < 1 || world > 8) fail(MR_ERR_INVALID_ARG, "bad member list");
+    for (int m = 0; m < world; m++)
+      if (!members[m] || members[m]->world != world || members[m]->rank != m)
+        fail(MR_ERR_INVALID_ARG, "members[%d] must be the group member of rank %d in a world of %d", m, m, world);
+    for (int a = 0; a < world; a++) {
+      mr_group *g = members[a];
+      MR_CUDA_CHECK(cudaSetDevice(g->ctx->device));
+      for (int b = 0; b < world; b++) {
+        const int db = members[b]->ctx->device;
+        if (db != g->ctx->device) {
+          int can = 0;
+          MR_CUDA_CHECK(cudaDeviceCanAccessPeer(&can, g->ctx->device, db));
+          if (!can) fail(MR_ERR_UNSUPPORTED, "device %d cannot access device %d's memory", g->ctx->device, db);
+          cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
+          if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+          else MR_CUDA_CHECK(e);
+        }
+        g->peer[b] = members[b]->xbuf;
+      }
+      g->connected = true;
+    }
+  });
+}
+
+mr_status mr_group_free(mr_group *g) {
+  if (!g) return MR_OK;
+  cudaSetDevice(g->ctx->device);
+  cudaDeviceSynchronize();
+  for (int m = 0; m < g->world; m++)
+    if (g->ipc_open[m]) cudaIpcCloseMemHandle(g->peer[m]);
+  if (g->xbuf) cudaFree(g->xbuf);
+  if (g->d_done) cudaFree(g->d_done);
+  if (g->d_order) cudaFree(g->d_order);
+  delete g;
+  return MR_OK;
+}
+
+void mr_group_slice(int32_t n_items, int32_t world, int32_t rank, int32_t *lo, int32_t *hi) {
+  int a = 0, b = 0;
+  if (world > 0 && rank >= 0 && rank < world && n_items >= 0) group_slice(n_items, world, rank, &a, &b);
+  if (lo) *lo = a;
+  if (hi) *hi = b;
+}
+
+mr_status mr_group_rank(mr_group *g, mr_state *st, mr_model *model, const mr_rank_batch *b, double *out_scores,
+                        int32_t *out_order) {
+  return guard([&] {
+    if (!b || !b->item_offsets) fail(MR_ERR_INVALID_ARG, "null argument");
+    const int N = b->n_requests == 1 ? b->item_offsets[1] - b->item_offsets[0] : 0;
+    group_check(g, st, model, b->n_requests, N);
+    if (b->item_offsets[0] != 0) fail(MR_ERR_INVALID_ARG, "item_offsets[0] must be 0");
+    if (N > 0 && (!b->item_ids || !out_scores)) fail(MR_ERR_INVALID_ARG, "null item / score arrays");
+    const Schema &S = st->store->schema;
+    if (!S.in_req_f64.empty() && !b->req_f64) fail(MR_ERR_INVALID_ARG, "schema needs req_f64 inputs");
+    if (!S.in_req_u64.empty() && !b->req_u64) fail(MR_ERR_INVALID_ARG, "schema needs req_u64 inputs");
+    if (!S.in_req_vec.empty() && (!b->req_vec || !b->req_vec_present)) fail(MR_ERR_INVALID_ARG, "schema needs req_vec inputs");
+    if (!S.in_req_tok.empty() && (!b->req_tok_offsets || !b->req_tok_hashes)) fail(MR_ERR_INVALID_ARG, "schema needs req_tok inputs");
+    std::lock_guard<std::mutex> one(g->mu);
+    InflightGuard ig(model);
+    MR_CUDA_CHECK(cudaSetDevice(g->ctx->device));
+    RankInFlight inflight(st);
+    std::shared_lock<std::shared_mutex> read_guard(st->store->mu);
+    GroupCall gc;
+    gc.N = N;
+    group_slice(N, g->world, g->rank, &gc.lo, &gc.hi);
+    // per-request aggregates (diversity, interacted_with histograms, cosine normalisation) read the WHOLE item list:
+    // such schemas assemble the full request on every member and only the scoring is split
+    gc.sliced = !S.needs_prepass;
+    const int a0 = gc.sliced ? gc.lo : 0, a1 = gc.sliced ? gc.hi : N, n_asm = a1 - a0;
+    LaneGuard lg(g->ctx);
+    Lane *lane = lg.lane.get();
+    struct Seg { const void *src; size_t bytes, off; };
+    Seg segs[12];
+    size_t in_bytes = 0;
+    int ns = 0;
+    auto seg = [&](const void *p, size_t bytes) { segs[ns] = Seg{p, p ? bytes : 0, in_bytes}; in_bytes += al(segs[ns].bytes); return ns++; };
+    const size_t nrf = S.in_req_f64.size(), nru = S.in_req_u64.size(), nrv = S.in_req_vec.size(), nif = S.in_item_f64.size(), ntk = S.in_req_tok.size();
+    const int s_ids = seg(b->item_ids ? b->item_ids + a0 : nullptr, (size_t)n_asm * 8);
+    const int s_usr = seg(b->user_ids, 8);
+    const int s_ses = seg(b->session_ids, 8);
+    const int s_rf = seg(b->req_f64, nrf * 8);
+    const int s_ru = seg(b->req_u64, nru * 8);
+    const int s_rv = seg(b->req_vec, (size_t)S.vec_stride * 4);
+    const int s_rp = seg(b->req_vec_present, nrv);
+    const int s_if = seg(b->item_f64 ? b->item_f64 + (size_t)a0 * nif : nullptr, (size_t)n_asm * nif * 8);
+    const bool has_tok = ntk > 0 && b->req_tok_offsets && b->req_tok_hashes;
+    const int32_t t1 = has_tok ? b->req_tok_offsets[ntk] : 0;
+    const int s_to = seg(has_tok ? b->req_tok_offsets : nullptr, (ntk + 1) * 4);
+    const int s_th = seg(has_tok ? b->req_tok_hashes : nullptr, (size_t)t1 * 8);
+    const int s_tw = seg(has_tok && b->req_tok_weights ? b->req_tok_weights : nullptr, (size_t)t1 * 8);
+    const bool fused = fused_codes(model);
+    const int n_sl = gc.hi - gc.lo;
+    const size_t leaf_bytes = (fused && n_sl > 0 && model->use_latency(n_sl)) ? latency_scratch_bytes(n_sl, (int)model->host.trees.size()) : 0;
+    ScratchPlan sp = plan_scratch(S, 1, std::max(n_asm, 1), st->hist_pool_per_hist, !fused, fused ? model->code_cols() : 0, leaf_bytes,
+                                  (size_t)std::max(n_sl, 1) * 8);
+    const size_t d_total = al(in_bytes) + sp.total + 256;
+    const size_t out_bytes = al((size_t)N * 8) + al((size_t)N * 4) + 256;
+    lane->ensure(in_bytes + out_bytes, d_total);
+    for (int k = 0; k < ns; k++)
+      if (segs[k].bytes) memcpy(lane->h_pinned + segs[k].off, segs[k].src, segs[k].bytes);
+    uint8_t *d_in = lane->d_buf, *scratch = lane->d_buf + al(in_bytes);
+    if (in_bytes) MR_CUDA_CHECK(cudaMemcpyAsync(d_in, lane->h_pinned, in_bytes, cudaMemcpyHostToDevice, lane->stream));
+    auto dp = [&](int si) -> const void * { return segs[si].bytes ? d_in + segs[si].off : nullptr; };
+    RankArgs a{};
+    fill_args(a, st, scratch, sp);
+    a.n_requests = 1;
+    a.total_items = n_asm;
+    a.item_ids = (const uint64_t *)dp(s_ids);
+    a.user_ids = (const uint64_t *)dp(s_usr);
+    a.session_ids = (const uint64_t *)dp(s_ses);
+    a.req_f64 = (const double *)dp(s_rf);
+    a.req_u64 = (const uint64_t *)dp(s_ru);
+    a.req_vec = (const float *)dp(s_rv);
+    a.req_vec_present = (const uint8_t *)dp(s_rp);
+    a.item_f64 = (const double *)dp(s_if);
+    a.req_tok_off = has_tok ? (const int32_t *)(d_in + segs[s_to].off) : nullptr;
+    a.req_tok_hash = (const uint64_t *)dp(s_th);
+    a.req_tok_w = (const double *)dp(s_tw);
+    a.req_tok_base = 0;
+    a.error_flag = (int32_t *)(lane->d_buf + al(in_bytes) + sp.total);
+    g->seq++;
+    group_enqueue(g, st, model, a, sp, scratch, gc, lane->stream);
+    uint8_t *h_out = lane->h_pinned + in_bytes;
+    const size_t ho_order = al((size_t)N * 8), ho_err = ho_order + al((size_t)N * 4);
+    const int parity = (int)(g->seq & 1u);
+    if (N > 0) MR_CUDA_CHECK(cudaMemcpyAsync(h_out, g->scores(g->rank, parity), (size_t)N * 8, cudaMemcpyDeviceToHost, lane->stream));
+    if (N > 0 && out_order) MR_CUDA_CHECK(cudaMemcpyAsync(h_out + ho_order, g->d_order, (size_t)N * 4, cudaMemcpyDeviceToHost, lane->stream));
+    MR_CUDA_CHECK(cudaMemcpyAsync(h_out + ho_err, a.error_flag, 4, cudaMemcpyDeviceToHost, lane->stream));
+    MR_CUDA_CHECK(cudaStreamSynchronize(lane->stream));
+    int32_t err;
+    memcpy(&err, h_out + ho_err, 4);
+    if (err == -2) fail(MR_ERR_CUDA, "a member of the group did not publish its slice within 2 s (peer process gone?)");
+    if (err == -1) { st->hist_pool_per_hist *= 4; fail(MR_ERR_UNSUPPORTED, "per-request tag histograms exceeded the scratch pool; pool grown, resubmit on every member"); }
+    if (err == MR_ERR_ARITHMETIC) fail(MR_ERR_ARITHMETIC, "/ by zero in normalized rate (global top counter is 0)");
+    if (N > 0) memcpy(out_scores, h_out, (size_t)N * 8);
+    if (N > 0 && out_order) memcpy(out_order, h_out + ho_order, (size_t)N * 4);
+  });
+}
+
+mr_status mr_group_rank_device(mr_group *g, mr_state *st, mr_model *model, const mr_rank_batch *b, int32_t total_items,
+                               double *d_out_scores, int32_t *d_out_order, void *cuda_stream) {
+  return guard([&] {
+    if (!b) fail(MR_ERR_INVALID_ARG, "null argument");
+    const int N = total_items;
+    group_check(g, st, model, b->n_requests, N);
+    const Schema &S = st->store->schema;
+    std::lock_guard<std::mutex> one(g->mu);
+    MR_CUDA_CHECK(cudaSetDevice(g->ctx->device));
+    RankInFlight inflight(st);
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    GroupCall gc;
+    gc.N = N;
+    group_slice(N, g->world, g->rank, &gc.lo, &gc.hi);
+    gc.sliced = !S.needs_prepass;
+    const int a0 = gc.sliced ? gc.lo : 0, a1 = gc.sliced ? gc.hi : N, n_asm = a1 - a0, n_sl = gc.hi - gc.lo;
+    const bool fused = fused_codes(model);
+    const size_t leaf_bytes = (fused && n_sl > 0 && model->use_latency(n_sl)) ? latency_scratch_bytes(n_sl, (int)model->host.trees.size()) : 0;
+    ScratchPlan sp = plan_scratch(S, 1, std::max(n_asm, 1), st->hist_pool_per_hist, !fused, fused ? model->code_cols() : 0, leaf_bytes,
+                                  (size_t)std::max(n_sl, 1) * 8);
+    if (sp.total > st->d_scratch_cap) {
+      MR_CUDA_CHECK(cudaDeviceSynchronize());
+      if (st->d_scratch) cudaFree(st->d_scratch);
+      st->d_scratch = nullptr;
+      MR_CUDA_CHECK(cudaMalloc((void **)&st->d_scratch, sp.total));
+      st->d_scratch_cap = sp.total;
+    }
+    const size_t nif = S.in_item_f64.size();
+    RankArgs a{};
+    fill_args(a, st, st->d_scratch, sp);
+    a.error_flag = st->d_error;
+    a.n_requests = 1;
+    a.total_items = n_asm;
+    a.item_ids = b->item_ids ? b->item_ids + a0 : nullptr;
+    a.user_ids = b->user_ids;
+    a.session_ids = b->session_ids;
+    a.req_f64 = b->req_f64;
+    a.req_u64 = b->req_u64;
+    a.req_vec = b->req_vec;
+    a.req_vec_present = b->req_vec_present;
+    a.item_f64 = b->item_f64 ? b->item_f64 + (size_t)a0 * nif : nullptr;
+    a.req_tok_off = (S.in_req_tok.empty() || !b->req_tok_hashes) ? nullptr : b->req_tok_offsets;
+    a.req_tok_hash = b->req_tok_hashes;
+    a.req_tok_w = b->req_tok_weights;
+    a.req_tok_base = 0;
+    g->seq++;
+    group_enqueue(g, st, model, a, sp, st->d_scratch, gc, stream);
+    const int parity = (int)(g->seq & 1u);
+    if (d_out_scores && N > 0) MR_CUDA_CHECK(cudaMemcpyAsync(d_out_scores, g->scores(g->rank, parity), (size_t)N * 8, cudaMemcpyDeviceToDevice, stream));
+    if (d_out_order && N > 0) MR_CUDA_CHECK(cudaMemcpyAsync(d_out_order, g->d_order, (size_t)N * 4, cudaMemcpyDeviceToDevice, stream));
   });
 }
 

@@ -470,7 +470,7 @@ Schema parse_schema_json(const char *json, size_t len) {
     if (d.kind == FK_COSINE) d.aux2 = n_cos++;
   }
   // fast columns: item-scoped entries whose every column is one row word (see FastCol)
-  if (S.tables[SC_ITEM].row_words <= 64 && S.dim <= 65535) {
+  if (S.tables[SC_ITEM].row_words <= 128 && S.dim <= 65535) {
     for (auto &d : S.plan) {
       d.fast = 0;
       d.pad = 0;

@@ -100,7 +100,7 @@ class RankBatch(C.Structure):
                 ("user_ids", C.c_void_p), ("session_ids", C.c_void_p), ("req_f64", C.c_void_p),
                 ("req_u64", C.c_void_p), ("req_vec", C.c_void_p), ("req_vec_present", C.c_void_p),
                 ("item_f64", C.c_void_p), ("req_tok_offsets", C.c_void_p), ("req_tok_hashes", C.c_void_p),
-                ("req_tok_weights", C.c_void_p)]
+                ("req_tok_weights", C.c_void_p), ("max_items_per_request", C.c_int32)]
 
 
 class StateInfo(C.Structure):
@@ -570,10 +570,12 @@ def pack_number_columns(names: list[str], ids_u64: np.ndarray, columns: np.ndarr
 
 def rank_device(state: DeviceState, model, n_requests: int, total_items: int, d_offsets: int, d_item_ids: int,
                 d_scores: int, d_order: int = 0, d_features: int = 0, stream: int = 0, d_user_ids: int = 0,
-                d_session_ids: int = 0) -> None:
-    """mr_rank_device: every pointer is a device address; enqueued on `stream`, no sync."""
+                d_session_ids: int = 0, max_items: int = 0) -> None:
+    """mr_rank_device: every pointer is a device address; enqueued on `stream`, no sync.
+    max_items: the largest request's item count when known (mr_rank_batch.max_items_per_request)."""
     b = RankBatch(n_requests, d_offsets, d_item_ids, d_user_ids or None, d_session_ids or None, None, None, None,
                   None, None)
+    b.max_items_per_request = int(max_items)
     check(lib().mr_rank_device(state._h, model._h if model is not None else None, C.byref(b),
                                C.c_int32(total_items), C.c_void_p(d_scores), C.c_void_p(d_order or None),
                                C.c_void_p(d_features or None), C.c_void_p(stream)))

@@ -196,3 +196,28 @@ void oracle_rank_order(const double *scores, int32_t n, int32_t *order, int32_t 
     memcpy(order, scratch, (unsigned long)n * 4);
   }
 }
+
+/* ---- CPU-arm helpers for bench.py (not restatements of reference code: the reference's feature assembly of
+ * stored scalars is a hash-map read per (item, feature), FeatureValueLoader.scala:11-25; a dense row gather is the
+ * CHEAPEST possible stand-in, so the CPU baseline is an upper bound on what the JVM path could do). */
+
+/* out[r, :] = cat[idx[r], :], rows in parallel (so that the baseline's assembly is not a single-threaded
+ * numpy fancy-index beside a multi-threaded scorer). */
+void oracle_gather_rows(const double *cat, const int64_t *idx, int32_t rows, int32_t cols, double *out, int32_t threads) {
+#ifdef _OPENMP
+  if (threads < 1) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(threads)
+#endif
+  for (int32_t r = 0; r < rows; r++) memcpy(out + (int64_t)r * cols, cat + idx[r] * (int64_t)cols, (size_t)cols * sizeof(double));
+}
+
+/* oracle_rank_order for n_requests back-to-back requests, requests in parallel. */
+void oracle_rank_order_batch(const double *scores, const int32_t *offsets, int32_t n_requests, int32_t *order,
+                             int32_t *scratch, int32_t threads) {
+#ifdef _OPENMP
+  if (threads < 1) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 16) num_threads(threads)
+#endif
+  for (int32_t r = 0; r < n_requests; r++)
+    oracle_rank_order(scores + offsets[r], offsets[r + 1] - offsets[r], order + offsets[r], scratch + offsets[r]);
+}

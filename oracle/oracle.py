@@ -123,3 +123,26 @@ def rank_order(scores) -> np.ndarray:
     lib().oracle_rank_order(C.c_void_p(scores.ctypes.data), C.c_int32(n), C.c_void_p(order.ctypes.data),
                             C.c_void_p(scratch.ctypes.data))
     return order
+
+
+def gather_rows(cat: np.ndarray, idx: np.ndarray, threads: int = 1, out: np.ndarray | None = None) -> np.ndarray:
+    """out[r] = cat[idx[r]] with the rows spread over `threads` (bench.py's CPU arm)."""
+    cat = np.ascontiguousarray(cat, dtype=np.float64)
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    rows, cols = idx.size, cat.shape[1]
+    if out is None:
+        out = np.empty((rows, cols), dtype=np.float64)
+    lib().oracle_gather_rows(C.c_void_p(cat.ctypes.data), C.c_void_p(idx.ctypes.data), C.c_int32(rows), C.c_int32(cols),
+                             C.c_void_p(out.ctypes.data), C.c_int32(threads))
+    return out
+
+
+def rank_order_batch(scores, offsets, threads: int = 1) -> np.ndarray:
+    """rank_order per request of a batch (offsets as in mr_rank_batch), requests in parallel."""
+    scores = np.ascontiguousarray(scores, dtype=np.float64)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+    order = np.empty(scores.size, dtype=np.int32)
+    scratch = np.empty(max(scores.size, 1), dtype=np.int32)
+    lib().oracle_rank_order_batch(C.c_void_p(scores.ctypes.data), C.c_void_p(offsets.ctypes.data), C.c_int32(offsets.size - 1),
+                                  C.c_void_p(order.ctypes.data), C.c_void_p(scratch.ctypes.data), C.c_int32(threads))
+    return order

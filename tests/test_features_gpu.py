@@ -303,34 +303,39 @@ def test_large_batch_is_sliced_and_pipelined(ctx):
     booster.free(); ds.free(); fm.free()
 
 
-def test_sharded_scorer_world1_matches_direct(ctx):
-    """metarank_b200/sharded.py with the CUDA slice scorer (single process: the gather is the identity)."""
+@pytest.mark.parametrize("n_feat", [63, 64, 100, 127, 140])
+def test_wide_item_rows_take_the_coalesced_gather(ctx, n_feat):
+    """Item rows of 65..128 words (64+ scalar features, BASELINE config #5) are gathered by the warp-per-row
+    kernels with up to four coalesced loads (code rows on the scored path, dense rows with explain); wider rows
+    fall back to the generic per-item kernel.  All three must equal the stored scalars / the oracle's scores."""
     import metarank_b200 as mb
-    from metarank_b200 import features as F, sharded
+    from metarank_b200 import features as F
 
-    names = [f"f{j}" for j in range(12)]
+    names = [f"f{j}" for j in range(n_feat)]
     fm = F.FeatureMapping(ctx, [dict(name=n, type="number", scope="item", source=f"metadata.{n}") for n in names], names)
     ds = F.DeviceState(ctx, fm)
-    cat = synth.feature_matrix(3000, 12, seed=9)
-    ids = np.arange(1, 3001, dtype=np.uint64) * np.uint64(40503)
-    ds.put_packed(F.pack_number_columns(names, ids, cat)); ds.flush()
-    blob = synth.lightgbm_model_text(300, 12, seed=10)
+    cat = synth.feature_matrix(700, n_feat, seed=n_feat)
+    ids = np.arange(1, 701, dtype=np.uint64) * np.uint64(40503)
+    for j0 in range(0, n_feat, 16):  # several upserts: rows are merged column group by column group
+        ds.put_packed(F.pack_number_columns(names[j0:j0 + 16], ids, cat[:, j0:j0 + 16]))
+    ds.flush()
+    blob = synth.lightgbm_model_text(60, n_feat, seed=11)
     booster = mb.LightGBMBooster(ctx, blob)
-    req = dict(event="ranking", id="mega", timestamp=0, user=None, session=None, fields=[],
-               items=[dict(id=None, fields=[]) for _ in range(2500)])
-    # the mapping packs ids by hashing strings; feed hashes directly instead
+    rng = np.random.Generator(np.random.PCG64(n_feat))
+    pick = rng.integers(0, 700, 5000)
+    offs = np.arange(0, 5001, 250, dtype=np.int32)
+    R = len(offs) - 1
+    arrays = dict(offsets=offs, ids=ids[pick], users=np.zeros(R, dtype=np.uint64), sessions=np.zeros(R, dtype=np.uint64),
+                  req_f64=np.zeros((R, 1)), req_u64=np.zeros((R, 1), dtype=np.uint64), req_vec=np.zeros((R, 1), dtype=np.float32),
+                  req_vp=np.zeros((R, 1), dtype=np.uint8), item_f64=None, n_requests=R, total_items=5000)
     rk = F.Ranker(fm, ds)
-    pick = np.random.Generator(np.random.PCG64(3)).choice(3000, 2500, replace=False)
-    arrays = dict(offsets=np.array([0, 2500], dtype=np.int32), ids=ids[pick], users=np.zeros(1, dtype=np.uint64),
-                  sessions=np.zeros(1, dtype=np.uint64), req_f64=np.zeros((1, 1)), req_u64=np.zeros((1, 1), dtype=np.uint64),
-                  req_vec=np.zeros((1, 1), dtype=np.float32), req_vp=np.zeros((1, 1), dtype=np.uint8), item_f64=None,
-                  n_requests=1, total_items=2500)
-    score_slice, n = sharded.cuda_slice_scorer(rk, booster, arrays)
-    assert n == 2500
-    scores, order = sharded.ShardedScorer(score_slice, ctx.rank_order).rerank(2500)
-    want = oracle.OracleBooster(0, blob).predictMat(cat[pick], 2500, 12)
-    assert _eq(scores, want) and np.array_equal(order, oracle.rank_order(want))
-    del req
+    want = oracle.OracleBooster(0, blob).predictMat(cat[pick], 5000, n_feat)
+    scores, order, _ = rk.rank_arrays(arrays, booster)                               # code rows -> code gather
+    assert _eq(scores, want)
+    scores2, _, feats = rk.rank_arrays(arrays, booster, want_features=True)          # explain: dense rows
+    assert _eq(feats, cat[pick]) and _eq(scores2, want)
+    for r in range(R):
+        assert np.array_equal(order[offs[r]:offs[r + 1]], oracle.rank_order(want[offs[r]:offs[r + 1]]))
     booster.free(); ds.free(); fm.free()
 
 
@@ -681,7 +686,7 @@ def test_ordering_edge_sizes_ties_and_specials(ctx):
         "leaf_count=1 1 1", "internal_value=0 0", "internal_weight=0 0", "internal_count=3 2", "is_linear=0", "shrinkage=1", "",
         "end of trees", ""]).encode()
     booster = mb.LightGBMBooster(ctx, model)
-    sizes = np.array([0, 1, 2, 3, 31, 32, 33, 100, 127, 128, 129, 130, 500, 1024, 4095, 4096, 4097, 5000, 0, 7], dtype=np.int64)
+    sizes = np.array([0, 1, 2, 3, 31, 32, 33, 100, 127, 128, 129, 130, 500, 1024, 4095, 4096, 4097, 5000, 0, 7, 9001, 4100, 1], dtype=np.int64)
     offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
     N, R = int(offs[-1]), len(sizes)
     pick = rng.integers(0, n_cat, N)
