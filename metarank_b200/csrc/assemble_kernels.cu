@@ -75,6 +75,23 @@ __global__ void lookup_kernel(RankArgs a) {
     const uint64_t u = a.user_ids ? __ldg(a.user_ids + i) : 0, s = a.session_ids ? __ldg(a.session_ids + i) : 0;
     a.visitor_row[2 * i] = u ? probe(a.st.t[SC_USER], u) : kNoRow;
     a.visitor_row[2 * i + 1] = s ? probe(a.st.t[SC_SESSION], s) : kNoRow;
+    if (a.n_cos > 0 && a.req_vec) {
+      // CosineDistance's aSum is a function of the request alone: once per request instead of once per item.
+      // query(i) * query(i) is a FLOAT product widened afterwards (S/ml/onnx/distance/DistanceFunction.scala:21)
+      int voff = 0;
+      for (int f = 0; f < a.n_plan; f++) {
+        const DFeature d = a.plan[f];
+        if (d.kind != FK_COSINE) continue;
+        const float *q = a.req_vec + (size_t)i * a.vec_stride + voff;
+        double as = 0.0;
+        for (int k = 0; k < d.aux0; k++) {
+          const float qk = __ldg(q + k);
+          as = __dadd_rn(as, (double)__fmul_rn(qk, qk));
+        }
+        a.qnorm[(size_t)i * a.n_cos + d.aux2] = as;
+        voff += d.aux0;
+      }
+    }
   }
   if (i == 0) {  // first kernel of every rank call: reset the per-call device state
     *a.hist_cursor = 0;
@@ -104,6 +121,7 @@ __global__ void __launch_bounds__(128) cosine_kernel(RankArgs a) {
     const bool ok = q_ok && ir != kNoRow && present(row_ptr(a.st.t[SC_ITEM], ir), d.b[0]);
     const float *q = a.req_vec + (size_t)r * a.vec_stride + voff;
     const double *side = a.st.side[(int)d.uparam];
+    if (!side) { voff += dim; continue; }  // stored as binary32: cosine_f32_kernel's
     double top = 0.0, as = 0.0, bs = 0.0;
     for (int d0 = 0; d0 < dim; d0 += 32) {
       const int nd = min(32, dim - d0);
@@ -127,6 +145,84 @@ __global__ void __launch_bounds__(128) cosine_kernel(RankArgs a) {
     }
     if (live) {
       const double out = ok ? __ddiv_rn(top, __dmul_rn(__dsqrt_rn(as), __dsqrt_rn(bs))) : nan_d();
+      a.cos[(size_t)d.aux2 * a.total_items + i] = out;
+      a.cos[(size_t)(a.n_cos + d.aux2) * a.total_items + i] = out;  // normalised copy (noop default)
+    }
+    voff += dim;
+  }
+}
+
+// Embeddings stored as binary32 (DState::side_f32): the kernel the bi-encoder configs run.  HBM-bound — an item costs
+// its 4 * dim bytes and nothing else: aSum comes from lookup_kernel (per request), bSum from the state (per item, computed
+// at upsert time), so only topSum = sum of (double)q[k] * (double)e[k] in index order is left, one DMUL + one DADD per element
+// (products rounded before the add, like the JVM).  A warp owns 32 items: their rows stream chunk by chunk through cp.async
+// (16 bytes per lane, a row segment per instruction, 32 rows in flight) into a padded tile, then lane j walks ITS item's
+// values in order.  The query is widened once per CTA into shared memory.
+constexpr int kCosChunk = 128;            // floats per row per stage
+constexpr int kCosPitch = kCosChunk + 4;  // 528-byte rows: 8 consecutive lanes read 16 bytes from 8 different bank groups
+
+__global__ void __launch_bounds__(128) cosine_f32_kernel(RankArgs a, int dim_max) {
+  extern __shared__ __align__(16) uint8_t s_cos_raw[];
+  double *s_q = reinterpret_cast<double *>(s_cos_raw);  // [dim_max] the CTA's first request's query, widened
+  float *s_tiles = reinterpret_cast<float *>(s_cos_raw + (((size_t)dim_max * 8 + 15) & ~size_t(15)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *tile = s_tiles + (size_t)warp * 32 * kCosPitch;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < a.total_items;
+  const int r = live ? a.item_req[i] : 0;
+  const int r0 = a.item_req[min(blockIdx.x * blockDim.x, (unsigned)a.total_items - 1u)];  // CTA-uniform
+  const uint32_t ir = live ? a.item_row[i] : kNoRow;
+  int voff = 0;
+  for (int f = 0; f < a.n_plan; f++) {
+    const DFeature d = a.plan[f];
+    if (d.kind != FK_COSINE) continue;
+    const int dim = d.aux0;
+    const float *side = a.st.side_f32[(int)d.uparam];
+    if (!side) { voff += dim; continue; }  // stored as f64: cosine_kernel's
+    __syncthreads();  // s_q of the previous feature is no longer read
+    {
+      const float *q0 = a.req_vec + (size_t)r0 * a.vec_stride + voff;
+      for (int k = threadIdx.x; k < dim; k += blockDim.x) s_q[k] = (double)__ldg(q0 + k);
+    }
+    __syncthreads();
+    const bool q_ok = live && a.req_vec_present && a.req_vec_present[(size_t)r * a.n_req_vec + d.in0];
+    const bool ok = q_ok && ir != kNoRow && present(row_ptr(a.st.t[SC_ITEM], ir), d.b[0]);
+    const float *q = a.req_vec + (size_t)r * a.vec_stride + voff;
+    const bool same_q = r == r0;
+    double top = 0.0;
+    for (int d0 = 0; d0 < dim; d0 += kCosChunk) {
+      const int nd = min(kCosChunk, dim - d0);  // a multiple of 4 (f32 mode requires dim % 4 == 0)
+      for (int j = 0; j < 32; j++) {
+        const uint32_t rj = __shfl_sync(0xFFFFFFFFu, ir, j);
+        const int okj = __shfl_sync(0xFFFFFFFFu, (int)ok, j);
+        if (okj && lane * 4 < nd)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(tile + j * kCosPitch + lane * 4)),
+                       "l"(side + (size_t)rj * dim + d0 + lane * 4)
+                       : "memory");
+      }
+      asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      if (ok) {
+        const float4 *row = reinterpret_cast<const float4 *>(tile + lane * kCosPitch);
+        for (int k4 = 0; k4 < nd / 4; k4++) {
+          const float4 e = row[k4];
+          const int k = d0 + k4 * 4;
+          const float ev[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            const double qd = same_q ? s_q[k + c] : (double)__ldg(q + k + c);
+            top = __dadd_rn(top, __dmul_rn(qd, (double)ev[c]));
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (live) {
+      double out = nan_d();
+      if (ok) {
+        const double as = a.qnorm[(size_t)r * a.n_cos + d.aux2], bs = __ldg(a.st.side_bs[(int)d.uparam] + ir);
+        out = __ddiv_rn(top, __dmul_rn(__dsqrt_rn(as), __dsqrt_rn(bs)));
+      }
       a.cos[(size_t)d.aux2 * a.total_items + i] = out;
       a.cos[(size_t)(a.n_cos + d.aux2) * a.total_items + i] = out;  // normalised copy (noop default)
     }
@@ -1098,15 +1194,16 @@ __global__ void __launch_bounds__(256) order_kernel(const double *scores, const 
   }
 }
 
-// Mega-requests (more items than the CTA sort holds; BASELINE config #5 is one 10 000-item request): the rank of
-// item j is the number of items that sort before it.  The n^2 comparisons are spread over the chip —
-// CTA (x, y) counts, for the 256 items of block x, the earlier items among split y of the request, staged through
-// shared memory as sortable keys — the partial counts meet in `rank` (zeroed by the launcher), and a second
-// kernel scatters.  Ties are broken by the index, i.e. the sort is stable like the reference's sortBy.
-constexpr int kBigOrderMin = 4096;   // requests above this size take this path
-constexpr int kBigOrderSplits = 16;
-constexpr int kBigOrderTile = 1024;  // keys staged per pass
-constexpr int kBigOrderJ = 4;        // items per thread: one staged key is compared against four registers
+// Mega-requests (more items than the CTA sort holds; BASELINE config #5 is one 10 000-item request), O(n log n) over
+// the whole chip instead of one CTA:
+//   1. order_big_sort_kernel   every 1024-item chunk of the request is sorted by its own CTA (bitonic network in shared
+//                              memory over (total-order key of -score, index in the request) pairs: all distinct, which is
+//                              the stability of the reference's sortBy) and written to scratch;
+//   2. order_big_merge_kernel  one thread per element: its final rank = its position in its own sorted chunk + for every
+//                              other chunk the number of elements that sort before it, found by binary search — keys <= its
+//                              key in chunks of LOWER item indices (ties lose to the earlier index), keys < its key in later ones.
+constexpr int kBigOrderMin = 4096;    // requests above this size take this path
+constexpr int kBigOrderChunk = 1024;  // items per sorted chunk (chunks are aligned to the batch's item index space)
 
 __device__ __forceinline__ int owning_request(const int32_t *offsets, int n_requests, int i) {
   int lo = 0, hi = n_requests;  // last r with off[r] <= i
@@ -1117,80 +1214,66 @@ __device__ __forceinline__ int owning_request(const int32_t *offsets, int n_requ
   return lo;
 }
 
-// total_order_key with NaN one below the maximum, so that `key + 1` never overflows (no finite key is that large)
-__device__ __forceinline__ long long big_order_key(double x) {
-  const long long k = total_order_key(x);
-  return k == 0x7FFFFFFFFFFFFFFFll ? 0x7FFFFFFFFFFFFFFEll : k;
-}
-
-// CTA (x, y): the 1024 items [1024 x, 1024 x + 1024) against split y of their request.  Thread t owns items
-// 1024 x + t + 256 m (m < 4).  q sorts before j iff key_q < key_j, or the keys tie and q < j: within a block of 256
-// staged keys that is `key_q < key_j + 1` for every q (block entirely before j), `key_q < key_j` for every q (block
-// entirely at or after j), or — only in the one block that holds j — decided per q.
-__global__ void __launch_bounds__(256) order_big_count_kernel(const double *scores, const int32_t *offsets, int n_requests,
-                                                              int total_items, int32_t *rank) {
-  __shared__ long long s_keys[kBigOrderTile];
-  const int j0 = blockIdx.x * (256 * kBigOrderJ), j1 = min(total_items, j0 + 256 * kBigOrderJ);
-  for (int r = owning_request(offsets, n_requests, j0); r < n_requests; r++) {
+__global__ void __launch_bounds__(256) order_big_sort_kernel(const double *scores, const int32_t *offsets, int n_requests,
+                                                             int total_items, long long *skeys, int32_t *sidx) {
+  __shared__ long long s_k[kBigOrderChunk];
+  __shared__ int s_i[kBigOrderChunk];
+  const int c0 = blockIdx.x * kBigOrderChunk, c1 = min(total_items, c0 + kBigOrderChunk);
+  for (int r = owning_request(offsets, n_requests, c0); r < n_requests; r++) {
     const int b = __ldg(offsets + r), n = __ldg(offsets + r + 1) - b;
-    if (b >= j1) break;
+    if (b >= c1) break;
     if (n <= kBigOrderMin) continue;
-    long long kj[kBigOrderJ];
-    int jj[kBigOrderJ], cnt[kBigOrderJ];
-    bool mine[kBigOrderJ];
-#pragma unroll
-    for (int m = 0; m < kBigOrderJ; m++) {
-      const int j = j0 + (int)threadIdx.x + 256 * m;
-      mine[m] = j < total_items && j >= b && j < b + n;
-      kj[m] = mine[m] ? big_order_key(-scores[j]) : 0;
-      jj[m] = j - b;
-      cnt[m] = 0;
+    const int lo = max(b, c0), hi = min(b + n, c1), m = hi - lo;  // this chunk's part of request r
+    if (m <= 0) continue;
+    int p2 = 1;
+    while (p2 < m) p2 <<= 1;
+    __syncthreads();  // the previous segment's read-out is complete
+    for (int j = threadIdx.x; j < p2; j += blockDim.x) {
+      s_k[j] = j < m ? total_order_key(-scores[lo + j]) : 0x7FFFFFFFFFFFFFFFll;
+      s_i[j] = j < m ? lo + j - b : 0x7FFFFFFF;
     }
-    const int per = (((n + gridDim.y - 1) / gridDim.y) + 255) & ~255;  // whole 256-key blocks per split
-    const int q0 = blockIdx.y * per, q1 = min(n, q0 + per);
-    for (int t0 = q0; t0 < q1; t0 += kBigOrderTile) {
-      const int nt = min(kBigOrderTile, q1 - t0);
-      __syncthreads();
-      for (int k = threadIdx.x; k < nt; k += blockDim.x) s_keys[k] = big_order_key(-scores[b + t0 + k]);
-      __syncthreads();
-      for (int c0 = 0; c0 < nt; c0 += 256) {
-        const int c1 = min(nt, c0 + 256), qa = t0 + c0, qb = t0 + c1;  // staged block = q in [qa, qb)
-        long long thr[kBigOrderJ];
-        bool partial = false;
-#pragma unroll
-        for (int m = 0; m < kBigOrderJ; m++) {
-          thr[m] = kj[m] + (jj[m] >= qb ? 1 : 0);
-          partial |= mine[m] && jj[m] > qa && jj[m] < qb;
-        }
-        if (!partial) {
-#pragma unroll 4
-          for (int k = c0; k < c1; k++) {
-            const long long kq = s_keys[k];
-#pragma unroll
-            for (int m = 0; m < kBigOrderJ; m++) cnt[m] += kq < thr[m];
-          }
-        } else {
-          for (int k = c0; k < c1; k++) {
-            const long long kq = s_keys[k];
-#pragma unroll
-            for (int m = 0; m < kBigOrderJ; m++) cnt[m] += kq < kj[m] || (kq == kj[m] && t0 + k < jj[m]);
+    __syncthreads();
+    for (int k = 2; k <= p2; k <<= 1) {
+      for (int jj = k >> 1; jj > 0; jj >>= 1) {
+        for (int i = threadIdx.x; i < p2; i += blockDim.x) {
+          const int l = i ^ jj;
+          if (l > i) {
+            const long long ki = s_k[i], kl = s_k[l];
+            const int ii = s_i[i], il = s_i[l];
+            const bool gt = ki > kl || (ki == kl && ii > il);
+            if (gt == ((i & k) == 0)) { s_k[i] = kl; s_k[l] = ki; s_i[i] = il; s_i[l] = ii; }
           }
         }
+        __syncthreads();
       }
     }
-#pragma unroll
-    for (int m = 0; m < kBigOrderJ; m++)
-      if (mine[m] && cnt[m]) atomicAdd(rank + j0 + (int)threadIdx.x + 256 * m, cnt[m]);
+    for (int j = threadIdx.x; j < m; j += blockDim.x) { skeys[lo + j] = s_k[j]; sidx[lo + j] = s_i[j]; }
   }
 }
 
-__global__ void __launch_bounds__(256) order_big_scatter_kernel(const int32_t *offsets, int n_requests, int total_items,
-                                                                const int32_t *rank, int32_t *order) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= total_items) return;
-  const int r = owning_request(offsets, n_requests, j);
+__global__ void __launch_bounds__(256) order_big_merge_kernel(const int32_t *offsets, int n_requests, int total_items,
+                                                              const long long *skeys, const int32_t *sidx, int32_t *order) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total_items) return;
+  const int r = owning_request(offsets, n_requests, g);
   const int b = __ldg(offsets + r), n = __ldg(offsets + r + 1) - b;
-  if (n > kBigOrderMin) order[b + rank[j]] = j - b;
+  if (n <= kBigOrderMin) return;
+  const int my_lo = max(b, (g / kBigOrderChunk) * kBigOrderChunk);
+  const long long kj = skeys[g];
+  int rank = g - my_lo;  // position inside its own sorted chunk
+  for (int c0 = (b / kBigOrderChunk) * kBigOrderChunk; c0 < b + n; c0 += kBigOrderChunk) {
+    const int lo = max(b, c0), hi = min(b + n, c0 + kBigOrderChunk);
+    if (lo == my_lo) continue;
+    const bool ties_before = lo < my_lo;  // the other chunk holds earlier item indices: equal keys sort before this element
+    int x = lo, y = hi;                   // first position whose key is > kj (ties_before) or >= kj
+    while (x < y) {
+      const int mid = (x + y) >> 1;
+      const long long km = __ldg(skeys + mid);
+      if (ties_before ? km <= kj : km < kj) x = mid + 1; else y = mid;
+    }
+    rank += x - lo;
+  }
+  order[b + rank] = sidx[g];
 }
 
 }  // namespace
@@ -1203,9 +1286,25 @@ void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t strea
   g_kernel_launches++;
   if (a.total_items <= 0) return;
   if (schema.needs_cosine) {
-    { ProfScope _ps("cosine_kernel", stream); cosine_kernel<<<(a.total_items + 127) / 128, 128, 0, stream>>>(a); }
-    MR_CUDA_CHECK(cudaGetLastError());
-    g_kernel_launches++;
+    bool any_f32 = false, any_f64 = false;
+    int dim_max = 0;
+    for (auto &d : schema.plan)
+      if (d.kind == FK_COSINE) {
+        if (a.st.side_f32[(int)d.uparam]) { any_f32 = true; dim_max = std::max(dim_max, (int)d.aux0); }
+        else any_f64 = true;
+      }
+    if (any_f32) {
+      const size_t smem = (((size_t)dim_max * 8 + 15) & ~size_t(15)) + (size_t)4 * 32 * kCosPitch * sizeof(float);
+      MR_CUDA_CHECK(cudaFuncSetAttribute(cosine_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      { ProfScope _ps("cosine_f32_kernel", stream); cosine_f32_kernel<<<(a.total_items + 127) / 128, 128, smem, stream>>>(a, dim_max); }
+      MR_CUDA_CHECK(cudaGetLastError());
+      g_kernel_launches++;
+    }
+    if (any_f64) {
+      { ProfScope _ps("cosine_kernel", stream); cosine_kernel<<<(a.total_items + 127) / 128, 128, 0, stream>>>(a); }
+      MR_CUDA_CHECK(cudaGetLastError());
+      g_kernel_launches++;
+    }
   }
   if (schema.needs_prepass && a.n_requests > 0) {
     int n_agg = 0;
@@ -1283,13 +1382,13 @@ void launch_rank_order(const double *d_scores, const int32_t *d_item_offsets, in
     g_kernel_launches++;
   }
   if ((unknown && total_items > kBigOrderMin) || max_items_hint > kBigOrderMin) {
-    int32_t *tmp = d_rank_tmp;
-    if (!tmp) MR_CUDA_CHECK(cudaMallocAsync((void **)&tmp, (size_t)total_items * 4, stream));
-    MR_CUDA_CHECK(cudaMemsetAsync(tmp, 0, (size_t)total_items * 4, stream));
-    const unsigned gx = (unsigned)((total_items + 255) / 256), gj = (unsigned)((total_items + 256 * kBigOrderJ - 1) / (256 * kBigOrderJ));
-    { ProfScope _ps("order_big_count_kernel", stream); order_big_count_kernel<<<dim3(gj, kBigOrderSplits), 256, 0, stream>>>(d_scores, d_item_offsets, n_requests, total_items, tmp); }
+    int32_t *tmp = d_rank_tmp;  // 3 ints per item: sorted keys (8 B) + their item indices (4 B)
+    if (!tmp) MR_CUDA_CHECK(cudaMallocAsync((void **)&tmp, (size_t)total_items * 12 + 16, stream));
+    long long *skeys = reinterpret_cast<long long *>(tmp);
+    int32_t *sidx = tmp + 2 * (size_t)total_items;
+    { ProfScope _ps("order_big_sort_kernel", stream); order_big_sort_kernel<<<(unsigned)((total_items + kBigOrderChunk - 1) / kBigOrderChunk), 256, 0, stream>>>(d_scores, d_item_offsets, n_requests, total_items, skeys, sidx); }
     MR_CUDA_CHECK(cudaGetLastError());
-    { ProfScope _ps("order_big_scatter_kernel", stream); order_big_scatter_kernel<<<gx, 256, 0, stream>>>(d_item_offsets, n_requests, total_items, tmp, d_order); }
+    { ProfScope _ps("order_big_merge_kernel", stream); order_big_merge_kernel<<<(unsigned)((total_items + 255) / 256), 256, 0, stream>>>(d_item_offsets, n_requests, total_items, skeys, sidx, d_order); }
     MR_CUDA_CHECK(cudaGetLastError());
     g_kernel_launches += 2;
     if (!d_rank_tmp) MR_CUDA_CHECK(cudaFreeAsync(tmp, stream));

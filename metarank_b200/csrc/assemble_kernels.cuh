@@ -33,6 +33,7 @@ struct RankArgs {
   uint32_t *item_row;     // [total_items] row in the item table or 0xFFFFFFFF
   uint32_t *visitor_row;  // [n_requests x 2] user row, session row
   double *cos;            // [2 x n_cos x total_items] raw, then normalised
+  double *qnorm;          // [n_requests x n_cos] CosineDistance's aSum of the request's query embedding (lookup_kernel)
   double *reqagg;         // [n_requests x n_reqagg x 4]
   uint2 *hist_desc;       // [n_requests x n_hist] {offset, length | unsorted << 31}
   uint64_t *hist_pool;
@@ -61,7 +62,7 @@ void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t strea
 void launch_code_rows(const RankArgs &a, uint32_t *code_rows, int code_row_words, uint32_t n_rows, const uint32_t *d_idx,
                       uint32_t n_idx, cudaStream_t stream);
 // max_items_hint: the largest request of the batch when the host knows it (0 = unknown: every size class is launched
-// and returns at once where it does not apply).  d_rank_tmp: total_items ints of scratch for the mega-request path
+// and returns at once where it does not apply).  d_rank_tmp: 3 * total_items ints (8-byte aligned) of scratch for the mega-request path
 // (nullptr: stream-ordered allocation when needed).
 void launch_rank_order(const double *d_scores, const int32_t *d_item_offsets, int n_requests, int total_items,
                        int32_t *d_order, cudaStream_t stream, int max_items_hint = 0, int32_t *d_rank_tmp = nullptr);

@@ -201,18 +201,21 @@ bool feature_value(In in, std::vector<uint8_t> &dst) {
       supported = false;
       break;
     }
-    case 6: {  // BoundedListValue: List[TimeValue(ts, Scalar)]; the readers want item ids (SString)
+    case 6: {  // BoundedListValue: List[TimeValue(ts, Scalar)].  The reader keeps the list and collects its SString
+               // entries only (S/feature/InteractedWithFeature.scala:117: values.map(_.value).collect { case SString(id) => id }):
+               // entries of another scalar kind are skipped, the rest of the history survives
       const int32_t n = in.varint();
       if (n < 0) fail(MR_ERR_PARSE, "negative list size");
-      out.put<uint8_t>(6); out.put<uint32_t>((uint32_t)n);
-      std::vector<uint8_t> one;
+      std::vector<uint8_t> one, kept;
       Out oo{one};
+      uint32_t n_kept = 0;
       for (int32_t k = 0; k < n; k++) {
         in.varlong();
         one.clear();
-        if (scalar(in, oo, tmp) == 0) out.bytes(one.data() + 1, 8);  // SString: drop the kind byte, keep the hash
-        else supported = false;
+        if (scalar(in, oo, tmp) == 0) { kept.insert(kept.end(), one.begin() + 1, one.begin() + 9); n_kept++; }  // drop the kind byte
       }
+      out.put<uint8_t>(6); out.put<uint32_t>(n_kept);
+      out.bytes(kept.data(), kept.size());
       break;
     }
   }

@@ -391,6 +391,8 @@ struct LParams {
   const uint32_t *tree_off;  // [n_trees] byte offset of the tree's chunk in `model`
   double *out;
   int rows, rows_padded, n_features, n_trees;
+  int n_chunks, chunks_per_cta;
+  uint32_t chunk_stride;  // bytes per chunk buffer
   float base_score;
 };
 
@@ -399,94 +401,136 @@ __global__ void __launch_bounds__(128) gbdt_leaves_kernel(const LParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int F = p.n_features;
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
-  const ChunkDesc cd = p.chunks[blockIdx.x];
-  uint8_t *cb = smem + 128;
-  uint8_t *xs = cb + ((cd.bytes + 127u) & ~127u);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);  // [0], [1]: chunk buffers; [2]: the code tile
+  const uint32_t stride = p.chunk_stride;
+  uint8_t *cbuf = smem + 128;
+  uint8_t *xs = cbuf + 2 * (size_t)stride;
   const int n_groups = (p.rows + 31) >> 5;
   const int g0 = blockIdx.y * 4, g1 = min(n_groups, g0 + 4);
+  // this CTA walks chunks [c_lo, c_hi) for its 128 items: the tile is staged once, the chunks stream through two buffers
+  const int c_lo = blockIdx.x * p.chunks_per_cta, c_hi = min(p.n_chunks, c_lo + p.chunks_per_cta);
   if (tid == 0) {
-    mbar_init(bar, 1);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
     fence_barrier_init();
     const uint32_t tile_bytes = (uint32_t)(g1 - g0) * (uint32_t)F * 64u;
-    mbar_arrive_expect_tx(bar, cd.bytes + tile_bytes);
-    tma_bulk_g2s(cb, p.model + cd.byte_off, cd.bytes, bar);
-    tma_bulk_g2s(xs, p.bins + (size_t)g0 * F * 32, tile_bytes, bar);
+    mbar_arrive_expect_tx(&bars[2], tile_bytes);
+    tma_bulk_g2s(xs, p.bins + (size_t)g0 * F * 32, tile_bytes, &bars[2]);
+    const ChunkDesc cd = p.chunks[c_lo];
+    mbar_arrive_expect_tx(&bars[0], cd.bytes);
+    tma_bulk_g2s(cbuf, p.model + cd.byte_off, cd.bytes, &bars[0]);
   }
   __syncthreads();
-  mbar_wait(bar, 0);
-  if (g0 + warp >= g1) return;
+  mbar_wait(&bars[2], 0);
+  const bool has_items = g0 + warp < g1;
   const int item = (g0 + warp) * 32 + lane;
   const uint8_t *xwarp = xs + (size_t)warp * F * 64;
   const uint32_t lane2 = (uint32_t)lane * 2u;
-  const int ntree = (int)*reinterpret_cast<const uint32_t *>(cb);
-  const uint32_t *roots = reinterpret_cast<const uint32_t *>(cb + 16);
-  for (int t = 0; t < ntree; t++) {
-    uint32_t n = roots[t];
-    while (!(n & 1u)) {
-      const uint2 nd = *reinterpret_cast<const uint2 *>(cb + (n & ~2u));  // bit 1 of a pointer: categorical target
-      const uint32_t code = *reinterpret_cast<const uint16_t *>(xwarp + ((nd.x & 0xFFC0u) | lane2));
-      bool left;
-      if (nd.x & 2u) {  // categorical bitset
-        left = false;
-        if (code != kBinNaN) {
-          const uint2 ct = reinterpret_cast<const uint2 *>(cb)[nd.x >> 16];
-          const uint32_t w = code >> 5;
-          if (w < ct.y) left = (reinterpret_cast<const uint32_t *>(cb)[ct.x + w] >> (code & 31u)) & 1u;
-        }
-      } else {
-        left = code <= (nd.x >> 16);  // NaN direction baked into the column
-      }
-      n = __byte_perm(nd.y, 0u, left ? 0x4410u : 0x4432u);
+  for (int c = c_lo, it = 0; c < c_hi; c++, it++) {
+    if (tid == 0 && c + 1 < c_hi) {  // prefetch the next chunk into the other buffer (its readers passed the barrier below)
+      const ChunkDesc nd = p.chunks[c + 1];
+      uint64_t *bar = &bars[(it + 1) & 1];
+      fence_proxy_async();
+      mbar_arrive_expect_tx(bar, nd.bytes);
+      tma_bulk_g2s(cbuf + (size_t)((it + 1) & 1) * stride, p.model + nd.byte_off, nd.bytes, bar);
     }
-    p.leafslots[(size_t)(cd.first_tree + t) * p.rows_padded + item] = (uint16_t)((n - 1u) >> 3);
+    mbar_wait(&bars[it & 1], (it >> 1) & 1);
+    const uint8_t *cb = cbuf + (size_t)(it & 1) * stride;
+    const uint32_t first_tree = p.chunks[c].first_tree;
+    if (has_items) {
+      const int ntree = (int)*reinterpret_cast<const uint32_t *>(cb);
+      const uint32_t *roots = reinterpret_cast<const uint32_t *>(cb + 16);
+      for (int t = 0; t < ntree; t++) {
+        uint32_t n = roots[t];
+        while (!(n & 1u)) {
+          const uint2 nd = *reinterpret_cast<const uint2 *>(cb + (n & ~2u));  // bit 1 of a pointer: categorical target
+          const uint32_t code = *reinterpret_cast<const uint16_t *>(xwarp + ((nd.x & 0xFFC0u) | lane2));
+          bool left;
+          if (nd.x & 2u) {  // categorical bitset
+            left = false;
+            if (code != kBinNaN) {
+              const uint2 ct = reinterpret_cast<const uint2 *>(cb)[nd.x >> 16];
+              const uint32_t w = code >> 5;
+              if (w < ct.y) left = (reinterpret_cast<const uint32_t *>(cb)[ct.x + w] >> (code & 31u)) & 1u;
+            }
+          } else {
+            left = code <= (nd.x >> 16);  // NaN direction baked into the column
+          }
+          n = __byte_perm(nd.y, 0u, left ? 0x4410u : 0x4432u);
+        }
+        p.leafslots[(size_t)(first_tree + t) * p.rows_padded + item] = (uint16_t)((n - 1u) >> 3);
+      }
+    }
+    __syncthreads();  // this buffer is refilled two chunks from now
   }
 }
 
 // In-order sum of the per-tree leaf values.  The adds are a dependent chain (tree order = the sequential reference's
-// rounding) but nothing else is: a warp owns 32 rows and streams their leaf SLOTS (2 bytes per row and tree — an
-// eighth of the f64 values themselves) through a kSumStages-deep cp.async pipeline of kSumTrees trees per stage,
-// 16 bytes per copy; the value behind a slot is read from the packed model (a few hundred KB, L1/L2 resident),
-// one 128-byte line per tree for the whole warp.  Small batches use one-warp CTAs so that a single mega-request
-// slice still spreads over the whole chip.
-constexpr int kSumTrees = 64, kSumStages = 4;  // 4 x 4 KB per warp
+// rounding) but nothing else is.  A warp owns 32 rows and runs a three-step software pipeline over groups of kSumTrees
+// trees, everything moved by cp.async so that no load waits on a register:
+//   A(g)  the rows' leaf SLOTS of group g (2 bytes per row and tree — an eighth of the f64 values), 16 bytes per copy;
+//   B(g)  with the slots in hand, the VALUES behind them: one 8-byte copy per (tree, row) out of the packed model
+//         (a few hundred KB, L2 resident) into a [tree][lane] tile — 64 copies per lane in flight, no register limit;
+//   C(g)  acc += value, tree by tree.
+// While C(g) adds, B(g + 1) and A(g + 2) are in flight.  One-warp CTAs, so that a single mega-request slice (a few
+// thousand rows) still spreads over the whole chip.
+constexpr int kSumTrees = 64;  // per warp: 2 x 4 KB of slots + 2 x 16 KB of values
 
 template <typename Real>
 __global__ void __launch_bounds__(128) gbdt_sum_kernel(const LParams p, const ScoreSinks sinks) {
-  extern __shared__ __align__(16) uint16_t s_slots[];  // [warps][kSumStages][kSumTrees][32]
+  extern __shared__ __align__(16) uint8_t s_sum_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr size_t kWarpBytes = 2 * kSumTrees * 32 * sizeof(uint16_t) + 2 * kSumTrees * 32 * sizeof(double);
+  uint16_t *s_slots = reinterpret_cast<uint16_t *>(s_sum_raw + (size_t)warp * kWarpBytes);        // [2][kSumTrees][32]
+  double *s_vals = reinterpret_cast<double *>(s_slots + 2 * kSumTrees * 32);                        // [2][kSumTrees][32]
   const int row0 = (blockIdx.x * (blockDim.x >> 5) + warp) * 32;
   const int item = row0 + lane;
   const bool live = item < p.rows, warp_live = row0 < p.rows;
-  uint16_t *tile = s_slots + (size_t)warp * kSumStages * kSumTrees * 32;
   const int n_groups = (p.n_trees + kSumTrees - 1) / kSumTrees;
-  auto issue = [&](int g) {
+  auto issue_slots = [&](int g) {  // A(g)
     if (g < n_groups && warp_live) {
       const int t0 = g * kSumTrees, nb = min(kSumTrees, p.n_trees - t0);
-      const uint32_t dst = smem_u32(tile + (size_t)(g % kSumStages) * kSumTrees * 32);
+      const uint32_t dst = smem_u32(s_slots + (size_t)(g & 1) * kSumTrees * 32);
       for (int k = lane; k < nb * 4; k += 32) {  // 16-byte piece k: tree k >> 2, rows (k & 3) * 8 .. + 8 of the warp's 32
         const uint16_t *src = p.leafslots + (size_t)(t0 + (k >> 2)) * p.rows_padded + row0 + (k & 3) * 8;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)k * 16u), "l"(src) : "memory");
       }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");  // an empty group keeps the wait count uniform
   };
-  Real acc = (sizeof(Real) == 4) ? (Real)p.base_score : (Real)0;
-  for (int g = 0; g < kSumStages - 1; g++) issue(g);
-  for (int g = 0; g < n_groups; g++) {
-    issue(g + kSumStages - 1);
-    asm volatile("cp.async.wait_group %0;" ::"n"(kSumStages - 1) : "memory");
-    __syncwarp();  // the stage was filled by all lanes' copies
-    const int t0 = g * kSumTrees, nb = min(kSumTrees, p.n_trees - t0);
-    const uint16_t *st = tile + (size_t)(g % kSumStages) * kSumTrees * 32 + lane;
-    if (live) {
-#pragma unroll 8
+  auto issue_values = [&](int g) {  // B(g): the slots of group g are in shared memory
+    if (g < n_groups && live) {
+      const int t0 = g * kSumTrees, nb = min(kSumTrees, p.n_trees - t0);
+      const uint16_t *sl = s_slots + (size_t)(g & 1) * kSumTrees * 32 + lane;
+      const uint32_t dst = smem_u32(s_vals + (size_t)(g & 1) * kSumTrees * 32 + lane);
+#pragma unroll 4
       for (int k = 0; k < nb; k++) {
-        const uint32_t slot = st[k * 32];
-        acc += *reinterpret_cast<const Real *>(p.model + __ldg(p.tree_off + t0 + k) + slot * 8u);
+        const uint8_t *src = p.model + __ldg(p.tree_off + t0 + k) + (uint32_t)sl[k * 32] * 8u;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (uint32_t)k * 256u), "l"(src) : "memory");
       }
     }
-    __syncwarp();  // before a later issue() overwrites this stage
+  };
+  auto fence = [&] {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    __syncwarp();  // copies issued by other lanes (the slots) are visible to all
+  };
+  Real acc = (sizeof(Real) == 4) ? (Real)p.base_score : (Real)0;
+  issue_slots(0);
+  fence();
+  issue_values(0);
+  issue_slots(1);
+  for (int g = 0; g < n_groups; g++) {
+    fence();                 // values of group g and slots of group g + 1 have landed
+    issue_values(g + 1);
+    issue_slots(g + 2);      // overwrites the slots of group g: B(g) read them when it was issued
+    if (live) {
+      const int nb = min(kSumTrees, p.n_trees - g * kSumTrees);
+      const double *sv = s_vals + (size_t)(g & 1) * kSumTrees * 32 + lane;
+      // the value slot holds the model's Real in its first bytes (f64, or f32 for XGBoost)
+#pragma unroll 8
+      for (int k = 0; k < nb; k++) acc += *reinterpret_cast<const Real *>(sv + k * 32);
+    }
+    __syncwarp();
   }
   if (live) store_score(p.out, sinks, item, (double)acc);
   if (sinks.n_peer) publish_when_last(sinks);
@@ -584,11 +628,17 @@ void launch_gbdt_latency(const BinnedLaunch &L, int n_trees, const uint32_t *d_t
   p.out = L.d_out;
   p.rows = L.rows; p.rows_padded = (L.rows + 127) & ~127; p.n_features = L.tile_cols; p.n_trees = n_trees;
   p.base_score = L.base_score;
-  const size_t smem = 128 + ((L.max_chunk_bytes + 127u) & ~127u) + (size_t)4 * L.tile_cols * 64;
-  dim3 grid((unsigned)L.n_chunks, (unsigned)((L.rows + 127) / 128));
+  p.n_chunks = L.n_chunks;
+  p.chunk_stride = (L.max_chunk_bytes + 127u) & ~127u;
+  // (chunk, 128-item group) pairs are the unit of parallelism; once there are more of them than ~16 per SM a CTA takes
+  // several chunks in a row for its group, so the code tile is staged once per CTA instead of once per 4 KB of trees
+  const int n_item_groups = (L.rows + 127) / 128;
+  p.chunks_per_cta = (int)std::max<long long>(1, std::min<long long>(16, ((long long)L.n_chunks * n_item_groups) / (148 * 16)));
+  const size_t smem = 128 + 2 * (size_t)p.chunk_stride + (size_t)4 * L.tile_cols * 64;
+  dim3 grid((unsigned)((L.n_chunks + p.chunks_per_cta - 1) / p.chunks_per_cta), (unsigned)n_item_groups);
   // the in-order sum: one-warp CTAs (16 KB of stages each) spread even a 1 000-row slice over 32 SMs
   const int sum_warps = 1;
-  const size_t sum_smem = (size_t)sum_warps * kSumStages * kSumTrees * 32 * sizeof(uint16_t);
+  const size_t sum_smem = (size_t)sum_warps * (2 * kSumTrees * 32 * sizeof(uint16_t) + 2 * kSumTrees * 32 * sizeof(double));
   const int n_warps = (L.rows + 31) / 32;
   auto go = [&](auto leaves, auto sum) {
     MR_CUDA_CHECK(cudaFuncSetAttribute(leaves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -140,15 +140,51 @@ HostModel parse_lightgbm_text(const uint8_t *blob, size_t len) {
   }
   size_t i = 0;
   int max_feature_idx = -1, num_class = 1, per_iter = 1;
+  long n_tree_sizes = -1, n_feature_names = -1;
+  std::string objective;
+  bool average_output = false;
+  auto count_tokens = [](const std::string &v) {
+    long n = 0;
+    bool in = false;
+    for (char ch : v) {
+      const bool sp = ch == ' ' || ch == '\t';
+      if (!sp && !in) n++;
+      in = !sp;
+    }
+    return n;
+  };
   for (; i < lines.size() && !starts(lines[i], "Tree="); i++) {
     std::string s(lines[i].p, lines[i].n);
     if (starts(lines[i], "max_feature_idx=")) max_feature_idx = atoi(s.c_str() + 16);
     else if (starts(lines[i], "num_class=")) num_class = atoi(s.c_str() + 10);
     else if (starts(lines[i], "num_tree_per_iteration=")) per_iter = atoi(s.c_str() + 23);
+    else if (starts(lines[i], "objective=")) objective = s.substr(10);
+    else if (s == "average_output") average_output = true;  // GBDT::SaveModelToString writes the bare word for rf boosting
+    else if (starts(lines[i], "tree_sizes=")) n_tree_sizes = count_tokens(s.substr(11));
+    else if (starts(lines[i], "feature_names=")) n_feature_names = count_tokens(s.substr(14));
   }
   if (max_feature_idx < 0) fail(MR_ERR_PARSE, "lightgbm: max_feature_idx missing (not a LightGBM model text)");
   if (num_class != 1 || per_iter != 1) fail(MR_ERR_UNSUPPORTED, "lightgbm: multiclass models are not supported");
   m.n_features = max_feature_idx + 1;
+  if (n_feature_names >= 0 && n_feature_names != m.n_features)
+    fail(MR_ERR_PARSE, "lightgbm: feature_names lists %ld names, max_feature_idx says %d features", n_feature_names, m.n_features);
+  if (average_output)
+    fail(MR_ERR_UNSUPPORTED, "lightgbm: average_output (random-forest boosting) models are not supported: the prediction is the "
+                             "MEAN of the trees, Metarank trains gbdt LambdaMART (S/ml/rank/LambdaMARTRanker.scala:96-118)");
+  {
+    // Booster.predictMat is a NORMAL prediction (LGBM_BoosterPredictForMat): the objective's ConvertOutput applies.  It is the
+    // identity for the ranking and plain regression objectives; everything else (sigmoid, exp, softmax, sqrt) is refused
+    // rather than silently returned as raw scores.  The line is "<name> [key:value ...]".
+    const std::string name = objective.substr(0, objective.find(' '));
+    static const char *identity[] = {"", "lambdarank", "rank_xendcg", "regression", "regression_l1", "huber", "fair", "quantile",
+                                     "mape", "custom"};
+    bool ok = false;
+    for (const char *k : identity) ok |= name == k;
+    if (ok && name == "regression" && objective.find("sqrt") != std::string::npos) ok = false;
+    if (!ok)
+      fail(MR_ERR_UNSUPPORTED, "lightgbm: objective '%s' transforms the raw score on prediction; only identity objectives "
+                               "(lambdarank, rank_xendcg, regression, ...) are supported", objective.c_str());
+  }
 
   std::unordered_map<std::string, std::string> kv;
   auto flush = [&]() {
@@ -208,22 +244,30 @@ HostModel parse_lightgbm_text(const uint8_t *blob, size_t len) {
     m.trees.push_back(std::move(t));
     kv.clear();
   };
-  bool in_tree = false;
+  bool in_tree = false, saw_end = false;
+  long next_tree = 0;
   for (; i < lines.size(); i++) {
     const Line &ln = lines[i];
     if (starts(ln, "Tree=")) {
       flush();
       in_tree = true;
       kv["Tree"] = std::string(ln.p + 5, ln.n - 5);
+      if (atol(kv["Tree"].c_str()) != next_tree) fail(MR_ERR_PARSE, "lightgbm: tree blocks out of order: 'Tree=%s' where Tree=%ld was expected", kv["Tree"].c_str(), next_tree);
+      next_tree++;
       continue;
     }
-    if (starts(ln, "end of trees")) break;
+    if (starts(ln, "end of trees")) { saw_end = true; break; }
     if (!in_tree) continue;
     const char *eq = (const char *)memchr(ln.p, '=', ln.n);
     if (!eq) continue;
     kv[std::string(ln.p, (size_t)(eq - ln.p))] = std::string(eq + 1, ln.n - (size_t)(eq - ln.p) - 1);
   }
   flush();
+  // SaveModelToString always closes the tree section; its absence means the blob was cut (a model file that lost
+  // its tail would otherwise load as a shorter, silently different ensemble)
+  if (!saw_end) fail(MR_ERR_PARSE, "lightgbm: 'end of trees' missing: the model text is truncated");
+  if (n_tree_sizes >= 0 && n_tree_sizes != (long)m.trees.size())
+    fail(MR_ERR_PARSE, "lightgbm: tree_sizes announces %ld trees, the text holds %zu", n_tree_sizes, m.trees.size());
   finalize(m);
   return m;
 }
@@ -234,6 +278,9 @@ HostModel parse_xgboost_model(const uint8_t *blob, size_t len) {
   m.blob.assign(blob, blob + len);
   size_t s = 0;
   while (s < len && (blob[s] == ' ' || blob[s] == '\n' || blob[s] == '\r' || blob[s] == '\t')) s++;
+  if (len - s >= 4 && (memcmp(blob + s, "binf", 4) == 0 || memcmp(blob + s, "bs64", 4) == 0))
+    fail(MR_ERR_UNSUPPORTED, "xgboost: this is the deprecated binary model format ('%.4s' header, XGBoost < 2.0 save_raw default); "
+                             "re-save the booster as JSON or UBJSON (booster.toByteArray(\"ubj\") / save_raw(raw_format='ubj'))", (const char *)blob + s);
   if (s >= len || blob[s] != '{')
     fail(MR_ERR_UNSUPPORTED, "xgboost: unsupported model encoding (only JSON and UBJSON; legacy binary is not)");
   JValue doc;
@@ -246,10 +293,40 @@ HostModel parse_xgboost_model(const uint8_t *blob, size_t len) {
   const JValue &gb = learner.at("gradient_booster");
   if (gb.at("name").str != "gbtree") fail(MR_ERR_UNSUPPORTED, "xgboost: booster '%s' not supported", gb.at("name").str.c_str());
   const JValue &lmp = learner.at("learner_model_param");
-  m.base_score = lmp.at("base_score").as_f32();
+  {
+    // base_score is written as a string: "5E-1" up to XGBoost 2.x, "[5E-1]" (a vector intercept, one entry per target)
+    // from 3.1 on; a number in hand-written files
+    const JValue &bs = lmp.at("base_score");
+    if (bs.kind == JValue::Str) {
+      std::string t = bs.str;
+      size_t a = 0, b = t.size();
+      while (a < b && (t[a] == ' ' || t[a] == '[')) a++;
+      while (b > a && (t[b - 1] == ' ' || t[b - 1] == ']')) b--;
+      t = t.substr(a, b - a);
+      if (t.find(',') != std::string::npos) fail(MR_ERR_UNSUPPORTED, "xgboost: multi-target base_score '%s' is not supported", bs.str.c_str());
+      char *end = nullptr;
+      m.base_score = strtof(t.c_str(), &end);
+      if (t.empty() || end == t.c_str() || *end != 0) fail(MR_ERR_PARSE, "xgboost: base_score '%s' is not a number", bs.str.c_str());
+    } else {
+      m.base_score = bs.as_f32();
+    }
+  }
   m.n_features = (int)lmp.at("num_feature").as_int();
   if (const JValue *nc = lmp.get("num_class"))
     if (nc->as_int() > 1) fail(MR_ERR_UNSUPPORTED, "xgboost: multiclass models are not supported");
+  if (const JValue *nt = lmp.get("num_target"))
+    if (nt->as_int() > 1) fail(MR_ERR_UNSUPPORTED, "xgboost: multi-target models are not supported");
+  if (const JValue *obj = learner.get("objective"))
+    if (const JValue *on = obj->get("name")) {
+      // Booster.predict applies the objective's PredTransform; it is the identity for rank:* and the plain regressions
+      // (and base_score needs no ProbToMargin for them).  Anything else is refused rather than returned as margins.
+      static const char *identity[] = {"rank:ndcg", "rank:pairwise", "rank:map", "reg:squarederror", "reg:linear",
+                                       "reg:absoluteerror", "reg:pseudohubererror", "reg:quantileerror"};
+      bool ok = false;
+      for (const char *k : identity) ok |= on->str == k;
+      if (!ok) fail(MR_ERR_UNSUPPORTED, "xgboost: objective '%s' transforms the margin on prediction; only rank:* and plain "
+                                       "regression objectives are supported", on->str.c_str());
+    }
   const JValue &trees = gb.at("model").at("trees");
   if (trees.kind != JValue::Arr) fail(MR_ERR_PARSE, "xgboost: trees is not an array");
   for (const JValue &jt : trees.arr) {
@@ -260,7 +337,13 @@ HostModel parse_xgboost_model(const uint8_t *blob, size_t len) {
       fail(MR_ERR_PARSE, "xgboost: tree arrays have inconsistent sizes");
     if (const JValue *st = jt.get("split_type"))
       for (auto &v : st->arr)
-        if (v.as_int() != 0) fail(MR_ERR_UNSUPPORTED, "xgboost: categorical splits are not supported");
+        if (v.as_int() != 0)
+          fail(MR_ERR_UNSUPPORTED, "xgboost: categorical splits are not supported (they need enable_categorical and typed "
+                                   "features; Metarank hands XGBoost a plain float matrix, S/ml/rank/LambdaMARTRanker.scala:119-140)");
+    if (const JValue *tp = jt.get("tree_param"))
+      if (const JValue *nn = tp->get("num_nodes"))
+        if ((size_t)nn->as_int() != L.size())
+          fail(MR_ERR_PARSE, "xgboost: tree_param.num_nodes = %lld but the tree's arrays hold %zu nodes", (long long)nn->as_int(), L.size());
     // renumber: internal nodes and leaves get separate index spaces
     std::vector<int32_t> id(n);
     int ni = 0, nl = 0;

@@ -239,7 +239,7 @@ struct mr_model {
   }
   bool use_latency(int rows) const {
     return lat.ok && rows <= latency_max_rows() && opt_variant < 0 && opt_threads == 0 &&
-           use_compact() && 128 + lat.packed.max_chunk_bytes + 128 + (size_t)4 * compact.tile_cols * 64 <= 200 * 1024;
+           use_compact() && 128 + 2 * ((size_t)lat.packed.max_chunk_bytes + 128) + (size_t)4 * compact.tile_cols * 64 <= 200 * 1024;
   }
   // true: score_codes() can store to peer sinks from inside the scoring kernel
   bool fuses_sinks(int rows) const { return use_latency(rows) || (use_binned() && use_compact()); }

@@ -60,9 +60,29 @@ struct JValue {
   }
 };
 
+// The JSON number grammar: -?(0|[1-9][0-9]*)(\.[0-9]+)?([eE][+-]?[0-9]+)?
+inline bool json_number_token_ok(const char *buf, size_t n) {
+  size_t k = 0;
+  auto dig = [&](size_t at) { return at < n && buf[at] >= '0' && buf[at] <= '9'; };
+  if (k < n && buf[k] == '-') k++;
+  if (!dig(k)) return false;
+  if (buf[k] == '0') k++;
+  else while (dig(k)) k++;
+  if (k < n && buf[k] == '.') { k++; if (!dig(k)) return false; while (dig(k)) k++; }
+  if (k < n && (buf[k] == 'e' || buf[k] == 'E')) {
+    k++;
+    if (k < n && (buf[k] == '+' || buf[k] == '-')) k++;
+    if (!dig(k)) return false;
+    while (dig(k)) k++;
+  }
+  return k == n;
+}
+
 class JsonParser {
  public:
-  JsonParser(const uint8_t *p, size_t n) : p_(p), e_(p + n) {}
+  // strict: numbers must follow the JSON grammar (request bodies, where the reference's jawn parser rejects
+  // '+1', '01', '1.', NaN); model files keep the lenient reader (XGBoost writes NaN / Infinity tokens)
+  JsonParser(const uint8_t *p, size_t n, bool strict = false) : p_(p), e_(p + n), strict_(strict) {}
   JValue parse() {
     JValue v = value(0);
     ws();
@@ -72,6 +92,7 @@ class JsonParser {
 
  private:
   const uint8_t *p_, *e_;
+  bool strict_ = false;
   void ws() {
     while (p_ < e_ && (*p_ == ' ' || *p_ == '\n' || *p_ == '\t' || *p_ == '\r')) p_++;
   }
@@ -152,6 +173,7 @@ class JsonParser {
     }
     if (n == 0) bad("unexpected character");
     buf[n] = 0;
+    if (strict_ && !json_number_token_ok(buf, n)) bad("bad number");
     JValue v;
     v.kind = JValue::Num;
     v.is_int = is_int;

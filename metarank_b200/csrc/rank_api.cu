@@ -3,6 +3,9 @@
 //   makeQuery  = lookup/cosine/prepass/assemble kernels over the device-resident state
 //   predict    = gbdt_score kernel on the assembled matrix (never leaves HBM)
 //   sortBy     = order kernel
+#include <chrono>
+#include <condition_variable>
+
 #include "assemble_kernels.cuh"
 #include "fv_codec.h"
 #include "request_codec.h"
@@ -57,7 +60,7 @@ namespace {
 inline size_t al(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct ScratchPlan {
-  size_t item_req, item_row, visitor_row, cos, reqagg, hist_desc, hist_pool, hist_cursor, error_flag, features, codes, leafvals, local_scores, total;
+  size_t item_req, item_row, visitor_row, cos, qnorm, reqagg, hist_desc, hist_pool, hist_cursor, error_flag, features, codes, leafvals, local_scores, total;
   uint32_t hist_pool_cap;
 };
 
@@ -72,6 +75,7 @@ ScratchPlan plan_scratch(const Schema &S, int n_requests, int total_items, uint3
   p.item_row = take((size_t)total_items * 4);
   p.visitor_row = take((size_t)n_requests * 8);
   p.cos = take((size_t)2 * n_cos * total_items * 8);
+  p.qnorm = take((size_t)n_requests * std::max(n_cos, 1) * 8);
   p.reqagg = take((size_t)n_requests * std::max(S.n_reqagg, 1) * 32);
   p.hist_desc = take((size_t)n_requests * std::max(S.n_hist, 1) * 8);
   uint64_t cap = (uint64_t)n_requests * S.n_hist * per_hist;
@@ -106,6 +110,7 @@ void fill_args(RankArgs &a, mr_state *st, uint8_t *scratch, const ScratchPlan &s
   a.item_row = (uint32_t *)(scratch + sp.item_row);
   a.visitor_row = (uint32_t *)(scratch + sp.visitor_row);
   a.cos = (double *)(scratch + sp.cos);
+  a.qnorm = (double *)(scratch + sp.qnorm);
   a.reqagg = (double *)(scratch + sp.reqagg);
   a.hist_desc = (uint2 *)(scratch + sp.hist_desc);
   a.hist_pool = (uint64_t *)(scratch + sp.hist_pool);
@@ -786,7 +791,25 @@ mr_status mr_rank_device_status(mr_state *st, void *cuda_stream) {
 //   +256   f64 score[2][cap]   double-buffered by request parity: a member may start request s+1 while a slow
 //                              peer still orders request s (it cannot reach s+2 before that peer published s+1,
 //                              which it does after it finished reading s)
+// Members of one process that SHARE a device (tests put a whole group on one GPU) meet here between publishing and
+// waiting: a host thread that allocates or frees device memory synchronises the device, so it would sit behind a
+// peer's wait kernel that in turn waits for this thread's publish.  With one member per GPU — the deployment — there
+// is nothing to meet about (a synchronising call only ever waits for its own device) and the pointer stays null.
+struct LocalRendezvous {
+  std::mutex m;
+  std::condition_variable cv;
+  int n = 0, arrived = 0;
+  uint64_t generation = 0;
+  void arrive_and_wait() {
+    std::unique_lock<std::mutex> lk(m);
+    const uint64_t gen = generation;
+    if (++arrived == n) { arrived = 0; generation++; cv.notify_all(); return; }
+    cv.wait_for(lk, std::chrono::seconds(3), [&] { return generation != gen; });  // bounded like the device-side wait
+  }
+};
+
 struct mr_group {
+  std::shared_ptr<LocalRendezvous> rendezvous;  // non-null only when local members share a device
   mr_ctx *ctx = nullptr;
   int rank = 0, world = 1, cap = 0;  // cap: item capacity (multiple of 128)
   uint8_t *xbuf = nullptr;
@@ -897,6 +920,7 @@ void group_enqueue(mr_group *g, mr_state *st, mr_model *model, RankArgs &a, cons
     MR_CUDA_CHECK(cudaGetLastError());
     g_kernel_launches++;
   }
+  if (g->rendezvous) g->rendezvous->arrive_and_wait();  // members sharing a device: everybody has published (see LocalRendezvous)
   { ProfScope _ps("group_wait_kernel", stream); group_wait_kernel<<<1, 32, 0, stream>>>(g->flag(g->rank, parity, 0), g->world, seq, a.error_flag, 2000000000ull); }
   MR_CUDA_CHECK(cudaGetLastError());
   launch_rank_order(g->scores(g->rank, parity), g->d_offs + 2, 1, gc.N, g->d_order, stream, gc.N, g->d_rank_tmp);
@@ -936,8 +960,8 @@ mr_status mr_group_create(mr_ctx *ctx, int32_t rank, int32_t world, int32_t max_
     MR_CUDA_CHECK(cudaMemset(g->d_done, 0, 256));
     g->d_offs = (int32_t *)((uint8_t *)g->d_done + 64);
     g->d_err = (int32_t *)((uint8_t *)g->d_done + 128);
-    MR_CUDA_CHECK(cudaMalloc((void **)&g->d_order, (size_t)g->cap * 4 * 2));
-    g->d_rank_tmp = g->d_order + g->cap;
+    MR_CUDA_CHECK(cudaMalloc((void **)&g->d_order, (size_t)g->cap * 4 * 4));
+    g->d_rank_tmp = g->d_order + g->cap;  // 3 ints per item, 8-byte aligned (cap is a multiple of 128)
     g->peer[rank] = g->xbuf;
     g->connected = world == 1;
     *out = g.release();
@@ -994,6 +1018,14 @@ mr_status mr_group_connect_local(mr_group *const *members, int32_t world) {
         g->peer[b] = members[b]->xbuf;
       }
       g->connected = true;
+    }
+    bool shared = false;
+    for (int a = 0; a < world; a++)
+      for (int b = a + 1; b < world; b++) shared |= members[a]->ctx->device == members[b]->ctx->device;
+    if (shared) {
+      auto rv = std::make_shared<LocalRendezvous>();
+      rv->n = world;
+      for (int a = 0; a < world; a++) members[a]->rendezvous = rv;
     }
   });
 }

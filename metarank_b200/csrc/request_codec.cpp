@@ -201,7 +201,8 @@ struct Cur {
     unsigned v = 0;
     for (int k = 0; k < 4; k++) {
       const uint8_t c = p[k];
-      v = v * 16 + (c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : 0);
+      if (!((c >= '0' && c <= '9') || (c >= 'a' && c <= 'f') || (c >= 'A' && c <= 'F'))) bad("bad \\u escape");  // jawn rejects it too
+      v = v * 16 + (c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c - 'A' + 10);
     }
     p += 4;
     return v;
@@ -260,6 +261,22 @@ struct Cur {
     }
     if (n == 0) bad("unexpected character");
     buf[n] = 0;
+    {  // the JSON grammar, as jawn enforces it: -?(0|[1-9][0-9]*)(\.[0-9]+)?([eE][+-]?[0-9]+)?  ('+1', '01', '1.', '.5' are not numbers)
+      size_t k = 0;
+      auto dig = [&](size_t at) { return at < n && buf[at] >= '0' && buf[at] <= '9'; };
+      if (buf[k] == '-') k++;
+      if (!dig(k)) bad("bad number");
+      if (buf[k] == '0') k++;
+      else while (dig(k)) k++;
+      if (k < n && buf[k] == '.') { k++; if (!dig(k)) bad("bad number"); while (dig(k)) k++; }
+      if (k < n && (buf[k] == 'e' || buf[k] == 'E')) {
+        k++;
+        if (k < n && (buf[k] == '+' || buf[k] == '-')) k++;
+        if (!dig(k)) bad("bad number");
+        while (dig(k)) k++;
+      }
+      if (k != n) bad("bad number");
+    }
     char *end = nullptr;
     d = strtod(buf, &end);
     if (end == buf || *end != 0) bad("bad number");
@@ -289,7 +306,7 @@ struct Cur {
   JValue dom() {  // a whole value through the shared reader (rare keys only)
     ws();
     if (p >= e) bad("unexpected end of input");
-    JsonParser jp(p, (size_t)(e - p));
+    JsonParser jp(p, (size_t)(e - p), /*strict=*/true);
     JValue v = jp.parse();
     p = jp.pos();
     return v;
@@ -383,7 +400,8 @@ Event decode_event(Cur &c) {
   Event e;
   bool has_id = false, has_ts = false, has_items = false, seen_user = false, seen_session = false, has_fields = false;
   c.object([&](const std::string &k) {
-    if (k == "id" && !has_id) {
+    // a repeated key overwrites the earlier one, as in circe's JsonObject (and json.loads)
+    if (k == "id") {
       if (c.peek() == '"') c.str(e.id);
       else {
         double d; bool ii; int64_t i;
@@ -392,21 +410,24 @@ Event decode_event(Cur &c) {
         e.id = std::to_string(i);
       }
       has_id = true;
-    } else if (k == "timestamp" && !has_ts) {
+    } else if (k == "timestamp") {
       e.ts = decode_timestamp(c.dom());
       has_ts = true;
-    } else if ((k == "user" && !seen_user) || (k == "session" && !seen_session)) {
+    } else if (k == "user" || k == "session") {
       const bool user = k == "user";
       (user ? seen_user : seen_session) = true;
+      (user ? e.has_user : e.has_session) = false;
       if (c.peek() == 'n') { if (!c.lit("null")) c.bad("bad literal"); return; }
       if (c.peek() != '"') fail(MR_ERR_PARSE, "'%s' must be a string", k.c_str());
       c.str(user ? e.user : e.session);
       (user ? e.has_user : e.has_session) = true;
-    } else if (k == "fields" && !has_fields) {
+    } else if (k == "fields") {
       has_fields = true;
+      e.fields.clear();
       stream_fields(c, e.fields);
-    } else if (k == "items" && !has_items) {
+    } else if (k == "items") {
       has_items = true;
+      e.items.clear();
       if (c.peek() != '[') fail(MR_ERR_PARSE, "items must be a non-empty list");
       c.array([&] {
         e.items.emplace_back();
@@ -414,20 +435,22 @@ Event decode_event(Cur &c) {
         bool has_iid = false, seen_rel = false, has_rel = false, has_ifields = false;
         double rel = 0;
         c.object([&](const std::string &ik) {
-          if (ik == "id" && !has_iid) {
+          if (ik == "id") {
             if (c.peek() != '"') fail(MR_ERR_PARSE, "item needs a string 'id'");
             c.str(I.id);
             has_iid = true;
-          } else if (ik == "relevancy" && !seen_rel) {
+          } else if (ik == "relevancy") {
             seen_rel = true;
+            has_rel = false;
             const char pk = c.peek();
             if (pk == 'n') { if (!c.lit("null")) c.bad("bad literal"); return; }
             if (pk == '"' || pk == '{' || pk == '[' || pk == 't' || pk == 'f') fail(MR_ERR_PARSE, "relevancy must be a number");
             bool ii; int64_t i;
             c.number(rel, ii, i);
             has_rel = true;
-          } else if (ik == "fields" && !has_ifields) {
+          } else if (ik == "fields") {
             has_ifields = true;
+            I.fields.clear();
             stream_fields(c, I.fields);
           } else {
             c.skip();  // label and anything else
@@ -441,9 +464,9 @@ Event decode_event(Cur &c) {
         }
       });
       if (e.items.empty()) fail(MR_ERR_PARSE, "items must be a non-empty list");  // NonEmptyList
-    } else if (k == "embeddings" && e.embeddings.kind == JValue::Null) {
+    } else if (k == "embeddings") {
       e.embeddings = c.dom();
-    } else if (k == "tokens" && e.tokens.kind == JValue::Null) {
+    } else if (k == "tokens") {
       e.tokens = c.dom();
     } else {
       c.skip();
@@ -600,6 +623,7 @@ void decode_requests(const Schema &S, const RequestPlan &rp, const char *json, s
   std::vector<Event> events;
   if (c.peek() == '[') c.array([&] { events.push_back(decode_event(c)); });
   else events.push_back(decode_event(c));
+  if (c.peek() != '\0' || c.p != c.e) fail(MR_ERR_PARSE, "json: trailing characters after the request");  // circe's parser fails on them
   const std::vector<ReqFeature> &plan = rp.features;
   const int R = (int)events.size();
   const size_t nrf = S.in_req_f64.size(), nru = S.in_req_u64.size(), nrv = S.in_req_vec.size(), nif = S.in_item_f64.size(), ntk = S.in_req_tok.size();

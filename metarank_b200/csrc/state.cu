@@ -63,6 +63,13 @@ StateStore::StateStore(const Schema &s) : schema(s) {
     T.sides.emplace_back();
     T.d_sides.push_back(nullptr);
     T.d_sides_cap.push_back(0);
+    T.side_bs.emplace_back();
+    T.side_is_f32.push_back(1);
+    T.side_dev_mode.push_back(0);
+    T.d_sides_f32.push_back(nullptr);
+    T.d_sides_f32_cap.push_back(0);
+    T.d_side_bs.push_back(nullptr);
+    T.d_side_bs_cap.push_back(0);
   }
   // the global scope always has its single row
   tables[SC_GLOBAL].find_or_insert(1);
@@ -75,6 +82,8 @@ StateStore::~StateStore() {
     if (T.d_rows) cudaFree(T.d_rows);
     if (T.d_pool) cudaFree(T.d_pool);
     for (auto p : T.d_sides) if (p) cudaFree(p);
+    for (auto p : T.d_sides_f32) if (p) cudaFree(p);
+    for (auto p : T.d_side_bs) if (p) cudaFree(p);
   }
 }
 
@@ -149,13 +158,29 @@ void StateStore::upsert(const uint8_t *buf, size_t len, int64_t *applied, int64_
       if (on) w[sl.bit >> 6] |= 1ull << (sl.bit & 63);
       else w[sl.bit >> 6] &= ~(1ull << (sl.bit & 63));
     };
-    auto put_list = [&](uint64_t *dst) {
-      const uint32_t off = (uint32_t)T.pool.size();
-      if (T.pool.size() + n > (size_t)UINT32_MAX) fail(MR_ERR_UNSUPPORTED, "state pool is full");
-      T.pool.resize(T.pool.size() + n);
-      if (n) memcpy(T.pool.data() + off, arr, (size_t)n * 8);
-      *dst = (uint64_t)off | ((uint64_t)n << 32);
+    // List payloads live in a per-(slot, row) region of the table's pool that is rewritten in place while the new
+    // list fits (FeatureValueSink re-emits the same keys continuously: appending every time would grow the pool
+    // without bound); a list that outgrows its region moves to a new one of twice the size.
+    const RawKey rk{((uint64_t)sl.table << 56) ^ ((uint64_t)it->second << 40) ^ (uint64_t)row};
+    auto put_words = [&](uint64_t *dst, const uint64_t *src, uint32_t cnt) {
+      auto reg = upsert_region.find(rk);
+      if (reg == upsert_region.end() || reg->second.second < cnt) {
+        const uint32_t cap = std::max<uint32_t>(cnt, reg == upsert_region.end() ? 0u : 2u * reg->second.second);
+        if (T.pool.size() + cap > (size_t)UINT32_MAX) fail(MR_ERR_UNSUPPORTED, "state pool is full");
+        const uint32_t off = (uint32_t)T.pool.size();
+        T.pool.resize(T.pool.size() + cap, 0);
+        if (reg == upsert_region.end()) reg = upsert_region.emplace(rk, std::make_pair(off, cap)).first;
+        else reg->second = std::make_pair(off, cap);
+      }
+      const uint32_t off = reg->second.first;
+      if (cnt) memcpy(T.pool.data() + off, src, (size_t)cnt * 8);
+      if (off < T.pool_uploaded && cnt) {
+        T.pool_dirty_lo = std::min<size_t>(T.pool_dirty_lo, off);
+        T.pool_dirty_hi = std::max<size_t>(T.pool_dirty_hi, std::min<size_t>((size_t)off + cnt, T.pool_uploaded));
+      }
+      *dst = (uint64_t)off | ((uint64_t)cnt << 32);
     };
+    auto put_list = [&](uint64_t *dst) { put_words(dst, reinterpret_cast<const uint64_t *>(arr), n); };
     bool ok = true;
     switch (sl.kind) {
       case SK_F64:
@@ -208,6 +233,7 @@ void StateStore::upsert(const uint8_t *buf, size_t len, int64_t *applied, int64_
         // of another length behaves as missing
         if (kind == 5 && (int)n == sl.p) { memcpy(&w[sl.word], arr, (size_t)n * 8); set_present(true); }
         else set_present(false);
+        buckets.erase(rk);  // the refreshed value supersedes the day buckets apply_writes kept (see apply_writes)
         break;
       case SK_STRLIST:
         if (kind == 2 && sl.p == 1) {
@@ -216,16 +242,15 @@ void StateStore::upsert(const uint8_t *buf, size_t len, int64_t *applied, int64_
           if (n) memcpy(v.data(), arr, (size_t)n * 8);
           std::sort(v.begin(), v.end());
           v.erase(std::unique(v.begin(), v.end()), v.end());
-          const uint32_t off = (uint32_t)T.pool.size();
-          if (T.pool.size() + v.size() > (size_t)UINT32_MAX) fail(MR_ERR_UNSUPPORTED, "state pool is full");
-          T.pool.insert(T.pool.end(), v.begin(), v.end());
-          w[sl.word] = (uint64_t)off | ((uint64_t)v.size() << 32);
+          put_words(&w[sl.word], v.data(), (uint32_t)v.size());
           set_present(true);
         } else if (kind == 2) { put_list(&w[sl.word]); set_present(true); }
         else set_present(false);  // InteractedWith / FieldMatch collect only SStringList
         break;
       case SK_BLIST:
         if (kind == 6) { put_list(&w[sl.word]); set_present(true); } else set_present(false);
+        lists.erase(rk);
+        list_region.erase(rk);
         break;
       case SK_F64LIST: {
         if (kind != 3) { set_present(false); break; }
@@ -235,6 +260,21 @@ void StateStore::upsert(const uint8_t *buf, size_t len, int64_t *applied, int64_
         auto &S = T.sides[local];
         if (S.size() < (size_t)T.n_rows * sl.p) S.resize((size_t)T.n_rows * sl.p, 0.0);
         memcpy(S.data() + (size_t)row * sl.p, arr, (size_t)n * 8);
+        {
+          auto &BS = T.side_bs[local];
+          if (BS.size() < T.n_rows) BS.resize(T.n_rows, 0.0);
+          // CosineDistance's bSum (S/ml/onnx/distance/DistanceFunction.scala:22): sequential, product rounded before the add
+          volatile double bs = 0.0;
+          bool f32 = T.side_is_f32[local] != 0;
+          const double *e = S.data() + (size_t)row * sl.p;
+          for (int k = 0; k < sl.p; k++) {
+            volatile double sq = e[k] * e[k];
+            bs = bs + sq;
+            f32 = f32 && ((double)(float)e[k] == e[k] || e[k] != e[k]);  // NaN payloads do not matter: NaN * x is NaN either way
+          }
+          BS[row] = bs;
+          T.side_is_f32[local] = f32;
+        }
         set_present(true);
         break;
       }
@@ -264,11 +304,12 @@ __global__ void scatter_rows_kernel(uint64_t *rows, int row_words, const uint32_
   const uint64_t *src = packed + (size_t)r * row_words;
   for (int w = threadIdx.x; w < row_words; w += blockDim.x) dst[w] = src[w];
 }
-__global__ void scatter_side_kernel(double *side, int dim, const uint32_t *idx, const double *packed, int n) {
+template <class V>
+__global__ void scatter_side_kernel(V *side, int dim, const uint32_t *idx, const V *packed, int n) {
   const int r = blockIdx.x;
   if (r >= n) return;
-  double *dst = side + (size_t)idx[r] * dim;
-  const double *src = packed + (size_t)r * dim;
+  V *dst = side + (size_t)idx[r] * dim;
+  const V *src = packed + (size_t)r * dim;
   for (int w = threadIdx.x; w < dim; w += blockDim.x) dst[w] = src[w];
 }
 
@@ -306,9 +347,19 @@ void StateStore::flush() {
       for (size_t s = 0; s < T.sides.size(); s++) {
         const int dim = schema.sides[T.side_ids[s]].dim;
         if (T.sides[s].size() < T.n_rows * (size_t)dim) T.sides[s].resize(T.n_rows * (size_t)dim, 0.0);
-        const size_t had_s = T.d_sides_cap[s];
-        ensure_dev(T.d_sides[s], T.d_sides_cap[s], T.sides[s].size(), 0, device_bytes);
-        realloc_any |= T.d_sides_cap[s] != had_s;
+        if (T.side_bs[s].size() < T.n_rows) T.side_bs[s].resize(T.n_rows, 0.0);
+        // binary32 on the device while every element round-trips (and rows stay 16-byte aligned for the kernel's copies)
+        const uint8_t mode = (T.side_is_f32[s] && dim % 4 == 0) ? 1 : 2;
+        if (mode != T.side_dev_mode[s]) {  // first upload, or an element that needs all 53 bits arrived: switch representation
+          realloc_any = true;
+          if (mode == 2 && T.d_sides_f32[s]) { cudaFree(T.d_sides_f32[s]); T.d_sides_f32[s] = nullptr; device_bytes -= (int64_t)T.d_sides_f32_cap[s] * 4; T.d_sides_f32_cap[s] = 0; }
+          T.side_dev_mode[s] = mode;
+        }
+        const size_t had_s = mode == 1 ? T.d_sides_f32_cap[s] : T.d_sides_cap[s], had_b = T.d_side_bs_cap[s];
+        if (mode == 1) ensure_dev(T.d_sides_f32[s], T.d_sides_f32_cap[s], T.sides[s].size(), 0, device_bytes);
+        else ensure_dev(T.d_sides[s], T.d_sides_cap[s], T.sides[s].size(), 0, device_bytes);
+        ensure_dev(T.d_side_bs[s], T.d_side_bs_cap[s], T.side_bs[s].size(), 0, device_bytes);
+        realloc_any |= (mode == 1 ? T.d_sides_f32_cap[s] : T.d_sides_cap[s]) != had_s || T.d_side_bs_cap[s] != had_b;
       }
       const size_t n_dirty = T.dirty_rows.size();
       const bool sparse = !realloc_any && n_dirty * 8 < (T.dirty_hi - T.dirty_lo);  // < 1/8 of the span touched
@@ -331,16 +382,23 @@ void StateStore::flush() {
         }
         for (size_t s = 0; s < T.sides.size(); s++) {
           const int dim = schema.sides[T.side_ids[s]].dim;
-          std::vector<double> packed(n_dirty * (size_t)dim);
-          for (size_t k = 0; k < n_dirty; k++)
-            memcpy(packed.data() + k * dim, T.sides[s].data() + (size_t)T.dirty_rows[k] * dim, (size_t)dim * 8);
-          double *d_packed = nullptr;
-          MR_CUDA_CHECK(cudaMalloc((void **)&d_packed, packed.size() * 8));
-          MR_CUDA_CHECK(cudaMemcpy(d_packed, packed.data(), packed.size() * 8, cudaMemcpyHostToDevice));
-          scatter_side_kernel<<<(unsigned)n_dirty, 128>>>(T.d_sides[s], dim, d_idx, d_packed, (int)n_dirty);
-          MR_CUDA_CHECK(cudaGetLastError());
-          MR_CUDA_CHECK(cudaDeviceSynchronize());
-          cudaFree(d_packed);
+          auto scatter = [&](auto *d_side, auto zero, int width, auto fetch) {
+            using V = decltype(zero);
+            std::vector<V> packed(n_dirty * (size_t)width);
+            for (size_t k = 0; k < n_dirty; k++)
+              for (int w = 0; w < width; w++) packed[k * width + w] = fetch((size_t)T.dirty_rows[k], w);
+            V *d_packed = nullptr;
+            MR_CUDA_CHECK(cudaMalloc((void **)&d_packed, packed.size() * sizeof(V)));
+            MR_CUDA_CHECK(cudaMemcpy(d_packed, packed.data(), packed.size() * sizeof(V), cudaMemcpyHostToDevice));
+            scatter_side_kernel<V><<<(unsigned)n_dirty, 128>>>(d_side, width, d_idx, d_packed, (int)n_dirty);
+            MR_CUDA_CHECK(cudaGetLastError());
+            MR_CUDA_CHECK(cudaDeviceSynchronize());
+            cudaFree(d_packed);
+          };
+          const std::vector<double> &S = T.sides[s], &BS = T.side_bs[s];
+          if (T.side_dev_mode[s] == 1) scatter(T.d_sides_f32[s], 0.0f, dim, [&](size_t r, int w) { return (float)S[r * dim + w]; });
+          else scatter(T.d_sides[s], 0.0, dim, [&](size_t r, int w) { return S[r * dim + w]; });
+          scatter(T.d_side_bs[s], 0.0, 1, [&](size_t r, int) { return BS[r]; });
         }
         cudaFree(d_idx);
       } else {
@@ -350,8 +408,16 @@ void StateStore::flush() {
                                  (hi - lo) * T.row_words * 8, cudaMemcpyHostToDevice));
         for (size_t s = 0; s < T.sides.size(); s++) {
           const int dim = schema.sides[T.side_ids[s]].dim;
-          MR_CUDA_CHECK(cudaMemcpy(T.d_sides[s] + lo * dim, T.sides[s].data() + lo * dim, (hi - lo) * dim * 8,
-                                   cudaMemcpyHostToDevice));
+          if (T.side_dev_mode[s] == 1) {
+            std::vector<float> f((hi - lo) * dim);
+            const double *src = T.sides[s].data() + lo * dim;
+            for (size_t k = 0; k < f.size(); k++) f[k] = (float)src[k];
+            MR_CUDA_CHECK(cudaMemcpy(T.d_sides_f32[s] + lo * dim, f.data(), f.size() * 4, cudaMemcpyHostToDevice));
+          } else {
+            MR_CUDA_CHECK(cudaMemcpy(T.d_sides[s] + lo * dim, T.sides[s].data() + lo * dim, (hi - lo) * dim * 8,
+                                     cudaMemcpyHostToDevice));
+          }
+          MR_CUDA_CHECK(cudaMemcpy(T.d_side_bs[s] + lo, T.side_bs[s].data() + lo, (hi - lo) * 8, cudaMemcpyHostToDevice));
         }
       }
       if (&T == &tables[SC_ITEM]) {
@@ -399,7 +465,9 @@ DState StateStore::view() const {
     v.t[t].pool = T.d_pool;
     v.t[t].row_words = T.row_words;
     for (size_t s = 0; s < T.side_ids.size(); s++) {
-      v.side[T.side_ids[s]] = T.d_sides[s];
+      v.side[T.side_ids[s]] = T.side_dev_mode[s] == 2 ? T.d_sides[s] : nullptr;
+      v.side_f32[T.side_ids[s]] = T.side_dev_mode[s] == 1 ? T.d_sides_f32[s] : nullptr;
+      v.side_bs[T.side_ids[s]] = T.d_side_bs[s];
       v.side_dim[T.side_ids[s]] = schema.sides[T.side_ids[s]].dim;
     }
   }
@@ -471,6 +539,13 @@ void StateStore::apply_writes(const uint8_t *buf, size_t len, int64_t *applied, 
     } else if (op == 2 && sl.kind == SK_PCOUNTER) {
       // MemPeriodicCounter.put: bucket = ts.toStartOfPeriod(period) = floor(ts.toDouble / period) * period
       const int64_t bucket = (int64_t)std::floor((double)ts / (double)sl.period_ms) * sl.period_ms;
+      const bool was_present = (w[sl.bit >> 6] >> (sl.bit & 63)) & 1;
+      if (was_present && buckets.find(rk) == buckets.end())
+        fail(MR_ERR_UNSUPPORTED,
+             "periodic counter '%s' of this key was loaded as a refreshed value (mr_state_upsert / mr_state_load_feature_values): "
+             "a PeriodicCounterValue carries window sums, not the day buckets behind them, so a PeriodicIncrement cannot continue "
+             "it without resetting the windows — feed a slot either refreshed values or raw writes, not both",
+             name.c_str());
       auto &m = buckets[rk];
       m[bucket] += inc;
       // PeriodicCounterFeature.fromMap: windows anchored at the LAST bucket,
@@ -487,6 +562,12 @@ void StateStore::apply_writes(const uint8_t *buf, size_t len, int64_t *applied, 
       // MemBoundedList.put: the first write is stored untrimmed; later ones prepend, drop entries
       // older than ts - duration, keep `count`
       auto lit = lists.find(rk);
+      if (lit == lists.end() && ((w[sl.bit >> 6] >> (sl.bit & 63)) & 1))
+        fail(MR_ERR_UNSUPPORTED,
+             "bounded list '%s' of this key was loaded as a refreshed value (mr_state_upsert / mr_state_load_feature_values): "
+             "its entries' timestamps are not part of the record, so an Append cannot age them — feed a slot either refreshed "
+             "values or raw writes, not both",
+             name.c_str());
       if (lit == lists.end()) {
         lists[rk].push_front({ts, item});
         lit = lists.find(rk);

@@ -34,7 +34,15 @@ struct DTable {  // device view, passed to kernels by value
 
 struct DState {
   DTable t[SC_N_TABLES];
+  // Embedding side arrays (one row of `dim` values per table row).  An array whose every element survives the
+  // round trip through binary32 — true for anything an ONNX encoder produced: the reference only ever widens f32
+  // outputs, S/model/Scalar.scala:16-33 — lives on the device as f32 (`side_f32`, half the bytes the cosine kernel
+  // streams) and is widened in registers, bit for bit the stored double; otherwise as f64 (`side`).  Exactly one of
+  // the two pointers is non-null.  side_bs[row] = sum of e*e in index order (CosineDistance's bSum, a function of the
+  // item alone, computed once at upsert time).
   const double *side[kMaxSides];
+  const float *side_f32[kMaxSides];
+  const double *side_bs[kMaxSides];
   int32_t side_dim[kMaxSides];
 };
 
@@ -57,6 +65,11 @@ struct HostTable {
   uint64_t *d_rows = nullptr; size_t d_rows_cap = 0;
   uint64_t *d_pool = nullptr; size_t d_pool_cap = 0, pool_uploaded = 0;
   std::vector<double *> d_sides; std::vector<size_t> d_sides_cap;
+  std::vector<std::vector<double>> side_bs;      // per row: sum of squares of the embedding, in index order
+  std::vector<uint8_t> side_is_f32;              // every element stored so far round-trips through binary32
+  std::vector<uint8_t> side_dev_mode;            // what the device holds: 0 nothing yet, 1 f32, 2 f64
+  std::vector<float *> d_sides_f32; std::vector<size_t> d_sides_f32_cap;
+  std::vector<double *> d_side_bs; std::vector<size_t> d_side_bs_cap;
   size_t d_keys_n = 0, d_n_rows = 0;  // what the device holds as of the last flush (ranking reads this snapshot)
   bool map_dirty = false;
   size_t dirty_lo = SIZE_MAX, dirty_hi = 0;  // row range touched since the last flush
@@ -99,6 +112,7 @@ struct StateStore {
   std::unordered_map<RawKey, std::map<int64_t, int64_t>, RawKeyHash> buckets;                // MemPeriodicCounter
   std::unordered_map<RawKey, std::deque<std::pair<int64_t, uint64_t>>, RawKeyHash> lists;     // MemBoundedList
   std::unordered_map<RawKey, uint32_t, RawKeyHash> list_region;  // pool offset of a list's fixed-capacity region
+  std::unordered_map<RawKey, std::pair<uint32_t, uint32_t>, RawKeyHash> upsert_region;  // upserted lists: {pool offset, capacity}
   void flush();
   DState view() const;
   // Item-table change log for consumers that keep derived per-row data on the device (the per-model

@@ -362,8 +362,9 @@ def to_state(values) -> dict:
         elif t == "pcounter":
             st[fv["key"]] = ("pcounter", [pv["value"] for pv in fv["values"]])
         elif t == "blist":
-            if all(isinstance(v, str) for _, v in fv["values"]):
-                st[fv["key"]] = ("blist", [v for _, v in fv["values"]])
+            # the reader keeps the list and collects its SString entries (InteractedWithFeature.scala:117:
+            # values.map(_.value).collect { case SString(id) => id }); other scalar kinds are skipped
+            st[fv["key"]] = ("blist", [v for _, v in fv["values"] if isinstance(v, str)])
     return st
 
 

@@ -65,7 +65,8 @@ int main(int argc, char **argv) {
     check(m != 0 && !env.ExceptionCheck(), "modelLoad", env.pending_message.c_str());
     const int rows = 5;
     const double X[rows * 2] = {0.5, -0.5, 0.6, -0.5, 0.0, 0.0, NAN, -1.0, 1.0, NAN};
-    const double want[rows] = {0.25 + 1, -0.75 + 1, 0.25 + 2, -0.75 + 1, -0.75 + 2};  // decision_type 2: missing NaN, default right
+    // decision_type 2 = default-left bit, missing type None: a NaN input is read as 0.0 (Tree::NumericalDecision)
+    const double want[rows] = {0.25 + 1, -0.75 + 1, 0.25 + 2, 0.25 + 1, -0.75 + 2};
     jdoubleArray v = env.NewDoubleArray(rows * 2);
     memcpy(v->data, X, sizeof X);
     jdoubleArray out = Java_ai_metarank_b200_Native_predictMat(&env, nullptr, m, v, rows, 2);

@@ -243,3 +243,70 @@ def test_parsers_survive_corrupted_models_and_schemas():
         else:
             err += 1
     assert ok > 0 and err > 0
+
+
+def test_real_file_quirks_of_the_booster_formats():
+    """No LightGBM / XGBoost build can be had in this image or on the GPU box (profiles/probe_r2_gbdt_libs.txt), so the
+    parsers are held to the quirks of the files those libraries really write, from their public formats:
+    LightGBM  the bare `average_output` word (rf boosting), objectives that transform the raw score, `tree_sizes` vs the
+              blocks present, a lost `end of trees`, out-of-order blocks, feature_names vs max_feature_idx;
+    XGBoost   base_score as a string ("5E-1", and "[5E-1]" from 3.1 on), booleans in default_left, tree_param.num_nodes,
+              transforming objectives, multi-target, the deprecated binary header."""
+    import json
+
+    lgb = synth.lightgbm_model_text(3, 4, seed=2)
+    assert inspect_model(0, lgb).n_trees == 3
+    assert inspect_model(0, lgb.replace(b"\n", b"\r\n")).n_trees == 3  # CRLF files
+    for text, status, word in [
+        (lgb.replace(b"objective=lambdarank", b"objective=lambdarank\naverage_output"), 5, "average_output"),
+        (lgb.replace(b"objective=lambdarank", b"objective=binary sigmoid:1"), 5, "binary"),
+        (lgb.replace(b"objective=lambdarank", b"objective=regression sqrt"), 5, "regression sqrt"),
+        (lgb.replace(b"objective=lambdarank", b"objective=poisson"), 5, "poisson"),
+        (lgb.replace(b"end of trees", b""), 2, "truncated"),
+        (lgb[: lgb.index(b"Tree=2")], 2, "truncated"),
+        (lgb.replace(b"Tree=1", b"Tree=7"), 2, "out of order"),
+        (lgb.replace(b"feature_names=", b"feature_names=extra "), 2, "feature_names"),
+    ]:
+        with pytest.raises(mb.MrError) as e:
+            inspect_model(0, text)
+        assert e.value.status == status and word in e.value.message, (word, e.value)
+    # tree_sizes disagreeing with the blocks present (a file cut between two trees and re-terminated)
+    cut = lgb[: lgb.index(b"Tree=2")] + b"end of trees\n"
+    with pytest.raises(mb.MrError) as e:
+        inspect_model(0, cut)
+    assert e.value.status == 2 and "tree_sizes" in e.value.message
+    for obj in (b"objective=rank_xendcg", b"objective=regression", b"objective=huber"):
+        assert inspect_model(0, lgb.replace(b"objective=lambdarank", obj)).n_trees == 3
+
+    doc = json.loads(synth.xgboost_model_json(3, 5, depth=3, seed=4))
+    lmp = doc["learner"]["learner_model_param"]
+
+    def with_(mut):
+        d = json.loads(json.dumps(doc))
+        mut(d)
+        return json.dumps(d).encode()
+
+    for bs in ("5E-1", "[5E-1]", " [ 2.5E-1 ] ", "0.5"):
+        assert inspect_model(1, with_(lambda d: d["learner"]["learner_model_param"].update(base_score=bs))).n_trees == 3
+    def bools(d):
+        for t in d["learner"]["gradient_booster"]["model"]["trees"]:
+            t["default_left"] = [bool(x) for x in t["default_left"]]
+    assert inspect_model(1, with_(bools)).n_trees == 3  # XGBoost 1.0-1.2 JSON wrote booleans
+    assert isinstance(lmp["base_score"], str)  # the synthetic writer uses the library's string form too
+    for mut, status, word in [
+        (lambda d: d["learner"]["learner_model_param"].update(base_score="[5E-1,2E-1]"), 5, "multi-target"),
+        (lambda d: d["learner"]["learner_model_param"].update(base_score="abc"), 2, "base_score"),
+        (lambda d: d["learner"]["learner_model_param"].update(num_target="2"), 5, "multi-target"),
+        (lambda d: d["learner"]["objective"].update(name="binary:logistic"), 5, "binary:logistic"),
+        (lambda d: d["learner"]["gradient_booster"].update(name="dart"), 5, "dart"),
+        (lambda d: d["learner"]["gradient_booster"]["model"]["trees"][1].setdefault("tree_param", {}).update(num_nodes="3"), 2, "num_nodes"),
+        (lambda d: d["learner"]["gradient_booster"]["model"]["trees"][0].update(
+            split_type=[1] * len(d["learner"]["gradient_booster"]["model"]["trees"][0]["left_children"])), 5, "categorical"),
+    ]:
+        with pytest.raises(mb.MrError) as e:
+            inspect_model(1, with_(mut))
+        assert e.value.status == status and word in e.value.message, (word, e.value)
+    for head in (b"binf\x00\x00\x00\x00", b"bs64AAAA"):
+        with pytest.raises(mb.MrError) as e:
+            inspect_model(1, head)
+        assert e.value.status == 5 and "deprecated binary" in e.value.message

@@ -85,7 +85,7 @@ def _sample_values():
     vals.append(dict(type="pcounter", key=key(), ts=5, values=[], expire_ms=7))
     vals.append(dict(type="blist", key=key(), ts=9, expire_ms=3, values=[(100 - j, f"p{j}") for j in range(12)]))
     vals.append(dict(type="blist", key=key(), ts=9, expire_ms=3, values=[]))
-    vals.append(dict(type="blist", key=key(), ts=9, expire_ms=3, values=[(1, "p1"), (2, 3.0)]))   # not item ids: no reader
+    vals.append(dict(type="blist", key=key(), ts=9, expire_ms=3, values=[(1, "p1"), (2, 3.0), (3, "p7")]))  # mixed: the ids survive
     vals.append(dict(type="numstats", key=key(), ts=1, min=0.5, max=9.0, quantiles={50: 3.0, 90: 8.0}, expire_ms=2))
     vals.append(dict(type="map", key=key(), ts=1, values={"a": 1.0, "b": "x", "c": ["y"]}, expire_ms=2))
     vals.append(dict(type="frequency", key=key(), ts=1, values={"x": 0.25, "y": 0.75}, expire_ms=2))
@@ -133,7 +133,7 @@ def test_native_decoder_emits_the_packers_upsert_records(legacy):
     recs, n, unsupported, consumed = F.transcode_feature_values(blob)
     state = co.to_state(co.decode_delimited(blob))
     assert n == len(vals) and consumed == len(blob)
-    assert unsupported == len(vals) - len(state) == 4            # numstats, map, frequency, the non-id list
+    assert unsupported == len(vals) - len(state) == 3            # numstats, map, frequency (a mixed list keeps its ids)
     assert recs == F.pack_feature_values(state)
     # a truncated trailing record ends the stream (BinaryVCodec.decodeDelimited -> Right(None))
     recs2, n2, _, consumed2 = F.transcode_feature_values(blob[:-2])

@@ -1089,3 +1089,141 @@ def test_golden_vectors_through_the_native_request_decoder(ctx, case):
         dec.free()
     finally:
         ds.free(); fm.free()
+
+
+def test_reupserted_lists_reuse_their_pool_region(ctx):
+    """FeatureValueSink re-emits the same keys continuously; list payloads (interacted_with bounded lists, tag
+    lists, token sets) must be rewritten in place instead of growing the pool with every upsert,
+    and what the kernels read must be the latest value, also when a list grows or shrinks."""
+    from metarank_b200 import features as F
+
+    feats = [dict(name="seen", type="interacted_with", interaction="click", field=["item.tags"], scope="session", count=50,
+                  duration="24h"),
+             dict(name="d", type="diversity", source="metadata.tags")]
+    model = ["seen", "d"]
+    mapping = fo.FeatureMapping(feats, model)
+    fm = F.FeatureMapping(ctx, feats, model)
+    ds = F.DeviceState(ctx, fm)
+    rng = np.random.Generator(np.random.PCG64(5))
+    items = [f"i{k}" for k in range(40)]
+    try:
+        state = {}
+        for it in items:
+            tags = [f"t{int(x)}" for x in rng.integers(0, 9, int(rng.integers(1, 5)))]
+            state[(("item", it), "seen_tags")] = ("scalar", tags)
+            state[(("item", it), "d")] = ("scalar", tags)
+        sizes = []
+        for rnd in range(60):
+            n = int(rng.integers(1, 40)) if rnd % 7 else 50  # grows and shrinks
+            state[(("session", "s"), "seen_interactions")] = ("blist", [items[int(j)] for j in rng.integers(0, 40, n)])
+            it = items[int(rng.integers(0, 40))]
+            tags = [f"t{int(x)}" for x in rng.integers(0, 9, int(rng.integers(1, 6)))]
+            state[(("item", it), "seen_tags")] = ("scalar", tags)
+            state[(("item", it), "d")] = ("scalar", tags)
+            ds.put(state)  # the WHOLE state again, like a sink that re-emits every key
+            ds.flush()
+            sizes.append(int(ds.info().device_bytes))
+            req = G.ranking(items[:25], session="s")
+            assert _eq(F.Ranker(fm, ds).make_query([req])[0], fo.dense_matrix(mapping, req, state)), rnd
+        # the pool settles: a list that outgrows its region moves to one of twice the size, so 60 re-emissions of the
+        # whole state cost a bounded factor — appending every time would have multiplied the pool 60-fold
+        assert sizes[-1] <= 1.5 * sizes[1] and sizes[-1] == sizes[-10], sizes
+    finally:
+        ds.free(); fm.free()
+
+
+def test_writes_cannot_silently_continue_loaded_values(ctx):
+    """A PeriodicCounterValue / BoundedListValue that arrived as a refreshed value does not carry the raw state
+    behind it (day buckets, entry timestamps): a PeriodicIncrement / Append on such a key must fail loudly instead
+    of resetting the windows / the history; the reverse — a refreshed value over written state —
+    simply supersedes it."""
+    import metarank_b200 as mb
+    from metarank_b200 import features as F
+
+    feats = [dict(name="wc", type="window_count", interaction="click", scope="item", bucket="24h", periods=[1, 7]),
+             dict(name="seen", type="interacted_with", interaction="click", field=["item.tags"], scope="session", count=5,
+                  duration="48h")]
+    model = ["wc", "seen"]
+    mapping = fo.FeatureMapping(feats, model)
+    flow = fo.FeatureValueFlow(mapping, always_refresh=True)
+    fm = F.FeatureMapping(ctx, feats, model)
+    ds = F.DeviceState(ctx, fm)
+    try:
+        ev = [G.item_event("a", [("tags", ["x", "y"])]), G.item_event("b", [("tags", ["y"])]),
+              G.interaction("a", "r", "click", session="s", ts=G.NOW - 3600_000),
+              G.interaction("b", "r", "click", session="s", ts=G.NOW)]
+        state = dict(flow.process(ev))
+        ds.apply_writes(flow.write_log)
+        ds.flush()
+        req = G.ranking(["a", "b"], session="s")
+        assert _eq(F.Ranker(fm, ds).make_query([req])[0], fo.dense_matrix(mapping, req, state))
+        # refreshed values over written state: they win, and from then on raw writes for those keys are refused
+        state[(("item", "a"), "wc")] = ("pcounter", [5, 9])
+        state[(("session", "s"), "seen_interactions")] = ("blist", ["b"])
+        ds.put({k: state[k] for k in [(("item", "a"), "wc"), (("session", "s"), "seen_interactions")]})
+        ds.flush()
+        assert _eq(F.Ranker(fm, ds).make_query([req])[0], fo.dense_matrix(mapping, req, state))
+        flow.write_log.clear()
+        flow.process([G.interaction("a", "r", "click", session="s", ts=G.NOW + 1000)])
+        hit = 0
+        for w in flow.write_log:
+            kind, (scope, name), ts, v = w
+            touches_loaded = (name == "wc" and scope == ("item", "a")) or (name == "seen_interactions" and scope == ("session", "s"))
+            if touches_loaded:
+                hit += 1
+                with pytest.raises(mb.MrError) as e:
+                    ds.apply_writes([w])
+                assert e.value.status == 5 and "refreshed value" in e.value.message
+        assert hit == 2
+        # a key that only ever saw raw writes keeps working
+        flow.write_log.clear()
+        flow.process([G.interaction("b", "r", "click", session="s2", ts=G.NOW + 2000)])
+        a, s = ds.apply_writes(flow.write_log)
+        assert a > 0
+    finally:
+        ds.free(); fm.free()
+
+
+@pytest.mark.parametrize("dim", [384, 20, 18, 132])
+def test_embedding_storage_switches_from_binary32_to_f64(ctx, dim):
+    """Embeddings whose every element round-trips through binary32 (anything an ONNX encoder produced) live on the
+    device as f32 and are scored by cosine_f32_kernel; the first element that needs all 53 bits switches the whole
+    array to f64 (sparse update -> full re-upload) and the old kernel.  Either way the column equals the reference's
+    sequential sums bit for bit.  Requests of 100 items put request boundaries inside the kernel's 128-item CTAs
+    (the per-CTA widened query vs the per-lane fallback); dim 18 is not a multiple of 4 (always f64), 132 has a
+    4-float tail chunk."""
+    feats = [dict(name="sim", type="field_match", rankingField="ranking.query", itemField="item.title",
+                  method=dict(type="bi-encoder", dim=dim), distance="cos")]
+    rng = np.random.Generator(np.random.PCG64(dim))
+    n = 700
+    state = {}
+    for k in range(n):
+        if rng.random() > 0.04:
+            state[(("item", f"i{k}"), "sim")] = ("scalar", rng.standard_normal(dim).astype(np.float32).astype(np.float64).tolist())
+    fm, ds, rk, _, _ = _device(ctx, feats, ["sim"], state)
+    mapping = fo.FeatureMapping(feats, ["sim"])
+
+    def check():
+        reqs = []
+        for r in range(7):
+            pick = rng.choice(n + 5, 100, replace=False)  # a few unknown items too
+            reqs.append(dict(event="ranking", id=f"r{r}", timestamp=0, user=None, session=None, fields=[("query", "q")],
+                             embeddings={} if r == 3 else {"sim": rng.standard_normal(dim).astype(np.float32)},
+                             items=[dict(id=f"i{int(j)}", fields=[]) for j in pick]))
+        got = rk.make_query(reqs)
+        for r, q in enumerate(reqs):
+            assert _eq(got[r], fo.dense_matrix(mapping, q, state)), r
+
+    try:
+        check()
+        upd = {(("item", "i9"), "sim"): ("scalar", rng.standard_normal(dim).astype(np.float32).astype(np.float64).tolist())}
+        state.update(upd); ds.put(upd); ds.flush()   # sparse update, still binary32
+        check()
+        upd = {(("item", "i11"), "sim"): ("scalar", (rng.standard_normal(dim) * (1 + 2.0**-40)).tolist())}
+        state.update(upd); ds.put(upd); ds.flush()   # needs 53 bits: the array becomes f64
+        check()
+        upd = {(("item", f"i{k}"), "sim"): ("scalar", rng.standard_normal(dim).tolist()) for k in (1, 2, n - 1)}
+        state.update(upd); ds.put(upd); ds.flush()
+        check()
+    finally:
+        ds.free(); fm.free()

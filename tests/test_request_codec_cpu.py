@@ -258,3 +258,36 @@ def test_native_decoder_survives_corrupted_bodies():
     with pytest.raises(_capi.MrError):  # a megabyte of '[' must not blow the stack
         F.DecodedRequests(fm, '{"id": "r", "timestamp": 1, "items": [{"id": "p"}], "junk": ' + "[" * 1_000_000)
     fm.free()
+
+
+def test_native_decoder_is_as_strict_as_jawn_and_takes_the_last_duplicate():
+    """duplicate keys resolve to the LAST occurrence (circe's JsonObject, json.loads), bytes after the
+    top-level value are a failure, and '+1', '01', '1.', '.5', \\uZZZZ are not JSON."""
+    fm = F.FeatureMapping(None, FEATS, MODEL)
+    base = '"items": [{"id": "p1"}, {"id": "p2", "relevancy": 1, "relevancy": 3}]'
+    body = '{"id": "a", "timestamp": 1000, "timestamp": 2000, "user": "u1", "user": null, "id": "b", ' + base + "}"
+    dec = F.DecodedRequests(fm, body)
+    want = fm.pack_requests([decode_ranking_event(body)])
+    got = dec.arrays()
+    assert dec.timestamp(0) == 2000 == decode_ranking_event(body)["timestamp"]
+    for k in ["offsets", "ids", "users", "sessions", "req_f64", "req_u64", "item_f64"]:
+        _same(got[k], want[k], k)
+    assert got["users"][0] == 0  # the later `null` wins
+    dec.free()
+    two_item_lists = '{"id": "a", "timestamp": 1, "items": [{"id": "x"}], "items": [{"id": "p1"}, {"id": "p2"}]}'
+    dec = F.DecodedRequests(fm, two_item_lists)
+    assert dec.total_items == 2 and [dec.item_id(i) for i in range(2)] == ["p1", "p2"]
+    dec.free()
+    ok = '{"id": "r", "timestamp": 1, "items": [{"id": "p"}]}'
+    for bad in [ok + " garbage", ok + "{}", ok + ",", "[" + ok + "] 1",
+                ok.replace('"timestamp": 1', '"timestamp": +1'), ok.replace('"timestamp": 1', '"timestamp": 01'),
+                ok.replace('"timestamp": 1', '"timestamp": 1.'), ok.replace('{"id": "p"}', '{"id": "p", "relevancy": .5}'),
+                ok.replace('{"id": "p"}', '{"id": "p", "relevancy": 1e}'), ok.replace('"id": "r"', '"id": "\\\\uZZZZ"'.replace("\\\\", "\\")),
+                ok.replace('{"id": "p"}', '{"id": "p", "relevancy": -}')]:
+        with pytest.raises(_capi.MrError):
+            F.DecodedRequests(fm, bad)
+        with pytest.raises(Exception):
+            decode_ranking_event(bad)
+    for good in [ok + "  \n\t ", ok.replace('{"id": "p"}', '{"id": "p", "relevancy": -0.5e+2}'), ok.replace('"timestamp": 1', '"timestamp": 0')]:
+        F.DecodedRequests(fm, good).free()
+    fm.free()
