@@ -600,29 +600,28 @@ def scorer_roofline(w, kernels, step_ms, sm_mhz):
     dom = max(kernels, key=lambda k: k["ms_per_step"])
     out = {"kernel": dom["kernel"], "kernel_ms": dom["ms_per_step"], "step_share": dom["ms_per_step"] / step_ms,
            "peak_source": peak_src}
-    if not dom["kernel"].startswith("gbdt_score_compact"):
+    slim = dom["kernel"].startswith("gbdt_score_slim")
+    if not (slim or dom["kernel"].startswith("gbdt_score_compact")):
         out.update({"bound": "hbm", "achieved": None, "peak": peak_hbm, "unit": "GB/s", "frac": None, "traffic": None,
                     "note": "dominant kernel is not the compact scorer; see `kernels` for its HBM fraction"})
         return out
-    # walk statistics on the codes of this very batch (first <= 262144 rows)
+    # walk statistics on this very batch (first <= 262144 rows)
     rows = min(w.rows, 262144)
     if getattr(w, "d_feat", None) is None:
         w.step(explain=True)
         w.status()
-    n_codes = b.codes_bytes(rows)
-    d_codes = torch.empty(n_codes, dtype=torch.uint8, device="cuda")
-    b.bin_device(w.d_feat.data_ptr(), rows, c["features"], d_codes.data_ptr(), w.stream)
     import metarank_b200 as mb
     lane, warp, wt = C.c_double(), C.c_double(), C.c_double()
-    mb._capi.check(mb._capi.lib().mr_model_walk_stats(b._h, C.c_void_p(d_codes.data_ptr()), C.c_int32(rows), C.byref(lane),
-                                                      C.byref(warp), C.byref(wt), C.c_void_p(w.stream)))
+    mb._capi.check(mb._capi.lib().mr_model_walk_stats(b._h, C.c_void_p(w.d_feat.data_ptr()), C.c_int32(rows), C.c_int32(c["features"]),
+                                                      C.byref(lane), C.byref(warp), C.byref(wt), C.c_void_p(w.stream)))
     scale = w.rows / rows
     levels_per_wt = warp.value / wt.value          # level steps a warp issues per tree (deepest lane)
     dbar = lane.value / (rows * c["trees"])        # mean path per item per tree
     lanes_active = lane.value / (32.0 * warp.value)
-    # wavefront floor of the lock-step walk: per level one node load (LDS.64, >= 1 wavefront) and one code load
-    # (LDS.U16, 1 wavefront); per tree one leaf value (LDS.64) and a quarter of a root load (LDS.128 per 4 trees)
-    wavefronts = (2.0 * warp.value + 1.25 * wt.value) * scale
+    # wavefront floor of the lock-step walk: per level one node load and one code load (1 wavefront each); per tree the leaf
+    # value (LDS.64: 1, or 2 once lanes sit on different leaves) and a quarter of a root-table load (LDS.128 per 4 trees);
+    # the slim layout also reads the root entry (1) and its leaf value as two half-warp passes (2)
+    wavefronts = (2.0 * warp.value + (3.25 if slim else 1.25) * wt.value) * scale
     t = dom["ms_per_step"] / 1e3
     smem_peak = SM_COUNT * 128.0 * clk / 1e9       # GB/s
     achieved = wavefronts * 128.0 / t / 1e9
@@ -637,7 +636,7 @@ def scorer_roofline(w, kernels, step_ms, sm_mhz):
     out.update({
         "bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
         "what": "shared-memory crossbar: wavefronts the lock-step walk needs at least (counted on this batch by "
-                "mr_model_walk_stats: 2 per warp level step + 1.25 per warp-tree) x 128 B / kernel time, against "
+                "mr_model_walk_stats: 2 per warp level step + 1.25 (8-byte nodes) or 3.25 (4-byte nodes) per warp-tree) x 128 B / kernel time, against "
                 "SMs x 128 B/clk x SM clock",
         "wavefronts_per_launch_floor": wavefronts, "warp_levels_per_tree": levels_per_wt, "mean_path": dbar,
         "lanes_active_of_32": 32.0 * lanes_active, "sm_clock_mhz": clk / 1e6,
@@ -678,7 +677,7 @@ def kernel_table(w, kernels):
             gbs = a / (k["ms_per_step"] / 1e3) / 1e9  # `a` = bytes per step over all launches of this kernel
             e.update({"bound": "hbm", "algorithmic_bytes": a, "achieved_gbs": gbs, "frac_hbm": gbs / peak_hbm})
         elif k["kernel"].startswith("gbdt_"):
-            e["bound"] = "smem" if "compact" in k["kernel"] or "leaves" in k["kernel"] else "latency"
+            e["bound"] = "smem" if any(x in k["kernel"] for x in ("compact", "slim", "leaves")) else "latency"
         out.append(e)
     return sorted(out, key=lambda e: -e["ms_per_step"])
 

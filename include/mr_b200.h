@@ -153,12 +153,12 @@ MR_API mr_status mr_model_inspect(int32_t kind, const uint8_t *blob, size_t len,
  * `rows` scored by mr_model_count_path(): the d̄ of SURVEY.md §8(d)'s B_item. */
 MR_API mr_status mr_model_count_path(mr_model *m, const double *values, int32_t rows, int32_t cols, double *mean_path);
 
-/* What the lock-step scorer executes on `rows` rows of codes (mr_model_bin_device layout; compact scorer only):
- * lane_levels = the sum of the rows' path lengths (internal nodes visited), warp_levels = the sum over (warp of 32
- * rows, tree) of the DEEPEST lane's path — the level steps a warp really issues — warp_trees = the number of
- * (warp, tree) pairs.  lane_levels / (32 * warp_levels) is the fraction of lanes doing useful work;
- * bench.py's shared-memory roofline is built from these counts.  Synchronous. */
-MR_API mr_status mr_model_walk_stats(mr_model *m, const void *d_codes, int32_t rows, double *lane_levels,
+/* What the lock-step scorers execute on a device-resident matrix (compact / slim scorers only): lane_levels = the sum of
+ * the rows' path lengths (internal nodes visited), warp_levels = the sum over (warp of 32 consecutive rows, tree) of the
+ * DEEPEST lane's path — the level steps a warp really issues — warp_trees = the number of (warp, tree) pairs.
+ * lane_levels / (32 * warp_levels) is the fraction of lanes doing useful work; bench.py's shared-memory roofline is built
+ * from these counts.  Synchronous. */
+MR_API mr_status mr_model_walk_stats(mr_model *m, const double *d_values, int32_t rows, int32_t cols, double *lane_levels,
                                      double *warp_levels, double *warp_trees, void *cuda_stream);
 
 /* Booster.close() / isClosed() (S/ml/rank/LambdaMARTRanker.scala:361-365).  close is
@@ -171,8 +171,8 @@ MR_API mr_status mr_model_free(mr_model *m);
 /* Tuning knobs for experiments (bench.py / tests); defaults are chosen per model.  Not synchronised
  * against concurrent predicts on the same handle: set them before serving.
  * key: "threads" (items per CTA, 0 = auto), "chunk_kb", "ilp" (trees in flight per thread, exact kernel: 2 | 4),
- * "variant" (-1 = auto, 0 = exact f64/f32 kernel, 2 = generic binned kernel, 4 = compact binned kernel; any
- * other value is MR_ERR_INVALID_ARG), "latency_rows" (largest batch the tree-parallel low-latency path takes,
+ * "variant" (-1 = auto, 0 = exact f64/f32 kernel, 2 = generic binned kernel, 4 = compact binned kernel with
+ * 8-byte nodes, 5 = slim kernel with 4-byte nodes where the model has that form; any other value is MR_ERR_INVALID_ARG), "latency_rows" (largest batch the tree-parallel low-latency path takes,
  * 0 = auto). */
 MR_API mr_status mr_model_set_option(mr_model *m, const char *key, int32_t value);
 

@@ -15,6 +15,11 @@ void check_model(mr_model *m) {
 
 namespace {
 
+__global__ void dyn_smem_base_probe(int *out) {
+  extern __shared__ uint8_t probe_smem[];
+  *out = (int)__cvta_generic_to_shared(probe_smem);
+}
+
 void check_matrix(mr_model *m, const void *values, int rows, int cols, const void *out) {
   if (rows < 0 || cols < 0) fail(MR_ERR_INVALID_ARG, "negative matrix dimension");
   if (rows > 0 && (!values || !out)) fail(MR_ERR_INVALID_ARG, "null matrix or output pointer");
@@ -87,6 +92,16 @@ mr_status mr_init(int32_t device, mr_ctx **out) {
     auto ctx = std::make_unique<mr_ctx>();
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
+    {  // where a kernel's dynamic shared window starts in the shared address space (the slim scorer wants to know)
+      int *d = nullptr, h = -1;
+      if (cudaMalloc((void **)&d, 4) == cudaSuccess) {
+        dyn_smem_base_probe<<<1, 32, 1024>>>(d);
+        if (cudaMemcpy(&h, d, 4, cudaMemcpyDeviceToHost) != cudaSuccess) h = -1;
+        cudaFree(d);
+      }
+      cudaGetLastError();
+      ctx->dyn_smem_base = h;
+    }
     *out = ctx.release();
   });
 }
@@ -263,6 +278,7 @@ mr_status mr_model_bin_device(mr_model *m, const double *d_values, int32_t rows,
     if (rows == 0) return;
     BinnedLaunch B = m->binned_desc();
     B.d_values = d_values; B.rows = rows; B.cols = cols; B.d_bins = (uint16_t *)d_codes; B.codes_only = true;
+    B.tile_T = m->code_layout(rows);  // what mr_model_score_codes_device will read for the same row count
     launch_gbdt_binned(B, m->ctx->num_sms, (cudaStream_t)cuda_stream);
   });
 }
@@ -332,19 +348,30 @@ mr_status mr_model_inspect(int32_t kind, const uint8_t *blob, size_t len, int32_
   });
 }
 
-mr_status mr_model_walk_stats(mr_model *m, const void *d_codes, int32_t rows, double *lane_levels, double *warp_levels,
-                              double *warp_trees, void *cuda_stream) {
+mr_status mr_model_walk_stats(mr_model *m, const double *d_values, int32_t rows, int32_t cols, double *lane_levels,
+                              double *warp_levels, double *warp_trees, void *cuda_stream) {
   return guard([&] {
     check_model(m);
-    if (!d_codes && rows > 0) fail(MR_ERR_INVALID_ARG, "null codes");
-    if (!m->use_binned() || !m->use_compact()) fail(MR_ERR_UNSUPPORTED, "walk statistics exist for the compact binned scorer only");
+    check_matrix(m, d_values, rows, cols, d_values);
+    if (!m->use_binned() || !m->use_compact()) fail(MR_ERR_UNSUPPORTED, "walk statistics exist for the compact binned scorers only");
     InflightGuard g(m);
     MR_CUDA_CHECK(cudaSetDevice(m->ctx->device));
-    BinnedLaunch B = m->binned_desc();
-    B.rows = rows;
-    B.d_bins = (uint16_t *)d_codes;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    BinnedLaunch B = m->binned_desc();  // the 8-byte compact form: same trees, same tile mapping as the slim one
+    B.d_values = d_values; B.rows = rows; B.cols = cols;
+    void *bins = nullptr;
+    MR_CUDA_CHECK(cudaMalloc(&bins, std::max<size_t>(binned_scratch_bytes(rows, m->code_cols()), 16)));
+    B.d_bins = (uint16_t *)bins;
+    B.codes_only = true;  // groups-of-32 layout (tile_T = 0)
     unsigned long long out[3] = {0, 0, 0};
-    compact_walk_stats(B, out, (cudaStream_t)cuda_stream);
+    try {
+      launch_gbdt_binned(B, m->ctx->num_sms, stream);
+      compact_walk_stats(B, out, stream);
+    } catch (...) {
+      cudaFree(bins);
+      throw;
+    }
+    cudaFree(bins);
     if (lane_levels) *lane_levels = (double)out[0];
     if (warp_levels) *warp_levels = (double)out[1];
     if (warp_trees) *warp_trees = (double)out[2];
@@ -359,7 +386,8 @@ mr_status mr_model_set_option(mr_model *m, const char *key, int32_t value) {
     std::string k(key);
     if (k == "threads") m->opt_threads = value;
     else if (k == "variant") {
-      if (value != -1 && value != 0 && value != 2 && value != 4) fail(MR_ERR_INVALID_ARG, "variant %d does not exist (-1 auto, 0 exact, 2 binned, 4 compact)", value);
+      if (value != -1 && value != 0 && value != 2 && value != 4 && value != 5)
+        fail(MR_ERR_INVALID_ARG, "variant %d does not exist (-1 auto, 0 exact, 2 binned, 4 compact, 5 slim)", value);
       m->opt_variant = value;
       m->code_gen = mr_model::next_code_gen();
     }

@@ -75,23 +75,6 @@ __global__ void lookup_kernel(RankArgs a) {
     const uint64_t u = a.user_ids ? __ldg(a.user_ids + i) : 0, s = a.session_ids ? __ldg(a.session_ids + i) : 0;
     a.visitor_row[2 * i] = u ? probe(a.st.t[SC_USER], u) : kNoRow;
     a.visitor_row[2 * i + 1] = s ? probe(a.st.t[SC_SESSION], s) : kNoRow;
-    if (a.n_cos > 0 && a.req_vec) {
-      // CosineDistance's aSum is a function of the request alone: once per request instead of once per item.
-      // query(i) * query(i) is a FLOAT product widened afterwards (S/ml/onnx/distance/DistanceFunction.scala:21)
-      int voff = 0;
-      for (int f = 0; f < a.n_plan; f++) {
-        const DFeature d = a.plan[f];
-        if (d.kind != FK_COSINE) continue;
-        const float *q = a.req_vec + (size_t)i * a.vec_stride + voff;
-        double as = 0.0;
-        for (int k = 0; k < d.aux0; k++) {
-          const float qk = __ldg(q + k);
-          as = __dadd_rn(as, (double)__fmul_rn(qk, qk));
-        }
-        a.qnorm[(size_t)i * a.n_cos + d.aux2] = as;
-        voff += d.aux0;
-      }
-    }
   }
   if (i == 0) {  // first kernel of every rank call: reset the per-call device state
     *a.hist_cursor = 0;
@@ -149,6 +132,30 @@ __global__ void __launch_bounds__(128) cosine_kernel(RankArgs a) {
       a.cos[(size_t)(a.n_cos + d.aux2) * a.total_items + i] = out;  // normalised copy (noop default)
     }
     voff += dim;
+  }
+}
+
+// CosineDistance's aSum (S/ml/onnx/distance/DistanceFunction.scala:21) is a function of the request alone: once per
+// (request, feature) instead of once per item.  query(i) * query(i) is a FLOAT product, widened and added in index order.
+// A warp per request: the query is staged coalesced, lane 0 walks it.
+__global__ void __launch_bounds__(128) cosine_qnorm_kernel(RankArgs a) {
+  extern __shared__ float s_qn[];  // [4 warps][vec_stride]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + warp;
+  if (r >= a.n_requests) return;
+  float *q = s_qn + (size_t)warp * a.vec_stride;
+  const float *src = a.req_vec + (size_t)r * a.vec_stride;
+  for (int k = lane; k < a.vec_stride; k += 32) q[k] = __ldg(src + k);
+  __syncwarp();
+  if (lane != 0) return;
+  int voff = 0;
+  for (int f = 0; f < a.n_plan; f++) {
+    const DFeature d = a.plan[f];
+    if (d.kind != FK_COSINE) continue;
+    double as = 0.0;
+    for (int k = 0; k < d.aux0; k++) as = __dadd_rn(as, (double)__fmul_rn(q[voff + k], q[voff + k]));
+    a.qnorm[(size_t)r * a.n_cos + d.aux2] = as;
+    voff += d.aux0;
   }
 }
 
@@ -714,14 +721,13 @@ __global__ void __launch_bounds__(kGatherWarps * 32) row_gather_kernel(RankArgs 
   }
   if (CODES) {
     __syncwarp();
-    uint16_t *out = a.codes + (size_t)g * bin.tile_cols * 32;
     for (int c = 0; c < a.n_fast; c++) {
       const int col = s_cols[c].col;
       const uint32_t dup = dup_col(bin.meta[col]);  // warp-uniform
       const uint32_t both = *reinterpret_cast<const uint32_t *>(tile + lane * tstride + 2 * c);
       if (lane < n_here) {
-        out[col * 32 + lane] = (uint16_t)both;
-        if (dup != kMetaNoDup) out[dup * 32 + lane] = (uint16_t)(both >> 16);
+        a.codes[code_index(bin.tile_T, bin.tile_cols, i0 + lane, col)] = (uint16_t)both;
+        if (dup != kMetaNoDup) a.codes[code_index(bin.tile_T, bin.tile_cols, i0 + lane, (int)dup)] = (uint16_t)(both >> 16);
       }
     }
   }
@@ -798,10 +804,17 @@ __global__ void __launch_bounds__(kGatherWarps * 32) code_gather_kernel(RankArgs
     }
   }
   __syncwarp();
-  uint16_t *out = a.codes + (size_t)g * a.bin.tile_cols * 32;
   const uint16_t *t16 = reinterpret_cast<const uint16_t *>(tile);
-  if (lane < n_here)
-    for (int c = 0; c < a.bin.tile_cols; c++) out[c * 32 + lane] = t16[lane * tw * 2 + c];
+  if (a.bin.tile_T == 0) {
+    uint16_t *out = a.codes + (size_t)g * a.bin.tile_cols * 32;
+    if (lane < n_here)
+      for (int c = 0; c < a.bin.tile_cols; c++) out[c * 32 + lane] = t16[lane * tw * 2 + c];
+  } else if (lane < n_here) {
+    // slim layout: a code row IS the sequence of its column pairs — one u32 per pair and lane, 128 bytes per warp store
+    const int T = a.bin.tile_T, n_pairs = (a.bin.tile_cols + 1) >> 1, item = i0 + lane;
+    uint32_t *out = reinterpret_cast<uint32_t *>(a.codes) + ((size_t)(item / T) * n_pairs) * T + (item % T);
+    for (int pr = 0; pr < n_pairs; pr++) out[(size_t)pr * T] = tile[lane * tw + pr];
+  }
 }
 
 // ------------------------------------------------------------------ assemble
@@ -845,13 +858,14 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
     double *row;
     uint16_t *codes;
     const BinParams *bp;
+    int item;
     __device__ __forceinline__ void operator()(int col, double v) const {
       if (row) row[col] = v;
       if (codes) {
         const BinMeta M = bp->meta[col];
         const uint16_t c = code_of_col(*bp, M, (M.flags & kMetaCat) != 0, v);
-        codes[(size_t)col * 32] = base_code(M, c);
-        if (dup_col(M) != kMetaNoDup) codes[(size_t)dup_col(M) * 32] = dup_code(c);
+        codes[code_index(bp->tile_T, bp->tile_cols, item, col)] = base_code(M, c);
+        if (dup_col(M) != kMetaNoDup) codes[code_index(bp->tile_T, bp->tile_cols, item, (int)dup_col(M))] = dup_code(c);
       }
     }
   };
@@ -863,8 +877,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
     const Emit *e;
     __device__ __forceinline__ OutProxy operator[](int col) const { return OutProxy{e, col}; }
   };
-  const Emit emit{a.out_features ? a.out_features + (size_t)i * a.dim : nullptr,
-                  a.codes ? a.codes + ((size_t)(i >> 5) * bin.tile_cols) * 32 + (i & 31) : nullptr, &bin};
+  const Emit emit{a.out_features ? a.out_features + (size_t)i * a.dim : nullptr, a.codes, &bin, i};
   const OutArr out{&emit};
 
   auto scoped_row = [&](int scope) -> const uint64_t * {
@@ -1294,6 +1307,9 @@ void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t strea
         else any_f64 = true;
       }
     if (any_f32) {
+      { ProfScope _ps("cosine_qnorm_kernel", stream); cosine_qnorm_kernel<<<(a.n_requests + 3) / 4, 128, (size_t)4 * std::max(a.vec_stride, 1) * sizeof(float), stream>>>(a); }
+      MR_CUDA_CHECK(cudaGetLastError());
+      g_kernel_launches++;
       const size_t smem = (((size_t)dim_max * 8 + 15) & ~size_t(15)) + (size_t)4 * 32 * kCosPitch * sizeof(float);
       MR_CUDA_CHECK(cudaFuncSetAttribute(cosine_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       { ProfScope _ps("cosine_f32_kernel", stream); cosine_f32_kernel<<<(a.total_items + 127) / 128, 128, smem, stream>>>(a, dim_max); }

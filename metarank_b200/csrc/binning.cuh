@@ -20,7 +20,18 @@ struct BinParams {
   int rows, cols, n_features;
   int tile_cols;  // columns of the code tile (>= n_features, see BinMeta::flags)
   int xgb;  // 1: round to binary32 first, strict less (upper_bound)
+  // Layout of `bins`.  0: [group of 32 items][tile column][lane] u16 (8-byte compact scorer, latency path).
+  // 512 | 256 | 128 = items per CTA of the slim scorer: [CTA tile][column pair][item of the tile] u32, the pair's even
+  // column in the low half — a CTA's tile is still ONE contiguous range, and a lane's read of any column hits its own bank.
+  int tile_T;
 };
+
+// index (in u16 units) of (item, tile column) in a code buffer of the given layout
+__device__ __forceinline__ size_t code_index(int tile_T, int tile_cols, int item, int col) {
+  if (tile_T == 0) return ((size_t)(item >> 5) * tile_cols + col) * 32 + (item & 31);
+  const int n_pairs = (tile_cols + 1) >> 1;
+  return (((size_t)(item / tile_T) * n_pairs + (col >> 1)) * tile_T + (item % tile_T)) * 2 + (col & 1);
+}
 
 // code of x in a column whose header (M, categorical flag) the caller already holds in registers
 template <bool XGB>

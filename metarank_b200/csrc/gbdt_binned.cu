@@ -46,11 +46,25 @@ __global__ void __launch_bounds__(256) bin_kernel(const BinParams p) {
   }
   __syncthreads();
   // phase 2: coalesced write in [group][column][lane] order
-  uint16_t *out = p.bins + (size_t)blockIdx.x * kBinGroups * T * 32;
-  const long long n_groups_total = (p.rows + 31) / 32;
-  for (int o = threadIdx.x; o < items_per_cta * T; o += blockDim.x) {
-    const int g = o / (T * 32), r = o - g * (T * 32), f = r >> 5, lane = r & 31;
-    if ((long long)blockIdx.x * kBinGroups + g < n_groups_total) out[o] = s_codes[f * pitch + g * 32 + lane];
+  if (p.tile_T == 0) {
+    uint16_t *out = p.bins + (size_t)blockIdx.x * kBinGroups * T * 32;
+    const long long n_groups_total = (p.rows + 31) / 32;
+    for (int o = threadIdx.x; o < items_per_cta * T; o += blockDim.x) {
+      const int g = o / (T * 32), r = o - g * (T * 32), f = r >> 5, lane = r & 31;
+      if ((long long)blockIdx.x * kBinGroups + g < n_groups_total) out[o] = s_codes[f * pitch + g * 32 + lane];
+    }
+  } else {
+    // slim layout: [CTA tile][column pair][item] u32 — consecutive threads write consecutive items of one pair
+    const int n_pairs = (T + 1) >> 1;
+    uint32_t *out = reinterpret_cast<uint32_t *>(p.bins);
+    for (int o = threadIdx.x; o < items_per_cta * n_pairs; o += blockDim.x) {
+      const int pr = o / items_per_cta, it = o - pr * items_per_cta;
+      const long long item = item0 + it;
+      if (item < (((long long)p.rows + 31) & ~31ll)) {
+        const uint32_t lo = s_codes[(2 * pr) * pitch + it], hi = (2 * pr + 1 < T) ? s_codes[(2 * pr + 1) * pitch + it] : 0u;
+        out[((size_t)(item / p.tile_T) * n_pairs + pr) * p.tile_T + (size_t)(item % p.tile_T)] = lo | (hi << 16);
+      }
+    }
   }
 }
 
@@ -377,6 +391,123 @@ __global__ void __launch_bounds__(1024) gbdt_score_compact_kernel(const BParams 
   if (p.sinks.n_peer) publish_when_last(p.sinks);
 }
 
+// ------------------------------------------------------------------ slim lock-step traversal (4-byte nodes)
+// The throughput scorer's fast path (gbdt_model.h SlimModel).  Same mapping as the compact kernel — thread per item,
+// trees in tree order, chunks double-buffered by TMA — with everything that cost a level an instruction or a
+// shared-memory wavefront taken out:
+//   * entries are 4 bytes: lanes on different nodes of a tree are served by ONE wavefront (an LDS.64 is two half-warp passes);
+//   * the code tile is [column pair][item of the CTA] u32 at absolute shared address (pair + 1) * 4T: the code's address is
+//     (entry & mask) | 4 * tid — one LOP3, no add, and lane l always reads bank l (no conflicts whatever the columns);
+//   * k is compared as a binary16 pattern straight out of the entry's high half: one HSETP2, no shift;
+//   * a child is (entry & mask) | block base, + 4 for the right one; a leaf is an entry with the sign bit set.
+// One level: LOP3, LDS.U16, HSETP2, LOP3, IADD (predicated), LDS.32, ISETP, BRA.
+template <int T> struct SlimConst {
+  static constexpr uint32_t kShift = T == 512 ? 11u : T == 256 ? 10u : 9u;
+  static constexpr uint32_t kColMask = ((0xFFFFu << kShift) & 0xFFFFu) | 2u;
+  static constexpr uint32_t kChildMask = ((1u << kShift) - 1u) & ~7u;
+};
+
+template <typename Real, int T>
+__global__ void __launch_bounds__(T) gbdt_score_slim_kernel(const BParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  using K = SlimConst<T>;
+  const int tid = threadIdx.x;
+  const uint32_t base = smem_u32(smem);         // absolute shared address of the dynamic window (small: asserted on the host)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+  const uint32_t tile_abs = (uint32_t)T * 4u;   // pair p of the tile lives at (p + 1) * 4T
+  const uint32_t n_pairs = (uint32_t)(p.n_features + 1) >> 1;
+  const uint32_t cb0_abs = (tile_abs * (n_pairs + 1u) + 2047u) & ~2047u, cb1_abs = cb0_abs + p.chunk_stride;
+  uint8_t *tile_ptr = smem + (tile_abs - base);
+  const bool resident = p.n_chunks == 1;
+  const uint32_t tid4 = (uint32_t)tid * 4u;
+
+  const int n_tiles = (p.rows + T - 1) / T;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0 && (int)blockIdx.x < n_tiles) {
+    const ChunkDesc cd = p.chunks[0];
+    mbar_arrive_expect_tx(&bars[0], cd.bytes);
+    tma_bulk_g2s(smem + (cb0_abs - base), p.model + cd.byte_off, cd.bytes, &bars[0]);
+  }
+  uint32_t it = 0, tile_it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+    if (tid == 0) {
+      const uint32_t bytes = n_pairs * (uint32_t)T * 4u;  // the whole CTA tile is one contiguous range (buffers are padded to whole tiles)
+      fence_proxy_async();
+      mbar_arrive_expect_tx(&bars[2], bytes);
+      tma_bulk_g2s(tile_ptr, reinterpret_cast<const uint8_t *>(p.bins) + (size_t)tile * bytes, bytes, &bars[2]);
+    }
+    mbar_wait(&bars[2], tile_it & 1);
+    const int item = tile * T + tid;
+    Real acc = (sizeof(Real) == 4) ? (Real)p.base_score : (Real)0;
+    for (int c = 0; c < p.n_chunks; ++c, ++it) {
+      if (!resident && tid == 0) {
+        const bool more = (c + 1 < p.n_chunks) || (tile + (int)gridDim.x < n_tiles);
+        if (more) {
+          const int nc = (c + 1 < p.n_chunks) ? c + 1 : 0;
+          const ChunkDesc cd = p.chunks[nc];
+          uint64_t *bar = &bars[(it + 1) & 1];
+          fence_proxy_async();
+          mbar_arrive_expect_tx(bar, cd.bytes);
+          tma_bulk_g2s(smem + ((((it + 1) & 1) ? cb1_abs : cb0_abs) - base), p.model + cd.byte_off, cd.bytes, bar);
+        }
+      }
+      if (!resident || it == 0) mbar_wait(&bars[it & 1], (it >> 1) & 1);
+      const uint32_t cb_abs = (!resident && (it & 1)) ? cb1_abs : cb0_abs;
+      const uint8_t *cb = smem + (cb_abs - base);
+      const int ntree = (int)*reinterpret_cast<const uint32_t *>(cb);
+      const uint32_t *roots = reinterpret_cast<const uint32_t *>(cb + 16);
+      auto walk = [&](uint32_t block_off) -> Real {
+        const uint32_t tb = cb_abs + block_off;  // absolute address of the tree's block, aligned to the block's size
+        uint32_t w;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(tb));
+        if ((int)w >= 0) {
+          asm volatile(
+              "{\n"
+              ".reg .pred pl, pq;\n"
+              ".reg .b32 off, code, n;\n"
+              ".reg .b16 wlo, whi, clo, chi;\n"
+              "SLVL:\n"
+              "lop3.b32 off, %0, %1, %2, 0xEA;\n"      // (w & column mask) | 4 * tid
+              "ld.shared.u16 code, [off];\n"
+              "mov.b32 {wlo, whi}, %0;\n"
+              "mov.b32 {clo, chi}, code;\n"
+              "setp.le.f16 pl, clo, whi;\n"            // code <= k on binary16 patterns; a NaN code goes right
+              "lop3.b32 n, %0, %3, %4, 0xEA;\n"        // (w & child mask) | block base
+              "@!pl add.u32 n, n, 4;\n"
+              "ld.shared.u32 %0, [n];\n"
+              "setp.ge.s32 pq, %0, 0;\n"
+              "@pq bra SLVL;\n"
+              "}\n"
+              : "+r"(w)
+              : "n"(K::kColMask), "r"(tid4), "n"(K::kChildMask), "r"(tb)
+              : "memory");
+        }
+        return *reinterpret_cast<const Real *>(smem + ((tb + (w & 0xFFFFu)) - base));
+      };
+      int t = 0;
+#pragma unroll 1
+      for (; t + 4 <= ntree; t += 4) {
+        const uint4 r = *reinterpret_cast<const uint4 *>(roots + t);
+        acc += walk(r.x);
+        acc += walk(r.y);
+        acc += walk(r.z);
+        acc += walk(r.w);
+      }
+#pragma unroll 1
+      for (; t < ntree; t++) acc += walk(roots[t]);
+      __syncthreads();
+    }
+    if (item < p.rows) store_score(p.out, p.sinks, item, (double)acc);
+  }
+  if (p.sinks.n_peer) publish_when_last(p.sinks);
+}
+
 // ------------------------------------------------------------------ low-latency path (small batches)
 // A single /rank request is 100 items: one thread per item walking 500 trees is a 100+ us dependent
 // chain on 4 warps of one SM.  For small batches the trees are spread over the chip instead: CTA
@@ -663,6 +794,7 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
   bp.meta = L.d_meta; bp.bucket_range = L.d_bucket_range;
   bp.bins = L.d_bins; bp.rows = L.rows; bp.cols = L.cols; bp.n_features = L.n_features; bp.tile_cols = F;
   bp.xgb = L.kind == MR_BOOSTER_XGBOOST;
+  bp.tile_T = L.tile_T;
   const int items_per_cta = kBinGroups * 32;
   const size_t bin_smem = (size_t)F * (items_per_cta + 2) * sizeof(uint16_t);
   if (bin_smem > 200 * 1024) fail(MR_ERR_UNSUPPORTED, "too many features for the binning kernel");
@@ -673,6 +805,38 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
   }
 
   if (L.codes_only) return;
+  if (L.tile_T) {
+    // ---- slim scorer: CTA = tile_T threads, tile at absolute shared address 4 * tile_T, two 2 KB-aligned chunk buffers
+    BParams p;
+    p.model = L.d_model; p.chunks = L.d_chunks; p.bins = L.d_bins; p.out = L.d_out;
+    p.n_chunks = L.n_chunks; p.chunk_stride = (L.max_chunk_bytes + 2047u) & ~2047u;
+    p.rows = L.rows; p.n_features = F; p.base_score = L.base_score;
+    p.sinks = L.sinks;
+    const int T = L.tile_T;
+    const size_t n_pairs = (size_t)(F + 1) / 2;
+    const size_t cb0 = (((size_t)T * 4 * (n_pairs + 1)) + 2047) & ~size_t(2047);
+    const size_t smem = cb0 + (size_t)p.chunk_stride * (L.n_chunks == 1 ? 1 : 2);  // the window starts at (or just above) address 0
+    auto go = [&](auto kern) {
+      MR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 0;
+      MR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
+      if (per_sm < 1) fail(MR_ERR_CUDA, "slim gbdt kernel does not fit on an SM (%zu B smem, %d threads)", smem, T);
+      per_sm = std::min(per_sm, std::max(1, 1536 / T));  // ~48 warps saturate the shared-memory pipe (profiles/sweep_r1.md)
+      const int n_tiles = (p.rows + T - 1) / T;
+      static const bool debug = getenv("MR_DEBUG_LAUNCH") != nullptr;
+      if (debug)
+        fprintf(stderr, "[mr] slim scorer: rows %d tile_cols %d chunks %d x %u B, %d threads x %d CTAs (%d/SM), %zu B smem\n", p.rows, F,
+                p.n_chunks, p.chunk_stride, T, std::max(1, std::min(n_tiles, num_sms * per_sm)), per_sm, smem);
+      { ProfScope _ps("gbdt_score_slim_kernel", stream); kern<<<std::max(1, std::min(n_tiles, num_sms * per_sm)), T, smem, stream>>>(p); }
+      MR_CUDA_CHECK(cudaGetLastError());
+      g_kernel_launches++;
+    };
+    const bool f32 = L.kind == MR_BOOSTER_XGBOOST;
+    if (T == 512) { if (f32) go(gbdt_score_slim_kernel<float, 512>); else go(gbdt_score_slim_kernel<double, 512>); }
+    else if (T == 256) { if (f32) go(gbdt_score_slim_kernel<float, 256>); else go(gbdt_score_slim_kernel<double, 256>); }
+    else { if (f32) go(gbdt_score_slim_kernel<float, 128>); else go(gbdt_score_slim_kernel<double, 128>); }
+    return;
+  }
   // ---- pass 2: traversal
   BParams p;
   p.model = L.d_model; p.chunks = L.d_chunks; p.bins = L.d_bins; p.out = L.d_out;

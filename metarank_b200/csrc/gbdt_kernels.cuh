@@ -68,10 +68,14 @@ struct BinnedLaunch {
   bool codes_only = false;              // run bin_kernel only (no traversal)
   bool codes_ready = false;             // d_bins already holds the codes (fused assemble): skip bin_kernel
   bool compact = false;                 // model bytes are pack_compact() chunks -> fast lock-step kernel
+  int tile_T = 0;                       // != 0: d_bins is in the slim layout and d_model / d_chunks are pack_slim() chunks
   ScoreSinks sinks;                     // compact + latency kernels only
 };
+// bytes of a code buffer for `rows` rows in either layout (BinParams::tile_T): whole groups of 32 / whole CTA tiles
 inline size_t binned_scratch_bytes(int rows, int tile_cols) {
-  return (size_t)((rows + 31) / 32) * (size_t)tile_cols * 32 * sizeof(uint16_t);
+  const size_t legacy = (size_t)((rows + 31) / 32) * (size_t)tile_cols * 32 * sizeof(uint16_t);
+  const size_t slim = (size_t)((rows + 511) / 512) * 512 * (size_t)((tile_cols + 1) / 2) * 4;
+  return legacy > slim ? legacy : slim;
 }
 void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream);
 // Low-latency path for small batches: the leaf every row reaches in every tree, spread over (chunk x item-group)

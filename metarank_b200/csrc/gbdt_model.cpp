@@ -759,4 +759,107 @@ BinnedModel pack_compact(const HostModel &m, const BinnedModel &bn, size_t chunk
   return C;
 }
 
+SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budget) {
+  SlimModel S;
+  if (!C.ok || m.has_cat || m.trees.empty()) return S;
+  const int F = m.n_features;
+  for (int f = 0; f < F; f++)
+    if (C.thr_off[f + 1] - C.thr_off[f] > 0x7C00u) return S;  // codes must stay below the binary16 NaN patterns
+  S.n_pairs = (C.tile_cols + 1) / 2;
+  size_t max_block = 16;
+  auto block_bytes = [](const HostTree &t) {
+    const size_t need = (2 + 2 * t.feat.size()) * 4 + t.leaf.size() * 8;  // entries (root pair + one pair per node) + leaf slots
+    size_t b = 16;
+    while (b < need) b <<= 1;
+    return b;
+  };
+  for (auto &t : m.trees) max_block = std::max(max_block, block_bytes(t));
+  for (int T : {512, 256, 128}) {
+    const int shift = T == 512 ? 11 : T == 256 ? 10 : 9;
+    if (S.n_pairs + 1 <= (1 << (16 - shift)) && max_block <= (size_t)T * 4) { S.tile_T = T; break; }
+  }
+  if (!S.tile_T) return S;
+  const int shift = S.tile_T == 512 ? 11 : S.tile_T == 256 ? 10 : 9;
+  const bool f32 = m.kind == MR_BOOSTER_XGBOOST;
+  if (chunk_budget == 0) {
+    // ~48 resident warps per SM: what their code tiles leave of the 227 KB, split over the CTAs' two chunk buffers
+    const int ctas = 1536 / S.tile_T;
+    const long long tile = (long long)(S.n_pairs + 1) * S.tile_T * 4;
+    const long long left = (225ll * 1024 / ctas - tile - 2048) / 2;
+    chunk_budget = (size_t)std::max<long long>(2048, std::min<long long>(24 * 1024, (left / 2048) * 2048));
+  }
+  chunk_budget = std::max<size_t>(chunk_budget, 2048);
+  PackedModel &pk = S.packed;
+  size_t i = 0, nt = m.trees.size();
+  while (i < nt) {
+    // greedy: header, then blocks, each aligned to its own size
+    size_t j = i, end = 0;
+    auto layout_end = [&](size_t from, size_t to) {
+      size_t off = 16 + al16((to - from) * 4);
+      for (size_t k = from; k < to; k++) {
+        const size_t b = block_bytes(m.trees[k]);
+        off = (off + b - 1) & ~(b - 1);
+        off += b;
+      }
+      return off;
+    };
+    while (j < nt) {
+      const size_t e = layout_end(i, j + 1);
+      if (j > i && e > chunk_budget) break;
+      end = e;
+      j++;
+    }
+    const size_t n = j - i, total = al16(end);
+    if (total > 65536) return S;
+    const size_t base = pk.bytes.size();
+    pk.bytes.resize(base + total, 0);
+    uint8_t *c = pk.bytes.data() + base;
+    const uint32_t hn = (uint32_t)n;
+    memcpy(c, &hn, 4);
+    uint32_t *roots = (uint32_t *)(c + 16);
+    size_t off = 16 + al16(n * 4);
+    for (size_t k = 0; k < n; k++) {
+      const HostTree &t = m.trees[i + k];
+      const size_t b = block_bytes(t), ni = t.feat.size();
+      off = (off + b - 1) & ~(b - 1);
+      roots[k] = (uint32_t)off;
+      uint32_t *e = (uint32_t *)(c + off);
+      const size_t leaf_base = (2 + 2 * ni) * 4;  // a multiple of 8
+      // breadth-first numbering of the child pairs: node q's children live in pair slot pair_of[q]
+      std::vector<uint32_t> entry_of_node(ni, 0);  // entry index of internal node q
+      uint32_t next_pair = 1;
+      std::vector<int> order;
+      if (ni) { order.push_back(0); entry_of_node[0] = 0; }
+      auto leaf_entry = [&](int cidx) { return 0x80000000u | (uint32_t)(leaf_base + (size_t)(~cidx) * 8); };
+      if (!ni) e[0] = leaf_entry(~0);
+      for (size_t h = 0; h < order.size(); h++) {
+        const int q = order[h];
+        const uint32_t pair = next_pair++;
+        const int f = t.feat[q];
+        const double *tb = C.thr.data() + C.thr_off[f], *te = C.thr.data() + C.thr_off[f + 1];
+        const uint32_t kk = (uint32_t)(std::lower_bound(tb, te, t.thr[q]) - tb);
+        const uint32_t dup = C.meta[f].flags >> 16;
+        const uint32_t col = ((t.flags[q] & NF_NAN_LEFT) && dup != kMetaNoDup) ? dup : (uint32_t)f;
+        e[entry_of_node[q]] = (kk << 16) | (((col >> 1) + 1u) << shift) | ((col & 1u) << 1) | (pair * 8u);
+        const int ch[2] = {t.left[q], t.right[q]};
+        for (int sd = 0; sd < 2; sd++) {
+          if (ch[sd] < 0) e[2 * pair + sd] = leaf_entry(ch[sd]);
+          else { entry_of_node[ch[sd]] = 2 * pair + sd; order.push_back(ch[sd]); }
+        }
+      }
+      uint8_t *lv = c + off + leaf_base;
+      for (size_t q = 0; q < t.leaf.size(); q++) {
+        if (f32) { const float v = (float)t.leaf[q]; memcpy(lv + q * 8, &v, 4); }
+        else memcpy(lv + q * 8, &t.leaf[q], 8);
+      }
+      off += b;
+    }
+    pk.chunks.push_back(ChunkDesc{(uint32_t)base, (uint32_t)total, (uint32_t)n, (uint32_t)i});
+    pk.max_chunk_bytes = std::max<uint32_t>(pk.max_chunk_bytes, (uint32_t)total);
+    i = j;
+  }
+  S.ok = true;
+  return S;
+}
+
 }  // namespace mr

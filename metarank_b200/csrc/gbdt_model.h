@@ -140,4 +140,29 @@ BinnedModel pack_binned(const HostModel &m, size_t chunk_budget);
 // chunk_budget 0 = sized from the code tile (what ~48 resident warps leave of the shared memory).
 BinnedModel pack_compact(const HostModel &m, const BinnedModel &binned, size_t chunk_budget);
 
+// "Slim" form of the compact model for the throughput scorer's fast path: 4-byte nodes, so that a warp whose lanes sit
+// on different nodes still reads them in ONE shared-memory wavefront (an 8-byte load splits into two half-warp passes).
+// A tree is a power-of-two sized and aligned BLOCK of 4-byte entries followed by its 8-byte leaf values:
+//   entry 0 = the root, entries (2j, 2j+1) for j >= 1 = the two children of an internal node, side by side;
+//   internal entry  bits 31..16  k as a binary16 bit pattern (k <= 0x7BFF: non-negative halves order like integers, and a
+//                                NaN code, 0xFFFF, fails every `<=`), compared by ONE HSETP2 against the code's low half
+//                   bits 15..s   (tile column pair + 1), i.e. the byte offset of that pair's row in the CTA's code tile
+//                                (s = log2(4 * tile_T): the tile is [column pair][item of the CTA] u32, pair p at (p+1) << s)
+//                   bits s-1..3  byte offset of the node's child pair inside the block (so blocks are <= 4 * tile_T bytes)
+//                   bit 1        which half of the pair's u32 holds this column (the byte offset 2)
+//   leaf entry      bit 31 set, bits 15..0 = byte offset of the leaf's 8-byte value slot inside the block
+// One level of a walk is LOP3 (code address) -> LDS.U16 -> HSETP2 -> LOP3 (child pair | block base) -> predicated +4 ->
+// LDS.32 (next entry) -> sign test -> branch: 8 instructions and 2 wavefronts, against 10 and ~3.4 for the 8-byte layout.
+//   chunk: +0 u32 n_trees, pad; +16 u32 block_offset[n_trees] (from the chunk start; chunk buffers are 2 KB aligned in
+//          shared memory and every block is aligned to its own size); then the blocks
+// ok == false (categorical splits, > 31 744 thresholds on a column, too many tile columns or too large a tree for any
+// tile_T): the 8-byte compact kernel scores the model.  The tile mapping (BinMeta, tile_cols) is the compact model's.
+struct SlimModel {
+  bool ok = false;
+  int tile_T = 0;       // items per CTA = threads per CTA: 512, 256 or 128
+  int n_pairs = 0;      // column pairs of the tile
+  PackedModel packed;
+};
+SlimModel pack_slim(const HostModel &m, const BinnedModel &compact, size_t chunk_budget);
+
 }  // namespace mr

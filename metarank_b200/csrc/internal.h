@@ -72,6 +72,8 @@ struct Lane {
 struct mr_ctx {
   int device = 0;
   int num_sms = 0;
+  int dyn_smem_base = -1;  // absolute shared-memory address of a kernel's dynamic window (probed by mr_init); the slim scorer
+                           // places its code tile at an absolute address and needs the window to start below it
   std::mutex mu;
   std::vector<std::unique_ptr<Lane>> free_lanes;
   std::atomic<int> live_models{0};
@@ -113,6 +115,9 @@ struct mr_model {
   ChunkDesc *d_chunks = nullptr;
   // binned form (exact integer traversal); binned.ok == false -> always the f64/f32 kernel
   BinnedModel binned, compact, lat;  // lat: compact layout in 4 KB chunks for the low-latency path
+  SlimModel slim;                    // 4-byte-node form of `compact` (same tile mapping) for the throughput scorer's fast path
+  uint8_t *d_smodel = nullptr;
+  ChunkDesc *d_schunks = nullptr;
   uint8_t *d_bmodel = nullptr, *d_cmodel = nullptr, *d_lmodel = nullptr;
   ChunkDesc *d_bchunks = nullptr, *d_cchunks = nullptr, *d_lchunks = nullptr;
   uint32_t *d_thr_off = nullptr;
@@ -146,10 +151,10 @@ struct mr_model {
   void free_binned() {
     for (void *p : {(void *)d_bmodel, (void *)d_bchunks, (void *)d_thr_off, (void *)d_thr, (void *)d_is_cat,
                     (void *)d_cmodel, (void *)d_cchunks, (void *)d_lmodel,
-                    (void *)d_lchunks, (void *)d_ltree_off, (void *)d_meta, (void *)d_cmeta, (void *)d_bucket_range})
+                    (void *)d_lchunks, (void *)d_ltree_off, (void *)d_smodel, (void *)d_schunks, (void *)d_meta, (void *)d_cmeta, (void *)d_bucket_range})
       if (p) cudaFree(p);
     d_bmodel = nullptr; d_bchunks = nullptr; d_thr_off = nullptr; d_thr = nullptr; d_is_cat = nullptr;
-    d_cmodel = nullptr; d_cchunks = nullptr; d_lmodel = nullptr; d_lchunks = nullptr; d_ltree_off = nullptr; d_meta = nullptr; d_cmeta = nullptr; d_bucket_range = nullptr;
+    d_cmodel = nullptr; d_cchunks = nullptr; d_lmodel = nullptr; d_lchunks = nullptr; d_ltree_off = nullptr; d_smodel = nullptr; d_schunks = nullptr; d_meta = nullptr; d_cmeta = nullptr; d_bucket_range = nullptr;
   }
   // identity of the current code mapping (thresholds + tile columns): consumers that cache codes key on it
   uint64_t code_gen = 0;
@@ -185,6 +190,14 @@ struct mr_model {
         d_cchunks = to_device(compact.packed.chunks);
         d_cmeta = to_device(compact.meta);
       }
+      slim = SlimModel{};
+      if (compact.ok) {
+        slim = pack_slim(host, compact, opt_chunk_kb > 0 ? budget : 0);
+        if (slim.ok) {
+          d_smodel = to_device(slim.packed.bytes);
+          d_schunks = to_device(slim.packed.chunks);
+        }
+      }
       lat = pack_compact(host, binned, 4 * 1024);
       if (lat.ok && !compact.ok) lat.ok = false;  // same tile mapping as `compact` (d_cmeta) by construction
       if (lat.ok) {
@@ -197,7 +210,17 @@ struct mr_model {
       }
     }
   }
-  bool use_compact() const { return compact.ok && (opt_variant == 4 || opt_variant < 0); }
+  bool use_compact() const { return compact.ok && (opt_variant == 4 || opt_variant == 5 || opt_variant < 0); }
+  // Layout of the code buffer a batch of `rows` rows is scored from (BinParams::tile_T): the slim scorer's CTA-tile layout
+  // when the model has a slim form, the batch is not one for the tree-parallel latency path, and the device's dynamic
+  // shared window starts below the tile's absolute address; else 0 (groups of 32 rows: compact kernel / latency path).
+  // variant 4 pins the 8-byte compact kernel, variant 5 the slim one (tests, A/B).
+  int code_layout(int rows) const {
+    if (!slim.ok || !use_binned() || !use_compact() || opt_variant == 4 || opt_threads != 0) return 0;
+    if (ctx->dyn_smem_base < 0 || ctx->dyn_smem_base + 64 > slim.tile_T * 4) return 0;
+    if (opt_variant < 0 && use_latency(rows)) return 0;
+    return slim.tile_T;
+  }
   // the code-based scorer that is active and the width of its code tile
   const BinnedModel &active_binned() const { return use_compact() ? compact : binned; }
   int code_cols() const { return active_binned().tile_cols; }
@@ -243,11 +266,22 @@ struct mr_model {
   }
   // true: score_codes() can store to peer sinks from inside the scoring kernel
   bool fuses_sinks(int rows) const { return use_latency(rows) || (use_binned() && use_compact()); }
+  // layout: the code buffer's layout — -1 = code_layout(rows) (what the producers were told for a batch of this size),
+  // 0 = groups of 32 rows whatever the size (mega-request slices)
   void score_codes(uint16_t *d_codes, int rows, double *d_out, cudaStream_t stream, void *d_leaf_scratch = nullptr,
-                   const ScoreSinks *sinks = nullptr) const {
+                   const ScoreSinks *sinks = nullptr, int layout = -1) const {
     BinnedLaunch B = binned_desc();
     B.rows = rows; B.cols = host.n_features; B.d_out = d_out; B.d_bins = d_codes; B.codes_ready = true;
     if (sinks) B.sinks = *sinks;
+    if (layout < 0) layout = code_layout(rows);
+    if (layout) {
+      B.tile_T = slim.tile_T;
+      B.d_model = d_smodel; B.d_chunks = d_schunks;
+      B.n_chunks = (int)slim.packed.chunks.size();
+      B.max_chunk_bytes = slim.packed.max_chunk_bytes;
+      launch_gbdt_binned(B, ctx->num_sms, stream);
+      return;
+    }
     if (use_latency(rows)) {
       B.d_model = d_lmodel; B.d_chunks = d_lchunks;
       B.n_chunks = (int)lat.packed.chunks.size();
@@ -272,7 +306,8 @@ struct mr_model {
       void *bins = nullptr;
       MR_CUDA_CHECK(cudaMallocAsync(&bins, std::max<size_t>(binned_scratch_bytes(rows, code_cols()), 16), stream));
       B.d_bins = (uint16_t *)bins;
-      if (use_latency(rows)) {
+      B.tile_T = code_layout(rows);
+      if (use_latency(rows) || B.tile_T) {
         B.codes_only = true;
         launch_gbdt_binned(B, ctx->num_sms, stream);
         score_codes(B.d_bins, rows, d_out, stream);

@@ -130,7 +130,8 @@ bool fused_codes(const mr_model *model) { return model && model->use_binned(); }
 
 const uint32_t *code_rows_for(mr_state *st, const mr_model *model, int *row_words_out);
 
-void set_codes(RankArgs &a, mr_state *st, const mr_model *model, uint8_t *scratch, const ScratchPlan &sp) {
+// legacy_layout: groups-of-32 codes whatever the batch size (mega-request slices are cut at 128-item boundaries of it)
+void set_codes(RankArgs &a, mr_state *st, const mr_model *model, uint8_t *scratch, const ScratchPlan &sp, bool legacy_layout = false) {
   a.codes = (uint16_t *)(scratch + sp.codes);
   a.bin = BinParams{};
   a.bin.thr_off = model->d_thr_off;
@@ -142,6 +143,7 @@ void set_codes(RankArgs &a, mr_state *st, const mr_model *model, uint8_t *scratc
   a.bin.n_features = model->host.n_features;
   a.bin.tile_cols = B.tile_cols;
   a.bin.xgb = model->host.kind == MR_BOOSTER_XGBOOST;
+  a.bin.tile_T = legacy_layout ? 0 : model->code_layout(a.total_items);
   a.code_rows = a.out_features ? nullptr : code_rows_for(st, model, &a.code_row_words);
 }
 
@@ -887,7 +889,7 @@ void group_enqueue(mr_group *g, mr_state *st, mr_model *model, RankArgs &a, cons
   MR_CUDA_CHECK(cudaGetLastError());
   a.item_offsets = g->d_offs;
   a.out_features = fused ? nullptr : (double *)(scratch + sp.features);
-  if (fused) set_codes(a, st, model, scratch, sp);
+  if (fused) set_codes(a, st, model, scratch, sp, /*legacy_layout=*/true);
   if (a.total_items > 0) launch_assemble(a, S, stream);
   else MR_CUDA_CHECK(cudaMemsetAsync(a.error_flag, 0, 4, stream));
   ScoreSinks sk;
@@ -903,11 +905,11 @@ void group_enqueue(mr_group *g, mr_state *st, mr_model *model, RankArgs &a, cons
   if (n_sl > 0) {
     if (fused && model->fuses_sinks(n_sl)) {
       uint16_t *codes = a.codes + (size_t)(first / 32) * model->code_cols() * 32;
-      model->score_codes(codes, n_sl, nullptr, stream, sp.leafvals ? scratch + sp.leafvals : nullptr, &sk);
+      model->score_codes(codes, n_sl, nullptr, stream, sp.leafvals ? scratch + sp.leafvals : nullptr, &sk, /*layout=*/0);
       published = true;
     } else {
       double *local = (double *)(scratch + sp.local_scores);
-      if (fused) model->score_codes(a.codes + (size_t)(first / 32) * model->code_cols() * 32, n_sl, local, stream);
+      if (fused) model->score_codes(a.codes + (size_t)(first / 32) * model->code_cols() * 32, n_sl, local, stream, nullptr, nullptr, /*layout=*/0);
       else model->score(a.out_features + (size_t)first * S.dim, n_sl, S.dim, local, stream);
       { ProfScope _ps("group_publish_kernel", stream); group_publish_kernel<<<(n_sl + 255) / 256, 256, 0, stream>>>(local, n_sl, sk); }
       MR_CUDA_CHECK(cudaGetLastError());

@@ -34,7 +34,7 @@ def _check(ctx, kind, blob, X, **opts):
     return got
 
 
-@pytest.mark.parametrize("variant,ilp", [(0, 2), (0, 4), (2, 2), (4, 1)])
+@pytest.mark.parametrize("variant,ilp", [(0, 2), (0, 4), (2, 2), (4, 1), (5, 1)])
 @pytest.mark.parametrize("threads", [32, 128, 256])
 def test_c2_lightgbm_100x30x500(ctx, variant, ilp, threads):
     blob = synth.lightgbm_model_text(500, 30, seed=1234 + 2)
@@ -42,7 +42,7 @@ def test_c2_lightgbm_100x30x500(ctx, variant, ilp, threads):
     _check(ctx, 0, blob, X, variant=variant, ilp=ilp, threads=threads)
 
 
-@pytest.mark.parametrize("variant", [0, 2, 4])
+@pytest.mark.parametrize("variant", [0, 2, 4, 5])
 @pytest.mark.parametrize("chunk_kb", [4, 32, 200])
 def test_chunking_is_invisible(ctx, chunk_kb, variant):
     blob = synth.lightgbm_model_text(500, 30, seed=7, stump_every=11)
@@ -93,7 +93,7 @@ def test_binned_codes_at_threshold_boundaries(ctx):
                 r[f] = v
                 rows.append(r)
     X = np.array(rows)
-    for v in (2, 4):
+    for v in (2, 4, 5):
         _check(ctx, 0, blob, X, variant=v)
     xb = synth.xgboost_model_json(30, 5, depth=5, seed=34)
     mx = model_parse.parse_xgboost(xb)
@@ -107,14 +107,14 @@ def test_binned_codes_at_threshold_boundaries(ctx):
                 r = np.zeros(5)
                 r[f] = v
                 rows.append(r)
-    for v in (2, 4):
+    for v in (2, 4, 5):
         _check(ctx, 1, xb, np.array(rows), variant=v)
 
 
 def test_deep_unbalanced_lightgbm(ctx):
     blob = synth.lightgbm_model_text(50, 20, num_leaves=255, max_depth=0, seed=21)
     X = synth.feature_matrix(777, 20, seed=22)
-    for v in (-1, 0, 2, 4):
+    for v in (-1, 0, 2, 4, 5):
         _check(ctx, 0, blob, X, variant=v)
     # one tree of 20 000 leaves: too large for the compact layout's 16-bit offsets -> generic binned kernel
     big = synth.lightgbm_model_text(2, 20, num_leaves=20000, max_depth=0, seed=23)
@@ -127,7 +127,7 @@ def test_c4_xgboost(ctx, fmt, depth, full):
     gen = synth.xgboost_model_json if fmt == "json" else synth.xgboost_model_ubj
     blob = gen(200, 16, depth=depth, seed=1234 + 4, full=full)
     X = synth.feature_matrix(256, 16, seed=42 + 4)
-    for variant in (-1, 0, 2, 4):  # -1 on 256 rows = the low-latency tree-parallel path
+    for variant in (-1, 0, 2, 4, 5):  # -1 on 256 rows = the low-latency tree-parallel path
         _check(ctx, 1, blob, X, variant=variant)
 
 
@@ -277,3 +277,28 @@ def test_removed_variants_are_rejected(ctx):
             b.set_option("variant", v)
         assert e.value.status == 1
     b.free()
+
+
+def test_slim_scorer_layouts_and_fallbacks(ctx):
+    """The 4-byte-node scorer (variant 5 / auto on large batches): every CTA-tile size it has (512 items up to 62 tile
+    columns, 256 up to 126, 128 up to 254), batches around the tile boundaries, XGBoost f32, single-leaf trees, NaN in
+    both directions on one feature (duplicated tile columns), models it must refuse (categorical splits -> the 8-byte
+    compact kernel) — all bit-identical to the oracle, like every other scorer."""
+    import metarank_b200 as mb
+
+    for n_feat, trees in ((30, 120), (70, 60), (120, 40), (200, 20), (300, 12)):
+        blob = synth.lightgbm_model_text(trees, n_feat, seed=500 + n_feat, stump_every=9)
+        for rows in (1, 127, 513, 5000, 40_000):
+            X = synth.feature_matrix(rows, n_feat, seed=rows + n_feat)
+            _check(ctx, 0, blob, X, variant=5)
+        _check(ctx, 0, blob, synth.feature_matrix(40_000, n_feat, seed=3))  # auto: 40 000 rows is the throughput path
+    for fmt in (synth.xgboost_model_json, synth.xgboost_model_ubj):
+        xb = fmt(90, 16, depth=6, seed=77)
+        for rows in (33, 4096, 40_000):
+            _check(ctx, 1, xb, synth.feature_matrix(rows, 16, seed=rows), variant=5)
+    deep = synth.lightgbm_model_text(40, 12, num_leaves=120, max_depth=0, seed=78)   # 2 KB tree blocks
+    _check(ctx, 0, deep, synth.feature_matrix(3000, 12, seed=4), variant=5)
+    huge = synth.lightgbm_model_text(6, 12, num_leaves=400, max_depth=0, seed=79)   # no slim form: silently the compact kernel
+    _check(ctx, 0, huge, synth.feature_matrix(3000, 12, seed=5), variant=5)
+    cat = synth.lightgbm_model_text(50, 10, seed=80, cat_features={3: 20})           # categorical: no slim form either
+    _check(ctx, 0, cat, synth.feature_matrix(3000, 10, seed=6), variant=5)
