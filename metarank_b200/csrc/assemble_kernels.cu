@@ -165,15 +165,16 @@ __global__ void __launch_bounds__(128) cosine_qnorm_kernel(RankArgs a) {
 // (products rounded before the add, like the JVM).  A warp owns 32 items: their rows stream chunk by chunk through cp.async
 // (16 bytes per lane, a row segment per instruction, 32 rows in flight) into a padded tile, then lane j walks ITS item's
 // values in order.  The query is widened once per CTA into shared memory.
-constexpr int kCosChunk = 128;            // floats per row per stage
-constexpr int kCosPitch = kCosChunk + 4;  // 528-byte rows: 8 consecutive lanes read 16 bytes from 8 different bank groups
+constexpr int kCosChunk = 64;             // floats per row per stage
+constexpr int kCosPitch = kCosChunk + 4;  // 272-byte rows: 8 consecutive lanes read 16 bytes from 8 different bank groups
+constexpr int kCosStages = 2;
 
 __global__ void __launch_bounds__(128) cosine_f32_kernel(RankArgs a, int dim_max) {
   extern __shared__ __align__(16) uint8_t s_cos_raw[];
   double *s_q = reinterpret_cast<double *>(s_cos_raw);  // [dim_max] the CTA's first request's query, widened
   float *s_tiles = reinterpret_cast<float *>(s_cos_raw + (((size_t)dim_max * 8 + 15) & ~size_t(15)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float *tile = s_tiles + (size_t)warp * 32 * kCosPitch;
+  float *tile = s_tiles + (size_t)warp * kCosStages * 32 * kCosPitch;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < a.total_items;
   const int r = live ? a.item_req[i] : 0;
@@ -186,6 +187,26 @@ __global__ void __launch_bounds__(128) cosine_f32_kernel(RankArgs a, int dim_max
     const int dim = d.aux0;
     const float *side = a.st.side_f32[(int)d.uparam];
     if (!side) { voff += dim; continue; }  // stored as f64: cosine_kernel's
+    // the rows do not wait for anything but the item's row index: start the first chunk before the query is staged and
+    // before the presence bits are read (a row without an embedding holds zeros; whether it counts is decided below)
+    const int n_chunks = (dim + kCosChunk - 1) / kCosChunk;
+    auto issue = [&](int c) {
+      if (c < n_chunks) {
+        const int d0 = c * kCosChunk, nd = min(kCosChunk, dim - d0);  // a multiple of 4 (f32 mode requires dim % 4 == 0)
+        float *st = tile + (size_t)(c % kCosStages) * 32 * kCosPitch;
+        // 16 lanes cover a row segment of 64 floats: two rows per instruction
+        const int half = lane >> 4, l16 = lane & 15;
+        for (int j = 0; j < 32; j += 2) {
+          const uint32_t rj = __shfl_sync(0xFFFFFFFFu, ir, j + half);
+          if (rj != kNoRow && l16 * 4 < nd)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(st + (j + half) * kCosPitch + l16 * 4)),
+                         "l"(side + (size_t)rj * dim + d0 + l16 * 4)
+                         : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(0);
     __syncthreads();  // s_q of the previous feature is no longer read
     {
       const float *q0 = a.req_vec + (size_t)r0 * a.vec_stride + voff;
@@ -197,33 +218,30 @@ __global__ void __launch_bounds__(128) cosine_f32_kernel(RankArgs a, int dim_max
     const float *q = a.req_vec + (size_t)r * a.vec_stride + voff;
     const bool same_q = r == r0;
     double top = 0.0;
-    for (int d0 = 0; d0 < dim; d0 += kCosChunk) {
-      const int nd = min(kCosChunk, dim - d0);  // a multiple of 4 (f32 mode requires dim % 4 == 0)
-      for (int j = 0; j < 32; j++) {
-        const uint32_t rj = __shfl_sync(0xFFFFFFFFu, ir, j);
-        const int okj = __shfl_sync(0xFFFFFFFFu, (int)ok, j);
-        if (okj && lane * 4 < nd)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(tile + j * kCosPitch + lane * 4)),
-                       "l"(side + (size_t)rj * dim + d0 + lane * 4)
-                       : "memory");
-      }
-      asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    for (int c = 0; c < n_chunks; c++) {
+      issue(c + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");  // chunk c has landed (chunk c + 1 may still be in flight)
       __syncwarp();
       if (ok) {
-        const float4 *row = reinterpret_cast<const float4 *>(tile + lane * kCosPitch);
+        const int d0 = c * kCosChunk, nd = min(kCosChunk, dim - d0);
+        const float4 *row = reinterpret_cast<const float4 *>(tile + (size_t)(c % kCosStages) * 32 * kCosPitch + lane * kCosPitch);
         for (int k4 = 0; k4 < nd / 4; k4++) {
           const float4 e = row[k4];
           const int k = d0 + k4 * 4;
           const float ev[4] = {e.x, e.y, e.z, e.w};
+          double pr[4];
 #pragma unroll
-          for (int c = 0; c < 4; c++) {
-            const double qd = same_q ? s_q[k + c] : (double)__ldg(q + k + c);
-            top = __dadd_rn(top, __dmul_rn(qd, (double)ev[c]));
+          for (int c4 = 0; c4 < 4; c4++) {
+            const double qd = same_q ? s_q[k + c4] : (double)__ldg(q + k + c4);
+            pr[c4] = __dmul_rn(qd, (double)ev[c4]);
           }
+#pragma unroll
+          for (int c4 = 0; c4 < 4; c4++) top = __dadd_rn(top, pr[c4]);
         }
       }
-      __syncwarp();
+      __syncwarp();  // before chunk c + 2 overwrites this stage
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (live) {
       double out = nan_d();
       if (ok) {
@@ -1310,7 +1328,7 @@ void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t strea
       { ProfScope _ps("cosine_qnorm_kernel", stream); cosine_qnorm_kernel<<<(a.n_requests + 3) / 4, 128, (size_t)4 * std::max(a.vec_stride, 1) * sizeof(float), stream>>>(a); }
       MR_CUDA_CHECK(cudaGetLastError());
       g_kernel_launches++;
-      const size_t smem = (((size_t)dim_max * 8 + 15) & ~size_t(15)) + (size_t)4 * 32 * kCosPitch * sizeof(float);
+      const size_t smem = (((size_t)dim_max * 8 + 15) & ~size_t(15)) + (size_t)4 * kCosStages * 32 * kCosPitch * sizeof(float);
       MR_CUDA_CHECK(cudaFuncSetAttribute(cosine_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       { ProfScope _ps("cosine_f32_kernel", stream); cosine_f32_kernel<<<(a.total_items + 127) / 128, 128, smem, stream>>>(a, dim_max); }
       MR_CUDA_CHECK(cudaGetLastError());

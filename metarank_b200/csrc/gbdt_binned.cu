@@ -420,6 +420,8 @@ __global__ void __launch_bounds__(T) gbdt_score_slim_kernel(const BParams p) {
   uint8_t *tile_ptr = smem + (tile_abs - base);
   const bool resident = p.n_chunks == 1;
   const uint32_t tid4 = (uint32_t)tid * 4u;
+  uint32_t lane_zero;
+  asm volatile("shr.u32 %0, %1, 31;" : "=r"(lane_zero) : "r"(tid4));
 
   const int n_tiles = (p.rows + T - 1) / T;
   if (tid == 0) {
@@ -462,45 +464,46 @@ __global__ void __launch_bounds__(T) gbdt_score_slim_kernel(const BParams p) {
       const uint8_t *cb = smem + (cb_abs - base);
       const int ntree = (int)*reinterpret_cast<const uint32_t *>(cb);
       const uint32_t *roots = reinterpret_cast<const uint32_t *>(cb + 16);
-      auto walk = [&](uint32_t block_off) -> Real {
-        const uint32_t tb = cb_abs + block_off;  // absolute address of the tree's block, aligned to the block's size
-        uint32_t w;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(tb));
-        if ((int)w >= 0) {
-          asm volatile(
-              "{\n"
-              ".reg .pred pl, pq;\n"
-              ".reg .b32 off, code, n;\n"
-              ".reg .b16 wlo, whi, clo, chi;\n"
-              "SLVL:\n"
-              "lop3.b32 off, %0, %1, %2, 0xEA;\n"      // (w & column mask) | 4 * tid
-              "ld.shared.u16 code, [off];\n"
-              "mov.b32 {wlo, whi}, %0;\n"
-              "mov.b32 {clo, chi}, code;\n"
-              "setp.le.f16 pl, clo, whi;\n"            // code <= k on binary16 patterns; a NaN code goes right
-              "lop3.b32 n, %0, %3, %4, 0xEA;\n"        // (w & child mask) | block base
-              "@!pl add.u32 n, n, 4;\n"
-              "ld.shared.u32 %0, [n];\n"
-              "setp.ge.s32 pq, %0, 0;\n"
-              "@pq bra SLVL;\n"
-              "}\n"
-              : "+r"(w)
-              : "n"(K::kColMask), "r"(tid4), "n"(K::kChildMask), "r"(tb)
-              : "memory");
-        }
-        return *reinterpret_cast<const Real *>(smem + ((tb + (w & 0xFFFFu)) - base));
+      auto walk = [&](uint32_t block_off, uint32_t w) -> Real {
+        // absolute address of the tree's block, aligned to the block's size.  `lane_zero` is 0, but only at run time: ptxas
+        // would otherwise prove the base warp-uniform, keep it in a uniform register — which a LOP3 cannot read — and
+        // re-materialise it with an extra move on every level; the three-input add costs nothing.  `w` is the root entry
+        // (always an internal one), delivered with the root table.
+        const uint32_t tb = cb_abs + block_off + lane_zero;
+        asm volatile(
+            "{\n"
+            ".reg .pred pl, pq;\n"
+            ".reg .b32 off, code, n;\n"
+            ".reg .b16 wlo, whi, clo, chi;\n"
+            "SLVL:\n"
+            "lop3.b32 off, %0, %1, %2, 0xEA;\n"      // (w & column mask) | 4 * tid
+            "ld.shared.u16 code, [off];\n"
+            "mov.b32 {wlo, whi}, %0;\n"
+            "mov.b32 {clo, chi}, code;\n"
+            "setp.le.f16 pl, clo, whi;\n"            // code <= k on binary16 patterns; a NaN code goes right
+            "lop3.b32 n, %0, %3, %4, 0xEA;\n"        // (w & child mask) | block base
+            "@!pl add.u32 n, n, 4;\n"
+            "ld.shared.u32 %0, [n];\n"
+            "setp.ge.s32 pq, %0, 0;\n"
+            "@pq bra SLVL;\n"
+            "}\n"
+            : "+r"(w)
+            : "n"(K::kColMask), "r"(tid4), "n"(K::kChildMask), "r"(tb)
+            : "memory");
+        return *reinterpret_cast<const Real *>(smem + (((w & 0xFFFFu) | tb) - base));
       };
+      // two trees per (warp-uniform) LDS.128: {block, root entry} x 2; the leaf values are still added one by one, in tree order
       int t = 0;
 #pragma unroll 1
       for (; t + 4 <= ntree; t += 4) {
-        const uint4 r = *reinterpret_cast<const uint4 *>(roots + t);
-        acc += walk(r.x);
-        acc += walk(r.y);
-        acc += walk(r.z);
-        acc += walk(r.w);
+        const uint4 r0 = *reinterpret_cast<const uint4 *>(roots + 2 * t), r1 = *reinterpret_cast<const uint4 *>(roots + 2 * t + 4);
+        acc += walk(r0.x, r0.y);
+        acc += walk(r0.z, r0.w);
+        acc += walk(r1.x, r1.y);
+        acc += walk(r1.z, r1.w);
       }
 #pragma unroll 1
-      for (; t < ntree; t++) acc += walk(roots[t]);
+      for (; t < ntree; t++) acc += walk(roots[2 * t], roots[2 * t + 1]);
       __syncthreads();
     }
     if (item < p.rows) store_score(p.out, p.sinks, item, (double)acc);
@@ -522,7 +525,7 @@ struct LParams {
   const uint32_t *tree_off;  // [n_trees] byte offset of the tree's chunk in `model`
   double *out;
   int rows, rows_padded, n_features, n_trees;
-  int n_chunks, chunks_per_cta;
+  int n_chunks, chunks_per_cta, has_cat;
   uint32_t chunk_stride;  // bytes per chunk buffer
   float base_score;
 };
@@ -572,25 +575,15 @@ __global__ void __launch_bounds__(128) gbdt_leaves_kernel(const LParams p) {
     if (has_items) {
       const int ntree = (int)*reinterpret_cast<const uint32_t *>(cb);
       const uint32_t *roots = reinterpret_cast<const uint32_t *>(cb + 16);
-      for (int t = 0; t < ntree; t++) {
-        uint32_t n = roots[t];
-        while (!(n & 1u)) {
-          const uint2 nd = *reinterpret_cast<const uint2 *>(cb + (n & ~2u));  // bit 1 of a pointer: categorical target
-          const uint32_t code = *reinterpret_cast<const uint16_t *>(xwarp + ((nd.x & 0xFFC0u) | lane2));
-          bool left;
-          if (nd.x & 2u) {  // categorical bitset
-            left = false;
-            if (code != kBinNaN) {
-              const uint2 ct = reinterpret_cast<const uint2 *>(cb)[nd.x >> 16];
-              const uint32_t w = code >> 5;
-              if (w < ct.y) left = (reinterpret_cast<const uint32_t *>(cb)[ct.x + w] >> (code & 31u)) & 1u;
-            }
-          } else {
-            left = code <= (nd.x >> 16);  // NaN direction baked into the column
-          }
-          n = __byte_perm(nd.y, 0u, left ? 0x4410u : 0x4432u);
-        }
-        p.leafslots[(size_t)(first_tree + t) * p.rows_padded + item] = (uint16_t)((n - 1u) >> 3);
+      const uint32_t cb_addr = smem_u32(cb), xwarp_addr = smem_u32(xwarp);
+      uint16_t *dst = p.leafslots + (size_t)first_tree * p.rows_padded + item;
+      // the compact scorer's hand-scheduled level loop (10 SASS instructions; nvcc's own schedule of the same walk is 18)
+      if (p.has_cat) {
+        for (int t = 0; t < ntree; t++)
+          dst[(size_t)t * p.rows_padded] = (uint16_t)((walk_tree<true, false>(roots[t], cb, cb_addr, xwarp, xwarp_addr, lane2) - 1u) >> 3);
+      } else {
+        for (int t = 0; t < ntree; t++)
+          dst[(size_t)t * p.rows_padded] = (uint16_t)((walk_tree<false, false>(roots[t], cb, cb_addr, xwarp, xwarp_addr, lane2) - 1u) >> 3);
       }
     }
     __syncthreads();  // this buffer is refilled two chunks from now
@@ -598,72 +591,91 @@ __global__ void __launch_bounds__(128) gbdt_leaves_kernel(const LParams p) {
 }
 
 // In-order sum of the per-tree leaf values.  The adds are a dependent chain (tree order = the sequential reference's
-// rounding) but nothing else is.  A warp owns 32 rows and runs a three-step software pipeline over groups of kSumTrees
-// trees, everything moved by cp.async so that no load waits on a register:
-//   A(g)  the rows' leaf SLOTS of group g (2 bytes per row and tree — an eighth of the f64 values), 16 bytes per copy;
-//   B(g)  with the slots in hand, the VALUES behind them: one 8-byte copy per (tree, row) out of the packed model
-//         (a few hundred KB, L2 resident) into a [tree][lane] tile — 64 copies per lane in flight, no register limit;
-//   C(g)  acc += value, tree by tree.
-// While C(g) adds, B(g + 1) and A(g + 2) are in flight.  One-warp CTAs, so that a single mega-request slice (a few
-// thousand rows) still spreads over the whole chip.
-constexpr int kSumTrees = 64;  // per warp: 2 x 4 KB of slots + 2 x 16 KB of values
+// rounding: ~2000 DADDs for BASELINE config #5) but nothing else is, so the CTA is a small producer / consumer machine
+// over groups of kSumTrees trees for its 32 rows:
+//   warps 1..3 (producers)  producer w owns ring buffer w and the groups g = w - 1 (mod 3): it copies the rows' leaf SLOTS
+//                           of the group (2 bytes per row and tree, 16 bytes per cp.async) and the trees' chunk offsets,
+//                           then — with the slots in hand — gathers the VALUES behind them, one 8-byte cp.async per
+//                           (tree, row) out of the packed model (a few hundred KB, L2 resident) into a [tree][lane] tile
+//                           (64 copies per lane in flight, no register limit), and raises the buffer's `full` barrier;
+//   warp 0 (consumer)       waits for `full`, acc += value tree by tree, raises `empty`.
+// Three groups are in flight while one is being added, so the L2 round trips hide behind the adds; a single
+// mega-request slice (a few thousand rows) still spreads over the whole chip, 32 rows per CTA.
+constexpr int kSumTrees = 64;
+constexpr int kSumRing = 3;
+constexpr size_t kSumBufBytes = (size_t)kSumTrees * 32 * sizeof(double) + (size_t)kSumTrees * 32 * sizeof(uint16_t) + kSumTrees * sizeof(uint32_t);
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 template <typename Real>
 __global__ void __launch_bounds__(128) gbdt_sum_kernel(const LParams p, const ScoreSinks sinks) {
   extern __shared__ __align__(16) uint8_t s_sum_raw[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(s_sum_raw), *empty = full + kSumRing;  // 2 x kSumRing barriers in the first 64 bytes
+  uint8_t *bufs = s_sum_raw + 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr size_t kWarpBytes = 2 * kSumTrees * 32 * sizeof(uint16_t) + 2 * kSumTrees * 32 * sizeof(double);
-  uint16_t *s_slots = reinterpret_cast<uint16_t *>(s_sum_raw + (size_t)warp * kWarpBytes);        // [2][kSumTrees][32]
-  double *s_vals = reinterpret_cast<double *>(s_slots + 2 * kSumTrees * 32);                        // [2][kSumTrees][32]
-  const int row0 = (blockIdx.x * (blockDim.x >> 5) + warp) * 32;
+  const int row0 = blockIdx.x * 32;
   const int item = row0 + lane;
-  const bool live = item < p.rows, warp_live = row0 < p.rows;
+  const bool live = item < p.rows;
   const int n_groups = (p.n_trees + kSumTrees - 1) / kSumTrees;
-  auto issue_slots = [&](int g) {  // A(g)
-    if (g < n_groups && warp_live) {
-      const int t0 = g * kSumTrees, nb = min(kSumTrees, p.n_trees - t0);
-      const uint32_t dst = smem_u32(s_slots + (size_t)(g & 1) * kSumTrees * 32);
-      for (int k = lane; k < nb * 4; k += 32) {  // 16-byte piece k: tree k >> 2, rows (k & 3) * 8 .. + 8 of the warp's 32
-        const uint16_t *src = p.leafslots + (size_t)(t0 + (k >> 2)) * p.rows_padded + row0 + (k & 3) * 8;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)k * 16u), "l"(src) : "memory");
-      }
-    }
-  };
-  auto issue_values = [&](int g) {  // B(g): the slots of group g are in shared memory
-    if (g < n_groups && live) {
-      const int t0 = g * kSumTrees, nb = min(kSumTrees, p.n_trees - t0);
-      const uint16_t *sl = s_slots + (size_t)(g & 1) * kSumTrees * 32 + lane;
-      const uint32_t dst = smem_u32(s_vals + (size_t)(g & 1) * kSumTrees * 32 + lane);
-#pragma unroll 4
-      for (int k = 0; k < nb; k++) {
-        const uint8_t *src = p.model + __ldg(p.tree_off + t0 + k) + (uint32_t)sl[k * 32] * 8u;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (uint32_t)k * 256u), "l"(src) : "memory");
-      }
-    }
-  };
-  auto fence = [&] {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-    __syncwarp();  // copies issued by other lanes (the slots) are visible to all
-  };
-  Real acc = (sizeof(Real) == 4) ? (Real)p.base_score : (Real)0;
-  issue_slots(0);
-  fence();
-  issue_values(0);
-  issue_slots(1);
-  for (int g = 0; g < n_groups; g++) {
-    fence();                 // values of group g and slots of group g + 1 have landed
-    issue_values(g + 1);
-    issue_slots(g + 2);      // overwrites the slots of group g: B(g) read them when it was issued
-    if (live) {
-      const int nb = min(kSumTrees, p.n_trees - g * kSumTrees);
-      const double *sv = s_vals + (size_t)(g & 1) * kSumTrees * 32 + lane;
-      // the value slot holds the model's Real in its first bytes (f64, or f32 for XGBoost)
-#pragma unroll 8
-      for (int k = 0; k < nb; k++) acc += *reinterpret_cast<const Real *>(sv + k * 32);
-    }
-    __syncwarp();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < kSumRing; k++) { mbar_init(&full[k], 1); mbar_init(&empty[k], 1); }
+    fence_barrier_init();
   }
-  if (live) store_score(p.out, sinks, item, (double)acc);
+  __syncthreads();
+  Real acc = (sizeof(Real) == 4) ? (Real)p.base_score : (Real)0;
+  if (warp > 0) {
+    // ---- producer of ring buffer b
+    const int b = warp - 1;
+    double *vals = reinterpret_cast<double *>(bufs + (size_t)b * kSumBufBytes);
+    uint16_t *slots = reinterpret_cast<uint16_t *>(vals + kSumTrees * 32);
+    uint32_t *toff = reinterpret_cast<uint32_t *>(slots + kSumTrees * 32);
+    for (int g = b, use = 0; g < n_groups; g += kSumRing, use++) {
+      if (use > 0) mbar_wait(&empty[b], (use - 1) & 1);  // the consumer is done with this buffer's previous group
+      const int t0 = g * kSumTrees, nb = min(kSumTrees, p.n_trees - t0);
+      {
+        const uint32_t dst = smem_u32(slots);
+        for (int k = lane; k < nb * 4; k += 32) {  // 16-byte piece k: tree k >> 2, rows (k & 3) * 8 .. + 8 of the CTA's 32
+          const uint16_t *src = p.leafslots + (size_t)(t0 + (k >> 2)) * p.rows_padded + row0 + (k & 3) * 8;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)k * 16u), "l"(src) : "memory");
+        }
+        if (lane * 4 < nb)  // the trees' chunk offsets, 4 per lane (the table is padded to whole groups)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(toff) + (uint32_t)lane * 16u),
+                       "l"(p.tree_off + t0 + lane * 4)
+                       : "memory");
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+      }
+      if (live) {
+        const uint32_t dst = smem_u32(vals + lane);
+#pragma unroll 8
+        for (int k = 0; k < nb; k++) {
+          const uint8_t *src = p.model + toff[k] + (uint32_t)slots[k * 32 + lane] * 8u;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (uint32_t)k * 256u), "l"(src) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[b]);
+    }
+  } else {
+    // ---- consumer
+    for (int g = 0; g < n_groups; g++) {
+      const int b = g % kSumRing, use = g / kSumRing;
+      mbar_wait(&full[b], use & 1);
+      if (live) {
+        const int nb = min(kSumTrees, p.n_trees - g * kSumTrees);
+        const double *sv = reinterpret_cast<const double *>(bufs + (size_t)b * kSumBufBytes) + lane;
+        // the value slot holds the model's Real in its first bytes (f64, or f32 for XGBoost)
+#pragma unroll 8
+        for (int k = 0; k < nb; k++) acc += *reinterpret_cast<const Real *>(sv + k * 32);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[b]);
+    }
+    if (live) store_score(p.out, sinks, item, (double)acc);
+  }
   if (sinks.n_peer) publish_when_last(sinks);
 }
 
@@ -760,6 +772,7 @@ void launch_gbdt_latency(const BinnedLaunch &L, int n_trees, const uint32_t *d_t
   p.rows = L.rows; p.rows_padded = (L.rows + 127) & ~127; p.n_features = L.tile_cols; p.n_trees = n_trees;
   p.base_score = L.base_score;
   p.n_chunks = L.n_chunks;
+  p.has_cat = L.has_cat ? 1 : 0;
   p.chunk_stride = (L.max_chunk_bytes + 127u) & ~127u;
   // (chunk, 128-item group) pairs are the unit of parallelism; once there are more of them than ~16 per SM a CTA takes
   // several chunks in a row for its group, so the code tile is staged once per CTA instead of once per 4 KB of trees
@@ -767,16 +780,16 @@ void launch_gbdt_latency(const BinnedLaunch &L, int n_trees, const uint32_t *d_t
   p.chunks_per_cta = (int)std::max<long long>(1, std::min<long long>(16, ((long long)L.n_chunks * n_item_groups) / (148 * 16)));
   const size_t smem = 128 + 2 * (size_t)p.chunk_stride + (size_t)4 * L.tile_cols * 64;
   dim3 grid((unsigned)((L.n_chunks + p.chunks_per_cta - 1) / p.chunks_per_cta), (unsigned)n_item_groups);
-  // the in-order sum: one-warp CTAs (16 KB of stages each) spread even a 1 000-row slice over 32 SMs
+  // the in-order sum: 32 rows per CTA (1 consumer + 3 producer warps), so even a 1 000-row slice spreads over 32 SMs
   const int sum_warps = 1;
-  const size_t sum_smem = (size_t)sum_warps * (2 * kSumTrees * 32 * sizeof(uint16_t) + 2 * kSumTrees * 32 * sizeof(double));
+  const size_t sum_smem = 64 + kSumRing * kSumBufBytes;
   const int n_warps = (L.rows + 31) / 32;
   auto go = [&](auto leaves, auto sum) {
     MR_CUDA_CHECK(cudaFuncSetAttribute(leaves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     { ProfScope _ps("gbdt_leaves_kernel", stream); leaves<<<grid, 128, smem, stream>>>(p); }
     MR_CUDA_CHECK(cudaGetLastError());
     MR_CUDA_CHECK(cudaFuncSetAttribute(sum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sum_smem));
-    { ProfScope _ps("gbdt_sum_kernel", stream); sum<<<(n_warps + sum_warps - 1) / sum_warps, sum_warps * 32, sum_smem, stream>>>(p, L.sinks); }
+    { ProfScope _ps("gbdt_sum_kernel", stream); sum<<<(n_warps + sum_warps - 1) / sum_warps, 128, sum_smem, stream>>>(p, L.sinks); }
     MR_CUDA_CHECK(cudaGetLastError());
     g_kernel_launches += 2;
   };

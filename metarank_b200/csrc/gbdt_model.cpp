@@ -768,7 +768,7 @@ SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budge
   S.n_pairs = (C.tile_cols + 1) / 2;
   size_t max_block = 16;
   auto block_bytes = [](const HostTree &t) {
-    const size_t need = (2 + 2 * t.feat.size()) * 4 + t.leaf.size() * 8;  // entries (root pair + one pair per node) + leaf slots
+    const size_t need = (2 + 2 * std::max<size_t>(t.feat.size(), 1)) * 4 + t.leaf.size() * 8;  // entries (root pair + one pair per node) + leaf slots
     size_t b = 16;
     while (b < need) b <<= 1;
     return b;
@@ -795,7 +795,7 @@ SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budge
     // greedy: header, then blocks, each aligned to its own size
     size_t j = i, end = 0;
     auto layout_end = [&](size_t from, size_t to) {
-      size_t off = 16 + al16((to - from) * 4);
+      size_t off = 16 + al16((to - from) * 8);
       for (size_t k = from; k < to; k++) {
         const size_t b = block_bytes(m.trees[k]);
         off = (off + b - 1) & ~(b - 1);
@@ -816,22 +816,26 @@ SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budge
     uint8_t *c = pk.bytes.data() + base;
     const uint32_t hn = (uint32_t)n;
     memcpy(c, &hn, 4);
-    uint32_t *roots = (uint32_t *)(c + 16);
-    size_t off = 16 + al16(n * 4);
+    uint32_t *roots = (uint32_t *)(c + 16);  // per tree: {block offset, copy of the root entry}
+    size_t off = 16 + al16(n * 8);
     for (size_t k = 0; k < n; k++) {
       const HostTree &t = m.trees[i + k];
       const size_t b = block_bytes(t), ni = t.feat.size();
       off = (off + b - 1) & ~(b - 1);
-      roots[k] = (uint32_t)off;
+      roots[2 * k] = (uint32_t)off;
       uint32_t *e = (uint32_t *)(c + off);
-      const size_t leaf_base = (2 + 2 * ni) * 4;  // a multiple of 8
+      const size_t leaf_base = (2 + 2 * std::max<size_t>(ni, 1)) * 4;  // a multiple of 8
       // breadth-first numbering of the child pairs: node q's children live in pair slot pair_of[q]
       std::vector<uint32_t> entry_of_node(ni, 0);  // entry index of internal node q
       uint32_t next_pair = 1;
       std::vector<int> order;
       if (ni) { order.push_back(0); entry_of_node[0] = 0; }
       auto leaf_entry = [&](int cidx) { return 0x80000000u | (uint32_t)(leaf_base + (size_t)(~cidx) * 8); };
-      if (!ni) e[0] = leaf_entry(~0);
+      if (!ni) {
+        // a single-leaf tree is a dummy split whose children both are its leaf: every walk starts at an internal entry
+        e[0] = (1u << shift) | (1u * 8u);  // k = 0 on tile column 0, child pair 1
+        e[2] = e[3] = leaf_entry(~0);
+      }
       for (size_t h = 0; h < order.size(); h++) {
         const int q = order[h];
         const uint32_t pair = next_pair++;
@@ -847,6 +851,7 @@ SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budge
           else { entry_of_node[ch[sd]] = 2 * pair + sd; order.push_back(ch[sd]); }
         }
       }
+      roots[2 * k + 1] = e[0];
       uint8_t *lv = c + off + leaf_base;
       for (size_t q = 0; q < t.leaf.size(); q++) {
         if (f32) { const float v = (float)t.leaf[q]; memcpy(lv + q * 8, &v, 4); }

@@ -153,8 +153,9 @@ BinnedModel pack_compact(const HostModel &m, const BinnedModel &binned, size_t c
 //   leaf entry      bit 31 set, bits 15..0 = byte offset of the leaf's 8-byte value slot inside the block
 // One level of a walk is LOP3 (code address) -> LDS.U16 -> HSETP2 -> LOP3 (child pair | block base) -> predicated +4 ->
 // LDS.32 (next entry) -> sign test -> branch: 8 instructions and 2 wavefronts, against 10 and ~3.4 for the 8-byte layout.
-//   chunk: +0 u32 n_trees, pad; +16 u32 block_offset[n_trees] (from the chunk start; chunk buffers are 2 KB aligned in
-//          shared memory and every block is aligned to its own size); then the blocks
+//   chunk: +0 u32 n_trees, pad; +16 per tree {u32 block offset from the chunk start, u32 copy of its root entry} (chunk
+//          buffers are 2 KB aligned in shared memory and every block is aligned to its own size; a single-leaf tree is a
+//          dummy split onto its leaf, so every walk starts at an internal entry that arrives with the table); then the blocks
 // ok == false (categorical splits, > 31 744 thresholds on a column, too many tile columns or too large a tree for any
 // tile_T): the 8-byte compact kernel scores the model.  The tile mapping (BinMeta, tile_cols) is the compact model's.
 struct SlimModel {

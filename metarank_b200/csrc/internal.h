@@ -203,7 +203,7 @@ struct mr_model {
       if (lat.ok) {
         d_lmodel = to_device(lat.packed.bytes);
         d_lchunks = to_device(lat.packed.chunks);
-        std::vector<uint32_t> toff(host.trees.size(), 0);
+        std::vector<uint32_t> toff(((host.trees.size() + 63) / 64) * 64 + 4, 0);  // padded: the sum kernel copies it 16 bytes at a time
         for (auto &cd : lat.packed.chunks)
           for (uint32_t t = 0; t < cd.n_trees; t++) toff[cd.first_tree + t] = cd.byte_off;
         d_ltree_off = to_device(toff);

@@ -129,6 +129,35 @@ def test_compact_level_loop_sass_instruction_budget():
         assert sum("LDS" in i for i in body) == 2 and not any(i.startswith(("DSETP", "DADD", "LDG")) for i in body), body
 
 
+def test_slim_level_loop_sass_instruction_budget():
+    """The 4-byte-node scorer's level loop is 8 SASS instructions — LOP3 (code address), LDS.U16, HSETP2 (k compared as a
+    binary16 pattern straight from the entry), LOP3 (child | block base), a predicated +4, LDS (next entry), ISETP (leaf =
+    sign bit), BRA — with two shared-memory loads and no 64-bit load (an LDS.64 costs two wavefronts once lanes diverge)."""
+    import os
+    import re
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    obj = os.path.join(root, "metarank_b200", "csrc", "build", "gbdt_binned.o")
+    if not os.path.exists(tool) or not os.path.exists(obj):
+        pytest.skip("cuobjdump or the object file is not available")
+    sass = subprocess.run([tool, "-sass", obj], capture_output=True, text=True).stdout
+    for T in (512, 256, 128):
+        m = re.search(r"Function : \S*slim_kernelIdLi%dEE\S*\n(.*?)(?:Function :|\Z)" % T, sass, re.S)
+        assert m, f"slim kernel <double, {T}> not found"
+        ins = [re.sub(r"/\*.*?\*/", "", ln).strip() for ln in m.group(1).split("\n") if re.search(r"/\*[0-9a-f]{4}\*/", ln)]
+        ins = [i for i in ins if i]
+        h = next(k for k, i in enumerate(ins) if i.startswith("HSETP2"))
+        start = h - 2
+        end = next(k for k in range(h, len(ins)) if "BRA" in ins[k])
+        body = ins[start:end + 1]
+        assert len(body) == 8, body
+        assert body[0].startswith("LOP3") and body[1].startswith("LDS.U16") and ".H0_H0" in body[2] and ".H1_H1" in body[2], body
+        assert sum(i.startswith("LDS") for i in body) == 2 and not any("LDS.64" in i or i.startswith(("SHF", "DADD", "LDG")) for i in body), body
+
+
 def test_ctypes_mirrors_match_the_header_layouts():
     """The Python ctypes structures (metarank_b200/features.py RankBatch, StateInfo) must have the header's
     layout: a C program prints sizeof / offsetof straight from include/mr_b200.h."""
