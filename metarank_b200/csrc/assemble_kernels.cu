@@ -165,8 +165,8 @@ __global__ void __launch_bounds__(128) cosine_qnorm_kernel(RankArgs a) {
 // (products rounded before the add, like the JVM).  A warp owns 32 items: their rows stream chunk by chunk through cp.async
 // (16 bytes per lane, a row segment per instruction, 32 rows in flight) into a padded tile, then lane j walks ITS item's
 // values in order.  The query is widened once per CTA into shared memory.
-constexpr int kCosChunk = 64;             // floats per row per stage
-constexpr int kCosPitch = kCosChunk + 4;  // 272-byte rows: 8 consecutive lanes read 16 bytes from 8 different bank groups
+constexpr int kCosChunk = 32;             // floats per row per stage (small stages: 5 CTAs = 20 warps per SM hide the L2 latency)
+constexpr int kCosPitch = kCosChunk + 4;  // 144-byte rows: 8 consecutive lanes read 16 bytes from 8 different bank groups
 constexpr int kCosStages = 2;
 
 __global__ void __launch_bounds__(128) cosine_f32_kernel(RankArgs a, int dim_max) {
@@ -194,13 +194,13 @@ __global__ void __launch_bounds__(128) cosine_f32_kernel(RankArgs a, int dim_max
       if (c < n_chunks) {
         const int d0 = c * kCosChunk, nd = min(kCosChunk, dim - d0);  // a multiple of 4 (f32 mode requires dim % 4 == 0)
         float *st = tile + (size_t)(c % kCosStages) * 32 * kCosPitch;
-        // 16 lanes cover a row segment of 64 floats: two rows per instruction
-        const int half = lane >> 4, l16 = lane & 15;
-        for (int j = 0; j < 32; j += 2) {
-          const uint32_t rj = __shfl_sync(0xFFFFFFFFu, ir, j + half);
-          if (rj != kNoRow && l16 * 4 < nd)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(st + (j + half) * kCosPitch + l16 * 4)),
-                         "l"(side + (size_t)rj * dim + d0 + l16 * 4)
+        // 8 lanes cover a row segment of 32 floats: four rows per instruction
+        const int quad = lane >> 3, l8 = lane & 7;
+        for (int j = 0; j < 32; j += 4) {
+          const uint32_t rj = __shfl_sync(0xFFFFFFFFu, ir, j + quad);
+          if (rj != kNoRow && l8 * 4 < nd)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(st + (j + quad) * kCosPitch + l8 * 4)),
+                         "l"(side + (size_t)rj * dim + d0 + l8 * 4)
                          : "memory");
         }
       }
@@ -217,6 +217,9 @@ __global__ void __launch_bounds__(128) cosine_f32_kernel(RankArgs a, int dim_max
     const bool ok = q_ok && ir != kNoRow && present(row_ptr(a.st.t[SC_ITEM], ir), d.b[0]);
     const float *q = a.req_vec + (size_t)r * a.vec_stride + voff;
     const bool same_q = r == r0;
+    // request boundaries inside a warp are rare (a CTA is 128 consecutive items): the whole warp takes the loop that
+    // reads the widened query from shared memory unless one of its lanes belongs to another request
+    const bool warp_same = __all_sync(0xFFFFFFFFu, same_q || !ok);
     double top = 0.0;
     for (int c = 0; c < n_chunks; c++) {
       issue(c + 1);
@@ -225,18 +228,26 @@ __global__ void __launch_bounds__(128) cosine_f32_kernel(RankArgs a, int dim_max
       if (ok) {
         const int d0 = c * kCosChunk, nd = min(kCosChunk, dim - d0);
         const float4 *row = reinterpret_cast<const float4 *>(tile + (size_t)(c % kCosStages) * 32 * kCosPitch + lane * kCosPitch);
-        for (int k4 = 0; k4 < nd / 4; k4++) {
-          const float4 e = row[k4];
-          const int k = d0 + k4 * 4;
-          const float ev[4] = {e.x, e.y, e.z, e.w};
-          double pr[4];
-#pragma unroll
-          for (int c4 = 0; c4 < 4; c4++) {
-            const double qd = same_q ? s_q[k + c4] : (double)__ldg(q + k + c4);
-            pr[c4] = __dmul_rn(qd, (double)ev[c4]);
+        if (warp_same) {
+#pragma unroll 2
+          for (int k4 = 0; k4 < nd / 4; k4++) {
+            const float4 e = row[k4];
+            const double *qd = s_q + d0 + k4 * 4;
+            const double p0 = __dmul_rn(qd[0], (double)e.x), p1 = __dmul_rn(qd[1], (double)e.y);
+            const double p2 = __dmul_rn(qd[2], (double)e.z), p3 = __dmul_rn(qd[3], (double)e.w);
+            top = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(top, p0), p1), p2), p3);
           }
+        } else {
+          for (int k4 = 0; k4 < nd / 4; k4++) {
+            const float4 e = row[k4];
+            const int k = d0 + k4 * 4;
+            const float ev[4] = {e.x, e.y, e.z, e.w};
 #pragma unroll
-          for (int c4 = 0; c4 < 4; c4++) top = __dadd_rn(top, pr[c4]);
+            for (int c4 = 0; c4 < 4; c4++) {
+              const double qd = same_q ? s_q[k + c4] : (double)__ldg(q + k + c4);
+              top = __dadd_rn(top, __dmul_rn(qd, (double)ev[c4]));
+            }
+          }
         }
       }
       __syncwarp();  // before chunk c + 2 overwrites this stage

@@ -407,7 +407,7 @@ template <int T> struct SlimConst {
   static constexpr uint32_t kChildMask = ((1u << kShift) - 1u) & ~7u;
 };
 
-template <typename Real, int T>
+template <typename Real, int T, bool HAS_CAT>
 __global__ void __launch_bounds__(T) gbdt_score_slim_kernel(const BParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   using K = SlimConst<T>;
@@ -470,26 +470,68 @@ __global__ void __launch_bounds__(T) gbdt_score_slim_kernel(const BParams p) {
         // re-materialise it with an extra move on every level; the three-input add costs nothing.  `w` is the root entry
         // (always an internal one), delivered with the root table.
         const uint32_t tb = cb_abs + block_off + lane_zero;
-        asm volatile(
-            "{\n"
-            ".reg .pred pl, pq;\n"
-            ".reg .b32 off, code, n;\n"
-            ".reg .b16 wlo, whi, clo, chi;\n"
-            "SLVL:\n"
-            "lop3.b32 off, %0, %1, %2, 0xEA;\n"      // (w & column mask) | 4 * tid
-            "ld.shared.u16 code, [off];\n"
-            "mov.b32 {wlo, whi}, %0;\n"
-            "mov.b32 {clo, chi}, code;\n"
-            "setp.le.f16 pl, clo, whi;\n"            // code <= k on binary16 patterns; a NaN code goes right
-            "lop3.b32 n, %0, %3, %4, 0xEA;\n"        // (w & child mask) | block base
-            "@!pl add.u32 n, n, 4;\n"
-            "ld.shared.u32 %0, [n];\n"
-            "setp.ge.s32 pq, %0, 0;\n"
-            "@pq bra SLVL;\n"
-            "}\n"
-            : "+r"(w)
-            : "n"(K::kColMask), "r"(tid4), "n"(K::kChildMask), "r"(tb)
-            : "memory");
+        if (!HAS_CAT) {
+          asm volatile(
+              "{\n"
+              ".reg .pred pl, pq;\n"
+              ".reg .b32 off, code, n;\n"
+              ".reg .b16 wlo, whi, clo, chi;\n"
+              "SLVL:\n"
+              "lop3.b32 off, %0, %1, %2, 0xEA;\n"      // (w & column mask) | 4 * tid
+              "ld.shared.u16 code, [off];\n"
+              "mov.b32 {wlo, whi}, %0;\n"
+              "mov.b32 {clo, chi}, code;\n"
+              "setp.le.f16 pl, clo, whi;\n"            // code <= k on binary16 patterns; a NaN code goes right
+              "lop3.b32 n, %0, %3, %4, 0xEA;\n"        // (w & child mask) | block base
+              "@!pl add.u32 n, n, 4;\n"
+              "ld.shared.u32 %0, [n];\n"
+              "setp.ge.s32 pq, %0, 0;\n"
+              "@pq bra SLVL;\n"
+              "}\n"
+              : "+r"(w)
+              : "n"(K::kColMask), "r"(tid4), "n"(K::kChildMask), "r"(tb)
+              : "memory");
+        } else {
+          // entries carry their kind: sign bit = leaf, bit 0 = categorical node.  The numeric loop runs until either shows up
+          // (one LOP3 with a predicate result instead of the sign test), categorical nodes are resolved here, then it re-enters
+          for (;;) {
+            if (!(w & 1u)) {
+              asm volatile(
+                  "{\n"
+                  ".reg .pred pl, pq;\n"
+                  ".reg .b32 off, code, n, tmp;\n"
+                  ".reg .b16 wlo, whi, clo, chi;\n"
+                  "SLVC:\n"
+                  "lop3.b32 off, %0, %1, %2, 0xEA;\n"
+                  "ld.shared.u16 code, [off];\n"
+                  "mov.b32 {wlo, whi}, %0;\n"
+                  "mov.b32 {clo, chi}, code;\n"
+                  "setp.le.f16 pl, clo, whi;\n"
+                  "lop3.b32 n, %0, %3, %4, 0xEA;\n"
+                  "@!pl add.u32 n, n, 4;\n"
+                  "ld.shared.u32 %0, [n];\n"
+                  "and.b32 tmp, %0, 0x80000001;\n"
+                  "setp.eq.u32 pq, tmp, 0;\n"
+                  "@pq bra SLVC;\n"
+                  "}\n"
+                  : "+r"(w)
+                  : "n"(K::kColMask), "r"(tid4), "n"(K::kChildMask), "r"(tb)
+                  : "memory");
+              if ((int)w < 0) break;
+            }
+            // categorical node (LightGBM CategoricalDecision): NaN / negative / beyond the bitset go right
+            const uint32_t code = *reinterpret_cast<const uint16_t *>(smem + (((w & K::kColMask) | tid4) - base));
+            bool left = false;
+            if (code != kBinNaN) {
+              const uint2 ct = *reinterpret_cast<const uint2 *>(smem + ((tb + ((w >> 16) & 0x7FFFu) * 8u) - base));
+              const uint32_t wd = code >> 5;
+              if (wd < ct.y) left = (*reinterpret_cast<const uint32_t *>(smem + ((tb + ct.x + wd * 4u) - base)) >> (code & 31u)) & 1u;
+            }
+            const uint32_t n = ((w & K::kChildMask) | tb) + (left ? 0u : 4u);
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(n));
+            if ((int)w < 0) break;
+          }
+        }
         return *reinterpret_cast<const Real *>(smem + (((w & 0xFFFFu) | tb) - base));
       };
       // two trees per (warp-uniform) LDS.128: {block, root entry} x 2; the leaf values are still added one by one, in tree order
@@ -591,85 +633,92 @@ __global__ void __launch_bounds__(128) gbdt_leaves_kernel(const LParams p) {
 }
 
 // In-order sum of the per-tree leaf values.  The adds are a dependent chain (tree order = the sequential reference's
-// rounding: ~2000 DADDs for BASELINE config #5) but nothing else is, so the CTA is a small producer / consumer machine
-// over groups of kSumTrees trees for its 32 rows:
-//   warps 1..3 (producers)  producer w owns ring buffer w and the groups g = w - 1 (mod 3): it copies the rows' leaf SLOTS
-//                           of the group (2 bytes per row and tree, 16 bytes per cp.async) and the trees' chunk offsets,
-//                           then — with the slots in hand — gathers the VALUES behind them, one 8-byte cp.async per
-//                           (tree, row) out of the packed model (a few hundred KB, L2 resident) into a [tree][lane] tile
-//                           (64 copies per lane in flight, no register limit), and raises the buffer's `full` barrier;
-//   warp 0 (consumer)       waits for `full`, acc += value tree by tree, raises `empty`.
-// Three groups are in flight while one is being added, so the L2 round trips hide behind the adds; a single
-// mega-request slice (a few thousand rows) still spreads over the whole chip, 32 rows per CTA.
-constexpr int kSumTrees = 64;
+// rounding: T dependent DADDs, 8.2 cycles each on B200 — tools/micro/fp64_latency.cu — i.e. 8 us for the 2000 trees of
+// BASELINE config #5) and everything else is arranged so that the chain is all that remains.  The model's small-chunk
+// packing is cut into GROUPS of consecutive chunks (<= 16 KB, <= 64 trees: one contiguous byte range).  A CTA is one
+// producer warp and 1 or 4 consumer warps of 32 rows each, around a ring of kSumRing group buffers:
+//   producer   per group ONE TMA bulk copy of the group's model bytes (leaf values included) plus 16-byte cp.async copies
+//              of the rows' leaf slots (2 bytes per row and tree) and of the trees' offsets inside the group; all of them
+//              complete on the buffer's `full` mbarrier, so the producer never waits for data — only for a free buffer;
+//   consumer   waits for `full`; per tree: slot (LDS.U16) -> value at group + tree offset + 8 * slot (LDS.64) -> acc += value;
+//              raises `empty`.  No per-lane gathers from global memory anywhere (8-byte cp.async gathers cost ~20 wavefronts
+//              an instruction and saturated the L1 pipe at 76 %: profiles/ncu_r2_summary.md).
 constexpr int kSumRing = 3;
-constexpr size_t kSumBufBytes = (size_t)kSumTrees * 32 * sizeof(double) + (size_t)kSumTrees * 32 * sizeof(uint16_t) + kSumTrees * sizeof(uint32_t);
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+struct SumParams {
+  const uint8_t *model;       // small-chunk compact packing
+  const uint16_t *leafslots;  // [n_trees][rows_padded]
+  const uint4 *groups;        // per group {first tree, n trees, byte offset in model, bytes}
+  const uint32_t *group_rel;  // [n_groups][kSumGroupTrees] byte offset of each tree's chunk inside its group
+  double *out;
+  int rows, rows_padded, n_groups;
+  uint32_t group_stride;      // bytes reserved per ring buffer for the model bytes (multiple of 128)
+  float base_score;
+};
+
 template <typename Real>
-__global__ void __launch_bounds__(128) gbdt_sum_kernel(const LParams p, const ScoreSinks sinks) {
-  extern __shared__ __align__(16) uint8_t s_sum_raw[];
-  uint64_t *full = reinterpret_cast<uint64_t *>(s_sum_raw), *empty = full + kSumRing;  // 2 x kSumRing barriers in the first 64 bytes
-  uint8_t *bufs = s_sum_raw + 64;
+__global__ void __launch_bounds__(160) gbdt_sum_kernel(const SumParams p, const ScoreSinks sinks) {
+  extern __shared__ __align__(128) uint8_t s_sum_raw[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(s_sum_raw), *empty = full + kSumRing;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * 32;
-  const int item = row0 + lane;
-  const bool live = item < p.rows;
-  const int n_groups = (p.n_trees + kSumTrees - 1) / kSumTrees;
+  const int C = (blockDim.x >> 5) - 1;  // consumer warps = 32-row slabs of this CTA
+  const int cta_rows = 32 * C;
+  const int row0 = blockIdx.x * cta_rows;
+  // ring buffer b: [model bytes: group_stride][slots: kSumGroupTrees x cta_rows u16][rel: kSumGroupTrees u32]
+  const size_t buf_bytes = (size_t)p.group_stride + (size_t)kSumGroupTrees * cta_rows * 2 + kSumGroupTrees * 4;
+  uint8_t *bufs = s_sum_raw + 128;
   if (threadIdx.x == 0) {
-    for (int k = 0; k < kSumRing; k++) { mbar_init(&full[k], 1); mbar_init(&empty[k], 1); }
+    for (int k = 0; k < kSumRing; k++) { mbar_init(&full[k], 33); mbar_init(&empty[k], C); }
     fence_barrier_init();
   }
   __syncthreads();
-  Real acc = (sizeof(Real) == 4) ? (Real)p.base_score : (Real)0;
-  if (warp > 0) {
-    // ---- producer of ring buffer b
-    const int b = warp - 1;
-    double *vals = reinterpret_cast<double *>(bufs + (size_t)b * kSumBufBytes);
-    uint16_t *slots = reinterpret_cast<uint16_t *>(vals + kSumTrees * 32);
-    uint32_t *toff = reinterpret_cast<uint32_t *>(slots + kSumTrees * 32);
-    for (int g = b, use = 0; g < n_groups; g += kSumRing, use++) {
-      if (use > 0) mbar_wait(&empty[b], (use - 1) & 1);  // the consumer is done with this buffer's previous group
-      const int t0 = g * kSumTrees, nb = min(kSumTrees, p.n_trees - t0);
-      {
-        const uint32_t dst = smem_u32(slots);
-        for (int k = lane; k < nb * 4; k += 32) {  // 16-byte piece k: tree k >> 2, rows (k & 3) * 8 .. + 8 of the CTA's 32
-          const uint16_t *src = p.leafslots + (size_t)(t0 + (k >> 2)) * p.rows_padded + row0 + (k & 3) * 8;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)k * 16u), "l"(src) : "memory");
-        }
-        if (lane * 4 < nb)  // the trees' chunk offsets, 4 per lane (the table is padded to whole groups)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(toff) + (uint32_t)lane * 16u),
-                       "l"(p.tree_off + t0 + lane * 4)
-                       : "memory");
-        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
+  if (warp == 0) {
+    // ---- producer
+    for (int g = 0; g < p.n_groups; g++) {
+      const int b = g % kSumRing, use = g / kSumRing;
+      if (use > 0) mbar_wait(&empty[b], (use - 1) & 1);
+      const uint4 gd = __ldg(p.groups + g);
+      uint8_t *mb = bufs + (size_t)b * buf_bytes;
+      uint16_t *slots = reinterpret_cast<uint16_t *>(mb + p.group_stride);
+      uint32_t *rel = reinterpret_cast<uint32_t *>(slots + (size_t)kSumGroupTrees * cta_rows);
+      if (lane == 0) {
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&full[b], gd.w);
+        tma_bulk_g2s(mb, p.model + gd.z, gd.w, &full[b]);
       }
-      if (live) {
-        const uint32_t dst = smem_u32(vals + lane);
-#pragma unroll 8
-        for (int k = 0; k < nb; k++) {
-          const uint8_t *src = p.model + toff[k] + (uint32_t)slots[k * 32 + lane] * 8u;
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (uint32_t)k * 256u), "l"(src) : "memory");
-        }
+      const int pieces_per_tree = cta_rows / 8;  // 16-byte pieces of 8 rows
+      const uint32_t dst = smem_u32(slots);
+      for (int k = lane; k < (int)gd.y * pieces_per_tree; k += 32) {
+        const int t = k / pieces_per_tree, part = k - t * pieces_per_tree;
+        const uint16_t *src = p.leafslots + (size_t)(gd.x + t) * p.rows_padded + row0 + part * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(t * cta_rows + part * 8) * 2u), "l"(src) : "memory");
       }
-      asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full[b]);
+      if (lane * 4 < (int)gd.y)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(rel) + (uint32_t)lane * 16u),
+                     "l"(p.group_rel + (size_t)g * kSumGroupTrees + lane * 4)
+                     : "memory");
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[b])) : "memory");
     }
   } else {
-    // ---- consumer
-    for (int g = 0; g < n_groups; g++) {
+    // ---- consumer of rows [row0 + 32 (warp - 1), + 32)
+    const int item = row0 + (warp - 1) * 32 + lane;
+    const bool live = item < p.rows;
+    Real acc = (sizeof(Real) == 4) ? (Real)p.base_score : (Real)0;
+    for (int g = 0; g < p.n_groups; g++) {
       const int b = g % kSumRing, use = g / kSumRing;
       mbar_wait(&full[b], use & 1);
+      const int nt = (int)__ldg(&p.groups[g].y);
       if (live) {
-        const int nb = min(kSumTrees, p.n_trees - g * kSumTrees);
-        const double *sv = reinterpret_cast<const double *>(bufs + (size_t)b * kSumBufBytes) + lane;
+        const uint8_t *mb = bufs + (size_t)b * buf_bytes;
+        const uint16_t *sl = reinterpret_cast<const uint16_t *>(mb + p.group_stride) + (warp - 1) * 32 + lane;
+        const uint32_t *rel = reinterpret_cast<const uint32_t *>(mb + p.group_stride + (size_t)kSumGroupTrees * cta_rows * 2);
         // the value slot holds the model's Real in its first bytes (f64, or f32 for XGBoost)
 #pragma unroll 8
-        for (int k = 0; k < nb; k++) acc += *reinterpret_cast<const Real *>(sv + k * 32);
+        for (int k = 0; k < nt; k++) acc += *reinterpret_cast<const Real *>(mb + rel[k] + (uint32_t)sl[(size_t)k * cta_rows] * 8u);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[b]);
@@ -763,11 +812,11 @@ void compact_walk_stats(const BinnedLaunch &L, unsigned long long out[3], cudaSt
   out[0] = h.lane_levels; out[1] = h.warp_levels; out[2] = h.warp_trees;
 }
 
-void launch_gbdt_latency(const BinnedLaunch &L, int n_trees, const uint32_t *d_tree_off, void *d_leafslots, cudaStream_t stream) {
+void launch_gbdt_latency(const BinnedLaunch &L, int n_trees, const SumPlan &sum, void *d_leafslots, cudaStream_t stream) {
   // L.d_model / d_chunks = the small-chunk compact packing; L.d_bins already holds the codes
   if (L.rows <= 0) return;
   LParams p;
-  p.model = L.d_model; p.chunks = L.d_chunks; p.bins = L.d_bins; p.leafslots = (uint16_t *)d_leafslots; p.tree_off = d_tree_off;
+  p.model = L.d_model; p.chunks = L.d_chunks; p.bins = L.d_bins; p.leafslots = (uint16_t *)d_leafslots; p.tree_off = nullptr;
   p.out = L.d_out;
   p.rows = L.rows; p.rows_padded = (L.rows + 127) & ~127; p.n_features = L.tile_cols; p.n_trees = n_trees;
   p.base_score = L.base_score;
@@ -780,16 +829,22 @@ void launch_gbdt_latency(const BinnedLaunch &L, int n_trees, const uint32_t *d_t
   p.chunks_per_cta = (int)std::max<long long>(1, std::min<long long>(16, ((long long)L.n_chunks * n_item_groups) / (148 * 16)));
   const size_t smem = 128 + 2 * (size_t)p.chunk_stride + (size_t)4 * L.tile_cols * 64;
   dim3 grid((unsigned)((L.n_chunks + p.chunks_per_cta - 1) / p.chunks_per_cta), (unsigned)n_item_groups);
-  // the in-order sum: 32 rows per CTA (1 consumer + 3 producer warps), so even a 1 000-row slice spreads over 32 SMs
-  const int sum_warps = 1;
-  const size_t sum_smem = 64 + kSumRing * kSumBufBytes;
-  const int n_warps = (L.rows + 31) / 32;
-  auto go = [&](auto leaves, auto sum) {
+  // the in-order sum: 32 rows per CTA while that keeps the chip busy (a mega-request slice of ~1 000 rows spreads over 32+
+  // SMs), 128 rows per CTA for larger batches so that the model bytes are staged once per four slabs
+  SumParams sp;
+  sp.model = L.d_model; sp.leafslots = (const uint16_t *)d_leafslots; sp.groups = sum.d_groups; sp.group_rel = sum.d_group_rel;
+  sp.out = L.d_out; sp.rows = L.rows; sp.rows_padded = p.rows_padded; sp.n_groups = sum.n_groups;
+  sp.group_stride = (sum.max_group_bytes + 127u) & ~127u;
+  sp.base_score = L.base_score;
+  const int consumers = L.rows <= 148 * 32 ? 1 : 4;
+  const int cta_rows = 32 * consumers;
+  const size_t sum_smem = 128 + kSumRing * ((size_t)sp.group_stride + (size_t)kSumGroupTrees * cta_rows * 2 + kSumGroupTrees * 4);
+  auto go = [&](auto leaves, auto sumk) {
     MR_CUDA_CHECK(cudaFuncSetAttribute(leaves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     { ProfScope _ps("gbdt_leaves_kernel", stream); leaves<<<grid, 128, smem, stream>>>(p); }
     MR_CUDA_CHECK(cudaGetLastError());
-    MR_CUDA_CHECK(cudaFuncSetAttribute(sum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sum_smem));
-    { ProfScope _ps("gbdt_sum_kernel", stream); sum<<<(n_warps + sum_warps - 1) / sum_warps, 128, sum_smem, stream>>>(p, L.sinks); }
+    MR_CUDA_CHECK(cudaFuncSetAttribute(sumk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sum_smem));
+    { ProfScope _ps("gbdt_sum_kernel", stream); sumk<<<(L.rows + cta_rows - 1) / cta_rows, 32 * (consumers + 1), sum_smem, stream>>>(sp, L.sinks); }
     MR_CUDA_CHECK(cudaGetLastError());
     g_kernel_launches += 2;
   };
@@ -844,10 +899,10 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
       MR_CUDA_CHECK(cudaGetLastError());
       g_kernel_launches++;
     };
-    const bool f32 = L.kind == MR_BOOSTER_XGBOOST;
-    if (T == 512) { if (f32) go(gbdt_score_slim_kernel<float, 512>); else go(gbdt_score_slim_kernel<double, 512>); }
-    else if (T == 256) { if (f32) go(gbdt_score_slim_kernel<float, 256>); else go(gbdt_score_slim_kernel<double, 256>); }
-    else { if (f32) go(gbdt_score_slim_kernel<float, 128>); else go(gbdt_score_slim_kernel<double, 128>); }
+    const bool f32 = L.kind == MR_BOOSTER_XGBOOST;  // (XGBoost categorical splits are refused at load time)
+    if (T == 512) { if (f32) go(gbdt_score_slim_kernel<float, 512, false>); else if (L.has_cat) go(gbdt_score_slim_kernel<double, 512, true>); else go(gbdt_score_slim_kernel<double, 512, false>); }
+    else if (T == 256) { if (f32) go(gbdt_score_slim_kernel<float, 256, false>); else if (L.has_cat) go(gbdt_score_slim_kernel<double, 256, true>); else go(gbdt_score_slim_kernel<double, 256, false>); }
+    else { if (f32) go(gbdt_score_slim_kernel<float, 128, false>); else if (L.has_cat) go(gbdt_score_slim_kernel<double, 128, true>); else go(gbdt_score_slim_kernel<double, 128, false>); }
     return;
   }
   // ---- pass 2: traversal

@@ -79,9 +79,18 @@ inline size_t binned_scratch_bytes(int rows, int tile_cols) {
 }
 void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream);
 // Low-latency path for small batches: the leaf every row reaches in every tree, spread over (chunk x item-group)
-// CTAs, then an in-order per-item sum of the values behind them.  d_leafslots: latency_scratch_bytes() of scratch;
-// d_tree_off: per tree, the byte offset of its chunk in L.d_model.
-void launch_gbdt_latency(const BinnedLaunch &L, int n_trees, const uint32_t *d_tree_off, void *d_leafslots, cudaStream_t stream);
+// CTAs, then an in-order per-item sum of the values behind them.  d_leafslots: latency_scratch_bytes() of scratch.
+// SumPlan: the small-chunk packing cut into groups of consecutive chunks for the sum kernel's staging
+// (groups[g] = {first tree, n trees, byte offset, bytes}; group_rel[g * kSumGroupTrees + k] = offset of tree k's chunk in its group).
+constexpr int kSumGroupTrees = 64;
+constexpr uint32_t kSumGroupBytes = 16 * 1024;
+struct SumPlan {
+  const uint4 *d_groups = nullptr;
+  const uint32_t *d_group_rel = nullptr;
+  int n_groups = 0;
+  uint32_t max_group_bytes = 0;
+};
+void launch_gbdt_latency(const BinnedLaunch &L, int n_trees, const SumPlan &sum, void *d_leafslots, cudaStream_t stream);
 // Level steps the lock-step scorer executes on the codes in L.d_bins (compact layout only): out = {sum of the lanes'
 // path lengths, sum over (warp, tree) of the deepest lane's path, number of (warp, tree) pairs}.  Synchronous.
 void compact_walk_stats(const BinnedLaunch &L, unsigned long long out[3], cudaStream_t stream);

@@ -761,14 +761,17 @@ BinnedModel pack_compact(const HostModel &m, const BinnedModel &bn, size_t chunk
 
 SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budget) {
   SlimModel S;
-  if (!C.ok || m.has_cat || m.trees.empty()) return S;
+  if (!C.ok || m.trees.empty()) return S;
   const int F = m.n_features;
   for (int f = 0; f < F; f++)
     if (C.thr_off[f + 1] - C.thr_off[f] > 0x7C00u) return S;  // codes must stay below the binary16 NaN patterns
   S.n_pairs = (C.tile_cols + 1) / 2;
   size_t max_block = 16;
-  auto block_bytes = [](const HostTree &t) {
-    const size_t need = (2 + 2 * std::max<size_t>(t.feat.size(), 1)) * 4 + t.leaf.size() * 8;  // entries (root pair + one pair per node) + leaf slots
+  auto n_cat_nodes = [](const HostTree &t) { size_t c = 0; for (auto fl : t.flags) c += (fl & NF_CATEGORICAL) != 0; return c; };
+  auto block_bytes = [&](const HostTree &t) {
+    // entries (root pair + one pair per node) + leaf slots + per categorical node {bitset byte offset, n words} + the bitsets
+    const size_t need = (2 + 2 * std::max<size_t>(t.feat.size(), 1)) * 4 + t.leaf.size() * 8 + n_cat_nodes(t) * 8 +
+                        ((t.cat_words.size() * 4 + 7) & ~size_t(7));
     size_t b = 16;
     while (b < need) b <<= 1;
     return b;
@@ -836,15 +839,28 @@ SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budge
         e[0] = (1u << shift) | (1u * 8u);  // k = 0 on tile column 0, child pair 1
         e[2] = e[3] = leaf_entry(~0);
       }
+      const size_t ctab_base = leaf_base + t.leaf.size() * 8, cw_base = ctab_base + n_cat_nodes(t) * 8;
+      uint32_t *ctab = (uint32_t *)(c + off + ctab_base);
+      size_t ci = 0;
       for (size_t h = 0; h < order.size(); h++) {
         const int q = order[h];
         const uint32_t pair = next_pair++;
         const int f = t.feat[q];
-        const double *tb = C.thr.data() + C.thr_off[f], *te = C.thr.data() + C.thr_off[f + 1];
-        const uint32_t kk = (uint32_t)(std::lower_bound(tb, te, t.thr[q]) - tb);
-        const uint32_t dup = C.meta[f].flags >> 16;
-        const uint32_t col = ((t.flags[q] & NF_NAN_LEFT) && dup != kMetaNoDup) ? dup : (uint32_t)f;
-        e[entry_of_node[q]] = (kk << 16) | (((col >> 1) + 1u) << shift) | ((col & 1u) << 1) | (pair * 8u);
+        if (t.flags[q] & NF_CATEGORICAL) {
+          // bit 0 = categorical: the level loop leaves on it (the same test that finds a leaf); the k field is the 8-byte
+          // index, inside the block, of the node's {bitset byte offset, n words}
+          ctab[2 * ci] = (uint32_t)(cw_base + (size_t)t.cat_begin[q] * 4);
+          ctab[2 * ci + 1] = (uint32_t)t.cat_n[q];
+          e[entry_of_node[q]] = (uint32_t)(((ctab_base + ci * 8) / 8) << 16) | ((((uint32_t)f >> 1) + 1u) << shift) |
+                                (((uint32_t)f & 1u) << 1) | (pair * 8u) | 1u;
+          ci++;
+        } else {
+          const double *tb = C.thr.data() + C.thr_off[f], *te = C.thr.data() + C.thr_off[f + 1];
+          const uint32_t kk = (uint32_t)(std::lower_bound(tb, te, t.thr[q]) - tb);
+          const uint32_t dup = C.meta[f].flags >> 16;
+          const uint32_t col = ((t.flags[q] & NF_NAN_LEFT) && dup != kMetaNoDup) ? dup : (uint32_t)f;
+          e[entry_of_node[q]] = (kk << 16) | (((col >> 1) + 1u) << shift) | ((col & 1u) << 1) | (pair * 8u);
+        }
         const int ch[2] = {t.left[q], t.right[q]};
         for (int sd = 0; sd < 2; sd++) {
           if (ch[sd] < 0) e[2 * pair + sd] = leaf_entry(ch[sd]);
@@ -852,6 +868,7 @@ SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budge
         }
       }
       roots[2 * k + 1] = e[0];
+      if (!t.cat_words.empty()) memcpy(c + off + cw_base, t.cat_words.data(), t.cat_words.size() * 4);
       uint8_t *lv = c + off + leaf_base;
       for (size_t q = 0; q < t.leaf.size(); q++) {
         if (f32) { const float v = (float)t.leaf[q]; memcpy(lv + q * 8, &v, 4); }

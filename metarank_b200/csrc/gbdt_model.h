@@ -156,7 +156,9 @@ BinnedModel pack_compact(const HostModel &m, const BinnedModel &binned, size_t c
 //   chunk: +0 u32 n_trees, pad; +16 per tree {u32 block offset from the chunk start, u32 copy of its root entry} (chunk
 //          buffers are 2 KB aligned in shared memory and every block is aligned to its own size; a single-leaf tree is a
 //          dummy split onto its leaf, so every walk starts at an internal entry that arrives with the table); then the blocks
-// ok == false (categorical splits, > 31 744 thresholds on a column, too many tile columns or too large a tree for any
+//   categorical entry: bit 0 set (the level loop leaves on it with the test that finds a leaf), bits 30..16 = 8-byte index
+//                   inside the block of the node's {bitset byte offset, n words}; column and child fields as above
+// ok == false (> 31 744 thresholds on a column, too many tile columns, or a tree — with its bitsets — too large for any
 // tile_T): the 8-byte compact kernel scores the model.  The tile mapping (BinMeta, tile_cols) is the compact model's.
 struct SlimModel {
   bool ok = false;

@@ -125,7 +125,9 @@ struct mr_model {
   uint8_t *d_is_cat = nullptr;
   BinMeta *d_meta = nullptr, *d_cmeta = nullptr;  // identity tile mapping (binned/threaded) / compact + lat mapping
   uint32_t *d_bucket_range = nullptr;
-  uint32_t *d_ltree_off = nullptr;  // per tree: byte offset of its chunk in d_lmodel (latency path)
+  uint32_t *d_ltree_off = nullptr;  // sum-kernel staging plan of the latency path: group_rel table
+  uint4 *d_lgroups = nullptr;
+  SumPlan sum_plan;
   std::atomic<bool> closed{false};
   std::atomic<int> inflight{0};
   std::mutex mu;  // guards repacking / device buffers
@@ -151,10 +153,10 @@ struct mr_model {
   void free_binned() {
     for (void *p : {(void *)d_bmodel, (void *)d_bchunks, (void *)d_thr_off, (void *)d_thr, (void *)d_is_cat,
                     (void *)d_cmodel, (void *)d_cchunks, (void *)d_lmodel,
-                    (void *)d_lchunks, (void *)d_ltree_off, (void *)d_smodel, (void *)d_schunks, (void *)d_meta, (void *)d_cmeta, (void *)d_bucket_range})
+                    (void *)d_lchunks, (void *)d_ltree_off, (void *)d_lgroups, (void *)d_smodel, (void *)d_schunks, (void *)d_meta, (void *)d_cmeta, (void *)d_bucket_range})
       if (p) cudaFree(p);
     d_bmodel = nullptr; d_bchunks = nullptr; d_thr_off = nullptr; d_thr = nullptr; d_is_cat = nullptr;
-    d_cmodel = nullptr; d_cchunks = nullptr; d_lmodel = nullptr; d_lchunks = nullptr; d_ltree_off = nullptr; d_smodel = nullptr; d_schunks = nullptr; d_meta = nullptr; d_cmeta = nullptr; d_bucket_range = nullptr;
+    d_cmodel = nullptr; d_cchunks = nullptr; d_lmodel = nullptr; d_lchunks = nullptr; d_ltree_off = nullptr; d_lgroups = nullptr; d_smodel = nullptr; d_schunks = nullptr; d_meta = nullptr; d_cmeta = nullptr; d_bucket_range = nullptr;
   }
   // identity of the current code mapping (thresholds + tile columns): consumers that cache codes key on it
   uint64_t code_gen = 0;
@@ -198,15 +200,39 @@ struct mr_model {
           d_schunks = to_device(slim.packed.chunks);
         }
       }
+      sum_plan = SumPlan{};
       lat = pack_compact(host, binned, 4 * 1024);
       if (lat.ok && !compact.ok) lat.ok = false;  // same tile mapping as `compact` (d_cmeta) by construction
       if (lat.ok) {
         d_lmodel = to_device(lat.packed.bytes);
         d_lchunks = to_device(lat.packed.chunks);
-        std::vector<uint32_t> toff(((host.trees.size() + 63) / 64) * 64 + 4, 0);  // padded: the sum kernel copies it 16 bytes at a time
-        for (auto &cd : lat.packed.chunks)
-          for (uint32_t t = 0; t < cd.n_trees; t++) toff[cd.first_tree + t] = cd.byte_off;
-        d_ltree_off = to_device(toff);
+        // groups of consecutive chunks (one contiguous byte range each) for the in-order sum's staging
+        std::vector<uint4> groups;
+        std::vector<uint32_t> rel;
+        const auto &ch = lat.packed.chunks;
+        for (size_t c = 0; c < ch.size();) {
+          size_t e = c + 1;
+          uint32_t bytes = ch[c].bytes, trees = ch[c].n_trees;
+          while (e < ch.size() && bytes + ch[e].bytes <= kSumGroupBytes && trees + ch[e].n_trees <= (uint32_t)kSumGroupTrees &&
+                 ch[e].byte_off == ch[e - 1].byte_off + ch[e - 1].bytes) {
+            bytes += ch[e].bytes; trees += ch[e].n_trees; e++;
+          }
+          if (trees > (uint32_t)kSumGroupTrees) { lat.ok = false; break; }  // a chunk of > 64 single-leaf trees: not worth a path
+          groups.push_back(make_uint4(ch[c].first_tree, trees, ch[c].byte_off, bytes));
+          rel.resize(groups.size() * kSumGroupTrees, 0);
+          uint32_t k = 0;
+          for (size_t q = c; q < e; q++)
+            for (uint32_t t = 0; t < ch[q].n_trees; t++) rel[(groups.size() - 1) * kSumGroupTrees + k++] = ch[q].byte_off - ch[c].byte_off;
+          sum_plan.max_group_bytes = std::max(sum_plan.max_group_bytes, bytes);
+          c = e;
+        }
+        if (lat.ok) {
+          d_lgroups = to_device(groups);
+          d_ltree_off = to_device(rel);
+          sum_plan.d_groups = d_lgroups;
+          sum_plan.d_group_rel = d_ltree_off;
+          sum_plan.n_groups = (int)groups.size();
+        }
       }
     }
   }
@@ -262,7 +288,8 @@ struct mr_model {
   }
   bool use_latency(int rows) const {
     return lat.ok && rows <= latency_max_rows() && opt_variant < 0 && opt_threads == 0 &&
-           use_compact() && 128 + 2 * ((size_t)lat.packed.max_chunk_bytes + 128) + (size_t)4 * compact.tile_cols * 64 <= 200 * 1024;
+           use_compact() && 128 + 2 * ((size_t)lat.packed.max_chunk_bytes + 128) + (size_t)4 * compact.tile_cols * 64 <= 200 * 1024 &&
+           128 + 3 * ((size_t)sum_plan.max_group_bytes + 128 + (size_t)kSumGroupTrees * 128 * 2 + kSumGroupTrees * 4) <= 220 * 1024;
   }
   // true: score_codes() can store to peer sinks from inside the scoring kernel
   bool fuses_sinks(int rows) const { return use_latency(rows) || (use_binned() && use_compact()); }
@@ -287,11 +314,11 @@ struct mr_model {
       B.n_chunks = (int)lat.packed.chunks.size();
       B.max_chunk_bytes = lat.packed.max_chunk_bytes;
       if (d_leaf_scratch) {
-        launch_gbdt_latency(B, (int)host.trees.size(), d_ltree_off, d_leaf_scratch, stream);
+        launch_gbdt_latency(B, (int)host.trees.size(), sum_plan, d_leaf_scratch, stream);
       } else {
         void *lv = nullptr;
         MR_CUDA_CHECK(cudaMallocAsync(&lv, latency_scratch_bytes(rows, (int)host.trees.size()), stream));
-        launch_gbdt_latency(B, (int)host.trees.size(), d_ltree_off, lv, stream);
+        launch_gbdt_latency(B, (int)host.trees.size(), sum_plan, lv, stream);
         MR_CUDA_CHECK(cudaFreeAsync(lv, stream));
       }
       return;

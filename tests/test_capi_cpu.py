@@ -145,7 +145,7 @@ def test_slim_level_loop_sass_instruction_budget():
         pytest.skip("cuobjdump or the object file is not available")
     sass = subprocess.run([tool, "-sass", obj], capture_output=True, text=True).stdout
     for T in (512, 256, 128):
-        m = re.search(r"Function : \S*slim_kernelIdLi%dEE\S*\n(.*?)(?:Function :|\Z)" % T, sass, re.S)
+        m = re.search(r"Function : \S*slim_kernelIdLi%dELb0EE\S*\n(.*?)(?:Function :|\Z)" % T, sass, re.S)
         assert m, f"slim kernel <double, {T}> not found"
         ins = [re.sub(r"/\*.*?\*/", "", ln).strip() for ln in m.group(1).split("\n") if re.search(r"/\*[0-9a-f]{4}\*/", ln)]
         ins = [i for i in ins if i]

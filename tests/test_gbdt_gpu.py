@@ -282,8 +282,8 @@ def test_removed_variants_are_rejected(ctx):
 def test_slim_scorer_layouts_and_fallbacks(ctx):
     """The 4-byte-node scorer (variant 5 / auto on large batches): every CTA-tile size it has (512 items up to 62 tile
     columns, 256 up to 126, 128 up to 254), batches around the tile boundaries, XGBoost f32, single-leaf trees, NaN in
-    both directions on one feature (duplicated tile columns), models it must refuse (categorical splits -> the 8-byte
-    compact kernel) — all bit-identical to the oracle, like every other scorer."""
+    both directions on one feature (duplicated tile columns), categorical splits, models it must refuse (trees or bitsets
+    too large for a block -> the 8-byte compact kernel) — all bit-identical to the oracle, like every other scorer."""
     import metarank_b200 as mb
 
     for n_feat, trees in ((30, 120), (70, 60), (120, 40), (200, 20), (300, 12)):
@@ -300,5 +300,14 @@ def test_slim_scorer_layouts_and_fallbacks(ctx):
     _check(ctx, 0, deep, synth.feature_matrix(3000, 12, seed=4), variant=5)
     huge = synth.lightgbm_model_text(6, 12, num_leaves=400, max_depth=0, seed=79)   # no slim form: silently the compact kernel
     _check(ctx, 0, huge, synth.feature_matrix(3000, 12, seed=5), variant=5)
-    cat = synth.lightgbm_model_text(50, 10, seed=80, cat_features={3: 20})           # categorical: no slim form either
-    _check(ctx, 0, cat, synth.feature_matrix(3000, 10, seed=6), variant=5)
+    # categorical splits: entries flagged in bit 0 leave the level loop and are resolved against the block's bitsets
+    for cats in ({3: 20}, {0: 7, 5: 300, 9: 33}):
+        cat = synth.lightgbm_model_text(50, 10, seed=80, cat_features=cats, stump_every=11)
+        Xc = synth.feature_matrix(6000, 10, seed=6)
+        for f, n in cats.items():  # integer category values, some NaN / negative / beyond the bitset
+            Xc[:, f] = np.random.Generator(np.random.PCG64(f)).integers(-2, n + 40, 6000)
+            Xc[::17, f] = np.nan
+        _check(ctx, 0, cat, Xc, variant=5)
+        _check(ctx, 0, cat, Xc, variant=4)
+    wide_cat = synth.lightgbm_model_text(20, 10, seed=81, cat_features={2: 40000})   # 5 KB bitsets: no slim form -> compact kernel
+    _check(ctx, 0, wide_cat, synth.feature_matrix(3000, 10, seed=7), variant=5)
