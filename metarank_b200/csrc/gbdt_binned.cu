@@ -621,11 +621,11 @@ __global__ void __launch_bounds__(128) gbdt_leaves_kernel(const LParams p) {
       uint16_t *dst = p.leafslots + (size_t)first_tree * p.rows_padded + item;
       // the compact scorer's hand-scheduled level loop (10 SASS instructions; nvcc's own schedule of the same walk is 18)
       if (p.has_cat) {
-        for (int t = 0; t < ntree; t++)
-          dst[(size_t)t * p.rows_padded] = (uint16_t)((walk_tree<true, false>(roots[t], cb, cb_addr, xwarp, xwarp_addr, lane2) - 1u) >> 3);
+        for (int t = 0; t < ntree; t++, dst += p.rows_padded)
+          *dst = (uint16_t)((walk_tree<true, false>(roots[t], cb, cb_addr, xwarp, xwarp_addr, lane2) - 1u) >> 3);
       } else {
-        for (int t = 0; t < ntree; t++)
-          dst[(size_t)t * p.rows_padded] = (uint16_t)((walk_tree<false, false>(roots[t], cb, cb_addr, xwarp, xwarp_addr, lane2) - 1u) >> 3);
+        for (int t = 0; t < ntree; t++, dst += p.rows_padded)
+          *dst = (uint16_t)((walk_tree<false, false>(roots[t], cb, cb_addr, xwarp, xwarp_addr, lane2) - 1u) >> 3);
       }
     }
     __syncthreads();  // this buffer is refilled two chunks from now
@@ -716,9 +716,21 @@ __global__ void __launch_bounds__(160) gbdt_sum_kernel(const SumParams p, const 
         const uint8_t *mb = bufs + (size_t)b * buf_bytes;
         const uint16_t *sl = reinterpret_cast<const uint16_t *>(mb + p.group_stride) + (warp - 1) * 32 + lane;
         const uint32_t *rel = reinterpret_cast<const uint32_t *>(mb + p.group_stride + (size_t)kSumGroupTrees * cta_rows * 2);
-        // the value slot holds the model's Real in its first bytes (f64, or f32 for XGBoost)
-#pragma unroll 8
-        for (int k = 0; k < nt; k++) acc += *reinterpret_cast<const Real *>(mb + rel[k] + (uint32_t)sl[(size_t)k * cta_rows] * 8u);
+        // Two dependent shared-memory reads per tree (slot, then the value behind it) — batches of 16 trees so that their
+        // latencies overlap: 16 slots, then 16 values, then the 16 adds in tree order.  The value slot holds the model's
+        // Real in its first bytes (f64, or f32 for XGBoost).
+        int k0 = 0;
+        for (; k0 + 16 <= nt; k0 += 16) {
+          uint32_t off[16];
+          Real v[16];
+#pragma unroll
+          for (int j = 0; j < 16; j++) off[j] = rel[k0 + j] + (uint32_t)sl[(size_t)(k0 + j) * cta_rows] * 8u;
+#pragma unroll
+          for (int j = 0; j < 16; j++) v[j] = *reinterpret_cast<const Real *>(mb + off[j]);
+#pragma unroll
+          for (int j = 0; j < 16; j++) acc += v[j];
+        }
+        for (; k0 < nt; k0++) acc += *reinterpret_cast<const Real *>(mb + rel[k0] + (uint32_t)sl[(size_t)k0 * cta_rows] * 8u);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[b]);

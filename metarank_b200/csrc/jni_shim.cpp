@@ -150,5 +150,51 @@ JNIEXPORT void JNICALL Java_ai_metarank_b200_Native_rank(JNIEnv *env, jclass, jl
                             (double *)addr(outFeatures)));
 }
 
+// ---- one mega-request across the GPUs of a box (mr_group_*)
+JNIEXPORT jlong JNICALL Java_ai_metarank_b200_Native_groupCreate(JNIEnv *env, jclass, jlong ctx, jint rank, jint world, jint maxItems) {
+  mr_group *g = nullptr;
+  throw_status(env, mr_group_create((mr_ctx *)ctx, rank, world, maxItems, &g));
+  return (jlong)g;
+}
+
+// members(i) = the group member of rank i, all created in this process
+JNIEXPORT void JNICALL Java_ai_metarank_b200_Native_groupConnectLocal(JNIEnv *env, jclass, jlongArray members) {
+  const jsize n = env->GetArrayLength(members);
+  jlong *p = env->GetLongArrayElements(members, nullptr);
+  mr_group *gs[8] = {};
+  for (jsize k = 0; k < n && k < 8; k++) gs[k] = (mr_group *)p[k];
+  env->ReleaseLongArrayElements(members, p, JNI_ABORT);
+  throw_status(env, n > 8 ? MR_ERR_INVALID_ARG : mr_group_connect_local(gs, n));
+}
+
+// Collective: every member calls it with the same request, concurrently (one blocking call per member).  Direct buffers;
+// every member receives the full scores and order.
+JNIEXPORT void JNICALL Java_ai_metarank_b200_Native_groupRank(JNIEnv *env, jclass, jlong group, jlong state, jlong model,
+                                                              jint nItems, jobject itemIds, jlong user, jlong session,
+                                                              jobject reqF64, jobject reqU64, jobject reqVec,
+                                                              jobject reqVecPresent, jobject itemF64, jobject outScores,
+                                                              jobject outOrder) {
+  auto addr = [&](jobject b) { return b ? env->GetDirectBufferAddress(b) : nullptr; };
+  int32_t offs[2] = {0, nItems};
+  uint64_t u = (uint64_t)user, se = (uint64_t)session;
+  mr_rank_batch b{};
+  b.n_requests = 1;
+  b.item_offsets = offs;
+  b.item_ids = (const uint64_t *)addr(itemIds);
+  b.user_ids = &u;
+  b.session_ids = &se;
+  b.req_f64 = (const double *)addr(reqF64);
+  b.req_u64 = (const uint64_t *)addr(reqU64);
+  b.req_vec = (const float *)addr(reqVec);
+  b.req_vec_present = (const uint8_t *)addr(reqVecPresent);
+  b.item_f64 = (const double *)addr(itemF64);
+  throw_status(env, mr_group_rank((mr_group *)group, (mr_state *)state, (mr_model *)model, &b, (double *)addr(outScores),
+                                  (int32_t *)addr(outOrder)));
+}
+
+JNIEXPORT void JNICALL Java_ai_metarank_b200_Native_groupFree(JNIEnv *env, jclass, jlong group) {
+  throw_status(env, mr_group_free((mr_group *)group));
+}
+
 }  // extern "C"
 #endif  // WITH_JNI

@@ -25,7 +25,7 @@ typedef jint jsize;
 #define JNICALL
 
 struct _jobject {
-  int kind;        /* 0 class, 1 byte[], 2 double[], 3 direct buffer */
+  int kind;        /* 0 class, 1 byte[], 2 double[], 3 direct buffer, 4 long[] */
   size_t len;      /* elements (arrays) / bytes (buffers) */
   void *data;
   std::string name; /* class name */
@@ -35,6 +35,7 @@ typedef jobject jclass;
 typedef jobject jarray;
 typedef jobject jbyteArray;
 typedef jobject jdoubleArray;
+typedef jobject jlongArray;
 
 struct JNIEnv {
   /* what the test inspects */
@@ -75,6 +76,19 @@ struct JNIEnv {
   }
   void ReleaseDoubleArrayElements(jdoubleArray a, jdouble *p, jint mode) {
     if (mode != JNI_ABORT) memcpy(a->data, p, a->len * sizeof(double));
+    free(p);
+    elements_out--;
+  }
+  jlongArray NewLongArray(jsize n) { return new _jobject{4, (size_t)n, calloc((size_t)n + 1, sizeof(jlong)), ""}; }
+  jlong *GetLongArrayElements(jlongArray a, jboolean *is_copy) {
+    if (is_copy) *is_copy = JNI_TRUE;
+    elements_out++;
+    jlong *p = (jlong *)malloc((a->len + 1) * sizeof(jlong));
+    memcpy(p, a->data, a->len * sizeof(jlong));
+    return p;
+  }
+  void ReleaseLongArrayElements(jlongArray a, jlong *p, jint mode) {
+    if (mode != JNI_ABORT) memcpy(a->data, p, a->len * sizeof(jlong));
     free(p);
     elements_out--;
   }
