@@ -632,22 +632,11 @@ __global__ void __launch_bounds__(256) prepass_kernel(RankArgs a) {
 }
 
 // number of occurrences of `tag` in histogram (r,h)
-// The sorted tag multisets of ONE request staged in shared memory (assemble_kernel: a CTA's 128 items almost always belong
-// to one request): every interacted_with / diversity column does a binary search per tag of the item, ~10^2 dependent
-// reads per item that are L2 round trips from global memory and 30-cycle LDS from here.
-constexpr uint32_t kHistStageCap = 3072;  // u64 entries (24 KB)
-struct HistStage {
-  int r = -1;               // request whose histograms are staged (-1: none)
-  const uint2 *desc = nullptr;     // [n_hist] {offset into pool, length | unsorted << 31} — offsets into `pool` below
-  const uint64_t *pool = nullptr;
-};
-
-__device__ __forceinline__ uint32_t hist_count(const RankArgs &a, const HistStage &hs, int r, int h, uint64_t tag) {
-  const bool staged = r == hs.r;
-  const uint2 hd = staged ? hs.desc[h] : a.hist_desc[(size_t)r * a.n_hist + h];
+__device__ __forceinline__ uint32_t hist_count(const RankArgs &a, int r, int h, uint64_t tag) {
+  const uint2 hd = a.hist_desc[(size_t)r * a.n_hist + h];
   const uint32_t n = hd.y & 0x7FFFFFFFu;
   if (n == 0) return 0;
-  const uint64_t *p = (staged ? hs.pool : a.hist_pool) + hd.x;
+  const uint64_t *p = a.hist_pool + hd.x;
   if (hd.y & 0x80000000u) {
     uint32_t c = 0;
     for (uint32_t k = 0; k < n; k++) c += p[k] == tag;
@@ -878,28 +867,6 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
     for (int k = threadIdx.x; k < n_words; k += blockDim.x) dst[k] = __ldg(src + k);
     bin.meta = reinterpret_cast<const BinMeta *>(s_meta_raw);
   }
-  // the tag multisets of the CTA's first request (see HistStage)
-  HistStage hstage;
-  if (a.n_hist > 0 && a.hist_stage_off) {
-    uint2 *s_hd = reinterpret_cast<uint2 *>(s_plan_raw + a.hist_stage_off);
-    uint64_t *s_hp = reinterpret_cast<uint64_t *>(s_hd + a.n_hist);
-    const int r0 = a.item_req[min(blockIdx.x * blockDim.x, (unsigned)a.total_items - 1u)];
-    uint32_t total = 0;
-    for (int h = 0; h < a.n_hist; h++) total += a.hist_desc[(size_t)r0 * a.n_hist + h].y & 0x7FFFFFFFu;  // CTA-uniform
-    if (total <= kHistStageCap) {
-      uint32_t at = 0;
-      for (int h = 0; h < a.n_hist; h++) {
-        const uint2 hd = a.hist_desc[(size_t)r0 * a.n_hist + h];
-        const uint32_t n = hd.y & 0x7FFFFFFFu;
-        for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) s_hp[at + k] = a.hist_pool[hd.x + k];
-        if (threadIdx.x == 0) s_hd[h] = make_uint2(at, hd.y);
-        at += n;
-      }
-      hstage.r = r0;
-      hstage.desc = s_hd;
-      hstage.pool = s_hp;
-    }
-  }
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.total_items) return;
@@ -1051,7 +1018,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
         if (irow && present(irow, d.b[0])) {
           const uint64_t desc = irow[d.w[0]];
           const uint32_t off = (uint32_t)desc, n = (uint32_t)(desc >> 32);
-          for (uint32_t k = 0; k < n; k++) cnt = __dadd_rn(cnt, (double)hist_count(a, hstage, r, d.aux0, IT.pool[off + k]));
+          for (uint32_t k = 0; k < n; k++) cnt = __dadd_rn(cnt, (double)hist_count(a, r, d.aux0, IT.pool[off + k]));
         }
         out[d.col] = cnt;
         break;
@@ -1143,7 +1110,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(RankArgs a) {
             const uint64_t desc = irow[d.w[0] + 1];
             const uint32_t off = (uint32_t)desc, n = (uint32_t)(desc >> 32);
             double s = 0.0;
-            for (uint32_t k = 0; k < n; k++) s = __dadd_rn(s, (double)hist_count(a, hstage, r, d.aux1, IT.pool[off + k]));
+            for (uint32_t k = 0; k < n; k++) s = __dadd_rn(s, (double)hist_count(a, r, d.aux1, IT.pool[off + k]));
             v = __ddiv_rn(s, agg[2]);
           } else v = kNaN;
         }
@@ -1427,16 +1394,7 @@ void launch_assemble(const RankArgs &a, const Schema &schema, cudaStream_t strea
       else go(row_gather_kernel<false, true, false>);
     }
     if (any_generic) {
-      size_t asm_smem = plan_bytes + (b.stage_meta ? meta_bytes : 0);
-      b.hist_stage_off = 0;
-      if (a.n_hist > 0) {
-        asm_smem = (asm_smem + 15) & ~size_t(15);
-        b.hist_stage_off = (int)asm_smem;
-        asm_smem += (size_t)a.n_hist * sizeof(uint2) + (size_t)kHistStageCap * 8;
-        if (asm_smem > 48 * 1024)
-          MR_CUDA_CHECK(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asm_smem));
-      }
-      { ProfScope _ps("assemble_kernel", stream); assemble_kernel<<<(a.total_items + 127) / 128, 128, asm_smem, stream>>>(b); }
+      { ProfScope _ps("assemble_kernel", stream); assemble_kernel<<<(a.total_items + 127) / 128, 128, plan_bytes + (b.stage_meta ? meta_bytes : 0), stream>>>(b); }
       MR_CUDA_CHECK(cudaGetLastError());
       g_kernel_launches++;
     }

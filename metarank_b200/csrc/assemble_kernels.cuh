@@ -46,7 +46,6 @@ struct RankArgs {
   uint16_t *codes;        // optional: u16 rank codes [group of 32 items][column][lane] for the binned scorer
   BinParams bin;          // thresholds of the model the codes are for (valid when codes != null)
   int stage_meta;         // set by launch_assemble: bucket-index headers staged in shared memory
-  int hist_stage_off;     // set by launch_assemble: byte offset of assemble_kernel's staged tag multisets in its shared memory (0: none)
   const FastCol *fast_cols;  // device copy of Schema::fast_cols (row_gather_kernel)
   int n_fast;
   // per-model code rows of the item table (rank_api.cu CodeCache): row r + 1 holds item row r's codes for

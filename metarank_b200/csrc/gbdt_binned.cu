@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(160) gbdt_sum_kernel(const SumParams p, const 
     // ---- producer
     for (int g = 0; g < p.n_groups; g++) {
       const int b = g % kSumRing, use = g / kSumRing;
-      if (use > 0) mbar_wait(&empty[b], (use - 1) & 1);
+      if (use > 0) mbar_wait_spin(&empty[b], (use - 1) & 1);
       const uint4 gd = __ldg(p.groups + g);
       uint8_t *mb = bufs + (size_t)b * buf_bytes;
       uint16_t *slots = reinterpret_cast<uint16_t *>(mb + p.group_stride);
@@ -690,12 +690,14 @@ __global__ void __launch_bounds__(160) gbdt_sum_kernel(const SumParams p, const 
         mbar_arrive_expect_tx(&full[b], gd.w);
         tma_bulk_g2s(mb, p.model + gd.z, gd.w, &full[b]);
       }
-      const int pieces_per_tree = cta_rows / 8;  // 16-byte pieces of 8 rows
+      // 16-byte pieces of 8 rows: 4 (one consumer) or 16 (four) per tree — a power of two, and piece k of the group lands
+      // at byte 16 k of the slot tile, so the loop is a shift, a mask and two adds per copy (this warp feeds four others)
+      const int pshift = C == 1 ? 2 : 4;
       const uint32_t dst = smem_u32(slots);
-      for (int k = lane; k < (int)gd.y * pieces_per_tree; k += 32) {
-        const int t = k / pieces_per_tree, part = k - t * pieces_per_tree;
-        const uint16_t *src = p.leafslots + (size_t)(gd.x + t) * p.rows_padded + row0 + part * 8;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(t * cta_rows + part * 8) * 2u), "l"(src) : "memory");
+      const uint16_t *src0 = p.leafslots + (size_t)gd.x * p.rows_padded + row0;
+      for (int k = lane; k < ((int)gd.y << pshift); k += 32) {
+        const uint16_t *src = src0 + (size_t)(k >> pshift) * p.rows_padded + (k & ((1 << pshift) - 1)) * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)k * 16u), "l"(src) : "memory");
       }
       if (lane * 4 < (int)gd.y)
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(rel) + (uint32_t)lane * 16u),
@@ -710,7 +712,7 @@ __global__ void __launch_bounds__(160) gbdt_sum_kernel(const SumParams p, const 
     Real acc = (sizeof(Real) == 4) ? (Real)p.base_score : (Real)0;
     for (int g = 0; g < p.n_groups; g++) {
       const int b = g % kSumRing, use = g / kSumRing;
-      mbar_wait(&full[b], use & 1);
+      mbar_wait_spin(&full[b], use & 1);
       const int nt = (int)__ldg(&p.groups[g].y);
       if (live) {
         const uint8_t *mb = bufs + (size_t)b * buf_bytes;

@@ -41,4 +41,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
 }
 
+// Polling wait: mbarrier.try_wait may suspend the thread for a system-dependent time before it re-checks, which is the
+// right thing when the data is normally there already (the scorers' prefetched chunks) and costs microseconds per wait
+// when the waiter is always ahead of the data (the in-order sum's consumer: 32 waits per CTA).  test_wait returns at once.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
 }  // namespace mr
