@@ -406,6 +406,42 @@ MR_API mr_status mr_group_rank(mr_group *g, mr_state *st, mr_model *model, const
 MR_API mr_status mr_group_rank_device(mr_group *g, mr_state *st, mr_model *model, const mr_rank_batch *d_batch,
                                       int32_t total_items, double *d_out_scores, int32_t *d_out_order, void *cuda_stream);
 
+/* ------------------------------------------------------------------ bi-encoder query forward
+ * OnnxBiEncoder.embed (S/ml/onnx/sbert/OnnxBiEncoder.scala:13-36): a BERT-shaped sentence encoder
+ * (sentence-transformers all-MiniLM-L6-v2 and relatives) run over the tokenized query, then avgpool (:38-60) over the
+ * first sum(attention_mask) tokens.  Tokenization stays with the caller (the reference's HuggingFaceTokenizer): the
+ * three int64 tensors are exactly what OnnxBiEncoder hands to OrtSession.run.  Dense layers run on the tcgen05 tensor
+ * cores in binary16 with f32 accumulation; the residual stream, LayerNorm, softmax and pooling are f32 (pooling sums in
+ * f64 like the reference).  Tolerance against an f32 evaluation of the same weights: 1e-3 on the cosine of two
+ * embeddings, the bar of the reference's own test (T/ml/onnx/sbert/OnnxBiencoderTest.scala:22-25). */
+typedef struct mr_encoder mr_encoder;
+
+/* Weights: the bytes of a HuggingFace `model.safetensors` of a BertModel (tensor names
+ * `embeddings.word_embeddings.weight`, `encoder.layer.<i>.attention.self.query.weight`, ...; an optional `bert.` prefix
+ * and the legacy LayerNorm.gamma / beta spellings are accepted; F32 or F16 tensors).  Shapes give hidden size, layer
+ * count, intermediate size, vocabulary and position count; `n_heads` and `layer_norm_eps` come from config.json
+ * (12 and 1e-12 for MiniLM-L6).  hidden % 64 == 0, intermediate % 64 == 0, hidden / n_heads == 32 or 64. */
+MR_API mr_status mr_encoder_load(mr_ctx *ctx, const uint8_t *safetensors, size_t len, int32_t n_heads, double layer_norm_eps,
+                                 mr_encoder **out);
+/* dim = OnnxSession.dim (the hidden size) */
+MR_API mr_status mr_encoder_info(const mr_encoder *e, int32_t *dim, int32_t *layers, int32_t *max_tokens, int32_t *vocab);
+/* embed(batch): input_ids / token_type_ids / attention_mask are [batch x seq] int64, row-major, padded to the longest
+ * sequence (`padding = true`); out = [batch x dim] f32.  Host buffers; copies are part of the call. */
+MR_API mr_status mr_encoder_embed(mr_encoder *e, const int64_t *input_ids, const int64_t *token_type_ids,
+                                  const int64_t *attention_mask, int32_t batch, int32_t seq, float *out);
+/* Same with device pointers, enqueued on `cuda_stream` without synchronising.  d_out_f64, when not null, also receives
+ * the embeddings widened to f64 — the query-embedding operand of mr_rank_batch. */
+MR_API mr_status mr_encoder_embed_device(mr_encoder *e, const int64_t *d_input_ids, const int64_t *d_token_type_ids,
+                                         const int64_t *d_attention_mask, int32_t batch, int32_t seq, float *d_out,
+                                         double *d_out_f64, void *cuda_stream);
+MR_API mr_status mr_encoder_free(mr_encoder *e);
+/* The dense layer of the forward on its own (diagnostics, tests, bench.py's tensor roofline): device pointers,
+ * C[M x N] = act(A[M x K] W[N x K]^T + bias) + residual with A, W binary16 (K contiguous), bias / residual / out_f32 f32,
+ * out_f16 binary16; any of bias, residual, out_f32, out_f16 may be null.  K % 64 == 0, N % 64 == 0. */
+MR_API mr_status mr_encoder_gemm_f16(mr_ctx *ctx, const void *d_a, const void *d_w, const float *d_bias, const float *d_residual,
+                                     float *d_out_f32, void *d_out_f16, int32_t m, int32_t n, int32_t k, int32_t gelu,
+                                     void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -267,25 +267,6 @@ __global__ void __launch_bounds__(128) cosine_f32_kernel(RankArgs a, int dim_max
 }
 
 // ------------------------------------------------------------------ per-request prepass
-constexpr int kSortCap = 4096;  // u64 keys sorted in shared memory (32 KB)
-
-__device__ void block_sort_u64(uint64_t *s, int n_pow2) {
-  // in-place bitonic sort of n_pow2 keys in shared memory
-  for (int k = 2; k <= n_pow2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
-        const int l = i ^ j;
-        if (l > i) {
-          const uint64_t x = s[i], y = s[l];
-          const bool up = (i & k) == 0;
-          if ((x > y) == up) { s[i] = y; s[l] = x; }
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
 // Reserves `n` pool entries for histogram (r,h); returns the offset or 0xFFFFFFFF on overflow.
 __device__ uint32_t hist_alloc(const RankArgs &a, uint32_t n) {
   __shared__ uint32_t s_off;
@@ -303,21 +284,36 @@ __device__ uint32_t hist_alloc(const RankArgs &a, uint32_t n) {
   return o;
 }
 
-__device__ void hist_finish(const RankArgs &a, int r, int h, uint32_t off, uint32_t n, uint64_t *s_sort) {
-  // sort the multiset so that per-item counting is two binary searches
-  uint32_t flags = 0;
-  if (n > 1 && n <= (uint32_t)kSortCap) {
-    int p2 = 1;
-    while (p2 < (int)n) p2 <<= 1;
-    for (int i = threadIdx.x; i < p2; i += blockDim.x) s_sort[i] = i < (int)n ? a.hist_pool[off + i] : ~0ull;
-    __syncthreads();
-    block_sort_u64(s_sort, p2);
-    for (int i = threadIdx.x; i < (int)n; i += blockDim.x) a.hist_pool[off + i] = s_sort[i];
-  } else if (n > (uint32_t)kSortCap) {
-    flags = 0x80000000u;  // too large for the shared-memory sort: readers scan linearly
+// A request's tag multiset is READ once per (item, tag) — 100-1000 items x a handful of tags — so it is stored as an
+// open-addressing table {tag, count}: a lookup is one or two 16-byte loads instead of the 2 log2(n) dependent 8-byte
+// loads of two binary searches over the sorted multiset (ncu_r2_asm: those searches were 35 % of assemble_kernel's stall
+// samples, and the kernel's time moves with the NUMBER of divergent loads, not with occupancy).  Layout in the pool, from
+// the allocation's start `off`: the n raw tags (fill order), then — 16-byte aligned — `slots` entries (slots = a power of
+// two >= 2 n) and one word counting tags equal to the empty marker itself.
+constexpr uint64_t kHistEmpty = ~0ull;
+__host__ __device__ inline uint32_t hist_slots(uint32_t n) {
+  uint32_t s = 2;
+  while (s < 2 * n) s <<= 1;
+  return s;
+}
+__host__ __device__ inline uint32_t hist_words(uint32_t n) { return n + 1 + 2 * hist_slots(n) + 2; }
+
+__device__ void hist_finish(const RankArgs &a, int r, int h, uint32_t off, uint32_t n) {
+  const uint32_t slots = hist_slots(n), toff = (off + n + 1) & ~1u, mask = slots - 1;
+  unsigned long long *tab = reinterpret_cast<unsigned long long *>(a.hist_pool + toff);
+  for (uint32_t i = threadIdx.x; i < slots; i += blockDim.x) { tab[2 * i] = kHistEmpty; tab[2 * i + 1] = 0; }
+  if (threadIdx.x == 0) tab[2 * slots] = 0;
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned long long tag = a.hist_pool[off + i];
+    if (tag == kHistEmpty) { atomicAdd(&tab[2 * slots], 1ull); continue; }
+    for (uint32_t sl = (uint32_t)mix64(tag) & mask;; sl = (sl + 1) & mask) {
+      const unsigned long long prev = atomicCAS(&tab[2 * sl], kHistEmpty, tag);
+      if (prev == kHistEmpty || prev == tag) { atomicAdd(&tab[2 * sl + 1], 1ull); break; }
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0) a.hist_desc[(size_t)r * a.n_hist + h] = make_uint2(off, n | flags);
+  if (threadIdx.x == 0) a.hist_desc[(size_t)r * a.n_hist + h] = make_uint2(toff, slots);
 }
 
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_scan, uint32_t *total) {
@@ -346,7 +342,6 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_scan
 }
 
 __global__ void __launch_bounds__(256) prepass_kernel(RankArgs a) {
-  __shared__ uint64_t s_sort[kSortCap];
   __shared__ uint32_t s_scan[32];
   __shared__ int s_i[4];
   __shared__ double s_d[4];
@@ -399,8 +394,8 @@ __global__ void __launch_bounds__(256) prepass_kernel(RankArgs a) {
         block_excl_scan(cnt, s_scan, &chunk_total);
         total += chunk_total;
       }
-      uint32_t off = total ? hist_alloc(a, total) : 0;
-      if (off == 0xFFFFFFFFu) { if (threadIdx.x == 0) a.hist_desc[(size_t)r * a.n_hist + d.aux0] = make_uint2(0, 0); continue; }
+      uint32_t off = total ? hist_alloc(a, hist_words(total)) : 0;
+      if (off == 0xFFFFFFFFu || total == 0) { if (threadIdx.x == 0) a.hist_desc[(size_t)r * a.n_hist + d.aux0] = make_uint2(0, 0); continue; }
       uint32_t run = 0;
       for (uint32_t base = 0; base < hlen && total; base += blockDim.x) {
         const uint32_t j = base + threadIdx.x;
@@ -418,7 +413,7 @@ __global__ void __launch_bounds__(256) prepass_kernel(RankArgs a) {
         run += chunk_total;
       }
       __syncthreads();
-      hist_finish(a, r, d.aux0, off, total, s_sort);
+      hist_finish(a, r, d.aux0, off, total);
     } else if (d.kind == FK_DIVERSITY) {
       // DiversityFeature.values (:67-130): items WITH state, in request order; the first one's
       // scalar type selects the mode; aggregates over the first `top` items of that type.
@@ -550,7 +545,7 @@ __global__ void __launch_bounds__(256) prepass_kernel(RankArgs a) {
           total += tt;
           run += ct;
         }
-        const uint32_t off = total ? hist_alloc(a, total) : 0;
+        const uint32_t off = total ? hist_alloc(a, hist_words(total)) : 0;
         if (off == 0xFFFFFFFFu) { if (threadIdx.x == 0) { agg[0] = 0; agg[1] = 0; agg[2] = 0; a.hist_desc[(size_t)r * a.n_hist + d.aux1] = make_uint2(0, 0); } continue; }
         uint32_t filled = 0;
         run = 0;
@@ -573,7 +568,8 @@ __global__ void __launch_bounds__(256) prepass_kernel(RankArgs a) {
           run += ct;
         }
         __syncthreads();
-        hist_finish(a, r, d.aux1, off, total, s_sort);
+        if (total) hist_finish(a, r, d.aux1, off, total);
+        else if (threadIdx.x == 0) a.hist_desc[(size_t)r * a.n_hist + d.aux1] = make_uint2(0, 0);
         if (threadIdx.x == 0) { agg[0] = 2.0; agg[1] = 0.0; agg[2] = (double)total; }
       }
     } else if (d.kind == FK_COSINE && d.aux1 != 0) {
@@ -631,23 +627,18 @@ __global__ void __launch_bounds__(256) prepass_kernel(RankArgs a) {
   }
 }
 
-// number of occurrences of `tag` in histogram (r,h)
+// number of occurrences of `tag` in histogram (r, h)
 __device__ __forceinline__ uint32_t hist_count(const RankArgs &a, int r, int h, uint64_t tag) {
   const uint2 hd = a.hist_desc[(size_t)r * a.n_hist + h];
-  const uint32_t n = hd.y & 0x7FFFFFFFu;
-  if (n == 0) return 0;
-  const uint64_t *p = a.hist_pool + hd.x;
-  if (hd.y & 0x80000000u) {
-    uint32_t c = 0;
-    for (uint32_t k = 0; k < n; k++) c += p[k] == tag;
-    return c;
+  if (hd.y == 0) return 0;
+  const uint32_t mask = hd.y - 1;
+  if (tag == kHistEmpty) return (uint32_t)a.hist_pool[hd.x + 2 * (size_t)hd.y];
+  const ulonglong2 *tab = reinterpret_cast<const ulonglong2 *>(a.hist_pool + hd.x);
+  for (uint32_t sl = (uint32_t)mix64(tag) & mask;; sl = (sl + 1) & mask) {
+    const ulonglong2 e = tab[sl];
+    if (e.x == tag) return (uint32_t)e.y;
+    if (e.x == kHistEmpty) return 0;
   }
-  uint32_t lo = 0, hi = n;  // lower_bound
-  while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (p[m] < tag) lo = m + 1; else hi = m; }
-  const uint32_t first = lo;
-  hi = n;  // upper_bound
-  while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (p[m] <= tag) lo = m + 1; else hi = m; }
-  return lo - first;
 }
 
 // ------------------------------------------------------------------ coalesced row gather (fast columns)
