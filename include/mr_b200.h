@@ -436,8 +436,9 @@ MR_API mr_status mr_encoder_embed_device(mr_encoder *e, const int64_t *d_input_i
                                          double *d_out_f64, void *cuda_stream);
 MR_API mr_status mr_encoder_free(mr_encoder *e);
 /* The dense layer of the forward on its own (diagnostics, tests, bench.py's tensor roofline): device pointers,
- * C[M x N] = act(A[M x K] W[N x K]^T + bias) + residual with A, W binary16 (K contiguous), bias / residual / out_f32 f32,
- * out_f16 binary16; any of bias, residual, out_f32, out_f16 may be null.  K % 64 == 0, N % 64 == 0. */
+ * C[M x N] = A[M x K] W[N x K]^T + bias, then either exact-erf GELU (`gelu`) or + residual, with A, W binary16
+ * (K contiguous), bias / residual / out_f32 f32, out_f16 binary16; any of bias, residual, out_f32, out_f16 may be null.
+ * K % 64 == 0, N % 64 == 0; GELU together with a residual is MR_ERR_INVALID_ARG. */
 MR_API mr_status mr_encoder_gemm_f16(mr_ctx *ctx, const void *d_a, const void *d_w, const float *d_bias, const float *d_residual,
                                      float *d_out_f32, void *d_out_f16, int32_t m, int32_t n, int32_t k, int32_t gelu,
                                      void *cuda_stream);

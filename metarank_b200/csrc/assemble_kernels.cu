@@ -288,30 +288,38 @@ __device__ uint32_t hist_alloc(const RankArgs &a, uint32_t n) {
 // open-addressing table {tag, count}: a lookup is one or two 16-byte loads instead of the 2 log2(n) dependent 8-byte
 // loads of two binary searches over the sorted multiset (ncu_r2_asm: those searches were 35 % of assemble_kernel's stall
 // samples, and the kernel's time moves with the NUMBER of divergent loads, not with occupancy).  Layout in the pool, from
-// the allocation's start `off`: the n raw tags (fill order), then — 16-byte aligned — `slots` entries (slots = a power of
-// two >= 2 n) and one word counting tags equal to the empty marker itself.
+// a 16-byte aligned start: `slots` entries (slots = a power of two >= 2 n, so it is never more than half full) and one
+// word counting tags equal to the empty marker itself.  Tags are inserted straight from the item rows (global atomics:
+// a few hundred per request), the multiset itself is never materialised.
 constexpr uint64_t kHistEmpty = ~0ull;
 __host__ __device__ inline uint32_t hist_slots(uint32_t n) {
   uint32_t s = 2;
   while (s < 2 * n) s <<= 1;
   return s;
 }
-__host__ __device__ inline uint32_t hist_words(uint32_t n) { return n + 1 + 2 * hist_slots(n) + 2; }
+__host__ __device__ inline uint32_t hist_words(uint32_t n) { return 1 + 2 * hist_slots(n) + 2; }
 
-__device__ void hist_finish(const RankArgs &a, int r, int h, uint32_t off, uint32_t n) {
-  const uint32_t slots = hist_slots(n), toff = (off + n + 1) & ~1u, mask = slots - 1;
+// Reserves and clears the table for a multiset of n tags (CTA-collective); returns its first word or 0xFFFFFFFF.
+__device__ uint32_t hist_begin(const RankArgs &a, uint32_t n) {
+  const uint32_t off = hist_alloc(a, hist_words(n));
+  if (off == 0xFFFFFFFFu) return off;
+  const uint32_t slots = hist_slots(n), toff = (off + 1) & ~1u;
   unsigned long long *tab = reinterpret_cast<unsigned long long *>(a.hist_pool + toff);
   for (uint32_t i = threadIdx.x; i < slots; i += blockDim.x) { tab[2 * i] = kHistEmpty; tab[2 * i + 1] = 0; }
   if (threadIdx.x == 0) tab[2 * slots] = 0;
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const unsigned long long tag = a.hist_pool[off + i];
-    if (tag == kHistEmpty) { atomicAdd(&tab[2 * slots], 1ull); continue; }
-    for (uint32_t sl = (uint32_t)mix64(tag) & mask;; sl = (sl + 1) & mask) {
-      const unsigned long long prev = atomicCAS(&tab[2 * sl], kHistEmpty, tag);
-      if (prev == kHistEmpty || prev == tag) { atomicAdd(&tab[2 * sl + 1], 1ull); break; }
-    }
+  return toff;
+}
+__device__ __forceinline__ void hist_insert(const RankArgs &a, uint32_t toff, uint32_t slots, unsigned long long tag) {
+  unsigned long long *tab = reinterpret_cast<unsigned long long *>(a.hist_pool + toff);
+  if (tag == kHistEmpty) { atomicAdd(&tab[2 * slots], 1ull); return; }
+  const uint32_t mask = slots - 1;
+  for (uint32_t sl = (uint32_t)mix64(tag) & mask;; sl = (sl + 1) & mask) {
+    const unsigned long long prev = atomicCAS(&tab[2 * sl], kHistEmpty, tag);
+    if (prev == kHistEmpty || prev == tag) { atomicAdd(&tab[2 * sl + 1], 1ull); return; }
   }
+}
+__device__ void hist_end(const RankArgs &a, int r, int h, uint32_t toff, uint32_t slots) {
   __syncthreads();
   if (threadIdx.x == 0) a.hist_desc[(size_t)r * a.n_hist + h] = make_uint2(toff, slots);
 }
@@ -394,10 +402,9 @@ __global__ void __launch_bounds__(256) prepass_kernel(RankArgs a) {
         block_excl_scan(cnt, s_scan, &chunk_total);
         total += chunk_total;
       }
-      uint32_t off = total ? hist_alloc(a, hist_words(total)) : 0;
+      const uint32_t off = total ? hist_begin(a, total) : 0, slots = hist_slots(total);
       if (off == 0xFFFFFFFFu || total == 0) { if (threadIdx.x == 0) a.hist_desc[(size_t)r * a.n_hist + d.aux0] = make_uint2(0, 0); continue; }
-      uint32_t run = 0;
-      for (uint32_t base = 0; base < hlen && total; base += blockDim.x) {
+      for (uint32_t base = 0; base < hlen; base += blockDim.x) {
         const uint32_t j = base + threadIdx.x;
         uint32_t cnt = 0, src = 0;
         if (j < hlen) {
@@ -407,13 +414,9 @@ __global__ void __launch_bounds__(256) prepass_kernel(RankArgs a) {
             if (present(rp, d.b[0])) { const uint64_t desc = rp[d.w[0]]; cnt = (uint32_t)(desc >> 32); src = (uint32_t)desc; }
           }
         }
-        uint32_t chunk_total;
-        const uint32_t my = block_excl_scan(cnt, s_scan, &chunk_total);
-        for (uint32_t k = 0; k < cnt; k++) a.hist_pool[off + run + my + k] = IT.pool[src + k];
-        run += chunk_total;
+        for (uint32_t k = 0; k < cnt; k++) hist_insert(a, off, slots, IT.pool[src + k]);
       }
-      __syncthreads();
-      hist_finish(a, r, d.aux0, off, total);
+      hist_end(a, r, d.aux0, off, slots);
     } else if (d.kind == FK_DIVERSITY) {
       // DiversityFeature.values (:67-130): items WITH state, in request order; the first one's
       // scalar type selects the mode; aggregates over the first `top` items of that type.
@@ -545,9 +548,8 @@ __global__ void __launch_bounds__(256) prepass_kernel(RankArgs a) {
           total += tt;
           run += ct;
         }
-        const uint32_t off = total ? hist_alloc(a, hist_words(total)) : 0;
+        const uint32_t off = total ? hist_begin(a, total) : 0, slots = hist_slots(total);
         if (off == 0xFFFFFFFFu) { if (threadIdx.x == 0) { agg[0] = 0; agg[1] = 0; agg[2] = 0; a.hist_desc[(size_t)r * a.n_hist + d.aux1] = make_uint2(0, 0); } continue; }
-        uint32_t filled = 0;
         run = 0;
         for (int base = 0; base < n_items && run < (uint32_t)top && total; base += blockDim.x) {
           const int j = base + threadIdx.x;
@@ -559,16 +561,13 @@ __global__ void __launch_bounds__(256) prepass_kernel(RankArgs a) {
               if (present(rp, d.b[0]) && rp[d.w[0]] == 2) { m = 1; const uint64_t ds = rp[d.w[0] + 1]; cnt = (uint32_t)(ds >> 32); src = (uint32_t)ds; }
             }
           }
-          uint32_t ct, tt;
+          uint32_t ct;
           const uint32_t ord = block_excl_scan(m, s_scan, &ct);
           if (!(m && run + ord < (uint32_t)top)) cnt = 0;
-          const uint32_t my = block_excl_scan(cnt, s_scan, &tt);
-          for (uint32_t k = 0; k < cnt; k++) a.hist_pool[off + filled + my + k] = IT.pool[src + k];
-          filled += tt;
+          for (uint32_t k = 0; k < cnt; k++) hist_insert(a, off, slots, IT.pool[src + k]);
           run += ct;
         }
-        __syncthreads();
-        if (total) hist_finish(a, r, d.aux1, off, total);
+        if (total) hist_end(a, r, d.aux1, off, slots);
         else if (threadIdx.x == 0) a.hist_desc[(size_t)r * a.n_hist + d.aux1] = make_uint2(0, 0);
         if (threadIdx.x == 0) { agg[0] = 2.0; agg[1] = 0.0; agg[2] = (double)total; }
       }

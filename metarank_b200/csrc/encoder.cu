@@ -122,7 +122,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half *qkv, const
 #pragma unroll
       for (int c = 0; c < D; c++) s = fmaf(qr[c], sk[j * P + c], s);
       s *= scale;
-      if (any && !smask[j]) s = -INFINITY;
+      if (!any) s = 0.f;  // every key masked: the additive -FLT_MAX absorbs the scores, softmax is uniform
+      else if (!smask[j]) s = -INFINITY;
       my[j] = s;
       mx = fmaxf(mx, s);
     }
@@ -139,6 +140,74 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half *qkv, const
       ctx[((size_t)b * S + q) * H + head * D + c0 + lane] = __float2half_rn(acc * inv);
     }
     __syncwarp();
+  }
+}
+
+// Queries are short (a search phrase is 5-20 tokens): for seq <= 32 and head dimension 32 a WARP owns one (sequence, head) and
+// nothing touches shared memory.  Lane j holds key row j, lane d holds column d of V (all keys), the query row arrives as a
+// broadcast load; scores, the two softmax reductions and the weights stay in registers (weights broadcast by shuffle).
+// Same operation order as attention_kernel — dot products by ascending dimension, reductions by the same xor tree, the
+// weighted sum by ascending key — so both kernels return the same bits.
+__global__ void __launch_bounds__(128, 5) attention_short_kernel(const __half *qkv, const int64_t *mask, int n_pairs, int heads, int S,
+                                                              int H, float scale, __half *ctx) {
+  constexpr int D = 32;
+  const int w = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (w >= n_pairs) return;
+  const int b = w / heads, head = w % heads;
+  const __half *base = qkv + (size_t)b * S * 3 * H + head * D;
+  const bool has = lane < S;
+  float k[D], vt[32];
+  {
+    const uint4 *kp = reinterpret_cast<const uint4 *>(base + (size_t)(has ? lane : 0) * 3 * H + H);
+#pragma unroll
+    for (int i = 0; i < D / 8; i++) {
+      const uint4 u = __ldg(kp + i);
+      const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; e++) { const float2 f = __half22float2(h[e]); k[8 * i + 2 * e] = f.x; k[8 * i + 2 * e + 1] = f.y; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j++) vt[j] = j < S ? __half2float(base[(size_t)j * 3 * H + 2 * H + lane]) : 0.f;
+  const bool m = has && mask[(size_t)b * S + (has ? lane : 0)] != 0;
+  const bool any = __ballot_sync(0xFFFFFFFFu, m) != 0;
+  uint4 qn[D / 8];  // the next query row, in flight while the current one is worked on
+#pragma unroll
+  for (int i = 0; i < D / 8; i++) qn[i] = __ldg(reinterpret_cast<const uint4 *>(base) + i);
+  for (int q = 0; q < S; q++) {
+    uint4 qc[D / 8];
+#pragma unroll
+    for (int i = 0; i < D / 8; i++) qc[i] = qn[i];
+    if (q + 1 < S) {
+      const uint4 *qp = reinterpret_cast<const uint4 *>(base + (size_t)(q + 1) * 3 * H);
+#pragma unroll
+      for (int i = 0; i < D / 8; i++) qn[i] = __ldg(qp + i);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < D / 8; i++) {
+      const uint4 u = qc[i];
+      const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; e++) { const float2 f = __half22float2(h[e]); s = fmaf(f.x, k[8 * i + 2 * e], s); s = fmaf(f.y, k[8 * i + 2 * e + 1], s); }
+    }
+    s *= scale;
+    if (!has) s = -INFINITY;
+    else if (!any) s = 0.f;
+    else if (!m) s = -INFINITY;
+    float mx = s;
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+    const float e = has ? __expf(s - mx) : 0.f;
+    float sum = e;
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    const float inv = 1.0f / sum;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      const float pj = __shfl_sync(0xFFFFFFFFu, e, j);
+      if (j < S) acc = fmaf(pj, vt[j], acc);
+    }
+    ctx[((size_t)b * S + q) * H + head * D + lane] = __float2half_rn(acc * inv);
   }
 }
 
@@ -264,8 +333,26 @@ struct mr_encoder {
   int64_t *d_in = nullptr; size_t d_in_cap = 0;
   float *d_out = nullptr; size_t d_out_cap = 0;
   cudaStream_t stream = nullptr;
+  // A forward is 7 L + 2 launches of a few microseconds each: for one query the launches ARE the latency.  Each
+  // (buffers, batch, seq) shape is captured once into a CUDA graph and replayed (tensor maps and pointers are baked
+  // into the nodes, so the key holds every pointer; growing the workspace drops the cache).
+  struct GraphKey {
+    const void *ids, *types, *mask, *out, *out64;
+    int B, S;
+    bool operator==(const GraphKey &o) const { return ids == o.ids && types == o.types && mask == o.mask && out == o.out && out64 == o.out64 && B == o.B && S == o.S; }
+  };
+  struct GraphEntry { GraphKey key; cudaGraphExec_t exec; uint64_t used; };
+  std::vector<GraphEntry> graphs;
+  uint64_t tick = 0;
+  static constexpr size_t kMaxGraphs = 16;
+
+  void drop_graphs() {
+    for (auto &g : graphs) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+  }
 
   ~mr_encoder() {
+    drop_graphs();
     cudaFree(d_f32); cudaFree(d_f16); cudaFree(x_f32); cudaFree(tmp); cudaFree(x_f16); cudaFree(qkv); cudaFree(ctxb); cudaFree(mid);
     cudaFree(d_error); cudaFree(d_in); cudaFree(d_out);
     if (h_error) cudaFreeHost(h_error);
@@ -275,6 +362,7 @@ struct mr_encoder {
   void reserve(size_t rows) {
     if (rows <= ws_rows) return;
     MR_CUDA_CHECK(cudaDeviceSynchronize());
+    drop_graphs();
     cudaFree(x_f32); cudaFree(tmp); cudaFree(x_f16); cudaFree(qkv); cudaFree(ctxb); cudaFree(mid);
     x_f32 = tmp = nullptr; x_f16 = qkv = ctxb = mid = nullptr; ws_rows = 0;
     const size_t r = (rows + 127) & ~(size_t)127;
@@ -287,10 +375,51 @@ struct mr_encoder {
     ws_rows = r;
   }
 
+  void run(const int64_t *ids, const int64_t *types, const int64_t *mask, int B, int S, float *out, double *out_f64, cudaStream_t st) {
+    reserve((size_t)B * S);
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (st == nullptr || profile_active() || cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      forward(ids, types, mask, B, S, out, out_f64, st);  // legacy stream / open profile / caller is capturing: plain launches
+      return;
+    }
+    const GraphKey key{ids, types, mask, out, out_f64, B, S};
+    for (auto &g : graphs)
+      if (g.key == key) {
+        g.used = ++tick;
+        MR_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
+        g_kernel_launches += 7 * L + 2;
+        return;
+      }
+    const long long before = g_kernel_launches;
+    MR_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    cudaGraph_t graph = nullptr;
+    try {
+      forward(ids, types, mask, B, S, out, out_f64, st);
+    } catch (...) {
+      cudaStreamEndCapture(st, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    g_kernel_launches = before;
+    MR_CUDA_CHECK(cudaStreamEndCapture(st, &graph));
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t err = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    MR_CUDA_CHECK(err);
+    if (graphs.size() >= kMaxGraphs) {
+      size_t lru = 0;
+      for (size_t i = 1; i < graphs.size(); i++) if (graphs[i].used < graphs[lru].used) lru = i;
+      cudaGraphExecDestroy(graphs[lru].exec);
+      graphs.erase(graphs.begin() + lru);
+    }
+    graphs.push_back({key, exec, ++tick});
+    MR_CUDA_CHECK(cudaGraphLaunch(exec, st));
+    g_kernel_launches += 7 * L + 2;
+  }
+
   void forward(const int64_t *ids, const int64_t *types, const int64_t *mask, int B, int S, float *out, double *out_f64,
                cudaStream_t st) {
     const int M = B * S;
-    reserve((size_t)M);
     { ProfScope _ps("embed_ln_kernel", st);
       embed_ln_kernel<<<(M + 3) / 4, 128, 0, st>>>(ids, types, M, S, H, vocab, n_types, word, pos, type, emb_g, emb_b, eps, x_f32, x_f16, d_error); }
     g_kernel_launches++;
@@ -299,7 +428,8 @@ struct mr_encoder {
     for (const Layer &ly : layers) {
       encoder_gemm(x_f16, ly.w_qkv, ly.b_qkv, nullptr, nullptr, qkv, M, 3 * H, H, false, st);
       { ProfScope _ps("attention_kernel", st);
-        if (D == 32) attention_kernel<32><<<dim3(heads, B), 128, att_smem, st>>>(qkv, mask, S, H, scale, ctxb);
+        if (D == 32 && S <= 32) attention_short_kernel<<<(B * heads + 3) / 4, 128, 0, st>>>(qkv, mask, B * heads, heads, S, H, scale, ctxb);
+        else if (D == 32) attention_kernel<32><<<dim3(heads, B), 128, att_smem, st>>>(qkv, mask, S, H, scale, ctxb);
         else attention_kernel<64><<<dim3(heads, B), 128, att_smem, st>>>(qkv, mask, S, H, scale, ctxb); }
       g_kernel_launches++;
       encoder_gemm(ctxb, ly.w_o, ly.b_o, x_f32, tmp, nullptr, M, H, H, false, st);
@@ -395,6 +525,7 @@ mr_status mr_encoder_load(mr_ctx *ctx, const uint8_t *blob, size_t len, int32_t 
       offs.push_back(o);
     }
     MR_CUDA_CHECK(cudaSetDevice(ctx->device));
+    encoder_gemm_init();
     MR_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     e->f32_count = f32.size();
     e->f16_count = mats.size();
@@ -446,7 +577,7 @@ mr_status mr_encoder_embed_device(mr_encoder *e, const int64_t *d_ids, const int
     if (!d_ids || !d_mask || !d_out) fail(MR_ERR_INVALID_ARG, "input_ids / attention_mask / out is null");
     std::lock_guard<std::mutex> g(e->mu);
     MR_CUDA_CHECK(cudaSetDevice(e->ctx->device));
-    e->forward(d_ids, d_types, d_mask, batch, seq, d_out, d_out_f64, (cudaStream_t)cuda_stream);
+    e->run(d_ids, d_types, d_mask, batch, seq, d_out, d_out_f64, (cudaStream_t)cuda_stream);
   });
 }
 
@@ -458,14 +589,14 @@ mr_status mr_encoder_embed(mr_encoder *e, const int64_t *ids, const int64_t *typ
     std::lock_guard<std::mutex> g(e->mu);
     MR_CUDA_CHECK(cudaSetDevice(e->ctx->device));
     const size_t n = (size_t)batch * seq;
-    if (3 * n > e->d_in_cap) { cudaFree(e->d_in); e->d_in = nullptr; e->d_in_cap = 0; MR_CUDA_CHECK(cudaMalloc(&e->d_in, 3 * n * 8)); e->d_in_cap = 3 * n; }
+    if (3 * n > e->d_in_cap) { MR_CUDA_CHECK(cudaStreamSynchronize(e->stream)); cudaFree(e->d_in); e->d_in = nullptr; e->d_in_cap = 0; MR_CUDA_CHECK(cudaMalloc(&e->d_in, 3 * n * 8)); e->d_in_cap = 3 * n; }
     const size_t no = (size_t)batch * e->H;
-    if (no > e->d_out_cap) { cudaFree(e->d_out); e->d_out = nullptr; e->d_out_cap = 0; MR_CUDA_CHECK(cudaMalloc(&e->d_out, no * 4)); e->d_out_cap = no; }
+    if (no > e->d_out_cap) { MR_CUDA_CHECK(cudaStreamSynchronize(e->stream)); cudaFree(e->d_out); e->d_out = nullptr; e->d_out_cap = 0; MR_CUDA_CHECK(cudaMalloc(&e->d_out, no * 4)); e->d_out_cap = no; }
     cudaStream_t st = e->stream;
     MR_CUDA_CHECK(cudaMemcpyAsync(e->d_in, ids, n * 8, cudaMemcpyHostToDevice, st));
     if (types) MR_CUDA_CHECK(cudaMemcpyAsync(e->d_in + n, types, n * 8, cudaMemcpyHostToDevice, st));
     MR_CUDA_CHECK(cudaMemcpyAsync(e->d_in + 2 * n, mask, n * 8, cudaMemcpyHostToDevice, st));
-    e->forward(e->d_in, types ? e->d_in + n : nullptr, e->d_in + 2 * n, batch, seq, e->d_out, nullptr, st);
+    e->run(e->d_in, types ? e->d_in + n : nullptr, e->d_in + 2 * n, batch, seq, e->d_out, nullptr, st);
     MR_CUDA_CHECK(cudaMemcpyAsync(out, e->d_out, no * 4, cudaMemcpyDeviceToHost, st));
     MR_CUDA_CHECK(cudaMemcpyAsync(e->h_error, e->d_error, 4, cudaMemcpyDeviceToHost, st));
     MR_CUDA_CHECK(cudaStreamSynchronize(st));

@@ -14,4 +14,7 @@ namespace mr {
 void encoder_gemm(const __half *A, const __half *W, const float *bias, const float *residual, float *out_f32, __half *out_f16,
                   int M, int N, int K, bool gelu, cudaStream_t stream);
 
+// Sets the kernels' shared-memory attributes (not a stream operation: done once, outside any graph capture).
+void encoder_gemm_init();
+
 }  // namespace mr

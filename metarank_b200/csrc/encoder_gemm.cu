@@ -3,15 +3,15 @@
 //
 //   C[M x N] = act( A[M x K] * W[N x K]^T + bias[N] ) (+ residual[M x N])      A, W: binary16, K-major; accumulate f32
 //
-// A persistent CTA per SM walks 128 x BLOCK_N output tiles; six warps with one role each (the canonical sm_100 shape):
+// A persistent CTA per SM walks 128 x BLOCK_N output tiles; ten warps in three roles (the canonical sm_100 shape):
 //   warp 0, one lane   TMA producer: per 64-element K block one `cp.async.bulk.tensor.2d` for the A tile and one for the
 //                      W tile, 128-byte swizzled, into a kStages-deep ring; completion on the stage's `full` mbarrier
 //   warp 1, one lane   MMA issuer: `tcgen05.mma.cta_group::1.kind::f16` (UMMA 128 x BLOCK_N x 16, operands straight from
 //                      shared memory through 64-bit matrix descriptors, accumulator in TENSOR MEMORY); `tcgen05.commit`
 //                      frees the stage for the producer and, after the last K block, hands the accumulator — one of
 //                      two TMEM buffers — to the epilogue, then starts the next tile in the other
-//   warps 2..5         epilogue: `tcgen05.ld` 32 lanes x 32 columns at a time -> bias, exact-erf GELU, residual ->
-//                      f32 and/or binary16 rows to global memory
+//   warps 2..9         epilogue: `tcgen05.ld` 32 lanes x 32 columns at a time -> bias, exact-erf GELU, residual ->
+//                      f32 and/or binary16 rows to global memory (two warps per TMEM lane quarter, half the columns each)
 // warp 1 also allocates / frees the TMEM columns.  SASS: UTMALDG (TMA), UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld).
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -105,8 +105,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // Persistent: one CTA per SM walks output tiles t = blockIdx.x, + gridDim.x, ... (n fastest, so the CTAs running together
 // share an A row block in L2).  The accumulator is double-buffered in tensor memory (2 x BLOCK_N columns): the epilogue
 // warps drain tile i while the MMA warp already accumulates tile i + 1, and the smem ring never drains between tiles.
-template <int BLOCK_N>
-__global__ void __launch_bounds__(192, 1) encoder_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
+// EPI: what the epilogue adds after the bias — compile-time, so that the plain layers carry neither 64 inlined erf
+// expansions to branch around (instruction-fetch stalls: ncu_r2_gemm2) nor predicated-off residual loads.
+enum { EPI_BIAS = 0, EPI_GELU = 1, EPI_RESIDUAL = 2 };
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(320, 1) encoder_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                               const __grid_constant__ CUtensorMap map_w, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // the 128-byte swizzle atoms (8 rows x 128 B) must start on 1024-byte boundaries of the shared-memory address space
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(192, 1) encoder_gemm_kernel(const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     for (uint32_t s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }  // 4 epilogue warps release a buffer
+    for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }  // 8 epilogue warps release a buffer
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -179,39 +183,52 @@ __global__ void __launch_bounds__(192, 1) encoder_gemm_kernel(const __grid_const
       }
     }
   } else {
-    // ===== epilogue: warp w reads TMEM lanes [32 (w % 4), +32) = rows of the tile, 32 columns at a time
-    const int quarter = warp & 3;
+    // ===== epilogue: 8 warps.  A warp may only read the TMEM lanes of its quarter (warp % 4): rows [32 (w % 4), +32) of the
+    // tile; the two warps of a quarter split the columns.  Everything that does not depend on the accumulator is fetched
+    // BEFORE the wait — the tile's bias slice (lane l holds column 32 c + l of each chunk, broadcast by shuffle later) and
+    // the thread's residual row — so the drain itself is TMEM load -> FADDs -> stores (ncu_r2_gemm: with the loads inside,
+    // their latency, 16 dependent round trips per tile, was the whole kernel).
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    constexpr int kChunks = BLOCK_N / 64;  // 32-column chunks per warp
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, lt++) {
-      const int m0 = (t / tiles_n) * kBlockM, n0 = (t % tiles_n) * BLOCK_N;
+      const int m0 = (t / tiles_n) * kBlockM, n0 = (t % tiles_n) * BLOCK_N + half * (BLOCK_N / 2);
       const uint32_t acc = lt & 1, acc_ph = (lt >> 1) & 1;
       const int row = m0 + quarter * 32 + lane;
-      mbar_wait(&acc_full[acc], acc_ph);
+      float bias_lane[kChunks];
+#pragma unroll
+      for (int c = 0; c < kChunks; c++) bias_lane[c] = p.bias ? __ldg(p.bias + n0 + 32 * c + lane) : 0.f;
+      if (lane == 0) mbar_wait_spin(&acc_full[acc], acc_ph);  // one polling lane per warp (try_wait's suspension oversleeps by microseconds)
+      __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+#pragma unroll
+      for (int c = 0; c < kChunks; c++) {
+        const int n = n0 + 32 * c;
+        float4 res[8];
+        if (EPI == EPI_RESIDUAL && row < p.M) {
+          const float4 *rs = reinterpret_cast<const float4 *>(p.residual + (size_t)row * p.N + n);
+#pragma unroll
+          for (int j = 0; j < 8; j++) res[j] = __ldg(rs + j);
+        }
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + (uint32_t)c0, v);
-        if (c0 + 32 == BLOCK_N) {
-          // every column of this tile is in registers: hand the accumulator back before the stores
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + (uint32_t)(half * (BLOCK_N / 2) + 32 * c), v);
+        if (c == kChunks - 1) {
+          // every column this warp owns is in registers: hand the accumulator back before the stores
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[acc]);
         }
+        float r[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          float x = __uint_as_float(v[j]) + __shfl_sync(0xFFFFFFFFu, bias_lane[c], j);
+          if (EPI == EPI_GELU) x = gelu_erf(x);
+          r[j] = x;
+        }
         if (row < p.M) {
-          const int n = n0 + c0;
-          float r[32];
+          if (EPI == EPI_RESIDUAL) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            float x = __uint_as_float(v[j]);
-            if (p.bias) x += __ldg(p.bias + n + j);
-            if (p.gelu) x = gelu_erf(x);
-            r[j] = x;
-          }
-          if (p.residual) {
-            const float4 *rs = reinterpret_cast<const float4 *>(p.residual + (size_t)row * p.N + n);
-#pragma unroll
-            for (int j = 0; j < 8; j++) { const float4 q = __ldg(rs + j); r[4 * j] += q.x; r[4 * j + 1] += q.y; r[4 * j + 2] += q.z; r[4 * j + 3] += q.w; }
+            for (int j = 0; j < 8; j++) { r[4 * j] += res[j].x; r[4 * j + 1] += res[j].y; r[4 * j + 2] += res[j].z; r[4 * j + 3] += res[j].w; }
           }
           if (p.out_f32) {
             float4 *o = reinterpret_cast<float4 *>(p.out_f32 + (size_t)row * p.N + n);
@@ -276,30 +293,53 @@ int num_sms() {
   return n;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N> constexpr size_t smem_bytes() {
+  return (size_t)StagesFor<BLOCK_N>::value * (kBlockM + BLOCK_N) * kBlockK * 2 + (2 * StagesFor<BLOCK_N>::value + 4) * 8 + 16 + 1024;  // + alignment slack
+}
+
+template <int BLOCK_N, int EPI>
 void launch(const __half *A, const __half *W, const GemmParams &p, cudaStream_t stream) {
   const CUtensorMap ma = make_map(A, p.M, p.K, kBlockM), mw = make_map(W, p.N, p.K, BLOCK_N);
-  constexpr int kStages = StagesFor<BLOCK_N>::value;
-  constexpr size_t smem = (size_t)kStages * (kBlockM + BLOCK_N) * kBlockK * 2 + (2 * kStages + 4) * 8 + 16 + 1024;  // + alignment slack
-  auto kern = encoder_gemm_kernel<BLOCK_N>;
-  static std::once_flag once;
-  std::call_once(once, [&] { MR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
+  constexpr size_t smem = smem_bytes<BLOCK_N>();
+  auto kern = encoder_gemm_kernel<BLOCK_N, EPI>;
   const int n_tiles = ((p.M + kBlockM - 1) / kBlockM) * (p.N / BLOCK_N);
   const unsigned grid = (unsigned)std::min(n_tiles, num_sms());
-  { ProfScope _ps("encoder_gemm_kernel", stream); kern<<<grid, 192, smem, stream>>>(ma, mw, p); }
+  { ProfScope _ps("encoder_gemm_kernel", stream); kern<<<grid, 320, smem, stream>>>(ma, mw, p); }
   MR_CUDA_CHECK(cudaGetLastError());
   g_kernel_launches++;
 }
 
+
+template <int BLOCK_N, int EPI> void set_smem() {
+  MR_CUDA_CHECK(cudaFuncSetAttribute(encoder_gemm_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BLOCK_N>()));
+}
 }  // namespace
+
+void encoder_gemm_init() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    set_smem<128, EPI_BIAS>(); set_smem<128, EPI_GELU>(); set_smem<128, EPI_RESIDUAL>();
+    set_smem<64, EPI_BIAS>(); set_smem<64, EPI_GELU>(); set_smem<64, EPI_RESIDUAL>();
+  });
+}
 
 void encoder_gemm(const __half *A, const __half *W, const float *bias, const float *residual, float *out_f32, __half *out_f16,
                   int M, int N, int K, bool gelu, cudaStream_t stream) {
   if (M <= 0) return;
   if (K % kBlockK != 0 || N % 64 != 0) fail(MR_ERR_INVALID_ARG, "encoder GEMM needs K %% 64 == 0 and N %% 64 == 0 (got N %d, K %d)", N, K);
+  encoder_gemm_init();
   GemmParams p{bias, residual, out_f32, out_f16, M, N, K, gelu ? 1 : 0};
-  if (N % 128 == 0) launch<128>(A, W, p, stream);
-  else launch<64>(A, W, p, stream);
+  if (gelu && residual) fail(MR_ERR_INVALID_ARG, "encoder GEMM: GELU and a residual in one epilogue are not built");
+  const int epi = gelu ? EPI_GELU : residual ? EPI_RESIDUAL : EPI_BIAS;
+  if (N % 128 == 0) {
+    if (epi == EPI_GELU) launch<128, EPI_GELU>(A, W, p, stream);
+    else if (epi == EPI_RESIDUAL) launch<128, EPI_RESIDUAL>(A, W, p, stream);
+    else launch<128, EPI_BIAS>(A, W, p, stream);
+  } else {
+    if (epi == EPI_GELU) launch<64, EPI_GELU>(A, W, p, stream);
+    else if (epi == EPI_RESIDUAL) launch<64, EPI_RESIDUAL>(A, W, p, stream);
+    else launch<64, EPI_BIAS>(A, W, p, stream);
+  }
 }
 
 }  // namespace mr

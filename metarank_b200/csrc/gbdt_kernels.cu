@@ -39,6 +39,8 @@ struct ProfRec { const char *name; cudaEvent_t e0, e1; };
 std::vector<ProfRec> g_prof;
 }  // namespace
 
+bool profile_active() { return g_prof_on.load(std::memory_order_relaxed); }
+
 ProfScope::ProfScope(const char *n, cudaStream_t s) : name(n), stream(s) {
   if (!g_prof_on.load(std::memory_order_relaxed)) return;
   if (cudaEventCreate(&e0) != cudaSuccess) { e0 = nullptr; return; }

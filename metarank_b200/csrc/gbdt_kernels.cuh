@@ -110,6 +110,7 @@ struct ProfScope {
   ~ProfScope();
 };
 void profile_begin();
+bool profile_active();  // launch sites that replay CUDA graphs fall back to plain launches while a profile is open
 // Waits for the device, then appends one JSON object per kernel name to `out`: {"kernel", "launches", "ms"}.
 void profile_end(std::string &out);
 

@@ -196,5 +196,32 @@ JNIEXPORT void JNICALL Java_ai_metarank_b200_Native_groupFree(JNIEnv *env, jclas
   throw_status(env, mr_group_free((mr_group *)group));
 }
 
+// OnnxBiEncoder (S/ml/onnx/sbert/OnnxBiEncoder.scala:11-36): weights = the model.safetensors bytes (direct buffer),
+// embed = session.run + avgpool over the three [batch x seq] long tensors the tokenizer produced (direct buffers, native order)
+JNIEXPORT jlong JNICALL Java_ai_metarank_b200_Native_encoderLoad(JNIEnv *env, jclass, jlong ctx, jobject weights, jlong len, jint nHeads,
+                                                                 jdouble layerNormEps) {
+  mr_encoder *e = nullptr;
+  throw_status(env, mr_encoder_load((mr_ctx *)ctx, (const uint8_t *)env->GetDirectBufferAddress(weights), (size_t)len, nHeads,
+                                    layerNormEps, &e));
+  return (jlong)e;
+}
+
+JNIEXPORT jint JNICALL Java_ai_metarank_b200_Native_encoderDim(JNIEnv *env, jclass, jlong enc) {
+  int32_t dim = 0;
+  throw_status(env, mr_encoder_info((const mr_encoder *)enc, &dim, nullptr, nullptr, nullptr));
+  return dim;
+}
+
+JNIEXPORT void JNICALL Java_ai_metarank_b200_Native_encoderEmbed(JNIEnv *env, jclass, jlong enc, jobject inputIds, jobject tokenTypeIds,
+                                                                 jobject attentionMask, jint batch, jint seq, jobject out) {
+  auto addr = [&](jobject b) { return b ? env->GetDirectBufferAddress(b) : nullptr; };
+  throw_status(env, mr_encoder_embed((mr_encoder *)enc, (const int64_t *)addr(inputIds), (const int64_t *)addr(tokenTypeIds),
+                                     (const int64_t *)addr(attentionMask), batch, seq, (float *)addr(out)));
+}
+
+JNIEXPORT void JNICALL Java_ai_metarank_b200_Native_encoderFree(JNIEnv *env, jclass, jlong enc) {
+  throw_status(env, mr_encoder_free((mr_encoder *)enc));
+}
+
 }  // extern "C"
 #endif  // WITH_JNI

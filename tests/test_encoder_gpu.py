@@ -51,11 +51,18 @@ def test_dense_layer_epilogues(ctx):
     r = torch.randn(M, N, generator=g).to(dev)
     o32 = torch.empty(M, N, device=dev)
     base = a.double() @ w.double().T
-    # exact-erf GELU (BertIntermediate), then residual added after the activation
-    E.gemm_f16_device(ctx, a.data_ptr(), w.data_ptr(), b.data_ptr(), r.data_ptr(), o32.data_ptr(), 0, M, N, K, gelu=True)
+    # exact-erf GELU (BertIntermediate)
+    E.gemm_f16_device(ctx, a.data_ptr(), w.data_ptr(), b.data_ptr(), 0, o32.data_ptr(), 0, M, N, K, gelu=True)
     torch.cuda.synchronize()
-    ref = torch.nn.functional.gelu(base + b.double()) + r.double()
+    ref = torch.nn.functional.gelu(base + b.double())
     assert (o32.double() - ref).abs().max().item() < 2e-4 * max(ref.abs().max().item(), 1.0)
+    # bias + residual (BertSelfOutput / BertOutput before their LayerNorm)
+    E.gemm_f16_device(ctx, a.data_ptr(), w.data_ptr(), b.data_ptr(), r.data_ptr(), o32.data_ptr(), 0, M, N, K)
+    torch.cuda.synchronize()
+    ref = base + b.double() + r.double()
+    assert (o32.double() - ref).abs().max().item() < 2e-4 * max(ref.abs().max().item(), 1.0)
+    with pytest.raises(_capi.MrError):  # the forward never needs both in one layer
+        E.gemm_f16_device(ctx, a.data_ptr(), w.data_ptr(), b.data_ptr(), r.data_ptr(), o32.data_ptr(), 0, M, N, K, gelu=True)
     E.gemm_f16_device(ctx, a.data_ptr(), w.data_ptr(), 0, 0, o32.data_ptr(), 0, M, N, K)
     torch.cuda.synchronize()
     assert (o32.double() - base).abs().max().item() < 2e-4 * max(base.abs().max().item(), 1.0)
@@ -136,6 +143,23 @@ def test_one_query_is_independent_of_its_batch(ctx):
         assert np.abs(alone[0] - full[b]).max() < 2e-3
         assert 1 - _cos(alone, full[b:b + 1])[0] < 1e-5
     enc.close()
+
+
+def test_short_and_general_attention_agree(ctx):
+    # seq <= 32 runs the register-resident warp-per-head kernel, anything longer the shared-memory one; one extra masked
+    # pad token moves a batch from the first to the second without changing the mathematics
+    w = E.synthetic_bert_weights(layers=2, seed=21)
+    enc = E.OnnxBiEncoder(ctx, E.write_safetensors(w), n_heads=12)
+    rng = np.random.default_rng(8)
+    ids = rng.integers(0, 30522, (5, 32))
+    lens = np.array([32, 17, 1, 31, 8])
+    mask = (np.arange(32)[None, :] < lens[:, None]).astype(np.int64)
+    tt = np.zeros_like(ids)
+    short = enc.embed(ids, tt, mask)
+    pad = lambda a: np.concatenate([a, np.zeros((5, 1), dtype=np.int64)], axis=1)  # noqa: E731
+    general = enc.embed(pad(ids), pad(tt), pad(mask))
+    enc.close()
+    assert np.abs(short - general).max() < 1e-5
 
 
 def test_argument_errors(ctx):

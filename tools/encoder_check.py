@@ -91,7 +91,8 @@ for (name, kw, heads, B, S) in [("tiny", dict(hidden=128, layers=2, intermediate
             i2 = rng.integers(0, 30522, (b, s)); m2 = np.ones((b, s), dtype=np.int64); t2 = np.zeros((b, s), dtype=np.int64)
             di, dm, dt = [torch.from_numpy(x).to(dev) for x in (i2, m2, t2)]
             out = torch.empty(b, 384, device=dev)
-            st = torch.cuda.current_stream().cuda_stream
+            side = torch.cuda.Stream(); torch.cuda.set_stream(side)
+            st = side.cuda_stream
             for _ in range(3): enc.embed_device(di.data_ptr(), dt.data_ptr(), dm.data_ptr(), b, s, out.data_ptr(), 0, st)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize(); e0.record()
@@ -102,6 +103,16 @@ for (name, kw, heads, B, S) in [("tiny", dict(hidden=128, layers=2, intermediate
             for _ in range(it): enc.embed(i2, t2, m2)
             host_ms = (time.perf_counter() - t0) / it * 1000
             flops = 2.0 * b * s * 6 * (4 * 384 * 384 + 2 * 384 * 1536)
+            if b in (1, 16384):
+                import ctypes as C
+                from metarank_b200 import _capi
+                lib = _capi.lib()
+                _capi.check(lib.mr_profile_begin())
+                for _ in range(3): enc.embed_device(di.data_ptr(), dt.data_ptr(), dm.data_ptr(), b, s, out.data_ptr(), 0, st)
+                buf = C.create_string_buffer(1 << 16); n = C.c_size_t()
+                _capi.check(lib.mr_profile_end(buf, C.c_size_t(len(buf)), C.byref(n)))
+                for k in json.loads(buf.value.decode()):
+                    print(f"      {k['kernel']}: {k['launches']} launches, {k['ms'] / k['launches'] * 1000:.1f} us each", flush=True)
             print(f"embed batch {b} x {s} tokens: device {ms:.3f} ms ({b/ms*1000:.0f} queries/s, {flops/ms/1e9:.1f} dense TFLOP/s), host call {host_ms:.3f} ms", flush=True)
             res.setdefault("embed_time", []).append({"batch": b, "seq": s, "device_ms": ms, "host_call_ms": host_ms, "dense_tflops": flops / ms / 1e9})
     enc.close()
