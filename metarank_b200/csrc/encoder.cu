@@ -428,7 +428,8 @@ struct mr_encoder {
     for (const Layer &ly : layers) {
       encoder_gemm(x_f16, ly.w_qkv, ly.b_qkv, nullptr, nullptr, qkv, M, 3 * H, H, false, st);
       { ProfScope _ps("attention_kernel", st);
-        if (D == 32 && S <= 32) attention_short_kernel<<<(B * heads + 3) / 4, 128, 0, st>>>(qkv, mask, B * heads, heads, S, H, scale, ctxb);
+        // a warp per head pays once there are enough heads to fill the chip
+        if (D == 32 && S <= 32 && B * heads >= 4096) attention_short_kernel<<<(B * heads + 3) / 4, 128, 0, st>>>(qkv, mask, B * heads, heads, S, H, scale, ctxb);
         else if (D == 32) attention_kernel<32><<<dim3(heads, B), 128, att_smem, st>>>(qkv, mask, S, H, scale, ctxb);
         else attention_kernel<64><<<dim3(heads, B), 128, att_smem, st>>>(qkv, mask, S, H, scale, ctxb); }
       g_kernel_launches++;

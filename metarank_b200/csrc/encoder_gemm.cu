@@ -331,7 +331,9 @@ void encoder_gemm(const __half *A, const __half *W, const float *bias, const flo
   GemmParams p{bias, residual, out_f32, out_f16, M, N, K, gelu ? 1 : 0};
   if (gelu && residual) fail(MR_ERR_INVALID_ARG, "encoder GEMM: GELU and a residual in one epilogue are not built");
   const int epi = gelu ? EPI_GELU : residual ? EPI_RESIDUAL : EPI_BIAS;
-  if (N % 128 == 0) {
+  // few row blocks (a handful of queries): narrower tiles put twice as many SMs on the weight stream
+  const bool wide = N % 128 == 0 && (long long)((M + kBlockM - 1) / kBlockM) * (N / 128) >= num_sms() / 2;
+  if (wide) {
     if (epi == EPI_GELU) launch<128, EPI_GELU>(A, W, p, stream);
     else if (epi == EPI_RESIDUAL) launch<128, EPI_RESIDUAL>(A, W, p, stream);
     else launch<128, EPI_BIAS>(A, W, p, stream);

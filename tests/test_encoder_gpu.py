@@ -110,6 +110,12 @@ def test_small_encoder_ragged_batch_and_token_types(ctx):
     _check(got, want)
 
 
+def test_large_batch_of_short_queries(ctx):
+    # 1024 queries x 4 heads: the register-resident attention kernel, against the fp32 restatement
+    got, want = _case(ctx, dict(hidden=128, layers=2, intermediate=256, vocab=1000, max_pos=64, seed=13), 4, 1024, 9, seed=4)
+    _check(got, want)
+
+
 def test_head_dimension_64(ctx):
     got, want = _case(ctx, dict(hidden=256, layers=2, intermediate=512, vocab=500, max_pos=32, seed=4), 4, 3, 17, seed=5)
     _check(got, want)
@@ -151,12 +157,14 @@ def test_short_and_general_attention_agree(ctx):
     w = E.synthetic_bert_weights(layers=2, seed=21)
     enc = E.OnnxBiEncoder(ctx, E.write_safetensors(w), n_heads=12)
     rng = np.random.default_rng(8)
-    ids = rng.integers(0, 30522, (5, 32))
-    lens = np.array([32, 17, 1, 31, 8])
+    n = 352  # x 12 heads >= 4096 (sequence, head) pairs: the batch size from which the warp-per-head kernel is chosen
+    ids = rng.integers(0, 30522, (n, 32))
+    lens = rng.integers(1, 33, n)
+    lens[:5] = [32, 17, 1, 31, 8]
     mask = (np.arange(32)[None, :] < lens[:, None]).astype(np.int64)
     tt = np.zeros_like(ids)
     short = enc.embed(ids, tt, mask)
-    pad = lambda a: np.concatenate([a, np.zeros((5, 1), dtype=np.int64)], axis=1)  # noqa: E731
+    pad = lambda a: np.concatenate([a, np.zeros((n, 1), dtype=np.int64)], axis=1)  # noqa: E731
     general = enc.embed(pad(ids), pad(tt), pad(mask))
     enc.close()
     assert np.abs(short - general).max() < 1e-5
