@@ -427,9 +427,12 @@ class GenericWorkload(Workload):
 
     def step(self, explain=False):
         import metarank_b200 as mb
+        import torch
+        if explain and getattr(self, "d_feat", None) is None:
+            self.d_feat = torch.empty(self.rows * self.c["features"], dtype=torch.float64, device="cuda")
         mb._capi.check(mb._capi.lib().mr_rank_device(self.state._h, self.booster._h, C.byref(self.batch), C.c_int32(self.rows),
-                                                     C.c_void_p(self.d_out.data_ptr()), C.c_void_p(self.d_order.data_ptr()), None,
-                                                     C.c_void_p(self.stream)))
+                                                     C.c_void_p(self.d_out.data_ptr()), C.c_void_p(self.d_order.data_ptr()),
+                                                     C.c_void_p(self.d_feat.data_ptr()) if explain else None, C.c_void_p(self.stream)))
 
     def status(self):
         from metarank_b200 import features as F
@@ -617,7 +620,8 @@ def scorer_roofline(w, kernels, step_ms, sm_mhz):
     out = {"kernel": dom["kernel"], "kernel_ms": dom["ms_per_step"], "step_share": dom["ms_per_step"] / step_ms,
            "peak_source": peak_src}
     slim = dom["kernel"].startswith("gbdt_score_slim")
-    if not (slim or dom["kernel"].startswith("gbdt_score_compact")):
+    leaves = dom["kernel"].startswith("gbdt_leaves")
+    if not (slim or leaves or dom["kernel"].startswith("gbdt_score_compact")):
         out.update({"bound": "hbm", "achieved": None, "peak": peak_hbm, "unit": "GB/s", "frac": None, "traffic": None,
                     "note": "dominant kernel is not the compact scorer; see `kernels` for its HBM fraction"})
         return out
@@ -637,7 +641,8 @@ def scorer_roofline(w, kernels, step_ms, sm_mhz):
     # wavefront floor of the lock-step walk: per level one node load and one code load (1 wavefront each); per tree the leaf
     # value (LDS.64: 1, or 2 once lanes sit on different leaves) and a quarter of a root-table load (LDS.128 per 4 trees);
     # the slim layout also reads the root entry (1) and its leaf value as two half-warp passes (2)
-    wavefronts = (2.0 * warp.value + (3.25 if slim else 1.25) * wt.value) * scale
+    # (the leaf-slot kernel of the low-latency path walks 8-byte nodes and stores a u16 slot per tree: 1 per warp-tree)
+    wavefronts = (2.0 * warp.value + (3.25 if slim else 1.0 if leaves else 1.25) * wt.value) * scale
     t = dom["ms_per_step"] / 1e3
     smem_peak = SM_COUNT * 128.0 * clk / 1e9       # GB/s
     achieved = wavefronts * 128.0 / t / 1e9
@@ -657,7 +662,7 @@ def scorer_roofline(w, kernels, step_ms, sm_mhz):
         "wavefronts_per_launch_floor": wavefronts, "warp_levels_per_tree": levels_per_wt, "mean_path": dbar,
         "lanes_active_of_32": 32.0 * lanes_active, "sm_clock_mhz": clk / 1e6,
         "issue": {"frac": None, "what": "see profiles/: issue-slot utilisation comes from ncu (sm__inst_executed), not from this run"},
-        "traffic": static.get("dominant_kernel_c2_bytes_per_launch"),
+        "traffic": static.get("dominant_kernel_c2_bytes_per_launch") if w.name == "C2" else None,
         "traffic_source": "static: profiles/traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of one capture), not measured in this run",
         "ncu_static": {k: static[k] for k in ("smem_wavefronts_per_launch", "l1tex_pipe_pct", "issue_active_pct", "source") if k in static},
         "algorithmic_gbs": b_item * w.rows / t / 1e9, "algorithmic_bytes_per_item": b_item,
@@ -682,6 +687,7 @@ def kernel_table(w, kernels):
         "code_gather_kernel": n * (2 * 2 * (tc or 0)) if tc else None,   # code row read + tile write
         "row_gather_kernel": n * (row_b + 2 * (tc or 0)) if tc else n * (row_b + 8 * w.c["features"]),
         "cosine_kernel": n * (8 * 384 + 16) if w.name == "C4" else None,
+        "cosine_f32_kernel": n * (4 * 384 + 8 + 8 + 8) if w.name == "C4" else None,   # f32 row + bSum + row index + the raw cosine out
         "order_small_kernel": n * 12,
         "order_kernel": n * 12,
     }
@@ -819,10 +825,17 @@ def measure(w, args, rank, world, dist, barrier, full=True):
         except Exception:
             w.tile_cols = None
         res["kernels"] = kernel_table(w, ks)
-        if full and w.name == "C2":
-            res["roofline"] = scorer_roofline(w, ks, total_ms / args.steps, (res.get("clocks") or {}).get("sm_mhz"))
+        dom = max(res["kernels"], key=lambda k: k["ms_per_step"])
+        walk = None
+        if dom["kernel"].startswith(("gbdt_score_slim", "gbdt_score_compact", "gbdt_leaves")):
+            try:
+                walk = scorer_roofline(w, ks, total_ms / args.steps, (res.get("clocks") or {}).get("sm_mhz"))
+            except Exception as ex:  # e.g. walk statistics not available for this model form
+                walk = None
+                res["roofline_note"] = f"walk statistics unavailable: {type(ex).__name__}: {ex}"[:200]
+        if walk is not None:
+            res["roofline"] = walk
         else:
-            dom = max(res["kernels"], key=lambda k: k["ms_per_step"])
             res["roofline"] = {"bound": dom.get("bound"), "kernel": dom["kernel"], "kernel_ms": dom["ms_per_step"],
                                "achieved": dom.get("achieved_gbs"), "peak": _peaks()[0], "unit": "GB/s", "frac": dom.get("frac_hbm"),
                                "traffic": None, "step_share": dom["ms_per_step"] / (total_ms / args.steps)}
@@ -858,7 +871,8 @@ def query_encoder_block(ctx, n_queries, seq=16):
     d_ids, d_tt, d_mask = (torch.from_numpy(x).to(dev) for x in (ids, tt, mask))
     out = torch.empty(n_queries, hidden, device=dev)
     out64 = torch.empty(n_queries, hidden, device=dev, dtype=torch.float64)
-    st = torch.cuda.current_stream()
+    st = torch.cuda.Stream()  # not the legacy stream: the library replays its CUDA graph of the forward on real streams only
+    torch.cuda.synchronize()
 
     def timed(b, iters):
         for _ in range(3):

@@ -98,6 +98,15 @@ struct GemmParams {
   int gelu;
 };
 
+// One lane of a converged warp, chosen by the hardware: unlike `lane == 0` the compiler knows the branch holds a single
+// thread and emits the tcgen05 / TMA instructions bare instead of wrapping each in an ELECT / BRA.U.ANY loop over the active
+// lanes (ncu_r2_gemm3: that wrapping was most of what the MMA-issuing thread executed).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xFFFFFFFF;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -144,7 +153,7 @@ __global__ void __launch_bounds__(320, 1) encoder_gemm_kernel(const __grid_const
   // `acc_empty` falls through.  Polling waits (mbar_wait_spin): the waiter is normally AHEAD of the data here, where
   // try_wait's suspension costs more than the spin.
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ===== TMA producer
       uint32_t it = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -159,7 +168,7 @@ __global__ void __launch_bounds__(320, 1) encoder_gemm_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ===== MMA issuer.  Instruction descriptor: D = f32, A = B = f16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
       const uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
       uint32_t it = 0, lt = 0;

@@ -14,4 +14,3 @@ run 8 C5 bench_r2_c5_n8.json "--steps 30"
 run 4 C5 bench_r2_c5_n4.json "--steps 30"
 run 2 C5 bench_r2_c5_n2b.json "--steps 30"
 run 1 C5 bench_r2_c5_n1b.json "--steps 30 --no-extras"
-run 8 C2 bench_r2_c2_n8.json "--steps 30"
