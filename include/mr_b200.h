@@ -430,7 +430,8 @@ MR_API mr_status mr_encoder_info(const mr_encoder *e, int32_t *dim, int32_t *lay
 MR_API mr_status mr_encoder_embed(mr_encoder *e, const int64_t *input_ids, const int64_t *token_type_ids,
                                   const int64_t *attention_mask, int32_t batch, int32_t seq, float *out);
 /* Same with device pointers, enqueued on `cuda_stream` without synchronising.  d_out_f64, when not null, also receives
- * the embeddings widened to f64 — the query-embedding operand of mr_rank_batch. */
+ * the embeddings widened to f64 — the query-embedding operand of mr_rank_batch.  A token / type id outside the tables,
+ * which fails the host entry point with MR_ERR_INVALID_ARG (ONNX Runtime's Gather fails the run), reads as id 0 here. */
 MR_API mr_status mr_encoder_embed_device(mr_encoder *e, const int64_t *d_input_ids, const int64_t *d_token_type_ids,
                                          const int64_t *d_attention_mask, int32_t batch, int32_t seq, float *d_out,
                                          double *d_out_f64, void *cuda_stream);

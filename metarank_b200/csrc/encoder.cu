@@ -211,6 +211,98 @@ __global__ void __launch_bounds__(128, 5) attention_short_kernel(const __half *q
   }
 }
 
+// seq <= 16 (the usual search phrase) and head dimension 32: the whole head is two tensor-core tiles.  A warp owns one
+// (sequence, head): S = Q K^T as 2 x 2 `mma.sync.m16n8k16` (Q rows = A fragments, K rows = B fragments, both straight from
+// global memory: a fragment register is two adjacent binary16 values of one row), softmax on the accumulator fragments
+// (a row lives in the four lanes of a quad: two xor-shuffles per reduction), P re-used in place as the A fragment of
+// O = P V (the accumulator layout of two 8-column tiles IS the A layout of a 16-deep step), V gathered as B fragments.
+// ~120 instructions per head instead of ~3000 scalar ones.  P is rounded to binary16 for the second product — the same
+// rounding the output gets anyway; tolerance in tests/test_encoder_gpu.py.  (tcgen05 has no shape this small: its minimum
+// tile is 64 x 8 x 16 per CTA and one accumulator round trip through TMEM costs more than this whole head.)
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+__global__ void __launch_bounds__(128) attention_mma16_kernel(const __half *qkv, const int64_t *mask, int n_pairs, int heads, int S,
+                                                              int H, float scale, __half *ctx) {
+  const int w = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (w >= n_pairs) return;
+  const int b = w / heads, head = w % heads, g = lane >> 2, t = lane & 3;
+  const __half *base = qkv + (size_t)b * S * 3 * H + head * 32;
+  const size_t pitch = (size_t)3 * H;
+  const int r0 = min(g, S - 1), r1 = min(g + 8, S - 1);  // rows / keys beyond the sequence read a valid row; their results are dropped
+  auto ld32 = [](const __half *p) { return __ldg(reinterpret_cast<const uint32_t *>(p)); };
+  // scores
+  float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+  for (int ks = 0; ks < 2; ks++) {
+    const int d0 = 16 * ks + 2 * t;
+    const uint32_t a[4] = {ld32(base + r0 * pitch + d0), ld32(base + r1 * pitch + d0), ld32(base + r0 * pitch + d0 + 8),
+                           ld32(base + r1 * pitch + d0 + 8)};
+    mma_16816(sc[0], a, ld32(base + r0 * pitch + H + d0), ld32(base + r0 * pitch + H + d0 + 8));  // keys 0..7: key g
+    mma_16816(sc[1], a, ld32(base + r1 * pitch + H + d0), ld32(base + r1 * pitch + H + d0 + 8));  // keys 8..15: key g + 8
+  }
+  // key validity of this lane's four columns: keys 2t, 2t+1, 8+2t, 9+2t
+  bool any_l = false, ok[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int j = (i >> 1) * 8 + 2 * t + (i & 1);
+    ok[i] = j < S && mask[(size_t)b * S + min(j, S - 1)] != 0;
+    any_l |= ok[i];
+  }
+  const bool any = __ballot_sync(0xFFFFFFFFu, any_l) != 0;
+  float p[2][4];  // [key tile][c0 c1 = row g, c2 c3 = row g + 8]
+#pragma unroll
+  for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int col = nt * 2 + (i & 1), j = nt * 8 + 2 * t + (i & 1);
+      float x = sc[nt][i] * scale;
+      if (j >= S) x = -INFINITY;
+      else if (!any) x = 0.f;
+      else if (!ok[col]) x = -INFINITY;
+      p[nt][i] = x;
+    }
+  float inv[2];
+#pragma unroll
+  for (int hrow = 0; hrow < 2; hrow++) {  // row g (values 0, 1 of both tiles), row g + 8 (values 2, 3)
+    float mx = fmaxf(fmaxf(p[0][2 * hrow], p[0][2 * hrow + 1]), fmaxf(p[1][2 * hrow], p[1][2 * hrow + 1]));
+    mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 2));
+    float sum = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+      for (int i = 0; i < 2; i++) { const float e = __expf(p[nt][2 * hrow + i] - mx); p[nt][2 * hrow + i] = e; sum += e; }
+    sum += __shfl_xor_sync(0xFFFFFFFFu, sum, 1);
+    sum += __shfl_xor_sync(0xFFFFFFFFu, sum, 2);
+    inv[hrow] = 1.0f / sum;
+  }
+  const uint32_t pa[4] = {pack_half2(p[0][0], p[0][1]), pack_half2(p[0][2], p[0][3]), pack_half2(p[1][0], p[1][1]),
+                          pack_half2(p[1][2], p[1][3])};
+  // O = P V: B fragment of dimension tile dt = {V[2t][d], V[2t+1][d]}, {V[2t+8][d], V[2t+9][d]} with d = 8 dt + g
+  const unsigned short *vb = reinterpret_cast<const unsigned short *>(base + 2 * H);
+  const size_t k0 = (size_t)min(2 * t, S - 1) * pitch, k1 = (size_t)min(2 * t + 1, S - 1) * pitch,
+               k2 = (size_t)min(2 * t + 8, S - 1) * pitch, k3 = (size_t)min(2 * t + 9, S - 1) * pitch;
+#pragma unroll
+  for (int dt = 0; dt < 4; dt++) {
+    const int d = 8 * dt + g;
+    const uint32_t b0 = (uint32_t)__ldg(vb + k0 + d) | (uint32_t)__ldg(vb + k1 + d) << 16;
+    const uint32_t b1 = (uint32_t)__ldg(vb + k2 + d) | (uint32_t)__ldg(vb + k3 + d) << 16;
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_16816(o, pa, b0, b1);
+    const int col = head * 32 + 8 * dt + 2 * t;
+    if (g < S) *reinterpret_cast<uint32_t *>(ctx + ((size_t)b * S + g) * H + col) = pack_half2(o[0] * inv[0], o[1] * inv[0]);
+    if (g + 8 < S) *reinterpret_cast<uint32_t *>(ctx + ((size_t)b * S + g + 8) * H + col) = pack_half2(o[2] * inv[1], o[3] * inv[1]);
+  }
+}
+
 // OnnxBiEncoder.avgpool (:38-60): per dimension, a double sum over the first tokenLengths = sum(attention_mask) tokens
 // divided by their count, narrowed to float; 0 tokens -> 0.0 / 0 = NaN, as in the reference.
 __global__ void __launch_bounds__(128) meanpool_kernel(const float *x, const int64_t *mask, int S, int H, float *out, double *out_f64) {
@@ -429,7 +521,8 @@ struct mr_encoder {
       encoder_gemm(x_f16, ly.w_qkv, ly.b_qkv, nullptr, nullptr, qkv, M, 3 * H, H, false, st);
       { ProfScope _ps("attention_kernel", st);
         // a warp per head pays once there are enough heads to fill the chip
-        if (D == 32 && S <= 32 && B * heads >= 4096) attention_short_kernel<<<(B * heads + 3) / 4, 128, 0, st>>>(qkv, mask, B * heads, heads, S, H, scale, ctxb);
+        if (D == 32 && S <= 16 && B * heads >= 1024) attention_mma16_kernel<<<(B * heads + 3) / 4, 128, 0, st>>>(qkv, mask, B * heads, heads, S, H, scale, ctxb);
+        else if (D == 32 && S <= 32 && B * heads >= 4096) attention_short_kernel<<<(B * heads + 3) / 4, 128, 0, st>>>(qkv, mask, B * heads, heads, S, H, scale, ctxb);
         else if (D == 32) attention_kernel<32><<<dim3(heads, B), 128, att_smem, st>>>(qkv, mask, S, H, scale, ctxb);
         else attention_kernel<64><<<dim3(heads, B), 128, att_smem, st>>>(qkv, mask, S, H, scale, ctxb); }
       g_kernel_launches++;

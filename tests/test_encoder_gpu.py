@@ -116,6 +116,13 @@ def test_large_batch_of_short_queries(ctx):
     _check(got, want)
 
 
+@pytest.mark.parametrize("S", [16, 8, 3, 1])
+def test_tensor_core_attention_for_short_sequences(ctx, S):
+    # seq <= 16 with >= 1024 (sequence, head) pairs: attention_mma16_kernel (mma.sync tiles, P rounded to binary16)
+    got, want = _case(ctx, dict(hidden=128, layers=2, intermediate=256, vocab=1000, max_pos=64, seed=15), 4, 300, S, seed=S)
+    _check(got, want)
+
+
 def test_head_dimension_64(ctx):
     got, want = _case(ctx, dict(hidden=256, layers=2, intermediate=512, vocab=500, max_pos=32, seed=4), 4, 3, 17, seed=5)
     _check(got, want)

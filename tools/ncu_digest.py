@@ -25,7 +25,7 @@ hi = next(i for i, x in enumerate(rows) if "# Samples" in x)
 hdr = rows[hi]
 si, ci, ei = hdr.index("# Samples"), hdr.index("Source"), hdr.index("Instructions Executed")
 stall = [(i, x) for i, x in enumerate(hdr) if x.startswith("stall_") and "Not Issued" not in x]
-data = rows[hi + 1:]
+data = [x for x in rows[hi + 1:] if len(x) > max(si, ci, ei)]
 tot = sum(float(x[si] or 0) for x in data) or 1.0
 agg = {}
 for x in data:
