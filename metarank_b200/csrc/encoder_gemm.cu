@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.h"
@@ -31,7 +32,9 @@ namespace {
 
 constexpr int kBlockM = 128, kBlockK = 64, kUmmaK = 16;
 // ring depth: 192 KB of operand stages either way (6 x 32 KB, 8 x 24 KB) — a whole K = 384 tile ahead of the MMA warp
-template <int BLOCK_N> struct StagesFor { static constexpr int value = BLOCK_N == 128 ? 6 : 8; };
+template <int BLOCK_N> struct StagesFor { static constexpr int value = BLOCK_N == 192 ? 5 : BLOCK_N == 128 ? 6 : 8; };  // 200 / 192 / 192 KB
+// TMEM columns are allocated in powers of two: the two accumulators of a 192-column tile sit 256 columns apart
+template <int BLOCK_N> struct AccStride { static constexpr uint32_t value = BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256; };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(320, 1) encoder_gemm_kernel(const __grid_const
   // [A stages: kStages x 128 x 128 B][W stages: kStages x BLOCK_N x 128 B][barriers][tmem address]
   constexpr uint32_t kStages = StagesFor<BLOCK_N>::value;
   constexpr uint32_t kABytes = kBlockM * kBlockK * 2, kWBytes = BLOCK_N * kBlockK * 2;
-  constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // a power of two >= 32
+  constexpr uint32_t kAccStride = AccStride<BLOCK_N>::value, kTmemCols = 2 * kAccStride;  // a power of two >= 32
   uint8_t *sa = smem, *sw = smem + kStages * kABytes;
   uint64_t *full = reinterpret_cast<uint64_t *>(sw + kStages * kWBytes), *empty = full + kStages;
   uint64_t *acc_full = empty + kStages, *acc_empty = acc_full + 2;
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(320, 1) encoder_gemm_kernel(const __grid_const
         const uint32_t acc = lt & 1, acc_ph = (lt >> 1) & 1;
         mbar_wait_spin(&acc_empty[acc], acc_ph ^ 1);  // the epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        const uint32_t tmem_d = tmem_base + acc * kAccStride;
         for (int kb = 0; kb < n_kblocks; kb++, it++) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1;
           mbar_wait_spin(&full[s], ph);
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(320, 1) encoder_gemm_kernel(const __grid_const
           for (int j = 0; j < 8; j++) res[j] = __ldg(rs + j);
         }
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + (uint32_t)(half * (BLOCK_N / 2) + 32 * c), v);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kAccStride + (uint32_t)(half * (BLOCK_N / 2) + 32 * c), v);
         if (c == kChunks - 1) {
           // every column this warp owns is in registers: hand the accumulator back before the stores
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -329,6 +332,7 @@ void encoder_gemm_init() {
   std::call_once(once, [] {
     set_smem<128, EPI_BIAS>(); set_smem<128, EPI_GELU>(); set_smem<128, EPI_RESIDUAL>();
     set_smem<64, EPI_BIAS>(); set_smem<64, EPI_GELU>(); set_smem<64, EPI_RESIDUAL>();
+    set_smem<192, EPI_BIAS>(); set_smem<192, EPI_GELU>(); set_smem<192, EPI_RESIDUAL>();
   });
 }
 
@@ -340,9 +344,18 @@ void encoder_gemm(const __half *A, const __half *W, const float *bias, const flo
   GemmParams p{bias, residual, out_f32, out_f16, M, N, K, gelu ? 1 : 0};
   if (gelu && residual) fail(MR_ERR_INVALID_ARG, "encoder GEMM: GELU and a residual in one epilogue are not built");
   const int epi = gelu ? EPI_GELU : residual ? EPI_RESIDUAL : EPI_BIAS;
-  // few row blocks (a handful of queries): narrower tiles put twice as many SMs on the weight stream
-  const bool wide = N % 128 == 0 && (long long)((M + kBlockM - 1) / kBlockM) * (N / 128) >= num_sms() / 2;
-  if (wide) {
+  // Tile width: 192 columns where N allows it (all BERT-small shapes: 384, 1152, 1536) — a third fewer re-reads of the A
+  // row block than 128 (the K = 384 layers are bound by L2 -> SM operand traffic, ncu_r2_summary.md); with only a few row
+  // blocks (a handful of queries) 64-column tiles put more SMs on the weight stream instead.  MR_GEMM_BN=64|128|192 forces one.
+  const long long row_blocks = (M + kBlockM - 1) / kBlockM;
+  static const int forced = [] { const char *e = getenv("MR_GEMM_BN"); return e ? atoi(e) : 0; }();
+  int bn = row_blocks * (N / 128 > 0 ? N / 128 : 1) < num_sms() / 2 ? 64 : N % 192 == 0 ? 192 : N % 128 == 0 ? 128 : 64;
+  if (forced && N % forced == 0 && (forced == 64 || forced == 128 || forced == 192)) bn = forced;
+  if (bn == 192) {
+    if (epi == EPI_GELU) launch<192, EPI_GELU>(A, W, p, stream);
+    else if (epi == EPI_RESIDUAL) launch<192, EPI_RESIDUAL>(A, W, p, stream);
+    else launch<192, EPI_BIAS>(A, W, p, stream);
+  } else if (bn == 128) {
     if (epi == EPI_GELU) launch<128, EPI_GELU>(A, W, p, stream);
     else if (epi == EPI_RESIDUAL) launch<128, EPI_RESIDUAL>(A, W, p, stream);
     else launch<128, EPI_BIAS>(A, W, p, stream);
