@@ -307,6 +307,42 @@ class C2(Workload):
         return {"p50_ms": float(np.percentile(ts, 50) * 1e3), "p99_ms": float(np.percentile(ts, 99) * 1e3),
                 "what": "mr_rank, 1 request x 100 items: id hashes in -> scores + order out, host buffers, via ctypes"}
 
+    def churn(self, steps=8, frac=0.01):
+        """State churn inside the timer: before every step `frac` of the catalogue's rows get new values
+        (mr_state_upsert of all 30 columns + mr_state_flush: host table update, scatter upload, and the per-model code rows
+        of the touched items re-derived on the next rank call), then the step runs.  Wall clock around upsert + flush + step
+        with a device sync per step; parity of the last step against the oracle on the updated values."""
+        import torch
+        from metarank_b200 import features as F
+        from oracle import oracle
+        c = self.c
+        names = [f"f{j}" for j in range(c["features"])]
+        n_upd = max(1, int(c["catalogue"] * frac))
+        rng = np.random.Generator(np.random.PCG64(c["data_seed"] + 77))
+        packs, rows_upd, vals_upd = [], [], []
+        for _ in range(steps + 1):
+            rows = rng.choice(c["catalogue"], n_upd, replace=False)
+            vals = rng.standard_normal((n_upd, c["features"]))
+            packs.append(F.pack_number_columns(names, self.item_ids[rows], vals))
+            rows_upd.append(rows); vals_upd.append(vals)
+        t_up = t_step = 0.0
+        for k in range(steps + 1):  # the first pass warms the path and is not counted
+            a = time.perf_counter()
+            self.state.put_packed(packs[k]); self.state.flush()
+            b = time.perf_counter()
+            self.step(); self.status(); torch.cuda.synchronize()
+            e = time.perf_counter()
+            self.cat[rows_upd[k]] = vals_upd[k]
+            if k:
+                t_up += b - a; t_step += e - b
+        n = min(2000, self.rows)
+        got = self.d_out[:n].cpu().numpy()
+        want = oracle.OracleBooster(0, self.blob).predictMat(np.ascontiguousarray(self.cat[self.pick[:n]]), n, c["features"])
+        return {"what": f"{frac:.0%} of the {c['catalogue']} item rows rewritten (all {c['features']} columns) + mr_state_flush before every step, "
+                        "inside the timer; wall clock, device sync per step", "steps": steps, "rows_updated_per_step": int(n_upd),
+                "value": self.rows * steps / (t_up + t_step), "unit": UNIT, "upsert_flush_ms_per_step": t_up / steps * 1e3,
+                "rank_ms_per_step": t_step / steps * 1e3, "scores_bit_identical_after_updates": bool(np.array_equal(got, want))}
+
     # --- CPU arm (oracle port): parallel row gather + C oracle scorer + per-request ordering
     def cpu_setup(self):
         from oracle import oracle
@@ -840,6 +876,11 @@ def measure(w, args, rank, world, dist, barrier, full=True):
                                "achieved": dom.get("achieved_gbs"), "peak": _peaks()[0], "unit": "GB/s", "frac": dom.get("frac_hbm"),
                                "traffic": None, "step_share": dom["ms_per_step"] / (total_ms / args.steps)}
         res["cpu_baseline"] = cpu_baseline(w, 12.0 if full else 4.0)
+        if w.name == "C2" and full:
+            try:
+                res["churn"] = w.churn()
+            except Exception as ex:
+                res["churn"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
         if w.name == "C4":
             try:
                 res["query_encoder"] = query_encoder_block(w.ctx, w.arrays["n_requests"])
@@ -992,6 +1033,8 @@ def main():
         }
         if res.get("query_encoder"):
             out["query_encoder"] = res["query_encoder"]
+        if res.get("churn"):
+            out["churn"] = res["churn"]
         if extras:
             out["other_configs"] = extras
         print(json.dumps(out), flush=True)
