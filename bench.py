@@ -678,7 +678,10 @@ def scorer_roofline(w, kernels, step_ms, sm_mhz):
     # value (LDS.64: 1, or 2 once lanes sit on different leaves) and a quarter of a root-table load (LDS.128 per 4 trees);
     # the slim layout also reads the root entry (1) and its leaf value as two half-warp passes (2)
     # (the leaf-slot kernel of the low-latency path walks 8-byte nodes and stores a u16 slot per tree: 1 per warp-tree)
-    wavefronts = (2.0 * warp.value + (3.25 if slim else 1.0 if leaves else 1.25) * wt.value) * scale
+    # with the root table in the kernel's parameter space (<= 1920 trees) level 0 has no node load and no root-table load:
+    # 2 per level step - 1 + the leaf value's 2
+    root_tab = slim and c["trees"] <= 1920
+    wavefronts = (2.0 * warp.value + (1.0 if root_tab else 3.25 if slim else 1.0 if leaves else 1.25) * wt.value) * scale
     t = dom["ms_per_step"] / 1e3
     smem_peak = SM_COUNT * 128.0 * clk / 1e9       # GB/s
     achieved = wavefronts * 128.0 / t / 1e9
@@ -693,7 +696,7 @@ def scorer_roofline(w, kernels, step_ms, sm_mhz):
     out.update({
         "bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
         "what": "shared-memory crossbar: wavefronts the lock-step walk needs at least (counted on this batch by "
-                "mr_model_walk_stats: 2 per warp level step + 1.25 (8-byte nodes) or 3.25 (4-byte nodes) per warp-tree) x 128 B / kernel time, against "
+                "mr_model_walk_stats: 2 per warp level step + per warp-tree 1 (4-byte nodes, root table in the parameter space), 3.25 (4-byte nodes) or 1.25 (8-byte nodes)) x 128 B / kernel time, against "
                 "SMs x 128 B/clk x SM clock",
         "wavefronts_per_launch_floor": wavefronts, "warp_levels_per_tree": levels_per_wt, "mean_path": dbar,
         "lanes_active_of_32": 32.0 * lanes_active, "sm_clock_mhz": clk / 1e6,
@@ -857,7 +860,7 @@ def measure(w, args, rank, world, dist, barrier, full=True):
     w.status()
     if rank == 0:
         try:
-            w.tile_cols = int(w.booster.codes_bytes(32) // 64) or None
+            w.tile_cols = int(round(w.booster.codes_bytes(1 << 16) / float(1 << 16) / 2.0)) or None  # u16 codes per item (whole CTA tiles: ask for many rows)
         except Exception:
             w.tile_cols = None
         res["kernels"] = kernel_table(w, ks)

@@ -149,6 +149,13 @@ MR_API mr_status mr_model_get_info(mr_model *m, mr_model_info *out);
  * parsers).  It does not score anything. */
 MR_API mr_status mr_model_inspect(int32_t kind, const uint8_t *blob, size_t len, int32_t chunk_kb, mr_model_info *out);
 
+/* Host-only consistency check of the throughput scorer's packing (4-byte entries, root table, in-entry bitsets): `samples`
+ * random code vectors are walked through the parsed trees and through the packed bytes the way the kernel reads them.
+ * *form: 0 = the model has no such packing (other scorers serve it), else 1 | 2 * (root table present) |
+ * 4 * (small-categorical codes); *mismatches: (sample, tree) pairs whose leaf differs — 0 for a sound packing.
+ * Validates layout on CPU-only CI; it scores nothing and is not a fallback. */
+MR_API mr_status mr_model_selfcheck(int32_t kind, const uint8_t *blob, size_t len, int32_t samples, int32_t *form, int64_t *mismatches);
+
 /* Mean evaluated path length (internal nodes visited per item per tree) of the last
  * `rows` scored by mr_model_count_path(): the d̄ of SURVEY.md §8(d)'s B_item. */
 MR_API mr_status mr_model_count_path(mr_model *m, const double *values, int32_t rows, int32_t cols, double *mean_path);

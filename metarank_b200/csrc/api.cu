@@ -348,6 +348,25 @@ mr_status mr_model_inspect(int32_t kind, const uint8_t *blob, size_t len, int32_
   });
 }
 
+mr_status mr_model_selfcheck(int32_t kind, const uint8_t *blob, size_t len, int32_t samples, int32_t *form, int64_t *mismatches) {
+  return guard([&] {
+    if (!blob || !form || !mismatches) fail(MR_ERR_INVALID_ARG, "null argument");
+    HostModel hm;
+    if (kind == MR_BOOSTER_LIGHTGBM) hm = parse_lightgbm_text(blob, len);
+    else if (kind == MR_BOOSTER_XGBOOST) hm = parse_xgboost_model(blob, len);
+    else fail(MR_ERR_UNSUPPORTED, "unsupported booster tag %d", kind);
+    *form = 0; *mismatches = 0;
+    const BinnedModel bn = pack_binned(hm, (size_t)(hm.n_features <= 32 ? 60 : 16) * 1024);
+    if (!bn.ok) return;
+    const BinnedModel cm = pack_compact(hm, bn, 0);
+    if (!cm.ok) return;
+    const SlimModel sl = pack_slim(hm, cm, 0);
+    if (!sl.ok) return;
+    *form = 1 | (sl.root_tab.empty() ? 0 : 2) | (sl.cat16 ? 4 : 0);
+    *mismatches = (int64_t)slim_pack_selfcheck(hm, cm, sl, std::max(1, samples), 0x9E3779B97F4A7C15ull);
+  });
+}
+
 mr_status mr_model_walk_stats(mr_model *m, const double *d_values, int32_t rows, int32_t cols, double *lane_levels,
                               double *warp_levels, double *warp_trees, void *cuda_stream) {
   return guard([&] {

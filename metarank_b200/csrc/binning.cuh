@@ -37,13 +37,14 @@ __device__ __forceinline__ size_t code_index(int tile_T, int tile_cols, int item
 template <bool XGB>
 __device__ __forceinline__ uint16_t code_of_col_t(const BinParams &p, const BinMeta &M, bool cat, double x) {
   if (XGB) x = (double)__double2float_rn(x);  // XGBoost compares binary32 values, strict less (upper_bound)
-  if (x != x) return kBinNaN;
   if (cat) {
-    // LightGBM CategoricalDecision: static_cast<int>(x), negative / out-of-int-range -> right
-    const bool in_range = (x < 2147483648.0) && (x > -2147483649.0);
+    // LightGBM CategoricalDecision: static_cast<int>(x), NaN / negative / out-of-int-range -> right
+    const bool in_range = (x < 2147483648.0) && (x > -2147483649.0);  // false for NaN
     const int iv = in_range ? __double2int_rz(x) : -1;
+    if (M.flags & kMetaCat16) return (iv >= 0 && iv < 16) ? (uint16_t)(kCat16Base | (uint32_t)iv) : kCat16Missing;
     return (iv >= 0 && iv < 65000) ? (uint16_t)iv : kBinNaN;
   }
+  if (x != x) return kBinNaN;
   // bucket(x) is monotone, so only the thresholds in x's own bucket need comparing
   uint32_t bk = 0;
   if (M.g > 1 && x > M.mn) {
@@ -86,6 +87,11 @@ __device__ __forceinline__ uint16_t code_of(const BinParams &p, int f, double x)
 // feature's nodes agree on; a feature with both NaN directions also fills its duplicate column.
 __device__ __forceinline__ uint16_t base_code(const BinMeta &M, uint16_t c) {
   return (c == kBinNaN && (M.flags & kMetaNanLow)) ? (uint16_t)0 : c;
+}
+// the category behind a categorical column's code (kBinNaN: goes right), whichever form the model's codes are in
+__device__ __forceinline__ uint32_t cat_of_code(uint32_t code, bool cat16) {
+  if (!cat16) return code;
+  return (code & 0xFFF0u) == kCat16Base ? (code & 15u) : (uint32_t)kBinNaN;
 }
 __device__ __forceinline__ uint32_t dup_col(const BinMeta &M) { return M.flags >> 16; }  // kMetaNoDup: none
 __device__ __forceinline__ uint16_t dup_code(uint16_t c) { return c == kBinNaN ? (uint16_t)0 : c; }

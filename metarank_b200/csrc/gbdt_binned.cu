@@ -15,6 +15,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <type_traits>
 
 #include "binning.cuh"
 #include "gbdt_kernels.cuh"
@@ -78,15 +80,17 @@ struct BParams {
   uint32_t chunk_stride;
   int rows, n_features;
   float base_score;
+  int cat16;  // categorical columns carry the small-categorical code form (gbdt_model.h kMetaCat16)
   ScoreSinks sinks;
 };
 
 template <bool HAS_CAT>
-__device__ __forceinline__ int bstep(const uint2 nd, const uint32_t code, const uint8_t *chunk) {
+__device__ __forceinline__ int bstep(const uint2 nd, uint32_t code, const uint8_t *chunk, bool cat16) {
   const uint32_t k = nd.x & 0xFFFFu, fl = nd.x >> 28;
   bool left;
   if (HAS_CAT && (fl & BF_CATEGORICAL)) {
     left = false;
+    code = cat_of_code(code, cat16);
     if (code != kBinNaN) {
       const uint2 ct = reinterpret_cast<const uint2 *>(chunk)[k];  // {bitset word offset, n words}
       const uint32_t w = code >> 5;
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(1024) gbdt_score_binned_kernel(const BParams p
           any = false;
 #pragma unroll
           for (int k = 0; k < ILP; k++) {
-            const int nx = bstep<HAS_CAT>(nd[k], code[k], cb);
+            const int nx = bstep<HAS_CAT>(nd[k], code[k], cb, p.cat16 != 0);
             n[k] = n[k] >= 0 ? nx : n[k];
             any |= n[k] >= 0;
           }
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(1024) gbdt_score_binned_kernel(const BParams p
         int n = 0;
         do {
           const uint2 nd = nodes[n];
-          n = bstep<HAS_CAT>(nd, xw[((nd.x >> 16) & 0xFFFu) << 5], cb);
+          n = bstep<HAS_CAT>(nd, xw[((nd.x >> 16) & 0xFFFu) << 5], cb, p.cat16 != 0);
         } while (n >= 0);
         acc += (AccT)leaves[~n];
       }
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(1024) gbdt_score_binned_kernel(const BParams p
 // trees are packed as a dummy split).
 template <bool HAS_CAT, bool ALIGNED>
 __device__ __forceinline__ uint32_t walk_tree(uint32_t n, const uint8_t *cb, uint32_t cb_addr, const uint8_t *xwarp,
-                                              uint32_t xwarp_addr, uint32_t lane2) {
+                                              uint32_t xwarp_addr, uint32_t lane2, bool cat16 = false) {
   if (HAS_CAT) {
     // pointers carry the kind of their target (bit 0 leaf, bit 1 categorical node): the numeric loop runs until
     // either bit shows up, categorical nodes are resolved here and the walk re-enters
@@ -249,7 +253,7 @@ __device__ __forceinline__ uint32_t walk_tree(uint32_t n, const uint8_t *cb, uin
       }
       // categorical node: NaN / negative / out-of-bitset go right (LightGBM CategoricalDecision)
       const uint2 nd = *reinterpret_cast<const uint2 *>(cb + (n & ~3u));
-      const uint32_t code = *reinterpret_cast<const uint16_t *>(xwarp + ((nd.x & 0xFFC0u) | lane2));
+      const uint32_t code = cat_of_code(*reinterpret_cast<const uint16_t *>(xwarp + ((nd.x & 0xFFC0u) | lane2)), cat16);
       bool left = false;
       if (code != kBinNaN) {
         const uint2 ct = reinterpret_cast<const uint2 *>(cb)[nd.x >> 16];
@@ -369,7 +373,7 @@ __global__ void __launch_bounds__(1024) gbdt_score_compact_kernel(const BParams 
       const uint32_t *roots = reinterpret_cast<const uint32_t *>(cb + 16);
       const uint32_t cb_addr = smem_u32(cb), xwarp_addr = smem_u32(xwarp);
       auto walk = [&](uint32_t root) -> Real {
-        const uint32_t n = walk_tree<HAS_CAT, ALIGNED>(root, cb, cb_addr, xwarp, xwarp_addr, lane2);
+        const uint32_t n = walk_tree<HAS_CAT, ALIGNED>(root, cb, cb_addr, xwarp, xwarp_addr, lane2, p.cat16 != 0);
         return *reinterpret_cast<const Real *>(cb + (n - 1u));
       };
       // four roots per (warp-uniform) LDS.128; the leaf values are still added one by one, in tree order
@@ -407,10 +411,69 @@ template <int T> struct SlimConst {
   static constexpr uint32_t kChildMask = ((1u << kShift) - 1u) & ~7u;
 };
 
-template <typename Real, int T, bool HAS_CAT>
-__global__ void __launch_bounds__(T) gbdt_score_slim_kernel(const BParams p) {
+// Root table as a kernel parameter (gbdt_model.h SlimModel::root_tab): NR entries of {block offset, root entry, left
+// child entry, right child entry}, read with warp-uniform indices from the constant bank.  NR == 0: the chunk's own
+// {block offset, root entry} table in shared memory.
+template <int NR> struct SlimRoots { uint4 e[NR > 0 ? NR : 1]; };
+
+// The numeric level of the walk, and the same level for models whose categorical nodes are in the in-loop form
+// (gbdt_model.h kMetaCat16): `entry >> (code & 31)` puts the node's bitset bit for this category at bit 0, `& entry & 1`
+// keeps it only at a categorical entry, and the compare takes it as its OR operand — a categorical code is a binary16 NaN,
+// so the numeric half of the OR is false there, and a numeric entry has bit 0 clear, so the categorical half is false here.
+#define MR_SLIM_TEST_NUM                                                                     \
+  "mov.b32 {wlo, whi}, %0;\n"                                                                \
+  "mov.b32 {clo, chi}, code;\n"                                                              \
+  "setp.le.f16 pl, clo, whi;\n"
+#define MR_SLIM_TEST_CAT16                                                                   \
+  "shf.r.wrap.b32 cb, %0, 0, code;\n"                                                        \
+  "and.b32 cb, cb, %0;\n"                                                                    \
+  "and.b32 cb, cb, 1;\n"                                                                     \
+  "setp.ne.u32 pc, cb, 0;\n"                                                                 \
+  "mov.b32 {wlo, whi}, %0;\n"                                                                \
+  "mov.b32 {clo, chi}, code;\n"                                                              \
+  "setp.le.or.f16 pl, clo, whi, pc;\n"
+// one level from the entry in %0 to the entry of the child taken; loops until a leaf entry (sign bit) arrives
+#define MR_SLIM_LOOP(LABEL, TEST)                                                            \
+  LABEL ":\n"                                                                                \
+  "lop3.b32 off, %0, %1, %2, 0xEA;\n" /* (entry & column mask) | 4 * tid */                  \
+  "ld.shared.u16 code, [off];\n"                                                             \
+  TEST                                                                                       \
+  "lop3.b32 n, %0, %3, %4, 0xEA;\n"   /* (entry & child mask) | block base */                \
+  "@!pl add.u32 n, n, 4;\n"                                                                  \
+  "ld.shared.u32 %0, [n];\n"                                                                 \
+  "setp.ge.s32 pq, %0, 0;\n"                                                                 \
+  "@pq bra " LABEL ";\n"
+// level 0 with the root entry (%5, warp-uniform) and both child entries (%6, %7) already in registers: no node load,
+// and no leaf test either — in a model with a root table the root's children are internal entries (pack_slim)
+#define MR_SLIM_ROOT(TEST0)                                                                  \
+  "lop3.b32 off, %5, %1, %2, 0xEA;\n"                                                        \
+  "ld.shared.u16 code, [off];\n"                                                             \
+  TEST0                                                                                      \
+  "selp.b32 %0, %6, %7, pl;\n"
+#define MR_SLIM_TEST0_NUM                                                                    \
+  "mov.b32 {wlo, whi}, %5;\n"                                                                \
+  "mov.b32 {clo, chi}, code;\n"                                                              \
+  "setp.le.f16 pl, clo, whi;\n"
+#define MR_SLIM_TEST0_CAT16                                                                  \
+  "shf.r.wrap.b32 cb, %5, 0, code;\n"                                                        \
+  "and.b32 cb, cb, %5;\n"                                                                    \
+  "and.b32 cb, cb, 1;\n"                                                                     \
+  "setp.ne.u32 pc, cb, 0;\n"                                                                 \
+  "mov.b32 {wlo, whi}, %5;\n"                                                                \
+  "mov.b32 {clo, chi}, code;\n"                                                              \
+  "setp.le.or.f16 pl, clo, whi, pc;\n"
+#define MR_SLIM_REGS                                                                         \
+  ".reg .pred pl, pq, pc;\n"                                                                 \
+  ".reg .b32 off, code, n, cb;\n"                                                            \
+  ".reg .b16 wlo, whi, clo, chi;\n"
+
+// CAT: 0 = no categorical node; 1 = categorical nodes with bitsets of any width (the loop leaves on them, they are resolved
+// in C++ and the loop is re-entered); 2 = small-categorical form, resolved inside the loop.
+template <typename Real, int T, int CAT, int NR>
+__global__ void __launch_bounds__(T) gbdt_score_slim_kernel(const __grid_constant__ BParams p, const __grid_constant__ SlimRoots<NR> rt) {
   extern __shared__ __align__(128) uint8_t smem[];
   using K = SlimConst<T>;
+  static_assert(NR == 0 || CAT != 1, "the parameter root table serves the in-loop forms only");
   const int tid = threadIdx.x;
   const uint32_t base = smem_u32(smem);         // absolute shared address of the dynamic window (small: asserted on the host)
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
@@ -463,89 +526,113 @@ __global__ void __launch_bounds__(T) gbdt_score_slim_kernel(const BParams p) {
       const uint32_t cb_abs = (!resident && (it & 1)) ? cb1_abs : cb0_abs;
       const uint8_t *cb = smem + (cb_abs - base);
       const int ntree = (int)*reinterpret_cast<const uint32_t *>(cb);
-      const uint32_t *roots = reinterpret_cast<const uint32_t *>(cb + 16);
-      auto walk = [&](uint32_t block_off, uint32_t w) -> Real {
-        // absolute address of the tree's block, aligned to the block's size.  `lane_zero` is 0, but only at run time: ptxas
-        // would otherwise prove the base warp-uniform, keep it in a uniform register — which a LOP3 cannot read — and
-        // re-materialise it with an extra move on every level; the three-input add costs nothing.  `w` is the root entry
-        // (always an internal one), delivered with the root table.
-        const uint32_t tb = cb_abs + block_off + lane_zero;
-        if (!HAS_CAT) {
-          asm volatile(
-              "{\n"
-              ".reg .pred pl, pq;\n"
-              ".reg .b32 off, code, n;\n"
-              ".reg .b16 wlo, whi, clo, chi;\n"
-              "SLVL:\n"
-              "lop3.b32 off, %0, %1, %2, 0xEA;\n"      // (w & column mask) | 4 * tid
-              "ld.shared.u16 code, [off];\n"
-              "mov.b32 {wlo, whi}, %0;\n"
-              "mov.b32 {clo, chi}, code;\n"
-              "setp.le.f16 pl, clo, whi;\n"            // code <= k on binary16 patterns; a NaN code goes right
-              "lop3.b32 n, %0, %3, %4, 0xEA;\n"        // (w & child mask) | block base
-              "@!pl add.u32 n, n, 4;\n"
-              "ld.shared.u32 %0, [n];\n"
-              "setp.ge.s32 pq, %0, 0;\n"
-              "@pq bra SLVL;\n"
-              "}\n"
-              : "+r"(w)
-              : "n"(K::kColMask), "r"(tid4), "n"(K::kChildMask), "r"(tb)
-              : "memory");
-        } else {
-          // entries carry their kind: sign bit = leaf, bit 0 = categorical node.  The numeric loop runs until either shows up
-          // (one LOP3 with a predicate result instead of the sign test), categorical nodes are resolved here, then it re-enters
-          for (;;) {
-            if (!(w & 1u)) {
-              asm volatile(
-                  "{\n"
-                  ".reg .pred pl, pq;\n"
-                  ".reg .b32 off, code, n, tmp;\n"
-                  ".reg .b16 wlo, whi, clo, chi;\n"
-                  "SLVC:\n"
-                  "lop3.b32 off, %0, %1, %2, 0xEA;\n"
-                  "ld.shared.u16 code, [off];\n"
-                  "mov.b32 {wlo, whi}, %0;\n"
-                  "mov.b32 {clo, chi}, code;\n"
-                  "setp.le.f16 pl, clo, whi;\n"
-                  "lop3.b32 n, %0, %3, %4, 0xEA;\n"
-                  "@!pl add.u32 n, n, 4;\n"
-                  "ld.shared.u32 %0, [n];\n"
-                  "and.b32 tmp, %0, 0x80000001;\n"
-                  "setp.eq.u32 pq, tmp, 0;\n"
-                  "@pq bra SLVC;\n"
-                  "}\n"
-                  : "+r"(w)
-                  : "n"(K::kColMask), "r"(tid4), "n"(K::kChildMask), "r"(tb)
-                  : "memory");
-              if ((int)w < 0) break;
-            }
-            // categorical node (LightGBM CategoricalDecision): NaN / negative / beyond the bitset go right
-            const uint32_t code = *reinterpret_cast<const uint16_t *>(smem + (((w & K::kColMask) | tid4) - base));
-            bool left = false;
-            if (code != kBinNaN) {
-              const uint2 ct = *reinterpret_cast<const uint2 *>(smem + ((tb + ((w >> 16) & 0x7FFFu) * 8u) - base));
-              const uint32_t wd = code >> 5;
-              if (wd < ct.y) left = (*reinterpret_cast<const uint32_t *>(smem + ((tb + ct.x + wd * 4u) - base)) >> (code & 31u)) & 1u;
-            }
-            const uint32_t n = ((w & K::kChildMask) | tb) + (left ? 0u : 4u);
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(n));
-            if ((int)w < 0) break;
-          }
-        }
+      auto leaf_value = [&](uint32_t tb, uint32_t w) -> Real {
         return *reinterpret_cast<const Real *>(smem + (((w & 0xFFFFu) | tb) - base));
       };
-      // two trees per (warp-uniform) LDS.128: {block, root entry} x 2; the leaf values are still added one by one, in tree order
-      int t = 0;
+      if (NR > 0) {
+        // level 0 from the parameter table: {block offset, root entry, left entry, right entry} of tree `first + t`
+        const uint4 *tab = rt.e + *reinterpret_cast<const uint32_t *>(cb + 4);
+        auto walk = [&](const uint4 r) -> Real {
+          // `lane_zero` is 0, but only at run time: ptxas would otherwise prove the block base warp-uniform, keep it in a
+          // uniform register — which a LOP3 cannot read — and re-materialise it with an extra move on every level
+          const uint32_t tb = cb_abs + r.x + lane_zero;
+          uint32_t w;
+          if (CAT == 0) {
+            asm volatile("{\n" MR_SLIM_REGS MR_SLIM_ROOT(MR_SLIM_TEST0_NUM) MR_SLIM_LOOP("SLVL", MR_SLIM_TEST_NUM) "}\n"
+                         : "=r"(w)
+                         : "n"(K::kColMask), "r"(tid4), "n"(K::kChildMask), "r"(tb), "r"(r.y), "r"(r.z), "r"(r.w)
+                         : "memory");
+          } else {
+            asm volatile("{\n" MR_SLIM_REGS MR_SLIM_ROOT(MR_SLIM_TEST0_CAT16) MR_SLIM_LOOP("SLVL", MR_SLIM_TEST_CAT16) "}\n"
+                         : "=r"(w)
+                         : "n"(K::kColMask), "r"(tid4), "n"(K::kChildMask), "r"(tb), "r"(r.y), "r"(r.z), "r"(r.w)
+                         : "memory");
+          }
+          return leaf_value(tb, w);
+        };
+        int t = 0;
 #pragma unroll 1
-      for (; t + 4 <= ntree; t += 4) {
-        const uint4 r0 = *reinterpret_cast<const uint4 *>(roots + 2 * t), r1 = *reinterpret_cast<const uint4 *>(roots + 2 * t + 4);
-        acc += walk(r0.x, r0.y);
-        acc += walk(r0.z, r0.w);
-        acc += walk(r1.x, r1.y);
-        acc += walk(r1.z, r1.w);
+        for (; t + 4 <= ntree; t += 4) {
+          const uint4 r0 = tab[t], r1 = tab[t + 1], r2 = tab[t + 2], r3 = tab[t + 3];
+          acc += walk(r0);
+          acc += walk(r1);
+          acc += walk(r2);
+          acc += walk(r3);
+        }
+#pragma unroll 1
+        for (; t < ntree; t++) acc += walk(tab[t]);
+      } else {
+        const uint32_t *roots = reinterpret_cast<const uint32_t *>(cb + 16);
+        auto walk = [&](uint32_t block_off, uint32_t w) -> Real {
+          // absolute address of the tree's block, aligned to the block's size (`lane_zero`: see above).  `w` is the root
+          // entry (always an internal one), delivered with the root table.
+          const uint32_t tb = cb_abs + block_off + lane_zero;
+          if (CAT == 0) {
+            asm volatile("{\n" MR_SLIM_REGS MR_SLIM_LOOP("SLVL", MR_SLIM_TEST_NUM) "}\n"
+                         : "+r"(w)
+                         : "n"(K::kColMask), "r"(tid4), "n"(K::kChildMask), "r"(tb)
+                         : "memory");
+          } else if (CAT == 2) {
+            asm volatile("{\n" MR_SLIM_REGS MR_SLIM_LOOP("SLVL", MR_SLIM_TEST_CAT16) "}\n"
+                         : "+r"(w)
+                         : "n"(K::kColMask), "r"(tid4), "n"(K::kChildMask), "r"(tb)
+                         : "memory");
+          } else {
+            // entries carry their kind: sign bit = leaf, bit 0 = categorical node.  The numeric loop runs until either shows up
+            // (one LOP3 with a predicate result instead of the sign test), categorical nodes are resolved here, then it re-enters
+            for (;;) {
+              if (!(w & 1u)) {
+                asm volatile(
+                    "{\n"
+                    ".reg .pred pl, pq;\n"
+                    ".reg .b32 off, code, n, tmp;\n"
+                    ".reg .b16 wlo, whi, clo, chi;\n"
+                    "SLVC:\n"
+                    "lop3.b32 off, %0, %1, %2, 0xEA;\n"
+                    "ld.shared.u16 code, [off];\n"
+                    "mov.b32 {wlo, whi}, %0;\n"
+                    "mov.b32 {clo, chi}, code;\n"
+                    "setp.le.f16 pl, clo, whi;\n"
+                    "lop3.b32 n, %0, %3, %4, 0xEA;\n"
+                    "@!pl add.u32 n, n, 4;\n"
+                    "ld.shared.u32 %0, [n];\n"
+                    "and.b32 tmp, %0, 0x80000001;\n"
+                    "setp.eq.u32 pq, tmp, 0;\n"
+                    "@pq bra SLVC;\n"
+                    "}\n"
+                    : "+r"(w)
+                    : "n"(K::kColMask), "r"(tid4), "n"(K::kChildMask), "r"(tb)
+                    : "memory");
+                if ((int)w < 0) break;
+              }
+              // categorical node (LightGBM CategoricalDecision): NaN / negative / beyond the bitset go right
+              const uint32_t code = *reinterpret_cast<const uint16_t *>(smem + (((w & K::kColMask) | tid4) - base));
+              bool left = false;
+              if (code != kBinNaN) {
+                const uint2 ct = *reinterpret_cast<const uint2 *>(smem + ((tb + ((w >> 16) & 0x7FFFu) * 8u) - base));
+                const uint32_t wd = code >> 5;
+                if (wd < ct.y) left = (*reinterpret_cast<const uint32_t *>(smem + ((tb + ct.x + wd * 4u) - base)) >> (code & 31u)) & 1u;
+              }
+              const uint32_t n = ((w & K::kChildMask) | tb) + (left ? 0u : 4u);
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(n));
+              if ((int)w < 0) break;
+            }
+          }
+          return leaf_value(tb, w);
+        };
+        // two trees per (warp-uniform) LDS.128: {block, root entry} x 2; the leaf values are still added one by one, in tree order
+        int t = 0;
+#pragma unroll 1
+        for (; t + 4 <= ntree; t += 4) {
+          const uint4 r0 = *reinterpret_cast<const uint4 *>(roots + 2 * t), r1 = *reinterpret_cast<const uint4 *>(roots + 2 * t + 4);
+          acc += walk(r0.x, r0.y);
+          acc += walk(r0.z, r0.w);
+          acc += walk(r1.x, r1.y);
+          acc += walk(r1.z, r1.w);
+        }
+#pragma unroll 1
+        for (; t < ntree; t++) acc += walk(roots[2 * t], roots[2 * t + 1]);
       }
-#pragma unroll 1
-      for (; t < ntree; t++) acc += walk(roots[2 * t], roots[2 * t + 1]);
       __syncthreads();
     }
     if (item < p.rows) store_score(p.out, p.sinks, item, (double)acc);
@@ -567,7 +654,7 @@ struct LParams {
   const uint32_t *tree_off;  // [n_trees] byte offset of the tree's chunk in `model`
   double *out;
   int rows, rows_padded, n_features, n_trees;
-  int n_chunks, chunks_per_cta, has_cat;
+  int n_chunks, chunks_per_cta, has_cat;  // has_cat: 0 none, 1 categorical nodes, 2 with small-categorical codes (kMetaCat16)
   uint32_t chunk_stride;  // bytes per chunk buffer
   float base_score;
 };
@@ -622,7 +709,7 @@ __global__ void __launch_bounds__(128) gbdt_leaves_kernel(const LParams p) {
       // the compact scorer's hand-scheduled level loop (10 SASS instructions; nvcc's own schedule of the same walk is 18)
       if (p.has_cat) {
         for (int t = 0; t < ntree; t++, dst += p.rows_padded)
-          *dst = (uint16_t)((walk_tree<true, false>(roots[t], cb, cb_addr, xwarp, xwarp_addr, lane2) - 1u) >> 3);
+          *dst = (uint16_t)((walk_tree<true, false>(roots[t], cb, cb_addr, xwarp, xwarp_addr, lane2, p.has_cat == 2) - 1u) >> 3);
       } else {
         for (int t = 0; t < ntree; t++, dst += p.rows_padded)
           *dst = (uint16_t)((walk_tree<false, false>(roots[t], cb, cb_addr, xwarp, xwarp_addr, lane2) - 1u) >> 3);
@@ -748,7 +835,7 @@ __global__ void __launch_bounds__(160) gbdt_sum_kernel(const SumParams p, const 
 // of them.  One thread per item straight from HBM/L2 (no staging): a measuring aid, not a scoring path.
 struct WalkStats { unsigned long long lane_levels, warp_levels, warp_trees; };
 
-__global__ void __launch_bounds__(128) compact_walk_stats_kernel(const uint8_t *model, const ChunkDesc *chunks, int n_chunks,
+__global__ void __launch_bounds__(128) compact_walk_stats_kernel(const bool cat16, const uint8_t *model, const ChunkDesc *chunks, int n_chunks,
                                                                  const uint16_t *bins, int rows, int F, WalkStats *out) {
   const int item = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -764,10 +851,11 @@ __global__ void __launch_bounds__(128) compact_walk_stats_kernel(const uint8_t *
       int depth = 0;
       while (live && !(n & 1u)) {
         const uint2 nd = *reinterpret_cast<const uint2 *>(cb + (n & ~2u));
-        const uint32_t code = xw[(nd.x & 0xFFC0u) >> 1];
+        uint32_t code = xw[(nd.x & 0xFFC0u) >> 1];
         bool left;
         if (nd.x & 2u) {
           left = false;
+          code = cat_of_code(code, cat16);
           if (code != kBinNaN) {
             const uint2 ct = reinterpret_cast<const uint2 *>(cb)[nd.x >> 16];
             const uint32_t w = code >> 5;
@@ -816,7 +904,7 @@ void compact_walk_stats(const BinnedLaunch &L, unsigned long long out[3], cudaSt
   MR_CUDA_CHECK(cudaMalloc((void **)&d, sizeof(WalkStats)));
   MR_CUDA_CHECK(cudaMemsetAsync(d, 0, sizeof(WalkStats), stream));
   if (L.rows > 0)
-    compact_walk_stats_kernel<<<(L.rows + 127) / 128, 128, 0, stream>>>(L.d_model, L.d_chunks, L.n_chunks, L.d_bins, L.rows, L.tile_cols, d);
+    compact_walk_stats_kernel<<<(L.rows + 127) / 128, 128, 0, stream>>>(L.cat16, L.d_model, L.d_chunks, L.n_chunks, L.d_bins, L.rows, L.tile_cols, d);
   cudaError_t e = cudaGetLastError();
   WalkStats h{};
   if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, stream);
@@ -835,7 +923,7 @@ void launch_gbdt_latency(const BinnedLaunch &L, int n_trees, const SumPlan &sum,
   p.rows = L.rows; p.rows_padded = (L.rows + 127) & ~127; p.n_features = L.tile_cols; p.n_trees = n_trees;
   p.base_score = L.base_score;
   p.n_chunks = L.n_chunks;
-  p.has_cat = L.has_cat ? 1 : 0;
+  p.has_cat = L.has_cat ? (L.cat16 ? 2 : 1) : 0;
   p.chunk_stride = (L.max_chunk_bytes + 127u) & ~127u;
   // (chunk, 128-item group) pairs are the unit of parallelism; once there are more of them than ~16 per SM a CTA takes
   // several chunks in a row for its group, so the code tile is staged once per CTA instead of once per 4 KB of trees
@@ -892,13 +980,13 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
     BParams p;
     p.model = L.d_model; p.chunks = L.d_chunks; p.bins = L.d_bins; p.out = L.d_out;
     p.n_chunks = L.n_chunks; p.chunk_stride = (L.max_chunk_bytes + 2047u) & ~2047u;
-    p.rows = L.rows; p.n_features = F; p.base_score = L.base_score;
+    p.rows = L.rows; p.n_features = F; p.base_score = L.base_score; p.cat16 = L.cat16 ? 1 : 0;
     p.sinks = L.sinks;
     const int T = L.tile_T;
     const size_t n_pairs = (size_t)(F + 1) / 2;
     const size_t cb0 = (((size_t)T * 4 * (n_pairs + 1)) + 2047) & ~size_t(2047);
     const size_t smem = cb0 + (size_t)p.chunk_stride * (L.n_chunks == 1 ? 1 : 2);  // the window starts at (or just above) address 0
-    auto go = [&](auto kern) {
+    auto go = [&](auto kern, const auto &roots) {
       MR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = 0;
       MR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
@@ -907,23 +995,44 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
       const int n_tiles = (p.rows + T - 1) / T;
       static const bool debug = getenv("MR_DEBUG_LAUNCH") != nullptr;
       if (debug)
-        fprintf(stderr, "[mr] slim scorer: rows %d tile_cols %d chunks %d x %u B, %d threads x %d CTAs (%d/SM), %zu B smem\n", p.rows, F,
-                p.n_chunks, p.chunk_stride, T, std::max(1, std::min(n_tiles, num_sms * per_sm)), per_sm, smem);
-      { ProfScope _ps("gbdt_score_slim_kernel", stream); kern<<<std::max(1, std::min(n_tiles, num_sms * per_sm)), T, smem, stream>>>(p); }
+        fprintf(stderr, "[mr] slim scorer: rows %d tile_cols %d chunks %d x %u B, %d threads x %d CTAs (%d/SM), %zu B smem, cat %d, root table %zu B\n",
+                p.rows, F, p.n_chunks, p.chunk_stride, T, std::max(1, std::min(n_tiles, num_sms * per_sm)), per_sm, smem,
+                L.has_cat ? (L.cat16 ? 2 : 1) : 0, sizeof(roots) > 16 ? sizeof(roots) : (size_t)0);
+      { ProfScope _ps("gbdt_score_slim_kernel", stream); kern<<<std::max(1, std::min(n_tiles, num_sms * per_sm)), T, smem, stream>>>(p, roots); }
       MR_CUDA_CHECK(cudaGetLastError());
       g_kernel_launches++;
     };
+    // CAT: 0 none, 1 bitsets of any width (the loop leaves on them), 2 small-categorical form resolved inside the loop
+    const int cat = !L.has_cat ? 0 : L.cat16 ? 2 : 1;
     const bool f32 = L.kind == MR_BOOSTER_XGBOOST;  // (XGBoost categorical splits are refused at load time)
-    if (T == 512) { if (f32) go(gbdt_score_slim_kernel<float, 512, false>); else if (L.has_cat) go(gbdt_score_slim_kernel<double, 512, true>); else go(gbdt_score_slim_kernel<double, 512, false>); }
-    else if (T == 256) { if (f32) go(gbdt_score_slim_kernel<float, 256, false>); else if (L.has_cat) go(gbdt_score_slim_kernel<double, 256, true>); else go(gbdt_score_slim_kernel<double, 256, false>); }
-    else { if (f32) go(gbdt_score_slim_kernel<float, 128, false>); else if (L.has_cat) go(gbdt_score_slim_kernel<double, 128, true>); else go(gbdt_score_slim_kernel<double, 128, false>); }
+    auto with_T = [&](auto tt) {
+      constexpr int TT = decltype(tt)::value;
+      auto with_roots = [&](auto nr) {
+        constexpr int NR = decltype(nr)::value;
+        SlimRoots<NR> roots;
+        if (NR > 0) memcpy(roots.e, L.h_root_tab, (size_t)L.n_root_tab * 16);
+        else roots.e[0] = make_uint4(0, 0, 0, 0);
+        if (f32) go(gbdt_score_slim_kernel<float, TT, 0, NR>, roots);
+        else if (cat == 2) go(gbdt_score_slim_kernel<double, TT, 2, NR>, roots);
+        else if (cat == 0) go(gbdt_score_slim_kernel<double, TT, 0, NR>, roots);
+        else if constexpr (NR == 0) go(gbdt_score_slim_kernel<double, TT, 1, 0>, roots);
+      };
+      // level 0 from a parameter-space root table when the model has one (<= kSlimRootTabMax trees, no wide bitsets)
+      const int n_tab = (L.h_root_tab && cat != 1) ? L.n_root_tab : 0;
+      if (n_tab > 0 && n_tab <= 512) with_roots(std::integral_constant<int, 512>{});
+      else if (n_tab > 0 && n_tab <= kSlimRootTabMax) with_roots(std::integral_constant<int, kSlimRootTabMax>{});
+      else with_roots(std::integral_constant<int, 0>{});
+    };
+    if (T == 512) with_T(std::integral_constant<int, 512>{});
+    else if (T == 256) with_T(std::integral_constant<int, 256>{});
+    else with_T(std::integral_constant<int, 128>{});
     return;
   }
   // ---- pass 2: traversal
   BParams p;
   p.model = L.d_model; p.chunks = L.d_chunks; p.bins = L.d_bins; p.out = L.d_out;
   p.n_chunks = L.n_chunks; p.chunk_stride = (L.max_chunk_bytes + 127u) & ~127u;
-  p.rows = L.rows; p.n_features = F; p.base_score = L.base_score;
+  p.rows = L.rows; p.n_features = F; p.base_score = L.base_score; p.cat16 = L.cat16 ? 1 : 0;
   p.sinks = L.sinks;
   const size_t kMaxSmem = 227 * 1024;
   const bool aligned_tile = L.compact && !L.has_cat && (F & (F - 1)) == 0;  // + slack to align the tile

@@ -57,6 +57,7 @@ struct BinnedLaunch {
   const uint32_t *d_bucket_range = nullptr;
   int kind = 0;
   bool has_cat = false;
+  bool cat16 = false;                   // categorical columns carry the small-categorical code form (kMetaCat16)
   float base_score = 0.f;
   int n_features = 0;
   int tile_cols = 0;                    // columns of the code tile (BinnedModel::tile_cols)
@@ -69,6 +70,8 @@ struct BinnedLaunch {
   bool codes_ready = false;             // d_bins already holds the codes (fused assemble): skip bin_kernel
   bool compact = false;                 // model bytes are pack_compact() chunks -> fast lock-step kernel
   int tile_T = 0;                       // != 0: d_bins is in the slim layout and d_model / d_chunks are pack_slim() chunks
+  const uint32_t *h_root_tab = nullptr;  // slim scorer: HOST copy of SlimModel::root_tab (4 words per tree), passed as a kernel parameter
+  int n_root_tab = 0;                   // trees in it (0: the chunks' own root tables)
   ScoreSinks sinks;                     // compact + latency kernels only
 };
 // bytes of a code buffer for `rows` rows in either layout (BinParams::tile_T): whole groups of 32 / whole CTA tiles

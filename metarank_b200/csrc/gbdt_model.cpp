@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <unordered_map>
@@ -520,17 +521,22 @@ BinnedModel pack_binned(const HostModel &m, size_t chunk_budget) {
   std::vector<std::vector<double>> thr(F);
   B.is_cat.assign(F, 0);
   std::vector<uint8_t> is_num(F, 0);
+  bool any_cat = false, small_cat = true;  // small_cat: every bitset lives in categories 0..15 (kMetaCat16)
   for (auto &t : m.trees)
     for (size_t q = 0; q < t.feat.size(); q++) {
       const int f = t.feat[q];
       if (t.flags[q] & NF_CATEGORICAL) {
         B.is_cat[f] = 1;
+        any_cat = true;
         if ((size_t)t.cat_n[q] * 32 > 65000) return B;  // category ids must fit the u16 code
+        for (int32_t wd = 0; wd < t.cat_n[q]; wd++)
+          if (t.cat_words[(size_t)t.cat_begin[q] + wd] & (wd == 0 ? 0xFFFF0000u : 0xFFFFFFFFu)) small_cat = false;
       } else {
         is_num[f] = 1;
         thr[f].push_back(t.thr[q]);
       }
     }
+  B.cat16 = any_cat && small_cat && getenv("MR_NO_CAT16") == nullptr;
   B.thr_off.assign(F + 1, 0);
   for (int f = 0; f < F; f++) {
     if (B.is_cat[f] && is_num[f]) return B;  // a column split both ways: not representable by one code
@@ -550,7 +556,7 @@ BinnedModel pack_binned(const HostModel &m, size_t chunk_budget) {
     const uint32_t mth = B.thr_off[f + 1] - B.thr_off[f];
     BinMeta &M = B.meta[f];
     M.mn = 0.0; M.scale = 0.0; M.g = 1; M.idx_off = (uint32_t)B.bucket_range.size();
-    M.thr_off = B.thr_off[f]; M.flags = (B.is_cat[f] ? kMetaCat : 0u) | (kMetaNoDup << 16);
+    M.thr_off = B.thr_off[f]; M.flags = (B.is_cat[f] ? (kMetaCat | (B.cat16 ? kMetaCat16 : 0u)) : 0u) | (kMetaNoDup << 16);
     if (mth >= 2 && std::isfinite(t[0]) && std::isfinite(t[mth - 1])) {
       const double span = t[mth - 1] - t[0];
       const uint32_t g = std::min<uint32_t>(4 * mth, 32768);
@@ -662,6 +668,7 @@ BinnedModel pack_compact(const HostModel &m, const BinnedModel &bn, size_t chunk
   C.thr_off = bn.thr_off;
   C.thr = bn.thr;
   C.is_cat = bn.is_cat;
+  C.cat16 = bn.cat16;
   C.meta = bn.meta;
   C.bucket_range = bn.bucket_range;
   // NaN direction per tile column (BinMeta::flags): a feature whose numerical nodes all send NaN the same
@@ -673,7 +680,7 @@ BinnedModel pack_compact(const HostModel &m, const BinnedModel &bn, size_t chunk
       if (!(t.flags[q] & NF_CATEGORICAL)) ((t.flags[q] & NF_NAN_LEFT) ? n_left : n_right)[t.feat[q]]++;
   C.tile_cols = F;
   for (int f = 0; f < F; f++) {
-    uint32_t fl = C.is_cat[f] ? kMetaCat : 0u, dup = kMetaNoDup;
+    uint32_t fl = C.is_cat[f] ? (kMetaCat | (C.cat16 ? kMetaCat16 : 0u)) : 0u, dup = kMetaNoDup;
     col_left[f] = (uint32_t)f;
     if (n_left[f] && !n_right[f]) fl |= kMetaNanLow;
     else if (n_left[f] && n_right[f]) { dup = (uint32_t)C.tile_cols++; col_left[f] = dup; }
@@ -766,12 +773,23 @@ SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budge
   for (int f = 0; f < F; f++)
     if (C.thr_off[f + 1] - C.thr_off[f] > 0x7C00u) return S;  // codes must stay below the binary16 NaN patterns
   S.n_pairs = (C.tile_cols + 1) / 2;
+  S.cat16 = C.cat16;
+  const bool cat16 = C.cat16;
+  // root table for the kernel's parameter space (SlimModel::root_tab).  With it, level 0 of a walk ends on the root's
+  // child entry and the level loop is entered without a leaf test: a leaf hanging directly off the root is reached
+  // through a dummy split (both children = the leaf), like the root of a single-leaf tree.
+  const bool want_tab = m.trees.size() <= (size_t)kSlimRootTabMax && (!m.has_cat || cat16) && getenv("MR_NO_ROOT_TAB") == nullptr;
+  auto n_dummy = [&](const HostTree &t) -> size_t {
+    if (!want_tab) return 0;
+    return t.feat.empty() ? 2 : (size_t)(t.left[0] < 0) + (size_t)(t.right[0] < 0);
+  };
   size_t max_block = 16;
   auto n_cat_nodes = [](const HostTree &t) { size_t c = 0; for (auto fl : t.flags) c += (fl & NF_CATEGORICAL) != 0; return c; };
   auto block_bytes = [&](const HostTree &t) {
     // entries (root pair + one pair per node) + leaf slots + per categorical node {bitset byte offset, n words} + the bitsets
-    const size_t need = (2 + 2 * std::max<size_t>(t.feat.size(), 1)) * 4 + t.leaf.size() * 8 + n_cat_nodes(t) * 8 +
-                        ((t.cat_words.size() * 4 + 7) & ~size_t(7));
+    // (cat16: the bitset is inside the entry)
+    const size_t need = (2 + 2 * (std::max<size_t>(t.feat.size(), 1) + n_dummy(t))) * 4 + t.leaf.size() * 8 +
+                        (cat16 ? 0 : n_cat_nodes(t) * 8 + ((t.cat_words.size() * 4 + 7) & ~size_t(7)));
     size_t b = 16;
     while (b < need) b <<= 1;
     return b;
@@ -794,6 +812,7 @@ SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budge
   chunk_budget = std::max<size_t>(chunk_budget, 2048);
   PackedModel &pk = S.packed;
   size_t i = 0, nt = m.trees.size();
+  if (want_tab) S.root_tab.reserve(nt * 4);
   while (i < nt) {
     // greedy: header, then blocks, each aligned to its own size
     size_t j = i, end = 0;
@@ -817,8 +836,8 @@ SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budge
     const size_t base = pk.bytes.size();
     pk.bytes.resize(base + total, 0);
     uint8_t *c = pk.bytes.data() + base;
-    const uint32_t hn = (uint32_t)n;
-    memcpy(c, &hn, 4);
+    const uint32_t hn[2] = {(uint32_t)n, (uint32_t)i};  // trees in the chunk, index of its first tree
+    memcpy(c, hn, 8);
     uint32_t *roots = (uint32_t *)(c + 16);  // per tree: {block offset, copy of the root entry}
     size_t off = 16 + al16(n * 8);
     for (size_t k = 0; k < n; k++) {
@@ -827,17 +846,23 @@ SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budge
       off = (off + b - 1) & ~(b - 1);
       roots[2 * k] = (uint32_t)off;
       uint32_t *e = (uint32_t *)(c + off);
-      const size_t leaf_base = (2 + 2 * std::max<size_t>(ni, 1)) * 4;  // a multiple of 8
+      const size_t leaf_base = (2 + 2 * (std::max<size_t>(ni, 1) + n_dummy(t))) * 4;  // a multiple of 8
       // breadth-first numbering of the child pairs: node q's children live in pair slot pair_of[q]
       std::vector<uint32_t> entry_of_node(ni, 0);  // entry index of internal node q
       uint32_t next_pair = 1;
       std::vector<int> order;
       if (ni) { order.push_back(0); entry_of_node[0] = 0; }
       auto leaf_entry = [&](int cidx) { return 0x80000000u | (uint32_t)(leaf_base + (size_t)(~cidx) * 8); };
+      const uint32_t dummy = 1u << shift;  // k = 0 on tile column 0; | child pair * 8
       if (!ni) {
         // a single-leaf tree is a dummy split whose children both are its leaf: every walk starts at an internal entry
-        e[0] = (1u << shift) | (1u * 8u);  // k = 0 on tile column 0, child pair 1
-        e[2] = e[3] = leaf_entry(~0);
+        e[0] = dummy | (1u * 8u);
+        if (want_tab) {
+          e[2] = dummy | (2u * 8u); e[3] = dummy | (3u * 8u);
+          e[4] = e[5] = e[6] = e[7] = leaf_entry(~0);
+        } else {
+          e[2] = e[3] = leaf_entry(~0);
+        }
       }
       const size_t ctab_base = leaf_base + t.leaf.size() * 8, cw_base = ctab_base + n_cat_nodes(t) * 8;
       uint32_t *ctab = (uint32_t *)(c + off + ctab_base);
@@ -846,7 +871,17 @@ SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budge
         const int q = order[h];
         const uint32_t pair = next_pair++;
         const int f = t.feat[q];
-        if (t.flags[q] & NF_CATEGORICAL) {
+        bool swapped = false;
+        if ((t.flags[q] & NF_CATEGORICAL) && cat16) {
+          // bit 0 = categorical, high half = the bitset itself (categories 0..15): resolved inside the level loop.  Bit 31 is
+          // the leaf flag, so a set holding category 15 is stored as its complement with the children exchanged — and with
+          // bit 2 set, the bit the missing code (kCat16Missing) tests, so that a missing value still reaches the right child
+          uint32_t bits = t.cat_n[q] > 0 ? (t.cat_words[(size_t)t.cat_begin[q]] & 0xFFFFu) : 0u;
+          swapped = (bits & 0x8000u) != 0;
+          if (swapped) bits = ~bits & 0xFFFFu;
+          e[entry_of_node[q]] = (bits << 16) | ((((uint32_t)f >> 1) + 1u) << shift) | (((uint32_t)f & 1u) << 1) | (pair * 8u) |
+                                (swapped ? 4u : 0u) | 1u;
+        } else if (t.flags[q] & NF_CATEGORICAL) {
           // bit 0 = categorical: the level loop leaves on it (the same test that finds a leaf); the k field is the 8-byte
           // index, inside the block, of the node's {bitset byte offset, n words}
           ctab[2 * ci] = (uint32_t)(cw_base + (size_t)t.cat_begin[q] * 4);
@@ -861,14 +896,20 @@ SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budge
           const uint32_t col = ((t.flags[q] & NF_NAN_LEFT) && dup != kMetaNoDup) ? dup : (uint32_t)f;
           e[entry_of_node[q]] = (kk << 16) | (((col >> 1) + 1u) << shift) | ((col & 1u) << 1) | (pair * 8u);
         }
-        const int ch[2] = {t.left[q], t.right[q]};
+        const int ch[2] = {swapped ? t.right[q] : t.left[q], swapped ? t.left[q] : t.right[q]};
         for (int sd = 0; sd < 2; sd++) {
-          if (ch[sd] < 0) e[2 * pair + sd] = leaf_entry(ch[sd]);
-          else { entry_of_node[ch[sd]] = 2 * pair + sd; order.push_back(ch[sd]); }
+          if (ch[sd] < 0 && h == 0 && want_tab) {
+            const uint32_t dp = next_pair++;
+            e[2 * pair + sd] = dummy | (dp * 8u);
+            e[2 * dp] = e[2 * dp + 1] = leaf_entry(ch[sd]);
+          } else if (ch[sd] < 0) {
+            e[2 * pair + sd] = leaf_entry(ch[sd]);
+          } else { entry_of_node[ch[sd]] = 2 * pair + sd; order.push_back(ch[sd]); }
         }
       }
       roots[2 * k + 1] = e[0];
-      if (!t.cat_words.empty()) memcpy(c + off + cw_base, t.cat_words.data(), t.cat_words.size() * 4);
+      if (want_tab) { S.root_tab.push_back((uint32_t)off); S.root_tab.push_back(e[0]); S.root_tab.push_back(e[2]); S.root_tab.push_back(e[3]); }
+      if (!cat16 && !t.cat_words.empty()) memcpy(c + off + cw_base, t.cat_words.data(), t.cat_words.size() * 4);
       uint8_t *lv = c + off + leaf_base;
       for (size_t q = 0; q < t.leaf.size(); q++) {
         if (f32) { const float v = (float)t.leaf[q]; memcpy(lv + q * 8, &v, 4); }
@@ -882,6 +923,119 @@ SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budge
   }
   S.ok = true;
   return S;
+}
+
+}  // namespace mr
+
+namespace mr {
+
+// Host-side consistency check of the slim packing (mr_model_selfcheck; CPU-only CI): random code vectors are walked
+// through (a) the parsed trees with the binned decision rule — `code <= k` on the node's tile column, bitset test on the
+// category — and (b) the packed 4-byte entries exactly as gbdt_score_slim_kernel reads them (root table or the chunk's own
+// table, masks of the tile size, dummy splits, in-entry bitsets).  Returns the number of (sample, tree) pairs whose leaf
+// value differs.  It validates LAYOUT, not arithmetic: nothing is scored here.
+size_t slim_pack_selfcheck(const HostModel &m, const BinnedModel &C, const SlimModel &S, int n_samples, uint64_t seed) {
+  if (!S.ok) return 0;
+  const int shift = S.tile_T == 512 ? 11 : S.tile_T == 256 ? 10 : 9;
+  const uint32_t col_mask = ((0xFFFFu << shift) & 0xFFFFu) | 2u, child_mask = ((1u << shift) - 1u) & ~7u;
+  auto rnd = [&]() { seed = seed * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(seed >> 33); };
+  auto f16_le = [](uint16_t a, uint16_t b) {  // binary16 `a <= b`, false if either is NaN (the kernel's HSETP2)
+    auto nan = [](uint16_t h) { return (h & 0x7C00u) == 0x7C00u && (h & 0x3FFu); };
+    if (nan(a) || nan(b)) return false;
+    auto key = [](uint16_t h) { return (h & 0x8000u) ? -(int)(h & 0x7FFFu) : (int)(h & 0x7FFFu); };
+    return key(a) <= key(b);
+  };
+  size_t bad = 0;
+  std::vector<uint16_t> tile((size_t)S.n_pairs * 2, 0);
+  std::vector<int> cat_val(m.n_features, -1);
+  std::vector<uint32_t> num_code(m.n_features, 0);
+  std::vector<uint8_t> is_nan(m.n_features, 0);
+  for (int s = 0; s < n_samples; s++) {
+    for (int f = 0; f < m.n_features; f++) {
+      const BinMeta &M = C.meta[f];
+      const uint32_t nthr = C.thr_off[f + 1] - C.thr_off[f];
+      is_nan[f] = rnd() % 8 == 0;
+      uint16_t code;
+      if (M.flags & kMetaCat) {
+        cat_val[f] = is_nan[f] ? -1 : (int)(rnd() % 24) - 2;
+        if (M.flags & kMetaCat16) code = (cat_val[f] >= 0 && cat_val[f] < 16) ? (uint16_t)(kCat16Base | cat_val[f]) : kCat16Missing;
+        else code = cat_val[f] >= 0 ? (uint16_t)cat_val[f] : kBinNaN;
+        tile[f] = code;
+      } else {
+        num_code[f] = rnd() % (nthr + 1);
+        code = is_nan[f] ? kBinNaN : (uint16_t)num_code[f];
+        tile[f] = (code == kBinNaN && (M.flags & kMetaNanLow)) ? 0 : code;
+        const uint32_t dup = M.flags >> 16;
+        if (dup != kMetaNoDup) tile[dup] = code == kBinNaN ? 0 : code;
+      }
+    }
+    for (size_t ci = 0; ci < S.packed.chunks.size(); ci++) {
+      const ChunkDesc &cd = S.packed.chunks[ci];
+      const uint8_t *cb = S.packed.bytes.data() + cd.byte_off;
+      const uint32_t *roots = (const uint32_t *)(cb + 16);
+      for (uint32_t k = 0; k < cd.n_trees; k++) {
+        const HostTree &t = m.trees[cd.first_tree + k];
+        // (a) the parsed tree
+        double want;
+        if (t.feat.empty()) want = t.leaf[0];
+        else {
+          int n = 0;
+          while (n >= 0) {
+            const int f = t.feat[n];
+            bool left;
+            if (t.flags[n] & NF_CATEGORICAL) {
+              const int cv = cat_val[f];
+              left = cv >= 0 && (cv >> 5) < t.cat_n[n] && ((t.cat_words[(size_t)t.cat_begin[n] + (cv >> 5)] >> (cv & 31)) & 1u);
+            } else if (is_nan[f]) {
+              left = (t.flags[n] & NF_NAN_LEFT) != 0;
+            } else {
+              const double *tb = C.thr.data() + C.thr_off[f], *te = C.thr.data() + C.thr_off[f + 1];
+              left = num_code[f] <= (uint32_t)(std::lower_bound(tb, te, t.thr[n]) - tb);
+            }
+            n = left ? t.left[n] : t.right[n];
+          }
+          want = t.leaf[~n];
+        }
+        // (b) the packed entries, the way the kernel walks them
+        auto code_at = [&](uint32_t w) { const uint32_t pair = ((w & col_mask) >> shift) - 1u; return tile[2 * pair + ((w >> 1) & 1u)]; };
+        auto goes_left = [&](uint32_t w, uint16_t code, const uint8_t *blk) {
+          if (S.cat16) {
+            const bool pc = ((w >> (code & 31u)) & w & 1u) != 0;
+            return pc || f16_le(code, (uint16_t)(w >> 16));
+          }
+          if (w & 1u) {  // wide categorical entry: {bitset byte offset, n words} at 8-byte index (w >> 16) & 0x7FFF
+            if (code == kBinNaN) return false;
+            const uint32_t *ct = (const uint32_t *)(blk + ((w >> 16) & 0x7FFFu) * 8u);
+            const uint32_t wd = code >> 5;
+            return wd < ct[1] && ((*(const uint32_t *)(blk + ct[0] + wd * 4u) >> (code & 31u)) & 1u) != 0;
+          }
+          return f16_le(code, (uint16_t)(w >> 16));
+        };
+        uint32_t block_off, w;
+        int guard = 0;
+        if (!S.root_tab.empty()) {
+          const uint32_t *r = S.root_tab.data() + 4 * (size_t)(cd.first_tree + k);
+          block_off = r[0];
+          w = goes_left(r[1], code_at(r[1]), cb + block_off) ? r[2] : r[3];
+          if ((int32_t)w < 0) { bad++; continue; }  // the root's children must be internal entries
+        } else {
+          block_off = roots[2 * k];
+          w = roots[2 * k + 1];
+        }
+        if (block_off != roots[2 * k] || ((const uint32_t *)(cb + 4))[0] != cd.first_tree) { bad++; continue; }
+        const uint8_t *blk = cb + block_off;
+        while ((int32_t)w >= 0 && guard++ < 100000) {
+          const uint32_t n = (w & child_mask) + (goes_left(w, code_at(w), blk) ? 0u : 4u);
+          w = *(const uint32_t *)(blk + n);
+        }
+        double got;
+        if (m.kind == MR_BOOSTER_XGBOOST) { float v; memcpy(&v, blk + (w & 0xFFFFu), 4); got = (double)v; want = (double)(float)want; }
+        else memcpy(&got, blk + (w & 0xFFFFu), 8);
+        if ((int32_t)w >= 0 || memcmp(&got, &want, 8) != 0) bad++;
+      }
+    }
+  }
+  return bad;
 }
 
 }  // namespace mr

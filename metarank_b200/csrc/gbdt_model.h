@@ -113,7 +113,14 @@ struct BinMeta {
   // With the direction baked into the column the traversal needs no NaN test at all.
   uint32_t flags;
 };
-constexpr uint32_t kMetaCat = 1u, kMetaNanLow = 2u, kMetaNoDup = 0xFFFFu;
+constexpr uint32_t kMetaCat = 1u, kMetaNanLow = 2u, kMetaCat16 = 4u, kMetaNoDup = 0xFFFFu;
+// Small-categorical code form (BinnedModel::cat16: every bitset of the model lives in categories 0..15).  A categorical
+// column's code is then 0xFFF0 | category, 0xFFE2 for NaN / negative / >= 16: both are binary16 NaN patterns, so the slim
+// scorer's numeric compare `code <= k` is false on them whatever the entry holds, and `code & 31` = 16 + category (2 for
+// the missing code) is the position, inside a categorical entry, of the node's bitset bit (the bitset sits in the entry's
+// high half; bit 2 of an entry is 0 — or 1 in an entry that stores the complement of its set, see pack_slim).  The level loop then resolves a categorical node with two more instructions
+// instead of leaving.  Every other consumer turns the code back into the category with cat_of_code().
+constexpr uint16_t kCat16Base = 0xFFF0u, kCat16Missing = 0xFFE2u;
 
 struct BinnedModel {
   bool ok = false;                 // false: model cannot be binned exactly -> use the f64/f32 kernel
@@ -122,6 +129,7 @@ struct BinnedModel {
   std::vector<BinMeta> meta;       // [n_features]
   std::vector<uint32_t> bucket_range;  // per bucket: first threshold index | one-past-last << 16 (within the column)
   std::vector<uint8_t> is_cat;     // [n_features] feature is split categorically
+  bool cat16 = false;              // categorical columns carry the small-categorical code form (kMetaCat16)
   int tile_cols = 0;               // columns of the code tile: n_features + duplicated (mixed NaN direction) columns
   PackedModel packed;              // chunks of BNodes (+ leaves, + categorical tables)
 };
@@ -160,12 +168,22 @@ BinnedModel pack_compact(const HostModel &m, const BinnedModel &binned, size_t c
 //                   inside the block of the node's {bitset byte offset, n words}; column and child fields as above
 // ok == false (> 31 744 thresholds on a column, too many tile columns, or a tree — with its bitsets — too large for any
 // tile_T): the 8-byte compact kernel scores the model.  The tile mapping (BinMeta, tile_cols) is the compact model's.
+//   cat16 models (kMetaCat16): a categorical entry is bit 0 set, bits 31..16 = the node's 16-bit bitset, column and child
+//                   fields as above, and nothing else in the block; the level loop handles it in place
+// root_tab (models of <= kSlimRootTabMax trees): per tree, in tree order, {block offset from the chunk start, root entry,
+// left child entry, right child entry}.  The scorer receives it as a kernel PARAMETER (constant bank): level 0 of every
+// walk then costs no node load and no root-table load on the shared-memory pipe — the root entry is warp-uniform anyway.
+constexpr int kSlimRootTabMax = 1920;  // 16 B per tree inside the 32 764-byte parameter space
 struct SlimModel {
   bool ok = false;
+  bool cat16 = false;   // categorical nodes are in the in-loop form (needs the compact model's cat16 codes)
   int tile_T = 0;       // items per CTA = threads per CTA: 512, 256 or 128
   int n_pairs = 0;      // column pairs of the tile
   PackedModel packed;
+  std::vector<uint32_t> root_tab;  // 4 words per tree, or empty (too many trees / wide categorical nodes)
 };
 SlimModel pack_slim(const HostModel &m, const BinnedModel &compact, size_t chunk_budget);
+// host-side layout check of pack_slim's output (mr_model_selfcheck): number of (sample, tree) leaf mismatches
+size_t slim_pack_selfcheck(const HostModel &m, const BinnedModel &compact, const SlimModel &slim, int n_samples, uint64_t seed);
 
 }  // namespace mr

@@ -272,7 +272,7 @@ struct mr_model {
     B.d_thr_off = d_thr_off; B.d_thr = d_thr; B.d_is_cat = d_is_cat;
     B.d_meta = cmp ? d_cmeta : d_meta; B.d_bucket_range = d_bucket_range;
     B.tile_cols = M.tile_cols;
-    B.kind = host.kind; B.has_cat = host.has_cat; B.base_score = host.base_score;
+    B.kind = host.kind; B.has_cat = host.has_cat; B.cat16 = M.cat16; B.base_score = host.base_score;
     B.n_features = host.n_features;
     B.threads = opt_threads; B.ilp = opt_ilp;
     return B;
@@ -306,6 +306,7 @@ struct mr_model {
       B.d_model = d_smodel; B.d_chunks = d_schunks;
       B.n_chunks = (int)slim.packed.chunks.size();
       B.max_chunk_bytes = slim.packed.max_chunk_bytes;
+      if (!slim.root_tab.empty()) { B.h_root_tab = slim.root_tab.data(); B.n_root_tab = (int)(slim.root_tab.size() / 4); }
       launch_gbdt_binned(B, ctx->num_sms, stream);
       return;
     }

@@ -108,6 +108,8 @@ def _grow_lightgbm_tree(rng, n_features, kinds, num_leaves, max_depth, cat_featu
             n_cat = cat_features[f]
             n_words = (n_cat + 31) // 32
             words = [int(rng.integers(0, 2**32)) for _ in range(n_words)]
+            if n_cat % 32:  # LightGBM's bitset ends at the largest category of the set: nothing beyond the feature's range
+                words[-1] &= (1 << (n_cat % 32)) - 1
             cat_idx = len(cat_b) - 1
             cat_t.extend(words)
             cat_b.append(len(cat_t))

@@ -132,7 +132,8 @@ def test_compact_level_loop_sass_instruction_budget():
 def test_slim_level_loop_sass_instruction_budget():
     """The 4-byte-node scorer's level loop is 8 SASS instructions — LOP3 (code address), LDS.U16, HSETP2 (k compared as a
     binary16 pattern straight from the entry), LOP3 (child | block base), a predicated +4, LDS (next entry), ISETP (leaf =
-    sign bit), BRA — with two shared-memory loads and no 64-bit load (an LDS.64 costs two wavefronts once lanes diverge)."""
+    sign bit), BRA — with two shared-memory loads and no 64-bit load (an LDS.64 costs two wavefronts once lanes diverge).
+    Models with small categorical bitsets pay two more (SHF, LOP3 with a predicate result) and never leave the loop."""
     import os
     import re
     import shutil
@@ -144,18 +145,37 @@ def test_slim_level_loop_sass_instruction_budget():
     if not os.path.exists(tool) or not os.path.exists(obj):
         pytest.skip("cuobjdump or the object file is not available")
     sass = subprocess.run([tool, "-sass", obj], capture_output=True, text=True).stdout
+    def level_loops(fn_body):
+        """[(instructions of a backward-branch loop)] of one function's SASS, innermost loops of <= 12 instructions."""
+        ins = []
+        for ln in fn_body.split("\n"):
+            a = re.search(r"/\*([0-9a-f]{4,5})\*/\s+(.*?);", ln)
+            if a:
+                ins.append((int(a.group(1), 16), a.group(2).strip()))
+        at = {addr: k for k, (addr, _) in enumerate(ins)}
+        loops = []
+        for k, (addr, text) in enumerate(ins):
+            b = re.search(r"BRA\s+(?:\S+,\s*)?0x([0-9a-f]+)", text)
+            if b and int(b.group(1), 16) in at and 0 < k - at[int(b.group(1), 16)] < 12 and "LDS" in " ".join(t for _, t in ins[at[int(b.group(1), 16)]:k]):
+                loops.append([t for _, t in ins[at[int(b.group(1), 16)]:k + 1]])
+        return loops
+
+    # <Real, T, CAT, NR>: smem root table / parameter root table (level 0 outside the loop), numeric and small-categorical
     for T in (512, 256, 128):
-        m = re.search(r"Function : \S*slim_kernelIdLi%dELb0EE\S*\n(.*?)(?:Function :|\Z)" % T, sass, re.S)
-        assert m, f"slim kernel <double, {T}> not found"
-        ins = [re.sub(r"/\*.*?\*/", "", ln).strip() for ln in m.group(1).split("\n") if re.search(r"/\*[0-9a-f]{4}\*/", ln)]
-        ins = [i for i in ins if i]
-        h = next(k for k, i in enumerate(ins) if i.startswith("HSETP2"))
-        start = h - 2
-        end = next(k for k in range(h, len(ins)) if "BRA" in ins[k])
-        body = ins[start:end + 1]
-        assert len(body) == 8, body
-        assert body[0].startswith("LOP3") and body[1].startswith("LDS.U16") and ".H0_H0" in body[2] and ".H1_H1" in body[2], body
-        assert sum(i.startswith("LDS") for i in body) == 2 and not any("LDS.64" in i or i.startswith(("SHF", "DADD", "LDG")) for i in body), body
+        for cat, nr, n_ins in ((0, 0, 8), (0, 512, 8), (0, 1920, 8), (2, 0, 10), (2, 512, 10)):
+            m = re.search(r"Function : \S*slim_kernelIdLi%dELi%dELi%dEE\S*\n(.*?)(?:Function :|\Z)" % (T, cat, nr), sass, re.S)
+            assert m, f"slim kernel <double, {T}, {cat}, {nr}> not found"
+            loops = [b for b in level_loops(m.group(1)) if any(i.startswith("HSETP2") for i in b)]
+            assert loops, (T, cat, nr)
+            for body in loops:
+                assert len(body) == n_ins, body
+                assert body[0].startswith("LOP3") and body[1].startswith("LDS.U16"), body
+                assert sum(i.startswith("LDS") for i in body) == 2 and not any("LDS.64" in i or i.startswith(("DADD", "LDG", "LDC")) for i in body), body
+                assert any(".H0_H0" in i and ".H1_H1" in i for i in body if i.startswith("HSETP2")), body
+                assert (sum(i.startswith("SHF") for i in body) == 1) == (cat == 2), body
+            if nr:
+                # level 0 comes from the constant bank: indexed LDC loads, no root-table LDS.128
+                assert "LDC.64" in m.group(1) and "LDS.128" not in m.group(1), (T, cat, nr)
 
 
 def test_ctypes_mirrors_match_the_header_layouts():
@@ -339,3 +359,31 @@ def test_real_file_quirks_of_the_booster_formats():
         with pytest.raises(mb.MrError) as e:
             inspect_model(1, head)
         assert e.value.status == 5 and "deprecated binary" in e.value.message
+
+
+@pytest.mark.parametrize("kind,blob,form", [
+    (0, synth.lightgbm_model_text(60, 30, seed=1, stump_every=7), 3),                       # numeric, root table
+    (0, synth.lightgbm_model_text(40, 12, num_leaves=2, seed=2), 3),                        # every leaf hangs off the root: dummy splits
+    (0, synth.lightgbm_model_text(30, 10, seed=3, cat_features={3: 16, 7: 5}, stump_every=5), 7),   # small categorical: in-loop form
+    (0, synth.lightgbm_model_text(30, 10, seed=4, cat_features={3: 40}), 1),                # categories beyond 15: wide form, no root table
+    (0, synth.lightgbm_model_text(2000, 8, num_leaves=4, seed=5), 1),                       # > 1920 trees: chunk-resident root tables
+    (0, synth.lightgbm_model_text(2000, 8, num_leaves=4, seed=6, cat_features={1: 9}), 5),
+    (0, synth.lightgbm_model_text(20, 200, seed=7), 3),                                     # 256-item tiles
+    (0, synth.lightgbm_model_text(12, 240, seed=8), 3),                                     # 128-item tiles
+    (1, synth.xgboost_model_json(50, 16, depth=6, seed=9), 3),
+])
+def test_slim_packing_walks_like_the_trees(kind, blob, form, monkeypatch):
+    """pack_slim's bytes, read the way gbdt_score_slim_kernel reads them (root table in the parameter space or in the
+    chunk, dummy splits under the root, in-entry bitsets of the small-categorical form), reach the leaf the parsed tree
+    reaches, on random code vectors incl. NaN / out-of-range categories — checked on the host, so that a packing bug shows
+    up without a GPU."""
+    from metarank_b200.booster import selfcheck_model
+
+    got_form, bad = selfcheck_model(kind, blob, 48)
+    assert got_form == form and bad == 0
+    monkeypatch.setenv("MR_NO_ROOT_TAB", "1")
+    got_form, bad = selfcheck_model(kind, blob, 16)
+    assert got_form == (form & ~2) and bad == 0
+    monkeypatch.setenv("MR_NO_CAT16", "1")
+    got_form, bad = selfcheck_model(kind, blob, 16)
+    assert got_form == (form & ~6) and bad == 0

@@ -311,3 +311,38 @@ def test_slim_scorer_layouts_and_fallbacks(ctx):
         _check(ctx, 0, cat, Xc, variant=4)
     wide_cat = synth.lightgbm_model_text(20, 10, seed=81, cat_features={2: 40000})   # 5 KB bitsets: no slim form -> compact kernel
     _check(ctx, 0, wide_cat, synth.feature_matrix(3000, 10, seed=7), variant=5)
+
+
+def test_small_categorical_in_loop_form_and_parameter_root_table(ctx, monkeypatch):
+    """Models whose bitsets all live in categories 0..15 carry `0xFFF0 | category` codes (gbdt_model.h kMetaCat16): the slim
+    scorer resolves their categorical nodes inside its level loop, every other scorer decodes the code back.  Level 0 of
+    the slim walk comes from a root table in the kernel's parameter space (<= 512 / <= 1920 trees; beyond that, or with
+    MR_NO_ROOT_TAB, from the chunk's own table).  Categories: in range, fractional (truncated like static_cast<int>),
+    negative, >= 16, beyond int range, NaN."""
+    rng = np.random.Generator(np.random.PCG64(91))
+    for cats, trees in (({3: 16}, 60), ({0: 7, 5: 12, 9: 16}, 40), ({1: 2}, 700), ({4: 16}, 2100)):
+        blob = synth.lightgbm_model_text(trees, 10, seed=90 + trees, cat_features=cats, stump_every=13)
+        X = synth.feature_matrix(6000, 10, seed=trees)
+        for f, n in cats.items():
+            X[:, f] = rng.integers(-2, n + 6, 6000)
+            X[::17, f] = np.nan
+            X[1::29, f] += 0.75
+            X[5::131, f] = 3e10
+            X[7::131, f] = -0.5   # static_cast<int>(-0.5) == 0: category 0
+        for variant in (5, 4, 2, 0):
+            _check(ctx, 0, blob, X, variant=variant)
+        _check(ctx, 0, blob, X[:300])                   # auto on a small batch: the tree-parallel latency path
+        _check(ctx, 0, blob, np.tile(X, (7, 1)))        # auto on 42 000 rows: the throughput path
+        monkeypatch.setenv("MR_NO_ROOT_TAB", "1")       # the same models through the chunk-resident root tables
+        _check(ctx, 0, blob, X, variant=5)
+        monkeypatch.delenv("MR_NO_ROOT_TAB")
+        monkeypatch.setenv("MR_NO_CAT16", "1")          # ... and through the wide-bitset form (the loop leaves on a categorical node)
+        _check(ctx, 0, blob, X, variant=5)
+        monkeypatch.delenv("MR_NO_CAT16")
+    # numeric models: leaves hanging directly off the root, single-leaf trees, both root-table sizes, XGBoost f32
+    for trees, leaves in ((30, 2), (300, 3), (513, 31), (1920, 8), (1921, 8)):
+        blob = synth.lightgbm_model_text(trees, 12, num_leaves=leaves, seed=trees, stump_every=5)
+        X = synth.feature_matrix(5000, 12, seed=trees + 1)
+        _check(ctx, 0, blob, X, variant=5)
+    xb = synth.xgboost_model_json(600, 16, depth=3, seed=92)
+    _check(ctx, 1, xb, synth.feature_matrix(5000, 16, seed=93), variant=5)
