@@ -151,10 +151,12 @@ MR_API mr_status mr_model_inspect(int32_t kind, const uint8_t *blob, size_t len,
 
 /* Host-only consistency check of the throughput scorer's packing (4-byte entries, root table, in-entry bitsets): `samples`
  * random code vectors are walked through the parsed trees and through the packed bytes the way the kernel reads them.
+ * max_tile: largest CTA tile to pack for (512 | 256 | 128; 0 = 512) — the library keeps one form per tile size.
  * *form: 0 = the model has no such packing (other scorers serve it), else 1 | 2 * (root table present) |
- * 4 * (small-categorical codes); *mismatches: (sample, tree) pairs whose leaf differs — 0 for a sound packing.
- * Validates layout on CPU-only CI; it scores nothing and is not a fallback. */
-MR_API mr_status mr_model_selfcheck(int32_t kind, const uint8_t *blob, size_t len, int32_t samples, int32_t *form, int64_t *mismatches);
+ * 4 * (small-categorical codes) | tile size << 8; *mismatches: (sample, tree) pairs whose leaf differs — 0 for a sound
+ * packing.  Validates layout on CPU-only CI; it scores nothing and is not a fallback. */
+MR_API mr_status mr_model_selfcheck(int32_t kind, const uint8_t *blob, size_t len, int32_t samples, int32_t max_tile, int32_t *form,
+                                    int64_t *mismatches);
 
 /* Mean evaluated path length (internal nodes visited per item per tree) of the last
  * `rows` scored by mr_model_count_path(): the d̄ of SURVEY.md §8(d)'s B_item. */

@@ -166,9 +166,10 @@ def inspect_model(kind: int, blob: bytes, chunk_kb: int = 0) -> _capi.ModelInfo:
     return inf
 
 
-def selfcheck_model(kind: int, blob: bytes, samples: int = 64) -> tuple[int, int]:
-    """Host-only layout check of the throughput scorer's packing (mr_model_selfcheck): (form bits, leaf mismatches)."""
+def selfcheck_model(kind: int, blob: bytes, samples: int = 64, max_tile: int = 0) -> tuple[int, int]:
+    """Host-only layout check of the throughput scorer's packing (mr_model_selfcheck): (form bits | tile size << 8, leaf
+    mismatches)."""
     form, bad = C.c_int32(), C.c_int64()
     buf = (C.c_uint8 * max(len(blob), 1)).from_buffer_copy(blob if blob else b"\0")
-    check(lib().mr_model_selfcheck(C.c_int32(kind), buf, C.c_size_t(len(blob)), C.c_int32(samples), C.byref(form), C.byref(bad)))
+    check(lib().mr_model_selfcheck(C.c_int32(kind), buf, C.c_size_t(len(blob)), C.c_int32(samples), C.c_int32(max_tile), C.byref(form), C.byref(bad)))
     return form.value, bad.value

@@ -348,7 +348,7 @@ mr_status mr_model_inspect(int32_t kind, const uint8_t *blob, size_t len, int32_
   });
 }
 
-mr_status mr_model_selfcheck(int32_t kind, const uint8_t *blob, size_t len, int32_t samples, int32_t *form, int64_t *mismatches) {
+mr_status mr_model_selfcheck(int32_t kind, const uint8_t *blob, size_t len, int32_t samples, int32_t max_tile, int32_t *form, int64_t *mismatches) {
   return guard([&] {
     if (!blob || !form || !mismatches) fail(MR_ERR_INVALID_ARG, "null argument");
     HostModel hm;
@@ -360,9 +360,9 @@ mr_status mr_model_selfcheck(int32_t kind, const uint8_t *blob, size_t len, int3
     if (!bn.ok) return;
     const BinnedModel cm = pack_compact(hm, bn, 0);
     if (!cm.ok) return;
-    const SlimModel sl = pack_slim(hm, cm, 0);
+    const SlimModel sl = pack_slim(hm, cm, 0, max_tile > 0 ? max_tile : 512, max_tile > 0 && max_tile < 512 ? 64 : 48);
     if (!sl.ok) return;
-    *form = 1 | (sl.root_tab.empty() ? 0 : 2) | (sl.cat16 ? 4 : 0);
+    *form = 1 | (sl.root_tab.empty() ? 0 : 2) | (sl.cat16 ? 4 : 0) | (sl.tile_T << 8);
     *mismatches = (int64_t)slim_pack_selfcheck(hm, cm, sl, std::max(1, samples), 0x9E3779B97F4A7C15ull);
   });
 }

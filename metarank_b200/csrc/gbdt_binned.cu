@@ -81,6 +81,7 @@ struct BParams {
   int rows, n_features;
   float base_score;
   int cat16;  // categorical columns carry the small-categorical code form (gbdt_model.h kMetaCat16)
+  int col_base;  // slim scorer: pair p of the code tile lives at absolute shared address (p + col_base) * 4T
   ScoreSinks sinks;
 };
 
@@ -477,9 +478,9 @@ __global__ void __launch_bounds__(T) gbdt_score_slim_kernel(const __grid_constan
   const int tid = threadIdx.x;
   const uint32_t base = smem_u32(smem);         // absolute shared address of the dynamic window (small: asserted on the host)
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
-  const uint32_t tile_abs = (uint32_t)T * 4u;   // pair p of the tile lives at (p + 1) * 4T
+  const uint32_t tile_abs = (uint32_t)T * 4u * (uint32_t)p.col_base;   // pair p of the tile lives at (p + col_base) * 4T
   const uint32_t n_pairs = (uint32_t)(p.n_features + 1) >> 1;
-  const uint32_t cb0_abs = (tile_abs * (n_pairs + 1u) + 2047u) & ~2047u, cb1_abs = cb0_abs + p.chunk_stride;
+  const uint32_t cb0_abs = ((uint32_t)T * 4u * (n_pairs + (uint32_t)p.col_base) + 2047u) & ~2047u, cb1_abs = cb0_abs + p.chunk_stride;
   uint8_t *tile_ptr = smem + (tile_abs - base);
   const bool resident = p.n_chunks == 1;
   const uint32_t tid4 = (uint32_t)tid * 4u;
@@ -984,14 +985,16 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
     p.sinks = L.sinks;
     const int T = L.tile_T;
     const size_t n_pairs = (size_t)(F + 1) / 2;
-    const size_t cb0 = (((size_t)T * 4 * (n_pairs + 1)) + 2047) & ~size_t(2047);
+    p.col_base = L.slim_col_base;
+    const size_t cb0 = (((size_t)T * 4 * (n_pairs + (size_t)L.slim_col_base)) + 2047) & ~size_t(2047);
     const size_t smem = cb0 + (size_t)p.chunk_stride * (L.n_chunks == 1 ? 1 : 2);  // the window starts at (or just above) address 0
     auto go = [&](auto kern, const auto &roots) {
       MR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = 0;
       MR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
       if (per_sm < 1) fail(MR_ERR_CUDA, "slim gbdt kernel does not fit on an SM (%zu B smem, %d threads)", smem, T);
-      per_sm = std::min(per_sm, std::max(1, 1536 / T));  // ~48 warps saturate the shared-memory pipe (profiles/sweep_r1.md)
+      // ~48 warps saturate the shared-memory pipe (profiles/sweep_r1.md); a batch that fits in one wave runs all its tiles at once
+      per_sm = std::min(per_sm, std::max(1, L.slim_per_sm > 0 ? L.slim_per_sm : 1536 / T));
       const int n_tiles = (p.rows + T - 1) / T;
       static const bool debug = getenv("MR_DEBUG_LAUNCH") != nullptr;
       if (debug)
@@ -1032,7 +1035,7 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
   BParams p;
   p.model = L.d_model; p.chunks = L.d_chunks; p.bins = L.d_bins; p.out = L.d_out;
   p.n_chunks = L.n_chunks; p.chunk_stride = (L.max_chunk_bytes + 127u) & ~127u;
-  p.rows = L.rows; p.n_features = F; p.base_score = L.base_score; p.cat16 = L.cat16 ? 1 : 0;
+  p.rows = L.rows; p.n_features = F; p.base_score = L.base_score; p.cat16 = L.cat16 ? 1 : 0; p.col_base = 1;
   p.sinks = L.sinks;
   const size_t kMaxSmem = 227 * 1024;
   const bool aligned_tile = L.compact && !L.has_cat && (F & (F - 1)) == 0;  // + slack to align the tile

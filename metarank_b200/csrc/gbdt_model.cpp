@@ -273,17 +273,144 @@ HostModel parse_lightgbm_text(const uint8_t *blob, size_t len) {
   return m;
 }
 
+// XGBoost's "deprecated" binary model: what Booster.toByteArray() / save_raw() / save_model("x.model") write by default
+// up to XGBoost 2.0 (JSON / UBJSON are opt-in there and the default from 2.1) — and therefore what a Metarank model trained
+// with ltrlib's xgboost4j holds.  Little-endian, fixed-size C structs (xgboost src/learner.cc LearnerModelParamLegacy,
+// src/gbm/gbtree_model.h GBTreeModelParam, include/xgboost/tree_model.h TreeParam / RegTree::Node / RTreeNodeStat):
+//   ["binf"]                                   optional 4-byte magic (0.4 - 0.9x save_raw)
+//   LearnerModelParamLegacy   136 B            f32 base_score, u32 num_feature, i32 num_class, i32 contain_extra_attrs,
+//                                              i32 contain_eval_metrics, u32 major, u32 minor, u32 num_target, i32 x 26
+//   u64 n + bytes             name_obj         ("rank:pairwise", "rank:ndcg", ...)
+//   u64 n + bytes             name_gbm         ("gbtree")
+//   GBTreeModelParam          160 B            i32 num_trees, i32 num_roots / num_parallel_tree, i32 num_feature, i32 pad,
+//                                              i64 num_pbuffer, i32 num_output_group, i32 size_leaf_vector, i32 x 32
+//   per tree: TreeParam       148 B            i32 num_roots, i32 num_nodes, i32 num_deleted, i32 max_depth, u32 num_feature,
+//                                              i32 size_leaf_vector, i32 x 31
+//             Node x num_nodes    20 B each    i32 parent, i32 cleft (-1: leaf), i32 cright, u32 sindex (bit 31 = default
+//                                              left, low 31 = feature; 0xFFFFFFFF = deleted), f32 leaf value | split condition
+//             Stat x num_nodes    16 B each    f32 loss_chg, f32 sum_hess, f32 base_weight, i32 leaf_child_cnt
+//             [u64 n + f32 x n]                leaf vector, only when size_leaf_vector != 0 (pre-1.0 multi-output; refused)
+//   i32 x num_trees           tree_info        output group of each tree
+//   (attributes, metrics, and from 1.0 a JSON configuration follow; prediction does not need them)
+// Unpinned like the rest of the scorer side: no file XGBoost wrote exists here; restated from the public
+// headers.  A node's test is the same as in the JSON form: missing -> default side, else left iff (f32)x < split condition.
+static HostModel parse_xgboost_binary(const uint8_t *blob, size_t len) {
+  HostModel m;
+  m.kind = MR_BOOSTER_XGBOOST;
+  m.blob.assign(blob, blob + len);
+  size_t p = 0;
+  auto need = [&](size_t n, const char *what) {
+    if (len - p < n) fail(MR_ERR_PARSE, "xgboost binary model: truncated in %s (offset %zu, %zu more bytes needed, %zu left)", what, p, n, len - p);
+  };
+  auto rd32 = [&](size_t off) { uint32_t v; memcpy(&v, blob + off, 4); return v; };
+  auto rdf = [&](size_t off) { float v; memcpy(&v, blob + off, 4); return v; };
+  auto rd64 = [&](size_t off) { uint64_t v; memcpy(&v, blob + off, 8); return v; };
+  if (len >= 4 && memcmp(blob, "binf", 4) == 0) p = 4;
+  need(136, "LearnerModelParam");
+  m.base_score = rdf(p);
+  const uint32_t num_feature = rd32(p + 4);
+  const int32_t num_class = (int32_t)rd32(p + 8);
+  const uint32_t major = rd32(p + 20), num_target = rd32(p + 28);
+  p += 136;
+  if (!(m.base_score == m.base_score) || num_feature == 0 || num_feature > (1u << 24) || major > 10)
+    fail(MR_ERR_UNSUPPORTED, "xgboost: unsupported model encoding (neither JSON / UBJSON nor a plausible binary header: num_feature %u, "
+                             "version %u)", num_feature, major);
+  if (num_class > 1) fail(MR_ERR_UNSUPPORTED, "xgboost: multiclass models are not supported");
+  if (num_target > 1) fail(MR_ERR_UNSUPPORTED, "xgboost: multi-target models are not supported");
+  auto rd_str = [&](const char *what) {
+    need(8, what);
+    const uint64_t n = rd64(p);
+    p += 8;
+    if (n > 256) fail(MR_ERR_PARSE, "xgboost binary model: %s is %llu bytes long", what, (unsigned long long)n);
+    need((size_t)n, what);
+    std::string v((const char *)blob + p, (size_t)n);
+    p += (size_t)n;
+    return v;
+  };
+  const std::string obj = rd_str("the objective name"), gbm = rd_str("the booster name");
+  {
+    static const char *identity[] = {"rank:ndcg", "rank:pairwise", "rank:map", "reg:squarederror", "reg:linear",
+                                     "reg:absoluteerror", "reg:pseudohubererror", "reg:quantileerror"};
+    bool ok = false;
+    for (const char *k : identity) ok |= obj == k;
+    if (!ok) fail(MR_ERR_UNSUPPORTED, "xgboost: objective '%s' transforms the margin on prediction; only rank:* and plain "
+                                     "regression objectives are supported", obj.c_str());
+  }
+  if (gbm != "gbtree") fail(MR_ERR_UNSUPPORTED, "xgboost: booster '%s' not supported", gbm.c_str());
+  m.n_features = (int)num_feature;
+  need(160, "GBTreeModelParam");
+  const int32_t num_trees = (int32_t)rd32(p), out_groups = (int32_t)rd32(p + 24), gb_leaf_vec = (int32_t)rd32(p + 28);
+  p += 160;
+  if (num_trees < 0 || (size_t)num_trees > len / 168) fail(MR_ERR_PARSE, "xgboost binary model: %d trees cannot fit %zu bytes", num_trees, len);
+  if (out_groups > 1 || gb_leaf_vec > 1) fail(MR_ERR_UNSUPPORTED, "xgboost: multi-output models are not supported");
+  for (int32_t ti = 0; ti < num_trees; ti++) {
+    need(148, "TreeParam");
+    const int32_t n = (int32_t)rd32(p + 4), leaf_vec = (int32_t)rd32(p + 20);
+    p += 148;
+    if (n < 1 || (size_t)n > (len - p) / 36) fail(MR_ERR_PARSE, "xgboost binary model: tree %d announces %d nodes", ti, n);
+    if (leaf_vec > 1) fail(MR_ERR_UNSUPPORTED, "xgboost: vector leaves are not supported");
+    need((size_t)n * 36, "a tree's nodes");
+    const size_t nodes = p;
+    p += (size_t)n * 36;
+    if (leaf_vec != 0) {  // pre-1.0 files carry an (empty or scalar) leaf vector here
+      need(8, "a tree's leaf vector");
+      const uint64_t lv = rd64(p);
+      p += 8;
+      need((size_t)lv * 4, "a tree's leaf vector");
+      p += (size_t)lv * 4;
+    }
+    // renumber from the root: deleted (pruned) nodes stay in the array but nothing points at them
+    std::vector<int32_t> id(n, INT32_MIN);
+    std::vector<int32_t> order;
+    std::vector<int32_t> st{0};
+    int ni = 0, nl = 0;
+    while (!st.empty()) {
+      const int32_t i = st.back();
+      st.pop_back();
+      if (i < 0 || i >= n) fail(MR_ERR_PARSE, "xgboost: child out of range");
+      if (id[i] != INT32_MIN) fail(MR_ERR_PARSE, "xgboost binary model: node %d of tree %d is reachable twice", i, ti);
+      const size_t o = nodes + (size_t)i * 20;
+      const int32_t cl = (int32_t)rd32(o + 4), cr = (int32_t)rd32(o + 8);
+      if (rd32(o + 12) == 0xFFFFFFFFu && cl != -1) fail(MR_ERR_PARSE, "xgboost binary model: tree %d reaches a deleted node", ti);
+      order.push_back(i);
+      if (cl == -1) id[i] = ~(nl++);
+      else { id[i] = ni++; st.push_back(cr); st.push_back(cl); }
+    }
+    HostTree t;
+    t.feat.resize(ni); t.thr.resize(ni); t.flags.resize(ni); t.left.resize(ni); t.right.resize(ni);
+    t.cat_begin.assign(ni, 0); t.cat_n.assign(ni, 0);
+    t.leaf.resize(nl);
+    for (int32_t i : order) {
+      const size_t o = nodes + (size_t)i * 20;
+      if (id[i] < 0) { t.leaf[~id[i]] = (double)rdf(o + 16); continue; }
+      const uint32_t sindex = rd32(o + 12);
+      const int k2 = id[i];
+      t.feat[k2] = (int32_t)(sindex & 0x7FFFFFFFu);
+      t.thr[k2] = (double)rdf(o + 16);
+      const bool dl = (sindex >> 31) != 0;
+      t.flags[k2] = (uint8_t)((dl ? NF_DEFAULT_LEFT | NF_NAN_LEFT : 0) | (2u << NF_MISSING_SHIFT));
+      t.left[k2] = id[(int32_t)rd32(o + 4)];
+      t.right[k2] = id[(int32_t)rd32(o + 8)];
+    }
+    m.trees.push_back(std::move(t));
+  }
+  need((size_t)num_trees * 4, "tree_info");
+  for (int32_t ti = 0; ti < num_trees; ti++)
+    if (rd32(p + (size_t)ti * 4) != 0) fail(MR_ERR_UNSUPPORTED, "xgboost: multi-group models are not supported");
+  finalize(m);
+  return m;
+}
+
 HostModel parse_xgboost_model(const uint8_t *blob, size_t len) {
   HostModel m;
   m.kind = MR_BOOSTER_XGBOOST;
   m.blob.assign(blob, blob + len);
   size_t s = 0;
   while (s < len && (blob[s] == ' ' || blob[s] == '\n' || blob[s] == '\r' || blob[s] == '\t')) s++;
-  if (len - s >= 4 && (memcmp(blob + s, "binf", 4) == 0 || memcmp(blob + s, "bs64", 4) == 0))
-    fail(MR_ERR_UNSUPPORTED, "xgboost: this is the deprecated binary model format ('%.4s' header, XGBoost < 2.0 save_raw default); "
-                             "re-save the booster as JSON or UBJSON (booster.toByteArray(\"ubj\") / save_raw(raw_format='ubj'))", (const char *)blob + s);
-  if (s >= len || blob[s] != '{')
-    fail(MR_ERR_UNSUPPORTED, "xgboost: unsupported model encoding (only JSON and UBJSON; legacy binary is not)");
+  if (len - s >= 4 && memcmp(blob + s, "bs64", 4) == 0)
+    fail(MR_ERR_UNSUPPORTED, "xgboost: base64-wrapped binary model ('bs64' header of old Python pickles); decode it, or re-save the "
+                             "booster (booster.toByteArray() / save_raw())");
+  if (s >= len || blob[s] != '{') return parse_xgboost_binary(blob, len);
   JValue doc;
   size_t k = s + 1;
   while (k < len && (blob[k] == ' ' || blob[k] == '\n' || blob[k] == '\r' || blob[k] == '\t')) k++;
@@ -766,7 +893,7 @@ BinnedModel pack_compact(const HostModel &m, const BinnedModel &bn, size_t chunk
   return C;
 }
 
-SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budget) {
+SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budget, int max_T, int warps_per_sm, uint32_t min_tile_addr) {
   SlimModel S;
   if (!C.ok || m.trees.empty()) return S;
   const int F = m.n_features;
@@ -796,18 +923,23 @@ SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budge
   };
   for (auto &t : m.trees) max_block = std::max(max_block, block_bytes(t));
   for (int T : {512, 256, 128}) {
+    if (T > max_T) continue;
     const int shift = T == 512 ? 11 : T == 256 ? 10 : 9;
-    if (S.n_pairs + 1 <= (1 << (16 - shift)) && max_block <= (size_t)T * 4) { S.tile_T = T; break; }
+    const int cbase = std::max(1, (int)((min_tile_addr + (uint32_t)T * 4u - 1u) / ((uint32_t)T * 4u)));
+    if (S.n_pairs + cbase <= (1 << (16 - shift)) && max_block <= (size_t)T * 4) { S.tile_T = T; S.col_base = cbase; break; }
   }
   if (!S.tile_T) return S;
   const int shift = S.tile_T == 512 ? 11 : S.tile_T == 256 ? 10 : 9;
   const bool f32 = m.kind == MR_BOOSTER_XGBOOST;
   if (chunk_budget == 0) {
-    // ~48 resident warps per SM: what their code tiles leave of the 227 KB, split over the CTAs' two chunk buffers
-    const int ctas = 1536 / S.tile_T;
-    const long long tile = (long long)(S.n_pairs + 1) * S.tile_T * 4;
+    // ~48 resident warps per SM (or what the caller plans for): what their code tiles leave of the 227 KB, split over
+    // the CTAs' two chunk buffers
+    const int ctas = std::max(1, warps_per_sm * 32 / S.tile_T);
+    const long long tile = (long long)(S.n_pairs + S.col_base) * S.tile_T * 4;
     const long long left = (225ll * 1024 / ctas - tile - 2048) / 2;
     chunk_budget = (size_t)std::max<long long>(2048, std::min<long long>(24 * 1024, (left / 2048) * 2048));
+    // a chunk is a TMA copy, an mbarrier wait and a CTA-wide barrier: at least ~8 trees between two of them
+    chunk_budget = std::max(chunk_budget, std::min<size_t>(8 * max_block + 2047, 16 * 1024) & ~size_t(2047));
   }
   chunk_budget = std::max<size_t>(chunk_budget, 2048);
   PackedModel &pk = S.packed;
@@ -853,7 +985,8 @@ SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budge
       std::vector<int> order;
       if (ni) { order.push_back(0); entry_of_node[0] = 0; }
       auto leaf_entry = [&](int cidx) { return 0x80000000u | (uint32_t)(leaf_base + (size_t)(~cidx) * 8); };
-      const uint32_t dummy = 1u << shift;  // k = 0 on tile column 0; | child pair * 8
+      const uint32_t cbase = (uint32_t)S.col_base;
+      const uint32_t dummy = cbase << shift;  // k = 0 on tile column 0; | child pair * 8
       if (!ni) {
         // a single-leaf tree is a dummy split whose children both are its leaf: every walk starts at an internal entry
         e[0] = dummy | (1u * 8u);
@@ -879,14 +1012,14 @@ SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budge
           uint32_t bits = t.cat_n[q] > 0 ? (t.cat_words[(size_t)t.cat_begin[q]] & 0xFFFFu) : 0u;
           swapped = (bits & 0x8000u) != 0;
           if (swapped) bits = ~bits & 0xFFFFu;
-          e[entry_of_node[q]] = (bits << 16) | ((((uint32_t)f >> 1) + 1u) << shift) | (((uint32_t)f & 1u) << 1) | (pair * 8u) |
+          e[entry_of_node[q]] = (bits << 16) | ((((uint32_t)f >> 1) + cbase) << shift) | (((uint32_t)f & 1u) << 1) | (pair * 8u) |
                                 (swapped ? 4u : 0u) | 1u;
         } else if (t.flags[q] & NF_CATEGORICAL) {
           // bit 0 = categorical: the level loop leaves on it (the same test that finds a leaf); the k field is the 8-byte
           // index, inside the block, of the node's {bitset byte offset, n words}
           ctab[2 * ci] = (uint32_t)(cw_base + (size_t)t.cat_begin[q] * 4);
           ctab[2 * ci + 1] = (uint32_t)t.cat_n[q];
-          e[entry_of_node[q]] = (uint32_t)(((ctab_base + ci * 8) / 8) << 16) | ((((uint32_t)f >> 1) + 1u) << shift) |
+          e[entry_of_node[q]] = (uint32_t)(((ctab_base + ci * 8) / 8) << 16) | ((((uint32_t)f >> 1) + cbase) << shift) |
                                 (((uint32_t)f & 1u) << 1) | (pair * 8u) | 1u;
           ci++;
         } else {
@@ -894,7 +1027,7 @@ SlimModel pack_slim(const HostModel &m, const BinnedModel &C, size_t chunk_budge
           const uint32_t kk = (uint32_t)(std::lower_bound(tb, te, t.thr[q]) - tb);
           const uint32_t dup = C.meta[f].flags >> 16;
           const uint32_t col = ((t.flags[q] & NF_NAN_LEFT) && dup != kMetaNoDup) ? dup : (uint32_t)f;
-          e[entry_of_node[q]] = (kk << 16) | (((col >> 1) + 1u) << shift) | ((col & 1u) << 1) | (pair * 8u);
+          e[entry_of_node[q]] = (kk << 16) | (((col >> 1) + cbase) << shift) | ((col & 1u) << 1) | (pair * 8u);
         }
         const int ch[2] = {swapped ? t.right[q] : t.left[q], swapped ? t.left[q] : t.right[q]};
         for (int sd = 0; sd < 2; sd++) {
@@ -997,7 +1130,7 @@ size_t slim_pack_selfcheck(const HostModel &m, const BinnedModel &C, const SlimM
           want = t.leaf[~n];
         }
         // (b) the packed entries, the way the kernel walks them
-        auto code_at = [&](uint32_t w) { const uint32_t pair = ((w & col_mask) >> shift) - 1u; return tile[2 * pair + ((w >> 1) & 1u)]; };
+        auto code_at = [&](uint32_t w) { const uint32_t pair = ((w & col_mask) >> shift) - (uint32_t)S.col_base; return tile[2 * pair + ((w >> 1) & 1u)]; };
         auto goes_left = [&](uint32_t w, uint16_t code, const uint8_t *blk) {
           if (S.cat16) {
             const bool pc = ((w >> (code & 31u)) & w & 1u) != 0;

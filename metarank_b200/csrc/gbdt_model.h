@@ -179,10 +179,15 @@ struct SlimModel {
   bool cat16 = false;   // categorical nodes are in the in-loop form (needs the compact model's cat16 codes)
   int tile_T = 0;       // items per CTA = threads per CTA: 512, 256 or 128
   int n_pairs = 0;      // column pairs of the tile
+  int col_base = 1;     // pair p of the CTA's code tile lives at absolute shared address (p + col_base) * 4 * tile_T
   PackedModel packed;
   std::vector<uint32_t> root_tab;  // 4 words per tree, or empty (too many trees / wide categorical nodes)
 };
-SlimModel pack_slim(const HostModel &m, const BinnedModel &compact, size_t chunk_budget);
+// max_T: largest tile size to consider; warps_per_sm: the residency the automatic chunk budget leaves room for;
+// min_tile_addr: lowest absolute shared address the code tile may start at (the kernel's dynamic window begins at 1 KB on
+// sm_100 and holds three mbarriers first) — the tile's pair p lives at (p + col_base) * 4 * tile_T.
+SlimModel pack_slim(const HostModel &m, const BinnedModel &compact, size_t chunk_budget, int max_T = 512, int warps_per_sm = 48,
+                    uint32_t min_tile_addr = 1088);
 // host-side layout check of pack_slim's output (mr_model_selfcheck): number of (sample, tree) leaf mismatches
 size_t slim_pack_selfcheck(const HostModel &m, const BinnedModel &compact, const SlimModel &slim, int n_samples, uint64_t seed);
 

@@ -322,6 +322,40 @@ def _ubj(obj, float_ctx: str | None = None) -> bytes:
     raise TypeError(type(obj))
 
 
+def xgboost_model_binary(n_trees: int, n_features: int, depth: int = 6, seed: int = 1234, full: bool = True,
+                         base_score: float = 0.5, shrinkage: float = 0.1, magic: bool = False, deleted: int = 0,
+                         objective: str = "rank:ndcg", with_attributes: bool = True) -> bytes:
+    """Same model as :func:`xgboost_model_json` in XGBoost's deprecated BINARY encoding — what ``Booster.toByteArray()`` /
+    ``save_raw()`` write by default up to XGBoost 2.0, i.e. what an xgboost4j-trained Metarank model holds
+    (LearnerModelParamLegacy 136 B, two length-prefixed names, GBTreeModelParam 160 B, per tree TreeParam 148 B + 20-byte
+    nodes + 16-byte stats, tree_info; little-endian).  magic: the 0.x ``binf`` prefix; deleted: pruned (unreachable) nodes
+    appended to every tree, as RegTree keeps them after pruning; with_attributes: the attribute block that follows."""
+    d = _xgb_model_dict(n_trees, n_features, depth, seed, full, base_score, shrinkage)
+    out = [b"binf"] if magic else []
+    out.append(struct.pack("<fIiiiIIIi", float(np.float32(base_score)), n_features, 0, 1 if with_attributes else 0, 0, 1, 7, 1, 1)
+               + b"\0" * (25 * 4))
+    for name in (objective, "gbtree"):
+        out.append(struct.pack("<Q", len(name)) + name.encode())
+    out.append(struct.pack("<iiiiqii", n_trees, 1, n_features, 0, 0, 1, 0) + b"\0" * (32 * 4))
+    for t in d["learner"]["gradient_booster"]["model"]["trees"]:
+        l, r, si, sc, dl, par = (t[k] for k in ("left_children", "right_children", "split_indices", "split_conditions",
+                                               "default_left", "parents"))
+        n = len(l)
+        out.append(struct.pack("<iiiiIi", 1, n + deleted, deleted, 0, n_features, 0) + b"\0" * (31 * 4))
+        for i in range(n):
+            parent = -1 if par[i] == 2147483647 else (par[i] | (0x80000000 if l[par[i]] == i else 0))
+            sindex = (si[i] | (0x80000000 if dl[i] else 0)) if l[i] >= 0 else 0
+            out.append(struct.pack("<IiiIf", parent & 0xFFFFFFFF, l[i], r[i] if l[i] >= 0 else 0, sindex, sc[i]))
+        for _ in range(deleted):
+            out.append(struct.pack("<IiiIf", 0xFFFFFFFF, -1, 0, 0xFFFFFFFF, 0.0))
+        out.append(struct.pack("<fffi", 0.0, 1.0, 0.0, 0) * (n + deleted))
+    out.append(struct.pack(f"<{n_trees}i", *([0] * n_trees)))
+    if with_attributes:
+        k, v = b"best_iteration", str(n_trees - 1).encode()
+        out.append(struct.pack("<Q", 1) + struct.pack("<Q", len(k)) + k + struct.pack("<Q", len(v)) + v)
+    return b"".join(out)
+
+
 def xgboost_model_ubj(n_trees: int, n_features: int, depth: int = 6, seed: int = 1234,
                       full: bool = True, base_score: float = 0.5, shrinkage: float = 0.1) -> bytes:
     """Same model as :func:`xgboost_model_json`, UBJSON-encoded (``save_raw("ubj")``)."""

@@ -187,8 +187,10 @@ def parse_xgboost(blob: bytes) -> dict:
         doc = json.loads(blob.decode("utf-8"), parse_float=lambda tok: float(np.float32(tok)))
     elif head == b"{":
         doc = _ubj_read(io.BytesIO(blob))
+    elif blob[:4] == b"bs64":
+        raise ValueError("base64-wrapped XGBoost binary model is not supported")
     else:
-        raise ValueError("unsupported XGBoost model encoding (legacy binary?)")
+        return _parse_xgboost_binary(blob)
     learner = doc["learner"]
     gb = learner["gradient_booster"]
     if gb["name"] != "gbtree":
@@ -212,6 +214,59 @@ def parse_xgboost(blob: bytes) -> dict:
         ))
     return dict(kind="xgboost", n_features=n_features, base_score=base_score, trees=trees,
                 objective=learner.get("objective", {}).get("name", ""))
+
+
+def _parse_xgboost_binary(blob: bytes) -> dict:
+    """XGBoost's deprecated binary encoding (the default of Booster.toByteArray() / save_raw() up to 2.0; restated from
+    xgboost's public headers: src/learner.cc LearnerModelParamLegacy (136 B), src/gbm/gbtree_model.h GBTreeModelParam
+    (160 B), include/xgboost/tree_model.h TreeParam (148 B), RegTree::Node (20 B: parent, cleft, cright, sindex with
+    the default-left flag in bit 31, leaf value | split condition) and RTreeNodeStat (16 B)).  Nodes keep their file
+    order; pruned nodes stay in the arrays, unreachable."""
+    import struct
+
+    p = 4 if blob[:4] == b"binf" else 0
+    if len(blob) < p + 136:
+        raise ValueError("unsupported XGBoost model encoding")
+    base_score, n_features, num_class = struct.unpack_from("<fIi", blob, p)
+    major, _, num_target = struct.unpack_from("<III", blob, p + 20)
+    p += 136
+    if not (base_score == base_score) or n_features == 0 or n_features > 1 << 24 or major > 10:
+        raise ValueError("unsupported XGBoost model encoding")
+    if num_class > 1 or num_target > 1:
+        raise ValueError("multi-output XGBoost models are not supported")
+    names = []
+    for _ in range(2):
+        (n,) = struct.unpack_from("<Q", blob, p)
+        if n > 256:
+            raise ValueError("XGBoost binary model: name too long")
+        names.append(blob[p + 8:p + 8 + n].decode())
+        p += 8 + n
+    if names[1] != "gbtree":
+        raise ValueError(f"booster {names[1]} not supported")
+    (n_trees,) = struct.unpack_from("<i", blob, p)
+    p += 160
+    trees = []
+    for _ in range(n_trees):
+        _, n, _, _, _, leaf_vec = struct.unpack_from("<iiiiIi", blob, p)
+        p += 148
+        if n < 1 or p + n * 36 > len(blob):
+            raise ValueError("XGBoost binary model: truncated tree")
+        nodes = np.frombuffer(blob, dtype=np.dtype([("parent", "<i4"), ("l", "<i4"), ("r", "<i4"), ("s", "<u4"), ("v", "<f4")]),
+                              count=n, offset=p)
+        p += n * 36
+        if leaf_vec != 0:
+            (lv,) = struct.unpack_from("<Q", blob, p)
+            p += 8 + 4 * lv
+        leaf = nodes["l"] == -1
+        trees.append(dict(
+            left=nodes["l"].astype(np.int32), right=np.where(leaf, -1, nodes["r"]).astype(np.int32),
+            split_index=np.where(leaf, 0, nodes["s"] & 0x7FFFFFFF).astype(np.int32),
+            split_cond=nodes["v"].astype(np.float32),
+            default_left=np.where(leaf, 0, nodes["s"] >> 31).astype(np.uint8),
+        ))
+    if p + 4 * n_trees > len(blob):
+        raise ValueError("XGBoost binary model: truncated tree_info")
+    return dict(kind="xgboost", n_features=int(n_features), base_score=np.float32(base_score), trees=trees, objective=names[0])
 
 
 # --------------------------------------------------------------------------- second opinion

@@ -58,7 +58,7 @@ def test_chunk_budget_controls_chunk_count():
 
 
 @pytest.mark.parametrize("kind,blob,status", [
-    (0, b"", 2), (0, b"tree\nversion=v4\n", 2), (1, b"binf....", 5), (1, b'{"learner": {}}', 2), (7, b"x", 5),
+    (0, b"", 2), (0, b"tree\nversion=v4\n", 2), (1, b"binf....", 2), (1, b"bs64\tAAAA", 5), (1, b"x" * 400, 5), (1, b'{"learner": {}}', 2), (7, b"x", 5),
     (0, synth.lightgbm_model_text(2, 3).replace(b"num_class=1", b"num_class=3"), 5),
     (0, synth.lightgbm_model_text(2, 3).replace(b"is_linear=0", b"is_linear=1"), 5),
     (0, synth.lightgbm_model_text(2, 3).replace(b"max_feature_idx=2", b"max_feature_idx=0"), 2),
@@ -355,10 +355,13 @@ def test_real_file_quirks_of_the_booster_formats():
         with pytest.raises(mb.MrError) as e:
             inspect_model(1, with_(mut))
         assert e.value.status == status and word in e.value.message, (word, e.value)
-    for head in (b"binf\x00\x00\x00\x00", b"bs64AAAA"):
-        with pytest.raises(mb.MrError) as e:
-            inspect_model(1, head)
-        assert e.value.status == 5 and "deprecated binary" in e.value.message
+    # the deprecated binary encoding is read (test_xgboost_deprecated_binary_encoding_is_read); its base64 wrapping is not
+    with pytest.raises(mb.MrError) as e:
+        inspect_model(1, b"bs64AAAA")
+    assert e.value.status == 5 and "base64" in e.value.message
+    with pytest.raises(mb.MrError) as e:
+        inspect_model(1, b"binf\x00\x00\x00\x00")
+    assert e.value.status == 2 and "truncated" in e.value.message
 
 
 @pytest.mark.parametrize("kind,blob,form", [
@@ -380,10 +383,38 @@ def test_slim_packing_walks_like_the_trees(kind, blob, form, monkeypatch):
     from metarank_b200.booster import selfcheck_model
 
     got_form, bad = selfcheck_model(kind, blob, 48)
-    assert got_form == form and bad == 0
+    tile = got_form >> 8
+    assert got_form & 255 == form and bad == 0 and tile in (512, 256, 128)
+    for smaller in (256, 128):   # the forms one-wave batches are scored from (mr_model::pick_slim)
+        if smaller < tile:
+            f2, bad = selfcheck_model(kind, blob, 16, max_tile=smaller)
+            assert bad == 0 and (f2 == 0 or (f2 & 255 == form and f2 >> 8 == smaller))
     monkeypatch.setenv("MR_NO_ROOT_TAB", "1")
     got_form, bad = selfcheck_model(kind, blob, 16)
-    assert got_form == (form & ~2) and bad == 0
+    assert got_form & 255 == (form & ~2) and bad == 0
     monkeypatch.setenv("MR_NO_CAT16", "1")
     got_form, bad = selfcheck_model(kind, blob, 16)
-    assert got_form == (form & ~6) and bad == 0
+    assert got_form & 255 == (form & ~6) and bad == 0
+
+
+def test_xgboost_deprecated_binary_encoding_is_read():
+    """Booster.toByteArray() of xgboost4j up to 2.0 — what a Metarank-trained XGBoost model holds — is the deprecated binary
+    encoding.  The same synthetic model written as JSON and as binary parses to the same shape on the host (and, in
+    tests/test_oracle_gbdt.py / test_gbdt_gpu.py, to the same scores); the `binf` prefix, pruned nodes left in the arrays
+    and a missing attribute block change nothing; every truncation point is a parse error, never a shorter model."""
+    j = synth.xgboost_model_json(12, 9, depth=5, seed=21, full=False)
+    ij = inspect_model(1, j)
+    for kw in ({}, {"magic": True}, {"deleted": 2}, {"with_attributes": False}, {"objective": "rank:pairwise"}):
+        b = synth.xgboost_model_binary(12, 9, depth=5, seed=21, full=False, **kw)
+        ib = inspect_model(1, b)
+        assert (ib.n_trees, ib.n_features, ib.n_internal_nodes, ib.max_leaves) == (ij.n_trees, ij.n_features, ij.n_internal_nodes, ij.max_leaves)
+    b = synth.xgboost_model_binary(12, 9, depth=5, seed=21, full=False, with_attributes=False)
+    for cut in list(range(0, 400, 7)) + [len(b) // 2, len(b) - 20, len(b) - 1]:
+        with pytest.raises(mb.MrError) as e:
+            inspect_model(1, b[:cut])
+        assert e.value.status in (2, 5), cut
+    for bad, status in ((synth.xgboost_model_binary(3, 4, objective="binary:logistic"), 5),
+                        (synth.xgboost_model_binary(3, 4).replace(b"gbtree", b"dart\0\0"), 5)):
+        with pytest.raises(mb.MrError) as e:
+            inspect_model(1, bad)
+        assert e.value.status == status

@@ -346,3 +346,47 @@ def test_small_categorical_in_loop_form_and_parameter_root_table(ctx, monkeypatc
         _check(ctx, 0, blob, X, variant=5)
     xb = synth.xgboost_model_json(600, 16, depth=3, seed=92)
     _check(ctx, 1, xb, synth.feature_matrix(5000, 16, seed=93), variant=5)
+
+
+def test_one_wave_batches_use_the_tile_size_that_balances_the_sms(ctx, monkeypatch):
+    """A batch the chip holds in one wave is scored from the slim form (512 / 256 / 128-item tiles) whose busiest SM holds the
+    fewest items (mr_model::pick_slim) — the same trees in another entry layout and another code-tile layout, so the scores
+    must not move: bit-identical to the oracle at sizes on both sides of every switch, with and without the smaller forms."""
+    import metarank_b200 as mb
+
+    models = [(0, synth.lightgbm_model_text(40, 24, seed=70, cat_features={7: 16}), 24),
+              (0, synth.lightgbm_model_text(40, 30, seed=71, stump_every=9), 30),
+              (1, synth.xgboost_model_json(30, 16, depth=6, seed=72), 16)]
+    for kind, blob, nf in models:
+        ob = oracle.OracleBooster(kind, blob)
+        X = synth.feature_matrix(300_000, nf, seed=nf)
+        if kind == 0 and nf == 24:
+            X[:, 7] = np.random.Generator(np.random.PCG64(1)).integers(-1, 18, len(X))
+            X[::37, 7] = np.nan
+        want = ob.predictMat(X, *X.shape, threads=0)
+        for alt in (True, False):
+            if not alt:
+                monkeypatch.setenv("MR_NO_SLIM_ALT", "1")
+            b = mb.B200Booster(ctx, blob, kind=kind, n_features=nf)
+            try:
+                for rows in (76_000, 131_072, 200_000, 256_000, 300_000):
+                    got = b.predictMat(X[:rows], rows, nf)
+                    assert np.array_equal(got, want[:rows]), (kind, nf, rows, alt)
+            finally:
+                b.free()
+            monkeypatch.delenv("MR_NO_SLIM_ALT", raising=False)
+
+
+def test_xgboost_deprecated_binary_model_scores_like_its_json_twin(ctx):
+    """The encoding xgboost4j's toByteArray() writes up to 2.0: the same synthetic ensemble as JSON and as binary (with the
+    `binf` prefix, with pruned nodes left in the arrays) gives the same bits through every scorer, and the oracle's own
+    reader of the format agrees."""
+    for depth, full, rows in ((6, True, 700), (8, False, 5000), (4, False, 40_000)):
+        j = synth.xgboost_model_json(80, 16, depth=depth, seed=60 + depth, full=full)
+        X = synth.feature_matrix(rows, 16, seed=depth)
+        X[::13, 3] = np.nan
+        want = _check(ctx, 1, j, X)
+        for kw in ({}, {"magic": True, "deleted": 2}):
+            b = synth.xgboost_model_binary(80, 16, depth=depth, seed=60 + depth, full=full, **kw)
+            for variant in (-1, 0, 5):
+                assert np.array_equal(_check(ctx, 1, b, X, variant=variant), want)
