@@ -836,11 +836,18 @@ __global__ void __launch_bounds__(kGatherWarps * 32) code_gather_kernel(RankArgs
 #pragma unroll 8
     for (int l = 0; l < crw; l++) tile[lane * tw + l] = __ldg(src + l);
   } else {
+    // the warp's 32 rows x crw words as ONE flattened range over the lanes: every load instruction is fully populated
+    // (a row of 21 words would leave a third of the lanes idle) and there are crw of them instead of 32
+    const int total = n_here * crw;
+    int j = lane / crw, l = lane - j * crw;   // element e = base + lane lives in row j, word l
 #pragma unroll 8
-    for (int j = 0; j < n_here; j++) {
-      const uint32_t r = __shfl_sync(0xFFFFFFFFu, my, j);
-      const uint32_t *src = a.code_rows + (size_t)r * crw;
-      for (int l = lane; l < crw; l += 32) tile[j * tw + l] = __ldg(src + l);
+    for (int base = 0; base < total; base += 32) {
+      const bool ok = base + lane < total;
+      const uint32_t r = __shfl_sync(0xFFFFFFFFu, my, ok ? j : 0);
+      if (ok) tile[j * tw + l] = __ldg(a.code_rows + (size_t)r * crw + l);
+      l += 32;
+      if (crw >= 16) { while (l >= crw) { l -= crw; j++; } }
+      else { const int q = l / crw; j += q; l -= q * crw; }
     }
   }
   __syncwarp();

@@ -993,8 +993,7 @@ void launch_gbdt_binned(const BinnedLaunch &L, int num_sms, cudaStream_t stream)
       int per_sm = 0;
       MR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
       if (per_sm < 1) fail(MR_ERR_CUDA, "slim gbdt kernel does not fit on an SM (%zu B smem, %d threads)", smem, T);
-      // ~48 warps saturate the shared-memory pipe (profiles/sweep_r1.md); a batch that fits in one wave runs all its tiles at once
-      per_sm = std::min(per_sm, std::max(1, L.slim_per_sm > 0 ? L.slim_per_sm : 1536 / T));
+      per_sm = std::min(per_sm, std::max(1, 1536 / T));  // ~48 warps saturate the shared-memory pipe (profiles/sweep_r1.md)
       const int n_tiles = (p.rows + T - 1) / T;
       static const bool debug = getenv("MR_DEBUG_LAUNCH") != nullptr;
       if (debug)

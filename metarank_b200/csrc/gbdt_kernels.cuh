@@ -73,7 +73,6 @@ struct BinnedLaunch {
   const uint32_t *h_root_tab = nullptr;  // slim scorer: HOST copy of SlimModel::root_tab (4 words per tree), passed as a kernel parameter
   int n_root_tab = 0;                   // trees in it (0: the chunks' own root tables)
   int slim_col_base = 1;                // slim scorer: SlimModel::col_base of the form in d_model
-  int slim_per_sm = 0;                  // slim scorer: CTAs per SM (0: ~48 warps); mr_model::pick_slim sets it for one-wave batches
   ScoreSinks sinks;                     // compact + latency kernels only
 };
 // bytes of a code buffer for `rows` rows in either layout (BinParams::tile_T): whole groups of 32 / whole CTA tiles

@@ -183,7 +183,8 @@ struct SlimModel {
   PackedModel packed;
   std::vector<uint32_t> root_tab;  // 4 words per tree, or empty (too many trees / wide categorical nodes)
 };
-// max_T: largest tile size to consider; warps_per_sm: the residency the automatic chunk budget leaves room for;
+// max_T: largest tile size to consider (mr_model_selfcheck packs the smaller ones too); warps_per_sm: the residency the
+// automatic chunk budget leaves room for;
 // min_tile_addr: lowest absolute shared address the code tile may start at (the kernel's dynamic window begins at 1 KB on
 // sm_100 and holds three mbarriers first) — the tile's pair p lives at (p + col_base) * 4 * tile_T.
 SlimModel pack_slim(const HostModel &m, const BinnedModel &compact, size_t chunk_budget, int max_T = 512, int warps_per_sm = 48,

@@ -118,11 +118,6 @@ struct mr_model {
   SlimModel slim;                    // 4-byte-node form of `compact` (same tile mapping) for the throughput scorer's fast path
   uint8_t *d_smodel = nullptr;
   ChunkDesc *d_schunks = nullptr;
-  // the same form at the smaller tile sizes (chunks sized for 64 resident warps): a batch that fits the chip in ONE wave is
-  // cut into the tile size that spreads it most evenly over the SMs (pick_slim)
-  SlimModel slim_alt[2];
-  uint8_t *d_salt_model[2] = {nullptr, nullptr};
-  ChunkDesc *d_salt_chunks[2] = {nullptr, nullptr};
   uint8_t *d_bmodel = nullptr, *d_cmodel = nullptr, *d_lmodel = nullptr;
   ChunkDesc *d_bchunks = nullptr, *d_cchunks = nullptr, *d_lchunks = nullptr;
   uint32_t *d_thr_off = nullptr;
@@ -158,10 +153,8 @@ struct mr_model {
   void free_binned() {
     for (void *p : {(void *)d_bmodel, (void *)d_bchunks, (void *)d_thr_off, (void *)d_thr, (void *)d_is_cat,
                     (void *)d_cmodel, (void *)d_cchunks, (void *)d_lmodel,
-                    (void *)d_lchunks, (void *)d_ltree_off, (void *)d_lgroups, (void *)d_smodel, (void *)d_schunks, (void *)d_meta, (void *)d_cmeta, (void *)d_bucket_range,
-                    (void *)d_salt_model[0], (void *)d_salt_model[1], (void *)d_salt_chunks[0], (void *)d_salt_chunks[1]})
+                    (void *)d_lchunks, (void *)d_ltree_off, (void *)d_lgroups, (void *)d_smodel, (void *)d_schunks, (void *)d_meta, (void *)d_cmeta, (void *)d_bucket_range})
       if (p) cudaFree(p);
-    d_salt_model[0] = d_salt_model[1] = nullptr; d_salt_chunks[0] = d_salt_chunks[1] = nullptr;
     d_bmodel = nullptr; d_bchunks = nullptr; d_thr_off = nullptr; d_thr = nullptr; d_is_cat = nullptr;
     d_cmodel = nullptr; d_cchunks = nullptr; d_lmodel = nullptr; d_lchunks = nullptr; d_ltree_off = nullptr; d_lgroups = nullptr; d_smodel = nullptr; d_schunks = nullptr; d_meta = nullptr; d_cmeta = nullptr; d_bucket_range = nullptr;
   }
@@ -207,17 +200,6 @@ struct mr_model {
           d_smodel = to_device(slim.packed.bytes);
           d_schunks = to_device(slim.packed.chunks);
         }
-        slim_alt[0] = slim_alt[1] = SlimModel{};
-        if (slim.ok && opt_chunk_kb <= 0 && getenv("MR_NO_SLIM_ALT") == nullptr) {
-          int k = 0;
-          for (int T = slim.tile_T / 2; T >= 128 && k < 2; T /= 2) {
-            SlimModel a = pack_slim(host, compact, 0, T, 64, min_tile);
-            if (!a.ok || a.tile_T != T) break;
-            d_salt_model[k] = to_device(a.packed.bytes);
-            d_salt_chunks[k] = to_device(a.packed.chunks);
-            slim_alt[k++] = std::move(a);
-          }
-        }
       }
       sum_plan = SumPlan{};
       lat = pack_compact(host, binned, 4 * 1024);
@@ -260,63 +242,18 @@ struct mr_model {
   // when the model has a slim form, the batch is not one for the tree-parallel latency path, and the device's dynamic
   // shared window starts below the tile's absolute address; else 0 (groups of 32 rows: compact kernel / latency path).
   // variant 4 pins the 8-byte compact kernel, variant 5 the slim one (tests, A/B).
-  // Which slim form scores a batch of `rows` rows, and with how many CTAs per SM.  Large batches: the largest tile, ~48
-  // resident warps, persistent CTAs (profiles/sweep_r1.md).  A batch the chip holds in ONE wave (<= 64 warps per SM) is a
-  // different problem — a second, nearly empty round costs as much as half a full one, because a thread's walk through the
-  // ensemble is a fixed dependent chain — so it is cut into the tile size whose busiest SM holds the fewest items, all
-  // tiles resident at once.
-  struct SlimPick { const SlimModel *form = nullptr; const uint8_t *d_model = nullptr; const ChunkDesc *d_chunks = nullptr; int per_sm = 0; };
-  SlimPick pick_slim(int rows) const {
-    SlimPick best;
-    if (!slim.ok) return best;
-    double best_cost = 0;
-    const int sms = ctx->num_sms;
-    for (int k = -1; k < 2; k++) {
-      const SlimModel &f = k < 0 ? slim : slim_alt[k];
-      if (!f.ok) continue;
-      const int T = f.tile_T;
-      if (ctx->dyn_smem_base < 0 || ctx->dyn_smem_base + 64 > f.col_base * T * 4) continue;
-      const long long tiles = ((long long)rows + T - 1) / T;
-      const size_t cb0 = (((size_t)T * 4 * ((size_t)f.n_pairs + f.col_base)) + 2047) & ~size_t(2047);
-      const size_t stride = ((size_t)f.packed.max_chunk_bytes + 2047u) & ~size_t(2047);
-      const size_t smem = cb0 + stride * (f.packed.chunks.size() == 1 ? 1 : 2) + 1024;
-      const int fit = (int)std::min<size_t>((size_t)(2048 / T), (227 * 1024) / smem);
-      if (fit < 1) continue;
-      const int base = std::max(1, std::min(fit, 1536 / T));
-      const long long per_wave = (long long)sms * base;
-      const int one_wave = (int)((tiles + sms - 1) / sms);  // CTAs on the busiest SM if every tile is resident at once
-      // persistent CTAs at ~48 warps: full rounds, then a last partial one that costs at least half a round (768 items'
-      // worth of time on an SM: the walk's dependent chain does not shorten with the load)
-      const long long full = tiles / per_wave, rem = tiles - full * per_wave;
-      double cost = (double)full * base * T + (rem ? std::max<double>((double)((rem + sms - 1) / sms) * T, 768.0) : 0.0);
-      int per_sm = base;
-      const bool one = one_wave <= fit;
-      if (one) {
-        // every tile resident at once: the busiest SM's items, a little slower per item beyond 48 warps (sweep_r1: 64 warps +8 %)
-        const double c1 = std::max<double>((double)one_wave * T * (1.0 + 0.005 * std::max(0, one_wave * T / 32 - 48)), 768.0);
-        if (c1 < cost) { cost = c1; per_sm = one_wave; }
-      }
-      if (k >= 0) {
-        // a smaller-tile form only where it was measured to pay: the whole batch in one wave (profiles/ncu_r2_summary.md:
-        // as persistent CTAs over several rounds its shorter chunks and 4-warp CTAs lose more than the balance wins), and
-        // only for a clear predicted gain
-        if (!one || per_sm != one_wave || T < 256 || (opt_variant == 5 && rows < 4096)) continue;
-        if (!(cost < best_cost * 0.9)) continue;
-      }
-      if (!best.form || cost < best_cost) {
-        best_cost = cost;
-        best.form = &f; best.per_sm = per_sm;
-        best.d_model = k < 0 ? d_smodel : d_salt_model[k];
-        best.d_chunks = k < 0 ? d_schunks : d_salt_chunks[k];
-      }
-    }
-    return best;
-  }
+  // Layout of the code buffer a batch of `rows` rows is scored from (BinParams::tile_T): the slim scorer's CTA-tile layout
+  // when the model has a slim form, the batch is not one for the tree-parallel latency path, and the device's dynamic
+  // shared window starts below the tile's absolute address; else 0 (groups of 32 rows: compact kernel / latency path).
+  // variant 4 pins the 8-byte compact kernel, variant 5 the slim one (tests, A/B).
+  // (Smaller-tile forms of the same model for batches that fit the chip in one wave were measured and dropped: a
+  // 256 000-row batch as 1000 x 256-item tiles, 7 CTAs per SM, took the 319 us the 500 x 512-item tiles take in two
+  // rounds — profiles/ncu_r2_summary.md section 1b.)
   int code_layout(int rows) const {
     if (!slim.ok || !use_binned() || !use_compact() || opt_variant == 4 || opt_threads != 0) return 0;
+    if (ctx->dyn_smem_base < 0 || ctx->dyn_smem_base + 64 > slim.col_base * slim.tile_T * 4) return 0;
     if (opt_variant < 0 && use_latency(rows)) return 0;
-    const SlimPick pk = pick_slim(rows);
-    return pk.form ? pk.form->tile_T : 0;
+    return slim.tile_T;
   }
   // the code-based scorer that is active and the width of its code tile
   const BinnedModel &active_binned() const { return use_compact() ? compact : binned; }
@@ -373,23 +310,12 @@ struct mr_model {
     if (sinks) B.sinks = *sinks;
     if (layout < 0) layout = code_layout(rows);
     if (layout) {
-      // the form of that tile size (the producers were told code_layout(rows); an explicit layout names a form directly)
-      SlimPick pk = pick_slim(rows);
-      if (!pk.form || pk.form->tile_T != layout) {
-        pk = SlimPick{};
-        for (int k = -1; k < 2; k++) {
-          const SlimModel &f = k < 0 ? slim : slim_alt[k];
-          if (f.ok && f.tile_T == layout) { pk.form = &f; pk.d_model = k < 0 ? d_smodel : d_salt_model[k]; pk.d_chunks = k < 0 ? d_schunks : d_salt_chunks[k]; }
-        }
-        if (!pk.form) fail(MR_ERR_INVALID_ARG, "no slim form with %d-item tiles", layout);
-      }
-      B.tile_T = pk.form->tile_T;
-      B.slim_col_base = pk.form->col_base;
-      B.slim_per_sm = pk.per_sm;
-      B.d_model = pk.d_model; B.d_chunks = pk.d_chunks;
-      B.n_chunks = (int)pk.form->packed.chunks.size();
-      B.max_chunk_bytes = pk.form->packed.max_chunk_bytes;
-      if (!pk.form->root_tab.empty()) { B.h_root_tab = pk.form->root_tab.data(); B.n_root_tab = (int)(pk.form->root_tab.size() / 4); }
+      B.tile_T = slim.tile_T;
+      B.slim_col_base = slim.col_base;
+      B.d_model = d_smodel; B.d_chunks = d_schunks;
+      B.n_chunks = (int)slim.packed.chunks.size();
+      B.max_chunk_bytes = slim.packed.max_chunk_bytes;
+      if (!slim.root_tab.empty()) { B.h_root_tab = slim.root_tab.data(); B.n_root_tab = (int)(slim.root_tab.size() / 4); }
       launch_gbdt_binned(B, ctx->num_sms, stream);
       return;
     }

@@ -121,32 +121,60 @@ uint32_t StateStore::row_for(const Slot &sl, int scope, uint64_t id0, uint64_t i
 
 void StateStore::upsert(const uint8_t *buf, size_t len, int64_t *applied, int64_t *skipped) {
   std::unique_lock<std::shared_mutex> g(mu);
+  // one record of the packed buffer (include/mr_b200.h "state record")
+  struct Rec { std::string name; uint8_t scope = 0, kind = 0; uint64_t id0 = 0, id1 = 0; double f64 = 0; uint64_t u64 = 0; int64_t i64 = 0;
+               uint32_t n = 0; const uint8_t *arr = nullptr; };
+  auto read_record = [](Reader &r, Rec &c) {
+    const uint16_t nl = r.get<uint16_t>();
+    c.name.assign((const char *)r.bytes(nl), nl);
+    c.scope = r.get<uint8_t>();
+    c.id0 = c.id1 = 0;
+    switch (c.scope) {
+      case SC_GLOBAL: break;
+      case SC_ITEM: case SC_USER: case SC_SESSION: case SC_RANKING: case SC_FIELD: c.id0 = r.get<uint64_t>(); break;
+      case SC_IRF: c.id0 = r.get<uint64_t>(); c.id1 = r.get<uint64_t>(); break;
+      default: fail(MR_ERR_PARSE, "state record: bad scope tag %d", (int)c.scope);
+    }
+    c.kind = r.get<uint8_t>();
+    c.f64 = 0; c.u64 = 0; c.i64 = 0; c.n = 0; c.arr = nullptr;
+    switch (c.kind) {
+      case 0: c.f64 = r.get<double>(); break;
+      case 1: c.u64 = r.get<uint64_t>(); break;
+      case 2: case 3: case 5: case 6: c.n = r.get<uint32_t>(); c.arr = r.bytes((size_t)c.n * 8); break;
+      case 4: c.i64 = r.get<int64_t>(); break;
+      case 7: c.u64 = r.get<uint8_t>(); break;  // SBoolean
+      default: fail(MR_ERR_PARSE, "state record: bad value kind %d", (int)c.kind);
+    }
+  };
+  // first pass: the whole buffer is checked (framing, tags, vector / embedding dims) before any table is touched, so a
+  // malformed or mismatching record later in the batch cannot leave the earlier ones half applied
+  {
+    Reader v{buf, buf + len};
+    Rec c;
+    while (v.p < v.e) {
+      read_record(v, c);
+      auto it = schema.slot_by_name.find(c.name);
+      if (it == schema.slot_by_name.end()) continue;
+      const Slot &sl = schema.slots[it->second];
+      if (sl.table != (int)c.scope || c.kind != 3) continue;
+      if (sl.kind == SK_F64VEC && (int)c.n != sl.p)
+        fail(MR_ERR_INVALID_ARG, "vector '%s' has %u values, the feature's dim is %d", c.name.c_str(), c.n, sl.p);
+      if (sl.kind == SK_F64LIST && (int)c.n != sl.p)
+        fail(MR_ERR_INVALID_ARG, "embedding '%s' has %u values, the schema says dim %d", c.name.c_str(), c.n, sl.p);
+    }
+  }
   Reader r{buf, buf + len};
   int64_t n_ok = 0, n_skip = 0;
+  Rec rec;
   while (r.p < r.e) {
-    const uint16_t nl = r.get<uint16_t>();
-    std::string name((const char *)r.bytes(nl), nl);
-    const uint8_t scope = r.get<uint8_t>();
-    uint64_t id0 = 0, id1 = 0;
-    switch (scope) {
-      case SC_GLOBAL: break;
-      case SC_ITEM: case SC_USER: case SC_SESSION: case SC_RANKING: case SC_FIELD: id0 = r.get<uint64_t>(); break;
-      case SC_IRF: id0 = r.get<uint64_t>(); id1 = r.get<uint64_t>(); break;
-      default: fail(MR_ERR_PARSE, "state record: bad scope tag %d", (int)scope);
-    }
-    const uint8_t kind = r.get<uint8_t>();
-    // payload view
-    double f64 = 0; uint64_t u64 = 0; int64_t i64 = 0; uint32_t n = 0; const uint8_t *arr = nullptr;
-    switch (kind) {
-      case 0: f64 = r.get<double>(); break;
-      case 1: u64 = r.get<uint64_t>(); break;
-      case 2: case 6: n = r.get<uint32_t>(); arr = r.bytes((size_t)n * 8); break;
-      case 3: n = r.get<uint32_t>(); arr = r.bytes((size_t)n * 8); break;
-      case 4: i64 = r.get<int64_t>(); break;
-      case 7: u64 = r.get<uint8_t>(); break;  // SBoolean
-      case 5: n = r.get<uint32_t>(); arr = r.bytes((size_t)n * 8); break;
-      default: fail(MR_ERR_PARSE, "state record: bad value kind %d", (int)kind);
-    }
+    read_record(r, rec);
+    const std::string &name = rec.name;
+    const uint8_t scope = rec.scope, kind = rec.kind;
+    const uint64_t id0 = rec.id0, id1 = rec.id1, u64 = rec.u64;
+    const double f64 = rec.f64;
+    const int64_t i64 = rec.i64;
+    uint32_t n = rec.n;
+    const uint8_t *arr = rec.arr;
     auto it = schema.slot_by_name.find(name);
     if (it == schema.slot_by_name.end()) { n_skip++; continue; }
     const Slot &sl = schema.slots[it->second];

@@ -1227,3 +1227,35 @@ def test_embedding_storage_switches_from_binary32_to_f64(ctx, dim):
         check()
     finally:
         ds.free(); fm.free()
+
+
+def test_upsert_batch_is_validated_before_anything_is_applied(ctx):
+    """A packed buffer whose LATER record is malformed (a vector of the wrong dim, a cut record) must not leave its earlier
+    records applied: the whole buffer is checked first."""
+    import metarank_b200 as mb
+    from metarank_b200 import features as F
+
+    feats = [dict(name="price", type="number", scope="item", source="metadata.price"),
+             dict(name="vec", type="vector", scope="item", source="metadata.vec", reduce=["vector3"])]
+    model = ["price", "vec"]
+    mapping = fo.FeatureMapping(feats, model)
+    fm = F.FeatureMapping(ctx, feats, model)
+    ds = F.DeviceState(ctx, fm)
+    try:
+        good = {(("item", "a"), "price"): ("scalar", 3.5), (("item", "a"), "vec"): ("scalar", [1.0, 2.0, 3.0])}
+        ds.put(good); ds.flush()
+        req = G.ranking(["a", "b"])
+        before = F.Ranker(fm, ds).make_query([req])[0]
+        assert _eq(before, fo.dense_matrix(mapping, req, good))
+        ok_rec = F.pack_feature_values({(("item", "b"), "price"): ("scalar", 9.0)})
+        bad_vec = F.pack_feature_values({(("item", "b"), "vec"): ("scalar", [1.0, 2.0])})      # dim 2, the feature says 3
+        for blob in (ok_rec + bad_vec, ok_rec + bad_vec[:-3], ok_rec + b"\x05\x00pri"):
+            with pytest.raises(mb.MrError):
+                ds.put_packed(blob)
+            ds.flush()
+            assert _eq(F.Ranker(fm, ds).make_query([req])[0], before)   # item b's price was NOT applied
+        ds.put_packed(ok_rec); ds.flush()
+        good[(("item", "b"), "price")] = ("scalar", 9.0)
+        assert _eq(F.Ranker(fm, ds).make_query([req])[0], fo.dense_matrix(mapping, req, good))
+    finally:
+        ds.free(); fm.free()

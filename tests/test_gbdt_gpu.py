@@ -348,10 +348,9 @@ def test_small_categorical_in_loop_form_and_parameter_root_table(ctx, monkeypatc
     _check(ctx, 1, xb, synth.feature_matrix(5000, 16, seed=93), variant=5)
 
 
-def test_one_wave_batches_use_the_tile_size_that_balances_the_sms(ctx, monkeypatch):
-    """A batch the chip holds in one wave is scored from the slim form (512 / 256 / 128-item tiles) whose busiest SM holds the
-    fewest items (mr_model::pick_slim) — the same trees in another entry layout and another code-tile layout, so the scores
-    must not move: bit-identical to the oracle at sizes on both sides of every switch, with and without the smaller forms."""
+def test_batches_of_several_hundred_thousand_rows(ctx):
+    """Batches around the chip's one-wave capacity (148 SMs x 1536 rows): partial last rounds of the persistent CTAs, the
+    small-categorical form, XGBoost f32 — bit-identical to the oracle at every size."""
     import metarank_b200 as mb
 
     models = [(0, synth.lightgbm_model_text(40, 24, seed=70, cat_features={7: 16}), 24),
@@ -364,17 +363,13 @@ def test_one_wave_batches_use_the_tile_size_that_balances_the_sms(ctx, monkeypat
             X[:, 7] = np.random.Generator(np.random.PCG64(1)).integers(-1, 18, len(X))
             X[::37, 7] = np.nan
         want = ob.predictMat(X, *X.shape, threads=0)
-        for alt in (True, False):
-            if not alt:
-                monkeypatch.setenv("MR_NO_SLIM_ALT", "1")
-            b = mb.B200Booster(ctx, blob, kind=kind, n_features=nf)
-            try:
-                for rows in (76_000, 131_072, 200_000, 256_000, 300_000):
-                    got = b.predictMat(X[:rows], rows, nf)
-                    assert np.array_equal(got, want[:rows]), (kind, nf, rows, alt)
-            finally:
-                b.free()
-            monkeypatch.delenv("MR_NO_SLIM_ALT", raising=False)
+        b = mb.B200Booster(ctx, blob, kind=kind, n_features=nf)
+        try:
+            for rows in (76_000, 131_072, 227_328, 256_000, 300_000):
+                got = b.predictMat(X[:rows], rows, nf)
+                assert np.array_equal(got, want[:rows]), (kind, nf, rows)
+        finally:
+            b.free()
 
 
 def test_xgboost_deprecated_binary_model_scores_like_its_json_twin(ctx):
