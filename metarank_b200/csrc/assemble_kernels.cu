@@ -1261,7 +1261,8 @@ __global__ void __launch_bounds__(256) order_kernel(const double *scores, const 
 //   2. order_big_merge_kernel  one thread per element: its final rank = its position in its own sorted chunk + for every
 //                              other chunk the number of elements that sort before it, found by binary search — keys <= its
 //                              key in chunks of LOWER item indices (ties lose to the earlier index), keys < its key in later ones.
-constexpr int kBigOrderMin = 4096;    // requests above this size take this path
+constexpr int kBigOrderMin = 4096;    // requests above this size take these paths:
+constexpr int kCountOrderMax = 20000; //   (kBigOrderMin, kCountOrderMax] items rank by counting (order_count_kernel), larger ones sort + merge
 constexpr int kBigOrderChunk = 1024;  // items per sorted chunk (chunks are aligned to the batch's item index space)
 
 __device__ __forceinline__ int owning_request(const int32_t *offsets, int n_requests, int i) {
@@ -1281,7 +1282,7 @@ __global__ void __launch_bounds__(256) order_big_sort_kernel(const double *score
   for (int r = owning_request(offsets, n_requests, c0); r < n_requests; r++) {
     const int b = __ldg(offsets + r), n = __ldg(offsets + r + 1) - b;
     if (b >= c1) break;
-    if (n <= kBigOrderMin) continue;
+    if (n <= kCountOrderMax) continue;  // order_small_kernel's / order_kernel's / order_count_kernel's
     const int lo = max(b, c0), hi = min(b + n, c1), m = hi - lo;  // this chunk's part of request r
     if (m <= 0) continue;
     int p2 = 1;
@@ -1316,7 +1317,7 @@ __global__ void __launch_bounds__(256) order_big_merge_kernel(const int32_t *off
   if (g >= total_items) return;
   const int r = owning_request(offsets, n_requests, g);
   const int b = __ldg(offsets + r), n = __ldg(offsets + r + 1) - b;
-  if (n <= kBigOrderMin) return;
+  if (n <= kCountOrderMax) return;
   const int my_lo = max(b, (g / kBigOrderChunk) * kBigOrderChunk);
   const long long kj = skeys[g];
   int rank = g - my_lo;  // position inside its own sorted chunk
@@ -1333,6 +1334,50 @@ __global__ void __launch_bounds__(256) order_big_merge_kernel(const int32_t *off
     rank += x - lo;
   }
   order[b + rank] = sidx[g];
+}
+
+// Requests of a few thousand to ~20 000 items (BASELINE config #5: one request of 10 000): the rank of an element IS the
+// number of elements that sort before it, and at this size counting them outright is cheaper than sorting — n^2 compares
+// spread over the whole chip (8 lanes per element, keys staged through shared memory in tiles every lane group of the
+// CTA reads) against a chunk sort plus ~n log^2 n dependent binary-search loads.  Same order as every other path: by the
+// total-order key of -score, ties by the earlier index (the stability of the reference's sortBy).
+constexpr int kCountLanes = 8;         // lanes that share one element's scan
+constexpr int kCountTile = 2048;       // keys per shared-memory tile
+
+__global__ void __launch_bounds__(256) order_count_kernel(const double *scores, const int32_t *offsets, int n_requests,
+                                                          int total_items, int32_t *order) {
+  __shared__ long long s_k[kCountTile];
+  constexpr int kPerCta = 256 / kCountLanes;  // elements per CTA
+  const int g0 = blockIdx.x * kPerCta, g1 = min(total_items, g0 + kPerCta);
+  const int sub = threadIdx.x % kCountLanes, mine = g0 + threadIdx.x / kCountLanes;
+  for (int r = owning_request(offsets, n_requests, g0); r < n_requests; r++) {
+    const int b = __ldg(offsets + r), n = __ldg(offsets + r + 1) - b;
+    if (b >= g1) break;
+    if (n <= kBigOrderMin || n > kCountOrderMax) continue;
+    const bool active = mine < g1 && mine >= b && mine < b + n;
+    const long long key = active ? total_order_key(-scores[mine]) : 0;
+    const int idx = mine - b;  // index inside the request
+    int cnt = 0;
+    for (int t0 = 0; t0 < n; t0 += kCountTile) {
+      const int m = min(kCountTile, n - t0);
+      __syncthreads();  // the previous tile has been read
+      for (int j = threadIdx.x; j < m; j += blockDim.x) s_k[j] = total_order_key(-scores[b + t0 + j]);
+      __syncthreads();
+      if (active) {
+        // elements of earlier index win ties (k_j <= key), later ones need k_j < key: one compare each side of `idx`
+        const int split = min(max(idx - t0, 0), m);  // tile positions [0, split) hold earlier indices
+#pragma unroll 4
+        for (int j = sub; j < split; j += kCountLanes) cnt += s_k[j] <= key;
+        const int start = split + ((idx >= t0 && idx - t0 < m) ? 1 : 0);  // the element itself is skipped
+        int j = start + ((sub - start) % kCountLanes + kCountLanes) % kCountLanes;  // first j >= start with j % lanes == sub
+#pragma unroll 4
+        for (; j < m; j += kCountLanes) cnt += s_k[j] < key;
+      }
+    }
+#pragma unroll
+    for (int o = kCountLanes / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+    if (active && sub == 0) order[b + cnt] = idx;
+  }
 }
 
 }  // namespace
@@ -1438,12 +1483,19 @@ void launch_rank_order(const double *d_scores, const int32_t *d_item_offsets, in
     MR_CUDA_CHECK(cudaGetLastError());
     g_kernel_launches++;
   }
-  if (unknown || max_items_hint > kSmallOrder) {  // larger requests: CTA-wide sort (small ones return at once)
+  const bool only_mega = !unknown && n_requests == 1 && max_items_hint > kBigOrderMin;  // one request, and it is a large one
+  if ((unknown || max_items_hint > kSmallOrder) && !only_mega) {  // larger requests: CTA-wide sort (small ones return at once)
     { ProfScope _ps("order_kernel", stream); order_kernel<<<std::min(n_requests, 148 * 4), 256, 4096 * (sizeof(long long) + sizeof(int)), stream>>>(d_scores, d_item_offsets, n_requests, d_order); }
     MR_CUDA_CHECK(cudaGetLastError());
     g_kernel_launches++;
   }
   if ((unknown && total_items > kBigOrderMin) || max_items_hint > kBigOrderMin) {
+    // (kBigOrderMin, kCountOrderMax] items: rank by counting; beyond: chunk sort + merge (each kernel skips the other's requests)
+    { ProfScope _ps("order_count_kernel", stream); order_count_kernel<<<(unsigned)((total_items + 256 / kCountLanes - 1) / (256 / kCountLanes)), 256, 0, stream>>>(d_scores, d_item_offsets, n_requests, total_items, d_order); }
+    MR_CUDA_CHECK(cudaGetLastError());
+    g_kernel_launches++;
+  }
+  if ((unknown && total_items > kCountOrderMax) || max_items_hint > kCountOrderMax) {
     int32_t *tmp = d_rank_tmp;  // 3 ints per item: sorted keys (8 B) + their item indices (4 B)
     if (!tmp) MR_CUDA_CHECK(cudaMallocAsync((void **)&tmp, (size_t)total_items * 12 + 16, stream));
     long long *skeys = reinterpret_cast<long long *>(tmp);

@@ -657,8 +657,8 @@ def test_two_contexts_in_one_process_on_two_gpus():
 
 
 def test_ordering_edge_sizes_ties_and_specials(ctx):
-    """Per-request ordering across the three device code paths (warp counting rank <= 128 items, CTA bitonic
-    sort <= 4096, counting from global memory beyond), with heavy ties and NaN scores; through mr_rank
+    """Per-request ordering across the four device code paths (warp bitonic network <= 128 items, CTA bitonic
+    sort <= 4096, chip-wide rank by counting <= 20 000, chunk sort + merge beyond), with heavy ties and NaN scores; through mr_rank
     (host offsets -> size hint) and mr_rank_device (no hint).  Oracle: stable sortBy(-score),
     S/ranking/Ranker.scala:58-60."""
     import torch
@@ -686,7 +686,8 @@ def test_ordering_edge_sizes_ties_and_specials(ctx):
         "leaf_count=1 1 1", "internal_value=0 0", "internal_weight=0 0", "internal_count=3 2", "is_linear=0", "shrinkage=1", "",
         "end of trees", ""]).encode()
     booster = mb.LightGBMBooster(ctx, model)
-    sizes = np.array([0, 1, 2, 3, 31, 32, 33, 100, 127, 128, 129, 130, 500, 1024, 4095, 4096, 4097, 5000, 0, 7, 9001, 4100, 1], dtype=np.int64)
+    sizes = np.array([0, 1, 2, 3, 31, 32, 33, 100, 127, 128, 129, 130, 500, 1024, 4095, 4096, 4097, 5000, 0, 7, 9001, 4100, 1,
+                      20000, 20001, 6, 23000], dtype=np.int64)  # (4096, 20000]: rank by counting; beyond: chunk sort + merge
     offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
     N, R = int(offs[-1]), len(sizes)
     pick = rng.integers(0, n_cat, N)
