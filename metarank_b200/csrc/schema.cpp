@@ -265,6 +265,28 @@ Schema parse_schema_json(const char *json, size_t len) {
         d.in0 = (int)S.in_item_f64.size();  // per-item override, already encoded by the caller
         for (int k = 0; k < d.dim; k++) S.in_item_f64.push_back(n);
       }
+    } else if (t == "referer") {
+      // RefererFeature (S/feature/RefererFeature.scala:39-110).  The referer URL is parsed when the event is WRITTEN
+      // (snowplow's referers.json, on the JVM: writeField :70-90 stores SString(medium) under the user or the session);
+      // the rank path only reads that string back and maps it through the fixed table :47-54 — unknown 0, search 1,
+      // internal 2, social 3, email 4, paid 5; absent / anything else -> CategoryValue("unknown", 0).  That is the
+      // string-index encoder (index + 1, 0 = nil) over the five named mediums, with no request-side override.
+      ScopeSpec sc = parse_scope(str_of(o, "scope", n), n);
+      (void)parse_field(str_of(o, "source", n), n);  // required by RefererSchema; read by the writer only
+      if (sc.scope != SC_USER && sc.scope != SC_SESSION)
+        fail(MR_ERR_UNSUPPORTED, "feature %s: referer is kept per user or per session (RefererFeature.writeField), scope %s has no key",
+             n.c_str(), str_of(o, "scope", n).c_str());
+      for (const char *m : {"search", "internal", "social", "email", "paid"}) {
+        fd.cat_values.push_back(m);
+        fd.cat_hashes.push_back(hash64(m, strlen(m)));
+      }
+      d.dim = 1;
+      d.aux0 = 0;
+      fd.scope = sc.scope;
+      d.kind = FK_CATEGORY;
+      d.scope = sc.scope;
+      bind(0, add_slot(fi, n, table_of(sc.scope), SK_CAT, 1, 0));
+      d.in0 = -1;
     } else if (t == "interaction_count") {
       ScopeSpec sc = parse_scope(str_of(o, "scope", n), n);
       if (sc.scope == SC_FIELD || sc.scope == SC_IRF || sc.scope == SC_RANKING)
@@ -433,7 +455,7 @@ Schema parse_schema_json(const char *json, size_t len) {
     if (d.scope == SC_USER || d.scope == SC_SESSION) S.needs_visitor = true;
     fd.dim = d.dim;
     fd.kind = d.kind;
-    if (t == "string") fd.kind = d.aux0 ? FK_ONEHOT : FK_CATEGORY;  // encoder kind, also when request-scoped
+    if (t == "string" || t == "referer") fd.kind = d.aux0 ? FK_ONEHOT : FK_CATEGORY;  // encoder kind, also when request-scoped
     S.plan.push_back(d);
     S.col_of[n] = {fd.col, fd.dim};
     col += d.dim;

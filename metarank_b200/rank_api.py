@@ -150,7 +150,10 @@ class RankApi:
                 continue
             o, d = od
             vals = [float(x) for x in row[o:o + d]]
-            if conf["type"] == "string" and conf.get("encode") == "index":
+            if conf["type"] == "referer":
+                idx = int(vals[0])
+                out[name] = f"{('unknown', 'search', 'internal', 'social', 'email', 'paid')[idx] if 0 <= idx <= 5 else 'unknown'}@{idx}"
+            elif conf["type"] == "string" and conf.get("encode") == "index":
                 idx = int(vals[0])
                 cat = conf["values"][idx - 1] if 1 <= idx <= len(conf["values"]) else "nil"
                 out[name] = f"{cat}@{idx}"  # CategoryValue

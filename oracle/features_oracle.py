@@ -300,6 +300,37 @@ class WordCountFeature(BaseFeature):
         return [NAN]
 
 
+class RefererFeature(BaseFeature):
+    """S/feature/RefererFeature.scala:39-110.  The URL is parsed at WRITE time (snowplow referers.json, a third-party
+    database that stays with the JVM): writeField :70-90 stores SString(medium) under the user or the session.  value()
+    :94-109 reads it back and maps it through `possibleValues` :47-54; absent / not a string / not in the table ->
+    CategoryValue("unknown", 0)."""
+
+    MEDIUMS = {"unknown": 0, "search": 1, "internal": 2, "social": 3, "email": 4, "paid": 5}
+
+    def __init__(self, c):
+        self.name = c["name"]
+        self.scope = parse_scope_type(c["scope"])
+        self.src_event, self.field = parse_field_name(c["source"])
+        self.dim = 1
+        self.categorical = True
+
+    def states(self):
+        return {self.name: dict(kind="scalar", scope=self.scope, refresh=0)}
+
+    def writes(self, ev, store):
+        return []  # the medium is written by the JVM's parser; tests put SString(medium) into the state directly
+
+    def value(self, req, state, item):
+        if self.scope[0] not in ("user", "session"):
+            return [0.0]
+        key = self.read_key(req, self.scope, self.name, item["id"])
+        fv = state.get(key) if key is not None else None
+        if fv is not None and fv[0] == "scalar" and isinstance(fv[1], str):
+            return [float(self.MEDIUMS.get(fv[1], 0))]
+        return [0.0]
+
+
 class StringFeature(BaseFeature):
     """S/feature/StringFeature.scala (index + onehot encoders)"""
 
@@ -1079,7 +1110,7 @@ class LocalDateTimeFeature(BaseFeature):
 
 
 FEATURE_TYPES = {
-    "number": NumberFeature, "word_count": WordCountFeature, "string": StringFeature,
+    "number": NumberFeature, "word_count": WordCountFeature, "string": StringFeature, "referer": RefererFeature,
     "interaction_count": InteractionCountFeature, "window_count": WindowInteractionCountFeature,
     "rate": RateFeature, "interacted_with": InteractedWithFeature, "relevancy": RelevancyFeature,
     "position": PositionFeature, "diversity": DiversityFeature, "boolean": BooleanFeature,

@@ -142,3 +142,21 @@ def test_token_match_schema_and_request_packing_on_the_host():
     with pytest.raises(_capi.MrError) as e:
         F.FeatureMapping(None, [dict(feats[2], method=dict(type="bm25", language="en"))], ["bm"])
     assert "avgdl" in str(e.value)
+
+
+def test_referer_reads_the_stored_medium():
+    """T/feature/RefererFeatureTest.scala:37-51: the write path (JVM: snowplow's referer database) stores
+    SString("search") under the user for http://www.google.com; the ranking then yields CategoryValue("search", 1).
+    The table S/feature/RefererFeature.scala:47-54 for the other mediums; absent / unknown strings -> 0."""
+    from oracle import features_oracle as fo
+
+    feats = [dict(name="ref_medium", type="referer", source="ranking.ref", scope="user")]
+    mapping = fo.FeatureMapping(feats, ["ref_medium"])
+    req = G.ranking(["p1", "p2"], user="u1")
+    state = {(("user", "u1"), "ref_medium"): ("scalar", "search")}
+    assert fo.dense_matrix(mapping, req, state).tolist() == [[1.0], [1.0]]
+    for medium, idx in (("unknown", 0), ("internal", 2), ("social", 3), ("email", 4), ("paid", 5), ("carrier pigeon", 0)):
+        state = {(("user", "u1"), "ref_medium"): ("scalar", medium)}
+        assert fo.dense_matrix(mapping, req, state).tolist() == [[float(idx)]] * 2
+    assert fo.dense_matrix(mapping, req, {}).tolist() == [[0.0], [0.0]]
+    assert fo.dense_matrix(mapping, G.ranking(["p1"], user=None), state).tolist() == [[0.0]]

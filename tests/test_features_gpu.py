@@ -1260,3 +1260,33 @@ def test_upsert_batch_is_validated_before_anything_is_applied(ctx):
         assert _eq(F.Ranker(fm, ds).make_query([req])[0], fo.dense_matrix(mapping, req, good))
     finally:
         ds.free(); fm.free()
+
+
+def test_referer_medium_from_user_and_session_state(ctx):
+    """`referer` (S/feature/RefererFeature.scala:94-109): the medium the JVM's parser stored under the user / the session,
+    through the fixed medium -> index table; the golden of T/feature/RefererFeatureTest.scala:46-50 (search -> 1) and every
+    other branch against the oracle."""
+    from metarank_b200 import features as F
+
+    feats = [dict(name="ref_medium", type="referer", source="ranking.ref", scope="user"),
+             dict(name="ref_s", type="referer", source="interaction:click.ref", scope="session"),
+             dict(name="price", type="number", scope="item", source="metadata.price")]
+    model = ["ref_medium", "price", "ref_s"]
+    mapping = fo.FeatureMapping(feats, model)
+    fm = F.FeatureMapping(ctx, feats, model)
+    ds = F.DeviceState(ctx, fm)
+    try:
+        state = {(("user", "u1"), "ref_medium"): ("scalar", "search"), (("item", "p1"), "price"): ("scalar", 2.5)}
+        for k, m in enumerate(("unknown", "search", "internal", "social", "email", "paid", "smoke signals")):
+            state[(("user", f"v{k}"), "ref_medium")] = ("scalar", m)
+            state[(("session", f"s{k}"), "ref_s")] = ("scalar", m)
+        ds.put(state); ds.flush()
+        reqs = [G.ranking(["p1", "p2"], user="u1", session="s3")]
+        reqs += [G.ranking(["p1"], user=f"v{k}", session=f"s{6 - k}") for k in range(7)]
+        reqs += [G.ranking(["p2", "p1"], user="nobody", session="nothing"), G.ranking(["p1"], user=None, session=None)]
+        got = F.Ranker(fm, ds).make_query(reqs)
+        assert got[0][:, 0].tolist() == [1.0, 1.0]   # RefererFeatureTest: CategoryValue("search", 1)
+        for q, g in zip(reqs, got):
+            assert _eq(g, fo.dense_matrix(mapping, q, state))
+    finally:
+        ds.free(); fm.free()

@@ -328,3 +328,31 @@ def test_oracle_nan_routing_against_hist_gradient_boosting():
     got = oracle.OracleBooster(0, blob).predictMat(np.ascontiguousarray(Xt), len(Xt), n_feat, threads=0)
     want = hgb.predict(Xt)
     assert np.array_equal(got, want), float(np.nanmax(np.abs(got - want)))
+
+
+def test_xgboost_binary_encoding_reads_like_json():
+    """The oracle's reader of XGBoost's deprecated binary encoding (xgboost4j's toByteArray() up to 2.0): the same synthetic
+    ensemble as JSON, UBJSON and binary — with the `binf` prefix, with pruned nodes left in the arrays, without the
+    attribute block — parses to the same arrays and scores to the same bits, through the C port and the pure-Python walk."""
+    j = synth.xgboost_model_json(25, 12, depth=5, seed=44, full=False)
+    pj = model_parse.parse_xgboost(j)
+    X = synth.feature_matrix(300, 12, seed=45)
+    X[::9, 2] = np.nan
+    want = oracle.OracleBooster(1, j).predictMat(X, 300, 12)
+    assert np.array_equal(oracle.OracleBooster(1, synth.xgboost_model_ubj(25, 12, depth=5, seed=44, full=False)).predictMat(X, 300, 12), want)
+    for kw in ({}, {"magic": True}, {"deleted": 3}, {"with_attributes": False}, {"objective": "rank:pairwise"}):
+        b = synth.xgboost_model_binary(25, 12, depth=5, seed=44, full=False, **kw)
+        pb = model_parse.parse_xgboost(b)
+        assert pb["n_features"] == pj["n_features"] and pb["base_score"] == pj["base_score"] and len(pb["trees"]) == len(pj["trees"])
+        nd = kw.get("deleted", 0)
+        for tb, tj in zip(pb["trees"], pj["trees"]):
+            n = len(tj["left"])
+            assert len(tb["left"]) == n + nd
+            for k in ("left", "right", "split_index", "split_cond", "default_left"):
+                assert np.array_equal(tb[k][:n], tj[k]), k
+        assert np.array_equal(oracle.OracleBooster(1, b).predictMat(X, 300, 12), want)
+        assert np.array_equal(model_parse.predict_python(pb, X[:40]), want[:40])
+    with pytest.raises(ValueError):
+        model_parse.parse_xgboost(b"bs64\tAAAA")
+    with pytest.raises(ValueError):
+        model_parse.parse_xgboost(b"not a model at all" * 20)
