@@ -1338,46 +1338,72 @@ __global__ void __launch_bounds__(256) order_big_merge_kernel(const int32_t *off
 
 // Requests of a few thousand to ~20 000 items (BASELINE config #5: one request of 10 000): the rank of an element IS the
 // number of elements that sort before it, and at this size counting them outright is cheaper than sorting — n^2 compares
-// spread over the whole chip (a warp per element, keys staged through shared memory in tiles every warp of the CTA
+// spread over the whole chip (four elements per warp, keys staged through shared memory in tiles every warp of the CTA
 // reads) against a chunk sort plus ~n log^2 n dependent binary-search loads.  Same order as every other path: by the
 // total-order key of -score, ties by the earlier index (the stability of the reference's sortBy).
-constexpr int kCountLanes = 32;        // lanes that share one element's scan: a warp (8 lanes per element left the chip at
-                                       // ~17 warps per SM on a 10 000-item request, latency-bound: 45 us against 11 us)
+constexpr int kCountPerWarp = 4;       // elements a warp ranks at once: one shared-memory read of a key serves four compares
 constexpr int kCountTile = 2048;       // keys per shared-memory tile
+constexpr int kCountPerCta = 8 * kCountPerWarp;
 
+// n^2 x 8 bytes through the shared-memory pipe is what a warp per element costs (10 000 items: 800 MB = 21 us at
+// 128 B/clk/SM; measured 45 us, the same as 8 lanes per element, which was latency-bound at 17 warps per SM) — so a warp
+// keeps FOUR consecutive elements in registers and every key it reads is compared against all four: 35 us on the
+// 10 000-item request, against 52 us for the chunk sort + merge it replaces there.  The tie rule depends on the side of the element a key comes from; the four elements are neighbours,
+// so all keys before the first of them take `<=`, all keys after the last take `<`, and only the 4 x 4 block in between
+// is compared with the index.
 __global__ void __launch_bounds__(256) order_count_kernel(const double *scores, const int32_t *offsets, int n_requests,
                                                           int total_items, int32_t *order) {
   __shared__ long long s_k[kCountTile];
-  constexpr int kPerCta = 256 / kCountLanes;  // elements per CTA
-  const int g0 = blockIdx.x * kPerCta, g1 = min(total_items, g0 + kPerCta);
-  const int sub = threadIdx.x % kCountLanes, mine = g0 + threadIdx.x / kCountLanes;
+  const int g0 = blockIdx.x * kCountPerCta, g1 = min(total_items, g0 + kCountPerCta);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w0 = g0 + warp * kCountPerWarp;  // this warp's elements: w0 .. w0 + 3 (batch item indices)
   for (int r = owning_request(offsets, n_requests, g0); r < n_requests; r++) {
     const int b = __ldg(offsets + r), n = __ldg(offsets + r + 1) - b;
     if (b >= g1) break;
     if (n <= kBigOrderMin || n > kCountOrderMax) continue;
-    const bool active = mine < g1 && mine >= b && mine < b + n;
-    const long long key = active ? total_order_key(-scores[mine]) : 0;
-    const int idx = mine - b;  // index inside the request
-    int cnt = 0;
+    // the warp's elements that belong to this request: [e_lo, e_hi) of its four
+    const int e_lo = max(0, b - w0), e_hi = min(kCountPerWarp, min(g1, b + n) - w0);
+    const bool any = e_lo < e_hi;
+    long long key[kCountPerWarp];
+    int cnt[kCountPerWarp];
+#pragma unroll
+    for (int e = 0; e < kCountPerWarp; e++) {
+      cnt[e] = 0;
+      key[e] = (e >= e_lo && e < e_hi) ? total_order_key(-scores[w0 + e]) : 0;
+    }
+    const int first = w0 + e_lo - b, last = w0 + e_hi - 1 - b;  // request-relative indices of the first / last active element
     for (int t0 = 0; t0 < n; t0 += kCountTile) {
       const int m = min(kCountTile, n - t0);
       __syncthreads();  // the previous tile has been read
       for (int j = threadIdx.x; j < m; j += blockDim.x) s_k[j] = total_order_key(-scores[b + t0 + j]);
       __syncthreads();
-      if (active) {
-        // elements of earlier index win ties (k_j <= key), later ones need k_j < key: one compare each side of `idx`
-        const int split = min(max(idx - t0, 0), m);  // tile positions [0, split) hold earlier indices
-#pragma unroll 4
-        for (int j = sub; j < split; j += kCountLanes) cnt += s_k[j] <= key;
-        const int start = split + ((idx >= t0 && idx - t0 < m) ? 1 : 0);  // the element itself is skipped
-        int j = start + ((sub - start) % kCountLanes + kCountLanes) % kCountLanes;  // first j >= start with j % lanes == sub
-#pragma unroll 4
-        for (; j < m; j += kCountLanes) cnt += s_k[j] < key;
+      if (!any) continue;
+      const int end_a = min(max(first - t0, 0), m);       // tile positions [0, end_a): items before all four -> ties count
+      const int beg_b = min(max(last + 1 - t0, 0), m);    // [beg_b, m): items after all four -> ties do not
+#pragma unroll 2
+      for (int j = lane; j < end_a; j += 32) {
+        const long long k = s_k[j];
+#pragma unroll
+        for (int e = 0; e < kCountPerWarp; e++) cnt[e] += k <= key[e];
+      }
+#pragma unroll 2
+      for (int j = beg_b + lane; j < m; j += 32) {
+        const long long k = s_k[j];
+#pragma unroll
+        for (int e = 0; e < kCountPerWarp; e++) cnt[e] += k < key[e];
+      }
+      const int j = end_a + lane;  // the block between them: at most four positions, compared with their index
+      if (j < beg_b) {
+        const long long k = s_k[j];
+#pragma unroll
+        for (int e = 0; e < kCountPerWarp; e++) cnt[e] += k < key[e] || (k == key[e] && t0 + j < w0 + e - b);
       }
     }
 #pragma unroll
-    for (int o = kCountLanes / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
-    if (active && sub == 0) order[b + cnt] = idx;
+    for (int e = 0; e < kCountPerWarp; e++) {
+      const int c = __reduce_add_sync(0xFFFFFFFFu, cnt[e]);
+      if (lane == 0 && e >= e_lo && e < e_hi) order[b + c] = w0 + e - b;
+    }
   }
 }
 
@@ -1492,7 +1518,7 @@ void launch_rank_order(const double *d_scores, const int32_t *d_item_offsets, in
   }
   if ((unknown && total_items > kBigOrderMin) || max_items_hint > kBigOrderMin) {
     // (kBigOrderMin, kCountOrderMax] items: rank by counting; beyond: chunk sort + merge (each kernel skips the other's requests)
-    { ProfScope _ps("order_count_kernel", stream); order_count_kernel<<<(unsigned)((total_items + 256 / kCountLanes - 1) / (256 / kCountLanes)), 256, 0, stream>>>(d_scores, d_item_offsets, n_requests, total_items, d_order); }
+    { ProfScope _ps("order_count_kernel", stream); order_count_kernel<<<(unsigned)((total_items + kCountPerCta - 1) / kCountPerCta), 256, 0, stream>>>(d_scores, d_item_offsets, n_requests, total_items, d_order); }
     MR_CUDA_CHECK(cudaGetLastError());
     g_kernel_launches++;
   }

@@ -731,7 +731,9 @@ __global__ void __launch_bounds__(128) gbdt_leaves_kernel(const LParams p) {
 //   consumer   waits for `full`; per tree: slot (LDS.U16) -> value at group + tree offset + 8 * slot (LDS.64) -> acc += value;
 //              raises `empty`.  No per-lane gathers from global memory anywhere (8-byte cp.async gathers cost ~20 wavefronts
 //              an instruction and saturated the L1 pipe at 76 %: profiles/ncu_r2_summary.md).
-constexpr int kSumRing = 3;
+constexpr int kSumRing = 3;     // ring depth when the grid is several CTAs per SM
+constexpr int kSumRingMax = 8;  // ... and the most a lone CTA per SM takes (mega-request slices: 79 CTAs on 148 SMs) — the ring
+                                // then hides the whole fetch latency of a group behind the groups in flight ahead of it
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -746,12 +748,14 @@ struct SumParams {
   int rows, rows_padded, n_groups;
   uint32_t group_stride;      // bytes reserved per ring buffer for the model bytes (multiple of 128)
   float base_score;
+  int ring;                   // ring depth (kSumRing .. kSumRingMax)
 };
 
 template <typename Real>
 __global__ void __launch_bounds__(160) gbdt_sum_kernel(const SumParams p, const ScoreSinks sinks) {
   extern __shared__ __align__(128) uint8_t s_sum_raw[];
-  uint64_t *full = reinterpret_cast<uint64_t *>(s_sum_raw), *empty = full + kSumRing;
+  uint64_t *full = reinterpret_cast<uint64_t *>(s_sum_raw), *empty = full + kSumRingMax;
+  const int ring = p.ring;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = (blockDim.x >> 5) - 1;  // consumer warps = 32-row slabs of this CTA
   const int cta_rows = 32 * C;
@@ -760,14 +764,14 @@ __global__ void __launch_bounds__(160) gbdt_sum_kernel(const SumParams p, const 
   const size_t buf_bytes = (size_t)p.group_stride + (size_t)kSumGroupTrees * cta_rows * 2 + kSumGroupTrees * 4;
   uint8_t *bufs = s_sum_raw + 128;
   if (threadIdx.x == 0) {
-    for (int k = 0; k < kSumRing; k++) { mbar_init(&full[k], 33); mbar_init(&empty[k], C); }
+    for (int k = 0; k < ring; k++) { mbar_init(&full[k], 33); mbar_init(&empty[k], C); }
     fence_barrier_init();
   }
   __syncthreads();
   if (warp == 0) {
     // ---- producer
     for (int g = 0; g < p.n_groups; g++) {
-      const int b = g % kSumRing, use = g / kSumRing;
+      const int b = g % ring, use = g / ring;
       if (use > 0) mbar_wait_spin(&empty[b], (use - 1) & 1);
       const uint4 gd = __ldg(p.groups + g);
       uint8_t *mb = bufs + (size_t)b * buf_bytes;
@@ -799,7 +803,7 @@ __global__ void __launch_bounds__(160) gbdt_sum_kernel(const SumParams p, const 
     const bool live = item < p.rows;
     Real acc = (sizeof(Real) == 4) ? (Real)p.base_score : (Real)0;
     for (int g = 0; g < p.n_groups; g++) {
-      const int b = g % kSumRing, use = g / kSumRing;
+      const int b = g % ring, use = g / ring;
       mbar_wait_spin(&full[b], use & 1);
       const int nt = (int)__ldg(&p.groups[g].y);
       if (live) {
@@ -941,7 +945,10 @@ void launch_gbdt_latency(const BinnedLaunch &L, int n_trees, const SumPlan &sum,
   sp.base_score = L.base_score;
   const int consumers = L.rows <= 148 * 32 ? 1 : 4;
   const int cta_rows = 32 * consumers;
-  const size_t sum_smem = 128 + kSumRing * ((size_t)sp.group_stride + (size_t)kSumGroupTrees * cta_rows * 2 + kSumGroupTrees * 4);
+  const size_t stage = (size_t)sp.group_stride + (size_t)kSumGroupTrees * cta_rows * 2 + kSumGroupTrees * 4;
+  const int n_sum_ctas = (L.rows + cta_rows - 1) / cta_rows;
+  sp.ring = n_sum_ctas <= 148 ? (int)std::max<size_t>(kSumRing, std::min<size_t>(kSumRingMax, (220 * 1024 - 128) / stage)) : kSumRing;
+  const size_t sum_smem = 128 + sp.ring * stage;
   auto go = [&](auto leaves, auto sumk) {
     MR_CUDA_CHECK(cudaFuncSetAttribute(leaves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     { ProfScope _ps("gbdt_leaves_kernel", stream); leaves<<<grid, 128, smem, stream>>>(p); }
