@@ -1342,16 +1342,18 @@ __global__ void __launch_bounds__(256) order_big_merge_kernel(const int32_t *off
 // reads) against a chunk sort plus ~n log^2 n dependent binary-search loads.  Same order as every other path: by the
 // total-order key of -score, ties by the earlier index (the stability of the reference's sortBy).
 constexpr int kCountPerWarp = 4;       // elements a warp ranks at once: one shared-memory read of a key serves four compares
-constexpr int kCountTile = 2048;       // keys per shared-memory tile
-constexpr int kCountPerCta = 8 * kCountPerWarp;
+constexpr int kCountThreads = 128;      // 4 warps = 16 elements per CTA: 625 CTAs for 10 000 items spread evenly enough over 148 SMs
+constexpr int kCountTile = 1024;       // keys per shared-memory tile
+constexpr int kCountPerCta = (kCountThreads / 32) * kCountPerWarp;
 
 // n^2 x 8 bytes through the shared-memory pipe is what a warp per element costs (10 000 items: 800 MB = 21 us at
 // 128 B/clk/SM; measured 45 us, the same as 8 lanes per element, which was latency-bound at 17 warps per SM) — so a warp
-// keeps FOUR consecutive elements in registers and every key it reads is compared against all four: 35 us on the
-// 10 000-item request, against 52 us for the chunk sort + merge it replaces there.  The tie rule depends on the side of the element a key comes from; the four elements are neighbours,
+// keeps FOUR consecutive elements in registers and every key it reads is compared against all four: 33-35 us on the
+// 10 000-item request, against 52 us for the chunk sort + merge it replaces there (16 half-rate ISETPs per two keys are
+// what is left: unrolled staging, predicated adds and smaller CTAs moved it by 2 us).  The tie rule depends on the side of the element a key comes from; the four elements are neighbours,
 // so all keys before the first of them take `<=`, all keys after the last take `<`, and only the 4 x 4 block in between
 // is compared with the index.
-__global__ void __launch_bounds__(256) order_count_kernel(const double *scores, const int32_t *offsets, int n_requests,
+__global__ void __launch_bounds__(kCountThreads) order_count_kernel(const double *scores, const int32_t *offsets, int n_requests,
                                                           int total_items, int32_t *order) {
   __shared__ long long s_k[kCountTile];
   const int g0 = blockIdx.x * kCountPerCta, g1 = min(total_items, g0 + kCountPerCta);
@@ -1375,22 +1377,40 @@ __global__ void __launch_bounds__(256) order_count_kernel(const double *scores, 
     for (int t0 = 0; t0 < n; t0 += kCountTile) {
       const int m = min(kCountTile, n - t0);
       __syncthreads();  // the previous tile has been read
-      for (int j = threadIdx.x; j < m; j += blockDim.x) s_k[j] = total_order_key(-scores[b + t0 + j]);
+      {
+        // all of a thread's loads first, then the keys: one memory latency per tile instead of one per element (as a
+        // plain loop the staging alone cost ~14 us of the kernel: 40 dependent L2 round trips per thread)
+        double v[kCountTile / kCountThreads];
+#pragma unroll
+        for (int q = 0; q < kCountTile / kCountThreads; q++) {
+          const int j = threadIdx.x + q * kCountThreads;
+          v[q] = j < m ? scores[b + t0 + j] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < kCountTile / kCountThreads; q++) {
+          const int j = threadIdx.x + q * kCountThreads;
+          if (j < m) s_k[j] = total_order_key(-v[q]);
+        }
+      }
       __syncthreads();
       if (!any) continue;
       const int end_a = min(max(first - t0, 0), m);       // tile positions [0, end_a): items before all four -> ties count
       const int beg_b = min(max(last + 1 - t0, 0), m);    // [beg_b, m): items after all four -> ties do not
+      // (a 64-bit compare is two ISETPs; the predicated add keeps the count at one instruction — `cnt += k <= key` compiles
+      // to an add plus a select)
 #pragma unroll 2
       for (int j = lane; j < end_a; j += 32) {
         const long long k = s_k[j];
 #pragma unroll
-        for (int e = 0; e < kCountPerWarp; e++) cnt[e] += k <= key[e];
+        for (int e = 0; e < kCountPerWarp; e++)
+          asm("{\n.reg .pred p;\nsetp.le.s64 p, %1, %2;\n@p add.s32 %0, %0, 1;\n}" : "+r"(cnt[e]) : "l"(k), "l"(key[e]));
       }
 #pragma unroll 2
       for (int j = beg_b + lane; j < m; j += 32) {
         const long long k = s_k[j];
 #pragma unroll
-        for (int e = 0; e < kCountPerWarp; e++) cnt[e] += k < key[e];
+        for (int e = 0; e < kCountPerWarp; e++)
+          asm("{\n.reg .pred p;\nsetp.lt.s64 p, %1, %2;\n@p add.s32 %0, %0, 1;\n}" : "+r"(cnt[e]) : "l"(k), "l"(key[e]));
       }
       const int j = end_a + lane;  // the block between them: at most four positions, compared with their index
       if (j < beg_b) {
@@ -1518,7 +1538,7 @@ void launch_rank_order(const double *d_scores, const int32_t *d_item_offsets, in
   }
   if ((unknown && total_items > kBigOrderMin) || max_items_hint > kBigOrderMin) {
     // (kBigOrderMin, kCountOrderMax] items: rank by counting; beyond: chunk sort + merge (each kernel skips the other's requests)
-    { ProfScope _ps("order_count_kernel", stream); order_count_kernel<<<(unsigned)((total_items + kCountPerCta - 1) / kCountPerCta), 256, 0, stream>>>(d_scores, d_item_offsets, n_requests, total_items, d_order); }
+    { ProfScope _ps("order_count_kernel", stream); order_count_kernel<<<(unsigned)((total_items + kCountPerCta - 1) / kCountPerCta), kCountThreads, 0, stream>>>(d_scores, d_item_offsets, n_requests, total_items, d_order); }
     MR_CUDA_CHECK(cudaGetLastError());
     g_kernel_launches++;
   }
