@@ -250,7 +250,7 @@ def test_malformed_tree_structures_are_rejected_not_walked():
 
 @pytest.mark.timeout(300)
 def test_parsers_survive_corrupted_models_and_schemas():
-    """Host-only fuzz: byte flips / truncations of model blobs (LightGBM text, XGBoost JSON and UBJSON) and of
+    """Host-only fuzz: byte flips / truncations of model blobs (LightGBM text, XGBoost JSON, UBJSON and binary) and of
     schema documents end in an MrError or a clean parse — never a crash, a hang or an out-of-bounds read."""
     import ctypes as C
     import json
@@ -260,7 +260,8 @@ def test_parsers_survive_corrupted_models_and_schemas():
 
     rng = np.random.Generator(np.random.PCG64(3))
     blobs = [(0, synth.lightgbm_model_text(6, 5, seed=1, cat_features={2: 8})), (1, synth.xgboost_model_json(5, 5, depth=3, seed=2)),
-             (1, synth.xgboost_model_ubj(5, 5, depth=3, seed=2))]
+             (1, synth.xgboost_model_ubj(5, 5, depth=3, seed=2)),
+             (1, synth.xgboost_model_binary(5, 5, depth=3, seed=2, deleted=1)), (1, synth.xgboost_model_binary(4, 6, depth=4, seed=3, magic=True))]
     ok = err = 0
     for kind, base in blobs:
         for _ in range(400):
@@ -271,6 +272,9 @@ def test_parsers_survive_corrupted_models_and_schemas():
                 b = b[:int(rng.integers(0, len(b)))]
             try:
                 B.inspect_model(kind, bytes(b))
+                # what parses must also pack, and its packing must walk like its trees (host-side layout check)
+                _, bad = B.selfcheck_model(kind, bytes(b), 4)
+                assert bad == 0
                 ok += 1
             except _capi.MrError:
                 err += 1
