@@ -1119,6 +1119,10 @@ def main():
             out["other_configs"] = extras
         print(json.dumps(out), flush=True)
 
+    if world > 1:
+        # the other ranks wait here while rank 0 writes its line: their NCCL teardown messages (NCCL_DEBUG=INFO prints to
+        # stdout) must not land in the middle of it
+        dist.barrier()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
