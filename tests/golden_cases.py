@@ -166,6 +166,41 @@ case("string_onehot", "S/util/OneHotEncoder.scala:12-24 (derived)",
      [item_event("p1", [("color", ["blue", "red", "pink"])])],
      ranking(["p1", "p2"]), {"color": [[1.0, 0.0, 1.0], [0.0, 0.0, 0.0]]})
 
+# More of the reference's own vectors for extractors whose cases above are derived from the source.  They pin the ORACLE
+# only (tests/test_features_golden.py): the device is held to the oracle on these extractors by the cases above and by the
+# randomised configs of tests/test_features_gpu.py.
+ORACLE_ONLY_CASES = []
+
+
+def oracle_case(name, ref, features, events, request, expected):
+    ORACLE_ONLY_CASES.append(dict(name=name, ref=ref, features=features, events=events, request=request, expected=expected,
+                                  model_features=[f["name"] for f in features]))
+
+
+_color = dict(name="color", type="string", scope="item", source="metadata.color", values=["red", "green", "blue"])
+oracle_case("string_item_onehot_default", "T/feature/StringFeatureTest.scala:101-108", [_color],
+            [item_event("p1", [("color", "green")])], ranking(["p1"]), {"color": [[0.0, 1.0, 0.0]]})
+oracle_case("string_from_ranking_field", "T/feature/StringFeatureTest.scala:110-125",
+            [dict(_color, source="ranking.color")], [], ranking(["p1"], [("color", "red")]), {"color": [[1.0, 0.0, 0.0]]})
+_click = dict(interaction("p1", "p0"), fields=[("country", "EU")])
+oracle_case("string_session_scope", "T/feature/StringFeatureTest.scala:127-144",
+            [dict(name="country", type="string", scope="session", source="interaction:click.country", values=["US", "EU"])],
+            [_click], ranking(["p1"]), {"country": [[0.0, 1.0]]})
+oracle_case("string_onehot_explicit", "T/feature/StringFeatureTest.scala:146-164",
+            [dict(name="country", type="string", scope="session", source="interaction:click.country", values=["us", "eu"],
+                  encode="onehot")],
+            [dict(interaction("p1", "p0"), fields=[("country", "eu")])], ranking(["p1"]), {"country": [[0.0, 1.0]]})
+oracle_case("string_override_from_rank_item", "T/feature/StringFeatureTest.scala:166-172", [_color], [],
+            ranking(["p1"], item_fields={"p1": [("color", "red")]}), {"color": [[1.0, 0.0, 0.0]]})
+_pop = dict(name="popularity", type="number", scope="item", source="metadata.popularity")
+oracle_case("number_item", "T/feature/NumberFeatureTest.scala:92-99", [_pop],
+            [item_event("p1", [("popularity", 100)])], ranking(["p1"]), {"popularity": [[100.0]]})
+oracle_case("number_override_from_rank_item", "T/feature/NumberFeatureTest.scala:101-109", [_pop], [],
+            ranking(["p1"], item_fields={"p1": [("popularity", 100)]}), {"popularity": [[100.0]]})
+oracle_case("number_ranking_scope", "T/feature/NumberFeatureTest.scala:111-126",
+            [dict(name="weather_temp", type="number", scope="ranking", source="ranking.temp")], [],
+            ranking(["p1"], [("temp", 10)]), {"weather_temp": [[10.0]]})
+
 # ClickthroughQuery dense layout: T/flow/ClickthroughQueryTest.scala:152-159
 LAYOUT_FEATURES = [
     dict(name="price", type="number", scope="item", source="metadata.price"),

@@ -12,7 +12,7 @@ def _same(a, b):
     return (a != a and b != b) or a == b
 
 
-@pytest.mark.parametrize("case", G.CASES, ids=[c["name"] for c in G.CASES])
+@pytest.mark.parametrize("case", G.CASES + G.ORACLE_ONLY_CASES, ids=[c["name"] for c in G.CASES + G.ORACLE_ONLY_CASES])
 def test_reference_golden_vector(case):
     mapping = fo.FeatureMapping(case["features"], case["model_features"])
     state = fo.FeatureValueFlow(mapping, always_refresh=True).process(case["events"])
