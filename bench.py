@@ -951,6 +951,9 @@ def measure(w, args, rank, world, dist, barrier, full=True):
                 res["roofline_note"] = f"walk statistics unavailable: {type(ex).__name__}: {ex}"[:200]
         if walk is not None:
             res["roofline"] = walk
+            for k in res["kernels"]:  # the per-kernel table names the same limiter as the roofline block
+                if k["kernel"] == walk.get("kernel") and walk.get("bound"):
+                    k["bound"] = walk["bound"]
         else:
             res["roofline"] = {"bound": dom.get("bound"), "kernel": dom["kernel"], "kernel_ms": dom["ms_per_step"],
                                "achieved": dom.get("achieved_gbs"), "peak": _peaks()[0], "unit": "GB/s", "frac": dom.get("frac_hbm"),
