@@ -14,6 +14,11 @@
 // and is what tests/test_request_codec_cpu.py compares this file with, array for array.
 #include "request_codec.h"
 
+#include <atomic>
+#include <exception>
+#include <mutex>
+#include <thread>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -492,6 +497,7 @@ struct ReqFeature {
   double docs = 0;
   std::unordered_map<std::string, double> termfreq;
   int s_f64 = -1, s_u64 = -1, s_item = -1, s_vec = -1, s_tok = -1, vec_off = 0, vec_dim = 0, dim = 1;
+  int item_kind = 0;  // what the per-item loop reads for this feature: 0 nothing, 1 relevancy, 2 number override, 3 string override
 };
 
 void split_field(const std::string &s, std::string &ev, std::string &fld) {
@@ -547,6 +553,8 @@ std::vector<ReqFeature> build_features(const Schema &S) {
       if (S.in_req_vec[k].feature == name) { f.s_vec = (int)k; f.vec_off = S.in_req_vec[k].offset; f.vec_dim = S.in_req_vec[k].dim; }
     auto c = S.col_of.find(name);
     if (c != S.col_of.end()) f.dim = c->second.second;
+    if (f.s_item >= 0)
+      f.item_kind = f.type == "relevancy" ? 1 : (f.type == "number" && f.scope != "ranking") ? 2 : (f.type == "string" && f.src_event != "ranking") ? 3 : 0;
     plan.push_back(std::move(f));
   }
   return plan;
@@ -618,11 +626,93 @@ std::shared_ptr<const RequestPlan> make_request_plan(const Schema &S) {
   return p;
 }
 
+// Element boundaries of a top-level JSON array: [begin, end) of every element, found by nesting depth outside strings.
+// Only a structural scan — no token is validated; returns false on anything it does not recognise (the caller then
+// walks the body sequentially, which also produces the error the reference's parser would).
+static bool split_top_level_array(const uint8_t *p, const uint8_t *e, std::vector<std::pair<const uint8_t *, const uint8_t *>> &out,
+                                  const uint8_t *&after) {
+  auto ws = [&] { while (p < e && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++; };
+  ws();
+  if (p >= e || *p != '[') return false;
+  p++;
+  ws();
+  if (p < e && *p == ']') { after = p + 1; return true; }
+  for (;;) {
+    ws();
+    const uint8_t *b = p;
+    int depth = 0;
+    for (;;) {
+      if (p >= e) return false;
+      const uint8_t ch = *p;
+      if (ch == '"') {
+        p++;
+        while (p < e && *p != '"') p += (*p == '\\' && p + 1 < e) ? 2 : 1;
+        if (p >= e) return false;
+        p++;
+      } else if (ch == '{' || ch == '[') { depth++; p++; }
+      else if (ch == '}' || ch == ']') {
+        if (depth == 0) { if (ch == '}') return false; break; }  // the array's own ']'
+        depth--; p++;
+      } else if (ch == ',' && depth == 0) break;
+      else p++;
+    }
+    const uint8_t *t = p;
+    while (t > b && (t[-1] == ' ' || t[-1] == '\n' || t[-1] == '\t' || t[-1] == '\r')) t--;
+    if (t == b) return false;  // empty element: let the sequential parser say what is wrong
+    out.emplace_back(b, t);
+    if (*p == ',') { p++; continue; }
+    after = p + 1;  // past ']'
+    return true;
+  }
+}
+
 void decode_requests(const Schema &S, const RequestPlan &rp, const char *json, size_t len, PackedRequests &P) {
   Cur c{(const uint8_t *)json, (const uint8_t *)json + len};
   std::vector<Event> events;
-  if (c.peek() == '[') c.array([&] { events.push_back(decode_event(c)); });
-  else events.push_back(decode_event(c));
+  bool parsed = false;
+  // A large batch (an array of events) is parsed by several threads: the elements are independent once their boundaries
+  // are known.  Anything unusual — a scan that does not end cleanly, an element that fails or is not consumed whole —
+  // drops back to the sequential walk below, so accepted bodies decode to the same batch and rejected ones get the same
+  // error either way.
+  const char *env_threads = getenv("MR_DECODE_THREADS");  // 1 = always sequential
+  const int max_threads = env_threads ? std::max(1, atoi(env_threads)) : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  if (max_threads > 1 && len >= (size_t)(256 << 10) && c.peek() == '[') {
+    std::vector<std::pair<const uint8_t *, const uint8_t *>> el;
+    const uint8_t *after = nullptr;
+    if (split_top_level_array(c.p, c.e, el, after) && el.size() >= 64) {
+      const size_t n = el.size();
+      const int nt = (int)std::min<size_t>((size_t)max_threads, n / 32);
+      events.resize(n);
+      std::atomic<size_t> next{0};
+      std::atomic<bool> failed{false};
+      auto work = [&] {
+        for (;;) {
+          const size_t i0 = next.fetch_add(16);
+          if (i0 >= n || failed.load(std::memory_order_relaxed)) return;
+          for (size_t i = i0; i < std::min(n, i0 + 16); i++) {
+            try {
+              Cur ci{el[i].first, el[i].second};
+              events[i] = decode_event(ci);
+              if (ci.peek() != '\0') { failed = true; return; }
+            } catch (...) {
+              failed = true;
+              return;
+            }
+          }
+        }
+      };
+      std::vector<std::thread> pool;
+      for (int t = 1; t < nt; t++) pool.emplace_back(work);
+      work();
+      for (auto &th : pool) th.join();
+      if (!failed) { c.p = after; parsed = true; }
+      else events.clear();
+    }
+  }
+  if (!parsed) {
+    if (c.peek() == '[') c.array([&] { events.push_back(decode_event(c)); });
+    else events.push_back(decode_event(c));
+  }
   if (c.peek() != '\0' || c.p != c.e) fail(MR_ERR_PARSE, "json: trailing characters after the request");  // circe's parser fails on them
   const std::vector<ReqFeature> &plan = rp.features;
   const int R = (int)events.size();
@@ -640,15 +730,27 @@ void decode_requests(const Schema &S, const RequestPlan &rp, const char *json, s
   P.req_u64.assign((size_t)std::max(R, 1) * std::max<size_t>(nru, 1), 0);
   P.req_vec.assign((size_t)std::max(R, 1) * std::max(S.vec_stride, 1), 0.f);
   P.req_vp.assign((size_t)std::max(R, 1) * std::max<size_t>(nrv, 1), 0);
-  P.item_f64.assign((size_t)std::max(N, 1) * std::max<size_t>(nif, 1), kNaN);
+  // the per-item override matrix is N x nif doubles (48 MB for 200 000 items x 30 features): only built when some item of
+  // the batch carries fields at all — otherwise mr_rank_batch.item_f64 is NULL anyway
+  bool any_item_fields = false;
+  for (int r = 0; r < R && !any_item_fields; r++)
+    for (auto &it : events[r].items)
+      if (!it.fields.empty()) { any_item_fields = true; break; }
+  if (any_item_fields || nif == 0) P.item_f64.assign((size_t)std::max(N, 1) * std::max<size_t>(nif, 1), kNaN);
   P.tok_off.assign(1, 0);
-  P.item_ids.reserve(N);
-  std::vector<std::vector<std::pair<uint64_t, double>>> tok((size_t)std::max<size_t>(ntk, 1));
-  bool any_item_f64 = false;
-  for (int r = 0; r < R; r++) {
-    const Event &q = events[r];
-    P.request_ids.push_back(q.id);
-    P.timestamps.push_back(q.ts);
+  P.item_ids.resize(N);
+  P.request_ids.resize(R);
+  P.timestamps.resize(R);
+  // per request and token slot: the (hash, weight) list; concatenated in request order once every request is packed
+  using TokList = std::vector<std::pair<uint64_t, double>>;
+  std::vector<std::vector<TokList>> req_tok(ntk ? (size_t)R : 0);
+  std::atomic<bool> any_item_f64{false};
+  // One request's slice of every output array (disjoint from every other request's, so requests pack in parallel).
+  auto pack_request = [&](int r) {
+    Event &q = events[r];
+    std::vector<TokList> tok((size_t)std::max<size_t>(ntk, 1));
+    P.request_ids[r] = q.id;
+    P.timestamps[r] = q.ts;
     if (q.has_user) P.users[r] = hash64(q.user.data(), q.user.size());
     if (q.has_session) P.sessions[r] = hash64(q.session.data(), q.session.size());
     auto last = [&](const std::string &n) -> const FieldVal * {  // RankingEvent.fieldsMap: last duplicate wins
@@ -660,7 +762,6 @@ void decode_requests(const Schema &S, const RequestPlan &rp, const char *json, s
       for (auto &f : q.fields) if (f.name == n) return &f.v;
       return nullptr;
     };
-    for (auto &t : tok) t.clear();
     for (auto &f : plan) {
       if ((f.type == "number" || f.type == "word_count") && f.scope == "ranking" && f.s_f64 >= 0) {
         const FieldVal *v = last(f.src_field);
@@ -712,25 +813,22 @@ void decode_requests(const Schema &S, const RequestPlan &rp, const char *json, s
         }
       }
     }
-    for (size_t s = 0; s < ntk; s++) {
-      for (auto &hw : tok[s]) { P.tok_hash.push_back(hw.first); P.tok_w.push_back(hw.second); }
-      P.tok_off.push_back((int32_t)P.tok_hash.size());
-    }
+    if (ntk) req_tok[r] = std::move(tok);
     for (size_t j = 0; j < q.items.size(); j++) {
-      const Item &it = q.items[j];
+      Item &it = q.items[j];
       const size_t i = (size_t)P.offsets[r] + j;
       P.ids[i] = hash64(it.id.data(), it.id.size());
-      P.item_ids.push_back(it.id);
+      if (it.fields.empty()) { P.item_ids[i] = std::move(it.id); continue; }  // nothing to override with
       for (auto &f : plan) {
-        if (f.s_item < 0) continue;
+        if (f.item_kind == 0) continue;
         double *dst = &P.item_f64[i * nif + f.s_item];
-        if (f.type == "relevancy") {
+        if (f.item_kind == 1) {
           for (auto &fl : it.fields)
             if (fl.name == "relevancy") { if (fl.v.is_num()) { *dst = fl.v.d; any_item_f64 = true; } break; }  // the FIRST one decides
-        } else if (f.type == "number" && f.scope != "ranking") {
+        } else if (f.item_kind == 2) {
           for (auto &fl : it.fields)
             if (fl.name == f.src_field && fl.v.is_num()) { *dst = fl.v.d; any_item_f64 = true; break; }
-        } else if (f.type == "string" && f.src_event != "ranking") {
+        } else if (f.item_kind == 3) {
           for (auto &fl : it.fields)
             if (fl.name == f.src_field && (fl.v.is_str() || fl.v.is_strlist())) {
               std::vector<std::string> vals = fl.v.is_str() ? std::vector<std::string>{fl.v.s} : fl.v.sl;
@@ -740,10 +838,45 @@ void decode_requests(const Schema &S, const RequestPlan &rp, const char *json, s
             }
         }
       }
+      P.item_ids[i] = std::move(it.id);
     }
+  };
+  const int pack_threads = (max_threads > 1 && R >= 64 && N >= 4096) ? (int)std::min<size_t>((size_t)max_threads, (size_t)R / 16) : 1;
+  if (pack_threads <= 1) {
+    for (int r = 0; r < R; r++) pack_request(r);
+  } else {
+    // a request the sequential walk would have failed on FIRST decides the error: keep the failure of the lowest index
+    std::atomic<int> next{0};
+    std::mutex err_mu;
+    int err_at = R;
+    std::exception_ptr err;
+    auto work = [&] {
+      for (;;) {
+        const int r0 = next.fetch_add(8);
+        if (r0 >= R) return;
+        for (int r = r0; r < std::min(R, r0 + 8); r++) {
+          try {
+            pack_request(r);
+          } catch (...) {
+            std::lock_guard<std::mutex> g(err_mu);
+            if (r < err_at) { err_at = r; err = std::current_exception(); }
+          }
+        }
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < pack_threads; t++) pool.emplace_back(work);
+    work();
+    for (auto &th : pool) th.join();
+    if (err) std::rethrow_exception(err);
   }
+  for (int r = 0; r < R && ntk; r++)
+    for (size_t sl = 0; sl < ntk; sl++) {
+      for (auto &hw : req_tok[r][sl]) { P.tok_hash.push_back(hw.first); P.tok_w.push_back(hw.second); }
+      P.tok_off.push_back((int32_t)P.tok_hash.size());
+    }
   if (ntk) { P.tok_hash.push_back(0); P.tok_w.push_back(0.0); }
-  P.has_item_f64 = nif > 0 && any_item_f64;
+  P.has_item_f64 = nif > 0 && any_item_f64.load();
   mr_rank_batch &b = P.batch;
   b.n_requests = R;
   b.item_offsets = P.offsets.data();

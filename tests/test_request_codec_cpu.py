@@ -291,3 +291,85 @@ def test_native_decoder_is_as_strict_as_jawn_and_takes_the_last_duplicate():
     for good in [ok + "  \n\t ", ok.replace('{"id": "p"}', '{"id": "p", "relevancy": -0.5e+2}'), ok.replace('"timestamp": 1', '"timestamp": 0')]:
         F.DecodedRequests(fm, good).free()
     fm.free()
+
+
+def _decode_all(fm, body, threads, monkeypatch):
+    monkeypatch.setenv("MR_DECODE_THREADS", str(threads))
+    dec = F.DecodedRequests(fm, body)
+    out = dec.arrays()
+    out["_ids"] = [dec.item_id(i) for i in range(dec.total_items)]
+    out["_ts"] = [dec.timestamp(r) for r in range(dec.n_requests)]
+    dec.free()
+    return out
+
+
+def test_large_batches_decode_the_same_on_several_threads(monkeypatch):
+    """A body of hundreds of events is split at its top-level element boundaries and parsed / packed by several threads
+    (request_codec.cpp decode_requests); the batch must be the one the sequential walk builds, array for array — with
+    brackets, commas and escaped quotes inside strings, nested arrays, duplicate fields, tokens and embeddings in play."""
+    rng = np.random.Generator(np.random.PCG64(77))
+    fm = F.FeatureMapping(None, FEATS, MODEL)
+    events = _random_body(rng, 900)
+    for k, tricky in enumerate(['a "quoted, [bracket]" \\ back', "]}],[{", 'x\\"y,z', "{\"k\": [1, 2]}"]):
+        events[50 * k + 3]["fields"].append(dict(name="query", value=tricky))
+        events[50 * k + 4]["items"][0]["id"] = tricky
+    for indent, ascii_ in ((None, True), (1, False)):
+        body = json.dumps(events, ensure_ascii=ascii_, indent=indent)
+        assert len(body) > 256 << 10
+        one = _decode_all(fm, body, 1, monkeypatch)
+        for threads in (2, 8):
+            many = _decode_all(fm, body, threads, monkeypatch)
+            assert many["n_requests"] == one["n_requests"] == 900 and many["total_items"] == one["total_items"]
+            for key in ["offsets", "ids", "users", "sessions", "req_f64", "req_u64", "req_vec", "req_vp", "item_f64", "tok_off",
+                        "tok_hash", "tok_w"]:
+                _same(many[key], one[key], key)
+            assert many["_ids"] == one["_ids"] and many["_ts"] == one["_ts"]
+    # no item carries fields: the override matrix is not built at all (mr_rank_batch.item_f64 == NULL) on either path
+    bare = [dict(id=f"r{r}", timestamp=1710716400123, items=[dict(id=f"i{r}_{j}") for j in range(40)]) for r in range(800)]
+    body = json.dumps(bare)
+    assert len(body) > 256 << 10
+    for threads in (1, 8):
+        got = _decode_all(fm, body, threads, monkeypatch)
+        assert got["item_f64"] is None and got["total_items"] == 32000
+    fm.free()
+
+
+def test_large_batches_fail_like_the_sequential_walk(monkeypatch):
+    """What the sequential decoder rejects, the threaded one rejects with the same status and message: it drops back to
+    the sequential walk on anything unusual, and a request-level error is the one of the FIRST offending request."""
+    rng = np.random.Generator(np.random.PCG64(78))
+    fm = F.FeatureMapping(None, FEATS, MODEL)
+    events = _random_body(rng, 700)
+    good = json.dumps(events)
+    assert len(good) > 256 << 10
+
+    def outcome(body, threads):
+        monkeypatch.setenv("MR_DECODE_THREADS", str(threads))
+        try:
+            F.DecodedRequests(fm, body).free()
+            return None
+        except _capi.MrError as ex:
+            return ex.status, ex.message
+
+    cut = good.index('{"id": "r350"')
+    bad_bodies = [
+        good[:cut] + '{"id": "r350", "items": []},' + good[cut:],                    # an event the decoder rejects, mid-array
+        good[:cut] + '{"id": "r350" "items": [{"id": "x"}], "timestamp": 1},' + good[cut:],   # malformed JSON inside one element
+        good[:-1] + ', 17]',                                                            # an element that is not an object
+        good + ' trailing',                                                             # bytes after the array
+        good[:-1],                                                                      # unterminated array
+        good[:cut] + ',' + good[cut:],                                                  # empty element
+    ]
+    import copy
+    wrong = copy.deepcopy(events)
+    for r, emb in ((10, [1.0, 2.0]), (600, [1.0])):   # wrong embedding dims in request 10 AND in request 600: the first decides
+        wrong[r]["embeddings"] = {"sim": emb}
+        wrong[r]["fields"].append(dict(name="query", value="red shoes"))
+    bad_bodies.append(json.dumps(wrong))
+    for body in bad_bodies:
+        want = outcome(body, 1)
+        assert want is not None, body[:80]
+        for threads in (2, 8):
+            assert outcome(body, threads) == want
+    assert outcome(good, 8) is None
+    fm.free()
