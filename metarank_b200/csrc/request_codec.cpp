@@ -17,6 +17,7 @@
 #include <atomic>
 #include <exception>
 #include <mutex>
+#include <system_error>
 #include <thread>
 
 #include <algorithm>
@@ -666,6 +667,18 @@ static bool split_top_level_array(const uint8_t *p, const uint8_t *e, std::vecto
   }
 }
 
+// `work` on nt threads (the caller's included).  A thread that cannot be started is simply not there: `work` pulls from
+// a shared counter, so the threads that do run finish the job.
+template <class F> static void run_on_threads(int nt, F &&work) {
+  std::vector<std::thread> pool;
+  try {
+    for (int t = 1; t < nt; t++) pool.emplace_back(work);
+  } catch (const std::system_error &) {
+  }
+  work();
+  for (auto &th : pool) th.join();
+}
+
 void decode_requests(const Schema &S, const RequestPlan &rp, const char *json, size_t len, PackedRequests &P) {
   Cur c{(const uint8_t *)json, (const uint8_t *)json + len};
   std::vector<Event> events;
@@ -701,10 +714,7 @@ void decode_requests(const Schema &S, const RequestPlan &rp, const char *json, s
           }
         }
       };
-      std::vector<std::thread> pool;
-      for (int t = 1; t < nt; t++) pool.emplace_back(work);
-      work();
-      for (auto &th : pool) th.join();
+      run_on_threads(nt, work);
       if (!failed) { c.p = after; parsed = true; }
       else events.clear();
     }
@@ -864,10 +874,7 @@ void decode_requests(const Schema &S, const RequestPlan &rp, const char *json, s
         }
       }
     };
-    std::vector<std::thread> pool;
-    for (int t = 1; t < pack_threads; t++) pool.emplace_back(work);
-    work();
-    for (auto &th : pool) th.join();
+    run_on_threads(pack_threads, work);
     if (err) std::rethrow_exception(err);
   }
   for (int r = 0; r < R && ntk; r++)
