@@ -12,12 +12,15 @@ Configs are BASELINE.json's (SURVEY.md §8 shorthand); the default and headline 
 One *step* = one pass of the hot path (lookup -> assemble -> score -> order) over one batch.
 
   value        whole-job items/s with inputs resident in HBM (device-timed with CUDA events, max over ranks)
-  e2e          the same metric through the C ABI with HOST buffers (H2D/D2H inside the timer)
+  e2e          the same metric through the C ABI with HOST buffers (H2D/D2H inside the timer), calls issued from two
+               worker threads the way a server issues them (`one_call_at_a_time`: a single thread)
   roofline     dominant kernel against the pipe that bounds it.  The GBDT scorer serves the ensemble from
-               shared memory (one TMA stage per chunk), so its bound is the SHARED-MEMORY pipe, not HBM:
-               achieved = wavefronts the walk needs (counted in-run by mr_model_walk_stats) x 128 B / kernel time,
-               peak = SMs x 128 B/clk x SM clock.  SURVEY.md 8(d)'s algorithmic-bytes figure is kept under
-               `algorithmic_gbs` (it exceeds the HBM peak by construction and is not a fraction of anything).
+               shared memory (one TMA stage per chunk), so its bound is not HBM but the busier of two on-chip pipes:
+               the SHARED-MEMORY crossbar — wavefronts the walk needs (counted in-run by mr_model_walk_stats) x 128 B /
+               kernel time against SMs x 128 B/clk x SM clock — or the ISSUE slots — warp instructions the walk needs
+               (SASS counts x the same statistics) against SMs x 4 schedulers x SM clock.  `frac` is the larger one, both
+               are in the block, next to the ncu values of one capture.  SURVEY.md 8(d)'s algorithmic-bytes figure is
+               kept under `algorithmic_gbs` (it exceeds the HBM peak by construction and is not a fraction of anything).
   kernels      every kernel of the step, device time from the library's own per-launch events
                (mr_profile_begin/end), with algorithmic HBM bytes and the HBM fraction for the HBM-bound ones
   cpu_baseline / --impl reference: the CPU oracle port (the reference's own scorer is a JNI jar that is not in
